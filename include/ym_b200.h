@@ -1,0 +1,98 @@
+/* libym_b200 — C ABI of the B200 (sm_100a) detection-forward hot path of YOLO-Master.
+ *
+ * The reference has no FFI on this path: every operator is an ATen call behind the `ultralytics.nn.modules`
+ * Python classes.  This header is therefore the boundary a maintainer would bind with
+ * ctypes: each entry point names the reference operator(s) it replaces (file:line under
+ * /root/reference/ultralytics).  Conventions:
+ *   - every function returns 0 on success, non-zero on error; `ym_last_error()` gives the thread-local message;
+ *   - all pointers are DEVICE pointers unless the name says `host`; no torch types cross the boundary;
+ *   - activations are NHWC fp16; `ld*` = row pitch in elements (lets a conv read/write a channel slice of a
+ *     wider concat buffer in place); `stream` is a cudaStream_t passed as void*;
+ *   - kernels never synchronise, allocate, or keep global mutable state (re-entrant, graph-capturable).
+ */
+#ifndef YM_B200_H
+#define YM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* ym_last_error(void);
+int ym_version(void);
+int ym_device_info(int* sm_major, int* sm_minor, int* sm_count, long long* l2_bytes);
+
+/* Conv (k x k, stride s, pad p, groups=1) + folded-BN bias + optional SiLU (+ residual add), implicit GEMM.
+ * Replaces Conv.forward / forward_fuse  nn/modules/conv.py:69-89 (+ fuse_conv_and_bn utils/torch_utils.py:315-349),
+ * Bottleneck's `x + cv2(cv1(x))` add  nn/modules/block.py:484-486, and bare nn.Conv2d(+bias) heads  nn/modules/head.py:104-119.
+ * w: packed fp16 [Cout][Kpad], k index = (ky*KW + kx)*Cin + ci, Kpad = ceil32(KH*KW*Cin) zero padded.
+ * out: fp16 (out_f32=0) or fp32 (out_f32=1) [B*Ho*Wo][ldo]; res: optional fp16 residual (same rows), act: 0 none, 1 SiLU. */
+int ym_conv2d_nhwc(const void* x, int ldx, int B, int H, int W, int Cin, const void* w, int Kpad, const float* bias,
+                   int Cout, int KH, int KW, int stride, int pad, void* out, int ldo, int out_f32, const void* res,
+                   int ldr, int act, void* stream);
+
+/* model.0 stem: Conv(Cin<=4 -> Cout in {16,32,64}, k3 s2 p1) + bias + SiLU reading the NCHW image (conv.py:69-89).
+ * in_dtype: 0 fp16, 1 fp32, 2 uint8 (x/255, engine/predictor.py:175).  wgt fp32 [Cin*9][Cout], out NHWC fp16. */
+int ym_stem_conv_nchw(const void* img, int in_dtype, int B, int Cin, int H, int W, const float* wgt, const float* bias,
+                      int Cout, void* out, int ldo, void* stream);
+
+/* Depthwise k x k (k in 3/5/7/9, stride 1, pad k/2) + bias (+SiLU) (+add).  Replaces DWConv conv.py:185-199,
+ * AAttn.pe block.py:1688,1731 and Attention.pe block.py:1311,1331 (reads V in place from the head-interleaved qkv:
+ * source channel of c = (c/grp_w)*grp_stride + grp_off + c%grp_w).  w: fp16 tap-major [k*k][C]. */
+int ym_dwconv_nhwc(const void* x, int ldx, int grp_w, int grp_stride, int grp_off, const void* w, const float* bias,
+                   int B, int H, int W, int C, int ksize, int act, const void* add, int ldadd, void* out, int ldo,
+                   void* stream);
+
+/* SPPF pooling: slots 1..3 of the [.., 4C] concat buffer = MaxPool(k) chained 1..3 times of slot 0 (block.py:237-242). */
+int ym_sppf_pool_nhwc(void* buf, int ld, int B, int H, int W, int C, int k, void* stream);
+
+/* nn.Upsample(nearest, up) + Concat(dim=1) of two tensors (conv.py:616-640); up=1 is a plain concat. */
+int ym_concat2_nhwc(const void* a, int lda, int Ca, int up, const void* b, int ldb, int Cb, void* out, int ldo, int B,
+                    int H, int W, void* stream);
+
+/* Fused multi-head attention O = softmax((Q*scale)^T K) V over token rows of the qkv conv output.
+ * Replaces AAttn.forward block.py:1708-1722 (batch = B*area, N = H*W/area) and Attention.forward block.py:1324-1331.
+ * d_qk must be 32; d_v 32 or 64.  Output channel = head*d_v + d. */
+int ym_attention_fwd(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
+                     int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream);
+
+/* EfficientSpatialRouter.forward + BaseRouter._process_logits (eval)  moe/routers.py:283-304, :185-265.
+ * w1: fp32 [9][C][Cr] (tap-major), scale1/shift1: folded BN1 [Cr]; w2: fp32 [E][Cr], scale2/shift2: folded BN2 [E].
+ * Writes idx int32 [B,topk] (descending prob), w fp32 [B,topk] (renormalised), probs fp32 [B,E] (nullable). */
+long long ym_router_scratch_floats(int B, int H, int W, int C, int Cr, int pool);
+int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* w1, int Cr,
+                   const float* scale1, const float* shift1, const float* w2, const float* scale2, const float* shift2,
+                   int E, int topk, float* scratch, int* idx_out, float* w_out, float* probs_out, void* stream);
+
+/* Routed expert GEMM, one problem per (image, k): replaces the per-expert Python loop + x[batch_idx] gather of
+ * OptimizedMOEImproved.forward moe/modules.py:1128-1142 for SimpleExpert's two 1x1 convs (moe/experts.py:79-85).
+ * Problem p: expert e = route_idx[p]; A = a + (p/a_div)*HW*lda [HW x K]; out + p*HW*ldo [HW x N] fp16.
+ * a_scale/a_shift (nullable, [P][K]): A := SiLU(A*scale + shift) (GroupNorm+SiLU of the hidden, fused on load).
+ * stats (nullable, [P][groups][2], zeroed here): per-(problem, group) sum / sum-of-squares of the stored output. */
+int ym_moe_expert_gemm(const void* a, int lda, int a_div, int P, int HW, int K, const void* w, int Kpad,
+                       long long w_expert_stride, const int* route_idx, int N, void* out, int ldo, const float* a_scale,
+                       const float* a_shift, float* stats, int groups, void* stream);
+
+/* GroupNorm statistics -> per-(problem, channel) affine: scale = rw*rstd*gamma[e], shift = rw*(beta[e] - mean*rstd*gamma[e])
+ * (nn.GroupNorm inside SimpleExpert, experts.py:81,84; rw = routing weight folds modules.py:1139-1142 into GN2). */
+int ym_gn_finalize(const float* stats, int P, int groups, int C, float count, float eps, const float* gamma,
+                   const float* beta, const int* route_idx, const float* route_w, float* scale, float* shift, void* stream);
+
+/* out = [x +] SiLU(BN(shared 1x1(x))) + sum_j (o_j*o_scale_j + o_shift_j): shared expert + weighted expert sum in fp32
+ * + ABlockMoE residual (moe/modules.py:1085,1147-1157,1256-1258). */
+int ym_moe_combine(const void* x, int ldx, int B, int HW, int C, const void* ws, int Kpad, const float* bias_s,
+                   const void* o, int ldo_o, const float* o_scale, const float* o_shift, int topk, void* out, int ldo,
+                   int add_residual, void* stream);
+
+/* Detect post-processing.  box[l]: fp32 [B, h_l*w_l, 4] ltrb distances; cls[l]: fp32 [B, h_l*w_l, nc] logits.
+ * ym_detect_topk: Detect._inference + postprocess + get_topk_index (end2end)  head.py:173-258, tal.py:398-423.
+ *   out fp32 [B, k, 6] = (x1,y1,x2,y2,score,cls), k = min(max_det, A), score-descending; out_anchor int32 [B,k] nullable.
+ * ym_detect_dense: Detect._inference -> y fp32 [B, 4+nc, A] (xyxy!=0: corner boxes, else xywh)  head.py:173-194. */
+int ym_detect_topk(int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
+                   const float* strides, int B, int nc, int max_det, float* out, int* out_anchor, void* stream);
+int ym_detect_dense(int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
+                    const float* strides, int B, int nc, int xyxy, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YM_B200_H */

@@ -1,0 +1,424 @@
+"""CPU oracle for the YOLO-Master detection forward pass.  TEST INFRASTRUCTURE ONLY.
+
+This file is a plain-PyTorch fp32 *restatement* of the reference's forward pass
+(`/root/reference/ultralytics/nn/...`, cited per function as file:line).  It is
+a checker: only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline
+/ `--impl reference` legs may import it.  The product package never does.
+
+Parity pinning: `tests/golden/make_golden.py` imports the real reference from
+`/root/reference` in the build container, fills its parameters with the
+deterministic generator in `oracle/synth.py`, and stores reference outputs in
+`tests/golden/*.pt`; `tests/test_oracle_golden.py` checks this file against them.
+
+Design: purely functional.  A model is (layer spec list, flat state_dict with
+the reference's *unfused* key names, e.g. `model.4.m.0.0.mlp.experts.2.conv.0.weight`).
+No nn.Module classes, no code shared with the product package.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-3  # utils/torch_utils.py:552-562 rewrites eps on every nn.BatchNorm2d
+GN_EPS = 1e-5  # nn.GroupNorm default, untouched by initialize_weights
+
+
+# ----------------------------------------------------------------------------
+# YAML -> layer spec (restates nn/tasks.py:2022-2275 parse_model and
+# nn/mixture_registry.py:84-156 adapt_mixture_args for the modules on the path)
+# ----------------------------------------------------------------------------
+def make_divisible(x: float, divisor: int) -> int:
+    """utils/ops.py make_divisible."""
+    return int(math.ceil(x / divisor) * divisor)
+
+
+_BASE = {"Conv", "C2f", "C3k2", "SPPF", "C2PSA", "A2C2f", "DWConv", "C3", "Bottleneck"}
+_REPEAT = {"C2f", "C3k2", "C2PSA", "A2C2f", "C3"}
+_MIX_BASE = {"A2C2fMoE", "ES_MOE"}
+_MIX_REPEAT = {"A2C2fMoE"}
+
+
+def parse_spec(d: dict, ch: int = 3, scale: str | None = None) -> dict:
+    """Return {'layers': [{'i','f','type','args','n'}], 'save': [...], 'nc','reg_max','end2end'}."""
+    nc, scales, end2end = d.get("nc"), d.get("scales"), d.get("end2end")
+    reg_max = d.get("reg_max", 16)
+    depth, width, max_channels = d.get("depth_multiple", 1.0), d.get("width_multiple", 1.0), float("inf")
+    scale = scale or d.get("scale")
+    if scales:
+        if not scale:
+            scale = next(iter(scales.keys()))
+        depth, width, max_channels = scales[scale]
+    chs = [ch]
+    layers, save = [], []
+    legacy = True
+    for i, (f, n, m, args) in enumerate(d["backbone"] + d["head"]):
+        args = list(args)
+        for j, a in enumerate(args):
+            if isinstance(a, str):
+                if a == "nc":
+                    args[j] = nc
+                elif a == "None":
+                    args[j] = None
+        n = max(round(n * depth), 1) if n > 1 else n
+        if m in _BASE:
+            c1, c2 = chs[f], args[0]
+            if c2 != nc:
+                c2 = make_divisible(min(c2, max_channels) * width, 8)
+            args = [c1, c2, *args[1:]]
+            if m in _REPEAT:
+                args.insert(2, n)
+                n = 1
+            if m == "C3k2":
+                legacy = False
+                if scale and scale in "mlx":
+                    args[3] = True
+            if m == "A2C2f":
+                legacy = False
+                if scale and scale in "lx":
+                    args.extend((True, 1.2))
+        elif m in _MIX_BASE:
+            c1, c2 = chs[f], args[0]
+            if c2 != nc:
+                c2 = make_divisible(min(c2, max_channels) * width, 8)
+            args = [c1, c2, *args[1:]]
+            if m in _MIX_REPEAT:
+                args.insert(2, n)
+                n = 1
+            if m == "A2C2fMoE":
+                legacy = False
+        elif m == "Concat":
+            c2 = sum(chs[x] for x in f)
+        elif m == "Detect":
+            args = [args[0], reg_max, end2end, [chs[x] for x in f]]
+            c2 = None
+        else:  # nn.Upsample etc.
+            c2 = chs[f]
+        layers.append({"i": i, "f": f, "type": m, "args": args, "n": n, "legacy": legacy})
+        save.extend(x % i for x in ([f] if isinstance(f, int) else f) if x != -1)
+        if i == 0:
+            chs = []
+        chs.append(c2)
+    return {"layers": layers, "save": sorted(set(save)), "nc": nc, "reg_max": reg_max, "end2end": bool(end2end)}
+
+
+# ----------------------------------------------------------------------------
+# leaf ops
+# ----------------------------------------------------------------------------
+def _bn(sd, p, x):
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        False, 0.0, BN_EPS)
+
+
+def conv_block(sd, p, x, s=1, g=1, act=True, pad=None):
+    """`Conv.forward` nn/modules/conv.py:69-78: act(bn(conv(x))), autopad :30-36."""
+    w = sd[p + ".conv.weight"]
+    k = w.shape[-1]
+    pad = k // 2 if pad is None else pad
+    y = F.conv2d(x, w, sd.get(p + ".conv.bias"), s, pad, 1, g)
+    y = _bn(sd, p + ".bn", y)
+    return F.silu(y) if act else y
+
+
+def dwconv_block(sd, p, x, act=True):
+    """`DWConv` conv.py:185-199: groups = gcd(c1, c2)."""
+    w = sd[p + ".conv.weight"]
+    g = math.gcd(x.shape[1], w.shape[0])
+    return conv_block(sd, p, x, 1, g, act)
+
+
+def bottleneck(sd, p, x, shortcut=True, g=1):
+    """`Bottleneck.forward` block.py:484-486 (k=(3,3); c1==c2 inside C3k2/C3k)."""
+    y = conv_block(sd, p + ".cv2", conv_block(sd, p + ".cv1", x), 1, g)
+    add = shortcut and x.shape[1] == y.shape[1]
+    return x + y if add else y
+
+
+def c3k(sd, p, x, n=2, shortcut=True, g=1):
+    """`C3k`/`C3.forward` block.py:348-350,1114-1131."""
+    a = conv_block(sd, p + ".cv1", x)
+    for j in range(n):
+        a = bottleneck(sd, f"{p}.m.{j}", a, shortcut, g)
+    return conv_block(sd, p + ".cv3", torch.cat((a, conv_block(sd, p + ".cv2", x)), 1))
+
+
+def attention(sd, p, x, num_heads, attn_ratio=0.5):
+    """`Attention.forward` block.py:1313-1333."""
+    B, C, H, W = x.shape
+    N = H * W
+    head_dim = C // num_heads
+    key_dim = int(head_dim * attn_ratio)
+    scale = key_dim ** -0.5
+    qkv = conv_block(sd, p + ".qkv", x, act=False)
+    q, k, v = qkv.view(B, num_heads, key_dim * 2 + head_dim, N).split([key_dim, key_dim, head_dim], dim=2)
+    attn = (q * scale).transpose(-2, -1) @ k
+    attn = attn.softmax(dim=-1)
+    o = (v @ attn.transpose(-2, -1)).view(B, C, H, W) + conv_block(sd, p + ".pe", v.reshape(B, C, H, W), 1, C, False)
+    return conv_block(sd, p + ".proj", o, act=False)
+
+
+def psablock(sd, p, x, num_heads, shortcut=True):
+    """`PSABlock.forward` block.py:1372-1383."""
+    a = attention(sd, p + ".attn", x, num_heads)
+    x = x + a if shortcut else a
+    f = conv_block(sd, p + ".ffn.1", conv_block(sd, p + ".ffn.0", x), act=False)
+    return x + f if shortcut else f
+
+
+def aattn(sd, p, x, num_heads, area=1):
+    """`AAttn.forward` block.py:1696-1732 (q scaled before q^T k; pe on V; head-interleaved qkv)."""
+    B, C, H, W = x.shape
+    N = H * W
+    hd = C // num_heads
+    qkv = conv_block(sd, p + ".qkv", x, act=False).flatten(2).transpose(1, 2)
+    Bq = B
+    if area > 1:
+        qkv = qkv.reshape(B * area, N // area, C * 3)
+        Bq, N = qkv.shape[0], qkv.shape[1]
+    q, k, v = qkv.view(Bq, N, num_heads, hd * 3).permute(0, 2, 3, 1).split([hd, hd, hd], dim=2)
+    attn = (q * (hd ** -0.5)).transpose(-2, -1) @ k
+    attn = attn.softmax(dim=-1)
+    o = (v @ attn.transpose(-2, -1)).permute(0, 3, 1, 2)
+    v = v.permute(0, 3, 1, 2)
+    if area > 1:
+        o = o.reshape(B, N * area, C)
+        v = v.reshape(B, N * area, C)
+    o = o.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+    v = v.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+    o = o + conv_block(sd, p + ".pe", v, 1, C, False, pad=3)
+    return conv_block(sd, p + ".proj", o, act=False)
+
+
+def get_safe_groups(channels: int, desired: int = 8) -> int:
+    """nn/modules/utils.py:108-115."""
+    if channels <= 0:
+        return 1
+    g = min(desired, channels)
+    while channels % g != 0:
+        g -= 1
+    return max(1, g)
+
+
+def simple_expert(sd, p, x):
+    """`SimpleExpert` moe/experts.py:73-88: 1x1 -> GN -> SiLU -> 1x1 -> GN."""
+    w1, w2 = sd[p + ".conv.0.weight"], sd[p + ".conv.3.weight"]
+    h = F.conv2d(x, w1)
+    h = F.group_norm(h, get_safe_groups(w1.shape[0]), sd[p + ".conv.1.weight"], sd[p + ".conv.1.bias"], GN_EPS)
+    h = F.silu(h)
+    o = F.conv2d(h, w2)
+    return F.group_norm(o, get_safe_groups(w2.shape[0]), sd[p + ".conv.4.weight"], sd[p + ".conv.4.bias"], GN_EPS)
+
+
+def efficient_spatial_router(sd, p, x, top_k, pool_scale=4):
+    """`EfficientSpatialRouter.forward` moe/routers.py:283-304 + `_process_logits` :185-265 (eval).
+
+    Returns (weights fp32 [B,k], indices int64 [B,k], probs fp32 [B,E]).
+    """
+    B, C, H, W = x.shape
+    xin = F.avg_pool2d(x, pool_scale, pool_scale) if (H > pool_scale and W > pool_scale) else x
+    h = F.conv2d(xin, sd[p + ".router.0.weight"], None, 1, 1)
+    h = F.silu(_bn(sd, p + ".router.1", h))
+    o = _bn(sd, p + ".router.4", F.conv2d(h, sd[p + ".router.3.weight"]))
+    logits = o.float().mean(dim=[2, 3])
+    probs = F.softmax(logits.float(), dim=1)
+    vals, idx = torch.topk(probs, top_k, dim=1)
+    vals = vals / vals.sum(dim=1, keepdim=True).clamp_min(1e-6)
+    return vals, idx, probs
+
+
+def optimized_moe_improved(sd, p, x, num_experts, top_k):
+    """`OptimizedMOEImproved.forward` moe/modules.py:1069-1157 (eval; add_residual=False under ABlockMoE)."""
+    B = x.shape[0]
+    w, idx, _ = efficient_spatial_router(sd, p + ".routing", x, top_k)
+    shared = F.silu(_bn(sd, p + ".shared_expert.1", F.conv2d(x, sd[p + ".shared_expert.0.weight"])))
+    out = torch.zeros_like(shared, dtype=torch.float32)
+    for e in range(num_experts):
+        mask = idx == e
+        if mask.any():
+            bi, ki = torch.where(mask)
+            o = simple_expert(sd, f"{p}.experts.{e}", x[bi])
+            out.index_add_(0, bi, o.float() * w[bi, ki].view(-1, 1, 1, 1))
+    return (shared.float() + out).to(x.dtype)
+
+
+def ablock_moe(sd, p, x, num_heads, area, num_experts, top_k):
+    """`ABlockMoE.forward` moe/modules.py:1247-1260."""
+    x = x + aattn(sd, p + ".attn", x, num_heads, area)
+    return x + optimized_moe_improved(sd, p + ".mlp", x, num_experts, top_k)
+
+
+# ----------------------------------------------------------------------------
+# top-level layers
+# ----------------------------------------------------------------------------
+def layer_conv(sd, p, x, c1, c2, k=1, s=1, pad=None, g=1, d=1, act=True):
+    return conv_block(sd, p, x, s, g, act is True, pad)
+
+
+def layer_c3k2(sd, p, x, c1, c2, n=1, c3k_=False, e=0.5, attn=False, g=1, shortcut=True):
+    """`C3k2` block.py:1074-1108 on top of `C2f.forward` :313-317."""
+    c = int(c2 * e)
+    y = list(conv_block(sd, p + ".cv1", x).chunk(2, 1))
+    for j in range(n):
+        q = f"{p}.m.{j}"
+        if attn:
+            t = bottleneck(sd, q + ".0", y[-1], shortcut, g)
+            t = psablock(sd, q + ".1", t, max(c // 64, 1))
+        elif c3k_:
+            t = c3k(sd, q, y[-1], 2, shortcut, g)
+        else:
+            t = bottleneck(sd, q, y[-1], shortcut, g)
+        y.append(t)
+    return conv_block(sd, p + ".cv2", torch.cat(y, 1))
+
+
+def layer_c2f(sd, p, x, c1, c2, n=1, shortcut=False, g=1, e=0.5):
+    """`C2f.forward` block.py:313-317."""
+    y = list(conv_block(sd, p + ".cv1", x).chunk(2, 1))
+    for j in range(n):
+        y.append(bottleneck(sd, f"{p}.m.{j}", y[-1], shortcut, g))
+    return conv_block(sd, p + ".cv2", torch.cat(y, 1))
+
+
+def layer_sppf(sd, p, x, c1, c2, k=5, n=3, shortcut=False):
+    """`SPPF.forward` block.py:237-242 (cv1 has act=False)."""
+    y = [conv_block(sd, p + ".cv1", x, act=False)]
+    for _ in range(n):
+        y.append(F.max_pool2d(y[-1], k, 1, k // 2))
+    o = conv_block(sd, p + ".cv2", torch.cat(y, 1))
+    return o + x if (shortcut and c1 == c2) else o
+
+
+def layer_c2psa(sd, p, x, c1, c2, n=1, e=0.5):
+    """`C2PSA.forward` block.py:1482-1493."""
+    c = int(c1 * e)
+    a, b = conv_block(sd, p + ".cv1", x).split((c, c), 1)
+    for j in range(n):
+        b = psablock(sd, f"{p}.m.{j}", b, c // 64)
+    return conv_block(sd, p + ".cv2", torch.cat((a, b), 1))
+
+
+def layer_a2c2f_moe(sd, p, x, c1, c2, n=1, a2=True, area=1, residual=False, mlp_ratio=2.0, e=0.5, g=1,
+                    shortcut=True, num_experts=4, top_k=2, expert_type="simple"):
+    """`A2C2fMoE` moe/modules.py:1268-1297 over `A2C2f.forward` block.py:1865-1879."""
+    c_ = int(c2 * e)
+    y = [conv_block(sd, p + ".cv1", x)]
+    for j in range(n):
+        t = y[-1]
+        if a2:
+            for r in range(2):
+                t = ablock_moe(sd, f"{p}.m.{j}.{r}", t, c_ // 32, area, num_experts, top_k)
+        else:
+            t = c3k(sd, f"{p}.m.{j}", t, 2, shortcut, g)
+        y.append(t)
+    o = conv_block(sd, p + ".cv2", torch.cat(y, 1))
+    if a2 and residual:
+        return x + sd[p + ".gamma"].view(1, -1, 1, 1) * o
+    return o
+
+
+def make_anchors(shapes, strides, offset=0.5):
+    """utils/tal.py:398-411."""
+    pts, st = [], []
+    for (h, w), s in zip(shapes, strides):
+        sx = torch.arange(w, dtype=torch.float32) + offset
+        sy = torch.arange(h, dtype=torch.float32) + offset
+        sy, sx = torch.meshgrid(sy, sx, indexing="ij")
+        pts.append(torch.stack((sx, sy), -1).view(-1, 2))
+        st.append(torch.full((h * w, 1), float(s)))
+    return torch.cat(pts), torch.cat(st)
+
+
+def detect_head_raw(sd, p, feats, nc, reg_max, end2end, legacy=False):
+    """`Detect.forward_head` head.py:146-155 on the one2one (end2end) or one2many towers."""
+    bs = feats[0].shape[0]
+    bp = p + (".one2one_cv2" if end2end else ".cv2")
+    cp = p + (".one2one_cv3" if end2end else ".cv3")
+    boxes, scores = [], []
+    for i, x in enumerate(feats):
+        b = conv_block(sd, f"{bp}.{i}.1", conv_block(sd, f"{bp}.{i}.0", x))
+        b = F.conv2d(b, sd[f"{bp}.{i}.2.weight"], sd[f"{bp}.{i}.2.bias"])
+        if legacy:
+            c = conv_block(sd, f"{cp}.{i}.1", conv_block(sd, f"{cp}.{i}.0", x))
+        else:
+            c = conv_block(sd, f"{cp}.{i}.0.1", dwconv_block(sd, f"{cp}.{i}.0.0", x))
+            c = conv_block(sd, f"{cp}.{i}.1.1", dwconv_block(sd, f"{cp}.{i}.1.0", c))
+        c = F.conv2d(c, sd[f"{cp}.{i}.2.weight"], sd[f"{cp}.{i}.2.bias"])
+        boxes.append(b.view(bs, 4 * reg_max, -1))
+        scores.append(c.view(bs, nc, -1))
+    return torch.cat(boxes, -1), torch.cat(scores, -1)
+
+
+def detect_decode(boxes, scores, shapes, strides, end2end, reg_max=1):
+    """`Detect._inference` head.py:173-194, `decode_bboxes` :210-217, `dist2bbox` tal.py:414-423.
+
+    Returns y (B, 4+nc, A): xyxy (end2end) or xywh boxes in pixels + sigmoid scores.
+    """
+    assert reg_max == 1, "DFL (reg_max>1) not on the yolo26 path"
+    anchors, st = make_anchors(shapes, strides)
+    anchors, st = anchors.t().unsqueeze(0), st.t()
+    lt, rb = boxes.chunk(2, 1)
+    x1y1, x2y2 = anchors - lt, anchors + rb
+    if end2end:
+        dbox = torch.cat((x1y1, x2y2), 1)
+    else:
+        dbox = torch.cat(((x1y1 + x2y2) / 2, x2y2 - x1y1), 1)
+    return torch.cat((dbox * st, scores.sigmoid()), 1)
+
+
+def detect_postprocess(y, nc, max_det=300):
+    """`Detect.postprocess` head.py:219-233 + `get_topk_index` :235-258 (non-agnostic)."""
+    preds = y.permute(0, 2, 1)
+    boxes, scores = preds.split([4, nc], dim=-1)
+    B, A, _ = scores.shape
+    k = min(max_det, A)
+    ori = scores.max(dim=-1)[0].topk(k)[1].unsqueeze(-1)
+    sc = scores.gather(1, ori.repeat(1, 1, nc))
+    sc, index = sc.flatten(1).topk(k)
+    idx = ori[torch.arange(B)[..., None], index // nc]
+    boxes = boxes.gather(1, idx.repeat(1, 1, 4))
+    return torch.cat([boxes, sc[..., None], (index % nc)[..., None].float()], dim=-1), idx.squeeze(-1)
+
+
+# ----------------------------------------------------------------------------
+# whole model (`BaseModel._predict_once` tasks.py:182-218)
+# ----------------------------------------------------------------------------
+_LAYER_FN = {"Conv": layer_conv, "C3k2": layer_c3k2, "C2f": layer_c2f, "SPPF": layer_sppf, "C2PSA": layer_c2psa,
+             "A2C2fMoE": layer_a2c2f_moe}
+
+
+def forward(spec: dict, sd: dict, x: torch.Tensor, img_hw=None, return_layers: bool = False,
+            end2end: bool | None = None) -> Any:
+    """Eval forward.  Returns (B,300,6) for end2end models, else (B,4+nc,A)."""
+    sd = {k: (v.float() if v.is_floating_point() else v) for k, v in sd.items()}
+    x = x.float()
+    H_in = x.shape[-2]
+    outs, ys = [], {}
+    for L in spec["layers"]:
+        i, f, t, args = L["i"], L["f"], L["type"], L["args"]
+        if isinstance(f, int):
+            xin = x if f == -1 else ys[f % i if f < 0 else f]
+        else:
+            xin = [x if j == -1 else ys[j] for j in f]
+        p = f"model.{i}"
+        if t in _LAYER_FN:
+            x = _LAYER_FN[t](sd, p, xin, *args)
+        elif t == "nn.Upsample":
+            x = F.interpolate(xin, scale_factor=float(args[1]), mode=args[2])
+        elif t == "Concat":
+            x = torch.cat(xin, args[0] if args else 1)
+        elif t == "Detect":
+            nc, reg_max, e2e, _ = args
+            e2e = bool(e2e) if end2end is None else end2end
+            shapes = [tuple(v.shape[2:]) for v in xin]
+            strides = [H_in / s[0] for s in shapes]
+            braw, sraw = detect_head_raw(sd, p, xin, nc, reg_max, e2e, L.get("legacy", False))
+            y = detect_decode(braw, sraw, shapes, strides, e2e, reg_max)
+            x = detect_postprocess(y, nc)[0] if e2e else y
+            ys["detect_raw"] = (braw, sraw, y)
+        else:
+            raise NotImplementedError(t)
+        ys[i] = x
+        outs.append(x)
+    return (x, ys) if return_layers else x

@@ -1,0 +1,42 @@
+"""Shared test helpers: deterministic weights (key-name generator + calibrated BN statistics) and tolerances."""
+import json
+import os
+
+import torch
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CFG_N = os.path.join(ROOT, "yolo-master_b200", "cfg", "models", "26", "yolo26-master-n.yaml")
+
+# BASELINE.json north_star: fp16 conv/attn outputs within 1e-3 abs / 1e-2 rel of the reference forward
+ATOL, RTOL = 1e-3, 1e-2
+
+
+def yaml_n():
+    return yaml.safe_load(open(CFG_N))
+
+
+def synth_sd_from_keys(seed=0, name="yolo26-master-n"):
+    """fp32 CPU state_dict rebuilt from the reference key table only (no model code involved)."""
+    from yolo_master_b200.utils.synth import fill_state_dict_, load_norm_stats_
+
+    keys = json.load(open(os.path.join(GOLD, f"{name}.keys.json")))
+    dt = {"torch.float32": torch.float32, "torch.int64": torch.int64}
+    sd = {k: torch.zeros(shape, dtype=dt[d]) for k, (shape, d) in keys.items()}
+    fill_state_dict_(sd, seed)
+    load_norm_stats_(sd, torch.load(os.path.join(GOLD, f"{name}.bnstats.pt")))
+    return sd
+
+
+def close_stats(a, b, atol=ATOL, rtol=RTOL):
+    """(max abs err, fraction of elements violating |a-b| <= atol + rtol*|b|)."""
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs()
+    bad = err > (atol + rtol * b.abs())
+    return float(err.max()) if err.numel() else 0.0, float(bad.float().mean()) if err.numel() else 0.0
+
+
+def assert_close(a, b, atol=ATOL, rtol=RTOL, max_bad_frac=0.0, what=""):
+    mx, bad = close_stats(a, b, atol, rtol)
+    assert bad <= max_bad_frac, f"{what}: max abs err {mx:.3e}, {bad * 100:.4f}% of elements outside atol={atol} rtol={rtol}"

@@ -1,0 +1,99 @@
+"""Generate golden fixtures from the REAL reference (run in the build container only; needs /root/reference).
+
+    YOLO_CONFIG_DIR=/tmp/ulcfg python tests/golden/make_golden.py
+
+Writes (all committed, all small):
+  yolo26-master-n.keys.json     reference state_dict key -> (shape, dtype)
+  yolo26-master-n.bnstats.pt    BatchNorm running statistics calibrated on synthetic images (fp32)
+  yolo26-master-n.golden.pt     reference outputs (fp32) for seeded inputs: per-layer activations, router decisions,
+                                raw Detect head outputs and the final (B,300,6) detections
+Weights are NOT stored: both sides regenerate them from state_dict key names with utils/synth.fill_state_dict_.
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+os.environ.setdefault("YOLO_CONFIG_DIR", "/tmp/ulcfg")
+
+from ultralytics.nn.modules.moe.routers import EfficientSpatialRouter  # noqa: E402
+from ultralytics.nn.tasks import DetectionModel  # noqa: E402
+
+from yolo_master_b200.utils.synth import fill_state_dict_, load_norm_stats_, synth_images  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+CFG = "/root/reference/ultralytics/cfg/models/26/yolo26-master-n.yaml"
+NAME = "yolo26-master-n"
+KEEP_LAYERS = [2, 4, 6, 8, 9, 10, 13, 16, 19, 22]
+
+
+def calibrated_reference(seed=0):
+    m = DetectionModel(CFG, verbose=False)
+    sd = m.state_dict()
+    fill_state_dict_(sd, seed)
+    m.load_state_dict(sd)
+    m.eval()
+    bns = [mod for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d)]
+    for b in bns:
+        b.train()
+        b.momentum = None
+        b.reset_running_stats()
+    with torch.no_grad():
+        m(synth_images(8, 320, 320, seed=7))
+    for b in bns:
+        b.eval()
+        b.momentum = 0.03
+    return m
+
+
+def run(m, x):
+    feats, routes = {}, {}
+    hooks = [mod.register_forward_hook(lambda mod, i, o, k=k: feats.__setitem__(k, o)) for k, mod in enumerate(m.model)]
+    for name, mod in m.named_modules():
+        if isinstance(mod, EfficientSpatialRouter):
+            hooks.append(mod.register_forward_hook(lambda mod, i, o, n=name: routes.__setitem__(n, (o[0].clone(), o[1].clone()))))
+    with torch.no_grad():
+        y, preds = m(x)
+    for h in hooks:
+        h.remove()
+    return y, preds, feats, routes
+
+
+def main():
+    torch.manual_seed(0)
+    m = calibrated_reference(0)
+    sd = m.state_dict()
+    json.dump({k: [list(v.shape), str(v.dtype)] for k, v in sd.items()}, open(f"{OUT}/{NAME}.keys.json", "w"))
+    stats = {k: v.clone() for k, v in sd.items() if k.endswith("running_mean") or k.endswith("running_var")}
+    torch.save(stats, f"{OUT}/{NAME}.bnstats.pt")
+
+    # the fixture must be reproducible from key names + stats alone
+    m2 = DetectionModel(CFG, verbose=False)
+    sd2 = m2.state_dict()
+    load_norm_stats_(fill_state_dict_(sd2, 0), stats)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd if sd[k].is_floating_point())
+
+    gold = {"cases": {}}
+    for tag, (B, H, W, seed) in {"b2_160": (2, 160, 160, 1), "b1_64": (1, 64, 64, 2)}.items():
+        x = synth_images(B, H, W, seed)
+        y, preds, feats, routes = run(m, x)
+        gold["cases"][tag] = {
+            "B": B, "H": H, "W": W, "seed": seed,
+            "final": y.clone(),
+            "layers": {i: feats[i].clone() for i in KEEP_LAYERS},
+            "routes": {n: (w.float(), i.int()) for n, (w, i) in routes.items()},
+            "head_boxes": preds["one2one"]["boxes"].clone(),
+            "head_scores": preds["one2one"]["scores"].clone(),
+        }
+        print(tag, "final", tuple(y.shape), "score range", float(y[..., 4].min()), float(y[..., 4].max()))
+    torch.save(gold, f"{OUT}/{NAME}.golden.pt")
+    for f in os.listdir(OUT):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

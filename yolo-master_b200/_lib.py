@@ -1,0 +1,61 @@
+"""ctypes binding of libym_b200.so (C ABI: include/ym_b200.h).  Fails loudly when the library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libym_b200.so")
+
+vp, ci, cf, cll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> (restype, argtypes).  Kept in one table so tests can check it against the header.
+SIGNATURES = {
+    "ym_last_error": (C.c_char_p, []),
+    "ym_version": (ci, []),
+    "ym_device_info": (ci, [C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(cll)]),
+    "ym_conv2d_nhwc": (ci, [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ci, ci, vp, ci, ci, vp]),
+    "ym_stem_conv_nchw": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, vp, ci, vp]),
+    "ym_dwconv_nhwc": (ci, [vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, vp, ci, vp]),
+    "ym_sppf_pool_nhwc": (ci, [vp, ci, ci, ci, ci, ci, ci, vp]),
+    "ym_concat2_nhwc": (ci, [vp, ci, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, vp]),
+    "ym_attention_fwd": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, cf, vp, ci, vp]),
+    "ym_router_scratch_floats": (cll, [ci, ci, ci, ci, ci, ci]),
+    "ym_router_topk": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, ci, vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]),
+    "ym_moe_expert_gemm": (ci, [vp, ci, ci, ci, ci, ci, vp, ci, cll, vp, ci, vp, ci, vp, vp, vp, ci, vp]),
+    "ym_gn_finalize": (ci, [vp, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp, vp]),
+    "ym_moe_combine": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, ci, vp, vp, ci, vp, ci, ci, vp]),
+    "ym_detect_topk": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp, vp]),
+    "ym_detect_dense": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp]),
+}
+
+_lib = None
+
+
+class YMLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises YMLibraryError if the CUDA extension is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise YMLibraryError(
+            f"{LIB_PATH} not found: build it with `make -C {os.path.join(_HERE, 'csrc')}` or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`.  There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().ym_last_error()
+        raise RuntimeError(f"libym_b200 {what} failed (rc={rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,32 @@
+// C-ABI plumbing: thread-local error string, version, device probe.
+#include <stdarg.h>
+
+#include "ym_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+extern "C" void ym_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* ym_last_error(void) { return g_err; }
+
+extern "C" int ym_version(void) { return 100; }
+
+// Returns 0 and fills sm_major/sm_minor/sm_count/l2_bytes for the current device.
+extern "C" int ym_device_info(int* sm_major, int* sm_minor, int* sm_count, long long* l2_bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { ym_set_error("ym_device_info: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) { ym_set_error("ym_device_info: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
+    if (sm_major) *sm_major = prop.major;
+    if (sm_minor) *sm_minor = prop.minor;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = (long long)prop.l2CacheSize;
+    return YM_OK;
+}

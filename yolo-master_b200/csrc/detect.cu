@@ -1,0 +1,265 @@
+// Detect head post-processing on device (head.py:173-258):
+//   anchors/strides (tal.py:398-411) + dist2bbox (tal.py:414-423) + sigmoid + end2end two-stage top-k
+//   (max over classes -> top-k anchors -> flatten k x nc -> top-k) in ONE kernel, one CTA per image.
+// Also the dense decode (B, 4+nc, A) used by the NMS path (head.py:173-184).
+//
+// Selection runs on the raw fp32 logits (sigmoid is monotonic), with radix-select thresholds and a final
+// 512-wide bitonic sort; scores are emitted as sigmoid(logit).  Ties are broken towards the lower index.
+#include "ym_common.cuh"
+
+namespace ym {
+
+struct DetectLevels {
+    const float* box[4];  // [B, hw_l, 4*reg_max] fp32 (reg_max == 1)
+    const float* cls[4];  // [B, hw_l, nc] fp32 logits
+    int h[4], w[4];
+    float stride[4];
+    int off[5];  // anchor offsets, off[nl] = A
+    int nl;
+};
+
+__device__ __forceinline__ uint32_t f2key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+// Block-wide: k-th largest key among keys[0..n).  Returns T; *take_eq = how many keys == T belong to the top-k.
+__device__ uint32_t radix_select_kth(const uint32_t* keys, int n, int k, uint32_t* hist, int* sh_misc, int* take_eq) {
+    uint32_t prefix = 0, mask = 0;
+    int remaining = k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t u = keys[i];
+            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int cum = 0, digit = 0;
+            for (int bin = 255; bin >= 0; --bin) {
+                const int hcount = (int)hist[bin];
+                if (cum + hcount >= remaining) { digit = bin; break; }
+                cum += hcount;
+            }
+            sh_misc[0] = digit;
+            sh_misc[1] = remaining - cum;
+        }
+        __syncthreads();
+        prefix |= ((uint32_t)sh_misc[0]) << shift;
+        mask |= 255u << shift;
+        remaining = sh_misc[1];
+        __syncthreads();
+    }
+    *take_eq = remaining;
+    return prefix;
+}
+
+// Collect the indices of the top-k keys into list[0..k): all keys > T (any order) then the first take_eq keys == T.
+__device__ void collect_topk(const uint32_t* keys, int n, uint32_t T, int take_eq, int* list, int* sh_cnt) {
+    if (threadIdx.x == 0) *sh_cnt = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (keys[i] > T) list[atomicAdd(sh_cnt, 1)] = i;
+    __syncthreads();
+    if (threadIdx.x < 32) {  // ordered scan of the equal keys by one warp
+        int base = *sh_cnt, taken = 0;
+        for (int i0 = 0; i0 < n && taken < take_eq; i0 += 32) {
+            const int i = i0 + threadIdx.x;
+            const bool eq = i < n && keys[i] == T;
+            const unsigned m = __ballot_sync(0xffffffffu, eq);
+            const int rank = __popc(m & ((1u << threadIdx.x) - 1u));
+            if (eq && taken + rank < take_eq) list[base + taken + rank] = i;
+            taken += __popc(m);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void anchor_of(const DetectLevels& L, int a, int& lvl, int& r) {
+    lvl = 0;
+    while (lvl + 1 < L.nl && a >= L.off[lvl + 1]) ++lvl;
+    r = a - L.off[lvl];
+}
+
+__global__ void __launch_bounds__(1024) detect_topk_kernel(const DetectLevels L, int nc, int kdet, float* __restrict__ out,
+                                                           int* __restrict__ out_anchor) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int A = L.off[L.nl];
+    const int nkeys_max = max(A, kdet * nc);
+    uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);              // [max(A, kdet*nc)]
+    int* cand = reinterpret_cast<int*>(keys + nkeys_max);               // [kdet] anchor ids
+    int* sel = cand + kdet;                                             // [kdet] flat ids
+    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(sel + kdet + ((nkeys_max + 2 * kdet) & 1));  // [512], 8-byte aligned
+    __shared__ uint32_t hist[256];
+    __shared__ int misc[4];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+
+    // ---- stage 1: per-anchor max logit (warp per anchor row)
+    for (int a = warp; a < A; a += nwarp) {
+        int lvl, r;
+        anchor_of(L, a, lvl, r);
+        const float* row = L.cls[lvl] + ((long long)b * L.h[lvl] * L.w[lvl] + r) * nc;
+        float m = -INFINITY;
+        for (int c = lane; c < nc; c += 32) m = fmaxf(m, row[c]);
+        m = warp_max(m);
+        if (lane == 0) keys[a] = f2key(m);
+    }
+    __syncthreads();
+    int take_eq;
+    uint32_t T = radix_select_kth(keys, A, kdet, hist, misc, &take_eq);
+    collect_topk(keys, A, T, take_eq, cand, &misc[2]);
+    // order candidates by (score desc, anchor asc) so that the flat index matches topk's sorted output
+    for (int i = tid; i < 512; i += blockDim.x)
+        sortbuf[i] = i < kdet ? (((unsigned long long)keys[cand[i]] << 32) | (uint32_t)(0x7fffffff - cand[i])) : 0ull;
+    __syncthreads();
+    for (int size = 2; size <= 512; size <<= 1) {
+        for (int strd = size >> 1; strd > 0; strd >>= 1) {
+            for (int i = tid; i < 256; i += blockDim.x) {
+                const int lo = 2 * i - (i & (strd - 1));
+                const int hi = lo + strd;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long x0 = sortbuf[lo], x1 = sortbuf[hi];
+                if ((x0 < x1) == desc) { sortbuf[lo] = x1; sortbuf[hi] = x0; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < kdet; i += blockDim.x) cand[i] = 0x7fffffff - (int)(sortbuf[i] & 0xffffffffull);
+    __syncthreads();
+
+    // ---- stage 2: gather kdet x nc logits, select top-kdet
+    const int n2 = kdet * nc;
+    for (int i = tid; i < n2; i += blockDim.x) {
+        const int ci = i / nc, c = i - ci * nc;
+        int lvl, r;
+        anchor_of(L, cand[ci], lvl, r);
+        keys[i] = f2key(L.cls[lvl][((long long)b * L.h[lvl] * L.w[lvl] + r) * nc + c]);
+    }
+    __syncthreads();
+    T = radix_select_kth(keys, n2, kdet, hist, misc, &take_eq);
+    collect_topk(keys, n2, T, take_eq, sel, &misc[2]);
+    for (int i = tid; i < 512; i += blockDim.x)
+        sortbuf[i] = i < kdet ? (((unsigned long long)keys[sel[i]] << 32) | (uint32_t)(0x7fffffff - sel[i])) : 0ull;
+    __syncthreads();
+    for (int size = 2; size <= 512; size <<= 1) {
+        for (int strd = size >> 1; strd > 0; strd >>= 1) {
+            for (int i = tid; i < 256; i += blockDim.x) {
+                const int lo = 2 * i - (i & (strd - 1));
+                const int hi = lo + strd;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long x0 = sortbuf[lo], x1 = sortbuf[hi];
+                if ((x0 < x1) == desc) { sortbuf[lo] = x1; sortbuf[hi] = x0; }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- emit
+    for (int i = tid; i < kdet; i += blockDim.x) {
+        const unsigned long long e = sortbuf[i];
+        const int flat = 0x7fffffff - (int)(e & 0xffffffffull);
+        const float logit = key2f((uint32_t)(e >> 32));
+        const int ci = flat / nc, c = flat - ci * nc;
+        const int a = cand[ci];
+        int lvl, r;
+        anchor_of(L, a, lvl, r);
+        const int ay = r / L.w[lvl], ax = r - ay * L.w[lvl];
+        const float4 d = *reinterpret_cast<const float4*>(L.box[lvl] + ((long long)b * L.h[lvl] * L.w[lvl] + r) * 4);
+        const float s = L.stride[lvl];
+        const float px = (float)ax + 0.5f, py = (float)ay + 0.5f;
+        float* o = out + ((long long)b * kdet + i) * 6;
+        o[0] = (px - d.x) * s;
+        o[1] = (py - d.y) * s;
+        o[2] = (px + d.z) * s;
+        o[3] = (py + d.w) * s;
+        o[4] = 1.f / (1.f + expf(-logit));
+        o[5] = (float)c;
+        if (out_anchor) out_anchor[(long long)b * kdet + i] = a;
+    }
+}
+
+// Dense decode: y[b, 0:4, a] = box (xyxy if xyxy else xywh) * stride, y[b, 4+c, a] = sigmoid(logit)   (head.py:173-194)
+__global__ void __launch_bounds__(256) detect_dense_kernel(const DetectLevels L, int nc, int xyxy, int B, float* __restrict__ y) {
+    const int A = L.off[L.nl];
+    const int no = 4 + nc;
+    const long long total = (long long)B * no * A;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int a = (int)(idx % A);
+    const int ch = (int)((idx / A) % no);
+    const int b = (int)(idx / ((long long)A * no));
+    int lvl, r;
+    anchor_of(L, a, lvl, r);
+    const long long row = (long long)b * L.h[lvl] * L.w[lvl] + r;
+    float v;
+    if (ch >= 4) {
+        v = 1.f / (1.f + expf(-L.cls[lvl][row * nc + (ch - 4)]));
+    } else {
+        const float4 d = *reinterpret_cast<const float4*>(L.box[lvl] + row * 4);
+        const int ay = r / L.w[lvl], ax = r - ay * L.w[lvl];
+        const float px = (float)ax + 0.5f, py = (float)ay + 0.5f, s = L.stride[lvl];
+        const float x1 = px - d.x, y1 = py - d.y, x2 = px + d.z, y2 = py + d.w;
+        if (xyxy) v = (ch == 0 ? x1 : ch == 1 ? y1 : ch == 2 ? x2 : y2) * s;
+        else v = (ch == 0 ? (x1 + x2) * 0.5f : ch == 1 ? (y1 + y2) * 0.5f : ch == 2 ? (x2 - x1) : (y2 - y1)) * s;
+    }
+    y[idx] = v;
+}
+
+}  // namespace ym
+
+using namespace ym;
+
+static int fill_levels(DetectLevels& L, int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
+                       const float* strides) {
+    if (nl < 1 || nl > 4) { ym_set_error("detect: 1..4 levels supported (got %d)", nl); return YM_ERR_ARG; }
+    memset(&L, 0, sizeof(L));
+    L.nl = nl;
+    int off = 0;
+    for (int i = 0; i < nl; ++i) {
+        if (!box[i] || !cls[i]) { ym_set_error("detect: null level pointer"); return YM_ERR_ARG; }
+        L.box[i] = (const float*)box[i]; L.cls[i] = (const float*)cls[i];
+        L.h[i] = hs[i]; L.w[i] = ws[i]; L.stride[i] = strides[i];
+        L.off[i] = off; off += hs[i] * ws[i];
+    }
+    L.off[nl] = off;
+    return YM_OK;
+}
+
+// out: [B, k, 6] fp32 (x1,y1,x2,y2,score,cls) with k = min(max_det, A); out_anchor (nullable): [B, k] int32
+extern "C" int ym_detect_topk(int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
+                              const float* strides, int B, int nc, int max_det, float* out, int* out_anchor, void* stream) {
+    YM_CHECK_ARG(out, "ym_detect_topk: null output");
+    DetectLevels L;
+    int rc = fill_levels(L, nl, box, cls, hs, ws, strides);
+    if (rc) return rc;
+    const int A = L.off[nl];
+    const int k = max_det < A ? max_det : A;
+    YM_CHECK_ARG(k >= 1 && k <= 512, "ym_detect_topk: max_det must be in 1..512 (got %d)", max_det);
+    YM_CHECK_ARG(nc >= 1, "ym_detect_topk: nc");
+    if (B == 0) return YM_OK;
+    const size_t nkeys = (size_t)(A > k * nc ? A : k * nc);
+    const size_t smem = nkeys * 4 + (size_t)k * 8 + 8 + 512 * 8;
+    YM_CHECK_ARG(smem <= 227 * 1024, "ym_detect_topk: %zu bytes of shared memory needed (A=%d) exceeds 227 KB", smem, A);
+    cudaError_t e = cudaFuncSetAttribute(detect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ym_set_error("ym_detect_topk: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
+    detect_topk_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(L, nc, k, out, out_anchor);
+    YM_CHECK_LAUNCH("detect_topk");
+    return YM_OK;
+}
+
+extern "C" int ym_detect_dense(int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
+                               const float* strides, int B, int nc, int xyxy, float* y, void* stream) {
+    YM_CHECK_ARG(y, "ym_detect_dense: null output");
+    DetectLevels L;
+    int rc = fill_levels(L, nl, box, cls, hs, ws, strides);
+    if (rc) return rc;
+    if (B == 0) return YM_OK;
+    const long long total = (long long)B * (4 + nc) * L.off[nl];
+    detect_dense_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(L, nc, xyxy, B, y);
+    YM_CHECK_LAUNCH("detect_dense");
+    return YM_OK;
+}

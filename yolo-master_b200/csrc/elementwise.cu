@@ -1,0 +1,292 @@
+// HBM-bound NHWC fp16 kernels: stem conv (NCHW image -> NHWC16), depthwise k x k, SPPF pooling,
+// nearest-upsample + concat.  All accesses are 16-byte vectors over the channel dimension.
+#include "ym_common.cuh"
+
+namespace ym {
+
+// ---------------------------------------------------------------------------------------------
+// Stem: Conv(3->COUT, k3 s2 p1) + folded BN + SiLU, reading the NCHW image directly (fp16 / fp32 / u8)
+// and writing NHWC fp16.  conv.py:69-89 for model.0; fuses the NCHW->NHWC layout change into the load.
+// ---------------------------------------------------------------------------------------------
+template <typename TIn>
+__device__ __forceinline__ float load_px(const TIn* p);
+template <>
+__device__ __forceinline__ float load_px<__half>(const __half* p) { return __half2float(*p); }
+template <>
+__device__ __forceinline__ float load_px<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float load_px<unsigned char>(const unsigned char* p) { return (float)(*p) * (1.0f / 255.0f); }
+
+template <typename TIn, int COUT>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const TIn* __restrict__ img, int B, int Cin, int H, int W,
+                                                        const float* __restrict__ wgt,   // [Cin*9][COUT]
+                                                        const float* __restrict__ bias,  // [COUT]
+                                                        __half* __restrict__ out, int ldo, int Ho, int Wo) {
+    __shared__ float sw[4 * 9 * COUT];
+    __shared__ float sb[COUT];
+    for (int i = threadIdx.x; i < Cin * 9 * COUT; i += blockDim.x) sw[i] = wgt[i];
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
+    __syncthreads();
+    const long long total = (long long)B * Ho * Wo;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ox = (int)(idx % Wo);
+    const int oy = (int)((idx / Wo) % Ho);
+    const int b = (int)(idx / ((long long)Wo * Ho));
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = sb[c];
+    for (int ci = 0; ci < Cin; ++ci) {
+        const TIn* plane = img + ((long long)b * Cin + ci) * H * W;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * 2 - 1 + ky;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * 2 - 1 + kx;
+                if (ix < 0 || ix >= W) continue;
+                const float v = load_px<TIn>(plane + (long long)iy * W + ix);
+                const float* wr = &sw[((ci * 3 + ky) * 3 + kx) * COUT];
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+            }
+        }
+    }
+    __half* dst = out + idx * ldo;
+#pragma unroll
+    for (int c = 0; c < COUT; c += 8) {
+        Half8 h;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h.v[q] = __floats2half2_rn(silu_f(acc[c + 2 * q]), silu_f(acc[c + 2 * q + 1]));
+        *reinterpret_cast<Half8*>(dst + c) = h;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depthwise k x k (stride 1, pad k/2) + bias (+SiLU) (+add), 8 channels per thread.
+// Source channel for output channel c: (c / grp_w) * grp_stride + grp_off + c % grp_w  -- lets `pe(v)` read V in place
+// from the head-interleaved qkv tensor (block.py:1688,1731; :1311,1331).  Weights tap-major [k*k][C] fp16.
+// ---------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256) dwconv_kernel(const __half* __restrict__ x, int ldx, int grp_w, int grp_stride,
+                                                     int grp_off, const __half* __restrict__ w, const float* __restrict__ bias,
+                                                     int B, int H, int W, int C, int act, const __half* __restrict__ add,
+                                                     int ldadd, __half* __restrict__ out, int ldo) {
+    const int chunks = C >> 3;
+    const long long total = (long long)B * H * W * chunks;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ch = (int)(idx % chunks);
+    const long long pix = idx / chunks;
+    const int ox = (int)(pix % W);
+    const int oy = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    const int c = ch * 8;
+    const int csrc = (c / grp_w) * grp_stride + grp_off + (c % grp_w);
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = bias ? bias[c + q] : 0.f;
+    constexpr int R = KS / 2;
+    const __half* xb = x + (long long)b * H * W * ldx + csrc;
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+        const int iy = oy + ky - R;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+            const int ix = ox + kx - R;
+            if (ix < 0 || ix >= W) continue;
+            const Half8 xv = *reinterpret_cast<const Half8*>(xb + ((long long)iy * W + ix) * ldx);
+            const Half8 wv = *reinterpret_cast<const Half8*>(w + (ky * KS + kx) * C + c);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 xf = __half22float2(xv.v[q]);
+                const float2 wf = __half22float2(wv.v[q]);
+                acc[2 * q] = fmaf(xf.x, wf.x, acc[2 * q]);
+                acc[2 * q + 1] = fmaf(xf.y, wf.y, acc[2 * q + 1]);
+            }
+        }
+    }
+    if (act == 1) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = silu_f(acc[q]);
+    }
+    if (add != nullptr) {
+        const Half8 av = *reinterpret_cast<const Half8*>(add + pix * ldadd + c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 af = __half22float2(av.v[q]);
+            acc[2 * q] += af.x;
+            acc[2 * q + 1] += af.y;
+        }
+    }
+    Half8 o;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o.v[q] = __floats2half2_rn(acc[2 * q], acc[2 * q + 1]);
+    *reinterpret_cast<Half8*>(out + pix * ldo + c) = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SPPF: three chained MaxPool(k, s1, p=k/2) of y0 == max over (k), (2k-1), (3k-2) windows of y0 (block.py:237-242).
+// y0 lives in channel slot 0 of the concat buffer; slots 1..3 are written here.  8 channels per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sppf_pool_kernel(__half* __restrict__ buf, int ld, int B, int H, int W, int C, int k) {
+    const int chunks = C >> 3;
+    const long long total = (long long)B * H * W * chunks;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ch = (int)(idx % chunks);
+    const long long pix = idx / chunks;
+    const int ox = (int)(pix % W);
+    const int oy = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    const int r1 = k / 2, r2 = 2 * r1, r3 = 3 * r1;
+    __half2 m1[4], m2[4], m3[4];
+    const __half2 ninf = __float2half2_rn(-65504.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) m1[q] = m2[q] = m3[q] = ninf;
+    const __half* xb = buf + (long long)b * H * W * ld + ch * 8;
+    for (int dy = -r3; dy <= r3; ++dy) {
+        const int iy = oy + dy;
+        if (iy < 0 || iy >= H) continue;
+        const int ady = dy < 0 ? -dy : dy;
+        for (int dx = -r3; dx <= r3; ++dx) {
+            const int ix = ox + dx;
+            if (ix < 0 || ix >= W) continue;
+            const int adx = dx < 0 ? -dx : dx;
+            const int rad = ady > adx ? ady : adx;
+            const Half8 v = *reinterpret_cast<const Half8*>(xb + ((long long)iy * W + ix) * ld);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                m3[q] = __hmax2(m3[q], v.v[q]);
+                if (rad <= r2) m2[q] = __hmax2(m2[q], v.v[q]);
+                if (rad <= r1) m1[q] = __hmax2(m1[q], v.v[q]);
+            }
+        }
+    }
+    __half* ob = buf + pix * ld + ch * 8;
+    Half8 o;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o.v[q] = m1[q];
+    *reinterpret_cast<Half8*>(ob + C) = o;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o.v[q] = m2[q];
+    *reinterpret_cast<Half8*>(ob + 2 * C) = o;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o.v[q] = m3[q];
+    *reinterpret_cast<Half8*>(ob + 3 * C) = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[..., 0:Ca] = a (optionally nearest-upsampled by `up`), out[..., Ca:Ca+Cb] = b     (nn.Upsample + Concat)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) concat2_kernel(const __half* __restrict__ a, int lda, int Ca, int up,
+                                                      const __half* __restrict__ bsrc, int ldb, int Cb,
+                                                      __half* __restrict__ out, int ldo, int B, int H, int W) {
+    const int chunks = (Ca + Cb) >> 3;
+    const long long total = (long long)B * H * W * chunks;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ch = (int)(idx % chunks);
+    const long long pix = idx / chunks;
+    const int c = ch * 8;
+    Half8 v;
+    if (c < Ca) {
+        long long sp = pix;
+        if (up > 1) {
+            const int ox = (int)(pix % W);
+            const int oy = (int)((pix / W) % H);
+            const int b = (int)(pix / ((long long)W * H));
+            sp = ((long long)b * (H / up) + oy / up) * (W / up) + ox / up;
+        }
+        v = *reinterpret_cast<const Half8*>(a + sp * lda + c);
+    } else {
+        v = *reinterpret_cast<const Half8*>(bsrc + pix * ldb + (c - Ca));
+    }
+    *reinterpret_cast<Half8*>(out + pix * ldo + c) = v;
+}
+
+}  // namespace ym
+
+using namespace ym;
+
+static inline int nblocks(long long total, int bs) { return (int)((total + bs - 1) / bs); }
+
+// in_dtype: 0 = fp16 NCHW, 1 = fp32 NCHW, 2 = uint8 NCHW (scaled by 1/255)
+extern "C" int ym_stem_conv_nchw(const void* img, int in_dtype, int B, int Cin, int H, int W, const float* wgt,
+                                 const float* bias, int Cout, void* out, int ldo, void* stream) {
+    YM_CHECK_ARG(img && wgt && bias && out, "ym_stem_conv_nchw: null pointer");
+    YM_CHECK_ARG(Cin >= 1 && Cin <= 4, "ym_stem_conv_nchw: Cin must be 1..4 (got %d)", Cin);
+    YM_CHECK_ARG(ldo % 8 == 0 && ((uintptr_t)out & 15) == 0, "ym_stem_conv_nchw: output alignment");
+    if (B == 0) return YM_OK;
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long total = (long long)B * Ho * Wo;
+    cudaStream_t st = (cudaStream_t)stream;
+#define YM_STEM(T, CO) stem_conv_kernel<T, CO><<<nblocks(total, 256), 256, 0, st>>>((const T*)img, B, Cin, H, W, wgt, bias, (__half*)out, ldo, Ho, Wo)
+#define YM_STEM_T(CO)                                   \
+    do {                                                \
+        if (in_dtype == 0) YM_STEM(__half, CO);         \
+        else if (in_dtype == 1) YM_STEM(float, CO);     \
+        else if (in_dtype == 2) YM_STEM(unsigned char, CO); \
+        else { ym_set_error("ym_stem_conv_nchw: bad in_dtype %d", in_dtype); return YM_ERR_ARG; } \
+    } while (0)
+    if (Cout == 16) YM_STEM_T(16);
+    else if (Cout == 32) YM_STEM_T(32);
+    else if (Cout == 64) YM_STEM_T(64);
+    else { ym_set_error("ym_stem_conv_nchw: Cout must be 16/32/64 (got %d)", Cout); return YM_ERR_UNSUPPORTED; }
+#undef YM_STEM_T
+#undef YM_STEM
+    YM_CHECK_LAUNCH("stem_conv");
+    return YM_OK;
+}
+
+extern "C" int ym_dwconv_nhwc(const void* x, int ldx, int grp_w, int grp_stride, int grp_off, const void* w,
+                              const float* bias, int B, int H, int W, int C, int ksize, int act, const void* add, int ldadd,
+                              void* out, int ldo, void* stream) {
+    YM_CHECK_ARG(x && w && out, "ym_dwconv_nhwc: null pointer");
+    YM_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && grp_w % 8 == 0 && grp_stride % 8 == 0 && grp_off % 8 == 0,
+                 "ym_dwconv_nhwc: channel counts/pitches must be multiples of 8");
+    YM_CHECK_ARG(add == nullptr || ldadd % 8 == 0, "ym_dwconv_nhwc: add pitch");
+    YM_CHECK_ARG((((uintptr_t)x | (uintptr_t)w | (uintptr_t)out | (uintptr_t)add) & 15) == 0, "ym_dwconv_nhwc: alignment");
+    if (B == 0) return YM_OK;
+    const long long total = (long long)B * H * W * (C / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+#define YM_DW(KS)                                                                                                    \
+    dwconv_kernel<KS><<<nblocks(total, 256), 256, 0, st>>>((const __half*)x, ldx, grp_w, grp_stride, grp_off,          \
+                                                           (const __half*)w, bias, B, H, W, C, act, (const __half*)add, \
+                                                           ldadd, (__half*)out, ldo)
+    switch (ksize) {
+        case 3: YM_DW(3); break;
+        case 5: YM_DW(5); break;
+        case 7: YM_DW(7); break;
+        case 9: YM_DW(9); break;
+        default: ym_set_error("ym_dwconv_nhwc: kernel size %d unsupported (3/5/7/9)", ksize); return YM_ERR_UNSUPPORTED;
+    }
+#undef YM_DW
+    YM_CHECK_LAUNCH("dwconv");
+    return YM_OK;
+}
+
+extern "C" int ym_sppf_pool_nhwc(void* buf, int ld, int B, int H, int W, int C, int k, void* stream) {
+    YM_CHECK_ARG(buf, "ym_sppf_pool_nhwc: null pointer");
+    YM_CHECK_ARG(C % 8 == 0 && ld % 8 == 0 && ld >= 4 * C && (k & 1), "ym_sppf_pool_nhwc: bad dims");
+    if (B == 0) return YM_OK;
+    const long long total = (long long)B * H * W * (C / 8);
+    sppf_pool_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>((__half*)buf, ld, B, H, W, C, k);
+    YM_CHECK_LAUNCH("sppf_pool");
+    return YM_OK;
+}
+
+extern "C" int ym_concat2_nhwc(const void* a, int lda, int Ca, int up, const void* b, int ldb, int Cb, void* out, int ldo,
+                               int B, int H, int W, void* stream) {
+    YM_CHECK_ARG(a && out && (b || Cb == 0), "ym_concat2_nhwc: null pointer");
+    YM_CHECK_ARG(Ca % 8 == 0 && Cb % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0, "ym_concat2_nhwc: multiples of 8");
+    YM_CHECK_ARG(up >= 1 && H % up == 0 && W % up == 0, "ym_concat2_nhwc: bad upsample factor");
+    if (B == 0) return YM_OK;
+    const long long total = (long long)B * H * W * ((Ca + Cb) / 8);
+    concat2_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)a, lda, Ca, up, (const __half*)b,
+                                                                         ldb, Cb, (__half*)out, ldo, B, H, W);
+    YM_CHECK_LAUNCH("concat2");
+    return YM_OK;
+}

@@ -1,0 +1,76 @@
+"""Shared plumbing for the accelerated modules: layout conversion at the module boundary and weight-pack caching."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+BN_EPS = 1e-3  # every nn.BatchNorm2d on the path runs with eps=1e-3 (reference utils/torch_utils.py:552-562)
+
+
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """NCHW-logical tensor -> (B,H,W,C) fp16 view (zero-copy when x is channels_last fp16)."""
+    if not x.is_cuda:
+        raise RuntimeError(
+            "yolo_master_b200 modules run on CUDA tensors only (hand-written sm_100a kernels; there is no CPU fallback)")
+    if x.dtype != torch.float16:
+        x = x.half()
+    v = x.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+def to_nchw(y: torch.Tensor) -> torch.Tensor:
+    """(B,H,W,C) -> NCHW-logical view (channels_last memory)."""
+    return y.permute(0, 3, 1, 2)
+
+
+def fold_bn(weight: torch.Tensor, conv_bias, bn: nn.BatchNorm2d | None):
+    """fp32 (w', b') with BatchNorm folded in: reference fuse_conv_and_bn utils/torch_utils.py:315-349."""
+    w = weight.detach().float()
+    b = torch.zeros(w.shape[0], device=w.device) if conv_bias is None else conv_bias.detach().float()
+    if bn is not None:
+        s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = w * s.view(-1, 1, 1, 1)
+        b = (b - bn.running_mean.detach().float()) * s + bn.bias.detach().float()
+    return w, b
+
+
+def pack_gemm_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Co,Ci,KH,KW] fp32 -> fp16 [Co, Kpad] with k = (ky*KW+kx)*Ci + ci, zero padded to a multiple of 32."""
+    Co = w.shape[0]
+    m = w.permute(0, 2, 3, 1).reshape(Co, -1)
+    K = m.shape[1]
+    Kpad = (K + 31) // 32 * 32
+    out = torch.zeros((Co, Kpad), dtype=torch.float16, device=w.device)
+    out[:, :K] = m.half()
+    return out.contiguous()
+
+
+def bn_affine(bn: nn.BatchNorm2d):
+    s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    return s.contiguous(), (bn.bias.detach().float() - bn.running_mean.detach().float() * s).contiguous()
+
+
+class PackCache:
+    """Derived (folded / repacked / fp16) weights, rebuilt when any source tensor changes version, storage or device."""
+
+    def _pack_sources(self):
+        return list(self.parameters(recurse=True)) + list(self.buffers(recurse=True))
+
+    def get_pack(self):
+        key = tuple((t.data_ptr(), t._version, str(t.device)) for t in self._pack_sources())
+        cached = self.__dict__.get("_ym_pack")
+        if cached is None or cached[0] != key:
+            with torch.no_grad():
+                cached = (key, self._build_pack())
+            self.__dict__["_ym_pack"] = cached
+        return cached[1]
+
+    def _build_pack(self):
+        raise NotImplementedError
+
+
+def require_eval(m: nn.Module):
+    if m.training:
+        raise RuntimeError(
+            f"{type(m).__name__}: the B200 path implements the inference forward only; call .eval() first "
+            "(training is out of scope, SURVEY.md §8)")

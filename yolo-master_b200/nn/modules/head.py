@@ -1,0 +1,108 @@
+"""Detect head with the reference's name, signature and state_dict keys (`ultralytics/nn/modules/head.py:37-262`).
+
+Towers run on the conv kernels (last 1x1 writes fp32 logits / distances), then ONE kernel per batch does
+anchors + dist2bbox + sigmoid + the end2end two-stage top-k (head.py:173-258), or the dense decode for the NMS path.
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ._base import require_eval, to_nhwc
+from .conv import Conv, DWConv, PlainConv2d
+
+__all__ = ("Detect",)
+
+
+class Detect(nn.Module):
+    """`Detect(nc=80, reg_max=16, end2end=False, ch=())`."""
+
+    dynamic = False
+    export = False
+    format = None
+    max_det = 300
+    agnostic_nms = False
+    shape = None
+    legacy = False
+    xyxy = False
+
+    def __init__(self, nc=80, reg_max=16, end2end=False, ch=()):
+        super().__init__()
+        self.nc = nc
+        self.nl = len(ch)
+        self.reg_max = reg_max
+        self.no = nc + self.reg_max * 4
+        self.stride = torch.zeros(self.nl)
+        c2, c3 = max((16, ch[0] // 4, self.reg_max * 4)), max(ch[0], min(self.nc, 100))
+        self.cv2 = nn.ModuleList(
+            nn.Sequential(Conv(x, c2, 3), Conv(c2, c2, 3), PlainConv2d(c2, 4 * self.reg_max, 1)) for x in ch)
+        self.cv3 = (
+            nn.ModuleList(nn.Sequential(Conv(x, c3, 3), Conv(c3, c3, 3), PlainConv2d(c3, self.nc, 1)) for x in ch)
+            if self.legacy
+            else nn.ModuleList(
+                nn.Sequential(
+                    nn.Sequential(DWConv(x, x, 3), Conv(x, c3, 1)),
+                    nn.Sequential(DWConv(c3, c3, 3), Conv(c3, c3, 1)),
+                    PlainConv2d(c3, self.nc, 1),
+                )
+                for x in ch
+            )
+        )
+        self.dfl = nn.Identity()
+        if end2end:
+            self.one2one_cv2 = copy.deepcopy(self.cv2)
+            self.one2one_cv3 = copy.deepcopy(self.cv3)
+
+    @property
+    def end2end(self):
+        return getattr(self, "_end2end", True) and hasattr(self, "one2one_cv2")
+
+    @end2end.setter
+    def end2end(self, value):
+        self._end2end = value
+
+    def fuse(self):
+        """Reference Detect.fuse() drops the one2many towers (head.py:260-262); they are simply not executed here."""
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _tower(seq, x, out_f32=True):
+        mods = list(seq)
+        for m in mods[:-1]:
+            if isinstance(m, nn.Sequential):
+                for mm in m:
+                    x = mm.fwd_nhwc(x)
+            else:
+                x = m.fwd_nhwc(x)
+        return mods[-1].fwd_nhwc(x, out_f32=out_f32)
+
+    def head_raw(self, feats_nhwc):
+        """Per level (boxes fp32 (B,h,w,4*reg_max), logits fp32 (B,h,w,nc)) from the active towers."""
+        e2e = self.end2end
+        box_head = self.one2one_cv2 if e2e else self.cv2
+        cls_head = self.one2one_cv3 if e2e else self.cv3
+        boxes = [self._tower(box_head[i], f) for i, f in enumerate(feats_nhwc)]
+        logits = [self._tower(cls_head[i], f) for i, f in enumerate(feats_nhwc)]
+        return boxes, logits
+
+    def forward(self, x):
+        require_eval(self)
+        if self.reg_max != 1:
+            raise NotImplementedError("Detect: DFL heads (reg_max > 1) are not on the B200 path (yolo26 uses reg_max=1)")
+        if self.agnostic_nms:
+            raise NotImplementedError("Detect: agnostic_nms top-k is not on the B200 path")
+        feats = [to_nhwc(f) for f in x]
+        boxes, logits = self.head_raw(feats)
+        strides = [float(s) for s in self.stride.tolist()]
+        if any(s <= 0 for s in strides):
+            raise RuntimeError("Detect.stride is not initialised (build the model through DetectionModel)")
+        if self.end2end:
+            y = ops.detect_topk(boxes, logits, strides, self.nc, self.max_det)
+        else:
+            y = ops.detect_dense(boxes, logits, strides, self.nc, xyxy=self.xyxy)
+        if self.export:
+            return y
+        return y, {"boxes": boxes, "scores": logits, "feats": x}

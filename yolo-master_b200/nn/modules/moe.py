@@ -1,0 +1,219 @@
+"""Routed MoE-FFN blocks with the reference's names, signatures and state_dict keys.
+
+Mirrors `ultralytics/nn/modules/moe/`: EfficientSpatialRouter routers.py:268-304, SimpleExpert experts.py:73-88,
+OptimizedMOEImproved modules.py:957-1180, ABlockMoE :1199-1260, A2C2fMoE :1268-1297.
+
+Routing is per IMAGE (routers.py:300), so an "expert batch" is a set of whole images.  Instead of the reference's
+Python loop over experts (`mask.any()` host sync, `x[batch_idx]` gather copy, `index_add_`), the router writes a
+device index table and one grouped GEMM per layer of the expert MLP runs all B*top_k (image, expert) problems with
+weight-pointer indirection; GroupNorm statistics are accumulated in the GEMM epilogues and applied on the next load.
+No host synchronisation happens anywhere in the block, so the forward is CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ._base import PackCache, bn_affine, fold_bn, pack_gemm_weight, require_eval, to_nchw, to_nhwc
+from .block import A2C2f, ABlock, C3k, _SeqNHWC
+
+__all__ = ("EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups")
+
+
+def get_safe_groups(channels: int, desired_groups: int = 8) -> int:
+    """Largest num_groups <= desired_groups dividing channels (reference nn/modules/utils.py:108-115)."""
+    if channels <= 0:
+        return 1
+    groups = min(desired_groups, channels)
+    while channels % groups != 0:
+        groups -= 1
+    return max(1, groups)
+
+
+class EfficientSpatialRouter(nn.Module, PackCache):
+    """`EfficientSpatialRouter(in_channels, num_experts, reduction=8, top_k=2, noise_std=1.0, pool_scale=4)`."""
+
+    def __init__(self, in_channels, num_experts, reduction=8, top_k=2, noise_std=1.0, pool_scale=4):
+        super().__init__()
+        self.num_experts = num_experts
+        self.top_k = top_k
+        self.noise_std = noise_std
+        self.pool_scale = pool_scale
+        self.capacity_factor = None
+        self.softmax = nn.Softmax(dim=1)
+        reduced_channels = max(in_channels // reduction, 8)
+        self.router = nn.Sequential(
+            nn.Conv2d(in_channels, reduced_channels, 3, padding=1, bias=False),
+            nn.BatchNorm2d(reduced_channels, eps=1e-3, momentum=0.03),
+            nn.SiLU(inplace=False),
+            nn.Conv2d(reduced_channels, num_experts, 1, bias=False),
+            nn.BatchNorm2d(num_experts, eps=1e-3, momentum=0.03),
+        )
+
+    def _build_pack(self):
+        c0, bn1, c3, bn2 = self.router[0], self.router[1], self.router[3], self.router[4]
+        Cr, C = c0.weight.shape[0], c0.weight.shape[1]
+        s1, h1 = bn_affine(bn1)
+        s2, h2 = bn_affine(bn2)
+        return {
+            "Cr": Cr, "E": c3.weight.shape[0],
+            "w1": c0.weight.detach().float().permute(2, 3, 1, 0).reshape(9, C, Cr).contiguous(),  # [tap][c][r]
+            "scale1": s1, "shift1": h1,
+            "w2": c3.weight.detach().float().reshape(c3.weight.shape[0], Cr).contiguous(),
+            "scale2": s2, "shift2": h2,
+        }
+
+    def route_nhwc(self, x, top_k=None):
+        k = self.top_k if top_k is None else max(1, min(int(top_k), self.num_experts))
+        return ops.router_topk(x, self.get_pack(), k, self.pool_scale)
+
+    def forward(self, x, top_k=None):
+        """Returns (weights fp32 [B,k], indices int64 [B,k], {}) like the reference's eval branch."""
+        require_eval(self)
+        if x.dim() != 4:
+            raise ValueError(f"Router input must be 4-D (NCHW), got {x.dim()}-D shape {tuple(x.shape)}")
+        if x.shape[1] != self.router[0].in_channels:
+            raise ValueError(f"router input: expected (N, {self.router[0].in_channels}, H, W), got {tuple(x.shape)}")
+        idx, w, _ = self.route_nhwc(to_nhwc(x), top_k)
+        return w, idx.long(), {}
+
+
+class SimpleExpert(nn.Module):
+    """`SimpleExpert(in_channels, out_channels, expand_ratio=2, num_groups=8)`: 1x1 -> GN -> SiLU -> 1x1 -> GN.
+
+    Parameter container only; the arithmetic runs batched over all routed (image, expert) problems in
+    `OptimizedMOEImproved.fwd_nhwc`."""
+
+    def __init__(self, in_channels, out_channels, expand_ratio=2, num_groups=8):
+        super().__init__()
+        hidden_dim = int(in_channels * expand_ratio)
+        self.conv = nn.Sequential(
+            nn.Conv2d(in_channels, hidden_dim, 1, bias=False),
+            nn.GroupNorm(get_safe_groups(hidden_dim, num_groups), hidden_dim),
+            nn.SiLU(inplace=True),
+            nn.Conv2d(hidden_dim, out_channels, 1, bias=False),
+            nn.GroupNorm(get_safe_groups(out_channels, num_groups), out_channels),
+        )
+
+    def forward(self, x):
+        raise RuntimeError("SimpleExpert runs only inside OptimizedMOEImproved on the B200 path (grouped expert GEMM)")
+
+
+class OptimizedMOEImproved(nn.Module, PackCache):
+    """Same constructor as the reference (modules.py:960-976); only expert_type='simple', router_type='efficient'."""
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, expert_type="simple", router_type="efficient",
+                 noise_std=1.0, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, expert_expand_ratio=2.0,
+                 progressive_sparsity=True, detach_routing=False, add_residual=True):
+        super().__init__()
+        if expert_type != "simple" or router_type != "efficient":
+            raise NotImplementedError("OptimizedMOEImproved: only expert_type='simple', router_type='efficient' are on the B200 path")
+        if in_channels != out_channels:
+            raise NotImplementedError("OptimizedMOEImproved: in_channels != out_channels is not on the B200 path")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_experts, self.top_k = num_experts, top_k
+        self.balance_loss_coeff, self.router_z_loss_coeff = balance_loss_coeff, router_z_loss_coeff
+        self.progressive_sparsity, self.add_residual, self.detach_routing = progressive_sparsity, add_residual, detach_routing
+        self.routing = EfficientSpatialRouter(in_channels, num_experts, top_k=top_k, noise_std=noise_std)
+        self.experts = nn.ModuleList(
+            SimpleExpert(in_channels, out_channels, expand_ratio=expert_expand_ratio) for _ in range(num_experts))
+        self.shared_expert = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, 1, bias=False), nn.BatchNorm2d(out_channels, eps=1e-3, momentum=0.03),
+            nn.SiLU(inplace=True))
+        self._init_weights()
+        self.last_routing_snapshot = {}
+
+    def _init_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        nn.init.normal_(self.routing.router[3].weight, mean=0, std=0.05)
+
+    def _pack_sources(self):  # the router keeps its own pack
+        return list(self.experts.parameters()) + list(self.shared_expert.parameters()) + list(self.shared_expert.buffers())
+
+    def _build_pack(self):
+        ex = list(self.experts)
+        w1 = torch.stack([pack_gemm_weight(e.conv[0].weight.detach().float()) for e in ex]).contiguous()  # [E][hid][Kpad]
+        w2 = torch.stack([pack_gemm_weight(e.conv[3].weight.detach().float()) for e in ex]).contiguous()  # [E][C][Kpad]
+        g1, g2 = ex[0].conv[1], ex[0].conv[4]
+        ws, bs = fold_bn(self.shared_expert[0].weight, None, self.shared_expert[1])
+        return {
+            "w1": w1, "w2": w2, "hid": w1.shape[1],
+            "gamma1": torch.stack([e.conv[1].weight.detach().float() for e in ex]).contiguous(),
+            "beta1": torch.stack([e.conv[1].bias.detach().float() for e in ex]).contiguous(),
+            "gamma2": torch.stack([e.conv[4].weight.detach().float() for e in ex]).contiguous(),
+            "beta2": torch.stack([e.conv[4].bias.detach().float() for e in ex]).contiguous(),
+            "G1": g1.num_groups, "G2": g2.num_groups, "eps1": g1.eps, "eps2": g2.eps,
+            "ws": pack_gemm_weight(ws), "bs": bs.contiguous(),
+        }
+
+    def fwd_nhwc(self, x, out=None, outer_residual=False):
+        """x: (B,H,W,C).  Returns shared(x) + sum_j w_j*expert_j(x) [+ x if add_residual or outer_residual]."""
+        require_eval(self)
+        B, H, W, C = x.shape
+        HW, k = H * W, self.top_k
+        pk = self.get_pack()
+        idx, w, probs = self.routing.route_nhwc(x, k)           # device index table, no host sync
+        ridx, rw = idx.view(-1), w.view(-1)
+        P, hid = B * k, pk["hid"]
+        ldx = ops.pitch(x)
+        # GEMM1: h[p] = x[p // k] @ W1[e_p]^T, GroupNorm-1 statistics in the epilogue
+        h, st1 = ops.moe_expert_gemm(x, ldx, k, P, HW, C, pk["w1"], ridx, hid, groups=pk["G1"])
+        sc1, sh1 = ops.gn_finalize(st1, hid, HW * (hid // pk["G1"]), pk["eps1"], pk["gamma1"], pk["beta1"], ridx)
+        # GEMM2: o[p] = SiLU(GN1(h[p])) @ W2[e_p]^T with GN+SiLU applied on the A-operand load; GN-2 statistics
+        o, st2 = ops.moe_expert_gemm(h, hid, 1, P, HW, hid, pk["w2"], ridx, C, a_scale=sc1, a_shift=sh1, groups=pk["G2"])
+        sc2, sh2 = ops.gn_finalize(st2, C, HW * (C // pk["G2"]), pk["eps2"], pk["gamma2"], pk["beta2"], ridx, route_w=rw)
+        # combine: shared expert GEMM + sum_j w_j*GN2(o_j) (+ residual), fp32 accumulate, one rounding
+        add_res = outer_residual or (self.add_residual and self.in_channels == self.out_channels)
+        y = ops.moe_combine(x, pk["ws"], pk["bs"], o, sc2, sh2, k, add_residual=add_res, out=out)
+        self.last_routing_snapshot = {"topk_indices": idx, "topk_weights": w, "router_probs": probs}  # device tensors, lazy
+        return y
+
+    def forward(self, x):
+        return to_nchw(self.fwd_nhwc(to_nhwc(x)))
+
+    @property
+    def aux_loss(self):
+        return torch.zeros((), device=self.shared_expert[0].weight.device)
+
+
+class ABlockMoE(ABlock):
+    """`ABlockMoE(dim, num_heads, mlp_ratio=1.2, area=1, num_experts=4, top_k=2, expert_type='simple')`."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=1.2, area=1, num_experts=4, top_k=2, expert_type="simple"):
+        super().__init__(dim, num_heads, mlp_ratio, area)
+        self.mlp = OptimizedMOEImproved(in_channels=dim, out_channels=dim, num_experts=num_experts, top_k=top_k,
+                                        expert_type=expert_type, expert_expand_ratio=mlp_ratio, progressive_sparsity=True,
+                                        add_residual=False)
+
+    def fwd_nhwc(self, x, out=None):
+        x = self.attn.fwd_nhwc(x, res=x)                              # x + attn(x)
+        return self.mlp.fwd_nhwc(x, out=out, outer_residual=True)    # x + mlp(x): residual fused in the combine epilogue
+
+    @property
+    def aux_loss(self):
+        return self.mlp.aux_loss
+
+
+class A2C2fMoE(A2C2f):
+    """`A2C2fMoE(c1, c2, n=1, a2=True, area=1, residual=False, mlp_ratio=2.0, e=0.5, g=1, shortcut=True,
+    num_experts=4, top_k=2, expert_type='simple')`."""
+
+    def __init__(self, c1, c2, n=1, a2=True, area=1, residual=False, mlp_ratio=2.0, e=0.5, g=1, shortcut=True,
+                 num_experts=4, top_k=2, expert_type="simple"):
+        super().__init__(c1, c2, n, a2, area, residual, mlp_ratio, e, g, shortcut)
+        c_ = int(c2 * e)
+        self.m = nn.ModuleList(
+            _SeqNHWC(*(ABlockMoE(c_, c_ // 32, mlp_ratio, area, num_experts, top_k, expert_type) for _ in range(2)))
+            if a2 else C3k(c_, c_, 2, shortcut, g)
+            for _ in range(n)
+        )
+
+    @property
+    def aux_loss(self):
+        return torch.zeros((), device=self.cv1.conv.weight.device)

@@ -1,0 +1,263 @@
+"""YAML -> model graph and the layer loop, mirroring `ultralytics/nn/tasks.py`.
+
+`parse_model` follows tasks.py:2022-2275 (+ mixture_registry.py:84-156 for the registered MoE modules) for the modules on
+the hot path; `DetectionModel` follows tasks.py:530-577 / `_predict_once` :182-218.  Differences, all deliberate:
+  * strides are derived analytically from the layer table (the reference runs a CPU forward, tasks.py:555-559);
+  * `nn.Upsample` + `Concat` pairs are executed as one kernel;
+  * the whole forward is host-sync free, so `graphed()` captures it into a CUDA graph per input shape.
+"""
+from __future__ import annotations
+
+import ast
+import contextlib
+import math
+import os
+from copy import deepcopy
+
+import torch
+import torch.nn as nn
+
+from . import modules as M
+
+_CFG_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cfg", "models")
+
+MODULES = {name: getattr(M, name) for name in M.__all__ if isinstance(getattr(M, name), type)}
+MIXTURE_MODULES = {"A2C2fMoE": M.A2C2fMoE}
+BASE_MODULES = frozenset({M.Conv, M.DWConv, M.Bottleneck, M.SPPF, M.C2PSA, M.C2f, M.C3k2, M.C3, M.A2C2f})
+REPEAT_MODULES = frozenset({M.C2f, M.C3k2, M.C3, M.C2PSA, M.A2C2f})
+MIXTURE_BASE_MODULES = frozenset(MIXTURE_MODULES.values())
+MIXTURE_REPEAT_MODULES = frozenset({M.A2C2fMoE})
+
+
+def make_divisible(x, divisor):
+    return int(math.ceil(x / divisor) * divisor)
+
+
+def yaml_model_load(path):
+    """Load a model YAML; bare names resolve against this package's cfg/models tree (e.g. 'yolo26-master-n.yaml')."""
+    import yaml
+
+    if not os.path.exists(path):
+        for root, _, files in os.walk(_CFG_ROOT):
+            if os.path.basename(path) in files:
+                path = os.path.join(root, os.path.basename(path))
+                break
+        else:
+            raise FileNotFoundError(path)
+    with open(path) as f:
+        d = yaml.safe_load(f)
+    d["yaml_file"] = path
+    return d
+
+
+def _resolve(name):
+    if name == "nn.Upsample":
+        return M.Upsample
+    if name.startswith("nn."):
+        return getattr(nn, name[3:])
+    if name in MODULES:
+        return MODULES[name]
+    if name in MIXTURE_MODULES:
+        return MIXTURE_MODULES[name]
+    raise KeyError(f"unknown model module {name!r} (not on the B200 hot path)")
+
+
+def parse_model(d, ch, verbose=False):
+    """Parse a YOLO model.yaml dictionary into (nn.Sequential, save list, per-layer output strides)."""
+    legacy = True
+    max_channels = float("inf")
+    nc, scales, end2end = (d.get(x) for x in ("nc", "scales", "end2end"))
+    reg_max = d.get("reg_max", 16)
+    depth, width = d.get("depth_multiple", 1.0), d.get("width_multiple", 1.0)
+    scale = d.get("scale")
+    if scales:
+        if not scale:
+            scale = next(iter(scales.keys()))
+        depth, width, max_channels = scales[scale]
+    if d.get("activation"):
+        raise NotImplementedError("custom default activations are not on the B200 path (SiLU only)")
+    ch = [ch]
+    strides = []
+    layers, save, c2 = [], [], ch[-1]
+    for i, (f, n, m, args) in enumerate(d["backbone"] + d["head"]):
+        m = _resolve(m)
+        args = list(args)
+        for j, a in enumerate(args):
+            if isinstance(a, str):
+                with contextlib.suppress(ValueError, SyntaxError):
+                    args[j] = {"nc": nc, "reg_max": reg_max, "end2end": end2end}[a] if a in ("nc", "reg_max", "end2end") \
+                        else ast.literal_eval(a)
+        n = n_ = max(round(n * depth), 1) if n > 1 else n
+        s_in = (1 if i == 0 else strides[f]) if isinstance(f, int) else strides[f[0]]
+        s_out = s_in
+        if m in BASE_MODULES:
+            c1, c2 = ch[f], args[0]
+            if c2 != nc:
+                c2 = make_divisible(min(c2, max_channels) * width, 8)
+            args = [c1, c2, *args[1:]]
+            if m in REPEAT_MODULES:
+                args.insert(2, n)
+                n = 1
+            if m is M.C3k2:
+                legacy = False
+                if scale and scale in "mlx":
+                    args[3] = True
+            if m is M.A2C2f:
+                legacy = False
+                if scale and scale in "lx":
+                    args.extend((True, 1.2))
+            if m in (M.Conv, M.DWConv) and len(args) > 3:
+                s_out = s_in * args[3]
+        elif m in MIXTURE_BASE_MODULES:
+            c1, c2 = ch[f], args[0]
+            if c2 != nc:
+                c2 = make_divisible(min(c2, max_channels) * width, 8)
+            args = [c1, c2, *args[1:]]
+            if m in MIXTURE_REPEAT_MODULES:
+                args.insert(2, n)
+                n = 1
+            if m is M.A2C2fMoE:
+                legacy = False
+        elif m is M.Concat:
+            c2 = sum(ch[x] for x in f)
+        elif m is M.Detect:
+            args.extend([reg_max, end2end, [ch[x] for x in f]])
+            m.legacy = legacy
+        elif m is M.Upsample:
+            c2 = ch[f]
+            s_out = s_in / float(args[1])
+        else:
+            c2 = ch[f]
+        m_ = nn.Sequential(*(m(*args) for _ in range(n))) if n > 1 else m(*args)
+        m_.np = sum(x.numel() for x in m_.parameters())
+        m_.i, m_.f, m_.type = i, f, m.__name__
+        if verbose:
+            print(f"{i:>3}{f!s:>20}{n_:>3}{m_.np:10.0f}  {m_.type:<20}{args!s:<30}")
+        save.extend(x % i for x in ([f] if isinstance(f, int) else f) if x != -1)
+        layers.append(m_)
+        if i == 0:
+            ch = []
+        ch.append(c2)
+        strides.append(s_out)
+    return nn.Sequential(*layers), sorted(save), strides
+
+
+class DetectionModel(nn.Module):
+    """`DetectionModel(cfg='yolo26-master-n.yaml', ch=3, nc=None, verbose=False)` — inference-only B200 model."""
+
+    def __init__(self, cfg="yolo26-master-n.yaml", ch=3, nc=None, verbose=False):
+        super().__init__()
+        self.yaml = cfg if isinstance(cfg, dict) else yaml_model_load(cfg)
+        self.yaml["channels"] = ch
+        if nc and nc != self.yaml["nc"]:
+            self.yaml["nc"] = nc
+        self.model, self.save, layer_strides = parse_model(deepcopy(self.yaml), ch=ch, verbose=verbose)
+        self.names = {i: f"{i}" for i in range(self.yaml["nc"])}
+        self.inplace = True
+        head = self.model[-1]
+        if isinstance(head, M.Detect):
+            head.stride = torch.tensor([float(layer_strides[j]) for j in head.f])
+            self.stride = head.stride
+        else:
+            self.stride = torch.tensor([32.0])
+        # Upsample immediately followed by Concat([-1, j]) and consumed by nothing else: executed as one kernel
+        self._fused_up = {}
+        for i, m in enumerate(self.model[:-1]):
+            nxt = self.model[i + 1]
+            if isinstance(m, M.Upsample) and isinstance(nxt, M.Concat) and isinstance(nxt.f, list) and nxt.f[0] == -1 \
+                    and i not in self.save and m.mode == "nearest" and float(m.scale_factor).is_integer():
+                self._fused_up[i] = int(m.scale_factor)
+        self._graphs = {}
+        self.eval()
+
+    @property
+    def end2end(self):
+        return getattr(self.model[-1], "end2end", False)
+
+    @end2end.setter
+    def end2end(self, value):
+        self.model[-1].end2end = value
+
+    def fuse(self, verbose=False):
+        """No-op kept for API parity: BatchNorm folding happens in each module's weight pack (tasks.py:285-320)."""
+        return self
+
+    def train(self, mode=True):
+        if mode:
+            raise RuntimeError("yolo_master_b200.DetectionModel is inference-only (training is out of scope)")
+        return super().train(False)
+
+    # ------------------------------------------------------------------------------------------
+    def _predict_once(self, x):
+        y = []
+        pending_up = 1
+        for i, m in enumerate(self.model):
+            if m.f != -1:
+                x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
+            if i in self._fused_up:
+                pending_up = self._fused_up[i]      # defer: the next Concat reads the low-res tensor directly
+                y.append(None)
+                continue
+            if pending_up > 1:
+                x = m(x, up_first=pending_up)
+                pending_up = 1
+            else:
+                x = m(x)
+            y.append(x if m.i in self.save else None)
+        return x
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("yolo_master_b200.DetectionModel.forward needs CUDA tensors (no CPU fallback)")
+        return self._predict_once(x)
+
+    predict = forward
+
+    # ------------------------------------------------------------------------------------------
+    def graphed(self, batch, height, width, dtype=torch.float16, warmup=3):
+        """CUDA-graph runner for a fixed input shape: returns `GraphedForward` (call with a device tensor)."""
+        key = (batch, height, width, dtype)
+        g = self._graphs.get(key)
+        if g is None:
+            g = GraphedForward(self, batch, height, width, dtype, warmup)
+            self._graphs[key] = g
+        return g
+
+
+class GraphedForward:
+    """Whole-forward CUDA graph with static input/output buffers (+ pinned host staging for the host-buffer API)."""
+
+    def __init__(self, model, batch, height, width, dtype, warmup=3):
+        dev = next(model.parameters()).device
+        self.model = model
+        self.static_in = torch.zeros((batch, model.yaml.get("channels", 3), height, width), dtype=dtype, device=dev)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            for _ in range(warmup):
+                out = model(self.static_in)
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        from .. import ops
+        k0 = ops.KERNELS
+        with torch.cuda.graph(self.graph, stream=self.stream), torch.no_grad():
+            out = model(self.static_in)
+        self.kernels_per_replay = ops.KERNELS - k0
+        self.static_out = out[0] if isinstance(out, tuple) else out
+        self.host_out = torch.empty(self.static_out.shape, dtype=self.static_out.dtype, pin_memory=True)
+
+    def __call__(self, x=None):
+        """x: device tensor of the captured shape (copied into the static input) or None (reuse the static input)."""
+        if x is not None:
+            self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+    def run_host(self, host_in):
+        """Host-buffer call: pinned host images -> H2D -> forward -> D2H into `self.host_out`; returns it (synchronised)."""
+        self.static_in.copy_(host_in, non_blocking=True)
+        self.graph.replay()
+        self.host_out.copy_(self.static_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.host_out

@@ -1,0 +1,240 @@
+"""Tensor-level wrappers over the C ABI (include/ym_b200.h).
+
+All activations are fp16 CUDA tensors of logical shape (B, H, W, C) whose channel dimension is dense
+(stride 1) — either contiguous NHWC or a channel slice of a wider NHWC buffer (pitch = stride of W).
+Nothing here falls back to torch: a missing library or a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_L = None
+LAUNCHES = 0  # number of kernel-launching C-ABI calls issued (bench.py reports kernels via LAUNCH_KERNELS)
+KERNELS = 0   # number of device kernels launched (a call may launch several)
+
+
+def lib():
+    global _L
+    if _L is None:
+        _L = _lib.load()
+    return _L
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _count(nkernels: int = 1):
+    global LAUNCHES, KERNELS
+    LAUNCHES += 1
+    KERNELS += nkernels
+
+
+def pitch(t: torch.Tensor, dtype=torch.float16) -> int:
+    """Row pitch (elements) of an NHWC activation view; validates the layout."""
+    if t.dim() != 4 or t.dtype != dtype or not t.is_cuda:
+        raise ValueError(f"expected a 4-D fp16 CUDA NHWC activation, got {tuple(t.shape)} {t.dtype} {t.device}")
+    B, H, W, Cc = t.shape
+    sb, sh, sw, sc = t.stride()
+    if Cc > 1 and sc != 1:
+        raise ValueError("NHWC activation must have a dense channel dimension")
+    ld = sw if W > 1 else (sh if H > 1 else (sb if B > 1 else Cc))
+    if (W > 1 and H > 1 and sh != W * ld) or (B > 1 and sb != H * W * ld):
+        raise ValueError(f"activation is not a (sliced) contiguous NHWC tensor: shape {tuple(t.shape)} strides {t.stride()}")
+    return ld
+
+
+def new_act(B, H, W, Cc, device) -> torch.Tensor:
+    return torch.empty((B, H, W, Cc), dtype=torch.float16, device=device)
+
+
+def conv2d(x, w_packed, bias, Cout, KH, KW, stride, pad, act, out=None, res=None, out_f32=False):
+    """ym_conv2d_nhwc.  x: (B,H,W,Cin) view.  Returns `out` (B,Ho,Wo,Cout)."""
+    B, H, W, Cin = x.shape
+    Ho = (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32 if out_f32 else torch.float16, device=x.device)
+        ldo = Cout
+    else:
+        ldo = pitch(out, torch.float32 if out_f32 else torch.float16)
+    if tuple(out.shape) != (B, Ho, Wo, Cout):
+        raise ValueError(f"conv2d: out shape {tuple(out.shape)} != {(B, Ho, Wo, Cout)}")
+    ldr = 0
+    rp = None
+    if res is not None:
+        if tuple(res.shape) != (B, Ho, Wo, Cout):
+            raise ValueError("conv2d: residual shape mismatch")
+        ldr = pitch(res)
+        rp = res.data_ptr()
+    _lib.check(lib().ym_conv2d_nhwc(x.data_ptr(), pitch(x), B, H, W, Cin, w_packed.data_ptr(), w_packed.shape[1],
+                                    None if bias is None else bias.data_ptr(), Cout, KH, KW, stride, pad,
+                                    out.data_ptr(), ldo, 1 if out_f32 else 0, rp, ldr, 1 if act else 0, _stream()),
+               "ym_conv2d_nhwc")
+    _count()
+    return out
+
+
+def stem_conv(img, wgt, bias, Cout, out=None):
+    """ym_stem_conv_nchw.  img: contiguous NCHW fp16/fp32/uint8."""
+    if not img.is_cuda or img.dim() != 4:
+        raise ValueError("stem_conv: expected a 4-D CUDA NCHW image batch")
+    img = img.contiguous()
+    dt = {torch.float16: 0, torch.float32: 1, torch.uint8: 2}.get(img.dtype)
+    if dt is None:
+        raise ValueError(f"stem_conv: unsupported image dtype {img.dtype}")
+    B, Cin, H, W = img.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if out is None:
+        out = new_act(B, Ho, Wo, Cout, img.device)
+    _lib.check(lib().ym_stem_conv_nchw(img.data_ptr(), dt, B, Cin, H, W, wgt.data_ptr(), bias.data_ptr(), Cout,
+                                       out.data_ptr(), pitch(out), _stream()), "ym_stem_conv_nchw")
+    _count()
+    return out
+
+
+def dwconv(x, w_taps, bias, ksize, act, C_out, grp_w=None, grp_stride=None, grp_off=0, add=None, out=None):
+    """ym_dwconv_nhwc.  x: (B,H,W,Cx) source view; output has C_out channels gathered per the group mapping."""
+    B, H, W, _ = x.shape
+    if grp_w is None:
+        grp_w, grp_stride = C_out, C_out
+    if out is None:
+        out = new_act(B, H, W, C_out, x.device)
+    _lib.check(lib().ym_dwconv_nhwc(x.data_ptr(), pitch(x), grp_w, grp_stride, grp_off, w_taps.data_ptr(),
+                                    None if bias is None else bias.data_ptr(), B, H, W, C_out, ksize, 1 if act else 0,
+                                    None if add is None else add.data_ptr(), 0 if add is None else pitch(add),
+                                    out.data_ptr(), pitch(out), _stream()), "ym_dwconv_nhwc")
+    _count()
+    return out
+
+
+def sppf_pool(buf, Cslot, k):
+    B, H, W, Ct = buf.shape
+    _lib.check(lib().ym_sppf_pool_nhwc(buf.data_ptr(), pitch(buf), B, H, W, Cslot, k, _stream()), "ym_sppf_pool_nhwc")
+    _count()
+    return buf
+
+
+def concat2(a, b, up=1, out=None):
+    """cat([upsample(a, up), b], channel).  b may be None (pure upsample / copy)."""
+    Ba, Ha, Wa, Ca = a.shape
+    H, W = Ha * up, Wa * up
+    Cb = 0 if b is None else b.shape[3]
+    if b is not None and tuple(b.shape[:3]) != (Ba, H, W):
+        raise ValueError(f"concat2: spatial mismatch {tuple(a.shape)} x{up} vs {tuple(b.shape)}")
+    if out is None:
+        out = new_act(Ba, H, W, Ca + Cb, a.device)
+    _lib.check(lib().ym_concat2_nhwc(a.data_ptr(), pitch(a), Ca, up, None if b is None else b.data_ptr(),
+                                     8 if b is None else pitch(b), Cb, out.data_ptr(), pitch(out), Ba, H, W, _stream()),
+               "ym_concat2_nhwc")
+    _count()
+    return out
+
+
+def attention(qkv, batch, N, heads, head_stride, q_off, k_off, v_off, d_qk, d_v, scale, out=None):
+    """ym_attention_fwd over the rows of `qkv` (B,H,W,Ctot) reinterpreted as (batch, N, Ctot)."""
+    B, H, W, _ = qkv.shape
+    if B * H * W != batch * N:
+        raise ValueError("attention: batch*N must equal the number of token rows")
+    if out is None:
+        out = new_act(B, H, W, heads * d_v, qkv.device)
+    _lib.check(lib().ym_attention_fwd(qkv.data_ptr(), pitch(qkv), batch, N, heads, head_stride, q_off, k_off, v_off, d_qk,
+                                      d_v, float(scale), out.data_ptr(), pitch(out), _stream()), "ym_attention_fwd")
+    _count()
+    return out
+
+
+def router_topk(x, pack, topk, pool=4):
+    """ym_router_topk.  Returns (idx int32 [B,k], w fp32 [B,k], probs fp32 [B,E])."""
+    B, H, W, Cc = x.shape
+    Cr, E = pack["Cr"], pack["E"]
+    n = lib().ym_router_scratch_floats(B, H, W, Cc, Cr, pool)
+    scratch = torch.empty((n,), dtype=torch.float32, device=x.device)
+    idx = torch.empty((B, topk), dtype=torch.int32, device=x.device)
+    w = torch.empty((B, topk), dtype=torch.float32, device=x.device)
+    probs = torch.empty((B, E), dtype=torch.float32, device=x.device)
+    _lib.check(lib().ym_router_topk(x.data_ptr(), pitch(x), B, H, W, Cc, pool, pack["w1"].data_ptr(), Cr,
+                                    pack["scale1"].data_ptr(), pack["shift1"].data_ptr(), pack["w2"].data_ptr(),
+                                    pack["scale2"].data_ptr(), pack["shift2"].data_ptr(), E, topk, scratch.data_ptr(),
+                                    idx.data_ptr(), w.data_ptr(), probs.data_ptr(), _stream()), "ym_router_topk")
+    _count(3)
+    return idx, w, probs
+
+
+def moe_expert_gemm(a, lda, a_div, P, HW, K, w_all, route_idx, N, a_scale=None, a_shift=None, groups=0):
+    """ym_moe_expert_gemm.  Returns (out fp16 [P,HW,N], stats fp32 [P,groups,2] or None)."""
+    dev = route_idx.device
+    out = torch.empty((P, HW, N), dtype=torch.float16, device=dev)
+    stats = torch.empty((P, groups, 2), dtype=torch.float32, device=dev) if groups else None
+    E, Nw, Kpad = w_all.shape
+    _lib.check(lib().ym_moe_expert_gemm(a.data_ptr(), lda, a_div, P, HW, K, w_all.data_ptr(), Kpad, Nw * Kpad,
+                                        route_idx.data_ptr(), N, out.data_ptr(), N,
+                                        None if a_scale is None else a_scale.data_ptr(),
+                                        None if a_shift is None else a_shift.data_ptr(),
+                                        None if stats is None else stats.data_ptr(), groups, _stream()),
+               "ym_moe_expert_gemm")
+    _count(2 if groups else 1)
+    return out, stats
+
+
+def gn_finalize(stats, C_, count, eps, gamma, beta, route_idx, route_w=None):
+    P, G, _ = stats.shape
+    scale = torch.empty((P, C_), dtype=torch.float32, device=stats.device)
+    shift = torch.empty((P, C_), dtype=torch.float32, device=stats.device)
+    _lib.check(lib().ym_gn_finalize(stats.data_ptr(), P, G, C_, float(count), float(eps), gamma.data_ptr(), beta.data_ptr(),
+                                    route_idx.data_ptr(), None if route_w is None else route_w.data_ptr(),
+                                    scale.data_ptr(), shift.data_ptr(), _stream()), "ym_gn_finalize")
+    _count()
+    return scale, shift
+
+
+def moe_combine(x, ws_packed, bias_s, o, o_scale, o_shift, topk, add_residual=True, out=None):
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = new_act(B, H, W, Cc, x.device)
+    _lib.check(lib().ym_moe_combine(x.data_ptr(), pitch(x), B, H * W, Cc, ws_packed.data_ptr(), ws_packed.shape[1],
+                                    bias_s.data_ptr(), o.data_ptr(), o.shape[2], o_scale.data_ptr(), o_shift.data_ptr(),
+                                    topk, out.data_ptr(), pitch(out), 1 if add_residual else 0, _stream()),
+               "ym_moe_combine")
+    _count()
+    return out
+
+
+def _level_arrays(boxes, logits, strides):
+    nl = len(boxes)
+    VP = C.c_void_p * nl
+    bp = VP(*[b.data_ptr() for b in boxes])
+    cp = VP(*[c.data_ptr() for c in logits])
+    hs = (C.c_int * nl)(*[b.shape[1] for b in boxes])
+    ws = (C.c_int * nl)(*[b.shape[2] for b in boxes])
+    st = (C.c_float * nl)(*[float(s) for s in strides])
+    return nl, bp, cp, hs, ws, st
+
+
+def detect_topk(boxes, logits, strides, nc, max_det=300, return_anchor=False):
+    """boxes[l]: fp32 (B,h,w,4); logits[l]: fp32 (B,h,w,nc).  Returns (B,k,6) fp32 [+ anchor ids (B,k) int32]."""
+    B = boxes[0].shape[0]
+    A = sum(b.shape[1] * b.shape[2] for b in boxes)
+    k = min(max_det, A)
+    out = torch.empty((B, k, 6), dtype=torch.float32, device=boxes[0].device)
+    anc = torch.empty((B, k), dtype=torch.int32, device=boxes[0].device) if return_anchor else None
+    nl, bp, cp, hs, ws, st = _level_arrays(boxes, logits, strides)
+    _lib.check(lib().ym_detect_topk(nl, bp, cp, hs, ws, st, B, nc, max_det, out.data_ptr(),
+                                    None if anc is None else anc.data_ptr(), _stream()), "ym_detect_topk")
+    _count()
+    return (out, anc) if return_anchor else out
+
+
+def detect_dense(boxes, logits, strides, nc, xyxy):
+    B = boxes[0].shape[0]
+    A = sum(b.shape[1] * b.shape[2] for b in boxes)
+    y = torch.empty((B, 4 + nc, A), dtype=torch.float32, device=boxes[0].device)
+    nl, bp, cp, hs, ws, st = _level_arrays(boxes, logits, strides)
+    _lib.check(lib().ym_detect_dense(nl, bp, cp, hs, ws, st, B, nc, 1 if xyxy else 0, y.data_ptr(), _stream()),
+               "ym_detect_dense")
+    _count()
+    return y
