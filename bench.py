@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: yolo26-master-n detection forward, synthetic 640x640 batches (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one forward pass of a batch of 32 synthetic images per GPU (weak scaling: per-GPU batch fixed).
+  value     images/s with the batch already resident in HBM (CUDA-graph replay of the whole forward, CUDA events,
+            max over ranks)
+  e2e       images/s through the host-buffer call: pinned host images -> H2D -> forward -> D2H of the (B,300,6) result
+  roofline  dominant kernel (area attention at P3) timed live with CUDA events, vs MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (port of the reference's PyTorch path) on a bounded sample, host cores stated
+`--impl reference` times the reference's own algorithm (oracle port, fp32 PyTorch-CPU, all host threads) on rank 0.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+METRIC = "images/sec @ 640x640 bs32"
+UNIT = "images/s"
+IMG = 640
+FLOPS_PER_IMAGE = 30.23e9      # conv 7.67 G + attention bmm 22.57 G (2*MAC)
+BYTES_PER_IMAGE = 139e6        # SURVEY.md §8d algorithmic fp16 bytes (unfused layer I/O + attention streams)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"], "tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+def synthetic_weights():
+    from _util import synth_sd_from_keys
+    return synth_sd_from_keys(0)
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/ym_clocks_{os.getpid()}.csv"
+
+    def __enter__(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.f.close()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            sm = sorted(float(r[1]) for r in rows)
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["samples"] = len(sm)
+                out["power_w_max"] = max(float(r[3]) for r in rows)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for j, n in enumerate(names):
+                    if any(r[5 + j].strip().lower().startswith("active") for r in rows):
+                        out["reasons"].append(n)
+            os.remove(self.path)
+        except Exception as e:  # clocks are evidence, never a reason to lose the number
+            out["error"] = str(e)
+        return out
+
+
+def run_reference(args):
+    """Reference arm: the reference's PyTorch-CPU algorithm (oracle port), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from _util import yaml_n
+    from oracle import yolo_master_oracle as O
+    from yolo_master_b200.utils.synth import synth_images
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec, sd = O.parse_spec(yaml_n()), synthetic_weights()
+    sample = args.ref_images
+    x = synth_images(sample, IMG, IMG, 0)
+    with torch.inference_mode():
+        for _ in range(args.warmup):
+            O.forward(spec, sd, x)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.forward(spec, sd, x)
+        dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "yolo26-master-n forward, 640x640, bs32 per GPU (configs[1])", "imgsz": IMG,
+                   "sample_images_per_step": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} synthetic 640x640 images per step (of the 32-image batch), fp32, oracle port of the reference PyTorch-CPU forward"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def time_attention_kernel(dev, batch, pk):
+    """Dominant kernel, timed alone on the launching stream: AAttn at P3 (80x80 tokens, 2 heads x 32) for the full batch."""
+    from yolo_master_b200 import ops
+    N, heads, hd = (IMG // 8) ** 2, 2, 32
+    qkv = torch.randn((batch, IMG // 8, IMG // 8, 3 * heads * hd), device=dev).half()
+    out = ops.new_act(batch, IMG // 8, IMG // 8, heads * hd, dev)
+    for _ in range(3):
+        ops.attention(qkv, batch, N, heads, 3 * hd, 0, hd, 2 * hd, hd, hd, hd ** -0.5, out=out)
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        ops.attention(qkv, batch, N, heads, 3 * hd, 0, hd, 2 * hd, hd, hd, hd ** -0.5, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 4.0 * N * N * hd * heads * batch
+    algo_bytes = 4.0 * N * hd * heads * batch * 2
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"kernel": "attention_fwd_kernel<32> (AAttn P3: N=6400, 2 heads x d32, whole batch)", "bound": "tensor",
+            "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": ach / pk["tflops_burst"], "traffic": None,
+            "ms_per_launch": ms, "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": algo_bytes,
+            "exp_per_launch": float(N) * N * heads * batch,
+            "note": "d=32 attention is bounded by MUFU exp throughput, not the tensor pipe (SURVEY.md §7); "
+                    "peak = cuBLAS bf16 burst " + pk["source"]}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from yolo_master_b200 import ops
+    from yolo_master_b200.nn.tasks import DetectionModel
+    from yolo_master_b200.utils.synth import synth_images
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    B = args.batch
+
+    # ---- model: rank 0 owns the (synthetic) checkpoint, weights broadcast over NCCL/NVLink once at start-up
+    model = DetectionModel("yolo26-master-n.yaml")
+    if rank == 0:
+        model.load_state_dict(synthetic_weights())
+    model.to(dev).eval()
+    if world > 1:
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=0)
+
+    # ---- CPU baseline (rank 0, N==1): oracle port on a bounded sample of the same workload
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from _util import yaml_n
+        from oracle import yolo_master_oracle as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        spec, sd = O.parse_spec(yaml_n()), synthetic_weights()
+        xs = synth_images(args.ref_images, IMG, IMG, 0)
+        with torch.inference_mode():
+            O.forward(spec, sd, xs[:1])
+            t0 = time.perf_counter()
+            reps = 0
+            while reps < 2 or time.perf_counter() - t0 < 10.0:
+                O.forward(spec, sd, xs)
+                reps += 1
+            dt = time.perf_counter() - t0
+        cpu_base = {"value": args.ref_images * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{reps} x {args.ref_images} synthetic 640x640 images, fp32 PyTorch-CPU oracle port ({dt:.1f} s)"}
+
+    # ---- inputs: 4 rotating device batches (315 MB > 126 MB L2) + pinned host copies for the e2e leg
+    nrot = 4
+    dev_in = [synth_images(B, IMG, IMG, seed=100 + rank * 10 + i).half().to(dev) for i in range(nrot)]
+    host_in = [synth_images(B, IMG, IMG, seed=200 + rank * 10 + i).half().pin_memory() for i in range(2)]
+    g = model.graphed(B, IMG, IMG, dtype=torch.float16)
+    kernels_per_step = g.kernels_per_replay
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with ClockSampler(local) as clk:
+        ms_dev = timed(lambda i: g(dev_in[i % nrot]), args.steps, args.warmup)
+    clocks = clk.summary()
+    ms_e2e = timed(lambda i: g.run_host(host_in[i % 2]), args.steps, args.warmup)
+
+    value = world * B * args.steps / (ms_dev * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    roof = time_attention_kernel(dev, B, pk) if rank == 0 else None
+
+    if rank == 0:
+        step_ms = ms_dev / args.steps
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": "yolo26-master-n forward, 640x640, bs32 per GPU (BASELINE.json configs[1]); random-init "
+                                   "weights (key-seeded) with calibrated BatchNorm statistics; ES-MoE top-2 of 4/8/16 experts",
+                       "global_batch": world * B, "imgsz": IMG, "parallelism": f"replicas x{world} (no data-path collective)",
+                       "l2": f"{nrot} rotating input batches ({nrot * B * 3 * IMG * IMG * 2 / 1e6:.0f} MB) and ~{BYTES_PER_IMAGE * B / 1e9:.1f} GB "
+                             "of per-step activations exceed the 126 MB L2",
+                       "execution": "CUDA graph of the whole forward"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * 3 * IMG * IMG * 2, "d2h_bytes_per_step": B * 300 * 6 * 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": kernels_per_step * args.steps,
+            "kernels_per_step": kernels_per_step,
+            "clocks": clocks,
+            "roofline": roof,
+            "model_roofline": {"flops_per_image": FLOPS_PER_IMAGE, "bytes_per_image": BYTES_PER_IMAGE,
+                               "tflops": FLOPS_PER_IMAGE * value / world / 1e12,
+                               "algorithmic_gbs": BYTES_PER_IMAGE * value / world / 1e9,
+                               "hbm_frac": BYTES_PER_IMAGE * value / world / 1e9 / pk["hbm_gbs"],
+                               "tensor_frac": FLOPS_PER_IMAGE * value / world / 1e12 / pk["tflops_sustained"]},
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--ref-images", type=int, default=4, help="images per CPU-oracle step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
