@@ -67,14 +67,16 @@ int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C, int pool,
  * OptimizedMOEImproved.forward moe/modules.py:1128-1142 for SimpleExpert's two 1x1 convs (moe/experts.py:79-85).
  * Problem p: expert e = route_idx[p]; A = a + (p/a_div)*HW*lda [HW x K]; out + p*HW*ldo [HW x N] fp16.
  * a_scale/a_shift (nullable, [P][K]): A := SiLU(A*scale + shift) (GroupNorm+SiLU of the hidden, fused on load).
- * stats (nullable, [P][groups][2], zeroed here): per-(problem, group) sum / sum-of-squares of the stored output. */
+ * stats (nullable, ym_moe_stats_floats(P,HW,N) floats): per-(problem, M tile, 8-channel tile) partial sum / sum-of-squares
+ * of the stored output, written without atomics so the statistics are bit-reproducible. */
+long long ym_moe_stats_floats(int P, int HW, int N);
 int ym_moe_expert_gemm(const void* a, int lda, int a_div, int P, int HW, int K, const void* w, int Kpad,
                        long long w_expert_stride, const int* route_idx, int N, void* out, int ldo, const float* a_scale,
                        const float* a_shift, float* stats, int groups, void* stream);
 
-/* GroupNorm statistics -> per-(problem, channel) affine: scale = rw*rstd*gamma[e], shift = rw*(beta[e] - mean*rstd*gamma[e])
+/* GroupNorm partial statistics (fixed-order reduction) -> per-(problem, channel) affine: scale = rw*rstd*gamma[e], shift = rw*(beta[e] - mean*rstd*gamma[e])
  * (nn.GroupNorm inside SimpleExpert, experts.py:81,84; rw = routing weight folds modules.py:1139-1142 into GN2). */
-int ym_gn_finalize(const float* stats, int P, int groups, int C, float count, float eps, const float* gamma,
+int ym_gn_finalize(const float* stats, int P, int HW, int groups, int C, float count, float eps, const float* gamma,
                    const float* beta, const int* route_idx, const float* route_w, float* scale, float* shift, void* stream);
 
 /* out = [x +] SiLU(BN(shared 1x1(x))) + sum_j (o_j*o_scale_j + o_shift_j): shared expert + weighted expert sum in fp32

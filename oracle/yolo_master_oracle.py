@@ -22,6 +22,28 @@ from typing import Any
 import torch
 import torch.nn.functional as F
 
+import contextlib
+
+_SIM_FP16 = False  # see fp16_storage()
+
+
+@contextlib.contextmanager
+def fp16_storage():
+    """Noise-floor model: same fp32 arithmetic, but every stored activation (conv / attention / expert outputs) is
+    rounded to fp16, as ANY fp16 execution of this graph (the reference's `.half()` path included) must do.  Tests use
+    |oracle_fp16_storage - oracle| as the yardstick for errors that accumulate across chained layers."""
+    global _SIM_FP16
+    old, _SIM_FP16 = _SIM_FP16, True
+    try:
+        yield
+    finally:
+        _SIM_FP16 = old
+
+
+def _st(t):
+    return t.half().float() if _SIM_FP16 else t
+
+
 BN_EPS = 1e-3  # utils/torch_utils.py:552-562 rewrites eps on every nn.BatchNorm2d
 GN_EPS = 1e-5  # nn.GroupNorm default, untouched by initialize_weights
 
@@ -119,7 +141,7 @@ def conv_block(sd, p, x, s=1, g=1, act=True, pad=None):
     pad = k // 2 if pad is None else pad
     y = F.conv2d(x, w, sd.get(p + ".conv.bias"), s, pad, 1, g)
     y = _bn(sd, p + ".bn", y)
-    return F.silu(y) if act else y
+    return _st(F.silu(y) if act else y)
 
 
 def dwconv_block(sd, p, x, act=True):
@@ -133,7 +155,7 @@ def bottleneck(sd, p, x, shortcut=True, g=1):
     """`Bottleneck.forward` block.py:484-486 (k=(3,3); c1==c2 inside C3k2/C3k)."""
     y = conv_block(sd, p + ".cv2", conv_block(sd, p + ".cv1", x), 1, g)
     add = shortcut and x.shape[1] == y.shape[1]
-    return x + y if add else y
+    return _st(x + y) if add else y
 
 
 def c3k(sd, p, x, n=2, shortcut=True, g=1):
@@ -155,16 +177,16 @@ def attention(sd, p, x, num_heads, attn_ratio=0.5):
     q, k, v = qkv.view(B, num_heads, key_dim * 2 + head_dim, N).split([key_dim, key_dim, head_dim], dim=2)
     attn = (q * scale).transpose(-2, -1) @ k
     attn = attn.softmax(dim=-1)
-    o = (v @ attn.transpose(-2, -1)).view(B, C, H, W) + conv_block(sd, p + ".pe", v.reshape(B, C, H, W), 1, C, False)
-    return conv_block(sd, p + ".proj", o, act=False)
+    o = _st((v @ attn.transpose(-2, -1)).view(B, C, H, W)) + conv_block(sd, p + ".pe", v.reshape(B, C, H, W), 1, C, False)
+    return conv_block(sd, p + ".proj", _st(o), act=False)
 
 
 def psablock(sd, p, x, num_heads, shortcut=True):
     """`PSABlock.forward` block.py:1372-1383."""
     a = attention(sd, p + ".attn", x, num_heads)
-    x = x + a if shortcut else a
+    x = _st(x + a) if shortcut else a
     f = conv_block(sd, p + ".ffn.1", conv_block(sd, p + ".ffn.0", x), act=False)
-    return x + f if shortcut else f
+    return _st(x + f) if shortcut else f
 
 
 def aattn(sd, p, x, num_heads, area=1):
@@ -180,14 +202,14 @@ def aattn(sd, p, x, num_heads, area=1):
     q, k, v = qkv.view(Bq, N, num_heads, hd * 3).permute(0, 2, 3, 1).split([hd, hd, hd], dim=2)
     attn = (q * (hd ** -0.5)).transpose(-2, -1) @ k
     attn = attn.softmax(dim=-1)
-    o = (v @ attn.transpose(-2, -1)).permute(0, 3, 1, 2)
+    o = _st(v @ attn.transpose(-2, -1)).permute(0, 3, 1, 2)
     v = v.permute(0, 3, 1, 2)
     if area > 1:
         o = o.reshape(B, N * area, C)
         v = v.reshape(B, N * area, C)
     o = o.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
     v = v.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
-    o = o + conv_block(sd, p + ".pe", v, 1, C, False, pad=3)
+    o = _st(o + conv_block(sd, p + ".pe", v, 1, C, False, pad=3))
     return conv_block(sd, p + ".proj", o, act=False)
 
 
@@ -204,10 +226,10 @@ def get_safe_groups(channels: int, desired: int = 8) -> int:
 def simple_expert(sd, p, x):
     """`SimpleExpert` moe/experts.py:73-88: 1x1 -> GN -> SiLU -> 1x1 -> GN."""
     w1, w2 = sd[p + ".conv.0.weight"], sd[p + ".conv.3.weight"]
-    h = F.conv2d(x, w1)
+    h = _st(F.conv2d(x, w1))
     h = F.group_norm(h, get_safe_groups(w1.shape[0]), sd[p + ".conv.1.weight"], sd[p + ".conv.1.bias"], GN_EPS)
     h = F.silu(h)
-    o = F.conv2d(h, w2)
+    o = _st(F.conv2d(h, w2))
     return F.group_norm(o, get_safe_groups(w2.shape[0]), sd[p + ".conv.4.weight"], sd[p + ".conv.4.bias"], GN_EPS)
 
 
@@ -240,13 +262,13 @@ def optimized_moe_improved(sd, p, x, num_experts, top_k):
             bi, ki = torch.where(mask)
             o = simple_expert(sd, f"{p}.experts.{e}", x[bi])
             out.index_add_(0, bi, o.float() * w[bi, ki].view(-1, 1, 1, 1))
-    return (shared.float() + out).to(x.dtype)
+    return _st((shared.float() + out).to(x.dtype))
 
 
 def ablock_moe(sd, p, x, num_heads, area, num_experts, top_k):
     """`ABlockMoE.forward` moe/modules.py:1247-1260."""
-    x = x + aattn(sd, p + ".attn", x, num_heads, area)
-    return x + optimized_moe_improved(sd, p + ".mlp", x, num_experts, top_k)
+    x = _st(x + aattn(sd, p + ".attn", x, num_heads, area))
+    return _st(x + optimized_moe_improved(sd, p + ".mlp", x, num_experts, top_k))
 
 
 # ----------------------------------------------------------------------------
@@ -386,6 +408,19 @@ def detect_postprocess(y, nc, max_det=300):
 # ----------------------------------------------------------------------------
 _LAYER_FN = {"Conv": layer_conv, "C3k2": layer_c3k2, "C2f": layer_c2f, "SPPF": layer_sppf, "C2PSA": layer_c2psa,
              "A2C2fMoE": layer_a2c2f_moe}
+
+
+def forward_layer(spec: dict, sd: dict, i: int, xin):
+    """Run ONE top-level layer (not Detect) on given input(s): used for teacher-forced per-layer parity."""
+    L = spec["layers"][i]
+    t, args = L["type"], L["args"]
+    if t in _LAYER_FN:
+        return _LAYER_FN[t](sd, f"model.{i}", xin, *args)
+    if t == "nn.Upsample":
+        return F.interpolate(xin, scale_factor=float(args[1]), mode=args[2])
+    if t == "Concat":
+        return torch.cat(xin, args[0] if args else 1)
+    raise NotImplementedError(t)
 
 
 def forward(spec: dict, sd: dict, x: torch.Tensor, img_hw=None, return_layers: bool = False,

@@ -40,3 +40,16 @@ def close_stats(a, b, atol=ATOL, rtol=RTOL):
 def assert_close(a, b, atol=ATOL, rtol=RTOL, max_bad_frac=0.0, what=""):
     mx, bad = close_stats(a, b, atol, rtol)
     assert bad <= max_bad_frac, f"{what}: max abs err {mx:.3e}, {bad * 100:.4f}% of elements outside atol={atol} rtol={rtol}"
+
+
+def assert_within_noise(y, ref, sim, what="", k_mean=2.0, k_max=3.0):
+    """Chained-op criterion: the CUDA path's deviation from the fp32 oracle must stay within a small multiple of the
+    deviation of the oracle's own fp16-storage model (`oracle.fp16_storage()`), i.e. within the noise ANY fp16 execution
+    of the same graph has.  Single kernels are held to the strict north-star tolerance instead (assert_close)."""
+    y, ref, sim = y.float().cpu(), ref.float(), sim.float()
+    e, n = (y - ref).abs(), (sim - ref).abs()
+    rms = float(ref.pow(2).mean().sqrt())
+    assert float(e.mean()) <= k_mean * float(n.mean()) + 2e-4 * rms, \
+        f"{what}: mean err {float(e.mean()):.3e} vs fp16-storage noise {float(n.mean()):.3e} (rms {rms:.3f})"
+    assert float(e.max()) <= k_max * float(n.max()) + 2e-3 * max(1.0, rms), \
+        f"{what}: max err {float(e.max()):.3e} vs fp16-storage noise max {float(n.max()):.3e} (rms {rms:.3f})"

@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-from _util import GOLD, close_stats, synth_sd_from_keys, yaml_n
+from _util import GOLD, assert_within_noise, close_stats, synth_sd_from_keys, yaml_n
 from oracle import yolo_master_oracle as O
 from yolo_master_b200.nn.tasks import DetectionModel
 from yolo_master_b200.utils.synth import synth_images
@@ -33,22 +33,31 @@ def _layers(m, x):
     return y[0], feats
 
 
-def _check_dets(y, ref, score_tol=1e-2, box_tol=1.0):
-    """Detections clear of the cut-off must be reproduced (same class, score within tol, box within tol pixels)."""
+def _repro_frac(y, ref, score_tol=1e-2, box_tol=1.0):
+    """Fraction of reference detections clear of the score cut-off that `y` reproduces (same class, score and box)."""
     y = y.float().cpu()
-    n_checked = 0
+    hit = tot = 0
     for b in range(y.shape[0]):
         kth = ref[b, -1, 4]
         for r in ref[b]:
             if r[4] < kth + 2 * score_tol:
                 continue
+            tot += 1
             same = (y[b, :, 5] == r[5]) & ((y[b, :, 4] - r[4]).abs() < score_tol)
-            assert same.any(), f"image {b}: reference detection {r.tolist()} not reproduced"
-            assert (y[b][same][:, :4] - r[:4]).abs().max(1)[0].min() < box_tol
-            n_checked += 1
-    assert n_checked > 0.5 * ref.shape[0] * ref.shape[1]
-    s1, s2 = y[..., 4].sort(dim=1, descending=True)[0], ref[..., 4].sort(dim=1, descending=True)[0]
-    assert (s1 - s2).abs().max() < score_tol
+            if same.any() and (y[b][same][:, :4] - r[:4]).abs().max(1)[0].min() < box_tol:
+                hit += 1
+    return hit / max(tot, 1), tot
+
+
+def _check_dets(y, ref, sim):
+    """Detections must agree with the fp32 oracle at least as well as the oracle's own fp16-storage model does."""
+    f_ours, tot = _repro_frac(y, ref)
+    f_sim, _ = _repro_frac(sim, ref)
+    assert tot > 0.3 * ref.shape[0] * ref.shape[1]
+    assert f_ours >= min(f_sim, 0.995) - 0.03 and f_ours > 0.85, f"reproduced {f_ours:.3f} of {tot} detections (fp16 noise floor {f_sim:.3f})"
+    s1, s2 = y.float().cpu()[..., 4].sort(dim=1, descending=True)[0], ref[..., 4].sort(dim=1, descending=True)[0]
+    s3 = sim[..., 4].sort(dim=1, descending=True)[0]
+    assert (s1 - s2).abs().max() <= 3 * (s3 - s2).abs().max() + 2e-3
 
 
 @pytest.mark.parametrize("tag", ["b2_160", "b1_64"])
@@ -58,12 +67,11 @@ def test_model_matches_reference_golden(model_and_sd, tag):
     c = torch.load(os.path.join(GOLD, "yolo26-master-n.golden.pt"))["cases"][tag]
     x = synth_images(c["B"], c["H"], c["W"], c["seed"]).half().to(DEV)
     y, feats = _layers(m, x)
+    with O.fp16_storage():   # noise floor of fp16 storage for this graph, from the oracle itself
+        ysim, sim = O.forward(O.parse_spec(yaml_n()), model_and_sd[1], x.float().cpu(), return_layers=True)
     for i, ref in c["layers"].items():
-        mx, _ = close_stats(feats[i], ref)
-        rms = float(ref.pow(2).mean().sqrt())
-        mean_err = float((feats[i].float().cpu() - ref).abs().mean())
-        assert mean_err < 4e-3 * rms and mx < 8e-2 * max(rms, 1.0), f"layer {i}: max {mx:.3e} mean {mean_err:.3e} rms {rms:.3f}"
-    _check_dets(y, c["final"])
+        assert_within_noise(feats[i], ref, sim[i], what=f"layer {i} vs reference golden")
+    _check_dets(y, c["final"], ysim)
     for name, (w_ref, i_ref) in c["routes"].items():
         mod = dict(m.named_modules())[name.replace(".routing", "")]
         snap = mod.last_routing_snapshot
@@ -76,15 +84,43 @@ def test_model_640_vs_oracle(model_and_sd):
     m, sd = model_and_sd
     x = synth_images(2, 640, 640, 3)
     y, feats = _layers(m, x.half().to(DEV))
-    ref, ys = O.forward(O.parse_spec(yaml_n()), sd, x.half().float(), return_layers=True)
+    spec = O.parse_spec(yaml_n())
+    ref, ys = O.forward(spec, sd, x.half().float(), return_layers=True)
+    with O.fp16_storage():
+        ysim, sim = O.forward(spec, sd, x.half().float(), return_layers=True)
     for i in range(23):
-        if feats[i] is None or ys[i] is None:
+        if feats.get(i) is None:
             continue
-        a, b = feats[i].float().cpu(), ys[i]
-        rms = float(b.pow(2).mean().sqrt())
-        mean_err = float((a - b).abs().mean())
-        assert mean_err < 4e-3 * rms, f"layer {i}: mean err {mean_err:.3e} rms {rms:.3f}"
-    _check_dets(y, ref)
+        assert_within_noise(feats[i], ys[i], sim[i], what=f"layer {i} (end to end)")
+    _check_dets(y, ref, ysim)
+
+
+def test_layers_teacher_forced_640(model_and_sd):
+    """Every top-level layer at the 640x640 geometry, fed the ORACLE's (fp16-rounded) input, against the oracle's output
+    for that same input: per-layer parity without error accumulation from earlier layers."""
+    m, sd = model_and_sd
+    spec = O.parse_spec(yaml_n())
+    x = synth_images(2, 640, 640, 4).half().float()
+    _, ys = O.forward(spec, sd, x, return_layers=True)
+    ys16 = {k: (v.half() if torch.is_tensor(v) else v) for k, v in ys.items()}
+    for i, L in enumerate(spec["layers"][:-1]):
+        f = L["f"]
+        src = (lambda j: x.half() if (i == 0 and j == -1) else ys16[i - 1 if j == -1 else j])
+        xin = src(f) if isinstance(f, int) else [src(j) for j in f]
+        to_dev = lambda t: t.to(DEV).contiguous(memory_format=torch.channels_last)
+        with torch.no_grad():
+            y = m.model[i](to_dev(xin) if torch.is_tensor(xin) else [to_dev(t) for t in xin])
+        xin32 = xin.float() if torch.is_tensor(xin) else [t.float() for t in xin]
+        ref = O.forward_layer(spec, sd, i, xin32)
+        with O.fp16_storage():
+            sim = O.forward_layer(spec, sd, i, xin32)
+        if L["type"] in ("Concat", "nn.Upsample"):
+            assert torch.equal(y.float().cpu(), ref), f"layer {i} {L['type']}"
+        else:
+            assert_within_noise(y, ref, sim, what=f"layer {i} {L['type']} (teacher forced)")
+            if L["type"] == "Conv":   # a single fused kernel: strict north-star tolerance
+                mx, bad = close_stats(y, ref)
+                assert bad == 0.0, f"layer {i} Conv: {bad:.2e} outside tolerance (max {mx:.2e})"
 
 
 def test_graph_replay_and_host_api(model_and_sd):

@@ -6,7 +6,7 @@ import math
 import pytest
 import torch
 
-from _util import ATOL, RTOL, assert_close, close_stats
+from _util import ATOL, RTOL, assert_close, assert_within_noise, close_stats
 from oracle import yolo_master_oracle as O
 from yolo_master_b200.nn import modules as M
 from yolo_master_b200.utils.synth import fill_state_dict_
@@ -27,6 +27,14 @@ def _prep(mod, seed=0):
 def _x(B, C, H, W, seed=0, scale=1.0):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn((B, C, H, W), generator=g) * scale).half()
+
+
+def _noise(fn, *a):
+    """(fp32 oracle, fp16-storage oracle) outputs of an oracle function."""
+    ref = fn(*a)
+    with O.fp16_storage():
+        sim = fn(*a)
+    return ref, sim
 
 
 def _run(mod, x):
@@ -94,22 +102,22 @@ def test_concat_and_upsample():
 
 def test_bottleneck_and_c3k2_variants():
     x = _x(2, 64, 24, 20, seed=6)
-    for args, oargs in [((64, 64, 1, False, 0.25), None), ((64, 128, 1, True), None), ((64, 64, 1, True, 0.5, True), None)]:
+    for args in [(64, 64, 1, False, 0.25), (64, 128, 1, True), (64, 256, 1, True, 0.5, True)]:
         m = M.C3k2(*args)
         sd = _prep(m, seed=len(args))
         y = _run(m, x)
-        ref = O.layer_c3k2(sd, "m", x.float(), *args)
-        assert_close(y, ref, what=f"C3k2{args}")
+        ref, sim = _noise(O.layer_c3k2, sd, "m", x.float(), *args)
+        assert_within_noise(y, ref, sim, what=f"C3k2{args}")
 
 
 def test_sppf_and_c2psa():
     x = _x(2, 256, 20, 20, seed=7)
     m = M.SPPF(256, 256, 5)
     sd = _prep(m, 3)
-    assert_close(_run(m, x), O.layer_sppf(sd, "m", x.float(), 256, 256, 5), what="SPPF")
+    assert_within_noise(_run(m, x), *_noise(O.layer_sppf, sd, "m", x.float(), 256, 256, 5), what="SPPF")
     m = M.C2PSA(256, 256, 1)
     sd = _prep(m, 4)
-    assert_close(_run(m, x), O.layer_c2psa(sd, "m", x.float(), 256, 256, 1), what="C2PSA")
+    assert_within_noise(_run(m, x), *_noise(O.layer_c2psa, sd, "m", x.float(), 256, 256, 1), what="C2PSA")
 
 
 @pytest.mark.parametrize("dim,heads,area,hw", [(64, 2, 1, (40, 40)), (64, 2, 1, (13, 17)), (128, 4, 1, (20, 20)),
@@ -119,15 +127,31 @@ def test_area_attention(dim, heads, area, hw):
     sd = _prep(m, seed=dim + area)
     x = _x(2, dim, *hw, seed=8)
     y = _run(m, x)
-    ref = O.aattn(sd, "m", x.float(), heads, area)
-    assert_close(y, ref, what=f"AAttn({dim},{heads},{area},{hw})")
+    ref, sim = _noise(O.aattn, sd, "m", x.float(), heads, area)
+    assert_within_noise(y, ref, sim, what=f"AAttn({dim},{heads},{area},{hw})")
+    assert close_stats(y, ref)[1] < 5e-3   # >99.5% of elements inside the single-op tolerance even after 4 chained ops
+
+
+@pytest.mark.parametrize("N,heads,dv,batch", [(400, 2, 32, 3), (1600, 2, 32, 2), (221, 4, 32, 2), (400, 2, 64, 2), (6400, 2, 32, 1)])
+def test_attention_kernel_alone_strict(N, heads, dv, batch):
+    """The fused attention kernel by itself (given fp16 q,k,v) meets the strict tolerance against fp32 softmax attention."""
+    from yolo_master_b200 import ops
+    hs = 64 + dv
+    g = torch.Generator().manual_seed(N + dv)
+    qkv = torch.randn((batch, N, 1, heads * hs), generator=g).half()
+    out = ops.attention(qkv.to(DEV), batch, N, heads, hs, 0, 32, 64, 32, dv, 32 ** -0.5)
+    t = qkv.float().view(batch, N, heads, hs).permute(0, 2, 1, 3)
+    q, k, v = t[..., :32], t[..., 32:64], t[..., 64:]
+    ref = torch.softmax((q * 32 ** -0.5) @ k.transpose(-1, -2), -1) @ v          # (b, h, N, dv)
+    ref = ref.permute(0, 2, 1, 3).reshape(batch, N, 1, heads * dv)
+    assert_close(out, ref, what=f"attention N={N} dv={dv}")
 
 
 def test_psa_attention():
     m = M.Attention(128, num_heads=2, attn_ratio=0.5)
     sd = _prep(m, 9)
     x = _x(2, 128, 20, 20, seed=9)
-    assert_close(_run(m, x), O.attention(sd, "m", x.float(), 2), what="Attention")
+    assert_within_noise(_run(m, x), *_noise(O.attention, sd, "m", x.float(), 2), what="Attention")
 
 
 @pytest.mark.parametrize("C,E,hw", [(64, 4, (40, 40)), (64, 8, (20, 20)), (128, 16, (10, 10)), (64, 4, (4, 4)), (64, 4, (9, 13))])
@@ -154,21 +178,20 @@ def test_moe_ffn_block(C, E, hw):
     sd = _prep(m, seed=E + 1)
     x = _x(4, C, *hw, seed=11)
     y = _run(m, x)
-    ref = O.optimized_moe_improved(sd, "m", x.float(), E, 2)
-    assert_close(y, ref, what=f"OptimizedMOEImproved({C},{E})")
+    ref, sim = _noise(O.optimized_moe_improved, sd, "m", x.float(), E, 2)
+    assert_within_noise(y, ref, sim, what=f"OptimizedMOEImproved({C},{E})")
+    assert close_stats(y, ref)[1] < 1e-3
 
 
 def test_ablock_moe_and_a2c2f_moe():
     x = _x(2, 64, 20, 20, seed=12)
     m = M.ABlockMoE(64, 2, 2.0, 1, 4, 2)
     sd = _prep(m, 5)
-    assert_close(_run(m, x), O.ablock_moe(sd, "m", x.float(), 2, 1, 4, 2), what="ABlockMoE")
+    assert_within_noise(_run(m, x), *_noise(O.ablock_moe, sd, "m", x.float(), 2, 1, 4, 2), what="ABlockMoE")
     args = (64, 128, 1, True, 1, False, 2.0, 0.5, 1, True, 4, 2)
     m = M.A2C2fMoE(*args)
     sd = _prep(m, 6)
-    y, ref = _run(m, x), O.layer_a2c2f_moe(sd, "m", x.float(), *args)
-    mx, bad = close_stats(y, ref)
-    assert bad < 2e-3 and mx < 3e-2, (mx, bad)   # 8 chained fp16 ops: a handful of near-zero elements exceed atol
+    assert_within_noise(_run(m, x), *_noise(O.layer_a2c2f_moe, sd, "m", x.float(), *args), what="A2C2fMoE")
 
 
 def _match_dets(y, ref, score_tol=2e-3, box_tol=0.3):

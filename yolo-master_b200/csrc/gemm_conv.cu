@@ -41,7 +41,7 @@ struct GemmConvParams {
     // A-operand GroupNorm+SiLU prologue: per (problem, k) scale/shift
     const float* a_scale; const float* a_shift;
     // stats epilogue
-    float* stats; int groups;  // [P][groups][2]
+    float* stats; int groups;  // partial sums [P][m tiles][Cout/8][2]
     // combine epilogue
     const __half* o; int ldo_o; const float* o_scale; const float* o_shift; int topk; int HW;
 };
@@ -75,9 +75,6 @@ __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParam
             sXf[i] = sc[i];
             sXf[p.K + i] = sh[i];
         }
-    }
-    if (EPI == EPI_STATS) {
-        if (tid < (BN / 8) * 2) sXf[(A_XFORM ? 2 * p.K : 0) + tid] = 0.f;
     }
 
     // ---- per-thread A-row bookkeeping: thread owns chunk c=tid%4 of rows tid/4 + 32*i
@@ -272,10 +269,10 @@ __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParam
         if (EPI == EPI_STATS) {
             ssum = warp_sum(ssum);
             ssq = warp_sum(ssq);
-            if (lane == 0) {
+            if (lane == 0) {  // one slot per (warp, n8 tile): no atomics -> bit-reproducible statistics
                 float* sS = sXf + (A_XFORM ? 2 * p.K : 0);
-                atomicAdd(&sS[ni * 2 + 0], ssum);
-                atomicAdd(&sS[ni * 2 + 1], ssq);
+                sS[(warp * NT + ni) * 2 + 0] = ssum;
+                sS[(warp * NT + ni) * 2 + 1] = ssq;
             }
         }
     }
@@ -284,12 +281,17 @@ __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParam
         if (tid < NT) {
             const int n = n0 + tid * 8;
             if (n < p.Cout) {
-                const int cpg = p.Cout / p.groups;
-                const int grp = n / cpg;
                 const float* sS = sXf + (A_XFORM ? 2 * p.K : 0);
-                float* dst = p.stats + ((long long)prob * p.groups + grp) * 2;
-                atomicAdd(dst + 0, sS[tid * 2 + 0]);
-                atomicAdd(dst + 1, sS[tid * 2 + 1]);
+                float a = 0.f, q = 0.f;
+#pragma unroll
+                for (int w = 0; w < NTHREADS / 32; ++w) {
+                    a += sS[(w * NT + tid) * 2 + 0];
+                    q += sS[(w * NT + tid) * 2 + 1];
+                }
+                // partial statistics: [problem][m tile][n8 tile][2], reduced in fixed order by gn_finalize
+                float* dst = p.stats + (((long long)prob * gridDim.x + blockIdx.x) * (p.Cout / 8) + (n >> 3)) * 2;
+                dst[0] = a;
+                dst[1] = q;
             }
         }
     }
@@ -299,7 +301,7 @@ template <int BN, int EPI, bool A_XFORM>
 static int launch_gemm(const GemmConvParams& p, int problems, cudaStream_t stream) {
     size_t smem = (size_t)STAGES * (BM + BN) * SK * sizeof(__half);
     if (A_XFORM) smem += 2 * (size_t)p.K * sizeof(float);
-    if (EPI == EPI_STATS) smem += (BN / 8) * 2 * sizeof(float);
+    if (EPI == EPI_STATS) smem += (NTHREADS / 32) * (BN / 8) * 2 * sizeof(float);
     auto kern = gemm_conv_kernel<BN, EPI, A_XFORM>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -375,8 +377,6 @@ extern "C" int ym_moe_expert_gemm(const void* a, int lda, int a_div, int P, int 
     p.a_scale = a_scale; p.a_shift = a_shift; p.stats = stats; p.groups = groups;
     cudaStream_t st = (cudaStream_t)stream;
     if (stats != nullptr) {
-        cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)P * groups * 2 * sizeof(float), st);
-        if (e != cudaSuccess) { ym_set_error("ym_moe_expert_gemm: memset: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
         if (a_scale) return dispatch_bn<EPI_STATS, true>(p, P, st);
         return dispatch_bn<EPI_STATS, false>(p, P, st);
     }
@@ -403,16 +403,25 @@ extern "C" int ym_moe_combine(const void* x, int ldx, int B, int HW, int C, cons
     return dispatch_bn<EPI_MOE_COMBINE, false>(p, 1, (cudaStream_t)stream);
 }
 
-// GroupNorm statistics -> per-(problem, channel) scale/shift.  scale = rw*rstd*gamma, shift = rw*(beta - mean*rstd*gamma)
-__global__ void gn_finalize_kernel(const float* __restrict__ stats, int P, int groups, int C, float count, float eps,
+// GroupNorm partial statistics [P][mtiles][C/8][2] -> per-(problem, channel) scale/shift (fixed-order reduction).
+// scale = rw*rstd*gamma, shift = rw*(beta - mean*rstd*gamma)
+__global__ void gn_finalize_kernel(const float* __restrict__ stats, int P, int mtiles, int groups, int C, float count, float eps,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    const int* __restrict__ route_idx, const float* __restrict__ route_w,
                                    float* __restrict__ scale, float* __restrict__ shift) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P * C) return;
     const int pr = i / C, c = i - pr * C;
-    const int grp = c / (C / groups);
-    const float s = stats[(pr * groups + grp) * 2 + 0], q = stats[(pr * groups + grp) * 2 + 1];
+    const int cpg = C / groups;
+    const int grp = c / cpg;
+    const int t0 = grp * cpg / 8, t1 = (grp + 1) * cpg / 8, nt = C / 8;
+    float s = 0.f, q = 0.f;
+    for (int mt = 0; mt < mtiles; ++mt)
+        for (int t = t0; t < t1; ++t) {
+            const float* src = stats + (((long long)pr * mtiles + mt) * nt + t) * 2;
+            s += src[0];
+            q += src[1];
+        }
     const float mean = s / count;
     const float var = fmaxf(q / count - mean * mean, 0.f);
     const float rstd = rsqrtf(var + eps);
@@ -423,14 +432,16 @@ __global__ void gn_finalize_kernel(const float* __restrict__ stats, int P, int g
     shift[i] = rw * (bt - mean * rstd * gm);
 }
 
-extern "C" int ym_gn_finalize(const float* stats, int P, int groups, int C, float count, float eps, const float* gamma,
+extern "C" long long ym_moe_stats_floats(int P, int HW, int N) { return (long long)P * ((HW + BM - 1) / BM) * (N / 8) * 2; }
+
+extern "C" int ym_gn_finalize(const float* stats, int P, int HW, int groups, int C, float count, float eps, const float* gamma,
                               const float* beta, const int* route_idx, const float* route_w, float* scale, float* shift,
                               void* stream) {
     YM_CHECK_ARG(stats && gamma && beta && route_idx && scale && shift, "ym_gn_finalize: null pointer");
-    YM_CHECK_ARG(groups > 0 && C % groups == 0, "ym_gn_finalize: bad groups");
+    YM_CHECK_ARG(groups > 0 && C % groups == 0 && (C / groups) % 8 == 0, "ym_gn_finalize: bad groups");
     if (P == 0) return YM_OK;
     const int n = P * C;
-    gn_finalize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(stats, P, groups, C, count, eps, gamma, beta,
+    gn_finalize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(stats, P, (HW + BM - 1) / BM, groups, C, count, eps, gamma, beta,
                                                                           route_idx, route_w, scale, shift);
     YM_CHECK_LAUNCH("gn_finalize");
     return YM_OK;

@@ -164,10 +164,10 @@ class OptimizedMOEImproved(nn.Module, PackCache):
         ldx = ops.pitch(x)
         # GEMM1: h[p] = x[p // k] @ W1[e_p]^T, GroupNorm-1 statistics in the epilogue
         h, st1 = ops.moe_expert_gemm(x, ldx, k, P, HW, C, pk["w1"], ridx, hid, groups=pk["G1"])
-        sc1, sh1 = ops.gn_finalize(st1, hid, HW * (hid // pk["G1"]), pk["eps1"], pk["gamma1"], pk["beta1"], ridx)
+        sc1, sh1 = ops.gn_finalize(st1, P, HW, pk["G1"], hid, HW * (hid // pk["G1"]), pk["eps1"], pk["gamma1"], pk["beta1"], ridx)
         # GEMM2: o[p] = SiLU(GN1(h[p])) @ W2[e_p]^T with GN+SiLU applied on the A-operand load; GN-2 statistics
         o, st2 = ops.moe_expert_gemm(h, hid, 1, P, HW, hid, pk["w2"], ridx, C, a_scale=sc1, a_shift=sh1, groups=pk["G2"])
-        sc2, sh2 = ops.gn_finalize(st2, C, HW * (C // pk["G2"]), pk["eps2"], pk["gamma2"], pk["beta2"], ridx, route_w=rw)
+        sc2, sh2 = ops.gn_finalize(st2, P, HW, pk["G2"], C, HW * (C // pk["G2"]), pk["eps2"], pk["gamma2"], pk["beta2"], ridx, route_w=rw)
         # combine: shared expert GEMM + sum_j w_j*GN2(o_j) (+ residual), fp32 accumulate, one rounding
         add_res = outer_residual or (self.add_residual and self.in_channels == self.out_channels)
         y = ops.moe_combine(x, pk["ws"], pk["bs"], o, sc2, sh2, k, add_residual=add_res, out=out)

@@ -166,10 +166,10 @@ def router_topk(x, pack, topk, pool=4):
 
 
 def moe_expert_gemm(a, lda, a_div, P, HW, K, w_all, route_idx, N, a_scale=None, a_shift=None, groups=0):
-    """ym_moe_expert_gemm.  Returns (out fp16 [P,HW,N], stats fp32 [P,groups,2] or None)."""
+    """ym_moe_expert_gemm.  Returns (out fp16 [P,HW,N], partial GroupNorm stats fp32 or None)."""
     dev = route_idx.device
     out = torch.empty((P, HW, N), dtype=torch.float16, device=dev)
-    stats = torch.empty((P, groups, 2), dtype=torch.float32, device=dev) if groups else None
+    stats = torch.empty((lib().ym_moe_stats_floats(P, HW, N),), dtype=torch.float32, device=dev) if groups else None
     E, Nw, Kpad = w_all.shape
     _lib.check(lib().ym_moe_expert_gemm(a.data_ptr(), lda, a_div, P, HW, K, w_all.data_ptr(), Kpad, Nw * Kpad,
                                         route_idx.data_ptr(), N, out.data_ptr(), N,
@@ -177,15 +177,14 @@ def moe_expert_gemm(a, lda, a_div, P, HW, K, w_all, route_idx, N, a_scale=None, 
                                         None if a_shift is None else a_shift.data_ptr(),
                                         None if stats is None else stats.data_ptr(), groups, _stream()),
                "ym_moe_expert_gemm")
-    _count(2 if groups else 1)
+    _count()
     return out, stats
 
 
-def gn_finalize(stats, C_, count, eps, gamma, beta, route_idx, route_w=None):
-    P, G, _ = stats.shape
+def gn_finalize(stats, P, HW, G, C_, count, eps, gamma, beta, route_idx, route_w=None):
     scale = torch.empty((P, C_), dtype=torch.float32, device=stats.device)
     shift = torch.empty((P, C_), dtype=torch.float32, device=stats.device)
-    _lib.check(lib().ym_gn_finalize(stats.data_ptr(), P, G, C_, float(count), float(eps), gamma.data_ptr(), beta.data_ptr(),
+    _lib.check(lib().ym_gn_finalize(stats.data_ptr(), P, HW, G, C_, float(count), float(eps), gamma.data_ptr(), beta.data_ptr(),
                                     route_idx.data_ptr(), None if route_w is None else route_w.data_ptr(),
                                     scale.data_ptr(), shift.data_ptr(), _stream()), "ym_gn_finalize")
     _count()
