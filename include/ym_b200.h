@@ -56,7 +56,7 @@ int ym_attention_fwd(const void* qkv, int ld, int batch, int N, int heads, int h
                      int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream);
 
 /* EfficientSpatialRouter.forward + BaseRouter._process_logits (eval)  moe/routers.py:283-304, :185-265.
- * w1: fp32 [9][C][Cr] (tap-major), scale1/shift1: folded BN1 [Cr]; w2: fp32 [E][Cr], scale2/shift2: folded BN2 [E].
+ * w1: fp32 [9][C/4][Cr][4] (tap-major, float4 over channels), scale1/shift1: folded BN1 [Cr]; w2: fp32 [E][Cr], scale2/shift2: folded BN2 [E].
  * Writes idx int32 [B,topk] (descending prob), w fp32 [B,topk] (renormalised), probs fp32 [B,E] (nullable). */
 long long ym_router_scratch_floats(int B, int H, int W, int C, int Cr, int pool);
 int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* w1, int Cr,
@@ -87,12 +87,27 @@ int ym_moe_combine(const void* x, int ldx, int B, int HW, int C, const void* ws,
 
 /* Detect post-processing.  box[l]: fp32 [B, h_l*w_l, 4] ltrb distances; cls[l]: fp32 [B, h_l*w_l, nc] logits.
  * ym_detect_topk: Detect._inference + postprocess + get_topk_index (end2end)  head.py:173-258, tal.py:398-423.
- *   out fp32 [B, k, 6] = (x1,y1,x2,y2,score,cls), k = min(max_det, A), score-descending; out_anchor int32 [B,k] nullable.
+ *   out fp32 [B, k, 6] = (x1,y1,x2,y2,score,cls), k = min(max_det, A), score-descending; out_anchor int32 [B,k] nullable;
+ *   scratch: B*A uint32 (per-anchor max-logit keys written by the first of the two kernels).
  * ym_detect_dense: Detect._inference -> y fp32 [B, 4+nc, A] (xyxy!=0: corner boxes, else xywh)  head.py:173-194. */
 int ym_detect_topk(int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
-                   const float* strides, int B, int nc, int max_det, float* out, int* out_anchor, void* stream);
+                   const float* strides, int B, int nc, int max_det, float* out, int* out_anchor, void* scratch,
+                   void* stream);
 int ym_detect_dense(int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
                     const float* strides, int B, int nc, int xyxy, float* y, void* stream);
+
+/* tcgen05 path (TMEM accumulators, swizzled smem operands, single-thread MMA issue).
+ * ym_tc_gemm_nt: out[M,N] = act(A[M,K] B[N,K]^T + bias) (+res) — the 1x1 Conv of conv.py:69-89 (a 1x1 conv on NHWC is
+ *   exactly this GEMM with A = activation rows, B = packed weights [Cout][K]).
+ * ym_moe_dispatch_tc: BatchedExpertComputation.compute_sparse_experts_batched  moe/utils.py:119-209 for 1x1-conv experts:
+ *   out[b] = clamp(sum_j fp16(fp16(x[b] W[idx[b,j]]^T) * w[b,j]), +-clamp), routes with w <= w_min dropped (:172-173);
+ *   x [B*HW][ldx] fp16, w_all [E][N][ldw] fp16, idx int32 [B,topk], w fp32 [B,topk], topk <= 2, N <= 256.
+ *   No gather / scatter copies: every 128-token tile is read once, both routed experts accumulate in TMEM. */
+int ym_tc_gemm_nt(const void* a, int lda, const void* b, int ldb, const float* bias, const void* res, int ldr, void* out,
+                  int ldo, int M, int N, int K, int act, void* stream);
+int ym_moe_dispatch_tc(const void* x, int ldx, int B, int HW, int C, const void* w_all, int ldw, long long w_expert_stride,
+                       const int* route_idx, const float* route_w, int topk, int N, float w_min, float clamp, void* out,
+                       int ldo, void* stream);
 
 #ifdef __cplusplus
 }

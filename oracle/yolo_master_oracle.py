@@ -7,7 +7,7 @@ a checker: only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baselin
 
 Parity pinning: `tests/golden/make_golden.py` imports the real reference from
 `/root/reference` in the build container, fills its parameters with the
-deterministic generator in `oracle/synth.py`, and stores reference outputs in
+deterministic generator in `yolo-master_b200/utils/synth.py`, and stores reference outputs in
 `tests/golden/*.pt`; `tests/test_oracle_golden.py` checks this file against them.
 
 Design: purely functional.  A model is (layer spec list, flat state_dict with
@@ -42,6 +42,27 @@ def fp16_storage():
 
 def _st(t):
     return t.half().float() if _SIM_FP16 else t
+
+
+_W16 = False  # see fp16_weights()
+
+
+@contextlib.contextmanager
+def fp16_weights():
+    """Model of the reference's deployed fp16 weights: `model.fuse().half()` folds BatchNorm into the conv weights
+    (utils/torch_utils.py:315-349) and rounds them to fp16 (nn/backends/pytorch.py:44-67).  Arithmetic stays fp32.
+    Used as the yardstick for single-kernel tests on activations with a large dynamic range, where fp16 weight
+    rounding (common to the reference's fp16 path and the CUDA path) is visible against an fp32-weight oracle."""
+    global _W16
+    old, _W16 = _W16, True
+    try:
+        yield
+    finally:
+        _W16 = old
+
+
+def _w(t):
+    return t.half().float() if _W16 else t
 
 
 BN_EPS = 1e-3  # utils/torch_utils.py:552-562 rewrites eps on every nn.BatchNorm2d
@@ -139,8 +160,14 @@ def conv_block(sd, p, x, s=1, g=1, act=True, pad=None):
     w = sd[p + ".conv.weight"]
     k = w.shape[-1]
     pad = k // 2 if pad is None else pad
-    y = F.conv2d(x, w, sd.get(p + ".conv.bias"), s, pad, 1, g)
-    y = _bn(sd, p + ".bn", y)
+    if _W16:  # fused + fp16-rounded weights, as deployed by the reference's fp16 backend
+        sc = sd[p + ".bn.weight"] / torch.sqrt(sd[p + ".bn.running_var"] + BN_EPS)
+        b0 = sd.get(p + ".conv.bias")
+        b0 = torch.zeros_like(sc) if b0 is None else b0
+        y = F.conv2d(x, _w(w * sc.view(-1, 1, 1, 1)), (b0 - sd[p + ".bn.running_mean"]) * sc + sd[p + ".bn.bias"], s, pad, 1, g)
+    else:
+        y = F.conv2d(x, w, sd.get(p + ".conv.bias"), s, pad, 1, g)
+        y = _bn(sd, p + ".bn", y)
     return _st(F.silu(y) if act else y)
 
 
@@ -226,10 +253,10 @@ def get_safe_groups(channels: int, desired: int = 8) -> int:
 def simple_expert(sd, p, x):
     """`SimpleExpert` moe/experts.py:73-88: 1x1 -> GN -> SiLU -> 1x1 -> GN."""
     w1, w2 = sd[p + ".conv.0.weight"], sd[p + ".conv.3.weight"]
-    h = _st(F.conv2d(x, w1))
+    h = _st(F.conv2d(x, _w(w1)))
     h = F.group_norm(h, get_safe_groups(w1.shape[0]), sd[p + ".conv.1.weight"], sd[p + ".conv.1.bias"], GN_EPS)
     h = F.silu(h)
-    o = _st(F.conv2d(h, w2))
+    o = _st(F.conv2d(h, _w(w2)))
     return F.group_norm(o, get_safe_groups(w2.shape[0]), sd[p + ".conv.4.weight"], sd[p + ".conv.4.bias"], GN_EPS)
 
 
@@ -254,7 +281,12 @@ def optimized_moe_improved(sd, p, x, num_experts, top_k):
     """`OptimizedMOEImproved.forward` moe/modules.py:1069-1157 (eval; add_residual=False under ABlockMoE)."""
     B = x.shape[0]
     w, idx, _ = efficient_spatial_router(sd, p + ".routing", x, top_k)
-    shared = F.silu(_bn(sd, p + ".shared_expert.1", F.conv2d(x, sd[p + ".shared_expert.0.weight"])))
+    if _W16:
+        sc = sd[p + ".shared_expert.1.weight"] / torch.sqrt(sd[p + ".shared_expert.1.running_var"] + BN_EPS)
+        shared = F.silu(F.conv2d(x, _w(sd[p + ".shared_expert.0.weight"] * sc.view(-1, 1, 1, 1)),
+                                 sd[p + ".shared_expert.1.bias"] - sd[p + ".shared_expert.1.running_mean"] * sc))
+    else:
+        shared = F.silu(_bn(sd, p + ".shared_expert.1", F.conv2d(x, sd[p + ".shared_expert.0.weight"])))
     out = torch.zeros_like(shared, dtype=torch.float32)
     for e in range(num_experts):
         mask = idx == e
@@ -360,13 +392,13 @@ def detect_head_raw(sd, p, feats, nc, reg_max, end2end, legacy=False):
     boxes, scores = [], []
     for i, x in enumerate(feats):
         b = conv_block(sd, f"{bp}.{i}.1", conv_block(sd, f"{bp}.{i}.0", x))
-        b = F.conv2d(b, sd[f"{bp}.{i}.2.weight"], sd[f"{bp}.{i}.2.bias"])
+        b = F.conv2d(b, _w(sd[f"{bp}.{i}.2.weight"]), sd[f"{bp}.{i}.2.bias"])
         if legacy:
             c = conv_block(sd, f"{cp}.{i}.1", conv_block(sd, f"{cp}.{i}.0", x))
         else:
             c = conv_block(sd, f"{cp}.{i}.0.1", dwconv_block(sd, f"{cp}.{i}.0.0", x))
             c = conv_block(sd, f"{cp}.{i}.1.1", dwconv_block(sd, f"{cp}.{i}.1.0", c))
-        c = F.conv2d(c, sd[f"{cp}.{i}.2.weight"], sd[f"{cp}.{i}.2.bias"])
+        c = F.conv2d(c, _w(sd[f"{cp}.{i}.2.weight"]), sd[f"{cp}.{i}.2.bias"])
         boxes.append(b.view(bs, 4 * reg_max, -1))
         scores.append(c.view(bs, nc, -1))
     return torch.cat(boxes, -1), torch.cat(scores, -1)

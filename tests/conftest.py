@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
+    import torch
+
+    # the fp32 CPU oracle (N x N attention) is memory bound: more than ~16 threads makes it slower on many-core hosts
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
 
 
 def pytest_collection_modifyitems(config, items):

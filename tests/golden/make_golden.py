@@ -95,5 +95,27 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def dispatch_golden():
+    """Reference BatchedExpertComputation (moe/utils.py:119-209) with 1x1-conv experts on small seeded cases."""
+    from ultralytics.nn.modules.moe.utils import BatchedExpertComputation
+    cases = []
+    for seed, (B, C, H, W, E, k) in enumerate([(6, 32, 5, 7, 4, 2), (9, 16, 4, 4, 8, 2), (4, 24, 3, 3, 3, 1)]):
+        g = torch.Generator().manual_seed(100 + seed)
+        x = torch.randn((B, C, H, W), generator=g)
+        Wt = torch.randn((E, C, C), generator=g) / C ** 0.5
+        experts = torch.nn.ModuleList([torch.nn.Conv2d(C, C, 1, bias=False) for _ in range(E)]).eval()
+        for e in range(E):
+            experts[e].weight.data.copy_(Wt[e].view(C, C, 1, 1))
+        idx = torch.stack([torch.randperm(E, generator=g)[:k] for _ in range(B)])
+        w = torch.rand((B, k), generator=g)
+        w = w / w.sum(1, keepdim=True)
+        w[0, -1] = 0.004
+        with torch.no_grad():
+            out = BatchedExpertComputation.compute_sparse_experts_batched(x, experts, w, idx, k, E)
+        cases.append({"x": x, "W": Wt, "w": w, "idx": idx, "out": out})
+    torch.save({"cases": cases}, f"{OUT}/dispatch.golden.pt")
+
+
 if __name__ == "__main__":
     main()
+    dispatch_golden()

@@ -67,7 +67,7 @@ def test_model_matches_reference_golden(model_and_sd, tag):
     c = torch.load(os.path.join(GOLD, "yolo26-master-n.golden.pt"))["cases"][tag]
     x = synth_images(c["B"], c["H"], c["W"], c["seed"]).half().to(DEV)
     y, feats = _layers(m, x)
-    with O.fp16_storage():   # noise floor of fp16 storage for this graph, from the oracle itself
+    with O.fp16_storage(), O.fp16_weights():   # noise floor of fp16 storage for this graph, from the oracle itself
         ysim, sim = O.forward(O.parse_spec(yaml_n()), model_and_sd[1], x.float().cpu(), return_layers=True)
     for i, ref in c["layers"].items():
         assert_within_noise(feats[i], ref, sim[i], what=f"layer {i} vs reference golden")
@@ -86,7 +86,7 @@ def test_model_640_vs_oracle(model_and_sd):
     y, feats = _layers(m, x.half().to(DEV))
     spec = O.parse_spec(yaml_n())
     ref, ys = O.forward(spec, sd, x.half().float(), return_layers=True)
-    with O.fp16_storage():
+    with O.fp16_storage(), O.fp16_weights():
         ysim, sim = O.forward(spec, sd, x.half().float(), return_layers=True)
     for i in range(23):
         if feats.get(i) is None:
@@ -112,14 +112,16 @@ def test_layers_teacher_forced_640(model_and_sd):
             y = m.model[i](to_dev(xin) if torch.is_tensor(xin) else [to_dev(t) for t in xin])
         xin32 = xin.float() if torch.is_tensor(xin) else [t.float() for t in xin]
         ref = O.forward_layer(spec, sd, i, xin32)
-        with O.fp16_storage():
+        with O.fp16_storage(), O.fp16_weights():
             sim = O.forward_layer(spec, sd, i, xin32)
         if L["type"] in ("Concat", "nn.Upsample"):
             assert torch.equal(y.float().cpu(), ref), f"layer {i} {L['type']}"
         else:
             assert_within_noise(y, ref, sim, what=f"layer {i} {L['type']} (teacher forced)")
-            if L["type"] == "Conv":   # a single fused kernel: strict north-star tolerance
-                mx, bad = close_stats(y, ref)
+            if L["type"] == "Conv":   # a single fused kernel: strict north-star tolerance vs the reference's fp16 weights
+                with O.fp16_weights():
+                    ref16 = O.forward_layer(spec, sd, i, xin32)
+                mx, bad = close_stats(y, ref16)
                 assert bad == 0.0, f"layer {i} Conv: {bad:.2e} outside tolerance (max {mx:.2e})"
 
 

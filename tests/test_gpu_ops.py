@@ -32,7 +32,7 @@ def _x(B, C, H, W, seed=0, scale=1.0):
 def _noise(fn, *a):
     """(fp32 oracle, fp16-storage oracle) outputs of an oracle function."""
     ref = fn(*a)
-    with O.fp16_storage():
+    with O.fp16_storage(), O.fp16_weights():
         sim = fn(*a)
     return ref, sim
 

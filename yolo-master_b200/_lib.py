@@ -26,7 +26,9 @@ SIGNATURES = {
     "ym_moe_stats_floats": (cll, [ci, ci, ci]),
     "ym_gn_finalize": (ci, [vp, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp, vp]),
     "ym_moe_combine": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, ci, vp, vp, ci, vp, ci, ci, vp]),
-    "ym_detect_topk": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp, vp]),
+    "ym_tc_gemm_nt": (ci, [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, vp]),
+    "ym_moe_dispatch_tc": (ci, [vp, ci, ci, ci, ci, vp, ci, cll, vp, vp, ci, ci, cf, cf, vp, ci, vp]),
+    "ym_detect_topk": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp, vp, vp]),
     "ym_detect_dense": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp]),
 }
 

@@ -86,8 +86,24 @@ __device__ __forceinline__ void anchor_of(const DetectLevels& L, int a, int& lvl
     r = a - L.off[lvl];
 }
 
+// Stage 1, full-GPU: per-anchor max logit over classes (warp per anchor row) -> sortable keys [B][A].
+__global__ void __launch_bounds__(256) detect_rowmax_kernel(const DetectLevels L, int nc, int B, uint32_t* __restrict__ keys) {
+    const int A = L.off[L.nl];
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= (long long)B * A) return;
+    const int b = (int)(row / A), a = (int)(row % A);
+    int lvl, r;
+    anchor_of(L, a, lvl, r);
+    const float* src = L.cls[lvl] + ((long long)b * L.h[lvl] * L.w[lvl] + r) * nc;
+    float m = -INFINITY;
+    for (int c = lane; c < nc; c += 32) m = fmaxf(m, src[c]);
+    m = warp_max(m);
+    if (lane == 0) keys[row] = f2key(m);
+}
+
 __global__ void __launch_bounds__(1024) detect_topk_kernel(const DetectLevels L, int nc, int kdet, float* __restrict__ out,
-                                                           int* __restrict__ out_anchor) {
+                                                           int* __restrict__ out_anchor, const uint32_t* __restrict__ keys_g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int A = L.off[L.nl];
     const int nkeys_max = max(A, kdet * nc);
@@ -97,18 +113,10 @@ __global__ void __launch_bounds__(1024) detect_topk_kernel(const DetectLevels L,
     unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(sel + kdet + ((nkeys_max + 2 * kdet) & 1));  // [512], 8-byte aligned
     __shared__ uint32_t hist[256];
     __shared__ int misc[4];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x;
 
-    // ---- stage 1: per-anchor max logit (warp per anchor row)
-    for (int a = warp; a < A; a += nwarp) {
-        int lvl, r;
-        anchor_of(L, a, lvl, r);
-        const float* row = L.cls[lvl] + ((long long)b * L.h[lvl] * L.w[lvl] + r) * nc;
-        float m = -INFINITY;
-        for (int c = lane; c < nc; c += 32) m = fmaxf(m, row[c]);
-        m = warp_max(m);
-        if (lane == 0) keys[a] = f2key(m);
-    }
+    // ---- stage 1 result (detect_rowmax_kernel): per-anchor max-logit keys
+    for (int a = tid; a < A; a += blockDim.x) keys[a] = keys_g[(long long)b * A + a];
     __syncthreads();
     int take_eq;
     uint32_t T = radix_select_kth(keys, A, kdet, hist, misc, &take_eq);
@@ -231,8 +239,9 @@ static int fill_levels(DetectLevels& L, int nl, const void* const* box, const vo
 
 // out: [B, k, 6] fp32 (x1,y1,x2,y2,score,cls) with k = min(max_det, A); out_anchor (nullable): [B, k] int32
 extern "C" int ym_detect_topk(int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
-                              const float* strides, int B, int nc, int max_det, float* out, int* out_anchor, void* stream) {
-    YM_CHECK_ARG(out, "ym_detect_topk: null output");
+                              const float* strides, int B, int nc, int max_det, float* out, int* out_anchor, void* scratch,
+                              void* stream) {
+    YM_CHECK_ARG(out && scratch, "ym_detect_topk: null output / scratch (B*A uint32)");
     DetectLevels L;
     int rc = fill_levels(L, nl, box, cls, hs, ws, strides);
     if (rc) return rc;
@@ -246,7 +255,10 @@ extern "C" int ym_detect_topk(int nl, const void* const* box, const void* const*
     YM_CHECK_ARG(smem <= 227 * 1024, "ym_detect_topk: %zu bytes of shared memory needed (A=%d) exceeds 227 KB", smem, A);
     cudaError_t e = cudaFuncSetAttribute(detect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ym_set_error("ym_detect_topk: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
-    detect_topk_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(L, nc, k, out, out_anchor);
+    const long long rows = (long long)B * A;
+    detect_rowmax_kernel<<<(int)((rows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(L, nc, B, (uint32_t*)scratch);
+    YM_CHECK_LAUNCH("detect_rowmax");
+    detect_topk_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(L, nc, k, out, out_anchor, (const uint32_t*)scratch);
     YM_CHECK_LAUNCH("detect_topk");
     return YM_OK;
 }

@@ -21,39 +21,46 @@ template <typename TIn, int COUT>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const TIn* __restrict__ img, int B, int Cin, int H, int W,
                                                         const float* __restrict__ wgt,   // [Cin*9][COUT]
                                                         const float* __restrict__ bias,  // [COUT]
-                                                        __half* __restrict__ out, int ldo, int Ho, int Wo) {
+                                                        __half* __restrict__ out, int ldo, int Ho, int Wo, int tiles_x) {
+    // CTA = 32 x 8 output pixels; the (65 x 17) x Cin input patch is staged in shared memory with coalesced row reads.
+    constexpr int TW = 32, TH = 8, IW = 2 * TW + 1, IH = 2 * TH + 1;
     __shared__ float sw[4 * 9 * COUT];
     __shared__ float sb[COUT];
-    for (int i = threadIdx.x; i < Cin * 9 * COUT; i += blockDim.x) sw[i] = wgt[i];
-    for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
+    __shared__ float sx[4][IH][IW + 1];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < Cin * 9 * COUT; i += 256) sw[i] = wgt[i];
+    for (int i = tid; i < COUT; i += 256) sb[i] = bias[i];
+    const int b = blockIdx.y;
+    const int oy0 = (blockIdx.x / tiles_x) * TH, ox0 = (blockIdx.x % tiles_x) * TW;
+    const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
+    for (int i = tid; i < Cin * IH * IW; i += 256) {
+        const int ci = i / (IH * IW), rem = i % (IH * IW);
+        const int ry = rem / IW, rx = rem % IW;
+        const int iy = iy0 + ry, ix = ix0 + rx;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = load_px<TIn>(img + (((long long)b * Cin + ci) * H + iy) * W + ix);
+        sx[ci][ry][rx] = v;
+    }
     __syncthreads();
-    const long long total = (long long)B * Ho * Wo;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int ox = (int)(idx % Wo);
-    const int oy = (int)((idx / Wo) % Ho);
-    const int b = (int)(idx / ((long long)Wo * Ho));
+    const int lx = tid % TW, ly = tid / TW;
+    const int ox = ox0 + lx, oy = oy0 + ly;
+    if (ox >= Wo || oy >= Ho) return;
     float acc[COUT];
 #pragma unroll
     for (int c = 0; c < COUT; ++c) acc[c] = sb[c];
     for (int ci = 0; ci < Cin; ++ci) {
-        const TIn* plane = img + ((long long)b * Cin + ci) * H * W;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-            const int iy = oy * 2 - 1 + ky;
-            if (iy < 0 || iy >= H) continue;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const int ix = ox * 2 - 1 + kx;
-                if (ix < 0 || ix >= W) continue;
-                const float v = load_px<TIn>(plane + (long long)iy * W + ix);
+                const float v = sx[ci][2 * ly + ky][2 * lx + kx];
                 const float* wr = &sw[((ci * 3 + ky) * 3 + kx) * COUT];
 #pragma unroll
                 for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
             }
         }
     }
-    __half* dst = out + idx * ldo;
+    __half* dst = out + (((long long)b * Ho + oy) * Wo + ox) * ldo;
 #pragma unroll
     for (int c = 0; c < COUT; c += 8) {
         Half8 h;
@@ -125,6 +132,116 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const __half* __restrict__ 
 #pragma unroll
     for (int q = 0; q < 4; ++q) o.v[q] = __floats2half2_rn(acc[2 * q], acc[2 * q + 1]);
     *reinterpret_cast<Half8*>(out + pix * ldo + c) = o;
+}
+
+// Shared-memory tiled variant (the fast path): a CTA computes TH x TW output pixels x CB channels from a haloed input
+// tile staged once in shared memory; each thread produces PX=4 horizontally adjacent pixels x 8 channels with a sliding
+// window in registers, so every staged input vector is reused up to min(KS,PX) times per row.  HBM traffic = one read of
+// the (haloed) input + one write of the output; the k x k re-reads are served from shared memory.
+template <int KS, int CHUNKS>
+__global__ void __launch_bounds__(256) dwconv_tiled_kernel(const __half* __restrict__ x, int ldx, int grp_w, int grp_stride,
+                                                           int grp_off, const __half* __restrict__ w,
+                                                           const float* __restrict__ bias, int H, int W, int C, int act,
+                                                           const __half* __restrict__ add, int ldadd, __half* __restrict__ out,
+                                                           int ldo, int tiles_x) {
+    constexpr int R = KS / 2, PX = 4, CB = CHUNKS * 8;
+    constexpr int GROUPS = 256 / CHUNKS;           // pixel groups per CTA
+    constexpr int TW = (CHUNKS == 8) ? 16 : 32;    // tile width
+    constexpr int GX = TW / PX;                    // groups per row
+    constexpr int TH = GROUPS / GX;                // tile height (8 or 16)
+    constexpr int HW_ = TW + 2 * R, HH_ = TH + 2 * R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __half* sx = reinterpret_cast<__half*>(smem_raw);            // [HH_][HW_][CB]
+    __half* sw = sx + HH_ * HW_ * CB;                            // [KS*KS][CB]
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x, b = blockIdx.y, cb0 = blockIdx.z * CB;
+    const int ty0 = (tile / tiles_x) * TH, tx0 = (tile % tiles_x) * TW;
+    const __half* xb = x + (long long)b * H * W * ldx;
+    // ---- stage weights + haloed input tile (zero outside the image)
+    for (int i = tid; i < KS * KS * CHUNKS; i += 256) {
+        const int tap = i / CHUNKS, ch = i % CHUNKS;
+        *reinterpret_cast<Half8*>(sw + tap * CB + ch * 8) = *reinterpret_cast<const Half8*>(w + tap * C + cb0 + ch * 8);
+    }
+    for (int i = tid; i < HH_ * HW_ * CHUNKS; i += 256) {
+        const int ch = i % CHUNKS, pp = i / CHUNKS;
+        const int hy = pp / HW_, hx = pp % HW_;
+        const int iy = ty0 + hy - R, ix = tx0 + hx - R;
+        const int c = cb0 + ch * 8;
+        const int csrc = (c / grp_w) * grp_stride + grp_off + (c % grp_w);
+        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        cp_async16(sx + pp * CB + ch * 8, ok ? xb + ((long long)iy * W + ix) * ldx + csrc : xb, ok ? 16 : 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    // ---- compute
+    const int ch = tid % CHUNKS, grp = tid / CHUNKS;
+    const int gy = grp / GX, gx = grp % GX;
+    const int c = cb0 + ch * 8;
+    float acc[PX][8];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[p][q] = bias ? bias[c + q] : 0.f;
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+        float wr[KS][8];
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+            const Half8 wv = *reinterpret_cast<const Half8*>(sw + (ky * KS + kx) * CB + ch * 8);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(wv.v[q]);
+                wr[kx][2 * q] = f.x;
+                wr[kx][2 * q + 1] = f.y;
+            }
+        }
+        const __half* row = sx + ((gy + ky) * HW_ + gx * PX) * CB + ch * 8;
+#pragma unroll
+        for (int j = 0; j < PX + KS - 1; ++j) {
+            const Half8 xv = *reinterpret_cast<const Half8*>(row + j * CB);
+            float xf[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(xv.v[q]);
+                xf[2 * q] = f.x;
+                xf[2 * q + 1] = f.y;
+            }
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+                const int kx = j - p;
+                if (kx >= 0 && kx < KS) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[p][q] = fmaf(xf[q], wr[kx][q], acc[p][q]);
+                }
+            }
+        }
+    }
+    // ---- epilogue
+    const int oy = ty0 + gy;
+    if (oy >= H) return;
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+        const int ox = tx0 + gx * PX + p;
+        if (ox >= W) continue;
+        const long long pix = ((long long)b * H + oy) * W + ox;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = act == 1 ? silu_f(acc[p][q]) : acc[p][q];
+        if (add != nullptr) {
+            const Half8 av = *reinterpret_cast<const Half8*>(add + pix * ldadd + c);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 af = __half22float2(av.v[q]);
+                v[2 * q] += af.x;
+                v[2 * q + 1] += af.y;
+            }
+        }
+        Half8 o;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o.v[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+        *reinterpret_cast<Half8*>(out + pix * ldo + c) = o;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -223,7 +340,10 @@ extern "C" int ym_stem_conv_nchw(const void* img, int in_dtype, int B, int Cin, 
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long total = (long long)B * Ho * Wo;
     cudaStream_t st = (cudaStream_t)stream;
-#define YM_STEM(T, CO) stem_conv_kernel<T, CO><<<nblocks(total, 256), 256, 0, st>>>((const T*)img, B, Cin, H, W, wgt, bias, (__half*)out, ldo, Ho, Wo)
+    const int tiles_x = (Wo + 31) / 32, tiles_y = (Ho + 7) / 8;
+    (void)total;
+    YM_CHECK_ARG(B <= 65535, "ym_stem_conv_nchw: batch too large");
+#define YM_STEM(T, CO) stem_conv_kernel<T, CO><<<dim3(tiles_x * tiles_y, B), 256, 0, st>>>((const T*)img, B, Cin, H, W, wgt, bias, (__half*)out, ldo, Ho, Wo, tiles_x)
 #define YM_STEM_T(CO)                                   \
     do {                                                \
         if (in_dtype == 0) YM_STEM(__half, CO);         \
@@ -252,6 +372,30 @@ extern "C" int ym_dwconv_nhwc(const void* x, int ldx, int grp_w, int grp_stride,
     if (B == 0) return YM_OK;
     const long long total = (long long)B * H * W * (C / 8);
     cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = (C % 64 == 0) ? 8 : ((C % 16 == 0) ? 2 : 0);  // source mapping is per 8-channel chunk
+    if (chunks && B <= 65535) {
+        const int TW = chunks == 8 ? 16 : 32, TH = chunks == 8 ? 8 : 16, CB = chunks * 8, R = ksize / 2;
+        const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+        const size_t smem = ((size_t)(TH + 2 * R) * (TW + 2 * R) * CB + (size_t)ksize * ksize * CB) * sizeof(__half);
+        dim3 grid(tiles_x * tiles_y, B, C / CB);
+#define YM_DWT(KS, CH)                                                                                                        \
+    do {                                                                                                                      \
+        auto kern = dwconv_tiled_kernel<KS, CH>;                                                                              \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+        kern<<<grid, 256, smem, st>>>((const __half*)x, ldx, grp_w, grp_stride, grp_off, (const __half*)w, bias, H, W, C, act, \
+                                      (const __half*)add, ldadd, (__half*)out, ldo, tiles_x);                                 \
+    } while (0)
+        bool done = true;
+        if (chunks == 8) {
+            switch (ksize) { case 3: YM_DWT(3, 8); break; case 5: YM_DWT(5, 8); break; case 7: YM_DWT(7, 8); break;
+                             case 9: YM_DWT(9, 8); break; default: done = false; }
+        } else {
+            switch (ksize) { case 3: YM_DWT(3, 2); break; case 5: YM_DWT(5, 2); break; case 7: YM_DWT(7, 2); break;
+                             case 9: YM_DWT(9, 2); break; default: done = false; }
+        }
+#undef YM_DWT
+        if (done) { YM_CHECK_LAUNCH("dwconv_tiled"); return YM_OK; }
+    }
 #define YM_DW(KS)                                                                                                    \
     dwconv_kernel<KS><<<nblocks(total, 256), 256, 0, st>>>((const __half*)x, ldx, grp_w, grp_stride, grp_off,          \
                                                            (const __half*)w, bias, B, H, W, C, act, (const __half*)add, \

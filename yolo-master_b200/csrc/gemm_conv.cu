@@ -209,11 +209,20 @@ __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParam
     cp_async_wait<0>();
 
     // ---------------- epilogue
+    // Phase 1: accumulators (+bias, +activation) -> warp-private fp32 staging tile in shared memory (reusing the
+    // pipeline buffers); GroupNorm statistics are taken here from the values as they will be stored.
+    // Phase 2: each lane owns one 16-byte (8-channel) chunk of an output row: residual / expert outputs are read and
+    // the result written with full 128-byte-line coalescing.
+    __syncthreads();  // every warp is done reading sA/sB
+    constexpr int SP = BN + 8;  // staging pitch (floats): == 8 mod 32 -> conflict-free float2 stores
+    float* stg = reinterpret_cast<float*>(smem_raw) + warp * 32 * SP;
     const int g = lane >> 2, t = lane & 3;
+    float* sS = sXf + (A_XFORM ? 2 * p.K : 0);
 #pragma unroll
     for (int ni = 0; ni < NT; ++ni) {
-        const int n = n0 + ni * 8 + 2 * t;
-        const bool nok = n < p.Cout;  // Cout % 8 == 0 -> pair is in or out together
+        const int nl = ni * 8 + 2 * t;
+        const int n = n0 + nl;
+        const bool nok = n < p.Cout;  // Cout is even -> the pair is in or out together
         float bias0 = 0.f, bias1 = 0.f;
         if (nok && p.bias != nullptr) {
             bias0 = p.bias[n];
@@ -224,14 +233,12 @@ __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParam
         for (int mi = 0; mi < 2; ++mi) {
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
-                const int m = m0 + warp * 32 + mi * 16 + g + hf * 8;
-                if (m >= p.M || !nok) continue;
+                const int rl = mi * 16 + g + hf * 8;
+                const int m = m0 + warp * 32 + rl;
                 float v0 = acc[mi][ni][hf * 2 + 0] + bias0;
                 float v1 = acc[mi][ni][hf * 2 + 1] + bias1;
-                if (EPI == EPI_STATS) {
-                    // statistics of the value as stored (fp16-rounded), matching GroupNorm on the stored tensor
-                    const __half2 hv = __floats2half2_rn(v0, v1);
-                    const float2 r = __half22float2(hv);
+                if (EPI == EPI_STATS && m < p.M && nok) {
+                    const float2 r = __half22float2(__floats2half2_rn(v0, v1));
                     ssum += r.x + r.y;
                     ssq += r.x * r.x + r.y * r.y;
                 }
@@ -239,40 +246,81 @@ __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParam
                     v0 = silu_f(v0);
                     v1 = silu_f(v1);
                 }
-                if (EPI == EPI_MOE_COMBINE) {
-                    const int b = m / p.HW;
-                    const int r = m - b * p.HW;
-                    for (int j = 0; j < p.topk; ++j) {
-                        const long long pr = (long long)b * p.topk + j;
-                        const __half2 ov = *reinterpret_cast<const __half2*>(p.o + (pr * p.HW + r) * p.ldo_o + n);
-                        const float2 of = __half22float2(ov);
-                        const float* sc = p.o_scale + pr * p.Cout + n;
-                        const float* sh = p.o_shift + pr * p.Cout + n;
-                        v0 += fmaf(of.x, sc[0], sh[0]);
-                        v1 += fmaf(of.y, sc[1], sh[1]);
-                    }
-                }
-                if (p.res != nullptr) {
-                    const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(p.res + (long long)m * p.ldr + n));
-                    v0 += rf.x;
-                    v1 += rf.y;
-                }
-                if (p.out_f32) {
-                    float2* dst = reinterpret_cast<float2*>(outb + ((long long)m * p.ldo + n) * 4);
-                    *dst = make_float2(v0, v1);
-                } else {
-                    __half2* dst = reinterpret_cast<__half2*>(outb + ((long long)m * p.ldo + n) * 2);
-                    *dst = __floats2half2_rn(v0, v1);
-                }
+                *reinterpret_cast<float2*>(stg + rl * SP + nl) = make_float2(v0, v1);
             }
         }
         if (EPI == EPI_STATS) {
             ssum = warp_sum(ssum);
             ssq = warp_sum(ssq);
             if (lane == 0) {  // one slot per (warp, n8 tile): no atomics -> bit-reproducible statistics
-                float* sS = sXf + (A_XFORM ? 2 * p.K : 0);
                 sS[(warp * NT + ni) * 2 + 0] = ssum;
                 sS[(warp * NT + ni) * 2 + 1] = ssq;
+            }
+        }
+    }
+    __syncwarp();
+    {
+        constexpr int CH = BN / 8;          // 16-byte chunks per row
+        constexpr int RPI = 32 / CH;        // rows per iteration (BN=64: 4, 32: 8, 16: 16, 8: 32)
+        const int ch = lane % CH, rsub = lane / CH;
+        const int n = n0 + ch * 8;
+#pragma unroll
+        for (int it = 0; it < 32 / RPI; ++it) {
+            const int rl = it * RPI + rsub;
+            const int m = m0 + warp * 32 + rl;
+            if (m >= p.M || n >= p.Cout) continue;
+            float v[8];
+            {
+                const float4 a0 = *reinterpret_cast<const float4*>(stg + rl * SP + ch * 8);
+                const float4 a1 = *reinterpret_cast<const float4*>(stg + rl * SP + ch * 8 + 4);
+                v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+            }
+            const bool full = n + 8 <= p.Cout;  // Cout % 8 != 0 only for tiny heads (e.g. 4 box channels)
+            if (EPI == EPI_MOE_COMBINE) {
+                const int bimg = m / p.HW;
+                const int r = m - bimg * p.HW;
+                for (int j = 0; j < p.topk; ++j) {
+                    const long long pr = (long long)bimg * p.topk + j;
+                    const Half8 ov = *reinterpret_cast<const Half8*>(p.o + (pr * p.HW + r) * p.ldo_o + n);
+                    const float4 s0 = *reinterpret_cast<const float4*>(p.o_scale + pr * p.Cout + n);
+                    const float4 s1 = *reinterpret_cast<const float4*>(p.o_scale + pr * p.Cout + n + 4);
+                    const float4 h0 = *reinterpret_cast<const float4*>(p.o_shift + pr * p.Cout + n);
+                    const float4 h1 = *reinterpret_cast<const float4*>(p.o_shift + pr * p.Cout + n + 4);
+                    const float2 o0 = __half22float2(ov.v[0]), o1 = __half22float2(ov.v[1]);
+                    const float2 o2 = __half22float2(ov.v[2]), o3 = __half22float2(ov.v[3]);
+                    v[0] += fmaf(o0.x, s0.x, h0.x); v[1] += fmaf(o0.y, s0.y, h0.y);
+                    v[2] += fmaf(o1.x, s0.z, h0.z); v[3] += fmaf(o1.y, s0.w, h0.w);
+                    v[4] += fmaf(o2.x, s1.x, h1.x); v[5] += fmaf(o2.y, s1.y, h1.y);
+                    v[6] += fmaf(o3.x, s1.z, h1.z); v[7] += fmaf(o3.y, s1.w, h1.w);
+                }
+            }
+            if (full) {
+                if (p.res != nullptr) {
+                    const Half8 rv = *reinterpret_cast<const Half8*>(p.res + (long long)m * p.ldr + n);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 rf = __half22float2(rv.v[q]);
+                        v[2 * q] += rf.x;
+                        v[2 * q + 1] += rf.y;
+                    }
+                }
+                if (p.out_f32) {
+                    float4* dst = reinterpret_cast<float4*>(outb + ((long long)m * p.ldo + n) * 4);
+                    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+                    Half8 o;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) o.v[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+                    *reinterpret_cast<Half8*>(outb + ((long long)m * p.ldo + n) * 2) = o;
+                }
+            } else {  // ragged channel tail: element-wise
+                for (int q = 0; q < 8 && n + q < p.Cout; ++q) {
+                    float r = v[q];
+                    if (p.res != nullptr) r += __half2float(p.res[(long long)m * p.ldr + n + q]);
+                    if (p.out_f32) reinterpret_cast<float*>(outb)[(long long)m * p.ldo + n + q] = r;
+                    else reinterpret_cast<__half*>(outb)[(long long)m * p.ldo + n + q] = __float2half_rn(r);
+                }
             }
         }
     }
@@ -281,7 +329,6 @@ __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParam
         if (tid < NT) {
             const int n = n0 + tid * 8;
             if (n < p.Cout) {
-                const float* sS = sXf + (A_XFORM ? 2 * p.K : 0);
                 float a = 0.f, q = 0.f;
 #pragma unroll
                 for (int w = 0; w < NTHREADS / 32; ++w) {
@@ -300,6 +347,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParam
 template <int BN, int EPI, bool A_XFORM>
 static int launch_gemm(const GemmConvParams& p, int problems, cudaStream_t stream) {
     size_t smem = (size_t)STAGES * (BM + BN) * SK * sizeof(__half);
+    static_assert((size_t)STAGES * (BM + BN) * SK * sizeof(__half) >= (size_t)BM * (BN + 8) * sizeof(float),
+                  "epilogue staging tile must fit in the pipeline buffers");
     if (A_XFORM) smem += 2 * (size_t)p.K * sizeof(float);
     if (EPI == EPI_STATS) smem += (NTHREADS / 32) * (BN / 8) * 2 * sizeof(float);
     auto kern = gemm_conv_kernel<BN, EPI, A_XFORM>;
@@ -333,12 +382,13 @@ extern "C" int ym_conv2d_nhwc(const void* x, int ldx, int B, int H, int W, int C
                               int out_f32, const void* res, int ldr, int act, void* stream) {
     YM_CHECK_ARG(x && w && out, "ym_conv2d_nhwc: null pointer");
     YM_CHECK_ARG(Cin % 8 == 0 && ldx % 8 == 0, "ym_conv2d_nhwc: Cin (%d) and ldx (%d) must be multiples of 8", Cin, ldx);
-    YM_CHECK_ARG(Cout % 2 == 0 && ldo % 2 == 0, "ym_conv2d_nhwc: Cout (%d)/ldo (%d) must be even", Cout, ldo);
+    YM_CHECK_ARG(Cout % 2 == 0, "ym_conv2d_nhwc: Cout (%d) must be even", Cout);
     YM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, "ym_conv2d_nhwc: x/w must be 16-byte aligned");
-    YM_CHECK_ARG(((uintptr_t)out & 3) == 0, "ym_conv2d_nhwc: out must be 4-byte aligned");
+    YM_CHECK_ARG(Cout % 8 != 0 || (((uintptr_t)out & 15) == 0 && ldo % (out_f32 ? 4 : 8) == 0),
+                 "ym_conv2d_nhwc: out must be 16-byte aligned with a pitch (%d) that keeps rows 16-byte aligned", ldo);
     YM_CHECK_ARG(Kpad % BK == 0 && Kpad >= KH * KW * Cin, "ym_conv2d_nhwc: bad Kpad %d", Kpad);
     YM_CHECK_ARG(stride >= 1 && KH >= 1 && KW >= 1 && pad >= 0, "ym_conv2d_nhwc: bad geometry");
-    YM_CHECK_ARG(res == nullptr || (ldr % 2 == 0 && ((uintptr_t)res & 3) == 0), "ym_conv2d_nhwc: bad residual");
+    YM_CHECK_ARG(res == nullptr || (ldr % 8 == 0 && ((uintptr_t)res & 15) == 0), "ym_conv2d_nhwc: residual must be 16-byte aligned");
     if (B == 0) return YM_OK;
     GemmConvParams p;
     memset(&p, 0, sizeof(p));
@@ -359,7 +409,8 @@ extern "C" int ym_moe_expert_gemm(const void* a, int lda, int a_div, int P, int 
                                   long long w_expert_stride, const int* route_idx, int N, void* out, int ldo,
                                   const float* a_scale, const float* a_shift, float* stats, int groups, void* stream) {
     YM_CHECK_ARG(a && w && out && route_idx, "ym_moe_expert_gemm: null pointer");
-    YM_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && N % 8 == 0 && ldo % 2 == 0, "ym_moe_expert_gemm: bad dims K=%d N=%d", K, N);
+    YM_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && N % 8 == 0 && ldo % 8 == 0, "ym_moe_expert_gemm: bad dims K=%d N=%d", K, N);
+    YM_CHECK_ARG((((uintptr_t)a | (uintptr_t)out) & 15) == 0, "ym_moe_expert_gemm: 16-byte alignment");
     YM_CHECK_ARG(Kpad % BK == 0 && Kpad >= K, "ym_moe_expert_gemm: bad Kpad");
     YM_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr), "ym_moe_expert_gemm: scale/shift mismatch");
     YM_CHECK_ARG(a_scale == nullptr || K % BK == 0, "ym_moe_expert_gemm: A prologue needs K %% 32 == 0");
@@ -389,7 +440,9 @@ extern "C" int ym_moe_combine(const void* x, int ldx, int B, int HW, int C, cons
                               const void* o, int ldo_o, const float* o_scale, const float* o_shift, int topk, void* out,
                               int ldo, int add_residual, void* stream) {
     YM_CHECK_ARG(x && ws && o && o_scale && o_shift && out, "ym_moe_combine: null pointer");
-    YM_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldo % 2 == 0 && ldo_o % 2 == 0, "ym_moe_combine: bad dims");
+    YM_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && ldo_o % 8 == 0, "ym_moe_combine: bad dims");
+    YM_CHECK_ARG((((uintptr_t)x | (uintptr_t)o | (uintptr_t)out | (uintptr_t)o_scale | (uintptr_t)o_shift) & 15) == 0,
+                 "ym_moe_combine: 16-byte alignment");
     YM_CHECK_ARG(Kpad % BK == 0 && Kpad >= C, "ym_moe_combine: bad Kpad");
     if (B == 0) return YM_OK;
     GemmConvParams p;
@@ -403,33 +456,38 @@ extern "C" int ym_moe_combine(const void* x, int ldx, int B, int HW, int C, cons
     return dispatch_bn<EPI_MOE_COMBINE, false>(p, 1, (cudaStream_t)stream);
 }
 
-// GroupNorm partial statistics [P][mtiles][C/8][2] -> per-(problem, channel) scale/shift (fixed-order reduction).
+// GroupNorm partial statistics [P][mtiles][C/8][2] -> per-(problem, channel) scale/shift.  One warp per (problem, group):
+// lanes stride over the partials, fixed-shape shuffle tree (deterministic), then write the group's channels.
 // scale = rw*rstd*gamma, shift = rw*(beta - mean*rstd*gamma)
-__global__ void gn_finalize_kernel(const float* __restrict__ stats, int P, int mtiles, int groups, int C, float count, float eps,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   const int* __restrict__ route_idx, const float* __restrict__ route_w,
-                                   float* __restrict__ scale, float* __restrict__ shift) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P * C) return;
-    const int pr = i / C, c = i - pr * C;
-    const int cpg = C / groups;
-    const int grp = c / cpg;
-    const int t0 = grp * cpg / 8, t1 = (grp + 1) * cpg / 8, nt = C / 8;
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ stats, int P, int mtiles, int groups, int C,
+                                                          float count, float eps, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const int* __restrict__ route_idx,
+                                                          const float* __restrict__ route_w, float* __restrict__ scale,
+                                                          float* __restrict__ shift) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= P * groups) return;
+    const int pr = wid / groups, grp = wid - pr * groups;
+    const int cpg = C / groups, tpg = cpg / 8, nt = C / 8;
     float s = 0.f, q = 0.f;
-    for (int mt = 0; mt < mtiles; ++mt)
-        for (int t = t0; t < t1; ++t) {
-            const float* src = stats + (((long long)pr * mtiles + mt) * nt + t) * 2;
-            s += src[0];
-            q += src[1];
-        }
+    for (int i = lane; i < mtiles * tpg; i += 32) {
+        const int mt = i / tpg, t = grp * tpg + i % tpg;
+        const float* src = stats + (((long long)pr * mtiles + mt) * nt + t) * 2;
+        s += src[0];
+        q += src[1];
+    }
+    s = ym::warp_sum(s);
+    q = ym::warp_sum(q);
     const float mean = s / count;
     const float var = fmaxf(q / count - mean * mean, 0.f);
     const float rstd = rsqrtf(var + eps);
     const int e = route_idx[pr];
-    const float gm = gamma[e * C + c], bt = beta[e * C + c];
     const float rw = route_w ? route_w[pr] : 1.f;
-    scale[i] = rw * rstd * gm;
-    shift[i] = rw * (bt - mean * rstd * gm);
+    for (int j = lane; j < cpg; j += 32) {
+        const int c = grp * cpg + j;
+        const float gm = gamma[e * C + c], bt = beta[e * C + c];
+        scale[(long long)pr * C + c] = rw * rstd * gm;
+        shift[(long long)pr * C + c] = rw * (bt - mean * rstd * gm);
+    }
 }
 
 extern "C" long long ym_moe_stats_floats(int P, int HW, int N) { return (long long)P * ((HW + BM - 1) / BM) * (N / 8) * 2; }
@@ -440,7 +498,7 @@ extern "C" int ym_gn_finalize(const float* stats, int P, int HW, int groups, int
     YM_CHECK_ARG(stats && gamma && beta && route_idx && scale && shift, "ym_gn_finalize: null pointer");
     YM_CHECK_ARG(groups > 0 && C % groups == 0 && (C / groups) % 8 == 0, "ym_gn_finalize: bad groups");
     if (P == 0) return YM_OK;
-    const int n = P * C;
+    const int n = P * groups * 32;
     gn_finalize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(stats, P, (HW + BM - 1) / BM, groups, C, count, eps, gamma, beta,
                                                                           route_idx, route_w, scale, shift);
     YM_CHECK_LAUNCH("gn_finalize");

@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(256) router_pool_kernel(const __half* __restri
 }
 
 // hidden[b, pix, r] = SiLU(scale1[r] * conv3x3(pooled)[pix, r] + shift1[r]); partial[b, blk, r] = sum over the block's pixels.
-// grid (nblk, B), block 256 = PIX_PER_BLOCK pixels x Cr lanes (Cr in {8,16,32}).  w1 layout [tap][c][r] fp32.
+// grid (nblk, B), block 256 = PIX_PER_BLOCK pixels x Cr lanes (Cr in {8,16,32,64}).  w1 layout [tap][c/4][r][4] fp32 so that
+// the Cr lanes of a pixel read consecutive float4 (coalesced) while the pooled input float4 is a broadcast.
 __global__ void __launch_bounds__(256) router_hidden_kernel(const float* __restrict__ pooled, int Hp, int Wp, int C, int Cr,
                                                             const float* __restrict__ w1, const float* __restrict__ scale1,
                                                             const float* __restrict__ shift1, float* __restrict__ partial,
@@ -41,22 +42,31 @@ __global__ void __launch_bounds__(256) router_hidden_kernel(const float* __restr
     const int r = threadIdx.x % Cr;
     const int pl = threadIdx.x / Cr;
     const int pix = blockIdx.x * ppb + pl;
+    const int C4 = C >> 2;
     float hval = 0.f;
     if (pix < Hp * Wp) {
         const int py = pix / Wp, px = pix % Wp;
-        float acc = 0.f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = py + ky - 1;
             if (iy < 0 || iy >= Hp) continue;
             for (int kx = 0; kx < 3; ++kx) {
                 const int ix = px + kx - 1;
                 if (ix < 0 || ix >= Wp) continue;
-                const float* pin = pooled + (((long long)b * Hp + iy) * Wp + ix) * C;
-                const float* pw = w1 + (long long)(ky * 3 + kx) * C * Cr + r;
-                for (int c = 0; c < C; ++c) acc = fmaf(pin[c], pw[(long long)c * Cr], acc);
+                const float4* pin = reinterpret_cast<const float4*>(pooled + (((long long)b * Hp + iy) * Wp + ix) * C);
+                const float4* pw = reinterpret_cast<const float4*>(w1) + (long long)(ky * 3 + kx) * C4 * Cr + r;
+#pragma unroll 4
+                for (int c4 = 0; c4 < C4; ++c4) {
+                    const float4 xv = __ldg(pin + c4);
+                    const float4 wv = __ldg(pw + (long long)c4 * Cr);
+                    a0 = fmaf(xv.x, wv.x, a0);
+                    a1 = fmaf(xv.y, wv.y, a1);
+                    a2 = fmaf(xv.z, wv.z, a2);
+                    a3 = fmaf(xv.w, wv.w, a3);
+                }
             }
         }
-        const float v = fmaf(acc, scale1[r], shift1[r]);
+        const float v = fmaf((a0 + a1) + (a2 + a3), scale1[r], shift1[r]);
         hval = v / (1.f + expf(-v));
     }
     red[threadIdx.x] = hval;
@@ -154,6 +164,7 @@ extern "C" int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C
     YM_CHECK_ARG(Cr == 8 || Cr == 16 || Cr == 32 || Cr == 64, "ym_router_topk: reduced channels must be 8/16/32/64 (got %d)", Cr);
     YM_CHECK_ARG(E >= 1 && E <= 64 && topk >= 1 && topk <= 8 && topk <= E, "ym_router_topk: need 1<=topk<=min(8,E), E<=64");
     YM_CHECK_ARG(pool >= 1, "ym_router_topk: pool");
+    YM_CHECK_ARG(C % 4 == 0, "ym_router_topk: C must be a multiple of 4");
     if (B == 0) return YM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool do_pool = H > pool && W > pool;  // routers.py:289-292

@@ -58,7 +58,8 @@ class EfficientSpatialRouter(nn.Module, PackCache):
         s2, h2 = bn_affine(bn2)
         return {
             "Cr": Cr, "E": c3.weight.shape[0],
-            "w1": c0.weight.detach().float().permute(2, 3, 1, 0).reshape(9, C, Cr).contiguous(),  # [tap][c][r]
+            # [tap][c/4][r][4]: the Cr lanes of one pixel read consecutive float4
+            "w1": c0.weight.detach().float().permute(2, 3, 1, 0).reshape(9, C // 4, 4, Cr).permute(0, 1, 3, 2).contiguous(),
             "scale1": s1, "shift1": h1,
             "w2": c3.weight.detach().float().reshape(c3.weight.shape[0], Cr).contiguous(),
             "scale2": s2, "shift2": h2,

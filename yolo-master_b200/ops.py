@@ -222,9 +222,10 @@ def detect_topk(boxes, logits, strides, nc, max_det=300, return_anchor=False):
     out = torch.empty((B, k, 6), dtype=torch.float32, device=boxes[0].device)
     anc = torch.empty((B, k), dtype=torch.int32, device=boxes[0].device) if return_anchor else None
     nl, bp, cp, hs, ws, st = _level_arrays(boxes, logits, strides)
+    scratch = torch.empty((B * A,), dtype=torch.int32, device=boxes[0].device)
     _lib.check(lib().ym_detect_topk(nl, bp, cp, hs, ws, st, B, nc, max_det, out.data_ptr(),
-                                    None if anc is None else anc.data_ptr(), _stream()), "ym_detect_topk")
-    _count()
+                                    None if anc is None else anc.data_ptr(), scratch.data_ptr(), _stream()), "ym_detect_topk")
+    _count(2)
     return (out, anc) if return_anchor else out
 
 
@@ -237,3 +238,31 @@ def detect_dense(boxes, logits, strides, nc, xyxy):
                "ym_detect_dense")
     _count()
     return y
+
+
+def tc_gemm_nt(a, b, bias=None, res=None, act=False, out=None):
+    """ym_tc_gemm_nt (tcgen05): a [M,K] fp16 (row pitch = stride(0)), b [N,K] fp16.  Returns out [M,N] fp16."""
+    M, K = a.shape
+    N = b.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float16, device=a.device)
+    _lib.check(lib().ym_tc_gemm_nt(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
+                                   None if bias is None else bias.data_ptr(), None if res is None else res.data_ptr(),
+                                   0 if res is None else res.stride(0), out.data_ptr(), out.stride(0), M, N, K,
+                                   1 if act else 0, _stream()), "ym_tc_gemm_nt")
+    _count()
+    return out
+
+
+def moe_dispatch(x, w_all, route_idx, route_w, w_min=0.01, clamp=1e4, out=None):
+    """ym_moe_dispatch_tc.  x: (B,H,W,C) fp16 NHWC; w_all: [E,N,C] fp16; route_idx int32 [B,k]; route_w fp32 [B,k]."""
+    B, H, W, Cc = x.shape
+    E, N, Kw = w_all.shape
+    k = route_idx.shape[1]
+    if out is None:
+        out = new_act(B, H, W, N, x.device)
+    _lib.check(lib().ym_moe_dispatch_tc(x.data_ptr(), pitch(x), B, H * W, Cc, w_all.data_ptr(), w_all.stride(1), w_all.stride(0),
+                                        route_idx.data_ptr(), route_w.data_ptr(), k, N, float(w_min), float(clamp),
+                                        out.data_ptr(), pitch(out), _stream()), "ym_moe_dispatch_tc")
+    _count()
+    return out
