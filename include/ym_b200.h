@@ -54,6 +54,12 @@ int ym_concat2_nhwc(const void* a, int lda, int Ca, int up, const void* b, int l
  * d_qk must be 32; d_v 32 or 64.  Output channel = head*d_v + d. */
 int ym_attention_fwd(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
                      int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream);
+/* Same contract on the tcgen05 path: S = QK^T and O += PV as tcgen05.mma with S/O in tensor memory, one query row per
+ * thread (shuffle-free softmax), lazy O rescaling.  ym_attention_fwd dispatches here by default;
+ * ym_set_attention_impl(0) selects the mma.sync kernel (returns the previous setting). */
+int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
+                        int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream);
+int ym_set_attention_impl(int impl);
 
 /* EfficientSpatialRouter.forward + BaseRouter._process_logits (eval)  moe/routers.py:283-304, :185-265.
  * w1: fp32 [9][C/4][Cr][4] (tap-major, float4 over channels), scale1/shift1: folded BN1 [Cr]; w2: fp32 [E][Cr], scale2/shift2: folded BN2 [E].

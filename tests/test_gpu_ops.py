@@ -134,12 +134,14 @@ def test_area_attention(dim, heads, area, hw):
 
 @pytest.mark.parametrize("N,heads,dv,batch", [(400, 2, 32, 3), (1600, 2, 32, 2), (221, 4, 32, 2), (400, 2, 64, 2), (6400, 2, 32, 1)])
 def test_attention_kernel_alone_strict(N, heads, dv, batch):
-    """The fused attention kernel by itself (given fp16 q,k,v) meets the strict tolerance against fp32 softmax attention."""
-    from yolo_master_b200 import ops
+    """The mma.sync attention kernel by itself (given fp16 q,k,v) meets the strict tolerance against fp32 softmax attention."""
+    from yolo_master_b200 import _lib, ops
+    prev = _lib.load().ym_set_attention_impl(0)
     hs = 64 + dv
     g = torch.Generator().manual_seed(N + dv)
     qkv = torch.randn((batch, N, 1, heads * hs), generator=g).half()
     out = ops.attention(qkv.to(DEV), batch, N, heads, hs, 0, 32, 64, 32, dv, 32 ** -0.5)
+    _lib.load().ym_set_attention_impl(prev)
     t = qkv.float().view(batch, N, heads, hs).permute(0, 2, 1, 3)
     q, k, v = t[..., :32], t[..., 32:64], t[..., 64:]
     ref = torch.softmax((q * 32 ** -0.5) @ k.transpose(-1, -2), -1) @ v          # (b, h, N, dv)

@@ -1,0 +1,261 @@
+// tcgen05 / TMEM fused attention forward (sm_100a):  O = softmax((Q*scale) K^T) V  for d_qk = 32, d_v in {32, 64}.
+//
+// Same contract as attention.cu (see there for the reference mapping, block.py:1708-1722 / :1324-1331); this is the
+// Blackwell-native data path:
+//   * S = Q K^T and O += P V run on the 5th-gen tensor cores (tcgen05.mma kind::f16, M = 128 query rows), issued by ONE
+//     thread; S (128 x 64 fp32) and O (128 x d_v fp32) live in tensor memory.
+//   * softmax: thread t of the CTA owns query row t: it reads its whole S row with one tcgen05.ld, so row max / row sum
+//     need no shuffles; exp2 on the MUFU; P is written as fp16 into a 128B-swizzled shared-memory tile that is the A
+//     operand of the PV MMA.
+//   * O is only rescaled when a row's running max grows by more than 2^8 (lazy rescaling): most KV tiles never touch O.
+//   * K/V tiles arrive by cp.async into 64B/128B-swizzled canonical UMMA layouts (3-stage ring).
+// One CTA = 128 threads, 128 TMEM columns (S 64 + O <= 64) and ~48 KB smem -> 4 CTAs per SM overlap each other's
+// MMA / softmax / load phases.
+#include "tc_common.cuh"
+
+namespace ym {
+
+constexpr int TA_BQ = 128, TA_BKV = 64, TA_THREADS = 128, TA_STAGES = 3;
+
+__device__ __forceinline__ float ta_exp2(float x) {
+    float y;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int DV>
+__global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* __restrict__ qkv, int ld, int N, int head_stride,
+                                                                 int q_off, int k_off, int v_off, float scale_log2,
+                                                                 __half* __restrict__ out, int ldo) {
+    constexpr int Q_BYTES = TA_BQ * 64, K_BYTES = TA_BKV * 64, V_BYTES = TA_BKV * DV * 2, P_BYTES = TA_BQ * 128;
+    constexpr uint32_t TMEM_COLS = 128;           // S: cols [0,64), O: cols [64, 64+DV)
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* sQ = smem;
+    unsigned char* sP = sQ + Q_BYTES;
+    unsigned char* sK = sP + P_BYTES;                      // [STAGES][K_BYTES]
+    unsigned char* sV = sK + TA_STAGES * K_BYTES;          // [STAGES][V_BYTES]
+    __shared__ uint64_t bar_s, bar_pv;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * TA_BQ, h = blockIdx.y, b = blockIdx.z;
+    const __half* base = qkv + (long long)b * N * ld + h * head_stride;
+    const __half* gQ = base + q_off;
+    const __half* gK = base + k_off;
+    const __half* gV = base + v_off;
+
+    if (tid == 0) {
+        tc::mbar_init(&bar_s, 1);
+        tc::mbar_init(&bar_pv, 1);
+        tc::fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
+
+    // ---- Q tile: 128 rows x 64 B (SW64)
+#pragma unroll
+    for (int i = 0; i < TA_BQ * 4 / TA_THREADS; ++i) {
+        const int idx = tid + i * TA_THREADS;
+        const int r = idx >> 2, c = idx & 3;
+        const bool ok = q0 + r < N;
+        cp_async16(sQ + tc::sw64_offset(r, c), ok ? gQ + (long long)(q0 + r) * ld + c * 8 : gQ, ok ? 16 : 0);
+    }
+    auto load_kv = [&](int t) {
+        const int st = t % TA_STAGES, kv0 = t * TA_BKV;
+        unsigned char* dK = sK + st * K_BYTES;
+        unsigned char* dV = sV + st * V_BYTES;
+#pragma unroll
+        for (int i = 0; i < TA_BKV * 4 / TA_THREADS; ++i) {
+            const int idx = tid + i * TA_THREADS;
+            const int r = idx >> 2, c = idx & 3;
+            const bool ok = kv0 + r < N;
+            cp_async16(dK + tc::sw64_offset(r, c), ok ? gK + (long long)(kv0 + r) * ld + c * 8 : gK, ok ? 16 : 0);
+        }
+        constexpr int VCH = DV / 8;
+#pragma unroll
+        for (int i = 0; i < TA_BKV * VCH / TA_THREADS; ++i) {
+            const int idx = tid + i * TA_THREADS;
+            const int r = idx / VCH, c = idx % VCH;
+            const bool ok = kv0 + r < N;
+            const uint32_t off = (DV == 32) ? tc::sw64_offset(r, c) : tc::sw128_offset(r, c);
+            cp_async16(dV + off, ok ? gV + (long long)(kv0 + r) * ld + c * 8 : gV, ok ? 16 : 0);
+        }
+    };
+    const int T = (N + TA_BKV - 1) / TA_BKV;
+    load_kv(0);
+    cp_async_commit();
+    if (T > 1) load_kv(1);
+    cp_async_commit();
+
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t t_s = tmem_base, t_o = tmem_base + 64;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+
+    const uint32_t idesc_qk = tc::make_idesc_f16(TA_BQ, TA_BKV, 0);
+    const uint32_t idesc_pv = tc::make_idesc_f16(TA_BQ, DV, 1);   // V is MN-major (d_v contiguous)
+    const uint64_t qdesc = tc::make_desc(smem_u32(sQ), 512, 4);
+    const uint64_t pdesc = tc::make_desc(smem_u32(sP), 1024, 2);
+
+    float m_used = -INFINITY, l_run = 0.f;
+    const int row = tid;                      // query row owned by this thread
+    unsigned char* prow = sP + row * 128;
+
+    for (int t = 0; t < T; ++t) {
+        // ---- (a) K_t / V_t have landed; make them visible to the async proxy
+        cp_async_wait<1>();
+        tc::fence_proxy_async();
+        __syncthreads();
+        // ---- (b) S = Q K_t^T
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint64_t kdesc = tc::make_desc(smem_u32(sK + (t % TA_STAGES) * K_BYTES), 512, 4);
+            tc::mma_f16_ss(t_s, qdesc, kdesc, idesc_qk, 0u);
+            tc::mma_f16_ss(t_s, qdesc + 2, kdesc + 2, idesc_qk, 1u);
+            tc::mma_commit(&bar_s);
+        }
+        // ---- (d) softmax of row `row`
+        tc::mbar_wait(&bar_s, t & 1);
+        tc::fence_after_sync();
+        uint32_t sr[64];
+        {
+            uint32_t lo[32], hi[32];
+            tc::tmem_ld32(t_s + lane_sel, lo);
+            tc::tmem_ld32(t_s + lane_sel + 32, hi);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { sr[i] = lo[i]; sr[32 + i] = hi[i]; }
+        }
+        const int kv0 = t * TA_BKV;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            float v = __uint_as_float(sr[i]);
+            if (kv0 + i >= N) v = -INFINITY;
+            sr[i] = __float_as_uint(v);
+            mx = fmaxf(mx, v);
+        }
+        const float m_tile = mx * scale_log2;
+        float alpha = 1.f;
+        const bool grow = m_tile > m_used + 8.f;     // also true on the first tile (m_used = -inf)
+        if (grow) {
+            alpha = ta_exp2(m_used - m_tile);        // 0 on the first tile
+            m_used = m_tile;
+            l_run *= alpha;
+        }
+        float rs = 0.f;
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float p0 = ta_exp2(fmaf(__uint_as_float(sr[2 * i]), scale_log2, -m_used));
+            const float p1 = ta_exp2(fmaf(__uint_as_float(sr[2 * i + 1]), scale_log2, -m_used));
+            rs += p0 + p1;
+            pk[i] = pack_half2(p0, p1);
+        }
+        l_run += rs;
+        // ---- (e) PV_{t-1} must be complete before O is rescaled, P overwritten, or its K/V stage reloaded
+        if (t > 0) {
+            tc::mbar_wait(&bar_pv, (t - 1) & 1);
+            tc::fence_after_sync();
+            if (__any_sync(0xffffffffu, grow)) {     // warp-collective TMEM round trip, lanes that did not grow use 1.0
+#pragma unroll
+                for (int c0 = 0; c0 < DV; c0 += 32) {
+                    uint32_t o[32];
+                    tc::tmem_ld32(t_o + lane_sel + c0, o);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tc::tmem_st32(t_o + lane_sel + c0, o);
+                }
+                tc::tmem_st_wait();
+            }
+        }
+        // ---- (c) prefetch tile t+2 into the ring stage last read by PV_{t-1} (complete: waited for just above)
+        if (t + 2 < T) load_kv(t + 2);
+        cp_async_commit();
+        // ---- P row -> swizzled smem (A operand, K-major, 64 keys = 128 B per row)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint4 v = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = v;
+        }
+        tc::fence_proxy_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        // ---- (f) O (+)= P V_t
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t va = smem_u32(sV + (t % TA_STAGES) * V_BYTES);
+            const uint64_t vdesc = (DV == 32) ? tc::make_desc(va, 512, 4) : tc::make_desc(va, 1024, 2);
+            constexpr uint32_t VSTEP = (16 * DV * 2) >> 4;    // 16 keys per MMA k-step, in 16-byte units
+#pragma unroll
+            for (int k = 0; k < TA_BKV / 16; ++k)
+                tc::mma_f16_ss(t_o, pdesc + 2 * k, vdesc + VSTEP * k, idesc_pv, (t | k) ? 1u : 0u);
+            tc::mma_commit(&bar_pv);
+        }
+    }
+    cp_async_wait<0>();
+    // ---- finalise: O / l -> global
+    tc::mbar_wait(&bar_pv, (T - 1) & 1);
+    tc::fence_after_sync();
+    const float inv = 1.f / l_run;
+    const int qrow = q0 + row;
+    __half* orow = out + ((long long)b * N + qrow) * ldo + h * DV;
+#pragma unroll
+    for (int c0 = 0; c0 < DV; c0 += 32) {
+        uint32_t o[32];
+        tc::tmem_ld32(t_o + lane_sel + c0, o);
+        tc::tmem_ld_wait();
+        if (qrow < N) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                Half8 hv;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    hv.v[q] = __floats2half2_rn(__uint_as_float(o[c * 8 + 2 * q]) * inv, __uint_as_float(o[c * 8 + 2 * q + 1]) * inv);
+                *reinterpret_cast<Half8*>(orow + c0 + c * 8) = hv;
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace ym
+
+using namespace ym;
+
+extern "C" int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
+                                   int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream) {
+    YM_CHECK_ARG(qkv && out, "ym_attention_fwd_tc: null pointer");
+    YM_CHECK_ARG(d_qk == 32, "ym_attention_fwd_tc: d_qk must be 32 (got %d)", d_qk);
+    YM_CHECK_ARG(d_v == 32 || d_v == 64, "ym_attention_fwd_tc: d_v must be 32 or 64 (got %d)", d_v);
+    YM_CHECK_ARG(ld % 8 == 0 && head_stride % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
+                 "ym_attention_fwd_tc: offsets/pitch must be multiples of 8 halves");
+    YM_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0 && ldo % 8 == 0, "ym_attention_fwd_tc: alignment");
+    YM_CHECK_ARG(N > 0 && heads > 0 && batch >= 0 && batch < 65536, "ym_attention_fwd_tc: bad sizes");
+    if (batch == 0) return YM_OK;
+    const float sl2 = scale * 1.4426950408889634f;
+    dim3 grid((N + TA_BQ - 1) / TA_BQ, heads, batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)TA_BQ * 64 + TA_BQ * 128 + TA_STAGES * (TA_BKV * 64 + TA_BKV * d_v * 2) + 1024;
+    cudaError_t e;
+    if (d_v == 32) {
+        e = cudaFuncSetAttribute(tc_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            tc_attention_kernel<32><<<grid, TA_THREADS, smem, st>>>((const __half*)qkv, ld, N, head_stride, q_off, k_off, v_off, sl2,
+                                                                  (__half*)out, ldo);
+    } else {
+        e = cudaFuncSetAttribute(tc_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            tc_attention_kernel<64><<<grid, TA_THREADS, smem, st>>>((const __half*)qkv, ld, N, head_stride, q_off, k_off, v_off, sl2,
+                                                                  (__half*)out, ldo);
+    }
+    if (e != cudaSuccess) { ym_set_error("ym_attention_fwd_tc: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
+    YM_CHECK_LAUNCH("tc_attention");
+    return YM_OK;
+}
