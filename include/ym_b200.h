@@ -115,6 +115,15 @@ int ym_moe_dispatch_tc(const void* x, int ldx, int B, int HW, int C, const void*
                        const int* route_idx, const float* route_w, int topk, int N, float w_min, float clamp, void* out,
                        int ldo, void* stream);
 
+/* TMA + tcgen05 convolution (same contract and weight packing as ym_conv2d_nhwc): the activation k-tiles are loaded by
+ * cp.async.bulk.tensor from a 4-D (C,W,H,B) tensor map at the tap-shifted origin (im2col-free, OOB zero fill = padding),
+ * MMAs are tcgen05.mma with the accumulator in TMEM.  Supported: k in {1,3} square, stride 1|2, pad k/2, Cin % 16 == 0,
+ * Cout % 8 == 0 (ym_conv2d_tc_supported returns 1); everything else goes through ym_conv2d_nhwc. */
+int ym_conv2d_tc_supported(int Cin, int Cout, int KH, int KW, int stride, int pad, int ldx);
+int ym_conv2d_tc(const void* x, int ldx, int B, int H, int W, int Cin, const void* w, int Kpad, const float* bias, int Cout,
+                 int KH, int KW, int stride, int pad, void* out, int ldo, int out_f32, const void* res, int ldr, int act,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

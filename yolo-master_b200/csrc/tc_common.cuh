@@ -13,10 +13,12 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 
-// Bounded wait (a lost arrive must not hang the GPU box): traps after ~2^26 polls.
+// Bounded wait: a lost arrive must not hang the GPU box.  try_wait suspends for a HW time slice per call, so the bound is
+// on wall-clock cycles (~1 s), not on the poll count; on timeout the kernel traps (the launch fails with an error).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
+    long long t0 = 0;
     for (uint32_t it = 0; !done; ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -25,7 +27,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
-        if (it > (1u << 26)) __trap();
+        if (!done && (it & 63u) == 63u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000LL) __trap();
+        }
     }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {

@@ -1,0 +1,317 @@
+// TMA-staged, im2col-free tcgen05 convolution for NHWC fp16 (sm_100a): Conv(k=1|3, s=1|2, groups=1) + folded-BN bias
+// + SiLU (+ residual), conv.py:69-89.
+//
+// The N-scale layers are HBM-bound on paper but *instruction-issue bound* with per-thread cp.async/ldmatrix/mma.sync
+// (ncu: sm__throughput ~50 %, dram ~18 %).  Here the whole main loop is issued by two threads:
+//   * producer (warp 0, one lane): one cp.async.bulk.tensor (TMA) per operand per k-tile.  The activation is a 4-D tensor
+//     map (C, W, H, B); the k-tile for filter tap (ky,kx) is the box [kc channels] x [TW x TH pixels] at the SHIFTED
+//     origin (x0*s + kx - pad, y0*s + ky - pad) with element strides (1, s, s, 1): no im2col buffer, padding comes from
+//     TMA out-of-bounds zero fill, and the box lands in shared memory already in the 32/64/128-byte swizzled K-major
+//     layout tcgen05 consumes.  1x1/stride-1 convs use a flat 2-D map (C, B*H*W) so tiles never straddle padding.
+//   * MMA issuer (warp 1, one lane): tcgen05.mma kind::f16, M = 128 pixels, N = BN output channels, accumulator in TMEM;
+//     tcgen05.commit releases the smem stage and finally signals the epilogue.
+//   * epilogue (all 4 warps): tcgen05.ld one accumulator row (= one output pixel) per thread, bias + SiLU (+ residual),
+//     16-byte vector stores.
+// Several CTAs are resident per SM (72 KB smem, <= 128 TMEM columns each) so one CTA's epilogue overlaps another's loads.
+#include <cuda.h>
+
+#include "tc_common.cuh"
+
+namespace ym {
+
+constexpr int CV_BM = 128, CV_THREADS = 128, CV_STAGES = 3;
+
+struct TcConvParams {
+    const float* bias;
+    const __half* res; int ldr;
+    void* out; int ldo; int out_f32;
+    int B, Ho, Wo, Cout, Cin, KH, KW, stride, pad;
+    int kc;            // channels per k-tile (16 / 32 / 64)
+    int tiles_x, tiles_y, TW, TH;   // patch mode
+    int M;             // flat mode: B*H*W rows
+    int act;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+template <int BN, bool FLAT>
+__global__ void __launch_bounds__(CV_THREADS) tc_conv_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                             const __grid_constant__ CUtensorMap map_b, const TcConvParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const int row_bytes = p.kc * 2;                       // 32 / 64 / 128
+    const int a_bytes = CV_BM * row_bytes, b_bytes = BN * row_bytes;
+    const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+    __shared__ uint64_t full_bar[CV_STAGES], empty_bar[CV_STAGES], done_bar;
+    __shared__ uint32_t tmem_slot;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < CV_STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        tc::mbar_init(&done_bar, 1);
+        tc::fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+
+    // ---- tile coordinates
+    const int n0 = blockIdx.y * BN;
+    int b = 0, oy0 = 0, ox0 = 0, m0 = 0;
+    if (FLAT) {
+        m0 = blockIdx.x * CV_BM;
+    } else {
+        const int tpi = p.tiles_x * p.tiles_y;
+        b = blockIdx.x / tpi;
+        const int t = blockIdx.x - b * tpi;
+        oy0 = (t / p.tiles_x) * p.TH;
+        ox0 = (t % p.tiles_x) * p.TW;
+    }
+    const int cchunks = p.Cin / p.kc;
+    const int KT = p.KH * p.KW * cchunks;
+    const uint32_t layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+    const uint32_t sbo = 8u * row_bytes;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer
+        for (int it = 0; it < KT; ++it) {
+            const int s = it % CV_STAGES;
+            if (it >= CV_STAGES) tc::mbar_wait(&empty_bar[s], ((it / CV_STAGES) - 1) & 1);
+            unsigned char* st = smem + s * stage_bytes;
+            const int tap = it / cchunks, c0 = (it - tap * cchunks) * p.kc;
+            mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + b_bytes));
+            if (FLAT) {
+                tma_load_2d(st, &map_a, c0, m0, &full_bar[s]);
+            } else {
+                const int ky = tap / p.KW, kx = tap - ky * p.KW;
+                tma_load_4d(st, &map_a, c0, ox0 * p.stride + kx - p.pad, oy0 * p.stride + ky - p.pad, b, &full_bar[s]);
+            }
+            tma_load_2d(st + a_bytes, &map_b, tap * p.Cin + c0, n0, &full_bar[s]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer
+        const uint32_t idesc = tc::make_idesc_f16(CV_BM, BN);
+        for (int it = 0; it < KT; ++it) {
+            const int s = it % CV_STAGES;
+            tc::mbar_wait(&full_bar[s], (it / CV_STAGES) & 1);
+            tc::fence_after_sync();
+            const uint32_t sa = smem_u32(smem + s * stage_bytes);
+            const uint64_t adesc = tc::make_desc(sa, sbo, layout_type), bdesc = tc::make_desc(sa + a_bytes, sbo, layout_type);
+            for (int k = 0; k < p.kc / 16; ++k) tc::mma_f16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) ? 1u : 0u);
+            tc::mma_commit(&empty_bar[s]);
+        }
+        tc::mma_commit(&done_bar);
+    }
+    __syncwarp();
+
+    // ===== epilogue: one output pixel (accumulator row) per thread
+    tc::mbar_wait(&done_bar, 0);
+    tc::fence_after_sync();
+    const int r = warp * 32 + lane;
+    long long opix;
+    bool rowok;
+    if (FLAT) {
+        opix = (long long)m0 + r;
+        rowok = opix < p.M;
+    } else {
+        const int ty = r / p.TW, tx = r - ty * p.TW;
+        const int oy = oy0 + ty, ox = ox0 + tx;
+        rowok = ty < p.TH && oy < p.Ho && ox < p.Wo;
+        opix = ((long long)b * p.Ho + oy) * p.Wo + ox;
+    }
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    constexpr int NCHUNK = BN < 16 ? 1 : BN / 16;
+#pragma unroll 1
+    for (int ci = 0; ci < NCHUNK; ++ci) {
+        uint32_t rr[16];
+        tc::tmem_ld16(lane_addr + ci * 16, rr);
+        tc::tmem_ld_wait();
+        const int n = n0 + ci * 16;
+        if (!rowok || n >= p.Cout) continue;
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            float x = __uint_as_float(rr[q]);
+            if (p.bias != nullptr && n + q < p.Cout) x += p.bias[n + q];
+            if (p.act == 1) x = silu_f(x);
+            v[q] = x;
+        }
+        if (n + 16 <= p.Cout) {
+            if (p.res != nullptr) {
+                const Half8 r0 = *reinterpret_cast<const Half8*>(p.res + opix * p.ldr + n);
+                const Half8 r1 = *reinterpret_cast<const Half8*>(p.res + opix * p.ldr + n + 8);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f0 = __half22float2(r0.v[q]), f1 = __half22float2(r1.v[q]);
+                    v[2 * q] += f0.x; v[2 * q + 1] += f0.y; v[8 + 2 * q] += f1.x; v[8 + 2 * q + 1] += f1.y;
+                }
+            }
+            if (p.out_f32) {
+                float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.ldo + n);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+                Half8 o0, o1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    o0.v[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+                    o1.v[q] = __floats2half2_rn(v[8 + 2 * q], v[8 + 2 * q + 1]);
+                }
+                __half* dst = reinterpret_cast<__half*>(p.out) + opix * p.ldo + n;
+                *reinterpret_cast<Half8*>(dst) = o0;
+                *reinterpret_cast<Half8*>(dst + 8) = o1;
+            }
+        } else {
+            for (int q = 0; q < 16 && n + q < p.Cout; ++q) {
+                float x = v[q];
+                if (p.res != nullptr) x += __half2float(p.res[opix * p.ldr + n + q]);
+                if (p.out_f32) reinterpret_cast<float*>(p.out)[opix * p.ldo + n + q] = x;
+                else reinterpret_cast<__half*>(p.out)[opix * p.ldo + n + q] = __float2half_rn(x);
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- host side: tensor-map encoding through the driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+    return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+template <int BN, bool FLAT>
+static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, dim3 grid, cudaStream_t st) {
+    const int row_bytes = p.kc * 2;
+    const int stage = ((CV_BM * row_bytes + BN * row_bytes + 1023) / 1024) * 1024;
+    const size_t smem = (size_t)CV_STAGES * stage + 1024;
+    auto kern = tc_conv_kernel<BN, FLAT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ym_set_error("tc_conv: smem attr %zu: %s", smem, cudaGetErrorString(e)); return YM_ERR_CUDA; }
+    kern<<<grid, CV_THREADS, smem, st>>>(ma, mb, p);
+    YM_CHECK_LAUNCH("tc_conv");
+    return YM_OK;
+}
+
+}  // namespace ym
+
+using namespace ym;
+
+// Returns 1 if ym_conv2d_tc supports this configuration (the Python layer falls back to ym_conv2d_nhwc otherwise).
+extern "C" int ym_conv2d_tc_supported(int Cin, int Cout, int KH, int KW, int stride, int pad, int ldx) {
+    if (!(KH == KW && (KH == 1 || KH == 3) && (stride == 1 || stride == 2) && pad == KH / 2)) return 0;
+    if (Cin % 16 != 0) return 0;
+    if (Cout % 8 != 0 || ldx % 8 != 0) return 0;
+    return get_encode() != nullptr;
+}
+
+extern "C" int ym_conv2d_tc(const void* x, int ldx, int B, int H, int W, int Cin, const void* w, int Kpad, const float* bias,
+                            int Cout, int KH, int KW, int stride, int pad, void* out, int ldo, int out_f32, const void* res,
+                            int ldr, int act, void* stream) {
+    YM_CHECK_ARG(x && w && out, "ym_conv2d_tc: null pointer");
+    YM_CHECK_ARG(ym_conv2d_tc_supported(Cin, Cout, KH, KW, stride, pad, ldx), "ym_conv2d_tc: unsupported configuration "
+                 "(Cin=%d Cout=%d k=%d s=%d p=%d); use ym_conv2d_nhwc", Cin, Cout, KH, stride, pad);
+    YM_CHECK_ARG((((uintptr_t)x | (uintptr_t)w | (uintptr_t)out | (uintptr_t)res) & 15) == 0, "ym_conv2d_tc: 16-byte alignment");
+    YM_CHECK_ARG(ldo % (out_f32 ? 4 : 8) == 0 && (res == nullptr || ldr % 8 == 0) && Kpad % 8 == 0, "ym_conv2d_tc: pitches");
+    if (B == 0) return YM_OK;
+    EncodeTiledFn enc = get_encode();
+    TcConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.bias = bias; p.res = (const __half*)res; p.ldr = ldr; p.out = out; p.ldo = ldo; p.out_f32 = out_f32;
+    p.B = B; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.act = act;
+    p.Ho = (H + 2 * pad - KH) / stride + 1;
+    p.Wo = (W + 2 * pad - KW) / stride + 1;
+    p.kc = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
+    const int row_bytes = p.kc * 2;
+    const bool flat = (KH == 1 && stride == 1);
+    int BN;
+    if (Cout <= 16) BN = 16; else if (Cout <= 32) BN = 32; else if (Cout <= 64) BN = 64;
+    else if (Cout <= 128 || Cout % 128 == 0) BN = 128; else BN = 64;
+    const int ntiles = (Cout + BN - 1) / BN;
+
+    CUtensorMap ma, mb;
+    CUresult cr;
+    if (flat) {
+        p.M = B * H * W;
+        cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)p.M};
+        cuuint64_t gstr[1] = {(cuuint64_t)ldx * 2};
+        cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)CV_BM};
+        cuuint32_t est[2] = {1, 1};
+        cr = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 swizzle_for(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        // output patch TH x TW = 128 pixels; prefer the wider tile unless the narrower one wastes fewer pixels
+        const int w16 = ((p.Wo + 15) / 16) * 16 * (((p.Ho + 7) / 8) * 8), w8 = ((p.Wo + 7) / 8) * 8 * (((p.Ho + 15) / 16) * 16);
+        p.TW = (w8 < w16) ? 8 : 16;
+        p.TH = CV_BM / p.TW;
+        p.tiles_x = (p.Wo + p.TW - 1) / p.TW;
+        p.tiles_y = (p.Ho + p.TH - 1) / p.TH;
+        cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)W * ldx * 2, (cuuint64_t)H * W * ldx * 2};
+        cuuint32_t box[4] = {(cuuint32_t)p.kc, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), 1};
+        cuuint32_t est[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        cr = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 swizzle_for(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (cr != CUDA_SUCCESS) { ym_set_error("ym_conv2d_tc: cuTensorMapEncodeTiled(activation) failed: %d", (int)cr); return YM_ERR_CUDA; }
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)Kpad, (cuuint64_t)Cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)Kpad * 2};
+        cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)BN};
+        cuuint32_t est[2] = {1, 1};
+        cr = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 swizzle_for(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (cr != CUDA_SUCCESS) { ym_set_error("ym_conv2d_tc: cuTensorMapEncodeTiled(weights) failed: %d", (int)cr); return YM_ERR_CUDA; }
+
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mtiles = flat ? (p.M + CV_BM - 1) / CV_BM : B * p.tiles_x * p.tiles_y;
+    dim3 grid(mtiles, ntiles, 1);
+#define YM_LC(BN_)                                                          \
+    (flat ? launch_conv<BN_, true>(ma, mb, p, grid, st) : launch_conv<BN_, false>(ma, mb, p, grid, st))
+    switch (BN) {
+        case 16: return YM_LC(16);
+        case 32: return YM_LC(32);
+        case 64: return YM_LC(64);
+        default: return YM_LC(128);
+    }
+#undef YM_LC
+}

@@ -13,6 +13,7 @@ import torch
 from . import _lib
 
 _L = None
+CONV_IMPL = "legacy"  # "tc": TMA + tcgen05 conv where supported (else the mma.sync implicit GEMM); "legacy": always mma.sync
 LAUNCHES = 0  # number of kernel-launching C-ABI calls issued (bench.py reports kernels via LAUNCH_KERNELS)
 KERNELS = 0   # number of device kernels launched (a call may launch several)
 
@@ -71,10 +72,14 @@ def conv2d(x, w_packed, bias, Cout, KH, KW, stride, pad, act, out=None, res=None
             raise ValueError("conv2d: residual shape mismatch")
         ldr = pitch(res)
         rp = res.data_ptr()
-    _lib.check(lib().ym_conv2d_nhwc(x.data_ptr(), pitch(x), B, H, W, Cin, w_packed.data_ptr(), w_packed.shape[1],
-                                    None if bias is None else bias.data_ptr(), Cout, KH, KW, stride, pad,
-                                    out.data_ptr(), ldo, 1 if out_f32 else 0, rp, ldr, 1 if act else 0, _stream()),
-               "ym_conv2d_nhwc")
+    ldx = pitch(x)
+    L = lib()
+    fn, name = L.ym_conv2d_nhwc, "ym_conv2d_nhwc"
+    if CONV_IMPL == "tc" and Cout % 8 == 0 and L.ym_conv2d_tc_supported(Cin, Cout, KH, KW, stride, pad, ldx):
+        fn, name = L.ym_conv2d_tc, "ym_conv2d_tc"
+    _lib.check(fn(x.data_ptr(), ldx, B, H, W, Cin, w_packed.data_ptr(), w_packed.shape[1],
+                  None if bias is None else bias.data_ptr(), Cout, KH, KW, stride, pad,
+                  out.data_ptr(), ldo, 1 if out_f32 else 0, rp, ldr, 1 if act else 0, _stream()), name)
     _count()
     return out
 
