@@ -54,9 +54,11 @@ def test_conv(c1, c2, k, s, act, hw):
     sd = _prep(m, seed=c1 * 7 + c2)
     x = _x(2, c1, *hw, seed=3)
     y = _run(m, x)
-    ref = O.conv_block(sd, "m", x.float(), s, 1, act)
+    with O.fp16_weights():   # the reference's deployed weights: BN folded, rounded to fp16 (model.fuse().half())
+        ref = O.conv_block(sd, "m", x.float(), s, 1, act)
     assert y.shape == ref.shape and y.dtype == torch.float16
     assert_close(y, ref, what=f"Conv({c1},{c2},{k},{s})")
+    assert_close(y, O.conv_block(sd, "m", x.float(), s, 1, act), max_bad_frac=1e-4, what="vs fp32-weight oracle")
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.uint8])
@@ -83,7 +85,8 @@ def test_dwconv(c, k, act):
     sd = _prep(m, seed=c + k)
     x = _x(2, c, 21, 19, seed=4)
     y = _run(m, x)
-    ref = O.conv_block(sd, "m", x.float(), 1, c, act)
+    with O.fp16_weights():
+        ref = O.conv_block(sd, "m", x.float(), 1, c, act)
     assert_close(y, ref, what=f"dw{k}")
 
 

@@ -129,8 +129,10 @@ def test_tc_conv_matches_oracle(c1, c2, k, s, act, hw):
     finally:
         ops.CONV_IMPL = old
     torch.cuda.synchronize()
-    ref = O.conv_block(sdo, "m", x.float(), s, 1, act)
+    with O.fp16_weights():   # the reference's deployed weights: BN folded, rounded to fp16
+        ref = O.conv_block(sdo, "m", x.float(), s, 1, act)
     assert_close(y_tc, ref, what=f"tc_conv({c1},{c2},{k},{s}) {hw}")
+    assert_close(y_tc, O.conv_block(sdo, "m", x.float(), s, 1, act), max_bad_frac=1e-4, what="vs fp32-weight oracle")
     assert_close(y_tc, y_lg.float().cpu(), atol=2e-3, rtol=2e-3, what="tc vs mma.sync")
 
 

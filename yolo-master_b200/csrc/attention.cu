@@ -209,7 +209,7 @@ using namespace ym;
 
 extern "C" int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
                                    int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream);
-static int g_attention_impl = 0;  // 1 = tcgen05/TMEM kernel (tc_attention.cu), 0 = mma.sync kernel (this file)
+static int g_attention_impl = 1;  // 1 = tcgen05/TMEM kernel (tc_attention.cu), 0 = mma.sync kernel (this file)
 extern "C" int ym_set_attention_impl(int impl) {
     const int old = g_attention_impl;
     if (impl == 0 || impl == 1) g_attention_impl = impl;

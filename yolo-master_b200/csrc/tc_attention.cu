@@ -7,7 +7,9 @@
 //   * softmax: thread t of the CTA owns query row t: it reads its whole S row with one tcgen05.ld, so row max / row sum
 //     need no shuffles; exp2 on the MUFU; P is written as fp16 into a 128B-swizzled shared-memory tile that is the A
 //     operand of the PV MMA.
-//   * O is only rescaled when a row's running max grows by more than 2^8 (lazy rescaling): most KV tiles never touch O.
+//   * the softmax row sums are accumulated by the tensor core as well (L += P * ones, a 128x16 accumulator) from the very
+//     fp16 P values that multiply V, so numerator and denominator are exactly consistent and no FADD is spent on them.
+//   * O / L are only rescaled when a row's running max grows by more than 2^8 (lazy rescaling): most KV tiles never do.
 //   * K/V tiles arrive by cp.async into 64B/128B-swizzled canonical UMMA layouts (3-stage ring).
 // One CTA = 128 threads, 128 TMEM columns (S 64 + O <= 64) and ~48 KB smem -> 4 CTAs per SM overlap each other's
 // MMA / softmax / load phases.
@@ -28,13 +30,16 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
                                                                  int q_off, int k_off, int v_off, float scale_log2,
                                                                  __half* __restrict__ out, int ldo) {
     constexpr int Q_BYTES = TA_BQ * 64, K_BYTES = TA_BKV * 64, V_BYTES = TA_BKV * DV * 2, P_BYTES = TA_BQ * 128;
-    constexpr uint32_t TMEM_COLS = 128;           // S: cols [0,64), O: cols [64, 64+DV)
+    constexpr int ONES_BYTES = 16 * 128;             // B operand of the row-sum MMA: 16 x 64 fp16 ones
+    // TMEM columns: S [0,64), O [64,64+DV), L (row sums, 16 cols) [64+DV, 80+DV)
+    constexpr uint32_t TMEM_COLS = (DV == 32) ? 128 : 256;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* sQ = smem;
     unsigned char* sP = sQ + Q_BYTES;
     unsigned char* sK = sP + P_BYTES;                      // [STAGES][K_BYTES]
     unsigned char* sV = sK + TA_STAGES * K_BYTES;          // [STAGES][V_BYTES]
+    unsigned char* sOnes = sV + TA_STAGES * V_BYTES;
     __shared__ uint64_t bar_s, bar_pv;
     __shared__ uint32_t tmem_slot;
 
@@ -52,6 +57,12 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
     }
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
+    {   // ones tile (layout-agnostic: every element is 1.0)
+        const __half2 one2 = __float2half2_rn(1.f);
+        uint4 v;
+        v.x = v.y = v.z = v.w = *reinterpret_cast<const uint32_t*>(&one2);
+        *reinterpret_cast<uint4*>(sOnes + tid * 16) = v;
+    }
 
     // ---- Q tile: 128 rows x 64 B (SW64)
 #pragma unroll
@@ -61,25 +72,41 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
         const bool ok = q0 + r < N;
         cp_async16(sQ + tc::sw64_offset(r, c), ok ? gQ + (long long)(q0 + r) * ld + c * 8 : gQ, ok ? 16 : 0);
     }
+    // per-thread constant parts of the K/V tile copies (2 K chunks and DV/16 V chunks per thread per tile)
+    constexpr int VCH = DV / 8, VIT = TA_BKV * VCH / TA_THREADS;
+    int k_row[2], v_row[VIT];
+    uint32_t k_dst[2], v_dst[VIT];
+    long long k_src[2], v_src[VIT];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = tid + i * TA_THREADS;
+        k_row[i] = idx >> 2;
+        k_dst[i] = tc::sw64_offset(idx >> 2, idx & 3);
+        k_src[i] = (long long)(idx >> 2) * ld + (idx & 3) * 8;
+    }
+#pragma unroll
+    for (int i = 0; i < VIT; ++i) {
+        const int idx = tid + i * TA_THREADS;
+        const int r = idx / VCH, c = idx % VCH;
+        v_row[i] = r;
+        v_dst[i] = (DV == 32) ? tc::sw64_offset(r, c) : tc::sw128_offset(r, c);
+        v_src[i] = (long long)r * ld + c * 8;
+    }
     auto load_kv = [&](int t) {
         const int st = t % TA_STAGES, kv0 = t * TA_BKV;
         unsigned char* dK = sK + st * K_BYTES;
         unsigned char* dV = sV + st * V_BYTES;
+        const __half* srcK = gK + (long long)kv0 * ld;
+        const __half* srcV = gV + (long long)kv0 * ld;
 #pragma unroll
-        for (int i = 0; i < TA_BKV * 4 / TA_THREADS; ++i) {
-            const int idx = tid + i * TA_THREADS;
-            const int r = idx >> 2, c = idx & 3;
-            const bool ok = kv0 + r < N;
-            cp_async16(dK + tc::sw64_offset(r, c), ok ? gK + (long long)(kv0 + r) * ld + c * 8 : gK, ok ? 16 : 0);
+        for (int i = 0; i < 2; ++i) {
+            const bool ok = kv0 + k_row[i] < N;
+            cp_async16(dK + k_dst[i], ok ? srcK + k_src[i] : gK, ok ? 16 : 0);
         }
-        constexpr int VCH = DV / 8;
 #pragma unroll
-        for (int i = 0; i < TA_BKV * VCH / TA_THREADS; ++i) {
-            const int idx = tid + i * TA_THREADS;
-            const int r = idx / VCH, c = idx % VCH;
-            const bool ok = kv0 + r < N;
-            const uint32_t off = (DV == 32) ? tc::sw64_offset(r, c) : tc::sw128_offset(r, c);
-            cp_async16(dV + off, ok ? gV + (long long)(kv0 + r) * ld + c * 8 : gV, ok ? 16 : 0);
+        for (int i = 0; i < VIT; ++i) {
+            const bool ok = kv0 + v_row[i] < N;
+            cp_async16(dV + v_dst[i], ok ? srcV + v_src[i] : gV, ok ? 16 : 0);
         }
     };
     const int T = (N + TA_BKV - 1) / TA_BKV;
@@ -87,37 +114,36 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
     cp_async_commit();
     if (T > 1) load_kv(1);
     cp_async_commit();
-
+    cp_async_wait<1>();                       // Q and K_0 / V_0 have landed
+    tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
-    const uint32_t t_s = tmem_base, t_o = tmem_base + 64;
+    const uint32_t t_s = tmem_base, t_o = tmem_base + 64, t_l = tmem_base + 64 + DV;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
 
     const uint32_t idesc_qk = tc::make_idesc_f16(TA_BQ, TA_BKV, 0);
     const uint32_t idesc_pv = tc::make_idesc_f16(TA_BQ, DV, 1);   // V is MN-major (d_v contiguous)
+    const uint32_t idesc_l = tc::make_idesc_f16(TA_BQ, 16, 0);
     const uint64_t qdesc = tc::make_desc(smem_u32(sQ), 512, 4);
     const uint64_t pdesc = tc::make_desc(smem_u32(sP), 1024, 2);
+    const uint64_t odesc = tc::make_desc(smem_u32(sOnes), 1024, 2);
 
-    float m_used = -INFINITY, l_run = 0.f;
+    auto issue_qk = [&](int t) {
+        const uint64_t kdesc = tc::make_desc(smem_u32(sK + (t % TA_STAGES) * K_BYTES), 512, 4);
+        tc::mma_f16_ss(t_s, qdesc, kdesc, idesc_qk, 0u);
+        tc::mma_f16_ss(t_s, qdesc + 2, kdesc + 2, idesc_qk, 1u);
+        tc::mma_commit(&bar_s);
+    };
+    if (tid == 0) issue_qk(0);
+
+    float m_used = -INFINITY;
     const int row = tid;                      // query row owned by this thread
     unsigned char* prow = sP + row * 128;
 
     for (int t = 0; t < T; ++t) {
-        // ---- (a) K_t / V_t have landed; make them visible to the async proxy
-        cp_async_wait<1>();
-        tc::fence_proxy_async();
-        __syncthreads();
-        // ---- (b) S = Q K_t^T
-        if (tid == 0) {
-            tc::fence_after_sync();
-            const uint64_t kdesc = tc::make_desc(smem_u32(sK + (t % TA_STAGES) * K_BYTES), 512, 4);
-            tc::mma_f16_ss(t_s, qdesc, kdesc, idesc_qk, 0u);
-            tc::mma_f16_ss(t_s, qdesc + 2, kdesc + 2, idesc_qk, 1u);
-            tc::mma_commit(&bar_s);
-        }
-        // ---- (d) softmax of row `row`
+        // ---- softmax of row `row` of S_t
         tc::mbar_wait(&bar_s, t & 1);
         tc::fence_after_sync();
         uint32_t sr[64];
@@ -130,33 +156,29 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
             for (int i = 0; i < 32; ++i) { sr[i] = lo[i]; sr[32 + i] = hi[i]; }
         }
         const int kv0 = t * TA_BKV;
+        if (kv0 + TA_BKV > N) {               // tail tile only: keys >= N do not exist
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+                if (kv0 + i >= N) sr[i] = 0xff800000u;   // -inf
+        }
         float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-            float v = __uint_as_float(sr[i]);
-            if (kv0 + i >= N) v = -INFINITY;
-            sr[i] = __float_as_uint(v);
-            mx = fmaxf(mx, v);
-        }
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
         const float m_tile = mx * scale_log2;
         float alpha = 1.f;
         const bool grow = m_tile > m_used + 8.f;     // also true on the first tile (m_used = -inf)
         if (grow) {
             alpha = ta_exp2(m_used - m_tile);        // 0 on the first tile
             m_used = m_tile;
-            l_run *= alpha;
         }
-        float rs = 0.f;
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const float p0 = ta_exp2(fmaf(__uint_as_float(sr[2 * i]), scale_log2, -m_used));
             const float p1 = ta_exp2(fmaf(__uint_as_float(sr[2 * i + 1]), scale_log2, -m_used));
-            rs += p0 + p1;
             pk[i] = pack_half2(p0, p1);
         }
-        l_run += rs;
-        // ---- (e) PV_{t-1} must be complete before O is rescaled, P overwritten, or its K/V stage reloaded
+        // ---- PV_{t-1} must be complete before O/L are rescaled, P is overwritten, or its K/V stage is reloaded
         if (t > 0) {
             tc::mbar_wait(&bar_pv, (t - 1) & 1);
             tc::fence_after_sync();
@@ -170,10 +192,16 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
                     for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                     tc::tmem_st32(t_o + lane_sel + c0, o);
                 }
+                uint32_t l16[16];
+                tc::tmem_ld16(t_l + lane_sel, l16);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) l16[i] = __float_as_uint(__uint_as_float(l16[i]) * alpha);
+                tc::tmem_st16(t_l + lane_sel, l16);
                 tc::tmem_st_wait();
             }
         }
-        // ---- (c) prefetch tile t+2 into the ring stage last read by PV_{t-1} (complete: waited for just above)
+        // ---- prefetch tile t+2 into the ring stage last read by PV_{t-1}
         if (t + 2 < T) load_kv(t + 2);
         cp_async_commit();
         // ---- P row -> swizzled smem (A operand, K-major, 64 keys = 128 B per row)
@@ -182,18 +210,22 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
             uint4 v = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = v;
         }
+        cp_async_wait<1>();                   // K_{t+1} / V_{t+1} have landed (only the newest group may be pending)
         tc::fence_proxy_async();
         tc::fence_before_sync();
         __syncthreads();
-        // ---- (f) O (+)= P V_t
+        // ---- S_{t+1} = Q K_{t+1}^T first (the next softmax waits on it), then O += P V_t and L += P 1
         if (tid == 0) {
             tc::fence_after_sync();
+            if (t + 1 < T) issue_qk(t + 1);
             const uint32_t va = smem_u32(sV + (t % TA_STAGES) * V_BYTES);
             const uint64_t vdesc = (DV == 32) ? tc::make_desc(va, 512, 4) : tc::make_desc(va, 1024, 2);
             constexpr uint32_t VSTEP = (16 * DV * 2) >> 4;    // 16 keys per MMA k-step, in 16-byte units
 #pragma unroll
-            for (int k = 0; k < TA_BKV / 16; ++k)
+            for (int k = 0; k < TA_BKV / 16; ++k) {
                 tc::mma_f16_ss(t_o, pdesc + 2 * k, vdesc + VSTEP * k, idesc_pv, (t | k) ? 1u : 0u);
+                tc::mma_f16_ss(t_l, pdesc + 2 * k, odesc + 2 * k, idesc_l, (t | k) ? 1u : 0u);
+            }
             tc::mma_commit(&bar_pv);
         }
     }
@@ -201,7 +233,13 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
     // ---- finalise: O / l -> global
     tc::mbar_wait(&bar_pv, (T - 1) & 1);
     tc::fence_after_sync();
-    const float inv = 1.f / l_run;
+    float inv;
+    {
+        uint32_t l16[16];
+        tc::tmem_ld16(t_l + lane_sel, l16);
+        tc::tmem_ld_wait();
+        inv = 1.f / __uint_as_float(l16[0]);
+    }
     const int qrow = q0 + row;
     __half* orow = out + ((long long)b * N + qrow) * ldo + h * DV;
 #pragma unroll
@@ -242,7 +280,7 @@ extern "C" int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, in
     const float sl2 = scale * 1.4426950408889634f;
     dim3 grid((N + TA_BQ - 1) / TA_BQ, heads, batch);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)TA_BQ * 64 + TA_BQ * 128 + TA_STAGES * (TA_BKV * 64 + TA_BKV * d_v * 2) + 1024;
+    const size_t smem = (size_t)TA_BQ * 64 + TA_BQ * 128 + TA_STAGES * (TA_BKV * 64 + TA_BKV * d_v * 2) + 16 * 128 + 1024;
     cudaError_t e;
     if (d_v == 32) {
         e = cudaFuncSetAttribute(tc_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 
 _L = None
-CONV_IMPL = "legacy"  # "tc": TMA + tcgen05 conv where supported (else the mma.sync implicit GEMM); "legacy": always mma.sync
+CONV_IMPL = "tc"  # "tc": TMA + tcgen05 conv where supported (else the mma.sync implicit GEMM); "legacy": always mma.sync
 LAUNCHES = 0  # number of kernel-launching C-ABI calls issued (bench.py reports kernels via LAUNCH_KERNELS)
 KERNELS = 0   # number of device kernels launched (a call may launch several)
 
