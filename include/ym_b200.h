@@ -120,6 +120,7 @@ int ym_moe_dispatch_tc(const void* x, int ldx, int B, int HW, int C, const void*
  * MMAs are tcgen05.mma with the accumulator in TMEM.  Supported: k in {1,3} square, stride 1|2, pad k/2, Cin % 16 == 0,
  * Cout % 8 == 0 (ym_conv2d_tc_supported returns 1); everything else goes through ym_conv2d_nhwc. */
 int ym_conv2d_tc_supported(int Cin, int Cout, int KH, int KW, int stride, int pad, int ldx);
+int ym_set_tc_conv_version(int v);   /* 2 (default): persistent, warp-specialised, TMA-store epilogue; 1: one tile per CTA */
 int ym_conv2d_tc(const void* x, int ldx, int B, int H, int W, int Cin, const void* w, int Kpad, const float* bias, int Cout,
                  int KH, int KW, int stride, int pad, void* out, int ldo, int out_f32, const void* res, int ldr, int act,
                  void* stream);

@@ -102,8 +102,10 @@ def test_tc_attention_large_logits_lazy_rescale():
     (128, 64, 3, 1, True), (80, 80, 1, 1, True), (256, 16, 3, 1, True), (32, 16, 1, 1, True),
 ])
 @pytest.mark.parametrize("hw", [(40, 40), (37, 23), (20, 20)])
-def test_tc_conv_matches_oracle(c1, c2, k, s, act, hw):
-    """TMA + tcgen05 convolution vs the CPU oracle (strict tolerance) and vs the mma.sync kernel."""
+@pytest.mark.parametrize("version", [2, 1])
+def test_tc_conv_matches_oracle(c1, c2, k, s, act, hw, version):
+    """TMA + tcgen05 convolution (v2: persistent warp-specialised + TMA store; v1: one tile per CTA) vs the CPU oracle
+    (strict tolerance) and vs the mma.sync kernel."""
     from oracle import yolo_master_oracle as O
     from yolo_master_b200 import ops
     from yolo_master_b200.nn import modules as M
@@ -119,6 +121,7 @@ def test_tc_conv_matches_oracle(c1, c2, k, s, act, hw):
     xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
     assert ops.lib().ym_conv2d_tc_supported(c1, c2, k, k, s, k // 2, c1) == 1
     old = ops.CONV_IMPL
+    oldv = ops.lib().ym_set_tc_conv_version(version)
     try:
         ops.CONV_IMPL = "tc"
         with torch.no_grad():
@@ -128,6 +131,7 @@ def test_tc_conv_matches_oracle(c1, c2, k, s, act, hw):
             y_lg = m(xd)
     finally:
         ops.CONV_IMPL = old
+        ops.lib().ym_set_tc_conv_version(oldv)
     torch.cuda.synchronize()
     with O.fp16_weights():   # the reference's deployed weights: BN folded, rounded to fp16
         ref = O.conv_block(sdo, "m", x.float(), s, 1, act)

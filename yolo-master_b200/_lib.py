@@ -16,6 +16,7 @@ SIGNATURES = {
     "ym_device_info": (ci, [C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(cll)]),
     "ym_conv2d_nhwc": (ci, [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ci, ci, vp, ci, ci, vp]),
     "ym_conv2d_tc_supported": (ci, [ci, ci, ci, ci, ci, ci, ci]),
+    "ym_set_tc_conv_version": (ci, [ci]),
     "ym_conv2d_tc": (ci, [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ci, ci, vp, ci, ci, vp]),
     "ym_stem_conv_nchw": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, vp, ci, vp]),
     "ym_dwconv_nhwc": (ci, [vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, vp, ci, vp]),

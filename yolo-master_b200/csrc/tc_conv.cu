@@ -197,6 +197,222 @@ __global__ void __launch_bounds__(CV_THREADS) tc_conv_kernel(const __grid_consta
     if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// =====================================================================================================================
+// v2: persistent, warp-specialised variant (the production path).
+//   warp 0 (one lane)  TMA producer  : per k-tile one bulk-tensor load for A (tap-shifted box) and one for B
+//   warp 1 (one lane)  MMA issuer    : tcgen05.mma into one of TWO TMEM accumulators (tile i+1 overlaps the epilogue of i)
+//   warps 2..5         epilogue      : tcgen05.ld (row per thread) -> bias/SiLU/residual -> fp16 -> 128B-swizzled smem
+//                                      staging tile -> ONE TMA store per tile (coalesced, clips image borders / ragged M)
+// CTAs are persistent (grid = 2 x #SMs at most) and walk the tile list with a static stride.
+// =====================================================================================================================
+constexpr int CV2_THREADS = 192, CV2_STAGES = 3, CV2_EPI_THREADS = 128;
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
+template <int BN, bool FLAT>
+__global__ void __launch_bounds__(CV2_THREADS) tc_conv2_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                               const __grid_constant__ CUtensorMap map_b,
+                                                               const __grid_constant__ CUtensorMap map_o, const TcConvParams p,
+                                                               int m_tiles, int n_tiles) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const int row_bytes = p.kc * 2;
+    const int a_bytes = CV_BM * row_bytes, b_bytes = BN * row_bytes;
+    const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
+    constexpr int OUT_ROW = BN * 2;                        // bytes per staged output row (32 / 64 / 128)
+    constexpr int OUT_BYTES = CV_BM * OUT_ROW;
+    unsigned char* stg = smem + CV2_STAGES * stage_bytes;  // [2][OUT_BYTES], 1024-aligned
+    __shared__ uint64_t full_bar[CV2_STAGES], empty_bar[CV2_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_slot;
+    constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < CV2_STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(&tfull_bar[a], 1);
+            tc::mbar_init(&tempty_bar[a], 4);          // one arrive per epilogue warp
+        }
+        tc::fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+
+    const int total_tiles = m_tiles * n_tiles;
+    const int cchunks = p.Cin / p.kc;
+    const int KT = p.KH * p.KW * cchunks;
+    const uint32_t layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+    const uint32_t sbo = 8u * row_bytes;
+
+    // tile -> coordinates
+    auto tile_coords = [&](int tile, int& n0, int& m0, int& b, int& oy0, int& ox0) {
+        const int mt = tile / n_tiles;
+        n0 = (tile - mt * n_tiles) * BN;
+        m0 = mt * CV_BM;
+        b = 0; oy0 = 0; ox0 = 0;
+        if (!FLAT) {
+            const int tpi = p.tiles_x * p.tiles_y;
+            b = mt / tpi;
+            const int t = mt - b * tpi;
+            oy0 = (t / p.tiles_x) * p.TH;
+            ox0 = (t % p.tiles_x) * p.TW;
+        }
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer
+            uint32_t kidx = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int n0, m0, b, oy0, ox0;
+                tile_coords(tile, n0, m0, b, oy0, ox0);
+                for (int it = 0; it < KT; ++it, ++kidx) {
+                    const int s = kidx % CV2_STAGES;
+                    tc::mbar_wait(&empty_bar[s], ((kidx / CV2_STAGES) & 1) ^ 1);
+                    unsigned char* st = smem + s * stage_bytes;
+                    const int tap = it / cchunks, c0 = (it - tap * cchunks) * p.kc;
+                    mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + b_bytes));
+                    if (FLAT) {
+                        tma_load_2d(st, &map_a, c0, m0, &full_bar[s]);
+                    } else {
+                        const int ky = tap / p.KW, kx = tap - ky * p.KW;
+                        tma_load_4d(st, &map_a, c0, ox0 * p.stride + kx - p.pad, oy0 * p.stride + ky - p.pad, b, &full_bar[s]);
+                    }
+                    tma_load_2d(st + a_bytes, &map_b, tap * p.Cin + c0, n0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer
+            const uint32_t idesc = tc::make_idesc_f16(CV_BM, BN < 16 ? 16 : BN);
+            uint32_t kidx = 0, titer = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
+                const uint32_t acc = titer & 1;
+                tc::mbar_wait(&tempty_bar[acc], ((titer >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+                tc::fence_after_sync();
+                const uint32_t tacc = tmem_base + acc * BN;
+                for (int it = 0; it < KT; ++it, ++kidx) {
+                    const int s = kidx % CV2_STAGES;
+                    tc::mbar_wait(&full_bar[s], (kidx / CV2_STAGES) & 1);
+                    tc::fence_after_sync();
+                    const uint32_t sa = smem_u32(smem + s * stage_bytes);
+                    const uint64_t adesc = tc::make_desc(sa, sbo, layout_type), bdesc = tc::make_desc(sa + a_bytes, sbo, layout_type);
+                    for (int k = 0; k < p.kc / 16; ++k) tc::mma_f16_ss(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) ? 1u : 0u);
+                    tc::mma_commit(&empty_bar[s]);
+                }
+                tc::mma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue warps (128 threads): accumulator row = (warp % 4) * 32 + lane
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool elected = (warp == 2 && lane == 0);
+        uint32_t titer = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
+            int n0, m0, b, oy0, ox0;
+            tile_coords(tile, n0, m0, b, oy0, ox0);
+            const uint32_t acc = titer & 1;
+            unsigned char* sbuf = stg + acc * OUT_BYTES;
+            long long opix;
+            bool rowok;
+            if (FLAT) {
+                opix = (long long)m0 + r;
+                rowok = opix < p.M;
+            } else {
+                const int ty = r / p.TW, tx = r - ty * p.TW;
+                const int oy = oy0 + ty, ox = ox0 + tx;
+                rowok = oy < p.Ho && ox < p.Wo;
+                opix = ((long long)b * p.Ho + oy) * p.Wo + ox;
+            }
+            tc::mbar_wait(&tfull_bar[acc], (titer >> 1) & 1);
+            tc::fence_after_sync();
+            constexpr int NCH = BN / 16;
+            uint32_t rr[NCH][16];
+#pragma unroll
+            for (int ci = 0; ci < NCH; ++ci) tc::tmem_ld16(lane_addr + acc * BN + ci * 16, rr[ci]);
+            tc::tmem_ld_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);   // accumulator free: the next-but-one tile's MMAs may start
+#pragma unroll
+            for (int ci = 0; ci < NCH; ++ci) {
+                const int n = n0 + ci * 16;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float x = __uint_as_float(rr[ci][j]);
+                    if (p.bias != nullptr && n + j < p.Cout) x += p.bias[n + j];
+                    if (p.act == 1) x = silu_f(x);
+                    v[j] = x;
+                }
+                if (p.res != nullptr && rowok && n + 16 <= p.Cout) {
+                    const Half8 r0 = *reinterpret_cast<const Half8*>(p.res + opix * p.ldr + n);
+                    const Half8 r1 = *reinterpret_cast<const Half8*>(p.res + opix * p.ldr + n + 8);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f0 = __half22float2(r0.v[j]), f1 = __half22float2(r1.v[j]);
+                        v[2 * j] += f0.x; v[2 * j + 1] += f0.y; v[8 + 2 * j] += f1.x; v[8 + 2 * j + 1] += f1.y;
+                    }
+                } else if (p.res != nullptr && rowok) {
+                    for (int j = 0; j < 16 && n + j < p.Cout; ++j) v[j] += __half2float(p.res[opix * p.ldr + n + j]);
+                }
+                // staged row r, 16-byte chunks (2*ci, 2*ci+1), swizzled like the TMA store expects
+#pragma unroll
+                for (int hc = 0; hc < 2; ++hc) {
+                    uint4 w;
+                    w.x = pack_half2(v[8 * hc + 0], v[8 * hc + 1]);
+                    w.y = pack_half2(v[8 * hc + 2], v[8 * hc + 3]);
+                    w.z = pack_half2(v[8 * hc + 4], v[8 * hc + 5]);
+                    w.w = pack_half2(v[8 * hc + 6], v[8 * hc + 7]);
+                    const int c = 2 * ci + hc;
+                    uint32_t off;
+                    if (OUT_ROW == 128) off = tc::sw128_offset(r, c);
+                    else if (OUT_ROW == 64) off = tc::sw64_offset(r, c);
+                    else off = (uint32_t)(r * 32 + ((c ^ ((r >> 2) & 1)) << 4));   // 32-byte swizzle
+                    *reinterpret_cast<uint4*>(sbuf + off) = w;
+                }
+            }
+            tc::fence_proxy_async();                       // staged tile -> visible to the TMA store
+            if (elected) tma_store_wait_read0();           // the previous tile's store has finished reading the OTHER buffer
+            epi_barrier();
+            if (elected) {
+                if (FLAT) tma_store_2d(&map_o, sbuf, n0, m0);
+                else tma_store_4d(&map_o, sbuf, n0, ox0, oy0, b);
+                tma_store_commit();
+            }
+        }
+        if (elected) tma_store_wait_all();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 // ---- host side: tensor-map encoding through the driver entry point (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -219,6 +435,29 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
 }
 
 template <int BN, bool FLAT>
+static int launch_conv2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const TcConvParams& p, int m_tiles,
+                        int n_tiles, cudaStream_t st) {
+    const int row_bytes = p.kc * 2;
+    const int stage = ((CV_BM * row_bytes + BN * row_bytes + 1023) / 1024) * 1024;
+    const size_t smem = (size_t)CV2_STAGES * stage + 2 * (size_t)CV_BM * BN * 2 + 1024;
+    auto kern = tc_conv2_kernel<BN, FLAT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ym_set_error("tc_conv2: smem attr %zu: %s", smem, cudaGetErrorString(e)); return YM_ERR_CUDA; }
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const int total = m_tiles * n_tiles;
+    const int grid = total < 2 * sms ? total : 2 * sms;
+    kern<<<grid, CV2_THREADS, smem, st>>>(ma, mb, mo, p, m_tiles, n_tiles);
+    YM_CHECK_LAUNCH("tc_conv2");
+    return YM_OK;
+}
+
+template <int BN, bool FLAT>
 static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const TcConvParams& p, dim3 grid, cudaStream_t st) {
     const int row_bytes = p.kc * 2;
     const int stage = ((CV_BM * row_bytes + BN * row_bytes + 1023) / 1024) * 1024;
@@ -234,6 +473,13 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const TcCon
 }  // namespace ym
 
 using namespace ym;
+
+static int g_tc_conv_version = 2;   // 2 = persistent warp-specialised kernel + TMA store, 1 = one tile per CTA
+extern "C" int ym_set_tc_conv_version(int v) {
+    const int old = g_tc_conv_version;
+    if (v == 1 || v == 2) g_tc_conv_version = v;
+    return old;
+}
 
 // Returns 1 if ym_conv2d_tc supports this configuration (the Python layer falls back to ym_conv2d_nhwc otherwise).
 extern "C" int ym_conv2d_tc_supported(int Cin, int Cout, int KH, int KW, int stride, int pad, int ldx) {
@@ -304,6 +550,50 @@ extern "C" int ym_conv2d_tc(const void* x, int ldx, int B, int H, int W, int Cin
 
     cudaStream_t st = (cudaStream_t)stream;
     const int mtiles = flat ? (p.M + CV_BM - 1) / CV_BM : B * p.tiles_x * p.tiles_y;
+    if (!out_f32 && Cout % 8 == 0 && g_tc_conv_version == 2) {
+        // persistent warp-specialised kernel with TMA-store epilogue (BN <= 64 keeps two CTAs per SM resident)
+        const int BN2 = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : 64);
+        const int nt2 = (Cout + BN2 - 1) / BN2;
+        CUtensorMap mb2, mo;
+        {
+            cuuint64_t gdim[2] = {(cuuint64_t)Kpad, (cuuint64_t)Cout};
+            cuuint64_t gstr[1] = {(cuuint64_t)Kpad * 2};
+            cuuint32_t box[2] = {(cuuint32_t)p.kc, (cuuint32_t)BN2};
+            cuuint32_t est[2] = {1, 1};
+            cr = enc(&mb2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_for(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) { ym_set_error("ym_conv2d_tc: cuTensorMapEncodeTiled(weights v2) failed: %d", (int)cr); return YM_ERR_CUDA; }
+        }
+        if (flat) {
+            cuuint64_t gdim[2] = {(cuuint64_t)Cout, (cuuint64_t)p.M};
+            cuuint64_t gstr[1] = {(cuuint64_t)ldo * 2};
+            cuuint32_t box[2] = {(cuuint32_t)BN2, (cuuint32_t)CV_BM};
+            cuuint32_t est[2] = {1, 1};
+            cr = enc(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_for(BN2 * 2), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)B};
+            cuuint64_t gstr[3] = {(cuuint64_t)ldo * 2, (cuuint64_t)p.Wo * ldo * 2, (cuuint64_t)p.Ho * p.Wo * ldo * 2};
+            cuuint32_t box[4] = {(cuuint32_t)BN2, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+            cuuint32_t est[4] = {1, 1, 1, 1};
+            cr = enc(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, out, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_for(BN2 * 2), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (cr != CUDA_SUCCESS) { ym_set_error("ym_conv2d_tc: cuTensorMapEncodeTiled(output) failed: %d", (int)cr); return YM_ERR_CUDA; }
+        if (flat) {
+            switch (BN2) {
+                case 16: return launch_conv2<16, true>(ma, mb2, mo, p, mtiles, nt2, st);
+                case 32: return launch_conv2<32, true>(ma, mb2, mo, p, mtiles, nt2, st);
+                default: return launch_conv2<64, true>(ma, mb2, mo, p, mtiles, nt2, st);
+            }
+        } else {
+            switch (BN2) {
+                case 16: return launch_conv2<16, false>(ma, mb2, mo, p, mtiles, nt2, st);
+                case 32: return launch_conv2<32, false>(ma, mb2, mo, p, mtiles, nt2, st);
+                default: return launch_conv2<64, false>(ma, mb2, mo, p, mtiles, nt2, st);
+            }
+        }
+    }
     dim3 grid(mtiles, ntiles, 1);
 #define YM_LC(BN_)                                                          \
     (flat ? launch_conv<BN_, true>(ma, mb, p, grid, st) : launch_conv<BN_, false>(ma, mb, p, grid, st))
