@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(CV_THREADS) tc_conv_kernel(const __grid_consta
 //                                      staging tile -> ONE TMA store per tile (coalesced, clips image borders / ragged M)
 // CTAs are persistent (grid = 2 x #SMs at most) and walk the tile list with a static stride.
 // =====================================================================================================================
-constexpr int CV2_THREADS = 192, CV2_STAGES = 3, CV2_EPI_THREADS = 128;
+constexpr int CV2_THREADS = 320, CV2_STAGES = 3, CV2_EPI_THREADS = 256;   // 2 control warps + 8 epilogue warps
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
@@ -222,10 +222,27 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+// SiLU over a register array, written stage by stage so that every stage is NC independent instructions (the MUFU and
+// FMA pipes stay busy instead of waiting on one element's ex2 -> add -> rcp -> mul chain).
+template <int NC>
+__device__ __forceinline__ void silu_array(float (&v)[NC]) {
+    float e[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) e[j] = v[j] * -1.4426950408889634f;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[j]) : "f"(e[j]));
+#pragma unroll
+    for (int j = 0; j < NC; ++j) e[j] += 1.0f;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(e[j]) : "f"(e[j]));
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] *= e[j];
+}
 
 template <int BN, bool FLAT>
-__global__ void __launch_bounds__(CV2_THREADS) tc_conv2_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                const __grid_constant__ CUtensorMap map_b,
                                                                const __grid_constant__ CUtensorMap map_o, const TcConvParams p,
                                                                int m_tiles, int n_tiles) {
@@ -239,9 +256,11 @@ __global__ void __launch_bounds__(CV2_THREADS) tc_conv2_kernel(const __grid_cons
     unsigned char* stg = smem + CV2_STAGES * stage_bytes;  // [2][OUT_BYTES], 1024-aligned
     __shared__ uint64_t full_bar[CV2_STAGES], empty_bar[CV2_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float sbias[1024 + 64];       // folded-BN bias, zero padded past Cout
     constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 1024 + 64; i += CV2_THREADS) sbias[i] = (p.bias != nullptr && i < p.Cout) ? p.bias[i] : 0.f;
     if (tid == 0) {
         for (int s = 0; s < CV2_STAGES; ++s) {
             tc::mbar_init(&full_bar[s], 1);
@@ -249,7 +268,7 @@ __global__ void __launch_bounds__(CV2_THREADS) tc_conv2_kernel(const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(&tfull_bar[a], 1);
-            tc::mbar_init(&tempty_bar[a], 4);          // one arrive per epilogue warp
+            tc::mbar_init(&tempty_bar[a], 8);          // one arrive per epilogue warp
         }
         tc::fence_mbar_init();
     }
@@ -266,7 +285,6 @@ __global__ void __launch_bounds__(CV2_THREADS) tc_conv2_kernel(const __grid_cons
     const uint32_t layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
     const uint32_t sbo = 8u * row_bytes;
 
-    // tile -> coordinates
     auto tile_coords = [&](int tile, int& n0, int& m0, int& b, int& oy0, int& ox0) {
         const int mt = tile / n_tiles;
         n0 = (tile - mt * n_tiles) * BN;
@@ -307,7 +325,7 @@ __global__ void __launch_bounds__(CV2_THREADS) tc_conv2_kernel(const __grid_cons
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer
-            const uint32_t idesc = tc::make_idesc_f16(CV_BM, BN < 16 ? 16 : BN);
+            const uint32_t idesc = tc::make_idesc_f16(CV_BM, BN);
             uint32_t kidx = 0, titer = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
                 const uint32_t acc = titer & 1;
@@ -327,10 +345,12 @@ __global__ void __launch_bounds__(CV2_THREADS) tc_conv2_kernel(const __grid_cons
             }
         }
     } else {
-        // ===== epilogue warps (128 threads): accumulator row = (warp % 4) * 32 + lane
-        const int q = warp & 3;
+        // ===== 8 epilogue warps: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4
+        constexpr int NC = BN / 2;                 // columns per thread: 8 / 16 / 32
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const int r = q * 32 + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int cbase = half * NC;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + cbase;
         const bool elected = (warp == 2 && lane == 0);
         uint32_t titer = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
@@ -338,6 +358,7 @@ __global__ void __launch_bounds__(CV2_THREADS) tc_conv2_kernel(const __grid_cons
             tile_coords(tile, n0, m0, b, oy0, ox0);
             const uint32_t acc = titer & 1;
             unsigned char* sbuf = stg + acc * OUT_BYTES;
+            const int n = n0 + cbase;
             long long opix;
             bool rowok;
             if (FLAT) {
@@ -349,56 +370,66 @@ __global__ void __launch_bounds__(CV2_THREADS) tc_conv2_kernel(const __grid_cons
                 rowok = oy < p.Ho && ox < p.Wo;
                 opix = ((long long)b * p.Ho + oy) * p.Wo + ox;
             }
+            // residual slice of this thread's row: issued before waiting for the accumulator, lands while the MMAs run
+            Half8 rv[NC / 8];
+            const bool has_res = p.res != nullptr && rowok && n + NC <= p.Cout;
+            if (has_res) {
+#pragma unroll
+                for (int c = 0; c < NC / 8; ++c) rv[c] = *reinterpret_cast<const Half8*>(p.res + opix * p.ldr + n + c * 8);
+            }
             tc::mbar_wait(&tfull_bar[acc], (titer >> 1) & 1);
             tc::fence_after_sync();
-            constexpr int NCH = BN / 16;
-            uint32_t rr[NCH][16];
-#pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) tc::tmem_ld16(lane_addr + acc * BN + ci * 16, rr[ci]);
+            uint32_t rr[NC];
+            if constexpr (NC == 32) tc::tmem_ld32(lane_addr + acc * BN, rr);
+            else if constexpr (NC == 16) tc::tmem_ld16(lane_addr + acc * BN, rr);
+            else tc::tmem_ld8(lane_addr + acc * BN, rr);
             tc::tmem_ld_wait();
             tc::fence_before_sync();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);   // accumulator free: the next-but-one tile's MMAs may start
+            if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);   // accumulator drained: the MMAs of tile i+2 may start
+            constexpr int CH = NC < 16 ? NC : 16;          // process 8 / 16 columns at a time (register budget: 2 CTAs/SM)
 #pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) {
-                const int n = n0 + ci * 16;
-                float v[16];
+            for (int c0 = 0; c0 < NC; c0 += CH) {
+                float v[CH];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float x = __uint_as_float(rr[ci][j]);
-                    if (p.bias != nullptr && n + j < p.Cout) x += p.bias[n + j];
-                    if (p.act == 1) x = silu_f(x);
-                    v[j] = x;
+                for (int j = 0; j < CH; j += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(&sbias[n + c0 + j]);
+                    v[j] = __uint_as_float(rr[c0 + j]) + bb.x;
+                    v[j + 1] = __uint_as_float(rr[c0 + j + 1]) + bb.y;
+                    v[j + 2] = __uint_as_float(rr[c0 + j + 2]) + bb.z;
+                    v[j + 3] = __uint_as_float(rr[c0 + j + 3]) + bb.w;
                 }
-                if (p.res != nullptr && rowok && n + 16 <= p.Cout) {
-                    const Half8 r0 = *reinterpret_cast<const Half8*>(p.res + opix * p.ldr + n);
-                    const Half8 r1 = *reinterpret_cast<const Half8*>(p.res + opix * p.ldr + n + 8);
+                if (p.act == 1) silu_array<CH>(v);
+                if (has_res) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f0 = __half22float2(r0.v[j]), f1 = __half22float2(r1.v[j]);
-                        v[2 * j] += f0.x; v[2 * j + 1] += f0.y; v[8 + 2 * j] += f1.x; v[8 + 2 * j + 1] += f1.y;
-                    }
+                    for (int c = 0; c < CH / 8; ++c)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = __half22float2(rv[c0 / 8 + c].v[j]);
+                            v[c * 8 + 2 * j] += f.x;
+                            v[c * 8 + 2 * j + 1] += f.y;
+                        }
                 } else if (p.res != nullptr && rowok) {
-                    for (int j = 0; j < 16 && n + j < p.Cout; ++j) v[j] += __half2float(p.res[opix * p.ldr + n + j]);
+                    for (int j = 0; j < CH && n + c0 + j < p.Cout; ++j) v[j] += __half2float(p.res[opix * p.ldr + n + c0 + j]);
                 }
-                // staged row r, 16-byte chunks (2*ci, 2*ci+1), swizzled like the TMA store expects
+                // staged row r, 16-byte chunks of this thread's column half, swizzled as the TMA store map expects
 #pragma unroll
-                for (int hc = 0; hc < 2; ++hc) {
+                for (int c = 0; c < CH / 8; ++c) {
                     uint4 w;
-                    w.x = pack_half2(v[8 * hc + 0], v[8 * hc + 1]);
-                    w.y = pack_half2(v[8 * hc + 2], v[8 * hc + 3]);
-                    w.z = pack_half2(v[8 * hc + 4], v[8 * hc + 5]);
-                    w.w = pack_half2(v[8 * hc + 6], v[8 * hc + 7]);
-                    const int c = 2 * ci + hc;
+                    w.x = pack_half2(v[8 * c + 0], v[8 * c + 1]);
+                    w.y = pack_half2(v[8 * c + 2], v[8 * c + 3]);
+                    w.z = pack_half2(v[8 * c + 4], v[8 * c + 5]);
+                    w.w = pack_half2(v[8 * c + 6], v[8 * c + 7]);
+                    const int ch = (cbase + c0) / 8 + c;
                     uint32_t off;
-                    if (OUT_ROW == 128) off = tc::sw128_offset(r, c);
-                    else if (OUT_ROW == 64) off = tc::sw64_offset(r, c);
-                    else off = (uint32_t)(r * 32 + ((c ^ ((r >> 2) & 1)) << 4));   // 32-byte swizzle
+                    if (OUT_ROW == 128) off = tc::sw128_offset(r, ch);
+                    else if (OUT_ROW == 64) off = tc::sw64_offset(r, ch);
+                    else off = (uint32_t)(r * 32 + ((ch ^ ((r >> 2) & 1)) << 4));   // 32-byte swizzle
                     *reinterpret_cast<uint4*>(sbuf + off) = w;
                 }
             }
             tc::fence_proxy_async();                       // staged tile -> visible to the TMA store
-            if (elected) tma_store_wait_read0();           // the previous tile's store has finished reading the OTHER buffer
+            if (elected) tma_store_wait_read0();           // the previous tile's store has released the other buffer
             epi_barrier();
             if (elected) {
                 if (FLAT) tma_store_2d(&map_o, sbuf, n0, m0);
