@@ -102,6 +102,22 @@ int ym_detect_topk(int nl, const void* const* box, const void* const* cls, const
 int ym_detect_dense(int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
                     const float* strides, int B, int nc, int xyxy, float* y, void* stream);
 
+/* Batched NMS / Cluster-Weighted NMS, one CTA per image, no host round trip.
+ * mode 0: non_max_suppression utils/nms.py:13-171 (single-label, class-aware) + TorchNMS.nms :245-302: candidates with
+ *   best-class conf > conf_thres, class offset cls*max_wh added in fp32 like the reference, greedy IoU > iou_thres,
+ *   first max_det survivors; out rows (x1,y1,x2,y2,conf,cls).
+ * mode 1: CW-NMS of examples/YOLO-Master-Cross-Platform-Edge-Deployment/cpp/src/common.cpp:56-198 (float64 IoU/offset,
+ *   conf >= conf_thres, w = s*exp(-(1-IoU)^2/sigma) over the top-3000 pool, clip to frame_w x frame_h, drop empty);
+ *   out rows (x,y,w,h,conf,cls); sigma <= 0 disables the refinement.
+ * pred fp32 [B][4+nc][A] (xywh-centre boxes, scores); out fp32 [B][max_det][6]; out_count int32 [B]; out_idx int32
+ * [B][max_det] anchor indices; scratch: ym_nms_scratch_bytes(B, A).  Images with more than 16384 candidates set the
+ * overflow flag (ym_nms_overflowed) and return count 0 instead of silently truncating. */
+long long ym_nms_scratch_bytes(int B, int A);
+int ym_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, float iou_thres, int max_det, int max_nms,
+                   float max_wh, int mode, float sigma, float frame_w, float frame_h, float* out, int* out_count, int* out_idx,
+                   void* scratch, void* stream);
+int ym_nms_overflowed(const void* scratch, int B, int A, void* stream);
+
 /* tcgen05 path (TMEM accumulators, swizzled smem operands, single-thread MMA issue).
  * ym_tc_gemm_nt: out[M,N] = act(A[M,K] B[N,K]^T + bias) (+res) — the 1x1 Conv of conv.py:69-89 (a 1x1 conv on NHWC is
  *   exactly this GEMM with A = activation rows, B = packed weights [Cout][K]).

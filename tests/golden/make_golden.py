@@ -116,6 +116,39 @@ def dispatch_golden():
     torch.save({"cases": cases}, f"{OUT}/dispatch.golden.pt")
 
 
+def synth_predictions(B, nc, A, seed, dense=True):
+    """Seeded (B, 4+nc, A) predictions: xywh boxes in a 640x640 frame, clustered so that NMS has work to do."""
+    g = torch.Generator().manual_seed(seed)
+    ncl = max(A // 12, 1)
+    centres = torch.rand((B, ncl, 2), generator=g) * 600 + 20
+    sizes = torch.exp(torch.randn((B, ncl, 2), generator=g) * 0.5 + 3.6)
+    which = torch.randint(0, ncl, (B, A), generator=g)
+    cxy = torch.gather(centres, 1, which[..., None].expand(-1, -1, 2)) + torch.randn((B, A, 2), generator=g) * (4 if dense else 40)
+    wh = torch.gather(sizes, 1, which[..., None].expand(-1, -1, 2)) * torch.exp(torch.randn((B, A, 2), generator=g) * 0.1)
+    cls_of_cluster = torch.randint(0, nc, (B, ncl), generator=g)
+    cl = torch.gather(cls_of_cluster, 1, which)
+    scores = torch.rand((B, nc, A), generator=g) * 0.05
+    peak = torch.rand((B, A), generator=g) ** 2
+    scores.scatter_(1, cl[:, None, :], peak[:, None, :])
+    return torch.cat([cxy.transpose(1, 2), wh.transpose(1, 2), scores], 1).contiguous()
+
+
+def nms_golden():
+    """Reference ultralytics.utils.nms.non_max_suppression (TorchNMS greedy kernel; torchvision not imported here)."""
+    assert "torchvision" not in sys.modules
+    from ultralytics.utils.nms import non_max_suppression
+    cases = []
+    for seed, (B, nc, A, conf, iou, max_det) in enumerate([(3, 80, 2100, 0.25, 0.7, 300), (2, 80, 8400, 0.25, 0.45, 300),
+                                                           (2, 3, 500, 0.05, 0.5, 20), (1, 80, 1000, 0.99, 0.7, 300)]):
+        pred = synth_predictions(B, nc, A, 500 + seed)
+        out, keep = non_max_suppression(pred.clone(), conf, iou, max_det=max_det, return_idxs=True)
+        cases.append({"B": B, "nc": nc, "A": A, "seed": 500 + seed, "conf": conf, "iou": iou, "max_det": max_det,
+                      "out": [o.clone() for o in out], "keep": [k.clone().long().view(-1) for k in keep]})
+        print("nms case", seed, [len(o) for o in out])
+    torch.save({"cases": cases}, f"{OUT}/nms.golden.pt")
+
+
 if __name__ == "__main__":
     main()
     dispatch_golden()
+    nms_golden()

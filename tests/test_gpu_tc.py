@@ -99,7 +99,8 @@ def test_tc_attention_large_logits_lazy_rescale():
 @pytest.mark.parametrize("c1,c2,k,s,act", [
     (64, 64, 1, 1, True), (64, 192, 1, 1, False), (384, 128, 1, 1, True), (48, 64, 1, 1, True), (96, 64, 1, 1, True),
     (16, 32, 3, 2, True), (64, 64, 3, 2, True), (32, 32, 3, 1, True), (16, 8, 3, 1, True), (128, 256, 3, 2, True),
-    (128, 64, 3, 1, True), (80, 80, 1, 1, True), (256, 16, 3, 1, True), (32, 16, 1, 1, True),
+    (128, 64, 3, 1, True), (80, 80, 1, 1, True), (256, 16, 3, 1, True), (32, 16, 1, 1, True), (24, 32, 3, 1, True),
+    (96, 64, 3, 1, True), (40, 64, 1, 1, True),
 ])
 @pytest.mark.parametrize("hw", [(40, 40), (37, 23), (20, 20)])
 @pytest.mark.parametrize("version", [2, 1])

@@ -31,6 +31,9 @@ SIGNATURES = {
     "ym_moe_stats_floats": (cll, [ci, ci, ci]),
     "ym_gn_finalize": (ci, [vp, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp, vp]),
     "ym_moe_combine": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, ci, vp, vp, ci, vp, ci, ci, vp]),
+    "ym_nms_scratch_bytes": (cll, [ci, ci]),
+    "ym_nms_batched": (ci, [vp, ci, ci, ci, cf, cf, ci, ci, cf, ci, cf, cf, cf, vp, vp, vp, vp, vp]),
+    "ym_nms_overflowed": (ci, [vp, ci, ci, vp]),
     "ym_tc_gemm_nt": (ci, [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, vp]),
     "ym_moe_dispatch_tc": (ci, [vp, ci, ci, ci, ci, vp, ci, cll, vp, vp, ci, ci, cf, cf, vp, ci, vp]),
     "ym_detect_topk": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp, vp, vp]),

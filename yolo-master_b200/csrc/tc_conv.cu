@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(CV_THREADS) tc_conv_kernel(const __grid_consta
         oy0 = (t / p.tiles_x) * p.TH;
         ox0 = (t % p.tiles_x) * p.TW;
     }
-    const int cchunks = p.Cin / p.kc;
+    const int cchunks = (p.Cin + p.kc - 1) / p.kc;
     const int KT = p.KH * p.KW * cchunks;
     const uint32_t layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
     const uint32_t sbo = 8u * row_bytes;
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
     const uint32_t tmem_base = tmem_slot;
 
     const int total_tiles = m_tiles * n_tiles;
-    const int cchunks = p.Cin / p.kc;
+    const int cchunks = (p.Cin + p.kc - 1) / p.kc;
     const int KT = p.KH * p.KW * cchunks;
     const uint32_t layout_type = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
     const uint32_t sbo = 8u * row_bytes;
@@ -515,7 +515,7 @@ extern "C" int ym_set_tc_conv_version(int v) {
 // Returns 1 if ym_conv2d_tc supports this configuration (the Python layer falls back to ym_conv2d_nhwc otherwise).
 extern "C" int ym_conv2d_tc_supported(int Cin, int Cout, int KH, int KW, int stride, int pad, int ldx) {
     if (!(KH == KW && (KH == 1 || KH == 3) && (stride == 1 || stride == 2) && pad == KH / 2)) return 0;
-    if (Cin % 16 != 0) return 0;
+    if (Cin % 8 != 0 || Cin < 16) return 0;
     if (Cout % 8 != 0 || ldx % 8 != 0) return 0;
     return get_encode() != nullptr;
 }
@@ -536,7 +536,9 @@ extern "C" int ym_conv2d_tc(const void* x, int ldx, int B, int H, int W, int Cin
     p.B = B; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.act = act;
     p.Ho = (H + 2 * pad - KH) / stride + 1;
     p.Wo = (W + 2 * pad - KW) / stride + 1;
-    p.kc = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
+    // channels per k-tile: a ragged last chunk (e.g. Cin = 48, 80, 96) is zero-filled by TMA out-of-bounds handling, so the
+    // box always spans a full 128-byte swizzle row once Cin > 32 (one bulk load per tap instead of several narrow ones)
+    p.kc = Cin > 32 ? 64 : (Cin > 16 ? 32 : 16);
     const int row_bytes = p.kc * 2;
     const bool flat = (KH == 1 && stride == 1);
     int BN;

@@ -271,3 +271,20 @@ def moe_dispatch(x, w_all, route_idx, route_w, w_min=0.01, clamp=1e4, out=None):
                                         out.data_ptr(), pitch(out), _stream()), "ym_moe_dispatch_tc")
     _count()
     return out
+
+
+def nms_batched(pred, conf_thres, iou_thres, max_det=300, max_nms=30000, max_wh=7680.0, mode=0, sigma=0.1, frame_wh=(0.0, 0.0)):
+    """ym_nms_batched.  pred: fp32 (B, 4+nc, A).  Returns (out (B,max_det,6), count (B,) int32, idx (B,max_det) int32)."""
+    if pred.dtype != torch.float32 or not pred.is_cuda or pred.dim() != 3:
+        raise ValueError("nms_batched: expected an fp32 CUDA tensor of shape (B, 4+nc, A)")
+    pred = pred.contiguous()
+    B, no, A = pred.shape
+    out = torch.empty((B, max_det, 6), dtype=torch.float32, device=pred.device)
+    cnt = torch.empty((B,), dtype=torch.int32, device=pred.device)
+    idx = torch.empty((B, max_det), dtype=torch.int32, device=pred.device)
+    scratch = torch.empty((lib().ym_nms_scratch_bytes(B, A),), dtype=torch.uint8, device=pred.device)
+    _lib.check(lib().ym_nms_batched(pred.data_ptr(), B, no - 4, A, float(conf_thres), float(iou_thres), max_det, max_nms,
+                                    float(max_wh), mode, float(sigma), float(frame_wh[0]), float(frame_wh[1]), out.data_ptr(),
+                                    cnt.data_ptr(), idx.data_ptr(), scratch.data_ptr(), _stream()), "ym_nms_batched")
+    _count(2)
+    return out, cnt, idx, scratch
