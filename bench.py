@@ -169,12 +169,72 @@ def time_attention_kernel(dev, batch, pk):
     flops = 4.0 * N * N * hd * heads * batch
     algo_bytes = 4.0 * N * hd * heads * batch * 2
     ach = flops / (ms * 1e-3) / 1e12
-    return {"kernel": "attention_fwd_kernel<32> (AAttn P3: N=6400, 2 heads x d32, whole batch)", "bound": "tensor",
-            "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": ach / pk["tflops_burst"], "traffic": None,
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["tc_attention_kernel<32>"]
+        if batch == 32:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]   # per launch, from the committed ncu --set full capture
+    except Exception:
+        pass
+    exps = float(N) * N * heads * batch
+    return {"kernel": "tc_attention_kernel<32> (tcgen05/TMEM; AAttn P3: N=6400, 2 heads x d32, whole batch)", "bound": "tensor",
+            "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": ach / pk["tflops_burst"], "traffic": traffic,
             "ms_per_launch": ms, "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": algo_bytes,
-            "exp_per_launch": float(N) * N * heads * batch,
-            "note": "d=32 attention is bounded by MUFU exp throughput, not the tensor pipe (SURVEY.md §7); "
+            "exp_per_launch": exps, "gexp_per_s": exps / (ms * 1e-3) / 1e9,
+            "mufu_frac": exps / (ms * 1e-3) / (148 * 16 * 1.965e9),
+            "note": "d=32 attention is bounded by the MUFU (one ex2 per score: 16 lanes/clk/SM x 148 SMs x 1.965 GHz = "
+                    "4.65 T exp/s), not by the tensor pipe (SURVEY.md §7): mufu_frac is the binding fraction; "
                     "peak = cuBLAS bf16 burst " + pk["source"]}
+
+
+def time_dispatch(dev, pk):
+    """ES-MoE dispatch microbench (BASELINE.json configs[4]): 65536 tokens x d=256, 8 experts, top-2, 1x1-conv experts
+    (BatchedExpertComputation semantics).  Algorithmic bytes = (k+1)*d*2 = 1536 B/token."""
+    from yolo_master_b200 import ops
+    B, C, H, W, E, K = 64, 256, 32, 32, 8, 2
+    g = torch.Generator().manual_seed(0)
+    nrot = 6                                   # 6 x 33.5 MB inputs + 6 outputs rotate through: > 126 MB L2
+    xs = [torch.randn((B, H, W, C), generator=g).half().to(dev) for _ in range(nrot)]
+    outs = [ops.new_act(B, H, W, C, dev) for _ in range(nrot)]
+    Wt = (torch.randn((E, C, C), generator=g) / C ** 0.5).half().to(dev)
+    idx = torch.stack([torch.randperm(E, generator=g)[:K] for _ in range(B)]).int().to(dev)
+    w = torch.rand((B, K), generator=g)
+    w = (w / w.sum(1, keepdim=True)).to(dev)
+    for i in range(3):
+        ops.moe_dispatch(xs[i % nrot], Wt, idx, w, out=outs[i % nrot])
+    reps = 30
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(reps):
+        ops.moe_dispatch(xs[i % nrot], Wt, idx, w, out=outs[i % nrot])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    tokens = B * H * W
+    gbs = 1536.0 * tokens / (ms * 1e-3) / 1e9
+    res = {"workload": "65536 tokens x d=256, 8 experts top-2, 1x1-conv experts (configs[4])", "kernel": "tc_gemm_kernel<256,true> (tcgen05, 2 TMEM accumulators)",
+           "ms": ms, "tokens_per_s": tokens / (ms * 1e-3), "algorithmic_gbs": gbs, "hbm_frac": gbs / pk["hbm_gbs"],
+           "tflops": 2.0 * K * C * C * tokens / (ms * 1e-3) / 1e12, "bytes_per_token": 1536}
+    # the reference's torch path on the same GPU (restated dispatcher on CUDA tensors, fp16): a baseline, not the product
+    try:
+        from oracle.moe_dispatch_oracle import compute_sparse_experts_batched, conv1x1_experts
+        xr = xs[0].permute(0, 3, 1, 2).contiguous()
+        ex = conv1x1_experts(Wt)
+        for _ in range(2):
+            compute_sparse_experts_batched(xr, ex, w, idx.long(), C)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            compute_sparse_experts_batched(xr, ex, w, idx.long(), C)
+        e1.record()
+        torch.cuda.synchronize()
+        mr = e0.elapsed_time(e1) / 5
+        res["torch_eager_gpu"] = {"ms": mr, "algorithmic_gbs": 1536.0 * tokens / (mr * 1e-3) / 1e9,
+                                  "note": "reference dispatcher (Python loop over experts, gather, conv, index_add_) on this GPU"}
+    except Exception as e:  # baseline only
+        res["torch_eager_gpu"] = {"error": str(e)[:200]}
+    return res
 
 
 def run_ours(args):
@@ -200,9 +260,8 @@ def run_ours(args):
     if rank == 0:
         model.load_state_dict(synthetic_weights())
     model.to(dev).eval()
-    if world > 1:
-        for t in list(model.parameters()) + list(model.buffers()):
-            dist.broadcast(t.data, src=0)
+    from yolo_master_b200 import parallel
+    parallel.broadcast_module_state(model, src=0)
 
     # ---- CPU baseline (rank 0, N==1): oracle port on a bounded sample of the same workload
     cpu_base = None
@@ -258,6 +317,7 @@ def run_ours(args):
     value = world * B * args.steps / (ms_dev * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     roof = time_attention_kernel(dev, B, pk) if rank == 0 else None
+    disp = time_dispatch(dev, pk) if rank == 0 else None
 
     if rank == 0:
         step_ms = ms_dev / args.steps
@@ -282,6 +342,7 @@ def run_ours(args):
                                "algorithmic_gbs": BYTES_PER_IMAGE * value / world / 1e9,
                                "hbm_frac": BYTES_PER_IMAGE * value / world / 1e9 / pk["hbm_gbs"],
                                "tensor_frac": FLOPS_PER_IMAGE * value / world / 1e12 / pk["tflops_sustained"]},
+            "dispatch": disp,
             "cpu_baseline": cpu_base,
         }
         print(json.dumps(out))
