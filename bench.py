@@ -219,6 +219,7 @@ def time_dispatch(dev, pk):
     # the reference's torch path on the same GPU (restated dispatcher on CUDA tensors, fp16): a baseline, not the product
     try:
         from oracle.moe_dispatch_oracle import compute_sparse_experts_batched, conv1x1_experts
+
         xr = xs[0].permute(0, 3, 1, 2).contiguous()
         ex = conv1x1_experts(Wt)
         for _ in range(2):

@@ -102,6 +102,25 @@ int ym_detect_topk(int nl, const void* const* box, const void* const* cls, const
 int ym_detect_dense(int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
                     const float* strides, int B, int nc, int xyxy, float* y, void* stream);
 
+/* ES_MOE (moe/modules.py:410-741, eval sparse path) on four entry points; the module is router -> per-expert depthwise k x k
+ * on the images that retained the expert -> grouped pointwise GEMM (+folded BN, SiLU, routing weight) -> sum + BN + SiLU.
+ * ym_esmoe_route: DynamicRoutingLayer.forward/_hard_top_k routers.py:458-496,519-527 + the top-k / dynamic-threshold /
+ *   renormalisation of ES_MOE._sparse_forward modules.py:659-684.  w1 fp32 [Cr][C], w2 fp32 [E][Cr].
+ *   idx int32 [B][topk] (descending weight, -1 = dropped by the threshold), w fp32 [B][topk], probs [B][E] nullable.
+ * ym_esmoe_dwconv: experts.py:284 depthwise for ONE expert over the images that retained it (slot b*topk+j of out).
+ * ym_esmoe_pointwise: experts.py:285-296 pointwise + BN + SiLU, scaled by the routing weight, one problem per slot.
+ * ym_esmoe_combine: modules.py:690-704 (sum over retained slots) + final BatchNorm + SiLU :496,581. */
+long long ym_esmoe_scratch_floats(int B, int HW, int C);
+int ym_esmoe_route(const void* x, int ldx, int B, int HW, int C, const float* w1, const float* b1, int Cr, const float* w2,
+                   const float* b2, int E, int topk, float dyn_thr, float* scratch, int* idx_out, float* w_out, float* probs_out,
+                   void* stream);
+int ym_esmoe_dwconv(const void* x, int ldx, const void* w, int B, int H, int W, int C, int ksize, const int* route_idx, int topk,
+                    int expert, void* out, int ldo, void* stream);
+int ym_esmoe_pointwise(const void* t, int ldt, int P, int HW, int K, const void* w, int Kpad, long long w_expert_stride,
+                       const float* bias_all, int N, const int* route_idx, const float* route_w, void* y, int ldy, void* stream);
+int ym_esmoe_combine(const void* y, int ldy, const int* route_idx, int topk, const float* scale, const float* shift, void* out,
+                     int ldo, int B, int HW, int C, void* stream);
+
 /* Batched NMS / Cluster-Weighted NMS, one CTA per image, no host round trip.
  * mode 0: non_max_suppression utils/nms.py:13-171 (single-label, class-aware) + TorchNMS.nms :245-302: candidates with
  *   best-class conf > conf_thres, class offset cls*max_wh added in fp32 like the reference, greedy IoU > iou_thres,

@@ -21,7 +21,7 @@ def compute_sparse_experts_batched(x: torch.Tensor, experts: Sequence[Callable[[
     wts = routing_weights.reshape(B, -1)[:, :k]
     thr = 0.0 if training else 0.01
     valid = wts > thr
-    out = torch.zeros(B, out_channels, H, W, dtype=x.dtype)
+    out = torch.zeros(B, out_channels, H, W, dtype=x.dtype, device=x.device)
     for e in range(len(experts)):
         mask = (idx == e) & valid
         if not mask.any():

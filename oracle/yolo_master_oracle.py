@@ -297,6 +297,70 @@ def optimized_moe_improved(sd, p, x, num_experts, top_k):
     return _st((shared.float() + out).to(x.dtype))
 
 
+def es_moe_kernel_sizes(num_experts, max_kernel_size=15, expert_kernel_sizes=None):
+    """`ES_MOE.__init__` moe/modules.py:478-493."""
+    if max_kernel_size % 2 == 0:
+        max_kernel_size -= 1
+    if expert_kernel_sizes is not None:
+        return [min(int(k) - (1 if int(k) % 2 == 0 else 0), max_kernel_size) for k in expert_kernel_sizes]
+    default = [3, 5, 7]
+    if num_experts <= len(default):
+        return [min(k, max_kernel_size) for k in default[:num_experts]]
+    return [min(3 + 2 * i, max_kernel_size) for i in range(num_experts)]
+
+
+def dynamic_routing_hard_topk(sd, p, x, top_k):
+    """`DynamicRoutingLayer.forward` + `_hard_top_k` moe/routers.py:458-496,519-527 (eval, Top-K enabled).
+
+    Returns per-image weights (B, E) fp32 (zero for unselected experts); they are spatially constant (:496)."""
+    pooled = x.mean(dim=(2, 3), keepdim=True)
+    h = F.silu(F.conv2d(pooled, sd[p + ".routing_network.0.weight"], sd[p + ".routing_network.0.bias"]))
+    logits = F.conv2d(h, sd[p + ".routing_network.2.weight"], sd[p + ".routing_network.2.bias"])
+    B, E = logits.shape[:2]
+    w = F.softmax(logits.reshape(B, E).float().clamp(-30.0, 30.0), dim=1)
+    vals, idx = torch.topk(w, top_k, dim=1)
+    vals = vals / vals.sum(dim=1, keepdim=True).clamp_min(1e-6)        # stable_normalize _numeric.py:85-90
+    return torch.zeros_like(w).scatter_(1, idx, vals)
+
+
+def es_moe(sd, p, x, c1, c2=None, num_experts=4, reduction=8, top_k=2, use_sparse_inference=True, dynamic_threshold=0.4,
+           max_kernel_size=15, expert_kernel_sizes=None):
+    """`ES_MOE.forward` (eval) moe/modules.py:535-583 with `_sparse_forward` :659-704: sample-level Top-K with the rank>=1
+    experts dropped when their renormalised weight < dynamic_threshold, expert = dw kxk -> 1x1 -> BN -> SiLU
+    (experts.py:280-296), fp32 here; final BN + SiLU (:496,581)."""
+    assert use_sparse_inference and top_k is not None and top_k < num_experts, "dense ES_MOE paths are not on the oracle"
+    c2 = c1 if c2 is None else c2
+    rw = dynamic_routing_hard_topk(sd, p + ".routing", x, top_k)                   # (B, E)
+    B, E = rw.shape
+    tv, ti = torch.topk(rw, top_k, dim=1)
+    ranks = torch.arange(top_k).view(1, -1)
+    keep = (ranks == 0) | (tv >= dynamic_threshold) if dynamic_threshold > 0 else torch.ones_like(ti, dtype=torch.bool)
+    retained = torch.zeros(B, E, dtype=torch.bool).scatter_(1, ti, keep)
+    w = rw * retained
+    w = w / w.sum(1, keepdim=True).clamp_min(torch.finfo(torch.float32).eps)
+    ks = es_moe_kernel_sizes(num_experts, max_kernel_size, expert_kernel_sizes)
+    out = torch.zeros(B, c2, x.shape[2], x.shape[3])
+    for e in range(E):
+        bi = torch.where(retained[:, e])[0]
+        if bi.numel() == 0:
+            continue
+        q = f"{p}.experts.{e}.conv"
+        t = F.conv2d(x[bi], _w(sd[q + ".depthwise.weight"]), None, 1, (ks[e] - 1) // 2, 1, x.shape[1])
+        t = _st(t)
+        if _W16:
+            sc = sd[q + ".bn.weight"] / torch.sqrt(sd[q + ".bn.running_var"] + BN_EPS)
+            y = F.conv2d(t, _w(sd[q + ".pointwise.weight"] * sc.view(-1, 1, 1, 1)), sd[q + ".bn.bias"] - sd[q + ".bn.running_mean"] * sc)
+        else:
+            y = _bn(sd, q + ".bn", F.conv2d(t, sd[q + ".pointwise.weight"]))
+        y = _st(F.silu(y))
+        out.index_add_(0, bi, y * w[bi, e].view(-1, 1, 1, 1))
+    return _st(F.silu(_bn(sd, p + ".norm.0", _st(out)))), (ti, w)
+
+
+def layer_es_moe(sd, p, x, *args):
+    return es_moe(sd, p, x, *args)[0]
+
+
 def ablock_moe(sd, p, x, num_heads, area, num_experts, top_k):
     """`ABlockMoE.forward` moe/modules.py:1247-1260."""
     x = _st(x + aattn(sd, p + ".attn", x, num_heads, area))
@@ -438,7 +502,7 @@ def detect_postprocess(y, nc, max_det=300):
 # ----------------------------------------------------------------------------
 # whole model (`BaseModel._predict_once` tasks.py:182-218)
 # ----------------------------------------------------------------------------
-_LAYER_FN = {"Conv": layer_conv, "C3k2": layer_c3k2, "C2f": layer_c2f, "SPPF": layer_sppf, "C2PSA": layer_c2psa,
+_LAYER_FN = {"ES_MOE": layer_es_moe, "Conv": layer_conv, "C3k2": layer_c3k2, "C2f": layer_c2f, "SPPF": layer_sppf, "C2PSA": layer_c2psa,
              "A2C2fMoE": layer_a2c2f_moe}
 
 

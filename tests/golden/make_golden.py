@@ -148,7 +148,37 @@ def nms_golden():
     torch.save({"cases": cases}, f"{OUT}/nms.golden.pt")
 
 
+ESMOE_CASES = [(64, 4, 2, 20, 24, 6), (32, 4, 2, 9, 7, 5), (128, 4, 2, 10, 10, 4)]   # C, E, top_k, H, W, B
+
+
+def esmoe_weights(sd, seed):
+    """Key-seeded fill + wider router logits so that the 0.4 dynamic threshold is exercised both ways."""
+    fill_state_dict_(sd, 40 + seed)
+    for k in sd:
+        if k.endswith("routing_network.2.weight"):
+            sd[k] *= 6
+    return sd
+
+
+def esmoe_golden():
+    """Reference ES_MOE (moe/modules.py:410-741) eval outputs; weights are regenerated from key names by the tests."""
+    from ultralytics.nn.modules.moe.modules import ES_MOE
+    from ultralytics.utils.torch_utils import initialize_weights
+    cases = []
+    for seed, (C, E, k, H, W, B) in enumerate(ESMOE_CASES):
+        m = ES_MOE(C, C, num_experts=E, top_k=k)
+        initialize_weights(m)
+        m.load_state_dict(esmoe_weights(m.state_dict(), seed))
+        m.eval()
+        x = torch.randn((B, C, H, W), generator=torch.Generator().manual_seed(seed))
+        with torch.no_grad():
+            y = m(x)
+        cases.append({"seed": seed, "keys": {kk: list(v.shape) for kk, v in m.state_dict().items()}, "y": y.clone()})
+    torch.save({"cases": cases}, f"{OUT}/esmoe.golden.pt")
+
+
 if __name__ == "__main__":
     main()
     dispatch_golden()
     nms_golden()
+    esmoe_golden()

@@ -258,3 +258,27 @@ def test_errors_are_loud():
     lib = _lib.load()
     rc = lib.ym_conv2d_nhwc(None, 8, 1, 1, 1, 8, None, 32, None, 8, 1, 1, 1, 0, None, 8, 0, None, 0, 0, None)
     assert rc != 0 and b"null" in lib.ym_last_error()
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_es_moe_vs_reference_golden_and_oracle(case):
+    """ES_MOE eval forward: CUDA path vs the REAL reference module's output (golden) and the oracle; routes exact."""
+    from test_esmoe_oracle import ESMOE_CASES, esmoe_case
+    C, E, k, H, W, B = ESMOE_CASES[case]
+    sd, x, yref = esmoe_case(case)
+    m = M.ES_MOE(C, C, num_experts=E, top_k=k)
+    assert set(m.state_dict()) == set(sd), "ES_MOE state_dict keys differ from the reference"
+    m.load_state_dict(sd)
+    m.eval().to(DEV)
+    xh = x.half()
+    y = _run(m, xh)
+    sdo = {"m." + kk: v for kk, v in sd.items()}
+    ref, (ti, w) = O.es_moe(sdo, "m", xh.float(), C, C, E, 8, k)
+    with O.fp16_storage(), O.fp16_weights():
+        sim, _ = O.es_moe(sdo, "m", xh.float(), C, C, E, 8, k)
+    assert_within_noise(y, ref, sim, what="ES_MOE")
+    assert close_stats(y, yref)[1] < 5e-3      # vs the real reference run on the fp32 input
+    snap = m.last_routing_snapshot
+    exp_idx = torch.where(w.gather(1, ti) > 0, ti, torch.full_like(ti, -1))
+    assert torch.equal(snap["topk_indices"].cpu().long(), exp_idx)          # retained experts (and drops) exact
+    torch.testing.assert_close(snap["topk_weights"].cpu(), w.gather(1, ti), atol=1e-5, rtol=1e-5)

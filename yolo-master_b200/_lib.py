@@ -31,6 +31,11 @@ SIGNATURES = {
     "ym_moe_stats_floats": (cll, [ci, ci, ci]),
     "ym_gn_finalize": (ci, [vp, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp, vp]),
     "ym_moe_combine": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, ci, vp, vp, ci, vp, ci, ci, vp]),
+    "ym_esmoe_scratch_floats": (cll, [ci, ci, ci]),
+    "ym_esmoe_route": (ci, [vp, ci, ci, ci, ci, vp, vp, ci, vp, vp, ci, ci, cf, vp, vp, vp, vp, vp]),
+    "ym_esmoe_dwconv": (ci, [vp, ci, vp, ci, ci, ci, ci, ci, vp, ci, ci, vp, ci, vp]),
+    "ym_esmoe_pointwise": (ci, [vp, ci, ci, ci, ci, vp, ci, cll, vp, ci, vp, vp, vp, ci, vp]),
+    "ym_esmoe_combine": (ci, [vp, ci, vp, ci, vp, vp, vp, ci, ci, ci, ci, vp]),
     "ym_nms_scratch_bytes": (cll, [ci, ci]),
     "ym_nms_batched": (ci, [vp, ci, ci, ci, cf, cf, ci, ci, cf, ci, cf, cf, cf, vp, vp, vp, vp, vp]),
     "ym_nms_overflowed": (ci, [vp, ci, ci, vp]),

@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const __half* __restr
                                                            int grp_off, const __half* __restrict__ w,
                                                            const float* __restrict__ bias, int H, int W, int C, int act,
                                                            const __half* __restrict__ add, int ldadd, __half* __restrict__ out,
-                                                           int ldo, int tiles_x) {
+                                                           int ldo, int tiles_x, const int* __restrict__ route_idx, int topk,
+                                                           int expert) {
     constexpr int R = KS / 2, PX = 4, CB = CHUNKS * 8;
     constexpr int GROUPS = 256 / CHUNKS;           // pixel groups per CTA
     constexpr int TW = (CHUNKS == 8) ? 16 : 32;    // tile width
@@ -155,6 +156,16 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const __half* __restr
     __half* sw = sx + HH_ * HW_ * CB;                            // [KS*KS][CB]
     const int tid = threadIdx.x;
     const int tile = blockIdx.x, b = blockIdx.y, cb0 = blockIdx.z * CB;
+    // routed mode (ES_MOE experts): image b is processed only if `expert` is among its retained routes; the output goes to
+    // slot b*topk + j of the per-route scratch tensor
+    int ob = b;
+    if (route_idx != nullptr) {
+        int j = -1;
+        for (int q = 0; q < topk; ++q)
+            if (route_idx[b * topk + q] == expert) j = q;
+        if (j < 0) return;
+        ob = b * topk + j;
+    }
     const int ty0 = (tile / tiles_x) * TH, tx0 = (tile % tiles_x) * TW;
     const __half* xb = x + (long long)b * H * W * ldx;
     // ---- stage weights + haloed input tile (zero outside the image)
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const __half* __restr
     for (int p = 0; p < PX; ++p) {
         const int ox = tx0 + gx * PX + p;
         if (ox >= W) continue;
-        const long long pix = ((long long)b * H + oy) * W + ox;
+        const long long pix = ((long long)ob * H + oy) * W + ox;
         float v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = act == 1 ? silu_f(acc[p][q]) : acc[p][q];
@@ -361,9 +372,28 @@ extern "C" int ym_stem_conv_nchw(const void* img, int in_dtype, int B, int Cin, 
     return YM_OK;
 }
 
+static int dwconv_impl(const void* x, int ldx, int grp_w, int grp_stride, int grp_off, const void* w, const float* bias, int B,
+                       int H, int W, int C, int ksize, int act, const void* add, int ldadd, void* out, int ldo,
+                       const int* route_idx, int topk, int expert, void* stream);
+
 extern "C" int ym_dwconv_nhwc(const void* x, int ldx, int grp_w, int grp_stride, int grp_off, const void* w,
                               const float* bias, int B, int H, int W, int C, int ksize, int act, const void* add, int ldadd,
                               void* out, int ldo, void* stream) {
+    return dwconv_impl(x, ldx, grp_w, grp_stride, grp_off, w, bias, B, H, W, C, ksize, act, add, ldadd, out, ldo, nullptr, 0, 0, stream);
+}
+
+// ES_MOE expert depthwise stage (experts.py:284): image b is convolved with expert `expert`'s k x k filter only if that
+// expert is one of its retained routes; the result lands in slot b*topk + j of out ([B*topk][H][W][C]).
+extern "C" int ym_esmoe_dwconv(const void* x, int ldx, const void* w, int B, int H, int W, int C, int ksize, const int* route_idx,
+                               int topk, int expert, void* out, int ldo, void* stream) {
+    YM_CHECK_ARG(route_idx && topk >= 1, "ym_esmoe_dwconv: routing table required");
+    YM_CHECK_ARG(C % 16 == 0, "ym_esmoe_dwconv: C must be a multiple of 16");
+    return dwconv_impl(x, ldx, C, C, 0, w, nullptr, B, H, W, C, ksize, 0, nullptr, 0, out, ldo, route_idx, topk, expert, stream);
+}
+
+static int dwconv_impl(const void* x, int ldx, int grp_w, int grp_stride, int grp_off, const void* w, const float* bias, int B,
+                       int H, int W, int C, int ksize, int act, const void* add, int ldadd, void* out, int ldo,
+                       const int* route_idx, int topk, int expert, void* stream) {
     YM_CHECK_ARG(x && w && out, "ym_dwconv_nhwc: null pointer");
     YM_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && grp_w % 8 == 0 && grp_stride % 8 == 0 && grp_off % 8 == 0,
                  "ym_dwconv_nhwc: channel counts/pitches must be multiples of 8");
@@ -383,7 +413,7 @@ extern "C" int ym_dwconv_nhwc(const void* x, int ldx, int grp_w, int grp_stride,
         auto kern = dwconv_tiled_kernel<KS, CH>;                                                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
         kern<<<grid, 256, smem, st>>>((const __half*)x, ldx, grp_w, grp_stride, grp_off, (const __half*)w, bias, H, W, C, act, \
-                                      (const __half*)add, ldadd, (__half*)out, ldo, tiles_x);                                 \
+                                      (const __half*)add, ldadd, (__half*)out, ldo, tiles_x, route_idx, topk, expert);        \
     } while (0)
         bool done = true;
         if (chunks == 8) {
@@ -396,6 +426,7 @@ extern "C" int ym_dwconv_nhwc(const void* x, int ldx, int grp_w, int grp_stride,
 #undef YM_DWT
         if (done) { YM_CHECK_LAUNCH("dwconv_tiled"); return YM_OK; }
     }
+    YM_CHECK_ARG(route_idx == nullptr, "dwconv: routed mode needs the tiled kernel (C %% 16 == 0, k in 3/5/7/9)");
 #define YM_DW(KS)                                                                                                    \
     dwconv_kernel<KS><<<nblocks(total, 256), 256, 0, st>>>((const __half*)x, ldx, grp_w, grp_stride, grp_off,          \
                                                            (const __half*)w, bias, B, H, W, C, act, (const __half*)add, \

@@ -35,9 +35,11 @@ struct GemmConvParams {
     int K;     // KH*KW*Cin
     int act;   // 0 none, 1 SiLU
     // grouped (problem = blockIdx.z)
-    const int* route_idx;      // expert per problem (null -> plain)
+    const int* route_idx;      // expert per problem (null -> plain); a negative entry = dropped route (CTA exits)
     long long w_expert_stride; // elements between experts' packed weights
     int a_div;                 // A problem = p / a_div
+    int bias_expert_stride;    // >0: bias + expert * stride (per-expert folded-BN bias, ES_MOE)
+    const float* prob_scale;   // optional per-problem output scale applied after the activation (routing weight)
     // A-operand GroupNorm+SiLU prologue: per (problem, k) scale/shift
     const float* a_scale; const float* a_shift;
     // stats epilogue
@@ -61,8 +63,13 @@ __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParam
     const __half* xb = p.x;
     const __half* wb = p.w;
     char* outb = reinterpret_cast<char*>(p.out);
+    const float* biasb = p.bias;
+    float pscale = 1.f;
     if (p.route_idx != nullptr) {
         const int e = p.route_idx[prob];
+        if (e < 0) return;                     // dropped route: nothing to compute, the combine kernel skips the slot
+        if (p.bias_expert_stride > 0 && biasb != nullptr) biasb += (long long)e * p.bias_expert_stride;
+        if (p.prob_scale != nullptr) pscale = p.prob_scale[prob];
         wb += (long long)e * p.w_expert_stride;
         xb += (long long)(prob / p.a_div) * p.M * p.ldx;
         outb += (long long)prob * p.M * p.ldo * (p.out_f32 ? 4 : 2);
@@ -224,9 +231,9 @@ __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParam
         const int n = n0 + nl;
         const bool nok = n < p.Cout;  // Cout is even -> the pair is in or out together
         float bias0 = 0.f, bias1 = 0.f;
-        if (nok && p.bias != nullptr) {
-            bias0 = p.bias[n];
-            bias1 = p.bias[n + 1];
+        if (nok && biasb != nullptr) {
+            bias0 = biasb[n];
+            bias1 = biasb[n + 1];
         }
         float ssum = 0.f, ssq = 0.f;
 #pragma unroll
@@ -246,6 +253,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParam
                     v0 = silu_f(v0);
                     v1 = silu_f(v1);
                 }
+                v0 *= pscale;
+                v1 *= pscale;
                 *reinterpret_cast<float2*>(stg + rl * SP + nl) = make_float2(v0, v1);
             }
         }
@@ -503,4 +512,25 @@ extern "C" int ym_gn_finalize(const float* stats, int P, int HW, int groups, int
                                                                           route_idx, route_w, scale, shift);
     YM_CHECK_LAUNCH("gn_finalize");
     return YM_OK;
+}
+
+
+// ES_MOE expert pointwise stage: y[p] = route_w[p] * SiLU(t[p] * Wpw[e_p]^T + bias[e_p])  (experts.py:280-296 with BN folded),
+// one problem per (image, k); problems whose route_idx is negative (dropped by the dynamic threshold) are skipped.
+extern "C" int ym_esmoe_pointwise(const void* t, int ldt, int P, int HW, int K, const void* w, int Kpad, long long w_expert_stride,
+                                  const float* bias_all, int N, const int* route_idx, const float* route_w, void* y, int ldy,
+                                  void* stream) {
+    YM_CHECK_ARG(t && w && bias_all && route_idx && route_w && y, "ym_esmoe_pointwise: null pointer");
+    YM_CHECK_ARG(K % 8 == 0 && ldt % 8 == 0 && N % 8 == 0 && ldy % 8 == 0, "ym_esmoe_pointwise: bad dims K=%d N=%d", K, N);
+    YM_CHECK_ARG(Kpad % BK == 0 && Kpad >= K, "ym_esmoe_pointwise: bad Kpad");
+    YM_CHECK_ARG((((uintptr_t)t | (uintptr_t)y | (uintptr_t)w) & 15) == 0, "ym_esmoe_pointwise: 16-byte alignment");
+    if (P == 0) return YM_OK;
+    GemmConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = (const __half*)t; p.ldx = ldt; p.w = (const __half*)w; p.Kpad = Kpad; p.bias = bias_all; p.bias_expert_stride = N;
+    p.out = y; p.ldo = ldy;
+    p.B = 1; p.H = HW; p.W = 1; p.Cin = K; p.KH = 1; p.KW = 1; p.stride = 1; p.pad = 0; p.Ho = HW; p.Wo = 1;
+    p.Cout = N; p.M = HW; p.K = K; p.act = 1;
+    p.route_idx = route_idx; p.w_expert_stride = w_expert_stride; p.a_div = 1; p.prob_scale = route_w;
+    return dispatch_bn<EPI_STD, false>(p, P, (cudaStream_t)stream);
 }

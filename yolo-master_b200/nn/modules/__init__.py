@@ -2,11 +2,13 @@
 from .block import A2C2f, AAttn, ABlock, Attention, Bottleneck, C2f, C2PSA, C3, C3k, C3k2, PSABlock, SPPF
 from .conv import Concat, Conv, DWConv, PlainConv2d, Upsample, autopad
 from .head import Detect
-from .moe import A2C2fMoE, ABlockMoE, EfficientSpatialRouter, OptimizedMOEImproved, SimpleExpert, get_safe_groups
+from .moe import (A2C2fMoE, ABlockMoE, DepthwiseSeparableConv, DynamicRoutingLayer, EfficientExpertGroup, EfficientSpatialRouter,
+                  ES_MOE, OptimizedMOEImproved, SimpleExpert, get_safe_groups)
 
 __all__ = (
     "Conv", "DWConv", "Concat", "Upsample", "PlainConv2d", "autopad",
     "Bottleneck", "C2f", "C3", "C3k", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA", "AAttn", "ABlock", "A2C2f",
     "EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups",
+    "DynamicRoutingLayer", "DepthwiseSeparableConv", "EfficientExpertGroup", "ES_MOE",
     "Detect",
 )

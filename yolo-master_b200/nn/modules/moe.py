@@ -18,7 +18,8 @@ from ... import ops
 from ._base import PackCache, bn_affine, fold_bn, pack_gemm_weight, require_eval, to_nchw, to_nhwc
 from .block import A2C2f, ABlock, C3k, _SeqNHWC
 
-__all__ = ("EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups")
+__all__ = ("EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups",
+           "DynamicRoutingLayer", "DepthwiseSeparableConv", "EfficientExpertGroup", "ES_MOE")
 
 
 def get_safe_groups(channels: int, desired_groups: int = 8) -> int:
@@ -218,3 +219,136 @@ class A2C2fMoE(A2C2f):
     @property
     def aux_loss(self):
         return torch.zeros((), device=self.cv1.conv.weight.device)
+
+
+# ======================================================================================================================
+# ES_MOE family (moe/routers.py:429-527, moe/experts.py:280-311, moe/modules.py:410-741)
+# ======================================================================================================================
+class DynamicRoutingLayer(nn.Module):
+    """`DynamicRoutingLayer(in_channels, num_experts=3, reduction=8, top_k=None)`: GAP -> 1x1 -> SiLU -> 1x1 (with biases).
+    Parameter container: the router arithmetic runs inside `ES_MOE.fwd_nhwc` (ym_esmoe_route)."""
+
+    def __init__(self, in_channels, num_experts=3, reduction=8, top_k=None):
+        super().__init__()
+        if num_experts < 1:
+            raise ValueError(f"num_experts must be positive, got {num_experts}")
+        if reduction < 1:
+            raise ValueError(f"reduction must be positive, got {reduction}")
+        if top_k is not None and not 1 <= top_k <= num_experts:
+            raise ValueError(f"top_k must be in [1, {num_experts}], got {top_k}")
+        reduced_channels = max(in_channels // reduction, 8)
+        self.in_channels = in_channels
+        self.num_experts = num_experts
+        self.top_k = min(top_k, num_experts) if top_k is not None else num_experts
+        self.use_top_k = top_k is not None
+        self.global_pool = nn.AdaptiveAvgPool2d(1)
+        self.routing_network = nn.Sequential(
+            nn.Conv2d(in_channels, reduced_channels, kernel_size=1), nn.SiLU(inplace=False),
+            nn.Conv2d(reduced_channels, num_experts, kernel_size=1))
+
+
+class DepthwiseSeparableConv(nn.Module):
+    """`DepthwiseSeparableConv(in_channels, out_channels, kernel_size, stride=1)`: dw kxk -> 1x1 -> BN -> SiLU."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1):
+        super().__init__()
+        if stride != 1:
+            raise NotImplementedError("DepthwiseSeparableConv: stride != 1 is not on the B200 path")
+        padding = (kernel_size - 1) // 2
+        self.depthwise = nn.Conv2d(in_channels, in_channels, kernel_size, stride=stride, padding=padding, groups=in_channels, bias=False)
+        self.pointwise = nn.Conv2d(in_channels, out_channels, kernel_size=1, bias=False)
+        self.bn = nn.BatchNorm2d(out_channels, eps=1e-3, momentum=0.03)
+        self.act = nn.SiLU(inplace=True)
+
+
+class EfficientExpertGroup(nn.Module):
+    """`EfficientExpertGroup(in_channels, out_channels, kernel_size, stride=1)`."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1):
+        super().__init__()
+        self.conv = DepthwiseSeparableConv(in_channels, out_channels, kernel_size, stride)
+
+
+class ES_MOE(nn.Module, PackCache):
+    """`ES_MOE(in_channels, out_channels=None, num_experts=4, reduction=8, top_k=2, use_sparse_inference=True,
+    dynamic_threshold=0.4, max_kernel_size=15, expert_kernel_sizes=None)` — eval sparse path only."""
+
+    def __init__(self, in_channels, out_channels=None, num_experts=4, reduction=8, top_k=2, use_sparse_inference=True,
+                 dynamic_threshold=0.4, max_kernel_size=15, expert_kernel_sizes=None):
+        super().__init__()
+        if in_channels < 1 or (out_channels is not None and out_channels < 1):
+            raise ValueError("in_channels and out_channels must be positive")
+        if num_experts < 1:
+            raise ValueError(f"num_experts must be positive, got {num_experts}")
+        if top_k is not None and not 1 <= top_k <= num_experts:
+            raise ValueError(f"top_k must be in [1, {num_experts}], got {top_k}")
+        if not 0.0 <= dynamic_threshold <= 1.0:
+            raise ValueError(f"dynamic_threshold must be in [0, 1], got {dynamic_threshold}")
+        if max_kernel_size < 3:
+            raise ValueError(f"max_kernel_size must be at least 3, got {max_kernel_size}")
+        max_kernel_size = int(max_kernel_size)
+        if max_kernel_size % 2 == 0:
+            max_kernel_size -= 1
+        out_channels = in_channels if out_channels is None else out_channels
+        self.in_channels, self.out_channels, self.num_experts, self.reduction = in_channels, out_channels, num_experts, reduction
+        self.top_k = min(top_k, num_experts) if top_k is not None else num_experts
+        self.use_top_k = top_k is not None
+        self.use_sparse_inference, self.dynamic_threshold, self.max_kernel_size = use_sparse_inference, dynamic_threshold, max_kernel_size
+        self.routing = DynamicRoutingLayer(in_channels, num_experts, reduction, top_k)
+        if expert_kernel_sizes is not None:
+            if len(expert_kernel_sizes) != num_experts:
+                raise ValueError(f"expert_kernel_sizes must have {num_experts} entries, got {len(expert_kernel_sizes)}")
+            ks = [min(int(k) - (1 if int(k) % 2 == 0 else 0), max_kernel_size) for k in expert_kernel_sizes]
+        else:
+            default = [3, 5, 7]
+            ks = [min(k, max_kernel_size) for k in default[:num_experts]] if num_experts <= len(default) \
+                else [min(3 + 2 * i, max_kernel_size) for i in range(num_experts)]
+        self.experts = nn.ModuleList([EfficientExpertGroup(in_channels, out_channels, kernel_size=k) for k in ks])
+        self.norm = nn.Sequential(nn.BatchNorm2d(out_channels, eps=1e-3, momentum=0.03), nn.SiLU(inplace=True))
+        self.register_buffer("load_balancing_loss", torch.tensor(0.0), persistent=False)
+        self.register_buffer("expert_usage_counts", torch.zeros(num_experts), persistent=False)
+        self.last_routing_snapshot = {}
+        self.balance_loss_coeff = 1.0
+
+    def _eager_sparse_enabled(self):
+        return bool(self.use_sparse_inference and self.use_top_k and self.top_k < self.num_experts)
+
+    def _pack_sources(self):
+        return [t for t in list(self.parameters()) + list(self.buffers()) if t is not self.load_balancing_loss and t is not self.expert_usage_counts]
+
+    def _build_pack(self):
+        ks = [e.conv.depthwise.kernel_size[0] for e in self.experts]
+        if any(k not in (3, 5, 7, 9) for k in ks):
+            raise NotImplementedError(f"ES_MOE: expert kernel sizes {ks} not on the B200 path (3/5/7/9)")
+        if self.in_channels % 16:
+            raise NotImplementedError("ES_MOE: in_channels must be a multiple of 16 on the B200 path")
+        r0, r2 = self.routing.routing_network[0], self.routing.routing_network[2]
+        pw, pb = [], []
+        for e in self.experts:
+            w, b = fold_bn(e.conv.pointwise.weight, None, e.conv.bn)
+            pw.append(pack_gemm_weight(w))
+            pb.append(b)
+        fs, fh = bn_affine(self.norm[0])
+        C = self.in_channels
+        return {
+            "E": self.num_experts, "N": self.out_channels, "Cr": r0.weight.shape[0], "ks": ks,
+            "rw1": r0.weight.detach().float().reshape(r0.weight.shape[0], C).contiguous(), "rb1": r0.bias.detach().float().contiguous(),
+            "rw2": r2.weight.detach().float().reshape(self.num_experts, -1).contiguous(), "rb2": r2.bias.detach().float().contiguous(),
+            "dw": [e.conv.depthwise.weight.detach().float().reshape(C, k * k).t().contiguous().half() for e, k in zip(self.experts, ks)],
+            "pw": torch.stack(pw).contiguous(), "pb": torch.stack(pb).contiguous(), "fscale": fs, "fshift": fh,
+        }
+
+    def fwd_nhwc(self, x, out=None):
+        require_eval(self)
+        if not self._eager_sparse_enabled():
+            raise NotImplementedError("ES_MOE: only the eval sparse path (top_k < num_experts, use_sparse_inference) is on the B200 path")
+        y, idx, w, probs = ops.esmoe_forward(x, self.get_pack(), self.top_k, self.dynamic_threshold, out=out)
+        self.last_routing_snapshot = {"topk_indices": idx, "topk_weights": w, "router_probs": probs}
+        return y
+
+    def forward(self, x):
+        return to_nchw(self.fwd_nhwc(to_nhwc(x)))
+
+    @property
+    def aux_loss(self):
+        return torch.zeros((), device=self.norm[0].weight.device)

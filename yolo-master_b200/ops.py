@@ -288,3 +288,36 @@ def nms_batched(pred, conf_thres, iou_thres, max_det=300, max_nms=30000, max_wh=
                                     cnt.data_ptr(), idx.data_ptr(), scratch.data_ptr(), _stream()), "ym_nms_batched")
     _count(2)
     return out, cnt, idx, scratch
+
+
+def esmoe_forward(x, pack, topk, dyn_thr, out=None):
+    """ES_MOE eval forward on the C ABI (ym_esmoe_route / _dwconv / _pointwise / _combine).  x: (B,H,W,C) fp16 view."""
+    B, H, W, Cc = x.shape
+    HW, E, N = H * W, pack["E"], pack["N"]
+    dev = x.device
+    L = lib()
+    st = _stream()
+    scratch = torch.empty((L.ym_esmoe_scratch_floats(B, HW, Cc),), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, topk), dtype=torch.int32, device=dev)
+    w = torch.empty((B, topk), dtype=torch.float32, device=dev)
+    probs = torch.empty((B, E), dtype=torch.float32, device=dev)
+    _lib.check(L.ym_esmoe_route(x.data_ptr(), pitch(x), B, HW, Cc, pack["rw1"].data_ptr(), pack["rb1"].data_ptr(), pack["Cr"],
+                                pack["rw2"].data_ptr(), pack["rb2"].data_ptr(), E, topk, float(dyn_thr), scratch.data_ptr(),
+                                idx.data_ptr(), w.data_ptr(), probs.data_ptr(), st), "ym_esmoe_route")
+    _count(2)
+    t = torch.empty((B * topk, HW, Cc), dtype=torch.float16, device=dev)
+    for e, (k, wdw) in enumerate(zip(pack["ks"], pack["dw"])):
+        _lib.check(L.ym_esmoe_dwconv(x.data_ptr(), pitch(x), wdw.data_ptr(), B, H, W, Cc, k, idx.data_ptr(), topk, e,
+                                     t.data_ptr(), Cc, st), "ym_esmoe_dwconv")
+        _count()
+    y = torch.empty((B * topk, HW, N), dtype=torch.float16, device=dev)
+    pw = pack["pw"]
+    _lib.check(L.ym_esmoe_pointwise(t.data_ptr(), Cc, B * topk, HW, Cc, pw.data_ptr(), pw.shape[2], pw.shape[1] * pw.shape[2],
+                                    pack["pb"].data_ptr(), N, idx.data_ptr(), w.data_ptr(), y.data_ptr(), N, st), "ym_esmoe_pointwise")
+    _count()
+    if out is None:
+        out = new_act(B, H, W, N, dev)
+    _lib.check(L.ym_esmoe_combine(y.data_ptr(), N, idx.data_ptr(), topk, pack["fscale"].data_ptr(), pack["fshift"].data_ptr(),
+                                  out.data_ptr(), pitch(out), B, HW, N, st), "ym_esmoe_combine")
+    _count()
+    return out, idx, w, probs
