@@ -149,6 +149,12 @@ int ym_tc_gemm_nt(const void* a, int lda, const void* b, int ldb, const float* b
 int ym_moe_dispatch_tc(const void* x, int ldx, int B, int HW, int C, const void* w_all, int ldw, long long w_expert_stride,
                        const int* route_idx, const float* route_w, int topk, int N, float w_min, float clamp, void* out,
                        int ldo, void* stream);
+/* Same contract, persistent warp-specialised kernel: x tiles and expert weight tiles arrive by TMA (weights [E*N][ldw]
+ * contiguous per expert), both routed experts accumulate in TMEM, output leaves by TMA store.  Shapes: HW % 128 == 0,
+ * C % 64 == 0 <= 256, N % 128 == 0 <= 256, top_k <= 2 (ym_moe_dispatch_v2_supported). */
+int ym_moe_dispatch_v2_supported(int HW, int C, int N, int topk, int ldx, int ldw, int ldo);
+int ym_moe_dispatch_v2(const void* x, int ldx, int B, int HW, int C, const void* w_all, int ldw, int E, const int* route_idx,
+                       const float* route_w, int topk, int N, float w_min, float clamp, void* out, int ldo, void* stream);
 
 /* TMA + tcgen05 convolution (same contract and weight packing as ym_conv2d_nhwc): the activation k-tiles are loaded by
  * cp.async.bulk.tensor from a 4-D (C,W,H,B) tensor map at the tap-shifted origin (im2col-free, OOB zero fill = padding),

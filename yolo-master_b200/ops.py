@@ -259,13 +259,23 @@ def tc_gemm_nt(a, b, bias=None, res=None, act=False, out=None):
     return out
 
 
+DISPATCH_IMPL = "v2"   # "v2": persistent TMA + tcgen05 kernel where supported; "v1": one tile per CTA (cp.async + tcgen05)
+
+
 def moe_dispatch(x, w_all, route_idx, route_w, w_min=0.01, clamp=1e4, out=None):
-    """ym_moe_dispatch_tc.  x: (B,H,W,C) fp16 NHWC; w_all: [E,N,C] fp16; route_idx int32 [B,k]; route_w fp32 [B,k]."""
+    """ES-MoE dispatch.  x: (B,H,W,C) fp16 NHWC; w_all: [E,N,C] fp16; route_idx int32 [B,k]; route_w fp32 [B,k]."""
     B, H, W, Cc = x.shape
     E, N, Kw = w_all.shape
     k = route_idx.shape[1]
     if out is None:
         out = new_act(B, H, W, N, x.device)
+    L = lib()
+    if DISPATCH_IMPL == "v2" and w_all.is_contiguous() and L.ym_moe_dispatch_v2_supported(H * W, Cc, N, k, pitch(x), w_all.stride(1), pitch(out)):
+        _lib.check(L.ym_moe_dispatch_v2(x.data_ptr(), pitch(x), B, H * W, Cc, w_all.data_ptr(), w_all.stride(1), E, route_idx.data_ptr(),
+                                        route_w.data_ptr(), k, N, float(w_min), float(clamp), out.data_ptr(), pitch(out), _stream()),
+                   "ym_moe_dispatch_v2")
+        _count()
+        return out
     _lib.check(lib().ym_moe_dispatch_tc(x.data_ptr(), pitch(x), B, H * W, Cc, w_all.data_ptr(), w_all.stride(1), w_all.stride(0),
                                         route_idx.data_ptr(), route_w.data_ptr(), k, N, float(w_min), float(clamp),
                                         out.data_ptr(), pitch(out), _stream()), "ym_moe_dispatch_tc")
