@@ -155,6 +155,17 @@ int ym_moe_dispatch_tc(const void* x, int ldx, int B, int HW, int C, const void*
 int ym_moe_dispatch_v2_supported(int HW, int C, int N, int topk, int ldx, int ldw, int ldo);
 int ym_moe_dispatch_v2(const void* x, int ldx, int B, int HW, int C, const void* w_all, int ldw, int E, const int* route_idx,
                        const float* route_w, int topk, int N, float w_min, float clamp, void* out, int ldo, void* stream);
+/* Same contract, CTA-pair kernel (2-CTA cluster, tcgen05.mma.cta_group::2, M = 256): each SM of a TPC pair keeps its own
+ * 128-token tile and loads only half of every expert weight tile, halving the L2 -> shared-memory weight traffic per token.
+ * Additionally requires HW % 256 == 0 and a device that can co-schedule 2-CTA clusters (ym_moe_dispatch_v3_supported). */
+int ym_moe_dispatch_v3_supported(int HW, int C, int N, int topk, int ldx, int ldw, int ldo);
+int ym_moe_dispatch_v3(const void* x, int ldx, int B, int HW, int C, const void* w_all, int ldw, int E, const int* route_idx,
+                       const float* route_w, int topk, int N, float w_min, float clamp, void* out, int ldo, void* stream);
+/* Profiling aid only (tools/profile_dispatch.py): a non-zero mask switches pipeline stages of the v2 kernel off so that
+ * their cost can be read off the kernel time; results are then wrong.  Default 0; the package never sets it. */
+void ym_set_dispatch_debug(int mask);
+int ym_dispatch_debug_mask(void);
+void ym_set_dispatch_trace(void* buf);   /* device int64[2][4][256]: clock64 timeline of CTAs 0/1 of the pair kernel, or NULL */
 
 /* TMA + tcgen05 convolution (same contract and weight packing as ym_conv2d_nhwc): the activation k-tiles are loaded by
  * cp.async.bulk.tensor from a 4-D (C,W,H,B) tensor map at the tap-shifted origin (im2col-free, OOB zero fill = padding),

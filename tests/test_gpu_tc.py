@@ -38,9 +38,10 @@ def test_tc_gemm_epilogue_and_pitched_views():
     assert float(obuf[:, :N].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("impl", ["v2", "v1"])
+@pytest.mark.parametrize("impl", ["v3", "v2", "v1"])
 @pytest.mark.parametrize("B,hw,C,E,k", [(8, (16, 16), 64, 4, 2), (64, (32, 32), 256, 8, 2), (5, (9, 13), 128, 8, 2), (6, (20, 20), 256, 16, 1),
-                                        (37, (16, 8), 128, 8, 2), (3, (64, 64), 256, 8, 2)])
+                                        (37, (16, 8), 128, 8, 2), (3, (64, 64), 256, 8, 2), (10, (16, 16), 128, 8, 2), (5, (32, 16), 256, 8, 1),
+                                        (151, (16, 16), 256, 8, 2)])
 def test_moe_dispatch_vs_oracle(B, hw, C, E, k, impl):
     """C5 configuration (x=(64,256,32,32), 8 experts, top-2) and ragged variants against the restated dispatcher."""
     from yolo_master_b200 import ops
@@ -51,12 +52,14 @@ def test_moe_dispatch_vs_oracle(B, hw, C, E, k, impl):
     w = torch.rand((B, k), generator=g)
     w = w / w.sum(1, keepdim=True)
     w[0, -1] = 0.005                                   # below the 0.01 eval threshold: that route must be dropped
+    if B > 2:
+        w[2, :] = 0.004                                # an image with no live route at all: its output is exactly zero
     ops.DISPATCH_IMPL = impl
     try:
         out = ops.moe_dispatch(x.to(DEV).permute(0, 2, 3, 1).contiguous(), W.to(DEV), idx.to(DEV), w.to(DEV))
         torch.cuda.synchronize()
     finally:
-        ops.DISPATCH_IMPL = "v2"
+        ops.DISPATCH_IMPL = "v3"
     ref = compute_sparse_experts_batched(x.float(), conv1x1_experts(W.float()), w, idx.long(), C)
     # the reference rounds every expert output to fp16 before weighting (utils.py:200-203); with two experts of opposite
     # sign that rounding is visible on the (small) sum, so a handful of elements may exceed the per-element bound vs fp32

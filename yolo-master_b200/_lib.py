@@ -43,6 +43,11 @@ SIGNATURES = {
     "ym_moe_dispatch_tc": (ci, [vp, ci, ci, ci, ci, vp, ci, cll, vp, vp, ci, ci, cf, cf, vp, ci, vp]),
     "ym_moe_dispatch_v2_supported": (ci, [ci, ci, ci, ci, ci, ci, ci]),
     "ym_moe_dispatch_v2": (ci, [vp, ci, ci, ci, ci, vp, ci, ci, vp, vp, ci, ci, cf, cf, vp, ci, vp]),
+    "ym_moe_dispatch_v3_supported": (ci, [ci, ci, ci, ci, ci, ci, ci]),
+    "ym_moe_dispatch_v3": (ci, [vp, ci, ci, ci, ci, vp, ci, ci, vp, vp, ci, ci, cf, cf, vp, ci, vp]),
+    "ym_set_dispatch_debug": (None, [ci]),
+    "ym_dispatch_debug_mask": (ci, []),
+    "ym_set_dispatch_trace": (None, [vp]),
     "ym_detect_topk": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp, vp, vp]),
     "ym_detect_dense": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp]),
 }

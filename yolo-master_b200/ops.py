@@ -259,7 +259,9 @@ def tc_gemm_nt(a, b, bias=None, res=None, act=False, out=None):
     return out
 
 
-DISPATCH_IMPL = "v2"   # "v2": persistent TMA + tcgen05 kernel where supported; "v1": one tile per CTA (cp.async + tcgen05)
+# "v3": CTA-pair kernel (tcgen05.mma.cta_group::2, half the weight traffic per SM) where supported, else "v2": persistent
+# single-CTA TMA + tcgen05 kernel where supported, else "v1": one tile per CTA (cp.async + tcgen05)
+DISPATCH_IMPL = "v3"
 
 
 def moe_dispatch(x, w_all, route_idx, route_w, w_min=0.01, clamp=1e4, out=None):
@@ -270,7 +272,13 @@ def moe_dispatch(x, w_all, route_idx, route_w, w_min=0.01, clamp=1e4, out=None):
     if out is None:
         out = new_act(B, H, W, N, x.device)
     L = lib()
-    if DISPATCH_IMPL == "v2" and w_all.is_contiguous() and L.ym_moe_dispatch_v2_supported(H * W, Cc, N, k, pitch(x), w_all.stride(1), pitch(out)):
+    if DISPATCH_IMPL == "v3" and w_all.is_contiguous() and L.ym_moe_dispatch_v3_supported(H * W, Cc, N, k, pitch(x), w_all.stride(1), pitch(out)):
+        _lib.check(L.ym_moe_dispatch_v3(x.data_ptr(), pitch(x), B, H * W, Cc, w_all.data_ptr(), w_all.stride(1), E, route_idx.data_ptr(),
+                                        route_w.data_ptr(), k, N, float(w_min), float(clamp), out.data_ptr(), pitch(out), _stream()),
+                   "ym_moe_dispatch_v3")
+        _count()
+        return out
+    if DISPATCH_IMPL in ("v2", "v3") and w_all.is_contiguous() and L.ym_moe_dispatch_v2_supported(H * W, Cc, N, k, pitch(x), w_all.stride(1), pitch(out)):
         _lib.check(L.ym_moe_dispatch_v2(x.data_ptr(), pitch(x), B, H * W, Cc, w_all.data_ptr(), w_all.stride(1), E, route_idx.data_ptr(),
                                         route_w.data_ptr(), k, N, float(w_min), float(clamp), out.data_ptr(), pitch(out), _stream()),
                    "ym_moe_dispatch_v2")
