@@ -91,16 +91,29 @@ int ym_moe_combine(const void* x, int ldx, int B, int HW, int C, const void* ws,
                    const void* o, int ldo_o, const float* o_scale, const float* o_shift, int topk, void* out, int ldo,
                    int add_residual, void* stream);
 
-/* Detect post-processing.  box[l]: fp32 [B, h_l*w_l, 4] ltrb distances; cls[l]: fp32 [B, h_l*w_l, nc] logits.
+/* Detect post-processing.  box[l]: fp32 [B, h_l*w_l, 4*reg_max] ltrb distances (reg_max == 1) or DFL bin logits,
+ * channel = side*reg_max + bin (block.py:63-85); cls[l]: fp32 [B, h_l*w_l, nc] logits.
  * ym_detect_topk: Detect._inference + postprocess + get_topk_index (end2end)  head.py:173-258, tal.py:398-423.
  *   out fp32 [B, k, 6] = (x1,y1,x2,y2,score,cls), k = min(max_det, A), score-descending; out_anchor int32 [B,k] nullable;
  *   scratch: B*A uint32 (per-anchor max-logit keys written by the first of the two kernels).
- * ym_detect_dense: Detect._inference -> y fp32 [B, 4+nc, A] (xyxy!=0: corner boxes, else xywh)  head.py:173-194. */
+ * ym_detect_dense: Detect._inference (+ DFL when reg_max > 1) -> y fp32 [B, 4+nc, A] (xyxy!=0: corner boxes, else xywh)
+ *   head.py:173-194. */
 int ym_detect_topk(int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
                    const float* strides, int B, int nc, int max_det, float* out, int* out_anchor, void* scratch,
                    void* stream);
 int ym_detect_dense(int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
-                    const float* strides, int B, int nc, int xyxy, float* y, void* stream);
+                    const float* strides, int B, int nc, int reg_max, int xyxy, float* y, void* stream);
+
+/* Element-wise glue of the residual / mixture blocks on NHWC fp16 rows (C % 8 == 0); a or b may be NULL (= 0) where allowed.
+ *   op 0  out = a + chan[c]*b            A2C2f layer-scale `x + gamma*y` block.py:1879; ls1/ls2 mot/experts.py:165,170;
+ *                                        ls_attn/ls_ffn moa/block.py:271-273                        (p0 = chan fp32[C])
+ *   op 1  out = a + tok[row*ldt+toff]*b  per-token routed accumulation mot/block.py:347-364, moa/block.py:232-244
+ *                                                                                                   (p0 = tok fp32)
+ *   op 2  out = sigmoid(a)*b             GLU gate mot/experts.py:168
+ *   op 3  out = gelu(a)                  exact (erf) nn.GELU mot/experts.py:225,365
+ *   op 4  out = [silu](a*sc[img,c] + sh[img,c]) + b   GroupNorm apply (img = row / rows_per_img; p0 = sc, p1 = sh fp32[imgs*C]) */
+int ym_ew_nhwc(int op, const void* a, int lda, const void* b, int ldb, const float* p0, const float* p1, int ldt, int toff,
+               int rows_per_img, int act, void* out, int ldo, long long rows, int C, void* stream);
 
 /* ES_MOE (moe/modules.py:410-741, eval sparse path) on four entry points; the module is router -> per-expert depthwise k x k
  * on the images that retained the expert -> grouped pointwise GEMM (+folded BN, SiLU, routing weight) -> sum + BN + SiLU.

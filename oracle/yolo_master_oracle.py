@@ -436,6 +436,30 @@ def layer_a2c2f_moe(sd, p, x, c1, c2, n=1, a2=True, area=1, residual=False, mlp_
     return o
 
 
+def ablock(sd, p, x, num_heads, area):
+    """`ABlock.forward` block.py:1787-1797: x + attn(x); x + mlp(x), mlp = Conv(c, c*r, 1) -> Conv(c*r, c, 1, act=False)."""
+    x = _st(x + aattn(sd, p + ".attn", x, num_heads, area))
+    return _st(x + conv_block(sd, p + ".mlp.1", conv_block(sd, p + ".mlp.0", x), act=False))
+
+
+def layer_a2c2f(sd, p, x, c1, c2, n=1, a2=True, area=1, residual=False, mlp_ratio=2.0, e=0.5, g=1, shortcut=True):
+    """`A2C2f.forward` block.py:1865-1879 (n x Sequential(ABlock, ABlock) or C3k; optional layer-scale residual)."""
+    c_ = int(c2 * e)
+    y = [conv_block(sd, p + ".cv1", x)]
+    for j in range(n):
+        t = y[-1]
+        if a2:
+            for r in range(2):
+                t = ablock(sd, f"{p}.m.{j}.{r}", t, c_ // 32, area)
+        else:
+            t = c3k(sd, f"{p}.m.{j}", t, 2, shortcut, g)
+        y.append(t)
+    o = conv_block(sd, p + ".cv2", torch.cat(y, 1))
+    if a2 and residual:
+        return _st(x + sd[p + ".gamma"].view(1, -1, 1, 1) * o)
+    return o
+
+
 def make_anchors(shapes, strides, offset=0.5):
     """utils/tal.py:398-411."""
     pts, st = [], []
@@ -473,7 +497,10 @@ def detect_decode(boxes, scores, shapes, strides, end2end, reg_max=1):
 
     Returns y (B, 4+nc, A): xyxy (end2end) or xywh boxes in pixels + sigmoid scores.
     """
-    assert reg_max == 1, "DFL (reg_max>1) not on the yolo26 path"
+    if reg_max > 1:  # `DFL.forward` block.py:80-85 (frozen arange weights; sd carries them as `dfl.conv.weight`)
+        b, _, a = boxes.shape
+        boxes = (boxes.view(b, 4, reg_max, a).transpose(2, 1).softmax(1)
+                 * torch.arange(reg_max, dtype=boxes.dtype).view(1, reg_max, 1, 1)).sum(1)
     anchors, st = make_anchors(shapes, strides)
     anchors, st = anchors.t().unsqueeze(0), st.t()
     lt, rb = boxes.chunk(2, 1)
@@ -503,7 +530,7 @@ def detect_postprocess(y, nc, max_det=300):
 # whole model (`BaseModel._predict_once` tasks.py:182-218)
 # ----------------------------------------------------------------------------
 _LAYER_FN = {"ES_MOE": layer_es_moe, "Conv": layer_conv, "C3k2": layer_c3k2, "C2f": layer_c2f, "SPPF": layer_sppf, "C2PSA": layer_c2psa,
-             "A2C2fMoE": layer_a2c2f_moe}
+             "A2C2fMoE": layer_a2c2f_moe, "A2C2f": layer_a2c2f}
 
 
 def forward_layer(spec: dict, sd: dict, i: int, xin):

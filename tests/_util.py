@@ -17,6 +17,11 @@ def yaml_n():
     return yaml.safe_load(open(CFG_N))
 
 
+def yaml_of(rel):
+    """A model YAML of this package's cfg tree, e.g. 'master/v0/det/yolo-master-n.yaml'."""
+    return yaml.safe_load(open(os.path.join(ROOT, "yolo-master_b200", "cfg", "models", rel)))
+
+
 def synth_sd_from_keys(seed=0, name="yolo26-master-n"):
     """fp32 CPU state_dict rebuilt from the reference key table only (no model code involved)."""
     from yolo_master_b200.utils.synth import fill_state_dict_, load_norm_stats_

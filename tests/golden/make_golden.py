@@ -31,8 +31,8 @@ NAME = "yolo26-master-n"
 KEEP_LAYERS = [2, 4, 6, 8, 9, 10, 13, 16, 19, 22]
 
 
-def calibrated_reference(seed=0):
-    m = DetectionModel(CFG, verbose=False)
+def calibrated_reference(seed=0, cfg=None):
+    m = DetectionModel(cfg or CFG, verbose=False)
     sd = m.state_dict()
     fill_state_dict_(sd, seed)
     m.load_state_dict(sd)
@@ -93,6 +93,39 @@ def main():
     torch.save(gold, f"{OUT}/{NAME}.golden.pt")
     for f in os.listdir(OUT):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+V0 = "/root/reference/ultralytics/cfg/models/master/v0/det/"
+EXTRA_MODELS = {
+    # name: (cfg, kept layers, {tag: (B, H, W, seed)})
+    "yolo-master-n-v0": (V0 + "yolo-master-n.yaml", [3, 6, 8, 9, 11, 12, 18, 21, 24], {"b2_128": (2, 128, 128, 3), "b1_64": (1, 64, 64, 4)}),
+    "yolo-master-l-v0": (V0 + "yolo-master-l.yaml", [8, 11, 12, 24], {"b1_64": (1, 64, 64, 5)}),
+}
+
+
+def extra_model_golden(name):
+    """v0 family (ES_MOE x4, A2C2f area attention with/without layer-scale residual, DFL Detect, no end2end): per-layer
+    activations, raw head outputs and the dense (B, 4+nc, A) prediction of the REAL reference."""
+    cfg, keep, cases = EXTRA_MODELS[name]
+    torch.manual_seed(0)
+    m = calibrated_reference(0, cfg)
+    sd = m.state_dict()
+    json.dump({k: [list(v.shape), str(v.dtype)] for k, v in sd.items()}, open(f"{OUT}/{name}.keys.json", "w"))
+    stats = {k: v.clone() for k, v in sd.items() if k.endswith("running_mean") or k.endswith("running_var")}
+    torch.save(stats, f"{OUT}/{name}.bnstats.pt")
+    gold = {"cases": {}}
+    for tag, (B, H, W, seed) in cases.items():
+        x = synth_images(B, H, W, seed)
+        y, preds, feats, _ = run(m, x)
+        pr = preds["one2one"] if "one2one" in preds else preds
+        gold["cases"][tag] = {"B": B, "H": H, "W": W, "seed": seed, "final": y.clone().half() if name.endswith("l-v0") else y.clone(),
+                              "layers": {i: feats[i].clone() for i in keep},
+                              "head_boxes": pr["boxes"].clone(), "head_scores": pr["scores"].clone()}
+        print(name, tag, "final", tuple(y.shape), "max score", float(y[:, 4:].max()))
+    torch.save(gold, f"{OUT}/{name}.golden.pt")
+    for f in sorted(os.listdir(OUT)):
+        if f.startswith(name):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
 def dispatch_golden():
@@ -178,7 +211,9 @@ def esmoe_golden():
 
 
 if __name__ == "__main__":
-    main()
-    dispatch_golden()
-    nms_golden()
-    esmoe_golden()
+    which = sys.argv[1:] or ["main", "dispatch", "nms", "esmoe", *EXTRA_MODELS]
+    for w in which:
+        if w in EXTRA_MODELS:
+            extra_model_golden(w)
+        else:
+            {"main": main, "dispatch": dispatch_golden, "nms": nms_golden, "esmoe": esmoe_golden}[w]()

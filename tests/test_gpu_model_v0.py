@@ -1,0 +1,117 @@
+"""GPU parity of the v0 family (yolo-master-n / -l: ES_MOE x4, A2C2f area attention with and without the layer-scale
+residual, C3k, DFL Detect, NMS post-processing) against the reference goldens and the CPU oracle, through the public API."""
+import os
+
+import pytest
+import torch
+
+from _util import GOLD, assert_within_noise, synth_sd_from_keys, yaml_of
+from oracle import nms_oracle as N
+from oracle import yolo_master_oracle as O
+from yolo_master_b200.nn.tasks import DetectionModel
+from yolo_master_b200.utils.nms import non_max_suppression
+from yolo_master_b200.utils.synth import synth_images
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+MODELS = {"yolo-master-n-v0": "master/v0/det/yolo-master-n.yaml", "yolo-master-l-v0": "master/v0/det/yolo-master-l.yaml"}
+
+
+@pytest.fixture(scope="module")
+def models():
+    out = {}
+    for name, cfg in MODELS.items():
+        sd = synth_sd_from_keys(0, name)
+        m = DetectionModel(os.path.basename(cfg))
+        missing, unexpected = m.load_state_dict(sd, strict=True)
+        out[name] = (m.to(DEV).eval(), sd, O.parse_spec(yaml_of(cfg)))
+    return out
+
+
+def _layers(m, x):
+    feats = {}
+    hooks = [mod.register_forward_hook(lambda mod, i, o, k=k: feats.__setitem__(k, o)) for k, mod in enumerate(m.model)]
+    with torch.no_grad():
+        y = m(x)
+    for h in hooks:
+        h.remove()
+    torch.cuda.synchronize()
+    return y[0], feats
+
+
+def _check_dense(y, ref, sim, what):
+    """Dense (B, 4+nc, A) prediction: boxes in pixels and sigmoid scores, within the fp16-storage noise of the graph."""
+    y = y.float().cpu()
+    assert y.shape == ref.shape
+    assert_within_noise(y[:, :4], ref[:, :4], sim[:, :4], what=what + " boxes")
+    assert_within_noise(y[:, 4:], ref[:, 4:], sim[:, 4:], what=what + " scores")
+
+
+@pytest.mark.parametrize("name,tag", [("yolo-master-n-v0", "b2_128"), ("yolo-master-n-v0", "b1_64"), ("yolo-master-l-v0", "b1_64")])
+def test_v0_model_matches_reference_golden(models, name, tag):
+    m, sd, spec = models[name]
+    c = torch.load(os.path.join(GOLD, f"{name}.golden.pt"))["cases"][tag]
+    x = synth_images(c["B"], c["H"], c["W"], c["seed"]).half()
+    y, feats = _layers(m, x.to(DEV))
+    ref, ys = O.forward(spec, sd, x.float(), return_layers=True)
+    with O.fp16_storage(), O.fp16_weights():
+        ysim, sim = O.forward(spec, sd, x.float(), return_layers=True)
+    for i, g in c["layers"].items():
+        assert_within_noise(feats[i], g, sim[i], what=f"{name} layer {i} vs reference golden")
+    _check_dense(y, ref, ysim, f"{name} {tag}")
+    if c["final"].dtype == torch.float32:
+        _check_dense(y, c["final"], ysim, f"{name} {tag} vs golden")
+
+
+def test_v0_layers_teacher_forced(models):
+    """Every top-level layer of yolo-master-n (v0) at 256x256, fed the oracle's fp16-rounded input."""
+    m, sd, spec = models["yolo-master-n-v0"]
+    x = synth_images(2, 256, 256, 9).half().float()
+    _, ys = O.forward(spec, sd, x, return_layers=True)
+    ys16 = {k: (v.half() if torch.is_tensor(v) else v) for k, v in ys.items()}
+    for i, L in enumerate(spec["layers"][:-1]):
+        f = L["f"]
+        src = (lambda j: x.half() if (i == 0 and j == -1) else ys16[i - 1 if j == -1 else j])
+        xin = src(f) if isinstance(f, int) else [src(j) for j in f]
+        to_dev = lambda t: t.to(DEV).contiguous(memory_format=torch.channels_last)
+        with torch.no_grad():
+            y = m.model[i](to_dev(xin) if torch.is_tensor(xin) else [to_dev(t) for t in xin])
+        xin32 = xin.float() if torch.is_tensor(xin) else [t.float() for t in xin]
+        ref = O.forward_layer(spec, sd, i, xin32)
+        with O.fp16_storage(), O.fp16_weights():
+            sim = O.forward_layer(spec, sd, i, xin32)
+        if L["type"] in ("Concat", "nn.Upsample"):
+            assert torch.equal(y.float().cpu(), ref), f"layer {i} {L['type']}"
+        else:
+            assert_within_noise(y, ref, sim, what=f"v0 layer {i} {L['type']} (teacher forced)")
+
+
+def test_v0_predict_pipeline_nms(models):
+    """model -> non_max_suppression (batched kernel) and -> CW-NMS: kept anchor indices bit-exact against the NMS oracle
+    run on the SAME dense prediction; CW-NMS keeps the same set and only moves the boxes."""
+    m, sd, spec = models["yolo-master-n-v0"]
+    x = synth_images(3, 320, 320, 11).half().to(DEV)
+    with torch.no_grad():
+        y = m(x)[0]
+    conf = float(y[:, 4:].amax(1).flatten().kthvalue(int(0.9 * y.shape[2] * y.shape[0]))[0])   # keep ~10 % of the anchors
+    out, keep = non_max_suppression(y, conf, 0.6, max_det=100, return_idxs=True)
+    ro, rk = N.non_max_suppression(y.float().cpu(), conf, 0.6, max_det=100)
+    for o, k, a, b in zip(out, keep, ro, rk):
+        assert torch.equal(k.cpu(), b)
+        torch.testing.assert_close(o.cpu(), a, atol=1e-4, rtol=1e-5)
+    assert sum(len(k) for k in keep) > 10
+    cw, ck = non_max_suppression(y, conf, 0.6, max_det=100, return_idxs=True, cluster=True, frame_wh=(320, 320))
+    for k, k2, o in zip(keep, ck, cw):
+        assert torch.equal(k, k2) or len(k2) <= len(k)      # clipping to the frame may drop empty boxes only
+        assert bool((o[:, 2:4] > 0).all())
+
+
+def test_v0_graph_replay(models):
+    m, _, _ = models["yolo-master-n-v0"]
+    x = synth_images(2, 256, 256, 5).half().to(DEV)
+    with torch.no_grad():
+        eager = m(x)[0].clone()
+    g = m.graphed(2, 256, 256)
+    out = g(x).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)

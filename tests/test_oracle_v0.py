@@ -1,0 +1,32 @@
+"""Pins the oracle's v0 family support (ES_MOE in-model, A2C2f area attention +/- layer-scale residual, C3k, DFL Detect)
+to outputs of the REAL reference (tests/golden/make_golden.py: yolo-master-n-v0 / yolo-master-l-v0)."""
+import os
+
+import pytest
+import torch
+
+from _util import GOLD, synth_sd_from_keys, yaml_of
+from oracle import yolo_master_oracle as O
+from yolo_master_b200.utils.synth import synth_images
+
+CASES = [("yolo-master-n-v0", "master/v0/det/yolo-master-n.yaml", "b2_128"), ("yolo-master-n-v0", "master/v0/det/yolo-master-n.yaml", "b1_64"),
+         ("yolo-master-l-v0", "master/v0/det/yolo-master-l.yaml", "b1_64")]
+
+
+@pytest.mark.parametrize("name,cfg,tag", CASES)
+def test_oracle_matches_reference_v0(name, cfg, tag):
+    c = torch.load(os.path.join(GOLD, f"{name}.golden.pt"))["cases"][tag]
+    sd = synth_sd_from_keys(0, name)
+    spec = O.parse_spec(yaml_of(cfg))
+    x = synth_images(c["B"], c["H"], c["W"], c["seed"])
+    y, ys = O.forward(spec, sd, x, return_layers=True)
+    for i, ref in c["layers"].items():
+        torch.testing.assert_close(ys[i], ref, atol=2e-4, rtol=1e-4, msg=lambda m, i=i: f"layer {i}: {m}")
+    braw, sraw, _ = ys["detect_raw"]
+    torch.testing.assert_close(braw, c["head_boxes"], atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(sraw, c["head_scores"], atol=2e-4, rtol=1e-4)
+    ref = c["final"].float()
+    tol = 2e-2 if c["final"].dtype == torch.float16 else 1e-3      # the L fixture stores the dense output in fp16
+    assert y.shape == ref.shape == (c["B"], 84, (c["H"] // 8) ** 2 + (c["H"] // 16) ** 2 + (c["H"] // 32) ** 2)
+    torch.testing.assert_close(y[:, :4], ref[:, :4], atol=tol, rtol=1e-3)        # xywh in pixels (DFL expectation)
+    torch.testing.assert_close(y[:, 4:], ref[:, 4:], atol=1e-3 if tol > 1e-3 else 1e-5, rtol=1e-3)

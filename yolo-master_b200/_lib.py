@@ -48,8 +48,9 @@ SIGNATURES = {
     "ym_set_dispatch_debug": (None, [ci]),
     "ym_dispatch_debug_mask": (ci, []),
     "ym_set_dispatch_trace": (None, [vp]),
+    "ym_ew_nhwc": (ci, [ci, vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, vp, ci, cll, ci, vp]),
     "ym_detect_topk": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp, vp, vp]),
-    "ym_detect_dense": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp]),
+    "ym_detect_dense": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, ci, vp, vp]),
 }
 
 _lib = None

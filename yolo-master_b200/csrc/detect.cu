@@ -191,7 +191,22 @@ __global__ void __launch_bounds__(1024) detect_topk_kernel(const DetectLevels L,
 }
 
 // Dense decode: y[b, 0:4, a] = box (xyxy if xyxy else xywh) * stride, y[b, 4+c, a] = sigmoid(logit)   (head.py:173-194)
-__global__ void __launch_bounds__(256) detect_dense_kernel(const DetectLevels L, int nc, int xyxy, int B, float* __restrict__ y) {
+// DFL (block.py:63-85): distance of one side = sum_i i * softmax_i(bins), bins = reg_max logits of that side.
+__device__ __forceinline__ float dfl_side(const float* __restrict__ p, int reg_max) {
+    if (reg_max == 1) return p[0];
+    float m = p[0];
+    for (int i = 1; i < reg_max; ++i) m = fmaxf(m, p[i]);
+    float s = 0.f, e = 0.f;
+    for (int i = 0; i < reg_max; ++i) {
+        const float w = expf(p[i] - m);
+        s += w;
+        e += w * (float)i;
+    }
+    return e / s;
+}
+
+__global__ void __launch_bounds__(256) detect_dense_kernel(const DetectLevels L, int nc, int reg_max, int xyxy, int B,
+                                                           float* __restrict__ y) {
     const int A = L.off[L.nl];
     const int no = 4 + nc;
     const long long total = (long long)B * no * A;
@@ -207,12 +222,15 @@ __global__ void __launch_bounds__(256) detect_dense_kernel(const DetectLevels L,
     if (ch >= 4) {
         v = 1.f / (1.f + expf(-L.cls[lvl][row * nc + (ch - 4)]));
     } else {
-        const float4 d = *reinterpret_cast<const float4*>(L.box[lvl] + row * 4);
+        // channel layout of the box tower: side * reg_max + bin, sides = (l, t, r, b)   head.py:186-194
+        const float* d = L.box[lvl] + row * 4 * reg_max;
+        const int axis = ch & 1;                       // 0: x (sides l,r), 1: y (sides t,b)
+        const float lo = dfl_side(d + axis * reg_max, reg_max), hi = dfl_side(d + (axis + 2) * reg_max, reg_max);
         const int ay = r / L.w[lvl], ax = r - ay * L.w[lvl];
-        const float px = (float)ax + 0.5f, py = (float)ay + 0.5f, s = L.stride[lvl];
-        const float x1 = px - d.x, y1 = py - d.y, x2 = px + d.z, y2 = py + d.w;
-        if (xyxy) v = (ch == 0 ? x1 : ch == 1 ? y1 : ch == 2 ? x2 : y2) * s;
-        else v = (ch == 0 ? (x1 + x2) * 0.5f : ch == 1 ? (y1 + y2) * 0.5f : ch == 2 ? (x2 - x1) : (y2 - y1)) * s;
+        const float pc = (float)(axis ? ay : ax) + 0.5f, s = L.stride[lvl];
+        const float c1 = pc - lo, c2 = pc + hi;
+        if (xyxy) v = (ch < 2 ? c1 : c2) * s;
+        else v = (ch < 2 ? (c1 + c2) * 0.5f : (c2 - c1)) * s;
     }
     y[idx] = v;
 }
@@ -264,14 +282,15 @@ extern "C" int ym_detect_topk(int nl, const void* const* box, const void* const*
 }
 
 extern "C" int ym_detect_dense(int nl, const void* const* box, const void* const* cls, const int* hs, const int* ws,
-                               const float* strides, int B, int nc, int xyxy, float* y, void* stream) {
+                               const float* strides, int B, int nc, int reg_max, int xyxy, float* y, void* stream) {
     YM_CHECK_ARG(y, "ym_detect_dense: null output");
+    YM_CHECK_ARG(reg_max >= 1 && reg_max <= 64, "ym_detect_dense: reg_max must be in 1..64 (got %d)", reg_max);
     DetectLevels L;
     int rc = fill_levels(L, nl, box, cls, hs, ws, strides);
     if (rc) return rc;
     if (B == 0) return YM_OK;
     const long long total = (long long)B * (4 + nc) * L.off[nl];
-    detect_dense_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(L, nc, xyxy, B, y);
+    detect_dense_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(L, nc, reg_max, xyxy, B, y);
     YM_CHECK_LAUNCH("detect_dense");
     return YM_OK;
 }

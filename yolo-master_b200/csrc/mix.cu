@@ -1,0 +1,107 @@
+// Element-wise glue of the mixture blocks (HBM-bound, 16-byte vectors, NHWC fp16 with row pitches).
+//   ym_ew_nhwc: layer-scale residuals, token-weighted expert accumulation, GLU gate, GELU, per-(image,channel) affine.
+#include "ym_common.cuh"
+
+namespace ym {
+
+enum EwOp {
+    EW_SCALE_RES = 0,   // out = a + chan[c] * b                       (A2C2f gamma block.py:1879; ls1/ls2, ls_attn/ls_ffn)
+    EW_TOKEN_ACC = 1,   // out = (a ? a : 0) + tok[row*ldt + toff] * b (MoT blend mot/block.py:347-364, MoA mix moa/block.py:232-244)
+    EW_GLU = 2,         // out = sigmoid(a) * b                        (mot/experts.py:168)
+    EW_GELU = 3,        // out = gelu(a) (exact, erf)                  (nn.GELU in mot/experts.py:225,365)
+    EW_AFFINE = 4,      // out = [silu](a * sc[img,c] + sh[img,c]) [+ b]   (GroupNorm apply; img = row / rows_per_img)
+};
+
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+
+template <int OP>
+__global__ void __launch_bounds__(256) ew_kernel(const __half* __restrict__ a, int lda, const __half* __restrict__ b, int ldb,
+                                                 const float* __restrict__ p0, const float* __restrict__ p1, int ldt, int toff,
+                                                 int rows_per_img, int act, __half* __restrict__ out, int ldo, long long rows,
+                                                 int C) {
+    const int cv = C >> 3;
+    const long long total = rows * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / cv;
+        const int c = (int)(i - row * cv) << 3;
+        float va[8], vb[8];
+        if (a) {
+            const Half8 h = *reinterpret_cast<const Half8*>(a + row * lda + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h.v[j]); va[2 * j] = f.x; va[2 * j + 1] = f.y; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) va[j] = 0.f;
+        }
+        if (b) {
+            const Half8 h = *reinterpret_cast<const Half8*>(b + row * ldb + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h.v[j]); vb[2 * j] = f.x; vb[2 * j + 1] = f.y; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vb[j] = 0.f;
+        }
+        float r[8];
+        if (OP == EW_SCALE_RES) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = fmaf(p0[c + j], vb[j], va[j]);
+        } else if (OP == EW_TOKEN_ACC) {
+            const float w = p0[row * ldt + toff];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = fmaf(w, vb[j], va[j]);
+        } else if (OP == EW_GLU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = vb[j] / (1.f + __expf(-va[j]));
+        } else if (OP == EW_GELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = gelu_f(va[j]);
+        } else {
+            const long long img = row / rows_per_img;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = fmaf(va[j], p0[img * C + c + j], p1[img * C + c + j]);
+                if (act) v = silu_f(v);
+                r[j] = v + vb[j];
+            }
+        }
+        Half8 o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o.v[j] = __floats2half2_rn(r[2 * j], r[2 * j + 1]);
+        *reinterpret_cast<Half8*>(out + row * ldo + c) = o;
+    }
+}
+
+}  // namespace ym
+
+using namespace ym;
+
+// a, b, out: fp16 [rows][ld*] (either of a/b may be null = zeros where the op allows); p0/p1: fp32 parameters of the op
+// (chan[C] | tok[rows*ldt] | scale,shift[imgs*C]).  C % 8 == 0, pitches % 8 == 0.
+extern "C" int ym_ew_nhwc(int op, const void* a, int lda, const void* b, int ldb, const float* p0, const float* p1, int ldt,
+                          int toff, int rows_per_img, int act, void* out, int ldo, long long rows, int C, void* stream) {
+    YM_CHECK_ARG(out, "ym_ew_nhwc: null output");
+    YM_CHECK_ARG(C % 8 == 0 && ldo % 8 == 0 && (!a || lda % 8 == 0) && (!b || ldb % 8 == 0), "ym_ew_nhwc: multiples of 8");
+    YM_CHECK_ARG(op >= 0 && op <= 4, "ym_ew_nhwc: unknown op %d", op);
+    YM_CHECK_ARG((op != EW_SCALE_RES && op != EW_TOKEN_ACC) || (p0 && b), "ym_ew_nhwc: op %d needs p0 and b", op);
+    YM_CHECK_ARG((op != EW_GLU) || (a && b), "ym_ew_nhwc: GLU needs a and b");
+    YM_CHECK_ARG((op != EW_GELU) || a, "ym_ew_nhwc: GELU needs a");
+    YM_CHECK_ARG((op != EW_AFFINE) || (a && p0 && p1 && rows_per_img > 0), "ym_ew_nhwc: affine needs a, scale, shift, rows_per_img");
+    if (rows == 0) return YM_OK;
+    const long long total = rows * (C / 8);
+    long long nb = (total + 255) / 256;
+    if (nb > 148LL * 16) nb = 148LL * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+#define EW_LAUNCH(OP)                                                                                                      \
+    ew_kernel<OP><<<(int)nb, 256, 0, st>>>((const __half*)a, lda, (const __half*)b, ldb, p0, p1, ldt, toff, rows_per_img, \
+                                           act, (__half*)out, ldo, rows, C)
+    switch (op) {
+        case EW_SCALE_RES: EW_LAUNCH(EW_SCALE_RES); break;
+        case EW_TOKEN_ACC: EW_LAUNCH(EW_TOKEN_ACC); break;
+        case EW_GLU: EW_LAUNCH(EW_GLU); break;
+        case EW_GELU: EW_LAUNCH(EW_GELU); break;
+        default: EW_LAUNCH(EW_AFFINE); break;
+    }
+#undef EW_LAUNCH
+    YM_CHECK_LAUNCH("ew_nhwc");
+    return YM_OK;
+}

@@ -69,6 +69,19 @@ class PackCache:
         raise NotImplementedError
 
 
+def cached_f32(owner: nn.Module, name: str, t: torch.Tensor, shape=None) -> torch.Tensor:
+    """Contiguous fp32 copy of a small parameter (layer-scale, norm affine ...), rebuilt when the source changes."""
+    key = (t.data_ptr(), t._version, str(t.device))
+    slot = owner.__dict__.setdefault("_ym_f32", {})
+    hit = slot.get(name)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            v = t.detach().float().reshape(shape if shape is not None else t.shape).contiguous()
+        hit = (key, v)
+        slot[name] = hit
+    return hit[1]
+
+
 def require_eval(m: nn.Module):
     if m.training:
         raise RuntimeError(

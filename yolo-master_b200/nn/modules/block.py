@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ._base import require_eval, to_nchw, to_nhwc
+from ._base import cached_f32, require_eval, to_nchw, to_nhwc
 from .conv import Conv
 
 __all__ = ("Bottleneck", "C2f", "C3", "C3k", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA", "AAttn", "ABlock", "A2C2f")
@@ -266,12 +266,13 @@ class A2C2f(_NHWCBlock):
         )
 
     def fwd_nhwc(self, x, out=None):
-        if self.gamma is not None:
-            raise NotImplementedError("A2C2f(residual=True) (layer-scale gamma, L/X scales) is not on the B200 path yet")
         B, H, W, _ = x.shape
         c_, n = self.cv1.conv.out_channels, len(self.m)
         cat = ops.new_act(B, H, W, (1 + n) * c_, x.device)
         self.cv1.fwd_nhwc(x, out=cat[..., :c_])
         for j, m in enumerate(self.m):
             m.fwd_nhwc(cat[..., j * c_:(j + 1) * c_], out=cat[..., (j + 1) * c_:(j + 2) * c_])
+        if self.gamma is not None:      # x + gamma * y  (block.py:1877-1879)
+            y = self.cv2.fwd_nhwc(cat)
+            return ops.ew(ops.EW_SCALE_RES, a=x, b=y, p0=cached_f32(self, 'gamma', self.gamma, (-1,)), out=out)
         return self.cv2.fwd_nhwc(cat, out=out)

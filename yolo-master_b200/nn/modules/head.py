@@ -14,7 +14,23 @@ from ... import ops
 from ._base import require_eval, to_nhwc
 from .conv import Conv, DWConv, PlainConv2d
 
-__all__ = ("Detect",)
+__all__ = ("Detect", "DFL")
+
+
+class DFL(nn.Module):
+    """`DFL(c1=16)` (block.py:63-85): frozen 1x1 conv with weights 0..c1-1 = expectation over the softmaxed bins.
+    Only holds the state_dict key (`dfl.conv.weight`); the arithmetic is fused into `ym_detect_dense`."""
+
+    def __init__(self, c1=16):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, 1, 1, bias=False).requires_grad_(False)
+        self.conv.weight.data[:] = torch.arange(c1, dtype=torch.float).view(1, c1, 1, 1)
+        self.c1 = c1
+
+    def check_frozen(self):
+        w = self.conv.weight.detach().float().view(-1).cpu()
+        if not torch.equal(w, torch.arange(self.c1, dtype=torch.float)):
+            raise NotImplementedError("DFL: conv.weight differs from arange(reg_max); only the reference's frozen DFL is supported")
 
 
 class Detect(nn.Module):
@@ -51,7 +67,8 @@ class Detect(nn.Module):
                 for x in ch
             )
         )
-        self.dfl = nn.Identity()
+        self.dfl = DFL(self.reg_max) if self.reg_max > 1 else nn.Identity()
+        self._dfl_checked = None
         if end2end:
             self.one2one_cv2 = copy.deepcopy(self.cv2)
             self.one2one_cv3 = copy.deepcopy(self.cv3)
@@ -90,8 +107,13 @@ class Detect(nn.Module):
 
     def forward(self, x):
         require_eval(self)
-        if self.reg_max != 1:
-            raise NotImplementedError("Detect: DFL heads (reg_max > 1) are not on the B200 path (yolo26 uses reg_max=1)")
+        if self.reg_max > 1:
+            if self.end2end:
+                raise NotImplementedError("Detect: end2end top-k with DFL (reg_max > 1) is not on the B200 path")
+            ver = self.dfl.conv.weight._version
+            if self._dfl_checked != ver:          # one host read per weight version, never inside a captured forward
+                self.dfl.check_frozen()
+                self._dfl_checked = ver
         if self.agnostic_nms:
             raise NotImplementedError("Detect: agnostic_nms top-k is not on the B200 path")
         feats = [to_nhwc(f) for f in x]
@@ -102,7 +124,7 @@ class Detect(nn.Module):
         if self.end2end:
             y = ops.detect_topk(boxes, logits, strides, self.nc, self.max_det)
         else:
-            y = ops.detect_dense(boxes, logits, strides, self.nc, xyxy=self.xyxy)
+            y = ops.detect_dense(boxes, logits, strides, self.nc, xyxy=self.xyxy, reg_max=self.reg_max)
         if self.export:
             return y
         return y, {"boxes": boxes, "scores": logits, "feats": x}

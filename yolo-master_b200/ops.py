@@ -234,12 +234,13 @@ def detect_topk(boxes, logits, strides, nc, max_det=300, return_anchor=False):
     return (out, anc) if return_anchor else out
 
 
-def detect_dense(boxes, logits, strides, nc, xyxy):
+def detect_dense(boxes, logits, strides, nc, xyxy, reg_max=1):
+    """boxes[l]: fp32 (B,h,w,4*reg_max) (DFL bin logits when reg_max > 1); returns y fp32 (B, 4+nc, A)."""
     B = boxes[0].shape[0]
     A = sum(b.shape[1] * b.shape[2] for b in boxes)
     y = torch.empty((B, 4 + nc, A), dtype=torch.float32, device=boxes[0].device)
     nl, bp, cp, hs, ws, st = _level_arrays(boxes, logits, strides)
-    _lib.check(lib().ym_detect_dense(nl, bp, cp, hs, ws, st, B, nc, 1 if xyxy else 0, y.data_ptr(), _stream()),
+    _lib.check(lib().ym_detect_dense(nl, bp, cp, hs, ws, st, B, nc, reg_max, 1 if xyxy else 0, y.data_ptr(), _stream()),
                "ym_detect_dense")
     _count()
     return y
@@ -339,3 +340,27 @@ def esmoe_forward(x, pack, topk, dyn_thr, out=None):
                                   out.data_ptr(), pitch(out), B, HW, N, st), "ym_esmoe_combine")
     _count()
     return out, idx, w, probs
+
+
+EW_SCALE_RES, EW_TOKEN_ACC, EW_GLU, EW_GELU, EW_AFFINE = 0, 1, 2, 3, 4
+
+
+def _rows(t):
+    return t.shape[0] * t.shape[1] * t.shape[2]
+
+
+def ew(op, a=None, b=None, p0=None, p1=None, ldt=0, toff=0, rows_per_img=1, act=False, out=None):
+    """ym_ew_nhwc on (B,H,W,C) views; see include/ym_b200.h for the op table."""
+    ref = a if a is not None else b
+    B, H, W, Cc = ref.shape
+    if out is None:
+        out = new_act(B, H, W, Cc, ref.device)
+    for p in (p0, p1):
+        if p is not None and (p.dtype != torch.float32 or not p.is_contiguous()):
+            raise ValueError("ew: parameters must be contiguous fp32")
+    _lib.check(lib().ym_ew_nhwc(op, None if a is None else a.data_ptr(), 0 if a is None else pitch(a),
+                                None if b is None else b.data_ptr(), 0 if b is None else pitch(b),
+                                None if p0 is None else p0.data_ptr(), None if p1 is None else p1.data_ptr(), ldt, toff,
+                                rows_per_img, 1 if act else 0, out.data_ptr(), pitch(out), B * H * W, Cc, _stream()), "ym_ew_nhwc")
+    _count()
+    return out

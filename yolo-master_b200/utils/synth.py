@@ -30,6 +30,8 @@ def fill_state_dict_(sd: dict, seed: int = 0, conv_gain: float = 1.0) -> dict:
         t = sd[key]
         if not torch.is_tensor(t) or not t.is_floating_point() or t.numel() == 0:
             continue
+        if key.endswith("dfl.conv.weight"):   # frozen arange(reg_max) in the reference (block.py:73-76): not a free parameter
+            continue
         g = _gen(key, seed)
         shape = tuple(t.shape)
         head_cls = _DET_CLS.search(key) is not None   # Detect's last 1x1 (no norm after it): keep logits un-saturated
