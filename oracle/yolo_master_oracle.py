@@ -580,3 +580,307 @@ def forward(spec: dict, sd: dict, x: torch.Tensor, img_hw=None, return_layers: b
         ys[i] = x
         outs.append(x)
     return (x, ys) if return_layers else x
+
+
+# ======================================================================================================================
+# Mixture-of-Transformers (nn/modules/mot/*) and Mixture-of-Attention (nn/modules/moa/*): eval forward
+# ======================================================================================================================
+ROUTE_TAP = None   # tests set this to a dict to capture MoT / MoA router outputs by module path
+
+
+def _gn(sd, p, x, groups, eps=1e-5):
+    return F.group_norm(x, groups, sd[p + ".weight"], sd[p + ".bias"], eps)
+
+
+def _ln(sd, p, x, eps=1e-5):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], eps)
+
+
+def _sdpa(q, k, v, scale):
+    """F.scaled_dot_product_attention(q, k, v, scale=scale) (mot/experts.py:37-69, moa/heads.py:37-52), math form."""
+    return ((q @ k.transpose(-2, -1)) * scale).softmax(dim=-1) @ v
+
+
+def _pad_to_window(x, win):
+    """`_WindowTransformerExpert._pad_to_window` mot/experts.py:236-244 on NHWC (zero pad bottom/right)."""
+    _, H, W, _ = x.shape
+    ph, pw = (win - H % win) % win, (win - W % win) % win
+    return F.pad(x, (0, 0, 0, pw, 0, ph)) if (ph or pw) else x
+
+
+def _win_part(x, win):
+    """[B,H,W,C] -> [B*nH*nW, win*win, C]  mot/experts.py:246-251."""
+    B, H, W, C = x.shape
+    return x.view(B, H // win, win, W // win, win, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, win * win, C)
+
+
+def _win_rev(w, win, H, W):
+    """mot/experts.py:253-261."""
+    B = w.shape[0] // ((H // win) * (W // win))
+    return w.view(B, H // win, W // win, win, win, -1).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, -1)
+
+
+def mot_local_expert(sd, p, x, nh, local_window=0):
+    """`_LocalConvTransformerExpert.forward` mot/experts.py:122-171."""
+    B, C, H, W = x.shape
+    N, hd = H * W, C // nh
+    g = get_safe_groups(C, 8)
+    xn = _gn(sd, p + ".norm1", x, g)
+    qkv = _st(F.conv2d(F.conv2d(xn, _w(sd[p + ".dw_mix.weight"]), None, 1, 1, 1, C), _w(sd[p + ".qkv.weight"])))
+    q, k, v = qkv.split(C, dim=1)
+    v = _st(v + F.conv2d(v, _w(sd[p + ".pe.weight"]), None, 1, 3, 1, C))
+    scale = hd ** -0.5
+    if local_window > 0 and N > local_window ** 2:
+        win = local_window
+        qw, kw, vw = (_win_part(_pad_to_window(t.permute(0, 2, 3, 1), win), win) for t in (q, k, v))
+        Hp, Wp = H + (win - H % win) % win, W + (win - W % win) % win
+        qw, kw, vw = (t.reshape(-1, win * win, nh, hd).permute(0, 2, 1, 3) for t in (qw, kw, vw))
+        o = _sdpa(qw, kw, vw, scale).transpose(1, 2).reshape(-1, win * win, C)
+        o = _win_rev(o, win, Hp, Wp)[:, :H, :W, :].permute(0, 3, 1, 2)
+    else:
+        th = lambda t: t.reshape(B, nh, hd, N).transpose(2, 3)
+        o = _sdpa(th(q), th(k), th(v), scale).transpose(2, 3).reshape(B, C, H, W)
+    x = _st(x + sd[p + ".ls1"] * F.conv2d(_st(o), _w(sd[p + ".proj.weight"])))
+    xn = _gn(sd, p + ".norm2", x, g)
+    ffn = _st(torch.sigmoid(conv_block(sd, p + ".ffn_gate.0", xn)) * conv_block(sd, p + ".ffn_val", xn))
+    return _st(x + sd[p + ".ls2"] * conv_block(sd, p + ".ffn_out", ffn, act=False))
+
+
+def mot_window_expert(sd, p, x, nh, win=7, shift=0):
+    """`_WindowTransformerExpert.forward` mot/experts.py:263-315 (pad before LayerNorm, roll without mask)."""
+    B, C, H0, W0 = x.shape
+    hd = C // nh
+    x = _pad_to_window(x.permute(0, 2, 3, 1), win)
+    H, W = x.shape[1:3]
+    if shift:
+        x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
+    w = _win_part(_ln(sd, p + ".norm1", x), win)
+    Bw = w.shape[0]
+    qkv = _st(F.linear(w, _w(sd[p + ".qkv.weight"]))).reshape(Bw, win * win, 3, nh, hd).permute(2, 0, 3, 1, 4)
+    o = _sdpa(qkv[0], qkv[1], qkv[2], hd ** -0.5).transpose(1, 2).reshape(Bw, win * win, C)
+    o = _win_rev(F.linear(_st(o), _w(sd[p + ".proj.weight"])), win, H, W)
+    if shift:
+        o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+        x = torch.roll(x, shifts=(shift, shift), dims=(1, 2))
+    x = _st(x[:, :H0, :W0] + sd[p + ".ls1"] * o[:, :H0, :W0])
+    h = _st(F.gelu(F.linear(_ln(sd, p + ".norm2", x), _w(sd[p + ".ffn.0.weight"]), sd[p + ".ffn.0.bias"])))
+    x = _st(x + sd[p + ".ls2"] * F.linear(h, _w(sd[p + ".ffn.3.weight"]), sd[p + ".ffn.3.bias"]))
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def mot_deform_expert(sd, p, x, nh, n_points=4, align_corners=True):
+    """`_DeformableTransformerExpert.forward/_deform_attn` mot/experts.py:394-496."""
+    B, C, H, W = x.shape
+    N, hd = H * W, C // nh
+    xf = x.flatten(2).transpose(1, 2)
+    xn = _ln(sd, p + ".norm1", xf)
+    q = _st(F.linear(xn, _w(sd[p + ".q_proj.weight"])))
+    off = F.linear(q, sd[p + ".offset_proj.weight"], sd[p + ".offset_proj.bias"]).reshape(B, N, nh, n_points, 2).tanh()
+    aw = F.linear(q, sd[p + ".attn_proj.weight"], sd[p + ".attn_proj.bias"]).reshape(B, N, nh, n_points).softmax(-1)
+    idx = torch.arange(N)
+    row = (idx // W).float() / max(H - 1, 1) * 2 - 1
+    col = (idx % W).float() / max(W - 1, 1) * 2 - 1
+    ref = torch.stack([col, row], -1)[None, :, None, None, :]
+    locs = (ref + off * 0.25).clamp(-1.0, 1.0)
+    v = _st(F.linear(xn, _w(sd[p + ".v_proj.weight"]))).permute(0, 2, 1).reshape(B * nh, hd, H, W)
+    samp = F.grid_sample(v, locs.permute(0, 2, 1, 3, 4).reshape(B * nh, N, n_points, 2), mode="bilinear",
+                         padding_mode="zeros", align_corners=align_corners)
+    samp = samp.reshape(B, nh, hd, N, n_points).permute(0, 3, 1, 4, 2)
+    o = _st((aw.unsqueeze(-1) * samp).sum(3).reshape(B, N, C))
+    xf = _st(xf + sd[p + ".ls1"] * F.linear(o, _w(sd[p + ".out_proj.weight"])))
+    h = _st(F.gelu(F.linear(_ln(sd, p + ".norm2", xf), _w(sd[p + ".ffn.0.weight"]), sd[p + ".ffn.0.bias"])))
+    xf = _st(xf + sd[p + ".ls2"] * F.linear(h, _w(sd[p + ".ffn.3.weight"]), sd[p + ".ffn.3.bias"]))
+    return xf.transpose(1, 2).reshape(B, C, H, W)
+
+
+def mot_router(sd, p, x, top_k, num_experts=3):
+    """`_MoTRouter.forward` mot/router.py:211-291 (spatial, fp32): returns dense weights [B,E,H,W], indices [B,k,H,W], logits."""
+    hidden = sd[p + ".router.0.weight"].shape[0]
+    h = F.conv2d(x.float(), sd[p + ".router.0.weight"])
+    h = F.silu(_gn(sd, p + ".router.1", h, get_safe_groups(hidden, 4)))
+    logits = F.conv2d(h, sd[p + ".router.3.weight"], sd[p + ".router.3.bias"])
+    w = F.softmax(logits / sd[p + ".temperature"].float(), dim=1)
+    if top_k < num_experts:
+        vals, idx = w.topk(top_k, dim=1)
+        vals = vals / vals.sum(1, keepdim=True).clamp_min(1e-6)
+        w = torch.zeros_like(w).scatter_(1, idx, vals)
+    else:
+        idx = torch.arange(num_experts).view(1, -1, 1, 1).expand(x.shape[0], -1, x.shape[2], x.shape[3])
+    return w, idx, logits
+
+
+def mot_block(sd, p, x, nh, top_k=2, win=7, n_points=4, shift=False, local_window=0, return_route=False):
+    """`MoTBlock.forward` mot/block.py:401-415 with the eval sample-sparse blend :347-364."""
+    w, idx, logits = mot_router(sd, p + ".router", x, top_k)
+    if ROUTE_TAP is not None:
+        ROUTE_TAP[p + ".router"] = (w, idx)
+    experts = (lambda t: mot_local_expert(sd, p + ".experts.0", t, nh, local_window),
+               lambda t: mot_window_expert(sd, p + ".experts.1", t, nh, win, win // 2 if shift else 0),
+               lambda t: mot_deform_expert(sd, p + ".experts.2", t, nh, n_points))
+    out = torch.zeros_like(x)
+    for e, fn in enumerate(experts):
+        active = (idx == e).reshape(x.shape[0], -1).any(1)
+        b = torch.nonzero(active, as_tuple=True)[0]
+        if b.numel():
+            out[b] = _st(out[b] + fn(x[b]) * _st(w[b, e:e + 1]))
+    C = x.shape[1]
+    o = _st(_gn(sd, p + ".out_norm", F.conv2d(out, _w(sd[p + ".out_proj.weight"])), get_safe_groups(C, 8)) + x)
+    return (o, w, idx, logits) if return_route else o
+
+
+def c2f_heads_mot(dim, num_heads):
+    """Head clamping of `C2fMoT.__init__` mot/wrappers.py:74-84."""
+    h = num_heads
+    while h > 1 and (dim % h != 0 or dim // h < 8):
+        h -= 1
+    return max(1, h)
+
+
+def layer_c2f_mot(sd, p, x, c1, c2, n=1, num_heads=6, top_k=2, window_size=7, n_points=4, mlp_ratio=2.0, temperature=1.0,
+                  balance_loss_coeff=0.01, e=0.5, *unused):
+    """`C2fMoT.forward` mot/wrappers.py:116-147."""
+    c = int(c2 * e)
+    nh = c2f_heads_mot(c, num_heads)
+    y = list(conv_block(sd, p + ".cv1", x).chunk(2, 1))
+    for j in range(n):
+        y.append(mot_block(sd, f"{p}.m.{j}", y[-1], nh, top_k, window_size, n_points, shift=bool(j % 2)))
+    return conv_block(sd, p + ".cv2", torch.cat(y, 1))
+
+
+# ---- MoA -------------------------------------------------------------------------------------------------------------
+def moa_router(sd, p, x, temperature):
+    """`_MoARouter.forward` moa/router.py:50-62 (fp32 soft routing over the 3 head groups)."""
+    hidden = sd[p + ".router.0.weight"].shape[0]
+    h = F.silu(_gn(sd, p + ".router.1", F.conv2d(x.float(), sd[p + ".router.0.weight"]), get_safe_groups(hidden, 4)))
+    logits = F.conv2d(h, sd[p + ".router.3.weight"], sd[p + ".router.3.bias"]) / max(temperature, 0.1)
+    return F.softmax(logits, dim=1)
+
+
+def _window_flash(q, k, v, scale, win, H, W):
+    """`_window_flash_attn` moa/heads.py:88-121 on [B,nh,N,hd] (zero pad, no mask)."""
+    B, nh, N, hd = q.shape
+    win = max(1, min(int(win), H, W))
+    ph, pw = (win - H % win) % win, (win - W % win) % win
+
+    def part(t):
+        t = F.pad(t.reshape(B, nh, H, W, hd), (0, 0, 0, pw, 0, ph))
+        Hp, Wp = t.shape[2:4]
+        return t.reshape(B, nh, Hp // win, win, Wp // win, win, hd).permute(0, 1, 2, 4, 3, 5, 6).reshape(-1, win * win, hd)
+
+    Hp, Wp = H + ph, W + pw
+    o = _sdpa(part(q), part(k), part(v), scale)
+    o = o.reshape(B, nh, Hp // win, Wp // win, win, win, hd).permute(0, 1, 2, 4, 3, 5, 6).reshape(B, nh, Hp, Wp, hd)
+    return o[:, :, :H, :W].reshape(B, nh, N, hd)
+
+
+def moa_local_head(sd, p, x, nh, hd, win=7):
+    """`_LocalAttnHead.forward` moa/heads.py:140-159."""
+    B, C, H, W = x.shape
+    N, inner = H * W, nh * hd
+    qkv = _st(F.conv2d(F.conv2d(x, _w(sd[p + ".qkv_dw.weight"]), None, 1, 1, 1, C), _w(sd[p + ".qkv_pw.weight"])))
+    q, k, v = qkv.split(inner, 1)
+    v = _st(v + F.conv2d(v, _w(sd[p + ".pe.weight"]), None, 1, 3, 1, inner))
+    th = lambda t: t.flatten(2).view(B, nh, hd, N).transpose(2, 3)
+    o = _window_flash(th(q), th(k), th(v), hd ** -0.5, win, H, W).transpose(2, 3).reshape(B, inner, H, W)
+    return _st(_gn(sd, p + ".norm", F.conv2d(_st(o), _w(sd[p + ".proj.weight"])), get_safe_groups(C, 8)))
+
+
+def moa_region_head(sd, p, x, nh, hd, pool_stride=2, max_kv=4096):
+    """`_RegionalAttnHead.forward` moa/heads.py:206-246."""
+    B, C, H, W = x.shape
+    inner = nh * hd
+    if min(H, W) <= 1:
+        kv = F.conv2d(x, _w(sd[p + ".kv_proj.weight"]))
+    else:
+        s = pool_stride
+        if max_kv is not None:
+            while max(1, H // s) * max(1, W // s) > max_kv:
+                s *= 2
+        kv = F.conv2d(_st(F.adaptive_avg_pool2d(x, (max(1, H // s), max(1, W // s)))), _w(sd[p + ".kv_proj.weight"]))
+    kv = _st(kv)
+    M = kv.shape[2] * kv.shape[3]
+    k, v = kv.split(inner, 1)
+    k = k.flatten(2).view(B, nh, hd, M).transpose(2, 3)
+    v = v.flatten(2).view(B, nh, hd, M).transpose(2, 3)
+    q = _st(F.conv2d(x, _w(sd[p + ".q_proj.weight"]))).flatten(2).view(B, nh, hd, H * W).transpose(2, 3)
+    o = _sdpa(q, k, v, hd ** -0.5).transpose(2, 3).reshape(B, inner, H, W)
+    return _st(_gn(sd, p + ".norm", F.conv2d(_st(o), _w(sd[p + ".proj.weight"])), get_safe_groups(C, 8)))
+
+
+def _linear_attn(q, k, v, rf, limit=1e4, eps=1e-6):
+    """`_GlobalAttnHead._linear_attn` moa/heads.py:318-352 (fp32, ReLU features on the persistent RF matrix)."""
+    B, nh, N, hd = q.shape
+    nb = rf.shape[0]
+    s = nb ** -0.5
+    qf = (F.relu(q @ rf.T * s) + eps).clamp(max=limit).reshape(B * nh, N, nb)
+    kf = (F.relu(k @ rf.T * s) + eps).clamp(max=limit).reshape(B * nh, N, nb)
+    vf = v.reshape(B * nh, N, hd)
+    kv = kf.transpose(1, 2) @ vf
+    numer = (qf @ kv).clamp(-limit, limit)
+    denom = (qf @ kf.sum(1).unsqueeze(-1)).clamp(min=eps)
+    return (numer / denom).reshape(B, nh, N, hd)
+
+
+def moa_global_head(sd, p, x, nh, hd, threshold=512, blend=64):
+    """`_GlobalAttnHead.forward` moa/heads.py:354-380."""
+    B, C, H, W = x.shape
+    N, inner = H * W, nh * hd
+    qkv = _st(F.conv2d(x, _w(sd[p + ".qkv.weight"]))).flatten(2)
+    th = lambda t: t.view(B, nh, hd, N).transpose(2, 3)
+    q, k, v = (th(t) for t in qkv.split(inner, 1))
+    rf = sd[p + "._rf_matrix"]
+    if N <= threshold:
+        o = _sdpa(q, k, v, hd ** -0.5)
+        if N > threshold - blend:
+            a = (N - (threshold - blend)) / blend
+            o = (1 - a) * o + a * _linear_attn(q, k, v, rf)
+    else:
+        o = _linear_attn(q, k, v, rf)
+    o = o.transpose(2, 3).reshape(B, inner, H, W)
+    return _st(_gn(sd, p + ".norm", F.conv2d(_st(o), _w(sd[p + ".proj.weight"])), get_safe_groups(C, 8)))
+
+
+def moa_block(sd, p, x, num_heads, temperature=1.0, shortcut=True, win=7, max_kv=4096, return_route=False):
+    """`MoABlock.forward` moa/block.py:167-278 (dense soft mixture of the three head groups, eval, sparse_inference=False)."""
+    C = x.shape[1]
+    hd, hpg = max(C // num_heads, 16), num_heads // 3
+    w = moa_router(sd, p + ".router", x, temperature)
+    if ROUTE_TAP is not None:
+        ROUTE_TAP[p + ".router"] = (w,)
+    mixed = _st(w[:, 0:1]) * moa_local_head(sd, p + ".local_head", x, hpg, hd, win)
+    mixed = mixed + _st(w[:, 1:2]) * moa_region_head(sd, p + ".region_head", x, hpg, hd, 2, max_kv)
+    mixed = _st(mixed + _st(w[:, 2:3]) * moa_global_head(sd, p + ".global_head", x, hpg, hd))
+    mixed = conv_block(sd, p + ".fusion", mixed, act=False)
+    if shortcut:
+        x = _st(x + sd[p + ".ls_attn"] * mixed)
+        x = _st(x + sd[p + ".ls_ffn"] * conv_block(sd, p + ".ffn.1", conv_block(sd, p + ".ffn.0", x), act=False))
+    else:
+        x = _st(sd[p + ".ls_attn"] * mixed)
+        x = _st(sd[p + ".ls_ffn"] * conv_block(sd, p + ".ffn.1", conv_block(sd, p + ".ffn.0", x), act=False))
+    return (x, w) if return_route else x
+
+
+def c2f_heads_moa(c, num_heads):
+    """Head adjustment of `C2fMoA.__init__` moa/wrappers.py:96-121."""
+    h = num_heads
+    while h % 3 != 0:
+        h += 1
+    while c // h < 16 and h > 3:
+        h -= 3
+    return max(h, 3)
+
+
+def layer_c2f_moa(sd, p, x, c1, c2, n=1, num_heads=6, mlp_ratio=2.0, temperature=1.0, shortcut=True, e=0.5,
+                  aux_loss_coeff=0.01, local_window_size=7, sequential_heads=True, regional_max_kv_tokens=4096, *unused):
+    """`C2fMoA.forward` moa/wrappers.py:147-186."""
+    c = int(c2 * e)
+    nh = c2f_heads_moa(c, num_heads)
+    y = list(conv_block(sd, p + ".cv1", x).chunk(2, 1))
+    for j in range(n):
+        y.append(moa_block(sd, f"{p}.m.{j}", y[-1], nh, temperature, shortcut, local_window_size, regional_max_kv_tokens))
+    return conv_block(sd, p + ".cv2", torch.cat(y, 1))
+
+
+_LAYER_FN.update({"C2fMoT": layer_c2f_mot, "C2fMoA": layer_c2f_moa})
+_MIX_BASE.update({"C2fMoT", "C2fMoA"})
+_MIX_REPEAT.update({"C2fMoT", "C2fMoA"})

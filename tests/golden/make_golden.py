@@ -100,7 +100,27 @@ EXTRA_MODELS = {
     # name: (cfg, kept layers, {tag: (B, H, W, seed)})
     "yolo-master-n-v0": (V0 + "yolo-master-n.yaml", [3, 6, 8, 9, 11, 12, 18, 21, 24], {"b2_128": (2, 128, 128, 3), "b1_64": (1, 64, 64, 4)}),
     "yolo-master-l-v0": (V0 + "yolo-master-l.yaml", [8, 11, 12, 24], {"b1_64": (1, 64, 64, 5)}),
+    # MoT + MoA neck (C2fMoT x3, C2fMoA x1), end2end head; "-s" = the same YAML with an injected s scale
+    "yolo26-master-moa-mot-n": ("/root/reference/ultralytics/cfg/models/26/yolo26-master-moa-mot-n.yaml", [6, 10, 13, 16, 19, 22],
+                                {"b2_224": (2, 224, 224, 6), "b1_96": (1, 96, 96, 7)}),
+    "yolo26-master-moa-mot-s": (("/root/reference/ultralytics/cfg/models/26/yolo26-master-moa-mot-n.yaml", "s", [0.50, 0.50, 1024]),
+                                [13, 16, 19, 22], {"b1_160": (1, 160, 160, 8)}),
 }
+
+
+def _route_hooks(m, routes):
+    """Capture MoT (dense weights, top-k indices) and MoA (soft weights) router outputs by module name."""
+    from ultralytics.nn.modules.moa.router import _MoARouter
+    from ultralytics.nn.modules.mot.router import _MoTRouter
+    hooks = []
+    for name, mod in m.named_modules():
+        if isinstance(mod, _MoTRouter):
+            hooks.append(mod.register_forward_hook(
+                lambda mod, i, o, n=name: routes.__setitem__(n, (o[0].float().clone(), o[1].to(torch.int8).clone()))))
+        elif isinstance(mod, _MoARouter):
+            hooks.append(mod.register_forward_hook(
+                lambda mod, i, o, n=name: routes.__setitem__(n, ((o[0] if isinstance(o, tuple) else o).float().clone(),))))
+    return hooks
 
 
 def extra_model_golden(name):
@@ -108,19 +128,32 @@ def extra_model_golden(name):
     activations, raw head outputs and the dense (B, 4+nc, A) prediction of the REAL reference."""
     cfg, keep, cases = EXTRA_MODELS[name]
     torch.manual_seed(0)
+    if isinstance(cfg, tuple):      # (yaml, scale key, scale constants): inject a scale without editing the YAML file
+        from ultralytics.nn.tasks import yaml_model_load
+        d = yaml_model_load(cfg[0])
+        d["scales"][cfg[1]] = cfg[2]
+        d["scale"] = cfg[1]
+        cfg = d
     m = calibrated_reference(0, cfg)
     sd = m.state_dict()
     json.dump({k: [list(v.shape), str(v.dtype)] for k, v in sd.items()}, open(f"{OUT}/{name}.keys.json", "w"))
-    stats = {k: v.clone() for k, v in sd.items() if k.endswith("running_mean") or k.endswith("running_var")}
+    # calibrated BatchNorm statistics + the constants the key-seeded generator leaves alone (router temperature buffers,
+    # the frozen DFL arange): everything a test needs besides key names to rebuild the exact state_dict
+    stats = {k: v.clone() for k, v in sd.items()
+             if k.endswith(("running_mean", "running_var", ".temperature", "dfl.conv.weight"))}
     torch.save(stats, f"{OUT}/{name}.bnstats.pt")
     gold = {"cases": {}}
     for tag, (B, H, W, seed) in cases.items():
         x = synth_images(B, H, W, seed)
+        routes = {}
+        hooks = _route_hooks(m, routes)
         y, preds, feats, _ = run(m, x)
+        for h in hooks:
+            h.remove()
         pr = preds["one2one"] if "one2one" in preds else preds
         gold["cases"][tag] = {"B": B, "H": H, "W": W, "seed": seed, "final": y.clone().half() if name.endswith("l-v0") else y.clone(),
                               "layers": {i: feats[i].clone() for i in keep},
-                              "head_boxes": pr["boxes"].clone(), "head_scores": pr["scores"].clone()}
+                              "head_boxes": pr["boxes"].clone(), "head_scores": pr["scores"].clone(), "routes": routes}
         print(name, tag, "final", tuple(y.shape), "max score", float(y[:, 4:].max()))
     torch.save(gold, f"{OUT}/{name}.golden.pt")
     for f in sorted(os.listdir(OUT)):

@@ -50,6 +50,8 @@ def fill_state_dict_(sd: dict, seed: int = 0, conv_gain: float = 1.0) -> dict:
             v = 0.5 + torch.rand(shape, generator=g)
         elif key.endswith("running_mean"):
             v = 0.2 * torch.randn(shape, generator=g)
+        elif key.rsplit(".", 1)[-1] in ("ls1", "ls2", "ls_attn", "ls_ffn"):   # layer-scale (init 0.1 in the reference)
+            v = 0.05 + 0.15 * torch.rand(shape, generator=g)
         elif key.endswith(".gamma"):
             v = 0.005 + 0.015 * torch.rand(shape, generator=g)
         elif key.endswith("weight"):  # norm scale
