@@ -108,12 +108,63 @@ int ym_detect_dense(int nl, const void* const* box, const void* const* cls, cons
  *   op 0  out = a + chan[c]*b            A2C2f layer-scale `x + gamma*y` block.py:1879; ls1/ls2 mot/experts.py:165,170;
  *                                        ls_attn/ls_ffn moa/block.py:271-273                        (p0 = chan fp32[C])
  *   op 1  out = a + tok[row*ldt+toff]*b  per-token routed accumulation mot/block.py:347-364, moa/block.py:232-244
- *                                                                                                   (p0 = tok fp32)
  *   op 2  out = sigmoid(a)*b             GLU gate mot/experts.py:168
  *   op 3  out = gelu(a)                  exact (erf) nn.GELU mot/experts.py:225,365
- *   op 4  out = [silu](a*sc[img,c] + sh[img,c]) + b   GroupNorm apply (img = row / rows_per_img; p0 = sc, p1 = sh fp32[imgs*C]) */
-int ym_ew_nhwc(int op, const void* a, int lda, const void* b, int ldb, const float* p0, const float* p1, int ldt, int toff,
-               int rows_per_img, int act, void* out, int ldo, long long rows, int C, void* stream);
+ *   op 4  out = tok * [silu](a*sc[img,c] + sh[img,c]) + b      GroupNorm apply (+ routed weight + accumulate);
+ *                                        img = row / rows_per_img; p0 = sc, p1 = sh fp32[imgs*C]; tok NULL = 1
+ *   op 5  out = t*a + (1-t)*b            scalar blend, t = p0[0] (moa/heads.py:371-375)
+ * tok: fp32 per-token weights [rows*ldt] read at column toff. */
+int ym_ew_nhwc(int op, const void* a, int lda, const void* b, int ldb, const float* p0, const float* p1, const float* tok,
+               int ldt, int toff, int rows_per_img, int act, void* out, int ldo, long long rows, int C, void* stream);
+
+/* ---- Mixture-of-Transformers / Mixture-of-Attention neck blocks (nn/modules/mot/*, nn/modules/moa/*) -------------------
+ * GroupNorm statistics -> per-(image, channel) affine (scale = rstd*gamma, shift = beta - mean*rstd*gamma) consumed by
+ * ym_ew_nhwc op 4.  Replaces nn.GroupNorm in mot/experts.py:99-100, mot/block.py:145, mot/router.py:109, moa/heads.py:137,203,284,
+ * moa/router.py:40.  x: fp16 (x_f32=0) or fp32 (x_f32=1) [B][HW][ld]; scale/shift fp32 [B][C]. */
+int ym_groupnorm_stats(const void* x, int x_f32, int ld, int B, int HW, int C, int G, float eps, const float* gamma,
+                       const float* beta, float* scale, float* shift, void* stream);
+
+/* nn.LayerNorm(C) per token row (mot/experts.py:215-216,355-356). */
+int ym_layernorm_nhwc(const void* x, int ldx, const float* gamma, const float* beta, float eps, void* out, int ldo,
+                      long long rows, int C, void* stream);
+
+/* softmax(q k^T * scale) v for small heads (padded head_dim hdp in 8/16/24/32), one query row per thread.
+ * q rows [batch*Nq][ldq], k/v rows [batch*Nkv][ld*]; head h = channels [h*hdp, (h+1)*hdp) of each pointer.
+ * Replaces F.scaled_dot_product_attention in _LocalConvTransformerExpert (global branch) mot/experts.py:159,
+ * _RegionalAttnHead moa/heads.py:243 (Nkv = pooled tokens), _GlobalAttnHead exact branch moa/heads.py:369. */
+int ym_attn_small(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int batch, int heads, int hdp,
+                  int Nq, int Nkv, float scale, void* out, int ldo, void* stream);
+
+/* Window attention over win x win tokens (win <= 8) with the reference's pad -> roll(-shift) -> partition token mapping done
+ * by index arithmetic (no copies); padding tokens carry padk/padv (NULL = zeros; the Window expert pads BEFORE LayerNorm so
+ * its padding tokens are qkv(LayerNorm(0)) = W_qkv . beta).  Outputs of padding queries are cropped by the reference and are
+ * never computed.  Replaces _WindowTransformerExpert.forward mot/experts.py:270-303, the windowed branch of the LocalConv
+ * expert :137-157 and _window_flash_attn moa/heads.py:88-121. */
+int ym_attn_window(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int B, int H, int W, int heads,
+                   int hdp, int win, int shift, const void* padq, const void* padk, const void* padv, float scale, void* out,
+                   int ldo, void* stream);
+
+/* Deformable sampling + point softmax (_DeformableTransformerExpert._deform_attn mot/experts.py:416-475).
+ * oa fp32 [rows][ldoa] = [offset logits (head, point, xy) | attention logits (head, point)]; v fp16 [B,H,W,heads*hd]. */
+int ym_deform_sample(const float* oa, int ldoa, const void* v, int ldv, int B, int H, int W, int heads, int hd, int np,
+                     int align_corners, void* out, int ldo, void* stream);
+
+/* Per-token router: 1x1 (C->HID) -> GroupNorm(G) -> SiLU -> 1x1 (HID->E)+b -> softmax(/T) -> [top-k, renormalise, scatter].
+ * _MoTRouter mot/router.py:211-291 (topk < E, temperature = device buffer temp_dev) and _MoARouter moa/router.py:50-62
+ * (topk == E, host temperature).  fp32 throughout.  weights fp32 [B*HW][E] dense (zeros off the top-k); idx int32 [B*HW][topk]
+ * (nullable).  scratch: ym_token_router_scratch_floats() floats. */
+long long ym_token_router_scratch_floats(int B, int HW, int HID);
+int ym_token_router(const void* x, int ldx, int B, int HW, int C, const float* w1, int HID, int G, const float* gn_w,
+                    const float* gn_b, float gn_eps, const float* w2, const float* b2, int E, int topk, const float* temp_dev,
+                    float temp, float* weights, int* idx, float* scratch, void* stream);
+
+/* Performer ReLU-feature linear attention of _GlobalAttnHead._linear_attn moa/heads.py:318-352 (fp32): rf fp32 [nb][hd]. */
+long long ym_linear_attn_scratch_floats(int batch, int heads, int hdp, int N);
+int ym_linear_attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int batch, int heads, int hdp, int hd,
+                   int nb, int N, const float* rf, float eps, float limit, float* scratch, void* out, int ldo, void* stream);
+
+/* F.adaptive_avg_pool2d (moa/heads.py:224). */
+int ym_adaptive_avgpool_nhwc(const void* x, int ldx, int B, int H, int W, int C, int h, int w, void* out, int ldo, void* stream);
 
 /* ES_MOE (moe/modules.py:410-741, eval sparse path) on four entry points; the module is router -> per-expert depthwise k x k
  * on the images that retained the expert -> grouped pointwise GEMM (+folded BN, SiLU, routing weight) -> sum + BN + SiLU.

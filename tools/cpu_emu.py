@@ -1,0 +1,251 @@
+"""DEV TOOL (never imported by the product): torch-CPU emulation of the C-ABI semantics of the MoT / MoA ops, monkey-patched
+over `yolo_master_b200.ops` so that the HOST wiring of the modules (weight packing, slicing, folding, op order) can be checked
+against the oracle in the GPU-less build container.  The kernels themselves are verified on the GPU by tests/test_gpu_mot.py.
+
+    python tools/cpu_emu.py
+"""
+import math
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import yolo_master_oracle as O  # noqa: E402
+from yolo_master_b200 import ops  # noqa: E402
+from yolo_master_b200.nn.modules import _base, block, conv, moa, mot  # noqa: E402
+from yolo_master_b200.utils.synth import fill_state_dict_  # noqa: E402
+
+
+def _out(y, out, dtype=torch.float16):
+    y = y.to(dtype)
+    if out is None:
+        return y.contiguous()
+    out.copy_(y)
+    return out
+
+
+def conv2d(x, w_packed, bias, Cout, KH, KW, stride, pad, act, out=None, res=None, out_f32=False):
+    B, H, W, Cin = x.shape
+    w = w_packed.float()[:, :KH * KW * Cin].reshape(Cout, KH, KW, Cin).permute(0, 3, 1, 2)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None if bias is None else bias.float(), stride, pad)
+    if act:
+        y = F.silu(y)
+    y = y.permute(0, 2, 3, 1)
+    if res is not None:
+        y = y + res.float()
+    return _out(y, out, torch.float32 if out_f32 else torch.float16)
+
+
+def dwconv(x, w_taps, bias, ksize, act, C_out, grp_w=None, grp_stride=None, grp_off=0, add=None, out=None):
+    assert grp_w is None or (grp_w == C_out and grp_off == 0)
+    w = w_taps.float().t().reshape(C_out, 1, ksize, ksize)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None if bias is None else bias.float(), 1, ksize // 2, 1, C_out)
+    if act:
+        y = F.silu(y)
+    y = y.permute(0, 2, 3, 1)
+    if add is not None:
+        y = y + add.float()
+    return _out(y, out)
+
+
+def ew(op, a=None, b=None, p0=None, p1=None, ldt=0, toff=0, rows_per_img=1, act=False, out=None, tok=None):
+    ref = a if a is not None else b
+    B, H, W, C = ref.shape
+    fa = torch.zeros(ref.shape) if a is None else a.float()
+    fb = torch.zeros(ref.shape) if b is None else b.float()
+    tw = None if tok is None else tok.view(B, H, W, ldt)[..., toff:toff + 1]
+    if op == ops.EW_SCALE_RES:
+        y = fa + p0.view(1, 1, 1, C) * fb
+    elif op == ops.EW_TOKEN_ACC:
+        y = fa + tw * fb
+    elif op == ops.EW_GLU:
+        y = torch.sigmoid(fa) * fb
+    elif op == ops.EW_GELU:
+        y = F.gelu(fa)
+    elif op == ops.EW_LERP:
+        y = p0[0] * fa + (1 - p0[0]) * fb
+    else:
+        assert rows_per_img == H * W
+        v = fa * p0.view(B, 1, 1, C) + p1.view(B, 1, 1, C)
+        if act:
+            v = F.silu(v)
+        y = (v if tw is None else tw * v) + fb
+    return _out(y, out)
+
+
+def groupnorm_stats(x, G, gamma, beta, eps=1e-5):
+    B, H, W, C = x.shape
+    xf = x.float().reshape(B, H * W, G, C // G)
+    mean = xf.mean((1, 3))
+    var = xf.var((1, 3), unbiased=False)
+    rstd = (var + eps).rsqrt()
+    sc = rstd.repeat_interleave(C // G, 1) * gamma
+    sh = beta - mean.repeat_interleave(C // G, 1) * sc
+    return sc.contiguous(), sh.contiguous()
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    return _out(F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps), out)
+
+
+def _h(t, nh, hdp):
+    B, H, W, _ = t.shape
+    return t.float().reshape(B, H * W, nh, hdp).permute(0, 2, 1, 3)
+
+
+def attn_small(q, k, v, heads, hdp, scale, out=None):
+    B, H, W, _ = q.shape
+    o = O._sdpa(_h(q, heads, hdp), _h(k, heads, hdp), _h(v, heads, hdp), scale)
+    return _out(o.permute(0, 2, 1, 3).reshape(B, H, W, heads * hdp), out)
+
+
+def attn_window(q, k, v, heads, hdp, win, shift, scale, padk=None, padv=None, out=None):
+    B, H, W, C = q.shape
+    Hp, Wp = math.ceil(H / win) * win, math.ceil(W / win) * win
+
+    def prep(t, pad):
+        full = (torch.zeros(C) if pad is None else pad.float()).view(1, 1, 1, C).expand(B, Hp, Wp, C).clone()
+        full[:, :H, :W] = t.float()
+        if shift:
+            full = torch.roll(full, (-shift, -shift), (1, 2))
+        return O._win_part(full, win).reshape(-1, win * win, heads, hdp).permute(0, 2, 1, 3)
+
+    o = O._sdpa(prep(q, None), prep(k, padk), prep(v, padv), scale).transpose(1, 2).reshape(-1, win * win, C)
+    o = O._win_rev(o, win, Hp, Wp)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    return _out(o[:, :H, :W], out)
+
+
+def deform_sample(oa, v, heads, hd, n_points, align_corners=True, out=None):
+    B, H, W, C = v.shape
+    N = H * W
+    off = oa[..., :heads * n_points * 2].reshape(B, N, heads, n_points, 2).tanh()
+    aw = oa[..., heads * n_points * 2:].reshape(B, N, heads, n_points).softmax(-1)
+    idx = torch.arange(N)
+    ref = torch.stack([(idx % W).float() / max(W - 1, 1) * 2 - 1, (idx // W).float() / max(H - 1, 1) * 2 - 1], -1)[None, :, None, None, :]
+    locs = (ref + off * 0.25).clamp(-1, 1)
+    v4 = v.float().reshape(B, N, heads, hd).permute(0, 2, 3, 1).reshape(B * heads, hd, H, W)
+    samp = F.grid_sample(v4, locs.permute(0, 2, 1, 3, 4).reshape(B * heads, N, n_points, 2), mode="bilinear", padding_mode="zeros",
+                         align_corners=align_corners)
+    o = (aw.unsqueeze(-1) * samp.reshape(B, heads, hd, N, n_points).permute(0, 3, 1, 4, 2)).sum(3)
+    return _out(o.reshape(B, H, W, C), out)
+
+
+def token_router(x, pk, topk, temp_dev=None, temp=1.0, want_idx=True):
+    B, H, W, C = x.shape
+    h = x.float().reshape(B, H * W, C) @ pk["w1"].t()
+    hid = h.shape[-1]
+    hn = F.group_norm(h.transpose(1, 2), pk["G"], pk["gn_w"], pk["gn_b"], 1e-5).transpose(1, 2)
+    lg = F.silu(hn) @ pk["w2"].t() + pk["b2"]
+    T = float(temp_dev[0]) if temp_dev is not None else temp
+    p = F.softmax(lg / T, -1)
+    E = p.shape[-1]
+    if topk < E:
+        vals, idx = p.topk(topk, -1)
+        vals = vals / vals.sum(-1, keepdim=True).clamp_min(1e-6)
+        p = torch.zeros_like(p).scatter_(-1, idx, vals)
+    else:
+        idx = torch.arange(E).expand(B, H * W, E)
+    return p.reshape(B, H, W, E).contiguous(), (idx.reshape(B, H, W, -1).int() if want_idx else None)
+
+
+def linear_attn(q, k, v, heads, hdp, hd, rf, eps=1e-6, limit=1e4, out=None):
+    B, H, W, _ = q.shape
+    o = O._linear_attn(_h(q, heads, hdp)[..., :hd], _h(k, heads, hdp)[..., :hd], _h(v, heads, hdp)[..., :hd], rf, limit, eps)
+    full = torch.zeros(B, heads, H * W, hdp)
+    full[..., :hd] = o
+    return _out(full.permute(0, 2, 1, 3).reshape(B, H, W, heads * hdp), out)
+
+
+def adaptive_avgpool(x, h, w, out=None):
+    return _out(F.adaptive_avg_pool2d(x.float().permute(0, 3, 1, 2), (h, w)).permute(0, 2, 3, 1), out)
+
+
+def install():
+    for name, fn in dict(conv2d=conv2d, dwconv=dwconv, ew=ew, groupnorm_stats=groupnorm_stats, layernorm=layernorm, attn_small=attn_small,
+                         attn_window=attn_window, deform_sample=deform_sample, token_router=token_router, linear_attn=linear_attn,
+                         adaptive_avgpool=adaptive_avgpool).items():
+        setattr(ops, name, fn)
+    ops.new_act = lambda B, H, W, C, device: torch.empty((B, H, W, C), dtype=torch.float16)
+
+    def to_nhwc(x):
+        v = x.half().permute(0, 2, 3, 1)
+        return v if v.is_contiguous() else v.contiguous()
+
+    for mod in (_base, block, conv, moa, mot):
+        if hasattr(mod, "to_nhwc"):
+            mod.to_nhwc = to_nhwc
+
+
+def seeded(module, seed):
+    sd = module.state_dict()
+    fill_state_dict_(sd, seed)
+    for k in sd:
+        if k.endswith("router.3.weight"):
+            sd[k] *= 3
+    module.load_state_dict(sd)
+    return module.eval(), {"m." + k: v.clone().float() for k, v in sd.items()}
+
+
+def report(name, y, ref, sim):
+    e, n = (y.float() - ref).abs(), (sim - ref).abs()
+    flag = "OK " if float(e.mean()) <= 2 * float(n.mean()) + 2e-4 * float(ref.pow(2).mean().sqrt()) and float(e.max()) <= 3 * float(n.max()) + 2e-3 else "BAD"
+    print(f"{flag} {name:44s} mean err {float(e.mean()):.2e} (noise {float(n.mean()):.2e})  max {float(e.max()):.2e} (noise {float(n.max()):.2e})")
+    return flag == "OK "
+
+
+def main():
+    install()
+    ok = True
+    g = torch.Generator().manual_seed(0)
+
+    def run(mod, fn, x, name):
+        nonlocal ok
+        with torch.no_grad():
+            y = mod.fwd_nhwc(x.half().permute(0, 2, 3, 1).contiguous()).float().permute(0, 3, 1, 2)
+        ref = fn(x)
+        with O.fp16_storage(), O.fp16_weights():
+            sim = fn(x)
+        ok &= report(name, y, ref, sim)
+
+    for dim, nh, H, W in [(64, 8, 20, 20), (128, 8, 10, 12), (64, 8, 7, 5)]:
+        x = torch.randn((2, dim, H, W), generator=g).half().float()
+        m, sd = seeded(mot._LocalConvTransformerExpert(dim, nh), 1)
+        run(m, lambda t: O.mot_local_expert(sd, "m", t, nh), x, f"LocalConv {dim} {H}x{W}")
+        m, sd = seeded(mot._LocalConvTransformerExpert(dim, nh, local_window_size=4), 2)
+        run(m, lambda t: O.mot_local_expert(sd, "m", t, nh, 4), x, f"LocalConv windowed {dim} {H}x{W}")
+        for shift in (0, 1):
+            m, sd = seeded(mot._WindowTransformerExpert(dim, nh, 7, shift_size=shift), 3 + shift)
+            run(m, lambda t: O.mot_window_expert(sd, "m", t, nh, 7, 3 if shift else 0), x, f"Window shift={shift} {dim} {H}x{W}")
+        m, sd = seeded(mot._DeformableTransformerExpert(dim, nh), 5)
+        run(m, lambda t: O.mot_deform_expert(sd, "m", t, nh), x, f"Deformable {dim} {H}x{W}")
+        m, sd = seeded(mot.MoTBlock(dim, nh, 2, temperature=0.8), 7)
+        run(m, lambda t: O.mot_block(sd, "m", t, nh, 2), x, f"MoTBlock {dim} {H}x{W}")
+    m, sd = seeded(mot.C2fMoT(64, 128, 2, 8, 2), 8)
+    x = torch.randn((2, 64, 14, 14), generator=g).half().float()
+    run(m, lambda t: O.layer_c2f_mot(sd, "m", t, 64, 128, 2, 8, 2), x, "C2fMoT n=2")
+    for dim, heads, H, W in [(32, 3, 40, 40), (32, 3, 12, 12), (32, 3, 22, 22), (64, 3, 24, 20), (96, 6, 9, 9)]:
+        x = torch.randn((2, dim, H, W), generator=g).half().float()
+        hd, hpg = max(dim // heads, 16), heads // 3
+        for cls, fn, nm in ((moa._LocalAttnHead, O.moa_local_head, "local"), (moa._RegionalAttnHead, O.moa_region_head, "regional"),
+                            (moa._GlobalAttnHead, O.moa_global_head, "global")):
+            m, sd = seeded(cls(dim, hpg, hd), 1)
+            m.fwd_nhwc = (lambda mm: lambda t: ops.groupnorm(mm.head_raw(t), mm.norm.num_groups, *mm.get_pack()["norm"]))(m)
+            run(m, lambda t: fn(sd, "m", t, hpg, hd), x, f"MoA {nm} head {dim} {H}x{W}")
+        m, sd = seeded(moa.MoABlock(dim, heads, temperature=0.8), 5)
+        run(m, lambda t: O.moa_block(sd, "m", t, heads, 0.8), x, f"MoABlock {dim} {H}x{W}")
+    m, sd = seeded(moa.C2fMoA(64, 64, 1, 3, 2.0, 0.8, True), 9)
+    x = torch.randn((2, 64, 24, 24), generator=g).half().float()
+    run(m, lambda t: O.layer_c2f_moa(sd, "m", t, 64, 64, 1, 3, 2.0, 0.8, True), x, "C2fMoA")
+    print("ALL OK" if ok else "FAILURES")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -48,7 +48,17 @@ SIGNATURES = {
     "ym_set_dispatch_debug": (None, [ci]),
     "ym_dispatch_debug_mask": (ci, []),
     "ym_set_dispatch_trace": (None, [vp]),
-    "ym_ew_nhwc": (ci, [ci, vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, vp, ci, cll, ci, vp]),
+    "ym_ew_nhwc": (ci, [ci, vp, ci, vp, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci, cll, ci, vp]),
+    "ym_groupnorm_stats": (ci, [vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, vp, vp, vp]),
+    "ym_layernorm_nhwc": (ci, [vp, ci, vp, vp, cf, vp, ci, cll, ci, vp]),
+    "ym_attn_small": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, cf, vp, ci, vp]),
+    "ym_attn_window": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, cf, vp, ci, vp]),
+    "ym_deform_sample": (ci, [vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, ci, vp]),
+    "ym_token_router_scratch_floats": (cll, [ci, ci, ci]),
+    "ym_token_router": (ci, [vp, ci, ci, ci, ci, vp, ci, ci, vp, vp, cf, vp, vp, ci, ci, vp, cf, vp, vp, vp, vp]),
+    "ym_linear_attn_scratch_floats": (cll, [ci, ci, ci, ci]),
+    "ym_linear_attn": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, vp, cf, cf, vp, vp, ci, vp]),
+    "ym_adaptive_avgpool_nhwc": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, vp, ci, vp]),
     "ym_detect_topk": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp, vp, vp]),
     "ym_detect_dense": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, ci, vp, vp]),
 }

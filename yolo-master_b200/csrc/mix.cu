@@ -9,14 +9,16 @@ enum EwOp {
     EW_TOKEN_ACC = 1,   // out = (a ? a : 0) + tok[row*ldt + toff] * b (MoT blend mot/block.py:347-364, MoA mix moa/block.py:232-244)
     EW_GLU = 2,         // out = sigmoid(a) * b                        (mot/experts.py:168)
     EW_GELU = 3,        // out = gelu(a) (exact, erf)                  (nn.GELU in mot/experts.py:225,365)
-    EW_AFFINE = 4,      // out = [silu](a * sc[img,c] + sh[img,c]) [+ b]   (GroupNorm apply; img = row / rows_per_img)
+    EW_AFFINE = 4,      // out = tok * [silu](a * sc[img,c] + sh[img,c]) + b   (GroupNorm apply; img = row / rows_per_img)
+    EW_LERP = 5,        // out = t*a + (1-t)*b, t = p0[0]              (moa/heads.py:371-375)
 };
 
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
 
 template <int OP>
 __global__ void __launch_bounds__(256) ew_kernel(const __half* __restrict__ a, int lda, const __half* __restrict__ b, int ldb,
-                                                 const float* __restrict__ p0, const float* __restrict__ p1, int ldt, int toff,
+                                                 const float* __restrict__ p0, const float* __restrict__ p1,
+                                                 const float* __restrict__ tok, int ldt, int toff,
                                                  int rows_per_img, int act, __half* __restrict__ out, int ldo, long long rows,
                                                  int C) {
     const int cv = C >> 3;
@@ -46,7 +48,7 @@ __global__ void __launch_bounds__(256) ew_kernel(const __half* __restrict__ a, i
 #pragma unroll
             for (int j = 0; j < 8; ++j) r[j] = fmaf(p0[c + j], vb[j], va[j]);
         } else if (OP == EW_TOKEN_ACC) {
-            const float w = p0[row * ldt + toff];
+            const float w = tok[row * ldt + toff];
 #pragma unroll
             for (int j = 0; j < 8; ++j) r[j] = fmaf(w, vb[j], va[j]);
         } else if (OP == EW_GLU) {
@@ -55,13 +57,18 @@ __global__ void __launch_bounds__(256) ew_kernel(const __half* __restrict__ a, i
         } else if (OP == EW_GELU) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) r[j] = gelu_f(va[j]);
+        } else if (OP == EW_LERP) {
+            const float t = p0[0];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = t * va[j] + (1.f - t) * vb[j];
         } else {
             const long long img = row / rows_per_img;
+            const float w = tok ? tok[row * ldt + toff] : 1.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float v = fmaf(va[j], p0[img * C + c + j], p1[img * C + c + j]);
                 if (act) v = silu_f(v);
-                r[j] = v + vb[j];
+                r[j] = fmaf(w, v, vb[j]);
             }
         }
         Half8 o;
@@ -76,13 +83,16 @@ __global__ void __launch_bounds__(256) ew_kernel(const __half* __restrict__ a, i
 using namespace ym;
 
 // a, b, out: fp16 [rows][ld*] (either of a/b may be null = zeros where the op allows); p0/p1: fp32 parameters of the op
-// (chan[C] | tok[rows*ldt] | scale,shift[imgs*C]).  C % 8 == 0, pitches % 8 == 0.
-extern "C" int ym_ew_nhwc(int op, const void* a, int lda, const void* b, int ldb, const float* p0, const float* p1, int ldt,
-                          int toff, int rows_per_img, int act, void* out, int ldo, long long rows, int C, void* stream) {
+// (chan[C] | scale,shift[imgs*C] | t); tok: fp32 per-token weights [rows*ldt].  C % 8 == 0, pitches % 8 == 0.
+extern "C" int ym_ew_nhwc(int op, const void* a, int lda, const void* b, int ldb, const float* p0, const float* p1,
+                          const float* tok, int ldt, int toff, int rows_per_img, int act, void* out, int ldo, long long rows, int C,
+                          void* stream) {
     YM_CHECK_ARG(out, "ym_ew_nhwc: null output");
     YM_CHECK_ARG(C % 8 == 0 && ldo % 8 == 0 && (!a || lda % 8 == 0) && (!b || ldb % 8 == 0), "ym_ew_nhwc: multiples of 8");
-    YM_CHECK_ARG(op >= 0 && op <= 4, "ym_ew_nhwc: unknown op %d", op);
-    YM_CHECK_ARG((op != EW_SCALE_RES && op != EW_TOKEN_ACC) || (p0 && b), "ym_ew_nhwc: op %d needs p0 and b", op);
+    YM_CHECK_ARG(op >= 0 && op <= 5, "ym_ew_nhwc: unknown op %d", op);
+    YM_CHECK_ARG(op != EW_SCALE_RES || (p0 && b), "ym_ew_nhwc: op 0 needs chan and b");
+    YM_CHECK_ARG(op != EW_TOKEN_ACC || (tok && b), "ym_ew_nhwc: op 1 needs tok and b");
+    YM_CHECK_ARG(op != EW_LERP || (p0 && a && b), "ym_ew_nhwc: op 5 needs t, a and b");
     YM_CHECK_ARG((op != EW_GLU) || (a && b), "ym_ew_nhwc: GLU needs a and b");
     YM_CHECK_ARG((op != EW_GELU) || a, "ym_ew_nhwc: GELU needs a");
     YM_CHECK_ARG((op != EW_AFFINE) || (a && p0 && p1 && rows_per_img > 0), "ym_ew_nhwc: affine needs a, scale, shift, rows_per_img");
@@ -92,13 +102,14 @@ extern "C" int ym_ew_nhwc(int op, const void* a, int lda, const void* b, int ldb
     if (nb > 148LL * 16) nb = 148LL * 16;
     cudaStream_t st = (cudaStream_t)stream;
 #define EW_LAUNCH(OP)                                                                                                      \
-    ew_kernel<OP><<<(int)nb, 256, 0, st>>>((const __half*)a, lda, (const __half*)b, ldb, p0, p1, ldt, toff, rows_per_img, \
-                                           act, (__half*)out, ldo, rows, C)
+    ew_kernel<OP><<<(int)nb, 256, 0, st>>>((const __half*)a, lda, (const __half*)b, ldb, p0, p1, tok, ldt, toff,          \
+                                           rows_per_img, act, (__half*)out, ldo, rows, C)
     switch (op) {
         case EW_SCALE_RES: EW_LAUNCH(EW_SCALE_RES); break;
         case EW_TOKEN_ACC: EW_LAUNCH(EW_TOKEN_ACC); break;
         case EW_GLU: EW_LAUNCH(EW_GLU); break;
         case EW_GELU: EW_LAUNCH(EW_GELU); break;
+        case EW_LERP: EW_LAUNCH(EW_LERP); break;
         default: EW_LAUNCH(EW_AFFINE); break;
     }
 #undef EW_LAUNCH

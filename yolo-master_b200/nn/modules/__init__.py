@@ -1,7 +1,9 @@
 """Operator library mirroring `ultralytics.nn.modules` (same class names / signatures / state_dict keys)."""
 from .block import A2C2f, AAttn, ABlock, Attention, Bottleneck, C2f, C2PSA, C3, C3k, C3k2, PSABlock, SPPF
 from .conv import Concat, Conv, DWConv, PlainConv2d, Upsample, autopad
-from .head import Detect
+from .head import DFL, Detect
+from .moa import C2fMoA, MoABlock
+from .mot import C2fMoT, MoTBlock
 from .moe import (A2C2fMoE, ABlockMoE, DepthwiseSeparableConv, DynamicRoutingLayer, EfficientExpertGroup, EfficientSpatialRouter,
                   ES_MOE, OptimizedMOEImproved, SimpleExpert, get_safe_groups)
 
@@ -10,5 +12,5 @@ __all__ = (
     "Bottleneck", "C2f", "C3", "C3k", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA", "AAttn", "ABlock", "A2C2f",
     "EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups",
     "DynamicRoutingLayer", "DepthwiseSeparableConv", "EfficientExpertGroup", "ES_MOE",
-    "Detect",
+    "Detect", "DFL", "C2fMoT", "MoTBlock", "C2fMoA", "MoABlock",
 )

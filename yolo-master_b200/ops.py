@@ -342,25 +342,124 @@ def esmoe_forward(x, pack, topk, dyn_thr, out=None):
     return out, idx, w, probs
 
 
-EW_SCALE_RES, EW_TOKEN_ACC, EW_GLU, EW_GELU, EW_AFFINE = 0, 1, 2, 3, 4
+EW_SCALE_RES, EW_TOKEN_ACC, EW_GLU, EW_GELU, EW_AFFINE, EW_LERP = 0, 1, 2, 3, 4, 5
 
 
 def _rows(t):
     return t.shape[0] * t.shape[1] * t.shape[2]
 
 
-def ew(op, a=None, b=None, p0=None, p1=None, ldt=0, toff=0, rows_per_img=1, act=False, out=None):
+def ew(op, a=None, b=None, p0=None, p1=None, ldt=0, toff=0, rows_per_img=1, act=False, out=None, tok=None):
     """ym_ew_nhwc on (B,H,W,C) views; see include/ym_b200.h for the op table."""
     ref = a if a is not None else b
     B, H, W, Cc = ref.shape
     if out is None:
         out = new_act(B, H, W, Cc, ref.device)
-    for p in (p0, p1):
+    for p in (p0, p1, tok):
         if p is not None and (p.dtype != torch.float32 or not p.is_contiguous()):
             raise ValueError("ew: parameters must be contiguous fp32")
     _lib.check(lib().ym_ew_nhwc(op, None if a is None else a.data_ptr(), 0 if a is None else pitch(a),
                                 None if b is None else b.data_ptr(), 0 if b is None else pitch(b),
-                                None if p0 is None else p0.data_ptr(), None if p1 is None else p1.data_ptr(), ldt, toff,
-                                rows_per_img, 1 if act else 0, out.data_ptr(), pitch(out), B * H * W, Cc, _stream()), "ym_ew_nhwc")
+                                None if p0 is None else p0.data_ptr(), None if p1 is None else p1.data_ptr(),
+                                None if tok is None else tok.data_ptr(), ldt, toff, rows_per_img, 1 if act else 0, out.data_ptr(), pitch(out), B * H * W, Cc, _stream()), "ym_ew_nhwc")
+    _count()
+    return out
+
+
+def groupnorm_stats(x, G, gamma, beta, eps=1e-5):
+    """ym_groupnorm_stats over a (B,H,W,C) fp16 view -> (scale, shift) fp32 (B, C)."""
+    B, H, W, Cc = x.shape
+    sc = torch.empty((B, Cc), dtype=torch.float32, device=x.device)
+    sh = torch.empty((B, Cc), dtype=torch.float32, device=x.device)
+    _lib.check(lib().ym_groupnorm_stats(x.data_ptr(), 0, pitch(x), B, H * W, Cc, G, eps, gamma.data_ptr(), beta.data_ptr(),
+                                        sc.data_ptr(), sh.data_ptr(), _stream()), "ym_groupnorm_stats")
+    _count()
+    return sc, sh
+
+
+def groupnorm(x, G, gamma, beta, eps=1e-5, act=False, tok=None, ldt=0, toff=0, add=None, out=None):
+    """GroupNorm (+SiLU) (* per-token weight) (+ add): statistics kernel + fused apply."""
+    sc, sh = groupnorm_stats(x, G, gamma, beta, eps)
+    return ew(EW_AFFINE, a=x, b=add, p0=sc, p1=sh, tok=tok, ldt=ldt, toff=toff, rows_per_img=x.shape[1] * x.shape[2], act=act, out=out)
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = new_act(B, H, W, Cc, x.device)
+    _lib.check(lib().ym_layernorm_nhwc(x.data_ptr(), pitch(x), gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(), pitch(out),
+                                       B * H * W, Cc, _stream()), "ym_layernorm_nhwc")
+    _count()
+    return out
+
+
+def attn_small(q, k, v, heads, hdp, scale, out=None):
+    """q: (B,H,W,heads*hdp) view; k, v: (B,h,w,heads*hdp) views (Nkv = h*w tokens per image)."""
+    B, H, W, _ = q.shape
+    Nkv = k.shape[1] * k.shape[2]
+    if out is None:
+        out = new_act(B, H, W, heads * hdp, q.device)
+    _lib.check(lib().ym_attn_small(q.data_ptr(), pitch(q), k.data_ptr(), pitch(k), v.data_ptr(), pitch(v), B, heads, hdp, H * W, Nkv,
+                                   scale, out.data_ptr(), pitch(out), _stream()), "ym_attn_small")
+    _count()
+    return out
+
+
+def attn_window(q, k, v, heads, hdp, win, shift, scale, padk=None, padv=None, out=None):
+    B, H, W, _ = q.shape
+    if out is None:
+        out = new_act(B, H, W, heads * hdp, q.device)
+    _lib.check(lib().ym_attn_window(q.data_ptr(), pitch(q), k.data_ptr(), pitch(k), v.data_ptr(), pitch(v), B, H, W, heads, hdp, win,
+                                    shift, None, None if padk is None else padk.data_ptr(), None if padv is None else padv.data_ptr(),
+                                    scale, out.data_ptr(), pitch(out), _stream()), "ym_attn_window")
+    _count()
+    return out
+
+
+def deform_sample(oa, v, heads, hd, n_points, align_corners=True, out=None):
+    """oa: fp32 (B,H,W,heads*n_points*3); v: fp16 (B,H,W,heads*hd)."""
+    B, H, W, Cc = v.shape
+    if out is None:
+        out = new_act(B, H, W, Cc, v.device)
+    _lib.check(lib().ym_deform_sample(oa.data_ptr(), pitch(oa, torch.float32), v.data_ptr(), pitch(v), B, H, W, heads, hd, n_points,
+                                      1 if align_corners else 0, out.data_ptr(), pitch(out), _stream()), "ym_deform_sample")
+    _count()
+    return out
+
+
+def token_router(x, pk, topk, temp_dev=None, temp=1.0, want_idx=True):
+    """ym_token_router.  pk: dict(w1 [HID,C], gn_w, gn_b, G, w2 [E,HID], b2) fp32.  Returns (weights fp32 (B,H,W,E), idx int32)."""
+    B, H, W, Cc = x.shape
+    HID, E = pk["w1"].shape[0], pk["w2"].shape[0]
+    wts = torch.empty((B, H, W, E), dtype=torch.float32, device=x.device)
+    idx = torch.empty((B, H, W, topk), dtype=torch.int32, device=x.device) if want_idx else None
+    scratch = torch.empty((lib().ym_token_router_scratch_floats(B, H * W, HID),), dtype=torch.float32, device=x.device)
+    _lib.check(lib().ym_token_router(x.data_ptr(), pitch(x), B, H * W, Cc, pk["w1"].data_ptr(), HID, pk["G"], pk["gn_w"].data_ptr(),
+                                     pk["gn_b"].data_ptr(), 1e-5, pk["w2"].data_ptr(), pk["b2"].data_ptr(), E, topk,
+                                     None if temp_dev is None else temp_dev.data_ptr(), float(temp), wts.data_ptr(),
+                                     None if idx is None else idx.data_ptr(), scratch.data_ptr(), _stream()), "ym_token_router")
+    _count(3)
+    return wts, idx
+
+
+def linear_attn(q, k, v, heads, hdp, hd, rf, eps=1e-6, limit=1e4, out=None):
+    B, H, W, _ = q.shape
+    N = H * W
+    if out is None:
+        out = new_act(B, H, W, heads * hdp, q.device)
+    scratch = torch.empty((lib().ym_linear_attn_scratch_floats(B, heads, hdp, N),), dtype=torch.float32, device=q.device)
+    _lib.check(lib().ym_linear_attn(q.data_ptr(), pitch(q), k.data_ptr(), pitch(k), v.data_ptr(), pitch(v), B, heads, hdp, hd,
+                                    rf.shape[0], N, rf.data_ptr(), eps, limit, scratch.data_ptr(), out.data_ptr(), pitch(out),
+                                    _stream()), "ym_linear_attn")
+    _count(2)
+    return out
+
+
+def adaptive_avgpool(x, h, w, out=None):
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = new_act(B, h, w, Cc, x.device)
+    _lib.check(lib().ym_adaptive_avgpool_nhwc(x.data_ptr(), pitch(x), B, H, W, Cc, h, w, out.data_ptr(), pitch(out), _stream()),
+               "ym_adaptive_avgpool_nhwc")
     _count()
     return out
