@@ -460,15 +460,15 @@ def layer_a2c2f(sd, p, x, c1, c2, n=1, a2=True, area=1, residual=False, mlp_rati
     return o
 
 
-def make_anchors(shapes, strides, offset=0.5):
-    """utils/tal.py:398-411."""
+def make_anchors(shapes, strides, offset=0.5, device=None, dtype=torch.float32):
+    """utils/tal.py:398-411 (anchors in the feature dtype/device, as the reference builds them)."""
     pts, st = [], []
     for (h, w), s in zip(shapes, strides):
-        sx = torch.arange(w, dtype=torch.float32) + offset
-        sy = torch.arange(h, dtype=torch.float32) + offset
+        sx = torch.arange(w, dtype=dtype, device=device) + offset
+        sy = torch.arange(h, dtype=dtype, device=device) + offset
         sy, sx = torch.meshgrid(sy, sx, indexing="ij")
         pts.append(torch.stack((sx, sy), -1).view(-1, 2))
-        st.append(torch.full((h * w, 1), float(s)))
+        st.append(torch.full((h * w, 1), float(s), dtype=dtype, device=device))
     return torch.cat(pts), torch.cat(st)
 
 
@@ -500,8 +500,8 @@ def detect_decode(boxes, scores, shapes, strides, end2end, reg_max=1):
     if reg_max > 1:  # `DFL.forward` block.py:80-85 (frozen arange weights; sd carries them as `dfl.conv.weight`)
         b, _, a = boxes.shape
         boxes = (boxes.view(b, 4, reg_max, a).transpose(2, 1).softmax(1)
-                 * torch.arange(reg_max, dtype=boxes.dtype).view(1, reg_max, 1, 1)).sum(1)
-    anchors, st = make_anchors(shapes, strides)
+                 * torch.arange(reg_max, dtype=boxes.dtype, device=boxes.device).view(1, reg_max, 1, 1)).sum(1)
+    anchors, st = make_anchors(shapes, strides, device=boxes.device, dtype=boxes.dtype)
     anchors, st = anchors.t().unsqueeze(0), st.t()
     lt, rb = boxes.chunk(2, 1)
     x1y1, x2y2 = anchors - lt, anchors + rb
@@ -521,7 +521,7 @@ def detect_postprocess(y, nc, max_det=300):
     ori = scores.max(dim=-1)[0].topk(k)[1].unsqueeze(-1)
     sc = scores.gather(1, ori.repeat(1, 1, nc))
     sc, index = sc.flatten(1).topk(k)
-    idx = ori[torch.arange(B)[..., None], index // nc]
+    idx = ori[torch.arange(B, device=y.device)[..., None], index // nc]
     boxes = boxes.gather(1, idx.repeat(1, 1, 4))
     return torch.cat([boxes, sc[..., None], (index % nc)[..., None].float()], dim=-1), idx.squeeze(-1)
 
@@ -547,10 +547,13 @@ def forward_layer(spec: dict, sd: dict, i: int, xin):
 
 
 def forward(spec: dict, sd: dict, x: torch.Tensor, img_hw=None, return_layers: bool = False,
-            end2end: bool | None = None) -> Any:
-    """Eval forward.  Returns (B,300,6) for end2end models, else (B,4+nc,A)."""
-    sd = {k: (v.float() if v.is_floating_point() else v) for k, v in sd.items()}
-    x = x.float()
+            end2end: bool | None = None, dtype: torch.dtype = torch.float32) -> Any:
+    """Eval forward.  Returns (B,300,6) for end2end models, else (B,4+nc,A).
+
+    dtype=torch.float16 with CUDA tensors reproduces the reference's torch-eager `.half().cuda()` path (the yolo26-master-n
+    layer types only); bench.py times that as the same-GPU baseline.  The parity oracle is the fp32 default."""
+    sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+    x = x.to(dtype)
     H_in = x.shape[-2]
     outs, ys = [], {}
     for L in spec["layers"]:

@@ -47,7 +47,7 @@ def assert_close(a, b, atol=ATOL, rtol=RTOL, max_bad_frac=0.0, what=""):
     assert bad <= max_bad_frac, f"{what}: max abs err {mx:.3e}, {bad * 100:.4f}% of elements outside atol={atol} rtol={rtol}"
 
 
-def assert_within_noise(y, ref, sim, what="", k_mean=2.0, k_max=3.0):
+def assert_within_noise(y, ref, sim, what="", k_mean=2.0, k_max=3.0, outlier_frac=0.0):
     """Chained-op criterion: the CUDA path's deviation from the fp32 oracle must stay within a small multiple of the
     deviation of the oracle's own fp16-storage model (`oracle.fp16_storage()`), i.e. within the noise ANY fp16 execution
     of the same graph has.  Single kernels are held to the strict north-star tolerance instead (assert_close)."""
@@ -56,5 +56,11 @@ def assert_within_noise(y, ref, sim, what="", k_mean=2.0, k_max=3.0):
     rms = float(ref.pow(2).mean().sqrt())
     assert float(e.mean()) <= k_mean * float(n.mean()) + 2e-4 * rms, \
         f"{what}: mean err {float(e.mean()):.3e} vs fp16-storage noise {float(n.mean()):.3e} (rms {rms:.3f})"
-    assert float(e.max()) <= k_max * float(n.max()) + 2e-3 * max(1.0, rms), \
-        f"{what}: max err {float(e.max()):.3e} vs fp16-storage noise max {float(n.max()):.3e} (rms {rms:.3f})"
+    emax = float(e.max())
+    if outlier_frac > 0 and e.numel() > 1:
+        # chains THROUGH a per-token discrete router: a token whose top-k margin is below the fp16 noise of its input may
+        # legitimately take another expert (in the reference's own fp16 execution too), which moves that token by O(1).
+        # The max criterion is then applied to the (1 - outlier_frac) quantile; the mean criterion above still covers all.
+        emax = float(e.flatten().kthvalue(max(1, int(e.numel() * (1.0 - outlier_frac))))[0])
+    assert emax <= k_max * float(n.max()) + 2e-3 * max(1.0, rms), \
+        f"{what}: max err {emax:.3e} (outlier_frac={outlier_frac}) vs fp16-storage noise max {float(n.max()):.3e} (rms {rms:.3f})"

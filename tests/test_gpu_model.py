@@ -148,3 +148,20 @@ def test_batch_sizes_and_empty(model_and_sd):
         y3 = m(synth_images(3, 96, 128, 1).half().to(DEV))[0]
     assert y1.shape == (1, 252, 6) and y3.shape == (3, 252, 6)
     assert torch.equal(y1[0], y3[0])                   # per-image independence (routing / GroupNorm are per sample)
+
+
+def test_stream_host_pipeline_uint8(model_and_sd):
+    """Pipelined host API (double-buffered H2D / compute / D2H) on uint8 frames returns, in order, exactly what the
+    synchronous call returns for each batch; uint8 input == the same frames as fp16 /255 up to the fp16 rounding of x/255."""
+    m, _ = model_and_sd
+    frames = [(synth_images(2, 256, 256, 40 + i) * 255).round().to(torch.uint8).pin_memory() for i in range(5)]
+    g8 = m.graphed(2, 256, 256, dtype=torch.uint8)
+    want = [g8.run_host(f).clone() for f in frames]
+    got = [o.clone() for o in g8.stream_host(iter(frames))]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    with torch.no_grad():
+        y16 = m((frames[0].float() / 255).half().to(DEV))[0].float().cpu()
+    s8, s16 = want[0][..., 4].sort(dim=1, descending=True)[0], y16[..., 4].sort(dim=1, descending=True)[0]
+    assert (s8 - s16).abs().max() < 2e-2

@@ -48,8 +48,8 @@ def test_mot_moa_model_matches_reference_golden(models, name, tag):
     y, feats = _layers(m, x.to(DEV))
     with O.fp16_storage(), O.fp16_weights():
         ysim, sim = O.forward(spec, sd, x.float(), return_layers=True)
-    for i, g in c["layers"].items():
-        assert_within_noise(feats[i], g, sim[i], what=f"{name} layer {i} vs reference golden")
+    for i, g in c["layers"].items():   # layers >= 13 sit behind per-token routers fed by fp16 activations: see outlier_frac
+        assert_within_noise(feats[i], g, sim[i], what=f"{name} layer {i} vs reference golden", outlier_frac=0.02 if i >= 13 else 0.0)
     _check_dets(y, c["final"], ysim)
     # router decisions: compared on the tokens whose reference margin is clear (upstream activations differ by fp16 noise)
     mods = dict(m.named_modules())

@@ -183,11 +183,11 @@ def run_mod(mod, x):
         return back(mod.fwd_nhwc(dev_nhwc(x)))
 
 
-def check_mod(y, fn, x, what):
+def check_mod(y, fn, x, what, outlier_frac=0.0):
     ref = fn(x)
     with O.fp16_storage(), O.fp16_weights():
         sim = fn(x)
-    assert_within_noise(y, ref, sim, what=what)
+    assert_within_noise(y, ref, sim, what=what, outlier_frac=outlier_frac)
 
 
 @pytest.mark.parametrize("dim,nh,H,W", [(64, 8, 20, 20), (128, 8, 10, 12), (64, 8, 7, 5)])
@@ -231,7 +231,8 @@ def test_mot_block_and_c2f(dim, nh, topk, H, W):
     check_mod(run_mod(m, x), lambda t: O.mot_block(sd, "m", t, nh, topk), x, "MoTBlock")
     m, sd = seeded(MT.C2fMoT(dim, 2 * dim, 2, 8, topk), 8)
     xin = h16(rnd(2, dim, H, W, seed=22))
-    check_mod(run_mod(m, xin), lambda t: O.layer_c2f_mot(sd, "m", t, dim, 2 * dim, 2, 8, topk), xin, "C2fMoT (n=2: shifted window block)")
+    check_mod(run_mod(m, xin), lambda t: O.layer_c2f_mot(sd, "m", t, dim, 2 * dim, 2, 8, topk), xin, "C2fMoT (n=2: shifted window block)",
+              outlier_frac=0.02)   # the 2nd block's router sees the 1st block's fp16 output: near-tie tokens may flip
 
 
 @pytest.mark.parametrize("dim,heads,H,W", [(32, 3, 40, 40), (32, 3, 12, 12), (32, 3, 22, 22), (64, 3, 24, 20), (96, 6, 9, 9)])

@@ -82,6 +82,18 @@ def cached_f32(owner: nn.Module, name: str, t: torch.Tensor, shape=None) -> torc
     return hit[1]
 
 
+def cached_pack(owner: nn.Module, name: str, sources, build):
+    """`build()` result cached on `owner` until any tensor in `sources` changes version, storage or device."""
+    key = tuple((t.data_ptr(), t._version, str(t.device)) for t in sources)
+    slot = owner.__dict__.setdefault("_ym_packs", {})
+    hit = slot.get(name)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            hit = (key, build())
+        slot[name] = hit
+    return hit[1]
+
+
 def require_eval(m: nn.Module):
     if m.training:
         raise RuntimeError(

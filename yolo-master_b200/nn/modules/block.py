@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ._base import cached_f32, require_eval, to_nchw, to_nhwc
+from ._base import cached_f32, cached_pack, fold_bn, pack_gemm_weight, require_eval, to_nchw, to_nhwc
 from .conv import Conv
 
 __all__ = ("Bottleneck", "C2f", "C3", "C3k", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA", "AAttn", "ABlock", "A2C2f")
@@ -245,8 +245,32 @@ class ABlock(_NHWCBlock):
             if m.bias is not None:
                 nn.init.constant_(m.bias, 0)
 
+    def _padded_mlp(self):
+        """mlp_ratio 1.2 (l/x scales) gives hidden widths such as int(256*1.2) = 307: zero-pad the hidden channels to a
+        multiple of 8 (padded units are SiLU(0) = 0 and meet zero columns of the second conv, so nothing changes)."""
+        c0, c1 = self.mlp[0], self.mlp[1]
+
+        def build():
+            w0, b0 = fold_bn(c0.conv.weight, None, c0.bn)
+            w1, b1 = fold_bn(c1.conv.weight, None, c1.bn)
+            hid = w0.shape[0]
+            hp = (hid + 7) // 8 * 8
+            w0p = torch.zeros((hp, *w0.shape[1:]), device=w0.device)
+            w0p[:hid] = w0
+            b0p = torch.zeros(hp, device=w0.device)
+            b0p[:hid] = b0
+            w1p = torch.zeros((w1.shape[0], hp, 1, 1), device=w1.device)
+            w1p[:, :hid] = w1
+            return {"w0": pack_gemm_weight(w0p), "b0": b0p.contiguous(), "w1": pack_gemm_weight(w1p), "b1": b1.contiguous(), "hp": hp}
+
+        return cached_pack(self, "mlp", [*c0.parameters(), *c0.buffers(), *c1.parameters(), *c1.buffers()], build)
+
     def fwd_nhwc(self, x, out=None):
         x = self.attn.fwd_nhwc(x, res=x)
+        if self.mlp[0].conv.out_channels % 8:
+            pk = self._padded_mlp()
+            h = ops.conv2d(x, pk["w0"], pk["b0"], pk["hp"], 1, 1, 1, 0, True)
+            return ops.conv2d(h, pk["w1"], pk["b1"], self.mlp[1].conv.out_channels, 1, 1, 1, 0, False, out=out, res=x)
         return self.mlp[1].fwd_nhwc(self.mlp[0].fwd_nhwc(x), out=out, res=x)
 
 

@@ -261,3 +261,52 @@ class GraphedForward:
         self.host_out.copy_(self.static_out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.host_out
+
+    # ------------------------------------------------------------------------------------------
+    def _pipeline(self):
+        p = self.__dict__.get("_pipe")
+        if p is None:
+            dev = self.static_in.device
+            ev = lambda: [torch.cuda.Event() for _ in range(2)]
+            p = {"h2d": torch.cuda.Stream(device=dev), "d2h": torch.cuda.Stream(device=dev),
+                 "stage": [torch.empty_like(self.static_in) for _ in range(2)],
+                 "dev_out": [torch.empty_like(self.static_out) for _ in range(2)],
+                 "host_out": [torch.empty(self.static_out.shape, dtype=self.static_out.dtype, pin_memory=True) for _ in range(2)],
+                 "h2d_done": ev(), "consumed": ev(), "fwd_done": ev(), "d2h_done": ev()}
+            self.__dict__["_pipe"] = p
+        return p
+
+    def stream_host(self, host_batches):
+        """Pipelined host-buffer API: for each pinned host batch (shape/dtype of the captured input) yields the pinned host
+        result `(B, n, 6)` in order.  The H2D copy of batch i+1 and the D2H copy of batch i-1 run on their own streams while
+        batch i computes (double-buffered staging), so a stream of batches runs at max(copy, compute) instead of their sum.
+        A yielded tensor is overwritten two batches later: consume or clone it before advancing twice."""
+        p = self._pipeline()
+        k = torch.cuda.current_stream(self.static_in.device)
+        pending = None
+        for i, hb in enumerate(host_batches):
+            s = i & 1
+            if i >= 2:
+                p["h2d"].wait_event(p["consumed"][s])          # staging slot s was drained by batch i-2
+            with torch.cuda.stream(p["h2d"]):
+                p["stage"][s].copy_(hb, non_blocking=True)
+                p["h2d_done"][s].record(p["h2d"])
+            k.wait_event(p["h2d_done"][s])
+            self.static_in.copy_(p["stage"][s], non_blocking=True)
+            p["consumed"][s].record(k)
+            self.graph.replay()
+            if i >= 2:
+                k.wait_event(p["d2h_done"][s])                 # dev_out[s] was read back by batch i-2
+            p["dev_out"][s].copy_(self.static_out, non_blocking=True)
+            p["fwd_done"][s].record(k)
+            p["d2h"].wait_event(p["fwd_done"][s])
+            with torch.cuda.stream(p["d2h"]):
+                p["host_out"][s].copy_(p["dev_out"][s], non_blocking=True)
+                p["d2h_done"][s].record(p["d2h"])
+            if pending is not None:
+                p["d2h_done"][pending].synchronize()
+                yield p["host_out"][pending]
+            pending = s
+        if pending is not None:
+            p["d2h_done"][pending].synchronize()
+            yield p["host_out"][pending]
