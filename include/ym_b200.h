@@ -59,6 +59,9 @@ int ym_attention_fwd(const void* qkv, int ld, int batch, int N, int heads, int h
  * ym_set_attention_impl(0) selects the mma.sync kernel (returns the previous setting). */
 int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
                         int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream);
+/* tcgen05 kernel only: compute every `every`-th softmax exponential with an FMA-pipe polynomial (2^f, |rel err| < 7.5e-5)
+ * instead of the MUFU, which is the binding pipe of d=32 attention; 0 = MUFU only.  Returns the previous setting. */
+int ym_set_attention_poly(int every);
 int ym_set_attention_impl(int impl);
 
 /* EfficientSpatialRouter.forward + BaseRouter._process_logits (eval)  moe/routers.py:283-304, :185-265.

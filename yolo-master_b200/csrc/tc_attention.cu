@@ -21,11 +21,24 @@ constexpr int TA_BQ = 128, TA_BKV = 64, TA_THREADS = 128, TA_STAGES = 3;
 
 __device__ __forceinline__ float ta_exp2(float x) {
     float y;
-    asm volatile("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
     return y;
 }
 
-template <int DV>
+// exp2 on the FMA / ALU pipes: round-to-nearest range reduction by the 1.5*2^23 magic add, degree-3 minimax polynomial of 2^f
+// on [-0.5, 0.5] (max relative error 7.5e-5, far below the fp16 rounding of P), exponent inserted by an integer add.
+// Used for every POLY-th score so that the 16-lane/clk MUFU is no longer the only pipe the softmax waits on.
+__device__ __forceinline__ float ta_exp2_poly(float x) {
+    x = fmaxf(x, -125.f);
+    const float t = x + 12582912.f;
+    const float f = x - (t - 12582912.f);
+    float p = fmaf(0.05517164617776871f, f, 0.2426111251115799f);
+    p = fmaf(p, f, 0.6932609677314758f);
+    p = fmaf(p, f, 0.9999280571937561f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <int DV, int POLY>
 __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* __restrict__ qkv, int ld, int N, int head_stride,
                                                                  int q_off, int k_off, int v_off, float scale_log2,
                                                                  __half* __restrict__ out, int ldo) {
@@ -174,8 +187,10 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            const float p0 = ta_exp2(fmaf(__uint_as_float(sr[2 * i]), scale_log2, -m_used));
-            const float p1 = ta_exp2(fmaf(__uint_as_float(sr[2 * i + 1]), scale_log2, -m_used));
+            const float x0 = fmaf(__uint_as_float(sr[2 * i]), scale_log2, -m_used);
+            const float x1 = fmaf(__uint_as_float(sr[2 * i + 1]), scale_log2, -m_used);
+            const float p0 = (POLY > 0 && (2 * i) % POLY == POLY - 1) ? ta_exp2_poly(x0) : ta_exp2(x0);
+            const float p1 = (POLY > 0 && (2 * i + 1) % POLY == POLY - 1) ? ta_exp2_poly(x1) : ta_exp2(x1);
             pk[i] = pack_half2(p0, p1);
         }
         // ---- PV_{t-1} must be complete before O/L are rescaled, P is overwritten, or its K/V stage is reloaded
@@ -267,6 +282,14 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
 
 using namespace ym;
 
+// Every POLY-th exponential of the softmax runs on the FMA pipe instead of the MUFU (0 = all on the MUFU; 2/3/4/6 supported).
+static int g_attention_poly = 0;
+extern "C" int ym_set_attention_poly(int every) {
+    const int old = g_attention_poly;
+    if (every == 0 || every == 2 || every == 3 || every == 4 || every == 6) g_attention_poly = every;
+    return old;
+}
+
 extern "C" int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
                                    int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream) {
     YM_CHECK_ARG(qkv && out, "ym_attention_fwd_tc: null pointer");
@@ -281,18 +304,25 @@ extern "C" int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, in
     dim3 grid((N + TA_BQ - 1) / TA_BQ, heads, batch);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)TA_BQ * 64 + TA_BQ * 128 + TA_STAGES * (TA_BKV * 64 + TA_BKV * d_v * 2) + 16 * 128 + 1024;
-    cudaError_t e;
-    if (d_v == 32) {
-        e = cudaFuncSetAttribute(tc_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            tc_attention_kernel<32><<<grid, TA_THREADS, smem, st>>>((const __half*)qkv, ld, N, head_stride, q_off, k_off, v_off, sl2,
-                                                                  (__half*)out, ldo);
-    } else {
-        e = cudaFuncSetAttribute(tc_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            tc_attention_kernel<64><<<grid, TA_THREADS, smem, st>>>((const __half*)qkv, ld, N, head_stride, q_off, k_off, v_off, sl2,
-                                                                  (__half*)out, ldo);
+    cudaError_t e = cudaSuccess;
+#define TA_LAUNCH(DV_, POLY_)                                                                                                  \
+    do {                                                                                                                       \
+        e = cudaFuncSetAttribute(tc_attention_kernel<DV_, POLY_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        if (e == cudaSuccess)                                                                                                  \
+            tc_attention_kernel<DV_, POLY_><<<grid, TA_THREADS, smem, st>>>((const __half*)qkv, ld, N, head_stride, q_off, k_off,  \
+                                                                           v_off, sl2, (__half*)out, ldo);                     \
+    } while (0)
+#define TA_LAUNCH_DV(DV_)                                          \
+    switch (g_attention_poly) {                                    \
+        case 2: TA_LAUNCH(DV_, 2); break;                          \
+        case 3: TA_LAUNCH(DV_, 3); break;                          \
+        case 4: TA_LAUNCH(DV_, 4); break;                          \
+        case 6: TA_LAUNCH(DV_, 6); break;                          \
+        default: TA_LAUNCH(DV_, 0); break;                         \
     }
+    if (d_v == 32) { TA_LAUNCH_DV(32) } else { TA_LAUNCH_DV(64) }
+#undef TA_LAUNCH_DV
+#undef TA_LAUNCH
     if (e != cudaSuccess) { ym_set_error("ym_attention_fwd_tc: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
     YM_CHECK_LAUNCH("tc_attention");
     return YM_OK;
