@@ -187,13 +187,13 @@ def time_attention_kernel(dev, batch, pk):
                     "peak = cuBLAS bf16 burst " + pk["source"]}
 
 
-def time_dispatch(dev, pk):
-    """ES-MoE dispatch microbench (BASELINE.json configs[4]): 65536 tokens x d=256, 8 experts, top-2, 1x1-conv experts
-    (BatchedExpertComputation semantics).  Algorithmic bytes = (k+1)*d*2 = 1536 B/token."""
+def time_dispatch(dev, pk, B=64, baseline=True):
+    """ES-MoE dispatch microbench (BASELINE.json configs[4]): B*1024 tokens (65536 at B=64) x d=256, 8 experts, top-2, 1x1-conv
+    experts (BatchedExpertComputation semantics).  Algorithmic bytes = (k+1)*d*2 = 1536 B/token."""
     from yolo_master_b200 import ops
-    B, C, H, W, E, K = 64, 256, 32, 32, 8, 2
+    C, H, W, E, K = 256, 32, 32, 8, 2
     g = torch.Generator().manual_seed(0)
-    nrot = 6                                   # 6 x 33.5 MB inputs + 6 outputs rotate through: > 126 MB L2
+    nrot = max(6, min(64, int(200e6 / (2 * B * H * W * C * 2)) + 1))   # rotating in/out buffers exceed the 126 MB L2 (6 x 33.5 MB x 2 at B=64)
     xs = [torch.randn((B, H, W, C), generator=g).half().to(dev) for _ in range(nrot)]
     outs = [ops.new_act(B, H, W, C, dev) for _ in range(nrot)]
     Wt = (torch.randn((E, C, C), generator=g) / C ** 0.5).half().to(dev)
@@ -221,9 +221,11 @@ def time_dispatch(dev, pk):
     ms = e0.elapsed_time(e1) / (reps * nrot)
     tokens = B * H * W
     gbs = 1536.0 * tokens / (ms * 1e-3) / 1e9
-    res = {"workload": "65536 tokens x d=256, 8 experts top-2, 1x1-conv experts (configs[4])", "kernel": "tc_dispatch2_kernel<256> (2-CTA clusters, tcgen05.mma.cta_group::2 M=256 N=256, TMA loads/stores, TMEM slot ring)",
+    res = {"workload": f"{B * H * W} tokens x d=256, 8 experts top-2, 1x1-conv experts (configs[4])", "kernel": "tc_dispatch2_kernel<256> (2-CTA clusters, tcgen05.mma.cta_group::2 M=256 N=256, TMA loads/stores, TMEM slot ring)",
            "ms": ms, "tokens_per_s": tokens / (ms * 1e-3), "algorithmic_gbs": gbs, "hbm_frac": gbs / pk["hbm_gbs"],
            "tflops": 2.0 * K * C * C * tokens / (ms * 1e-3) / 1e12, "bytes_per_token": 1536}
+    if not baseline:
+        return res
     # the reference's torch path on the same GPU (restated dispatcher on CUDA tensors, fp16): a baseline, not the product
     try:
         from oracle.moe_dispatch_oracle import compute_sparse_experts_batched, conv1x1_experts
@@ -379,6 +381,11 @@ def run_ours(args):
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     roof = time_attention_kernel(dev, B, pk) if rank == 0 else None
     disp = time_dispatch(dev, pk) if rank == 0 else None
+    if disp is not None:   # token sweep of the same microbench (4096 ... 262144 tokens): fixed launch / pipeline-fill cost vs size
+        disp["sweep"] = []
+        for nb in (4, 16, 64, 256):
+            r = disp if nb == 64 else time_dispatch(dev, pk, B=nb, baseline=False)
+            disp["sweep"].append({"tokens": nb * 1024, "ms": r["ms"], "algorithmic_gbs": r["algorithmic_gbs"], "hbm_frac": r["hbm_frac"]})
     eager = time_torch_eager_gpu(dev, B) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
     if rank == 0:

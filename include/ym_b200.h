@@ -31,9 +31,11 @@ int ym_conv2d_nhwc(const void* x, int ldx, int B, int H, int W, int Cin, const v
                    int ldr, int act, void* stream);
 
 /* model.0 stem: Conv(Cin<=4 -> Cout in {16,32,64}, k3 s2 p1) + bias + SiLU reading the NCHW image (conv.py:69-89).
- * in_dtype: 0 fp16, 1 fp32, 2 uint8 (x/255, engine/predictor.py:175).  wgt fp32 [Cin*9][Cout], out NHWC fp16. */
-int ym_stem_conv_nchw(const void* img, int in_dtype, int B, int Cin, int H, int W, const float* wgt, const float* bias,
-                      int Cout, void* out, int ldo, void* stream);
+ * in_dtype: 0 fp16, 1 fp32, 2 uint8 (x/255, engine/predictor.py:175).  out NHWC fp16.
+ * wgt_host fp32 [Cin*9][Cout] and bias_host fp32 [Cout] are HOST pointers: the (<= 9.3 KB of) weights ride in the kernel's
+ * parameter block so that every FFMA reads its weight from the constant bank (baked in at capture time under a CUDA graph). */
+int ym_stem_conv_nchw(const void* img, int in_dtype, int B, int Cin, int H, int W, const float* wgt_host,
+                      const float* bias_host, int Cout, void* out, int ldo, void* stream);
 
 /* Depthwise k x k (k in 3/5/7/9, stride 1, pad k/2) + bias (+SiLU) (+add).  Replaces DWConv conv.py:185-199,
  * AAttn.pe block.py:1688,1731 and Attention.pe block.py:1311,1331 (reads V in place from the head-interleaved qkv:
@@ -60,7 +62,9 @@ int ym_attention_fwd(const void* qkv, int ld, int batch, int N, int heads, int h
 int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
                         int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream);
 /* tcgen05 kernel only: compute every `every`-th softmax exponential with an FMA-pipe polynomial (2^f, |rel err| < 7.5e-5)
- * instead of the MUFU, which is the binding pipe of d=32 attention; 0 = MUFU only.  Returns the previous setting. */
+ * instead of the MUFU (0 = MUFU only, the default).  Measured on B200 (P3 shape, bs32): 1.005 ms at 0, 1.001 / 1.015 / 1.018 /
+ * 1.099 ms at 6 / 4 / 3 / 2 - the kernel's per-tile dependency chain, not the MUFU rate, sets its time.  Returns the previous
+ * setting. */
 int ym_set_attention_poly(int every);
 int ym_set_attention_impl(int impl);
 

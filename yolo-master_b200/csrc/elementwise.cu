@@ -17,19 +17,23 @@ __device__ __forceinline__ float load_px<float>(const float* p) { return *p; }
 template <>
 __device__ __forceinline__ float load_px<unsigned char>(const unsigned char* p) { return (float)(*p) * (1.0f / 255.0f); }
 
+// Weights travel as a __grid_constant__ kernel parameter: every FFMA then takes its weight straight from the constant bank
+// (uniform address), so the inner loop is 1 shared-memory load + COUT FFMAs per tap.  (Round-1 history: weights in shared
+// memory cost 4 broadcast LDS.128 per tap and made the kernel LSU-bound at 0.63 TB/s, profiles/r01_launch_roofline.txt.)
+template <int COUT>
+struct StemWeights {
+    float w[4 * 9 * COUT];   // [(ci*3+ky)*3+kx][COUT], rows ci >= Cin unused
+    float b[COUT];
+};
+
 template <typename TIn, int COUT>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const TIn* __restrict__ img, int B, int Cin, int H, int W,
-                                                        const float* __restrict__ wgt,   // [Cin*9][COUT]
-                                                        const float* __restrict__ bias,  // [COUT]
+                                                        const __grid_constant__ StemWeights<COUT> sw,
                                                         __half* __restrict__ out, int ldo, int Ho, int Wo, int tiles_x) {
     // CTA = 32 x 8 output pixels; the (65 x 17) x Cin input patch is staged in shared memory with coalesced row reads.
     constexpr int TW = 32, TH = 8, IW = 2 * TW + 1, IH = 2 * TH + 1;
-    __shared__ float sw[4 * 9 * COUT];
-    __shared__ float sb[COUT];
     __shared__ float sx[4][IH][IW + 1];
     const int tid = threadIdx.x;
-    for (int i = tid; i < Cin * 9 * COUT; i += 256) sw[i] = wgt[i];
-    for (int i = tid; i < COUT; i += 256) sb[i] = bias[i];
     const int b = blockIdx.y;
     const int oy0 = (blockIdx.x / tiles_x) * TH, ox0 = (blockIdx.x % tiles_x) * TW;
     const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
@@ -47,16 +51,18 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const TIn* __restrict__ 
     if (ox >= Wo || oy >= Ho) return;
     float acc[COUT];
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[c] = sb[c];
-    for (int ci = 0; ci < Cin; ++ci) {
+    for (int c = 0; c < COUT; ++c) acc[c] = sw.b[c];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+    for (int ci = 0; ci < 4; ++ci) {
+        if (ci < Cin) {
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const float v = sx[ci][2 * ly + ky][2 * lx + kx];
-                const float* wr = &sw[((ci * 3 + ky) * 3 + kx) * COUT];
+            for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float v = sx[ci][2 * ly + ky][2 * lx + kx];
+#pragma unroll
+                    for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v, sw.w[((ci * 3 + ky) * 3 + kx) * COUT + c], acc[c]);
+                }
             }
         }
     }
@@ -341,33 +347,40 @@ using namespace ym;
 
 static inline int nblocks(long long total, int bs) { return (int)((total + bs - 1) / bs); }
 
-// in_dtype: 0 = fp16 NCHW, 1 = fp32 NCHW, 2 = uint8 NCHW (scaled by 1/255)
-extern "C" int ym_stem_conv_nchw(const void* img, int in_dtype, int B, int Cin, int H, int W, const float* wgt,
-                                 const float* bias, int Cout, void* out, int ldo, void* stream) {
-    YM_CHECK_ARG(img && wgt && bias && out, "ym_stem_conv_nchw: null pointer");
+// in_dtype: 0 = fp16 NCHW, 1 = fp32 NCHW, 2 = uint8 NCHW (scaled by 1/255).  wgt_host / bias_host are HOST pointers (fp32
+// [Cin*9][Cout] and [Cout]): they are copied into the kernel's parameter block (constant bank) at launch, i.e. at capture
+// time under a CUDA graph.
+template <int CO>
+static int stem_launch(const void* img, int in_dtype, int B, int Cin, int H, int W, const float* wgt_host, const float* bias_host,
+                       void* out, int ldo, int Ho, int Wo, cudaStream_t st) {
+    StemWeights<CO> sw;
+    memset(&sw, 0, sizeof(sw));
+    memcpy(sw.w, wgt_host, sizeof(float) * (size_t)Cin * 9 * CO);
+    memcpy(sw.b, bias_host, sizeof(float) * CO);
+    const int tiles_x = (Wo + 31) / 32, tiles_y = (Ho + 7) / 8;
+    const dim3 grid(tiles_x * tiles_y, B);
+    if (in_dtype == 0) stem_conv_kernel<__half, CO><<<grid, 256, 0, st>>>((const __half*)img, B, Cin, H, W, sw, (__half*)out, ldo, Ho, Wo, tiles_x);
+    else if (in_dtype == 1) stem_conv_kernel<float, CO><<<grid, 256, 0, st>>>((const float*)img, B, Cin, H, W, sw, (__half*)out, ldo, Ho, Wo, tiles_x);
+    else if (in_dtype == 2) stem_conv_kernel<unsigned char, CO><<<grid, 256, 0, st>>>((const unsigned char*)img, B, Cin, H, W, sw, (__half*)out, ldo, Ho, Wo, tiles_x);
+    else { ym_set_error("ym_stem_conv_nchw: bad in_dtype %d", in_dtype); return YM_ERR_ARG; }
+    return YM_OK;
+}
+
+extern "C" int ym_stem_conv_nchw(const void* img, int in_dtype, int B, int Cin, int H, int W, const float* wgt_host,
+                                 const float* bias_host, int Cout, void* out, int ldo, void* stream) {
+    YM_CHECK_ARG(img && wgt_host && bias_host && out, "ym_stem_conv_nchw: null pointer");
     YM_CHECK_ARG(Cin >= 1 && Cin <= 4, "ym_stem_conv_nchw: Cin must be 1..4 (got %d)", Cin);
     YM_CHECK_ARG(ldo % 8 == 0 && ((uintptr_t)out & 15) == 0, "ym_stem_conv_nchw: output alignment");
     if (B == 0) return YM_OK;
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-    const long long total = (long long)B * Ho * Wo;
     cudaStream_t st = (cudaStream_t)stream;
-    const int tiles_x = (Wo + 31) / 32, tiles_y = (Ho + 7) / 8;
-    (void)total;
     YM_CHECK_ARG(B <= 65535, "ym_stem_conv_nchw: batch too large");
-#define YM_STEM(T, CO) stem_conv_kernel<T, CO><<<dim3(tiles_x * tiles_y, B), 256, 0, st>>>((const T*)img, B, Cin, H, W, wgt, bias, (__half*)out, ldo, Ho, Wo, tiles_x)
-#define YM_STEM_T(CO)                                   \
-    do {                                                \
-        if (in_dtype == 0) YM_STEM(__half, CO);         \
-        else if (in_dtype == 1) YM_STEM(float, CO);     \
-        else if (in_dtype == 2) YM_STEM(unsigned char, CO); \
-        else { ym_set_error("ym_stem_conv_nchw: bad in_dtype %d", in_dtype); return YM_ERR_ARG; } \
-    } while (0)
-    if (Cout == 16) YM_STEM_T(16);
-    else if (Cout == 32) YM_STEM_T(32);
-    else if (Cout == 64) YM_STEM_T(64);
+    int rc;
+    if (Cout == 16) rc = stem_launch<16>(img, in_dtype, B, Cin, H, W, wgt_host, bias_host, out, ldo, Ho, Wo, st);
+    else if (Cout == 32) rc = stem_launch<32>(img, in_dtype, B, Cin, H, W, wgt_host, bias_host, out, ldo, Ho, Wo, st);
+    else if (Cout == 64) rc = stem_launch<64>(img, in_dtype, B, Cin, H, W, wgt_host, bias_host, out, ldo, Ho, Wo, st);
     else { ym_set_error("ym_stem_conv_nchw: Cout must be 16/32/64 (got %d)", Cout); return YM_ERR_UNSUPPORTED; }
-#undef YM_STEM_T
-#undef YM_STEM
+    if (rc) return rc;
     YM_CHECK_LAUNCH("stem_conv");
     return YM_OK;
 }

@@ -5,76 +5,107 @@
 // The reference applies conv1x1+BN per pooled pixel and then takes the fp32 spatial mean (routers.py:300); both are
 // affine, so mean(BN(conv1x1(h))) == BN(conv1x1(mean(h))) and the [B,E,H',W'] map is never materialised.  All router
 // arithmetic here is fp32 on the fp16 activations (the reference's own fp32 contract covers mean/softmax/top-k).
-// Replaces ~10 launches + 3 host syncs (routers.py:51,295,301) with 3 small launches and no sync: routing stays on
+// Replaces ~10 launches + 3 host syncs (routers.py:51,295,301) with 2 small launches and no sync: routing stays on
 // the device as an index table consumed by ym_moe_expert_gemm.
 #include "ym_common.cuh"
 
 namespace ym {
 
-// pooled[b, py, px, c] = mean over the ps x ps block (F.avg_pool2d, floor semantics), fp32
-__global__ void __launch_bounds__(256) router_pool_kernel(const __half* __restrict__ x, int ldx, int B, int H, int W, int C,
-                                                          int ps, int Hp, int Wp, float* __restrict__ pooled) {
-    const long long total = (long long)B * Hp * Wp * C;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c = (int)(idx % C);
-    const long long pp = idx / C;
-    const int px = (int)(pp % Wp);
-    const int py = (int)((pp / Wp) % Hp);
-    const int b = (int)(pp / ((long long)Wp * Hp));
-    const __half* xb = x + ((long long)b * H * W) * ldx + c;
-    float s = 0.f;
-    for (int dy = 0; dy < ps; ++dy)
-        for (int dx = 0; dx < ps; ++dx) s += __half2float(xb[((long long)(py * ps + dy) * W + (px * ps + dx)) * ldx]);
-    pooled[idx] = s / (float)(ps * ps);
-}
+// Fused avg-pool + conv3x3 + BN + SiLU + per-tile sums.  (Round-1 history: separate pool / hidden kernels ran at 41 GB/s,
+// L1-instruction bound - two 16-byte loads per four FMAs - with the pooled map making a round trip through global memory;
+// profiles/r01_launch_roofline.txt.)  w1 layout [tap][c/4][r][4] fp32: the Cr lanes of a quad read consecutive float4.
+// One CTA = a 4 x 16 tile of POOLED pixels of one image:
+//   phase 1: the haloed 6 x 18 pooled tile is averaged straight from the fp16 activation into shared memory (fp32);
+//   phase 2: each thread owns one reduced channel r and FOUR horizontally adjacent pixels: per (ky, c4) it loads 6 input
+//            float4 (shared memory, broadcast across the r lanes) and 3 weight float4 (L1) for 48 FMAs (was 2 loads per 4).
+// partial[b, tile, r] = sum over the tile's pixels of SiLU(scale1*conv + shift1); router_finish_kernel is unchanged.
+constexpr int RT_TY = 4, RT_TX = 16, RT_HY = RT_TY + 2, RT_HX = RT_TX + 2;
 
-// hidden[b, pix, r] = SiLU(scale1[r] * conv3x3(pooled)[pix, r] + shift1[r]); partial[b, blk, r] = sum over the block's pixels.
-// grid (nblk, B), block 256 = PIX_PER_BLOCK pixels x Cr lanes (Cr in {8,16,32,64}).  w1 layout [tap][c/4][r][4] fp32 so that
-// the Cr lanes of a pixel read consecutive float4 (coalesced) while the pooled input float4 is a broadcast.
-__global__ void __launch_bounds__(256) router_hidden_kernel(const float* __restrict__ pooled, int Hp, int Wp, int C, int Cr,
-                                                            const float* __restrict__ w1, const float* __restrict__ scale1,
-                                                            const float* __restrict__ shift1, float* __restrict__ partial,
-                                                            int nblk) {
-    __shared__ float red[256];
+__global__ void __launch_bounds__(256) router_fused_kernel(const __half* __restrict__ x, int ldx, int H, int W, int C, int ps,
+                                                           int Hp, int Wp, int Cr, const float* __restrict__ w1,
+                                                           const float* __restrict__ scale1, const float* __restrict__ shift1,
+                                                           float* __restrict__ partial, int tiles_x, int nblk) {
+    extern __shared__ float rsm[];
+    float* sp = rsm;                                   // [RT_HY][RT_HX][C] pooled tile with halo (zero outside the map)
+    float* red = rsm + RT_HY * RT_HX * C;              // [16 quads][Cr]
     const int b = blockIdx.y;
-    const int ppb = 256 / Cr;
-    const int r = threadIdx.x % Cr;
-    const int pl = threadIdx.x / Cr;
-    const int pix = blockIdx.x * ppb + pl;
+    const int ty0 = (blockIdx.x / tiles_x) * RT_TY, tx0 = (blockIdx.x % tiles_x) * RT_TX;
+    const int C8 = C >> 3;
+    const float inv = 1.f / (float)(ps * ps);
+    const __half* xb = x + (long long)b * H * W * ldx;
+    for (int i = threadIdx.x; i < RT_HY * RT_HX * C8; i += blockDim.x) {
+        const int c8 = i % C8, pp = i / C8;
+        const int hy = pp / RT_HX, hx = pp - hy * RT_HX;
+        const int py = ty0 + hy - 1, px = tx0 + hx - 1;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        if (py >= 0 && py < Hp && px >= 0 && px < Wp) {
+            for (int dy = 0; dy < ps; ++dy)
+                for (int dx = 0; dx < ps; ++dx) {
+                    const Half8 h = *reinterpret_cast<const Half8*>(xb + ((long long)(py * ps + dy) * W + (px * ps + dx)) * ldx + c8 * 8);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __half22float2(h.v[j]);
+                        acc[2 * j] += f.x;
+                        acc[2 * j + 1] += f.y;
+                    }
+                }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] *= inv;
+        }
+        float4* dst = reinterpret_cast<float4*>(sp + (size_t)pp * C + c8 * 8);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncthreads();
     const int C4 = C >> 2;
-    float hval = 0.f;
-    if (pix < Hp * Wp) {
-        const int py = pix / Wp, px = pix % Wp;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const int nitems = 16 * Cr;                         // (quad, r)
+    for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
+        const int r = it % Cr, quad = it / Cr;
+        const int qy = quad >> 2, qx = quad & 3;        // pixels (ty0 + qy, tx0 + 4*qx + 0..3)
+        float a[4][4];
+#pragma unroll
+        for (int pxl = 0; pxl < 4; ++pxl)
+#pragma unroll
+            for (int l = 0; l < 4; ++l) a[pxl][l] = 0.f;
+        const float4* wbase = reinterpret_cast<const float4*>(w1) + r;
         for (int ky = 0; ky < 3; ++ky) {
-            const int iy = py + ky - 1;
-            if (iy < 0 || iy >= Hp) continue;
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix = px + kx - 1;
-                if (ix < 0 || ix >= Wp) continue;
-                const float4* pin = reinterpret_cast<const float4*>(pooled + (((long long)b * Hp + iy) * Wp + ix) * C);
-                const float4* pw = reinterpret_cast<const float4*>(w1) + (long long)(ky * 3 + kx) * C4 * Cr + r;
-#pragma unroll 4
-                for (int c4 = 0; c4 < C4; ++c4) {
-                    const float4 xv = __ldg(pin + c4);
-                    const float4 wv = __ldg(pw + (long long)c4 * Cr);
-                    a0 = fmaf(xv.x, wv.x, a0);
-                    a1 = fmaf(xv.y, wv.y, a1);
-                    a2 = fmaf(xv.z, wv.z, a2);
-                    a3 = fmaf(xv.w, wv.w, a3);
+            const float* srow = sp + (size_t)((qy + ky) * RT_HX + 4 * qx) * C;
+            for (int c4 = 0; c4 < C4; ++c4) {
+                float4 xv[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) xv[j] = *reinterpret_cast<const float4*>(srow + (size_t)j * C + c4 * 4);
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 wv = __ldg(wbase + ((long long)(ky * 3 + kx) * C4 + c4) * Cr);
+#pragma unroll
+                    for (int pxl = 0; pxl < 4; ++pxl) {
+                        a[pxl][0] = fmaf(xv[pxl + kx].x, wv.x, a[pxl][0]);
+                        a[pxl][1] = fmaf(xv[pxl + kx].y, wv.y, a[pxl][1]);
+                        a[pxl][2] = fmaf(xv[pxl + kx].z, wv.z, a[pxl][2]);
+                        a[pxl][3] = fmaf(xv[pxl + kx].w, wv.w, a[pxl][3]);
+                    }
                 }
             }
         }
-        const float v = fmaf((a0 + a1) + (a2 + a3), scale1[r], shift1[r]);
-        hval = v / (1.f + expf(-v));
+        const float sc = scale1[r], sh = shift1[r];
+        float hsum = 0.f;
+#pragma unroll
+        for (int pxl = 0; pxl < 4; ++pxl) {
+            const int py = ty0 + qy, px = tx0 + 4 * qx + pxl;
+            if (py < Hp && px < Wp) {
+                const float v = fmaf((a[pxl][0] + a[pxl][1]) + (a[pxl][2] + a[pxl][3]), sc, sh);
+                hsum += v / (1.f + expf(-v));
+            }
+        }
+        red[quad * Cr + r] = hsum;
     }
-    red[threadIdx.x] = hval;
     __syncthreads();
-    if (threadIdx.x < Cr) {  // fixed-order (deterministic) reduction over the block's pixels
-        float s = 0.f;
-        for (int i = 0; i < ppb; ++i) s += red[i * Cr + threadIdx.x];
-        partial[((long long)b * nblk + blockIdx.x) * Cr + threadIdx.x] = s;
+    if ((int)threadIdx.x < Cr) {   // fixed-order (deterministic) reduction over the tile's 16 quads
+        float s2 = 0.f;
+        for (int q = 0; q < 16; ++q) s2 += red[q * Cr + threadIdx.x];
+        partial[((long long)b * nblk + blockIdx.x) * Cr + threadIdx.x] = s2;
     }
 }
 
@@ -164,21 +195,26 @@ extern "C" int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C
     YM_CHECK_ARG(Cr == 8 || Cr == 16 || Cr == 32 || Cr == 64, "ym_router_topk: reduced channels must be 8/16/32/64 (got %d)", Cr);
     YM_CHECK_ARG(E >= 1 && E <= 64 && topk >= 1 && topk <= 8 && topk <= E, "ym_router_topk: need 1<=topk<=min(8,E), E<=64");
     YM_CHECK_ARG(pool >= 1, "ym_router_topk: pool");
-    YM_CHECK_ARG(C % 4 == 0, "ym_router_topk: C must be a multiple of 4");
     if (B == 0) return YM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool do_pool = H > pool && W > pool;  // routers.py:289-292
     const int ps = do_pool ? pool : 1;
     const int Hp = H / ps, Wp = W / ps;
-    float* pooled = scratch;
-    const long long npool = (long long)B * Hp * Wp * C;
-    float* partial = scratch + npool;
-    router_pool_kernel<<<(int)((npool + 255) / 256), 256, 0, st>>>((const __half*)x, ldx, B, H, W, C, ps, Hp, Wp, pooled);
-    YM_CHECK_LAUNCH("router_pool");
-    const int ppb = 256 / Cr;
-    const int nblk = (Hp * Wp + ppb - 1) / ppb;
-    router_hidden_kernel<<<dim3(nblk, B), 256, 0, st>>>(pooled, Hp, Wp, C, Cr, w1, scale1, shift1, partial, nblk);
-    YM_CHECK_LAUNCH("router_hidden");
+    YM_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && (((uintptr_t)x) & 15) == 0, "ym_router_topk: C / pitch must be multiples of 8 halves");
+    const int tiles_x = (Wp + RT_TX - 1) / RT_TX, tiles_y = (Hp + RT_TY - 1) / RT_TY;
+    const int nblk = tiles_x * tiles_y;
+    float* partial = scratch;
+    const size_t smem = ((size_t)RT_HY * RT_HX * C + 16 * (size_t)Cr) * sizeof(float);
+    YM_CHECK_ARG(smem <= 200 * 1024, "ym_router_topk: C=%d too wide for the fused router tile", C);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(router_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { ym_set_error("ym_router_topk: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
+        smem_set = smem;
+    }
+    router_fused_kernel<<<dim3(nblk, B), 256, smem, st>>>((const __half*)x, ldx, H, W, C, ps, Hp, Wp, Cr, w1, scale1, shift1, partial,
+                                                         tiles_x, nblk);
+    YM_CHECK_LAUNCH("router_fused");
     router_finish_kernel<<<B, 32, 0, st>>>(partial, nblk, Cr, Hp * Wp, w2, scale2, shift2, E, topk, idx_out, w_out, probs_out);
     YM_CHECK_LAUNCH("router_finish");
     return YM_OK;

@@ -66,9 +66,10 @@ class Conv(nn.Module, PackCache):
         elif kind == "dw":
             C, _, k, _ = w.shape
             pk["w"] = w.reshape(C, k * k).t().contiguous().half()  # tap-major [k*k][C]
-        else:  # stem: fp32 [Cin*9][Cout], k index = (ci*3+ky)*3+kx
+        else:  # stem: fp32 [Cin*9][Cout], k index = (ci*3+ky)*3+kx; HOST copies (they ride in the kernel's parameter block)
             Co = w.shape[0]
-            pk["w"] = w.reshape(Co, -1).t().contiguous()
+            pk["w"] = w.reshape(Co, -1).t().contiguous().cpu()
+            pk["bias"] = pk["bias"].cpu()
         return pk
 
     # ---- forward ------------------------------------------------------------------------------

@@ -85,7 +85,9 @@ def conv2d(x, w_packed, bias, Cout, KH, KW, stride, pad, act, out=None, res=None
 
 
 def stem_conv(img, wgt, bias, Cout, out=None):
-    """ym_stem_conv_nchw.  img: contiguous NCHW fp16/fp32/uint8."""
+    """ym_stem_conv_nchw.  img: contiguous NCHW fp16/fp32/uint8; wgt / bias: contiguous fp32 HOST tensors."""
+    if wgt.is_cuda or bias.is_cuda or wgt.dtype != torch.float32 or bias.dtype != torch.float32 or not wgt.is_contiguous():
+        raise ValueError("stem_conv: weights and bias must be contiguous fp32 host tensors")
     if not img.is_cuda or img.dim() != 4:
         raise ValueError("stem_conv: expected a 4-D CUDA NCHW image batch")
     img = img.contiguous()
@@ -166,7 +168,7 @@ def router_topk(x, pack, topk, pool=4):
                                     pack["scale1"].data_ptr(), pack["shift1"].data_ptr(), pack["w2"].data_ptr(),
                                     pack["scale2"].data_ptr(), pack["shift2"].data_ptr(), E, topk, scratch.data_ptr(),
                                     idx.data_ptr(), w.data_ptr(), probs.data_ptr(), _stream()), "ym_router_topk")
-    _count(3)
+    _count(2)
     return idx, w, probs
 
 
