@@ -30,6 +30,7 @@ struct TcConvParams {
     int tiles_x, tiles_y, TW, TH;   // patch mode
     int M;             // flat mode: B*H*W rows
     int act;
+    int stages;        // operand ring depth of the persistent kernel (set by launch_conv2)
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -205,7 +206,16 @@ __global__ void __launch_bounds__(CV_THREADS) tc_conv_kernel(const __grid_consta
 //                                      staging tile -> ONE TMA store per tile (coalesced, clips image borders / ragged M)
 // CTAs are persistent (grid = 2 x #SMs at most) and walk the tile list with a static stride.
 // =====================================================================================================================
-constexpr int CV2_THREADS = 320, CV2_STAGES = 3, CV2_EPI_THREADS = 256;   // 2 control warps + 8 epilogue warps
+constexpr int CV2_THREADS = 320, CV2_EPI_THREADS = 256;   // 2 control warps + 8 epilogue warps
+// Operand ring depth is chosen per launch (TcConvParams::stages): a k-tile of a low-channel layer is only 4-6 KB (Cin = 16:
+// 128 rows x 32 B + weights), and with 3 stages a CTA had ~15 KB in flight - far too little to cover the ~1 us L2/HBM latency
+// (profiles/r01_launch_roofline.txt: the P1/P2 convs ran at 0.5-1.2 TB/s).  The ring now takes up to ~64 KB: 3 stages of
+// 24 KB at Cin >= 64, 6 at Cin = 32, 12 at Cin = 16.
+constexpr int CV2_MIN_STAGES = 3, CV2_MAX_STAGES = 12, CV2_RING_BYTES = 64 * 1024;
+static inline int cv2_stages(int stage_bytes) {
+    int n = CV2_RING_BYTES / stage_bytes;
+    return n < CV2_MIN_STAGES ? CV2_MIN_STAGES : (n > CV2_MAX_STAGES ? CV2_MAX_STAGES : n);
+}
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
@@ -253,8 +263,9 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
     const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
     constexpr int OUT_ROW = BN * 2;                        // bytes per staged output row (32 / 64 / 128)
     constexpr int OUT_BYTES = CV_BM * OUT_ROW;
-    unsigned char* stg = smem + CV2_STAGES * stage_bytes;  // [2][OUT_BYTES], 1024-aligned
-    __shared__ uint64_t full_bar[CV2_STAGES], empty_bar[CV2_STAGES], tfull_bar[2], tempty_bar[2];
+    const int nst = p.stages;
+    unsigned char* stg = smem + nst * stage_bytes;         // [2][OUT_BYTES], 1024-aligned
+    __shared__ uint64_t full_bar[CV2_MAX_STAGES], empty_bar[CV2_MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float sbias[1024 + 64];       // folded-BN bias, zero padded past Cout
     constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < 1024 + 64; i += CV2_THREADS) sbias[i] = (p.bias != nullptr && i < p.Cout) ? p.bias[i] : 0.f;
     if (tid == 0) {
-        for (int s = 0; s < CV2_STAGES; ++s) {
+        for (int s = 0; s < nst; ++s) {
             tc::mbar_init(&full_bar[s], 1);
             tc::mbar_init(&empty_bar[s], 1);
         }
@@ -302,13 +313,13 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer
-            uint32_t kidx = 0;
+            int s = 0;
+            uint32_t ph = 0;                               // ring position and its phase bit
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int n0, m0, b, oy0, ox0;
                 tile_coords(tile, n0, m0, b, oy0, ox0);
-                for (int it = 0; it < KT; ++it, ++kidx) {
-                    const int s = kidx % CV2_STAGES;
-                    tc::mbar_wait(&empty_bar[s], ((kidx / CV2_STAGES) & 1) ^ 1);
+                for (int it = 0; it < KT; ++it) {
+                    tc::mbar_wait(&empty_bar[s], ph ^ 1);
                     unsigned char* st = smem + s * stage_bytes;
                     const int tap = it / cchunks, c0 = (it - tap * cchunks) * p.kc;
                     mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + b_bytes));
@@ -319,6 +330,7 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
                         tma_load_4d(st, &map_a, c0, ox0 * p.stride + kx - p.pad, oy0 * p.stride + ky - p.pad, b, &full_bar[s]);
                     }
                     tma_load_2d(st + a_bytes, &map_b, tap * p.Cin + c0, n0, &full_bar[s]);
+                    if (++s == nst) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -326,20 +338,21 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
         if (lane == 0) {
             // ===== MMA issuer
             const uint32_t idesc = tc::make_idesc_f16(CV_BM, BN);
-            uint32_t kidx = 0, titer = 0;
+            uint32_t titer = 0, ph = 0;
+            int s = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
                 const uint32_t acc = titer & 1;
                 tc::mbar_wait(&tempty_bar[acc], ((titer >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
                 tc::fence_after_sync();
                 const uint32_t tacc = tmem_base + acc * BN;
-                for (int it = 0; it < KT; ++it, ++kidx) {
-                    const int s = kidx % CV2_STAGES;
-                    tc::mbar_wait(&full_bar[s], (kidx / CV2_STAGES) & 1);
+                for (int it = 0; it < KT; ++it) {
+                    tc::mbar_wait(&full_bar[s], ph);
                     tc::fence_after_sync();
                     const uint32_t sa = smem_u32(smem + s * stage_bytes);
                     const uint64_t adesc = tc::make_desc(sa, sbo, layout_type), bdesc = tc::make_desc(sa + a_bytes, sbo, layout_type);
                     for (int k = 0; k < p.kc / 16; ++k) tc::mma_f16_ss(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) ? 1u : 0u);
                     tc::mma_commit(&empty_bar[s]);
+                    if (++s == nst) { s = 0; ph ^= 1; }
                 }
                 tc::mma_commit(&tfull_bar[acc]);
             }
@@ -466,11 +479,13 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
 }
 
 template <int BN, bool FLAT>
-static int launch_conv2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const TcConvParams& p, int m_tiles,
+static int launch_conv2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const TcConvParams& p_in, int m_tiles,
                         int n_tiles, cudaStream_t st) {
+    TcConvParams p = p_in;
     const int row_bytes = p.kc * 2;
     const int stage = ((CV_BM * row_bytes + BN * row_bytes + 1023) / 1024) * 1024;
-    const size_t smem = (size_t)CV2_STAGES * stage + 2 * (size_t)CV_BM * BN * 2 + 1024;
+    p.stages = cv2_stages(stage);
+    const size_t smem = (size_t)p.stages * stage + 2 * (size_t)CV_BM * BN * 2 + 1024;
     auto kern = tc_conv2_kernel<BN, FLAT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ym_set_error("tc_conv2: smem attr %zu: %s", smem, cudaGetErrorString(e)); return YM_ERR_CUDA; }
