@@ -37,30 +37,13 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const TIn* __restrict__ 
     const int b = blockIdx.y;
     const int oy0 = (blockIdx.x / tiles_x) * TH, ox0 = (blockIdx.x % tiles_x) * TW;
     const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
-    // all of a thread's patch elements are loaded before any is stored: 18 independent loads in flight per thread instead of
-    // a load -> convert -> store chain that exposed the full DRAM latency 13 times per CTA
-    constexpr int PER = (4 * IH * IW + 255) / 256;
-    float vals[PER];
-    const int npatch = Cin * IH * IW;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int i = tid + k * 256;
+    for (int i = tid; i < Cin * IH * IW; i += 256) {
+        const int ci = i / (IH * IW), rem = i % (IH * IW);
+        const int ry = rem / IW, rx = rem % IW;
+        const int iy = iy0 + ry, ix = ix0 + rx;
         float v = 0.f;
-        if (i < npatch) {
-            const int ci = i / (IH * IW), rem = i % (IH * IW);
-            const int ry = rem / IW, rx = rem % IW;
-            const int iy = iy0 + ry, ix = ix0 + rx;
-            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = load_px<TIn>(img + (((long long)b * Cin + ci) * H + iy) * W + ix);
-        }
-        vals[k] = v;
-    }
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int i = tid + k * 256;
-        if (i < npatch) {
-            const int ci = i / (IH * IW), rem = i % (IH * IW);
-            sx[ci][rem / IW][rem % IW] = vals[k];
-        }
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = load_px<TIn>(img + (((long long)b * Cin + ci) * H + iy) * W + ix);
+        sx[ci][ry][rx] = v;
     }
     __syncthreads();
     const int lx = tid % TW, ly = tid / TW;

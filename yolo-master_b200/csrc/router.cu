@@ -41,33 +41,16 @@ __global__ void __launch_bounds__(256) router_fused_kernel(const __half* __restr
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
         if (py >= 0 && py < Hp && px >= 0 && px < Wp) {
-            const __half* src = xb + ((long long)(py * ps) * W + px * ps) * ldx + c8 * 8;
-            if (ps == 4) {   // the usual case: all 16 loads are issued before the first add (one memory latency, not sixteen)
-                Half8 h[16];
-#pragma unroll
-                for (int dy = 0; dy < 4; ++dy)
-#pragma unroll
-                    for (int dx = 0; dx < 4; ++dx) h[dy * 4 + dx] = *reinterpret_cast<const Half8*>(src + ((long long)dy * W + dx) * ldx);
-#pragma unroll
-                for (int t = 0; t < 16; ++t)
+            for (int dy = 0; dy < ps; ++dy)
+                for (int dx = 0; dx < ps; ++dx) {
+                    const Half8 h = *reinterpret_cast<const Half8*>(xb + ((long long)(py * ps + dy) * W + (px * ps + dx)) * ldx + c8 * 8);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float2 f = __half22float2(h[t].v[j]);
+                        const float2 f = __half22float2(h.v[j]);
                         acc[2 * j] += f.x;
                         acc[2 * j + 1] += f.y;
                     }
-            } else {
-                for (int dy = 0; dy < ps; ++dy)
-                    for (int dx = 0; dx < ps; ++dx) {
-                        const Half8 h = *reinterpret_cast<const Half8*>(src + ((long long)dy * W + dx) * ldx);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f = __half22float2(h.v[j]);
-                            acc[2 * j] += f.x;
-                            acc[2 * j + 1] += f.y;
-                        }
-                    }
-            }
+                }
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] *= inv;
         }
@@ -89,7 +72,6 @@ __global__ void __launch_bounds__(256) router_fused_kernel(const __half* __restr
         const float4* wbase = reinterpret_cast<const float4*>(w1) + r;
         for (int ky = 0; ky < 3; ++ky) {
             const float* srow = sp + (size_t)((qy + ky) * RT_HX + 4 * qx) * C;
-#pragma unroll 2
             for (int c4 = 0; c4 < C4; ++c4) {
                 float4 xv[6];
 #pragma unroll
