@@ -14,12 +14,12 @@ namespace ym {
 // Fused avg-pool + conv3x3 + BN + SiLU + per-tile sums.  (Round-1 history: separate pool / hidden kernels ran at 41 GB/s,
 // L1-instruction bound - two 16-byte loads per four FMAs - with the pooled map making a round trip through global memory;
 // profiles/r01_launch_roofline.txt.)  w1 layout [tap][c/4][r][4] fp32: the Cr lanes of a quad read consecutive float4.
-// One CTA = a 4 x 16 tile of POOLED pixels of one image:
-//   phase 1: the haloed 6 x 18 pooled tile is averaged straight from the fp16 activation into shared memory (fp32);
+// One CTA = a 2 x 16 tile of POOLED pixels of one image (small tiles: the maps are 5x5 .. 40x40, the grid must fill 148 SMs):
+//   phase 1: the haloed 4 x 18 pooled tile is averaged straight from the fp16 activation into shared memory (fp32);
 //   phase 2: each thread owns one reduced channel r and FOUR horizontally adjacent pixels: per (ky, c4) it loads 6 input
 //            float4 (shared memory, broadcast across the r lanes) and 3 weight float4 (L1) for 48 FMAs (was 2 loads per 4).
 // partial[b, tile, r] = sum over the tile's pixels of SiLU(scale1*conv + shift1); router_finish_kernel is unchanged.
-constexpr int RT_TY = 4, RT_TX = 16, RT_HY = RT_TY + 2, RT_HX = RT_TX + 2;
+constexpr int RT_TY = 2, RT_TX = 16, RT_HY = RT_TY + 2, RT_HX = RT_TX + 2, RT_QUADS = RT_TY * (RT_TX / 4);
 
 __global__ void __launch_bounds__(256) router_fused_kernel(const __half* __restrict__ x, int ldx, int H, int W, int C, int ps,
                                                            int Hp, int Wp, int Cr, const float* __restrict__ w1,
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) router_fused_kernel(const __half* __restr
                                                            float* __restrict__ partial, int tiles_x, int nblk) {
     extern __shared__ float rsm[];
     float* sp = rsm;                                   // [RT_HY][RT_HX][C] pooled tile with halo (zero outside the map)
-    float* red = rsm + RT_HY * RT_HX * C;              // [16 quads][Cr]
+    float* red = rsm + RT_HY * RT_HX * C;              // [RT_QUADS][Cr]
     const int b = blockIdx.y;
     const int ty0 = (blockIdx.x / tiles_x) * RT_TY, tx0 = (blockIdx.x % tiles_x) * RT_TX;
     const int C8 = C >> 3;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) router_fused_kernel(const __half* __restr
     }
     __syncthreads();
     const int C4 = C >> 2;
-    const int nitems = 16 * Cr;                         // (quad, r)
+    const int nitems = RT_QUADS * Cr;                   // (quad, r)
     for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
         const int r = it % Cr, quad = it / Cr;
         const int qy = quad >> 2, qx = quad & 3;        // pixels (ty0 + qy, tx0 + 4*qx + 0..3)
@@ -102,9 +102,9 @@ __global__ void __launch_bounds__(256) router_fused_kernel(const __half* __restr
         red[quad * Cr + r] = hsum;
     }
     __syncthreads();
-    if ((int)threadIdx.x < Cr) {   // fixed-order (deterministic) reduction over the tile's 16 quads
+    if ((int)threadIdx.x < Cr) {   // fixed-order (deterministic) reduction over the tile's quads
         float s2 = 0.f;
-        for (int q = 0; q < 16; ++q) s2 += red[q * Cr + threadIdx.x];
+        for (int q = 0; q < RT_QUADS; ++q) s2 += red[q * Cr + threadIdx.x];
         partial[((long long)b * nblk + blockIdx.x) * Cr + threadIdx.x] = s2;
     }
 }
@@ -204,7 +204,7 @@ extern "C" int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C
     const int tiles_x = (Wp + RT_TX - 1) / RT_TX, tiles_y = (Hp + RT_TY - 1) / RT_TY;
     const int nblk = tiles_x * tiles_y;
     float* partial = scratch;
-    const size_t smem = ((size_t)RT_HY * RT_HX * C + 16 * (size_t)Cr) * sizeof(float);
+    const size_t smem = ((size_t)RT_HY * RT_HX * C + RT_QUADS * (size_t)Cr) * sizeof(float);
     YM_CHECK_ARG(smem <= 200 * 1024, "ym_router_topk: C=%d too wide for the fused router tile", C);
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
