@@ -323,6 +323,20 @@ def dynamic_routing_hard_topk(sd, p, x, top_k):
     return torch.zeros_like(w).scatter_(1, idx, vals)
 
 
+def es_moe_retained_weights(rw, top_k, dynamic_threshold):
+    """Sample-level part of `ES_MOE._sparse_forward` moe/modules.py:659-684: Top-K over the (spatially constant) importance,
+    rank >= 1 experts dropped below `dynamic_threshold`, retained mass renormalised.  rw (B, E) -> (indices (B,k), w (B,E),
+    retained mask (B,E)).  Known answer of the reference (tests/test_moe.py:409-420): (0.6, 0.4, 0), k=2, thr 0.5 -> (1, 0, 0)."""
+    B, E = rw.shape
+    tv, ti = torch.topk(rw, top_k, dim=1)
+    ranks = torch.arange(top_k, device=rw.device).view(1, -1)
+    keep = (ranks == 0) | (tv >= dynamic_threshold) if dynamic_threshold > 0 else torch.ones_like(ti, dtype=torch.bool)
+    retained = torch.zeros(B, E, dtype=torch.bool, device=rw.device).scatter_(1, ti, keep)
+    w = rw * retained
+    w = w / w.sum(1, keepdim=True).clamp_min(torch.finfo(torch.float32).eps)
+    return ti, w, retained
+
+
 def es_moe(sd, p, x, c1, c2=None, num_experts=4, reduction=8, top_k=2, use_sparse_inference=True, dynamic_threshold=0.4,
            max_kernel_size=15, expert_kernel_sizes=None):
     """`ES_MOE.forward` (eval) moe/modules.py:535-583 with `_sparse_forward` :659-704: sample-level Top-K with the rank>=1
@@ -332,12 +346,7 @@ def es_moe(sd, p, x, c1, c2=None, num_experts=4, reduction=8, top_k=2, use_spars
     c2 = c1 if c2 is None else c2
     rw = dynamic_routing_hard_topk(sd, p + ".routing", x, top_k)                   # (B, E)
     B, E = rw.shape
-    tv, ti = torch.topk(rw, top_k, dim=1)
-    ranks = torch.arange(top_k).view(1, -1)
-    keep = (ranks == 0) | (tv >= dynamic_threshold) if dynamic_threshold > 0 else torch.ones_like(ti, dtype=torch.bool)
-    retained = torch.zeros(B, E, dtype=torch.bool).scatter_(1, ti, keep)
-    w = rw * retained
-    w = w / w.sum(1, keepdim=True).clamp_min(torch.finfo(torch.float32).eps)
+    ti, w, retained = es_moe_retained_weights(rw, top_k, dynamic_threshold)
     ks = es_moe_kernel_sizes(num_experts, max_kernel_size, expert_kernel_sizes)
     out = torch.zeros(B, c2, x.shape[2], x.shape[3])
     for e in range(E):

@@ -75,7 +75,12 @@ def conv2d(x, w_packed, bias, Cout, KH, KW, stride, pad, act, out=None, res=None
     ldx = pitch(x)
     L = lib()
     fn, name = L.ym_conv2d_nhwc, "ym_conv2d_nhwc"
-    if CONV_IMPL == "tc" and Cout % 8 == 0 and L.ym_conv2d_tc_supported(Cin, Cout, KH, KW, stride, pad, ldx):
+    # 3x3 convs over <= 16 input channels stay on the mma.sync implicit GEMM: a k-tile is then 128 rows of 32 bytes and the TMA
+    # unit, fed one 32-byte row at a time for each of the 9 taps, is slower than 16-byte cp.async gathers (measured at bs32:
+    # 93.8 vs 82.7 us for 16->32 s2 @320^2, 86.0 vs 62.3 us for 16->8 @160^2; profiles/r01_conv_impl_table.json).  The rule
+    # depends on the layer only, never on the batch, so results stay bit-identical across batch sizes.
+    small_k = KH == 3 and Cin <= 16
+    if CONV_IMPL == "tc" and not small_k and Cout % 8 == 0 and L.ym_conv2d_tc_supported(Cin, Cout, KH, KW, stride, pad, ldx):
         fn, name = L.ym_conv2d_tc, "ym_conv2d_tc"
     _lib.check(fn(x.data_ptr(), ldx, B, H, W, Cin, w_packed.data_ptr(), w_packed.shape[1],
                   None if bias is None else bias.data_ptr(), Cout, KH, KW, stride, pad,
