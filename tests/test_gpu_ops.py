@@ -282,3 +282,22 @@ def test_es_moe_vs_reference_golden_and_oracle(case):
     exp_idx = torch.where(w.gather(1, ti) > 0, ti, torch.full_like(ti, -1))
     assert torch.equal(snap["topk_indices"].cpu().long(), exp_idx)          # retained experts (and drops) exact
     torch.testing.assert_close(snap["topk_weights"].cpu(), w.gather(1, ti), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("H,W,C,k", [(20, 20, 128, 5), (13, 17, 64, 5), (40, 40, 32, 5), (7, 9, 16, 3), (112, 96, 8, 5)])
+def test_sppf_pool_exact(H, W, C, k):
+    """Chained MaxPool(k) x3 into slots 1..3 of the concat buffer: max is exact in fp16, so bit-identical to F.max_pool2d
+    (separable shared-memory kernel for P5-sized maps, direct window kernel for the large-map fallback)."""
+    import torch.nn.functional as F
+    from yolo_master_b200 import ops
+    g = torch.Generator().manual_seed(H * W + C)
+    y0 = torch.randn((3, H, W, C), generator=g).half()
+    buf = torch.zeros((3, H, W, 4 * C), dtype=torch.float16)
+    buf[..., :C] = y0
+    d = buf.to(DEV)
+    ops.sppf_pool(d, C, k)
+    cur = y0.permute(0, 3, 1, 2).float()
+    for s in range(1, 4):
+        cur = F.max_pool2d(cur, k, 1, k // 2)
+        assert torch.equal(d[..., s * C:(s + 1) * C].float().cpu(), cur.permute(0, 2, 3, 1)), f"slot {s}"
+    assert torch.equal(d[..., :C].cpu(), y0)

@@ -39,15 +39,30 @@ __device__ uint32_t radix_select_kth(const uint32_t* keys, int n, int k, uint32_
             if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int cum = 0, digit = 0;
-            for (int bin = 255; bin >= 0; --bin) {
-                const int hcount = (int)hist[bin];
-                if (cum + hcount >= remaining) { digit = bin; break; }
-                cum += hcount;
+        if (threadIdx.x < 32) {
+            // descending scan of the 256 bins by one warp: lane l owns bins 255-8l .. 248-8l (a single thread walking the bins
+            // was ~30 us of dependent shared-memory reads per image over the 8 digit passes of the two selections)
+            const int lane = threadIdx.x;
+            int local[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { local[j] = (int)hist[255 - (lane * 8 + j)]; sum += local[j]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
             }
-            sh_misc[0] = digit;
-            sh_misc[1] = remaining - cum;
+            const int excl = incl - sum;
+            if (excl < remaining && remaining <= incl) {      // exactly one lane: its bins contain the remaining-th largest key
+                int cum = excl, digit = 255 - lane * 8 - 7, left = remaining - excl;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (cum + local[j] >= remaining) { digit = 255 - (lane * 8 + j); left = remaining - cum; break; }
+                    cum += local[j];
+                }
+                sh_misc[0] = digit;
+                sh_misc[1] = left;
+            }
         }
         __syncthreads();
         prefix |= ((uint32_t)sh_misc[0]) << shift;

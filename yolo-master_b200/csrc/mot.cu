@@ -22,27 +22,55 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // GroupNorm statistics -> per (image, channel) affine: scale = rstd*gamma, shift = beta - mean*rstd*gamma.
-template <typename T>
+// One CTA per (group, image); VEC consecutive channels of a pixel are read with one 2*VEC- or 4*VEC-byte load (the scalar
+// version ran at 158 GB/s: profiles/r01_launch_roofline_moa_mot_n.txt).  Two passes (mean, then centred squares) for accuracy.
+template <typename T, int VEC>
+__device__ __forceinline__ void gn_load(const T* __restrict__ p, float (&v)[VEC]) {
+    if constexpr (sizeof(T) == 2 && VEC == 8) {
+        const Half8 h = *reinterpret_cast<const Half8*>(p);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h.v[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+    } else if constexpr (sizeof(T) == 2 && VEC == 4) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const float2 f0 = unpack_half2(u.x), f1 = unpack_half2(u.y);
+        v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+    } else if constexpr (sizeof(T) == 4 && VEC == 4) {
+        const float4 f = *reinterpret_cast<const float4*>(p);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v[j] = (float)p[j];
+    }
+}
+
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, int ld, int HW, int C, int G, float eps,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float* __restrict__ scale, float* __restrict__ shift) {
     __shared__ float red[8];
     const int g = blockIdx.x, b = blockIdx.y, cpg = C / G;
     const T* xb = x + (size_t)b * HW * ld + g * cpg;
-    const int n = HW * cpg;
+    const int vpr = cpg / VEC;                  // vectors per pixel
+    const int nv = HW * vpr;
+    const float n = (float)HW * (float)cpg;
     float s = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int r = i / cpg, c = i - r * cpg;
-        s += (float)xb[(size_t)r * ld + c];
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const int r = i / vpr, c = (i - r * vpr) * VEC;
+        float v[VEC];
+        gn_load<T, VEC>(xb + (size_t)r * ld + c, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) s += v[j];
     }
-    const float mean = block_sum(s, red) / (float)n;
+    const float mean = block_sum(s, red) / n;
     float q = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int r = i / cpg, c = i - r * cpg;
-        const float d = (float)xb[(size_t)r * ld + c] - mean;
-        q += d * d;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        const int r = i / vpr, c = (i - r * vpr) * VEC;
+        float v[VEC];
+        gn_load<T, VEC>(xb + (size_t)r * ld + c, v);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { const float d = v[j] - mean; q += d * d; }
     }
-    const float var = block_sum(q, red) / (float)n;
+    const float var = block_sum(q, red) / n;
     const float rstd = rsqrtf(var + eps);
     if (threadIdx.x < cpg) {
         const int c = g * cpg + threadIdx.x;
@@ -50,6 +78,20 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
         scale[(size_t)b * C + c] = rstd * ga;
         shift[(size_t)b * C + c] = be - mean * rstd * ga;
     }
+}
+
+template <typename T>
+static void gn_stats_launch(const T* x, int ld, int B, int HW, int C, int G, float eps, const float* gamma, const float* beta,
+                            float* scale, float* shift, cudaStream_t st) {
+    const int cpg = C / G;
+    const dim3 grid(G, B);
+    const bool al = (((uintptr_t)x) % 16 == 0) && (ld * (int)sizeof(T)) % 16 == 0 && (cpg * (int)sizeof(T)) % 8 == 0;
+    if (sizeof(T) == 2 && al && cpg % 8 == 0 && (cpg * 2) % 16 == 0)
+        gn_stats_kernel<T, 8><<<grid, 256, 0, st>>>(x, ld, HW, C, G, eps, gamma, beta, scale, shift);
+    else if (al && cpg % 4 == 0 && (sizeof(T) == 2 || (cpg * 4) % 16 == 0))
+        gn_stats_kernel<T, 4><<<grid, 256, 0, st>>>(x, ld, HW, C, G, eps, gamma, beta, scale, shift);
+    else
+        gn_stats_kernel<T, 1><<<grid, 256, 0, st>>>(x, ld, HW, C, G, eps, gamma, beta, scale, shift);
 }
 
 // LayerNorm over C per token row: one warp per row.
@@ -112,45 +154,71 @@ __device__ __forceinline__ void load_row(float (&dst)[HDP], const __half* __rest
     }
 }
 
-// consume `nk` keys (multiple of 8 slots; keys >= nvalid are masked) held in shared memory as fp16 [.][HDP]
-template <int HDP>
-__device__ __forceinline__ void attend_tile(RowState<HDP>& st, const __half* __restrict__ sk, const __half* __restrict__ sv,
+// K / V tiles live in shared memory as fp32 [keys][HDP] (converted once per tile): the inner loops then read whole rows with
+// 16-byte broadcast loads and contain no conversions.  (First version: fp16 tiles read as half2 - 8 LDS + 8 cvt per 16 FMA at
+// head_dim 8 - ran at 0.6 T scores/s, LSU / conversion bound; profiles/r01_launch_roofline_moa_mot_n.txt.)
+// consume `nk` keys (multiple of 8 slots; keys >= nvalid are masked) for QPT query rows held by this thread
+template <int HDP, int QPT>
+__device__ __forceinline__ void attend_tile(RowState<HDP> (&st)[QPT], const float* __restrict__ sk, const float* __restrict__ sv,
                                             int nk, int nvalid) {
     for (int j0 = 0; j0 < nk && j0 < nvalid; j0 += 8) {
-        float s[8];
-        float mx = -INFINITY;
+        float s[QPT][8];
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-            const __half2* kr = reinterpret_cast<const __half2*>(sk + (j0 + jj) * HDP);
-            float a = 0.f;
+            float kr[HDP];
 #pragma unroll
-            for (int d = 0; d < HDP / 2; ++d) {
-                const float2 f = __half22float2(kr[d]);
-                a = fmaf(st.q[2 * d], f.x, a);
-                a = fmaf(st.q[2 * d + 1], f.y, a);
+            for (int d = 0; d < HDP; d += 4) {
+                const float4 f = *reinterpret_cast<const float4*>(sk + (j0 + jj) * HDP + d);
+                kr[d] = f.x; kr[d + 1] = f.y; kr[d + 2] = f.z; kr[d + 3] = f.w;
             }
-            s[jj] = (j0 + jj < nvalid) ? a : -INFINITY;
-            mx = fmaxf(mx, s[jj]);
+            const bool ok = j0 + jj < nvalid;
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq) {
+                float a = 0.f;
+#pragma unroll
+                for (int d = 0; d < HDP; ++d) a = fmaf(st[qq].q[d], kr[d], a);
+                s[qq][jj] = ok ? a : -INFINITY;
+            }
         }
-        const float mn = fmaxf(st.m, mx);
-        const float corr = exp2f(st.m - mn);   // st.m == -inf on the first group: exp2(-inf) = 0
-        st.m = mn;
-        st.l *= corr;
 #pragma unroll
-        for (int d = 0; d < HDP; ++d) st.acc[d] *= corr;
+        for (int qq = 0; qq < QPT; ++qq) {
+            float mx = s[qq][0];
+#pragma unroll
+            for (int jj = 1; jj < 8; ++jj) mx = fmaxf(mx, s[qq][jj]);
+            const float mn = fmaxf(st[qq].m, mx);
+            const float corr = exp2f(st[qq].m - mn);   // m == -inf on the first group: exp2(-inf) = 0
+            st[qq].m = mn;
+            st[qq].l *= corr;
+#pragma unroll
+            for (int d = 0; d < HDP; ++d) st[qq].acc[d] *= corr;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                s[qq][jj] = exp2f(s[qq][jj] - mn);
+                st[qq].l += s[qq][jj];
+            }
+        }
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-            const float p = exp2f(s[jj] - mn);
-            st.l += p;
-            const __half2* vr = reinterpret_cast<const __half2*>(sv + (j0 + jj) * HDP);
+            float vr[HDP];
 #pragma unroll
-            for (int d = 0; d < HDP / 2; ++d) {
-                const float2 f = __half22float2(vr[d]);
-                st.acc[2 * d] = fmaf(p, f.x, st.acc[2 * d]);
-                st.acc[2 * d + 1] = fmaf(p, f.y, st.acc[2 * d + 1]);
+            for (int d = 0; d < HDP; d += 4) {
+                const float4 f = *reinterpret_cast<const float4*>(sv + (j0 + jj) * HDP + d);
+                vr[d] = f.x; vr[d + 1] = f.y; vr[d + 2] = f.z; vr[d + 3] = f.w;
             }
+#pragma unroll
+            for (int qq = 0; qq < QPT; ++qq)
+#pragma unroll
+                for (int d = 0; d < HDP; ++d) st[qq].acc[d] = fmaf(s[qq][jj], vr[d], st[qq].acc[d]);
         }
     }
+}
+
+template <int HDP>
+__device__ __forceinline__ void init_row(RowState<HDP>& st) {
+    st.m = -INFINITY;
+    st.l = 0.f;
+#pragma unroll
+    for (int d = 0; d < HDP; ++d) { st.acc[d] = 0.f; st.q[d] = 0.f; }
 }
 
 template <int HDP>
@@ -165,24 +233,33 @@ __device__ __forceinline__ void store_row(const RowState<HDP>& st, __half* __res
     }
 }
 
-constexpr int AT_TK = 64;   // keys per shared-memory tile
+// 8 fp16 channels -> 8 fp32 in a shared-memory row
+__device__ __forceinline__ void stage8(float* __restrict__ dst, const Half8& h) {
+    const float2 f0 = __half22float2(h.v[0]), f1 = __half22float2(h.v[1]), f2 = __half22float2(h.v[2]), f3 = __half22float2(h.v[3]);
+    *reinterpret_cast<float4*>(dst) = make_float4(f0.x, f0.y, f1.x, f1.y);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+}
+
+constexpr int AT_TK = 64;        // keys per shared-memory tile
+constexpr int AT_THREADS = 128;
 
 // Global attention: q rows [batch*Nq], k/v rows [batch*Nkv]; head h uses channels [h*HDP, (h+1)*HDP) of each pointer.
-template <int HDP>
-__global__ void __launch_bounds__(128) attn_small_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k,
-                                                         int ldk, const __half* __restrict__ v, int ldv, int Nq, int Nkv,
-                                                         float scale_log2, __half* __restrict__ out, int ldo) {
-    __shared__ __align__(16) __half sk[AT_TK * HDP];
-    __shared__ __align__(16) __half sv[AT_TK * HDP];
+// Each thread owns QPT query rows (qi, qi + 128, ...): a K / V row read from shared memory is used QPT times.
+template <int HDP, int QPT>
+__global__ void __launch_bounds__(AT_THREADS) attn_small_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k,
+                                                                int ldk, const __half* __restrict__ v, int ldv, int Nq, int Nkv,
+                                                                float scale_log2, __half* __restrict__ out, int ldo) {
+    __shared__ __align__(16) float sk[AT_TK * HDP];
+    __shared__ __align__(16) float sv[AT_TK * HDP];
     const int h = blockIdx.y, b = blockIdx.z;
-    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = qi < Nq;
-    RowState<HDP> st;
-    st.m = -INFINITY;
-    st.l = 0.f;
+    const int q0 = blockIdx.x * (AT_THREADS * QPT) + threadIdx.x;
+    RowState<HDP> st[QPT];
 #pragma unroll
-    for (int d = 0; d < HDP; ++d) st.acc[d] = 0.f;
-    load_row<HDP>(st.q, q + ((size_t)b * Nq + (live ? qi : 0)) * ldq + h * HDP, scale_log2);
+    for (int qq = 0; qq < QPT; ++qq) {
+        init_row<HDP>(st[qq]);
+        const int qi = q0 + qq * AT_THREADS;
+        load_row<HDP>(st[qq].q, q + ((size_t)b * Nq + (qi < Nq ? qi : 0)) * ldq + h * HDP, scale_log2);
+    }
     constexpr int VPR = HDP / 8;   // 16-byte vectors per row
     for (int k0 = 0; k0 < Nkv; k0 += AT_TK) {
         __syncthreads();
@@ -197,26 +274,30 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const __half* __restric
 #pragma unroll
                 for (int j = 0; j < 4; ++j) hk.v[j] = hv.v[j] = __floats2half2_rn(0.f, 0.f);
             }
-            *reinterpret_cast<Half8*>(sk + r * HDP + part * 8) = hk;
-            *reinterpret_cast<Half8*>(sv + r * HDP + part * 8) = hv;
+            stage8(sk + r * HDP + part * 8, hk);
+            stage8(sv + r * HDP + part * 8, hv);
         }
         __syncthreads();
-        attend_tile<HDP>(st, sk, sv, AT_TK, Nkv - k0);
+        attend_tile<HDP, QPT>(st, sk, sv, AT_TK, Nkv - k0);
     }
-    if (live) store_row<HDP>(st, out + ((size_t)b * Nq + qi) * ldo + h * HDP);
+#pragma unroll
+    for (int qq = 0; qq < QPT; ++qq) {
+        const int qi = q0 + qq * AT_THREADS;
+        if (qi < Nq) store_row<HDP>(st[qq], out + ((size_t)b * Nq + qi) * ldo + h * HDP);
+    }
 }
 
 // Window attention (win*win <= 64 tokens per window) with the reference's pad-then-roll token mapping:
 // window (wy,wx) token (iy,ix) -> padded-rolled position (py,px) -> source ((py+shift)%Hp, (px+shift)%Wp); sources outside
-// HxW are padding tokens whose q/k/v are `padvec` (3 pointers' worth: [q | k | v] per head layout) or zeros.
+// HxW are padding tokens whose k/v are `padk` / `padv` (per head layout) or zeros.
 template <int HDP>
 __global__ void __launch_bounds__(64) attn_window_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k,
                                                          int ldk, const __half* __restrict__ v, int ldv, int H, int W, int win,
                                                          int shift, const __half* __restrict__ padq,
                                                          const __half* __restrict__ padk, const __half* __restrict__ padv,
                                                          float scale_log2, __half* __restrict__ out, int ldo) {
-    __shared__ __align__(16) __half sk[64 * HDP];
-    __shared__ __align__(16) __half sv[64 * HDP];
+    __shared__ __align__(16) float sk[64 * HDP];
+    __shared__ __align__(16) float sv[64 * HDP];
     const int Hp = (H + win - 1) / win * win, Wp = (W + win - 1) / win * win;
     const int nwx = Wp / win;
     const int wy = blockIdx.x / nwx, wx = blockIdx.x - wy * nwx;
@@ -229,11 +310,8 @@ __global__ void __launch_bounds__(64) attn_window_kernel(const __half* __restric
     const bool tok = t < WT;
     const bool real = tok && sy < H && sx < W;
     const size_t row = (size_t)b * H * W + (size_t)sy * W + sx;
-    RowState<HDP> st;
-    st.m = -INFINITY;
-    st.l = 0.f;
-#pragma unroll
-    for (int d = 0; d < HDP; ++d) { st.acc[d] = 0.f; st.q[d] = 0.f; }
+    RowState<HDP> st[1];
+    init_row<HDP>(st[0]);
     constexpr int VPR = HDP / 8;
     {
         const __half* kp = real ? k + row * ldk + h * HDP : (padk ? padk + h * HDP : nullptr);
@@ -245,16 +323,16 @@ __global__ void __launch_bounds__(64) attn_window_kernel(const __half* __restric
             for (int j = 0; j < 4; ++j) hk.v[j] = hv.v[j] = __floats2half2_rn(0.f, 0.f);
             if (tok && kp) hk = *reinterpret_cast<const Half8*>(kp + part * 8);
             if (tok && vp) hv = *reinterpret_cast<const Half8*>(vp + part * 8);
-            *reinterpret_cast<Half8*>(sk + t * HDP + part * 8) = hk;
-            *reinterpret_cast<Half8*>(sv + t * HDP + part * 8) = hv;
+            stage8(sk + t * HDP + part * 8, hk);
+            stage8(sv + t * HDP + part * 8, hv);
         }
-        if (real) load_row<HDP>(st.q, q + row * ldq + h * HDP, scale_log2);
+        if (real) load_row<HDP>(st[0].q, q + row * ldq + h * HDP, scale_log2);
     }
     (void)padq;   // padding queries produce rows that the reference crops away: never computed
     __syncthreads();
     if (!real) return;
-    attend_tile<HDP>(st, sk, sv, 64, WT);
-    store_row<HDP>(st, out + row * ldo + h * HDP);
+    attend_tile<HDP, 1>(st, sk, sv, 64, WT);
+    store_row<HDP>(st[0], out + row * ldo + h * HDP);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -552,11 +630,8 @@ extern "C" int ym_groupnorm_stats(const void* x, int x_f32, int ld, int B, int H
     YM_CHECK_ARG(x && scale && shift, "ym_groupnorm_stats: null pointer");
     YM_CHECK_ARG(G >= 1 && C % G == 0 && C / G <= 256, "ym_groupnorm_stats: C=%d must be divisible by G=%d (<=256 channels per group)", C, G);
     if (B == 0) return YM_OK;
-    dim3 grid(G, B);
-    if (x_f32)
-        gn_stats_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, ld, HW, C, G, eps, gamma, beta, scale, shift);
-    else
-        gn_stats_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, ld, HW, C, G, eps, gamma, beta, scale, shift);
+    if (x_f32) gn_stats_launch<float>((const float*)x, ld, B, HW, C, G, eps, gamma, beta, scale, shift, (cudaStream_t)stream);
+    else gn_stats_launch<__half>((const __half*)x, ld, B, HW, C, G, eps, gamma, beta, scale, shift, (cudaStream_t)stream);
     YM_CHECK_LAUNCH("groupnorm_stats");
     return YM_OK;
 }
@@ -583,17 +658,21 @@ extern "C" int ym_attn_small(const void* q, int ldq, const void* k, int ldk, con
     ATTN_ARGS_OK("ym_attn_small");
     YM_CHECK_ARG(Nq >= 1 && Nkv >= 1 && heads >= 1, "ym_attn_small: empty problem");
     if (batch == 0) return YM_OK;
-    dim3 grid((Nq + 127) / 128, heads, batch);
     cudaStream_t st = (cudaStream_t)stream;
     const float sl = scale * LOG2E;
-#define AS_LAUNCH(H)                                                                                                         \
-    attn_small_kernel<H><<<grid, 128, 0, st>>>((const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, Nq, Nkv, sl, \
-                                               (__half*)out, ldo)
+    // two query rows per thread where the register budget allows it (head_dim <= 16) and the problem is large enough to
+    // still fill the GPU with 256-query CTAs
+    const bool two = hdp <= 16 && (long long)((Nq + 255) / 256) * heads * batch >= 2 * 148;
+    const int qpc = two ? 256 : 128;
+    dim3 grid((Nq + qpc - 1) / qpc, heads, batch);
+#define AS_LAUNCH(H, Q)                                                                                                      \
+    attn_small_kernel<H, Q><<<grid, AT_THREADS, 0, st>>>((const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, Nq, \
+                                                         Nkv, sl, (__half*)out, ldo)
     switch (hdp) {
-        case 8: AS_LAUNCH(8); break;
-        case 16: AS_LAUNCH(16); break;
-        case 24: AS_LAUNCH(24); break;
-        default: AS_LAUNCH(32); break;
+        case 8: if (two) AS_LAUNCH(8, 2); else AS_LAUNCH(8, 1); break;
+        case 16: if (two) AS_LAUNCH(16, 2); else AS_LAUNCH(16, 1); break;
+        case 24: AS_LAUNCH(24, 1); break;
+        default: AS_LAUNCH(32, 1); break;
     }
 #undef AS_LAUNCH
     YM_CHECK_LAUNCH("attn_small");
@@ -658,7 +737,7 @@ extern "C" int ym_token_router(const void* x, int ldx, int B, int HW, int C, con
     float* sh = sc + (size_t)B * HID;
     token_router_hidden_kernel<<<(int)((rows + 127) / 128), 128, (size_t)HID * C * 4, st>>>((const __half*)x, ldx, w1, C, HID, hidden, rows);
     YM_CHECK_LAUNCH("token_router_hidden");
-    gn_stats_kernel<float><<<dim3(G, B), 256, 0, st>>>(hidden, HID, HW, HID, G, gn_eps, gn_w, gn_b, sc, sh);
+    gn_stats_launch<float>(hidden, HID, B, HW, HID, G, gn_eps, gn_w, gn_b, sc, sh, st);
     YM_CHECK_LAUNCH("token_router_gn");
     token_router_finish_kernel<<<(int)((rows + 127) / 128), 128, 0, st>>>(hidden, sc, sh, w2, b2, HID, E, topk, temp_dev, temp, HW,
                                                                            weights, idx, rows);
