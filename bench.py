@@ -182,9 +182,10 @@ def time_attention_kernel(dev, batch, pk):
             "ms_per_launch": ms, "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": algo_bytes,
             "exp_per_launch": exps, "gexp_per_s": exps / (ms * 1e-3) / 1e9,
             "mufu_frac": exps / (ms * 1e-3) / (148 * 16 * 1.965e9),
-            "note": "d=32 attention is bounded by the MUFU (one ex2 per score: 16 lanes/clk/SM x 148 SMs x 1.965 GHz = "
-                    "4.65 T exp/s), not by the tensor pipe (SURVEY.md §7): mufu_frac is the binding fraction; "
-                    "peak = cuBLAS bf16 burst " + pk["source"]}
+            "note": "d=32 attention has two equal non-tensor ceilings of 16 scores/clk/SM (4.65 T scores/s): one ex2 per score on "
+                    "the MUFU (16 lanes/clk/SM) and one fp32 score read back from tensor memory (tcgen05.ld: 64 B/clk/SM); "
+                    "mufu_frac is the fraction of that ceiling (an FMA-pipe exp2 offload was measured and gives no gain, "
+                    "profiles/r01_attention_poly_sweep.json); peak = cuBLAS bf16 burst " + pk["source"]}
 
 
 def time_dispatch(dev, pk, B=64, baseline=True):
