@@ -66,6 +66,10 @@ int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, int heads, in
  * 1.099 ms at 6 / 4 / 3 / 2 - the kernel's per-tile dependency chain, not the MUFU rate, sets its time.  Returns the previous
  * setting. */
 int ym_set_attention_poly(int every);
+/* tcgen05 kernel only: read each S row from tensor memory in four 16-column chunks and run the exponentials of one chunk while
+ * the next is in flight (running maximum updated per chunk, already-packed P values rescaled on growth).  Returns the previous
+ * setting. */
+int ym_set_attention_chunked(int on);
 int ym_set_attention_impl(int impl);
 
 /* EfficientSpatialRouter.forward + BaseRouter._process_logits (eval)  moe/routers.py:283-304, :185-265.

@@ -70,9 +70,18 @@ def test_moe_dispatch_vs_oracle(B, hw, C, E, k, impl):
     assert_close(out.permute(0, 3, 1, 2), ref16, max_bad_frac=2e-6, what="moe_dispatch vs fp16-expert-output oracle")
 
 
+@pytest.fixture(params=[0, 1], ids=["rowwise", "chunked"])
+def softmax_mode(request):
+    """Both softmax schedules of the tcgen05 attention kernel (ym_set_attention_chunked)."""
+    from yolo_master_b200 import _lib
+    prev = _lib.load().ym_set_attention_chunked(request.param)
+    yield request.param
+    _lib.load().ym_set_attention_chunked(prev)
+
+
 @pytest.mark.parametrize("N,heads,dv,batch", [(64, 1, 32, 1), (128, 2, 32, 2), (400, 2, 32, 3), (1600, 2, 32, 2), (221, 4, 32, 2),
-                                              (400, 2, 64, 2), (100, 2, 64, 1), (6400, 2, 32, 1)])
-def test_tc_attention_strict(N, heads, dv, batch):
+                                              (400, 2, 64, 2), (100, 2, 64, 1), (6400, 2, 32, 1), (40, 1, 32, 1), (17, 2, 32, 2)])
+def test_tc_attention_strict(N, heads, dv, batch, softmax_mode):
     """tcgen05 attention kernel alone vs fp32 softmax attention (strict tolerance), incl. ragged N and d_v = 64."""
     from yolo_master_b200 import _lib, ops
     hs = 64 + dv
@@ -88,8 +97,8 @@ def test_tc_attention_strict(N, heads, dv, batch):
     assert_close(out, ref, what=f"tc attention N={N} dv={dv}")
 
 
-def test_tc_attention_large_logits_lazy_rescale():
-    """Rows whose running max keeps growing exercise the lazy O rescaling path."""
+def test_tc_attention_large_logits_lazy_rescale(softmax_mode):
+    """Rows whose running max keeps growing exercise the lazy O rescaling path (and, chunked, the in-row P rescale)."""
     from yolo_master_b200 import _lib
     N, heads, dv, hs = 512, 1, 32, 96
     g = torch.Generator().manual_seed(3)

@@ -17,8 +17,13 @@ qkv = torch.randn((B, 80, 80, 3 * heads * hd), device=dev).half()
 L = ops.lib()
 res = {}
 ref = None
-for poly in (0, 6, 4, 3, 2, 0):
-    L.ym_set_attention_poly(poly)
+for poly in (0, 6, 4, "chunked", 0, "chunked"):
+    if poly == "chunked":
+        L.ym_set_attention_poly(0)
+        L.ym_set_attention_chunked(1)
+    else:
+        L.ym_set_attention_chunked(0)
+        L.ym_set_attention_poly(poly)
     out = ops.new_act(B, 80, 80, heads * hd, dev)
     for _ in range(3):
         ops.attention(qkv, B, N, heads, 3 * hd, 0, hd, 2 * hd, hd, hd, hd ** -0.5, out=out)
@@ -35,4 +40,5 @@ for poly in (0, 6, 4, 3, 2, 0):
     err = float((out.float() - ref).abs().max())
     res[f"poly{poly}" + ("_again" if f"poly{poly}" in res else "")] = {"ms": ms, "max_abs_dev_vs_mufu": err}
 L.ym_set_attention_poly(0)
+L.ym_set_attention_chunked(0)
 print(json.dumps(res))

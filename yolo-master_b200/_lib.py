@@ -26,6 +26,7 @@ SIGNATURES = {
     "ym_attention_fwd_tc": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, cf, vp, ci, vp]),
     "ym_set_attention_impl": (ci, [ci]),
     "ym_set_attention_poly": (ci, [ci]),
+    "ym_set_attention_chunked": (ci, [ci]),
     "ym_router_scratch_floats": (cll, [ci, ci, ci, ci, ci, ci]),
     "ym_router_topk": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, ci, vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]),
     "ym_moe_expert_gemm": (ci, [vp, ci, ci, ci, ci, ci, vp, ci, cll, vp, ci, vp, ci, vp, vp, vp, ci, vp]),

@@ -38,7 +38,12 @@ __device__ __forceinline__ float ta_exp2_poly(float x) {
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-template <int DV, int POLY>
+// CHUNK: the S row is read from tensor memory in four 16-column chunks; the exponentials of chunk c run while chunk c+1 is in
+// flight (tcgen05.ld is asynchronous until tcgen05.wait::ld), so the two 16-scores/clk/SM resources of this kernel - the
+// tensor-memory read port and the MUFU - overlap inside every warp instead of alternating.  The running maximum is updated
+// chunk by chunk with the same 2^8 slack as the lazy rescale; when a later chunk raises it, the fp16 P values already packed
+// for this row are multiplied by the same factor as O / L, so the row stays exactly consistent.
+template <int DV, int POLY, bool CHUNK>
 __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* __restrict__ qkv, int ld, int N, int head_stride,
                                                                  int q_off, int k_off, int v_off, float scale_log2,
                                                                  __half* __restrict__ out, int ldo) {
@@ -159,39 +164,83 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
         // ---- softmax of row `row` of S_t
         tc::mbar_wait(&bar_s, t & 1);
         tc::fence_after_sync();
-        uint32_t sr[64];
-        {
-            uint32_t lo[32], hi[32];
-            tc::tmem_ld32(t_s + lane_sel, lo);
-            tc::tmem_ld32(t_s + lane_sel + 32, hi);
+        const int kv0 = t * TA_BKV;
+        float alpha = 1.f;
+        bool grow = false;
+        uint32_t pk[32];
+        if constexpr (CHUNK) {
+            uint32_t cur[16];
+            tc::tmem_ld16(t_s + lane_sel, cur);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { sr[i] = lo[i]; sr[32 + i] = hi[i]; }
-        }
-        const int kv0 = t * TA_BKV;
-        if (kv0 + TA_BKV > N) {               // tail tile only: keys >= N do not exist
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t nxt[16];
+                if (ch < 3) tc::tmem_ld16(t_s + lane_sel + 16 * (ch + 1), nxt);      // lands while this chunk's exps run
+                if (kv0 + TA_BKV > N) {           // tail tile only: keys >= N do not exist
 #pragma unroll
-            for (int i = 0; i < 64; ++i)
-                if (kv0 + i >= N) sr[i] = 0xff800000u;   // -inf
-        }
-        float mx = -INFINITY;
+                    for (int i = 0; i < 16; ++i)
+                        if (kv0 + ch * 16 + i >= N) cur[i] = 0xff800000u;   // -inf
+                }
+                float mx = __uint_as_float(cur[0]);
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
-        const float m_tile = mx * scale_log2;
-        float alpha = 1.f;
-        const bool grow = m_tile > m_used + 8.f;     // also true on the first tile (m_used = -inf)
-        if (grow) {
-            alpha = ta_exp2(m_used - m_tile);        // 0 on the first tile
-            m_used = m_tile;
-        }
-        uint32_t pk[32];
+                for (int i = 1; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
+                const float cm = mx * scale_log2;
+                if (cm > m_used + 8.f) {          // first chunk of the first tile (m_used = -inf), then rare
+                    const float a = ta_exp2(m_used - cm);
+                    m_used = cm;
+                    alpha *= a;
+                    grow = true;
+                    const __half2 a2 = __float2half2_rn(a);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const float x0 = fmaf(__uint_as_float(sr[2 * i]), scale_log2, -m_used);
-            const float x1 = fmaf(__uint_as_float(sr[2 * i + 1]), scale_log2, -m_used);
-            const float p0 = (POLY > 0 && (2 * i) % POLY == POLY - 1) ? ta_exp2_poly(x0) : ta_exp2(x0);
-            const float p1 = (POLY > 0 && (2 * i + 1) % POLY == POLY - 1) ? ta_exp2_poly(x1) : ta_exp2(x1);
-            pk[i] = pack_half2(p0, p1);
+                    for (int i = 0; i < ch * 8; ++i) {
+                        const __half2 v = __hmul2(*reinterpret_cast<const __half2*>(&pk[i]), a2);
+                        pk[i] = *reinterpret_cast<const uint32_t*>(&v);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float p0 = ta_exp2(fmaf(__uint_as_float(cur[2 * i]), scale_log2, -m_used));
+                    const float p1 = ta_exp2(fmaf(__uint_as_float(cur[2 * i + 1]), scale_log2, -m_used));
+                    pk[ch * 8 + i] = pack_half2(p0, p1);
+                }
+                if (ch < 3) {
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+                }
+            }
+        } else {
+            uint32_t sr[64];
+            {
+                uint32_t lo[32], hi[32];
+                tc::tmem_ld32(t_s + lane_sel, lo);
+                tc::tmem_ld32(t_s + lane_sel + 32, hi);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { sr[i] = lo[i]; sr[32 + i] = hi[i]; }
+            }
+            if (kv0 + TA_BKV > N) {               // tail tile only: keys >= N do not exist
+#pragma unroll
+                for (int i = 0; i < 64; ++i)
+                    if (kv0 + i >= N) sr[i] = 0xff800000u;   // -inf
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+            const float m_tile = mx * scale_log2;
+            grow = m_tile > m_used + 8.f;         // also true on the first tile (m_used = -inf)
+            if (grow) {
+                alpha = ta_exp2(m_used - m_tile);        // 0 on the first tile
+                m_used = m_tile;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float x0 = fmaf(__uint_as_float(sr[2 * i]), scale_log2, -m_used);
+                const float x1 = fmaf(__uint_as_float(sr[2 * i + 1]), scale_log2, -m_used);
+                const float p0 = (POLY > 0 && (2 * i) % POLY == POLY - 1) ? ta_exp2_poly(x0) : ta_exp2(x0);
+                const float p1 = (POLY > 0 && (2 * i + 1) % POLY == POLY - 1) ? ta_exp2_poly(x1) : ta_exp2(x1);
+                pk[i] = pack_half2(p0, p1);
+            }
         }
         // ---- PV_{t-1} must be complete before O/L are rescaled, P is overwritten, or its K/V stage is reloaded
         if (t > 0) {
@@ -290,6 +339,14 @@ extern "C" int ym_set_attention_poly(int every) {
     return old;
 }
 
+// Chunked softmax (tensor-memory reads overlapped with the exponentials inside each warp): 1 = on, 0 = whole-row softmax.
+static int g_attention_chunked = 0;
+extern "C" int ym_set_attention_chunked(int on) {
+    const int old = g_attention_chunked;
+    if (on == 0 || on == 1) g_attention_chunked = on;
+    return old;
+}
+
 extern "C" int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
                                    int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream) {
     YM_CHECK_ARG(qkv && out, "ym_attention_fwd_tc: null pointer");
@@ -305,20 +362,21 @@ extern "C" int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, in
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)TA_BQ * 64 + TA_BQ * 128 + TA_STAGES * (TA_BKV * 64 + TA_BKV * d_v * 2) + 16 * 128 + 1024;
     cudaError_t e = cudaSuccess;
-#define TA_LAUNCH(DV_, POLY_)                                                                                                  \
+#define TA_LAUNCH(DV_, POLY_, CH_)                                                                                             \
     do {                                                                                                                       \
-        e = cudaFuncSetAttribute(tc_attention_kernel<DV_, POLY_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        e = cudaFuncSetAttribute(tc_attention_kernel<DV_, POLY_, CH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e == cudaSuccess)                                                                                                  \
-            tc_attention_kernel<DV_, POLY_><<<grid, TA_THREADS, smem, st>>>((const __half*)qkv, ld, N, head_stride, q_off, k_off,  \
-                                                                           v_off, sl2, (__half*)out, ldo);                     \
+            tc_attention_kernel<DV_, POLY_, CH_><<<grid, TA_THREADS, smem, st>>>((const __half*)qkv, ld, N, head_stride, q_off,    \
+                                                                               k_off, v_off, sl2, (__half*)out, ldo);          \
     } while (0)
 #define TA_LAUNCH_DV(DV_)                                          \
-    switch (g_attention_poly) {                                    \
-        case 2: TA_LAUNCH(DV_, 2); break;                          \
-        case 3: TA_LAUNCH(DV_, 3); break;                          \
-        case 4: TA_LAUNCH(DV_, 4); break;                          \
-        case 6: TA_LAUNCH(DV_, 6); break;                          \
-        default: TA_LAUNCH(DV_, 0); break;                         \
+    if (g_attention_chunked) { TA_LAUNCH(DV_, 0, true); }          \
+    else switch (g_attention_poly) {                               \
+        case 2: TA_LAUNCH(DV_, 2, false); break;                   \
+        case 3: TA_LAUNCH(DV_, 3, false); break;                   \
+        case 4: TA_LAUNCH(DV_, 4, false); break;                   \
+        case 6: TA_LAUNCH(DV_, 6, false); break;                   \
+        default: TA_LAUNCH(DV_, 0, false); break;                  \
     }
     if (d_v == 32) { TA_LAUNCH_DV(32) } else { TA_LAUNCH_DV(64) }
 #undef TA_LAUNCH_DV
