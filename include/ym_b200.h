@@ -66,10 +66,13 @@ int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, int heads, in
  * 1.099 ms at 6 / 4 / 3 / 2 - the kernel's per-tile dependency chain, not the MUFU rate, sets its time.  Returns the previous
  * setting. */
 int ym_set_attention_poly(int every);
-/* tcgen05 kernel only: read each S row from tensor memory in four 16-column chunks and run the exponentials of one chunk while
- * the next is in flight (running maximum updated per chunk, already-packed P values rescaled on growth).  Returns the previous
- * setting. */
-int ym_set_attention_chunked(int on);
+/* tcgen05 kernel only, schedule selector (returns the previous setting):
+ *   0  whole-row softmax; P through shared memory (SS-mode MMAs, row sums as a P x ones MMA)
+ *   1  chunked softmax: each S row is read from tensor memory in four 16-column chunks and the exponentials of one chunk run
+ *      while the next is in flight (running maximum per chunk, already-packed P values rescaled on growth)
+ *   2  whole-row softmax; P written to tensor memory (tcgen05.st) and consumed by a TS-mode tcgen05.mma, row sums in registers
+ *   3  1 + 2 */
+int ym_set_attention_chunked(int mode);
 int ym_set_attention_impl(int impl);
 
 /* EfficientSpatialRouter.forward + BaseRouter._process_logits (eval)  moe/routers.py:283-304, :185-265.

@@ -70,7 +70,7 @@ def test_moe_dispatch_vs_oracle(B, hw, C, E, k, impl):
     assert_close(out.permute(0, 3, 1, 2), ref16, max_bad_frac=2e-6, what="moe_dispatch vs fp16-expert-output oracle")
 
 
-@pytest.fixture(params=[0, 1], ids=["rowwise", "chunked"])
+@pytest.fixture(params=[0, 1, 2, 3], ids=["rowwise", "chunked", "tmemP", "chunked+tmemP"])
 def softmax_mode(request):
     """Both softmax schedules of the tcgen05 attention kernel (ym_set_attention_chunked)."""
     from yolo_master_b200 import _lib

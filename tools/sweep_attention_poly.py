@@ -17,10 +17,10 @@ qkv = torch.randn((B, 80, 80, 3 * heads * hd), device=dev).half()
 L = ops.lib()
 res = {}
 ref = None
-for poly in (0, 6, 4, "chunked", 0, "chunked"):
-    if poly == "chunked":
+for poly in (0, "mode1", "mode2", "mode3", 0, "mode2"):
+    if isinstance(poly, str):
         L.ym_set_attention_poly(0)
-        L.ym_set_attention_chunked(1)
+        L.ym_set_attention_chunked(int(poly[-1]))
     else:
         L.ym_set_attention_chunked(0)
         L.ym_set_attention_poly(poly)

@@ -43,7 +43,12 @@ __device__ __forceinline__ float ta_exp2_poly(float x) {
 // tensor-memory read port and the MUFU - overlap inside every warp instead of alternating.  The running maximum is updated
 // chunk by chunk with the same 2^8 slack as the lazy rescale; when a later chunk raises it, the fp16 P values already packed
 // for this row are multiplied by the same factor as O / L, so the row stays exactly consistent.
-template <int DV, int POLY, bool CHUNK>
+// TSP: P never touches shared memory.  Each thread writes its packed fp16 P row into tensor memory (tcgen05.st, 256 B/clk) and
+// O += P V runs as a TS-mode tcgen05.mma whose A operand is read from tensor memory; the row sums are plain fp32 adds in
+// registers instead of a second (P x ones) MMA.  Per CTA-tile this removes the 16 KB P store, the 2 x 16 KB of P operand reads
+// and the ones operand from the shared-memory pipe: 74 KB -> 24 KB per tile, where 128 B/clk of shared-memory bandwidth
+// (580 clk per tile) had been a tighter ceiling than the MUFU and the tensor-memory read port (512 clk each).
+template <int DV, int POLY, bool CHUNK, bool TSP>
 __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* __restrict__ qkv, int ld, int N, int head_stride,
                                                                  int q_off, int k_off, int v_off, float scale_log2,
                                                                  __half* __restrict__ out, int ldo) {
@@ -139,6 +144,8 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
     const uint32_t t_s = tmem_base, t_o = tmem_base + 64, t_l = tmem_base + 64 + DV;
+    const uint32_t t_p = tmem_base + 64 + DV;          // TSP: 32 columns of packed fp16 P (takes the place of L)
+    float l_run = 0.f;                                 // TSP: running row sum
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
 
     const uint32_t idesc_qk = tc::make_idesc_f16(TA_BQ, TA_BKV, 0);
@@ -242,6 +249,15 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
                 pk[i] = pack_half2(p0, p1);
             }
         }
+        if constexpr (TSP) {                      // row sum of the fp16-rounded P values that multiply V
+            float ls = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float2 f = unpack_half2(pk[i]);
+                ls += f.x + f.y;
+            }
+            l_run = l_run * alpha + ls;
+        }
         // ---- PV_{t-1} must be complete before O/L are rescaled, P is overwritten, or its K/V stage is reloaded
         if (t > 0) {
             tc::mbar_wait(&bar_pv, (t - 1) & 1);
@@ -256,23 +272,31 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
                     for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                     tc::tmem_st32(t_o + lane_sel + c0, o);
                 }
-                uint32_t l16[16];
-                tc::tmem_ld16(t_l + lane_sel, l16);
-                tc::tmem_ld_wait();
+                if constexpr (!TSP) {
+                    uint32_t l16[16];
+                    tc::tmem_ld16(t_l + lane_sel, l16);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) l16[i] = __float_as_uint(__uint_as_float(l16[i]) * alpha);
-                tc::tmem_st16(t_l + lane_sel, l16);
+                    for (int i = 0; i < 16; ++i) l16[i] = __float_as_uint(__uint_as_float(l16[i]) * alpha);
+                    tc::tmem_st16(t_l + lane_sel, l16);
+                }
                 tc::tmem_st_wait();
             }
         }
         // ---- prefetch tile t+2 into the ring stage last read by PV_{t-1}
         if (t + 2 < T) load_kv(t + 2);
         cp_async_commit();
-        // ---- P row -> swizzled smem (A operand, K-major, 64 keys = 128 B per row)
+        if constexpr (TSP) {
+            // ---- P row -> tensor memory (A operand of the TS-mode MMA: lane = query row, column c = keys 2c, 2c+1)
+            tc::tmem_st32(t_p + lane_sel, pk);
+            tc::tmem_st_wait();
+        } else {
+            // ---- P row -> swizzled smem (A operand, K-major, 64 keys = 128 B per row)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint4 v = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-            *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = v;
+            for (int c = 0; c < 8; ++c) {
+                uint4 v = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = v;
+            }
         }
         cp_async_wait<1>();                   // K_{t+1} / V_{t+1} have landed (only the newest group may be pending)
         tc::fence_proxy_async();
@@ -287,8 +311,12 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
             constexpr uint32_t VSTEP = (16 * DV * 2) >> 4;    // 16 keys per MMA k-step, in 16-byte units
 #pragma unroll
             for (int k = 0; k < TA_BKV / 16; ++k) {
-                tc::mma_f16_ss(t_o, pdesc + 2 * k, vdesc + VSTEP * k, idesc_pv, (t | k) ? 1u : 0u);
-                tc::mma_f16_ss(t_l, pdesc + 2 * k, odesc + 2 * k, idesc_l, (t | k) ? 1u : 0u);
+                if constexpr (TSP) {
+                    tc::mma_f16_ts(t_o, t_p + 8 * k, vdesc + VSTEP * k, idesc_pv, (t | k) ? 1u : 0u);   // 16 keys = 8 columns
+                } else {
+                    tc::mma_f16_ss(t_o, pdesc + 2 * k, vdesc + VSTEP * k, idesc_pv, (t | k) ? 1u : 0u);
+                    tc::mma_f16_ss(t_l, pdesc + 2 * k, odesc + 2 * k, idesc_l, (t | k) ? 1u : 0u);
+                }
             }
             tc::mma_commit(&bar_pv);
         }
@@ -298,7 +326,9 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
     tc::mbar_wait(&bar_pv, (T - 1) & 1);
     tc::fence_after_sync();
     float inv;
-    {
+    if constexpr (TSP) {
+        inv = 1.f / l_run;
+    } else {
         uint32_t l16[16];
         tc::tmem_ld16(t_l + lane_sel, l16);
         tc::tmem_ld_wait();
@@ -339,11 +369,13 @@ extern "C" int ym_set_attention_poly(int every) {
     return old;
 }
 
-// Chunked softmax (tensor-memory reads overlapped with the exponentials inside each warp): 1 = on, 0 = whole-row softmax.
+// Softmax / PV schedule: 0 = whole-row softmax, P through shared memory (SS-mode MMAs, row sums on the tensor core);
+// 1 = chunked softmax (tensor-memory reads overlapped with the exponentials inside each warp), P through shared memory;
+// 2 = whole-row softmax, P through tensor memory (TS-mode PV MMA, row sums in registers); 3 = chunked + tensor-memory P.
 static int g_attention_chunked = 0;
 extern "C" int ym_set_attention_chunked(int on) {
     const int old = g_attention_chunked;
-    if (on == 0 || on == 1) g_attention_chunked = on;
+    if (on >= 0 && on <= 3) g_attention_chunked = on;
     return old;
 }
 
@@ -362,21 +394,23 @@ extern "C" int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, in
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)TA_BQ * 64 + TA_BQ * 128 + TA_STAGES * (TA_BKV * 64 + TA_BKV * d_v * 2) + 16 * 128 + 1024;
     cudaError_t e = cudaSuccess;
-#define TA_LAUNCH(DV_, POLY_, CH_)                                                                                             \
-    do {                                                                                                                       \
-        e = cudaFuncSetAttribute(tc_attention_kernel<DV_, POLY_, CH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e == cudaSuccess)                                                                                                  \
-            tc_attention_kernel<DV_, POLY_, CH_><<<grid, TA_THREADS, smem, st>>>((const __half*)qkv, ld, N, head_stride, q_off,    \
-                                                                               k_off, v_off, sl2, (__half*)out, ldo);          \
+#define TA_LAUNCH(DV_, POLY_, CH_, TS_)                                                                                            \
+    do {                                                                                                                           \
+        e = cudaFuncSetAttribute(tc_attention_kernel<DV_, POLY_, CH_, TS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess)                                                                                                      \
+            tc_attention_kernel<DV_, POLY_, CH_, TS_><<<grid, TA_THREADS, smem, st>>>((const __half*)qkv, ld, N, head_stride, q_off,   \
+                                                                                    k_off, v_off, sl2, (__half*)out, ldo);         \
     } while (0)
-#define TA_LAUNCH_DV(DV_)                                          \
-    if (g_attention_chunked) { TA_LAUNCH(DV_, 0, true); }          \
-    else switch (g_attention_poly) {                               \
-        case 2: TA_LAUNCH(DV_, 2, false); break;                   \
-        case 3: TA_LAUNCH(DV_, 3, false); break;                   \
-        case 4: TA_LAUNCH(DV_, 4, false); break;                   \
-        case 6: TA_LAUNCH(DV_, 6, false); break;                   \
-        default: TA_LAUNCH(DV_, 0, false); break;                  \
+#define TA_LAUNCH_DV(DV_)                                                  \
+    if (g_attention_chunked == 2) { TA_LAUNCH(DV_, 0, false, true); }      \
+    else if (g_attention_chunked == 3) { TA_LAUNCH(DV_, 0, true, true); }  \
+    else if (g_attention_chunked == 1) { TA_LAUNCH(DV_, 0, true, false); } \
+    else switch (g_attention_poly) {                                       \
+        case 2: TA_LAUNCH(DV_, 2, false, false); break;                    \
+        case 3: TA_LAUNCH(DV_, 3, false, false); break;                    \
+        case 4: TA_LAUNCH(DV_, 4, false, false); break;                    \
+        case 6: TA_LAUNCH(DV_, 6, false, false); break;                    \
+        default: TA_LAUNCH(DV_, 0, false, false); break;                   \
     }
     if (d_v == 32) { TA_LAUNCH_DV(32) } else { TA_LAUNCH_DV(64) }
 #undef TA_LAUNCH_DV
