@@ -177,7 +177,8 @@ def time_attention_kernel(dev, batch, pk):
     except Exception:
         pass
     exps = float(N) * N * heads * batch
-    return {"kernel": "tc_attention_kernel<32> (tcgen05/TMEM; AAttn P3: N=6400, 2 heads x d32, whole batch)", "bound": "tensor",
+    return {"kernel": "tc_attention_kernel<32> (tcgen05: S = QK^T SS-mode, O += PV TS-mode with P in tensor memory; AAttn P3: N=6400, "
+                      "2 heads x d32, whole batch)", "bound": "tensor",
             "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": ach / pk["tflops_burst"], "traffic": traffic,
             "ms_per_launch": ms, "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": algo_bytes,
             "exp_per_launch": exps, "gexp_per_s": exps / (ms * 1e-3) / 1e9,

@@ -76,7 +76,7 @@ def softmax_mode(request):
     from yolo_master_b200 import _lib
     prev = _lib.load().ym_set_attention_chunked(request.param)
     yield request.param
-    _lib.load().ym_set_attention_chunked(prev)
+    assert _lib.load().ym_set_attention_chunked(prev) == request.param
 
 
 @pytest.mark.parametrize("N,heads,dv,batch", [(64, 1, 32, 1), (128, 2, 32, 2), (400, 2, 32, 3), (1600, 2, 32, 2), (221, 4, 32, 2),
