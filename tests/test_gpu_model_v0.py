@@ -88,7 +88,7 @@ def test_v0_layers_teacher_forced(models):
 
 def test_v0_predict_pipeline_nms(models):
     """model -> non_max_suppression (batched kernel) and -> CW-NMS: kept anchor indices bit-exact against the NMS oracle
-    run on the SAME dense prediction; CW-NMS keeps the same set and only moves the boxes."""
+    run on the SAME dense prediction; CW-NMS keeps (up to threshold ties) the same set and only moves the boxes."""
     m, sd, spec = models["yolo-master-n-v0"]
     x = synth_images(3, 320, 320, 11).half().to(DEV)
     with torch.no_grad():
@@ -102,7 +102,10 @@ def test_v0_predict_pipeline_nms(models):
     assert sum(len(k) for k in keep) > 10
     cw, ck = non_max_suppression(y, conf, 0.6, max_det=100, return_idxs=True, cluster=True, frame_wh=(320, 320))
     for k, k2, o in zip(keep, ck, cw):
-        assert torch.equal(k, k2) or len(k2) <= len(k)      # clipping to the frame may drop empty boxes only
+        # same greedy per-class suppression; CW-NMS differs in the class offset (common.cpp:138) and computes IoU in double, so a
+        # pair sitting exactly at the threshold may flip (CW-NMS kernel vs its own oracle is bit-checked in test_gpu_nms.py)
+        sa, sb = set(k.tolist()), set(k2.tolist())
+        assert len(sa & sb) >= 0.9 * max(len(sa), len(sb))
         assert bool((o[:, 2:4] > 0).all())
 
 
