@@ -90,3 +90,43 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(root, f)
+
+
+@pytest.mark.parametrize("name,cfg,scale", [
+    ("yolo-master-n-v0", "yolo-master-n.yaml", None), ("yolo-master-l-v0", "yolo-master-l.yaml", None),
+    ("yolo26-master-moa-mot-n", "yolo26-master-moa-mot-n.yaml", None), ("yolo26-master-moa-mot-s", "yolo26-master-moa-mot-n.yaml", [0.50, 0.50, 1024])])
+def test_state_dict_keys_match_reference_all_families(name, cfg, scale):
+    """Stock YAMLs of the v0 (ES_MOE / A2C2f / DFL) and MoT + MoA families build with the reference's exact state_dict layout
+    (key tables exported from the real reference by tests/golden/make_golden.py)."""
+    from yolo_master_b200.nn.tasks import DetectionModel, yaml_model_load
+
+    d = yaml_model_load(cfg)
+    if scale is not None:
+        d["scales"]["s"] = scale
+        d["scale"] = "s"
+    m = DetectionModel(d)
+    ref = json.load(open(os.path.join(GOLD, f"{name}.keys.json")))
+    sd = m.state_dict()
+    assert set(sd) == set(ref), sorted(set(sd) ^ set(ref))[:10]
+    for k, (shape, dt) in ref.items():
+        assert list(sd[k].shape) == shape and str(sd[k].dtype) == dt, k
+    assert m.stride.tolist() == [8.0, 16.0, 32.0]
+    assert m.end2end is ("moa-mot" in name)
+
+
+def test_mixture_module_signatures_match_reference():
+    from yolo_master_b200.nn import modules as M
+
+    expect = {
+        "ES_MOE": ["in_channels", "out_channels", "num_experts", "reduction", "top_k", "use_sparse_inference", "dynamic_threshold",
+                   "max_kernel_size", "expert_kernel_sizes"],
+        "C2fMoT": ["c1", "c2", "n", "num_heads", "top_k", "window_size", "n_points", "mlp_ratio", "temperature", "balance_loss_coeff", "e",
+                   "sparse_train", "scene_aware_router", "scene_hidden_dim", "scene_consistency_coeff", "sparse_train_warmup_steps",
+                   "scene_inference_mode", "local_attn_window"],
+        "C2fMoA": ["c1", "c2", "n", "num_heads", "mlp_ratio", "temperature", "shortcut", "e", "aux_loss_coeff", "local_window_size",
+                   "sequential_heads", "regional_max_kv_tokens", "sparse_inference", "sparse_inference_threshold",
+                   "inference_sparse_threshold"],
+    }
+    for name, params in expect.items():
+        got = [p for p in inspect.signature(getattr(M, name).__init__).parameters if p != "self"]
+        assert got == params, (name, got)
