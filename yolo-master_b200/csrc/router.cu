@@ -14,12 +14,12 @@ namespace ym {
 // Fused avg-pool + conv3x3 + BN + SiLU + per-tile sums.  (Round-1 history: separate pool / hidden kernels ran at 41 GB/s,
 // L1-instruction bound - two 16-byte loads per four FMAs - with the pooled map making a round trip through global memory;
 // profiles/r01_launch_roofline.txt.)  w1 layout [tap][c/4][r][4] fp32: the Cr lanes of a quad read consecutive float4.
-// One CTA = a 2 x 16 tile of POOLED pixels of one image (small tiles: the maps are 5x5 .. 40x40, the grid must fill 148 SMs):
-//   phase 1: the haloed 4 x 18 pooled tile is averaged straight from the fp16 activation into shared memory (fp32);
+// One CTA = a 4 x 16 tile of POOLED pixels of one image (a 2 x 16 tile was measured: more CTAs but 2.25x halo re-reads, 36 -> 54 us at P3):
+//   phase 1: the haloed 6 x 18 pooled tile is averaged straight from the fp16 activation into shared memory (fp32);
 //   phase 2: each thread owns one reduced channel r and FOUR horizontally adjacent pixels: per (ky, c4) it loads 6 input
 //            float4 (shared memory, broadcast across the r lanes) and 3 weight float4 (L1) for 48 FMAs (was 2 loads per 4).
 // partial[b, tile, r] = sum over the tile's pixels of SiLU(scale1*conv + shift1); router_finish_kernel is unchanged.
-constexpr int RT_TY = 2, RT_TX = 16, RT_HY = RT_TY + 2, RT_HX = RT_TX + 2, RT_QUADS = RT_TY * (RT_TX / 4);
+constexpr int RT_TY = 4, RT_TX = 16, RT_HY = RT_TY + 2, RT_HX = RT_TX + 2, RT_QUADS = RT_TY * (RT_TX / 4);
 
 __global__ void __launch_bounds__(256) router_fused_kernel(const __half* __restrict__ x, int ldx, int H, int W, int C, int ps,
                                                            int Hp, int Wp, int Cr, const float* __restrict__ w1,
