@@ -165,3 +165,14 @@ def test_stream_host_pipeline_uint8(model_and_sd):
         y16 = m((frames[0].float() / 255).half().to(DEV))[0].float().cpu()
     s8, s16 = want[0][..., 4].sort(dim=1, descending=True)[0], y16[..., 4].sort(dim=1, descending=True)[0]
     assert (s8 - s16).abs().max() < 2e-2
+
+
+def test_empty_batch_and_bad_rank(model_and_sd):
+    m, _ = model_and_sd
+    with torch.no_grad():
+        y, aux = m(torch.zeros((0, 3, 96, 128), dtype=torch.float16, device=DEV))
+    assert y.shape == (0, 252, 6) and aux["boxes"] == []
+    with pytest.raises(ValueError):
+        m(torch.zeros((3, 96, 128), dtype=torch.float16, device=DEV))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros((1, 3, 96, 128), dtype=torch.float16))      # CPU tensor: no fallback

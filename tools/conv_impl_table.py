@@ -32,9 +32,7 @@ def spy(x, w_packed, bias, Cout, KH, KW, stride, pad, act, out=None, res=None, o
     return orig(x, w_packed, bias, Cout, KH, KW, stride, pad, act, out=out, res=res, out_f32=out_f32)
 
 
-ops.conv2d = spy
-for mod in sys.modules.values():   # modules bound `ops` by reference, so patching the attribute is enough
-    pass
+ops.conv2d = spy          # the modules call `ops.conv2d(...)` through the module attribute, so patching it is enough
 with torch.no_grad():
     m(synth_images(B, 640, 640, 1).half().cuda())
 ops.conv2d = orig

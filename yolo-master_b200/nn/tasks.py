@@ -209,7 +209,21 @@ class DetectionModel(nn.Module):
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("yolo_master_b200.DetectionModel.forward needs CUDA tensors (no CPU fallback)")
+        if x.dim() != 4:
+            raise ValueError(f"expected a (B, C, H, W) image batch, got shape {tuple(x.shape)}")
+        if x.shape[0] == 0:                       # empty batch: nothing to launch, shapes as the reference would return them
+            return self._empty_result(x)
         return self._predict_once(x)
+
+    def _empty_result(self, x):
+        head = self.model[-1]
+        H, W = x.shape[2:]
+        A = sum(math.ceil(H / float(s)) * math.ceil(W / float(s)) for s in self.stride.tolist())
+        if getattr(head, "end2end", False):
+            y = torch.zeros((0, min(head.max_det, A), 6), dtype=torch.float32, device=x.device)
+        else:
+            y = torch.zeros((0, 4 + self.yaml["nc"], A), dtype=torch.float32, device=x.device)
+        return y, {"boxes": [], "scores": [], "feats": []}
 
     predict = forward
 
