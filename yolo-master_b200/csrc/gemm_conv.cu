@@ -49,9 +49,9 @@ struct GemmConvParams {
 };
 
 template <int BN, int EPI, bool A_XFORM>
-// BN = 64 tiles ran 4 CTAs per SM at 124-128 registers (ncu: 24 % warps active on the MoE expert GEMMs); capping them at
-// 96 registers costs 16-88 bytes of spill and lets a fifth CTA onto the SM.
-__global__ void __launch_bounds__(NTHREADS, BN >= 32 ? 5 : (BN == 16 ? 6 : 8)) gemm_conv_kernel(const GemmConvParams p) {
+// (A register cap of 96 for the BN = 64 tiles - 5 instead of 4 CTAs per SM at 16-88 bytes of spill - was measured: the whole
+// step got 1 % slower, so the kernel keeps the compiler's 124-128 registers.)
+__global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* sA = reinterpret_cast<__half*>(smem_raw);                 // [STAGES][BM][SK]
     __half* sB = sA + STAGES * BM * SK;                               // [STAGES][BN][SK]
