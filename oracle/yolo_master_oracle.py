@@ -896,3 +896,166 @@ def layer_c2f_moa(sd, p, x, c1, c2, n=1, num_heads=6, mlp_ratio=2.0, temperature
 _LAYER_FN.update({"C2fMoT": layer_c2f_mot, "C2fMoA": layer_c2f_moa})
 _MIX_BASE.update({"C2fMoT", "C2fMoA"})
 _MIX_REPEAT.update({"C2fMoT", "C2fMoA"})
+
+
+# ======================================================================================================================
+# Gated MoE family (nn/modules/moe/gated.py): `VisualEnhancedAdaptiveGateMoE` as used by the v0_10 model zoo - eval forward.
+# restated and pinned ahead of the CUDA path (no product code consumes this yet).
+# ======================================================================================================================
+def _gn_na(x, groups, eps=1e-5):
+    return F.group_norm(x, groups, None, None, eps)
+
+
+def gated_se_gate(sd, p, x):
+    """`se_gate` gated.py:325-332: GAP -> Linear(no bias) -> SiLU -> Linear -> Sigmoid.  Returns [B, C]."""
+    g = x.mean((2, 3))
+    g = F.silu(F.linear(g, sd[p + ".2.weight"]))
+    return torch.sigmoid(F.linear(g, sd[p + ".4.weight"], sd[p + ".4.bias"]))
+
+
+def visual_detail_gate(sd, p, x, groups=8):
+    """`VisualDetailGate.forward` gated.py:1154-1178: x * (1 + tanh(scale) * gate(x - avgpool3(x)))."""
+    C = x.shape[1]
+    d = x - F.avg_pool2d(x, 3, 1, 1)
+    t = F.conv2d(d, _w(sd[p + ".detail_filter.0.weight"]), None, 1, 1, 1, C)
+    t = F.silu(_gn(sd, p + ".detail_filter.1", t, get_safe_groups(C, groups)))
+    t = F.silu(F.conv2d(t, _w(sd[p + ".detail_filter.3.weight"])))
+    gate = torch.sigmoid(F.conv2d(t, _w(sd[p + ".detail_filter.5.weight"]), sd[p + ".detail_filter.5.bias"]))
+    return _st(x * (1 + torch.tanh(sd[p + ".detail_scale"]) * gate))
+
+
+def dual_stream_gate_router(sd, p, x, top_k, temperature, pool_scale=4):
+    """`DualStreamGateRouter.forward` gated.py:129-160 (fp32): global mean/std statistics + pooled local conv stream, blended by
+    sigmoid(alpha), clamp +-30, softmax(/T), top-k, renormalise with +1e-6.  Returns (weights [B,k], indices [B,k], probs)."""
+    B, C, H, W = x.shape
+    xf = x.float()
+    mean = xf.mean((2, 3))
+    std = xf.std((2, 3), unbiased=False) if H * W > 1 else torch.zeros_like(mean)
+    gl = F.linear(torch.cat([mean, std], 1), sd[p + ".global_fc.weight"])
+    xl = F.avg_pool2d(xf, pool_scale, pool_scale) if (H > pool_scale and W > pool_scale) else xf
+    t = F.conv2d(xl, sd[p + ".local_conv.0.weight"], None, 1, 1, 1, C)
+    t = F.silu(_gn(sd, p + ".local_conv.1", t, get_safe_groups(C, 8)))
+    t = F.conv2d(t, sd[p + ".local_conv.3.weight"])
+    t = F.silu(_gn(sd, p + ".local_conv.4", t, get_safe_groups(t.shape[1], 4)))
+    ll = F.conv2d(t, sd[p + ".local_conv.6.weight"], sd[p + ".local_conv.6.bias"]).mean((2, 3))
+    a = torch.sigmoid(sd[p + ".alpha"])
+    logits = (a * gl + (1 - a) * ll).clamp(-30.0, 30.0)
+    probs = F.softmax(logits / temperature, dim=1)
+    w, idx = torch.topk(probs, top_k, dim=1)
+    return w / (w.sum(1, keepdim=True) + 1e-6), idx, probs
+
+
+def complexity_gate(w, complexity):
+    """`AdaptiveGateMoE._apply_complexity_gate` gated.py:469-490: keep the round(c * k) best ranks (c clamped to [0.3, 1.5]),
+    renormalise.  `complexity` is ONE scalar for the whole batch (gated.py:455-461)."""
+    k = w.shape[1]
+    if k <= 1:
+        return w
+    c = torch.nan_to_num(complexity, nan=1.0, posinf=1.0, neginf=1.0).clamp(0.3, 1.5)
+    keep = torch.round(c * k).clamp(1, k)
+    mask = (torch.arange(1, k + 1, dtype=keep.dtype).view(1, k) <= keep).to(w.dtype)
+    w = w * mask
+    return w / w.sum(1, keepdim=True).clamp_min(1e-6)
+
+
+def fused_expert_group(sd, p, x, w, idx, num_experts, out_channels, num_groups=8):
+    """`FusedExpertGroup.forward` gated.py:1061-1081: one grouped 3x3 conv computes every expert, the top-k outputs are gathered,
+    GroupNorm (no affine) + per-expert affine + SiLU, weighted sum."""
+    B, C, H, W = x.shape
+    fw = sd[p + ".fused_conv.weight"]
+    groups = C // fw.shape[1]
+    fo = _st(F.conv2d(x, _w(fw), None, 1, 1, 1, groups)).view(B, num_experts, out_channels, H, W)
+    k = idx.shape[1]
+    sel = torch.gather(fo, 1, idx.view(B, k, 1, 1, 1).expand(B, k, out_channels, H, W))
+    nrm = _gn_na(sel.reshape(B * k, out_channels, H, W), get_safe_groups(out_channels, num_groups)).view(B, k, out_channels, H, W)
+    nrm = nrm * sd[p + ".expert_norm_weight"][idx].view(B, k, out_channels, 1, 1) + sd[p + ".expert_norm_bias"][idx].view(B, k, out_channels, 1, 1)
+    return _st((F.silu(nrm) * w.view(B, k, 1, 1, 1)).sum(1))
+
+
+def low_rank_fused_expert_group(sd, p, x, w, idx, num_experts, out_channels, num_groups=8):
+    """`LowRankFusedExpertGroup.forward` gated.py:1101-1147: shared 1x1 bottleneck -> GN -> SiLU -> FusedExpertGroup."""
+    t = F.conv2d(x, _w(sd[p + ".bottleneck.0.weight"]))
+    t = _st(F.silu(_gn(sd, p + ".bottleneck.1", t, get_safe_groups(t.shape[1], num_groups))))
+    return fused_expert_group(sd, p + ".fused", t, w, idx, num_experts, out_channels, num_groups)
+
+
+def shared_inverted_expert_group(sd, p, x, w, idx, num_experts, out_channels):
+    """`SharedInvertedExpertGroup.forward` moe/experts.py:235-269: shared expand 1x1 -> GN -> SiLU -> dw3x3 -> GN -> SiLU, then a
+    1x1 + GN projection per ACTIVE expert, weighted index_add (routes with weight <= 0 are dropped)."""
+    B, C, H, W = x.shape
+    t = F.conv2d(x, _w(sd[p + ".shared_feature.0.weight"]))
+    hid = t.shape[1]
+    t = F.silu(_gn(sd, p + ".shared_feature.1", t, get_safe_groups(hid, 8)))
+    t = F.conv2d(_st(t), _w(sd[p + ".shared_feature.3.weight"]), None, 1, 1, 1, hid)
+    feat = _st(F.silu(_gn(sd, p + ".shared_feature.4", t, get_safe_groups(hid, 8))))
+    out = torch.zeros(B, out_channels, H, W)
+    valid = w > 0.0
+    for e in torch.unique(idx[valid]).tolist():
+        bi, ki = torch.where((idx == e) & valid)
+        y = _gn(sd, f"{p}.expert_projections.{e}.1", F.conv2d(feat[bi], _w(sd[f"{p}.expert_projections.{e}.0.weight"])),
+                get_safe_groups(out_channels, 8))
+        out.index_add_(0, bi, _st(y) * w[bi, ki].view(-1, 1, 1, 1))
+    return _st(out)
+
+
+def pyramid_context_mixer(sd, p, x, groups=8, pool_scales=(2, 4)):
+    """`PyramidContextMixer.forward` gated.py:1210-1221."""
+    B, C, H, W = x.shape
+    g = get_safe_groups(C, groups)
+    ctx = [F.silu(_gn(sd, p + ".local_context.1", F.conv2d(x, _w(sd[p + ".local_context.0.weight"]), None, 1, 1, 1, C), g))]
+    for i, s in enumerate(pool_scales):
+        h, w = max(1, H // s), max(1, W // s)
+        pooled = x if (H, W) == (h, w) else F.adaptive_avg_pool2d(x, (h, w))
+        t = F.silu(_gn(sd, f"{p}.pool_projections.{i}.1", F.conv2d(pooled, _w(sd[f"{p}.pool_projections.{i}.0.weight"])), g))
+        ctx.append(F.interpolate(t, size=(H, W), mode="nearest"))
+    c = torch.stack(ctx, 0).mean(0)
+    gate = torch.sigmoid(F.conv2d(c, _w(sd[p + ".context_gate.0.weight"]), sd[p + ".context_gate.0.bias"]))
+    return _st(x + torch.tanh(sd[p + ".context_scale"]) * c * gate)
+
+
+def feature_refine(sd, p, x, groups=8):
+    """`FeatureRefinementHook` moe/hooks.py:50-57: x + tanh(scale) * refiner(x) * gate(x)."""
+    C = x.shape[1]
+    r = F.silu(_gn(sd, p + ".feature_refiner.1", F.conv2d(x, _w(sd[p + ".feature_refiner.0.weight"]), None, 1, 1, 1, C), get_safe_groups(C, groups)))
+    g = F.silu(F.conv2d(x.mean((2, 3), keepdim=True), _w(sd[p + ".feature_gate.1.weight"])))
+    g = torch.sigmoid(F.conv2d(g, _w(sd[p + ".feature_gate.3.weight"]), sd[p + ".feature_gate.3.bias"]))
+    return _st(x + torch.tanh(sd[p + ".refine_scale"]) * r * g)
+
+
+def layer_visual_enhanced_gate_moe(sd, p, x, c1, c2, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.2,
+                                   final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+                                   fused_expert_threshold=8, shuffle_groups=2, *unused, return_route=False):
+    """`VisualEnhancedAdaptiveGateMoE.forward` = `run_visual_hybrid_moe_forward` moe/_gated_visual.py:33-86 with the hooks
+    detail (pre_route), context + refine (post_fusion) of gated.py:1749-1755."""
+    dyn = int(c1 * split_ratio)
+    st_c = c1 - dyn
+    out_dyn = int(c2 * split_ratio)
+    gate = gated_se_gate(sd, p + ".se_gate", x)
+    xs = _st(x[:, :st_c] * gate[:, :st_c, None, None])
+    xd = _st(x[:, st_c:] * gate[:, st_c:, None, None])
+    xd = visual_detail_gate(sd, p + ".detail_gate", xd, num_groups)
+    # static path: dw3x3 -> BN -> SiLU -> 1x1 -> BN -> SiLU (gated.py:335-344)
+    t = F.silu(_bn(sd, p + ".static_net.1", F.conv2d(xs, _w(sd[p + ".static_net.0.weight"]), None, 1, 1, 1, st_c)))
+    out_s = _st(F.silu(_bn(sd, p + ".static_net.4", F.conv2d(_st(t), _w(sd[p + ".static_net.3.weight"])))))
+    # batch-level complexity scalar (gated.py:455-461): sigmoid(conv1x1(GAP(x_dynamic))) averaged over the WHOLE batch
+    cx = torch.sigmoid(F.conv2d(xd.mean((2, 3), keepdim=True), sd[p + ".complexity_estimator.1.weight"], sd[p + ".complexity_estimator.1.bias"])).mean()
+    cx = cx.clamp(0.3, 1.5) if bool(torch.isfinite(cx)) else torch.tensor(1.0)
+    w, idx, probs = dual_stream_gate_router(sd, p + ".routing", xd, top_k, max(float(initial_temperature), 1e-3))
+    w = complexity_gate(w, cx)
+    if num_experts <= fused_expert_threshold:
+        out_d = low_rank_fused_expert_group(sd, p + ".fused_experts", xd, w, idx, num_experts, out_dyn, num_groups)
+    else:
+        out_d = shared_inverted_expert_group(sd, p + ".fused_experts", xd, w, idx, num_experts, out_dyn)
+    cat = torch.cat([out_s, out_d], 1)
+    sg = shuffle_groups if c2 % shuffle_groups == 0 else 1
+    if sg > 1:
+        B, C, H, W = cat.shape
+        cat = cat.view(B, sg, C // sg, H, W).transpose(1, 2).reshape(B, C, H, W)
+    cat = pyramid_context_mixer(sd, p + ".context_mixer", cat, num_groups)
+    cat = feature_refine(sd, p, cat, num_groups)
+    out = _st(_gn(sd, p + ".bn", F.conv2d(cat, _w(sd[p + ".proj.weight"])), get_safe_groups(c2, num_groups)) + x)
+    return (out, w, idx, probs) if return_route else out
+
+
+_LAYER_FN["VisualEnhancedAdaptiveGateMoE"] = layer_visual_enhanced_gate_moe
+_MIX_BASE.add("VisualEnhancedAdaptiveGateMoE")

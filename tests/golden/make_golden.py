@@ -103,6 +103,10 @@ EXTRA_MODELS = {
     # MoT + MoA neck (C2fMoT x3, C2fMoA x1), end2end head; "-s" = the same YAML with an injected s scale
     "yolo26-master-moa-mot-n": ("/root/reference/ultralytics/cfg/models/26/yolo26-master-moa-mot-n.yaml", [6, 10, 13, 16, 19, 22],
                                 {"b2_224": (2, 224, 224, 6), "b1_96": (1, 96, 96, 7)}),
+    # gated MoE family: oracle pinned ahead of the CUDA path
+    "yolo-master-n-v0_10": ("/root/reference/ultralytics/cfg/models/master/v0_10/det/yolo-master-n.yaml", [5, 8, 11, 17, 20, 23],
+                            {"b2_160": (2, 160, 160, 9), "b1_128": (1, 128, 128, 10)}),   # (B=1 with a 5..7-pixel P4/P5 map makes the
+                            # reference itself raise: its router GroupNorm then sees one value per group, gated.py:113)
     "yolo26-master-moa-mot-s": (("/root/reference/ultralytics/cfg/models/26/yolo26-master-moa-mot-n.yaml", "s", [0.50, 0.50, 1024]),
                                 [13, 16, 19, 22], {"b1_160": (1, 160, 160, 8)}),
 }
@@ -140,7 +144,8 @@ def extra_model_golden(name):
     # calibrated BatchNorm statistics + the constants the key-seeded generator leaves alone (router temperature buffers,
     # the frozen DFL arange): everything a test needs besides key names to rebuild the exact state_dict
     stats = {k: v.clone() for k, v in sd.items()
-             if k.endswith(("running_mean", "running_var", ".temperature", "dfl.conv.weight"))}
+             if k.endswith(("running_mean", "running_var", ".temperature", "dfl.conv.weight"))
+             or (v.is_floating_point() and v.dim() == 0)}        # scalar gates / scales keep their constructor values
     torch.save(stats, f"{OUT}/{name}.bnstats.pt")
     gold = {"cases": {}}
     for tag, (B, H, W, seed) in cases.items():
