@@ -1,0 +1,75 @@
+"""CPU oracle for the predictor's pre-processing - TEST INFRASTRUCTURE ONLY, groundwork for a device
+letterbox kernel (no product code consumes it yet).
+
+Restates, in integer arithmetic, what `LetterBox.__call__` (ultralytics/data/augment.py:1705-1800: `get_params` :1742-1786, then
+cv2.resize(INTER_LINEAR) + cv2.copyMakeBorder(value=114)) and `BasePredictor.preprocess` (engine/predictor.py:155-176: BGR->RGB,
+HWC->CHW) do to one uint8 frame.  cv2.resize on 8-bit data is third-party code (opencv-python, version floor only in the
+reference's pyproject.toml); its generic kernel (modules/imgproc/src/resize.cpp: `HResizeLinear` + `VResizeLinear<uchar,int,short>`)
+is restated here from its published algorithm:
+  * source coordinate fx = (float)((dx + 0.5) * scale - 0.5), floor, clamp to the image;
+  * 11-bit fixed-point coefficients a = saturate_cast<short>(w * 2048) (round half to even), horizontal pass in int32;
+  * vertical pass  dst = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+  * an exact 2x downscale in both axes takes the INTER_AREA fast path: (a + b + c + d + 2) >> 2.
+Pinned (tests/test_letterbox_oracle.py, fixtures generated with cv2 4.13 by tests/golden/make_golden.py): bit-exact for
+downscales, identity and single-axis resizes.  PARITY PARTIAL for two-axis upscales: this cv2 wheel's SIMD dispatch differs from
+the generic kernel by 1 LSB on 0.05-0.4 % of the pixels, so those cases are held to |diff| <= 1.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def letterbox_params(shape_hw, new_shape=(640, 640), scaleup=True, center=True):
+    """`LetterBox.get_params` augment.py:1742-1786 (auto=False, scale_fill=False): returns (new_unpad (w, h), top, bottom, left, right)."""
+    h, w = shape_hw
+    r = min(new_shape[0] / h, new_shape[1] / w)
+    if not scaleup:
+        r = min(r, 1.0)
+    new_unpad = (round(w * r), round(h * r))
+    dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
+    if center:
+        dw /= 2
+        dh /= 2
+    top, bottom = (round(dh - 0.1) if center else 0), round(dh + 0.1)
+    left, right = (round(dw - 0.1) if center else 0), round(dw + 0.1)
+    return new_unpad, top, bottom, left, right
+
+
+def _coeffs(dn, sn, scale):
+    d = np.arange(dn, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    lo = s < 0
+    f[lo], s[lo] = 0, 0
+    hi = s >= sn - 1
+    f[hi], s[hi] = 0, sn - 1
+    a0 = np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int32)
+    a1 = np.rint(f * np.float32(2048)).astype(np.int32)
+    return s, np.minimum(s + 1, sn - 1), a0, a1
+
+
+def resize_linear_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR) for uint8 HxWxC images (generic OpenCV kernel)."""
+    sh, sw = src.shape[:2]
+    if (dw, dh) == (sw, sh):
+        return src.copy()
+    sx, sy = 1.0 / (dw / sw), 1.0 / (dh / sh)
+    if sx == 2.0 and sy == 2.0:
+        s = src.astype(np.int32)
+        return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    x0, x1, ax0, ax1 = _coeffs(dw, sw, sx)
+    y0, y1, ay0, ay1 = _coeffs(dh, sh, sy)
+    s = src.astype(np.int32)
+    rows = s[:, x0] * ax0[None, :, None] + s[:, x1] * ax1[None, :, None]
+    out = ((((ay0[:, None, None] * (rows[y0] >> 4)) >> 16) + ((ay1[:, None, None] * (rows[y1] >> 4)) >> 16) + 2) >> 2)
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def preprocess_frame(img_bgr_hwc: np.ndarray, new_shape=(640, 640), pad_value=114) -> np.ndarray:
+    """One frame through LetterBox + the predictor's layout change: uint8 HWC BGR -> uint8 CHW RGB of `new_shape`."""
+    (nw, nh), top, bottom, left, right = letterbox_params(img_bgr_hwc.shape[:2], new_shape)
+    img = img_bgr_hwc if img_bgr_hwc.shape[:2] == (nh, nw) else resize_linear_u8(img_bgr_hwc, nw, nh)
+    out = np.full((nh + top + bottom, nw + left + right, img.shape[2]), pad_value, dtype=np.uint8)
+    out[top:top + nh, left:left + nw] = img
+    return np.ascontiguousarray(out[..., ::-1].transpose(2, 0, 1))

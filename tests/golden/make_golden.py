@@ -248,10 +248,33 @@ def esmoe_golden():
     torch.save({"cases": cases}, f"{OUT}/esmoe.golden.pt")
 
 
+LETTERBOX_CASES = [(480, 640), (720, 1280), (1080, 1920), (1200, 1600), (427, 640), (640, 480), (333, 500), (100, 37), (64, 64)]
+
+
+def letterbox_golden():
+    """Reference pre-processing of one seeded uint8 BGR frame per case: the REAL `LetterBox` (cv2.resize INTER_LINEAR +
+    copyMakeBorder 114) followed by the predictor's BGR->RGB / HWC->CHW (engine/predictor.py:164-170).  Stores only a CRC and a
+    coarse 16x16 block-mean thumbnail per case (the expected tensors are 1.2 MB each) plus the cv2 version."""
+    import zlib
+
+    import cv2
+    import numpy as np
+    from ultralytics.data.augment import LetterBox
+    cases = []
+    for seed, (h, w) in enumerate(LETTERBOX_CASES):
+        img = np.random.default_rng(900 + seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        out = LetterBox((640, 640), auto=False, stride=32)(image=img)
+        chw = np.ascontiguousarray(out[..., ::-1].transpose(2, 0, 1))
+        cases.append({"h": h, "w": w, "seed": 900 + seed, "crc": zlib.crc32(chw.tobytes()), "shape": list(chw.shape),
+                      "thumb": torch.from_numpy(chw.reshape(3, 40, 16, 40, 16).astype(np.float32).mean((2, 4)))})
+        print("letterbox", (h, w), chw.shape, cases[-1]["crc"])
+    torch.save({"cv2": cv2.__version__, "cases": cases}, f"{OUT}/letterbox.golden.pt")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["main", "dispatch", "nms", "esmoe", *EXTRA_MODELS]
+    which = sys.argv[1:] or ["main", "dispatch", "nms", "esmoe", "letterbox", *EXTRA_MODELS]
     for w in which:
         if w in EXTRA_MODELS:
             extra_model_golden(w)
         else:
-            {"main": main, "dispatch": dispatch_golden, "nms": nms_golden, "esmoe": esmoe_golden}[w]()
+            {"main": main, "dispatch": dispatch_golden, "nms": nms_golden, "esmoe": esmoe_golden, "letterbox": letterbox_golden}[w]()
