@@ -6,13 +6,13 @@ cv2.resize(INTER_LINEAR) + cv2.copyMakeBorder(value=114)) and `BasePredictor.pre
 HWC->CHW) do to one uint8 frame.  cv2.resize on 8-bit data is third-party code (opencv-python, version floor only in the
 reference's pyproject.toml); its generic kernel (modules/imgproc/src/resize.cpp: `HResizeLinear` + `VResizeLinear<uchar,int,short>`)
 is restated here from its published algorithm:
-  * source coordinate fx = (float)((dx + 0.5) * scale - 0.5), floor, clamp to the image;
+  * source coordinate fx = (float)((dx + 0.5) * scale - 0.5), floor; at the border x clamps index AND weight (fx = 0), y clips only
+    the two row indices and keeps the weights (the border row is blended with itself);
   * 11-bit fixed-point coefficients a = saturate_cast<short>(w * 2048) (round half to even), horizontal pass in int32;
   * vertical pass  dst = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
   * an exact 2x downscale in both axes takes the INTER_AREA fast path: (a + b + c + d + 2) >> 2.
-Pinned (tests/test_letterbox_oracle.py, fixtures generated with cv2 4.13 by tests/golden/make_golden.py): bit-exact for
-downscales, identity and single-axis resizes.  PARITY PARTIAL for two-axis upscales: this cv2 wheel's SIMD dispatch differs from
-the generic kernel by 1 LSB on 0.05-0.4 % of the pixels, so those cases are held to |diff| <= 1.
+Pinned (tests/test_letterbox_oracle.py, fixtures generated with cv2 4.13 by tests/golden/make_golden.py): bit-exact (CRC) for
+every fixture - downscales, identity, single-axis and two-axis upscales.
 """
 from __future__ import annotations
 
@@ -35,18 +35,22 @@ def letterbox_params(shape_hw, new_shape=(640, 640), scaleup=True, center=True):
     return new_unpad, top, bottom, left, right
 
 
-def _coeffs(dn, sn, scale):
+def _coeffs(dn, sn, scale, clamp_weights):
+    """Source indices and 11-bit weights of one axis.  OpenCV clamps the WEIGHTS at the image border only along x
+    (resize.cpp: `if (sx < 0) fx = 0, sx = 0`); along y the two row indices are clipped (`clip(sy0 + k, 0, height)`) but the
+    fractional weights are kept, so a border row is blended with itself through two separately truncated products."""
     d = np.arange(dn, dtype=np.float64)
     f = ((d + 0.5) * scale - 0.5).astype(np.float32)
     s = np.floor(f).astype(np.int64)
     f = (f - s.astype(np.float32)).astype(np.float32)
-    lo = s < 0
-    f[lo], s[lo] = 0, 0
-    hi = s >= sn - 1
-    f[hi], s[hi] = 0, sn - 1
+    if clamp_weights:
+        lo = s < 0
+        f[lo], s[lo] = 0, 0
+        hi = s >= sn - 1
+        f[hi], s[hi] = 0, sn - 1
     a0 = np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int32)
     a1 = np.rint(f * np.float32(2048)).astype(np.int32)
-    return s, np.minimum(s + 1, sn - 1), a0, a1
+    return np.clip(s, 0, sn - 1), np.clip(s + 1, 0, sn - 1), a0, a1
 
 
 def resize_linear_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
@@ -58,8 +62,8 @@ def resize_linear_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
     if sx == 2.0 and sy == 2.0:
         s = src.astype(np.int32)
         return ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
-    x0, x1, ax0, ax1 = _coeffs(dw, sw, sx)
-    y0, y1, ay0, ay1 = _coeffs(dh, sh, sy)
+    x0, x1, ax0, ax1 = _coeffs(dw, sw, sx, True)
+    y0, y1, ay0, ay1 = _coeffs(dh, sh, sy, False)
     s = src.astype(np.int32)
     rows = s[:, x0] * ax0[None, :, None] + s[:, x1] * ax1[None, :, None]
     out = ((((ay0[:, None, None] * (rows[y0] >> 4)) >> 16) + ((ay1[:, None, None] * (rows[y1] >> 4)) >> 16) + 2) >> 2)

@@ -1,6 +1,6 @@
 """Pins oracle/letterbox_oracle.py (integer restatement of LetterBox + cv2.resize INTER_LINEAR + the predictor's BGR->RGB /
 HWC->CHW) to the REAL reference pipeline (fixtures: tests/golden/make_golden.py letterbox, cv2 4.13): bit-exact (CRC) for
-downscales / identity, within 1 LSB for the two-axis upscales where this cv2 wheel's SIMD dispatch departs from the generic kernel."""
+every case - downscales, identity, one- and two-axis upscales."""
 import os
 import zlib
 
@@ -20,11 +20,9 @@ def test_letterbox_oracle_matches_reference(case):
     img = np.random.default_rng(case["seed"]).integers(0, 256, (h, w, 3), dtype=np.uint8)
     out = L.preprocess_frame(img, (640, 640))
     assert list(out.shape) == case["shape"] and out.dtype == np.uint8
-    upscale = min(640 / h, 640 / w) > 1.0
-    if not upscale:
-        assert zlib.crc32(out.tobytes()) == case["crc"]                      # bit-exact
     thumb = out.reshape(3, 40, 16, 40, 16).astype(np.float32).mean((2, 4))
-    assert float(np.abs(thumb - case["thumb"].numpy()).max()) <= (0.25 if upscale else 0.0)   # 16x16 block means; 1-LSB pixels cluster
+    assert float(np.abs(thumb - case["thumb"].numpy()).max()) == 0.0         # 16x16 block means: localises a mismatch
+    assert zlib.crc32(out.tobytes()) == case["crc"]                          # bit-exact
 
 
 def test_letterbox_params_known_answers():
@@ -35,12 +33,14 @@ def test_letterbox_params_known_answers():
     assert L.letterbox_params((100, 37)) == ((237, 640), 0, 0, 201, 202)
 
 
-def test_two_axis_upscale_is_within_one_lsb_of_cv2():
+def test_resize_matches_cv2_bit_exact():
+    """Direct comparison when cv2 is importable (it is in the build container).  The upscales exercise the y-border rule: the two
+    clipped row indices keep their fractional weights, so a border row is blended with itself through two truncated products."""
     cv2 = pytest.importorskip("cv2")
-    img = np.random.default_rng(5).integers(0, 256, (64, 64, 3), dtype=np.uint8)
-    ref = cv2.resize(img, (640, 640), interpolation=cv2.INTER_LINEAR)
-    d = np.abs(ref.astype(int) - L.resize_linear_u8(img, 640, 640).astype(int))
-    assert d.max() <= 1 and (d > 0).mean() < 0.01
+    rng = np.random.default_rng(5)
+    for (sh, sw, dh, dw) in ((64, 64, 640, 640), (100, 37, 640, 237), (31, 57, 352, 640), (7, 5, 640, 457), (2, 2, 9, 9), (1, 8, 5, 16)):
+        img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR), L.resize_linear_u8(img, dw, dh)), (sh, sw, dh, dw)
     big = np.random.default_rng(6).integers(0, 256, (300, 400, 3), dtype=np.uint8)
     for dw, dh in ((320, 240), (400, 100), (137, 300), (200, 150), (399, 299), (57, 31)):   # downscale / single-axis / exact 2x
         assert np.array_equal(cv2.resize(big, (dw, dh), interpolation=cv2.INTER_LINEAR), L.resize_linear_u8(big, dw, dh)), (dw, dh)
