@@ -181,6 +181,26 @@ int ym_linear_attn(const void* q, int ldq, const void* k, int ldk, const void* v
 /* F.adaptive_avg_pool2d (moa/heads.py:224). */
 int ym_adaptive_avgpool_nhwc(const void* x, int ldx, int B, int H, int W, int C, int h, int w, void* out, int ldo, void* stream);
 
+/* Predictor pre-processing of B same-sized uint8 HWC frames.  Replaces, fused into one pass,
+ * LetterBox.apply_image data/augment.py:1792-1822 (cv2.resize INTER_LINEAR + copyMakeBorder BORDER_CONSTANT) and
+ * BasePredictor.preprocess engine/predictor.py:166-175 (BGR->RGB, BHWC->BCHW, .half()/.float(), /255).
+ *   src uint8 [B][sh][src_pitch] (3 interleaved channels; frame b at src + b*src_stride bytes);
+ *   xtab [nw], ytab [nh]: DEVICE tables of {uint32 i0 | i1<<16, uint32 a0 | a1<<16}: the clipped source indices and 11-bit
+ *     weights (a0+a1 = 2048) of cv2's fixed-point bilinear kernel, built on the host from LetterBox.get_params
+ *     (augment.py:1742-1786); ignored when area2x != 0 (exact 2x downscale in both axes = cv2's INTER_AREA fast path);
+ *   the resized nh x nw image lands at (top, left) of the H x W output, everything else is pad_value;
+ *   out: chw ? [B][3][H][W] : [B][H][W][3];  out_dtype 0 uint8, 1 fp16 (v/255), 2 fp32 (v/255);  swap_rb reverses the channels. */
+int ym_letterbox_u8(const void* src, long long src_stride, int B, int sh, int sw, int src_pitch, const void* xtab,
+                    const void* ytab, int area2x, int nw, int nh, int top, int left, int pad_value, int swap_rb, void* out,
+                    int out_dtype, int chw, int H, int W, void* stream);
+
+/* ops.scale_boxes + clip_boxes utils/ops.py:119-158,174-201 (DetectionPredictor.construct_result
+ * models/yolo/detect/predict.py:107-125), in place on n fp32 rows [ld >= 4]: (b - pad) / gain, then clamp to the original
+ * frame unless xywh.  Image of row i = row_img ? row_img[i] : i / rows_per_img.  params_host: HOST fp32 [n_img][5] =
+ * (gain, pad_x, pad_y, w0, h0), n_img <= 128 (rides in the kernel's parameter block: no upload, graph-capturable). */
+int ym_scale_boxes(float* boxes, int ld, long long n, int rows_per_img, const int* row_img, int n_img,
+                   const float* params_host, int padding, int xywh, void* stream);
+
 /* ES_MOE (moe/modules.py:410-741, eval sparse path) on four entry points; the module is router -> per-expert depthwise k x k
  * on the images that retained the expert -> grouped pointwise GEMM (+folded BN, SiLU, routing weight) -> sum + BN + SiLU.
  * ym_esmoe_route: DynamicRoutingLayer.forward/_hard_top_k routers.py:458-496,519-527 + the top-k / dynamic-threshold /

@@ -1,5 +1,5 @@
-"""CPU oracle for the predictor's pre-processing - TEST INFRASTRUCTURE ONLY, groundwork for a device
-letterbox kernel (no product code consumes it yet).
+"""CPU oracle for the predictor's pre- and post-processing - TEST INFRASTRUCTURE ONLY: the checker of
+`ym_letterbox_u8` / `ym_scale_boxes` and of the host mirror in yolo-master_b200/{data,engine,utils/ops.py}.
 
 Restates, in integer arithmetic, what `LetterBox.__call__` (ultralytics/data/augment.py:1705-1800: `get_params` :1742-1786, then
 cv2.resize(INTER_LINEAR) + cv2.copyMakeBorder(value=114)) and `BasePredictor.preprocess` (engine/predictor.py:155-176: BGR->RGB,
@@ -19,14 +19,19 @@ from __future__ import annotations
 import numpy as np
 
 
-def letterbox_params(shape_hw, new_shape=(640, 640), scaleup=True, center=True):
-    """`LetterBox.get_params` augment.py:1742-1786 (auto=False, scale_fill=False): returns (new_unpad (w, h), top, bottom, left, right)."""
+def letterbox_params(shape_hw, new_shape=(640, 640), scaleup=True, center=True, auto=False, scale_fill=False, stride=32):
+    """`LetterBox.get_params` augment.py:1742-1790: returns (new_unpad (w, h), top, bottom, left, right)."""
     h, w = shape_hw
     r = min(new_shape[0] / h, new_shape[1] / w)
     if not scaleup:
         r = min(r, 1.0)
     new_unpad = (round(w * r), round(h * r))
     dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
+    if auto:
+        dw, dh = dw % stride, dh % stride
+    elif scale_fill:
+        dw, dh = 0.0, 0.0
+        new_unpad = (new_shape[1], new_shape[0])
     if center:
         dw /= 2
         dh /= 2
@@ -70,10 +75,38 @@ def resize_linear_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
     return np.clip(out, 0, 255).astype(np.uint8)
 
 
-def preprocess_frame(img_bgr_hwc: np.ndarray, new_shape=(640, 640), pad_value=114) -> np.ndarray:
-    """One frame through LetterBox + the predictor's layout change: uint8 HWC BGR -> uint8 CHW RGB of `new_shape`."""
-    (nw, nh), top, bottom, left, right = letterbox_params(img_bgr_hwc.shape[:2], new_shape)
-    img = img_bgr_hwc if img_bgr_hwc.shape[:2] == (nh, nw) else resize_linear_u8(img_bgr_hwc, nw, nh)
+def preprocess_frame(img_bgr_hwc: np.ndarray, new_shape=(640, 640), pad_value=114, **lb) -> np.ndarray:
+    """One frame through LetterBox + the predictor's layout change: uint8 HWC BGR -> uint8 CHW RGB (`lb`: LetterBox options)."""
+    out = letterbox_frame(img_bgr_hwc, new_shape, pad_value, **lb)
+    return np.ascontiguousarray(out[..., ::-1].transpose(2, 0, 1))
+
+
+def letterbox_frame(img: np.ndarray, new_shape=(640, 640), pad_value=114, **lb) -> np.ndarray:
+    """`LetterBox.apply_image` augment.py:1792-1822: resize if needed, constant border; HWC in, HWC out."""
+    (nw, nh), top, bottom, left, right = letterbox_params(img.shape[:2], new_shape, **lb)
+    if img.shape[:2] != (nh, nw):
+        img = resize_linear_u8(img, nw, nh)
     out = np.full((nh + top + bottom, nw + left + right, img.shape[2]), pad_value, dtype=np.uint8)
     out[top:top + nh, left:left + nw] = img
-    return np.ascontiguousarray(out[..., ::-1].transpose(2, 0, 1))
+    return out
+
+
+def scale_boxes(img1_shape, boxes: np.ndarray, img0_shape, padding=True, xywh=False) -> np.ndarray:
+    """`ops.scale_boxes` + `clip_boxes` utils/ops.py:119-158,174-201 on fp32 rows (n, >= 4); returns a new array.
+    fp32 arithmetic in the reference's order: subtract the integer padding, divide by float32(gain), clamp to the original frame."""
+    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+    pad_x = round((img1_shape[1] - round(img0_shape[1] * gain)) / 2 - 0.1)
+    pad_y = round((img1_shape[0] - round(img0_shape[0] * gain)) / 2 - 0.1)
+    b = boxes.astype(np.float32).copy()
+    if padding:
+        b[..., 0] -= np.float32(pad_x)
+        b[..., 1] -= np.float32(pad_y)
+        if not xywh:
+            b[..., 2] -= np.float32(pad_x)
+            b[..., 3] -= np.float32(pad_y)
+    b[..., :4] = b[..., :4] / np.float32(gain)
+    if not xywh:
+        h, w = img0_shape[:2]
+        b[..., [0, 2]] = b[..., [0, 2]].clip(0, w)
+        b[..., [1, 3]] = b[..., [1, 3]].clip(0, h)
+    return b

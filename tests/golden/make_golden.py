@@ -251,6 +251,13 @@ def esmoe_golden():
 LETTERBOX_CASES = [(480, 640), (720, 1280), (1080, 1920), (1200, 1600), (427, 640), (640, 480), (333, 500), (100, 37), (64, 64)]
 
 
+LETTERBOX_VARIANTS = [(300, 400, (640, 640), {"auto": True}), (500, 333, (640, 640), {"auto": True}),
+                      (200, 300, (640, 640), {"scaleup": False}), (375, 500, (640, 640), {"scale_fill": True}),
+                      (480, 640, (640, 640), {"center": False}), (1080, 1920, (384, 640), {}), (97, 211, (320, 416), {"auto": True})]
+SCALE_BOX_CASES = [((640, 640), (480, 640)), ((640, 640), (1080, 1920)), ((384, 640), (720, 1280)), ((640, 640), (100, 37)),
+                   ((640, 640), (333, 500, 3))]
+
+
 def letterbox_golden():
     """Reference pre-processing of one seeded uint8 BGR frame per case: the REAL `LetterBox` (cv2.resize INTER_LINEAR +
     copyMakeBorder 114) followed by the predictor's BGR->RGB / HWC->CHW (engine/predictor.py:164-170).  Stores only a CRC and a
@@ -268,7 +275,26 @@ def letterbox_golden():
         cases.append({"h": h, "w": w, "seed": 900 + seed, "crc": zlib.crc32(chw.tobytes()), "shape": list(chw.shape),
                       "thumb": torch.from_numpy(chw.reshape(3, 40, 16, 40, 16).astype(np.float32).mean((2, 4)))})
         print("letterbox", (h, w), chw.shape, cases[-1]["crc"])
-    torch.save({"cv2": cv2.__version__, "cases": cases}, f"{OUT}/letterbox.golden.pt")
+    # LetterBox option variants (HWC output of the transform itself) and `ops.scale_boxes` on seeded boxes
+    from ultralytics.utils import ops
+    variants = []
+    for seed, (h, w, new_shape, kw) in enumerate(LETTERBOX_VARIANTS):
+        img = np.random.default_rng(950 + seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        lb = LetterBox(new_shape, stride=32, **kw)
+        out = lb(image=img)
+        prm = lb.get_params({"img": img})
+        variants.append({"h": h, "w": w, "seed": 950 + seed, "new_shape": new_shape, "kw": kw, "shape": list(out.shape),
+                         "crc": zlib.crc32(np.ascontiguousarray(out).tobytes()),
+                         "params": [list(prm["new_unpad"]), prm["top"], prm["bottom"], prm["left"], prm["right"]]})
+        print("letterbox variant", (h, w), new_shape, kw, out.shape)
+    boxes = []
+    for seed, (img1, img0) in enumerate(SCALE_BOX_CASES):
+        g = torch.Generator().manual_seed(970 + seed)
+        b = torch.rand((64, 6), generator=g) * torch.tensor([img1[1], img1[0], img1[1], img1[0], 1, 80]) * 1.1 - 8.0
+        for xywh in (False, True):
+            boxes.append({"img1": img1, "img0": img0, "seed": 970 + seed, "xywh": xywh,
+                          "out": ops.scale_boxes(img1, b[:, :4].clone(), img0, xywh=xywh)})
+    torch.save({"cv2": cv2.__version__, "cases": cases, "variants": variants, "scale_boxes": boxes}, f"{OUT}/letterbox.golden.pt")
 
 
 if __name__ == "__main__":

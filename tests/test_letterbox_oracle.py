@@ -44,3 +44,25 @@ def test_resize_matches_cv2_bit_exact():
     big = np.random.default_rng(6).integers(0, 256, (300, 400, 3), dtype=np.uint8)
     for dw, dh in ((320, 240), (400, 100), (137, 300), (200, 150), (399, 299), (57, 31)):   # downscale / single-axis / exact 2x
         assert np.array_equal(cv2.resize(big, (dw, dh), interpolation=cv2.INTER_LINEAR), L.resize_linear_u8(big, dw, dh)), (dw, dh)
+
+
+@pytest.mark.parametrize("case", GOLDEN["variants"], ids=lambda c: f"{c['h']}x{c['w']}-{'-'.join(c['kw']) or 'rect'}")
+def test_letterbox_variants_match_reference(case):
+    """auto (minimum rectangle) / scaleup=False / scale_fill / center=False / non-square target: geometry and pixels of the
+    transform itself (HWC, BGR) against the real LetterBox."""
+    img = np.random.default_rng(case["seed"]).integers(0, 256, (case["h"], case["w"], 3), dtype=np.uint8)
+    prm = L.letterbox_params(img.shape[:2], tuple(case["new_shape"]), **case["kw"])
+    assert [list(prm[0]), *prm[1:]] == case["params"]
+    out = L.letterbox_frame(img, tuple(case["new_shape"]), **case["kw"])
+    assert list(out.shape) == case["shape"]
+    assert zlib.crc32(np.ascontiguousarray(out).tobytes()) == case["crc"]
+
+
+@pytest.mark.parametrize("case", GOLDEN["scale_boxes"], ids=lambda c: f"{c['img0'][0]}x{c['img0'][1]}-{'xywh' if c['xywh'] else 'xyxy'}")
+def test_scale_boxes_oracle_matches_reference(case):
+    """ops.scale_boxes (+ clip_boxes) of the reference on seeded boxes that straddle the frame: bit-exact fp32."""
+    g = torch.Generator().manual_seed(case["seed"])
+    img1 = case["img1"]
+    b = torch.rand((64, 6), generator=g) * torch.tensor([img1[1], img1[0], img1[1], img1[0], 1, 80]) * 1.1 - 8.0
+    out = L.scale_boxes(img1, b[:, :4].numpy(), case["img0"], xywh=case["xywh"])
+    assert np.array_equal(out, case["out"].numpy())

@@ -1,0 +1,140 @@
+// Predictor pre- and post-processing around the forward pass.  HBM-bound byte / index work:
+//   ym_letterbox_u8   LetterBox (cv2.resize INTER_LINEAR fixed point + constant border) + BGR->RGB + HWC->CHW (+ /255, fp16)
+//   ym_scale_boxes    ops.scale_boxes + clip_boxes on the (B, K, 6) / ragged NMS result rows
+#include "preproc_core.cuh"
+#include "ym_common.cuh"
+
+namespace ym {
+
+constexpr int LB_TX = 64, LB_TY = 4, LB_PX = 4;   // 256 threads, each 4 consecutive output pixels of one row
+
+template <typename T>
+__device__ __forceinline__ T lb_cvt(int v);
+template <>
+__device__ __forceinline__ uint8_t lb_cvt<uint8_t>(int v) { return (uint8_t)v; }
+template <>
+__device__ __forceinline__ float lb_cvt<float>(int v) { return __fdiv_rn((float)v, 255.f); }   // im.float() / 255 predictor.py:173-175
+template <>
+__device__ __forceinline__ __half lb_cvt<__half>(int v) { return __float2half_rn(__fdiv_rn((float)v, 255.f)); }
+
+template <typename T>
+struct alignas(sizeof(T) * 4) Vec4 {
+    T v[4];
+};
+
+// out: CHW ? [B][3][H][W] : [B][H][W][3].  grid = (ceil(W / 256), ceil(H / 4), B).
+template <typename T, bool CHW>
+__global__ void __launch_bounds__(LB_TX* LB_TY) letterbox_kernel(const uint8_t* __restrict__ src, long long src_stride,
+                                                                 const LbTap* __restrict__ xt, const LbTap* __restrict__ yt,
+                                                                 T* __restrict__ out, const LbGeom g) {
+    const int dy = blockIdx.y * LB_TY + threadIdx.y;
+    const int dx0 = (blockIdx.x * LB_TX + threadIdx.x) * LB_PX;
+    if (dy >= g.H || dx0 >= g.W) return;
+    const uint8_t* s = src + (long long)blockIdx.z * src_stride;
+    T* o = out + (long long)blockIdx.z * 3 * g.H * g.W;
+    int v[LB_PX][3];
+#pragma unroll
+    for (int j = 0; j < LB_PX; ++j) {
+        if (dx0 + j < g.W) lb_output_pixel(s, g, xt, yt, dx0 + j, dy, v[j]);
+        else v[j][0] = v[j][1] = v[j][2] = 0;
+    }
+    if (CHW) {
+        const bool vec = (g.W % LB_PX) == 0;   // rows and planes then start on a 4-element boundary
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            T* row = o + ((long long)c * g.H + dy) * g.W + dx0;
+            if (vec) {
+                Vec4<T> pk;
+#pragma unroll
+                for (int j = 0; j < LB_PX; ++j) pk.v[j] = lb_cvt<T>(v[j][c]);
+                *reinterpret_cast<Vec4<T>*>(row) = pk;
+            } else {
+#pragma unroll
+                for (int j = 0; j < LB_PX; ++j)
+                    if (dx0 + j < g.W) row[j] = lb_cvt<T>(v[j][c]);
+            }
+        }
+    } else {
+        T* row = o + ((long long)dy * g.W + dx0) * 3;
+#pragma unroll
+        for (int j = 0; j < LB_PX; ++j)
+            if (dx0 + j < g.W) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) row[3 * j + c] = lb_cvt<T>(v[j][c]);
+            }
+    }
+}
+
+constexpr int SB_MAX_IMG = 128;
+struct ScaleBoxParams {
+    float p[SB_MAX_IMG][5];   // gain, pad_x, pad_y, w0, h0 of each image
+};
+
+struct DivRn {
+    __device__ __forceinline__ float operator()(float a, float b) const { return __fdiv_rn(a, b); }
+};
+
+__global__ void __launch_bounds__(256) scale_boxes_kernel(float* __restrict__ boxes, int ld, long long n, int rows_per_img,
+                                                          const int* __restrict__ row_img, int padding, int xywh,
+                                                          const __grid_constant__ ScaleBoxParams sp) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int img = row_img ? row_img[i] : (int)(i / rows_per_img);
+    scale_box(boxes + i * ld, sp.p[img], padding, xywh, DivRn());
+}
+
+}  // namespace ym
+
+using namespace ym;
+
+extern "C" int ym_letterbox_u8(const void* src, long long src_stride, int B, int sh, int sw, int src_pitch, const void* xtab,
+                               const void* ytab, int area2x, int nw, int nh, int top, int left, int pad_value, int swap_rb,
+                               void* out, int out_dtype, int chw, int H, int W, void* stream) {
+    YM_CHECK_ARG(src && out, "ym_letterbox_u8: null pointer");
+    YM_CHECK_ARG(B >= 0 && B <= 65535, "ym_letterbox_u8: 0 <= B <= 65535 (got %d)", B);
+    YM_CHECK_ARG(sh > 0 && sw > 0 && sh <= 65535 && sw <= 65535 && src_pitch >= 3 * sw, "ym_letterbox_u8: bad source %dx%d pitch %d",
+                 sh, sw, src_pitch);
+    YM_CHECK_ARG(nw > 0 && nh > 0 && top >= 0 && left >= 0 && top + nh <= H && left + nw <= W,
+                 "ym_letterbox_u8: resized %dx%d at (%d,%d) does not fit %dx%d", nh, nw, top, left, H, W);
+    YM_CHECK_ARG(area2x ? (sw == 2 * nw && sh == 2 * nh) : (xtab && ytab), "ym_letterbox_u8: tables missing / not an exact 2x downscale");
+    YM_CHECK_ARG(out_dtype >= 0 && out_dtype <= 2, "ym_letterbox_u8: out_dtype 0 uint8, 1 fp16, 2 fp32");
+    YM_CHECK_ARG(pad_value >= 0 && pad_value <= 255, "ym_letterbox_u8: pad value");
+    if (B == 0) return YM_OK;
+    LbGeom g;
+    g.sh = sh; g.sw = sw; g.src_pitch = src_pitch; g.nw = nw; g.nh = nh; g.top = top; g.left = left; g.H = H; g.W = W;
+    g.pad = pad_value; g.swap_rb = swap_rb ? 1 : 0; g.area2x = area2x ? 1 : 0;
+    dim3 grid((W + LB_TX * LB_PX - 1) / (LB_TX * LB_PX), (H + LB_TY - 1) / LB_TY, B), block(LB_TX, LB_TY);
+    YM_CHECK_ARG(grid.y <= 65535, "ym_letterbox_u8: output too tall");
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint8_t* s = (const uint8_t*)src;
+    const LbTap *xt = (const LbTap*)xtab, *yt = (const LbTap*)ytab;
+#define LB_LAUNCH(T, CHW) letterbox_kernel<T, CHW><<<grid, block, 0, st>>>(s, src_stride, xt, yt, (T*)out, g)
+    if (chw) {
+        if (out_dtype == 0) LB_LAUNCH(uint8_t, true);
+        else if (out_dtype == 1) LB_LAUNCH(__half, true);
+        else LB_LAUNCH(float, true);
+    } else {
+        if (out_dtype == 0) LB_LAUNCH(uint8_t, false);
+        else if (out_dtype == 1) LB_LAUNCH(__half, false);
+        else LB_LAUNCH(float, false);
+    }
+#undef LB_LAUNCH
+    YM_CHECK_LAUNCH("letterbox_u8");
+    return YM_OK;
+}
+
+extern "C" int ym_scale_boxes(float* boxes, int ld, long long n, int rows_per_img, const int* row_img, int n_img,
+                              const float* params_host, int padding, int xywh, void* stream) {
+    YM_CHECK_ARG(n == 0 || boxes, "ym_scale_boxes: null boxes");
+    YM_CHECK_ARG(ld >= 4, "ym_scale_boxes: row pitch >= 4");
+    YM_CHECK_ARG(n_img >= 1 && n_img <= SB_MAX_IMG && params_host, "ym_scale_boxes: 1..%d images per call", SB_MAX_IMG);
+    YM_CHECK_ARG(row_img || (rows_per_img > 0 && n <= (long long)rows_per_img * n_img), "ym_scale_boxes: rows_per_img * n_img < n");
+    if (n == 0) return YM_OK;
+    ScaleBoxParams sp;
+    memset(&sp, 0, sizeof(sp));
+    memcpy(sp.p, params_host, sizeof(float) * 5 * n_img);
+    scale_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(boxes, ld, n, rows_per_img, row_img,
+                                                                                     padding, xywh, sp);
+    YM_CHECK_LAUNCH("scale_boxes");
+    return YM_OK;
+}

@@ -1,0 +1,137 @@
+"""`Results` / `Boxes` containers with the attribute names of ultralytics/engine/results.py:184-300,860-1100 (detection subset).
+Plain holders: the tensors stay wherever the predictor produced them (CUDA) until `.cpu()` / `.numpy()` is asked for."""
+from __future__ import annotations
+
+import torch
+
+
+def _xyxy2xywh(x):
+    y = torch.empty_like(x)
+    y[..., 0] = (x[..., 0] + x[..., 2]) / 2
+    y[..., 1] = (x[..., 1] + x[..., 3]) / 2
+    y[..., 2] = x[..., 2] - x[..., 0]
+    y[..., 3] = x[..., 3] - x[..., 1]
+    return y
+
+
+class Boxes:
+    """(n, 6) rows (x1, y1, x2, y2, conf, cls) in pixels of the original frame (results.py:860-1100)."""
+
+    def __init__(self, boxes, orig_shape):
+        if boxes.ndim == 1:
+            boxes = boxes[None, :]
+        if boxes.shape[-1] not in (6, 7):
+            raise ValueError(f"expected 6 or 7 values but got {boxes.shape[-1]}")
+        self.data = boxes
+        self.orig_shape = tuple(orig_shape)
+        self.is_track = boxes.shape[-1] == 7
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    @property
+    def xyxy(self):
+        return self.data[:, :4]
+
+    @property
+    def conf(self):
+        return self.data[:, -2]
+
+    @property
+    def cls(self):
+        return self.data[:, -1]
+
+    @property
+    def id(self):
+        return self.data[:, -3] if self.is_track else None
+
+    @property
+    def xywh(self):
+        return _xyxy2xywh(self.xyxy)
+
+    @property
+    def xyxyn(self):
+        xyxy = self.xyxy.clone()
+        xyxy[..., [0, 2]] /= self.orig_shape[1]
+        xyxy[..., [1, 3]] /= self.orig_shape[0]
+        return xyxy
+
+    @property
+    def xywhn(self):
+        xywh = self.xywh
+        xywh[..., [0, 2]] /= self.orig_shape[1]
+        xywh[..., [1, 3]] /= self.orig_shape[0]
+        return xywh
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        return Boxes(self.data[idx], self.orig_shape)
+
+    def cpu(self):
+        return Boxes(self.data.cpu(), self.orig_shape)
+
+    def cuda(self):
+        return Boxes(self.data.cuda(), self.orig_shape)
+
+    def to(self, *args, **kwargs):
+        return Boxes(self.data.to(*args, **kwargs), self.orig_shape)
+
+    def numpy(self):
+        b = Boxes.__new__(Boxes)
+        b.data, b.orig_shape, b.is_track = self.data.cpu().numpy(), self.orig_shape, self.is_track
+        return b
+
+
+class Results:
+    """One image's detections (results.py:184-300): `orig_img`, `orig_shape`, `boxes`, `names`, `path`, `speed`."""
+
+    def __init__(self, orig_img, path=None, names=None, boxes=None, speed=None):
+        self.orig_img = orig_img
+        self.orig_shape = tuple(orig_img.shape[:2])
+        self.boxes = Boxes(boxes, self.orig_shape) if boxes is not None else None
+        self.masks = self.probs = self.keypoints = self.obb = None
+        self.speed = speed if speed is not None else {"preprocess": None, "inference": None, "postprocess": None}
+        self.names = names
+        self.path = path
+        self.save_dir = None
+        self._keys = ("boxes",)
+
+    def __len__(self):
+        return 0 if self.boxes is None else len(self.boxes)
+
+    def __getitem__(self, idx):
+        return Results(self.orig_img, self.path, self.names, None if self.boxes is None else self.boxes.data[idx], self.speed)
+
+    def _apply(self, fn, *args, **kwargs):
+        r = Results(self.orig_img, self.path, self.names, None, self.speed)
+        if self.boxes is not None:
+            r.boxes = getattr(self.boxes, fn)(*args, **kwargs)
+        return r
+
+    def cpu(self):
+        return self._apply("cpu")
+
+    def numpy(self):
+        return self._apply("numpy")
+
+    def cuda(self):
+        return self._apply("cuda")
+
+    def to(self, *args, **kwargs):
+        return self._apply("to", *args, **kwargs)
+
+    def summary(self, normalize: bool = False, decimals: int = 5):
+        """results.py:606-660 (detection rows): list of {name, class, confidence, box}."""
+        out = []
+        if self.boxes is None:
+            return out
+        h, w = self.orig_shape if normalize else (1, 1)
+        for row in self.boxes.data.cpu().tolist():
+            c = int(row[5])
+            out.append({"name": (self.names or {}).get(c, str(c)), "class": c, "confidence": round(row[4], decimals),
+                        "box": {"x1": round(row[0] / w, decimals), "y1": round(row[1] / h, decimals),
+                                "x2": round(row[2] / w, decimals), "y2": round(row[3] / h, decimals)}})
+        return out

@@ -470,3 +470,61 @@ def adaptive_avgpool(x, h, w, out=None):
                "ym_adaptive_avgpool_nhwc")
     _count()
     return out
+
+
+_LB_DTYPES = {torch.uint8: 0, torch.float16: 1, torch.float32: 2}
+
+
+def letterbox(src, xtab, ytab, area2x, nw, nh, top, left, H, W, pad_value=114, swap_rb=True, chw=True, dtype=torch.uint8, out=None):
+    """ym_letterbox_u8.  src: uint8 CUDA (B, sh, sw, 3) frames with dense rows; xtab / ytab: int32 CUDA (n, 2) tap tables
+    (None when area2x).  Returns (B, 3, H, W) (chw) or (B, H, W, 3) of `dtype` (fp16 / fp32 are scaled by 1/255)."""
+    if not src.is_cuda or src.dtype != torch.uint8 or src.dim() != 4 or src.shape[3] != 3:
+        raise ValueError(f"letterbox: expected uint8 CUDA frames (B, H, W, 3), got {tuple(src.shape)} {src.dtype} {src.device}")
+    if src.stride(3) != 1 or src.stride(2) != 3:
+        raise ValueError("letterbox: frames must have dense interleaved rows")
+    B, sh, sw, _ = src.shape
+    if dtype not in _LB_DTYPES:
+        raise ValueError(f"letterbox: unsupported output dtype {dtype}")
+    if not area2x:
+        for t, n in ((xtab, nw), (ytab, nh)):
+            if t is None or not t.is_cuda or t.dtype != torch.int32 or tuple(t.shape) != (n, 2) or not t.is_contiguous():
+                raise ValueError("letterbox: tap tables must be contiguous int32 CUDA tensors of shape (n, 2)")
+    shape = (B, 3, H, W) if chw else (B, H, W, 3)
+    if out is None:
+        out = torch.empty(shape, dtype=dtype, device=src.device)
+    elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous() or not out.is_cuda:
+        raise ValueError(f"letterbox: out must be a contiguous {dtype} CUDA tensor of shape {shape}")
+    _lib.check(lib().ym_letterbox_u8(src.data_ptr(), src.stride(0) if B > 1 else 0, B, sh, sw, src.stride(1) if sh > 1 else 3 * sw,
+                                     None if area2x else xtab.data_ptr(), None if area2x else ytab.data_ptr(), 1 if area2x else 0,
+                                     nw, nh, top, left, int(pad_value), 1 if swap_rb else 0, out.data_ptr(), _LB_DTYPES[dtype],
+                                     1 if chw else 0, H, W, _stream()), "ym_letterbox_u8")
+    _count()
+    return out
+
+
+def scale_boxes(boxes, params, rows_per_img=0, row_img=None, padding=True, xywh=False):
+    """ym_scale_boxes, in place.  boxes: fp32 CUDA (..., ld >= 4) rows with a dense last dimension; params: fp32 HOST (n_img, 5)
+    = (gain, pad_x, pad_y, w0, h0); image of a row = row_img[row] (int32 CUDA) or row // rows_per_img."""
+    if not boxes.is_cuda or boxes.dtype != torch.float32 or boxes.dim() < 2 or boxes.shape[-1] < 4:
+        raise ValueError("scale_boxes: expected an fp32 CUDA tensor (..., >= 4)")
+    if boxes.dim() == 2 and boxes.stride(1) == 1 and (boxes.shape[0] == 1 or boxes.stride(0) >= boxes.shape[1]):
+        ld = boxes.stride(0) if boxes.shape[0] > 1 else boxes.shape[1]   # e.g. the [:, :4] view of (n, 6) result rows
+    elif boxes.is_contiguous():
+        ld = boxes.shape[-1]
+    else:
+        raise ValueError("scale_boxes: rows must be dense with a constant pitch")
+    if params.is_cuda or params.dtype != torch.float32 or params.dim() != 2 or params.shape[1] != 5 or not params.is_contiguous():
+        raise ValueError("scale_boxes: params must be a contiguous fp32 HOST tensor (n_img, 5)")
+    n = boxes.numel() // boxes.shape[-1]
+    n_img = params.shape[0]
+    if row_img is not None:
+        if not row_img.is_cuda or row_img.dtype != torch.int32 or row_img.numel() != n or not row_img.is_contiguous():
+            raise ValueError("scale_boxes: row_img must be a contiguous int32 CUDA tensor with one entry per row")
+    elif rows_per_img <= 0 or n > rows_per_img * n_img:
+        raise ValueError("scale_boxes: rows_per_img * n_img must cover every row")
+    if n_img > 128:
+        raise ValueError("scale_boxes: at most 128 images per call")
+    _lib.check(lib().ym_scale_boxes(boxes.data_ptr(), ld, n, rows_per_img, None if row_img is None else row_img.data_ptr(), n_img,
+                                    params.data_ptr(), 1 if padding else 0, 1 if xywh else 0, _stream()), "ym_scale_boxes")
+    _count()
+    return boxes
