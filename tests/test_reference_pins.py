@@ -69,3 +69,52 @@ def test_router_fp32_contract():
     w, idx, probs = O.efficient_spatial_router(sd, "model.4.m.0.0.mlp.routing", x, 2)
     assert w.dtype == torch.float32 and idx.dtype == torch.int64 and probs.dtype == torch.float32
     assert torch.allclose(w.sum(1), torch.ones(3)) and torch.allclose(probs.sum(1), torch.ones(3), atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Error conventions of the routed modules: tests/test_moe_router_boundaries.py:66-112,175-190 of the reference,
+# replayed on this package's router.  All of these fire before any kernel is launched, so they run without a GPU.
+def test_router_input_validation_matches_reference_error_types():
+    import pytest
+
+    from yolo_master_b200.nn.modules.moe import EfficientSpatialRouter, _validate_router_input
+    from yolo_master_b200.utils.errors import MoERouterError, ShapeMismatchError, YOLOMasterError
+    C = 64
+    _validate_router_input(torch.randn(2, C, 16, 16), C)                                   # valid: no exception
+    for bad in (torch.randn(2, C, 16), torch.randn(2, C, 16, 16, 1)):
+        with pytest.raises(MoERouterError, match="4-D"):
+            _validate_router_input(bad, C)
+    with pytest.raises(ShapeMismatchError) as e:
+        _validate_router_input(torch.randn(2, 32, 16, 16), C)
+    assert e.value.expected == "(N, 64, H, W)" and e.value.actual == (2, 32, 16, 16) and "router input" in str(e.value)
+    for v in (float("nan"), float("inf")):
+        x = torch.randn(2, C, 16, 16)
+        x[0, 0, 0, 0] = v
+        with pytest.raises(MoERouterError, match="NaN"):
+            _validate_router_input(x, C)
+    assert issubclass(MoERouterError, YOLOMasterError) and issubclass(ShapeMismatchError, YOLOMasterError)
+    router = EfficientSpatialRouter(C, 4, top_k=2).eval()
+    with pytest.raises(MoERouterError, match="4-D"):
+        router(torch.randn(2, C, 16))
+    with pytest.raises(ShapeMismatchError):
+        router(torch.randn(2, 128, 16, 16))
+    for v in (float("nan"), float("inf")):
+        router.noise_std = v
+        with pytest.raises(MoERouterError, match="noise_std"):
+            router(torch.randn(2, C, 16, 16))
+
+
+def test_error_types_are_the_references_when_it_is_importable():
+    """Inside the reference tree the package re-exports ultralytics' own classes (identity, so `except` clauses written against
+    ultralytics.utils.errors keep working); standalone it defines equivalents."""
+    import importlib
+    import sys
+
+    from yolo_master_b200.utils import errors
+    if "ultralytics" in sys.modules or importlib.util.find_spec("ultralytics") is not None:
+        from ultralytics.utils.errors import MoERouterError
+        assert errors.MoERouterError is MoERouterError
+    else:
+        assert errors.MoERouterError.__module__ == "yolo_master_b200.utils.errors"
+        e = errors.ShapeMismatchError("(N, 8, H, W)", (1, 4, 2, 2), "ctx")
+        assert str(e) == "Shape mismatch: expected (N, 8, H, W), got (1, 4, 2, 2) [ctx]"

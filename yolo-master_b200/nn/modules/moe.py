@@ -11,10 +11,13 @@ No host synchronisation happens anywhere in the block, so the forward is CUDA-gr
 """
 from __future__ import annotations
 
+import math
+
 import torch
 import torch.nn as nn
 
 from ... import ops
+from ...utils.errors import MoERouterError, ShapeMismatchError
 from ._base import PackCache, bn_affine, fold_bn, pack_gemm_weight, require_eval, to_nchw, to_nhwc
 from .block import A2C2f, ABlock, C3k, _SeqNHWC
 
@@ -30,6 +33,18 @@ def get_safe_groups(channels: int, desired_groups: int = 8) -> int:
     while channels % groups != 0:
         groups -= 1
     return max(1, groups)
+
+
+def _validate_router_input(x: torch.Tensor, expected_channels: int, context: str = "") -> None:
+    """routers.py:33-52: rank, channel count, finiteness (the last one reads the tensor and synchronises, as the reference does;
+    it runs only at a router's public `forward`, never inside a block's fused path)."""
+    tag = f" [{context}]" if context else ""
+    if x.dim() != 4:
+        raise MoERouterError(f"Router input must be 4-D (NCHW), got {x.dim()}-D shape {tuple(x.shape)}{tag}")
+    if expected_channels > 0 and x.shape[1] != expected_channels:
+        raise ShapeMismatchError(expected=f"(N, {expected_channels}, H, W)", actual=tuple(x.shape), context=context or "router input")
+    if not bool(torch.isfinite(x).all()):
+        raise MoERouterError(f"Router input contains NaN/Inf values{tag}")
 
 
 class EfficientSpatialRouter(nn.Module, PackCache):
@@ -73,11 +88,12 @@ class EfficientSpatialRouter(nn.Module, PackCache):
     def forward(self, x, top_k=None):
         """Returns (weights fp32 [B,k], indices int64 [B,k], {}) like the reference's eval branch."""
         require_eval(self)
-        if x.dim() != 4:
-            raise ValueError(f"Router input must be 4-D (NCHW), got {x.dim()}-D shape {tuple(x.shape)}")
-        if x.shape[1] != self.router[0].in_channels:
-            raise ValueError(f"router input: expected (N, {self.router[0].in_channels}, H, W), got {tuple(x.shape)}")
+        _validate_router_input(x, self.router[0].in_channels, context="EfficientSpatialRouter")
+        if not math.isfinite(float(self.noise_std)):
+            raise MoERouterError("EfficientSpatialRouter noise_std must be finite")
         idx, w, _ = self.route_nhwc(to_nhwc(x), top_k)
+        if not bool(torch.isfinite(w).all()):     # routers.py:295-302: non-finite weights / statistics inside the router
+            raise MoERouterError("EfficientSpatialRouter internal output contains NaN/Inf")
         return w, idx.long(), {}
 
 
@@ -177,7 +193,14 @@ class OptimizedMOEImproved(nn.Module, PackCache):
         return y
 
     def forward(self, x):
-        return to_nchw(self.fwd_nhwc(to_nhwc(x)))
+        """Standalone NCHW entry.  The reference guards four intermediate tensors (modules.py:1086,1144,1148,1151); the fused
+        path has one place to look - the block output - and raises the same RuntimeError type there.  Inside A2C2fMoE the block
+        runs through `fwd_nhwc` with no host synchronisation."""
+        y = self.fwd_nhwc(to_nhwc(x))
+        if not torch.cuda.is_current_stream_capturing() and not bool(torch.isfinite(y).all()):
+            raise RuntimeError("OptimizedMOEImproved final output contains NaN/Inf (shared expert / sparse expert aggregation / "
+                               "dtype conversion)")
+        return to_nchw(y)
 
     @property
     def aux_loss(self):
