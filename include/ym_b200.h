@@ -128,6 +128,9 @@ int ym_detect_dense(int nl, const void* const* box, const void* const* cls, cons
  *   op 4  out = tok * [silu](a*sc[img,c] + sh[img,c]) + b      GroupNorm apply (+ routed weight + accumulate);
  *                                        img = row / rows_per_img; p0 = sc, p1 = sh fp32[imgs*C]; tok NULL = 1
  *   op 5  out = t*a + (1-t)*b            scalar blend, t = p0[0] (moa/heads.py:371-375)
+ *   op 6  out = sigmoid(a)               gate heads of moe/gated.py:1165-1172,1206-1208
+ *   op 7  out = a * (1 + t*b)            VisualDetailGate gated.py:1176-1178, t = p0[0] = tanh(detail_scale)
+ *   op 8  out = a * b                    context * gate gated.py:1219-1221
  * tok: fp32 per-token weights [rows*ldt] read at column toff. */
 int ym_ew_nhwc(int op, const void* a, int lda, const void* b, int ldb, const float* p0, const float* p1, const float* tok,
                int ldt, int toff, int rows_per_img, int act, void* out, int ldo, long long rows, int C, void* stream);
@@ -180,6 +183,35 @@ int ym_linear_attn(const void* q, int ldq, const void* k, int ldk, const void* v
 
 /* F.adaptive_avg_pool2d (moa/heads.py:224). */
 int ym_adaptive_avgpool_nhwc(const void* x, int ldx, int B, int H, int W, int C, int h, int w, void* out, int ldo, void* stream);
+
+/* ---- Gated MoE family (VisualEnhancedAdaptiveGateMoE, nn/modules/moe/gated.py) ----------------------
+ * ym_gate_router: DualStreamGateRouter.forward gated.py:129-151 (fp32 throughout, as the reference's FP32RouterMixin) followed by
+ *   AdaptiveGateMoE._safe_complexity / _apply_complexity_gate gated.py:455-490.  x: fp16 [B][H*W][ldx] (the dynamic channel half).
+ *   global stream: [mean | population std] over H*W per channel -> global_fc fp32 [E][2C];
+ *   local stream : avg_pool(pool) when H,W > pool -> dw3x3 (dw fp32 [C][9]) -> GN(G1) -> SiLU -> 1x1 (pw1 [R][C]) -> GN(G2) -> SiLU
+ *                  -> 1x1 (pw2 [E][R]) + b2 -> spatial mean;
+ *   logits = clamp(alpha*global + (1-alpha)*local, +-30) (alpha = sigmoid(self.alpha), passed as a value), softmax(/temperature),
+ *   top-k, w / (sum + 1e-6); complexity c = clamp(mean over the BATCH of sigmoid(cx_w . mean_c + cx_b), 0.3, 1.5) keeps the
+ *   round(c*topk) best ranks and renormalises.  Outputs: w fp32 [B][topk], idx int32 [B][topk], probs fp32 [B][E] (nullable).
+ *   scratch: ym_gate_router_scratch_floats() floats.  Three kernels, no host synchronisation.
+ * ym_fc_gate: out[b][o] = scale * sigmoid(b2[o] + w2[o] . silu(w1 . v[b]))   v fp16 [B][ldv] (a 1x1 adaptive average pool):
+ *   se_gate gated.py:325-332 (scale 1), feature_gate moe/hooks.py:50-57 (scale = tanh(refine_scale)); consumed by ym_ew_nhwc op 4.
+ * ym_gated_select: FusedExpertGroup.forward gated.py:1061-1081 after the all-expert grouped conv: fo fp16 [B][HW][ldf] holds
+ *   expert e in channels [e*oc, (e+1)*oc); for the routed experts: GroupNorm(G, no affine) over the slice, gamma/beta fp32 [E][oc],
+ *   SiLU, sum_j w[b][j] * (.) -> out fp16 [B][HW][ldo].  scratch: 2*B*topk*oc floats.
+ * ym_ctx_mean3: PyramidContextMixer gated.py:1213-1219: (a + nearest_up(b) + nearest_up(c)) / 3 with b (h2,w2), c (h4,w4). */
+long long ym_gate_router_scratch_floats(int B, int H, int W, int C, int R, int E, int pool);
+int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* global_fc, const float* dw,
+                   const float* gn1_w, const float* gn1_b, int G1, const float* pw1, int R, const float* gn2_w,
+                   const float* gn2_b, int G2, const float* pw2, const float* b2, int E, float gn_eps, float alpha,
+                   float temperature, const float* cx_w, float cx_b, int topk, float* scratch, float* w_out, int* idx_out,
+                   float* probs_out, void* stream);
+int ym_fc_gate(const void* v, int ldv, int B, int Cin, const float* w1, int Cr, const float* w2, const float* b2, int Cout,
+               float scale, float* out, void* stream);
+int ym_gated_select(const void* fo, int ldf, int B, int HW, int E, int oc, int G, float eps, const int* idx, const float* w,
+                    int topk, const float* gamma, const float* beta, float* scratch, void* out, int ldo, void* stream);
+int ym_ctx_mean3(const void* a, int lda, const void* b, int ldb, const void* c, int ldc, int B, int H, int W, int C, int h2,
+                 int w2, int h4, int w4, void* out, int ldo, void* stream);
 
 /* Predictor pre-processing of B same-sized uint8 HWC frames.  Replaces, fused into one pass,
  * LetterBox.apply_image data/augment.py:1792-1822 (cv2.resize INTER_LINEAR + copyMakeBorder BORDER_CONSTANT) and

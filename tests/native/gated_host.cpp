@@ -1,0 +1,88 @@
+// TEST INFRASTRUCTURE (g++ only, no CUDA): runs the phase functions of yolo-master_b200/csrc/gated_core.cuh on the host - for
+// each CTA, every phase is executed for tid = 0..NTHR-1 before the next phase starts, which is what __syncthreads() gives the
+// kernels in gated.cu - so tests/test_gated_host.py can compare the arithmetic of ym_gate_router / ym_fc_gate / ym_gated_select /
+// ym_ctx_mean3 with the oracle in the GPU-less build container.  Same argument lists as the C ABI, minus the stream.
+#include <vector>
+
+#include "gated_core.cuh"
+
+using namespace ym::gated;
+
+extern "C" int host_gate_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* global_fc,
+                                const float* dw, const float* gn1_w, const float* gn1_b, int G1, const float* pw1, int R,
+                                const float* gn2_w, const float* gn2_b, int G2, const float* pw2, const float* b2, int E,
+                                float gn_eps, float alpha, float temperature, const float* cx_w, float cx_b, int topk,
+                                float* w_out, int* idx_out, float* probs_out) {
+    const bool pooling = pool > 1 && H > pool && W > pool;
+    const int eff = pooling ? pool : 1, Hp = H / eff, Wp = W / eff;
+    const long long N = (long long)Hp * Wp;
+    std::vector<float> stats((size_t)B * 2 * C), pooled((size_t)B * N * C), t1((size_t)B * N * C), t2((size_t)B * N * R),
+        ll((size_t)B * E), cx(B);
+    R0Args a0;
+    a0.x = (const ym_half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = eff; a0.Hp = Hp; a0.Wp = Wp;
+    a0.inv_area = 1.f / (float)(eff * eff); a0.stats = stats.data(); a0.pooled = pooled.data();
+    std::vector<float> sm(r0_smem_floats(C, NTHR) + r1_smem_floats(R, NTHR) + 16);
+    for (int b = 0; b < B; ++b)
+        for (int ph = 0; ph < R0_PHASES; ++ph)
+            for (int t = 0; t < NTHR; ++t) r0_phase(ph, a0, b, t, NTHR, sm.data());
+    R1Args a1;
+    a1.pooled = pooled.data(); a1.t1 = t1.data(); a1.t2 = t2.data(); a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E;
+    a1.G1 = G1; a1.G2 = G2; a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w;
+    a1.g2b = gn2_b; a1.pw2 = pw2; a1.b2 = b2; a1.ll = ll.data();
+    for (int b = 0; b < B; ++b) {
+        for (int ph = 0; ph < R1_PHASES; ++ph)
+            for (int t = 0; t < NTHR; ++t) r1_phase(ph, a1, b, t, NTHR, sm.data());
+        for (int ph = 0; ph < R1_TAIL_PHASES; ++ph)
+            for (int t = 0; t < NTHR; ++t) r1_tail_phase(ph, a1, b, t, NTHR, sm.data());
+    }
+    R2Args a2;
+    a2.stats = stats.data(); a2.ll = ll.data(); a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha;
+    a2.inv_temp = 1.f / temperature; a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.cx = cx.data(); a2.w = w_out;
+    a2.probs = probs_out; a2.idx = idx_out;
+    for (int ph = 0; ph < R2_PHASES; ++ph)
+        for (int t = 0; t < NTHR; ++t) r2_phase(ph, a2, t, NTHR, sm.data());
+    return 0;
+}
+
+extern "C" int host_fc_gate(const void* v, int ldv, int B, int Cin, const float* w1, int Cr, const float* w2, const float* b2,
+                            int Cout, float scale, float* out) {
+    FcArgs a;
+    a.v = (const ym_half*)v; a.ldv = ldv; a.Cin = Cin; a.Cr = Cr; a.Cout = Cout; a.w1 = w1; a.w2 = w2; a.b2 = b2; a.scale = scale;
+    a.out = out;
+    std::vector<float> sm(fc_smem_floats(Cr) + 1);
+    for (int b = 0; b < B; ++b)
+        for (int ph = 0; ph < FC_PHASES; ++ph)
+            for (int t = 0; t < NTHR; ++t) fc_phase(ph, a, b, t, NTHR, sm.data());
+    return 0;
+}
+
+extern "C" int host_gated_select(const void* fo, int ldf, int B, int HW, int E, int oc, int G, float eps, const int* idx,
+                                 const float* w, int topk, const float* gamma, const float* beta, void* out, int ldo) {
+    std::vector<float> sc((size_t)B * topk * oc), sh((size_t)B * topk * oc), sm(s0_smem_floats(NTHR));
+    S0Args a;
+    a.fo = (const ym_half*)fo; a.ldf = ldf; a.HW = HW; a.oc = oc; a.G = G; a.topk = topk; a.eps = eps; a.idx = idx; a.gamma = gamma;
+    a.beta = beta; a.sc = sc.data(); a.sh = sh.data();
+    for (int r = 0; r < B * topk; ++r)
+        for (int ph = 0; ph < S0_PHASES; ++ph)
+            for (int t = 0; t < NTHR; ++t) s0_phase(ph, a, r, t, NTHR, sm.data());
+    ym_half* o = (ym_half*)out;
+    for (int b = 0; b < B; ++b)
+        for (int p = 0; p < HW; ++p)
+            for (int c = 0; c < oc; ++c) o[((long long)b * HW + p) * ldo + c] = ym_f2h(s1_element(a, w, b, p, c));
+    (void)E;
+    return 0;
+}
+
+extern "C" int host_ctx_mean3(const void* a, int lda, const void* b, int ldb, const void* c, int ldc, int B, int H, int W, int C,
+                              int h2, int w2, int h4, int w4, void* out, int ldo) {
+    CtxArgs g;
+    g.a = (const ym_half*)a; g.b = (const ym_half*)b; g.c = (const ym_half*)c; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    g.H = H; g.W = W; g.C = C; g.h2 = h2; g.w2 = w2; g.h4 = h4; g.w4 = w4;
+    g.sy2 = (float)h2 / (float)H; g.sx2 = (float)w2 / (float)W; g.sy4 = (float)h4 / (float)H; g.sx4 = (float)w4 / (float)W;
+    ym_half* o = (ym_half*)out;
+    for (int img = 0; img < B; ++img)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x)
+                for (int ch = 0; ch < C; ++ch) o[((long long)(img * H + y) * W + x) * ldo + ch] = ym_f2h(ctx_element(g, img, y, x, ch));
+    return 0;
+}

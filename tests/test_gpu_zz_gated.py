@@ -1,0 +1,144 @@
+"""GPU parity of the gated MoE family: `ym_gate_router`, `ym_fc_gate`, `ym_gated_select`, `ym_ctx_mean3`,
+the new `ym_ew_nhwc` ops and the `VisualEnhancedAdaptiveGateMoE` block / the v0_10 yolo-master-n model against the oracle and
+the reference goldens, through the public API.
+
+Written after round 1's GPU budget was spent: the kernel bodies and the host wiring are verified on the host
+(tests/test_gated_host.py runs the same phase functions under g++ and the block against the oracle), the CUDA launches have not
+run on hardware yet.  Until they have, the module is marked xfail(strict=False) - XPASS means the marker can go - and the file
+name sorts it after the verified suites."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _util import GOLD, assert_within_noise, synth_sd_from_keys, yaml_of
+from oracle import yolo_master_oracle as O
+from yolo_master_b200 import ops
+from yolo_master_b200.nn.modules.gated import VisualEnhancedAdaptiveGateMoE
+from yolo_master_b200.nn.tasks import DetectionModel
+from yolo_master_b200.utils.synth import fill_state_dict_, synth_images
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first hardware run of the gated-MoE kernels (host-verified only)")]
+DEV = "cuda"
+CFG = "master/v0_10/det/yolo-master-n.yaml"
+NAME = "yolo-master-n-v0_10"
+
+
+def _block(c, E, k, seed):
+    m = VisualEnhancedAdaptiveGateMoE(c, c, E, k, 0.5)
+    sd = m.state_dict()
+    fill_state_dict_(sd, seed)
+    m.load_state_dict(sd)
+    return m.to(DEV).eval(), {"m." + k_: v.clone().float() for k_, v in sd.items()}
+
+
+@pytest.mark.parametrize("c,E,k,H,W", [(128, 4, 2, 80, 80), (128, 8, 2, 40, 40), (256, 16, 2, 20, 20), (64, 4, 1, 4, 4), (64, 8, 2, 9, 7)])
+def test_gate_router_kernels(c, E, k, H, W):
+    m, sd = _block(c, E, k, 11)
+    xd = torch.randn((3, c // 2, H, W), generator=torch.Generator().manual_seed(5)).half()
+    idx, w, probs = ops.gate_router(xd.to(DEV).permute(0, 2, 3, 1).contiguous(), m.get_pack()["router"], k)
+    xf = xd.float()
+    cx = torch.sigmoid(F.conv2d(xf.mean((2, 3), keepdim=True), sd["m.complexity_estimator.1.weight"], sd["m.complexity_estimator.1.bias"])).mean()
+    rw, ri, rp = O.dual_stream_gate_router(sd, "m.routing", xf, k, 1.2)
+    rw = O.complexity_gate(rw, cx.clamp(0.3, 1.5))
+    assert torch.equal(idx.long().cpu(), ri)
+    torch.testing.assert_close(probs.cpu(), rp, atol=1e-5, rtol=1e-3)
+    torch.testing.assert_close(w.cpu(), rw, atol=1e-5, rtol=1e-3)
+
+
+def test_fc_gate_select_ctx_kernels():
+    g = torch.Generator().manual_seed(9)
+    m, sd = _block(128, 4, 2, 7)
+    pk = m.get_pack()
+    v = torch.randn((3, 1, 1, 128), generator=g).half()
+    got = ops.fc_gate(v.to(DEV), pk["se_w1"], pk["se_w2"], pk["se_b2"]).cpu()
+    want = torch.sigmoid(F.linear(F.silu(F.linear(v.view(3, 128).float(), sd["m.se_gate.2.weight"])), sd["m.se_gate.4.weight"], sd["m.se_gate.4.bias"]))
+    torch.testing.assert_close(got, want, atol=1e-5, rtol=1e-4)
+    B, H, W, E, oc, G = 3, 17, 13, 4, 64, 8
+    buf = torch.randn((B, H, W, E * oc + 8), generator=g).half()
+    idx = torch.tensor([[2, 0], [1, 3], [0, 2]], dtype=torch.int32)
+    w = torch.tensor([[0.7, 0.3], [0.55, 0.45], [1.0, 0.0]])
+    gamma, beta = torch.randn((E, oc), generator=g), torch.randn((E, oc), generator=g)
+    got = ops.gated_select(buf.to(DEV)[..., :E * oc], idx.to(DEV), w.to(DEV), gamma.to(DEV), beta.to(DEV), E, oc, G).float().cpu()
+    f5 = buf[..., :E * oc].float().permute(0, 3, 1, 2).reshape(B, E, oc, H, W)
+    sel = torch.gather(f5, 1, idx.long().view(B, 2, 1, 1, 1).expand(B, 2, oc, H, W))
+    nrm = F.group_norm(sel.reshape(B * 2, oc, H, W), G).view(B, 2, oc, H, W)
+    nrm = nrm * gamma[idx.long()].view(B, 2, oc, 1, 1) + beta[idx.long()].view(B, 2, oc, 1, 1)
+    want = (F.silu(nrm) * w.view(B, 2, 1, 1, 1)).sum(1).permute(0, 2, 3, 1)
+    torch.testing.assert_close(got, want, atol=4e-3, rtol=2e-3)
+    for H, W in ((8, 12), (5, 7), (3, 3), (1, 2)):
+        a = torch.randn((2, H, W, 16), generator=g).half()
+        h2, w2, h4, w4 = max(1, H // 2), max(1, W // 2), max(1, H // 4), max(1, W // 4)
+        b, c = torch.randn((2, h2, w2, 16), generator=g).half(), torch.randn((2, h4, w4, 16), generator=g).half()
+        up = lambda t: F.interpolate(t.float().permute(0, 3, 1, 2), size=(H, W), mode="nearest").permute(0, 2, 3, 1)
+        want = torch.stack([a.float(), up(b), up(c)]).mean(0)
+        torch.testing.assert_close(ops.ctx_mean3(a.to(DEV), b.to(DEV), c.to(DEV)).float().cpu(), want, atol=2e-3, rtol=1e-3)
+
+
+def test_new_elementwise_ops():
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.randn((2, 5, 7, 16), generator=g).half(), torch.randn((2, 5, 7, 16), generator=g).half()
+    t = torch.tensor([0.37])
+    da, db = a.to(DEV), b.to(DEV)
+    torch.testing.assert_close(ops.ew(ops.EW_SIGMOID, a=da).float().cpu(), torch.sigmoid(a.float()), atol=1e-3, rtol=1e-3)
+    torch.testing.assert_close(ops.ew(ops.EW_MUL_GATE, a=da, b=db, p0=t.to(DEV)).float().cpu(), a.float() * (1 + 0.37 * b.float()), atol=2e-3, rtol=2e-3)
+    torch.testing.assert_close(ops.ew(ops.EW_MUL, a=da, b=db).float().cpu(), a.float() * b.float(), atol=2e-3, rtol=2e-3)
+
+
+@pytest.mark.parametrize("c,E,k,H,W,seed", [(128, 4, 2, 40, 40, 1), (128, 8, 2, 20, 24, 2), (256, 16, 2, 10, 10, 3)])
+def test_block_matches_oracle(c, E, k, H, W, seed):
+    m, sd = _block(c, E, k, seed)
+    x = torch.randn((2, c, H, W), generator=torch.Generator().manual_seed(20 + seed)).half().float()
+    fn = lambda t, **kw: O.layer_visual_enhanced_gate_moe(sd, "m", t, c, c, E, k, 0.5, **kw)
+    with torch.no_grad():
+        y = m(x.half().to(DEV).contiguous(memory_format=torch.channels_last))
+    ref, rw, ri, _ = fn(x, return_route=True)
+    assert torch.equal(m.last_routing_snapshot["topk_indices"].long().cpu(), ri)
+    with O.fp16_storage(), O.fp16_weights():
+        sim = fn(x)
+    assert_within_noise(y, ref, sim, what=f"VisualEnhancedAdaptiveGateMoE c{c} E{E}")
+
+
+@pytest.fixture(scope="module")
+def model():
+    m = DetectionModel(CFG)
+    sd = synth_sd_from_keys(0, NAME)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval(), sd, O.parse_spec(yaml_of(CFG))
+
+
+@pytest.mark.parametrize("tag", ["b2_160", "b1_128"])
+def test_v0_10_model_matches_reference_golden(model, tag):
+    m, sd, spec = model
+    c = torch.load(os.path.join(GOLD, f"{NAME}.golden.pt"))["cases"][tag]
+    x = synth_images(c["B"], c["H"], c["W"], c["seed"]).half()
+    feats = {}
+    hooks = [mod.register_forward_hook(lambda mod, i, o, k=k: feats.__setitem__(k, o)) for k, mod in enumerate(m.model)]
+    with torch.no_grad():
+        y = m(x.to(DEV))[0]
+    for h in hooks:
+        h.remove()
+    ref, ys = O.forward(spec, sd, x.float(), return_layers=True)
+    with O.fp16_storage(), O.fp16_weights():
+        ysim, sim = O.forward(spec, sd, x.float(), return_layers=True)
+    for i, g in c["layers"].items():
+        assert_within_noise(feats[i], g, sim[i], what=f"{NAME} layer {i} vs reference golden", outlier_frac=0.02)
+    y = y.float().cpu()
+    assert_within_noise(y[:, :4], ref[:, :4], ysim[:, :4], what=f"{NAME} {tag} boxes", outlier_frac=0.02)
+    assert_within_noise(y[:, 4:], ref[:, 4:], ysim[:, 4:], what=f"{NAME} {tag} scores", outlier_frac=0.02)
+
+
+def test_v0_10_graph_replay_and_batch_dependence(model):
+    """CUDA-graph replay equals eager.  Unlike every other family the gated blocks are NOT per-image independent in the reference
+    itself: the complexity scalar is a mean over the batch (gated.py:455-461), so only determinism is asserted here."""
+    m, _, _ = model
+    x = synth_images(2, 256, 256, 5).half().to(DEV)
+    with torch.no_grad():
+        eager = m(x)[0].clone()
+        again = m(x)[0].clone()
+    assert torch.equal(eager, again)
+    out = m.graphed(2, 256, 256)(x).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)

@@ -69,6 +69,12 @@ def ew(op, a=None, b=None, p0=None, p1=None, ldt=0, toff=0, rows_per_img=1, act=
         y = F.gelu(fa)
     elif op == ops.EW_LERP:
         y = p0[0] * fa + (1 - p0[0]) * fb
+    elif op == ops.EW_SIGMOID:
+        y = torch.sigmoid(fa)
+    elif op == ops.EW_MUL_GATE:
+        y = fa * (1 + p0[0] * fb)
+    elif op == ops.EW_MUL:
+        y = fa * fb
     else:
         assert rows_per_img == H * W
         v = fa * p0.view(B, 1, 1, C) + p1.view(B, 1, 1, C)
@@ -165,6 +171,87 @@ def linear_attn(q, k, v, heads, hdp, hd, rf, eps=1e-6, limit=1e4, out=None):
 
 def adaptive_avgpool(x, h, w, out=None):
     return _out(F.adaptive_avg_pool2d(x.float().permute(0, 3, 1, 2), (h, w)).permute(0, 2, 3, 1), out)
+
+
+def moe_expert_gemm(a, lda, a_div, P, HW, K, w_all, route_idx, N, a_scale=None, a_shift=None, groups=0):
+    """out[p] = A[p // a_div] @ W[route_idx[p]]^T (optionally A := SiLU(A*scale + shift)); the "stats" handle is the stored output."""
+    A = a.reshape(-1, HW, a.shape[-1])[..., :K].float()
+    outs = []
+    for p in range(P):
+        Ap = A[p // a_div]
+        if a_scale is not None:
+            Ap = F.silu(Ap * a_scale[p].view(1, K) + a_shift[p].view(1, K))
+        outs.append(Ap @ w_all[int(route_idx[p])].float()[:N, :K].t())
+    out = torch.stack(outs).half()
+    return out, (out if groups else None)
+
+
+def gn_finalize(stats, P, HW, G, C_, count, eps, gamma, beta, route_idx, route_w=None):
+    o = stats.float().reshape(P, HW, G, C_ // G)
+    mean = o.mean((1, 3))
+    rstd = 1.0 / torch.sqrt(o.var((1, 3), unbiased=False) + eps)
+    e = route_idx.long()
+    rw = torch.ones(P) if route_w is None else route_w.float()
+    g, b = gamma[e].float(), beta[e].float()
+    mean, rstd = mean.repeat_interleave(C_ // G, 1), rstd.repeat_interleave(C_ // G, 1)
+    return (rw[:, None] * rstd * g).contiguous(), (rw[:, None] * (b - mean * rstd * g)).contiguous()
+
+
+def install_gated(host):
+    """Gated-family ops backed by the HOST build of their kernel bodies (tests/native/gated_host.cpp): `host` is its ctypes handle."""
+    import ctypes as C
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    host.host_gate_router.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, ci, cf, cf, cf, vp, cf,
+                                      ci, vp, vp, vp]
+    host.host_fc_gate.argtypes = [vp, ci, ci, ci, vp, ci, vp, vp, ci, cf, vp]
+    host.host_gated_select.argtypes = [vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, ci, vp, vp, vp, ci]
+    host.host_ctx_mean3.argtypes = [vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, ci]
+
+    def ld(t):   # row pitch of a (B,H,W,C) view with a dense channel dimension (what ops.pitch validates on the GPU path)
+        assert t.dtype == torch.float16 and t.stride(3) == 1
+        return t.stride(2) if t.shape[2] > 1 else (t.stride(1) if t.shape[1] > 1 else (t.stride(0) if t.shape[0] > 1 else t.shape[3]))
+
+    def gate_router(x, pk, topk):
+        B, H, W, Cc = x.shape
+        w = torch.empty((B, topk), dtype=torch.float32)
+        idx = torch.empty((B, topk), dtype=torch.int32)
+        probs = torch.empty((B, pk["E"]), dtype=torch.float32)
+        host.host_gate_router(x.data_ptr(), ld(x), B, H, W, Cc, pk["pool"], pk["global_fc"].data_ptr(), pk["dw"].data_ptr(),
+                              pk["gn1_w"].data_ptr(), pk["gn1_b"].data_ptr(), pk["G1"], pk["pw1"].data_ptr(), pk["R"],
+                              pk["gn2_w"].data_ptr(), pk["gn2_b"].data_ptr(), pk["G2"], pk["pw2"].data_ptr(), pk["b2"].data_ptr(), pk["E"],
+                              pk["eps"], pk["alpha"], pk["temperature"], pk["cx_w"].data_ptr(), pk["cx_b"], topk, w.data_ptr(),
+                              idx.data_ptr(), probs.data_ptr())
+        return idx, w, probs
+
+    def fc_gate(v, w1, w2, b2, scale=1.0):
+        B, Cin = v.shape[0], v.shape[3]
+        out = torch.empty((B, w2.shape[0]), dtype=torch.float32)
+        host.host_fc_gate(v.data_ptr(), ld(v), B, Cin, w1.data_ptr(), w1.shape[0], w2.data_ptr(), None if b2 is None else b2.data_ptr(),
+                          w2.shape[0], float(scale), out.data_ptr())
+        return out
+
+    def gated_select(fo, idx, w, gamma, beta, E, oc, G, eps=1e-5, out=None):
+        B, H, W, _ = fo.shape
+        if out is None:
+            out = torch.empty((B, H, W, oc), dtype=torch.float16)
+        host.host_gated_select(fo.data_ptr(), ld(fo), B, H * W, E, oc, G, eps, idx.data_ptr(), w.data_ptr(), idx.shape[1], gamma.data_ptr(),
+                               beta.data_ptr(), out.data_ptr(), ld(out))
+        return out
+
+    def ctx_mean3(a, b, c, out=None):
+        B, H, W, Cc = a.shape
+        if out is None:
+            out = torch.empty((B, H, W, Cc), dtype=torch.float16)
+        host.host_ctx_mean3(a.data_ptr(), ld(a), b.data_ptr(), ld(b), c.data_ptr(), ld(c), B, H, W, Cc, b.shape[1], b.shape[2],
+                            c.shape[1], c.shape[2], out.data_ptr(), ld(out))
+        return out
+
+    for name, fn in dict(gate_router=gate_router, fc_gate=fc_gate, gated_select=gated_select, ctx_mean3=ctx_mean3,
+                         moe_expert_gemm=moe_expert_gemm, gn_finalize=gn_finalize).items():
+        setattr(ops, name, fn)
+    ops.pitch = lambda t, dtype=torch.float16: ld(t)
+    from yolo_master_b200.nn.modules import gated
+    gated.to_nhwc = _base.to_nhwc
 
 
 def install():

@@ -1,0 +1,190 @@
+// Gated MoE family (VisualEnhancedAdaptiveGateMoE, nn/modules/moe/gated.py): the small fp32 kernels
+// between the convolutions.  The kernel bodies are in gated_core.cuh (phase functions shared with the host-side check).
+//   ym_gate_router    DualStreamGateRouter + batch complexity gate -> per-image top-k experts and weights
+//   ym_fc_gate        SE gate / feature gate: two-layer MLP on a pooled vector -> per-(image, channel) multiplier
+//   ym_gated_select   FusedExpertGroup tail: GroupNorm of the routed experts' channel slices, affine, SiLU, weighted sum
+//   ym_ctx_mean3      PyramidContextMixer: mean of the local map and two nearest-upsampled pooled maps
+#include "gated_core.cuh"
+#include "ym_common.cuh"
+
+namespace ym {
+using namespace gated;
+
+__global__ void __launch_bounds__(NTHR) gate_r0_kernel(const R0Args a) {
+    extern __shared__ float sm[];
+    for (int ph = 0; ph < R0_PHASES; ++ph) {
+        r0_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(NTHR) gate_r1_kernel(const R1Args a) {
+    extern __shared__ float sm[];
+    for (int ph = 0; ph < R1_PHASES; ++ph) {
+        r1_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
+        __syncthreads();
+    }
+    for (int ph = 0; ph < R1_TAIL_PHASES; ++ph) {
+        r1_tail_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(NTHR) gate_r2_kernel(const R2Args a) {
+    __shared__ float sm[4];
+    for (int ph = 0; ph < R2_PHASES; ++ph) {
+        r2_phase(ph, a, threadIdx.x, NTHR, sm);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(NTHR) fc_gate_kernel(const FcArgs a) {
+    extern __shared__ float sm[];
+    for (int ph = 0; ph < FC_PHASES; ++ph) {
+        fc_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(NTHR) select_s0_kernel(const S0Args a) {
+    extern __shared__ float sm[];
+    for (int ph = 0; ph < S0_PHASES; ++ph) {
+        s0_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
+        __syncthreads();
+    }
+}
+
+// one thread per 8 consecutive channels of one output pixel
+__global__ void __launch_bounds__(256) select_s1_kernel(const S0Args a, const float* __restrict__ w, __half* __restrict__ out,
+                                                        int ldo, long long total) {
+    const int cv = a.oc >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / cv;
+        const int c = (int)(i - row * cv) << 3, b = (int)(row / a.HW), p = (int)(row - (long long)b * a.HW);
+        Half8 o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            o.v[j] = __floats2half2_rn(s1_element(a, w, b, p, c + 2 * j), s1_element(a, w, b, p, c + 2 * j + 1));
+        *reinterpret_cast<Half8*>(out + row * ldo + c) = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) ctx_mean3_kernel(const CtxArgs a, __half* __restrict__ out, int ldo, long long total) {
+    const int cv = a.C >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / cv;
+        const int c = (int)(i - row * cv) << 3;
+        const int img = (int)(row / ((long long)a.H * a.W)), rem = (int)(row - (long long)img * a.H * a.W);
+        const int y = rem / a.W, x = rem - y * a.W;
+        Half8 o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            o.v[j] = __floats2half2_rn(ctx_element(a, img, y, x, c + 2 * j), ctx_element(a, img, y, x, c + 2 * j + 1));
+        *reinterpret_cast<Half8*>(out + row * ldo + c) = o;
+    }
+}
+
+static int grid_for(long long total) {
+    long long nb = (total + 255) / 256;
+    return (int)(nb > 148LL * 16 ? 148LL * 16 : (nb < 1 ? 1 : nb));
+}
+
+}  // namespace ym
+
+using namespace ym;
+
+static void pooled_dims(int H, int W, int pool, int* Hp, int* Wp, int* eff) {
+    const bool pooling = pool > 1 && H > pool && W > pool;   // gated.py:139-142
+    *eff = pooling ? pool : 1;
+    *Hp = H / *eff;
+    *Wp = W / *eff;
+}
+
+extern "C" long long ym_gate_router_scratch_floats(int B, int H, int W, int C, int R, int E, int pool) {
+    int Hp, Wp, eff;
+    pooled_dims(H, W, pool, &Hp, &Wp, &eff);
+    const long long N = (long long)Hp * Wp;
+    return (long long)B * (2LL * C + N * C * 2 + N * R + E + 1);
+}
+
+extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* global_fc,
+                              const float* dw, const float* gn1_w, const float* gn1_b, int G1, const float* pw1, int R,
+                              const float* gn2_w, const float* gn2_b, int G2, const float* pw2, const float* b2, int E,
+                              float gn_eps, float alpha, float temperature, const float* cx_w, float cx_b, int topk,
+                              float* scratch, float* w_out, int* idx_out, float* probs_out, void* stream) {
+    YM_CHECK_ARG(x && scratch && w_out && idx_out, "ym_gate_router: null pointer");
+    YM_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R > 0, "ym_gate_router: empty problem");
+    YM_CHECK_ARG(E >= 1 && E <= MAXE && topk >= 1 && topk <= E, "ym_gate_router: 1 <= topk <= E <= %d", MAXE);
+    YM_CHECK_ARG(G1 >= 1 && G1 <= MAXG && C % G1 == 0 && G2 >= 1 && G2 <= MAXG && R % G2 == 0, "ym_gate_router: GroupNorm groups");
+    YM_CHECK_ARG(temperature > 0.f, "ym_gate_router: temperature must be positive");
+    int Hp, Wp, eff;
+    pooled_dims(H, W, pool, &Hp, &Wp, &eff);
+    const long long N = (long long)Hp * Wp;
+    float* stats = scratch;
+    float* pooled = stats + (long long)B * 2 * C;
+    float* t1 = pooled + (long long)B * N * C;
+    float* t2 = t1 + (long long)B * N * C;
+    float* ll = t2 + (long long)B * N * R;
+    float* cx = ll + (long long)B * E;
+    cudaStream_t st = (cudaStream_t)stream;
+    R0Args a0;
+    a0.x = (const __half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = eff; a0.Hp = Hp; a0.Wp = Wp;
+    a0.inv_area = 1.f / (float)(eff * eff); a0.stats = stats; a0.pooled = pooled;
+    gate_r0_kernel<<<B, NTHR, r0_smem_floats(C, NTHR) * sizeof(float), st>>>(a0);
+    R1Args a1;
+    a1.pooled = pooled; a1.t1 = t1; a1.t2 = t2; a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E; a1.G1 = G1; a1.G2 = G2;
+    a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w; a1.g2b = gn2_b; a1.pw2 = pw2;
+    a1.b2 = b2; a1.ll = ll;
+    gate_r1_kernel<<<B, NTHR, r1_smem_floats(R, NTHR) * sizeof(float), st>>>(a1);
+    R2Args a2;
+    a2.stats = stats; a2.ll = ll; a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha; a2.inv_temp = 1.f / temperature;
+    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
+    gate_r2_kernel<<<1, NTHR, 0, st>>>(a2);
+    YM_CHECK_LAUNCH("gate_router");
+    return YM_OK;
+}
+
+extern "C" int ym_fc_gate(const void* v, int ldv, int B, int Cin, const float* w1, int Cr, const float* w2, const float* b2,
+                          int Cout, float scale, float* out, void* stream) {
+    YM_CHECK_ARG(v && w1 && w2 && out, "ym_fc_gate: null pointer");
+    YM_CHECK_ARG(B > 0 && Cin > 0 && Cr > 0 && Cr <= 8192 && Cout > 0 && ldv >= Cin, "ym_fc_gate: bad sizes");
+    FcArgs a;
+    a.v = (const __half*)v; a.ldv = ldv; a.Cin = Cin; a.Cr = Cr; a.Cout = Cout; a.w1 = w1; a.w2 = w2; a.b2 = b2; a.scale = scale;
+    a.out = out;
+    fc_gate_kernel<<<B, NTHR, fc_smem_floats(Cr) * sizeof(float), (cudaStream_t)stream>>>(a);
+    YM_CHECK_LAUNCH("fc_gate");
+    return YM_OK;
+}
+
+extern "C" int ym_gated_select(const void* fo, int ldf, int B, int HW, int E, int oc, int G, float eps, const int* idx,
+                               const float* w, int topk, const float* gamma, const float* beta, float* scratch, void* out,
+                               int ldo, void* stream) {
+    YM_CHECK_ARG(fo && idx && w && gamma && beta && scratch && out, "ym_gated_select: null pointer");
+    YM_CHECK_ARG(B > 0 && HW > 0 && E >= 1 && topk >= 1 && topk <= E, "ym_gated_select: bad sizes");
+    YM_CHECK_ARG(oc % 8 == 0 && ldo % 8 == 0 && ldf >= E * oc, "ym_gated_select: oc, ldo multiples of 8; ldf >= E*oc");
+    YM_CHECK_ARG(G >= 1 && G <= MAXG && oc % G == 0, "ym_gated_select: GroupNorm groups");
+    S0Args a;
+    a.fo = (const __half*)fo; a.ldf = ldf; a.HW = HW; a.oc = oc; a.G = G; a.topk = topk; a.eps = eps; a.idx = idx; a.gamma = gamma;
+    a.beta = beta; a.sc = scratch; a.sh = scratch + (long long)B * topk * oc;
+    cudaStream_t st = (cudaStream_t)stream;
+    select_s0_kernel<<<B * topk, NTHR, s0_smem_floats(NTHR) * sizeof(float), st>>>(a);
+    const long long total = (long long)B * HW * (oc / 8);
+    select_s1_kernel<<<grid_for(total), 256, 0, st>>>(a, w, (__half*)out, ldo, total);
+    YM_CHECK_LAUNCH("gated_select");
+    return YM_OK;
+}
+
+extern "C" int ym_ctx_mean3(const void* a, int lda, const void* b, int ldb, const void* c, int ldc, int B, int H, int W, int C,
+                            int h2, int w2, int h4, int w4, void* out, int ldo, void* stream) {
+    YM_CHECK_ARG(a && b && c && out, "ym_ctx_mean3: null pointer");
+    YM_CHECK_ARG(B > 0 && H > 0 && W > 0 && h2 > 0 && w2 > 0 && h4 > 0 && w4 > 0, "ym_ctx_mean3: empty map");
+    YM_CHECK_ARG(C % 8 == 0 && ldo % 8 == 0, "ym_ctx_mean3: C, ldo multiples of 8");
+    CtxArgs g;
+    g.a = (const __half*)a; g.b = (const __half*)b; g.c = (const __half*)c; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    g.H = H; g.W = W; g.C = C; g.h2 = h2; g.w2 = w2; g.h4 = h4; g.w4 = w4;
+    g.sy2 = (float)h2 / (float)H; g.sx2 = (float)w2 / (float)W; g.sy4 = (float)h4 / (float)H; g.sx4 = (float)w4 / (float)W;
+    const long long total = (long long)B * H * W * (C / 8);
+    ctx_mean3_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(g, (__half*)out, ldo, total);
+    YM_CHECK_LAUNCH("ctx_mean3");
+    return YM_OK;
+}

@@ -1,0 +1,444 @@
+// Gated MoE family (nn/modules/moe/gated.py): bodies of the small fp32 kernels in gated.cu.
+//
+// Every kernel here is "one CTA per image (or per route), a fixed sequence of phases separated by __syncthreads()", and each
+// phase is written as a function of (tid, nthr) that only reads what earlier phases wrote.  That makes the bodies runnable on
+// the host by looping tid inside each phase (tests/native/gated_host.cpp, g++), so the arithmetic is compared with the oracle
+// in the GPU-less build container.  No warp intrinsics, no atomics: reductions go through shared memory in a fixed order.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#include <cuda_fp16.h>
+#ifndef YM_HD
+#define YM_HD __host__ __device__ __forceinline__
+#endif
+typedef __half ym_half;
+YM_HD float ym_h2f(ym_half h) { return __half2float(h); }
+YM_HD ym_half ym_f2h(float f) { return __float2half_rn(f); }
+#else
+#ifndef YM_HD
+#define YM_HD inline
+#endif
+typedef _Float16 ym_half;
+YM_HD float ym_h2f(ym_half h) { return (float)h; }
+YM_HD ym_half ym_f2h(float f) { return (ym_half)f; }
+#endif
+
+namespace ym {
+namespace gated {
+
+constexpr int NTHR = 256;      // threads per CTA of every kernel in this file
+constexpr int MAXG = 8;        // GroupNorm groups (get_safe_groups(c, 8) <= 8)
+constexpr int MAXE = 64;       // experts
+
+YM_HD float sigmoid_f(float v) { return 1.f / (1.f + expf(-v)); }
+YM_HD float silu_f32(float v) { return v / (1.f + expf(-v)); }
+
+// Thread t of a CTA owns "column" c0 = t % Cg and row lane pl = t / Cg of a [rows][cols] reduction (Cg = min(cols, nthr)).
+struct ColLane {
+    int Cg, NL, c0, pl;
+    YM_HD ColLane(int cols, int tid, int nthr) {
+        Cg = cols < nthr ? cols : nthr;
+        NL = nthr / Cg;
+        c0 = tid % Cg;
+        pl = tid / Cg;
+    }
+    YM_HD bool active() const { return pl < NL; }
+};
+YM_HD int col_lane_floats(int cols, int nthr) { return cols > nthr ? cols : nthr; }   // NL * cols <= max(cols, nthr)
+
+// --------------------------------------------------------------------------------------------------------------------
+// R0: per-image channel statistics (mean, population std) of x and the pooled fp32 map the local stream reads
+//     (DualStreamGateRouter.forward gated.py:129-142).
+struct R0Args {
+    const ym_half* x;   // [B][H*W][ldx]
+    int ldx, H, W, C, pool, Hp, Wp;
+    float inv_area;     // 1 / (pool*pool), 1 when the map is not pooled
+    float* stats;       // [B][2C]: mean | std
+    float* pooled;      // [B][Hp*Wp][C]
+};
+constexpr int R0_PHASES = 5;
+YM_HD int r0_smem_floats(int C, int nthr) { return col_lane_floats(C, nthr) + C; }
+
+YM_HD void r0_phase(int ph, const R0Args& a, int img, int tid, int nthr, float* sm) {
+    const int HW = a.H * a.W, C = a.C;
+    const ym_half* x = a.x + (long long)img * HW * a.ldx;
+    float* part = sm;
+    float* mean = sm + col_lane_floats(C, nthr);
+    const ColLane cl(C, tid, nthr);
+    if (ph == 0 || ph == 2) {   // partial sums of x (ph 0) or (x - mean)^2 (ph 2)
+        if (!cl.active()) return;
+        for (int c = cl.c0; c < C; c += cl.Cg) {
+            const float m = ph == 2 ? mean[c] : 0.f;
+            float s = 0.f;
+            for (int p = cl.pl; p < HW; p += cl.NL) {
+                const float v = ym_h2f(x[(long long)p * a.ldx + c]) - m;
+                s += ph == 2 ? v * v : v;
+            }
+            part[cl.pl * C + c] = s;
+        }
+    } else if (ph == 1 || ph == 3) {
+        for (int c = tid; c < C; c += nthr) {
+            float s = 0.f;
+            for (int l = 0; l < cl.NL; ++l) s += part[l * C + c];
+            s /= (float)HW;
+            if (ph == 1) {
+                mean[c] = s;
+                a.stats[(long long)img * 2 * C + c] = s;
+            } else {
+                a.stats[(long long)img * 2 * C + C + c] = HW > 1 ? sqrtf(s) : 0.f;
+            }
+        }
+    } else {   // ph 4: avg_pool2d(kernel = stride = pool), floor mode, or a plain fp32 copy
+        float* out = a.pooled + (long long)img * a.Hp * a.Wp * C;
+        const int n = a.Hp * a.Wp * C;
+        for (int e = tid; e < n; e += nthr) {
+            const int c = e % C, pp = e / C, py = pp / a.Wp, px = pp % a.Wp;
+            float s = 0.f;
+            for (int dy = 0; dy < a.pool; ++dy)
+                for (int dx = 0; dx < a.pool; ++dx)
+                    s += ym_h2f(x[(long long)((py * a.pool + dy) * a.W + px * a.pool + dx) * a.ldx + c]);
+            out[e] = s * a.inv_area;
+        }
+    }
+}
+
+// GroupNorm statistics of a [N][Cc] fp32 map in two passes; element e belongs to group (e % Cc) / cpg.
+// pass 0: per-thread partial sums -> part[tid*MAXG + g];   pass 1: partial sums of (v - mean[g])^2.
+YM_HD void gn_partials(const float* t, int N, int Cc, int cpg, const float* mean, int tid, int nthr, float* part) {
+    float acc[MAXG];
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g) acc[g] = 0.f;
+    const int n = N * Cc;
+    for (int e = tid; e < n; e += nthr) {
+        const int g = (e % Cc) / cpg;
+        float v = t[e];
+        if (mean) {
+            float m = 0.f;
+#pragma unroll
+            for (int gg = 0; gg < MAXG; ++gg) m = g == gg ? mean[gg] : m;
+            v = (v - m) * (v - m);
+        }
+#pragma unroll
+        for (int gg = 0; gg < MAXG; ++gg) acc[gg] += g == gg ? v : 0.f;
+    }
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g) part[tid * MAXG + g] = acc[g];
+}
+// Fixed-order reduction of the partials by thread g: returns sum / count.
+YM_HD float gn_reduce(const float* part, int g, int nthr, float count) {
+    float s = 0.f;
+    for (int t = 0; t < nthr; ++t) s += part[t * MAXG + g];
+    return s / count;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// R1: local stream on the pooled map (gated.py:109-118,144-145): dw3x3 -> GN -> SiLU -> 1x1 -> GN -> SiLU -> 1x1 + bias -> mean.
+struct R1Args {
+    const float* pooled;   // [B][N][C]
+    float *t1, *t2;        // scratch [B][N][C], [B][N][R]
+    int Hp, Wp, C, R, E, G1, G2;
+    float eps;
+    const float *dw;       // [C][9]
+    const float *g1w, *g1b;   // [C]
+    const float* pw1;      // [R][C]
+    const float *g2w, *g2b;   // [R]
+    const float *pw2, *b2;    // [E][R], [E]
+    float* ll;             // [B][E] local logits
+};
+constexpr int R1_PHASES = 10;
+YM_HD int r1_smem_floats(int R, int nthr) { return nthr * MAXG + 2 * MAXG + col_lane_floats(R, nthr); }
+
+YM_HD void r1_phase(int ph, const R1Args& a, int img, int tid, int nthr, float* sm) {
+    const int N = a.Hp * a.Wp, C = a.C, R = a.R;
+    const float* src = a.pooled + (long long)img * N * C;
+    float* t1 = a.t1 + (long long)img * N * C;
+    float* t2 = a.t2 + (long long)img * N * R;
+    float* part = sm;
+    float* mean = sm + nthr * MAXG;
+    float* rstd = mean + MAXG;
+    const int cpg1 = C / a.G1, cpg2 = R / a.G2;
+    switch (ph) {
+        case 0: {   // depthwise 3x3, zero padding
+            for (int e = tid; e < N * C; e += nthr) {
+                const int c = e % C, p = e / C, y = p / a.Wp, x = p % a.Wp;
+                float s = 0.f;
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int yy = y + ky - 1;
+                    if (yy < 0 || yy >= a.Hp) continue;
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int xx = x + kx - 1;
+                        if (xx < 0 || xx >= a.Wp) continue;
+                        s += a.dw[c * 9 + ky * 3 + kx] * src[(long long)(yy * a.Wp + xx) * C + c];
+                    }
+                }
+                t1[e] = s;
+            }
+            break;
+        }
+        case 1: gn_partials(t1, N, C, cpg1, nullptr, tid, nthr, part); break;
+        case 2: if (tid < a.G1) mean[tid] = gn_reduce(part, tid, nthr, (float)N * cpg1); break;
+        case 3: gn_partials(t1, N, C, cpg1, mean, tid, nthr, part); break;
+        case 4: if (tid < a.G1) rstd[tid] = 1.f / sqrtf(gn_reduce(part, tid, nthr, (float)N * cpg1) + a.eps); break;
+        case 5: {   // GN1 apply + SiLU in place, then nothing else reads the raw t1
+            for (int e = tid; e < N * C; e += nthr) {
+                const int c = e % C, g = c / cpg1;
+                t1[e] = silu_f32((t1[e] - mean[g]) * rstd[g] * a.g1w[c] + a.g1b[c]);
+            }
+            break;
+        }
+        case 6: {   // 1x1: C -> R
+            for (int e = tid; e < N * R; e += nthr) {
+                const int r = e % R, p = e / R;
+                const float* row = t1 + (long long)p * C;
+                const float* w = a.pw1 + (long long)r * C;
+                float s = 0.f;
+                for (int c = 0; c < C; ++c) s += w[c] * row[c];
+                t2[e] = s;
+            }
+            break;
+        }
+        case 7: gn_partials(t2, N, R, cpg2, nullptr, tid, nthr, part); break;
+        case 8: if (tid < a.G2) mean[tid] = gn_reduce(part, tid, nthr, (float)N * cpg2); break;
+        case 9: gn_partials(t2, N, R, cpg2, mean, tid, nthr, part); break;
+        default: break;
+    }
+}
+// The tail needs two more barriers; kept separate so that R1_PHASES stays a plain loop bound.
+constexpr int R1_TAIL_PHASES = 3;
+YM_HD void r1_tail_phase(int ph, const R1Args& a, int img, int tid, int nthr, float* sm) {
+    const int N = a.Hp * a.Wp, R = a.R;
+    const float* t2 = a.t2 + (long long)img * N * R;
+    float* part = sm;
+    float* mean = sm + nthr * MAXG;
+    float* rstd = mean + MAXG;
+    float* colp = rstd + MAXG;
+    const int cpg2 = R / a.G2;
+    if (ph == 0) {
+        if (tid < a.G2) rstd[tid] = 1.f / sqrtf(gn_reduce(part, tid, nthr, (float)N * cpg2) + a.eps);
+    } else if (ph == 1) {   // column sums over the pixels of SiLU(GN2(t2)): the last 1x1 and the spatial mean commute
+        const ColLane cl(R, tid, nthr);
+        if (!cl.active()) return;
+        for (int r = cl.c0; r < R; r += cl.Cg) {
+            const int g = r / cpg2;
+            float s = 0.f;
+            for (int p = cl.pl; p < N; p += cl.NL) s += silu_f32((t2[(long long)p * R + r] - mean[g]) * rstd[g] * a.g2w[r] + a.g2b[r]);
+            colp[cl.pl * R + r] = s;
+        }
+    } else {
+        const ColLane cl(R, tid, nthr);
+        for (int e = tid; e < a.E; e += nthr) {
+            float s = a.b2[e];
+            for (int r = 0; r < R; ++r) {
+                float m = 0.f;
+                for (int l = 0; l < cl.NL; ++l) m += colp[l * R + r];
+                s += a.pw2[e * R + r] * (m / (float)N);
+            }
+            a.ll[(long long)img * a.E + e] = s;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// R2 (one CTA for the whole batch): batch-level complexity scalar (gated.py:455-461), stream blend, softmax(/T), top-k,
+// renormalisation (gated.py:147-151) and the complexity gate (gated.py:469-490).
+struct R2Args {
+    const float* stats;   // [B][2C]
+    const float* ll;      // [B][E]
+    const float* wg;      // [E][2C] global_fc
+    const float *wc;      // [C] complexity_estimator conv weight
+    float bc, alpha, inv_temp;   // alpha = sigmoid(self.alpha)
+    int B, C, E, topk;
+    float* cx;            // scratch [B]
+    float *w, *probs;     // [B][topk], [B][E] (probs nullable)
+    int* idx;             // [B][topk]
+};
+constexpr int R2_PHASES = 3;
+YM_HD int r2_smem_floats() { return 4; }
+
+YM_HD void r2_phase(int ph, const R2Args& a, int tid, int nthr, float* sm) {
+    if (ph == 0) {
+        for (int b = tid; b < a.B; b += nthr) {
+            float s = a.bc;
+            for (int c = 0; c < a.C; ++c) s += a.wc[c] * a.stats[(long long)b * 2 * a.C + c];
+            a.cx[b] = sigmoid_f(s);
+        }
+    } else if (ph == 1) {
+        if (tid != 0) return;
+        float s = 0.f;
+        for (int b = 0; b < a.B; ++b) s += a.cx[b];
+        s /= (float)a.B;
+        if (!(s == s) || s > 3.0e38f || s < -3.0e38f) s = 1.f;      // non-finite -> 1.0
+        s = s < 0.3f ? 0.3f : (s > 1.5f ? 1.5f : s);
+        float keep = rintf(s * (float)a.topk);                        // torch.round: half to even
+        keep = keep < 1.f ? 1.f : (keep > (float)a.topk ? (float)a.topk : keep);
+        sm[0] = keep;
+    } else {
+        const float keep = sm[0];
+        for (int b = tid; b < a.B; b += nthr) {
+            float p[MAXE];
+            float mx = -3.0e38f;
+            for (int e = 0; e < a.E; ++e) {
+                float gl = 0.f;
+                const float* w = a.wg + (long long)e * 2 * a.C;
+                const float* st = a.stats + (long long)b * 2 * a.C;
+                for (int j = 0; j < 2 * a.C; ++j) gl += w[j] * st[j];
+                float l = a.alpha * gl + (1.f - a.alpha) * a.ll[(long long)b * a.E + e];
+                l = l < -30.f ? -30.f : (l > 30.f ? 30.f : l);
+                p[e] = l * a.inv_temp;
+                mx = p[e] > mx ? p[e] : mx;
+            }
+            float den = 0.f;
+            for (int e = 0; e < a.E; ++e) {
+                p[e] = expf(p[e] - mx);
+                den += p[e];
+            }
+            for (int e = 0; e < a.E; ++e) {
+                p[e] /= den;
+                if (a.probs) a.probs[(long long)b * a.E + e] = p[e];
+            }
+            float wsel[MAXE];
+            float tot = 0.f;
+            for (int j = 0; j < a.topk; ++j) {
+                int best = -1;
+                for (int e = 0; e < a.E; ++e)
+                    if (p[e] >= 0.f && (best < 0 || p[e] > p[best])) best = e;
+                if (best < 0) best = j;                               // all-NaN row: keep the indices valid
+                a.idx[(long long)b * a.topk + j] = best;
+                wsel[j] = p[best];
+                tot += p[best];
+                p[best] = -1.f;                                       // taken
+            }
+            float tot2 = 0.f;
+            for (int j = 0; j < a.topk; ++j) {
+                wsel[j] /= tot + 1e-6f;
+                if (a.topk > 1 && (float)(j + 1) > keep) wsel[j] = 0.f;
+                tot2 += wsel[j];
+            }
+            for (int j = 0; j < a.topk; ++j)
+                a.w[(long long)b * a.topk + j] = a.topk > 1 ? wsel[j] / (tot2 < 1e-6f ? 1e-6f : tot2) : wsel[j];
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// Per-image two-layer gate on a pooled vector: out = scale * sigmoid(W2 . silu(W1 . v) + b2)
+// (se_gate gated.py:325-332; feature_gate moe/hooks.py:50-57 with scale = tanh(refine_scale)).
+struct FcArgs {
+    const ym_half* v;   // [B][ldv]
+    int ldv, Cin, Cr, Cout;
+    const float *w1, *w2, *b2;   // [Cr][Cin], [Cout][Cr], [Cout] (nullable)
+    float scale;
+    float* out;         // [B][Cout]
+};
+constexpr int FC_PHASES = 2;
+YM_HD int fc_smem_floats(int Cr) { return Cr; }
+
+YM_HD void fc_phase(int ph, const FcArgs& a, int img, int tid, int nthr, float* sm) {
+    const ym_half* v = a.v + (long long)img * a.ldv;
+    if (ph == 0) {
+        for (int r = tid; r < a.Cr; r += nthr) {
+            float s = 0.f;
+            for (int c = 0; c < a.Cin; ++c) s += a.w1[(long long)r * a.Cin + c] * ym_h2f(v[c]);
+            sm[r] = silu_f32(s);
+        }
+    } else {
+        for (int o = tid; o < a.Cout; o += nthr) {
+            float s = a.b2 ? a.b2[o] : 0.f;
+            for (int r = 0; r < a.Cr; ++r) s += a.w2[(long long)o * a.Cr + r] * sm[r];
+            a.out[(long long)img * a.Cout + o] = a.scale * sigmoid_f(s);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// FusedExpertGroup tail (gated.py:1061-1081): for route (b, j) with expert e = idx[b][j], GroupNorm (no affine) over the
+// expert's channel slice of the all-expert conv output, then the expert's affine; S0 produces per-(route, channel) scale/shift.
+struct S0Args {
+    const ym_half* fo;   // [B][HW][ldf], expert e occupies channels [e*oc, (e+1)*oc)
+    int ldf, HW, oc, G, topk;
+    float eps;
+    const int* idx;      // [B][topk]
+    const float *gamma, *beta;   // [E][oc]
+    float *sc, *sh;      // [B*topk][oc]
+};
+constexpr int S0_PHASES = 5;
+YM_HD int s0_smem_floats(int nthr) { return nthr * MAXG + 2 * MAXG; }
+
+YM_HD void s0_partials(const ym_half* base, int ldf, int HW, int oc, int cpg, const float* mean, int tid, int nthr, float* part) {
+    float acc[MAXG];
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g) acc[g] = 0.f;
+    const int n = HW * oc;
+    for (int e = tid; e < n; e += nthr) {
+        const int c = e % oc, p = e / oc, g = c / cpg;
+        float v = ym_h2f(base[(long long)p * ldf + c]);
+        if (mean) {
+            float m = 0.f;
+#pragma unroll
+            for (int gg = 0; gg < MAXG; ++gg) m = g == gg ? mean[gg] : m;
+            v = (v - m) * (v - m);
+        }
+#pragma unroll
+        for (int gg = 0; gg < MAXG; ++gg) acc[gg] += g == gg ? v : 0.f;
+    }
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g) part[tid * MAXG + g] = acc[g];
+}
+
+YM_HD void s0_phase(int ph, const S0Args& a, int route, int tid, int nthr, float* sm) {
+    const int b = route / a.topk, ex = a.idx[route], cpg = a.oc / a.G;
+    const ym_half* base = a.fo + (long long)b * a.HW * a.ldf + (long long)ex * a.oc;
+    float* part = sm;
+    float* mean = sm + nthr * MAXG;
+    float* rstd = mean + MAXG;
+    const float cnt = (float)a.HW * cpg;
+    if (ph == 0) s0_partials(base, a.ldf, a.HW, a.oc, cpg, nullptr, tid, nthr, part);
+    else if (ph == 1) { if (tid < a.G) mean[tid] = gn_reduce(part, tid, nthr, cnt); }
+    else if (ph == 2) s0_partials(base, a.ldf, a.HW, a.oc, cpg, mean, tid, nthr, part);
+    else if (ph == 3) { if (tid < a.G) rstd[tid] = 1.f / sqrtf(gn_reduce(part, tid, nthr, cnt) + a.eps); }
+    else {
+        for (int c = tid; c < a.oc; c += nthr) {
+            const int g = c / cpg;
+            const float gm = a.gamma[(long long)ex * a.oc + c];
+            a.sc[(long long)route * a.oc + c] = rstd[g] * gm;
+            a.sh[(long long)route * a.oc + c] = a.beta[(long long)ex * a.oc + c] - mean[g] * rstd[g] * gm;
+        }
+    }
+}
+
+// S1, one output element: sum_j w[b][j] * SiLU(fo[b, p, e_j*oc + c] * sc[route][c] + sh[route][c]).
+YM_HD float s1_element(const S0Args& a, const float* w, int b, int p, int c) {
+    float s = 0.f;
+    for (int j = 0; j < a.topk; ++j) {
+        const int route = b * a.topk + j, ex = a.idx[route];
+        const float v = ym_h2f(a.fo[((long long)b * a.HW + p) * a.ldf + (long long)ex * a.oc + c]);
+        s += w[route] * silu_f32(v * a.sc[(long long)route * a.oc + c] + a.sh[(long long)route * a.oc + c]);
+    }
+    return s;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// PyramidContextMixer mean of the three context maps (gated.py:1213-1219): a full-res, b and c at (h2,w2) / (h4,w4), upsampled
+// with F.interpolate(mode="nearest"): src = min(floor(dst * in / out), in - 1), the ratio in float32.
+struct CtxArgs {
+    const ym_half *a, *b, *c;
+    int lda, ldb, ldc, H, W, C, h2, w2, h4, w4;
+    float sy2, sx2, sy4, sx4;   // (float)in / out per axis
+};
+YM_HD int nearest_src(int dst, float scale, int in) {
+    const int s = (int)floorf((float)dst * scale);
+    return s < in - 1 ? s : in - 1;
+}
+YM_HD float ctx_element(const CtxArgs& a, int img, int y, int x, int ch) {
+    const float va = ym_h2f(a.a[((long long)(img * a.H + y) * a.W + x) * a.lda + ch]);
+    const int y2 = nearest_src(y, a.sy2, a.h2), x2 = nearest_src(x, a.sx2, a.w2);
+    const int y4 = nearest_src(y, a.sy4, a.h4), x4 = nearest_src(x, a.sx4, a.w4);
+    const float vb = ym_h2f(a.b[((long long)(img * a.h2 + y2) * a.w2 + x2) * a.ldb + ch]);
+    const float vc = ym_h2f(a.c[((long long)(img * a.h4 + y4) * a.w4 + x4) * a.ldc + ch]);
+    return (va + vb + vc) / 3.f;
+}
+
+}  // namespace gated
+}  // namespace ym

@@ -1,5 +1,6 @@
 // Element-wise glue of the mixture blocks (HBM-bound, 16-byte vectors, NHWC fp16 with row pitches).
-//   ym_ew_nhwc: layer-scale residuals, token-weighted expert accumulation, GLU gate, GELU, per-(image,channel) affine.
+//   ym_ew_nhwc: layer-scale residuals, token-weighted expert accumulation, GLU gate, GELU, per-(image,channel) affine,
+//               sigmoid / multiplicative gates of the gated MoE family.
 #include "ym_common.cuh"
 
 namespace ym {
@@ -11,6 +12,9 @@ enum EwOp {
     EW_GELU = 3,        // out = gelu(a) (exact, erf)                  (nn.GELU in mot/experts.py:225,365)
     EW_AFFINE = 4,      // out = tok * [silu](a * sc[img,c] + sh[img,c]) + b   (GroupNorm apply; img = row / rows_per_img)
     EW_LERP = 5,        // out = t*a + (1-t)*b, t = p0[0]              (moa/heads.py:371-375)
+    EW_SIGMOID = 6,     // out = sigmoid(a)                            (gate heads of moe/gated.py:1165-1172,1206-1208)
+    EW_MUL_GATE = 7,    // out = a * (1 + t*b), t = p0[0]              (VisualDetailGate gated.py:1176-1178, t = tanh(detail_scale))
+    EW_MUL = 8,         // out = a * b                                 (context * gate, gated.py:1219-1221)
 };
 
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
@@ -61,6 +65,16 @@ __global__ void __launch_bounds__(256) ew_kernel(const __half* __restrict__ a, i
             const float t = p0[0];
 #pragma unroll
             for (int j = 0; j < 8; ++j) r[j] = t * va[j] + (1.f - t) * vb[j];
+        } else if (OP == EW_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = 1.f / (1.f + __expf(-va[j]));
+        } else if (OP == EW_MUL_GATE) {
+            const float t = p0[0];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = va[j] * fmaf(t, vb[j], 1.f);
+        } else if (OP == EW_MUL) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = va[j] * vb[j];
         } else {
             const long long img = row / rows_per_img;
             const float w = tok ? tok[row * ldt + toff] : 1.f;
@@ -89,12 +103,14 @@ extern "C" int ym_ew_nhwc(int op, const void* a, int lda, const void* b, int ldb
                           void* stream) {
     YM_CHECK_ARG(out, "ym_ew_nhwc: null output");
     YM_CHECK_ARG(C % 8 == 0 && ldo % 8 == 0 && (!a || lda % 8 == 0) && (!b || ldb % 8 == 0), "ym_ew_nhwc: multiples of 8");
-    YM_CHECK_ARG(op >= 0 && op <= 5, "ym_ew_nhwc: unknown op %d", op);
+    YM_CHECK_ARG(op >= 0 && op <= 8, "ym_ew_nhwc: unknown op %d", op);
     YM_CHECK_ARG(op != EW_SCALE_RES || (p0 && b), "ym_ew_nhwc: op 0 needs chan and b");
     YM_CHECK_ARG(op != EW_TOKEN_ACC || (tok && b), "ym_ew_nhwc: op 1 needs tok and b");
     YM_CHECK_ARG(op != EW_LERP || (p0 && a && b), "ym_ew_nhwc: op 5 needs t, a and b");
     YM_CHECK_ARG((op != EW_GLU) || (a && b), "ym_ew_nhwc: GLU needs a and b");
-    YM_CHECK_ARG((op != EW_GELU) || a, "ym_ew_nhwc: GELU needs a");
+    YM_CHECK_ARG((op != EW_GELU && op != EW_SIGMOID) || a, "ym_ew_nhwc: GELU / sigmoid need a");
+    YM_CHECK_ARG(op != EW_MUL_GATE || (p0 && a && b), "ym_ew_nhwc: op 7 needs t, a and b");
+    YM_CHECK_ARG(op != EW_MUL || (a && b), "ym_ew_nhwc: op 8 needs a and b");
     YM_CHECK_ARG((op != EW_AFFINE) || (a && p0 && p1 && rows_per_img > 0), "ym_ew_nhwc: affine needs a, scale, shift, rows_per_img");
     if (rows == 0) return YM_OK;
     const long long total = rows * (C / 8);
@@ -110,6 +126,9 @@ extern "C" int ym_ew_nhwc(int op, const void* a, int lda, const void* b, int ldb
         case EW_GLU: EW_LAUNCH(EW_GLU); break;
         case EW_GELU: EW_LAUNCH(EW_GELU); break;
         case EW_LERP: EW_LAUNCH(EW_LERP); break;
+        case EW_SIGMOID: EW_LAUNCH(EW_SIGMOID); break;
+        case EW_MUL_GATE: EW_LAUNCH(EW_MUL_GATE); break;
+        case EW_MUL: EW_LAUNCH(EW_MUL); break;
         default: EW_LAUNCH(EW_AFFINE); break;
     }
 #undef EW_LAUNCH

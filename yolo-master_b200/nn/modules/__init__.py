@@ -1,6 +1,8 @@
 """Operator library mirroring `ultralytics.nn.modules` (same class names / signatures / state_dict keys)."""
 from .block import A2C2f, AAttn, ABlock, Attention, Bottleneck, C2f, C2PSA, C3, C3k, C3k2, PSABlock, SPPF
 from .conv import Concat, Conv, DWConv, PlainConv2d, Upsample, autopad
+from .gated import (DualStreamGateRouter, FusedExpertGroup, LowRankFusedExpertGroup, PyramidContextMixer, SharedInvertedExpertGroup,
+                    VisualDetailGate, VisualEnhancedAdaptiveGateMoE)
 from .head import DFL, Detect
 from .moa import C2fMoA, MoABlock
 from .mot import C2fMoT, MoTBlock
@@ -13,4 +15,6 @@ __all__ = (
     "EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups",
     "DynamicRoutingLayer", "DepthwiseSeparableConv", "EfficientExpertGroup", "ES_MOE",
     "Detect", "DFL", "C2fMoT", "MoTBlock", "C2fMoA", "MoABlock",
+    "VisualEnhancedAdaptiveGateMoE", "DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup",
+    "VisualDetailGate", "PyramidContextMixer",
 )

@@ -1,0 +1,351 @@
+"""Gated MoE family with the reference's names, constructor signatures and state_dict keys
+(`ultralytics/nn/modules/moe/gated.py`) - eval forward of `VisualEnhancedAdaptiveGateMoE`, the block of the
+v0_10 model zoo (`run_visual_hybrid_moe_forward`, moe/_gated_visual.py:33-86).
+
+Per block: SE gate (pooled vector -> two-layer MLP, `ym_fc_gate`) scales the channels, which split into a static half
+(depthwise 3x3 -> 1x1, BatchNorm folded) and a dynamic half (detail gate -> per-IMAGE top-k routing, `ym_gate_router`, fp32 ->
+routed experts); the halves are concatenated, channel-shuffled, mixed with pyramid context, refined, projected and added to the
+input.  Routing never touches the host: expert indices and weights stay in device tables.
+
+Expert back-ends, chosen like the reference (gated.py:1318-1331,1498-1507):
+  * E <= fused_expert_threshold: `LowRankFusedExpertGroup` - shared 1x1 bottleneck, then ONE 3x3 conv produces every expert (the
+    reference's grouped conv, run here as a dense conv with block-diagonal weights) and `ym_gated_select` normalises and sums the
+    routed experts' channel slices;
+  * E >  fused_expert_threshold: `SharedInvertedExpertGroup` - shared expand / depthwise features, then the routed experts'
+    1x1 + GroupNorm projections through the expert-indexed grouped GEMM of the MoE-FFN path (`ym_moe_expert_gemm`).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ._base import PackCache, fold_bn, pack_gemm_weight, require_eval, to_nchw, to_nhwc
+from .moe import get_safe_groups
+from .mot import _f32, _pack_dw, _pack_linear
+
+__all__ = ("DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup", "VisualDetailGate",
+           "PyramidContextMixer", "VisualEnhancedAdaptiveGateMoE")
+
+
+def _gn(channels: int, groups: int = 8) -> nn.GroupNorm:
+    return nn.GroupNorm(get_safe_groups(channels, groups), channels)
+
+
+class DualStreamGateRouter(nn.Module):
+    """`DualStreamGateRouter(in_channels, num_experts, top_k, temperature=1.0, local_reduction=16, pool_scale=4)` (gated.py:82-165)."""
+
+    def __init__(self, in_channels, num_experts, top_k, temperature=1.0, local_reduction=16, pool_scale=4):
+        super().__init__()
+        self.num_experts = num_experts
+        self.top_k = top_k
+        self.temperature = max(float(temperature), 1e-3)
+        self.pool_scale = pool_scale
+        self.global_fc = nn.Linear(2 * in_channels, num_experts, bias=False)
+        reduced = max(in_channels // local_reduction, 4)
+        self.local_conv = nn.Sequential(
+            nn.Conv2d(in_channels, in_channels, 3, padding=1, groups=in_channels, bias=False),
+            _gn(in_channels, 8),
+            nn.SiLU(inplace=False),
+            nn.Conv2d(in_channels, reduced, 1, bias=False),
+            _gn(reduced, 4),
+            nn.SiLU(inplace=False),
+            nn.Conv2d(reduced, num_experts, 1, bias=True),
+        )
+        self.alpha = nn.Parameter(torch.tensor(0.5))
+
+    def pack(self):
+        lc = self.local_conv
+        C, R, E = lc[0].weight.shape[0], lc[3].weight.shape[0], self.num_experts
+        return {
+            "E": E, "R": R, "pool": int(self.pool_scale), "G1": lc[1].num_groups, "G2": lc[4].num_groups, "eps": float(lc[1].eps),
+            "global_fc": _f32(self.global_fc.weight), "dw": _f32(lc[0].weight).reshape(C, 9).contiguous(),
+            "gn1_w": _f32(lc[1].weight), "gn1_b": _f32(lc[1].bias), "pw1": _f32(lc[3].weight).reshape(R, C).contiguous(),
+            "gn2_w": _f32(lc[4].weight), "gn2_b": _f32(lc[4].bias), "pw2": _f32(lc[6].weight).reshape(E, R).contiguous(),
+            "b2": _f32(lc[6].bias), "alpha": float(torch.sigmoid(self.alpha.detach().float())), "temperature": float(self.temperature),
+        }
+
+
+class FusedExpertGroup(nn.Module):
+    """`FusedExpertGroup(in_channels, out_channels, num_experts, num_groups=8, top_k=2)` (gated.py:1003-1081)."""
+
+    def __init__(self, in_channels, out_channels, num_experts, num_groups=8, top_k=2):
+        super().__init__()
+        self.in_channels, self.out_channels, self.num_experts = in_channels, out_channels, num_experts
+        self.top_k = min(int(top_k), num_experts)
+        fused_out = out_channels * num_experts
+        conv_groups = min(get_safe_groups(in_channels, num_groups), fused_out)
+        while conv_groups > 1 and (in_channels % conv_groups != 0 or fused_out % conv_groups != 0):
+            conv_groups -= 1
+        self.num_groups = max(1, conv_groups)
+        self.fused_conv = nn.Conv2d(in_channels, fused_out, 3, padding=1, groups=self.num_groups, bias=False)
+        self.norm_groups = get_safe_groups(out_channels, num_groups)
+        self.expert_norm_weight = nn.Parameter(torch.ones(num_experts, out_channels))
+        self.expert_norm_bias = nn.Parameter(torch.zeros(num_experts, out_channels))
+
+    def dense_weight(self) -> torch.Tensor:
+        """The grouped conv as a dense [E*oc, Cin, 3, 3] weight: output o of group g reads input slice g, zeros elsewhere."""
+        w = self.fused_conv.weight.detach().float()
+        Co, cpg = w.shape[0], w.shape[1]
+        g = self.num_groups
+        dense = torch.zeros((Co, self.in_channels, 3, 3), dtype=torch.float32, device=w.device)
+        opg = Co // g
+        for k in range(g):
+            dense[k * opg:(k + 1) * opg, k * cpg:(k + 1) * cpg] = w[k * opg:(k + 1) * opg]
+        return dense
+
+
+class LowRankFusedExpertGroup(nn.Module):
+    """`LowRankFusedExpertGroup(in_channels, out_channels, num_experts, num_groups=8, top_k=2, bottleneck_ratio=0.5,
+    min_channels=16)` (gated.py:1101-1147)."""
+
+    def __init__(self, in_channels, out_channels, num_experts, num_groups=8, top_k=2, bottleneck_ratio=0.5, min_channels=16):
+        super().__init__()
+        self.in_channels, self.out_channels, self.num_experts = in_channels, out_channels, num_experts
+        self.top_k = min(int(top_k), num_experts)
+        self.bottleneck_channels = min(in_channels, max(min_channels, int(round(in_channels * bottleneck_ratio))))
+        self.bottleneck = nn.Sequential(
+            nn.Conv2d(in_channels, self.bottleneck_channels, 1, bias=False),
+            _gn(self.bottleneck_channels, num_groups),
+            nn.SiLU(inplace=False),
+        )
+        self.fused = FusedExpertGroup(self.bottleneck_channels, out_channels, num_experts, num_groups, top_k=top_k)
+
+
+class SharedInvertedExpertGroup(nn.Module):
+    """`SharedInvertedExpertGroup(in_channels, out_channels, num_experts, expand_ratio=2.0, kernel_size=3, top_k=2,
+    weight_threshold=0.0)` (moe/experts.py:176-269)."""
+
+    def __init__(self, in_channels, out_channels, num_experts, expand_ratio=2.0, kernel_size=3, top_k=2, weight_threshold=0.0):
+        super().__init__()
+        if kernel_size != 3:
+            raise NotImplementedError("SharedInvertedExpertGroup: only kernel_size=3 is on the B200 path")
+        self.in_channels, self.out_channels, self.num_experts = in_channels, out_channels, num_experts
+        self.top_k, self.weight_threshold = top_k, weight_threshold
+        hidden = max(1, int(in_channels * expand_ratio))
+        self.shared_feature = nn.Sequential(
+            nn.Conv2d(in_channels, hidden, 1, bias=False), _gn(hidden), nn.SiLU(inplace=True),
+            nn.Conv2d(hidden, hidden, kernel_size, padding=kernel_size // 2, groups=hidden, bias=False), _gn(hidden), nn.SiLU(inplace=True),
+        )
+        self.expert_projections = nn.ModuleList(
+            nn.Sequential(nn.Conv2d(hidden, out_channels, 1, bias=False), _gn(out_channels)) for _ in range(num_experts))
+
+
+class VisualDetailGate(nn.Module):
+    """`VisualDetailGate(channels, num_groups=8, reduction=8)` (gated.py:1154-1178)."""
+
+    def __init__(self, channels, num_groups=8, reduction=8):
+        super().__init__()
+        hidden = max(channels // reduction, 8)
+        self.detail_filter = nn.Sequential(
+            nn.Conv2d(channels, channels, 3, padding=1, groups=channels, bias=False), _gn(channels, num_groups), nn.SiLU(inplace=False),
+            nn.Conv2d(channels, hidden, 1, bias=False), nn.SiLU(inplace=False),
+            nn.Conv2d(hidden, channels, 1, bias=True), nn.Sigmoid(),
+        )
+        self.detail_scale = nn.Parameter(torch.tensor(0.1))
+
+
+class PyramidContextMixer(nn.Module):
+    """`PyramidContextMixer(channels, num_groups=8, pool_scales=(2, 4))` (gated.py:1184-1221)."""
+
+    def __init__(self, channels, num_groups=8, pool_scales=(2, 4)):
+        super().__init__()
+        self.pool_scales = tuple(pool_scales)
+        if len(self.pool_scales) != 2:
+            raise NotImplementedError("PyramidContextMixer: exactly two pool scales are on the B200 path")
+        self.local_context = nn.Sequential(
+            nn.Conv2d(channels, channels, 3, padding=1, groups=channels, bias=False), _gn(channels, num_groups), nn.SiLU(inplace=False))
+        self.pool_projections = nn.ModuleList(
+            nn.Sequential(nn.Conv2d(channels, channels, 1, bias=False), _gn(channels, num_groups), nn.SiLU(inplace=False))
+            for _ in self.pool_scales)
+        self.context_gate = nn.Sequential(nn.Conv2d(channels, channels, 1, bias=True), nn.Sigmoid())
+        self.context_scale = nn.Parameter(torch.tensor(0.1))
+
+
+def _gn_args(gn: nn.GroupNorm):
+    return gn.num_groups, _f32(gn.weight), _f32(gn.bias), float(gn.eps)
+
+
+def _norm(x, args, act=False, add=None, out=None):
+    G, w, b, eps = args
+    return ops.groupnorm(x, G, w, b, eps=eps, act=act, add=add, out=out)
+
+
+class VisualEnhancedAdaptiveGateMoE(nn.Module, PackCache):
+    """`VisualEnhancedAdaptiveGateMoE(in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8,
+    initial_temperature=1.2, final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+    fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5, refine_reduction=8, detail_reduction=8)` (gated.py:1703-1756)."""
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.2,
+                 final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+                 fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5, refine_reduction=8, detail_reduction=8):
+        super().__init__()
+        if in_channels != out_channels:
+            raise ValueError("VisualEnhancedAdaptiveGateMoE: the residual `proj(...) + x` needs in_channels == out_channels")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_experts, self.top_k, self.num_groups = num_experts, top_k, num_groups
+        self.initial_temperature, self.final_temperature = initial_temperature, final_temperature
+        self.dynamic_channels = int(in_channels * split_ratio)
+        self.static_channels = in_channels - self.dynamic_channels
+        self.out_dynamic = int(out_channels * split_ratio)
+        self.out_static = out_channels - self.out_dynamic
+        for n in (self.dynamic_channels, self.static_channels, self.out_dynamic, self.out_static):
+            if n % 8:
+                raise NotImplementedError("VisualEnhancedAdaptiveGateMoE: channel halves must be multiples of 8 on the B200 path")
+        se_hidden = max(in_channels // 4, 4)
+        self.se_gate = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(in_channels, se_hidden, bias=False),
+                                     nn.SiLU(inplace=False), nn.Linear(se_hidden, in_channels, bias=True), nn.Sigmoid())
+        sc = self.static_channels
+        self.static_net = nn.Sequential(
+            nn.Conv2d(sc, sc, 3, padding=1, groups=sc, bias=False), nn.BatchNorm2d(sc), nn.SiLU(inplace=False),
+            nn.Conv2d(sc, self.out_static, 1, bias=False), nn.BatchNorm2d(self.out_static), nn.SiLU(inplace=False))
+        self.routing = DualStreamGateRouter(self.dynamic_channels, num_experts, top_k, temperature=initial_temperature)
+        self.fused_expert_threshold = fused_expert_threshold
+        self.shuffle_groups = shuffle_groups if out_channels % shuffle_groups == 0 else 1
+        if num_experts <= fused_expert_threshold:
+            self.expert_backend = "low_rank_fused"
+            self.fused_experts = LowRankFusedExpertGroup(self.dynamic_channels, self.out_dynamic, num_experts, num_groups,
+                                                         top_k=top_k, bottleneck_ratio=bottleneck_ratio)
+        else:
+            self.expert_backend = "shared_inverted"
+            self.fused_experts = SharedInvertedExpertGroup(self.dynamic_channels, self.out_dynamic, num_experts, top_k=top_k,
+                                                           weight_threshold=0.0)
+        self.complexity_estimator = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(self.dynamic_channels, 1, 1), nn.Sigmoid())
+        self.proj = nn.Conv2d(out_channels, out_channels, 1, bias=False)
+        self.bn = _gn(out_channels, num_groups)
+        oc = out_channels
+        hidden = max(oc // refine_reduction, 8)
+        self.feature_refiner = nn.Sequential(nn.Conv2d(oc, oc, 3, padding=1, groups=oc, bias=False), _gn(oc, num_groups), nn.SiLU(inplace=False))
+        self.feature_gate = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(oc, hidden, 1, bias=False), nn.SiLU(inplace=False),
+                                          nn.Conv2d(hidden, oc, 1, bias=True), nn.Sigmoid())
+        self.refine_scale = nn.Parameter(torch.tensor(0.1))
+        self.context_mixer = PyramidContextMixer(oc, num_groups)
+        self.detail_gate = VisualDetailGate(self.dynamic_channels, num_groups, detail_reduction)
+        self.last_routing_snapshot: dict = {}
+
+    # ------------------------------------------------------------------------------------------------------------ weights
+    def _build_pack(self):
+        dev = self.proj.weight.device
+        C, dyn = self.out_channels, self.dynamic_channels
+        pk = {}
+        pk["se_w1"], pk["se_w2"], pk["se_b2"] = _f32(self.se_gate[2].weight), _f32(self.se_gate[4].weight), _f32(self.se_gate[4].bias)
+        # x - avg_pool3(x) as ONE depthwise 3x3 (centre 8/9, neighbours -1/9; avg_pool2d counts the padding, so borders agree)
+        hp = torch.full((9, dyn), -1.0 / 9.0, dtype=torch.float32, device=dev)
+        hp[4] = 8.0 / 9.0
+        pk["detail_hp"] = hp.half().contiguous()
+        df = self.detail_gate.detail_filter
+        pk["df0"], pk["df1"] = _pack_dw(df[0].weight), _gn_args(df[1])
+        pk["df3"], pk["df5"] = _pack_linear(df[3].weight), _pack_linear(df[5].weight, df[5].bias)
+        pk["detail_t"] = torch.tanh(self.detail_gate.detail_scale.detach().float()).reshape(1).contiguous()
+        w, b = fold_bn(self.static_net[0].weight, None, self.static_net[1])
+        pk["st_dw"], pk["st_dw_b"] = _pack_dw(w), b.contiguous()
+        w, b = fold_bn(self.static_net[3].weight, None, self.static_net[4])
+        pk["st_pw"] = (pack_gemm_weight(w), b.contiguous())
+        r = self.routing.pack()
+        ce = self.complexity_estimator[1]
+        r["cx_w"], r["cx_b"] = _f32(ce.weight).reshape(-1).contiguous(), float(ce.bias.detach().float())
+        pk["router"] = r
+        fe = self.fused_experts
+        if self.expert_backend == "low_rank_fused":
+            pk["bn0"], pk["bn1"] = _pack_linear(fe.bottleneck[0].weight), _gn_args(fe.bottleneck[1])
+            pk["fused_w"] = pack_gemm_weight(fe.fused.dense_weight())
+            pk["fused_gamma"], pk["fused_beta"] = _f32(fe.fused.expert_norm_weight), _f32(fe.fused.expert_norm_bias)
+        else:
+            sf = fe.shared_feature
+            pk["sf0"], pk["sf1"], pk["sf3"], pk["sf4"] = _pack_linear(sf[0].weight), _gn_args(sf[1]), _pack_dw(sf[3].weight), _gn_args(sf[4])
+            pk["proj_w"] = torch.stack([pack_gemm_weight(p[0].weight.detach().float()) for p in fe.expert_projections]).contiguous()
+            pk["proj_gamma"] = torch.stack([_f32(p[1].weight) for p in fe.expert_projections]).contiguous()
+            pk["proj_beta"] = torch.stack([_f32(p[1].bias) for p in fe.expert_projections]).contiguous()
+            pk["proj_G"], pk["proj_eps"] = fe.expert_projections[0][1].num_groups, float(fe.expert_projections[0][1].eps)
+        sg = self.shuffle_groups
+        if sg > 1:   # channel shuffle as a permutation GEMM: new channel i*sg + g <- old channel g*(C/sg) + i  (gated.py:1334-1338)
+            perm = torch.zeros((C, C), dtype=torch.float32, device=dev)
+            old = torch.arange(C, device=dev)
+            perm[(old % (C // sg)) * sg + old // (C // sg), old] = 1.0
+            pk["shuffle"] = pack_gemm_weight(perm.reshape(C, C, 1, 1))
+        cm = self.context_mixer
+        pk["lc0"], pk["lc1"] = _pack_dw(cm.local_context[0].weight), _gn_args(cm.local_context[1])
+        pk["pp"] = [(_pack_linear(p[0].weight), _gn_args(p[1])) for p in cm.pool_projections]
+        pk["cg"] = _pack_linear(cm.context_gate[0].weight, cm.context_gate[0].bias)
+        pk["ctx_t"] = torch.tanh(cm.context_scale.detach().float()).reshape(1).expand(C).contiguous()
+        pk["fr0"], pk["fr1"] = _pack_dw(self.feature_refiner[0].weight), _gn_args(self.feature_refiner[1])
+        fg = self.feature_gate
+        pk["fg_w1"] = _f32(fg[1].weight).reshape(fg[1].weight.shape[0], C).contiguous()
+        pk["fg_w2"], pk["fg_b2"] = _f32(fg[3].weight).reshape(C, -1).contiguous(), _f32(fg[3].bias)
+        pk["refine_t"] = float(torch.tanh(self.refine_scale.detach().float()))
+        pk["proj"], pk["bn"] = _pack_linear(self.proj.weight), _gn_args(self.bn)
+        return pk
+
+    # ------------------------------------------------------------------------------------------------------------ forward
+    def _experts(self, xd, idx, w, pk, out):
+        B, H, W, _ = xd.shape
+        fe = self.fused_experts
+        if self.expert_backend == "low_rank_fused":
+            t = _norm(ops.conv2d(xd, *pk["bn0"], pk["bn0"][0].shape[0], 1, 1, 1, 0, False), pk["bn1"], act=True)
+            E, oc = self.num_experts, self.out_dynamic
+            fo = ops.conv2d(t, pk["fused_w"], None, E * oc, 3, 3, 1, 1, False)            # every expert, one dense conv
+            return ops.gated_select(fo, idx, w, pk["fused_gamma"], pk["fused_beta"], E, oc, fe.fused.norm_groups, 1e-5, out=out)
+        hid = pk["sf0"][0].shape[0]
+        h = _norm(ops.conv2d(xd, *pk["sf0"], hid, 1, 1, 1, 0, False), pk["sf1"], act=True)
+        feat = _norm(ops.dwconv(h, pk["sf3"], None, 3, False, hid), pk["sf4"], act=True)
+        oc, G, HW = self.out_dynamic, pk["proj_G"], H * W
+        acc = None
+        for j in range(idx.shape[1]):                       # one grouped GEMM per routing rank; a zero weight contributes zero
+            rj, wj = idx[:, j].contiguous(), w[:, j].contiguous()
+            o, st = ops.moe_expert_gemm(feat, ops.pitch(feat), 1, B, HW, hid, pk["proj_w"], rj, oc, groups=G)
+            sc, sh = ops.gn_finalize(st, B, HW, G, oc, HW * (oc // G), pk["proj_eps"], pk["proj_gamma"], pk["proj_beta"], rj, route_w=wj)
+            last = j == idx.shape[1] - 1
+            acc = ops.ew(ops.EW_AFFINE, a=o.view(B, H, W, oc), b=acc, p0=sc, p1=sh, rows_per_img=HW, act=False, out=out if last else None)
+        return acc
+
+    def fwd_nhwc(self, x, out=None):
+        require_eval(self)
+        B, H, W, C = x.shape
+        HW, st_c = H * W, self.static_channels
+        pk = self.get_pack()
+        zero = torch.zeros((B, C), dtype=torch.float32, device=x.device)
+        # SE-gated split (gated.py:325-332, _gated_visual.py:40-45)
+        gate = ops.fc_gate(ops.adaptive_avgpool(x, 1, 1), pk["se_w1"], pk["se_w2"], pk["se_b2"])
+        xg = ops.ew(ops.EW_AFFINE, a=x, p0=gate, p1=zero, rows_per_img=HW)
+        xs, xd = xg[..., :st_c], xg[..., st_c:]
+        # detail gate on the dynamic half (gated.py:1174-1178)
+        t = ops.dwconv(ops.dwconv(xd, pk["detail_hp"], None, 3, False, xd.shape[3]), pk["df0"], None, 3, False, xd.shape[3])
+        t = _norm(t, pk["df1"], act=True)
+        t = ops.conv2d(t, *pk["df3"], pk["df3"][0].shape[0], 1, 1, 1, 0, True)
+        g = ops.ew(ops.EW_SIGMOID, a=ops.conv2d(t, *pk["df5"], xd.shape[3], 1, 1, 1, 0, False))
+        xd = ops.ew(ops.EW_MUL_GATE, a=xd, b=g, p0=pk["detail_t"])
+        # static path straight into its half of the concatenation buffer
+        cat = ops.new_act(B, H, W, C, x.device)
+        ts = ops.dwconv(xs, pk["st_dw"], pk["st_dw_b"], 3, True, st_c)
+        ops.conv2d(ts, *pk["st_pw"], self.out_static, 1, 1, 1, 0, True, out=cat[..., :self.out_static])
+        # routing (+ batch-level complexity gate) and routed experts into the other half
+        idx, w, probs = ops.gate_router(xd, pk["router"], self.top_k)
+        self.last_routing_snapshot = {"topk_indices": idx, "topk_weights": w, "router_probs": probs}   # device tensors, lazy
+        self._experts(xd, idx, w, pk, cat[..., self.out_static:])
+        if self.shuffle_groups > 1:
+            cat = ops.conv2d(cat, pk["shuffle"], None, C, 1, 1, 1, 0, False)
+        # pyramid context (gated.py:1210-1221)
+        lc = _norm(ops.dwconv(cat, pk["lc0"], None, 3, False, C), pk["lc1"], act=True)
+        ctx = [lc]
+        for s, (pw, gn) in zip(self.context_mixer.pool_scales, pk["pp"]):
+            h, w_ = max(1, H // s), max(1, W // s)
+            pooled = cat if (h, w_) == (H, W) else ops.adaptive_avgpool(cat, h, w_)
+            ctx.append(_norm(ops.conv2d(pooled, *pw, C, 1, 1, 1, 0, False), gn, act=True))
+        c = ops.ctx_mean3(*ctx)
+        cgate = ops.ew(ops.EW_SIGMOID, a=ops.conv2d(c, *pk["cg"], C, 1, 1, 1, 0, False))
+        cat = ops.ew(ops.EW_SCALE_RES, a=cat, b=ops.ew(ops.EW_MUL, a=c, b=cgate), p0=pk["ctx_t"])
+        # feature refinement (moe/hooks.py:50-57): cat + tanh(scale) * refiner(cat) * gate(cat)
+        r = _norm(ops.dwconv(cat, pk["fr0"], None, 3, False, C), pk["fr1"], act=True)
+        fg = ops.fc_gate(ops.adaptive_avgpool(cat, 1, 1), pk["fg_w1"], pk["fg_w2"], pk["fg_b2"], scale=pk["refine_t"])
+        cat = ops.ew(ops.EW_AFFINE, a=r, b=cat, p0=fg, p1=zero, rows_per_img=HW)
+        # projection + GroupNorm + residual
+        return _norm(ops.conv2d(cat, *pk["proj"], C, 1, 1, 1, 0, False), pk["bn"], add=x, out=out)
+
+    def forward(self, x):
+        return to_nchw(self.fwd_nhwc(to_nhwc(x)))
+
+    @property
+    def aux_loss(self):
+        return torch.zeros((), device=self.proj.weight.device)

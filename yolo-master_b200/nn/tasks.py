@@ -22,7 +22,8 @@ from . import modules as M
 _CFG_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cfg", "models")
 
 MODULES = {name: getattr(M, name) for name in M.__all__ if isinstance(getattr(M, name), type)}
-MIXTURE_MODULES = {"A2C2fMoE": M.A2C2fMoE, "ES_MOE": M.ES_MOE, "C2fMoT": M.C2fMoT, "C2fMoA": M.C2fMoA}
+MIXTURE_MODULES = {"A2C2fMoE": M.A2C2fMoE, "ES_MOE": M.ES_MOE, "C2fMoT": M.C2fMoT, "C2fMoA": M.C2fMoA,
+                   "VisualEnhancedAdaptiveGateMoE": M.VisualEnhancedAdaptiveGateMoE}
 BASE_MODULES = frozenset({M.Conv, M.DWConv, M.Bottleneck, M.SPPF, M.C2PSA, M.C2f, M.C3k2, M.C3, M.A2C2f})
 REPEAT_MODULES = frozenset({M.C2f, M.C3k2, M.C3, M.C2PSA, M.A2C2f})
 MIXTURE_BASE_MODULES = frozenset(MIXTURE_MODULES.values())
@@ -38,12 +39,16 @@ def yaml_model_load(path):
     import yaml
 
     if not os.path.exists(path):
-        for root, _, files in os.walk(_CFG_ROOT):
-            if os.path.basename(path) in files:
-                path = os.path.join(root, os.path.basename(path))
-                break
-        else:
-            raise FileNotFoundError(path)
+        if os.path.exists(os.path.join(_CFG_ROOT, path)):          # 'master/v0_10/det/yolo-master-n.yaml'
+            path = os.path.join(_CFG_ROOT, path)
+        else:                                                     # bare name: first match of a sorted walk (v0 before v0_10)
+            for root, dirs, files in os.walk(_CFG_ROOT):
+                dirs.sort()
+                if os.path.basename(path) in files:
+                    path = os.path.join(root, os.path.basename(path))
+                    break
+            else:
+                raise FileNotFoundError(path)
     with open(path) as f:
         d = yaml.safe_load(f)
     d["yaml_file"] = path

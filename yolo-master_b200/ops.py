@@ -528,3 +528,62 @@ def scale_boxes(boxes, params, rows_per_img=0, row_img=None, padding=True, xywh=
                                     params.data_ptr(), 1 if padding else 0, 1 if xywh else 0, _stream()), "ym_scale_boxes")
     _count()
     return boxes
+
+
+EW_SIGMOID, EW_MUL_GATE, EW_MUL = 6, 7, 8
+
+
+def gate_router(x, pk, topk):
+    """ym_gate_router.  x: (B,H,W,C) fp16 view (the dynamic channel half); pk: fp32 parameter pack of DualStreamGateRouter +
+    complexity estimator (see VisualEnhancedAdaptiveGateMoE._build_pack).  Returns (idx int32 [B,k], w fp32 [B,k], probs [B,E])."""
+    B, H, W, Cc = x.shape
+    E, R = pk["E"], pk["R"]
+    dev = x.device
+    w = torch.empty((B, topk), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, topk), dtype=torch.int32, device=dev)
+    probs = torch.empty((B, E), dtype=torch.float32, device=dev)
+    scratch = torch.empty((lib().ym_gate_router_scratch_floats(B, H, W, Cc, R, E, pk["pool"]),), dtype=torch.float32, device=dev)
+    _lib.check(lib().ym_gate_router(x.data_ptr(), pitch(x), B, H, W, Cc, pk["pool"], pk["global_fc"].data_ptr(), pk["dw"].data_ptr(),
+                                    pk["gn1_w"].data_ptr(), pk["gn1_b"].data_ptr(), pk["G1"], pk["pw1"].data_ptr(), R,
+                                    pk["gn2_w"].data_ptr(), pk["gn2_b"].data_ptr(), pk["G2"], pk["pw2"].data_ptr(), pk["b2"].data_ptr(),
+                                    E, pk["eps"], pk["alpha"], pk["temperature"], pk["cx_w"].data_ptr(), pk["cx_b"], topk,
+                                    scratch.data_ptr(), w.data_ptr(), idx.data_ptr(), probs.data_ptr(), _stream()), "ym_gate_router")
+    _count(3)
+    return idx, w, probs
+
+
+def fc_gate(v, w1, w2, b2, scale=1.0):
+    """ym_fc_gate.  v: (B,1,1,Cin) fp16 pooled vector; w1 fp32 [Cr,Cin], w2 fp32 [Cout,Cr], b2 fp32 [Cout] or None -> fp32 (B, Cout)."""
+    B, Cin = v.shape[0], v.shape[3]
+    if v.shape[1] != 1 or v.shape[2] != 1:
+        raise ValueError("fc_gate: expected a (B,1,1,C) pooled vector")
+    out = torch.empty((B, w2.shape[0]), dtype=torch.float32, device=v.device)
+    _lib.check(lib().ym_fc_gate(v.data_ptr(), pitch(v), B, Cin, w1.data_ptr(), w1.shape[0], w2.data_ptr(),
+                                None if b2 is None else b2.data_ptr(), w2.shape[0], float(scale), out.data_ptr(), _stream()), "ym_fc_gate")
+    _count()
+    return out
+
+
+def gated_select(fo, idx, w, gamma, beta, E, oc, G, eps=1e-5, out=None):
+    """ym_gated_select.  fo: (B,H,W,E*oc) fp16 all-expert conv output; idx int32 / w fp32 [B,k]; gamma, beta fp32 [E,oc]."""
+    B, H, W, _ = fo.shape
+    k = idx.shape[1]
+    if out is None:
+        out = new_act(B, H, W, oc, fo.device)
+    scratch = torch.empty((2 * B * k * oc,), dtype=torch.float32, device=fo.device)
+    _lib.check(lib().ym_gated_select(fo.data_ptr(), pitch(fo), B, H * W, E, oc, G, eps, idx.data_ptr(), w.data_ptr(), k,
+                                     gamma.data_ptr(), beta.data_ptr(), scratch.data_ptr(), out.data_ptr(), pitch(out), _stream()),
+               "ym_gated_select")
+    _count(2)
+    return out
+
+
+def ctx_mean3(a, b, c, out=None):
+    """ym_ctx_mean3: (a + nearest_up(b) + nearest_up(c)) / 3 on (B,H,W,C) fp16 views."""
+    B, H, W, Cc = a.shape
+    if out is None:
+        out = new_act(B, H, W, Cc, a.device)
+    _lib.check(lib().ym_ctx_mean3(a.data_ptr(), pitch(a), b.data_ptr(), pitch(b), c.data_ptr(), pitch(c), B, H, W, Cc,
+                                  b.shape[1], b.shape[2], c.shape[1], c.shape[2], out.data_ptr(), pitch(out), _stream()), "ym_ctx_mean3")
+    _count()
+    return out
