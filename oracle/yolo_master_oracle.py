@@ -1022,40 +1022,89 @@ def feature_refine(sd, p, x, groups=8):
     return _st(x + torch.tanh(sd[p + ".refine_scale"]) * r * g)
 
 
-def layer_visual_enhanced_gate_moe(sd, p, x, c1, c2, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.2,
-                                   final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
-                                   fused_expert_threshold=8, shuffle_groups=2, *unused, return_route=False):
-    """`VisualEnhancedAdaptiveGateMoE.forward` = `run_visual_hybrid_moe_forward` moe/_gated_visual.py:33-86 with the hooks
-    detail (pre_route), context + refine (post_fusion) of gated.py:1749-1755."""
+def gated_moe_forward(sd, p, x, c1, c2, num_experts, top_k, split_ratio, num_groups, temperature, backend, shuffle_groups, hooks,
+                      return_route=False):
+    """Eval forward shared by the whole AdaptiveGateMoE line: `AdaptiveGateMoE.forward` gated.py:508-555 (v0.4, v0.5),
+    `HybridAdaptiveGateMoE.forward` :1340-1386 (v0.6, v0.7: + channel shuffle) and `run_visual_hybrid_moe_forward`
+    moe/_gated_visual.py:33-86 (v0.8 ... v0.10: + hooks).  `backend` in {"shared_inverted", "fused", "low_rank_fused"}; `hooks` is the
+    ordered subset of ("detail", "context", "refine") the class configures (detail runs before routing, the others after the
+    concatenation; the complexity scalar is taken from the dynamic half the router sees)."""
     dyn = int(c1 * split_ratio)
     st_c = c1 - dyn
     out_dyn = int(c2 * split_ratio)
     gate = gated_se_gate(sd, p + ".se_gate", x)
     xs = _st(x[:, :st_c] * gate[:, :st_c, None, None])
     xd = _st(x[:, st_c:] * gate[:, st_c:, None, None])
-    xd = visual_detail_gate(sd, p + ".detail_gate", xd, num_groups)
+    if "detail" in hooks:
+        xd = visual_detail_gate(sd, p + ".detail_gate", xd, num_groups)
     # static path: dw3x3 -> BN -> SiLU -> 1x1 -> BN -> SiLU (gated.py:335-344)
     t = F.silu(_bn(sd, p + ".static_net.1", F.conv2d(xs, _w(sd[p + ".static_net.0.weight"]), None, 1, 1, 1, st_c)))
     out_s = _st(F.silu(_bn(sd, p + ".static_net.4", F.conv2d(_st(t), _w(sd[p + ".static_net.3.weight"])))))
     # batch-level complexity scalar (gated.py:455-461): sigmoid(conv1x1(GAP(x_dynamic))) averaged over the WHOLE batch
     cx = torch.sigmoid(F.conv2d(xd.mean((2, 3), keepdim=True), sd[p + ".complexity_estimator.1.weight"], sd[p + ".complexity_estimator.1.bias"])).mean()
     cx = cx.clamp(0.3, 1.5) if bool(torch.isfinite(cx)) else torch.tensor(1.0)
-    w, idx, probs = dual_stream_gate_router(sd, p + ".routing", xd, top_k, max(float(initial_temperature), 1e-3))
+    w, idx, probs = dual_stream_gate_router(sd, p + ".routing", xd, top_k, max(float(temperature), 1e-3))
     w = complexity_gate(w, cx)
-    if num_experts <= fused_expert_threshold:
+    if backend == "low_rank_fused":
         out_d = low_rank_fused_expert_group(sd, p + ".fused_experts", xd, w, idx, num_experts, out_dyn, num_groups)
+    elif backend == "fused":
+        out_d = fused_expert_group(sd, p + ".fused_experts", xd, w, idx, num_experts, out_dyn, num_groups)
     else:
         out_d = shared_inverted_expert_group(sd, p + ".fused_experts", xd, w, idx, num_experts, out_dyn)
     cat = torch.cat([out_s, out_d], 1)
-    sg = shuffle_groups if c2 % shuffle_groups == 0 else 1
+    sg = shuffle_groups if (shuffle_groups and c2 % shuffle_groups == 0) else 1
     if sg > 1:
         B, C, H, W = cat.shape
         cat = cat.view(B, sg, C // sg, H, W).transpose(1, 2).reshape(B, C, H, W)
-    cat = pyramid_context_mixer(sd, p + ".context_mixer", cat, num_groups)
-    cat = feature_refine(sd, p, cat, num_groups)
+    for h in hooks:
+        if h == "context":
+            cat = pyramid_context_mixer(sd, p + ".context_mixer", cat, num_groups)
+        elif h == "refine":
+            cat = feature_refine(sd, p, cat, num_groups)
     out = _st(_gn(sd, p + ".bn", F.conv2d(cat, _w(sd[p + ".proj.weight"])), get_safe_groups(c2, num_groups)) + x)
     return (out, w, idx, probs) if return_route else out
 
 
-_LAYER_FN["VisualEnhancedAdaptiveGateMoE"] = layer_visual_enhanced_gate_moe
-_MIX_BASE.add("VisualEnhancedAdaptiveGateMoE")
+# class name -> (default initial_temperature, hybrid back-end choice?, low-rank?, shuffle?, hooks): the constructor defaults and
+# the forward each class of the line uses (gated.py:268-1766)
+GATED_VARIANTS = {
+    "AdaptiveGateMoE": (1.0, False, False, False, ()),                                               # v0.4
+    "FusedAdaptiveGateMoE": (1.0, None, False, False, ()),                                           # v0.5: always fused
+    "HybridAdaptiveGateMoE": (1.2, True, False, True, ()),                                           # v0.6
+    "LowRankHybridAdaptiveGateMoE": (1.2, True, True, True, ()),                                     # v0.7
+    "RefinedLowRankHybridAdaptiveGateMoE": (1.2, True, True, True, ("refine",)),                     # v0.8
+    "DetailAwareLowRankHybridAdaptiveGateMoE": (1.2, True, True, True, ("detail",)),                 # v0.9
+    "ContextRefinedLowRankHybridAdaptiveGateMoE": (1.2, True, True, True, ("context", "refine")),
+    "VisualEnhancedAdaptiveGateMoE": (1.2, True, True, True, ("detail", "context", "refine")),       # v0.10
+}
+
+
+def gated_backend(name, num_experts, fused_expert_threshold=8):
+    _, hybrid, low_rank, _, _ = GATED_VARIANTS[name]
+    if hybrid is None:
+        return "fused"
+    if not hybrid or num_experts > fused_expert_threshold:
+        return "shared_inverted"
+    return "low_rank_fused" if low_rank else "fused"
+
+
+def _gated_layer(name):
+    temp0, _, _, shuffle, hooks = GATED_VARIANTS[name]
+
+    def layer(sd, p, x, c1, c2, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=temp0,
+              final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+              fused_expert_threshold=8, shuffle_groups=2, *unused, return_route=False):
+        return gated_moe_forward(sd, p, x, c1, c2, num_experts, top_k, split_ratio, num_groups, initial_temperature,
+                                 gated_backend(name, num_experts, fused_expert_threshold), shuffle_groups if shuffle else 1, hooks,
+                                 return_route=return_route)
+    layer.__name__ = "layer_" + name
+    layer.__doc__ = f"`{name}.forward` (nn/modules/moe/gated.py), eval; see gated_moe_forward."
+    return layer
+
+
+layer_visual_enhanced_gate_moe = _gated_layer("VisualEnhancedAdaptiveGateMoE")
+for _name in GATED_VARIANTS:
+    _LAYER_FN[_name] = _gated_layer(_name)
+    _MIX_BASE.add(_name)
+
+

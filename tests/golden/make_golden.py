@@ -297,10 +297,46 @@ def letterbox_golden():
     torch.save({"cv2": cv2.__version__, "cases": cases, "variants": variants, "scale_boxes": boxes}, f"{OUT}/letterbox.golden.pt")
 
 
+GATED_FAMILY = ["AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
+                "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE",
+                "ContextRefinedLowRankHybridAdaptiveGateMoE", "VisualEnhancedAdaptiveGateMoE"]
+
+
+def gated_family_golden():
+    """Module-level goldens of every class of the AdaptiveGateMoE line (v0_4 ... v0_10 model zoos): the REAL reference module
+    (c1 = c2 = 64, top-2 of 4 and of 16 experts, key-seeded weights) on a seeded (2, 64, 12, 12) input -> output, router decisions
+    before the complexity gate, and the state-dict key table."""
+    from ultralytics.nn.modules.moe import gated as G
+    out = {}
+    for ci, name in enumerate(GATED_FAMILY):
+        for E in (4, 16):
+            torch.manual_seed(0)
+            m = getattr(G, name)(64, 64, E, 2, 0.5).eval()
+            for mod in m.modules():                      # inside a model every BatchNorm2d runs with eps = 1e-3
+                if isinstance(mod, torch.nn.BatchNorm2d):   # (initialize_weights, utils/torch_utils.py:552-562)
+                    mod.eps = 1e-3
+            sd = m.state_dict()
+            fill_state_dict_(sd, 300 + ci)
+            m.load_state_dict(sd)
+            x = torch.randn((2, 64, 12, 12), generator=torch.Generator().manual_seed(400 + ci))
+            route = {}
+            h = m.routing.register_forward_hook(lambda mod, i, o: route.update(w=o[0].flatten(1).clone(), idx=o[1].flatten(1).clone()))
+            with torch.no_grad():
+                y = m(x)
+            h.remove()
+            out[f"{name}/E{E}"] = {"seed": 300 + ci, "xseed": 400 + ci, "y": y.clone(), "route_w": route["w"], "route_idx": route["idx"],
+                                   "keys": {k: list(v.shape) for k, v in sd.items()},
+                                   "scalars": {k: v.clone() for k, v in sd.items() if v.dim() == 0 and v.is_floating_point()},   # left at init
+                                   "backend": getattr(m, "expert_backend", "shared_inverted")}
+            print("gated", name, E, out[f"{name}/E{E}"]["backend"], float(y.abs().mean()))
+    torch.save(out, f"{OUT}/gated_family.golden.pt")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["main", "dispatch", "nms", "esmoe", "letterbox", *EXTRA_MODELS]
+    which = sys.argv[1:] or ["main", "dispatch", "nms", "esmoe", "letterbox", "gated_family", *EXTRA_MODELS]
     for w in which:
         if w in EXTRA_MODELS:
             extra_model_golden(w)
         else:
-            {"main": main, "dispatch": dispatch_golden, "nms": nms_golden, "esmoe": esmoe_golden, "letterbox": letterbox_golden}[w]()
+            {"main": main, "dispatch": dispatch_golden, "nms": nms_golden, "esmoe": esmoe_golden, "letterbox": letterbox_golden,
+             "gated_family": gated_family_golden}[w]()

@@ -152,6 +152,38 @@ def test_block_host_wiring_matches_oracle(emu, c, E, k, H, W, seed):
     assert emu.report(f"VisualEnhancedAdaptiveGateMoE c{c} E{E}", y, ref, sim)
 
 
+FAMILY = torch.load(os.path.join(GOLD, "gated_family.golden.pt"))
+
+
+@pytest.mark.parametrize("key", sorted(FAMILY), ids=lambda k: k.replace("AdaptiveGateMoE", "AGM"))
+def test_family_class_matches_reference_module_golden(emu, key):
+    """Every class of the AdaptiveGateMoE line (v0_4 ... v0_10 zoos), top-2 of 4 and of 16 experts: state-dict keys equal the
+    reference module's, and the host mirror (emulated ops) reproduces the REAL module's output within the fp16 noise floor of the
+    oracle with identical expert choices."""
+    from yolo_master_b200.nn.modules import gated
+    from yolo_master_b200.utils.synth import fill_state_dict_
+    name, E = key.split("/E")
+    c = FAMILY[key]
+    m = getattr(gated, name)(64, 64, int(E), 2, 0.5)
+    assert m.expert_backend == c["backend"]
+    sd = m.state_dict()
+    assert {k: list(v.shape) for k, v in sd.items()} == c["keys"]
+    fill_state_dict_(sd, c["seed"])
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    sdm = {"m." + k: v.clone().float() for k, v in sd.items()}
+    x = torch.randn((2, 64, 12, 12), generator=torch.Generator().manual_seed(c["xseed"]))
+    with torch.no_grad():
+        y = m.fwd_nhwc(x.half().permute(0, 2, 3, 1).contiguous()).float().permute(0, 3, 1, 2)
+    xq = x.half().float()
+    ref, _, ri, _ = O._LAYER_FN[name](sdm, "m", xq, 64, 64, int(E), 2, 0.5, return_route=True)
+    assert torch.equal(m.last_routing_snapshot["topk_indices"].long(), ri)
+    with O.fp16_storage(), O.fp16_weights():
+        sim = O._LAYER_FN[name](sdm, "m", xq, 64, 64, int(E), 2, 0.5)
+    assert emu.report(key, y, ref, sim)
+    assert float((y - c["y"]).abs().max()) < 3e-2               # and stays close to the reference module's own fp32 output
+
+
 def test_fused_group_dense_weight_equals_grouped_conv():
     from yolo_master_b200.nn.modules.gated import FusedExpertGroup
     g = FusedExpertGroup(32, 16, 4)
@@ -177,3 +209,23 @@ def test_v0_10_model_builds_and_loads_reference_keys():
     assert [L["type"] for L in spec["layers"]].count("VisualEnhancedAdaptiveGateMoE") == 3
     for sc in "smlx":
         assert DetectionModel(f"master/v0_10/det/yolo-master-{sc}.yaml") is not None
+
+
+def test_gated_zoo_yamls_build():
+    """v0_4 ... v0_10 model zoos (35 stock YAMLs): every file parses into its family's block with the reference's back-end choice and
+    parameter count (reference counts taken with ultralytics' own DetectionModel on the n scale)."""
+    from yolo_master_b200.nn.tasks import DetectionModel
+    want = {"v0_4": ("AdaptiveGateMoE", ["shared_inverted"] * 3, None), "v0_5": ("FusedAdaptiveGateMoE", ["fused"] * 3, None),
+            "v0_6": ("HybridAdaptiveGateMoE", ["fused", "fused", "shared_inverted"], None),
+            "v0_7": ("LowRankHybridAdaptiveGateMoE", ["low_rank_fused", "low_rank_fused", "shared_inverted"], 3106914),
+            "v0_8": ("RefinedLowRankHybridAdaptiveGateMoE", ["low_rank_fused", "low_rank_fused", "shared_inverted"], 3137637),
+            "v0_9": ("DetailAwareLowRankHybridAdaptiveGateMoE", ["low_rank_fused", "low_rank_fused", "shared_inverted"], 3116133),
+            "v0_10": ("VisualEnhancedAdaptiveGateMoE", ["low_rank_fused", "low_rank_fused", "shared_inverted"], 3449963)}
+    for ver, (cls, backends, nparam) in want.items():
+        m = DetectionModel(f"master/{ver}/det/yolo-master-n.yaml")
+        assert [type(m.model[i]).__name__ for i in (5, 8, 11)] == [cls] * 3
+        assert [m.model[i].expert_backend for i in (5, 8, 11)] == backends
+        if nparam:
+            assert sum(p.numel() for p in m.parameters()) == nparam
+        assert DetectionModel(f"master/{ver}/det/yolo-master-s.yaml").model[5].in_channels == 256
+    assert type(DetectionModel("yolo-master-n.yaml").model[3]).__name__ == "ES_MOE"        # a bare name still resolves to the v0 zoo

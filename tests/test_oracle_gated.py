@@ -71,3 +71,25 @@ def test_complexity_gate_known_answers():
     assert torch.allclose(O.complexity_gate(w, torch.tensor(0.76)), w)
     assert torch.allclose(O.complexity_gate(w, torch.tensor(0.75)), w)
     assert torch.allclose(O.complexity_gate(w, torch.tensor(float("nan"))), w)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The whole AdaptiveGateMoE line (v0_4 ... v0_10 zoos): module-level goldens of the REAL reference classes
+# (tests/golden/make_golden.py gated_family), top-2 of 4 (fused / low-rank back-ends) and of 16 (shared-inverted) experts.
+FAMILY = torch.load(os.path.join(GOLD, "gated_family.golden.pt"))
+
+
+@pytest.mark.parametrize("key", sorted(FAMILY), ids=lambda k: k.replace("AdaptiveGateMoE", "AGM"))
+def test_gated_family_oracle_matches_reference_module(key):
+    from yolo_master_b200.utils.synth import fill_state_dict_
+    name, E = key.split("/E")
+    c = FAMILY[key]
+    sd = {k: torch.zeros(shape, dtype=torch.int64 if k.endswith("num_batches_tracked") else torch.float32) for k, shape in c["keys"].items()}
+    fill_state_dict_(sd, c["seed"])
+    sd.update(c["scalars"])                                      # 0-dim parameters (alpha, *_scale) stay at their init values
+    sd = {"m." + k: v for k, v in sd.items()}
+    x = torch.randn((2, 64, 12, 12), generator=torch.Generator().manual_seed(c["xseed"]))
+    assert O.gated_backend(name, int(E)) == c["backend"]
+    y, w, idx, _ = O._LAYER_FN[name](sd, "m", x, 64, 64, int(E), 2, 0.5, return_route=True)
+    assert torch.equal(idx, c["route_idx"])                      # router choices (taken before the complexity gate in the fixture)
+    torch.testing.assert_close(y, c["y"], atol=2e-4, rtol=2e-4)

@@ -1,7 +1,9 @@
 """Operator library mirroring `ultralytics.nn.modules` (same class names / signatures / state_dict keys)."""
 from .block import A2C2f, AAttn, ABlock, Attention, Bottleneck, C2f, C2PSA, C3, C3k, C3k2, PSABlock, SPPF
 from .conv import Concat, Conv, DWConv, PlainConv2d, Upsample, autopad
-from .gated import (DualStreamGateRouter, FusedExpertGroup, LowRankFusedExpertGroup, PyramidContextMixer, SharedInvertedExpertGroup,
+from .gated import (AdaptiveGateMoE, ContextRefinedLowRankHybridAdaptiveGateMoE, DetailAwareLowRankHybridAdaptiveGateMoE,
+                    DualStreamGateRouter, FusedAdaptiveGateMoE, FusedExpertGroup, HybridAdaptiveGateMoE, LowRankFusedExpertGroup,
+                    LowRankHybridAdaptiveGateMoE, PyramidContextMixer, RefinedLowRankHybridAdaptiveGateMoE, SharedInvertedExpertGroup,
                     VisualDetailGate, VisualEnhancedAdaptiveGateMoE)
 from .head import DFL, Detect
 from .moa import C2fMoA, MoABlock
@@ -15,6 +17,8 @@ __all__ = (
     "EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups",
     "DynamicRoutingLayer", "DepthwiseSeparableConv", "EfficientExpertGroup", "ES_MOE",
     "Detect", "DFL", "C2fMoT", "MoTBlock", "C2fMoA", "MoABlock",
+    "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
+    "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE", "ContextRefinedLowRankHybridAdaptiveGateMoE",
     "VisualEnhancedAdaptiveGateMoE", "DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup",
     "VisualDetailGate", "PyramidContextMixer",
 )

@@ -1,6 +1,10 @@
 """Gated MoE family with the reference's names, constructor signatures and state_dict keys
-(`ultralytics/nn/modules/moe/gated.py`) - eval forward of `VisualEnhancedAdaptiveGateMoE`, the block of the
-v0_10 model zoo (`run_visual_hybrid_moe_forward`, moe/_gated_visual.py:33-86).
+(`ultralytics/nn/modules/moe/gated.py`) - eval forward of the whole AdaptiveGateMoE line: `AdaptiveGateMoE`
+(v0_4 zoo), `FusedAdaptiveGateMoE` (v0_5), `HybridAdaptiveGateMoE` (v0_6), `LowRankHybridAdaptiveGateMoE` (v0_7),
+`RefinedLowRankHybridAdaptiveGateMoE` (v0_8), `DetailAwareLowRankHybridAdaptiveGateMoE` (v0_9),
+`ContextRefinedLowRankHybridAdaptiveGateMoE` and `VisualEnhancedAdaptiveGateMoE` (v0_10).  The classes differ in the expert
+back-end, the channel shuffle and which of the detail / context / refine stages they carry (gated.py:508-555, :1340-1386,
+moe/_gated_visual.py:33-86); one implementation serves them all.
 
 Per block: SE gate (pooled vector -> two-layer MLP, `ym_fc_gate`) scales the channels, which split into a static half
 (depthwise 3x3 -> 1x1, BatchNorm folded) and a dynamic half (detail gate -> per-IMAGE top-k routing, `ym_gate_router`, fp32 ->
@@ -27,7 +31,9 @@ from .moe import get_safe_groups
 from .mot import _f32, _pack_dw, _pack_linear
 
 __all__ = ("DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup", "VisualDetailGate",
-           "PyramidContextMixer", "VisualEnhancedAdaptiveGateMoE")
+           "PyramidContextMixer", "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
+           "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE",
+           "ContextRefinedLowRankHybridAdaptiveGateMoE", "VisualEnhancedAdaptiveGateMoE")
 
 
 def _gn(channels: int, groups: int = 8) -> nn.GroupNorm:
@@ -173,17 +179,16 @@ def _norm(x, args, act=False, add=None, out=None):
     return ops.groupnorm(x, G, w, b, eps=eps, act=act, add=add, out=out)
 
 
-class VisualEnhancedAdaptiveGateMoE(nn.Module, PackCache):
-    """`VisualEnhancedAdaptiveGateMoE(in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8,
-    initial_temperature=1.2, final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
-    fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5, refine_reduction=8, detail_reduction=8)` (gated.py:1703-1756)."""
+class _GatedMoE(nn.Module, PackCache):
+    """Shared body of the AdaptiveGateMoE line.  `backend` in {"shared_inverted", "fused", "low_rank_fused"}; `hooks` is the ordered
+    subset of ("detail", "context", "refine") (detail before routing, the others after the concatenation, in this order)."""
 
-    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.2,
-                 final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
-                 fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5, refine_reduction=8, detail_reduction=8):
+    def __init__(self, in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
+                 backend, shuffle_groups=1, bottleneck_ratio=0.5, hooks=(), refine_reduction=8, detail_reduction=8,
+                 fused_expert_threshold=8):
         super().__init__()
         if in_channels != out_channels:
-            raise ValueError("VisualEnhancedAdaptiveGateMoE: the residual `proj(...) + x` needs in_channels == out_channels")
+            raise ValueError(f"{type(self).__name__}: the residual `proj(...) + x` needs in_channels == out_channels")
         self.in_channels, self.out_channels = in_channels, out_channels
         self.num_experts, self.top_k, self.num_groups = num_experts, top_k, num_groups
         self.initial_temperature, self.final_temperature = initial_temperature, final_temperature
@@ -193,7 +198,7 @@ class VisualEnhancedAdaptiveGateMoE(nn.Module, PackCache):
         self.out_static = out_channels - self.out_dynamic
         for n in (self.dynamic_channels, self.static_channels, self.out_dynamic, self.out_static):
             if n % 8:
-                raise NotImplementedError("VisualEnhancedAdaptiveGateMoE: channel halves must be multiples of 8 on the B200 path")
+                raise NotImplementedError(f"{type(self).__name__}: channel halves must be multiples of 8 on the B200 path")
         se_hidden = max(in_channels // 4, 4)
         self.se_gate = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(in_channels, se_hidden, bias=False),
                                      nn.SiLU(inplace=False), nn.Linear(se_hidden, in_channels, bias=True), nn.Sigmoid())
@@ -203,26 +208,34 @@ class VisualEnhancedAdaptiveGateMoE(nn.Module, PackCache):
             nn.Conv2d(sc, self.out_static, 1, bias=False), nn.BatchNorm2d(self.out_static), nn.SiLU(inplace=False))
         self.routing = DualStreamGateRouter(self.dynamic_channels, num_experts, top_k, temperature=initial_temperature)
         self.fused_expert_threshold = fused_expert_threshold
-        self.shuffle_groups = shuffle_groups if out_channels % shuffle_groups == 0 else 1
-        if num_experts <= fused_expert_threshold:
-            self.expert_backend = "low_rank_fused"
+        self.shuffle_groups = shuffle_groups if (shuffle_groups and out_channels % shuffle_groups == 0) else 1
+        self.expert_backend = backend
+        if backend == "low_rank_fused":
             self.fused_experts = LowRankFusedExpertGroup(self.dynamic_channels, self.out_dynamic, num_experts, num_groups,
                                                          top_k=top_k, bottleneck_ratio=bottleneck_ratio)
-        else:
-            self.expert_backend = "shared_inverted"
+        elif backend == "fused":
+            self.fused_experts = FusedExpertGroup(self.dynamic_channels, self.out_dynamic, num_experts, num_groups, top_k=top_k)
+        elif backend == "shared_inverted":
             self.fused_experts = SharedInvertedExpertGroup(self.dynamic_channels, self.out_dynamic, num_experts, top_k=top_k,
                                                            weight_threshold=0.0)
+        else:
+            raise ValueError(f"unknown expert back-end {backend!r}")
         self.complexity_estimator = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(self.dynamic_channels, 1, 1), nn.Sigmoid())
         self.proj = nn.Conv2d(out_channels, out_channels, 1, bias=False)
         self.bn = _gn(out_channels, num_groups)
+        self.router_hook_names = tuple(hooks)
         oc = out_channels
-        hidden = max(oc // refine_reduction, 8)
-        self.feature_refiner = nn.Sequential(nn.Conv2d(oc, oc, 3, padding=1, groups=oc, bias=False), _gn(oc, num_groups), nn.SiLU(inplace=False))
-        self.feature_gate = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(oc, hidden, 1, bias=False), nn.SiLU(inplace=False),
-                                          nn.Conv2d(hidden, oc, 1, bias=True), nn.Sigmoid())
-        self.refine_scale = nn.Parameter(torch.tensor(0.1))
-        self.context_mixer = PyramidContextMixer(oc, num_groups)
-        self.detail_gate = VisualDetailGate(self.dynamic_channels, num_groups, detail_reduction)
+        if "refine" in hooks:
+            hidden = max(oc // refine_reduction, 8)
+            self.feature_refiner = nn.Sequential(nn.Conv2d(oc, oc, 3, padding=1, groups=oc, bias=False), _gn(oc, num_groups),
+                                                 nn.SiLU(inplace=False))
+            self.feature_gate = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(oc, hidden, 1, bias=False), nn.SiLU(inplace=False),
+                                              nn.Conv2d(hidden, oc, 1, bias=True), nn.Sigmoid())
+            self.refine_scale = nn.Parameter(torch.tensor(0.1))
+        if "context" in hooks:
+            self.context_mixer = PyramidContextMixer(oc, num_groups)
+        if "detail" in hooks:
+            self.detail_gate = VisualDetailGate(self.dynamic_channels, num_groups, detail_reduction)
         self.last_routing_snapshot: dict = {}
 
     # ------------------------------------------------------------------------------------------------------------ weights
@@ -231,14 +244,15 @@ class VisualEnhancedAdaptiveGateMoE(nn.Module, PackCache):
         C, dyn = self.out_channels, self.dynamic_channels
         pk = {}
         pk["se_w1"], pk["se_w2"], pk["se_b2"] = _f32(self.se_gate[2].weight), _f32(self.se_gate[4].weight), _f32(self.se_gate[4].bias)
-        # x - avg_pool3(x) as ONE depthwise 3x3 (centre 8/9, neighbours -1/9; avg_pool2d counts the padding, so borders agree)
-        hp = torch.full((9, dyn), -1.0 / 9.0, dtype=torch.float32, device=dev)
-        hp[4] = 8.0 / 9.0
-        pk["detail_hp"] = hp.half().contiguous()
-        df = self.detail_gate.detail_filter
-        pk["df0"], pk["df1"] = _pack_dw(df[0].weight), _gn_args(df[1])
-        pk["df3"], pk["df5"] = _pack_linear(df[3].weight), _pack_linear(df[5].weight, df[5].bias)
-        pk["detail_t"] = torch.tanh(self.detail_gate.detail_scale.detach().float()).reshape(1).contiguous()
+        if "detail" in self.router_hook_names:
+            # x - avg_pool3(x) as ONE depthwise 3x3 (centre 8/9, neighbours -1/9; avg_pool2d counts the padding, so borders agree)
+            hp = torch.full((9, dyn), -1.0 / 9.0, dtype=torch.float32, device=dev)
+            hp[4] = 8.0 / 9.0
+            pk["detail_hp"] = hp.half().contiguous()
+            df = self.detail_gate.detail_filter
+            pk["df0"], pk["df1"] = _pack_dw(df[0].weight), _gn_args(df[1])
+            pk["df3"], pk["df5"] = _pack_linear(df[3].weight), _pack_linear(df[5].weight, df[5].bias)
+            pk["detail_t"] = torch.tanh(self.detail_gate.detail_scale.detach().float()).reshape(1).contiguous()
         w, b = fold_bn(self.static_net[0].weight, None, self.static_net[1])
         pk["st_dw"], pk["st_dw_b"] = _pack_dw(w), b.contiguous()
         w, b = fold_bn(self.static_net[3].weight, None, self.static_net[4])
@@ -250,8 +264,10 @@ class VisualEnhancedAdaptiveGateMoE(nn.Module, PackCache):
         fe = self.fused_experts
         if self.expert_backend == "low_rank_fused":
             pk["bn0"], pk["bn1"] = _pack_linear(fe.bottleneck[0].weight), _gn_args(fe.bottleneck[1])
-            pk["fused_w"] = pack_gemm_weight(fe.fused.dense_weight())
-            pk["fused_gamma"], pk["fused_beta"] = _f32(fe.fused.expert_norm_weight), _f32(fe.fused.expert_norm_bias)
+        if self.expert_backend in ("low_rank_fused", "fused"):
+            fused = fe.fused if self.expert_backend == "low_rank_fused" else fe
+            pk["fused_w"] = pack_gemm_weight(fused.dense_weight())
+            pk["fused_gamma"], pk["fused_beta"] = _f32(fused.expert_norm_weight), _f32(fused.expert_norm_bias)
         else:
             sf = fe.shared_feature
             pk["sf0"], pk["sf1"], pk["sf3"], pk["sf4"] = _pack_linear(sf[0].weight), _gn_args(sf[1]), _pack_dw(sf[3].weight), _gn_args(sf[4])
@@ -265,16 +281,18 @@ class VisualEnhancedAdaptiveGateMoE(nn.Module, PackCache):
             old = torch.arange(C, device=dev)
             perm[(old % (C // sg)) * sg + old // (C // sg), old] = 1.0
             pk["shuffle"] = pack_gemm_weight(perm.reshape(C, C, 1, 1))
-        cm = self.context_mixer
-        pk["lc0"], pk["lc1"] = _pack_dw(cm.local_context[0].weight), _gn_args(cm.local_context[1])
-        pk["pp"] = [(_pack_linear(p[0].weight), _gn_args(p[1])) for p in cm.pool_projections]
-        pk["cg"] = _pack_linear(cm.context_gate[0].weight, cm.context_gate[0].bias)
-        pk["ctx_t"] = torch.tanh(cm.context_scale.detach().float()).reshape(1).expand(C).contiguous()
-        pk["fr0"], pk["fr1"] = _pack_dw(self.feature_refiner[0].weight), _gn_args(self.feature_refiner[1])
-        fg = self.feature_gate
-        pk["fg_w1"] = _f32(fg[1].weight).reshape(fg[1].weight.shape[0], C).contiguous()
-        pk["fg_w2"], pk["fg_b2"] = _f32(fg[3].weight).reshape(C, -1).contiguous(), _f32(fg[3].bias)
-        pk["refine_t"] = float(torch.tanh(self.refine_scale.detach().float()))
+        if "context" in self.router_hook_names:
+            cm = self.context_mixer
+            pk["lc0"], pk["lc1"] = _pack_dw(cm.local_context[0].weight), _gn_args(cm.local_context[1])
+            pk["pp"] = [(_pack_linear(p[0].weight), _gn_args(p[1])) for p in cm.pool_projections]
+            pk["cg"] = _pack_linear(cm.context_gate[0].weight, cm.context_gate[0].bias)
+            pk["ctx_t"] = torch.tanh(cm.context_scale.detach().float()).reshape(1).expand(C).contiguous()
+        if "refine" in self.router_hook_names:
+            pk["fr0"], pk["fr1"] = _pack_dw(self.feature_refiner[0].weight), _gn_args(self.feature_refiner[1])
+            fg = self.feature_gate
+            pk["fg_w1"] = _f32(fg[1].weight).reshape(fg[1].weight.shape[0], C).contiguous()
+            pk["fg_w2"], pk["fg_b2"] = _f32(fg[3].weight).reshape(C, -1).contiguous(), _f32(fg[3].bias)
+            pk["refine_t"] = float(torch.tanh(self.refine_scale.detach().float()))
         pk["proj"], pk["bn"] = _pack_linear(self.proj.weight), _gn_args(self.bn)
         return pk
 
@@ -282,11 +300,13 @@ class VisualEnhancedAdaptiveGateMoE(nn.Module, PackCache):
     def _experts(self, xd, idx, w, pk, out):
         B, H, W, _ = xd.shape
         fe = self.fused_experts
-        if self.expert_backend == "low_rank_fused":
-            t = _norm(ops.conv2d(xd, *pk["bn0"], pk["bn0"][0].shape[0], 1, 1, 1, 0, False), pk["bn1"], act=True)
+        if self.expert_backend in ("low_rank_fused", "fused"):
+            t, fused = xd, fe
+            if self.expert_backend == "low_rank_fused":
+                t, fused = _norm(ops.conv2d(xd, *pk["bn0"], pk["bn0"][0].shape[0], 1, 1, 1, 0, False), pk["bn1"], act=True), fe.fused
             E, oc = self.num_experts, self.out_dynamic
             fo = ops.conv2d(t, pk["fused_w"], None, E * oc, 3, 3, 1, 1, False)            # every expert, one dense conv
-            return ops.gated_select(fo, idx, w, pk["fused_gamma"], pk["fused_beta"], E, oc, fe.fused.norm_groups, 1e-5, out=out)
+            return ops.gated_select(fo, idx, w, pk["fused_gamma"], pk["fused_beta"], E, oc, fused.norm_groups, 1e-5, out=out)
         hid = pk["sf0"][0].shape[0]
         h = _norm(ops.conv2d(xd, *pk["sf0"], hid, 1, 1, 1, 0, False), pk["sf1"], act=True)
         feat = _norm(ops.dwconv(h, pk["sf3"], None, 3, False, hid), pk["sf4"], act=True)
@@ -310,12 +330,12 @@ class VisualEnhancedAdaptiveGateMoE(nn.Module, PackCache):
         gate = ops.fc_gate(ops.adaptive_avgpool(x, 1, 1), pk["se_w1"], pk["se_w2"], pk["se_b2"])
         xg = ops.ew(ops.EW_AFFINE, a=x, p0=gate, p1=zero, rows_per_img=HW)
         xs, xd = xg[..., :st_c], xg[..., st_c:]
-        # detail gate on the dynamic half (gated.py:1174-1178)
-        t = ops.dwconv(ops.dwconv(xd, pk["detail_hp"], None, 3, False, xd.shape[3]), pk["df0"], None, 3, False, xd.shape[3])
-        t = _norm(t, pk["df1"], act=True)
-        t = ops.conv2d(t, *pk["df3"], pk["df3"][0].shape[0], 1, 1, 1, 0, True)
-        g = ops.ew(ops.EW_SIGMOID, a=ops.conv2d(t, *pk["df5"], xd.shape[3], 1, 1, 1, 0, False))
-        xd = ops.ew(ops.EW_MUL_GATE, a=xd, b=g, p0=pk["detail_t"])
+        if "detail" in self.router_hook_names:   # detail gate on the dynamic half (gated.py:1174-1178)
+            t = ops.dwconv(ops.dwconv(xd, pk["detail_hp"], None, 3, False, xd.shape[3]), pk["df0"], None, 3, False, xd.shape[3])
+            t = _norm(t, pk["df1"], act=True)
+            t = ops.conv2d(t, *pk["df3"], pk["df3"][0].shape[0], 1, 1, 1, 0, True)
+            g = ops.ew(ops.EW_SIGMOID, a=ops.conv2d(t, *pk["df5"], xd.shape[3], 1, 1, 1, 0, False))
+            xd = ops.ew(ops.EW_MUL_GATE, a=xd, b=g, p0=pk["detail_t"])
         # static path straight into its half of the concatenation buffer
         cat = ops.new_act(B, H, W, C, x.device)
         ts = ops.dwconv(xs, pk["st_dw"], pk["st_dw_b"], 3, True, st_c)
@@ -326,20 +346,21 @@ class VisualEnhancedAdaptiveGateMoE(nn.Module, PackCache):
         self._experts(xd, idx, w, pk, cat[..., self.out_static:])
         if self.shuffle_groups > 1:
             cat = ops.conv2d(cat, pk["shuffle"], None, C, 1, 1, 1, 0, False)
-        # pyramid context (gated.py:1210-1221)
-        lc = _norm(ops.dwconv(cat, pk["lc0"], None, 3, False, C), pk["lc1"], act=True)
-        ctx = [lc]
-        for s, (pw, gn) in zip(self.context_mixer.pool_scales, pk["pp"]):
-            h, w_ = max(1, H // s), max(1, W // s)
-            pooled = cat if (h, w_) == (H, W) else ops.adaptive_avgpool(cat, h, w_)
-            ctx.append(_norm(ops.conv2d(pooled, *pw, C, 1, 1, 1, 0, False), gn, act=True))
-        c = ops.ctx_mean3(*ctx)
-        cgate = ops.ew(ops.EW_SIGMOID, a=ops.conv2d(c, *pk["cg"], C, 1, 1, 1, 0, False))
-        cat = ops.ew(ops.EW_SCALE_RES, a=cat, b=ops.ew(ops.EW_MUL, a=c, b=cgate), p0=pk["ctx_t"])
-        # feature refinement (moe/hooks.py:50-57): cat + tanh(scale) * refiner(cat) * gate(cat)
-        r = _norm(ops.dwconv(cat, pk["fr0"], None, 3, False, C), pk["fr1"], act=True)
-        fg = ops.fc_gate(ops.adaptive_avgpool(cat, 1, 1), pk["fg_w1"], pk["fg_w2"], pk["fg_b2"], scale=pk["refine_t"])
-        cat = ops.ew(ops.EW_AFFINE, a=r, b=cat, p0=fg, p1=zero, rows_per_img=HW)
+        for hook in self.router_hook_names:
+            if hook == "context":     # pyramid context (gated.py:1210-1221)
+                lc = _norm(ops.dwconv(cat, pk["lc0"], None, 3, False, C), pk["lc1"], act=True)
+                ctx = [lc]
+                for s, (pw, gn) in zip(self.context_mixer.pool_scales, pk["pp"]):
+                    h, w_ = max(1, H // s), max(1, W // s)
+                    pooled = cat if (h, w_) == (H, W) else ops.adaptive_avgpool(cat, h, w_)
+                    ctx.append(_norm(ops.conv2d(pooled, *pw, C, 1, 1, 1, 0, False), gn, act=True))
+                c = ops.ctx_mean3(*ctx)
+                cgate = ops.ew(ops.EW_SIGMOID, a=ops.conv2d(c, *pk["cg"], C, 1, 1, 1, 0, False))
+                cat = ops.ew(ops.EW_SCALE_RES, a=cat, b=ops.ew(ops.EW_MUL, a=c, b=cgate), p0=pk["ctx_t"])
+            elif hook == "refine":    # feature refinement (moe/hooks.py:50-57): cat + tanh(scale) * refiner(cat) * gate(cat)
+                r = _norm(ops.dwconv(cat, pk["fr0"], None, 3, False, C), pk["fr1"], act=True)
+                fg = ops.fc_gate(ops.adaptive_avgpool(cat, 1, 1), pk["fg_w1"], pk["fg_w2"], pk["fg_b2"], scale=pk["refine_t"])
+                cat = ops.ew(ops.EW_AFFINE, a=r, b=cat, p0=fg, p1=zero, rows_per_img=HW)
         # projection + GroupNorm + residual
         return _norm(ops.conv2d(cat, *pk["proj"], C, 1, 1, 1, 0, False), pk["bn"], add=x, out=out)
 
@@ -349,3 +370,98 @@ class VisualEnhancedAdaptiveGateMoE(nn.Module, PackCache):
     @property
     def aux_loss(self):
         return torch.zeros((), device=self.proj.weight.device)
+
+
+_LOSS_ARGS = "balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01"   # accepted and unused at inference
+
+
+class AdaptiveGateMoE(_GatedMoE):
+    """`AdaptiveGateMoE(in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.0,
+    final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01, router_hooks=None,
+    detail_reduction=8, refine_reduction=8)` (gated.py:268-640): shared-inverted experts, no shuffle."""
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.0,
+                 final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01, router_hooks=None,
+                 detail_reduction=8, refine_reduction=8):
+        hooks = tuple(router_hooks or ())
+        if any(h not in ("detail", "context", "refine") for h in hooks):
+            raise NotImplementedError(f"AdaptiveGateMoE: router hooks {hooks} are not on the B200 path (detail / context / refine)")
+        super().__init__(in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
+                         "shared_inverted", 1, hooks=hooks, refine_reduction=refine_reduction, detail_reduction=detail_reduction)
+
+
+class FusedAdaptiveGateMoE(_GatedMoE):
+    """`FusedAdaptiveGateMoE(in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8,
+    initial_temperature=1.0, final_temperature=0.5, <loss coefficients>)` (gated.py:1232-1274): always the fused expert group."""
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.0,
+                 final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01):
+        super().__init__(in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
+                         "fused", 1)
+
+
+def _hybrid_backend(num_experts, threshold, low_rank):
+    if num_experts > threshold:
+        return "shared_inverted"
+    return "low_rank_fused" if low_rank else "fused"
+
+
+class HybridAdaptiveGateMoE(_GatedMoE):
+    """`HybridAdaptiveGateMoE(in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8,
+    initial_temperature=1.2, final_temperature=0.5, <loss coefficients>, fused_expert_threshold=8, shuffle_groups=2)`
+    (gated.py:1277-1386): fused experts up to the threshold, shared-inverted above; channel shuffle."""
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.2,
+                 final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+                 fused_expert_threshold=8, shuffle_groups=2):
+        super().__init__(in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
+                         _hybrid_backend(num_experts, fused_expert_threshold, False), shuffle_groups,
+                         fused_expert_threshold=fused_expert_threshold)
+
+
+class LowRankHybridAdaptiveGateMoE(_GatedMoE):
+    """`LowRankHybridAdaptiveGateMoE(..., fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5)` (gated.py:1455-1508)."""
+    HOOKS = ()
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.2,
+                 final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+                 fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5, refine_reduction=8, detail_reduction=8):
+        super().__init__(in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
+                         _hybrid_backend(num_experts, fused_expert_threshold, True), shuffle_groups, bottleneck_ratio, self.HOOKS,
+                         refine_reduction, detail_reduction, fused_expert_threshold)
+
+
+class RefinedLowRankHybridAdaptiveGateMoE(LowRankHybridAdaptiveGateMoE):
+    """`RefinedLowRankHybridAdaptiveGateMoE(..., bottleneck_ratio=0.5, refine_reduction=8)` (gated.py:1511-1585): + refinement."""
+    HOOKS = ("refine",)
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.2,
+                 final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+                 fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5, refine_reduction=8):
+        super().__init__(in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
+                         balance_loss_coeff, router_z_loss_coeff, entropy_loss_coeff, fused_expert_threshold, shuffle_groups,
+                         bottleneck_ratio, refine_reduction)
+
+
+class DetailAwareLowRankHybridAdaptiveGateMoE(LowRankHybridAdaptiveGateMoE):
+    """`DetailAwareLowRankHybridAdaptiveGateMoE(..., bottleneck_ratio=0.5, detail_reduction=8)` (gated.py:1588-1642): + detail gate."""
+    HOOKS = ("detail",)
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.2,
+                 final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+                 fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5, detail_reduction=8):
+        super().__init__(in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
+                         balance_loss_coeff, router_z_loss_coeff, entropy_loss_coeff, fused_expert_threshold, shuffle_groups,
+                         bottleneck_ratio, 8, detail_reduction)
+
+
+class ContextRefinedLowRankHybridAdaptiveGateMoE(RefinedLowRankHybridAdaptiveGateMoE):
+    """`ContextRefinedLowRankHybridAdaptiveGateMoE(..., bottleneck_ratio=0.5, refine_reduction=8)` (gated.py:1645-1700): + pyramid context."""
+    HOOKS = ("context", "refine")
+
+
+class VisualEnhancedAdaptiveGateMoE(LowRankHybridAdaptiveGateMoE):
+    """`VisualEnhancedAdaptiveGateMoE(in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8,
+    initial_temperature=1.2, final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+    fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5, refine_reduction=8, detail_reduction=8)` (gated.py:1703-1756)."""
+    HOOKS = ("detail", "context", "refine")

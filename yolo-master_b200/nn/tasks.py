@@ -22,8 +22,11 @@ from . import modules as M
 _CFG_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cfg", "models")
 
 MODULES = {name: getattr(M, name) for name in M.__all__ if isinstance(getattr(M, name), type)}
-MIXTURE_MODULES = {"A2C2fMoE": M.A2C2fMoE, "ES_MOE": M.ES_MOE, "C2fMoT": M.C2fMoT, "C2fMoA": M.C2fMoA,
-                   "VisualEnhancedAdaptiveGateMoE": M.VisualEnhancedAdaptiveGateMoE}
+MIXTURE_MODULES = {"A2C2fMoE": M.A2C2fMoE, "ES_MOE": M.ES_MOE, "C2fMoT": M.C2fMoT, "C2fMoA": M.C2fMoA}
+MIXTURE_MODULES.update({n: getattr(M, n) for n in (          # the AdaptiveGateMoE line, v0_4 ... v0_10 zoos (nn/modules/gated.py)
+    "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
+    "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE", "ContextRefinedLowRankHybridAdaptiveGateMoE",
+    "VisualEnhancedAdaptiveGateMoE")})
 BASE_MODULES = frozenset({M.Conv, M.DWConv, M.Bottleneck, M.SPPF, M.C2PSA, M.C2f, M.C3k2, M.C3, M.A2C2f})
 REPEAT_MODULES = frozenset({M.C2f, M.C3k2, M.C3, M.C2PSA, M.A2C2f})
 MIXTURE_BASE_MODULES = frozenset(MIXTURE_MODULES.values())
