@@ -297,6 +297,13 @@ def optimized_moe_improved(sd, p, x, num_experts, top_k):
     return _st((shared.float() + out).to(x.dtype))
 
 
+def layer_modular_router_expert_moe(sd, p, x, c1, c2, num_experts=4, top_k=2, *unused):
+    """`ModularRouterExpertMoE` (= `OptimizedMOEImproved`, moe/modules.py:1745) as a top-level YAML layer (v0_1 zoo): the block
+    owns its residual, `final_output + x` when in == out channels (modules.py:1156-1159)."""
+    y = optimized_moe_improved(sd, p, x, num_experts, top_k)
+    return _st(y + x) if c1 == c2 else y
+
+
 def es_moe_kernel_sizes(num_experts, max_kernel_size=15, expert_kernel_sizes=None):
     """`ES_MOE.__init__` moe/modules.py:478-493."""
     if max_kernel_size % 2 == 0:
@@ -1103,6 +1110,9 @@ def _gated_layer(name):
 
 
 layer_visual_enhanced_gate_moe = _gated_layer("VisualEnhancedAdaptiveGateMoE")
+for _name in ("ModularRouterExpertMoE", "OptimizedMOEImproved"):
+    _LAYER_FN[_name] = layer_modular_router_expert_moe
+    _MIX_BASE.add(_name)
 for _name in GATED_VARIANTS:
     _LAYER_FN[_name] = _gated_layer(_name)
     _MIX_BASE.add(_name)

@@ -107,6 +107,9 @@ EXTRA_MODELS = {
     "yolo-master-n-v0_10": ("/root/reference/ultralytics/cfg/models/master/v0_10/det/yolo-master-n.yaml", [5, 8, 11, 17, 20, 23],
                             {"b2_160": (2, 160, 160, 9), "b1_128": (1, 128, 128, 10)}),   # (B=1 with a 5..7-pixel P4/P5 map makes the
                             # reference itself raise: its router GroupNorm then sees one value per group, gated.py:113)
+    # ModularRouterExpertMoE (= OptimizedMOEImproved) as a top-level layer that owns its residual: the v0_1 zoo
+    "yolo-master-n-v0_1": ("/root/reference/ultralytics/cfg/models/master/v0_1/det/yolo-master-n.yaml", [5, 8, 11, 23],
+                           {"b2_128": (2, 128, 128, 12)}),
     "yolo26-master-moa-mot-s": (("/root/reference/ultralytics/cfg/models/26/yolo26-master-moa-mot-n.yaml", "s", [0.50, 0.50, 1024]),
                                 [13, 16, 19, 22], {"b1_160": (1, 160, 160, 8)}),
 }

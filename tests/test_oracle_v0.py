@@ -10,7 +10,9 @@ from oracle import yolo_master_oracle as O
 from yolo_master_b200.utils.synth import synth_images
 
 CASES = [("yolo-master-n-v0", "master/v0/det/yolo-master-n.yaml", "b2_128"), ("yolo-master-n-v0", "master/v0/det/yolo-master-n.yaml", "b1_64"),
-         ("yolo-master-l-v0", "master/v0/det/yolo-master-l.yaml", "b1_64")]
+         ("yolo-master-l-v0", "master/v0/det/yolo-master-l.yaml", "b1_64"),
+         # v0_1 zoo: ModularRouterExpertMoE (= OptimizedMOEImproved) as a top-level layer that owns its residual
+         ("yolo-master-n-v0_1", "master/v0_1/det/yolo-master-n.yaml", "b2_128")]
 
 
 @pytest.mark.parametrize("name,cfg,tag", CASES)

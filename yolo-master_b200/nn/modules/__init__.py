@@ -11,7 +11,10 @@ from .mot import C2fMoT, MoTBlock
 from .moe import (A2C2fMoE, ABlockMoE, DepthwiseSeparableConv, DynamicRoutingLayer, EfficientExpertGroup, EfficientSpatialRouter,
                   ES_MOE, OptimizedMOEImproved, SimpleExpert, get_safe_groups)
 
+ModularRouterExpertMoE = OptimizedMOEImproved   # alias of the reference (moe/modules.py:1745), the block of the v0_1 zoo
+
 __all__ = (
+    "ModularRouterExpertMoE",
     "Conv", "DWConv", "Concat", "Upsample", "PlainConv2d", "autopad",
     "Bottleneck", "C2f", "C3", "C3k", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA", "AAttn", "ABlock", "A2C2f",
     "EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups",
