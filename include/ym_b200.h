@@ -263,6 +263,13 @@ int ym_esmoe_combine(const void* y, int ldy, const int* route_idx, int topk, con
  * [B][max_det] anchor indices; scratch: ym_nms_scratch_bytes(B, A).  Images with more than 16384 candidates set the
  * overflow flag (ym_nms_overflowed) and return count 0 instead of silently truncating. */
 long long ym_nms_scratch_bytes(int B, int A);
+
+/* Large-candidate path of mode 0 (same outputs as ym_nms_batched): keys, boxes and suppression flags in global scratch, any number
+ * of candidates per image, the first max_nms by score enter the suppression (utils/nms.py:142-146: validation at conf 0.001).
+ * utils/nms.py takes it when ym_nms_overflowed() reports more than 16384 candidates in some image. */
+long long ym_nms_large_scratch_bytes(int B, int A);
+int ym_nms_batched_large(const float* pred, int B, int nc, int A, float conf_thres, float iou_thres, int max_det, int max_nms,
+                         float max_wh, float* out, int* out_count, int* out_idx, void* scratch, void* stream);
 int ym_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, float iou_thres, int max_det, int max_nms,
                    float max_wh, int mode, float sigma, float frame_w, float frame_h, float* out, int* out_count, int* out_idx,
                    void* scratch, void* stream);

@@ -41,6 +41,8 @@ SIGNATURES = {
     "ym_nms_scratch_bytes": (cll, [ci, ci]),
     "ym_nms_batched": (ci, [vp, ci, ci, ci, cf, cf, ci, ci, cf, ci, cf, cf, cf, vp, vp, vp, vp, vp]),
     "ym_nms_overflowed": (ci, [vp, ci, ci, vp]),
+    "ym_nms_large_scratch_bytes": (cll, [ci, ci]),
+    "ym_nms_batched_large": (ci, [vp, ci, ci, ci, cf, cf, ci, ci, cf, vp, vp, vp, vp, vp]),
     "ym_tc_gemm_nt": (ci, [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, vp]),
     "ym_moe_dispatch_tc": (ci, [vp, ci, ci, ci, ci, vp, ci, cll, vp, vp, ci, ci, cf, cf, vp, ci, vp]),
     "ym_moe_dispatch_v2_supported": (ci, [ci, ci, ci, ci, ci, ci, ci]),

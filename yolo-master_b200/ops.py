@@ -316,6 +316,23 @@ def nms_batched(pred, conf_thres, iou_thres, max_det=300, max_nms=30000, max_wh=
     return out, cnt, idx, scratch
 
 
+def nms_batched_large(pred, conf_thres, iou_thres, max_det=300, max_nms=30000, max_wh=7680.0):
+    """ym_nms_batched_large: mode 0 of nms_batched without the 16384-candidate limit.  Returns (out, count, idx)."""
+    if pred.dtype != torch.float32 or not pred.is_cuda or pred.dim() != 3:
+        raise ValueError("nms_batched_large: expected an fp32 CUDA tensor of shape (B, 4+nc, A)")
+    pred = pred.contiguous()
+    B, no, A = pred.shape
+    out = torch.empty((B, max_det, 6), dtype=torch.float32, device=pred.device)
+    cnt = torch.empty((B,), dtype=torch.int32, device=pred.device)
+    idx = torch.empty((B, max_det), dtype=torch.int32, device=pred.device)
+    scratch = torch.empty((lib().ym_nms_large_scratch_bytes(B, A),), dtype=torch.uint8, device=pred.device)
+    _lib.check(lib().ym_nms_batched_large(pred.data_ptr(), B, no - 4, A, float(conf_thres), float(iou_thres), max_det, max_nms,
+                                          float(max_wh), out.data_ptr(), cnt.data_ptr(), idx.data_ptr(), scratch.data_ptr(), _stream()),
+               "ym_nms_batched_large")
+    _count(2)
+    return out, cnt, idx
+
+
 def esmoe_forward(x, pack, topk, dyn_thr, out=None):
     """ES_MOE eval forward on the C ABI (ym_esmoe_route / _dwconv / _pointwise / _combine).  x: (B,H,W,C) fp16 view."""
     B, H, W, Cc = x.shape

@@ -39,7 +39,10 @@ def non_max_suppression(prediction, conf_thres: float = 0.25, iou_thres: float =
                                              1 if cluster else 0, sigma, frame_wh or (0.0, 0.0))
     B, _, A = prediction.shape
     if ops.lib().ym_nms_overflowed(scratch.data_ptr(), B, A, torch.cuda.current_stream().cuda_stream):
-        raise RuntimeError("non_max_suppression: more than 16384 candidates above conf_thres in one image (raise conf_thres)")
+        # some image has more candidates than the shared-memory sorter holds (validation at conf 0.001): global-memory path
+        if cluster:
+            raise RuntimeError("non_max_suppression(cluster=True): more than 16384 candidates above conf_thres in one image")
+        out, cnt, idx = ops.nms_batched_large(prediction.float(), conf_thres, iou_thres, max_det, max_nms, float(max_wh))
     counts = cnt.tolist()  # the reference returns ragged Python lists: one host read of B integers
     output = [out[b, :n] for b, n in enumerate(counts)]
     if return_idxs:
