@@ -206,6 +206,14 @@ int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C, int pool,
                    const float* gn2_b, int G2, const float* pw2, const float* b2, int E, float gn_eps, float alpha,
                    float temperature, const float* cx_w, float cx_b, int topk, float* scratch, float* w_out, int* idx_out,
                    float* probs_out, void* stream);
+/* ZeroCostRouter.forward gated.py:953-968 (UltraLightRouter of UltimateOptimizedMoE, v0_3 zoo) + the complexity SCALE of
+ * UltimateOptimizedMoE.forward modules.py:1663-1670: probs = softmax(clamp(softmax(fc . [mean | std]) / T, +-30)), top-k,
+ * w / (sum + 1e-6), then w *= clamp(mean over the batch of sigmoid(cx_w . mean_c + cx_b), 0.3, 1.5).  fc fp32 [E][2C].
+ * scratch: ym_zero_cost_router_scratch_floats() floats. */
+long long ym_zero_cost_router_scratch_floats(int B, int C);
+int ym_zero_cost_router(const void* x, int ldx, int B, int H, int W, int C, const float* fc, int E, float temperature,
+                        const float* cx_w, float cx_b, int topk, float* scratch, float* w_out, int* idx_out, float* probs_out,
+                        void* stream);
 int ym_fc_gate(const void* v, int ldv, int B, int Cin, const float* w1, int Cr, const float* w2, const float* b2, int Cout,
                float scale, float* out, void* stream);
 int ym_gated_select(const void* fo, int ldf, int B, int HW, int E, int oc, int G, float eps, const int* idx, const float* w,

@@ -1086,6 +1086,44 @@ GATED_VARIANTS = {
 }
 
 
+def zero_cost_router(sd, p, x, top_k, temperature):
+    """`ZeroCostRouter.forward` gated.py:953-968 (fp32): `router` = Linear -> Softmax, whose OUTPUT is divided by T, clamped and
+    sent through softmax again; top-k; renormalise with +1e-6.  Returns (weights [B,k], indices [B,k], probs)."""
+    B, C, H, W = x.shape
+    xf = x.float()
+    mean = xf.mean((2, 3))
+    std = xf.std((2, 3), unbiased=False) if H * W > 1 else torch.zeros_like(mean)
+    p0 = F.softmax(F.linear(torch.cat([mean, std], 1), sd[p + ".router.0.weight"]), dim=1)
+    probs = F.softmax((p0 / temperature).clamp(-30.0, 30.0), dim=1)
+    w, idx = torch.topk(probs, top_k, dim=1)
+    return w / (w.sum(1, keepdim=True) + 1e-6), idx, probs
+
+
+def layer_ultimate_optimized_moe(sd, p, x, c1, c2, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, use_routing_cache=True,
+                                 capacity_factor=1.5, initial_temperature=2.0, *unused, return_route=False):
+    """`UltimateOptimizedMoE.forward` moe/modules.py:1653-1680 (v0_3 zoo), eval: un-gated channel split, static path, ZeroCostRouter
+    on the dynamic half, routing weights SCALED by the batch-level complexity (clamped to [0.3, 1.5]), FusedExpertGroup,
+    concatenation, 1x1 projection, GroupNorm, residual."""
+    dyn = int(c1 * split_ratio)
+    st_c = c1 - dyn
+    out_dyn = int(c2 * split_ratio)
+    xs, xd = x[:, :st_c], x[:, st_c:]
+    cx = torch.sigmoid(F.conv2d(xd.mean((2, 3), keepdim=True), sd[p + ".complexity_estimator.1.weight"], sd[p + ".complexity_estimator.1.bias"])).mean()
+    cx = torch.nan_to_num(cx, nan=1.0, posinf=1.5, neginf=0.3).clamp(0.3, 1.5)
+    t = F.silu(_bn(sd, p + ".static_net.1", F.conv2d(xs, _w(sd[p + ".static_net.0.weight"]), None, 1, 1, 1, st_c)))
+    out_s = _st(F.silu(_bn(sd, p + ".static_net.4", F.conv2d(_st(t), _w(sd[p + ".static_net.3.weight"])))))
+    w, idx, probs = zero_cost_router(sd, p + ".routing", xd, top_k, float(initial_temperature))
+    w = w * cx
+    out_d = fused_expert_group(sd, p + ".fused_experts", xd, w, idx, num_experts, out_dyn, num_groups)
+    cat = torch.cat([out_s, out_d], 1)
+    out = _st(_gn(sd, p + ".bn", F.conv2d(cat, _w(sd[p + ".proj.weight"])), get_safe_groups(c2, num_groups)) + x)
+    return (out, w, idx, probs) if return_route else out
+
+
+_LAYER_FN["UltimateOptimizedMoE"] = layer_ultimate_optimized_moe
+_MIX_BASE.add("UltimateOptimizedMoE")
+
+
 def gated_backend(name, num_experts, fused_expert_threshold=8):
     _, hybrid, low_rank, _, _ = GATED_VARIANTS[name]
     if hybrid is None:

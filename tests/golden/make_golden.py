@@ -311,10 +311,11 @@ def gated_family_golden():
     before the complexity gate, and the state-dict key table."""
     from ultralytics.nn.modules.moe import gated as G
     out = {}
-    for ci, name in enumerate(GATED_FAMILY):
+    from ultralytics.nn.modules.moe import modules as MM
+    for ci, name in enumerate(GATED_FAMILY + ["UltimateOptimizedMoE"]):
         for E in (4, 16):
             torch.manual_seed(0)
-            m = getattr(G, name)(64, 64, E, 2, 0.5).eval()
+            m = getattr(G if hasattr(G, name) and name != "UltimateOptimizedMoE" else MM, name)(64, 64, E, 2, 0.5).eval()
             for mod in m.modules():                      # inside a model every BatchNorm2d runs with eps = 1e-3
                 if isinstance(mod, torch.nn.BatchNorm2d):   # (initialize_weights, utils/torch_utils.py:552-562)
                     mod.eps = 1e-3
@@ -330,7 +331,7 @@ def gated_family_golden():
             out[f"{name}/E{E}"] = {"seed": 300 + ci, "xseed": 400 + ci, "y": y.clone(), "route_w": route["w"], "route_idx": route["idx"],
                                    "keys": {k: list(v.shape) for k, v in sd.items()},
                                    "scalars": {k: v.clone() for k, v in sd.items() if v.dim() == 0 and v.is_floating_point()},   # left at init
-                                   "backend": getattr(m, "expert_backend", "shared_inverted")}
+                                   "backend": getattr(m, "expert_backend", "fused" if name == "UltimateOptimizedMoE" else "shared_inverted")}
             print("gated", name, E, out[f"{name}/E{E}"]["backend"], float(y.abs().mean()))
     torch.save(out, f"{OUT}/gated_family.golden.pt")
 

@@ -37,8 +37,26 @@ extern "C" int host_gate_router(const void* x, int ldx, int B, int H, int W, int
     }
     R2Args a2;
     a2.stats = stats.data(); a2.ll = ll.data(); a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha;
-    a2.inv_temp = 1.f / temperature; a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.cx = cx.data(); a2.w = w_out;
+    a2.inv_temp = 1.f / temperature; a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.cx = cx.data(); a2.w = w_out;
     a2.probs = probs_out; a2.idx = idx_out;
+    for (int ph = 0; ph < R2_PHASES; ++ph)
+        for (int t = 0; t < NTHR; ++t) r2_phase(ph, a2, t, NTHR, sm.data());
+    return 0;
+}
+
+extern "C" int host_zero_cost_router(const void* x, int ldx, int B, int H, int W, int C, const float* fc, int E, float temperature,
+                                     const float* cx_w, float cx_b, int topk, float* w_out, int* idx_out, float* probs_out) {
+    std::vector<float> stats((size_t)B * 2 * C), cx(B), sm(r0_smem_floats(C, NTHR) + 16);
+    R0Args a0;
+    a0.x = (const ym_half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = 1; a0.Hp = H; a0.Wp = W; a0.inv_area = 1.f;
+    a0.stats = stats.data(); a0.pooled = nullptr;
+    for (int b = 0; b < B; ++b)
+        for (int ph = 0; ph < R0_PHASES; ++ph)
+            for (int t = 0; t < NTHR; ++t) r0_phase(ph, a0, b, t, NTHR, sm.data());
+    R2Args a2;
+    a2.stats = stats.data(); a2.ll = nullptr; a2.wg = fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = 1.f; a2.inv_temp = 1.f / temperature;
+    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.cx = cx.data(); a2.w = w_out; a2.probs = probs_out;
+    a2.idx = idx_out;
     for (int ph = 0; ph < R2_PHASES; ++ph)
         for (int t = 0; t < NTHR; ++t) r2_phase(ph, a2, t, NTHR, sm.data());
     return 0;

@@ -229,6 +229,9 @@ def test_gated_zoo_yamls_build():
             assert sum(p.numel() for p in m.parameters()) == nparam
         assert DetectionModel(f"master/{ver}/det/yolo-master-s.yaml").model[5].in_channels == 256
     assert type(DetectionModel("yolo-master-n.yaml").model[3]).__name__ == "ES_MOE"        # a bare name still resolves to the v0 zoo
+    for sc in "nsmlx":                                          # v0_3 zoo: UltimateOptimizedMoE
+        m = DetectionModel(f"master/v0_3/det/yolo-master-{sc}.yaml")
+        assert [type(m.model[i]).__name__ for i in (5, 8, 11)] == ["UltimateOptimizedMoE"] * 3
     for sc in "nsmlx":                                          # v0_1 zoo: ModularRouterExpertMoE is OptimizedMOEImproved
         m = DetectionModel(f"master/v0_1/det/yolo-master-{sc}.yaml")
         assert [type(m.model[i]).__name__ for i in (5, 8, 11)] == ["OptimizedMOEImproved"] * 3 and m.model[5].add_residual

@@ -203,6 +203,7 @@ def install_gated(host):
     vp, ci, cf = C.c_void_p, C.c_int, C.c_float
     host.host_gate_router.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, ci, cf, cf, cf, vp, cf,
                                       ci, vp, vp, vp]
+    host.host_zero_cost_router.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci, cf, vp, cf, ci, vp, vp, vp]
     host.host_fc_gate.argtypes = [vp, ci, ci, ci, vp, ci, vp, vp, ci, cf, vp]
     host.host_gated_select.argtypes = [vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, ci, vp, vp, vp, ci]
     host.host_ctx_mean3.argtypes = [vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, ci]
@@ -221,6 +222,15 @@ def install_gated(host):
                               pk["gn2_w"].data_ptr(), pk["gn2_b"].data_ptr(), pk["G2"], pk["pw2"].data_ptr(), pk["b2"].data_ptr(), pk["E"],
                               pk["eps"], pk["alpha"], pk["temperature"], pk["cx_w"].data_ptr(), pk["cx_b"], topk, w.data_ptr(),
                               idx.data_ptr(), probs.data_ptr())
+        return idx, w, probs
+
+    def zero_cost_router(x, fc, temperature, cx_w, cx_b, topk):
+        B, H, W, Cc = x.shape
+        w = torch.empty((B, topk), dtype=torch.float32)
+        idx = torch.empty((B, topk), dtype=torch.int32)
+        probs = torch.empty((B, fc.shape[0]), dtype=torch.float32)
+        host.host_zero_cost_router(x.data_ptr(), ld(x), B, H, W, Cc, fc.data_ptr(), fc.shape[0], float(temperature), cx_w.data_ptr(),
+                                   float(cx_b), topk, w.data_ptr(), idx.data_ptr(), probs.data_ptr())
         return idx, w, probs
 
     def fc_gate(v, w1, w2, b2, scale=1.0):
@@ -246,7 +256,7 @@ def install_gated(host):
                             c.shape[1], c.shape[2], out.data_ptr(), ld(out))
         return out
 
-    for name, fn in dict(gate_router=gate_router, fc_gate=fc_gate, gated_select=gated_select, ctx_mean3=ctx_mean3,
+    for name, fn in dict(gate_router=gate_router, zero_cost_router=zero_cost_router, fc_gate=fc_gate, gated_select=gated_select, ctx_mean3=ctx_mean3,
                          moe_expert_gemm=moe_expert_gemm, gn_finalize=gn_finalize).items():
         setattr(ops, name, fn)
     ops.pitch = lambda t, dtype=torch.float16: ld(t)

@@ -138,9 +138,33 @@ extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C
     gate_r1_kernel<<<B, NTHR, r1_smem_floats(R, NTHR) * sizeof(float), st>>>(a1);
     R2Args a2;
     a2.stats = stats; a2.ll = ll; a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha; a2.inv_temp = 1.f / temperature;
-    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
+    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
     gate_r2_kernel<<<1, NTHR, 0, st>>>(a2);
     YM_CHECK_LAUNCH("gate_router");
+    return YM_OK;
+}
+
+extern "C" long long ym_zero_cost_router_scratch_floats(int B, int C) { return (long long)B * (2LL * C + 1); }
+
+extern "C" int ym_zero_cost_router(const void* x, int ldx, int B, int H, int W, int C, const float* fc, int E, float temperature,
+                                   const float* cx_w, float cx_b, int topk, float* scratch, float* w_out, int* idx_out,
+                                   float* probs_out, void* stream) {
+    YM_CHECK_ARG(x && fc && cx_w && scratch && w_out && idx_out, "ym_zero_cost_router: null pointer");
+    YM_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "ym_zero_cost_router: empty problem");
+    YM_CHECK_ARG(E >= 1 && E <= MAXE && topk >= 1 && topk <= E, "ym_zero_cost_router: 1 <= topk <= E <= %d", MAXE);
+    YM_CHECK_ARG(temperature > 0.f, "ym_zero_cost_router: temperature must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* stats = scratch;
+    float* cx = stats + (long long)B * 2 * C;
+    R0Args a0;
+    a0.x = (const __half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = 1; a0.Hp = H; a0.Wp = W; a0.inv_area = 1.f;
+    a0.stats = stats; a0.pooled = nullptr;
+    gate_r0_kernel<<<B, NTHR, r0_smem_floats(C, NTHR) * sizeof(float), st>>>(a0);
+    R2Args a2;
+    a2.stats = stats; a2.ll = nullptr; a2.wg = fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = 1.f; a2.inv_temp = 1.f / temperature;
+    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
+    gate_r2_kernel<<<1, NTHR, 0, st>>>(a2);
+    YM_CHECK_LAUNCH("zero_cost_router");
     return YM_OK;
 }
 

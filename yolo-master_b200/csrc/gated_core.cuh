@@ -56,7 +56,7 @@ struct R0Args {
     int ldx, H, W, C, pool, Hp, Wp;
     float inv_area;     // 1 / (pool*pool), 1 when the map is not pooled
     float* stats;       // [B][2C]: mean | std
-    float* pooled;      // [B][Hp*Wp][C]
+    float* pooled;      // [B][Hp*Wp][C], or null: statistics only
 };
 constexpr int R0_PHASES = 5;
 YM_HD int r0_smem_floats(int C, int nthr) { return col_lane_floats(C, nthr) + C; }
@@ -91,6 +91,7 @@ YM_HD void r0_phase(int ph, const R0Args& a, int img, int tid, int nthr, float* 
             }
         }
     } else {   // ph 4: avg_pool2d(kernel = stride = pool), floor mode, or a plain fp32 copy
+        if (!a.pooled) return;                                        // statistics only (ZeroCostRouter)
         float* out = a.pooled + (long long)img * a.Hp * a.Wp * C;
         const int n = a.Hp * a.Wp * C;
         for (int e = tid; e < n; e += nthr) {
@@ -250,6 +251,8 @@ struct R2Args {
     const float *wc;      // [C] complexity_estimator conv weight
     float bc, alpha, inv_temp;   // alpha = sigmoid(self.alpha)
     int B, C, E, topk;
+    int zero_cost;        // 0: DualStreamGateRouter + complexity GATE (ranks dropped);  1: ZeroCostRouter (gated.py:953-968: softmax of
+                          //    the global stream, / T, clamp, softmax again) + complexity SCALE (weights multiplied, modules.py:1663-1670)
     float* cx;            // scratch [B]
     float *w, *probs;     // [B][topk], [B][E] (probs nullable)
     int* idx;             // [B][topk]
@@ -274,8 +277,9 @@ YM_HD void r2_phase(int ph, const R2Args& a, int tid, int nthr, float* sm) {
         float keep = rintf(s * (float)a.topk);                        // torch.round: half to even
         keep = keep < 1.f ? 1.f : (keep > (float)a.topk ? (float)a.topk : keep);
         sm[0] = keep;
+        sm[1] = s;                                                    // the clamped complexity itself (zero-cost mode scales by it)
     } else {
-        const float keep = sm[0];
+        const float keep = sm[0], cscale = sm[1];
         for (int b = tid; b < a.B; b += nthr) {
             float p[MAXE];
             float mx = -3.0e38f;
@@ -284,9 +288,12 @@ YM_HD void r2_phase(int ph, const R2Args& a, int tid, int nthr, float* sm) {
                 const float* w = a.wg + (long long)e * 2 * a.C;
                 const float* st = a.stats + (long long)b * 2 * a.C;
                 for (int j = 0; j < 2 * a.C; ++j) gl += w[j] * st[j];
-                float l = a.alpha * gl + (1.f - a.alpha) * a.ll[(long long)b * a.E + e];
-                l = l < -30.f ? -30.f : (l > 30.f ? 30.f : l);
-                p[e] = l * a.inv_temp;
+                float l = a.zero_cost ? gl : a.alpha * gl + (1.f - a.alpha) * a.ll[(long long)b * a.E + e];
+                if (!a.zero_cost) {
+                    l = l < -30.f ? -30.f : (l > 30.f ? 30.f : l);
+                    l *= a.inv_temp;
+                }
+                p[e] = l;
                 mx = p[e] > mx ? p[e] : mx;
             }
             float den = 0.f;
@@ -294,10 +301,24 @@ YM_HD void r2_phase(int ph, const R2Args& a, int tid, int nthr, float* sm) {
                 p[e] = expf(p[e] - mx);
                 den += p[e];
             }
-            for (int e = 0; e < a.E; ++e) {
-                p[e] /= den;
-                if (a.probs) a.probs[(long long)b * a.E + e] = p[e];
+            for (int e = 0; e < a.E; ++e) p[e] /= den;
+            if (a.zero_cost) {   // the Sequential already ends in a Softmax: its output / T, clamped, goes through softmax again
+                mx = -3.0e38f;
+                for (int e = 0; e < a.E; ++e) {
+                    float l = p[e] * a.inv_temp;
+                    l = l < -30.f ? -30.f : (l > 30.f ? 30.f : l);
+                    p[e] = l;
+                    mx = l > mx ? l : mx;
+                }
+                den = 0.f;
+                for (int e = 0; e < a.E; ++e) {
+                    p[e] = expf(p[e] - mx);
+                    den += p[e];
+                }
+                for (int e = 0; e < a.E; ++e) p[e] /= den;
             }
+            if (a.probs)
+                for (int e = 0; e < a.E; ++e) a.probs[(long long)b * a.E + e] = p[e];
             float wsel[MAXE];
             float tot = 0.f;
             for (int j = 0; j < a.topk; ++j) {
@@ -313,11 +334,15 @@ YM_HD void r2_phase(int ph, const R2Args& a, int tid, int nthr, float* sm) {
             float tot2 = 0.f;
             for (int j = 0; j < a.topk; ++j) {
                 wsel[j] /= tot + 1e-6f;
-                if (a.topk > 1 && (float)(j + 1) > keep) wsel[j] = 0.f;
+                if (!a.zero_cost && a.topk > 1 && (float)(j + 1) > keep) wsel[j] = 0.f;
                 tot2 += wsel[j];
             }
-            for (int j = 0; j < a.topk; ++j)
-                a.w[(long long)b * a.topk + j] = a.topk > 1 ? wsel[j] / (tot2 < 1e-6f ? 1e-6f : tot2) : wsel[j];
+            for (int j = 0; j < a.topk; ++j) {
+                float v = wsel[j];
+                if (a.zero_cost) v *= cscale;
+                else if (a.topk > 1) v /= tot2 < 1e-6f ? 1e-6f : tot2;
+                a.w[(long long)b * a.topk + j] = v;
+            }
         }
     }
 }

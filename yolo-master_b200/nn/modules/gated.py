@@ -33,7 +33,7 @@ from .mot import _f32, _pack_dw, _pack_linear
 __all__ = ("DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup", "VisualDetailGate",
            "PyramidContextMixer", "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
            "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE",
-           "ContextRefinedLowRankHybridAdaptiveGateMoE", "VisualEnhancedAdaptiveGateMoE")
+           "ContextRefinedLowRankHybridAdaptiveGateMoE", "VisualEnhancedAdaptiveGateMoE", "ZeroCostRouter", "UltimateOptimizedMoE")
 
 
 def _gn(channels: int, groups: int = 8) -> nn.GroupNorm:
@@ -465,3 +465,93 @@ class VisualEnhancedAdaptiveGateMoE(LowRankHybridAdaptiveGateMoE):
     initial_temperature=1.2, final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
     fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5, refine_reduction=8, detail_reduction=8)` (gated.py:1703-1756)."""
     HOOKS = ("detail", "context", "refine")
+
+
+class ZeroCostRouter(nn.Module):
+    """`ZeroCostRouter(in_channels, num_experts, top_k, temperature=1.0)` (gated.py:938-1000; `UltraLightRouter` :2710-2724 adds
+    nothing at inference): Linear over [mean | std] -> Softmax, executed inside `ym_zero_cost_router`."""
+
+    def __init__(self, in_channels, num_experts, top_k, temperature=1.0, use_cache=True):
+        super().__init__()
+        self.num_experts, self.top_k, self.temperature = num_experts, top_k, temperature
+        self.router = nn.Sequential(nn.Linear(2 * in_channels, num_experts, bias=False), nn.Softmax(dim=1))
+
+
+class _BalanceController(nn.Module):
+    """State of `AdaptiveBalanceController` (gated.py:1767-1843): one parameter, used by the training loss only."""
+
+    def __init__(self, num_experts):
+        super().__init__()
+        self.expert_importance = nn.Parameter(torch.ones(num_experts))
+
+
+class UltimateOptimizedMoE(nn.Module, PackCache):
+    """`UltimateOptimizedMoE(in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, use_routing_cache=True,
+    capacity_factor=1.5, initial_temperature=2.0, final_temperature=0.5, entropy_coeff=0.01)` (moe/modules.py:1534-1742, v0_3 zoo):
+    plain channel split, static path, ZeroCostRouter, complexity-scaled weights, fused expert group, projection + GroupNorm + x."""
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, use_routing_cache=True,
+                 capacity_factor=1.5, initial_temperature=2.0, final_temperature=0.5, entropy_coeff=0.01):
+        super().__init__()
+        if in_channels != out_channels:
+            raise ValueError("UltimateOptimizedMoE: the residual `proj(...) + x` needs in_channels == out_channels")
+        self.in_channels, self.out_channels, self.num_experts, self.top_k = in_channels, out_channels, num_experts, top_k
+        self.initial_temperature, self.final_temperature = initial_temperature, final_temperature
+        self.dynamic_channels = int(in_channels * split_ratio)
+        self.static_channels = in_channels - self.dynamic_channels
+        self.out_dynamic = int(out_channels * split_ratio)
+        self.out_static = out_channels - self.out_dynamic
+        for n in (self.dynamic_channels, self.static_channels, self.out_dynamic, self.out_static):
+            if n % 8:
+                raise NotImplementedError("UltimateOptimizedMoE: channel halves must be multiples of 8 on the B200 path")
+        sc = self.static_channels
+        self.static_net = nn.Sequential(
+            nn.Conv2d(sc, sc, 3, padding=1, groups=sc, bias=False), nn.BatchNorm2d(sc), nn.SiLU(inplace=True),
+            nn.Conv2d(sc, self.out_static, 1, bias=False), nn.BatchNorm2d(self.out_static), nn.SiLU(inplace=True))
+        self.routing = ZeroCostRouter(self.dynamic_channels, num_experts, top_k, temperature=initial_temperature, use_cache=use_routing_cache)
+        self.fused_experts = FusedExpertGroup(self.dynamic_channels, self.out_dynamic, num_experts, num_groups)
+        self.complexity_estimator = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(self.dynamic_channels, 1, 1), nn.Sigmoid())
+        self.register_buffer("current_top_k", torch.tensor(num_experts))
+        self.balance_controller = _BalanceController(num_experts)
+        self.proj = nn.Conv2d(out_channels, out_channels, 1, bias=False)
+        self.bn = _gn(out_channels, num_groups)
+        self.expert_backend = "fused"
+        self.last_routing_snapshot: dict = {}
+
+    def _build_pack(self):
+        pk = {}
+        w, b = fold_bn(self.static_net[0].weight, None, self.static_net[1])
+        pk["st_dw"], pk["st_dw_b"] = _pack_dw(w), b.contiguous()
+        w, b = fold_bn(self.static_net[3].weight, None, self.static_net[4])
+        pk["st_pw"] = (pack_gemm_weight(w), b.contiguous())
+        pk["fc"] = _f32(self.routing.router[0].weight)
+        ce = self.complexity_estimator[1]
+        pk["cx_w"], pk["cx_b"] = _f32(ce.weight).reshape(-1).contiguous(), float(ce.bias.detach().float())
+        pk["fused_w"] = pack_gemm_weight(self.fused_experts.dense_weight())
+        pk["fused_gamma"], pk["fused_beta"] = _f32(self.fused_experts.expert_norm_weight), _f32(self.fused_experts.expert_norm_bias)
+        pk["proj"], pk["bn"] = _pack_linear(self.proj.weight), _gn_args(self.bn)
+        return pk
+
+    def fwd_nhwc(self, x, out=None):
+        require_eval(self)
+        B, H, W, C = x.shape
+        st_c = self.static_channels
+        pk = self.get_pack()
+        xs, xd = x[..., :st_c], x[..., st_c:]
+        cat = ops.new_act(B, H, W, C, x.device)
+        ts = ops.dwconv(xs, pk["st_dw"], pk["st_dw_b"], 3, True, st_c)
+        ops.conv2d(ts, *pk["st_pw"], self.out_static, 1, 1, 1, 0, True, out=cat[..., :self.out_static])
+        idx, w, probs = ops.zero_cost_router(xd, pk["fc"], self.routing.temperature, pk["cx_w"], pk["cx_b"], self.top_k)
+        self.last_routing_snapshot = {"topk_indices": idx, "topk_weights": w, "router_probs": probs}
+        E, oc = self.num_experts, self.out_dynamic
+        fo = ops.conv2d(xd, pk["fused_w"], None, E * oc, 3, 3, 1, 1, False)
+        ops.gated_select(fo, idx, w, pk["fused_gamma"], pk["fused_beta"], E, oc, self.fused_experts.norm_groups, 1e-5,
+                         out=cat[..., self.out_static:])
+        return _norm(ops.conv2d(cat, *pk["proj"], C, 1, 1, 1, 0, False), pk["bn"], add=x, out=out)
+
+    def forward(self, x):
+        return to_nchw(self.fwd_nhwc(to_nhwc(x)))
+
+    @property
+    def aux_loss(self):
+        return torch.zeros((), device=self.proj.weight.device)

@@ -569,6 +569,21 @@ def gate_router(x, pk, topk):
     return idx, w, probs
 
 
+def zero_cost_router(x, fc, temperature, cx_w, cx_b, topk):
+    """ym_zero_cost_router.  x: (B,H,W,C) fp16 view; fc fp32 [E,2C]; cx_w fp32 [C].  Returns (idx int32 [B,k], w fp32 [B,k], probs)."""
+    B, H, W, Cc = x.shape
+    E = fc.shape[0]
+    w = torch.empty((B, topk), dtype=torch.float32, device=x.device)
+    idx = torch.empty((B, topk), dtype=torch.int32, device=x.device)
+    probs = torch.empty((B, E), dtype=torch.float32, device=x.device)
+    scratch = torch.empty((lib().ym_zero_cost_router_scratch_floats(B, Cc),), dtype=torch.float32, device=x.device)
+    _lib.check(lib().ym_zero_cost_router(x.data_ptr(), pitch(x), B, H, W, Cc, fc.data_ptr(), E, float(temperature), cx_w.data_ptr(),
+                                         float(cx_b), topk, scratch.data_ptr(), w.data_ptr(), idx.data_ptr(), probs.data_ptr(), _stream()),
+               "ym_zero_cost_router")
+    _count(2)
+    return idx, w, probs
+
+
 def fc_gate(v, w1, w2, b2, scale=1.0):
     """ym_fc_gate.  v: (B,1,1,Cin) fp16 pooled vector; w1 fp32 [Cr,Cin], w2 fp32 [Cout,Cr], b2 fp32 [Cout] or None -> fp32 (B, Cout)."""
     B, Cin = v.shape[0], v.shape[3]
