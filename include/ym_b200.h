@@ -192,7 +192,9 @@ int ym_adaptive_avgpool_nhwc(const void* x, int ldx, int B, int H, int W, int C,
  *                  -> 1x1 (pw2 [E][R]) + b2 -> spatial mean;
  *   logits = clamp(alpha*global + (1-alpha)*local, +-30) (alpha = sigmoid(self.alpha), passed as a value), softmax(/temperature),
  *   top-k, w / (sum + 1e-6); complexity c = clamp(mean over the BATCH of sigmoid(cx_w . mean_c + cx_b), 0.3, 1.5) keeps the
- *   round(c*topk) best ranks and renormalises.  Outputs: w fp32 [B][topk], idx int32 [B][topk], probs fp32 [B][E] (nullable).
+ *   round(c*topk) best ranks and renormalises.  DualStreamGateRouterV2 (gated.py:181-260, v0_11 / v0_12 zoos): ln_w / ln_b fp32 [2C]
+ *   (nullable pair) = LayerNorm over the statistics in front of global_fc, prior fp32 [E] (nullable) added to the blended logits
+ *   before the clamp.  Outputs: w fp32 [B][topk], idx int32 [B][topk], probs fp32 [B][E] (nullable).
  *   scratch: ym_gate_router_scratch_floats() floats.  Three kernels, no host synchronisation.
  * ym_fc_gate: out[b][o] = scale * sigmoid(b2[o] + w2[o] . silu(w1 . v[b]))   v fp16 [B][ldv] (a 1x1 adaptive average pool):
  *   se_gate gated.py:325-332 (scale 1), feature_gate moe/hooks.py:50-57 (scale = tanh(refine_scale)); consumed by ym_ew_nhwc op 4.
@@ -204,8 +206,8 @@ long long ym_gate_router_scratch_floats(int B, int H, int W, int C, int R, int E
 int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* global_fc, const float* dw,
                    const float* gn1_w, const float* gn1_b, int G1, const float* pw1, int R, const float* gn2_w,
                    const float* gn2_b, int G2, const float* pw2, const float* b2, int E, float gn_eps, float alpha,
-                   float temperature, const float* cx_w, float cx_b, int topk, float* scratch, float* w_out, int* idx_out,
-                   float* probs_out, void* stream);
+                   float temperature, const float* cx_w, float cx_b, int topk, const float* ln_w, const float* ln_b, float ln_eps,
+                   const float* prior, float* scratch, float* w_out, int* idx_out, float* probs_out, void* stream);
 /* ZeroCostRouter.forward gated.py:953-968 (UltraLightRouter of UltimateOptimizedMoE, v0_3 zoo) + the complexity SCALE of
  * UltimateOptimizedMoE.forward modules.py:1663-1670: probs = softmax(clamp(softmax(fc . [mean | std]) / T, +-30)), top-k,
  * w / (sum + 1e-6), then w *= clamp(mean over the batch of sigmoid(cx_w . mean_c + cx_b), 0.3, 1.5).  fc fp32 [E][2C].

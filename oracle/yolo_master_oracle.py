@@ -938,7 +938,10 @@ def dual_stream_gate_router(sd, p, x, top_k, temperature, pool_scale=4):
     xf = x.float()
     mean = xf.mean((2, 3))
     std = xf.std((2, 3), unbiased=False) if H * W > 1 else torch.zeros_like(mean)
-    gl = F.linear(torch.cat([mean, std], 1), sd[p + ".global_fc.weight"])
+    stats = torch.cat([mean, std], 1)
+    if p + ".stat_norm.weight" in sd:      # DualStreamGateRouterV2 gated.py:181-260 (v0_11 / v0_12): LayerNorm on the statistics
+        stats = F.layer_norm(stats, (2 * C,), sd[p + ".stat_norm.weight"], sd[p + ".stat_norm.bias"], 1e-5)
+    gl = F.linear(stats, sd[p + ".global_fc.weight"])
     xl = F.avg_pool2d(xf, pool_scale, pool_scale) if (H > pool_scale and W > pool_scale) else xf
     t = F.conv2d(xl, sd[p + ".local_conv.0.weight"], None, 1, 1, 1, C)
     t = F.silu(_gn(sd, p + ".local_conv.1", t, get_safe_groups(C, 8)))
@@ -946,7 +949,10 @@ def dual_stream_gate_router(sd, p, x, top_k, temperature, pool_scale=4):
     t = F.silu(_gn(sd, p + ".local_conv.4", t, get_safe_groups(t.shape[1], 4)))
     ll = F.conv2d(t, sd[p + ".local_conv.6.weight"], sd[p + ".local_conv.6.bias"]).mean((2, 3))
     a = torch.sigmoid(sd[p + ".alpha"])
-    logits = (a * gl + (1 - a) * ll).clamp(-30.0, 30.0)
+    logits = a * gl + (1 - a) * ll
+    if p + ".expert_prior" in sd:          # ... and a learnable per-expert prior, added before the clamp
+        logits = logits + sd[p + ".expert_prior"].view(1, -1)
+    logits = logits.clamp(-30.0, 30.0)
     probs = F.softmax(logits / temperature, dim=1)
     w, idx = torch.topk(probs, top_k, dim=1)
     return w / (w.sum(1, keepdim=True) + 1e-6), idx, probs
@@ -1029,6 +1035,16 @@ def feature_refine(sd, p, x, groups=8):
     return _st(x + torch.tanh(sd[p + ".refine_scale"]) * r * g)
 
 
+def light_refine(sd, p, x, groups=8):
+    """`OptimalHybridGateMoE._apply_refine` gated.py:1958-1961 (v0_12): x + tanh(scale) * GN(dw3x3(x)) * SE(x) - no activation on
+    the depthwise branch, unlike `feature_refine`."""
+    C = x.shape[1]
+    r = _gn(sd, p + ".refine_dw.1", F.conv2d(x, _w(sd[p + ".refine_dw.0.weight"]), None, 1, 1, 1, C), get_safe_groups(C, groups))
+    g = F.silu(F.conv2d(x.mean((2, 3), keepdim=True), _w(sd[p + ".refine_gate.1.weight"])))
+    g = torch.sigmoid(F.conv2d(g, _w(sd[p + ".refine_gate.3.weight"]), sd[p + ".refine_gate.3.bias"]))
+    return _st(x + torch.tanh(sd[p + ".refine_scale"]) * r * g)
+
+
 def gated_moe_forward(sd, p, x, c1, c2, num_experts, top_k, split_ratio, num_groups, temperature, backend, shuffle_groups, hooks,
                       return_route=False):
     """Eval forward shared by the whole AdaptiveGateMoE line: `AdaptiveGateMoE.forward` gated.py:508-555 (v0.4, v0.5),
@@ -1068,6 +1084,8 @@ def gated_moe_forward(sd, p, x, c1, c2, num_experts, top_k, split_ratio, num_gro
             cat = pyramid_context_mixer(sd, p + ".context_mixer", cat, num_groups)
         elif h == "refine":
             cat = feature_refine(sd, p, cat, num_groups)
+        elif h == "light_refine":
+            cat = light_refine(sd, p, cat, num_groups)
     out = _st(_gn(sd, p + ".bn", F.conv2d(cat, _w(sd[p + ".proj.weight"])), get_safe_groups(c2, num_groups)) + x)
     return (out, w, idx, probs) if return_route else out
 
@@ -1083,6 +1101,8 @@ GATED_VARIANTS = {
     "DetailAwareLowRankHybridAdaptiveGateMoE": (1.2, True, True, True, ("detail",)),                 # v0.9
     "ContextRefinedLowRankHybridAdaptiveGateMoE": (1.2, True, True, True, ("context", "refine")),
     "VisualEnhancedAdaptiveGateMoE": (1.2, True, True, True, ("detail", "context", "refine")),       # v0.10
+    "HybridAdaptiveGateMoEv2": (1.2, True, False, True, ()),                 # v0.11: v0.6 + DualStreamGateRouterV2 (keys in the sd)
+    "OptimalHybridGateMoE": (1.2, True, False, True, ("light_refine",)),     # v0.12: + depthwise refinement
 }
 
 

@@ -312,10 +312,11 @@ def gated_family_golden():
     from ultralytics.nn.modules.moe import gated as G
     out = {}
     from ultralytics.nn.modules.moe import modules as MM
-    for ci, name in enumerate(GATED_FAMILY + ["UltimateOptimizedMoE"]):
+    for ci, name in enumerate(GATED_FAMILY + ["UltimateOptimizedMoE", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE"]):
         for E in (4, 16):
             torch.manual_seed(0)
-            m = getattr(G if hasattr(G, name) and name != "UltimateOptimizedMoE" else MM, name)(64, 64, E, 2, 0.5).eval()
+            split = 0.375 if (E == 16 and name in ("HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE")) else 0.5   # the v0_11 / v0_12 P5 setting
+            m = getattr(G if hasattr(G, name) and name != "UltimateOptimizedMoE" else MM, name)(64, 64, E, 2, split).eval()
             for mod in m.modules():                      # inside a model every BatchNorm2d runs with eps = 1e-3
                 if isinstance(mod, torch.nn.BatchNorm2d):   # (initialize_weights, utils/torch_utils.py:552-562)
                     mod.eps = 1e-3
@@ -328,7 +329,7 @@ def gated_family_golden():
             with torch.no_grad():
                 y = m(x)
             h.remove()
-            out[f"{name}/E{E}"] = {"seed": 300 + ci, "xseed": 400 + ci, "y": y.clone(), "route_w": route["w"], "route_idx": route["idx"],
+            out[f"{name}/E{E}"] = {"seed": 300 + ci, "xseed": 400 + ci, "split": split, "y": y.clone(), "route_w": route["w"], "route_idx": route["idx"],
                                    "keys": {k: list(v.shape) for k, v in sd.items()},
                                    "scalars": {k: v.clone() for k, v in sd.items() if v.dim() == 0 and v.is_floating_point()},   # left at init
                                    "backend": getattr(m, "expert_backend", "fused" if name == "UltimateOptimizedMoE" else "shared_inverted")}

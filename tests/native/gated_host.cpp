@@ -12,7 +12,8 @@ extern "C" int host_gate_router(const void* x, int ldx, int B, int H, int W, int
                                 const float* dw, const float* gn1_w, const float* gn1_b, int G1, const float* pw1, int R,
                                 const float* gn2_w, const float* gn2_b, int G2, const float* pw2, const float* b2, int E,
                                 float gn_eps, float alpha, float temperature, const float* cx_w, float cx_b, int topk,
-                                float* w_out, int* idx_out, float* probs_out) {
+                                const float* ln_w, const float* ln_b, float ln_eps, const float* prior, float* w_out, int* idx_out,
+                                float* probs_out) {
     const bool pooling = pool > 1 && H > pool && W > pool;
     const int eff = pooling ? pool : 1, Hp = H / eff, Wp = W / eff;
     const long long N = (long long)Hp * Wp;
@@ -38,7 +39,7 @@ extern "C" int host_gate_router(const void* x, int ldx, int B, int H, int W, int
     R2Args a2;
     a2.stats = stats.data(); a2.ll = ll.data(); a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha;
     a2.inv_temp = 1.f / temperature; a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.cx = cx.data(); a2.w = w_out;
-    a2.probs = probs_out; a2.idx = idx_out;
+    a2.probs = probs_out; a2.idx = idx_out; a2.ln_w = ln_w; a2.ln_b = ln_b; a2.ln_eps = ln_eps; a2.prior = prior;
     for (int ph = 0; ph < R2_PHASES; ++ph)
         for (int t = 0; t < NTHR; ++t) r2_phase(ph, a2, t, NTHR, sm.data());
     return 0;
@@ -56,7 +57,7 @@ extern "C" int host_zero_cost_router(const void* x, int ldx, int B, int H, int W
     R2Args a2;
     a2.stats = stats.data(); a2.ll = nullptr; a2.wg = fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = 1.f; a2.inv_temp = 1.f / temperature;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.cx = cx.data(); a2.w = w_out; a2.probs = probs_out;
-    a2.idx = idx_out;
+    a2.idx = idx_out; a2.ln_w = nullptr; a2.ln_b = nullptr; a2.ln_eps = 0.f; a2.prior = nullptr;
     for (int ph = 0; ph < R2_PHASES; ++ph)
         for (int t = 0; t < NTHR; ++t) r2_phase(ph, a2, t, NTHR, sm.data());
     return 0;

@@ -164,7 +164,7 @@ def test_family_class_matches_reference_module_golden(emu, key):
     from yolo_master_b200.utils.synth import fill_state_dict_
     name, E = key.split("/E")
     c = FAMILY[key]
-    m = getattr(gated, name)(64, 64, int(E), 2, 0.5)
+    m = getattr(gated, name)(64, 64, int(E), 2, c["split"])
     assert m.expert_backend == c["backend"]
     sd = m.state_dict()
     assert {k: list(v.shape) for k, v in sd.items()} == c["keys"]
@@ -176,10 +176,10 @@ def test_family_class_matches_reference_module_golden(emu, key):
     with torch.no_grad():
         y = m.fwd_nhwc(x.half().permute(0, 2, 3, 1).contiguous()).float().permute(0, 3, 1, 2)
     xq = x.half().float()
-    ref, _, ri, _ = O._LAYER_FN[name](sdm, "m", xq, 64, 64, int(E), 2, 0.5, return_route=True)
+    ref, _, ri, _ = O._LAYER_FN[name](sdm, "m", xq, 64, 64, int(E), 2, c["split"], return_route=True)
     assert torch.equal(m.last_routing_snapshot["topk_indices"].long(), ri)
     with O.fp16_storage(), O.fp16_weights():
-        sim = O._LAYER_FN[name](sdm, "m", xq, 64, 64, int(E), 2, 0.5)
+        sim = O._LAYER_FN[name](sdm, "m", xq, 64, 64, int(E), 2, c["split"])
     assert emu.report(key, y, ref, sim)
     assert float((y - c["y"]).abs().max()) < 3e-2               # and stays close to the reference module's own fp32 output
 
@@ -229,6 +229,10 @@ def test_gated_zoo_yamls_build():
             assert sum(p.numel() for p in m.parameters()) == nparam
         assert DetectionModel(f"master/{ver}/det/yolo-master-s.yaml").model[5].in_channels == 256
     assert type(DetectionModel("yolo-master-n.yaml").model[3]).__name__ == "ES_MOE"        # a bare name still resolves to the v0 zoo
+    for cfg, cls in (("master/v0_12/det/yolo-master-n.yaml", "OptimalHybridGateMoE"), ("master/exp/yolo-master-v0_11.yaml", "HybridAdaptiveGateMoEv2")):
+        m = DetectionModel(cfg)
+        assert [type(m.model[i]).__name__ for i in (5, 8, 11)] == [cls] * 3 and m.model[11].dynamic_channels == 96
+        assert type(m.model[5].routing).__name__ == "DualStreamGateRouterV2"
     for sc in "nsmlx":                                          # v0_3 zoo: UltimateOptimizedMoE
         m = DetectionModel(f"master/v0_3/det/yolo-master-{sc}.yaml")
         assert [type(m.model[i]).__name__ for i in (5, 8, 11)] == ["UltimateOptimizedMoE"] * 3

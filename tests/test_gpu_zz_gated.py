@@ -111,7 +111,7 @@ def test_family_class_matches_reference_module_golden(key):
     from yolo_master_b200.nn.modules import gated
     name, E = key.split("/E")
     c = FAMILY[key]
-    m = getattr(gated, name)(64, 64, int(E), 2, 0.5)
+    m = getattr(gated, name)(64, 64, int(E), 2, c["split"])
     sd = m.state_dict()
     fill_state_dict_(sd, c["seed"])
     m.load_state_dict(sd, strict=True)
@@ -120,10 +120,10 @@ def test_family_class_matches_reference_module_golden(key):
     x = torch.randn((2, 64, 12, 12), generator=torch.Generator().manual_seed(c["xseed"])).half().float()
     with torch.no_grad():
         y = m(x.half().to(DEV).contiguous(memory_format=torch.channels_last))
-    ref, _, ri, _ = O._LAYER_FN[name](sdm, "m", x, 64, 64, int(E), 2, 0.5, return_route=True)
+    ref, _, ri, _ = O._LAYER_FN[name](sdm, "m", x, 64, 64, int(E), 2, c["split"], return_route=True)
     assert torch.equal(m.last_routing_snapshot["topk_indices"].long().cpu(), ri)
     with O.fp16_storage(), O.fp16_weights():
-        sim = O._LAYER_FN[name](sdm, "m", x, 64, 64, int(E), 2, 0.5)
+        sim = O._LAYER_FN[name](sdm, "m", x, 64, 64, int(E), 2, c["split"])
     assert_within_noise(y, ref, sim, what=key)
     assert float((y.float().cpu() - c["y"]).abs().max()) < 3e-2
 

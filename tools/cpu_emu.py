@@ -202,7 +202,7 @@ def install_gated(host):
     import ctypes as C
     vp, ci, cf = C.c_void_p, C.c_int, C.c_float
     host.host_gate_router.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, ci, cf, cf, cf, vp, cf,
-                                      ci, vp, vp, vp]
+                                      ci, vp, vp, cf, vp, vp, vp, vp]
     host.host_zero_cost_router.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci, cf, vp, cf, ci, vp, vp, vp]
     host.host_fc_gate.argtypes = [vp, ci, ci, ci, vp, ci, vp, vp, ci, cf, vp]
     host.host_gated_select.argtypes = [vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, ci, vp, vp, vp, ci]
@@ -217,10 +217,13 @@ def install_gated(host):
         w = torch.empty((B, topk), dtype=torch.float32)
         idx = torch.empty((B, topk), dtype=torch.int32)
         probs = torch.empty((B, pk["E"]), dtype=torch.float32)
+        ln, prior = pk.get("stat_norm"), pk.get("prior")
         host.host_gate_router(x.data_ptr(), ld(x), B, H, W, Cc, pk["pool"], pk["global_fc"].data_ptr(), pk["dw"].data_ptr(),
                               pk["gn1_w"].data_ptr(), pk["gn1_b"].data_ptr(), pk["G1"], pk["pw1"].data_ptr(), pk["R"],
                               pk["gn2_w"].data_ptr(), pk["gn2_b"].data_ptr(), pk["G2"], pk["pw2"].data_ptr(), pk["b2"].data_ptr(), pk["E"],
-                              pk["eps"], pk["alpha"], pk["temperature"], pk["cx_w"].data_ptr(), pk["cx_b"], topk, w.data_ptr(),
+                              pk["eps"], pk["alpha"], pk["temperature"], pk["cx_w"].data_ptr(), pk["cx_b"], topk,
+                              None if ln is None else ln[0].data_ptr(), None if ln is None else ln[1].data_ptr(),
+                              0.0 if ln is None else ln[2], None if prior is None else prior.data_ptr(), w.data_ptr(),
                               idx.data_ptr(), probs.data_ptr())
         return idx, w, probs
 

@@ -111,12 +111,14 @@ extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C
                               const float* dw, const float* gn1_w, const float* gn1_b, int G1, const float* pw1, int R,
                               const float* gn2_w, const float* gn2_b, int G2, const float* pw2, const float* b2, int E,
                               float gn_eps, float alpha, float temperature, const float* cx_w, float cx_b, int topk,
-                              float* scratch, float* w_out, int* idx_out, float* probs_out, void* stream) {
+                              const float* ln_w, const float* ln_b, float ln_eps, const float* prior, float* scratch,
+                              float* w_out, int* idx_out, float* probs_out, void* stream) {
     YM_CHECK_ARG(x && scratch && w_out && idx_out, "ym_gate_router: null pointer");
     YM_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R > 0, "ym_gate_router: empty problem");
     YM_CHECK_ARG(E >= 1 && E <= MAXE && topk >= 1 && topk <= E, "ym_gate_router: 1 <= topk <= E <= %d", MAXE);
     YM_CHECK_ARG(G1 >= 1 && G1 <= MAXG && C % G1 == 0 && G2 >= 1 && G2 <= MAXG && R % G2 == 0, "ym_gate_router: GroupNorm groups");
     YM_CHECK_ARG(temperature > 0.f, "ym_gate_router: temperature must be positive");
+    YM_CHECK_ARG((ln_w == nullptr) == (ln_b == nullptr), "ym_gate_router: LayerNorm weight and bias come together");
     int Hp, Wp, eff;
     pooled_dims(H, W, pool, &Hp, &Wp, &eff);
     const long long N = (long long)Hp * Wp;
@@ -139,6 +141,7 @@ extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C
     R2Args a2;
     a2.stats = stats; a2.ll = ll; a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha; a2.inv_temp = 1.f / temperature;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
+    a2.ln_w = ln_w; a2.ln_b = ln_b; a2.ln_eps = ln_eps; a2.prior = prior;
     gate_r2_kernel<<<1, NTHR, 0, st>>>(a2);
     YM_CHECK_LAUNCH("gate_router");
     return YM_OK;
@@ -163,6 +166,7 @@ extern "C" int ym_zero_cost_router(const void* x, int ldx, int B, int H, int W, 
     R2Args a2;
     a2.stats = stats; a2.ll = nullptr; a2.wg = fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = 1.f; a2.inv_temp = 1.f / temperature;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
+    a2.ln_w = nullptr; a2.ln_b = nullptr; a2.ln_eps = 0.f; a2.prior = nullptr;
     gate_r2_kernel<<<1, NTHR, 0, st>>>(a2);
     YM_CHECK_LAUNCH("zero_cost_router");
     return YM_OK;

@@ -250,6 +250,9 @@ struct R2Args {
     const float* wg;      // [E][2C] global_fc
     const float *wc;      // [C] complexity_estimator conv weight
     float bc, alpha, inv_temp;   // alpha = sigmoid(self.alpha)
+    const float *ln_w, *ln_b;    // [2C] LayerNorm over the statistics in front of global_fc (DualStreamGateRouterV2 gated.py:215,226), or null
+    float ln_eps;
+    const float* prior;          // [E] learnable expert prior added to the blended logits before the clamp (gated.py:216,238), or null
     int B, C, E, topk;
     int zero_cost;        // 0: DualStreamGateRouter + complexity GATE (ranks dropped);  1: ZeroCostRouter (gated.py:953-968: softmax of
                           //    the global stream, / T, clamp, softmax again) + complexity SCALE (weights multiplied, modules.py:1663-1670)
@@ -283,12 +286,24 @@ YM_HD void r2_phase(int ph, const R2Args& a, int tid, int nthr, float* sm) {
         for (int b = tid; b < a.B; b += nthr) {
             float p[MAXE];
             float mx = -3.0e38f;
+            const float* st = a.stats + (long long)b * 2 * a.C;
+            float lm = 0.f, lr = 1.f;
+            if (a.ln_w) {                                             // LayerNorm statistics of this image's [mean | std] row
+                for (int j = 0; j < 2 * a.C; ++j) lm += st[j];
+                lm /= (float)(2 * a.C);
+                float v = 0.f;
+                for (int j = 0; j < 2 * a.C; ++j) v += (st[j] - lm) * (st[j] - lm);
+                lr = 1.f / sqrtf(v / (float)(2 * a.C) + a.ln_eps);
+            }
             for (int e = 0; e < a.E; ++e) {
                 float gl = 0.f;
                 const float* w = a.wg + (long long)e * 2 * a.C;
-                const float* st = a.stats + (long long)b * 2 * a.C;
-                for (int j = 0; j < 2 * a.C; ++j) gl += w[j] * st[j];
+                if (a.ln_w)
+                    for (int j = 0; j < 2 * a.C; ++j) gl += w[j] * ((st[j] - lm) * lr * a.ln_w[j] + a.ln_b[j]);
+                else
+                    for (int j = 0; j < 2 * a.C; ++j) gl += w[j] * st[j];
                 float l = a.zero_cost ? gl : a.alpha * gl + (1.f - a.alpha) * a.ll[(long long)b * a.E + e];
+                if (a.prior) l += a.prior[e];
                 if (!a.zero_cost) {
                     l = l < -30.f ? -30.f : (l > 30.f ? 30.f : l);
                     l *= a.inv_temp;

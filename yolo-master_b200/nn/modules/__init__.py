@@ -4,7 +4,8 @@ from .conv import Concat, Conv, DWConv, PlainConv2d, Upsample, autopad
 from .gated import (AdaptiveGateMoE, ContextRefinedLowRankHybridAdaptiveGateMoE, DetailAwareLowRankHybridAdaptiveGateMoE,
                     DualStreamGateRouter, FusedAdaptiveGateMoE, FusedExpertGroup, HybridAdaptiveGateMoE, LowRankFusedExpertGroup,
                     LowRankHybridAdaptiveGateMoE, PyramidContextMixer, RefinedLowRankHybridAdaptiveGateMoE, SharedInvertedExpertGroup,
-                    UltimateOptimizedMoE, VisualDetailGate, VisualEnhancedAdaptiveGateMoE, ZeroCostRouter)
+                    UltimateOptimizedMoE, VisualDetailGate, VisualEnhancedAdaptiveGateMoE, ZeroCostRouter, DualStreamGateRouterV2,
+                    HybridAdaptiveGateMoEv2, OptimalHybridGateMoE)
 from .head import DFL, Detect
 from .moa import C2fMoA, MoABlock
 from .mot import C2fMoT, MoTBlock
@@ -22,6 +23,7 @@ __all__ = (
     "Detect", "DFL", "C2fMoT", "MoTBlock", "C2fMoA", "MoABlock",
     "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
     "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE", "ContextRefinedLowRankHybridAdaptiveGateMoE",
-    "VisualEnhancedAdaptiveGateMoE", "UltimateOptimizedMoE", "ZeroCostRouter", "DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup",
+    "VisualEnhancedAdaptiveGateMoE", "UltimateOptimizedMoE", "ZeroCostRouter", "DualStreamGateRouterV2", "HybridAdaptiveGateMoEv2",
+    "OptimalHybridGateMoE", "DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup",
     "VisualDetailGate", "PyramidContextMixer",
 )

@@ -33,7 +33,7 @@ from .mot import _f32, _pack_dw, _pack_linear
 __all__ = ("DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup", "VisualDetailGate",
            "PyramidContextMixer", "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
            "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE",
-           "ContextRefinedLowRankHybridAdaptiveGateMoE", "VisualEnhancedAdaptiveGateMoE", "ZeroCostRouter", "UltimateOptimizedMoE")
+           "ContextRefinedLowRankHybridAdaptiveGateMoE", "VisualEnhancedAdaptiveGateMoE", "ZeroCostRouter", "UltimateOptimizedMoE", "DualStreamGateRouterV2", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE")
 
 
 def _gn(channels: int, groups: int = 8) -> nn.GroupNorm:
@@ -72,6 +72,22 @@ class DualStreamGateRouter(nn.Module):
             "gn2_w": _f32(lc[4].weight), "gn2_b": _f32(lc[4].bias), "pw2": _f32(lc[6].weight).reshape(E, R).contiguous(),
             "b2": _f32(lc[6].bias), "alpha": float(torch.sigmoid(self.alpha.detach().float())), "temperature": float(self.temperature),
         }
+
+
+class DualStreamGateRouterV2(DualStreamGateRouter):
+    """`DualStreamGateRouterV2(in_channels, num_experts, top_k, temperature=1.0, local_reduction=16, pool_scale=4, noise_std=0.1)`
+    (gated.py:181-260, v0_11 / v0_12 zoos): LayerNorm on the channel statistics + a learnable expert prior on the logits."""
+
+    def __init__(self, in_channels, num_experts, top_k, temperature=1.0, local_reduction=16, pool_scale=4, noise_std=0.1):
+        super().__init__(in_channels, num_experts, top_k, temperature, local_reduction, pool_scale)
+        self.stat_norm = nn.LayerNorm(2 * in_channels)
+        self.expert_prior = nn.Parameter(torch.zeros(num_experts))
+
+    def pack(self):
+        pk = super().pack()
+        pk["stat_norm"] = (_f32(self.stat_norm.weight), _f32(self.stat_norm.bias), float(self.stat_norm.eps))
+        pk["prior"] = _f32(self.expert_prior)
+        return pk
 
 
 class FusedExpertGroup(nn.Module):
@@ -185,7 +201,7 @@ class _GatedMoE(nn.Module, PackCache):
 
     def __init__(self, in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
                  backend, shuffle_groups=1, bottleneck_ratio=0.5, hooks=(), refine_reduction=8, detail_reduction=8,
-                 fused_expert_threshold=8):
+                 fused_expert_threshold=8, router_v2=False):
         super().__init__()
         if in_channels != out_channels:
             raise ValueError(f"{type(self).__name__}: the residual `proj(...) + x` needs in_channels == out_channels")
@@ -206,7 +222,8 @@ class _GatedMoE(nn.Module, PackCache):
         self.static_net = nn.Sequential(
             nn.Conv2d(sc, sc, 3, padding=1, groups=sc, bias=False), nn.BatchNorm2d(sc), nn.SiLU(inplace=False),
             nn.Conv2d(sc, self.out_static, 1, bias=False), nn.BatchNorm2d(self.out_static), nn.SiLU(inplace=False))
-        self.routing = DualStreamGateRouter(self.dynamic_channels, num_experts, top_k, temperature=initial_temperature)
+        self.routing = (DualStreamGateRouterV2 if router_v2 else DualStreamGateRouter)(self.dynamic_channels, num_experts, top_k,
+                                                                                        temperature=initial_temperature)
         self.fused_expert_threshold = fused_expert_threshold
         self.shuffle_groups = shuffle_groups if (shuffle_groups and out_channels % shuffle_groups == 0) else 1
         self.expert_backend = backend
@@ -231,6 +248,12 @@ class _GatedMoE(nn.Module, PackCache):
                                                  nn.SiLU(inplace=False))
             self.feature_gate = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(oc, hidden, 1, bias=False), nn.SiLU(inplace=False),
                                               nn.Conv2d(hidden, oc, 1, bias=True), nn.Sigmoid())
+            self.refine_scale = nn.Parameter(torch.tensor(0.1))
+        if "light_refine" in hooks:   # OptimalHybridGateMoE gated.py:1927-1943: depthwise + GroupNorm (no activation), SE gate
+            hidden = max(oc // refine_reduction, 8)
+            self.refine_dw = nn.Sequential(nn.Conv2d(oc, oc, 3, padding=1, groups=oc, bias=False), _gn(oc, num_groups))
+            self.refine_gate = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(oc, hidden, 1, bias=False), nn.SiLU(inplace=False),
+                                             nn.Conv2d(hidden, oc, 1, bias=True), nn.Sigmoid())
             self.refine_scale = nn.Parameter(torch.tensor(0.1))
         if "context" in hooks:
             self.context_mixer = PyramidContextMixer(oc, num_groups)
@@ -287,9 +310,10 @@ class _GatedMoE(nn.Module, PackCache):
             pk["pp"] = [(_pack_linear(p[0].weight), _gn_args(p[1])) for p in cm.pool_projections]
             pk["cg"] = _pack_linear(cm.context_gate[0].weight, cm.context_gate[0].bias)
             pk["ctx_t"] = torch.tanh(cm.context_scale.detach().float()).reshape(1).expand(C).contiguous()
-        if "refine" in self.router_hook_names:
-            pk["fr0"], pk["fr1"] = _pack_dw(self.feature_refiner[0].weight), _gn_args(self.feature_refiner[1])
-            fg = self.feature_gate
+        if "refine" in self.router_hook_names or "light_refine" in self.router_hook_names:
+            light = "light_refine" in self.router_hook_names
+            dw, fg = (self.refine_dw, self.refine_gate) if light else (self.feature_refiner, self.feature_gate)
+            pk["fr0"], pk["fr1"] = _pack_dw(dw[0].weight), _gn_args(dw[1])
             pk["fg_w1"] = _f32(fg[1].weight).reshape(fg[1].weight.shape[0], C).contiguous()
             pk["fg_w2"], pk["fg_b2"] = _f32(fg[3].weight).reshape(C, -1).contiguous(), _f32(fg[3].bias)
             pk["refine_t"] = float(torch.tanh(self.refine_scale.detach().float()))
@@ -357,8 +381,8 @@ class _GatedMoE(nn.Module, PackCache):
                 c = ops.ctx_mean3(*ctx)
                 cgate = ops.ew(ops.EW_SIGMOID, a=ops.conv2d(c, *pk["cg"], C, 1, 1, 1, 0, False))
                 cat = ops.ew(ops.EW_SCALE_RES, a=cat, b=ops.ew(ops.EW_MUL, a=c, b=cgate), p0=pk["ctx_t"])
-            elif hook == "refine":    # feature refinement (moe/hooks.py:50-57): cat + tanh(scale) * refiner(cat) * gate(cat)
-                r = _norm(ops.dwconv(cat, pk["fr0"], None, 3, False, C), pk["fr1"], act=True)
+            elif hook in ("refine", "light_refine"):   # cat + tanh(scale) * refiner(cat) * gate(cat)  (moe/hooks.py:50-57; the v0_12
+                r = _norm(ops.dwconv(cat, pk["fr0"], None, 3, False, C), pk["fr1"], act=hook == "refine")   # variant has no SiLU)
                 fg = ops.fc_gate(ops.adaptive_avgpool(cat, 1, 1), pk["fg_w1"], pk["fg_w2"], pk["fg_b2"], scale=pk["refine_t"])
                 cat = ops.ew(ops.EW_AFFINE, a=r, b=cat, p0=fg, p1=zero, rows_per_img=HW)
         # projection + GroupNorm + residual
@@ -465,6 +489,27 @@ class VisualEnhancedAdaptiveGateMoE(LowRankHybridAdaptiveGateMoE):
     initial_temperature=1.2, final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
     fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5, refine_reduction=8, detail_reduction=8)` (gated.py:1703-1756)."""
     HOOKS = ("detail", "context", "refine")
+
+
+class HybridAdaptiveGateMoEv2(_GatedMoE):
+    """`HybridAdaptiveGateMoEv2(..., fused_expert_threshold=8, shuffle_groups=2)` (gated.py:1389-1452, v0_11): `HybridAdaptiveGateMoE`
+    with `DualStreamGateRouterV2`."""
+    HOOKS = ()
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.2,
+                 final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+                 fused_expert_threshold=8, shuffle_groups=2, refine=True, refine_reduction=8):
+        super().__init__(in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
+                         _hybrid_backend(num_experts, fused_expert_threshold, False), shuffle_groups,
+                         hooks=self.HOOKS if refine else (), refine_reduction=refine_reduction,
+                         fused_expert_threshold=fused_expert_threshold, router_v2=True)
+        self.refine = bool(refine) and bool(self.HOOKS)
+
+
+class OptimalHybridGateMoE(HybridAdaptiveGateMoEv2):
+    """`OptimalHybridGateMoE(..., fused_expert_threshold=8, shuffle_groups=2, refine=True, refine_reduction=8)` (gated.py:1846-2023,
+    v0_12): v0_11 plus a depthwise refinement gated by a global SE vector."""
+    HOOKS = ("light_refine",)
 
 
 class ZeroCostRouter(nn.Module):

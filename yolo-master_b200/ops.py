@@ -560,10 +560,13 @@ def gate_router(x, pk, topk):
     idx = torch.empty((B, topk), dtype=torch.int32, device=dev)
     probs = torch.empty((B, E), dtype=torch.float32, device=dev)
     scratch = torch.empty((lib().ym_gate_router_scratch_floats(B, H, W, Cc, R, E, pk["pool"]),), dtype=torch.float32, device=dev)
+    ln, prior = pk.get("stat_norm"), pk.get("prior")          # DualStreamGateRouterV2: (weight, bias, eps) and the expert prior
     _lib.check(lib().ym_gate_router(x.data_ptr(), pitch(x), B, H, W, Cc, pk["pool"], pk["global_fc"].data_ptr(), pk["dw"].data_ptr(),
                                     pk["gn1_w"].data_ptr(), pk["gn1_b"].data_ptr(), pk["G1"], pk["pw1"].data_ptr(), R,
                                     pk["gn2_w"].data_ptr(), pk["gn2_b"].data_ptr(), pk["G2"], pk["pw2"].data_ptr(), pk["b2"].data_ptr(),
                                     E, pk["eps"], pk["alpha"], pk["temperature"], pk["cx_w"].data_ptr(), pk["cx_b"], topk,
+                                    None if ln is None else ln[0].data_ptr(), None if ln is None else ln[1].data_ptr(),
+                                    0.0 if ln is None else ln[2], None if prior is None else prior.data_ptr(),
                                     scratch.data_ptr(), w.data_ptr(), idx.data_ptr(), probs.data_ptr(), _stream()), "ym_gate_router")
     _count(3)
     return idx, w, probs
