@@ -931,6 +931,36 @@ def visual_detail_gate(sd, p, x, groups=8):
     return _st(x * (1 + torch.tanh(sd[p + ".detail_scale"]) * gate))
 
 
+def _multi_head_global_logits(sd, p, stats):
+    """Global branch of `MultiHeadRouterV3.forward` gated.py:2123-2140 (v0_13): a dense projection blended with per-head projections
+    of consecutive chunks of the normalised statistics."""
+    B = stats.shape[0]
+    nh = sum(1 for k in sd if k.startswith(p + ".heads.") and k.endswith(".weight"))
+    hd = sd[p + ".heads.0.weight"].shape[1]
+    hw = torch.sigmoid(sd[p + ".head_alpha"])
+    hw = hw / (hw.sum() + 1e-6)
+    gw = torch.sigmoid(sd[p + ".global_weight"])
+    if stats.shape[1] < hd * nh:
+        padded = F.pad(stats, (0, hd * nh - stats.shape[1]))
+    else:
+        padded = stats[:, :hd * nh]
+    chunks = padded.view(B, nh, hd)
+    out = gw * F.linear(stats, sd[p + ".global_proj.weight"])
+    for i in range(nh):
+        out = out + (1 - gw) * hw[i] * F.linear(chunks[:, i], sd[f"{p}.heads.{i}.weight"])
+    return out
+
+
+def cross_path_gate(sd, p, cat):
+    """`CrossPathGate.forward` gated.py:2396-2412 (v0_15) on the concatenated [static | dynamic] outputs: per-(image, channel) gate
+    0.5 + tanh(gate_scale) * 0.5 * sigmoid(MLP(GAP(cat))); only the first C of the MLP's 2C outputs are used."""
+    C = cat.shape[1]
+    g = F.silu(F.linear(cat.mean((2, 3)), sd[p + ".gate_net.2.weight"]))
+    g = F.linear(g, sd[p + ".gate_net.4.weight"], sd[p + ".gate_net.4.bias"])
+    gate = 0.5 + torch.tanh(sd[p + ".gate_scale"]) * 0.5 * torch.sigmoid(g)
+    return _st(cat * gate[:, :C, None, None])
+
+
 def dual_stream_gate_router(sd, p, x, top_k, temperature, pool_scale=4):
     """`DualStreamGateRouter.forward` gated.py:129-160 (fp32): global mean/std statistics + pooled local conv stream, blended by
     sigmoid(alpha), clamp +-30, softmax(/T), top-k, renormalise with +1e-6.  Returns (weights [B,k], indices [B,k], probs)."""
@@ -941,7 +971,7 @@ def dual_stream_gate_router(sd, p, x, top_k, temperature, pool_scale=4):
     stats = torch.cat([mean, std], 1)
     if p + ".stat_norm.weight" in sd:      # DualStreamGateRouterV2 gated.py:181-260 (v0_11 / v0_12): LayerNorm on the statistics
         stats = F.layer_norm(stats, (2 * C,), sd[p + ".stat_norm.weight"], sd[p + ".stat_norm.bias"], 1e-5)
-    gl = F.linear(stats, sd[p + ".global_fc.weight"])
+    gl = _multi_head_global_logits(sd, p, stats) if p + ".heads.0.weight" in sd else F.linear(stats, sd[p + ".global_fc.weight"])
     xl = F.avg_pool2d(xf, pool_scale, pool_scale) if (H > pool_scale and W > pool_scale) else xf
     t = F.conv2d(xl, sd[p + ".local_conv.0.weight"], None, 1, 1, 1, C)
     t = F.silu(_gn(sd, p + ".local_conv.1", t, get_safe_groups(C, 8)))
@@ -1075,6 +1105,8 @@ def gated_moe_forward(sd, p, x, c1, c2, num_experts, top_k, split_ratio, num_gro
     else:
         out_d = shared_inverted_expert_group(sd, p + ".fused_experts", xd, w, idx, num_experts, out_dyn)
     cat = torch.cat([out_s, out_d], 1)
+    if p + ".cross_gate.gate_scale" in sd:     # GatedFusionMoE gated.py:2652-2653 (v0_15): content-aware gate on both paths
+        cat = cross_path_gate(sd, p + ".cross_gate", cat)
     sg = shuffle_groups if (shuffle_groups and c2 % shuffle_groups == 0) else 1
     if sg > 1:
         B, C, H, W = cat.shape
@@ -1103,6 +1135,8 @@ GATED_VARIANTS = {
     "VisualEnhancedAdaptiveGateMoE": (1.2, True, True, True, ("detail", "context", "refine")),       # v0.10
     "HybridAdaptiveGateMoEv2": (1.2, True, False, True, ()),                 # v0.11: v0.6 + DualStreamGateRouterV2 (keys in the sd)
     "OptimalHybridGateMoE": (1.2, True, False, True, ("light_refine",)),     # v0.12: + depthwise refinement
+    "MultiHeadRouterMoE": (1.2, True, False, True, ("light_refine",)),       # v0.13: v0.12 + MultiHeadRouterV3 (keys in the sd)
+    "GatedFusionMoE": (1.2, True, False, True, ("light_refine",)),           # v0.15: v0.12 + CrossPathGate (keys in the sd)
 }
 
 

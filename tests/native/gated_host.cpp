@@ -64,10 +64,10 @@ extern "C" int host_zero_cost_router(const void* x, int ldx, int B, int H, int W
 }
 
 extern "C" int host_fc_gate(const void* v, int ldv, int B, int Cin, const float* w1, int Cr, const float* w2, const float* b2,
-                            int Cout, float scale, float* out) {
+                            int Cout, float scale, float offset, float* out) {
     FcArgs a;
     a.v = (const ym_half*)v; a.ldv = ldv; a.Cin = Cin; a.Cr = Cr; a.Cout = Cout; a.w1 = w1; a.w2 = w2; a.b2 = b2; a.scale = scale;
-    a.out = out;
+    a.offset = offset; a.out = out;
     std::vector<float> sm(fc_smem_floats(Cr) + 1);
     for (int b = 0; b < B; ++b)
         for (int ph = 0; ph < FC_PHASES; ++ph)

@@ -169,6 +169,7 @@ def test_family_class_matches_reference_module_golden(emu, key):
     sd = m.state_dict()
     assert {k: list(v.shape) for k, v in sd.items()} == c["keys"]
     fill_state_dict_(sd, c["seed"])
+    sd.update({k: v.clone() for k, v in c["scalars"].items()})    # 0-dim parameters (and CrossPathGate's bias) as the fixture had them
     m.load_state_dict(sd, strict=True)
     m.eval()
     sdm = {"m." + k: v.clone().float() for k, v in sd.items()}
@@ -229,10 +230,11 @@ def test_gated_zoo_yamls_build():
             assert sum(p.numel() for p in m.parameters()) == nparam
         assert DetectionModel(f"master/{ver}/det/yolo-master-s.yaml").model[5].in_channels == 256
     assert type(DetectionModel("yolo-master-n.yaml").model[3]).__name__ == "ES_MOE"        # a bare name still resolves to the v0 zoo
-    for cfg, cls in (("master/v0_12/det/yolo-master-n.yaml", "OptimalHybridGateMoE"), ("master/exp/yolo-master-v0_11.yaml", "HybridAdaptiveGateMoEv2")):
+    for cfg, cls in (("master/v0_12/det/yolo-master-n.yaml", "OptimalHybridGateMoE"), ("master/exp/yolo-master-v0_11.yaml", "HybridAdaptiveGateMoEv2"),
+                     ("master/v0_13/det/yolo-master-n.yaml", "MultiHeadRouterMoE"), ("master/v0_15/det/yolo-master-n.yaml", "GatedFusionMoE")):
         m = DetectionModel(cfg)
         assert [type(m.model[i]).__name__ for i in (5, 8, 11)] == [cls] * 3 and m.model[11].dynamic_channels == 96
-        assert type(m.model[5].routing).__name__ == "DualStreamGateRouterV2"
+        assert type(m.model[5].routing).__name__ == ("MultiHeadRouterV3" if cls == "MultiHeadRouterMoE" else "DualStreamGateRouterV2")
     for sc in "nsmlx":                                          # v0_3 zoo: UltimateOptimizedMoE
         m = DetectionModel(f"master/v0_3/det/yolo-master-{sc}.yaml")
         assert [type(m.model[i]).__name__ for i in (5, 8, 11)] == ["UltimateOptimizedMoE"] * 3

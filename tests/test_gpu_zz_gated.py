@@ -114,6 +114,7 @@ def test_family_class_matches_reference_module_golden(key):
     m = getattr(gated, name)(64, 64, int(E), 2, c["split"])
     sd = m.state_dict()
     fill_state_dict_(sd, c["seed"])
+    sd.update({k: v.clone() for k, v in c["scalars"].items()})    # 0-dim parameters (and CrossPathGate's bias) as the fixture had them
     m.load_state_dict(sd, strict=True)
     m = m.to(DEV).eval()
     sdm = {"m." + k: v.clone().float() for k, v in sd.items()}

@@ -204,7 +204,7 @@ def install_gated(host):
     host.host_gate_router.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, ci, cf, cf, cf, vp, cf,
                                       ci, vp, vp, cf, vp, vp, vp, vp]
     host.host_zero_cost_router.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci, cf, vp, cf, ci, vp, vp, vp]
-    host.host_fc_gate.argtypes = [vp, ci, ci, ci, vp, ci, vp, vp, ci, cf, vp]
+    host.host_fc_gate.argtypes = [vp, ci, ci, ci, vp, ci, vp, vp, ci, cf, cf, vp]
     host.host_gated_select.argtypes = [vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, ci, vp, vp, vp, ci]
     host.host_ctx_mean3.argtypes = [vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, ci]
 
@@ -236,11 +236,11 @@ def install_gated(host):
                                    float(cx_b), topk, w.data_ptr(), idx.data_ptr(), probs.data_ptr())
         return idx, w, probs
 
-    def fc_gate(v, w1, w2, b2, scale=1.0):
+    def fc_gate(v, w1, w2, b2, scale=1.0, offset=0.0):
         B, Cin = v.shape[0], v.shape[3]
         out = torch.empty((B, w2.shape[0]), dtype=torch.float32)
         host.host_fc_gate(v.data_ptr(), ld(v), B, Cin, w1.data_ptr(), w1.shape[0], w2.data_ptr(), None if b2 is None else b2.data_ptr(),
-                          w2.shape[0], float(scale), out.data_ptr())
+                          w2.shape[0], float(scale), float(offset), out.data_ptr())
         return out
 
     def gated_select(fo, idx, w, gamma, beta, E, oc, G, eps=1e-5, out=None):

@@ -173,12 +173,12 @@ extern "C" int ym_zero_cost_router(const void* x, int ldx, int B, int H, int W, 
 }
 
 extern "C" int ym_fc_gate(const void* v, int ldv, int B, int Cin, const float* w1, int Cr, const float* w2, const float* b2,
-                          int Cout, float scale, float* out, void* stream) {
+                          int Cout, float scale, float offset, float* out, void* stream) {
     YM_CHECK_ARG(v && w1 && w2 && out, "ym_fc_gate: null pointer");
     YM_CHECK_ARG(B > 0 && Cin > 0 && Cr > 0 && Cr <= 8192 && Cout > 0 && ldv >= Cin, "ym_fc_gate: bad sizes");
     FcArgs a;
     a.v = (const __half*)v; a.ldv = ldv; a.Cin = Cin; a.Cr = Cr; a.Cout = Cout; a.w1 = w1; a.w2 = w2; a.b2 = b2; a.scale = scale;
-    a.out = out;
+    a.offset = offset; a.out = out;
     fc_gate_kernel<<<B, NTHR, fc_smem_floats(Cr) * sizeof(float), (cudaStream_t)stream>>>(a);
     YM_CHECK_LAUNCH("fc_gate");
     return YM_OK;

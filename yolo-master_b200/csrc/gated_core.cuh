@@ -363,13 +363,14 @@ YM_HD void r2_phase(int ph, const R2Args& a, int tid, int nthr, float* sm) {
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-// Per-image two-layer gate on a pooled vector: out = scale * sigmoid(W2 . silu(W1 . v) + b2)
-// (se_gate gated.py:325-332; feature_gate moe/hooks.py:50-57 with scale = tanh(refine_scale)).
+// Per-image two-layer gate on a pooled vector: out = offset + scale * sigmoid(W2 . silu(W1 . v) + b2)
+// (se_gate gated.py:325-332; feature_gate moe/hooks.py:50-57 with scale = tanh(refine_scale); CrossPathGate gated.py:2402-2404 with
+// offset 0.5 and scale 0.5 * tanh(gate_scale)).
 struct FcArgs {
     const ym_half* v;   // [B][ldv]
     int ldv, Cin, Cr, Cout;
     const float *w1, *w2, *b2;   // [Cr][Cin], [Cout][Cr], [Cout] (nullable)
-    float scale;
+    float scale, offset;
     float* out;         // [B][Cout]
 };
 constexpr int FC_PHASES = 2;
@@ -387,7 +388,7 @@ YM_HD void fc_phase(int ph, const FcArgs& a, int img, int tid, int nthr, float* 
         for (int o = tid; o < a.Cout; o += nthr) {
             float s = a.b2 ? a.b2[o] : 0.f;
             for (int r = 0; r < a.Cr; ++r) s += a.w2[(long long)o * a.Cr + r] * sm[r];
-            a.out[(long long)img * a.Cout + o] = a.scale * sigmoid_f(s);
+            a.out[(long long)img * a.Cout + o] = a.offset + a.scale * sigmoid_f(s);
         }
     }
 }

@@ -33,7 +33,8 @@ from .mot import _f32, _pack_dw, _pack_linear
 __all__ = ("DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup", "VisualDetailGate",
            "PyramidContextMixer", "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
            "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE",
-           "ContextRefinedLowRankHybridAdaptiveGateMoE", "VisualEnhancedAdaptiveGateMoE", "ZeroCostRouter", "UltimateOptimizedMoE", "DualStreamGateRouterV2", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE")
+           "ContextRefinedLowRankHybridAdaptiveGateMoE", "VisualEnhancedAdaptiveGateMoE", "ZeroCostRouter", "UltimateOptimizedMoE", "DualStreamGateRouterV2", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE", "MultiHeadRouterV3", "CrossPathGate",
+           "MultiHeadRouterMoE", "GatedFusionMoE")
 
 
 def _gn(channels: int, groups: int = 8) -> nn.GroupNorm:
@@ -88,6 +89,75 @@ class DualStreamGateRouterV2(DualStreamGateRouter):
         pk["stat_norm"] = (_f32(self.stat_norm.weight), _f32(self.stat_norm.bias), float(self.stat_norm.eps))
         pk["prior"] = _f32(self.expert_prior)
         return pk
+
+
+class MultiHeadRouterV3(nn.Module):
+    """`MultiHeadRouterV3(in_channels, num_experts, top_k, temperature=1.0, num_heads=4, local_reduction=16, pool_scale=4,
+    noise_std=0.1, expert_dropout=0.1)` (gated.py:2026-2211, v0_13 zoo).  Its global branch is linear in the normalised statistics
+    (a dense projection blended with per-head projections of consecutive chunks), so it packs into ONE effective [E, 2C] matrix
+    and runs on the same kernels as `DualStreamGateRouterV2`."""
+
+    def __init__(self, in_channels, num_experts, top_k, temperature=1.0, num_heads=4, local_reduction=16, pool_scale=4, noise_std=0.1,
+                 expert_dropout=0.1):
+        super().__init__()
+        self.num_experts, self.top_k = num_experts, top_k
+        self.temperature = max(float(temperature), 1e-3)
+        self.pool_scale = pool_scale
+        self.num_heads = max(1, min(num_heads, num_experts))
+        stat_dim = 2 * in_channels
+        self.stat_norm = nn.LayerNorm(stat_dim)
+        self._head_dim = max(stat_dim // self.num_heads, 4)
+        self.heads = nn.ModuleList([nn.Linear(self._head_dim, num_experts, bias=False) for _ in range(self.num_heads)])
+        self.global_proj = nn.Linear(stat_dim, num_experts, bias=False)
+        self.head_alpha = nn.Parameter(torch.ones(self.num_heads) / self.num_heads)
+        self.global_weight = nn.Parameter(torch.tensor(0.1))
+        self.expert_prior = nn.Parameter(torch.zeros(num_experts))
+        reduced = max(in_channels // local_reduction, 4)
+        self.local_conv = nn.Sequential(
+            nn.Conv2d(in_channels, in_channels, 3, padding=1, groups=in_channels, bias=False), _gn(in_channels, 8), nn.SiLU(inplace=False),
+            nn.Conv2d(in_channels, reduced, 1, bias=False), _gn(reduced, 4), nn.SiLU(inplace=False),
+            nn.Conv2d(reduced, num_experts, 1, bias=True))
+        self.alpha = nn.Parameter(torch.tensor(0.5))
+
+    def effective_global_weight(self) -> torch.Tensor:
+        """[E, 2C]: gw * global_proj + (1 - gw) * hw_i * heads[i] on the columns of chunk i (gated.py:2123-2140)."""
+        gw = torch.sigmoid(self.global_weight.detach().float())
+        hw = torch.sigmoid(self.head_alpha.detach().float())
+        hw = hw / (hw.sum() + 1e-6)
+        w = gw * self.global_proj.weight.detach().float()
+        sd, hd = w.shape[1], self._head_dim
+        for i, h in enumerate(self.heads):
+            lo, hi = i * hd, min((i + 1) * hd, sd)          # columns past 2C are zero padding in the reference
+            if lo < hi:
+                w[:, lo:hi] += (1 - gw) * hw[i] * h.weight.detach().float()[:, :hi - lo]
+        return w.contiguous()
+
+    def pack(self):
+        lc = self.local_conv
+        C, R, E = lc[0].weight.shape[0], lc[3].weight.shape[0], self.num_experts
+        return {
+            "E": E, "R": R, "pool": int(self.pool_scale), "G1": lc[1].num_groups, "G2": lc[4].num_groups, "eps": float(lc[1].eps),
+            "global_fc": self.effective_global_weight(), "dw": _f32(lc[0].weight).reshape(C, 9).contiguous(),
+            "gn1_w": _f32(lc[1].weight), "gn1_b": _f32(lc[1].bias), "pw1": _f32(lc[3].weight).reshape(R, C).contiguous(),
+            "gn2_w": _f32(lc[4].weight), "gn2_b": _f32(lc[4].bias), "pw2": _f32(lc[6].weight).reshape(E, R).contiguous(),
+            "b2": _f32(lc[6].bias), "alpha": float(torch.sigmoid(self.alpha.detach().float())), "temperature": float(self.temperature),
+            "stat_norm": (_f32(self.stat_norm.weight), _f32(self.stat_norm.bias), float(self.stat_norm.eps)),
+            "prior": _f32(self.expert_prior),
+        }
+
+
+class CrossPathGate(nn.Module):
+    """`CrossPathGate(static_channels, dynamic_channels, out_channels, num_groups=8, drop_prob=0.1)` (gated.py:2347-2412, v0_15)."""
+
+    def __init__(self, static_channels, dynamic_channels, out_channels, num_groups=8, drop_prob=0.1):
+        super().__init__()
+        self.static_channels, self.dynamic_channels, self.out_channels = static_channels, dynamic_channels, out_channels
+        stat_dim = static_channels + dynamic_channels
+        hidden = max(stat_dim // 4, 8)
+        self.gate_net = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(stat_dim, hidden, bias=False),
+                                      nn.SiLU(inplace=False), nn.Linear(hidden, out_channels * 2, bias=True))
+        self.gate_scale = nn.Parameter(torch.tensor(0.0))
+        self.drop_scale = nn.Parameter(torch.tensor(1.0))
 
 
 class FusedExpertGroup(nn.Module):
@@ -201,7 +271,7 @@ class _GatedMoE(nn.Module, PackCache):
 
     def __init__(self, in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
                  backend, shuffle_groups=1, bottleneck_ratio=0.5, hooks=(), refine_reduction=8, detail_reduction=8,
-                 fused_expert_threshold=8, router_v2=False):
+                 fused_expert_threshold=8, router_v2=False, router=None, cross_gate=False):
         super().__init__()
         if in_channels != out_channels:
             raise ValueError(f"{type(self).__name__}: the residual `proj(...) + x` needs in_channels == out_channels")
@@ -222,8 +292,8 @@ class _GatedMoE(nn.Module, PackCache):
         self.static_net = nn.Sequential(
             nn.Conv2d(sc, sc, 3, padding=1, groups=sc, bias=False), nn.BatchNorm2d(sc), nn.SiLU(inplace=False),
             nn.Conv2d(sc, self.out_static, 1, bias=False), nn.BatchNorm2d(self.out_static), nn.SiLU(inplace=False))
-        self.routing = (DualStreamGateRouterV2 if router_v2 else DualStreamGateRouter)(self.dynamic_channels, num_experts, top_k,
-                                                                                        temperature=initial_temperature)
+        self.routing = router if router is not None else (DualStreamGateRouterV2 if router_v2 else DualStreamGateRouter)(
+            self.dynamic_channels, num_experts, top_k, temperature=initial_temperature)
         self.fused_expert_threshold = fused_expert_threshold
         self.shuffle_groups = shuffle_groups if (shuffle_groups and out_channels % shuffle_groups == 0) else 1
         self.expert_backend = backend
@@ -240,6 +310,8 @@ class _GatedMoE(nn.Module, PackCache):
         self.complexity_estimator = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(self.dynamic_channels, 1, 1), nn.Sigmoid())
         self.proj = nn.Conv2d(out_channels, out_channels, 1, bias=False)
         self.bn = _gn(out_channels, num_groups)
+        if cross_gate:
+            self.cross_gate = CrossPathGate(self.out_static, self.out_dynamic, out_channels, num_groups)
         self.router_hook_names = tuple(hooks)
         oc = out_channels
         if "refine" in hooks:
@@ -298,6 +370,10 @@ class _GatedMoE(nn.Module, PackCache):
             pk["proj_gamma"] = torch.stack([_f32(p[1].weight) for p in fe.expert_projections]).contiguous()
             pk["proj_beta"] = torch.stack([_f32(p[1].bias) for p in fe.expert_projections]).contiguous()
             pk["proj_G"], pk["proj_eps"] = fe.expert_projections[0][1].num_groups, float(fe.expert_projections[0][1].eps)
+        if hasattr(self, "cross_gate"):   # only the first C of the gate MLP's 2C outputs are used (gated.py:2404-2408)
+            cg = self.cross_gate
+            pk["xg_w1"], pk["xg_w2"], pk["xg_b2"] = _f32(cg.gate_net[2].weight), _f32(cg.gate_net[4].weight[:C]), _f32(cg.gate_net[4].bias[:C])
+            pk["xg_scale"] = 0.5 * float(torch.tanh(cg.gate_scale.detach().float()))
         sg = self.shuffle_groups
         if sg > 1:   # channel shuffle as a permutation GEMM: new channel i*sg + g <- old channel g*(C/sg) + i  (gated.py:1334-1338)
             perm = torch.zeros((C, C), dtype=torch.float32, device=dev)
@@ -368,6 +444,9 @@ class _GatedMoE(nn.Module, PackCache):
         idx, w, probs = ops.gate_router(xd, pk["router"], self.top_k)
         self.last_routing_snapshot = {"topk_indices": idx, "topk_weights": w, "router_probs": probs}   # device tensors, lazy
         self._experts(xd, idx, w, pk, cat[..., self.out_static:])
+        if "xg_w1" in pk:   # CrossPathGate: cat * (0.5 + 0.5 * tanh(gate_scale) * sigmoid(MLP(GAP(cat))))
+            xg = ops.fc_gate(ops.adaptive_avgpool(cat, 1, 1), pk["xg_w1"], pk["xg_w2"], pk["xg_b2"], scale=pk["xg_scale"], offset=0.5)
+            cat = ops.ew(ops.EW_AFFINE, a=cat, p0=xg, p1=zero, rows_per_img=HW)
         if self.shuffle_groups > 1:
             cat = ops.conv2d(cat, pk["shuffle"], None, C, 1, 1, 1, 0, False)
         for hook in self.router_hook_names:
@@ -510,6 +589,37 @@ class OptimalHybridGateMoE(HybridAdaptiveGateMoEv2):
     """`OptimalHybridGateMoE(..., fused_expert_threshold=8, shuffle_groups=2, refine=True, refine_reduction=8)` (gated.py:1846-2023,
     v0_12): v0_11 plus a depthwise refinement gated by a global SE vector."""
     HOOKS = ("light_refine",)
+
+
+class MultiHeadRouterMoE(_GatedMoE):
+    """`MultiHeadRouterMoE(..., fused_expert_threshold=8, shuffle_groups=2, refine=True, refine_reduction=8, num_heads=4,
+    expert_dropout=0.05)` (gated.py:2430-2496, v0_13): `OptimalHybridGateMoE` with `MultiHeadRouterV3`."""
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.2,
+                 final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+                 fused_expert_threshold=8, shuffle_groups=2, refine=True, refine_reduction=8, num_heads=4, expert_dropout=0.05):
+        router = MultiHeadRouterV3(int(in_channels * split_ratio), num_experts, top_k, temperature=initial_temperature,
+                                   num_heads=num_heads, expert_dropout=expert_dropout)
+        super().__init__(in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
+                         _hybrid_backend(num_experts, fused_expert_threshold, False), shuffle_groups,
+                         hooks=("light_refine",) if refine else (), refine_reduction=refine_reduction,
+                         fused_expert_threshold=fused_expert_threshold, router=router)
+        self.refine = bool(refine)
+
+
+class GatedFusionMoE(_GatedMoE):
+    """`GatedFusionMoE(..., fused_expert_threshold=8, shuffle_groups=2, refine=True, refine_reduction=8, drop_prob=0.05)`
+    (gated.py:2564-2707, v0_15): `OptimalHybridGateMoE` with a `CrossPathGate` on the concatenated paths (stochastic depth is a
+    training-time feature)."""
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.2,
+                 final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+                 fused_expert_threshold=8, shuffle_groups=2, refine=True, refine_reduction=8, drop_prob=0.05):
+        super().__init__(in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
+                         _hybrid_backend(num_experts, fused_expert_threshold, False), shuffle_groups,
+                         hooks=("light_refine",) if refine else (), refine_reduction=refine_reduction,
+                         fused_expert_threshold=fused_expert_threshold, router_v2=True, cross_gate=True)
+        self.refine = bool(refine)
 
 
 class ZeroCostRouter(nn.Module):

@@ -27,7 +27,8 @@ MIXTURE_MODULES.update({"ModularRouterExpertMoE": M.OptimizedMOEImproved, "Optim
 MIXTURE_MODULES.update({n: getattr(M, n) for n in (          # the AdaptiveGateMoE line, v0_4 ... v0_10 zoos (nn/modules/gated.py)
     "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
     "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE", "ContextRefinedLowRankHybridAdaptiveGateMoE",
-    "VisualEnhancedAdaptiveGateMoE", "UltimateOptimizedMoE", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE")})                                      # + the v0_3 zoo block
+    "VisualEnhancedAdaptiveGateMoE", "UltimateOptimizedMoE", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE", "MultiHeadRouterMoE",
+    "GatedFusionMoE")})                                      # + the v0_3 zoo block
 BASE_MODULES = frozenset({M.Conv, M.DWConv, M.Bottleneck, M.SPPF, M.C2PSA, M.C2f, M.C3k2, M.C3, M.A2C2f})
 REPEAT_MODULES = frozenset({M.C2f, M.C3k2, M.C3, M.C2PSA, M.A2C2f})
 MIXTURE_BASE_MODULES = frozenset(MIXTURE_MODULES.values())

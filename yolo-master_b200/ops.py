@@ -587,14 +587,16 @@ def zero_cost_router(x, fc, temperature, cx_w, cx_b, topk):
     return idx, w, probs
 
 
-def fc_gate(v, w1, w2, b2, scale=1.0):
-    """ym_fc_gate.  v: (B,1,1,Cin) fp16 pooled vector; w1 fp32 [Cr,Cin], w2 fp32 [Cout,Cr], b2 fp32 [Cout] or None -> fp32 (B, Cout)."""
+def fc_gate(v, w1, w2, b2, scale=1.0, offset=0.0):
+    """ym_fc_gate.  v: (B,1,1,Cin) fp16 pooled vector; w1 fp32 [Cr,Cin], w2 fp32 [Cout,Cr], b2 fp32 [Cout] or None -> fp32 (B, Cout)
+    = offset + scale * sigmoid(w2 . silu(w1 . v) + b2)."""
     B, Cin = v.shape[0], v.shape[3]
     if v.shape[1] != 1 or v.shape[2] != 1:
         raise ValueError("fc_gate: expected a (B,1,1,C) pooled vector")
     out = torch.empty((B, w2.shape[0]), dtype=torch.float32, device=v.device)
     _lib.check(lib().ym_fc_gate(v.data_ptr(), pitch(v), B, Cin, w1.data_ptr(), w1.shape[0], w2.data_ptr(),
-                                None if b2 is None else b2.data_ptr(), w2.shape[0], float(scale), out.data_ptr(), _stream()), "ym_fc_gate")
+                                None if b2 is None else b2.data_ptr(), w2.shape[0], float(scale), float(offset), out.data_ptr(), _stream()),
+               "ym_fc_gate")
     _count()
     return out
 
