@@ -1,7 +1,8 @@
 """Device-resident CUDA-graph throughput of every supported model family (not the bench.py line, which is yolo26-master-n):
     python tools/bench_models.py [batch] > gpurun_out/models.json
 Variants: yolo26-master-n (A2C2fMoE), yolo-master-{n,s,l} v0 (ES_MOE + A2C2f + DFL), yolo26-master-moa-mot-{n,s} (C2fMoT/C2fMoA),
-plus configs[2] (s MoT+MoA bs64) and configs[3] (l @1280, 16 images = one rank's shard)."""
+plus configs[2] (s MoT+MoA bs64) and configs[3] (l @1280, 16 images = one rank's shard), the v0_1 zoo (ModularRouterExpertMoE) and the
+v0_10 zoo (VisualEnhancedAdaptiveGateMoE)."""
 import json
 import os
 import sys
@@ -30,7 +31,10 @@ CASES = [("yolo26-master-n", "yolo26-master-n.yaml", "yolo26-master-n", B0, 640)
          ("yolo-master-n-v0", "yolo-master-n.yaml", "yolo-master-n-v0", B0, 640),
          ("yolo-master-l-v0 @1280 (configs[3] shard)", "yolo-master-l.yaml", "yolo-master-l-v0", 16, 1280),
          ("yolo26-master-moa-mot-n", moamot(False), "yolo26-master-moa-mot-n", B0, 640),
-         ("yolo26-master-moa-mot-s bs64 (configs[2])", moamot(True), "yolo26-master-moa-mot-s", 64, 640)]
+         ("yolo26-master-moa-mot-s bs64 (configs[2])", moamot(True), "yolo26-master-moa-mot-s", 64, 640),
+         # families added after round 1's GPU budget (first hardware numbers pending): v0_1 ModularRouterExpertMoE, v0_10 gated MoE
+         ("yolo-master-n-v0_1", "master/v0_1/det/yolo-master-n.yaml", "yolo-master-n-v0_1", B0, 640),
+         ("yolo-master-n-v0_10", "master/v0_10/det/yolo-master-n.yaml", "yolo-master-n-v0_10", B0, 640)]
 res = {}
 for tag, cfg, keys, B, S in CASES:
     try:
