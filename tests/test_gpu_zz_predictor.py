@@ -80,7 +80,7 @@ def test_scale_boxes_batch_and_ragged():
     g = torch.Generator().manual_seed(4)
     shapes = [(480, 640), (1080, 1920), (100, 37), (333, 500)] * 40                   # 160 images: two parameter blocks
     b = torch.rand((len(shapes), 300, 6), generator=g) * 700 - 30
-    dev = b.to(DEV)
+    dev = b.clone().to(DEV)
     box_ops.scale_boxes_batch((640, 640), dev, shapes)
     for i, s in enumerate(shapes):
         assert np.array_equal(dev[i, :, :4].cpu().numpy(), L.scale_boxes((640, 640), b[i, :, :4].numpy(), s)), i
@@ -88,7 +88,7 @@ def test_scale_boxes_batch_and_ragged():
     counts = [7, 0, 31, 2]
     flat = torch.rand((sum(counts), 6), generator=g) * 700 - 30
     row_img = torch.repeat_interleave(torch.arange(4, dtype=torch.int32), torch.tensor(counts)).to(DEV)
-    dev = flat.to(DEV)
+    dev = flat.clone().to(DEV)
     box_ops.scale_boxes_batch((640, 640), dev, shapes[:4], row_img=row_img)
     lo = 0
     for i, n in enumerate(counts):
