@@ -42,9 +42,14 @@ def conv2d(x, w_packed, bias, Cout, KH, KW, stride, pad, act, out=None, res=None
 
 
 def dwconv(x, w_taps, bias, ksize, act, C_out, grp_w=None, grp_stride=None, grp_off=0, add=None, out=None):
-    assert grp_w is None or (grp_w == C_out and grp_off == 0)
+    xs = x.float()
+    if grp_w is not None and not (grp_w == C_out and grp_off == 0):   # source channel of c = (c/grp_w)*grp_stride + grp_off + c%grp_w
+        src = torch.tensor([(c // grp_w) * grp_stride + grp_off + c % grp_w for c in range(C_out)])
+        xs = xs[..., src]
+    else:
+        xs = xs[..., :C_out]
     w = w_taps.float().t().reshape(C_out, 1, ksize, ksize)
-    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None if bias is None else bias.float(), 1, ksize // 2, 1, C_out)
+    y = F.conv2d(xs.permute(0, 3, 1, 2), w, None if bias is None else bias.float(), 1, ksize // 2, 1, C_out)
     if act:
         y = F.silu(y)
     y = y.permute(0, 2, 3, 1)
@@ -265,6 +270,99 @@ def install_gated(host):
     ops.pitch = lambda t, dtype=torch.float16: ld(t)
     from yolo_master_b200.nn.modules import gated
     gated.to_nhwc = _base.to_nhwc
+
+
+# ---- the remaining ops of a whole model (stem, area attention, upsample+concat, SPPF pooling, image router, MoE combine, Detect):
+# with these, DetectionModel forwards run end to end on the CPU emulation (tests/test_host_model_wiring.py)
+def stem_conv(img, wgt, bias, Cout, out=None):
+    B, Cin, H, W = img.shape
+    x = img.float() / 255 if img.dtype == torch.uint8 else img.float()
+    w = wgt.float().reshape(Cin, 3, 3, Cout).permute(3, 0, 1, 2)                  # [Cin*9][Cout], k = (ci*3+ky)*3+kx
+    y = F.silu(F.conv2d(x, w, bias.float(), 2, 1)).permute(0, 2, 3, 1)
+    return _out(y, out)
+
+
+def attention(qkv, batch, N, heads, head_stride, q_off, k_off, v_off, d_qk, d_v, scale, out=None):
+    B, H, W, Ct = qkv.shape
+    rows = qkv.reshape(batch, N, Ct).float()
+    outs = []
+    for h in range(heads):
+        b0 = h * head_stride
+        q, k, v = rows[..., b0 + q_off:b0 + q_off + d_qk], rows[..., b0 + k_off:b0 + k_off + d_qk], rows[..., b0 + v_off:b0 + v_off + d_v]
+        outs.append(torch.softmax((q * scale) @ k.transpose(1, 2), -1) @ v)
+    y = torch.cat(outs, -1).reshape(B, H, W, heads * d_v)
+    return _out(y, out)
+
+
+def concat2(a, b, up=1, out=None):
+    ya = a.float()
+    if up > 1:
+        ya = ya.repeat_interleave(up, 1).repeat_interleave(up, 2)
+    y = ya if b is None else torch.cat([ya, b.float()], 3)
+    return _out(y, out)
+
+
+def sppf_pool(buf, Cslot, k):
+    t = buf[..., :Cslot].float().permute(0, 3, 1, 2)
+    for i in range(1, 4):
+        t = F.max_pool2d(t, k, 1, k // 2)
+        buf[..., i * Cslot:(i + 1) * Cslot] = t.permute(0, 2, 3, 1).half()
+    return buf
+
+
+def router_topk(x, pack, topk, pool=4):
+    B, H, W, C = x.shape
+    Cr, E = pack["Cr"], pack["E"]
+    xin = x.float().permute(0, 3, 1, 2)
+    if H > pool and W > pool:
+        xin = F.avg_pool2d(xin, pool, pool)
+    w1 = pack["w1"].permute(0, 1, 3, 2).reshape(3, 3, C, Cr).permute(3, 2, 0, 1)   # [tap][c/4][r][4] -> [r][c][ky][kx]
+    h = F.silu(F.conv2d(xin, w1, None, 1, 1) * pack["scale1"].view(1, -1, 1, 1) + pack["shift1"].view(1, -1, 1, 1))
+    o = F.conv2d(h, pack["w2"].view(E, Cr, 1, 1)) * pack["scale2"].view(1, -1, 1, 1) + pack["shift2"].view(1, -1, 1, 1)
+    probs = torch.softmax(o.mean((2, 3)), 1)
+    w, idx = torch.topk(probs, topk, 1)
+    return idx.int(), (w / w.sum(1, keepdim=True).clamp_min(1e-6)).contiguous(), probs
+
+
+def moe_combine(x, ws_packed, bias_s, o, o_scale, o_shift, topk, add_residual=True, out=None):
+    B, H, W, C = x.shape
+    shared = F.silu(x.float() @ ws_packed.float()[:, :C].t() + bias_s.view(1, 1, 1, -1))
+    e = (o.float() * o_scale.view(B * topk, 1, -1) + o_shift.view(B * topk, 1, -1)).reshape(B, topk, H, W, C).sum(1)
+    y = shared + e + (x.float() if add_residual else 0)
+    return _out(y, out)
+
+
+def detect_dense(boxes, logits, strides, nc, xyxy, reg_max=1):
+    lv = [b.shape[1:3] for b in boxes]
+    bx = torch.cat([b.float().reshape(b.shape[0], -1, b.shape[3]).transpose(1, 2) for b in boxes], 2)
+    sc = torch.cat([c.float().reshape(c.shape[0], -1, c.shape[3]).transpose(1, 2) for c in logits], 2)
+    return O.detect_decode(bx, sc, lv, [float(s) for s in strides], xyxy, reg_max)
+
+
+def detect_topk(boxes, logits, strides, nc, max_det=300, return_anchor=False):
+    r, idx = O.detect_postprocess(detect_dense(boxes, logits, strides, nc, True, 1), nc, max_det)
+    return (r, idx.int()) if return_anchor else r
+
+
+def install_model():
+    """Everything `install()` covers plus the whole-model ops above."""
+    install()
+    for name, fn in dict(stem_conv=stem_conv, attention=attention, concat2=concat2, sppf_pool=sppf_pool, router_topk=router_topk,
+                         moe_combine=moe_combine, moe_expert_gemm=moe_expert_gemm, gn_finalize=gn_finalize, detect_dense=detect_dense,
+                         detect_topk=detect_topk).items():
+        setattr(ops, name, fn)
+    ops.pitch = lambda t, dtype=torch.float16: (t.stride(2) if t.shape[2] > 1 else (t.stride(1) if t.shape[1] > 1 else (t.stride(0) if t.shape[0] > 1 else t.shape[3])))
+    from yolo_master_b200.nn.modules import gated, head, moe
+    for mod in (gated, head, moe):
+        if hasattr(mod, "to_nhwc"):
+            mod.to_nhwc = _base.to_nhwc
+
+    def conv_forward(self, x):                   # Conv.forward without its "CUDA tensors only" guard on the stem
+        pk = self.get_pack()
+        if pk["kind"] == "stem":
+            return _base.to_nchw(ops.stem_conv(x, pk["w"], pk["bias"], self.conv.out_channels))
+        return _base.to_nchw(self.fwd_nhwc(conv.to_nhwc(x)))
+    conv.Conv.forward = conv.Conv.forward_fuse = conv_forward
 
 
 def install():

@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ._base import PackCache, fold_bn, pack_gemm_weight, require_eval, to_nchw, to_nhwc
+from ._base import BN_EPS, PackCache, fold_bn, pack_gemm_weight, require_eval, to_nchw, to_nhwc
 from .moe import get_safe_groups
 from .mot import _f32, _pack_dw, _pack_linear
 
@@ -290,8 +290,8 @@ class _GatedMoE(nn.Module, PackCache):
                                      nn.SiLU(inplace=False), nn.Linear(se_hidden, in_channels, bias=True), nn.Sigmoid())
         sc = self.static_channels
         self.static_net = nn.Sequential(
-            nn.Conv2d(sc, sc, 3, padding=1, groups=sc, bias=False), nn.BatchNorm2d(sc), nn.SiLU(inplace=False),
-            nn.Conv2d(sc, self.out_static, 1, bias=False), nn.BatchNorm2d(self.out_static), nn.SiLU(inplace=False))
+            nn.Conv2d(sc, sc, 3, padding=1, groups=sc, bias=False), nn.BatchNorm2d(sc, eps=BN_EPS, momentum=0.03), nn.SiLU(inplace=False),
+            nn.Conv2d(sc, self.out_static, 1, bias=False), nn.BatchNorm2d(self.out_static, eps=BN_EPS, momentum=0.03), nn.SiLU(inplace=False))
         self.routing = router if router is not None else (DualStreamGateRouterV2 if router_v2 else DualStreamGateRouter)(
             self.dynamic_channels, num_experts, top_k, temperature=initial_temperature)
         self.fused_expert_threshold = fused_expert_threshold
@@ -661,8 +661,8 @@ class UltimateOptimizedMoE(nn.Module, PackCache):
                 raise NotImplementedError("UltimateOptimizedMoE: channel halves must be multiples of 8 on the B200 path")
         sc = self.static_channels
         self.static_net = nn.Sequential(
-            nn.Conv2d(sc, sc, 3, padding=1, groups=sc, bias=False), nn.BatchNorm2d(sc), nn.SiLU(inplace=True),
-            nn.Conv2d(sc, self.out_static, 1, bias=False), nn.BatchNorm2d(self.out_static), nn.SiLU(inplace=True))
+            nn.Conv2d(sc, sc, 3, padding=1, groups=sc, bias=False), nn.BatchNorm2d(sc, eps=BN_EPS, momentum=0.03), nn.SiLU(inplace=True),
+            nn.Conv2d(sc, self.out_static, 1, bias=False), nn.BatchNorm2d(self.out_static, eps=BN_EPS, momentum=0.03), nn.SiLU(inplace=True))
         self.routing = ZeroCostRouter(self.dynamic_channels, num_experts, top_k, temperature=initial_temperature, use_cache=use_routing_cache)
         self.fused_experts = FusedExpertGroup(self.dynamic_channels, self.out_dynamic, num_experts, num_groups)
         self.complexity_estimator = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(self.dynamic_channels, 1, 1), nn.Sigmoid())

@@ -197,7 +197,8 @@ class OptimizedMOEImproved(nn.Module, PackCache):
         path has one place to look - the block output - and raises the same RuntimeError type there.  Inside A2C2fMoE the block
         runs through `fwd_nhwc` with no host synchronisation."""
         y = self.fwd_nhwc(to_nhwc(x))
-        if not torch.cuda.is_current_stream_capturing() and not bool(torch.isfinite(y).all()):
+        capturing = y.is_cuda and torch.cuda.is_current_stream_capturing()      # a host read would break a graph capture
+        if not capturing and not bool(torch.isfinite(y).all()):
             raise RuntimeError("OptimizedMOEImproved final output contains NaN/Inf (shared expert / sparse expert aggregation / "
                                "dtype conversion)")
         return to_nchw(y)
