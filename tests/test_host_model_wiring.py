@@ -116,3 +116,41 @@ def test_zoo_model_host_wiring_matches_oracle(emu, cfg):
         assert_within_noise(feats[i], ys[i], sim[i], what=f"{cfg} layer {i}", outlier_frac=0.02)
     assert_within_noise(y[:, :4], ref[:, :4], ysim[:, :4], what=f"{cfg} boxes", outlier_frac=0.02)
     assert_within_noise(y[:, 4:], ref[:, 4:], ysim[:, 4:], what=f"{cfg} scores", outlier_frac=0.02)
+
+
+def test_predictor_pipeline_on_emulated_model(emu, tmp_path_factory, monkeypatch):
+    """frames -> DetectionPredictor (letterbox -> model -> confidence filter -> rescale -> Results) with the model on emulated ops and
+    the two predictor kernels on their g++ build, against: oracle pre-processing -> the same model -> oracle rescale (exact)."""
+    import numpy as np
+
+    from oracle import letterbox_oracle as L
+    from yolo_master_b200 import ops
+    from yolo_master_b200.engine import DetectionPredictor
+    from yolo_master_b200.nn.tasks import DetectionModel
+    import test_preproc_host as ph
+    so = str(tmp_path_factory.mktemp("preproc_host_m") / "libpreproc_host.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "yolo-master_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "native", "preproc_host.cpp"), "-o", so], check=True)
+    lib = C.CDLL(so)
+    lib.host_letterbox_u8.argtypes = [ph.vp, ph.ci, ph.ci, ph.ci, ph.vp, ph.vp] + [ph.ci] * 7 + [ph.vp, ph.ci, ph.ci, ph.ci]
+    lib.host_scale_boxes.argtypes = [ph.vp, ph.ci, ph.cll, ph.ci, ph.vp, ph.vp, ph.ci, ph.ci]
+    monkeypatch.setattr(ops, "letterbox", ph._emu_letterbox(lib))
+    monkeypatch.setattr(ops, "scale_boxes", ph._emu_scale_boxes(lib))
+    monkeypatch.setattr(DetectionModel, "forward", lambda self, x: self._predict_once(x))      # skip the CUDA-only guard
+    m = DetectionModel("yolo26-master-n.yaml")
+    m.load_state_dict(synth_sd_from_keys(0), strict=True)
+    m.eval()
+    shapes = [(240, 320), (360, 640), (240, 320)]
+    frames = [np.random.default_rng(100 + i).integers(0, 256, (h, w, 3), dtype=np.uint8) for i, (h, w) in enumerate(shapes)]
+    pred = DetectionPredictor(m, imgsz=320, conf=0.0, device="cpu")
+    results = pred(frames)
+    batch = torch.from_numpy(np.stack([L.preprocess_frame(f, (320, 320)) for f in frames]))
+    assert torch.equal(pred.preprocess(frames), batch)
+    with torch.no_grad():
+        y = m(batch)[0].float()
+    for i, (r, f) in enumerate(zip(results, frames)):
+        keep = y[i][y[i][:, 4] > 0.0]
+        want = keep.clone()
+        want[:, :4] = torch.from_numpy(L.scale_boxes((320, 320), keep[:, :4].numpy(), f.shape))
+        assert torch.equal(r.boxes.data, want), i
+        assert r.orig_shape == f.shape[:2]
