@@ -184,6 +184,11 @@ int ym_linear_attn(const void* q, int ldq, const void* k, int ldk, const void* v
 /* F.adaptive_avg_pool2d (moa/heads.py:224). */
 int ym_adaptive_avgpool_nhwc(const void* x, int ldx, int B, int H, int W, int C, int h, int w, void* out, int ldo, void* stream);
 
+/* Pose.kpts_decode head.py:644-664: per level kpt fp32 [B][h][w][nk] (the pose tower's output) ->
+ * y fp32 [B][nk][A], A = sum h*w: x, y = (v*2 + grid coordinate) * stride, visibility (ndim 3) = sigmoid. */
+int ym_kpts_decode(int nl, const void* const* kpt, const int* hs, const int* ws, const float* strides, int B, int nk, int ndim,
+                   float* y, void* stream);
+
 /* ---- Gated MoE family (VisualEnhancedAdaptiveGateMoE, nn/modules/moe/gated.py) ----------------------
  * ym_gate_router: DualStreamGateRouter.forward gated.py:129-151 (fp32 throughout, as the reference's FP32RouterMixin) followed by
  *   AdaptiveGateMoE._safe_complexity / _apply_complexity_gate gated.py:455-490.  x: fp16 [B][H*W][ldx] (the dynamic channel half).

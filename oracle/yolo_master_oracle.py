@@ -137,6 +137,9 @@ def parse_spec(d: dict, ch: int = 3, scale: str | None = None) -> dict:
         elif m == "Detect":
             args = [args[0], reg_max, end2end, [chs[x] for x in f]]
             c2 = None
+        elif m == "Pose":
+            args = [args[0], tuple(d["kpt_shape"]), reg_max, end2end, [chs[x] for x in f]]
+            c2 = None
         else:  # nn.Upsample etc.
             c2 = chs[f]
         layers.append({"i": i, "f": f, "type": m, "args": args, "n": n, "legacy": legacy})
@@ -508,6 +511,23 @@ def detect_head_raw(sd, p, feats, nc, reg_max, end2end, legacy=False):
     return torch.cat(boxes, -1), torch.cat(scores, -1)
 
 
+def pose_kpts(sd, p, feats, kpt_shape, shapes, strides):
+    """`Pose.forward_head` head.py:613-621 (one2many keypoint towers) + `kpts_decode` :644-664.  Returns (B, nk, A)."""
+    bs, nk, ndim = feats[0].shape[0], kpt_shape[0] * kpt_shape[1], kpt_shape[1]
+    raw = []
+    for i, x in enumerate(feats):
+        t = conv_block(sd, f"{p}.cv4.{i}.1", conv_block(sd, f"{p}.cv4.{i}.0", x))
+        raw.append(F.conv2d(t, _w(sd[f"{p}.cv4.{i}.2.weight"]), sd[f"{p}.cv4.{i}.2.bias"]).view(bs, nk, -1))
+    y = torch.cat(raw, 2).clone()
+    anchors, st = make_anchors(shapes, strides, device=y.device, dtype=y.dtype)
+    anchors, st = anchors.t(), st.t()
+    if ndim == 3:
+        y[:, 2::ndim] = y[:, 2::ndim].sigmoid()
+    y[:, 0::ndim] = (y[:, 0::ndim] * 2.0 + (anchors[0] - 0.5)) * st
+    y[:, 1::ndim] = (y[:, 1::ndim] * 2.0 + (anchors[1] - 0.5)) * st
+    return y
+
+
 def detect_decode(boxes, scores, shapes, strides, end2end, reg_max=1):
     """`Detect._inference` head.py:173-194, `decode_bboxes` :210-217, `dist2bbox` tal.py:414-423.
 
@@ -593,6 +613,14 @@ def forward(spec: dict, sd: dict, x: torch.Tensor, img_hw=None, return_layers: b
             braw, sraw = detect_head_raw(sd, p, xin, nc, reg_max, e2e, L.get("legacy", False))
             y = detect_decode(braw, sraw, shapes, strides, e2e, reg_max)
             x = detect_postprocess(y, nc)[0] if e2e else y
+            ys["detect_raw"] = (braw, sraw, y)
+        elif t == "Pose":      # Detect + decoded keypoints appended to the dense prediction (head.py:608-611); one2many head
+            nc, kpt_shape, reg_max, e2e, _ = args
+            shapes = [tuple(v.shape[2:]) for v in xin]
+            strides = [H_in / s[0] for s in shapes]
+            braw, sraw = detect_head_raw(sd, p, xin, nc, reg_max, False, L.get("legacy", False))
+            y = detect_decode(braw, sraw, shapes, strides, False, reg_max)
+            x = torch.cat([y, pose_kpts(sd, p, xin, kpt_shape, shapes, strides)], 1)
             ys["detect_raw"] = (braw, sraw, y)
         else:
             raise NotImplementedError(t)

@@ -110,6 +110,9 @@ EXTRA_MODELS = {
     # ModularRouterExpertMoE (= OptimizedMOEImproved) as a top-level layer that owns its residual: the v0_1 zoo
     "yolo-master-n-v0_1": ("/root/reference/ultralytics/cfg/models/master/v0_1/det/yolo-master-n.yaml", [5, 8, 11, 23],
                            {"b2_128": (2, 128, 128, 12)}),
+    # Pose head on the v0_1 backbone: built with the reference's PoseModel
+    "yolo-master-pose-n-v0_1": ("/root/reference/ultralytics/cfg/models/master/v0_1/pose/yolo-master-pose-n.yaml", [11, 23],
+                                {"b2_128": (2, 128, 128, 14)}),
     "yolo26-master-moa-mot-s": (("/root/reference/ultralytics/cfg/models/26/yolo26-master-moa-mot-n.yaml", "s", [0.50, 0.50, 1024]),
                                 [13, 16, 19, 22], {"b1_160": (1, 160, 160, 8)}),
 }

@@ -1,6 +1,8 @@
 // TEST INFRASTRUCTURE (g++ only, no CUDA): runs the per-pixel / per-box code of yolo-master_b200/csrc/preproc_core.cuh on the
 // host, over the same index space the kernels cover, so tests/test_preproc_host.py can compare the integer arithmetic of
 // ym_letterbox_u8 / ym_scale_boxes with the oracle in the GPU-less build container.  Built by the test into a temp dir.
+#include <math.h>
+
 #include "preproc_core.cuh"
 
 using namespace ym;
@@ -20,6 +22,19 @@ extern "C" void host_letterbox_u8(const uint8_t* src, int sh, int sw, int src_pi
                 else out[((long long)dy * W + dx) * 3 + c] = (uint8_t)v[c];
             }
         }
+}
+
+struct SigmoidHost {
+    float operator()(float v) const { return 1.f / (1.f + expf(-v)); }
+};
+
+// one level at a time: kpt fp32 [B][h][w][nk] -> y[b][k][a0 + p] of the [B][nk][A] output
+extern "C" void host_kpts_decode_level(const float* kpt, int h, int w, float stride, int a0, int B, int nk, int ndim, int A, float* y) {
+    for (int b = 0; b < B; ++b)
+        for (int k = 0; k < nk; ++k)
+            for (int p = 0; p < h * w; ++p)
+                y[((long long)b * nk + k) * A + a0 + p] =
+                    kpt_decode_value(kpt[((long long)b * h * w + p) * nk + k], k % ndim, ndim, p % w, p / w, stride, SigmoidHost());
 }
 
 struct DivHost {

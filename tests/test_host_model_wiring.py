@@ -48,7 +48,8 @@ def emu(host):
 CASES = [("yolo-master-n-v0_1", "master/v0_1/det/yolo-master-n.yaml", "b2_128"),
          ("yolo-master-n-v0_10", "master/v0_10/det/yolo-master-n.yaml", "b2_160"),
          ("yolo26-master-n", "26/yolo26-master-n.yaml", None),
-         ("yolo26-master-moa-mot-n", "26/yolo26-master-moa-mot-n.yaml", "b1_96")]
+         ("yolo26-master-moa-mot-n", "26/yolo26-master-moa-mot-n.yaml", "b1_96"),
+         ("yolo-master-pose-n-v0_1", "master/v0_1/pose/yolo-master-pose-n.yaml", "b2_128")]
 
 
 @pytest.mark.parametrize("name,cfg,tag", CASES, ids=[c[0] for c in CASES])

@@ -12,7 +12,9 @@ from yolo_master_b200.utils.synth import synth_images
 CASES = [("yolo-master-n-v0", "master/v0/det/yolo-master-n.yaml", "b2_128"), ("yolo-master-n-v0", "master/v0/det/yolo-master-n.yaml", "b1_64"),
          ("yolo-master-l-v0", "master/v0/det/yolo-master-l.yaml", "b1_64"),
          # v0_1 zoo: ModularRouterExpertMoE (= OptimizedMOEImproved) as a top-level layer that owns its residual
-         ("yolo-master-n-v0_1", "master/v0_1/det/yolo-master-n.yaml", "b2_128")]
+         ("yolo-master-n-v0_1", "master/v0_1/det/yolo-master-n.yaml", "b2_128"),
+         # Pose head on the v0_1 backbone (reference PoseModel): (B, 4 + nc + 17*3, A)
+         ("yolo-master-pose-n-v0_1", "master/v0_1/pose/yolo-master-pose-n.yaml", "b2_128")]
 
 
 @pytest.mark.parametrize("name,cfg,tag", CASES)
@@ -29,6 +31,9 @@ def test_oracle_matches_reference_v0(name, cfg, tag):
     torch.testing.assert_close(sraw, c["head_scores"], atol=2e-4, rtol=1e-4)
     ref = c["final"].float()
     tol = 2e-2 if c["final"].dtype == torch.float16 else 1e-3      # the L fixture stores the dense output in fp16
-    assert y.shape == ref.shape == (c["B"], 84, (c["H"] // 8) ** 2 + (c["H"] // 16) ** 2 + (c["H"] // 32) ** 2)
+    rows = 5 + 51 if "pose" in name else 84
+    assert y.shape == ref.shape == (c["B"], rows, (c["H"] // 8) ** 2 + (c["H"] // 16) ** 2 + (c["H"] // 32) ** 2)
     torch.testing.assert_close(y[:, :4], ref[:, :4], atol=tol, rtol=1e-3)        # xywh in pixels (DFL expectation)
-    torch.testing.assert_close(y[:, 4:], ref[:, 4:], atol=1e-3 if tol > 1e-3 else 1e-5, rtol=1e-3)
+    nsc = 1 if "pose" in name else 80
+    torch.testing.assert_close(y[:, 4:4 + nsc], ref[:, 4:4 + nsc], atol=1e-3 if tol > 1e-3 else 1e-5, rtol=1e-3)
+    torch.testing.assert_close(y[:, 4 + nsc:], ref[:, 4 + nsc:], atol=2e-3, rtol=1e-3)     # decoded keypoints (pixels / visibility)

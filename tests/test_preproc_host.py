@@ -33,7 +33,8 @@ def host(tmp_path_factory):
     lib = C.CDLL(so)
     lib.host_letterbox_u8.argtypes = [vp, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, ci, ci, ci]
     lib.host_scale_boxes.argtypes = [vp, ci, cll, ci, vp, vp, ci, ci]
-    lib.host_letterbox_u8.restype = lib.host_scale_boxes.restype = None
+    lib.host_kpts_decode_level.argtypes = [vp, ci, ci, C.c_float, ci, ci, ci, ci, ci, vp]
+    lib.host_letterbox_u8.restype = lib.host_scale_boxes.restype = lib.host_kpts_decode_level.restype = None
     return lib
 
 
@@ -243,3 +244,27 @@ def test_letterbox_rejects_unsupported():
         LetterBox()(image=np.zeros((4, 4), np.uint8))
     with pytest.raises(ValueError):
         LetterBox((96, 128)).plan((2, 900), "cpu")           # would resize to zero rows (cv2.resize raises there too)
+
+
+def test_kpts_decode_body_matches_reference_formula(host):
+    """`ym_kpts_decode`'s per-element function (g++ build) against Pose.kpts_decode head.py:644-664 written with torch, for
+    (x, y, visibility) and (x, y) keypoints over three levels."""
+    from oracle import yolo_master_oracle as O
+    g = torch.Generator().manual_seed(6)
+    for ndim in (3, 2):
+        nk, B, shapes, strides = 17 * ndim, 2, [(8, 6), (4, 3), (2, 2)], [8.0, 16.0, 32.0]
+        A = sum(h * w for h, w in shapes)
+        levels = [torch.randn((B, h, w, nk), generator=g) for h, w in shapes]
+        y = torch.empty((B, nk, A))
+        a0 = 0
+        for t, (h, w), s in zip(levels, shapes, strides):
+            host.host_kpts_decode_level(t.data_ptr(), h, w, s, a0, B, nk, ndim, A, y.data_ptr())
+            a0 += h * w
+        raw = torch.cat([t.reshape(B, -1, nk).transpose(1, 2) for t in levels], 2)
+        anchors, st = O.make_anchors(shapes, strides)
+        want = raw.clone()
+        if ndim == 3:
+            want[:, 2::ndim] = want[:, 2::ndim].sigmoid()
+        want[:, 0::ndim] = (raw[:, 0::ndim] * 2.0 + (anchors.t()[0] - 0.5)) * st.t()
+        want[:, 1::ndim] = (raw[:, 1::ndim] * 2.0 + (anchors.t()[1] - 0.5)) * st.t()
+        torch.testing.assert_close(y, want, atol=1e-6, rtol=1e-6)

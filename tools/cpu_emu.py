@@ -344,12 +344,28 @@ def detect_topk(boxes, logits, strides, nc, max_det=300, return_anchor=False):
     return (r, idx.int()) if return_anchor else r
 
 
+def kpts_decode(kpts, strides, ndim):
+    B, nk = kpts[0].shape[0], kpts[0].shape[3]
+    outs = []
+    for t, s in zip(kpts, strides):
+        h, w = t.shape[1:3]
+        y = t.float().reshape(B, h * w, nk).transpose(1, 2).clone()                 # (B, nk, h*w)
+        gx = torch.arange(w, dtype=torch.float32).repeat(h)
+        gy = torch.arange(h, dtype=torch.float32).repeat_interleave(w)
+        y[:, 0::ndim] = (y[:, 0::ndim] * 2.0 + gx) * float(s)
+        y[:, 1::ndim] = (y[:, 1::ndim] * 2.0 + gy) * float(s)
+        if ndim == 3:
+            y[:, 2::ndim] = torch.sigmoid(y[:, 2::ndim])
+        outs.append(y)
+    return torch.cat(outs, 2)
+
+
 def install_model():
     """Everything `install()` covers plus the whole-model ops above."""
     install()
     for name, fn in dict(stem_conv=stem_conv, attention=attention, concat2=concat2, sppf_pool=sppf_pool, router_topk=router_topk,
                          moe_combine=moe_combine, moe_expert_gemm=moe_expert_gemm, gn_finalize=gn_finalize, detect_dense=detect_dense,
-                         detect_topk=detect_topk).items():
+                         detect_topk=detect_topk, kpts_decode=kpts_decode).items():
         setattr(ops, name, fn)
     ops.pitch = lambda t, dtype=torch.float16: (t.stride(2) if t.shape[2] > 1 else (t.stride(1) if t.shape[1] > 1 else (t.stride(0) if t.shape[0] > 1 else t.shape[3])))
     from yolo_master_b200.nn.modules import gated, head, moe

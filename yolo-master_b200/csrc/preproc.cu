@@ -83,9 +83,56 @@ __global__ void __launch_bounds__(256) scale_boxes_kernel(float* __restrict__ bo
     scale_box(boxes + i * ld, sp.p[img], padding, xywh, DivRn());
 }
 
+constexpr int KPT_MAX_LEVELS = 8;
+struct KptLevels {
+    const float* kpt[KPT_MAX_LEVELS];   // fp32 [B][h][w][nk]
+    int h[KPT_MAX_LEVELS], w[KPT_MAX_LEVELS], a0[KPT_MAX_LEVELS + 1];   // a0 = first anchor of the level
+    float stride[KPT_MAX_LEVELS];
+    int nl;
+};
+struct SigmoidRn {
+    __device__ __forceinline__ float operator()(float v) const { return __fdiv_rn(1.f, 1.f + expf(-v)); }
+};
+
+// y fp32 [B][nk][A]; one thread per element, anchor fastest (coalesced stores)
+__global__ void __launch_bounds__(256) kpts_decode_kernel(const KptLevels lv, int B, int nk, int ndim, int A, float* __restrict__ y) {
+    const long long total = (long long)B * nk * A;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(i % A), k = (int)((i / A) % nk), b = (int)(i / ((long long)A * nk));
+        int l = 0;
+        while (l + 1 < lv.nl && a >= lv.a0[l + 1]) ++l;
+        const int p = a - lv.a0[l], gy = p / lv.w[l], gx = p - gy * lv.w[l];
+        const float raw = lv.kpt[l][((long long)b * lv.h[l] * lv.w[l] + p) * nk + k];
+        y[i] = kpt_decode_value(raw, k % ndim, ndim, gx, gy, lv.stride[l], SigmoidRn());
+    }
+}
+
 }  // namespace ym
 
 using namespace ym;
+
+extern "C" int ym_kpts_decode(int nl, const void* const* kpt, const int* hs, const int* ws, const float* strides, int B, int nk,
+                              int ndim, float* y, void* stream) {
+    YM_CHECK_ARG(kpt && hs && ws && strides && y, "ym_kpts_decode: null pointer");
+    YM_CHECK_ARG(nl >= 1 && nl <= KPT_MAX_LEVELS && nk >= 1 && (ndim == 2 || ndim == 3) && nk % ndim == 0,
+                 "ym_kpts_decode: 1..%d levels, ndim 2 or 3 dividing nk", KPT_MAX_LEVELS);
+    if (B <= 0) return YM_OK;
+    KptLevels lv;
+    lv.nl = nl;
+    int A = 0;
+    for (int l = 0; l < nl; ++l) {
+        YM_CHECK_ARG(kpt[l] && hs[l] > 0 && ws[l] > 0, "ym_kpts_decode: bad level %d", l);
+        lv.kpt[l] = (const float*)kpt[l]; lv.h[l] = hs[l]; lv.w[l] = ws[l]; lv.stride[l] = strides[l]; lv.a0[l] = A;
+        A += hs[l] * ws[l];
+    }
+    lv.a0[nl] = A;
+    const long long total = (long long)B * nk * A;
+    long long nb = (total + 255) / 256;
+    if (nb > 148LL * 16) nb = 148LL * 16;
+    kpts_decode_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(lv, B, nk, ndim, A, y);
+    YM_CHECK_LAUNCH("kpts_decode");
+    return YM_OK;
+}
 
 extern "C" int ym_letterbox_u8(const void* src, long long src_stride, int B, int sh, int sw, int src_pitch, const void* xtab,
                                const void* ytab, int area2x, int nw, int nh, int top, int left, int pad_value, int swap_rb,

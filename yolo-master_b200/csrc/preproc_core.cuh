@@ -98,4 +98,13 @@ YM_HD void scale_box(float* b, const float* p, int padding, int xywh, Div div) {
     b[3] = y2;
 }
 
+// Pose.kpts_decode head.py:644-664 for one output element y[b][k][a] (k = keypoint*ndim + d): x / y are (v*2 + grid coordinate) *
+// stride (the reference's anchor - 0.5 IS the integer grid coordinate), the optional visibility channel is a sigmoid.
+// v points at the level's fp32 NHWC tower output [B][h][w][nk]; (gx, gy) is the anchor's cell, `sig` an IEEE-accurate sigmoid.
+template <typename Sig>
+YM_HD float kpt_decode_value(float raw, int d, int ndim, int gx, int gy, float stride, Sig sig) {
+    if (ndim == 3 && d == 2) return sig(raw);
+    return (raw * 2.0f + (float)(d == 0 ? gx : gy)) * stride;
+}
+
 }  // namespace ym

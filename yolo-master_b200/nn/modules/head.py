@@ -14,7 +14,7 @@ from ... import ops
 from ._base import require_eval, to_nhwc
 from .conv import Conv, DWConv, PlainConv2d
 
-__all__ = ("Detect", "DFL")
+__all__ = ("Detect", "DFL", "Pose")
 
 
 class DFL(nn.Module):
@@ -128,3 +128,27 @@ class Detect(nn.Module):
         if self.export:
             return y
         return y, {"boxes": boxes, "scores": logits, "feats": x}
+
+
+class Pose(Detect):
+    """`Pose(nc=80, kpt_shape=(17, 3), reg_max=16, end2end=False, ch=())` (head.py:558-664): Detect plus a keypoint tower per level;
+    the dense output gains `nk` rows of decoded keypoints (`ym_kpts_decode`): (B, 4 + nc + nk, A)."""
+
+    def __init__(self, nc=80, kpt_shape=(17, 3), reg_max=16, end2end=False, ch=()):
+        super().__init__(nc, reg_max, end2end, ch)
+        self.kpt_shape = tuple(kpt_shape)
+        self.nk = self.kpt_shape[0] * self.kpt_shape[1]
+        c4 = max(ch[0] // 4, self.nk)
+        self.cv4 = nn.ModuleList(nn.Sequential(Conv(x, c4, 3), Conv(c4, c4, 3), PlainConv2d(c4, self.nk, 1)) for x in ch)
+        if end2end:
+            self.one2one_cv4 = copy.deepcopy(self.cv4)
+
+    def forward(self, x):
+        if self.end2end:
+            raise NotImplementedError("Pose: the end2end (one2one) head is not on the B200 path")
+        y, aux = super().forward(x)
+        feats = [to_nhwc(f) for f in x]
+        kpts = [self._tower(self.cv4[i], f) for i, f in enumerate(feats)]
+        ky = ops.kpts_decode(kpts, [float(s) for s in self.stride.tolist()], self.kpt_shape[1])
+        aux["kpts"] = kpts
+        return torch.cat([y, ky], 1), aux

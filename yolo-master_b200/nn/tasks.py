@@ -95,8 +95,8 @@ def parse_model(d, ch, verbose=False):
         for j, a in enumerate(args):
             if isinstance(a, str):
                 with contextlib.suppress(ValueError, SyntaxError):
-                    args[j] = {"nc": nc, "reg_max": reg_max, "end2end": end2end}[a] if a in ("nc", "reg_max", "end2end") \
-                        else ast.literal_eval(a)
+                    named = {"nc": nc, "reg_max": reg_max, "end2end": end2end, "kpt_shape": d.get("kpt_shape")}
+                    args[j] = named[a] if a in named else ast.literal_eval(a)
         n = n_ = max(round(n * depth), 1) if n > 1 else n
         s_in = (1 if i == 0 else strides[f]) if isinstance(f, int) else strides[f[0]]
         s_out = s_in
@@ -130,7 +130,7 @@ def parse_model(d, ch, verbose=False):
                 legacy = False
         elif m is M.Concat:
             c2 = sum(ch[x] for x in f)
-        elif m is M.Detect:
+        elif m in (M.Detect, M.Pose):
             args.extend([reg_max, end2end, [ch[x] for x in f]])
             m.legacy = legacy
         elif m is M.Upsample:
@@ -246,6 +246,17 @@ class DetectionModel(nn.Module):
             g = GraphedForward(self, batch, height, width, dtype, warmup)
             self._graphs[key] = g
         return g
+
+
+class PoseModel(DetectionModel):
+    """`PoseModel(cfg, ch=3, nc=None, data_kpt_shape=(None, None))` (tasks.py:801-846): a DetectionModel whose head is `Pose`."""
+
+    def __init__(self, cfg="yolo-master-pose-n.yaml", ch=3, nc=None, data_kpt_shape=(None, None), verbose=False):
+        cfg = cfg if isinstance(cfg, dict) else yaml_model_load(cfg)
+        if any(data_kpt_shape) and list(data_kpt_shape) != list(cfg["kpt_shape"]):
+            cfg["kpt_shape"] = list(data_kpt_shape)
+        super().__init__(cfg, ch=ch, nc=nc, verbose=verbose)
+        self.kpt_shape = tuple(self.yaml["kpt_shape"])
 
 
 class GraphedForward:

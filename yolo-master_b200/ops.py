@@ -624,3 +624,14 @@ def ctx_mean3(a, b, c, out=None):
                                   b.shape[1], b.shape[2], c.shape[1], c.shape[2], out.data_ptr(), pitch(out), _stream()), "ym_ctx_mean3")
     _count()
     return out
+
+
+def kpts_decode(kpts, strides, ndim):
+    """ym_kpts_decode.  kpts[l]: fp32 (B,h,w,nk) pose-tower outputs -> fp32 (B, nk, A)."""
+    B, nk = kpts[0].shape[0], kpts[0].shape[3]
+    A = sum(k.shape[1] * k.shape[2] for k in kpts)
+    y = torch.empty((B, nk, A), dtype=torch.float32, device=kpts[0].device)
+    nl, kp, _, hs, ws, st = _level_arrays(kpts, kpts, strides)
+    _lib.check(lib().ym_kpts_decode(nl, kp, hs, ws, st, B, nk, ndim, y.data_ptr(), _stream()), "ym_kpts_decode")
+    _count()
+    return y

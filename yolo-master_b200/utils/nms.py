@@ -31,8 +31,12 @@ def non_max_suppression(prediction, conf_thres: float = 0.25, iou_thres: float =
         return (output, keepi) if return_idxs else output
     if classes is not None or agnostic or multi_label or rotated or len(labels):
         raise NotImplementedError("non_max_suppression: classes / agnostic / multi_label / rotated / labels are not on the B200 path")
-    if nc and prediction.shape[1] - 4 != nc:
-        raise NotImplementedError("non_max_suppression: mask coefficients (nc < channels-4) are not on the B200 path")
+    extra = None
+    if nc and prediction.shape[1] - 4 != nc:      # rows past 4 + nc (keypoints, mask coefficients) ride along with the kept anchors
+        if cluster:
+            raise NotImplementedError("non_max_suppression(cluster=True) with extra columns is not on the B200 path")
+        extra = prediction[:, 4 + nc:]
+        prediction = prediction[:, :4 + nc].contiguous()
     if cluster and frame_wh is None:
         raise ValueError("non_max_suppression(cluster=True) needs frame_wh=(width, height)")
     out, cnt, idx, scratch = ops.nms_batched(prediction.float(), conf_thres, iou_thres, max_det, max_nms, float(max_wh),
@@ -45,6 +49,8 @@ def non_max_suppression(prediction, conf_thres: float = 0.25, iou_thres: float =
         out, cnt, idx = ops.nms_batched_large(prediction.float(), conf_thres, iou_thres, max_det, max_nms, float(max_wh))
     counts = cnt.tolist()  # the reference returns ragged Python lists: one host read of B integers
     output = [out[b, :n] for b, n in enumerate(counts)]
+    if extra is not None:                       # nms.py:124-131: x = cat(box, conf, cls, mask) - gathered by the kept anchor indices
+        output = [torch.cat([o, extra[b][:, idx[b, :n].long()].t().to(o.dtype)], 1) for b, (o, n) in enumerate(zip(output, counts))]
     if return_idxs:
         return output, [idx[b, :n].long() for b, n in enumerate(counts)]
     return output
