@@ -185,7 +185,8 @@ int ym_linear_attn(const void* q, int ldq, const void* k, int ldk, const void* v
 int ym_adaptive_avgpool_nhwc(const void* x, int ldx, int B, int H, int W, int C, int h, int w, void* out, int ldo, void* stream);
 
 /* Pose.kpts_decode head.py:644-664: per level kpt fp32 [B][h][w][nk] (the pose tower's output) ->
- * y fp32 [B][nk][A], A = sum h*w: x, y = (v*2 + grid coordinate) * stride, visibility (ndim 3) = sigmoid. */
+ * y fp32 [B][nk][A], A = sum h*w: x, y = (v*2 + grid coordinate) * stride, visibility (ndim 3) = sigmoid.  ndim 1 copies the values
+ * unchanged: the mask-coefficient rows of Segment._inference head.py:332-344. */
 int ym_kpts_decode(int nl, const void* const* kpt, const int* hs, const int* ws, const float* strides, int B, int nk, int ndim,
                    float* y, void* stream);
 

@@ -140,6 +140,9 @@ def parse_spec(d: dict, ch: int = 3, scale: str | None = None) -> dict:
         elif m == "Pose":
             args = [args[0], tuple(d["kpt_shape"]), reg_max, end2end, [chs[x] for x in f]]
             c2 = None
+        elif m == "Segment":
+            args = [args[0], args[1], make_divisible(min(args[2], max_channels) * width, 8), reg_max, end2end, [chs[x] for x in f]]
+            c2 = None
         else:  # nn.Upsample etc.
             c2 = chs[f]
         layers.append({"i": i, "f": f, "type": m, "args": args, "n": n, "legacy": legacy})
@@ -528,6 +531,20 @@ def pose_kpts(sd, p, feats, kpt_shape, shapes, strides):
     return y
 
 
+def segment_extras(sd, p, feats, nm):
+    """`Segment.forward_head` head.py:337-345 (one2many mask-coefficient towers) and `Proto.forward` block.py:105-107.
+    Returns (mask coefficients (B, nm, A), prototypes (B, nm, 2h, 2w))."""
+    bs = feats[0].shape[0]
+    mc = []
+    for i, x in enumerate(feats):
+        t = conv_block(sd, f"{p}.cv4.{i}.1", conv_block(sd, f"{p}.cv4.{i}.0", x))
+        mc.append(F.conv2d(t, _w(sd[f"{p}.cv4.{i}.2.weight"]), sd[f"{p}.cv4.{i}.2.bias"]).view(bs, nm, -1))
+    t = conv_block(sd, p + ".proto.cv1", feats[0])
+    t = _st(F.conv_transpose2d(t, _w(sd[p + ".proto.upsample.weight"]), sd[p + ".proto.upsample.bias"], 2, 0))
+    proto = conv_block(sd, p + ".proto.cv3", conv_block(sd, p + ".proto.cv2", t))
+    return torch.cat(mc, 2), proto
+
+
 def detect_decode(boxes, scores, shapes, strides, end2end, reg_max=1):
     """`Detect._inference` head.py:173-194, `decode_bboxes` :210-217, `dist2bbox` tal.py:414-423.
 
@@ -614,6 +631,15 @@ def forward(spec: dict, sd: dict, x: torch.Tensor, img_hw=None, return_layers: b
             y = detect_decode(braw, sraw, shapes, strides, e2e, reg_max)
             x = detect_postprocess(y, nc)[0] if e2e else y
             ys["detect_raw"] = (braw, sraw, y)
+        elif t == "Segment":   # Detect + mask coefficients appended to the dense prediction, prototypes alongside (head.py:317-335)
+            nc, nm, npr, reg_max, e2e, _ = args
+            shapes = [tuple(v.shape[2:]) for v in xin]
+            strides = [H_in / s[0] for s in shapes]
+            braw, sraw = detect_head_raw(sd, p, xin, nc, reg_max, False, L.get("legacy", False))
+            y = detect_decode(braw, sraw, shapes, strides, False, reg_max)
+            mc, proto = segment_extras(sd, p, xin, nm)
+            x = torch.cat([y, mc], 1)
+            ys["detect_raw"], ys["proto"] = (braw, sraw, y), proto
         elif t == "Pose":      # Detect + decoded keypoints appended to the dense prediction (head.py:608-611); one2many head
             nc, kpt_shape, reg_max, e2e, _ = args
             shapes = [tuple(v.shape[2:]) for v in xin]

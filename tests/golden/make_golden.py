@@ -113,6 +113,9 @@ EXTRA_MODELS = {
     # Pose head on the v0_1 backbone: built with the reference's PoseModel
     "yolo-master-pose-n-v0_1": ("/root/reference/ultralytics/cfg/models/master/v0_1/pose/yolo-master-pose-n.yaml", [11, 23],
                                 {"b2_128": (2, 128, 128, 14)}),
+    # Segment head + Proto on the v0_1 backbone (reference model built from the seg YAML)
+    "yolo-master-seg-n-v0_1": ("/root/reference/ultralytics/cfg/models/master/v0_1/seg/yolo-master-seg-n.yaml", [23],
+                               {"b2_96": (2, 96, 96, 15)}),
     "yolo26-master-moa-mot-s": (("/root/reference/ultralytics/cfg/models/26/yolo26-master-moa-mot-n.yaml", "s", [0.50, 0.50, 1024]),
                                 [13, 16, 19, 22], {"b1_160": (1, 160, 160, 8)}),
 }
@@ -161,10 +164,15 @@ def extra_model_golden(name):
         y, preds, feats, _ = run(m, x)
         for h in hooks:
             h.remove()
+        proto = None
+        if isinstance(y, tuple):            # Segment: (dense prediction + mask coefficients, prototypes)
+            y, proto = y
         pr = preds["one2one"] if "one2one" in preds else preds
         gold["cases"][tag] = {"B": B, "H": H, "W": W, "seed": seed, "final": y.clone().half() if name.endswith("l-v0") else y.clone(),
                               "layers": {i: feats[i].clone() for i in keep},
                               "head_boxes": pr["boxes"].clone(), "head_scores": pr["scores"].clone(), "routes": routes}
+        if proto is not None:
+            gold["cases"][tag]["proto"] = proto.clone()
         print(name, tag, "final", tuple(y.shape), "max score", float(y[:, 4:].max()))
     torch.save(gold, f"{OUT}/{name}.golden.pt")
     for f in sorted(os.listdir(OUT)):

@@ -49,7 +49,8 @@ CASES = [("yolo-master-n-v0_1", "master/v0_1/det/yolo-master-n.yaml", "b2_128"),
          ("yolo-master-n-v0_10", "master/v0_10/det/yolo-master-n.yaml", "b2_160"),
          ("yolo26-master-n", "26/yolo26-master-n.yaml", None),
          ("yolo26-master-moa-mot-n", "26/yolo26-master-moa-mot-n.yaml", "b1_96"),
-         ("yolo-master-pose-n-v0_1", "master/v0_1/pose/yolo-master-pose-n.yaml", "b2_128")]
+         ("yolo-master-pose-n-v0_1", "master/v0_1/pose/yolo-master-pose-n.yaml", "b2_128"),
+         ("yolo-master-seg-n-v0_1", "master/v0_1/seg/yolo-master-seg-n.yaml", "b2_96")]
 
 
 @pytest.mark.parametrize("name,cfg,tag", CASES, ids=[c[0] for c in CASES])
@@ -65,13 +66,18 @@ def test_model_host_wiring_matches_reference_golden(emu, name, cfg, tag):
     feats = {}
     hooks = [mod.register_forward_hook(lambda mod, i, o, k=k: feats.__setitem__(k, o)) for k, mod in enumerate(m.model)]
     with torch.no_grad():
-        y = m._predict_once(x)[0].float()
+        y = m._predict_once(x)[0]
     for h in hooks:
         h.remove()
     spec = O.parse_spec(yaml_of(cfg))
-    ref, _ = O.forward(spec, sd, x.float(), return_layers=True)
+    ref, rys = O.forward(spec, sd, x.float(), return_layers=True)
     with O.fp16_storage(), O.fp16_weights():
         ysim, sim = O.forward(spec, sd, x.float(), return_layers=True)
+    if isinstance(y, tuple):      # Segment: (dense prediction + mask coefficients, prototypes)
+        y, proto = y
+        assert_within_noise(proto, c["proto"], sim["proto"], what=f"{name} prototypes vs reference golden")
+        assert_within_noise(proto, rys["proto"], sim["proto"], what=f"{name} prototypes")
+    y = y.float()
     for i, g in c["layers"].items():
         assert_within_noise(feats[i], g, sim[i], what=f"{name} layer {i} vs reference golden", outlier_frac=0.02)
     if ref.shape[-1] == 6:        # end2end (B, 300, 6): rows are a top-k selection, compare the score column and the best boxes

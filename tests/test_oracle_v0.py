@@ -37,3 +37,18 @@ def test_oracle_matches_reference_v0(name, cfg, tag):
     nsc = 1 if "pose" in name else 80
     torch.testing.assert_close(y[:, 4:4 + nsc], ref[:, 4:4 + nsc], atol=1e-3 if tol > 1e-3 else 1e-5, rtol=1e-3)
     torch.testing.assert_close(y[:, 4 + nsc:], ref[:, 4 + nsc:], atol=2e-3, rtol=1e-3)     # decoded keypoints (pixels / visibility)
+
+
+def test_oracle_matches_reference_segment():
+    """Segment head + Proto on the v0_1 backbone: dense prediction with the 32 mask coefficients appended, and the prototypes."""
+    name, cfg = "yolo-master-seg-n-v0_1", "master/v0_1/seg/yolo-master-seg-n.yaml"
+    c = torch.load(os.path.join(GOLD, f"{name}.golden.pt"))["cases"]["b2_96"]
+    sd = synth_sd_from_keys(0, name)
+    y, ys = O.forward(O.parse_spec(yaml_of(cfg)), sd, synth_images(c["B"], c["H"], c["W"], c["seed"]), return_layers=True)
+    ref = c["final"].float()
+    assert y.shape == ref.shape == (2, 4 + 80 + 32, 12 * 12 + 6 * 6 + 3 * 3)
+    torch.testing.assert_close(y[:, :4], ref[:, :4], atol=1e-3, rtol=1e-3)
+    torch.testing.assert_close(y[:, 4:84], ref[:, 4:84], atol=1e-5, rtol=1e-3)
+    torch.testing.assert_close(y[:, 84:], ref[:, 84:], atol=3e-4, rtol=1e-3)          # mask coefficients
+    assert ys["proto"].shape == c["proto"].shape == (2, 32, 24, 24)
+    torch.testing.assert_close(ys["proto"], c["proto"], atol=3e-4, rtol=1e-3)

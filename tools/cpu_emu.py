@@ -350,10 +350,11 @@ def kpts_decode(kpts, strides, ndim):
     for t, s in zip(kpts, strides):
         h, w = t.shape[1:3]
         y = t.float().reshape(B, h * w, nk).transpose(1, 2).clone()                 # (B, nk, h*w)
-        gx = torch.arange(w, dtype=torch.float32).repeat(h)
-        gy = torch.arange(h, dtype=torch.float32).repeat_interleave(w)
-        y[:, 0::ndim] = (y[:, 0::ndim] * 2.0 + gx) * float(s)
-        y[:, 1::ndim] = (y[:, 1::ndim] * 2.0 + gy) * float(s)
+        if ndim > 1:                                                                # ndim 1: plain gather (mask coefficients)
+            gx = torch.arange(w, dtype=torch.float32).repeat(h)
+            gy = torch.arange(h, dtype=torch.float32).repeat_interleave(w)
+            y[:, 0::ndim] = (y[:, 0::ndim] * 2.0 + gx) * float(s)
+            y[:, 1::ndim] = (y[:, 1::ndim] * 2.0 + gy) * float(s)
         if ndim == 3:
             y[:, 2::ndim] = torch.sigmoid(y[:, 2::ndim])
         outs.append(y)

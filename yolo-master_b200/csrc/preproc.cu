@@ -114,8 +114,8 @@ using namespace ym;
 extern "C" int ym_kpts_decode(int nl, const void* const* kpt, const int* hs, const int* ws, const float* strides, int B, int nk,
                               int ndim, float* y, void* stream) {
     YM_CHECK_ARG(kpt && hs && ws && strides && y, "ym_kpts_decode: null pointer");
-    YM_CHECK_ARG(nl >= 1 && nl <= KPT_MAX_LEVELS && nk >= 1 && (ndim == 2 || ndim == 3) && nk % ndim == 0,
-                 "ym_kpts_decode: 1..%d levels, ndim 2 or 3 dividing nk", KPT_MAX_LEVELS);
+    YM_CHECK_ARG(nl >= 1 && nl <= KPT_MAX_LEVELS && nk >= 1 && ndim >= 1 && ndim <= 3 && nk % ndim == 0,
+                 "ym_kpts_decode: 1..%d levels, ndim 1 (copy), 2 or 3 dividing nk", KPT_MAX_LEVELS);
     if (B <= 0) return YM_OK;
     KptLevels lv;
     lv.nl = nl;

@@ -103,6 +103,7 @@ YM_HD void scale_box(float* b, const float* p, int padding, int xywh, Div div) {
 // v points at the level's fp32 NHWC tower output [B][h][w][nk]; (gx, gy) is the anchor's cell, `sig` an IEEE-accurate sigmoid.
 template <typename Sig>
 YM_HD float kpt_decode_value(float raw, int d, int ndim, int gx, int gy, float stride, Sig sig) {
+    if (ndim == 1) return raw;                       // plain NHWC levels -> (B, n, A) gather: Segment's mask coefficients
     if (ndim == 3 && d == 2) return sig(raw);
     return (raw * 2.0f + (float)(d == 0 ? gx : gy)) * stride;
 }

@@ -11,10 +11,10 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ._base import require_eval, to_nhwc
+from ._base import PackCache, pack_gemm_weight, require_eval, to_nchw, to_nhwc
 from .conv import Conv, DWConv, PlainConv2d
 
-__all__ = ("Detect", "DFL", "Pose")
+__all__ = ("Detect", "DFL", "Pose", "Proto", "Segment")
 
 
 class DFL(nn.Module):
@@ -152,3 +152,62 @@ class Pose(Detect):
         ky = ops.kpts_decode(kpts, [float(s) for s in self.stride.tolist()], self.kpt_shape[1])
         aux["kpts"] = kpts
         return torch.cat([y, ky], 1), aux
+
+
+class Proto(nn.Module, PackCache):
+    """`Proto(c1, c_=256, c2=32)` (block.py:88-107): Conv 3x3 -> ConvTranspose2d(2, stride 2) -> Conv 3x3 -> Conv 1x1.
+    A 2x2 stride-2 transposed convolution writes each input pixel to its own 2x2 output block, so it runs as a 1x1 convolution
+    to 4*c_ channels (one group per (dy, dx)) followed by a depth-to-space rearrangement."""
+
+    def __init__(self, c1, c_=256, c2=32):
+        super().__init__()
+        self.cv1 = Conv(c1, c_, k=3)
+        self.upsample = nn.ConvTranspose2d(c_, c_, 2, 2, 0, bias=True)
+        self.cv2 = Conv(c_, c_, k=3)
+        self.cv3 = Conv(c_, c2)
+
+    def _pack_sources(self):
+        return [self.upsample.weight, self.upsample.bias]
+
+    def _build_pack(self):
+        w = self.upsample.weight.detach().float()                          # [ci][co][dy][dx]
+        c = w.shape[1]
+        w4 = w.permute(2, 3, 1, 0).reshape(4 * c, w.shape[0], 1, 1)        # row (dy*2+dx)*c + co
+        return {"w": pack_gemm_weight(w4), "b": self.upsample.bias.detach().float().repeat(4).contiguous(), "c": c}
+
+    def fwd_nhwc(self, x):
+        pk = self.get_pack()
+        t = self.cv1.fwd_nhwc(x)
+        B, H, W, _ = t.shape
+        c = pk["c"]
+        t = ops.conv2d(t, pk["w"], pk["b"], 4 * c, 1, 1, 1, 0, False)      # (B,H,W,[dy][dx][c])
+        t = t.view(B, H, W, 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, c)   # depth-to-space (a copy)
+        return self.cv3.fwd_nhwc(self.cv2.fwd_nhwc(t))
+
+    def forward(self, x):
+        require_eval(self)
+        return to_nchw(self.fwd_nhwc(to_nhwc(x)))
+
+
+class Segment(Detect):
+    """`Segment(nc=80, nm=32, npr=256, reg_max=16, end2end=False, ch=())` (head.py:265-346): Detect plus a mask-coefficient tower per
+    level and a prototype branch on the first level.  Eval output: ((y (B, 4 + nc + nm, A), proto (B, nm, 2h, 2w)), aux)."""
+
+    def __init__(self, nc=80, nm=32, npr=256, reg_max=16, end2end=False, ch=()):
+        super().__init__(nc, reg_max, end2end, ch)
+        self.nm, self.npr = nm, npr
+        self.proto = Proto(ch[0], self.npr, self.nm)
+        c4 = max(ch[0] // 4, self.nm)
+        self.cv4 = nn.ModuleList(nn.Sequential(Conv(x, c4, 3), Conv(c4, c4, 3), PlainConv2d(c4, self.nm, 1)) for x in ch)
+        if end2end:
+            self.one2one_cv4 = copy.deepcopy(self.cv4)
+
+    def forward(self, x):
+        if self.end2end:
+            raise NotImplementedError("Segment: the end2end (one2one) head is not on the B200 path")
+        y, aux = super().forward(x)
+        feats = [to_nhwc(f) for f in x]
+        mc = ops.kpts_decode([self._tower(self.cv4[i], f) for i, f in enumerate(feats)], [float(s) for s in self.stride.tolist()], 1)
+        proto = to_nchw(self.proto.fwd_nhwc(feats[0]))
+        aux["mask_coefficient"], aux["proto"] = mc, proto
+        return (torch.cat([y, mc], 1), proto), aux

@@ -130,8 +130,10 @@ def parse_model(d, ch, verbose=False):
                 legacy = False
         elif m is M.Concat:
             c2 = sum(ch[x] for x in f)
-        elif m in (M.Detect, M.Pose):
+        elif m in (M.Detect, M.Pose, M.Segment):
             args.extend([reg_max, end2end, [ch[x] for x in f]])
+            if m is M.Segment:
+                args[2] = make_divisible(min(args[2], max_channels) * width, 8)      # npr scales with the width (tasks.py:2224-2225)
             m.legacy = legacy
         elif m is M.Upsample:
             c2 = ch[f]
@@ -257,6 +259,11 @@ class PoseModel(DetectionModel):
             cfg["kpt_shape"] = list(data_kpt_shape)
         super().__init__(cfg, ch=ch, nc=nc, verbose=verbose)
         self.kpt_shape = tuple(self.yaml["kpt_shape"])
+
+
+class SegmentationModel(DetectionModel):
+    """`SegmentationModel(cfg, ch=3, nc=None)` (tasks.py:775-798): a DetectionModel whose head is `Segment`; the eval forward returns
+    ((y, proto), aux)."""
 
 
 class GraphedForward:
