@@ -190,6 +190,11 @@ int ym_adaptive_avgpool_nhwc(const void* x, int ldx, int B, int H, int W, int C,
 int ym_kpts_decode(int nl, const void* const* kpt, const int* hs, const int* ws, const float* strides, int B, int nk, int ndim,
                    float* y, void* stream);
 
+/* OBB head head.py:477-500 + dist2rbox utils/tal.py:447-453 on top of ym_detect_dense's xywh decode: angle fp32 [B][h][w][1] per level
+ * (raw tower output), yin fp32 [B][4+nc][A] -> yout fp32 [B][4+nc+1][A] = rotated centre, w, h, class scores, angle = (sigmoid - 0.25)*pi. */
+int ym_obb_finish(int nl, const void* const* angle, const int* hs, const int* ws, const float* strides, int B, int nc,
+                  const float* yin, float* yout, void* stream);
+
 /* ---- Gated MoE family (VisualEnhancedAdaptiveGateMoE, nn/modules/moe/gated.py) ----------------------
  * ym_gate_router: DualStreamGateRouter.forward gated.py:129-151 (fp32 throughout, as the reference's FP32RouterMixin) followed by
  *   AdaptiveGateMoE._safe_complexity / _apply_complexity_gate gated.py:455-490.  x: fp16 [B][H*W][ldx] (the dynamic channel half).

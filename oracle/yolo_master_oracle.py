@@ -140,6 +140,9 @@ def parse_spec(d: dict, ch: int = 3, scale: str | None = None) -> dict:
         elif m == "Pose":
             args = [args[0], tuple(d["kpt_shape"]), reg_max, end2end, [chs[x] for x in f]]
             c2 = None
+        elif m == "OBB":
+            args = [args[0], args[1], reg_max, end2end, [chs[x] for x in f]]
+            c2 = None
         elif m == "Segment":
             args = [args[0], args[1], make_divisible(min(args[2], max_channels) * width, 8), reg_max, end2end, [chs[x] for x in f]]
             c2 = None
@@ -545,6 +548,29 @@ def segment_extras(sd, p, feats, nm):
     return torch.cat(mc, 2), proto
 
 
+def obb_decode(sd, p, feats, boxes, scores, shapes, strides, reg_max):
+    """`OBB.forward_head` head.py:484-496 (angle towers, (sigmoid - 0.25) * pi), `OBB.decode_bboxes` = `dist2rbox` utils/tal.py:447-453 and
+    `OBB._inference` head.py:477-482.  Returns (B, 4 + nc + 1, A): rotated cx, cy, w, h in pixels, sigmoid scores, angle."""
+    bs = feats[0].shape[0]
+    ang = []
+    for i, x in enumerate(feats):
+        t = conv_block(sd, f"{p}.cv4.{i}.1", conv_block(sd, f"{p}.cv4.{i}.0", x))
+        ang.append(F.conv2d(t, _w(sd[f"{p}.cv4.{i}.2.weight"]), sd[f"{p}.cv4.{i}.2.bias"]).view(bs, 1, -1))
+    angle = (torch.cat(ang, 2).sigmoid() - 0.25) * math.pi
+    if reg_max > 1:
+        b, _, a = boxes.shape
+        boxes = (boxes.view(b, 4, reg_max, a).transpose(2, 1).softmax(1)
+                 * torch.arange(reg_max, dtype=boxes.dtype).view(1, reg_max, 1, 1)).sum(1)
+    anchors, st = make_anchors(shapes, strides, dtype=boxes.dtype)
+    anchors, st = anchors.t().unsqueeze(0), st.t()
+    lt, rb = boxes.split(2, 1)
+    cos, sin = torch.cos(angle), torch.sin(angle)
+    xf, yf = ((rb - lt) / 2).split(1, 1)
+    xy = torch.cat([xf * cos - yf * sin, xf * sin + yf * cos], 1) + anchors
+    dbox = torch.cat([xy, lt + rb], 1) * st
+    return torch.cat([dbox, scores.sigmoid(), angle], 1)
+
+
 def detect_decode(boxes, scores, shapes, strides, end2end, reg_max=1):
     """`Detect._inference` head.py:173-194, `decode_bboxes` :210-217, `dist2bbox` tal.py:414-423.
 
@@ -631,6 +657,13 @@ def forward(spec: dict, sd: dict, x: torch.Tensor, img_hw=None, return_layers: b
             y = detect_decode(braw, sraw, shapes, strides, e2e, reg_max)
             x = detect_postprocess(y, nc)[0] if e2e else y
             ys["detect_raw"] = (braw, sraw, y)
+        elif t == "OBB":       # rotated boxes + angle row (head.py:477-500); one2many head
+            nc, ne, reg_max, e2e, _ = args
+            shapes = [tuple(v.shape[2:]) for v in xin]
+            strides = [H_in / s[0] for s in shapes]
+            braw, sraw = detect_head_raw(sd, p, xin, nc, reg_max, False, L.get("legacy", False))
+            x = obb_decode(sd, p, xin, braw, sraw, shapes, strides, reg_max)
+            ys["detect_raw"] = (braw, sraw, x)
         elif t == "Segment":   # Detect + mask coefficients appended to the dense prediction, prototypes alongside (head.py:317-335)
             nc, nm, npr, reg_max, e2e, _ = args
             shapes = [tuple(v.shape[2:]) for v in xin]

@@ -116,6 +116,9 @@ EXTRA_MODELS = {
     # Segment head + Proto on the v0_1 backbone (reference model built from the seg YAML)
     "yolo-master-seg-n-v0_1": ("/root/reference/ultralytics/cfg/models/master/v0_1/seg/yolo-master-seg-n.yaml", [23],
                                {"b2_96": (2, 96, 96, 15)}),
+    # OBB head on the v0_1 backbone (rotated boxes + angle row)
+    "yolo-master-obb-n-v0_1": ("/root/reference/ultralytics/cfg/models/master/v0_1/obb/yolo-master-obb-n.yaml", [23],
+                               {"b2_96": (2, 96, 96, 16)}),
     "yolo26-master-moa-mot-s": (("/root/reference/ultralytics/cfg/models/26/yolo26-master-moa-mot-n.yaml", "s", [0.50, 0.50, 1024]),
                                 [13, 16, 19, 22], {"b1_160": (1, 160, 160, 8)}),
 }

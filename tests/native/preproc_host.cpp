@@ -37,6 +37,26 @@ extern "C" void host_kpts_decode_level(const float* kpt, int h, int w, float str
                     kpt_decode_value(kpt[((long long)b * h * w + p) * nk + k], k % ndim, ndim, p % w, p / w, stride, SigmoidHost());
 }
 
+struct SinCosHost {
+    void operator()(float a, float* s, float* c) const { *s = sinf(a); *c = cosf(a); }
+};
+
+// one level: angle fp32 [B][h][w][1]; yin [B][rows][A] -> yout [B][rows+1][A] for the anchors a0 .. a0 + h*w
+extern "C" void host_obb_finish_level(const float* angle, int h, int w, float stride, int a0, int B, int nc, int A, const float* yin,
+                                      float* yout) {
+    const int rows = 4 + nc;
+    for (int b = 0; b < B; ++b)
+        for (int p = 0; p < h * w; ++p) {
+            const float* src = yin + (long long)b * rows * A + a0 + p;
+            float* dst = yout + (long long)b * (rows + 1) * A + a0 + p;
+            float ox, oy, ang;
+            obb_rotate(src[0], src[A], angle[(long long)b * h * w + p], p % w, p / w, stride, &ox, &oy, &ang, SigmoidHost(), SinCosHost());
+            dst[0] = ox; dst[A] = oy;
+            for (int r = 2; r < rows; ++r) dst[(long long)r * A] = src[(long long)r * A];
+            dst[(long long)rows * A] = ang;
+        }
+}
+
 struct DivHost {
     float operator()(float a, float b) const { return a / b; }
 };

@@ -52,3 +52,18 @@ def test_oracle_matches_reference_segment():
     torch.testing.assert_close(y[:, 84:], ref[:, 84:], atol=3e-4, rtol=1e-3)          # mask coefficients
     assert ys["proto"].shape == c["proto"].shape == (2, 32, 24, 24)
     torch.testing.assert_close(ys["proto"], c["proto"], atol=3e-4, rtol=1e-3)
+
+
+def test_oracle_matches_reference_obb():
+    """OBB head on the v0_1 backbone: rotated (cx, cy, w, h), class scores and the angle row."""
+    name, cfg = "yolo-master-obb-n-v0_1", "master/v0_1/obb/yolo-master-obb-n.yaml"
+    c = torch.load(os.path.join(GOLD, f"{name}.golden.pt"))["cases"]["b2_96"]
+    sd = synth_sd_from_keys(0, name)
+    y = O.forward(O.parse_spec(yaml_of(cfg)), sd, synth_images(c["B"], c["H"], c["W"], c["seed"]))
+    ref = c["final"].float()
+    nc = ref.shape[1] - 5
+    assert y.shape == ref.shape and ref.shape[2] == 12 * 12 + 6 * 6 + 3 * 3
+    torch.testing.assert_close(y[:, :4], ref[:, :4], atol=1e-3, rtol=1e-3)
+    torch.testing.assert_close(y[:, 4:4 + nc], ref[:, 4:4 + nc], atol=1e-5, rtol=1e-3)
+    torch.testing.assert_close(y[:, -1], ref[:, -1], atol=1e-5, rtol=1e-4)             # angle in [-pi/4, 3pi/4]
+    assert float(y[:, -1].min()) >= -0.7854 and float(y[:, -1].max()) <= 2.3562

@@ -34,7 +34,8 @@ def host(tmp_path_factory):
     lib.host_letterbox_u8.argtypes = [vp, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, ci, ci, ci]
     lib.host_scale_boxes.argtypes = [vp, ci, cll, ci, vp, vp, ci, ci]
     lib.host_kpts_decode_level.argtypes = [vp, ci, ci, C.c_float, ci, ci, ci, ci, ci, vp]
-    lib.host_letterbox_u8.restype = lib.host_scale_boxes.restype = lib.host_kpts_decode_level.restype = None
+    lib.host_obb_finish_level.argtypes = [vp, ci, ci, C.c_float, ci, ci, ci, ci, vp, vp]
+    lib.host_letterbox_u8.restype = lib.host_scale_boxes.restype = lib.host_kpts_decode_level.restype = lib.host_obb_finish_level.restype = None
     return lib
 
 
@@ -268,3 +269,31 @@ def test_kpts_decode_body_matches_reference_formula(host):
         want[:, 0::ndim] = (raw[:, 0::ndim] * 2.0 + (anchors.t()[0] - 0.5)) * st.t()
         want[:, 1::ndim] = (raw[:, 1::ndim] * 2.0 + (anchors.t()[1] - 0.5)) * st.t()
         torch.testing.assert_close(y, want, atol=1e-6, rtol=1e-6)
+
+
+def test_obb_finish_body_matches_dist2rbox(host):
+    """`ym_obb_finish`'s per-anchor function (g++ build) applied to an axis-aligned xywh decode against dist2rbox (utils/tal.py:447-453)
+    evaluated directly on the distances: rotated centres agree to fp32 rounding, w / h / scores are copied, the angle row is appended."""
+    import math
+    from oracle import yolo_master_oracle as O
+    g = torch.Generator().manual_seed(8)
+    B, nc, shapes, strides = 2, 3, [(6, 5), (3, 3)], [8.0, 16.0]
+    A = sum(h * w for h, w in shapes)
+    dist = torch.rand((B, 4, A), generator=g) * 3                                   # l, t, r, b in grid units
+    scores = torch.rand((B, nc, A), generator=g)
+    raw = [torch.randn((B, h, w, 1), generator=g) for h, w in shapes]
+    anchors, st = O.make_anchors(shapes, strides)
+    anchors, st = anchors.t().unsqueeze(0), st.t()
+    lt, rb = dist.split(2, 1)
+    yin = torch.cat([((anchors - lt) + (anchors + rb)) / 2 * st, (lt + rb) * st, scores], 1).contiguous()   # what ym_detect_dense emits
+    yout = torch.empty((B, 4 + nc + 1, A))
+    a0 = 0
+    for t, (h, w), s in zip(raw, shapes, strides):
+        host.host_obb_finish_level(t.data_ptr(), h, w, s, a0, B, nc, A, yin.data_ptr(), yout.data_ptr())
+        a0 += h * w
+    angle = (torch.cat([t.reshape(B, -1, 1).transpose(1, 2) for t in raw], 2).sigmoid() - 0.25) * math.pi
+    xf, yf = ((rb - lt) / 2).split(1, 1)
+    xy = (torch.cat([xf * angle.cos() - yf * angle.sin(), xf * angle.sin() + yf * angle.cos()], 1) + anchors) * st
+    torch.testing.assert_close(yout[:, :2], xy, atol=2e-4, rtol=1e-5)
+    assert torch.equal(yout[:, 2:4 + nc], yin[:, 2:])
+    torch.testing.assert_close(yout[:, -1:], angle, atol=1e-6, rtol=1e-6)

@@ -361,12 +361,27 @@ def kpts_decode(kpts, strides, ndim):
     return torch.cat(outs, 2)
 
 
+def obb_finish(y, angles, strides, nc):
+    B, rows, A = y.shape
+    raw = torch.cat([t.float().reshape(B, -1, 1).transpose(1, 2) for t in angles], 2)      # (B, 1, A)
+    ang = (torch.sigmoid(raw) - 0.25) * math.pi
+    ax = torch.cat([(torch.arange(t.shape[2], dtype=torch.float32) + 0.5).repeat(t.shape[1]) for t in angles])
+    ay = torch.cat([(torch.arange(t.shape[1], dtype=torch.float32) + 0.5).repeat_interleave(t.shape[2]) for t in angles])
+    st = torch.cat([torch.full((t.shape[1] * t.shape[2],), float(s)) for t, s in zip(angles, strides)])
+    xf, yf = y[:, 0] / st - ax, y[:, 1] / st - ay
+    c, s_ = torch.cos(ang[:, 0]), torch.sin(ang[:, 0])
+    out = torch.cat([y, ang], 1).clone()
+    out[:, 0] = (xf * c - yf * s_ + ax) * st
+    out[:, 1] = (xf * s_ + yf * c + ay) * st
+    return out
+
+
 def install_model():
     """Everything `install()` covers plus the whole-model ops above."""
     install()
     for name, fn in dict(stem_conv=stem_conv, attention=attention, concat2=concat2, sppf_pool=sppf_pool, router_topk=router_topk,
                          moe_combine=moe_combine, moe_expert_gemm=moe_expert_gemm, gn_finalize=gn_finalize, detect_dense=detect_dense,
-                         detect_topk=detect_topk, kpts_decode=kpts_decode).items():
+                         detect_topk=detect_topk, kpts_decode=kpts_decode, obb_finish=obb_finish).items():
         setattr(ops, name, fn)
     ops.pitch = lambda t, dtype=torch.float16: (t.stride(2) if t.shape[2] > 1 else (t.stride(1) if t.shape[1] > 1 else (t.stride(0) if t.shape[0] > 1 else t.shape[3])))
     from yolo_master_b200.nn.modules import gated, head, moe

@@ -107,9 +107,55 @@ __global__ void __launch_bounds__(256) kpts_decode_kernel(const KptLevels lv, in
     }
 }
 
+struct SinCosDev {
+    __device__ __forceinline__ void operator()(float a, float* s, float* c) const { sincosf(a, s, c); }
+};
+
+// yin fp32 [B][4+nc][A] (xywh dense decode) -> yout fp32 [B][4+nc+1][A]: rotated centre, w, h, class scores, angle
+__global__ void __launch_bounds__(256) obb_finish_kernel(const KptLevels lv, int B, int nc, int A, const float* __restrict__ yin,
+                                                         float* __restrict__ yout) {
+    const int rows = 4 + nc;
+    const long long total = (long long)B * A;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(i % A), b = (int)(i / A);
+        int l = 0;
+        while (l + 1 < lv.nl && a >= lv.a0[l + 1]) ++l;
+        const int p = a - lv.a0[l], gy = p / lv.w[l], gx = p - gy * lv.w[l];
+        const float* src = yin + (long long)b * rows * A + a;
+        float* dst = yout + (long long)b * (rows + 1) * A + a;
+        float ox, oy, ang;
+        obb_rotate(src[0], src[A], lv.kpt[l][(long long)b * lv.h[l] * lv.w[l] + p], gx, gy, lv.stride[l], &ox, &oy, &ang, SigmoidRn(), SinCosDev());
+        dst[0] = ox;
+        dst[A] = oy;
+        for (int r = 2; r < rows; ++r) dst[(long long)r * A] = src[(long long)r * A];
+        dst[(long long)rows * A] = ang;
+    }
+}
+
 }  // namespace ym
 
 using namespace ym;
+
+extern "C" int ym_obb_finish(int nl, const void* const* angle, const int* hs, const int* ws, const float* strides, int B, int nc,
+                             const float* yin, float* yout, void* stream) {
+    YM_CHECK_ARG(angle && hs && ws && strides && yin && yout, "ym_obb_finish: null pointer");
+    YM_CHECK_ARG(nl >= 1 && nl <= KPT_MAX_LEVELS && nc >= 1, "ym_obb_finish: 1..%d levels", KPT_MAX_LEVELS);
+    if (B <= 0) return YM_OK;
+    KptLevels lv;
+    lv.nl = nl;
+    int A = 0;
+    for (int l = 0; l < nl; ++l) {
+        YM_CHECK_ARG(angle[l] && hs[l] > 0 && ws[l] > 0, "ym_obb_finish: bad level %d", l);
+        lv.kpt[l] = (const float*)angle[l]; lv.h[l] = hs[l]; lv.w[l] = ws[l]; lv.stride[l] = strides[l]; lv.a0[l] = A;
+        A += hs[l] * ws[l];
+    }
+    lv.a0[nl] = A;
+    long long nb = ((long long)B * A + 255) / 256;
+    if (nb > 148LL * 16) nb = 148LL * 16;
+    obb_finish_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(lv, B, nc, A, yin, yout);
+    YM_CHECK_LAUNCH("obb_finish");
+    return YM_OK;
+}
 
 extern "C" int ym_kpts_decode(int nl, const void* const* kpt, const int* hs, const int* ws, const float* strides, int B, int nk,
                               int ndim, float* y, void* stream) {

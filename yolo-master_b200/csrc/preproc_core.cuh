@@ -108,4 +108,19 @@ YM_HD float kpt_decode_value(float raw, int d, int ndim, int gx, int gy, float s
     return (raw * 2.0f + (float)(d == 0 ? gx : gy)) * stride;
 }
 
+// OBB head (head.py:477-500, dist2rbox utils/tal.py:447-453) for one anchor, applied to the axis-aligned dense decode: the centre offset
+// (xf, yf) = (rb - lt) / 2 is recovered from the decoded centre, rotated by the predicted angle and re-anchored; w, h stay.
+//   angle = (sigmoid(raw) - 0.25) * pi;  x' = (xf cos - yf sin + ax) * s;  y' = (xf sin + yf cos + ay) * s,  anchor (ax, ay) = cell + 0.5.
+template <typename Sig, typename SinCos>
+YM_HD void obb_rotate(float cx, float cy, float raw, int gx, int gy, float stride, float* ox, float* oy, float* oang, Sig sig, SinCos sc) {
+    const float ang = (sig(raw) - 0.25f) * 3.14159265358979323846f;
+    const float ax = (float)gx + 0.5f, ay = (float)gy + 0.5f;
+    const float xf = cx / stride - ax, yf = cy / stride - ay;
+    float s, c;
+    sc(ang, &s, &c);
+    *ox = (xf * c - yf * s + ax) * stride;
+    *oy = (xf * s + yf * c + ay) * stride;
+    *oang = ang;
+}
+
 }  // namespace ym

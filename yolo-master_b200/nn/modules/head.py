@@ -14,7 +14,7 @@ from ... import ops
 from ._base import PackCache, pack_gemm_weight, require_eval, to_nchw, to_nhwc
 from .conv import Conv, DWConv, PlainConv2d
 
-__all__ = ("Detect", "DFL", "Pose", "Proto", "Segment")
+__all__ = ("Detect", "DFL", "Pose", "Proto", "Segment", "OBB")
 
 
 class DFL(nn.Module):
@@ -211,3 +211,27 @@ class Segment(Detect):
         proto = to_nchw(self.proto.fwd_nhwc(feats[0]))
         aux["mask_coefficient"], aux["proto"] = mc, proto
         return (torch.cat([y, mc], 1), proto), aux
+
+
+class OBB(Detect):
+    """`OBB(nc=80, ne=1, reg_max=16, end2end=False, ch=())` (head.py:428-520): Detect plus an angle tower per level; boxes are decoded
+    as rotated (cx, cy, w, h) and the angle is appended: (B, 4 + nc + 1, A).  Rotated NMS is left to the caller."""
+
+    def __init__(self, nc=80, ne=1, reg_max=16, end2end=False, ch=()):
+        super().__init__(nc, reg_max, end2end, ch)
+        if ne != 1:
+            raise NotImplementedError("OBB: only one extra parameter (the angle) is on the B200 path")
+        self.ne = ne
+        c4 = max(ch[0] // 4, self.ne)
+        self.cv4 = nn.ModuleList(nn.Sequential(Conv(x, c4, 3), Conv(c4, c4, 3), PlainConv2d(c4, self.ne, 1)) for x in ch)
+        if end2end:
+            self.one2one_cv4 = copy.deepcopy(self.cv4)
+
+    def forward(self, x):
+        if self.end2end:
+            raise NotImplementedError("OBB: the end2end (one2one) head is not on the B200 path")
+        y, aux = super().forward(x)
+        feats = [to_nhwc(f) for f in x]
+        angles = [self._tower(self.cv4[i], f) for i, f in enumerate(feats)]
+        aux["angle"] = angles
+        return ops.obb_finish(y, angles, [float(s) for s in self.stride.tolist()], self.nc), aux

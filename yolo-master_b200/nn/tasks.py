@@ -130,7 +130,7 @@ def parse_model(d, ch, verbose=False):
                 legacy = False
         elif m is M.Concat:
             c2 = sum(ch[x] for x in f)
-        elif m in (M.Detect, M.Pose, M.Segment):
+        elif m in (M.Detect, M.Pose, M.Segment, M.OBB):
             args.extend([reg_max, end2end, [ch[x] for x in f]])
             if m is M.Segment:
                 args[2] = make_divisible(min(args[2], max_channels) * width, 8)      # npr scales with the width (tasks.py:2224-2225)
@@ -264,6 +264,10 @@ class PoseModel(DetectionModel):
 class SegmentationModel(DetectionModel):
     """`SegmentationModel(cfg, ch=3, nc=None)` (tasks.py:775-798): a DetectionModel whose head is `Segment`; the eval forward returns
     ((y, proto), aux)."""
+
+
+class OBBModel(DetectionModel):
+    """`OBBModel(cfg, ch=3, nc=None)` (tasks.py:749-772): a DetectionModel whose head is `OBB`."""
 
 
 class GraphedForward:

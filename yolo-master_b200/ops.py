@@ -635,3 +635,13 @@ def kpts_decode(kpts, strides, ndim):
     _lib.check(lib().ym_kpts_decode(nl, kp, hs, ws, st, B, nk, ndim, y.data_ptr(), _stream()), "ym_kpts_decode")
     _count()
     return y
+
+
+def obb_finish(y, angles, strides, nc):
+    """ym_obb_finish.  y: fp32 (B, 4+nc, A) xywh dense decode; angles[l]: fp32 (B,h,w,1) raw angle-tower outputs -> fp32 (B, 4+nc+1, A)."""
+    B, rows, A = y.shape
+    out = torch.empty((B, rows + 1, A), dtype=torch.float32, device=y.device)
+    nl, ap, _, hs, ws, st = _level_arrays(angles, angles, strides)
+    _lib.check(lib().ym_obb_finish(nl, ap, hs, ws, st, B, nc, y.contiguous().data_ptr(), out.data_ptr(), _stream()), "ym_obb_finish")
+    _count()
+    return out
