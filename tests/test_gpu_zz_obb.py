@@ -34,7 +34,6 @@ def test_obb_model_matches_reference_golden():
     assert_within_noise(y[:, 4:-1], ref[:, 4:-1], sim[:, 4:-1], what="obb scores")
     assert_within_noise(y[:, -1:], ref[:, -1:], sim[:, -1:], what="obb angle")
     assert_within_noise(y, c["final"].float(), sim, what="obb vs reference golden")
-    g = m.graphed(2, 96, 96)
-    out = g(x.to(DEV)).clone() if hasattr(g, "__call__") else None
+    out = m.graphed(2, 96, 96)(x.to(DEV)).clone()                  # whole forward as one CUDA graph
     torch.cuda.synchronize()
     assert torch.equal(out.float().cpu(), y)

@@ -290,8 +290,9 @@ class GraphedForward:
         with torch.cuda.graph(self.graph, stream=self.stream), torch.no_grad():
             out = model(self.static_in)
         self.kernels_per_replay = ops.KERNELS - k0
-        self.static_out = out[0] if isinstance(out, tuple) else out
-        self.host_out = torch.empty(self.static_out.shape, dtype=self.static_out.dtype, pin_memory=True)
+        self.static_out = out[0] if isinstance(out, tuple) else out                  # Segment: (prediction, prototypes)
+        self._lead = self.static_out[0] if isinstance(self.static_out, tuple) else self.static_out
+        self.host_out = torch.empty(self._lead.shape, dtype=self._lead.dtype, pin_memory=True)
 
     def __call__(self, x=None):
         """x: device tensor of the captured shape (copied into the static input) or None (reuse the static input)."""
@@ -304,7 +305,7 @@ class GraphedForward:
         """Host-buffer call: pinned host images -> H2D -> forward -> D2H into `self.host_out`; returns it (synchronised)."""
         self.static_in.copy_(host_in, non_blocking=True)
         self.graph.replay()
-        self.host_out.copy_(self.static_out, non_blocking=True)
+        self.host_out.copy_(self._lead, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.host_out
 
