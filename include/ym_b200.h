@@ -184,6 +184,11 @@ int ym_linear_attn(const void* q, int ldq, const void* k, int ldk, const void* v
 /* F.adaptive_avg_pool2d (moa/heads.py:224). */
 int ym_adaptive_avgpool_nhwc(const void* x, int ldx, int B, int H, int W, int C, int h, int w, void* out, int ldo, void* stream);
 
+/* Classify tail nn/modules/head.py:823-832 on the pooled feature vector v fp16 [B][ldv]: logits = w . v + b (w fp32 [nc][Cin]) and
+ * probs = softmax(logits), both fp32 [B][nc]. */
+int ym_classify_head(const void* v, int ldv, int B, int Cin, const float* w, const float* b, int nc, float* logits, float* probs,
+                     void* stream);
+
 /* Pose.kpts_decode head.py:644-664: per level kpt fp32 [B][h][w][nk] (the pose tower's output) ->
  * y fp32 [B][nk][A], A = sum h*w: x, y = (v*2 + grid coordinate) * stride, visibility (ndim 3) = sigmoid.  ndim 1 copies the values
  * unchanged: the mask-coefficient rows of Segment._inference head.py:332-344. */

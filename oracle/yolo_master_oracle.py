@@ -65,7 +65,9 @@ def _w(t):
     return t.half().float() if _W16 else t
 
 
-BN_EPS = 1e-3  # utils/torch_utils.py:552-562 rewrites eps on every nn.BatchNorm2d
+BN_EPS = 1e-3  # utils/torch_utils.py:552-562 (`initialize_weights`, called by DetectionModel tasks.py:565) rewrites eps on every
+#                nn.BatchNorm2d; ClassificationModel (tasks.py:947-964) never calls it, so its BatchNorms keep torch's default 1e-5:
+#                `forward` switches this module constant for the duration of a classification model's pass
 GN_EPS = 1e-5  # nn.GroupNorm default, untouched by initialize_weights
 
 
@@ -78,7 +80,7 @@ def make_divisible(x: float, divisor: int) -> int:
     return int(math.ceil(x / divisor) * divisor)
 
 
-_BASE = {"Conv", "C2f", "C3k2", "SPPF", "C2PSA", "A2C2f", "DWConv", "C3", "Bottleneck"}
+_BASE = {"Conv", "C2f", "C3k2", "SPPF", "C2PSA", "A2C2f", "DWConv", "C3", "Bottleneck", "Classify"}
 _REPEAT = {"C2f", "C3k2", "C2PSA", "A2C2f", "C3"}
 _MIX_BASE = {"A2C2fMoE", "ES_MOE"}
 _MIX_REPEAT = {"A2C2fMoE"}
@@ -631,6 +633,13 @@ def forward(spec: dict, sd: dict, x: torch.Tensor, img_hw=None, return_layers: b
 
     dtype=torch.float16 with CUDA tensors reproduces the reference's torch-eager `.half().cuda()` path (the yolo26-master-n
     layer types only); bench.py times that as the same-GPU baseline.  The parity oracle is the fp32 default."""
+    global BN_EPS
+    if spec["layers"][-1]["type"] == "Classify" and BN_EPS != 1e-5:
+        BN_EPS = 1e-5
+        try:
+            return forward(spec, sd, x, img_hw, return_layers, end2end, dtype)
+        finally:
+            BN_EPS = 1e-3
     sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
     x = x.to(dtype)
     H_in = x.shape[-2]
@@ -657,6 +666,12 @@ def forward(spec: dict, sd: dict, x: torch.Tensor, img_hw=None, return_layers: b
             y = detect_decode(braw, sraw, shapes, strides, e2e, reg_max)
             x = detect_postprocess(y, nc)[0] if e2e else y
             ys["detect_raw"] = (braw, sraw, y)
+        elif t == "Classify":  # head.py:825-832: Conv -> global average pool -> Linear -> softmax; the model output is the probabilities
+            c1, c2 = args[0], args[1]
+            t_ = conv_block(sd, p + ".conv", xin)
+            logits = F.linear(_st(t_.mean((2, 3))), _w(sd[p + ".linear.weight"]), sd[p + ".linear.bias"])
+            x = logits.softmax(1)
+            ys["logits"] = logits
         elif t == "OBB":       # rotated boxes + angle row (head.py:477-500); one2many head
             nc, ne, reg_max, e2e, _ = args
             shapes = [tuple(v.shape[2:]) for v in xin]

@@ -314,6 +314,42 @@ def letterbox_golden():
     torch.save({"cv2": cv2.__version__, "cases": cases, "variants": variants, "scale_boxes": boxes}, f"{OUT}/letterbox.golden.pt")
 
 
+def cls_golden():
+    """Reference ClassificationModel (v0_1 cls n: ModularRouterExpertMoE backbone + Classify) on seeded 64x64 images: probabilities,
+    logits and the layer-11 feature; key table + calibrated BatchNorm statistics like the other model fixtures."""
+    from ultralytics.nn.tasks import ClassificationModel
+    name = "yolo-master-cls-n-v0_1"
+    m = ClassificationModel("/root/reference/ultralytics/cfg/models/master/v0_1/cls/yolo-master-cls-n.yaml", verbose=False)
+    sd = m.state_dict()
+    fill_state_dict_(sd, 0)
+    m.load_state_dict(sd)
+    m.eval()
+    bns = [mod for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d)]
+    for b in bns:
+        b.train()
+        b.momentum = None
+        b.reset_running_stats()
+    with torch.no_grad():
+        m(synth_images(8, 128, 128, seed=7))
+    for b in bns:
+        b.eval()
+        b.momentum = 0.03
+    sd = m.state_dict()
+    json.dump({k: [list(v.shape), str(v.dtype)] for k, v in sd.items()}, open(f"{OUT}/{name}.keys.json", "w"))
+    stats = {k: v.clone() for k, v in sd.items() if k.endswith(("running_mean", "running_var", "num_batches_tracked"))
+             or (v.dim() == 0 and v.is_floating_point())}
+    torch.save(stats, f"{OUT}/{name}.bnstats.pt")
+    x = synth_images(3, 64, 64, 21)
+    feats = {}
+    h = m.model[11].register_forward_hook(lambda mod, i, o: feats.__setitem__(11, o.clone()))
+    with torch.no_grad():
+        y, logits = m(x)
+    h.remove()
+    torch.save({"cases": {"b3_64": {"B": 3, "H": 64, "W": 64, "seed": 21, "final": y.clone(), "logits": logits.clone(), "layers": feats}}},
+               f"{OUT}/{name}.golden.pt")
+    print(name, tuple(y.shape), float(y.max()), [os.path.getsize(f"{OUT}/{name}{e}") for e in (".golden.pt", ".bnstats.pt", ".keys.json")])
+
+
 GATED_FAMILY = ["AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
                 "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE",
                 "ContextRefinedLowRankHybridAdaptiveGateMoE", "VisualEnhancedAdaptiveGateMoE"]
@@ -358,10 +394,10 @@ def gated_family_golden():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["main", "dispatch", "nms", "esmoe", "letterbox", "gated_family", *EXTRA_MODELS]
+    which = sys.argv[1:] or ["main", "dispatch", "nms", "esmoe", "letterbox", "gated_family", "cls", *EXTRA_MODELS]
     for w in which:
         if w in EXTRA_MODELS:
             extra_model_golden(w)
         else:
             {"main": main, "dispatch": dispatch_golden, "nms": nms_golden, "esmoe": esmoe_golden, "letterbox": letterbox_golden,
-             "gated_family": gated_family_golden}[w]()
+             "gated_family": gated_family_golden, "cls": cls_golden}[w]()

@@ -75,6 +75,17 @@ extern "C" int host_fc_gate(const void* v, int ldv, int B, int Cin, const float*
     return 0;
 }
 
+extern "C" int host_classify_head(const void* v, int ldv, int B, int Cin, const float* w, const float* b, int nc, float* logits,
+                                  float* probs) {
+    ClsArgs a;
+    a.v = (const ym_half*)v; a.ldv = ldv; a.Cin = Cin; a.nc = nc; a.w = w; a.b = b; a.logits = logits; a.probs = probs;
+    std::vector<float> sm(cls_smem_floats(NTHR));
+    for (int i = 0; i < B; ++i)
+        for (int ph = 0; ph < CLS_PHASES; ++ph)
+            for (int t = 0; t < NTHR; ++t) cls_phase(ph, a, i, t, NTHR, sm.data());
+    return 0;
+}
+
 extern "C" int host_gated_select(const void* fo, int ldf, int B, int HW, int E, int oc, int G, float eps, const int* idx,
                                  const float* w, int topk, const float* gamma, const float* beta, void* out, int ldo) {
     std::vector<float> sc((size_t)B * topk * oc), sh((size_t)B * topk * oc), sm(s0_smem_floats(NTHR));

@@ -162,3 +162,26 @@ def test_predictor_pipeline_on_emulated_model(emu, tmp_path_factory, monkeypatch
         want[:, :4] = torch.from_numpy(L.scale_boxes((320, 320), keep[:, :4].numpy(), f.shape))
         assert torch.equal(r.boxes.data, want), i
         assert r.orig_shape == f.shape[:2]
+
+
+def test_classification_model_host_wiring(emu):
+    """ClassificationModel (v0_1 cls n) on emulated ops, the Classify tail on the g++ build of its kernel body: logits within the
+    fp16 noise floor of the oracle and of the reference golden, probabilities sum to one, top-1 agrees."""
+    from yolo_master_b200.nn.tasks import ClassificationModel
+    name, cfg = "yolo-master-cls-n-v0_1", "master/v0_1/cls/yolo-master-cls-n.yaml"
+    m = ClassificationModel(cfg)
+    sd = synth_sd_from_keys(0, name)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    c = torch.load(os.path.join(GOLD, f"{name}.golden.pt"))["cases"]["b3_64"]
+    x = synth_images(c["B"], c["H"], c["W"], c["seed"]).half()
+    with torch.no_grad():
+        y, logits = m._predict_once(x)
+    spec = O.parse_spec(yaml_of(cfg))
+    ref, rys = O.forward(spec, sd, x.float(), return_layers=True)
+    with O.fp16_storage(), O.fp16_weights():
+        _, sim = O.forward(spec, sd, x.float(), return_layers=True)
+    assert_within_noise(logits, rys["logits"], sim["logits"], what="cls logits")
+    assert_within_noise(logits, c["logits"], sim["logits"], what="cls logits vs reference golden")
+    torch.testing.assert_close(y.sum(1), torch.ones(3), atol=1e-5, rtol=0)
+    torch.testing.assert_close(y, torch.softmax(logits, 1), atol=1e-7, rtol=1e-5)

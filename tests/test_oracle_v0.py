@@ -67,3 +67,16 @@ def test_oracle_matches_reference_obb():
     torch.testing.assert_close(y[:, 4:4 + nc], ref[:, 4:4 + nc], atol=1e-5, rtol=1e-3)
     torch.testing.assert_close(y[:, -1], ref[:, -1], atol=1e-5, rtol=1e-4)             # angle in [-pi/4, 3pi/4]
     assert float(y[:, -1].min()) >= -0.7854 and float(y[:, -1].max()) <= 2.3562
+
+
+def test_oracle_matches_reference_classify():
+    """Classify head on the v0_1 backbone (reference ClassificationModel): logits and softmax probabilities over 1000 classes."""
+    name, cfg = "yolo-master-cls-n-v0_1", "master/v0_1/cls/yolo-master-cls-n.yaml"
+    c = torch.load(os.path.join(GOLD, f"{name}.golden.pt"))["cases"]["b3_64"]
+    sd = synth_sd_from_keys(0, name)
+    y, ys = O.forward(O.parse_spec(yaml_of(cfg)), sd, synth_images(c["B"], c["H"], c["W"], c["seed"]), return_layers=True)
+    assert y.shape == (3, 1000)
+    torch.testing.assert_close(ys[11], c["layers"][11], atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(ys["logits"], c["logits"], atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(y, c["final"], atol=1e-6, rtol=1e-4)
+    assert torch.equal(y.argmax(1), c["final"].argmax(1))

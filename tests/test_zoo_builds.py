@@ -15,6 +15,7 @@ def test_stock_detection_yamls_construct():
     from yolo_master_b200.nn import tasks
     supported = set(tasks.MODULES) | set(tasks.MIXTURE_MODULES) | {"nn.Upsample"}
     files = sorted(glob.glob(f"{REF}/master/**/*.yaml", recursive=True) + glob.glob(f"{REF}/26/*master*.yaml"))
+    other = [f for f in files if any(f"/{t}/" in f for t in ("seg", "pose", "obb", "cls")) and f.endswith("-n.yaml")]
     files = [f for f in files if "/det/" in f or "/26/" in f or "/exp/" in f]
     built, skipped, raised = 0, 0, []
     for f in files:
@@ -29,6 +30,11 @@ def test_stock_detection_yamls_construct():
             built += 1
         except NotImplementedError as e:
             raised.append((os.path.relpath(f, REF), str(e)))
-    assert built >= 25, (built, skipped)
+    for f in other:                                               # the n file of every seg / pose / obb / cls zoo constructs too
+        d = yaml.safe_load(open(f))
+        if not ({layer[2] for layer in d.get("backbone", []) + d.get("head", [])} - supported):
+            tasks.DetectionModel(f)
+            built += 1
+    assert built >= 60, (built, skipped)
     assert [r[0] for r in raised] == ["master/v0_10/det/yolo-master-mot-scene-n.yaml"], raised
     assert skipped <= 14, skipped                                 # 102 detection YAMLs in the zoo, 88 on the path

@@ -209,6 +209,7 @@ def install_gated(host):
     host.host_gate_router.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, ci, cf, cf, cf, vp, cf,
                                       ci, vp, vp, cf, vp, vp, vp, vp]
     host.host_zero_cost_router.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci, cf, vp, cf, ci, vp, vp, vp]
+    host.host_classify_head.argtypes = [vp, ci, ci, ci, vp, vp, ci, vp, vp]
     host.host_fc_gate.argtypes = [vp, ci, ci, ci, vp, ci, vp, vp, ci, cf, cf, vp]
     host.host_gated_select.argtypes = [vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, ci, vp, vp, vp, ci]
     host.host_ctx_mean3.argtypes = [vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, ci]
@@ -248,6 +249,13 @@ def install_gated(host):
                           w2.shape[0], float(scale), float(offset), out.data_ptr())
         return out
 
+    def classify_head(v, w, b):
+        B, Cin, nc = v.shape[0], v.shape[3], w.shape[0]
+        logits, probs = torch.empty((B, nc), dtype=torch.float32), torch.empty((B, nc), dtype=torch.float32)
+        host.host_classify_head(v.data_ptr(), ld(v), B, Cin, w.data_ptr(), None if b is None else b.data_ptr(), nc, logits.data_ptr(),
+                                probs.data_ptr())
+        return probs, logits
+
     def gated_select(fo, idx, w, gamma, beta, E, oc, G, eps=1e-5, out=None):
         B, H, W, _ = fo.shape
         if out is None:
@@ -264,7 +272,7 @@ def install_gated(host):
                             c.shape[1], c.shape[2], out.data_ptr(), ld(out))
         return out
 
-    for name, fn in dict(gate_router=gate_router, zero_cost_router=zero_cost_router, fc_gate=fc_gate, gated_select=gated_select, ctx_mean3=ctx_mean3,
+    for name, fn in dict(gate_router=gate_router, zero_cost_router=zero_cost_router, fc_gate=fc_gate, classify_head=classify_head, gated_select=gated_select, ctx_mean3=ctx_mean3,
                          moe_expert_gemm=moe_expert_gemm, gn_finalize=gn_finalize).items():
         setattr(ops, name, fn)
     ops.pitch = lambda t, dtype=torch.float16: ld(t)

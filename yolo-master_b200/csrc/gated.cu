@@ -46,6 +46,14 @@ __global__ void __launch_bounds__(NTHR) fc_gate_kernel(const FcArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(NTHR) classify_kernel(const ClsArgs a) {
+    extern __shared__ float sm[];
+    for (int ph = 0; ph < CLS_PHASES; ++ph) {
+        cls_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(NTHR) select_s0_kernel(const S0Args a) {
     extern __shared__ float sm[];
     for (int ph = 0; ph < S0_PHASES; ++ph) {
@@ -181,6 +189,17 @@ extern "C" int ym_fc_gate(const void* v, int ldv, int B, int Cin, const float* w
     a.offset = offset; a.out = out;
     fc_gate_kernel<<<B, NTHR, fc_smem_floats(Cr) * sizeof(float), (cudaStream_t)stream>>>(a);
     YM_CHECK_LAUNCH("fc_gate");
+    return YM_OK;
+}
+
+extern "C" int ym_classify_head(const void* v, int ldv, int B, int Cin, const float* w, const float* b, int nc, float* logits,
+                                float* probs, void* stream) {
+    YM_CHECK_ARG(v && w && logits && probs, "ym_classify_head: null pointer");
+    YM_CHECK_ARG(B > 0 && Cin > 0 && nc > 0 && ldv >= Cin, "ym_classify_head: bad sizes");
+    ClsArgs a;
+    a.v = (const __half*)v; a.ldv = ldv; a.Cin = Cin; a.nc = nc; a.w = w; a.b = b; a.logits = logits; a.probs = probs;
+    classify_kernel<<<B, NTHR, cls_smem_floats(NTHR) * sizeof(float), (cudaStream_t)stream>>>(a);
+    YM_CHECK_LAUNCH("classify_head");
     return YM_OK;
 }
 

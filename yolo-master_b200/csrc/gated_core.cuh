@@ -394,6 +394,52 @@ YM_HD void fc_phase(int ph, const FcArgs& a, int img, int tid, int nthr, float* 
 }
 
 // --------------------------------------------------------------------------------------------------------------------
+// Classify tail (nn/modules/head.py:823-832): logits = W . v + b on the pooled vector, probs = softmax(logits).  One CTA per image.
+struct ClsArgs {
+    const ym_half* v;   // [B][ldv] pooled features
+    int ldv, Cin, nc;
+    const float *w, *b;   // [nc][Cin], [nc]
+    float *logits, *probs;   // [B][nc]
+};
+constexpr int CLS_PHASES = 4;
+YM_HD int cls_smem_floats(int nthr) { return nthr + 2; }
+
+YM_HD void cls_phase(int ph, const ClsArgs& a, int img, int tid, int nthr, float* sm) {
+    const ym_half* v = a.v + (long long)img * a.ldv;
+    float* lg = a.logits + (long long)img * a.nc;
+    float* pr = a.probs + (long long)img * a.nc;
+    if (ph == 0) {          // logits, per-thread running maximum
+        float mx = -3.0e38f;
+        for (int o = tid; o < a.nc; o += nthr) {
+            float s = a.b ? a.b[o] : 0.f;
+            const float* w = a.w + (long long)o * a.Cin;
+            for (int c = 0; c < a.Cin; ++c) s += w[c] * ym_h2f(v[c]);
+            lg[o] = s;
+            mx = s > mx ? s : mx;
+        }
+        sm[tid] = mx;
+    } else if (ph == 1) {   // row maximum
+        if (tid != 0) return;
+        float mx = sm[0];
+        for (int t = 1; t < nthr; ++t) mx = sm[t] > mx ? sm[t] : mx;
+        sm[nthr] = mx;
+    } else if (ph == 2) {   // exponentials, per-thread partial sums (barrier before sm[tid] is overwritten: sm[nthr] already read)
+        const float mx = sm[nthr];
+        float s = 0.f;
+        for (int o = tid; o < a.nc; o += nthr) {
+            const float e = expf(lg[o] - mx);
+            pr[o] = e;
+            s += e;
+        }
+        sm[tid] = s;
+    } else {                // normalise; every thread re-adds the partial sums in the same fixed order
+        float den = 0.f;
+        for (int t = 0; t < nthr; ++t) den += sm[t];
+        for (int o = tid; o < a.nc; o += nthr) pr[o] /= den;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
 // FusedExpertGroup tail (gated.py:1061-1081): for route (b, j) with expert e = idx[b][j], GroupNorm (no affine) over the
 // expert's channel slice of the all-expert conv output, then the expert's affine; S0 produces per-(route, channel) scale/shift.
 struct S0Args {

@@ -6,7 +6,7 @@ from .gated import (AdaptiveGateMoE, ContextRefinedLowRankHybridAdaptiveGateMoE,
                     LowRankHybridAdaptiveGateMoE, PyramidContextMixer, RefinedLowRankHybridAdaptiveGateMoE, SharedInvertedExpertGroup,
                     UltimateOptimizedMoE, VisualDetailGate, VisualEnhancedAdaptiveGateMoE, ZeroCostRouter, DualStreamGateRouterV2,
                     HybridAdaptiveGateMoEv2, OptimalHybridGateMoE, MultiHeadRouterMoE, GatedFusionMoE, MultiHeadRouterV3, CrossPathGate)
-from .head import DFL, OBB, Detect, Pose, Proto, Segment
+from .head import DFL, OBB, Classify, Detect, Pose, Proto, Segment
 from .moa import C2fMoA, MoABlock
 from .mot import C2fMoT, MoTBlock
 from .moe import (A2C2fMoE, ABlockMoE, DepthwiseSeparableConv, DynamicRoutingLayer, EfficientExpertGroup, EfficientSpatialRouter,
@@ -20,7 +20,7 @@ __all__ = (
     "Bottleneck", "C2f", "C3", "C3k", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA", "AAttn", "ABlock", "A2C2f",
     "EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups",
     "DynamicRoutingLayer", "DepthwiseSeparableConv", "EfficientExpertGroup", "ES_MOE",
-    "Detect", "DFL", "Pose", "Proto", "Segment", "OBB", "C2fMoT", "MoTBlock", "C2fMoA", "MoABlock",
+    "Detect", "DFL", "Pose", "Proto", "Segment", "OBB", "Classify", "C2fMoT", "MoTBlock", "C2fMoA", "MoABlock",
     "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
     "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE", "ContextRefinedLowRankHybridAdaptiveGateMoE",
     "VisualEnhancedAdaptiveGateMoE", "UltimateOptimizedMoE", "ZeroCostRouter", "DualStreamGateRouterV2", "HybridAdaptiveGateMoEv2",

@@ -11,10 +11,10 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ._base import PackCache, pack_gemm_weight, require_eval, to_nchw, to_nhwc
+from ._base import PackCache, cached_f32, pack_gemm_weight, require_eval, to_nchw, to_nhwc
 from .conv import Conv, DWConv, PlainConv2d
 
-__all__ = ("Detect", "DFL", "Pose", "Proto", "Segment", "OBB")
+__all__ = ("Detect", "DFL", "Pose", "Proto", "Segment", "OBB", "Classify")
 
 
 class DFL(nn.Module):
@@ -235,3 +235,29 @@ class OBB(Detect):
         angles = [self._tower(self.cv4[i], f) for i, f in enumerate(feats)]
         aux["angle"] = angles
         return ops.obb_finish(y, angles, [float(s) for s in self.stride.tolist()], self.nc), aux
+
+
+class Classify(nn.Module):
+    """`Classify(c1, c2, k=1, s=1, p=None, g=1)` (head.py:791-832): Conv to 1280 channels -> global average pool -> Linear -> softmax.
+    Eval output: (probabilities (B, c2), logits (B, c2))."""
+
+    export = False
+
+    def __init__(self, c1, c2, k=1, s=1, p=None, g=1):
+        super().__init__()
+        c_ = 1280
+        self.conv = Conv(c1, c_, k, s, p, g)
+        self.pool = nn.AdaptiveAvgPool2d(1)
+        self.drop = nn.Dropout(p=0.0, inplace=True)
+        self.linear = nn.Linear(c_, c2)
+
+    def forward(self, x):
+        require_eval(self)
+        if isinstance(x, list):
+            x = torch.cat(x, 1)
+        t = self.conv.fwd_nhwc(to_nhwc(x))
+        v = ops.adaptive_avgpool(t, 1, 1)
+        w = cached_f32(self, "w", self.linear.weight)
+        b = cached_f32(self, "b", self.linear.bias) if self.linear.bias is not None else None
+        y, logits = ops.classify_head(v, w, b)
+        return y if self.export else (y, logits)

@@ -29,7 +29,7 @@ MIXTURE_MODULES.update({n: getattr(M, n) for n in (          # the AdaptiveGateM
     "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE", "ContextRefinedLowRankHybridAdaptiveGateMoE",
     "VisualEnhancedAdaptiveGateMoE", "UltimateOptimizedMoE", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE", "MultiHeadRouterMoE",
     "GatedFusionMoE")})                                      # + the v0_3 zoo block
-BASE_MODULES = frozenset({M.Conv, M.DWConv, M.Bottleneck, M.SPPF, M.C2PSA, M.C2f, M.C3k2, M.C3, M.A2C2f})
+BASE_MODULES = frozenset({M.Conv, M.DWConv, M.Bottleneck, M.SPPF, M.C2PSA, M.C2f, M.C3k2, M.C3, M.A2C2f, M.Classify})
 REPEAT_MODULES = frozenset({M.C2f, M.C3k2, M.C3, M.C2PSA, M.A2C2f})
 MIXTURE_BASE_MODULES = frozenset(MIXTURE_MODULES.values())
 MIXTURE_REPEAT_MODULES = frozenset({M.A2C2fMoE, M.C2fMoA, M.C2fMoT})
@@ -268,6 +268,19 @@ class SegmentationModel(DetectionModel):
 
 class OBBModel(DetectionModel):
     """`OBBModel(cfg, ch=3, nc=None)` (tasks.py:749-772): a DetectionModel whose head is `OBB`."""
+
+
+class ClassificationModel(DetectionModel):
+    """`ClassificationModel(cfg, ch=3, nc=None)` (tasks.py:913-990): backbone + `Classify`; the eval forward returns (probs, logits).
+
+    The reference's DetectionModel rewrites every BatchNorm2d to eps = 1e-3 (`initialize_weights`, tasks.py:565); its
+    ClassificationModel does not, so BatchNorms keep torch's default eps of 1e-5 - mirrored here (the weight packs read `bn.eps`)."""
+
+    def __init__(self, cfg="yolo-master-cls-n.yaml", ch=3, nc=None, verbose=False):
+        super().__init__(cfg, ch=ch, nc=nc, verbose=verbose)
+        for mod in self.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.eps = 1e-5
 
 
 class GraphedForward:

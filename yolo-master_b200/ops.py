@@ -645,3 +645,14 @@ def obb_finish(y, angles, strides, nc):
     _lib.check(lib().ym_obb_finish(nl, ap, hs, ws, st, B, nc, y.contiguous().data_ptr(), out.data_ptr(), _stream()), "ym_obb_finish")
     _count()
     return out
+
+
+def classify_head(v, w, b):
+    """ym_classify_head.  v: (B,1,1,Cin) fp16 pooled features; w fp32 [nc,Cin], b fp32 [nc] -> (probs, logits) fp32 (B, nc)."""
+    B, Cin, nc = v.shape[0], v.shape[3], w.shape[0]
+    logits = torch.empty((B, nc), dtype=torch.float32, device=v.device)
+    probs = torch.empty((B, nc), dtype=torch.float32, device=v.device)
+    _lib.check(lib().ym_classify_head(v.data_ptr(), pitch(v), B, Cin, w.data_ptr(), None if b is None else b.data_ptr(), nc,
+                                      logits.data_ptr(), probs.data_ptr(), _stream()), "ym_classify_head")
+    _count()
+    return probs, logits
