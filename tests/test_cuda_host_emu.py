@@ -1,0 +1,198 @@
+"""The extern "C" entry points written after round 1's GPU budget, exercised END TO END without a GPU: the real .cu translation units
+(preproc.cu, gated.cu, nms_large.cu, mix.cu) are compiled with g++ against tests/native/cuda_host_emu.h - a CUDA execution model on
+host threads (one OS thread per CUDA thread of a block, std::barrier for __syncthreads, thread_local blockIdx / threadIdx) - and
+called through the real `yolo_master_b200.ops` wrappers with CPU tensors.  Unlike the phase / per-element harnesses this covers
+the argument checks, the launch geometry, the shared-memory sizing, the grid-stride loops and the vectorised stores of the kernels
+themselves, and the ctypes marshalling of `ops.py`.  What it cannot cover: timing, sm_100a code generation, fast-math rounding."""
+import ctypes as C
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _util import GOLD, ROOT
+from oracle import letterbox_oracle as L
+from oracle import nms_oracle as N
+from oracle import yolo_master_oracle as O
+from yolo_master_b200 import _lib, ops
+
+CSRC = os.path.join(ROOT, "yolo-master_b200", "csrc")
+UNITS = ["preproc.cu", "gated.cu", "nms_large.cu", "mix.cu"]
+SYMBOLS = ["ym_letterbox_u8", "ym_scale_boxes", "ym_kpts_decode", "ym_obb_finish", "ym_gate_router", "ym_gate_router_scratch_floats",
+           "ym_zero_cost_router", "ym_zero_cost_router_scratch_floats", "ym_fc_gate", "ym_classify_head", "ym_gated_select",
+           "ym_ctx_mean3", "ym_nms_batched_large", "ym_nms_large_scratch_bytes", "ym_ew_nhwc", "ym_last_error"]
+
+
+@pytest.fixture(scope="module")
+def emu_lib(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("ym_emu") / "libym_emu.so")
+    cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-DYM_HOST_EMU", "-I", os.path.join(ROOT, "tests", "native"),
+           "-I", CSRC, "-x", "c++", *[os.path.join(CSRC, u) for u in UNITS], os.path.join(ROOT, "tests", "native", "emu_api.cpp"), "-o", so]
+    subprocess.run(cmd, check=True)
+    lib = C.CDLL(so)
+    for name in SYMBOLS:
+        res, args = _lib.SIGNATURES[name]
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+@pytest.fixture()
+def emu(emu_lib, monkeypatch):
+    monkeypatch.setattr(ops, "lib", lambda: emu_lib)
+    monkeypatch.setattr(_lib, "load", lambda: emu_lib)
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(ops, "REQUIRE_CUDA", False)
+    return emu_lib
+
+
+def test_argument_checks_report_through_ym_last_error(emu):
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        ops.ew(ops.EW_SIGMOID, a=torch.zeros((1, 2, 2, 12), dtype=torch.float16))
+    with pytest.raises(RuntimeError, match="does not fit"):
+        ops.letterbox(torch.zeros((1, 4, 4, 3), dtype=torch.uint8), torch.zeros((8, 2), dtype=torch.int32), torch.zeros((8, 2), dtype=torch.int32),
+                      False, 8, 8, 2, 0, 8, 8)
+
+
+def test_letterbox_kernel_geometry(emu):
+    """Vector (W % 4 == 0) and scalar store paths, CHW / HWC, the three output types, B > 1, the 2x area path - whole kernels."""
+    from yolo_master_b200.data.augment import LetterBox
+    rng = np.random.default_rng(3)
+    for (h, w, new_shape) in ((60, 80, (96, 96)), (33, 7, (70, 50)), (250, 250, (125, 125)), (90, 160, (101, 203)), (64, 64, (64, 64))):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = L.preprocess_frame(img, new_shape)
+        lb = LetterBox(new_shape)
+        src = torch.from_numpy(img)[None]
+        assert np.array_equal(lb.apply_batch(src, swap_rb=True, chw=True)[0].numpy(), want), (h, w, new_shape)
+        assert np.array_equal(lb.apply_batch(src)[0].numpy(), L.letterbox_frame(img, new_shape)), (h, w, new_shape)
+        u8 = torch.from_numpy(want)
+        assert torch.equal(lb.apply_batch(src, swap_rb=True, chw=True, dtype=torch.float16)[0], u8.half() / 255)
+        assert torch.equal(lb.apply_batch(src, swap_rb=True, chw=True, dtype=torch.float32)[0], u8.float() / 255)
+    frames = np.stack([rng.integers(0, 256, (45, 60, 3), dtype=np.uint8) for _ in range(3)])
+    out = LetterBox((64, 64)).apply_batch(torch.from_numpy(frames), swap_rb=True, chw=True).numpy()
+    for i in range(3):
+        assert np.array_equal(out[i], L.preprocess_frame(frames[i], (64, 64))), i
+    case = torch.load(os.path.join(GOLD, "letterbox.golden.pt"))["cases"][7]             # 100 x 37 -> 640 x 640, the reference's CRC
+    img = np.random.default_rng(case["seed"]).integers(0, 256, (case["h"], case["w"], 3), dtype=np.uint8)
+    full = LetterBox((640, 640)).apply_batch(torch.from_numpy(img)[None], swap_rb=True, chw=True)[0].numpy()
+    assert zlib.crc32(full.tobytes()) == case["crc"]
+
+
+def test_scale_boxes_kpts_obb_kernels(emu):
+    from yolo_master_b200.utils import ops as box_ops
+    g = torch.Generator().manual_seed(4)
+    shapes = [(480, 640), (1080, 1920), (100, 37)] * 50                                   # 150 images: two parameter blocks
+    b = torch.rand((len(shapes), 7, 6), generator=g) * 700 - 30
+    dev = b.clone()
+    box_ops.scale_boxes_batch((640, 640), dev, shapes)
+    for i in (0, 1, 2, 127, 128, 149):
+        assert np.array_equal(dev[i, :, :4].numpy(), L.scale_boxes((640, 640), b[i, :, :4].numpy(), shapes[i])), i
+    nk, B, lv, strides = 51, 2, [(8, 6), (4, 3), (2, 2)], [8.0, 16.0, 32.0]
+    levels = [torch.randn((B, h, w, nk), generator=g) for h, w in lv]
+    y = ops.kpts_decode(levels, strides, 3)
+    raw = torch.cat([t.reshape(B, -1, nk).transpose(1, 2) for t in levels], 2)
+    anchors, st = O.make_anchors(lv, strides)
+    want = raw.clone()
+    want[:, 2::3] = want[:, 2::3].sigmoid()
+    want[:, 0::3] = (raw[:, 0::3] * 2.0 + (anchors.t()[0] - 0.5)) * st.t()
+    want[:, 1::3] = (raw[:, 1::3] * 2.0 + (anchors.t()[1] - 0.5)) * st.t()
+    torch.testing.assert_close(y, want, atol=1e-6, rtol=1e-6)
+    assert torch.equal(ops.kpts_decode(levels, strides, 1), raw)                          # ndim 1: the plain gather Segment uses
+    A, nc = raw.shape[2], 3
+    yin = torch.rand((B, 4 + nc, A), generator=g) * 50
+    ang = [torch.randn((B, h, w, 1), generator=g) for h, w in lv]
+    out = ops.obb_finish(yin, ang, strides, nc)
+    assert out.shape == (B, 4 + nc + 1, A) and torch.equal(out[:, 2:4 + nc], yin[:, 2:])
+    a = (torch.cat([t.reshape(B, -1, 1).transpose(1, 2) for t in ang], 2).sigmoid() - 0.25) * 3.14159265358979
+    torch.testing.assert_close(out[:, -1:], a, atol=1e-6, rtol=1e-6)
+
+
+def test_gated_kernels(emu):
+    """Router (three kernels, dynamic shared memory), gates, select, context mean, classifier - against the oracle functions."""
+    from yolo_master_b200.nn.modules.gated import OptimalHybridGateMoE, UltimateOptimizedMoE, VisualEnhancedAdaptiveGateMoE
+    from yolo_master_b200.utils.synth import fill_state_dict_
+    g = torch.Generator().manual_seed(5)
+    for cls, c, E, k, H, W in ((VisualEnhancedAdaptiveGateMoE, 128, 4, 2, 20, 24), (OptimalHybridGateMoE, 64, 16, 2, 9, 7)):
+        m = cls(c, c, E, k, 0.5)
+        sd = m.state_dict()
+        fill_state_dict_(sd, 11)
+        m.load_state_dict(sd)
+        sdm = {"m." + k_: v.float() for k_, v in sd.items()}
+        xd = torch.randn((3, c // 2, H, W), generator=g).half()
+        idx, w, probs = ops.gate_router(xd.permute(0, 2, 3, 1).contiguous(), m.eval().get_pack()["router"], k)
+        cx = torch.sigmoid(F.conv2d(xd.float().mean((2, 3), keepdim=True), sdm["m.complexity_estimator.1.weight"], sdm["m.complexity_estimator.1.bias"])).mean()
+        rw, ri, rp = O.dual_stream_gate_router(sdm, "m.routing", xd.float(), k, 1.2)
+        assert torch.equal(idx.long(), ri)
+        torch.testing.assert_close(probs, rp, atol=2e-6, rtol=1e-4)
+        torch.testing.assert_close(w, O.complexity_gate(rw, cx.clamp(0.3, 1.5)), atol=2e-6, rtol=1e-4)
+    m = UltimateOptimizedMoE(64, 64, 4, 2, 0.5)
+    sd = m.state_dict()
+    fill_state_dict_(sd, 3)
+    m.load_state_dict(sd)
+    pk = m.eval().get_pack()
+    xd = torch.randn((2, 32, 6, 5), generator=g).half()
+    idx, w, _ = ops.zero_cost_router(xd.permute(0, 2, 3, 1).contiguous(), pk["fc"], 2.0, pk["cx_w"], pk["cx_b"], 2)
+    rw, ri, _ = O.zero_cost_router({"m." + k_: v.float() for k_, v in sd.items()}, "m.routing", xd.float(), 2, 2.0)
+    assert torch.equal(idx.long(), ri) and bool((w > 0).all())
+    # select + context mean + classifier + fc gate with a strided input view
+    B, H, W, E, oc, G = 2, 7, 5, 4, 16, 8
+    buf = torch.randn((B, H, W, E * oc + 8), generator=g).half()
+    idx = torch.tensor([[2, 0], [1, 3]], dtype=torch.int32)
+    ww = torch.tensor([[0.7, 0.3], [1.0, 0.0]])
+    gamma, beta = torch.randn((E, oc), generator=g), torch.randn((E, oc), generator=g)
+    got = ops.gated_select(buf[..., :E * oc], idx, ww, gamma, beta, E, oc, G).float()
+    f5 = buf[..., :E * oc].float().permute(0, 3, 1, 2).reshape(B, E, oc, H, W)
+    sel = torch.gather(f5, 1, idx.long().view(B, 2, 1, 1, 1).expand(B, 2, oc, H, W))
+    nrm = F.group_norm(sel.reshape(B * 2, oc, H, W), G).view(B, 2, oc, H, W) * gamma[idx.long()].view(B, 2, oc, 1, 1) + beta[idx.long()].view(B, 2, oc, 1, 1)
+    torch.testing.assert_close(got, (F.silu(nrm) * ww.view(B, 2, 1, 1, 1)).sum(1).permute(0, 2, 3, 1), atol=4e-3, rtol=2e-3)
+    a = torch.randn((2, 5, 7, 16), generator=g).half()
+    b, c_ = torch.randn((2, 2, 3, 16), generator=g).half(), torch.randn((2, 1, 1, 16), generator=g).half()
+    up = lambda t: F.interpolate(t.float().permute(0, 3, 1, 2), size=(5, 7), mode="nearest").permute(0, 2, 3, 1)
+    torch.testing.assert_close(ops.ctx_mean3(a, b, c_).float(), torch.stack([a.float(), up(b), up(c_)]).mean(0), atol=2e-3, rtol=1e-3)
+    v = torch.randn((3, 1, 1, 96), generator=g).half()
+    wl, bl = torch.randn((10, 96), generator=g) * 0.1, torch.randn((10,), generator=g)
+    probs, logits = ops.classify_head(v, wl, bl)
+    torch.testing.assert_close(logits, v.view(3, 96).float() @ wl.t() + bl, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(probs, torch.softmax(logits, 1), atol=1e-7, rtol=1e-5)
+    w1, w2, b2 = torch.randn((8, 96), generator=g) * 0.1, torch.randn((12, 8), generator=g), torch.randn((12,), generator=g)
+    got = ops.fc_gate(v, w1, w2, b2, scale=0.4, offset=0.5)
+    torch.testing.assert_close(got, 0.5 + 0.4 * torch.sigmoid(F.linear(F.silu(F.linear(v.view(3, 96).float(), w1)), w2, b2)), atol=1e-6, rtol=1e-5)
+
+
+def test_elementwise_ops_including_the_verified_ones(emu):
+    """mix.cu through the same launch macro as on the GPU: the three new ops and, as a sanity check of the emulation itself, ops
+    whose GPU behaviour is already established."""
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.randn((2, 5, 7, 16), generator=g).half(), torch.randn((2, 5, 7, 16), generator=g).half()
+    t, chan = torch.tensor([0.37]), torch.randn((16,), generator=g)
+    torch.testing.assert_close(ops.ew(ops.EW_SIGMOID, a=a).float(), torch.sigmoid(a.float()), atol=1e-3, rtol=1e-3)
+    torch.testing.assert_close(ops.ew(ops.EW_MUL_GATE, a=a, b=b, p0=t).float(), a.float() * (1 + 0.37 * b.float()), atol=2e-3, rtol=2e-3)
+    torch.testing.assert_close(ops.ew(ops.EW_MUL, a=a, b=b).float(), a.float() * b.float(), atol=2e-3, rtol=2e-3)
+    torch.testing.assert_close(ops.ew(ops.EW_SCALE_RES, a=a, b=b, p0=chan).float(), a.float() + chan * b.float(), atol=2e-3, rtol=2e-3)
+    torch.testing.assert_close(ops.ew(ops.EW_GLU, a=a, b=b).float(), torch.sigmoid(a.float()) * b.float(), atol=2e-3, rtol=2e-3)
+    sc, sh = torch.rand((2, 16), generator=g), torch.randn((2, 16), generator=g)
+    want = F.silu(a.float() * sc.view(2, 1, 1, 16) + sh.view(2, 1, 1, 16)) + b.float()
+    torch.testing.assert_close(ops.ew(ops.EW_AFFINE, a=a, b=b, p0=sc, p1=sh, rows_per_img=35, act=True).float(), want, atol=4e-3, rtol=2e-3)
+    wide = torch.randn((2, 5, 7, 32), generator=g).half()                                # channel-slice views in and out
+    out = torch.zeros((2, 5, 7, 32), dtype=torch.float16)
+    ops.ew(ops.EW_MUL, a=wide[..., 16:], b=b, out=out[..., :16])
+    torch.testing.assert_close(out[..., :16].float(), wide[..., 16:].float() * b.float(), atol=2e-3, rtol=2e-3)
+    assert bool((out[..., 16:] == 0).all())
+
+
+def test_large_nms_kernel(emu):
+    """The whole ym_nms_batched_large call (best-class kernel + 1024-thread per-image kernel with its static shared block)."""
+    g = torch.Generator().manual_seed(17)
+    B, nc, A = 2, 3, 1500
+    centres = torch.rand((B, 2, A // 20 + 1), generator=g) * 320
+    cxy = centres.repeat_interleave(20, 2)[:, :, :A] + torch.randn((B, 2, A), generator=g) * 6
+    pred = torch.cat([cxy, torch.exp(torch.randn((B, 2, A), generator=g) * 0.5 + 3.0), torch.rand((B, nc, A), generator=g) ** 4], 1).contiguous()
+    out, cnt, idx = ops.nms_batched_large(pred, 0.05, 0.6, 50, 1000)
+    ro, rk = N.non_max_suppression(pred, 0.05, 0.6, max_det=50, max_nms=1000)
+    for b in range(B):
+        n = int(cnt[b])
+        assert n == len(rk[b]) and torch.equal(idx[b, :n].long(), rk[b]) and torch.equal(out[b, :n], ro[b])

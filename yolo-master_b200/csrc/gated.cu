@@ -4,14 +4,15 @@
 //   ym_fc_gate        SE gate / feature gate: two-layer MLP on a pooled vector -> per-(image, channel) multiplier
 //   ym_gated_select   FusedExpertGroup tail: GroupNorm of the routed experts' channel slices, affine, SiLU, weighted sum
 //   ym_ctx_mean3      PyramidContextMixer: mean of the local map and two nearest-upsampled pooled maps
-#include "gated_core.cuh"
 #include "ym_common.cuh"
+
+#include "gated_core.cuh"
 
 namespace ym {
 using namespace gated;
 
 __global__ void __launch_bounds__(NTHR) gate_r0_kernel(const R0Args a) {
-    extern __shared__ float sm[];
+    YM_DYN_SMEM(float, sm);
     for (int ph = 0; ph < R0_PHASES; ++ph) {
         r0_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
         __syncthreads();
@@ -19,7 +20,7 @@ __global__ void __launch_bounds__(NTHR) gate_r0_kernel(const R0Args a) {
 }
 
 __global__ void __launch_bounds__(NTHR) gate_r1_kernel(const R1Args a) {
-    extern __shared__ float sm[];
+    YM_DYN_SMEM(float, sm);
     for (int ph = 0; ph < R1_PHASES; ++ph) {
         r1_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
         __syncthreads();
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(NTHR) gate_r2_kernel(const R2Args a) {
 }
 
 __global__ void __launch_bounds__(NTHR) fc_gate_kernel(const FcArgs a) {
-    extern __shared__ float sm[];
+    YM_DYN_SMEM(float, sm);
     for (int ph = 0; ph < FC_PHASES; ++ph) {
         fc_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
         __syncthreads();
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(NTHR) fc_gate_kernel(const FcArgs a) {
 }
 
 __global__ void __launch_bounds__(NTHR) classify_kernel(const ClsArgs a) {
-    extern __shared__ float sm[];
+    YM_DYN_SMEM(float, sm);
     for (int ph = 0; ph < CLS_PHASES; ++ph) {
         cls_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
         __syncthreads();
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(NTHR) classify_kernel(const ClsArgs a) {
 }
 
 __global__ void __launch_bounds__(NTHR) select_s0_kernel(const S0Args a) {
-    extern __shared__ float sm[];
+    YM_DYN_SMEM(float, sm);
     for (int ph = 0; ph < S0_PHASES; ++ph) {
         s0_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
         __syncthreads();
@@ -140,17 +141,17 @@ extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C
     R0Args a0;
     a0.x = (const __half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = eff; a0.Hp = Hp; a0.Wp = Wp;
     a0.inv_area = 1.f / (float)(eff * eff); a0.stats = stats; a0.pooled = pooled;
-    gate_r0_kernel<<<B, NTHR, r0_smem_floats(C, NTHR) * sizeof(float), st>>>(a0);
+    YM_LAUNCH(gate_r0_kernel, B, NTHR, r0_smem_floats(C, NTHR) * sizeof(float), st, a0);
     R1Args a1;
     a1.pooled = pooled; a1.t1 = t1; a1.t2 = t2; a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E; a1.G1 = G1; a1.G2 = G2;
     a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w; a1.g2b = gn2_b; a1.pw2 = pw2;
     a1.b2 = b2; a1.ll = ll;
-    gate_r1_kernel<<<B, NTHR, r1_smem_floats(R, NTHR) * sizeof(float), st>>>(a1);
+    YM_LAUNCH(gate_r1_kernel, B, NTHR, r1_smem_floats(R, NTHR) * sizeof(float), st, a1);
     R2Args a2;
     a2.stats = stats; a2.ll = ll; a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha; a2.inv_temp = 1.f / temperature;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
     a2.ln_w = ln_w; a2.ln_b = ln_b; a2.ln_eps = ln_eps; a2.prior = prior;
-    gate_r2_kernel<<<1, NTHR, 0, st>>>(a2);
+    YM_LAUNCH(gate_r2_kernel, 1, NTHR, 0, st, a2);
     YM_CHECK_LAUNCH("gate_router");
     return YM_OK;
 }
@@ -170,12 +171,12 @@ extern "C" int ym_zero_cost_router(const void* x, int ldx, int B, int H, int W, 
     R0Args a0;
     a0.x = (const __half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = 1; a0.Hp = H; a0.Wp = W; a0.inv_area = 1.f;
     a0.stats = stats; a0.pooled = nullptr;
-    gate_r0_kernel<<<B, NTHR, r0_smem_floats(C, NTHR) * sizeof(float), st>>>(a0);
+    YM_LAUNCH(gate_r0_kernel, B, NTHR, r0_smem_floats(C, NTHR) * sizeof(float), st, a0);
     R2Args a2;
     a2.stats = stats; a2.ll = nullptr; a2.wg = fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = 1.f; a2.inv_temp = 1.f / temperature;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
     a2.ln_w = nullptr; a2.ln_b = nullptr; a2.ln_eps = 0.f; a2.prior = nullptr;
-    gate_r2_kernel<<<1, NTHR, 0, st>>>(a2);
+    YM_LAUNCH(gate_r2_kernel, 1, NTHR, 0, st, a2);
     YM_CHECK_LAUNCH("zero_cost_router");
     return YM_OK;
 }
@@ -187,7 +188,7 @@ extern "C" int ym_fc_gate(const void* v, int ldv, int B, int Cin, const float* w
     FcArgs a;
     a.v = (const __half*)v; a.ldv = ldv; a.Cin = Cin; a.Cr = Cr; a.Cout = Cout; a.w1 = w1; a.w2 = w2; a.b2 = b2; a.scale = scale;
     a.offset = offset; a.out = out;
-    fc_gate_kernel<<<B, NTHR, fc_smem_floats(Cr) * sizeof(float), (cudaStream_t)stream>>>(a);
+    YM_LAUNCH(fc_gate_kernel, B, NTHR, fc_smem_floats(Cr) * sizeof(float), (cudaStream_t)stream, a);
     YM_CHECK_LAUNCH("fc_gate");
     return YM_OK;
 }
@@ -198,7 +199,7 @@ extern "C" int ym_classify_head(const void* v, int ldv, int B, int Cin, const fl
     YM_CHECK_ARG(B > 0 && Cin > 0 && nc > 0 && ldv >= Cin, "ym_classify_head: bad sizes");
     ClsArgs a;
     a.v = (const __half*)v; a.ldv = ldv; a.Cin = Cin; a.nc = nc; a.w = w; a.b = b; a.logits = logits; a.probs = probs;
-    classify_kernel<<<B, NTHR, cls_smem_floats(NTHR) * sizeof(float), (cudaStream_t)stream>>>(a);
+    YM_LAUNCH(classify_kernel, B, NTHR, cls_smem_floats(NTHR) * sizeof(float), (cudaStream_t)stream, a);
     YM_CHECK_LAUNCH("classify_head");
     return YM_OK;
 }
@@ -214,9 +215,9 @@ extern "C" int ym_gated_select(const void* fo, int ldf, int B, int HW, int E, in
     a.fo = (const __half*)fo; a.ldf = ldf; a.HW = HW; a.oc = oc; a.G = G; a.topk = topk; a.eps = eps; a.idx = idx; a.gamma = gamma;
     a.beta = beta; a.sc = scratch; a.sh = scratch + (long long)B * topk * oc;
     cudaStream_t st = (cudaStream_t)stream;
-    select_s0_kernel<<<B * topk, NTHR, s0_smem_floats(NTHR) * sizeof(float), st>>>(a);
+    YM_LAUNCH(select_s0_kernel, B * topk, NTHR, s0_smem_floats(NTHR) * sizeof(float), st, a);
     const long long total = (long long)B * HW * (oc / 8);
-    select_s1_kernel<<<grid_for(total), 256, 0, st>>>(a, w, (__half*)out, ldo, total);
+    YM_LAUNCH(select_s1_kernel, grid_for(total), 256, 0, st, a, w, (__half*)out, ldo, total);
     YM_CHECK_LAUNCH("gated_select");
     return YM_OK;
 }
@@ -231,7 +232,7 @@ extern "C" int ym_ctx_mean3(const void* a, int lda, const void* b, int ldb, cons
     g.H = H; g.W = W; g.C = C; g.h2 = h2; g.w2 = w2; g.h4 = h4; g.w4 = w4;
     g.sy2 = (float)h2 / (float)H; g.sx2 = (float)w2 / (float)W; g.sy4 = (float)h4 / (float)H; g.sx4 = (float)w4 / (float)W;
     const long long total = (long long)B * H * W * (C / 8);
-    ctx_mean3_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(g, (__half*)out, ldo, total);
+    YM_LAUNCH(ctx_mean3_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, g, (__half*)out, ldo, total);
     YM_CHECK_LAUNCH("ctx_mean3");
     return YM_OK;
 }

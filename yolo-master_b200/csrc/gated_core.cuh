@@ -8,10 +8,16 @@
 #include <math.h>
 #include <stdint.h>
 
+#if defined(__CUDACC__) || defined(YM_HOST_EMU)   // nvcc, or g++ with tests/native/cuda_host_emu.h already included
 #ifdef __CUDACC__
 #include <cuda_fp16.h>
+#endif
 #ifndef YM_HD
+#ifdef __CUDACC__
 #define YM_HD __host__ __device__ __forceinline__
+#else
+#define YM_HD inline
+#endif
 #endif
 typedef __half ym_half;
 YM_HD float ym_h2f(ym_half h) { return __half2float(h); }

@@ -117,9 +117,12 @@ extern "C" int ym_ew_nhwc(int op, const void* a, int lda, const void* b, int ldb
     long long nb = (total + 255) / 256;
     if (nb > 148LL * 16) nb = 148LL * 16;
     cudaStream_t st = (cudaStream_t)stream;
-#define EW_LAUNCH(OP)                                                                                                      \
-    ew_kernel<OP><<<(int)nb, 256, 0, st>>>((const __half*)a, lda, (const __half*)b, ldb, p0, p1, tok, ldt, toff,          \
-                                           rows_per_img, act, (__half*)out, ldo, rows, C)
+#define EW_LAUNCH(OP)                                                                                                       \
+    do {                                                                                                                    \
+        auto kfn = ew_kernel<OP>;                                                                                           \
+        YM_LAUNCH(kfn, (int)nb, 256, 0, st, (const __half*)a, lda, (const __half*)b, ldb, p0, p1, tok, ldt, toff, rows_per_img, \
+                  act, (__half*)out, ldo, rows, C);                                                                         \
+    } while (0)
     switch (op) {
         case EW_SCALE_RES: EW_LAUNCH(EW_SCALE_RES); break;
         case EW_TOKEN_ACC: EW_LAUNCH(EW_TOKEN_ACC); break;

@@ -1,7 +1,8 @@
 // Batched NMS, large-candidate path (see nms_large_core.cuh): taken by utils/nms.py only for batches in which some image exceeds
 // the 16384-candidate capacity of the shared-memory kernel in nms.cu (validation at conf 0.001, utils/nms.py:142-146).
-#include "nms_large_core.cuh"
 #include "ym_common.cuh"
+
+#include "nms_large_core.cuh"
 
 namespace ym {
 
@@ -9,7 +10,7 @@ struct CtaExec {
     int nthr;
     template <class F>
     __host__ __device__ __forceinline__ void all(F f) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(YM_HOST_EMU)
         f((int)threadIdx.x);
         __syncthreads();
 #endif
@@ -76,9 +77,9 @@ extern "C" int ym_nms_batched_large(const float* pred, int B, int nc, int A, flo
     cudaMemsetAsync(out, 0, (size_t)B * max_det * 6 * sizeof(float), st);
     cudaMemsetAsync(out_idx, 0xff, (size_t)B * max_det * sizeof(int), st);
     const long long total = (long long)B * A;
-    nmsl_best_class_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(pred, B, nc, A, conf, cls);
+    YM_LAUNCH(nmsl_best_class_kernel, (int)((total + 255) / 256), 256, 0, st, pred, B, nc, A, conf, cls);
     YM_CHECK_LAUNCH("nmsl_best_class");
-    nms_large_kernel<<<B, 1024, 0, st>>>(a);
+    YM_LAUNCH(nms_large_kernel, B, 1024, 0, st, a);
     YM_CHECK_LAUNCH("nms_large");
     return YM_OK;
 }

@@ -1,8 +1,9 @@
 // Predictor pre- and post-processing around the forward pass.  HBM-bound byte / index work:
 //   ym_letterbox_u8   LetterBox (cv2.resize INTER_LINEAR fixed point + constant border) + BGR->RGB + HWC->CHW (+ /255, fp16)
 //   ym_scale_boxes    ops.scale_boxes + clip_boxes on the (B, K, 6) / ragged NMS result rows
-#include "preproc_core.cuh"
 #include "ym_common.cuh"
+
+#include "preproc_core.cuh"
 
 namespace ym {
 
@@ -152,7 +153,7 @@ extern "C" int ym_obb_finish(int nl, const void* const* angle, const int* hs, co
     lv.a0[nl] = A;
     long long nb = ((long long)B * A + 255) / 256;
     if (nb > 148LL * 16) nb = 148LL * 16;
-    obb_finish_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(lv, B, nc, A, yin, yout);
+    YM_LAUNCH(obb_finish_kernel, (int)nb, 256, 0, (cudaStream_t)stream, lv, B, nc, A, yin, yout);
     YM_CHECK_LAUNCH("obb_finish");
     return YM_OK;
 }
@@ -175,7 +176,7 @@ extern "C" int ym_kpts_decode(int nl, const void* const* kpt, const int* hs, con
     const long long total = (long long)B * nk * A;
     long long nb = (total + 255) / 256;
     if (nb > 148LL * 16) nb = 148LL * 16;
-    kpts_decode_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(lv, B, nk, ndim, A, y);
+    YM_LAUNCH(kpts_decode_kernel, (int)nb, 256, 0, (cudaStream_t)stream, lv, B, nk, ndim, A, y);
     YM_CHECK_LAUNCH("kpts_decode");
     return YM_OK;
 }
@@ -201,7 +202,11 @@ extern "C" int ym_letterbox_u8(const void* src, long long src_stride, int B, int
     cudaStream_t st = (cudaStream_t)stream;
     const uint8_t* s = (const uint8_t*)src;
     const LbTap *xt = (const LbTap*)xtab, *yt = (const LbTap*)ytab;
-#define LB_LAUNCH(T, CHW) letterbox_kernel<T, CHW><<<grid, block, 0, st>>>(s, src_stride, xt, yt, (T*)out, g)
+#define LB_LAUNCH(T, CHW)                                                      \
+    do {                                                                       \
+        auto kfn = letterbox_kernel<T, CHW>;                                   \
+        YM_LAUNCH(kfn, grid, block, 0, st, s, src_stride, xt, yt, (T*)out, g); \
+    } while (0)
     if (chw) {
         if (out_dtype == 0) LB_LAUNCH(uint8_t, true);
         else if (out_dtype == 1) LB_LAUNCH(__half, true);
@@ -226,8 +231,8 @@ extern "C" int ym_scale_boxes(float* boxes, int ld, long long n, int rows_per_im
     ScaleBoxParams sp;
     memset(&sp, 0, sizeof(sp));
     memcpy(sp.p, params_host, sizeof(float) * 5 * n_img);
-    scale_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(boxes, ld, n, rows_per_img, row_img,
-                                                                                     padding, xywh, sp);
+    YM_LAUNCH(scale_boxes_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, boxes, ld, n, rows_per_img, row_img, padding,
+              xywh, sp);
     YM_CHECK_LAUNCH("scale_boxes");
     return YM_OK;
 }

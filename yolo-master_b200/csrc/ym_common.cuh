@@ -1,10 +1,17 @@
 // Shared device/host helpers for libym_b200 (sm_100a only).
 #pragma once
+#ifdef YM_HOST_EMU          // tests/native/cuda_host_emu.h: the CUDA execution model on host threads (GPU-less verification)
+#include "cuda_host_emu.h"
+#else
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+// kernel launch / dynamic shared memory through macros, so that a translation unit can also be built for the host emulation
+#define YM_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define YM_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
 
 #define YM_OK 0
 #define YM_ERR_ARG 1
@@ -33,6 +40,7 @@ extern "C" void ym_set_error(const char* fmt, ...);
 
 namespace ym {
 
+#ifndef YM_HOST_EMU   // inline PTX: real GPU builds only
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -70,6 +78,8 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+#endif
+
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -81,6 +91,7 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t v) {
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
+#ifndef YM_HOST_EMU   // warp shuffles: real GPU builds only
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -91,6 +102,7 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+#endif
 
 struct alignas(16) Half8 {
     __half2 v[4];

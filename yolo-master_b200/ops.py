@@ -18,6 +18,14 @@ LAUNCHES = 0  # number of kernel-launching C-ABI calls issued (bench.py reports 
 KERNELS = 0   # number of device kernels launched (a call may launch several)
 
 
+REQUIRE_CUDA = True   # tests/test_cuda_host_emu.py clears this to drive the host-emulated build of the library with CPU tensors
+
+
+def _dev(t) -> bool:
+    """True where a tensor is acceptable as device memory for the C ABI."""
+    return t.is_cuda or not REQUIRE_CUDA
+
+
 def lib():
     global _L
     if _L is None:
@@ -37,7 +45,7 @@ def _count(nkernels: int = 1):
 
 def pitch(t: torch.Tensor, dtype=torch.float16) -> int:
     """Row pitch (elements) of an NHWC activation view; validates the layout."""
-    if t.dim() != 4 or t.dtype != dtype or not t.is_cuda:
+    if t.dim() != 4 or t.dtype != dtype or not _dev(t):
         raise ValueError(f"expected a 4-D fp16 CUDA NHWC activation, got {tuple(t.shape)} {t.dtype} {t.device}")
     B, H, W, Cc = t.shape
     sb, sh, sw, sc = t.stride()
@@ -318,7 +326,7 @@ def nms_batched(pred, conf_thres, iou_thres, max_det=300, max_nms=30000, max_wh=
 
 def nms_batched_large(pred, conf_thres, iou_thres, max_det=300, max_nms=30000, max_wh=7680.0):
     """ym_nms_batched_large: mode 0 of nms_batched without the 16384-candidate limit.  Returns (out, count, idx)."""
-    if pred.dtype != torch.float32 or not pred.is_cuda or pred.dim() != 3:
+    if pred.dtype != torch.float32 or not _dev(pred) or pred.dim() != 3:
         raise ValueError("nms_batched_large: expected an fp32 CUDA tensor of shape (B, 4+nc, A)")
     pred = pred.contiguous()
     B, no, A = pred.shape
@@ -495,7 +503,7 @@ _LB_DTYPES = {torch.uint8: 0, torch.float16: 1, torch.float32: 2}
 def letterbox(src, xtab, ytab, area2x, nw, nh, top, left, H, W, pad_value=114, swap_rb=True, chw=True, dtype=torch.uint8, out=None):
     """ym_letterbox_u8.  src: uint8 CUDA (B, sh, sw, 3) frames with dense rows; xtab / ytab: int32 CUDA (n, 2) tap tables
     (None when area2x).  Returns (B, 3, H, W) (chw) or (B, H, W, 3) of `dtype` (fp16 / fp32 are scaled by 1/255)."""
-    if not src.is_cuda or src.dtype != torch.uint8 or src.dim() != 4 or src.shape[3] != 3:
+    if not _dev(src) or src.dtype != torch.uint8 or src.dim() != 4 or src.shape[3] != 3:
         raise ValueError(f"letterbox: expected uint8 CUDA frames (B, H, W, 3), got {tuple(src.shape)} {src.dtype} {src.device}")
     if src.stride(3) != 1 or src.stride(2) != 3:
         raise ValueError("letterbox: frames must have dense interleaved rows")
@@ -504,12 +512,12 @@ def letterbox(src, xtab, ytab, area2x, nw, nh, top, left, H, W, pad_value=114, s
         raise ValueError(f"letterbox: unsupported output dtype {dtype}")
     if not area2x:
         for t, n in ((xtab, nw), (ytab, nh)):
-            if t is None or not t.is_cuda or t.dtype != torch.int32 or tuple(t.shape) != (n, 2) or not t.is_contiguous():
+            if t is None or not _dev(t) or t.dtype != torch.int32 or tuple(t.shape) != (n, 2) or not t.is_contiguous():
                 raise ValueError("letterbox: tap tables must be contiguous int32 CUDA tensors of shape (n, 2)")
     shape = (B, 3, H, W) if chw else (B, H, W, 3)
     if out is None:
         out = torch.empty(shape, dtype=dtype, device=src.device)
-    elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous() or not out.is_cuda:
+    elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous() or not _dev(out):
         raise ValueError(f"letterbox: out must be a contiguous {dtype} CUDA tensor of shape {shape}")
     _lib.check(lib().ym_letterbox_u8(src.data_ptr(), src.stride(0) if B > 1 else 0, B, sh, sw, src.stride(1) if sh > 1 else 3 * sw,
                                      None if area2x else xtab.data_ptr(), None if area2x else ytab.data_ptr(), 1 if area2x else 0,
@@ -522,7 +530,7 @@ def letterbox(src, xtab, ytab, area2x, nw, nh, top, left, H, W, pad_value=114, s
 def scale_boxes(boxes, params, rows_per_img=0, row_img=None, padding=True, xywh=False):
     """ym_scale_boxes, in place.  boxes: fp32 CUDA (..., ld >= 4) rows with a dense last dimension; params: fp32 HOST (n_img, 5)
     = (gain, pad_x, pad_y, w0, h0); image of a row = row_img[row] (int32 CUDA) or row // rows_per_img."""
-    if not boxes.is_cuda or boxes.dtype != torch.float32 or boxes.dim() < 2 or boxes.shape[-1] < 4:
+    if not _dev(boxes) or boxes.dtype != torch.float32 or boxes.dim() < 2 or boxes.shape[-1] < 4:
         raise ValueError("scale_boxes: expected an fp32 CUDA tensor (..., >= 4)")
     if boxes.dim() == 2 and boxes.stride(1) == 1 and (boxes.shape[0] == 1 or boxes.stride(0) >= boxes.shape[1]):
         ld = boxes.stride(0) if boxes.shape[0] > 1 else boxes.shape[1]   # e.g. the [:, :4] view of (n, 6) result rows
@@ -535,7 +543,7 @@ def scale_boxes(boxes, params, rows_per_img=0, row_img=None, padding=True, xywh=
     n = boxes.numel() // boxes.shape[-1]
     n_img = params.shape[0]
     if row_img is not None:
-        if not row_img.is_cuda or row_img.dtype != torch.int32 or row_img.numel() != n or not row_img.is_contiguous():
+        if not _dev(row_img) or row_img.dtype != torch.int32 or row_img.numel() != n or not row_img.is_contiguous():
             raise ValueError("scale_boxes: row_img must be a contiguous int32 CUDA tensor with one entry per row")
     elif rows_per_img <= 0 or n > rows_per_img * n_img:
         raise ValueError("scale_boxes: rows_per_img * n_img must cover every row")
