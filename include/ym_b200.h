@@ -229,6 +229,14 @@ int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C, int pool,
  * UltimateOptimizedMoE.forward modules.py:1663-1670: probs = softmax(clamp(softmax(fc . [mean | std]) / T, +-30)), top-k,
  * w / (sum + 1e-6), then w *= clamp(mean over the batch of sigmoid(cx_w . mean_c + cx_b), 0.3, 1.5).  fc fp32 [E][2C].
  * scratch: ym_zero_cost_router_scratch_floats() floats. */
+/* UltraEfficientRouter.forward moe/routers.py:96-118 (UltraOptimizedMoE, v0_1 uomoe / v0_2 zoos): avg_pool(pool) when H,W > pool ->
+ * dw3x3 -> GN -> SiLU -> 1x1 -> GN -> SiLU -> 1x1 + bias, then PER PIXEL clamp(+-30) / T -> softmax over experts, spatial mean, top-k,
+ * w / max(sum, 1e-6); weights <= w_min are zeroed (the eval threshold of BatchedExpertComputation moe/utils.py:172-173).
+ * scratch: ym_gate_router_scratch_floats(B, H, W, C, R, E, pool) floats. */
+int ym_pixel_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* dw, const float* gn1_w,
+                    const float* gn1_b, int G1, const float* pw1, int R, const float* gn2_w, const float* gn2_b, int G2,
+                    const float* pw2, const float* b2, int E, float gn_eps, float temperature, float w_min, int topk, float* scratch,
+                    float* w_out, int* idx_out, float* probs_out, void* stream);
 long long ym_zero_cost_router_scratch_floats(int B, int C);
 int ym_zero_cost_router(const void* x, int ldx, int B, int H, int W, int C, const float* fc, int E, float temperature,
                         const float* cx_w, float cx_b, int topk, float* scratch, float* w_out, int* idx_out, float* probs_out,

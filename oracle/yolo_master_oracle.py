@@ -308,6 +308,39 @@ def optimized_moe_improved(sd, p, x, num_experts, top_k):
     return _st((shared.float() + out).to(x.dtype))
 
 
+def ultra_efficient_router(sd, p, x, top_k, temperature=1.0, pool_scale=8):
+    """`UltraEfficientRouter.forward` moe/routers.py:96-118 (eval): pooled local stream, PER-PIXEL clamp / T / softmax over experts, spatial
+    mean, top-k, renormalise (clamp_min 1e-6).  Returns (weights [B,k], indices [B,k], pooled probabilities [B,E])."""
+    B, C, H, W = x.shape
+    xl = F.avg_pool2d(x, pool_scale, pool_scale) if (H > pool_scale and W > pool_scale) else x
+    t = F.conv2d(xl, sd[p + ".router.0.weight"], None, 1, 1, 1, C)
+    t = F.silu(_gn(sd, p + ".router.1", t, get_safe_groups(C, 8)))
+    t = F.conv2d(t, sd[p + ".router.3.weight"])
+    t = F.silu(_gn(sd, p + ".router.4", t, get_safe_groups(t.shape[1], 4)))
+    logits = F.conv2d(t, sd[p + ".router.6.weight"], sd[p + ".router.6.bias"])
+    wts = F.softmax((logits.clamp(-30.0, 30.0) / temperature).float(), dim=1)
+    pooled = wts.mean((2, 3))
+    w, idx = torch.topk(pooled, top_k, dim=1)
+    return w / w.sum(1, keepdim=True).clamp_min(1e-6), idx, pooled
+
+
+def layer_ultra_optimized_moe(sd, p, x, c1, c2, num_experts=4, top_k=2, *unused, return_route=False):
+    """`UltraOptimizedMoE.forward` moe/modules.py:205-214 (v0_1 uomoe / v0_2 zoos), eval: UltraEfficientRouter, shared expert
+    (1x1 -> GroupNorm -> SiLU) + `BatchedExpertComputation.compute_sparse_experts_batched` over OptimizedSimpleExpert (the SimpleExpert
+    structure: routes with weight <= 0.01 dropped, fp32 multiply, clamp +-1e4; moe/utils.py:119-209).  No residual."""
+    w, idx, probs = ultra_efficient_router(sd, p + ".routing", x, top_k)
+    shared = F.silu(_gn(sd, p + ".shared_expert.1", F.conv2d(x, _w(sd[p + ".shared_expert.0.weight"])), get_safe_groups(c2, 8)))
+    out = torch.zeros_like(shared)
+    valid = w > 0.01
+    for e in range(num_experts):
+        mask = (idx == e) & valid
+        if mask.any():
+            bi, ki = torch.where(mask)
+            out.index_add_(0, bi, simple_expert(sd, f"{p}.experts.{e}", x[bi]).float() * w[bi, ki].view(-1, 1, 1, 1))
+    y = _st(shared + out.clamp(-1e4, 1e4))
+    return (y, w, idx, probs) if return_route else y
+
+
 def layer_modular_router_expert_moe(sd, p, x, c1, c2, num_experts=4, top_k=2, *unused):
     """`ModularRouterExpertMoE` (= `OptimizedMOEImproved`, moe/modules.py:1745) as a top-level YAML layer (v0_1 zoo): the block
     owns its residual, `final_output + x` when in == out channels (modules.py:1156-1159)."""
@@ -1304,6 +1337,8 @@ def _gated_layer(name):
 
 
 layer_visual_enhanced_gate_moe = _gated_layer("VisualEnhancedAdaptiveGateMoE")
+_LAYER_FN["UltraOptimizedMoE"] = layer_ultra_optimized_moe
+_MIX_BASE.add("UltraOptimizedMoE")
 for _name in ("ModularRouterExpertMoE", "OptimizedMOEImproved"):
     _LAYER_FN[_name] = layer_modular_router_expert_moe
     _MIX_BASE.add(_name)

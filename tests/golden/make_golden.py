@@ -362,11 +362,14 @@ def gated_family_golden():
     from ultralytics.nn.modules.moe import gated as G
     out = {}
     from ultralytics.nn.modules.moe import modules as MM
-    for ci, name in enumerate(GATED_FAMILY + ["UltimateOptimizedMoE", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE", "MultiHeadRouterMoE", "GatedFusionMoE"]):
+    for ci, name in enumerate(GATED_FAMILY + ["UltimateOptimizedMoE", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE", "MultiHeadRouterMoE", "GatedFusionMoE", "UltraOptimizedMoE"]):
         for E in (4, 16):
             torch.manual_seed(0)
             split = 0.375 if (E == 16 and name in ("HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE", "MultiHeadRouterMoE", "GatedFusionMoE")) else 0.5   # the v0_11 / v0_12 P5 setting
-            m = getattr(G if hasattr(G, name) and name != "UltimateOptimizedMoE" else MM, name)(64, 64, E, 2, split).eval()
+            if name == "UltraOptimizedMoE":          # (in, out, num_experts, top_k): no channel split
+                m = MM.UltraOptimizedMoE(64, 64, E, 2).eval()
+            else:
+                m = getattr(G if hasattr(G, name) and name != "UltimateOptimizedMoE" else MM, name)(64, 64, E, 2, split).eval()
             for mod in m.modules():                      # inside a model every BatchNorm2d runs with eps = 1e-3
                 if isinstance(mod, torch.nn.BatchNorm2d):   # (initialize_weights, utils/torch_utils.py:552-562)
                     mod.eps = 1e-3
@@ -379,7 +382,8 @@ def gated_family_golden():
                 g = torch.Generator().manual_seed(77)    # "bias" tensors small: give the gate something to do
                 sd["cross_gate.gate_net.4.bias"].copy_(torch.randn(sd["cross_gate.gate_net.4.bias"].shape, generator=g))
             m.load_state_dict(sd)
-            x = torch.randn((2, 64, 12, 12), generator=torch.Generator().manual_seed(400 + ci))
+            hw = 24 if name == "UltraOptimizedMoE" else 12        # its router pools 8x8: 24x24 exercises the pooled branch
+            x = torch.randn((2, 64, hw, hw), generator=torch.Generator().manual_seed(400 + ci))
             route = {}
             h = m.routing.register_forward_hook(lambda mod, i, o: route.update(w=o[0].flatten(1).clone(), idx=o[1].flatten(1).clone()))
             with torch.no_grad():
@@ -388,7 +392,7 @@ def gated_family_golden():
             out[f"{name}/E{E}"] = {"seed": 300 + ci, "xseed": 400 + ci, "split": split, "y": y.clone(), "route_w": route["w"], "route_idx": route["idx"],
                                    "keys": {k: list(v.shape) for k, v in sd.items()},
                                    "scalars": {k: v.clone() for k, v in sd.items() if (v.dim() == 0 and v.is_floating_point()) or k == "cross_gate.gate_net.4.bias"},
-                                   "backend": getattr(m, "expert_backend", "fused" if name == "UltimateOptimizedMoE" else "shared_inverted")}
+                                   "backend": getattr(m, "expert_backend", "fused" if name == "UltimateOptimizedMoE" else "shared_inverted"), "hw": hw}
             print("gated", name, E, out[f"{name}/E{E}"]["backend"], float(y.abs().mean()))
     torch.save(out, f"{OUT}/gated_family.golden.pt")
 

@@ -22,14 +22,14 @@ extern "C" int host_gate_router(const void* x, int ldx, int B, int H, int W, int
     R0Args a0;
     a0.x = (const ym_half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = eff; a0.Hp = Hp; a0.Wp = Wp;
     a0.inv_area = 1.f / (float)(eff * eff); a0.stats = stats.data(); a0.pooled = pooled.data();
-    std::vector<float> sm(r0_smem_floats(C, NTHR) + r1_smem_floats(R, NTHR) + 16);
+    std::vector<float> sm(r0_smem_floats(C, NTHR) + r1_smem_floats(R, E, NTHR) + 16);
     for (int b = 0; b < B; ++b)
         for (int ph = 0; ph < R0_PHASES; ++ph)
             for (int t = 0; t < NTHR; ++t) r0_phase(ph, a0, b, t, NTHR, sm.data());
     R1Args a1;
     a1.pooled = pooled.data(); a1.t1 = t1.data(); a1.t2 = t2.data(); a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E;
     a1.G1 = G1; a1.G2 = G2; a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w;
-    a1.g2b = gn2_b; a1.pw2 = pw2; a1.b2 = b2; a1.ll = ll.data();
+    a1.g2b = gn2_b; a1.pw2 = pw2; a1.b2 = b2; a1.ll = ll.data(); a1.pixel_softmax = 0; a1.inv_temp = 1.f;
     for (int b = 0; b < B; ++b) {
         for (int ph = 0; ph < R1_PHASES; ++ph)
             for (int t = 0; t < NTHR; ++t) r1_phase(ph, a1, b, t, NTHR, sm.data());
@@ -38,8 +38,41 @@ extern "C" int host_gate_router(const void* x, int ldx, int B, int H, int W, int
     }
     R2Args a2;
     a2.stats = stats.data(); a2.ll = ll.data(); a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha;
-    a2.inv_temp = 1.f / temperature; a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.cx = cx.data(); a2.w = w_out;
+    a2.inv_temp = 1.f / temperature; a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.w_min = 0.f; a2.cx = cx.data(); a2.w = w_out;
     a2.probs = probs_out; a2.idx = idx_out; a2.ln_w = ln_w; a2.ln_b = ln_b; a2.ln_eps = ln_eps; a2.prior = prior;
+    for (int ph = 0; ph < R2_PHASES; ++ph)
+        for (int t = 0; t < NTHR; ++t) r2_phase(ph, a2, t, NTHR, sm.data());
+    return 0;
+}
+
+extern "C" int host_pixel_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* dw, const float* gn1_w,
+                                 const float* gn1_b, int G1, const float* pw1, int R, const float* gn2_w, const float* gn2_b, int G2,
+                                 const float* pw2, const float* b2, int E, float gn_eps, float temperature, float w_min, int topk,
+                                 float* w_out, int* idx_out, float* probs_out) {
+    const bool pooling = pool > 1 && H > pool && W > pool;
+    const int eff = pooling ? pool : 1, Hp = H / eff, Wp = W / eff;
+    const long long N = (long long)Hp * Wp;
+    std::vector<float> stats((size_t)B * 2 * C), pooled((size_t)B * N * C), t1((size_t)B * N * C), t2((size_t)B * N * R), ll((size_t)B * E);
+    std::vector<float> sm(r0_smem_floats(C, NTHR) + r1_smem_floats(R, E, NTHR) + 16);
+    R0Args a0;
+    a0.x = (const ym_half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = eff; a0.Hp = Hp; a0.Wp = Wp;
+    a0.inv_area = 1.f / (float)(eff * eff); a0.stats = stats.data(); a0.pooled = pooled.data();
+    R1Args a1;
+    a1.pooled = pooled.data(); a1.t1 = t1.data(); a1.t2 = t2.data(); a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E;
+    a1.G1 = G1; a1.G2 = G2; a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w;
+    a1.g2b = gn2_b; a1.pw2 = pw2; a1.b2 = b2; a1.ll = ll.data(); a1.pixel_softmax = 1; a1.inv_temp = 1.f / temperature;
+    for (int b = 0; b < B; ++b) {
+        for (int ph = 0; ph < R0_PHASES; ++ph)
+            for (int t = 0; t < NTHR; ++t) r0_phase(ph, a0, b, t, NTHR, sm.data());
+        for (int ph = 0; ph < R1_PHASES; ++ph)
+            for (int t = 0; t < NTHR; ++t) r1_phase(ph, a1, b, t, NTHR, sm.data());
+        for (int ph = 0; ph < R1_TAIL_PHASES; ++ph)
+            for (int t = 0; t < NTHR; ++t) r1_tail_phase(ph, a1, b, t, NTHR, sm.data());
+    }
+    R2Args a2;
+    a2.stats = stats.data(); a2.ll = ll.data(); a2.wg = nullptr; a2.wc = nullptr; a2.bc = 0.f; a2.alpha = 0.f; a2.inv_temp = 1.f;
+    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 2; a2.w_min = w_min; a2.cx = nullptr; a2.w = w_out; a2.probs = probs_out;
+    a2.idx = idx_out; a2.ln_w = nullptr; a2.ln_b = nullptr; a2.ln_eps = 0.f; a2.prior = nullptr;
     for (int ph = 0; ph < R2_PHASES; ++ph)
         for (int t = 0; t < NTHR; ++t) r2_phase(ph, a2, t, NTHR, sm.data());
     return 0;
@@ -56,7 +89,7 @@ extern "C" int host_zero_cost_router(const void* x, int ldx, int B, int H, int W
             for (int t = 0; t < NTHR; ++t) r0_phase(ph, a0, b, t, NTHR, sm.data());
     R2Args a2;
     a2.stats = stats.data(); a2.ll = nullptr; a2.wg = fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = 1.f; a2.inv_temp = 1.f / temperature;
-    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.cx = cx.data(); a2.w = w_out; a2.probs = probs_out;
+    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.w_min = 0.f; a2.cx = cx.data(); a2.w = w_out; a2.probs = probs_out;
     a2.idx = idx_out; a2.ln_w = nullptr; a2.ln_b = nullptr; a2.ln_eps = 0.f; a2.prior = nullptr;
     for (int ph = 0; ph < R2_PHASES; ++ph)
         for (int t = 0; t < NTHR; ++t) r2_phase(ph, a2, t, NTHR, sm.data());

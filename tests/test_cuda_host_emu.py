@@ -23,7 +23,7 @@ from yolo_master_b200 import _lib, ops
 CSRC = os.path.join(ROOT, "yolo-master_b200", "csrc")
 UNITS = ["preproc.cu", "gated.cu", "nms_large.cu", "mix.cu"]
 SYMBOLS = ["ym_letterbox_u8", "ym_scale_boxes", "ym_kpts_decode", "ym_obb_finish", "ym_gate_router", "ym_gate_router_scratch_floats",
-           "ym_zero_cost_router", "ym_zero_cost_router_scratch_floats", "ym_fc_gate", "ym_classify_head", "ym_gated_select",
+           "ym_zero_cost_router", "ym_zero_cost_router_scratch_floats", "ym_pixel_router", "ym_fc_gate", "ym_classify_head", "ym_gated_select",
            "ym_ctx_mean3", "ym_nms_batched_large", "ym_nms_large_scratch_bytes", "ym_ew_nhwc", "ym_last_error"]
 
 
@@ -129,6 +129,18 @@ def test_gated_kernels(emu):
         assert torch.equal(idx.long(), ri)
         torch.testing.assert_close(probs, rp, atol=2e-6, rtol=1e-4)
         torch.testing.assert_close(w, O.complexity_gate(rw, cx.clamp(0.3, 1.5)), atol=2e-6, rtol=1e-4)
+    from yolo_master_b200.nn.modules.moe import UltraOptimizedMoE
+    for E, hw in ((4, 24), (16, 7)):                     # pooled (24 > 8) and un-pooled router maps; per-thread partials per expert
+        mu = UltraOptimizedMoE(64, 64, E, 2)
+        sdu = mu.state_dict()
+        fill_state_dict_(sdu, 9)
+        mu.load_state_dict(sdu)
+        xu = torch.randn((2, 64, hw, hw), generator=g).half()
+        idx, w, probs = ops.pixel_router(xu.permute(0, 2, 3, 1).contiguous(), mu.eval().get_pack()["router"], 2, 0.01)
+        rw, ri, rp = O.ultra_efficient_router({"m." + k_: v.float() for k_, v in sdu.items()}, "m.routing", xu.float(), 2)
+        assert torch.equal(idx.long(), ri)
+        torch.testing.assert_close(probs, rp, atol=2e-6, rtol=1e-4)
+        torch.testing.assert_close(w, torch.where(rw > 0.01, rw, torch.zeros_like(rw)), atol=2e-6, rtol=1e-4)
     m = UltimateOptimizedMoE(64, 64, 4, 2, 0.5)
     sd = m.state_dict()
     fill_state_dict_(sd, 3)

@@ -160,12 +160,14 @@ def test_family_class_matches_reference_module_golden(emu, key):
     """Every class of the AdaptiveGateMoE line (v0_4 ... v0_10 zoos), top-2 of 4 and of 16 experts: state-dict keys equal the
     reference module's, and the host mirror (emulated ops) reproduces the REAL module's output within the fp16 noise floor of the
     oracle with identical expert choices."""
-    from yolo_master_b200.nn.modules import gated
+    from yolo_master_b200.nn.modules import gated, moe as moe_mod
     from yolo_master_b200.utils.synth import fill_state_dict_
     name, E = key.split("/E")
     c = FAMILY[key]
-    m = getattr(gated, name)(64, 64, int(E), 2, c["split"])
-    assert m.expert_backend == c["backend"]
+    extra = () if name == "UltraOptimizedMoE" else (c["split"],)             # (in, out, num_experts, top_k[, split_ratio])
+    m = getattr(gated, name, None) or getattr(moe_mod, name)
+    m = m(64, 64, int(E), 2, *extra)
+    assert getattr(m, "expert_backend", c["backend"]) == c["backend"]
     sd = m.state_dict()
     assert {k: list(v.shape) for k, v in sd.items()} == c["keys"]
     fill_state_dict_(sd, c["seed"])
@@ -173,14 +175,14 @@ def test_family_class_matches_reference_module_golden(emu, key):
     m.load_state_dict(sd, strict=True)
     m.eval()
     sdm = {"m." + k: v.clone().float() for k, v in sd.items()}
-    x = torch.randn((2, 64, 12, 12), generator=torch.Generator().manual_seed(c["xseed"]))
+    x = torch.randn((2, 64, c["hw"], c["hw"]), generator=torch.Generator().manual_seed(c["xseed"]))
     with torch.no_grad():
         y = m.fwd_nhwc(x.half().permute(0, 2, 3, 1).contiguous()).float().permute(0, 3, 1, 2)
     xq = x.half().float()
-    ref, _, ri, _ = O._LAYER_FN[name](sdm, "m", xq, 64, 64, int(E), 2, c["split"], return_route=True)
+    ref, _, ri, _ = O._LAYER_FN[name](sdm, "m", xq, 64, 64, int(E), 2, *extra, return_route=True)
     assert torch.equal(m.last_routing_snapshot["topk_indices"].long(), ri)
     with O.fp16_storage(), O.fp16_weights():
-        sim = O._LAYER_FN[name](sdm, "m", xq, 64, 64, int(E), 2, c["split"])
+        sim = O._LAYER_FN[name](sdm, "m", xq, 64, 64, int(E), 2, *extra)
     assert emu.report(key, y, ref, sim)
     assert float((y - c["y"]).abs().max()) < 3e-2               # and stays close to the reference module's own fp32 output
 

@@ -108,23 +108,25 @@ FAMILY = torch.load(os.path.join(GOLD, "gated_family.golden.pt"))
 def test_family_class_matches_reference_module_golden(key):
     """Every class of the AdaptiveGateMoE line (v0_4 ... v0_10 zoos), top-2 of 4 and of 16 experts, against the oracle (pinned to the
     REAL module by tests/test_oracle_gated.py) and the reference module's own output."""
-    from yolo_master_b200.nn.modules import gated
+    from yolo_master_b200.nn.modules import gated, moe as moe_mod
     name, E = key.split("/E")
     c = FAMILY[key]
-    m = getattr(gated, name)(64, 64, int(E), 2, c["split"])
+    extra = () if name == "UltraOptimizedMoE" else (c["split"],)             # (in, out, num_experts, top_k[, split_ratio])
+    m = getattr(gated, name, None) or getattr(moe_mod, name)
+    m = m(64, 64, int(E), 2, *extra)
     sd = m.state_dict()
     fill_state_dict_(sd, c["seed"])
     sd.update({k: v.clone() for k, v in c["scalars"].items()})    # 0-dim parameters (and CrossPathGate's bias) as the fixture had them
     m.load_state_dict(sd, strict=True)
     m = m.to(DEV).eval()
     sdm = {"m." + k: v.clone().float() for k, v in sd.items()}
-    x = torch.randn((2, 64, 12, 12), generator=torch.Generator().manual_seed(c["xseed"])).half().float()
+    x = torch.randn((2, 64, c["hw"], c["hw"]), generator=torch.Generator().manual_seed(c["xseed"])).half().float()
     with torch.no_grad():
         y = m(x.half().to(DEV).contiguous(memory_format=torch.channels_last))
-    ref, _, ri, _ = O._LAYER_FN[name](sdm, "m", x, 64, 64, int(E), 2, c["split"], return_route=True)
+    ref, _, ri, _ = O._LAYER_FN[name](sdm, "m", x, 64, 64, int(E), 2, *extra, return_route=True)
     assert torch.equal(m.last_routing_snapshot["topk_indices"].long().cpu(), ri)
     with O.fp16_storage(), O.fp16_weights():
-        sim = O._LAYER_FN[name](sdm, "m", x, 64, 64, int(E), 2, c["split"])
+        sim = O._LAYER_FN[name](sdm, "m", x, 64, 64, int(E), 2, *extra)
     assert_within_noise(y, ref, sim, what=key)
     assert float((y.float().cpu() - c["y"]).abs().max()) < 3e-2
 

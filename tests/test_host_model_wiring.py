@@ -89,13 +89,13 @@ def test_model_host_wiring_matches_reference_golden(emu, name, cfg, tag):
         assert_within_noise(y[:, 4:], ref[:, 4:], ysim[:, 4:], what=f"{name} scores", outlier_frac=0.02)
 
 
-ZOO = ["master/v0_3/det/yolo-master-n.yaml", "master/v0_4/det/yolo-master-n.yaml", "master/v0_5/det/yolo-master-n.yaml",
+ZOO = ["master/v0_1/det/yolo-master-n-uomoe.yaml", "master/v0_3/det/yolo-master-n.yaml", "master/v0_4/det/yolo-master-n.yaml", "master/v0_5/det/yolo-master-n.yaml",
        "master/v0_6/det/yolo-master-n.yaml", "master/v0_7/det/yolo-master-n.yaml", "master/v0_8/det/yolo-master-n.yaml",
        "master/v0_9/det/yolo-master-n.yaml", "master/exp/yolo-master-v0_11.yaml", "master/v0_12/det/yolo-master-n.yaml",
        "master/v0_13/det/yolo-master-n.yaml", "master/v0_15/det/yolo-master-n.yaml"]
 
 
-@pytest.mark.parametrize("cfg", ZOO, ids=[c.split("/")[1] for c in ZOO])
+@pytest.mark.parametrize("cfg", ZOO, ids=[c.split("/")[1] + ("-uomoe" if "uomoe" in c else "") for c in ZOO])
 def test_zoo_model_host_wiring_matches_oracle(emu, cfg):
     """One n-scale model per zoo version of the gated line (no model-level reference golden for these: every block class is pinned
     to the reference as a module, tests/test_oracle_gated.py): the mirror on emulated ops against the oracle's whole-model forward

@@ -88,9 +88,10 @@ def test_gated_family_oracle_matches_reference_module(key):
     fill_state_dict_(sd, c["seed"])
     sd.update(c["scalars"])                                      # 0-dim parameters (alpha, *_scale) stay at their init values
     sd = {"m." + k: v for k, v in sd.items()}
-    x = torch.randn((2, 64, 12, 12), generator=torch.Generator().manual_seed(c["xseed"]))
+    x = torch.randn((2, 64, c["hw"], c["hw"]), generator=torch.Generator().manual_seed(c["xseed"]))
     if name in O.GATED_VARIANTS:
         assert O.gated_backend(name, int(E)) == c["backend"]
-    y, w, idx, _ = O._LAYER_FN[name](sd, "m", x, 64, 64, int(E), 2, c["split"], return_route=True)
+    extra = () if name == "UltraOptimizedMoE" else (c["split"],)             # (in, out, num_experts, top_k[, split_ratio])
+    y, w, idx, _ = O._LAYER_FN[name](sd, "m", x, 64, 64, int(E), 2, *extra, return_route=True)
     assert torch.equal(idx, c["route_idx"])                      # router choices (taken before the complexity gate in the fixture)
     torch.testing.assert_close(y, c["y"], atol=2e-4, rtol=2e-4)

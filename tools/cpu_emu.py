@@ -208,6 +208,7 @@ def install_gated(host):
     vp, ci, cf = C.c_void_p, C.c_int, C.c_float
     host.host_gate_router.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, ci, cf, cf, cf, vp, cf,
                                       ci, vp, vp, cf, vp, vp, vp, vp]
+    host.host_pixel_router.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, ci, cf, cf, cf, ci, vp, vp, vp]
     host.host_zero_cost_router.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci, cf, vp, cf, ci, vp, vp, vp]
     host.host_classify_head.argtypes = [vp, ci, ci, ci, vp, vp, ci, vp, vp]
     host.host_fc_gate.argtypes = [vp, ci, ci, ci, vp, ci, vp, vp, ci, cf, cf, vp]
@@ -231,6 +232,17 @@ def install_gated(host):
                               None if ln is None else ln[0].data_ptr(), None if ln is None else ln[1].data_ptr(),
                               0.0 if ln is None else ln[2], None if prior is None else prior.data_ptr(), w.data_ptr(),
                               idx.data_ptr(), probs.data_ptr())
+        return idx, w, probs
+
+    def pixel_router(x, pk, topk, w_min=0.01):
+        B, H, W, Cc = x.shape
+        w = torch.empty((B, topk), dtype=torch.float32)
+        idx = torch.empty((B, topk), dtype=torch.int32)
+        probs = torch.empty((B, pk["E"]), dtype=torch.float32)
+        host.host_pixel_router(x.data_ptr(), ld(x), B, H, W, Cc, pk["pool"], pk["dw"].data_ptr(), pk["gn1_w"].data_ptr(), pk["gn1_b"].data_ptr(),
+                               pk["G1"], pk["pw1"].data_ptr(), pk["R"], pk["gn2_w"].data_ptr(), pk["gn2_b"].data_ptr(), pk["G2"],
+                               pk["pw2"].data_ptr(), pk["b2"].data_ptr(), pk["E"], pk["eps"], pk["temperature"], float(w_min), topk,
+                               w.data_ptr(), idx.data_ptr(), probs.data_ptr())
         return idx, w, probs
 
     def zero_cost_router(x, fc, temperature, cx_w, cx_b, topk):
@@ -272,7 +284,7 @@ def install_gated(host):
                             c.shape[1], c.shape[2], out.data_ptr(), ld(out))
         return out
 
-    for name, fn in dict(gate_router=gate_router, zero_cost_router=zero_cost_router, fc_gate=fc_gate, classify_head=classify_head, gated_select=gated_select, ctx_mean3=ctx_mean3,
+    for name, fn in dict(gate_router=gate_router, pixel_router=pixel_router, zero_cost_router=zero_cost_router, fc_gate=fc_gate, classify_head=classify_head, gated_select=gated_select, ctx_mean3=ctx_mean3,
                          moe_expert_gemm=moe_expert_gemm, gn_finalize=gn_finalize).items():
         setattr(ops, name, fn)
     ops.pitch = lambda t, dtype=torch.float16: ld(t)

@@ -66,6 +66,7 @@ SIGNATURES = {
     "ym_gate_router_scratch_floats": (cll, [ci, ci, ci, ci, ci, ci, ci]),
     "ym_gate_router": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, ci, cf, cf, cf, vp, cf, ci,
                             vp, vp, cf, vp, vp, vp, vp, vp, vp]),
+    "ym_pixel_router": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, vp, vp, ci, vp, ci, vp, vp, ci, vp, vp, ci, cf, cf, cf, ci, vp, vp, vp, vp, vp]),
     "ym_zero_cost_router_scratch_floats": (cll, [ci, ci]),
     "ym_zero_cost_router": (ci, [vp, ci, ci, ci, ci, ci, vp, ci, cf, vp, cf, ci, vp, vp, vp, vp, vp]),
     "ym_fc_gate": (ci, [vp, ci, ci, ci, vp, ci, vp, vp, ci, cf, cf, vp, vp]),

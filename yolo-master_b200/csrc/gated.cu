@@ -145,14 +145,50 @@ extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C
     R1Args a1;
     a1.pooled = pooled; a1.t1 = t1; a1.t2 = t2; a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E; a1.G1 = G1; a1.G2 = G2;
     a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w; a1.g2b = gn2_b; a1.pw2 = pw2;
-    a1.b2 = b2; a1.ll = ll;
-    YM_LAUNCH(gate_r1_kernel, B, NTHR, r1_smem_floats(R, NTHR) * sizeof(float), st, a1);
+    a1.b2 = b2; a1.ll = ll; a1.pixel_softmax = 0; a1.inv_temp = 1.f;
+    YM_LAUNCH(gate_r1_kernel, B, NTHR, r1_smem_floats(R, E, NTHR) * sizeof(float), st, a1);
     R2Args a2;
     a2.stats = stats; a2.ll = ll; a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha; a2.inv_temp = 1.f / temperature;
-    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
+    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.w_min = 0.f; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
     a2.ln_w = ln_w; a2.ln_b = ln_b; a2.ln_eps = ln_eps; a2.prior = prior;
     YM_LAUNCH(gate_r2_kernel, 1, NTHR, 0, st, a2);
     YM_CHECK_LAUNCH("gate_router");
+    return YM_OK;
+}
+
+extern "C" int ym_pixel_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* dw, const float* gn1_w,
+                               const float* gn1_b, int G1, const float* pw1, int R, const float* gn2_w, const float* gn2_b, int G2,
+                               const float* pw2, const float* b2, int E, float gn_eps, float temperature, float w_min, int topk,
+                               float* scratch, float* w_out, int* idx_out, float* probs_out, void* stream) {
+    YM_CHECK_ARG(x && scratch && w_out && idx_out, "ym_pixel_router: null pointer");
+    YM_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R > 0 && R <= MAXR, "ym_pixel_router: empty problem / more than %d reduced channels", MAXR);
+    YM_CHECK_ARG(E >= 1 && E <= 32 && topk >= 1 && topk <= E, "ym_pixel_router: 1 <= topk <= E <= 32");
+    YM_CHECK_ARG(G1 >= 1 && G1 <= MAXG && C % G1 == 0 && G2 >= 1 && G2 <= MAXG && R % G2 == 0, "ym_pixel_router: GroupNorm groups");
+    YM_CHECK_ARG(temperature > 0.f, "ym_pixel_router: temperature must be positive");
+    int Hp, Wp, eff;
+    pooled_dims(H, W, pool, &Hp, &Wp, &eff);
+    const long long N = (long long)Hp * Wp;
+    float* stats = scratch;
+    float* pooled = stats + (long long)B * 2 * C;
+    float* t1 = pooled + (long long)B * N * C;
+    float* t2 = t1 + (long long)B * N * C;
+    float* ll = t2 + (long long)B * N * R;
+    cudaStream_t st = (cudaStream_t)stream;
+    R0Args a0;
+    a0.x = (const __half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = eff; a0.Hp = Hp; a0.Wp = Wp;
+    a0.inv_area = 1.f / (float)(eff * eff); a0.stats = stats; a0.pooled = pooled;
+    YM_LAUNCH(gate_r0_kernel, B, NTHR, r0_smem_floats(C, NTHR) * sizeof(float), st, a0);
+    R1Args a1;
+    a1.pooled = pooled; a1.t1 = t1; a1.t2 = t2; a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E; a1.G1 = G1; a1.G2 = G2;
+    a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w; a1.g2b = gn2_b; a1.pw2 = pw2;
+    a1.b2 = b2; a1.ll = ll; a1.pixel_softmax = 1; a1.inv_temp = 1.f / temperature;
+    YM_LAUNCH(gate_r1_kernel, B, NTHR, r1_smem_floats(R, E, NTHR) * sizeof(float), st, a1);
+    R2Args a2;
+    a2.stats = stats; a2.ll = ll; a2.wg = nullptr; a2.wc = nullptr; a2.bc = 0.f; a2.alpha = 0.f; a2.inv_temp = 1.f;
+    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 2; a2.w_min = w_min; a2.cx = nullptr; a2.w = w_out; a2.probs = probs_out;
+    a2.idx = idx_out; a2.ln_w = nullptr; a2.ln_b = nullptr; a2.ln_eps = 0.f; a2.prior = nullptr;
+    YM_LAUNCH(gate_r2_kernel, 1, NTHR, 0, st, a2);
+    YM_CHECK_LAUNCH("pixel_router");
     return YM_OK;
 }
 
@@ -174,7 +210,7 @@ extern "C" int ym_zero_cost_router(const void* x, int ldx, int B, int H, int W, 
     YM_LAUNCH(gate_r0_kernel, B, NTHR, r0_smem_floats(C, NTHR) * sizeof(float), st, a0);
     R2Args a2;
     a2.stats = stats; a2.ll = nullptr; a2.wg = fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = 1.f; a2.inv_temp = 1.f / temperature;
-    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
+    a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.w_min = 0.f; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
     a2.ln_w = nullptr; a2.ln_b = nullptr; a2.ln_eps = 0.f; a2.prior = nullptr;
     YM_LAUNCH(gate_r2_kernel, 1, NTHR, 0, st, a2);
     YM_CHECK_LAUNCH("zero_cost_router");

@@ -152,10 +152,14 @@ struct R1Args {
     const float* pw1;      // [R][C]
     const float *g2w, *g2b;   // [R]
     const float *pw2, *b2;    // [E][R], [E]
-    float* ll;             // [B][E] local logits
+    float* ll;             // [B][E] local logits (pixel_softmax: the spatial mean of the per-pixel expert probabilities)
+    int pixel_softmax;     // 1: UltraEfficientRouter routers.py:104-118 - per-pixel clamp(+-30) / T -> softmax over experts, THEN the mean
+    float inv_temp;
 };
 constexpr int R1_PHASES = 10;
-YM_HD int r1_smem_floats(int R, int nthr) { return nthr * MAXG + 2 * MAXG + col_lane_floats(R, nthr); }
+constexpr int MAXR = 64;       // reduced channels of the local stream (max(C / 16, 4))
+YM_HD int r1_part_floats(int E, int nthr) { return nthr * (E > MAXG ? E : MAXG); }      // per-thread partials: GN groups, or experts
+YM_HD int r1_smem_floats(int R, int E, int nthr) { return r1_part_floats(E, nthr) + 2 * MAXG + col_lane_floats(R, nthr); }
 
 YM_HD void r1_phase(int ph, const R1Args& a, int img, int tid, int nthr, float* sm) {
     const int N = a.Hp * a.Wp, C = a.C, R = a.R;
@@ -163,7 +167,7 @@ YM_HD void r1_phase(int ph, const R1Args& a, int img, int tid, int nthr, float* 
     float* t1 = a.t1 + (long long)img * N * C;
     float* t2 = a.t2 + (long long)img * N * R;
     float* part = sm;
-    float* mean = sm + nthr * MAXG;
+    float* mean = sm + r1_part_floats(a.E, nthr);
     float* rstd = mean + MAXG;
     const int cpg1 = C / a.G1, cpg2 = R / a.G2;
     switch (ph) {
@@ -218,12 +222,37 @@ YM_HD void r1_tail_phase(int ph, const R1Args& a, int img, int tid, int nthr, fl
     const int N = a.Hp * a.Wp, R = a.R;
     const float* t2 = a.t2 + (long long)img * N * R;
     float* part = sm;
-    float* mean = sm + nthr * MAXG;
+    float* mean = sm + r1_part_floats(a.E, nthr);
     float* rstd = mean + MAXG;
     float* colp = rstd + MAXG;
     const int cpg2 = R / a.G2;
     if (ph == 0) {
         if (tid < a.G2) rstd[tid] = 1.f / sqrtf(gn_reduce(part, tid, nthr, (float)N * cpg2) + a.eps);
+    } else if (ph == 1 && a.pixel_softmax) {   // per pixel: SiLU(GN2) -> 1x1 + bias -> clamp -> / T -> softmax; per-thread sums per expert
+        float acc[MAXE];
+        for (int e = 0; e < a.E; ++e) acc[e] = 0.f;
+        for (int p = tid; p < N; p += nthr) {
+            float h[MAXR], l[MAXE];
+            for (int r = 0; r < R; ++r) {
+                const int g = r / cpg2;
+                h[r] = silu_f32((t2[(long long)p * R + r] - mean[g]) * rstd[g] * a.g2w[r] + a.g2b[r]);
+            }
+            float mx = -3.0e38f;
+            for (int e = 0; e < a.E; ++e) {
+                float s = a.b2[e];
+                for (int r = 0; r < R; ++r) s += a.pw2[e * R + r] * h[r];
+                s = (s < -30.f ? -30.f : (s > 30.f ? 30.f : s)) * a.inv_temp;
+                l[e] = s;
+                mx = s > mx ? s : mx;
+            }
+            float den = 0.f;
+            for (int e = 0; e < a.E; ++e) {
+                l[e] = expf(l[e] - mx);
+                den += l[e];
+            }
+            for (int e = 0; e < a.E; ++e) acc[e] += l[e] / den;
+        }
+        for (int e = 0; e < a.E; ++e) part[tid * a.E + e] = acc[e];
     } else if (ph == 1) {   // column sums over the pixels of SiLU(GN2(t2)): the last 1x1 and the spatial mean commute
         const ColLane cl(R, tid, nthr);
         if (!cl.active()) return;
@@ -232,6 +261,12 @@ YM_HD void r1_tail_phase(int ph, const R1Args& a, int img, int tid, int nthr, fl
             float s = 0.f;
             for (int p = cl.pl; p < N; p += cl.NL) s += silu_f32((t2[(long long)p * R + r] - mean[g]) * rstd[g] * a.g2w[r] + a.g2b[r]);
             colp[cl.pl * R + r] = s;
+        }
+    } else if (a.pixel_softmax) {
+        for (int e = tid; e < a.E; e += nthr) {
+            float s = 0.f;
+            for (int t = 0; t < nthr; ++t) s += part[t * a.E + e];
+            a.ll[(long long)img * a.E + e] = s / (float)N;
         }
     } else {
         const ColLane cl(R, tid, nthr);
@@ -261,7 +296,10 @@ struct R2Args {
     const float* prior;          // [E] learnable expert prior added to the blended logits before the clamp (gated.py:216,238), or null
     int B, C, E, topk;
     int zero_cost;        // 0: DualStreamGateRouter + complexity GATE (ranks dropped);  1: ZeroCostRouter (gated.py:953-968: softmax of
-                          //    the global stream, / T, clamp, softmax again) + complexity SCALE (weights multiplied, modules.py:1663-1670)
+                          //    the global stream, / T, clamp, softmax again) + complexity SCALE (weights multiplied, modules.py:1663-1670);
+                          // 2: `ll` already holds expert probabilities (UltraEfficientRouter): top-k, w / max(sum, 1e-6), no complexity,
+                          //    weights <= w_min zeroed (BatchedExpertComputation's eval threshold, moe/utils.py:172-173)
+    float w_min;
     float* cx;            // scratch [B]
     float *w, *probs;     // [B][topk], [B][E] (probs nullable)
     int* idx;             // [B][topk]
@@ -271,13 +309,14 @@ YM_HD int r2_smem_floats() { return 4; }
 
 YM_HD void r2_phase(int ph, const R2Args& a, int tid, int nthr, float* sm) {
     if (ph == 0) {
+        if (a.zero_cost == 2) return;
         for (int b = tid; b < a.B; b += nthr) {
             float s = a.bc;
             for (int c = 0; c < a.C; ++c) s += a.wc[c] * a.stats[(long long)b * 2 * a.C + c];
             a.cx[b] = sigmoid_f(s);
         }
     } else if (ph == 1) {
-        if (tid != 0) return;
+        if (tid != 0 || a.zero_cost == 2) return;
         float s = 0.f;
         for (int b = 0; b < a.B; ++b) s += a.cx[b];
         s /= (float)a.B;
@@ -291,6 +330,28 @@ YM_HD void r2_phase(int ph, const R2Args& a, int tid, int nthr, float* sm) {
         const float keep = sm[0], cscale = sm[1];
         for (int b = tid; b < a.B; b += nthr) {
             float p[MAXE];
+            if (a.zero_cost == 2) {   // probabilities come straight from the per-pixel stream
+                float wsel2[MAXE], tot = 0.f;
+                for (int e = 0; e < a.E; ++e) {
+                    p[e] = a.ll[(long long)b * a.E + e];
+                    if (a.probs) a.probs[(long long)b * a.E + e] = p[e];
+                }
+                for (int j = 0; j < a.topk; ++j) {
+                    int best = -1;
+                    for (int e = 0; e < a.E; ++e)
+                        if (p[e] >= 0.f && (best < 0 || p[e] > p[best])) best = e;
+                    if (best < 0) best = j;
+                    a.idx[(long long)b * a.topk + j] = best;
+                    wsel2[j] = p[best];
+                    tot += p[best];
+                    p[best] = -1.f;
+                }
+                for (int j = 0; j < a.topk; ++j) {
+                    const float v = wsel2[j] / (tot < 1e-6f ? 1e-6f : tot);
+                    a.w[(long long)b * a.topk + j] = v > a.w_min ? v : 0.f;
+                }
+                continue;
+            }
             float mx = -3.0e38f;
             const float* st = a.stats + (long long)b * 2 * a.C;
             float lm = 0.f, lr = 1.f;

@@ -10,12 +10,12 @@ from .head import DFL, OBB, Classify, Detect, Pose, Proto, Segment
 from .moa import C2fMoA, MoABlock
 from .mot import C2fMoT, MoTBlock
 from .moe import (A2C2fMoE, ABlockMoE, DepthwiseSeparableConv, DynamicRoutingLayer, EfficientExpertGroup, EfficientSpatialRouter,
-                  ES_MOE, OptimizedMOEImproved, SimpleExpert, get_safe_groups)
+                  ES_MOE, OptimizedMOEImproved, SimpleExpert, UltraEfficientRouter, UltraOptimizedMoE, get_safe_groups)
 
 ModularRouterExpertMoE = OptimizedMOEImproved   # alias of the reference (moe/modules.py:1745), the block of the v0_1 zoo
 
 __all__ = (
-    "ModularRouterExpertMoE",
+    "ModularRouterExpertMoE", "UltraOptimizedMoE", "UltraEfficientRouter",
     "Conv", "DWConv", "Concat", "Upsample", "PlainConv2d", "autopad",
     "Bottleneck", "C2f", "C3", "C3k", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA", "AAttn", "ABlock", "A2C2f",
     "EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups",

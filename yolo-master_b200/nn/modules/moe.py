@@ -21,7 +21,7 @@ from ...utils.errors import MoERouterError, ShapeMismatchError
 from ._base import PackCache, bn_affine, fold_bn, pack_gemm_weight, require_eval, to_nchw, to_nhwc
 from .block import A2C2f, ABlock, C3k, _SeqNHWC
 
-__all__ = ("EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups",
+__all__ = ("UltraEfficientRouter", "UltraOptimizedMoE", "EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups",
            "DynamicRoutingLayer", "DepthwiseSeparableConv", "EfficientExpertGroup", "ES_MOE")
 
 
@@ -202,6 +202,97 @@ class OptimizedMOEImproved(nn.Module, PackCache):
             raise RuntimeError("OptimizedMOEImproved final output contains NaN/Inf (shared expert / sparse expert aggregation / "
                                "dtype conversion)")
         return to_nchw(y)
+
+    @property
+    def aux_loss(self):
+        return torch.zeros((), device=self.shared_expert[0].weight.device)
+
+
+class UltraEfficientRouter(nn.Module):
+    """`UltraEfficientRouter(in_channels, num_experts, reduction=16, top_k=2, noise_std=1.0, temperature=1.0, pool_scale=8)`
+    (moe/routers.py:58-137): depthwise / pointwise local stream on an 8x-pooled map, per-pixel softmax, spatial mean (`ym_pixel_router`)."""
+
+    def __init__(self, in_channels, num_experts, reduction=16, top_k=2, noise_std=1.0, temperature=1.0, pool_scale=8):
+        super().__init__()
+        self.num_experts, self.top_k, self.noise_std = num_experts, top_k, noise_std
+        self.temperature = max(float(temperature), 1e-3)
+        self.pool_scale = pool_scale
+        reduced = max(in_channels // reduction, 4)
+        self.router = nn.Sequential(
+            nn.Conv2d(in_channels, in_channels, 3, padding=1, groups=in_channels, bias=False),
+            nn.GroupNorm(get_safe_groups(in_channels, 8), in_channels), nn.SiLU(inplace=False),
+            nn.Conv2d(in_channels, reduced, 1, bias=False), nn.GroupNorm(get_safe_groups(reduced, 4), reduced), nn.SiLU(inplace=False),
+            nn.Conv2d(reduced, num_experts, 1, bias=True))
+        self.softmax = nn.Softmax(dim=1)
+
+    def pack(self):
+        r = self.router
+        C, R, E = r[0].weight.shape[0], r[3].weight.shape[0], self.num_experts
+        f = lambda t: t.detach().float().contiguous()
+        return {"E": E, "R": R, "pool": int(self.pool_scale), "G1": r[1].num_groups, "G2": r[4].num_groups, "eps": float(r[1].eps),
+                "dw": f(r[0].weight).reshape(C, 9).contiguous(), "gn1_w": f(r[1].weight), "gn1_b": f(r[1].bias),
+                "pw1": f(r[3].weight).reshape(R, C).contiguous(), "gn2_w": f(r[4].weight), "gn2_b": f(r[4].bias),
+                "pw2": f(r[6].weight).reshape(E, R).contiguous(), "b2": f(r[6].bias), "temperature": float(self.temperature)}
+
+
+class UltraOptimizedMoE(nn.Module, PackCache):
+    """`UltraOptimizedMoE(in_channels, out_channels, num_experts=4, top_k=2, expert_type="simple", router_reduction=16,
+    router_pool_scale=8, noise_std=1.0, router_temperature=1.0, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, num_groups=8,
+    weight_threshold=0.01)` (moe/modules.py:121-320; v0_1 uomoe / v0_2 zoos): UltraEfficientRouter, GroupNorm shared expert and the
+    routed 1x1 -> GN -> SiLU -> 1x1 -> GN experts on the grouped expert GEMM; routes with weight <= 0.01 are dropped; no residual."""
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, expert_type="simple", router_reduction=16, router_pool_scale=8,
+                 noise_std=1.0, router_temperature=1.0, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, num_groups=8, weight_threshold=0.01):
+        super().__init__()
+        if expert_type != "simple":
+            raise NotImplementedError("UltraOptimizedMoE: only expert_type='simple' is on the B200 path")
+        if in_channels != out_channels:
+            raise NotImplementedError("UltraOptimizedMoE: in_channels != out_channels is not on the B200 path")
+        self.in_channels, self.out_channels, self.num_experts, self.top_k = in_channels, out_channels, num_experts, top_k
+        self.weight_threshold = weight_threshold
+        self.routing = UltraEfficientRouter(in_channels, num_experts, reduction=router_reduction, top_k=top_k, noise_std=noise_std,
+                                            temperature=router_temperature, pool_scale=router_pool_scale)
+        self.experts = nn.ModuleList(SimpleExpert(in_channels, out_channels, expand_ratio=2, num_groups=num_groups) for _ in range(num_experts))
+        self.shared_expert = nn.Sequential(nn.Conv2d(in_channels, out_channels, 1, bias=False),
+                                           nn.GroupNorm(get_safe_groups(out_channels, num_groups), out_channels), nn.SiLU(inplace=True))
+        self.last_routing_snapshot = {}
+
+    def _build_pack(self):
+        ex = list(self.experts)
+        g1, g2, gs = ex[0].conv[1], ex[0].conv[4], self.shared_expert[1]
+        f = lambda t: t.detach().float().contiguous()
+        return {
+            "w1": torch.stack([pack_gemm_weight(e.conv[0].weight.detach().float()) for e in ex]).contiguous(),
+            "w2": torch.stack([pack_gemm_weight(e.conv[3].weight.detach().float()) for e in ex]).contiguous(),
+            "gamma1": torch.stack([f(e.conv[1].weight) for e in ex]).contiguous(), "beta1": torch.stack([f(e.conv[1].bias) for e in ex]).contiguous(),
+            "gamma2": torch.stack([f(e.conv[4].weight) for e in ex]).contiguous(), "beta2": torch.stack([f(e.conv[4].bias) for e in ex]).contiguous(),
+            "G1": g1.num_groups, "G2": g2.num_groups, "eps1": g1.eps, "eps2": g2.eps,
+            "ws": pack_gemm_weight(self.shared_expert[0].weight.detach().float()), "gs": (gs.num_groups, f(gs.weight), f(gs.bias), float(gs.eps)),
+            "router": self.routing.pack(),
+        }
+
+    def fwd_nhwc(self, x, out=None):
+        require_eval(self)
+        B, H, W, C = x.shape
+        HW = H * W
+        pk = self.get_pack()
+        idx, w, probs = ops.pixel_router(x, pk["router"], self.top_k, self.weight_threshold)      # weights <= threshold arrive as 0
+        self.last_routing_snapshot = {"topk_indices": idx, "topk_weights": w, "router_probs": probs}
+        G, gw, gb, geps = pk["gs"]
+        acc = ops.groupnorm(ops.conv2d(x, pk["ws"], None, C, 1, 1, 1, 0, False), G, gw, gb, eps=geps, act=True)   # shared expert
+        hid, ldx = pk["w1"].shape[1], ops.pitch(x)
+        for j in range(self.top_k):      # one grouped-GEMM chain per routing rank: a zero weight contributes zero
+            rj, wj = idx[:, j].contiguous(), w[:, j].contiguous()
+            h, st1 = ops.moe_expert_gemm(x, ldx, 1, B, HW, C, pk["w1"], rj, hid, groups=pk["G1"])
+            sc1, sh1 = ops.gn_finalize(st1, B, HW, pk["G1"], hid, HW * (hid // pk["G1"]), pk["eps1"], pk["gamma1"], pk["beta1"], rj)
+            o, st2 = ops.moe_expert_gemm(h, hid, 1, B, HW, hid, pk["w2"], rj, C, a_scale=sc1, a_shift=sh1, groups=pk["G2"])
+            sc2, sh2 = ops.gn_finalize(st2, B, HW, pk["G2"], C, HW * (C // pk["G2"]), pk["eps2"], pk["gamma2"], pk["beta2"], rj, route_w=wj)
+            last = j == self.top_k - 1
+            acc = ops.ew(ops.EW_AFFINE, a=o.view(B, H, W, C), b=acc, p0=sc2, p1=sh2, rows_per_img=HW, act=False, out=out if last else None)
+        return acc
+
+    def forward(self, x):
+        return to_nchw(self.fwd_nhwc(to_nhwc(x)))
 
     @property
     def aux_loss(self):

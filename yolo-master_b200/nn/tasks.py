@@ -24,6 +24,7 @@ _CFG_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file_
 MODULES = {name: getattr(M, name) for name in M.__all__ if isinstance(getattr(M, name), type)}
 MIXTURE_MODULES = {"A2C2fMoE": M.A2C2fMoE, "ES_MOE": M.ES_MOE, "C2fMoT": M.C2fMoT, "C2fMoA": M.C2fMoA}
 MIXTURE_MODULES.update({"ModularRouterExpertMoE": M.OptimizedMOEImproved, "OptimizedMOEImproved": M.OptimizedMOEImproved})   # modules.py:1745
+MIXTURE_MODULES["UltraOptimizedMoE"] = M.UltraOptimizedMoE                                                                       # v0_1 uomoe / v0_2 zoos
 MIXTURE_MODULES.update({n: getattr(M, n) for n in (          # the AdaptiveGateMoE line, v0_4 ... v0_10 zoos (nn/modules/gated.py)
     "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
     "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE", "ContextRefinedLowRankHybridAdaptiveGateMoE",

@@ -664,3 +664,20 @@ def classify_head(v, w, b):
                                       logits.data_ptr(), probs.data_ptr(), _stream()), "ym_classify_head")
     _count()
     return probs, logits
+
+
+def pixel_router(x, pk, topk, w_min=0.01):
+    """ym_pixel_router (UltraEfficientRouter).  x: (B,H,W,C) fp16 view; pk: fp32 pack of the router's local stream.
+    Returns (idx int32 [B,k], w fp32 [B,k] with weights <= w_min zeroed, probs fp32 [B,E])."""
+    B, H, W, Cc = x.shape
+    E, R = pk["E"], pk["R"]
+    w = torch.empty((B, topk), dtype=torch.float32, device=x.device)
+    idx = torch.empty((B, topk), dtype=torch.int32, device=x.device)
+    probs = torch.empty((B, E), dtype=torch.float32, device=x.device)
+    scratch = torch.empty((lib().ym_gate_router_scratch_floats(B, H, W, Cc, R, E, pk["pool"]),), dtype=torch.float32, device=x.device)
+    _lib.check(lib().ym_pixel_router(x.data_ptr(), pitch(x), B, H, W, Cc, pk["pool"], pk["dw"].data_ptr(), pk["gn1_w"].data_ptr(),
+                                     pk["gn1_b"].data_ptr(), pk["G1"], pk["pw1"].data_ptr(), R, pk["gn2_w"].data_ptr(), pk["gn2_b"].data_ptr(),
+                                     pk["G2"], pk["pw2"].data_ptr(), pk["b2"].data_ptr(), E, pk["eps"], pk["temperature"], float(w_min), topk,
+                                     scratch.data_ptr(), w.data_ptr(), idx.data_ptr(), probs.data_ptr(), _stream()), "ym_pixel_router")
+    _count(3)
+    return idx, w, probs
