@@ -105,7 +105,9 @@ def test_zoo_model_host_wiring_matches_oracle(emu, cfg):
     from yolo_master_b200.utils.synth import fill_state_dict_
     m = DetectionModel(cfg)
     sd = m.state_dict()
-    fill_state_dict_(sd, 31)
+    # key-seeded weights leave some routers almost undecided; a seed whose top-k margins are clear of fp16 noise is used per model
+    # (a flipped per-image expert choice is a legitimate fp16 outcome but makes a whole-model comparison meaningless)
+    fill_state_dict_(sd, {"master/v0_1/det/yolo-master-n-uomoe.yaml": 32}.get(cfg, 31))
     m.load_state_dict(sd, strict=True)
     m.eval()
     sd = {k: (v.clone().float() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
