@@ -1272,6 +1272,7 @@ GATED_VARIANTS = {
     "OptimalHybridGateMoE": (1.2, True, False, True, ("light_refine",)),     # v0.12: + depthwise refinement
     "MultiHeadRouterMoE": (1.2, True, False, True, ("light_refine",)),       # v0.13: v0.12 + MultiHeadRouterV3 (keys in the sd)
     "GatedFusionMoE": (1.2, True, False, True, ("light_refine",)),           # v0.15: v0.12 + CrossPathGate (keys in the sd)
+    "SharedExpertMoE": (1.2, True, True, True, ()),       # moe/shared_expert_moe.py: v0.7 blocks sharing one expert group per pool_id
 }
 
 

@@ -237,6 +237,12 @@ def test_gated_zoo_yamls_build():
         m = DetectionModel(cfg)
         assert [type(m.model[i]).__name__ for i in (5, 8, 11)] == [cls] * 3 and m.model[11].dynamic_channels == 96
         assert type(m.model[5].routing).__name__ == ("MultiHeadRouterV3" if cls == "MultiHeadRouterMoE" else "DualStreamGateRouterV2")
+    from yolo_master_b200.nn.modules.gated import SharedExpertMoE
+    SharedExpertMoE.reset_shared_pools()                        # v0_8 shared-expert model: two blocks, one expert group, 2 618 441 parameters
+    m = DetectionModel("master/v0_8/det/yolo-master-moe-mot-shared-n.yaml")
+    assert m.model[5].fused_experts is m.model[8].fused_experts and (m.model[5]._is_pool_owner, m.model[8]._is_pool_owner) == (True, False)
+    assert sum(p.numel() for p in m.parameters()) == 2618441 and len(m.state_dict()) == 838
+    SharedExpertMoE.reset_shared_pools()
     for sc in "nsmlx":                                          # v0_3 zoo: UltimateOptimizedMoE
         m = DetectionModel(f"master/v0_3/det/yolo-master-{sc}.yaml")
         assert [type(m.model[i]).__name__ for i in (5, 8, 11)] == ["UltimateOptimizedMoE"] * 3

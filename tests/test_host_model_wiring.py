@@ -89,20 +89,22 @@ def test_model_host_wiring_matches_reference_golden(emu, name, cfg, tag):
         assert_within_noise(y[:, 4:], ref[:, 4:], ysim[:, 4:], what=f"{name} scores", outlier_frac=0.02)
 
 
-ZOO = ["master/v0_1/det/yolo-master-n-uomoe.yaml", "master/v0_3/det/yolo-master-n.yaml", "master/v0_4/det/yolo-master-n.yaml", "master/v0_5/det/yolo-master-n.yaml",
+ZOO = ["master/v0_1/det/yolo-master-n-uomoe.yaml", "master/v0_8/det/yolo-master-moe-mot-shared-n.yaml", "master/v0_3/det/yolo-master-n.yaml", "master/v0_4/det/yolo-master-n.yaml", "master/v0_5/det/yolo-master-n.yaml",
        "master/v0_6/det/yolo-master-n.yaml", "master/v0_7/det/yolo-master-n.yaml", "master/v0_8/det/yolo-master-n.yaml",
        "master/v0_9/det/yolo-master-n.yaml", "master/exp/yolo-master-v0_11.yaml", "master/v0_12/det/yolo-master-n.yaml",
        "master/v0_13/det/yolo-master-n.yaml", "master/v0_15/det/yolo-master-n.yaml"]
 
 
-@pytest.mark.parametrize("cfg", ZOO, ids=[c.split("/")[1] + ("-uomoe" if "uomoe" in c else "") for c in ZOO])
+@pytest.mark.parametrize("cfg", ZOO, ids=[c.split("/")[1] + ("-uomoe" if "uomoe" in c else "-shared" if "shared" in c else "") for c in ZOO])
 def test_zoo_model_host_wiring_matches_oracle(emu, cfg):
     """One n-scale model per zoo version of the gated line (no model-level reference golden for these: every block class is pinned
     to the reference as a module, tests/test_oracle_gated.py): the mirror on emulated ops against the oracle's whole-model forward
     with the mirror's own key-seeded state dict - YAML parsing, per-layer argument plumbing (split ratios, expert counts, back-ends)
     and the Detect head."""
     from yolo_master_b200.nn.tasks import DetectionModel
+    from yolo_master_b200.nn.modules.gated import SharedExpertMoE
     from yolo_master_b200.utils.synth import fill_state_dict_
+    SharedExpertMoE.reset_shared_pools()        # build-time registry of shared expert groups (moe/shared_expert_moe.py:114-117)
     m = DetectionModel(cfg)
     sd = m.state_dict()
     # key-seeded weights leave some routers almost undecided; a seed whose top-k margins are clear of fp16 noise is used per model
@@ -122,7 +124,7 @@ def test_zoo_model_host_wiring_matches_oracle(emu, cfg):
     ref, ys = O.forward(spec, sd, x.float(), return_layers=True)
     with O.fp16_storage(), O.fp16_weights():
         ysim, sim = O.forward(spec, sd, x.float(), return_layers=True)
-    for i in (5, 8, 11, 23):
+    for i in ((5, 8, 13, 22) if "shared" in cfg else (5, 8, 11, 23)):
         assert_within_noise(feats[i], ys[i], sim[i], what=f"{cfg} layer {i}", outlier_frac=0.02)
     assert_within_noise(y[:, :4], ref[:, :4], ysim[:, :4], what=f"{cfg} boxes", outlier_frac=0.02)
     assert_within_noise(y[:, 4:], ref[:, 4:], ysim[:, 4:], what=f"{cfg} scores", outlier_frac=0.02)

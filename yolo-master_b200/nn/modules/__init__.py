@@ -5,7 +5,8 @@ from .gated import (AdaptiveGateMoE, ContextRefinedLowRankHybridAdaptiveGateMoE,
                     DualStreamGateRouter, FusedAdaptiveGateMoE, FusedExpertGroup, HybridAdaptiveGateMoE, LowRankFusedExpertGroup,
                     LowRankHybridAdaptiveGateMoE, PyramidContextMixer, RefinedLowRankHybridAdaptiveGateMoE, SharedInvertedExpertGroup,
                     UltimateOptimizedMoE, VisualDetailGate, VisualEnhancedAdaptiveGateMoE, ZeroCostRouter, DualStreamGateRouterV2,
-                    HybridAdaptiveGateMoEv2, OptimalHybridGateMoE, MultiHeadRouterMoE, GatedFusionMoE, MultiHeadRouterV3, CrossPathGate)
+                    HybridAdaptiveGateMoEv2, OptimalHybridGateMoE, MultiHeadRouterMoE, GatedFusionMoE, MultiHeadRouterV3, CrossPathGate,
+                    SharedExpertMoE)
 from .head import DFL, OBB, Classify, Detect, Pose, Proto, Segment
 from .moa import C2fMoA, MoABlock
 from .mot import C2fMoT, MoTBlock
@@ -24,6 +25,6 @@ __all__ = (
     "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
     "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE", "ContextRefinedLowRankHybridAdaptiveGateMoE",
     "VisualEnhancedAdaptiveGateMoE", "UltimateOptimizedMoE", "ZeroCostRouter", "DualStreamGateRouterV2", "HybridAdaptiveGateMoEv2",
-    "OptimalHybridGateMoE", "MultiHeadRouterMoE", "GatedFusionMoE", "MultiHeadRouterV3", "CrossPathGate", "DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup",
+    "OptimalHybridGateMoE", "MultiHeadRouterMoE", "GatedFusionMoE", "SharedExpertMoE", "MultiHeadRouterV3", "CrossPathGate", "DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup",
     "VisualDetailGate", "PyramidContextMixer",
 )

@@ -34,7 +34,7 @@ __all__ = ("DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup"
            "PyramidContextMixer", "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
            "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE",
            "ContextRefinedLowRankHybridAdaptiveGateMoE", "VisualEnhancedAdaptiveGateMoE", "ZeroCostRouter", "UltimateOptimizedMoE", "DualStreamGateRouterV2", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE", "MultiHeadRouterV3", "CrossPathGate",
-           "MultiHeadRouterMoE", "GatedFusionMoE")
+           "MultiHeadRouterMoE", "GatedFusionMoE", "SharedExpertMoE")
 
 
 def _gn(channels: int, groups: int = 8) -> nn.GroupNorm:
@@ -532,6 +532,39 @@ class LowRankHybridAdaptiveGateMoE(_GatedMoE):
         super().__init__(in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
                          _hybrid_backend(num_experts, fused_expert_threshold, True), shuffle_groups, bottleneck_ratio, self.HOOKS,
                          refine_reduction, detail_reduction, fused_expert_threshold)
+
+
+_SHARED_EXPERT_POOLS: dict = {}
+
+
+class SharedExpertMoE(LowRankHybridAdaptiveGateMoE):
+    """`SharedExpertMoE(..., fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5, pool_id="shared")`
+    (moe/shared_expert_moe.py:27-129): `LowRankHybridAdaptiveGateMoE` blocks with the same `pool_id` share ONE expert group module (the
+    first block built owns it), so the state dict carries the same tensors under both blocks' keys, as in the reference."""
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, initial_temperature=1.2,
+                 final_temperature=0.5, balance_loss_coeff=1.0, router_z_loss_coeff=1.0, entropy_loss_coeff=0.01,
+                 fused_expert_threshold=8, shuffle_groups=2, bottleneck_ratio=0.5, pool_id="shared"):
+        super().__init__(in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, initial_temperature, final_temperature,
+                         balance_loss_coeff, router_z_loss_coeff, entropy_loss_coeff, fused_expert_threshold, shuffle_groups, bottleneck_ratio)
+        self.pool_id, self.bottleneck_ratio = pool_id, bottleneck_ratio
+        sig = {"in_channels": self.dynamic_channels, "out_channels": self.out_dynamic, "num_experts": num_experts, "top_k": top_k,
+               "bottleneck_ratio": bottleneck_ratio}
+        pool = _SHARED_EXPERT_POOLS.get(pool_id)
+        if pool is None:
+            _SHARED_EXPERT_POOLS[pool_id] = {**sig, "fused_experts": self.fused_experts}
+            self._is_pool_owner = True
+        else:
+            for k, v in sig.items():
+                if pool[k] != v:
+                    raise ValueError(f"SharedExpertMoE pool '{pool_id}' parameter mismatch: {k} expected {pool[k]}, got {v}")
+            self.fused_experts = pool["fused_experts"]
+            self._is_pool_owner = False
+
+    @classmethod
+    def reset_shared_pools(cls):
+        """Clear the build-time registry before or after constructing a model (shared_expert_moe.py:114-117)."""
+        _SHARED_EXPERT_POOLS.clear()
 
 
 class RefinedLowRankHybridAdaptiveGateMoE(LowRankHybridAdaptiveGateMoE):
