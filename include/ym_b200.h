@@ -184,6 +184,13 @@ int ym_linear_attn(const void* q, int ldq, const void* k, int ldk, const void* v
 /* F.adaptive_avg_pool2d (moa/heads.py:224). */
 int ym_adaptive_avgpool_nhwc(const void* x, int ldx, int B, int H, int W, int C, int h, int w, void* out, int ldo, void* stream);
 
+/* LatentRouter.forward nn/modules/latent_mixture.py:219-241 (per_token = False) for LatentMixture (:721-734): T pooled token vectors
+ * fp16 [B][ld_t] -> mean over tokens of (token + emb[t]) -> LayerNorm -> Linear(C, hid) + SiLU -> Linear(hid, C) + SiLU ->
+ * Linear(C, E) -> nan_to_num / clamp(+-30) -> softmax(/ max(temperature, 0.1)).  logits, probs fp32 [B][E]. */
+int ym_latent_router(int T, const void* const* tokens, const int* lds, int B, int C, const float* emb, const float* ln_w,
+                     const float* ln_b, float ln_eps, const float* w1, const float* b1, int hid, const float* w2, const float* b2,
+                     const float* wh, const float* bh, int E, float temperature, float* logits, float* probs, void* stream);
+
 /* Classify tail nn/modules/head.py:823-832 on the pooled feature vector v fp16 [B][ldv]: logits = w . v + b (w fp32 [nc][Cin]) and
  * probs = softmax(logits), both fp32 [B][nc]. */
 int ym_classify_head(const void* v, int ldv, int B, int Cin, const float* w, const float* b, int nc, float* logits, float* probs,

@@ -136,6 +136,11 @@ def parse_spec(d: dict, ch: int = 3, scale: str | None = None) -> dict:
                 legacy = False
         elif m == "Concat":
             c2 = sum(chs[x] for x in f)
+        elif m == "LatentMixture":     # multi-input mixture module (mixture_registry.py:96-141)
+            c2 = args[0]
+            if c2 != nc:
+                c2 = make_divisible(min(c2, max_channels) * width, 8)
+            args = [[chs[x] for x in f], c2, *args[1:]]
         elif m == "Detect":
             args = [args[0], reg_max, end2end, [chs[x] for x in f]]
             c2 = None
@@ -306,6 +311,44 @@ def optimized_moe_improved(sd, p, x, num_experts, top_k):
             o = simple_expert(sd, f"{p}.experts.{e}", x[bi])
             out.index_add_(0, bi, o.float() * w[bi, ki].view(-1, 1, 1, 1))
     return _st((shared.float() + out).to(x.dtype))
+
+
+def _conv1x1_gn(sd, p, x):
+    """`_conv1x1` latent_mixture.py:48-53: 1x1 -> GroupNorm(1) -> SiLU."""
+    return _st(F.silu(_gn(sd, p + ".1", F.conv2d(x, _w(sd[p + ".0.weight"])), 1)))
+
+
+def latent_router(sd, p, tokens, temperature):
+    """`LatentRouter.forward` latent_mixture.py:219-241 (per_token = False, fp32): mean over tokens of (token + scale embedding) ->
+    LayerNorm -> Linear + SiLU -> Linear + SiLU -> expert head -> nan_to_num / clamp(+-30) -> softmax(/ max(T, 0.1))."""
+    x = tokens.float()
+    if p + ".scale_embedding" in sd:
+        x = x + sd[p + ".scale_embedding"].unsqueeze(0)
+    r = F.layer_norm(x.mean(1), (x.shape[-1],), sd[p + ".norm.weight"], sd[p + ".norm.bias"], 1e-5)
+    h = F.silu(F.linear(r, sd[p + ".trunk.0.weight"], sd[p + ".trunk.0.bias"]))
+    h = F.silu(F.linear(h, sd[p + ".trunk.2.weight"], sd[p + ".trunk.2.bias"]))
+    logits = torch.nan_to_num(F.linear(h, sd[p + ".expert_head.weight"], sd[p + ".expert_head.bias"]), nan=0.0, posinf=30.0, neginf=-30.0).clamp(-30.0, 30.0)
+    return logits, F.softmax(logits / max(float(temperature), 0.1), dim=-1)
+
+
+def layer_latent_mixture(sd, p, xs, in_channels, c2, num_experts=4, expert_ratio=0.25, router_hidden_dim=None, temperature=1.0, *unused,
+                         return_route=False):
+    """`LatentMixture.forward` latent_mixture.py:721-800 (eval, dense dispatch, router_only fusion): projected tokens -> router ->
+    base + residual_gain * sum_e probs[:, e] * DenseChannelExpert_e(base)."""
+    proj = [x if c == c2 else _conv1x1_gn(sd, f"{p}.token_projs.{i}", x) for i, (x, c) in enumerate(zip(xs, in_channels))]
+    base = xs[0] if in_channels[0] == c2 else _conv1x1_gn(sd, p + ".base_proj", xs[0])
+    tokens = torch.stack([_st(t.mean((2, 3))).float() for t in proj], 1)
+    T = float(sd[p + ".router._temperature"]) if p + ".router._temperature" in sd else float(temperature)
+    logits, probs = latent_router(sd, p + ".router", tokens, T)
+    mixed = torch.zeros_like(base)
+    for e in range(num_experts):
+        q = f"{p}.experts.{e}.net"
+        hid = sd[q + ".0.weight"].shape[0]
+        t = _st(F.silu(_gn(sd, q + ".1", F.conv2d(base, _w(sd[q + ".0.weight"])), 1)))
+        t = _st(F.silu(_gn(sd, q + ".4", F.conv2d(t, _w(sd[q + ".3.weight"]), None, 1, 1, 1, hid), 1)))
+        mixed = mixed + _st(F.conv2d(t, _w(sd[q + ".6.weight"]))) * probs[:, e].view(-1, 1, 1, 1)
+    out = _st(base + sd[p + ".residual_gain"] * mixed)
+    return (out, probs, logits) if return_route else out
 
 
 def ultra_efficient_router(sd, p, x, top_k, temperature=1.0, pool_scale=8):
@@ -1338,6 +1381,7 @@ def _gated_layer(name):
 
 
 layer_visual_enhanced_gate_moe = _gated_layer("VisualEnhancedAdaptiveGateMoE")
+_LAYER_FN["LatentMixture"] = layer_latent_mixture
 _LAYER_FN["UltraOptimizedMoE"] = layer_ultra_optimized_moe
 _MIX_BASE.add("UltraOptimizedMoE")
 for _name in ("ModularRouterExpertMoE", "OptimizedMOEImproved"):

@@ -119,6 +119,9 @@ EXTRA_MODELS = {
     # OBB head on the v0_1 backbone (rotated boxes + angle row)
     "yolo-master-obb-n-v0_1": ("/root/reference/ultralytics/cfg/models/master/v0_1/obb/yolo-master-obb-n.yaml", [23],
                                {"b2_96": (2, 96, 96, 16)}),
+    # LatentMixture (multi-input latent-routed mixture on every Detect input); residual_init 0.01 so that the experts contribute
+    "yolo26-master-latent-n": ("/root/reference/ultralytics/cfg/models/26/yolo26-master-latent-n-resinit010.yaml", [22, 23, 24, 25],
+                               {"b2_128": (2, 128, 128, 17)}),
     "yolo26-master-moa-mot-s": (("/root/reference/ultralytics/cfg/models/26/yolo26-master-moa-mot-n.yaml", "s", [0.50, 0.50, 1024]),
                                 [13, 16, 19, 22], {"b1_160": (1, 160, 160, 8)}),
 }
@@ -152,12 +155,12 @@ def extra_model_golden(name):
         cfg = d
     m = calibrated_reference(0, cfg)
     sd = m.state_dict()
-    json.dump({k: [list(v.shape), str(v.dtype)] for k, v in sd.items()}, open(f"{OUT}/{name}.keys.json", "w"))
+    json.dump({k: [list(v.shape), str(v.dtype)] for k, v in sd.items() if torch.is_tensor(v)}, open(f"{OUT}/{name}.keys.json", "w"))
     # calibrated BatchNorm statistics + the constants the key-seeded generator leaves alone (router temperature buffers,
     # the frozen DFL arange): everything a test needs besides key names to rebuild the exact state_dict
-    stats = {k: v.clone() for k, v in sd.items()
-             if k.endswith(("running_mean", "running_var", ".temperature", "dfl.conv.weight"))
-             or (v.is_floating_point() and v.dim() == 0)}        # scalar gates / scales keep their constructor values
+    stats = {k: v.clone() for k, v in sd.items() if torch.is_tensor(v) and (
+             k.endswith(("running_mean", "running_var", ".temperature", "dfl.conv.weight"))
+             or (v.is_floating_point() and v.dim() == 0))}       # scalar gates / scales keep their constructor values
     torch.save(stats, f"{OUT}/{name}.bnstats.pt")
     gold = {"cases": {}}
     for tag, (B, H, W, seed) in cases.items():
@@ -335,7 +338,7 @@ def cls_golden():
         b.eval()
         b.momentum = 0.03
     sd = m.state_dict()
-    json.dump({k: [list(v.shape), str(v.dtype)] for k, v in sd.items()}, open(f"{OUT}/{name}.keys.json", "w"))
+    json.dump({k: [list(v.shape), str(v.dtype)] for k, v in sd.items() if torch.is_tensor(v)}, open(f"{OUT}/{name}.keys.json", "w"))
     stats = {k: v.clone() for k, v in sd.items() if k.endswith(("running_mean", "running_var", "num_batches_tracked"))
              or (v.dim() == 0 and v.is_floating_point())}
     torch.save(stats, f"{OUT}/{name}.bnstats.pt")

@@ -23,7 +23,7 @@ from yolo_master_b200 import _lib, ops
 CSRC = os.path.join(ROOT, "yolo-master_b200", "csrc")
 UNITS = ["preproc.cu", "gated.cu", "nms_large.cu", "mix.cu"]
 SYMBOLS = ["ym_letterbox_u8", "ym_scale_boxes", "ym_kpts_decode", "ym_obb_finish", "ym_gate_router", "ym_gate_router_scratch_floats",
-           "ym_zero_cost_router", "ym_zero_cost_router_scratch_floats", "ym_pixel_router", "ym_fc_gate", "ym_classify_head", "ym_gated_select",
+           "ym_zero_cost_router", "ym_zero_cost_router_scratch_floats", "ym_pixel_router", "ym_latent_router", "ym_fc_gate", "ym_classify_head", "ym_gated_select",
            "ym_ctx_mean3", "ym_nms_batched_large", "ym_nms_large_scratch_bytes", "ym_ew_nhwc", "ym_last_error"]
 
 
@@ -208,3 +208,22 @@ def test_large_nms_kernel(emu):
     for b in range(B):
         n = int(cnt[b])
         assert n == len(rk[b]) and torch.equal(idx[b, :n].long(), rk[b]) and torch.equal(out[b, :n], ro[b])
+
+
+def test_latent_router_kernel(emu):
+    """ym_latent_router (LayerNorm + two-layer MLP + head + softmax in one CTA per image, dynamic shared memory sized from C / hidden /
+    E) against the oracle's LatentRouter, for 2 and 3 tokens, default and explicit hidden width, T < 0.1 clamped."""
+    from yolo_master_b200.nn.modules.latent import LatentMixture
+    from yolo_master_b200.utils.synth import fill_state_dict_
+    g = torch.Generator().manual_seed(12)
+    for in_ch, oc, hid, temp in (((64, 32), 64, None, 1.0), ((128, 64, 128), 128, 48, 0.5), ((256, 256), 256, None, 0.05)):
+        m = LatentMixture(list(in_ch), oc, 4, 0.25, hid, temp)
+        sd = m.state_dict()
+        fill_state_dict_({k: v for k, v in sd.items() if torch.is_tensor(v)}, 7)
+        m.load_state_dict(sd)
+        sdm = {"m." + k: v.float() for k, v in sd.items() if torch.is_tensor(v)}
+        tokens = [torch.randn((3, 1, 1, oc), generator=g).half() for _ in in_ch]
+        probs, logits = ops.latent_router(tokens, m.eval().get_pack()["router"])
+        rl, rp = O.latent_router(sdm, "m.router", torch.stack([t.view(3, oc) for t in tokens], 1), temp)
+        torch.testing.assert_close(logits, rl, atol=2e-5, rtol=1e-4)
+        torch.testing.assert_close(probs, rp, atol=2e-6, rtol=1e-4)

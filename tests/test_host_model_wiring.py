@@ -51,7 +51,8 @@ CASES = [("yolo-master-n-v0_1", "master/v0_1/det/yolo-master-n.yaml", "b2_128"),
          ("yolo26-master-moa-mot-n", "26/yolo26-master-moa-mot-n.yaml", "b1_96"),
          ("yolo-master-pose-n-v0_1", "master/v0_1/pose/yolo-master-pose-n.yaml", "b2_128"),
          ("yolo-master-seg-n-v0_1", "master/v0_1/seg/yolo-master-seg-n.yaml", "b2_96"),
-         ("yolo-master-obb-n-v0_1", "master/v0_1/obb/yolo-master-obb-n.yaml", "b2_96")]
+         ("yolo-master-obb-n-v0_1", "master/v0_1/obb/yolo-master-obb-n.yaml", "b2_96"),
+         ("yolo26-master-latent-n", "26/yolo26-master-latent-n-resinit010.yaml", "b2_128")]
 
 
 @pytest.mark.parametrize("name,cfg,tag", CASES, ids=[c[0] for c in CASES])

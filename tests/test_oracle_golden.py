@@ -64,3 +64,18 @@ def test_oracle_router_indices_exact(gold, sd, tag):
             else:
                 t = t + O.optimized_moe_improved(sd, p + ".mlp", t, a[10], a[11])
     assert seen == len(c["routes"]) == 6
+
+
+def test_oracle_matches_reference_latent_mixture():
+    """yolo26-master-latent-n (residual gain 0.01): LatentMixture on every Detect input - multi-input tokens, latent router, dense
+    channel experts - pinned to the real reference model, layers 22-25 and the end-to-end detections."""
+    from _util import yaml_of
+    name, cfg = "yolo26-master-latent-n", "26/yolo26-master-latent-n-resinit010.yaml"
+    c = torch.load(os.path.join(GOLD, f"{name}.golden.pt"))["cases"]["b2_128"]
+    sd = synth_sd_from_keys(0, name)
+    y, ys = O.forward(O.parse_spec(yaml_of(cfg)), sd, synth_images(c["B"], c["H"], c["W"], c["seed"]), return_layers=True)
+    for i, ref in c["layers"].items():
+        torch.testing.assert_close(ys[i], ref, atol=1e-4, rtol=1e-4, msg=lambda m, i=i: f"layer {i}: {m}")
+    assert float((ys[23] - ys[16]).abs().max()) > 1e-4            # the mixture does contribute (residual gain 0.01)
+    torch.testing.assert_close(y, c["final"], atol=1e-3, rtol=1e-4)
+    assert torch.equal(y[..., 5], c["final"][..., 5])

@@ -396,16 +396,26 @@ def obb_finish(y, angles, strides, nc):
     return out
 
 
+def latent_router(tokens, pk):
+    x = torch.stack([t.float().reshape(t.shape[0], -1) for t in tokens], 1)
+    if pk.get("emb") is not None:
+        x = x + pk["emb"].unsqueeze(0)
+    r = F.layer_norm(x.mean(1), (x.shape[-1],), pk["ln_w"], pk["ln_b"], pk["ln_eps"])
+    h = F.silu(F.linear(F.silu(F.linear(r, pk["w1"], pk["b1"])), pk["w2"], pk["b2"]))
+    logits = torch.nan_to_num(F.linear(h, pk["wh"], pk["bh"]), nan=0.0, posinf=30.0, neginf=-30.0).clamp(-30.0, 30.0)
+    return torch.softmax(logits / max(pk["temperature"], 0.1), -1), logits
+
+
 def install_model():
     """Everything `install()` covers plus the whole-model ops above."""
     install()
     for name, fn in dict(stem_conv=stem_conv, attention=attention, concat2=concat2, sppf_pool=sppf_pool, router_topk=router_topk,
                          moe_combine=moe_combine, moe_expert_gemm=moe_expert_gemm, gn_finalize=gn_finalize, detect_dense=detect_dense,
-                         detect_topk=detect_topk, kpts_decode=kpts_decode, obb_finish=obb_finish).items():
+                         detect_topk=detect_topk, kpts_decode=kpts_decode, obb_finish=obb_finish, latent_router=latent_router).items():
         setattr(ops, name, fn)
     ops.pitch = lambda t, dtype=torch.float16: (t.stride(2) if t.shape[2] > 1 else (t.stride(1) if t.shape[1] > 1 else (t.stride(0) if t.shape[0] > 1 else t.shape[3])))
-    from yolo_master_b200.nn.modules import gated, head, moe
-    for mod in (gated, head, moe):
+    from yolo_master_b200.nn.modules import gated, head, latent, moe
+    for mod in (gated, head, latent, moe):
         if hasattr(mod, "to_nhwc"):
             mod.to_nhwc = _base.to_nhwc
 

@@ -47,6 +47,14 @@ __global__ void __launch_bounds__(NTHR) fc_gate_kernel(const FcArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(NTHR) latent_router_kernel(const LrArgs a) {
+    YM_DYN_SMEM(float, sm);
+    for (int ph = 0; ph < LR_PHASES; ++ph) {
+        lr_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(NTHR) classify_kernel(const ClsArgs a) {
     YM_DYN_SMEM(float, sm);
     for (int ph = 0; ph < CLS_PHASES; ++ph) {
@@ -226,6 +234,28 @@ extern "C" int ym_fc_gate(const void* v, int ldv, int B, int Cin, const float* w
     a.offset = offset; a.out = out;
     YM_LAUNCH(fc_gate_kernel, B, NTHR, fc_smem_floats(Cr) * sizeof(float), (cudaStream_t)stream, a);
     YM_CHECK_LAUNCH("fc_gate");
+    return YM_OK;
+}
+
+extern "C" int ym_latent_router(int T, const void* const* tokens, const int* lds, int B, int C, const float* emb, const float* ln_w,
+                                const float* ln_b, float ln_eps, const float* w1, const float* b1, int hid, const float* w2,
+                                const float* b2, const float* wh, const float* bh, int E, float temperature, float* logits,
+                                float* probs, void* stream) {
+    YM_CHECK_ARG(tokens && lds && ln_w && ln_b && w1 && b1 && w2 && b2 && wh && bh && logits && probs, "ym_latent_router: null pointer");
+    YM_CHECK_ARG(T >= 1 && T <= LR_MAX_TOKENS && B > 0 && C > 0 && hid > 0 && E >= 1 && E <= MAXE, "ym_latent_router: 1..%d tokens, E <= %d",
+                 LR_MAX_TOKENS, MAXE);
+    YM_CHECK_ARG(lr_smem_floats(C, hid, E, NTHR) * sizeof(float) <= 48 * 1024, "ym_latent_router: latent / hidden width too large");
+    LrArgs a;
+    for (int t = 0; t < T; ++t) {
+        YM_CHECK_ARG(tokens[t] && lds[t] >= C, "ym_latent_router: bad token %d", t);
+        a.tok[t] = (const __half*)tokens[t];
+        a.ld[t] = lds[t];
+    }
+    a.T = T; a.C = C; a.hid = hid; a.E = E; a.emb = emb; a.ln_w = ln_w; a.ln_b = ln_b; a.ln_eps = ln_eps;
+    a.inv_temp = 1.f / (temperature < 0.1f ? 0.1f : temperature);
+    a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.wh = wh; a.bh = bh; a.logits = logits; a.probs = probs;
+    YM_LAUNCH(latent_router_kernel, B, NTHR, lr_smem_floats(C, hid, E, NTHR) * sizeof(float), (cudaStream_t)stream, a);
+    YM_CHECK_LAUNCH("latent_router");
     return YM_OK;
 }
 

@@ -461,6 +461,94 @@ YM_HD void fc_phase(int ph, const FcArgs& a, int img, int tid, int nthr, float* 
 }
 
 // --------------------------------------------------------------------------------------------------------------------
+// LatentRouter.forward (nn/modules/latent_mixture.py:219-241, per_token = False) on the pooled scale tokens of LatentMixture: mean over
+// tokens of (token + scale embedding) -> LayerNorm -> Linear + SiLU -> Linear + SiLU -> expert head -> clamp(+-30) -> softmax(/ T).
+constexpr int LR_MAX_TOKENS = 4;
+struct LrArgs {
+    const ym_half* tok[LR_MAX_TOKENS];   // [B][ld] pooled token vectors (fp16, as adaptive_avg_pool2d of an fp16 map leaves them)
+    int ld[LR_MAX_TOKENS];
+    int T, C, hid, E;
+    const float* emb;                    // [T][C] scale embedding, or null
+    const float *ln_w, *ln_b;            // [C]
+    float ln_eps, inv_temp;              // inv_temp = 1 / max(temperature, 0.1)
+    const float *w1, *b1, *w2, *b2, *wh, *bh;   // [hid][C],[hid]  [C][hid],[C]  [E][C],[E]
+    float *logits, *probs;               // [B][E]
+};
+constexpr int LR_PHASES = 9;
+YM_HD int lr_smem_floats(int C, int hid, int E, int nthr) { return 2 * C + hid + E + nthr + 2; }
+
+YM_HD void lr_phase(int ph, const LrArgs& a, int img, int tid, int nthr, float* sm) {
+    const int C = a.C;
+    float* r = sm;
+    float* h2 = r + C;
+    float* h1 = h2 + C;
+    float* lg = h1 + a.hid;
+    float* red = lg + a.E;
+    float* st = red + nthr;
+    switch (ph) {
+        case 0: case 2: {
+            float s = 0.f;
+            for (int c = tid; c < C; c += nthr) {
+                if (ph == 0) {
+                    float v = 0.f;
+                    for (int t = 0; t < a.T; ++t) v += ym_h2f(a.tok[t][(long long)img * a.ld[t] + c]) + (a.emb ? a.emb[t * C + c] : 0.f);
+                    r[c] = v / (float)a.T;
+                    s += r[c];
+                } else {
+                    const float d = r[c] - st[0];
+                    s += d * d;
+                }
+            }
+            red[tid] = s;
+            break;
+        }
+        case 1: case 3: {
+            if (tid != 0) return;
+            float s = 0.f;
+            for (int t = 0; t < nthr; ++t) s += red[t];
+            if (ph == 1) st[0] = s / (float)C;
+            else st[1] = 1.f / sqrtf(s / (float)C + a.ln_eps);
+            break;
+        }
+        case 4:
+            for (int c = tid; c < C; c += nthr) r[c] = (r[c] - st[0]) * st[1] * a.ln_w[c] + a.ln_b[c];
+            break;
+        case 5:
+            for (int j = tid; j < a.hid; j += nthr) {
+                float s = a.b1[j];
+                for (int c = 0; c < C; ++c) s += a.w1[(long long)j * C + c] * r[c];
+                h1[j] = silu_f32(s);
+            }
+            break;
+        case 6:
+            for (int c = tid; c < C; c += nthr) {
+                float s = a.b2[c];
+                for (int j = 0; j < a.hid; ++j) s += a.w2[(long long)c * a.hid + j] * h1[j];
+                h2[c] = silu_f32(s);
+            }
+            break;
+        case 7:
+            for (int e = tid; e < a.E; e += nthr) {
+                float s = a.bh[e];
+                for (int c = 0; c < C; ++c) s += a.wh[(long long)e * C + c] * h2[c];
+                if (!(s == s)) s = 0.f;                                   // nan_to_num(nan = 0), then the +-30 clamp covers +-inf
+                lg[e] = s < -30.f ? -30.f : (s > 30.f ? 30.f : s);
+            }
+            break;
+        default: {
+            if (tid != 0) return;
+            float mx = -3.0e38f, den = 0.f;
+            for (int e = 0; e < a.E; ++e) mx = lg[e] * a.inv_temp > mx ? lg[e] * a.inv_temp : mx;
+            for (int e = 0; e < a.E; ++e) den += expf(lg[e] * a.inv_temp - mx);
+            for (int e = 0; e < a.E; ++e) {
+                a.logits[(long long)img * a.E + e] = lg[e];
+                a.probs[(long long)img * a.E + e] = expf(lg[e] * a.inv_temp - mx) / den;
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
 // Classify tail (nn/modules/head.py:823-832): logits = W . v + b on the pooled vector, probs = softmax(logits).  One CTA per image.
 struct ClsArgs {
     const ym_half* v;   // [B][ldv] pooled features

@@ -8,6 +8,7 @@ from .gated import (AdaptiveGateMoE, ContextRefinedLowRankHybridAdaptiveGateMoE,
                     HybridAdaptiveGateMoEv2, OptimalHybridGateMoE, MultiHeadRouterMoE, GatedFusionMoE, MultiHeadRouterV3, CrossPathGate,
                     SharedExpertMoE)
 from .head import DFL, OBB, Classify, Detect, Pose, Proto, Segment
+from .latent import DenseChannelExpert, LatentMixture, LatentRouter
 from .moa import C2fMoA, MoABlock
 from .mot import C2fMoT, MoTBlock
 from .moe import (A2C2fMoE, ABlockMoE, DepthwiseSeparableConv, DynamicRoutingLayer, EfficientExpertGroup, EfficientSpatialRouter,
@@ -16,7 +17,7 @@ from .moe import (A2C2fMoE, ABlockMoE, DepthwiseSeparableConv, DynamicRoutingLay
 ModularRouterExpertMoE = OptimizedMOEImproved   # alias of the reference (moe/modules.py:1745), the block of the v0_1 zoo
 
 __all__ = (
-    "ModularRouterExpertMoE", "UltraOptimizedMoE", "UltraEfficientRouter",
+    "ModularRouterExpertMoE", "UltraOptimizedMoE", "UltraEfficientRouter", "LatentMixture", "LatentRouter", "DenseChannelExpert",
     "Conv", "DWConv", "Concat", "Upsample", "PlainConv2d", "autopad",
     "Bottleneck", "C2f", "C3", "C3k", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA", "AAttn", "ABlock", "A2C2f",
     "EfficientSpatialRouter", "SimpleExpert", "OptimizedMOEImproved", "ABlockMoE", "A2C2fMoE", "get_safe_groups",

@@ -119,6 +119,11 @@ def parse_model(d, ch, verbose=False):
                     args.extend((True, 1.2))
             if m in (M.Conv, M.DWConv) and len(args) > 3:
                 s_out = s_in * args[3]
+        elif m is M.LatentMixture:                 # multi-input mixture module (mixture_registry.py:96-141): [in_channels list, c2, *rest]
+            c2 = args[0]
+            if c2 != nc:
+                c2 = make_divisible(min(c2, max_channels) * width, 8)
+            args = [[ch[x] for x in f], c2, *args[1:]]
         elif m in MIXTURE_BASE_MODULES:
             c1, c2 = ch[f], args[0]
             if c2 != nc:

@@ -681,3 +681,20 @@ def pixel_router(x, pk, topk, w_min=0.01):
                                      scratch.data_ptr(), w.data_ptr(), idx.data_ptr(), probs.data_ptr(), _stream()), "ym_pixel_router")
     _count(3)
     return idx, w, probs
+
+
+def latent_router(tokens, pk):
+    """ym_latent_router.  tokens: list of (B,1,1,C) fp16 pooled vectors; pk: fp32 pack of LatentRouter.  Returns (probs, logits) (B, E)."""
+    T, B, Cc = len(tokens), tokens[0].shape[0], tokens[0].shape[3]
+    E = pk["wh"].shape[0]
+    logits = torch.empty((B, E), dtype=torch.float32, device=tokens[0].device)
+    probs = torch.empty((B, E), dtype=torch.float32, device=tokens[0].device)
+    tp = (C.c_void_p * T)(*[t.data_ptr() for t in tokens])
+    lds = (C.c_int * T)(*[pitch(t) for t in tokens])
+    emb = pk.get("emb")
+    _lib.check(lib().ym_latent_router(T, tp, lds, B, Cc, None if emb is None else emb.data_ptr(), pk["ln_w"].data_ptr(), pk["ln_b"].data_ptr(),
+                                      pk["ln_eps"], pk["w1"].data_ptr(), pk["b1"].data_ptr(), pk["w1"].shape[0], pk["w2"].data_ptr(),
+                                      pk["b2"].data_ptr(), pk["wh"].data_ptr(), pk["bh"].data_ptr(), E, pk["temperature"],
+                                      logits.data_ptr(), probs.data_ptr(), _stream()), "ym_latent_router")
+    _count()
+    return probs, logits
