@@ -184,6 +184,10 @@ int ym_linear_attn(const void* q, int ldq, const void* k, int ldk, const void* v
 /* F.adaptive_avg_pool2d (moa/heads.py:224). */
 int ym_adaptive_avgpool_nhwc(const void* x, int ldx, int B, int H, int W, int C, int h, int w, void* out, int ldo, void* stream);
 
+/* nn.AdaptiveAvgPool2d(1) of an NHWC fp16 map x [B][HW][ldx] -> fp16 [B][ldo] (SE / feature / cross gates of the gated MoE family, the
+ * latent tokens, Classify): one CTA per (image, 64-channel slab), fixed-order reduction. */
+int ym_gap_nhwc(const void* x, int ldx, int B, int HW, int C, void* out, int ldo, void* stream);
+
 /* LatentRouter.forward nn/modules/latent_mixture.py:219-241 (per_token = False) for LatentMixture (:721-734): T pooled token vectors
  * fp16 [B][ld_t] -> mean over tokens of (token + emb[t]) -> LayerNorm -> Linear(C, hid) + SiLU -> Linear(hid, C) + SiLU ->
  * Linear(C, E) -> nan_to_num / clamp(+-30) -> softmax(/ max(temperature, 0.1)).  logits, probs fp32 [B][E]. */

@@ -24,7 +24,7 @@ CSRC = os.path.join(ROOT, "yolo-master_b200", "csrc")
 UNITS = ["preproc.cu", "gated.cu", "nms_large.cu", "mix.cu"]
 SYMBOLS = ["ym_letterbox_u8", "ym_scale_boxes", "ym_kpts_decode", "ym_obb_finish", "ym_gate_router", "ym_gate_router_scratch_floats",
            "ym_zero_cost_router", "ym_zero_cost_router_scratch_floats", "ym_pixel_router", "ym_latent_router", "ym_fc_gate", "ym_classify_head", "ym_gated_select",
-           "ym_ctx_mean3", "ym_nms_batched_large", "ym_nms_large_scratch_bytes", "ym_ew_nhwc", "ym_last_error"]
+           "ym_ctx_mean3", "ym_gap_nhwc", "ym_nms_batched_large", "ym_nms_large_scratch_bytes", "ym_ew_nhwc", "ym_last_error"]
 
 
 @pytest.fixture(scope="module")
@@ -227,3 +227,24 @@ def test_latent_router_kernel(emu):
         rl, rp = O.latent_router(sdm, "m.router", torch.stack([t.view(3, oc) for t in tokens], 1), temp)
         torch.testing.assert_close(logits, rl, atol=2e-5, rtol=1e-4)
         torch.testing.assert_close(probs, rp, atol=2e-6, rtol=1e-4)
+
+
+def test_global_average_pool_kernel(emu):
+    """ym_gap_nhwc (one CTA per image x 64-channel slab, 8 octets x 32 pixel lanes, fixed-order reduction) against a float64 mean: ragged
+    last slab, a channel-slice view (pitch > C), HW smaller than the lane count, and a pre-allocated output slice."""
+    g = torch.Generator().manual_seed(3)
+    for B, H, W, Cc, ld in ((2, 5, 7, 64, 64), (3, 20, 20, 72, 96), (1, 2, 3, 8, 8), (2, 9, 4, 200, 200)):
+        buf = torch.randn((B, H, W, ld), generator=g).half()
+        x = buf[..., :Cc]
+        out = ops.gap(x)
+        ref = x.double().mean((1, 2), keepdim=True)
+        assert out.shape == (B, 1, 1, Cc)
+        torch.testing.assert_close(out.double(), ref, atol=1e-3, rtol=1e-3)
+        assert torch.equal(out, x.float().mean((1, 2), keepdim=True).half()) or (out.float() - ref.float()).abs().max() < 1e-3
+    wide = torch.zeros((2, 1, 1, 96), dtype=torch.float16)
+    x = torch.randn((2, 6, 6, 32), generator=g).half()
+    ops.gap(x, out=wide[..., 64:96])
+    torch.testing.assert_close(wide[..., 64:96].float(), x.float().mean((1, 2), keepdim=True), atol=1e-3, rtol=1e-3)
+    assert not wide[..., :64].any()
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        ops.gap(torch.zeros((1, 2, 2, 12), dtype=torch.float16))

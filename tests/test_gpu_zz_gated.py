@@ -77,6 +77,16 @@ def test_fc_gate_select_ctx_kernels():
         torch.testing.assert_close(ops.ctx_mean3(a.to(DEV), b.to(DEV), c.to(DEV)).float().cpu(), want, atol=2e-3, rtol=1e-3)
 
 
+def test_global_average_pool_kernel():
+    g = torch.Generator().manual_seed(3)
+    for B, H, W, Cc, ld in ((2, 5, 7, 64, 64), (3, 20, 20, 72, 96), (1, 2, 3, 8, 8), (32, 80, 80, 128, 128)):
+        buf = torch.randn((B, H, W, ld), generator=g).half().cuda()
+        x = buf[..., :Cc]
+        out = ops.gap(x)
+        assert out.shape == (B, 1, 1, Cc)
+        torch.testing.assert_close(out.double().cpu(), x.double().mean((1, 2), keepdim=True).cpu(), atol=1e-3, rtol=1e-3)
+
+
 def test_new_elementwise_ops():
     g = torch.Generator().manual_seed(3)
     a, b = torch.randn((2, 5, 7, 16), generator=g).half(), torch.randn((2, 5, 7, 16), generator=g).half()

@@ -174,6 +174,10 @@ def linear_attn(q, k, v, heads, hdp, hd, rf, eps=1e-6, limit=1e4, out=None):
     return _out(full.permute(0, 2, 1, 3).reshape(B, H, W, heads * hdp), out)
 
 
+def gap(x, out=None):
+    return _out(x.float().mean((1, 2), keepdim=True), out)
+
+
 def adaptive_avgpool(x, h, w, out=None):
     return _out(F.adaptive_avg_pool2d(x.float().permute(0, 3, 1, 2), (h, w)).permute(0, 2, 3, 1), out)
 
@@ -430,7 +434,7 @@ def install_model():
 def install():
     for name, fn in dict(conv2d=conv2d, dwconv=dwconv, ew=ew, groupnorm_stats=groupnorm_stats, layernorm=layernorm, attn_small=attn_small,
                          attn_window=attn_window, deform_sample=deform_sample, token_router=token_router, linear_attn=linear_attn,
-                         adaptive_avgpool=adaptive_avgpool).items():
+                         adaptive_avgpool=adaptive_avgpool, gap=gap).items():
         setattr(ops, name, fn)
     ops.new_act = lambda B, H, W, C, device: torch.empty((B, H, W, C), dtype=torch.float16)
 

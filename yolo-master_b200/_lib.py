@@ -72,6 +72,7 @@ SIGNATURES = {
     "ym_fc_gate": (ci, [vp, ci, ci, ci, vp, ci, vp, vp, ci, cf, cf, vp, vp]),
     "ym_gated_select": (ci, [vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, ci, vp, vp, vp, vp, ci, vp]),
     "ym_ctx_mean3": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, ci, vp]),
+    "ym_gap_nhwc": (ci, [vp, ci, ci, ci, ci, vp, ci, vp]),
     "ym_latent_router": (ci, [ci, C.POINTER(vp), C.POINTER(ci), ci, ci, vp, vp, vp, cf, vp, vp, ci, vp, vp, vp, vp, ci, cf, vp, vp, vp]),
     "ym_classify_head": (ci, [vp, ci, ci, ci, vp, vp, ci, vp, vp, vp]),
     "ym_obb_finish": (ci, [ci, C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, vp, vp, vp]),

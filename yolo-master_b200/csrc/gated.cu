@@ -47,6 +47,14 @@ __global__ void __launch_bounds__(NTHR) fc_gate_kernel(const FcArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(NTHR) gap_kernel(const GapArgs a) {   // grid = (channel slabs, B)
+    YM_DYN_SMEM(float, sm);
+    for (int ph = 0; ph < GAP_PHASES; ++ph) {
+        gap_phase(ph, a, blockIdx.y, blockIdx.x, threadIdx.x, NTHR, sm);
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(NTHR) latent_router_kernel(const LrArgs a) {
     YM_DYN_SMEM(float, sm);
     for (int ph = 0; ph < LR_PHASES; ++ph) {
@@ -234,6 +242,16 @@ extern "C" int ym_fc_gate(const void* v, int ldv, int B, int Cin, const float* w
     a.offset = offset; a.out = out;
     YM_LAUNCH(fc_gate_kernel, B, NTHR, fc_smem_floats(Cr) * sizeof(float), (cudaStream_t)stream, a);
     YM_CHECK_LAUNCH("fc_gate");
+    return YM_OK;
+}
+
+extern "C" int ym_gap_nhwc(const void* x, int ldx, int B, int HW, int C, void* out, int ldo, void* stream) {
+    YM_CHECK_ARG(x && out, "ym_gap_nhwc: null pointer");
+    YM_CHECK_ARG(B > 0 && B <= 65535 && HW > 0 && C > 0 && C % 8 == 0 && ldx >= C && ldo >= C, "ym_gap_nhwc: bad sizes (C multiple of 8)");
+    GapArgs a;
+    a.x = (const __half*)x; a.ldx = ldx; a.HW = HW; a.C = C; a.out = (__half*)out; a.ldo = ldo;
+    YM_LAUNCH(gap_kernel, dim3((C + GAP_SLAB - 1) / GAP_SLAB, B), NTHR, gap_smem_floats(NTHR) * sizeof(float), (cudaStream_t)stream, a);
+    YM_CHECK_LAUNCH("gap_nhwc");
     return YM_OK;
 }
 

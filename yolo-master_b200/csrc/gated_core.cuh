@@ -461,6 +461,45 @@ YM_HD void fc_phase(int ph, const FcArgs& a, int img, int tid, int nthr, float* 
 }
 
 // --------------------------------------------------------------------------------------------------------------------
+// Global average pool of an NHWC fp16 map -> fp16 [B][ldo] (nn.AdaptiveAvgPool2d(1) of the SE / feature / cross gates, the latent
+// tokens and Classify).  One CTA per (image, 64-channel slab): 8 channel octets x 32 pixel lanes, 16-byte loads, fixed-order reduction.
+struct GapArgs {
+    const ym_half* x;   // [B][HW][ldx]
+    int ldx, HW, C;
+    ym_half* out;       // [B][ldo]
+    int ldo;
+};
+constexpr int GAP_SLAB = 64;     // channels per CTA
+constexpr int GAP_PHASES = 2;
+YM_HD int gap_smem_floats(int nthr) { return nthr * 8; }
+
+YM_HD void gap_phase(int ph, const GapArgs& a, int img, int slab, int tid, int nthr, float* sm) {
+    const int c0 = slab * GAP_SLAB, oct = tid & 7, lane = tid >> 3, nl = nthr >> 3;    // 8 octets x nl pixel lanes
+    const int c = c0 + oct * 8;
+    if (ph == 0) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        if (c < a.C) {
+            const ym_half* base = a.x + (long long)img * a.HW * a.ldx + c;
+            for (int p = lane; p < a.HW; p += nl) {
+                const ym_half* v = base + (long long)p * a.ldx;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += ym_h2f(v[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm[tid * 8 + j] = acc[j];
+    } else {
+        if (tid >= GAP_SLAB || c0 + tid >= a.C) return;
+        const int o = tid >> 3, j = tid & 7;                  // channel c0 + tid lives in octet o, slot j
+        float s = 0.f;
+        for (int l = 0; l < nl; ++l) s += sm[(l * 8 + o) * 8 + j];
+        a.out[(long long)img * a.ldo + c0 + tid] = ym_f2h(s / (float)a.HW);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
 // LatentRouter.forward (nn/modules/latent_mixture.py:219-241, per_token = False) on the pooled scale tokens of LatentMixture: mean over
 // tokens of (token + scale embedding) -> LayerNorm -> Linear + SiLU -> Linear + SiLU -> expert head -> clamp(+-30) -> softmax(/ T).
 constexpr int LR_MAX_TOKENS = 4;

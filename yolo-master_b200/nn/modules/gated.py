@@ -427,7 +427,7 @@ class _GatedMoE(nn.Module, PackCache):
         pk = self.get_pack()
         zero = torch.zeros((B, C), dtype=torch.float32, device=x.device)
         # SE-gated split (gated.py:325-332, _gated_visual.py:40-45)
-        gate = ops.fc_gate(ops.adaptive_avgpool(x, 1, 1), pk["se_w1"], pk["se_w2"], pk["se_b2"])
+        gate = ops.fc_gate(ops.gap(x), pk["se_w1"], pk["se_w2"], pk["se_b2"])
         xg = ops.ew(ops.EW_AFFINE, a=x, p0=gate, p1=zero, rows_per_img=HW)
         xs, xd = xg[..., :st_c], xg[..., st_c:]
         if "detail" in self.router_hook_names:   # detail gate on the dynamic half (gated.py:1174-1178)
@@ -445,7 +445,7 @@ class _GatedMoE(nn.Module, PackCache):
         self.last_routing_snapshot = {"topk_indices": idx, "topk_weights": w, "router_probs": probs}   # device tensors, lazy
         self._experts(xd, idx, w, pk, cat[..., self.out_static:])
         if "xg_w1" in pk:   # CrossPathGate: cat * (0.5 + 0.5 * tanh(gate_scale) * sigmoid(MLP(GAP(cat))))
-            xg = ops.fc_gate(ops.adaptive_avgpool(cat, 1, 1), pk["xg_w1"], pk["xg_w2"], pk["xg_b2"], scale=pk["xg_scale"], offset=0.5)
+            xg = ops.fc_gate(ops.gap(cat), pk["xg_w1"], pk["xg_w2"], pk["xg_b2"], scale=pk["xg_scale"], offset=0.5)
             cat = ops.ew(ops.EW_AFFINE, a=cat, p0=xg, p1=zero, rows_per_img=HW)
         if self.shuffle_groups > 1:
             cat = ops.conv2d(cat, pk["shuffle"], None, C, 1, 1, 1, 0, False)
@@ -462,7 +462,7 @@ class _GatedMoE(nn.Module, PackCache):
                 cat = ops.ew(ops.EW_SCALE_RES, a=cat, b=ops.ew(ops.EW_MUL, a=c, b=cgate), p0=pk["ctx_t"])
             elif hook in ("refine", "light_refine"):   # cat + tanh(scale) * refiner(cat) * gate(cat)  (moe/hooks.py:50-57; the v0_12
                 r = _norm(ops.dwconv(cat, pk["fr0"], None, 3, False, C), pk["fr1"], act=hook == "refine")   # variant has no SiLU)
-                fg = ops.fc_gate(ops.adaptive_avgpool(cat, 1, 1), pk["fg_w1"], pk["fg_w2"], pk["fg_b2"], scale=pk["refine_t"])
+                fg = ops.fc_gate(ops.gap(cat), pk["fg_w1"], pk["fg_w2"], pk["fg_b2"], scale=pk["refine_t"])
                 cat = ops.ew(ops.EW_AFFINE, a=r, b=cat, p0=fg, p1=zero, rows_per_img=HW)
         # projection + GroupNorm + residual
         return _norm(ops.conv2d(cat, *pk["proj"], C, 1, 1, 1, 0, False), pk["bn"], add=x, out=out)

@@ -256,7 +256,7 @@ class Classify(nn.Module):
         if isinstance(x, list):
             x = torch.cat(x, 1)
         t = self.conv.fwd_nhwc(to_nhwc(x))
-        v = ops.adaptive_avgpool(t, 1, 1)
+        v = ops.gap(t)
         w = cached_f32(self, "w", self.linear.weight)
         b = cached_f32(self, "b", self.linear.bias) if self.linear.bias is not None else None
         y, logits = ops.classify_head(v, w, b)

@@ -140,7 +140,7 @@ class LatentMixture(nn.Module, PackCache):
         for x, c in zip(xs, self.in_channels):
             if tuple(x.shape[:3]) != (B, H, W) or x.shape[3] != c:
                 raise ValueError(f"LatentMixture: inputs must share the spatial size and carry {self.in_channels} channels")
-        tokens = [ops.adaptive_avgpool(self._project(x, p), 1, 1) for x, p in zip(xs, pk["tok"])]
+        tokens = [ops.gap(self._project(x, p)) for x, p in zip(xs, pk["tok"])]
         base = self._project(xs[0], pk["base"])
         probs, logits = ops.latent_router(tokens, pk["router"])
         self.last_routing_snapshot = {"router_probs": probs, "router_logits": logits}

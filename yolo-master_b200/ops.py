@@ -698,3 +698,13 @@ def latent_router(tokens, pk):
                                       logits.data_ptr(), probs.data_ptr(), _stream()), "ym_latent_router")
     _count()
     return probs, logits
+
+
+def gap(x, out=None):
+    """ym_gap_nhwc: global average pool of a (B,H,W,C) fp16 view -> (B,1,1,C) fp16."""
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = new_act(B, 1, 1, Cc, x.device)
+    _lib.check(lib().ym_gap_nhwc(x.data_ptr(), pitch(x), B, H * W, Cc, out.data_ptr(), pitch(out), _stream()), "ym_gap_nhwc")
+    _count()
+    return out
