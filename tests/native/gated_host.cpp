@@ -8,6 +8,19 @@
 
 using namespace ym::gated;
 
+// gate_r0_kernel (grid = slabs x images) followed by gate_r0m_kernel (grid = images), as launch_r0 in gated.cu issues them.
+static void host_r0(R0Args& a, int B, std::vector<float>& part, float* sm) {
+    r0_slabs(a.Hp, &a.S, &a.PR);
+    part.assign((size_t)B * a.S * 2 * a.C, 0.f);
+    a.part = part.data();
+    for (int b = 0; b < B; ++b)
+        for (int s = 0; s < a.S; ++s)
+            for (int ph = 0; ph < R0_PHASES; ++ph)
+                for (int t = 0; t < NTHR; ++t) r0_phase(ph, a, b, s, t, NTHR, sm);
+    for (int b = 0; b < B; ++b)
+        for (int t = 0; t < NTHR; ++t) r0m_phase(a, b, t, NTHR);
+}
+
 extern "C" int host_gate_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* global_fc,
                                 const float* dw, const float* gn1_w, const float* gn1_b, int G1, const float* pw1, int R,
                                 const float* gn2_w, const float* gn2_b, int G2, const float* pw2, const float* b2, int E,
@@ -23,9 +36,8 @@ extern "C" int host_gate_router(const void* x, int ldx, int B, int H, int W, int
     a0.x = (const ym_half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = eff; a0.Hp = Hp; a0.Wp = Wp;
     a0.inv_area = 1.f / (float)(eff * eff); a0.stats = stats.data(); a0.pooled = pooled.data();
     std::vector<float> sm(r0_smem_floats(C, NTHR) + r1_smem_floats(R, E, NTHR) + 16);
-    for (int b = 0; b < B; ++b)
-        for (int ph = 0; ph < R0_PHASES; ++ph)
-            for (int t = 0; t < NTHR; ++t) r0_phase(ph, a0, b, t, NTHR, sm.data());
+    std::vector<float> part;
+    host_r0(a0, B, part, sm.data());
     R1Args a1;
     a1.pooled = pooled.data(); a1.t1 = t1.data(); a1.t2 = t2.data(); a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E;
     a1.G1 = G1; a1.G2 = G2; a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w;
@@ -61,9 +73,9 @@ extern "C" int host_pixel_router(const void* x, int ldx, int B, int H, int W, in
     a1.pooled = pooled.data(); a1.t1 = t1.data(); a1.t2 = t2.data(); a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E;
     a1.G1 = G1; a1.G2 = G2; a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w;
     a1.g2b = gn2_b; a1.pw2 = pw2; a1.b2 = b2; a1.ll = ll.data(); a1.pixel_softmax = 1; a1.inv_temp = 1.f / temperature;
+    std::vector<float> part;
+    host_r0(a0, B, part, sm.data());
     for (int b = 0; b < B; ++b) {
-        for (int ph = 0; ph < R0_PHASES; ++ph)
-            for (int t = 0; t < NTHR; ++t) r0_phase(ph, a0, b, t, NTHR, sm.data());
         for (int ph = 0; ph < R1_PHASES; ++ph)
             for (int t = 0; t < NTHR; ++t) r1_phase(ph, a1, b, t, NTHR, sm.data());
         for (int ph = 0; ph < R1_TAIL_PHASES; ++ph)
@@ -84,9 +96,8 @@ extern "C" int host_zero_cost_router(const void* x, int ldx, int B, int H, int W
     R0Args a0;
     a0.x = (const ym_half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = 1; a0.Hp = H; a0.Wp = W; a0.inv_area = 1.f;
     a0.stats = stats.data(); a0.pooled = nullptr;
-    for (int b = 0; b < B; ++b)
-        for (int ph = 0; ph < R0_PHASES; ++ph)
-            for (int t = 0; t < NTHR; ++t) r0_phase(ph, a0, b, t, NTHR, sm.data());
+    std::vector<float> part;
+    host_r0(a0, B, part, sm.data());
     R2Args a2;
     a2.stats = stats.data(); a2.ll = nullptr; a2.wg = fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = 1.f; a2.inv_temp = 1.f / temperature;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.w_min = 0.f; a2.cx = cx.data(); a2.w = w_out; a2.probs = probs_out;

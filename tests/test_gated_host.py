@@ -37,10 +37,7 @@ def emu(host):
     spec.loader.exec_module(mod)
     from yolo_master_b200 import ops
     from yolo_master_b200.nn.modules import _base, block, conv, gated, moa, mot
-    names = ("conv2d", "dwconv", "ew", "groupnorm_stats", "layernorm", "attn_small", "attn_window", "deform_sample", "token_router",
-             "linear_attn", "adaptive_avgpool", "new_act", "gate_router", "fc_gate", "gated_select", "ctx_mean3", "moe_expert_gemm",
-             "gn_finalize", "pitch")
-    saved_ops = {k: getattr(ops, k) for k in names}
+    saved_ops = {k: v for k, v in vars(ops).items() if callable(v) and not k.startswith("_")}
     saved_nhwc = {m: m.to_nhwc for m in (_base, block, conv, moa, mot, gated) if hasattr(m, "to_nhwc")}
     mod.install()
     mod.install_gated(host)

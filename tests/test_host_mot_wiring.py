@@ -20,8 +20,7 @@ def emu():
     spec.loader.exec_module(mod)
     from yolo_master_b200 import ops
     from yolo_master_b200.nn.modules import _base, block, conv, moa, mot
-    saved_ops = {k: getattr(ops, k) for k in ("conv2d", "dwconv", "ew", "groupnorm_stats", "layernorm", "attn_small", "attn_window",
-                                               "deform_sample", "token_router", "linear_attn", "adaptive_avgpool", "new_act")}
+    saved_ops = {k: v for k, v in vars(ops).items() if callable(v) and not k.startswith("_")}
     saved_nhwc = {m: m.to_nhwc for m in (_base, block, conv, moa, mot) if hasattr(m, "to_nhwc")}
     mod.install()
     yield mod

@@ -11,12 +11,22 @@
 namespace ym {
 using namespace gated;
 
-__global__ void __launch_bounds__(NTHR) gate_r0_kernel(const R0Args a) {
+__global__ void __launch_bounds__(NTHR) gate_r0_kernel(const R0Args a) {   // grid = (slabs, B)
     YM_DYN_SMEM(float, sm);
     for (int ph = 0; ph < R0_PHASES; ++ph) {
-        r0_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
+        r0_phase(ph, a, blockIdx.y, blockIdx.x, threadIdx.x, NTHR, sm);
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(NTHR) gate_r0m_kernel(const R0Args a) { r0m_phase(a, blockIdx.x, threadIdx.x, NTHR); }
+
+// Statistics + pooled map of every image: slab kernel, then the per-image merge.
+static void launch_r0(R0Args& a, int B, float* part, cudaStream_t st) {
+    a.part = part;
+    r0_slabs(a.Hp, &a.S, &a.PR);
+    YM_LAUNCH(gate_r0_kernel, dim3(a.S, B), NTHR, r0_smem_floats(a.C, NTHR) * sizeof(float), st, a);
+    YM_LAUNCH(gate_r0m_kernel, B, NTHR, 0, st, a);
 }
 
 __global__ void __launch_bounds__(NTHR) gate_r1_kernel(const R1Args a) {
@@ -129,7 +139,7 @@ extern "C" long long ym_gate_router_scratch_floats(int B, int H, int W, int C, i
     int Hp, Wp, eff;
     pooled_dims(H, W, pool, &Hp, &Wp, &eff);
     const long long N = (long long)Hp * Wp;
-    return (long long)B * (2LL * C + N * C * 2 + N * R + E + 1);
+    return (long long)B * (2LL * C + N * C * 2 + N * R + E + 1 + 2LL * R0_MAX_SLABS * C);
 }
 
 extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* global_fc,
@@ -139,7 +149,8 @@ extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C
                               const float* ln_w, const float* ln_b, float ln_eps, const float* prior, float* scratch,
                               float* w_out, int* idx_out, float* probs_out, void* stream) {
     YM_CHECK_ARG(x && scratch && w_out && idx_out, "ym_gate_router: null pointer");
-    YM_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R > 0, "ym_gate_router: empty problem");
+    YM_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && C > 0 && R > 0, "ym_gate_router: empty problem");
+    YM_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldx >= C, "ym_gate_router: C and the pitch must be multiples of 8");
     YM_CHECK_ARG(E >= 1 && E <= MAXE && topk >= 1 && topk <= E, "ym_gate_router: 1 <= topk <= E <= %d", MAXE);
     YM_CHECK_ARG(G1 >= 1 && G1 <= MAXG && C % G1 == 0 && G2 >= 1 && G2 <= MAXG && R % G2 == 0, "ym_gate_router: GroupNorm groups");
     YM_CHECK_ARG(temperature > 0.f, "ym_gate_router: temperature must be positive");
@@ -153,11 +164,12 @@ extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C
     float* t2 = t1 + (long long)B * N * C;
     float* ll = t2 + (long long)B * N * R;
     float* cx = ll + (long long)B * E;
+    float* part = cx + B;
     cudaStream_t st = (cudaStream_t)stream;
     R0Args a0;
     a0.x = (const __half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = eff; a0.Hp = Hp; a0.Wp = Wp;
     a0.inv_area = 1.f / (float)(eff * eff); a0.stats = stats; a0.pooled = pooled;
-    YM_LAUNCH(gate_r0_kernel, B, NTHR, r0_smem_floats(C, NTHR) * sizeof(float), st, a0);
+    launch_r0(a0, B, part, st);
     R1Args a1;
     a1.pooled = pooled; a1.t1 = t1; a1.t2 = t2; a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E; a1.G1 = G1; a1.G2 = G2;
     a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w; a1.g2b = gn2_b; a1.pw2 = pw2;
@@ -177,7 +189,8 @@ extern "C" int ym_pixel_router(const void* x, int ldx, int B, int H, int W, int 
                                const float* pw2, const float* b2, int E, float gn_eps, float temperature, float w_min, int topk,
                                float* scratch, float* w_out, int* idx_out, float* probs_out, void* stream) {
     YM_CHECK_ARG(x && scratch && w_out && idx_out, "ym_pixel_router: null pointer");
-    YM_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && R > 0 && R <= MAXR, "ym_pixel_router: empty problem / more than %d reduced channels", MAXR);
+    YM_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && C > 0 && R > 0 && R <= MAXR, "ym_pixel_router: empty problem / more than %d reduced channels", MAXR);
+    YM_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldx >= C, "ym_pixel_router: C and the pitch must be multiples of 8");
     YM_CHECK_ARG(E >= 1 && E <= 32 && topk >= 1 && topk <= E, "ym_pixel_router: 1 <= topk <= E <= 32");
     YM_CHECK_ARG(G1 >= 1 && G1 <= MAXG && C % G1 == 0 && G2 >= 1 && G2 <= MAXG && R % G2 == 0, "ym_pixel_router: GroupNorm groups");
     YM_CHECK_ARG(temperature > 0.f, "ym_pixel_router: temperature must be positive");
@@ -189,11 +202,12 @@ extern "C" int ym_pixel_router(const void* x, int ldx, int B, int H, int W, int 
     float* t1 = pooled + (long long)B * N * C;
     float* t2 = t1 + (long long)B * N * C;
     float* ll = t2 + (long long)B * N * R;
+    float* part = ll + (long long)B * E + B;
     cudaStream_t st = (cudaStream_t)stream;
     R0Args a0;
     a0.x = (const __half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = eff; a0.Hp = Hp; a0.Wp = Wp;
     a0.inv_area = 1.f / (float)(eff * eff); a0.stats = stats; a0.pooled = pooled;
-    YM_LAUNCH(gate_r0_kernel, B, NTHR, r0_smem_floats(C, NTHR) * sizeof(float), st, a0);
+    launch_r0(a0, B, part, st);
     R1Args a1;
     a1.pooled = pooled; a1.t1 = t1; a1.t2 = t2; a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E; a1.G1 = G1; a1.G2 = G2;
     a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w; a1.g2b = gn2_b; a1.pw2 = pw2;
@@ -208,22 +222,24 @@ extern "C" int ym_pixel_router(const void* x, int ldx, int B, int H, int W, int 
     return YM_OK;
 }
 
-extern "C" long long ym_zero_cost_router_scratch_floats(int B, int C) { return (long long)B * (2LL * C + 1); }
+extern "C" long long ym_zero_cost_router_scratch_floats(int B, int C) { return (long long)B * (2LL * C + 1 + 2LL * R0_MAX_SLABS * C); }
 
 extern "C" int ym_zero_cost_router(const void* x, int ldx, int B, int H, int W, int C, const float* fc, int E, float temperature,
                                    const float* cx_w, float cx_b, int topk, float* scratch, float* w_out, int* idx_out,
                                    float* probs_out, void* stream) {
     YM_CHECK_ARG(x && fc && cx_w && scratch && w_out && idx_out, "ym_zero_cost_router: null pointer");
-    YM_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "ym_zero_cost_router: empty problem");
+    YM_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && C > 0, "ym_zero_cost_router: empty problem");
+    YM_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldx >= C, "ym_zero_cost_router: C and the pitch must be multiples of 8");
     YM_CHECK_ARG(E >= 1 && E <= MAXE && topk >= 1 && topk <= E, "ym_zero_cost_router: 1 <= topk <= E <= %d", MAXE);
     YM_CHECK_ARG(temperature > 0.f, "ym_zero_cost_router: temperature must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     float* stats = scratch;
     float* cx = stats + (long long)B * 2 * C;
+    float* part = cx + B;
     R0Args a0;
     a0.x = (const __half*)x; a0.ldx = ldx; a0.H = H; a0.W = W; a0.C = C; a0.pool = 1; a0.Hp = H; a0.Wp = W; a0.inv_area = 1.f;
     a0.stats = stats; a0.pooled = nullptr;
-    YM_LAUNCH(gate_r0_kernel, B, NTHR, r0_smem_floats(C, NTHR) * sizeof(float), st, a0);
+    launch_r0(a0, B, part, st);
     R2Args a2;
     a2.stats = stats; a2.ll = nullptr; a2.wg = fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = 1.f; a2.inv_temp = 1.f / temperature;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.w_min = 0.f; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;

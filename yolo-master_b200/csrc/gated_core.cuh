@@ -56,58 +56,123 @@ YM_HD int col_lane_floats(int cols, int nthr) { return cols > nthr ? cols : nthr
 
 // --------------------------------------------------------------------------------------------------------------------
 // R0: per-image channel statistics (mean, population std) of x and the pooled fp32 map the local stream reads
-//     (DualStreamGateRouter.forward gated.py:129-142).
+//     (DualStreamGateRouter.forward gated.py:129-142).  The map is cut into S slabs of whole pooled rows, one CTA each (grid S x B):
+//     the CTA reduces its slab to (mean_s, M2_s) per channel in two passes over data it has just pulled into L1/L2 and writes its pooled
+//     rows; r0m_phase then merges the S partials of an image in slab order (Chan's parallel-variance update), so the result does not
+//     depend on scheduling.  Eight channels per thread per load (C and the pitch are multiples of 8, as for every activation here).
 struct R0Args {
     const ym_half* x;   // [B][H*W][ldx]
     int ldx, H, W, C, pool, Hp, Wp;
     float inv_area;     // 1 / (pool*pool), 1 when the map is not pooled
     float* stats;       // [B][2C]: mean | std
     float* pooled;      // [B][Hp*Wp][C], or null: statistics only
+    float* part;        // [B][S][2C]: slab mean | slab M2
+    int S, PR;          // slabs per image, pooled rows per slab (the last slab also takes the H % pool leftover rows)
 };
+constexpr int R0_MAX_SLABS = 32;
 constexpr int R0_PHASES = 5;
-YM_HD int r0_smem_floats(int C, int nthr) { return col_lane_floats(C, nthr) + C; }
+YM_HD void r0_slabs(int Hp, int* S, int* PR) {
+    const int want = Hp < R0_MAX_SLABS ? Hp : R0_MAX_SLABS;
+    *PR = (Hp + want - 1) / want;
+    *S = (Hp + *PR - 1) / *PR;
+}
+YM_HD int r0_smem_floats(int C, int nthr) { return (C > nthr * 8 ? C : nthr * 8) + C; }
 
-YM_HD void r0_phase(int ph, const R0Args& a, int img, int tid, int nthr, float* sm) {
-    const int HW = a.H * a.W, C = a.C;
-    const ym_half* x = a.x + (long long)img * HW * a.ldx;
+YM_HD void ym_load8(const ym_half* p, float (&f)[8]) {
+#if defined(__CUDA_ARCH__)
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 v = __half22float2(h[j]);
+        f[2 * j] = v.x;
+        f[2 * j + 1] = v.y;
+    }
+#else
+    for (int j = 0; j < 8; ++j) f[j] = ym_h2f(p[j]);
+#endif
+}
+
+YM_HD void r0_phase(int ph, const R0Args& a, int img, int slab, int tid, int nthr, float* sm) {
+    const int C = a.C, OC = C >> 3;
+    const int y0 = slab * a.PR * a.pool, y1 = slab == a.S - 1 ? a.H : (slab + 1) * a.PR * a.pool;
+    const int n = (y1 - y0) * a.W;                                     // pixels of this slab
+    const ym_half* x = a.x + ((long long)img * a.H * a.W + (long long)y0 * a.W) * a.ldx;
     float* part = sm;
-    float* mean = sm + col_lane_floats(C, nthr);
-    const ColLane cl(C, tid, nthr);
-    if (ph == 0 || ph == 2) {   // partial sums of x (ph 0) or (x - mean)^2 (ph 2)
+    float* mean = sm + (C > nthr * 8 ? C : nthr * 8);
+    const ColLane cl(OC, tid, nthr);                                   // column = channel octet, lane = pixel lane
+    float* slab_out = a.part + ((long long)img * a.S + slab) * 2 * C;
+    if (ph == 0 || ph == 2) {   // partial sums of x (ph 0) or (x - slab mean)^2 (ph 2)
         if (!cl.active()) return;
-        for (int c = cl.c0; c < C; c += cl.Cg) {
-            const float m = ph == 2 ? mean[c] : 0.f;
-            float s = 0.f;
-            for (int p = cl.pl; p < HW; p += cl.NL) {
-                const float v = ym_h2f(x[(long long)p * a.ldx + c]) - m;
-                s += ph == 2 ? v * v : v;
+        for (int o = cl.c0; o < OC; o += cl.Cg) {
+            float m[8], acc[8], v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                m[j] = ph == 2 ? mean[o * 8 + j] : 0.f;
+                acc[j] = 0.f;
             }
-            part[cl.pl * C + c] = s;
+            for (int p = cl.pl; p < n; p += cl.NL) {
+                ym_load8(x + (long long)p * a.ldx + o * 8, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float d = v[j] - m[j];
+                    acc[j] += ph == 2 ? d * d : d;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part[cl.pl * C + o * 8 + j] = acc[j];
         }
     } else if (ph == 1 || ph == 3) {
         for (int c = tid; c < C; c += nthr) {
             float s = 0.f;
             for (int l = 0; l < cl.NL; ++l) s += part[l * C + c];
-            s /= (float)HW;
             if (ph == 1) {
+                s /= (float)n;
                 mean[c] = s;
-                a.stats[(long long)img * 2 * C + c] = s;
+                slab_out[c] = s;
             } else {
-                a.stats[(long long)img * 2 * C + C + c] = HW > 1 ? sqrtf(s) : 0.f;
+                slab_out[C + c] = s;
             }
         }
-    } else {   // ph 4: avg_pool2d(kernel = stride = pool), floor mode, or a plain fp32 copy
+    } else {   // ph 4: avg_pool2d(kernel = stride = pool), floor mode, or a plain fp32 copy - this slab's pooled rows
         if (!a.pooled) return;                                        // statistics only (ZeroCostRouter)
-        float* out = a.pooled + (long long)img * a.Hp * a.Wp * C;
-        const int n = a.Hp * a.Wp * C;
-        for (int e = tid; e < n; e += nthr) {
-            const int c = e % C, pp = e / C, py = pp / a.Wp, px = pp % a.Wp;
-            float s = 0.f;
+        const int r0 = slab * a.PR, r1 = (slab + 1) * a.PR < a.Hp ? (slab + 1) * a.PR : a.Hp;
+        float* out = a.pooled + ((long long)img * a.Hp + r0) * a.Wp * C;
+        const int ne = (r1 - r0) * a.Wp * OC;
+        for (int e = tid; e < ne; e += nthr) {
+            const int o = e % OC, pp = e / OC, py = pp / a.Wp, px = pp % a.Wp;
+            float s[8], v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = 0.f;
             for (int dy = 0; dy < a.pool; ++dy)
-                for (int dx = 0; dx < a.pool; ++dx)
-                    s += ym_h2f(x[(long long)((py * a.pool + dy) * a.W + px * a.pool + dx) * a.ldx + c]);
-            out[e] = s * a.inv_area;
+                for (int dx = 0; dx < a.pool; ++dx) {
+                    ym_load8(x + (long long)((py * a.pool + dy) * a.W + px * a.pool + dx) * a.ldx + o * 8, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) s[j] += v[j];
+                }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) out[(long long)pp * C + o * 8 + j] = s[j] * a.inv_area;
         }
+    }
+}
+
+// Merge of the slab partials of one image, in slab order: n <- n + n_s, delta = mean_s - mean, mean += delta n_s / n,
+// M2 += M2_s + delta^2 n_old n_s / n.
+YM_HD void r0m_phase(const R0Args& a, int img, int tid, int nthr) {
+    const int C = a.C;
+    for (int c = tid; c < C; c += nthr) {
+        float cnt = 0.f, mean = 0.f, m2 = 0.f;
+        for (int s = 0; s < a.S; ++s) {
+            const int y0 = s * a.PR * a.pool, y1 = s == a.S - 1 ? a.H : (s + 1) * a.PR * a.pool;
+            const float ns = (float)((y1 - y0) * a.W);
+            const float* ps = a.part + ((long long)img * a.S + s) * 2 * C;
+            const float tot = cnt + ns, delta = ps[c] - mean;
+            mean += delta * (ns / tot);
+            m2 += ps[C + c] + delta * delta * (cnt * ns / tot);
+            cnt = tot;
+        }
+        a.stats[(long long)img * 2 * C + c] = mean;
+        a.stats[(long long)img * 2 * C + C + c] = cnt > 1.f ? sqrtf(m2 / cnt) : 0.f;
     }
 }
 
