@@ -222,13 +222,15 @@ int ym_obb_finish(int nl, const void* const* angle, const int* hs, const int* ws
  *   round(c*topk) best ranks and renormalises.  DualStreamGateRouterV2 (gated.py:181-260, v0_11 / v0_12 zoos): ln_w / ln_b fp32 [2C]
  *   (nullable pair) = LayerNorm over the statistics in front of global_fc, prior fp32 [E] (nullable) added to the blended logits
  *   before the clamp.  Outputs: w fp32 [B][topk], idx int32 [B][topk], probs fp32 [B][E] (nullable).
- *   scratch: ym_gate_router_scratch_floats() floats.  Three kernels, no host synchronisation.
+ *   scratch: ym_gate_router_scratch_floats() floats.  Four kernels (slab statistics, their merge, local stream, finish), no host
+ *   synchronisation.
  * ym_fc_gate: out[b][o] = offset + scale * sigmoid(b2[o] + w2[o] . silu(w1 . v[b]))   v fp16 [B][ldv] (a 1x1 adaptive average pool):
  *   se_gate gated.py:325-332 (scale 1), feature_gate moe/hooks.py:50-57 (scale = tanh(refine_scale)), CrossPathGate gated.py:2396-2412
  *   (offset 0.5, scale 0.5*tanh(gate_scale), v0_15 zoo); consumed by ym_ew_nhwc op 4.
  * ym_gated_select: FusedExpertGroup.forward gated.py:1061-1081 after the all-expert grouped conv: fo fp16 [B][HW][ldf] holds
  *   expert e in channels [e*oc, (e+1)*oc); for the routed experts: GroupNorm(G, no affine) over the slice, gamma/beta fp32 [E][oc],
- *   SiLU, sum_j w[b][j] * (.) -> out fp16 [B][HW][ldo].  scratch: 2*B*topk*oc floats.
+ *   SiLU, sum_j w[b][j] * (.) -> out fp16 [B][HW][ldo].  scratch: ym_gated_select_scratch_floats() floats.  The statistics run on a
+ *   (pixel slabs x routes) grid and are merged per route in slab order; three kernels.
  * ym_ctx_mean3: PyramidContextMixer gated.py:1213-1219: (a + nearest_up(b) + nearest_up(c)) / 3 with b (h2,w2), c (h4,w4). */
 long long ym_gate_router_scratch_floats(int B, int H, int W, int C, int R, int E, int pool);
 int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* global_fc, const float* dw,
@@ -254,6 +256,7 @@ int ym_zero_cost_router(const void* x, int ldx, int B, int H, int W, int C, cons
                         void* stream);
 int ym_fc_gate(const void* v, int ldv, int B, int Cin, const float* w1, int Cr, const float* w2, const float* b2, int Cout,
                float scale, float offset, float* out, void* stream);
+long long ym_gated_select_scratch_floats(int B, int topk, int oc);
 int ym_gated_select(const void* fo, int ldf, int B, int HW, int E, int oc, int G, float eps, const int* idx, const float* w,
                     int topk, const float* gamma, const float* beta, float* scratch, void* out, int ldo, void* stream);
 int ym_ctx_mean3(const void* a, int lda, const void* b, int ldb, const void* c, int ldc, int B, int H, int W, int C, int h2,

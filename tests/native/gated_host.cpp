@@ -132,13 +132,20 @@ extern "C" int host_classify_head(const void* v, int ldv, int B, int Cin, const 
 
 extern "C" int host_gated_select(const void* fo, int ldf, int B, int HW, int E, int oc, int G, float eps, const int* idx,
                                  const float* w, int topk, const float* gamma, const float* beta, void* out, int ldo) {
-    std::vector<float> sc((size_t)B * topk * oc), sh((size_t)B * topk * oc), sm(s0_smem_floats(NTHR));
+    std::vector<float> sc((size_t)B * topk * oc), sh((size_t)B * topk * oc), sm(s0_smem_floats(oc, NTHR));
     S0Args a;
+    s0_slabs(HW, &a.S, &a.PS);
+    std::vector<float> part((size_t)B * topk * a.S * 2 * G);
+    a.part = part.data();
     a.fo = (const ym_half*)fo; a.ldf = ldf; a.HW = HW; a.oc = oc; a.G = G; a.topk = topk; a.eps = eps; a.idx = idx; a.gamma = gamma;
     a.beta = beta; a.sc = sc.data(); a.sh = sh.data();
     for (int r = 0; r < B * topk; ++r)
-        for (int ph = 0; ph < S0_PHASES; ++ph)
-            for (int t = 0; t < NTHR; ++t) s0_phase(ph, a, r, t, NTHR, sm.data());
+        for (int s = 0; s < a.S; ++s)
+            for (int ph = 0; ph < S0_PHASES; ++ph)
+                for (int t = 0; t < NTHR; ++t) s0_phase(ph, a, r, s, t, NTHR, sm.data());
+    for (int r = 0; r < B * topk; ++r)
+        for (int ph = 0; ph < S0M_PHASES; ++ph)
+            for (int t = 0; t < NTHR; ++t) s0m_phase(ph, a, r, t, NTHR, sm.data());
     ym_half* o = (ym_half*)out;
     for (int b = 0; b < B; ++b)
         for (int p = 0; p < HW; ++p)

@@ -23,7 +23,7 @@ from yolo_master_b200 import _lib, ops
 CSRC = os.path.join(ROOT, "yolo-master_b200", "csrc")
 UNITS = ["preproc.cu", "gated.cu", "nms_large.cu", "mix.cu"]
 SYMBOLS = ["ym_letterbox_u8", "ym_scale_boxes", "ym_kpts_decode", "ym_obb_finish", "ym_gate_router", "ym_gate_router_scratch_floats",
-           "ym_zero_cost_router", "ym_zero_cost_router_scratch_floats", "ym_pixel_router", "ym_latent_router", "ym_fc_gate", "ym_classify_head", "ym_gated_select",
+           "ym_zero_cost_router", "ym_zero_cost_router_scratch_floats", "ym_pixel_router", "ym_latent_router", "ym_fc_gate", "ym_classify_head", "ym_gated_select", "ym_gated_select_scratch_floats",
            "ym_ctx_mean3", "ym_gap_nhwc", "ym_nms_batched_large", "ym_nms_large_scratch_bytes", "ym_ew_nhwc", "ym_last_error"]
 
 
@@ -173,6 +173,34 @@ def test_gated_kernels(emu):
     w1, w2, b2 = torch.randn((8, 96), generator=g) * 0.1, torch.randn((12, 8), generator=g), torch.randn((12,), generator=g)
     got = ops.fc_gate(v, w1, w2, b2, scale=0.4, offset=0.5)
     torch.testing.assert_close(got, 0.5 + 0.4 * torch.sigmoid(F.linear(F.silu(F.linear(v.view(3, 96).float(), w1)), w2, b2)), atol=1e-6, rtol=1e-5)
+
+
+def test_slab_statistics_merge(emu):
+    """The slab-parallel statistics (gate_r0 + merge, select_s0 + merge) with several slabs per image, a ragged last slab and a mean far
+    from zero (where a naive sum-of-squares would cancel): the zero-cost router sees mean | std directly, the select sees GroupNorm."""
+    from yolo_master_b200.nn.modules.gated import UltimateOptimizedMoE
+    from yolo_master_b200.utils.synth import fill_state_dict_
+    g = torch.Generator().manual_seed(8)
+    m = UltimateOptimizedMoE(64, 64, 4, 2, 0.5)
+    sd = m.state_dict()
+    fill_state_dict_(sd, 3)
+    m.load_state_dict(sd)
+    pk = m.eval().get_pack()
+    xd = (torch.randn((2, 32, 45, 11), generator=g) * 0.25 + 6.0).half()          # 45 rows -> 23 slabs of 2 rows, the last of 1
+    idx, w, probs = ops.zero_cost_router(xd.permute(0, 2, 3, 1).contiguous(), pk["fc"], 2.0, pk["cx_w"], pk["cx_b"], 2)
+    rw, ri, rp = O.zero_cost_router({"m." + k_: v.float() for k_, v in sd.items()}, "m.routing", xd.float(), 2, 2.0)
+    assert torch.equal(idx.long(), ri)
+    torch.testing.assert_close(probs, rp, atol=5e-6, rtol=2e-4)
+    B, H, W, E, oc, G = 2, 27, 23, 4, 32, 8                                        # 621 pixels -> 3 slabs of 207
+    buf = (torch.randn((B, H, W, E * oc), generator=g) * 0.5 + 4.0).half()
+    idx = torch.tensor([[2, 0], [1, 3]], dtype=torch.int32)
+    ww = torch.tensor([[0.7, 0.3], [0.4, 0.6]])
+    gamma, beta = torch.randn((E, oc), generator=g), torch.randn((E, oc), generator=g)
+    got = ops.gated_select(buf, idx, ww, gamma, beta, E, oc, G).float()
+    f5 = buf.double().permute(0, 3, 1, 2).reshape(B, E, oc, H, W)
+    sel = torch.gather(f5, 1, idx.long().view(B, 2, 1, 1, 1).expand(B, 2, oc, H, W))
+    nrm = F.group_norm(sel.reshape(B * 2, oc, H, W), G).view(B, 2, oc, H, W) * gamma[idx.long()].double().view(B, 2, oc, 1, 1) + beta[idx.long()].double().view(B, 2, oc, 1, 1)
+    torch.testing.assert_close(got, (F.silu(nrm) * ww.double().view(B, 2, 1, 1, 1)).sum(1).permute(0, 2, 3, 1).float(), atol=4e-3, rtol=2e-3)
 
 
 def test_elementwise_ops_including_the_verified_ones(emu):

@@ -70,6 +70,7 @@ SIGNATURES = {
     "ym_zero_cost_router_scratch_floats": (cll, [ci, ci]),
     "ym_zero_cost_router": (ci, [vp, ci, ci, ci, ci, ci, vp, ci, cf, vp, cf, ci, vp, vp, vp, vp, vp]),
     "ym_fc_gate": (ci, [vp, ci, ci, ci, vp, ci, vp, vp, ci, cf, cf, vp, vp]),
+    "ym_gated_select_scratch_floats": (C.c_longlong, [ci, ci, ci]),
     "ym_gated_select": (ci, [vp, ci, ci, ci, ci, ci, ci, cf, vp, vp, ci, vp, vp, vp, vp, ci, vp]),
     "ym_ctx_mean3": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, ci, vp]),
     "ym_gap_nhwc": (ci, [vp, ci, ci, ci, ci, vp, ci, vp]),

@@ -81,15 +81,22 @@ __global__ void __launch_bounds__(NTHR) classify_kernel(const ClsArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(NTHR) select_s0_kernel(const S0Args a) {
+__global__ void __launch_bounds__(NTHR) select_s0_kernel(const S0Args a) {   // grid = (slabs, routes)
     YM_DYN_SMEM(float, sm);
     for (int ph = 0; ph < S0_PHASES; ++ph) {
-        s0_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
+        s0_phase(ph, a, blockIdx.y, blockIdx.x, threadIdx.x, NTHR, sm);
         __syncthreads();
     }
 }
 
-// one thread per 8 consecutive channels of one output pixel
+__global__ void __launch_bounds__(NTHR) select_s0m_kernel(const S0Args a) {   // grid = routes
+    __shared__ float sm[2 * MAXG];
+    for (int ph = 0; ph < S0M_PHASES; ++ph) {
+        s0m_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) select_s1_kernel(const S0Args a, const float* __restrict__ w, __half* __restrict__ out,
                                                         int ldo, long long total) {
     const int cv = a.oc >> 3;
@@ -304,18 +311,22 @@ extern "C" int ym_classify_head(const void* v, int ldv, int B, int Cin, const fl
     return YM_OK;
 }
 
+extern "C" long long ym_gated_select_scratch_floats(int B, int topk, int oc) { return s0_scratch_floats(B, topk, oc); }
+
 extern "C" int ym_gated_select(const void* fo, int ldf, int B, int HW, int E, int oc, int G, float eps, const int* idx,
                                const float* w, int topk, const float* gamma, const float* beta, float* scratch, void* out,
                                int ldo, void* stream) {
     YM_CHECK_ARG(fo && idx && w && gamma && beta && scratch && out, "ym_gated_select: null pointer");
-    YM_CHECK_ARG(B > 0 && HW > 0 && E >= 1 && topk >= 1 && topk <= E, "ym_gated_select: bad sizes");
-    YM_CHECK_ARG(oc % 8 == 0 && ldo % 8 == 0 && ldf >= E * oc, "ym_gated_select: oc, ldo multiples of 8; ldf >= E*oc");
+    YM_CHECK_ARG(B > 0 && HW > 0 && E >= 1 && topk >= 1 && topk <= E && (long long)B * topk <= 65535, "ym_gated_select: bad sizes");
+    YM_CHECK_ARG(oc % 8 == 0 && oc <= 8 * NTHR && ldo % 8 == 0 && ldf % 8 == 0 && ldf >= E * oc, "ym_gated_select: oc, ldf, ldo multiples of 8; ldf >= E*oc");
     YM_CHECK_ARG(G >= 1 && G <= MAXG && oc % G == 0, "ym_gated_select: GroupNorm groups");
     S0Args a;
     a.fo = (const __half*)fo; a.ldf = ldf; a.HW = HW; a.oc = oc; a.G = G; a.topk = topk; a.eps = eps; a.idx = idx; a.gamma = gamma;
-    a.beta = beta; a.sc = scratch; a.sh = scratch + (long long)B * topk * oc;
+    a.beta = beta; a.sc = scratch; a.sh = scratch + (long long)B * topk * oc; a.part = a.sh + (long long)B * topk * oc;
+    s0_slabs(HW, &a.S, &a.PS);
     cudaStream_t st = (cudaStream_t)stream;
-    YM_LAUNCH(select_s0_kernel, B * topk, NTHR, s0_smem_floats(NTHR) * sizeof(float), st, a);
+    YM_LAUNCH(select_s0_kernel, dim3(a.S, B * topk), NTHR, s0_smem_floats(oc, NTHR) * sizeof(float), st, a);
+    YM_LAUNCH(select_s0m_kernel, B * topk, NTHR, 0, st, a);
     const long long total = (long long)B * HW * (oc / 8);
     YM_LAUNCH(select_s1_kernel, grid_for(total), 256, 0, st, a, w, (__half*)out, ldo, total);
     YM_CHECK_LAUNCH("gated_select");

@@ -708,43 +708,90 @@ struct S0Args {
     const int* idx;      // [B][topk]
     const float *gamma, *beta;   // [E][oc]
     float *sc, *sh;      // [B*topk][oc]
+    float* part;         // [B*topk][S][2G]: slab mean | slab M2 per group
+    int S, PS;           // pixel slabs per route, pixels per slab
 };
-constexpr int S0_PHASES = 5;
-YM_HD int s0_smem_floats(int nthr) { return nthr * MAXG + 2 * MAXG; }
+constexpr int S0_MAX_SLABS = 32;
+constexpr int S0_PHASES = 6;
+constexpr int S0M_PHASES = 2;
+YM_HD void s0_slabs(int HW, int* S, int* PS) {   // about 256 pixels per CTA
+    int want = (HW + 255) / 256;
+    want = want < 1 ? 1 : (want > S0_MAX_SLABS ? S0_MAX_SLABS : want);
+    *PS = (HW + want - 1) / want;
+    *S = (HW + *PS - 1) / *PS;
+}
+YM_HD int s0_smem_floats(int oc, int nthr) { return nthr * 8 + oc + 2 * MAXG; }   // oc <= 8 * nthr
+YM_HD long long s0_scratch_floats(int B, int topk, int oc) { return (long long)B * topk * (2LL * oc + 2LL * S0_MAX_SLABS * MAXG); }
 
-YM_HD void s0_partials(const ym_half* base, int ldf, int HW, int oc, int cpg, const float* mean, int tid, int nthr, float* part) {
-    float acc[MAXG];
+// Slab CTA (route, slab): per-group (mean, M2) of the slab's pixels of the selected expert's channel slice, two passes.
+YM_HD void s0_phase(int ph, const S0Args& a, int route, int slab, int tid, int nthr, float* sm) {
+    const int b = route / a.topk, ex = a.idx[route], cpg = a.oc / a.G, OC = a.oc >> 3;
+    const int p0 = slab * a.PS, p1 = p0 + a.PS < a.HW ? p0 + a.PS : a.HW, n = p1 - p0;
+    const ym_half* base = a.fo + ((long long)b * a.HW + p0) * a.ldf + (long long)ex * a.oc;
+    float* part = sm;                 // [lanes][oc]
+    float* chs = sm + nthr * 8;       // [oc]
+    float* mean = chs + a.oc;         // [G]
+    const ColLane cl(OC, tid, nthr);
+    if (ph == 0 || ph == 3) {
+        if (!cl.active()) return;
+        for (int o = cl.c0; o < OC; o += cl.Cg) {
+            float m[8], acc[8], v[8];
 #pragma unroll
-    for (int g = 0; g < MAXG; ++g) acc[g] = 0.f;
-    const int n = HW * oc;
-    for (int e = tid; e < n; e += nthr) {
-        const int c = e % oc, p = e / oc, g = c / cpg;
-        float v = ym_h2f(base[(long long)p * ldf + c]);
-        if (mean) {
-            float m = 0.f;
+            for (int j = 0; j < 8; ++j) {
+                m[j] = ph == 3 ? mean[(o * 8 + j) / cpg] : 0.f;
+                acc[j] = 0.f;
+            }
+            for (int p = cl.pl; p < n; p += cl.NL) {
+                ym_load8(base + (long long)p * a.ldf + o * 8, v);
 #pragma unroll
-            for (int gg = 0; gg < MAXG; ++gg) m = g == gg ? mean[gg] : m;
-            v = (v - m) * (v - m);
+                for (int j = 0; j < 8; ++j) {
+                    const float d = v[j] - m[j];
+                    acc[j] += ph == 3 ? d * d : d;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part[cl.pl * a.oc + o * 8 + j] = acc[j];
         }
-#pragma unroll
-        for (int gg = 0; gg < MAXG; ++gg) acc[gg] += g == gg ? v : 0.f;
+    } else if (ph == 1 || ph == 4) {
+        for (int c = tid; c < a.oc; c += nthr) {
+            float s = 0.f;
+            for (int l = 0; l < cl.NL; ++l) s += part[l * a.oc + c];
+            chs[c] = s;
+        }
+    } else if (tid < a.G) {           // ph 2: slab mean of group tid; ph 5: slab M2, both to the partials
+        float s = 0.f;
+        for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) s += chs[c];
+        float* out = a.part + ((long long)route * a.S + slab) * 2 * a.G;
+        if (ph == 2) {
+            s /= (float)n * cpg;
+            mean[tid] = s;
+            out[tid] = s;
+        } else {
+            out[a.G + tid] = s;
+        }
     }
-#pragma unroll
-    for (int g = 0; g < MAXG; ++g) part[tid * MAXG + g] = acc[g];
 }
 
-YM_HD void s0_phase(int ph, const S0Args& a, int route, int tid, int nthr, float* sm) {
-    const int b = route / a.topk, ex = a.idx[route], cpg = a.oc / a.G;
-    const ym_half* base = a.fo + (long long)b * a.HW * a.ldf + (long long)ex * a.oc;
-    float* part = sm;
-    float* mean = sm + nthr * MAXG;
-    float* rstd = mean + MAXG;
-    const float cnt = (float)a.HW * cpg;
-    if (ph == 0) s0_partials(base, a.ldf, a.HW, a.oc, cpg, nullptr, tid, nthr, part);
-    else if (ph == 1) { if (tid < a.G) mean[tid] = gn_reduce(part, tid, nthr, cnt); }
-    else if (ph == 2) s0_partials(base, a.ldf, a.HW, a.oc, cpg, mean, tid, nthr, part);
-    else if (ph == 3) { if (tid < a.G) rstd[tid] = 1.f / sqrtf(gn_reduce(part, tid, nthr, cnt) + a.eps); }
-    else {
+// Merge CTA (route): slab partials in slab order (Chan), then the per-channel scale / shift of GroupNorm + the expert's affine.
+YM_HD void s0m_phase(int ph, const S0Args& a, int route, int tid, int nthr, float* sm) {
+    const int ex = a.idx[route], cpg = a.oc / a.G;
+    float* mean = sm;
+    float* rstd = sm + MAXG;
+    if (ph == 0) {
+        if (tid >= a.G) return;
+        float cnt = 0.f, mu = 0.f, m2 = 0.f;
+        for (int s = 0; s < a.S; ++s) {
+            const int p0 = s * a.PS, p1 = p0 + a.PS < a.HW ? p0 + a.PS : a.HW;
+            const float ns = (float)(p1 - p0) * cpg;
+            const float* ps = a.part + ((long long)route * a.S + s) * 2 * a.G;
+            const float tot = cnt + ns, delta = ps[tid] - mu;
+            mu += delta * (ns / tot);
+            m2 += ps[a.G + tid] + delta * delta * (cnt * ns / tot);
+            cnt = tot;
+        }
+        mean[tid] = mu;
+        rstd[tid] = 1.f / sqrtf(m2 / cnt + a.eps);
+    } else {
         for (int c = tid; c < a.oc; c += nthr) {
             const int g = c / cpg;
             const float gm = a.gamma[(long long)ex * a.oc + c];

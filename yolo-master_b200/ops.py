@@ -576,7 +576,7 @@ def gate_router(x, pk, topk):
                                     None if ln is None else ln[0].data_ptr(), None if ln is None else ln[1].data_ptr(),
                                     0.0 if ln is None else ln[2], None if prior is None else prior.data_ptr(),
                                     scratch.data_ptr(), w.data_ptr(), idx.data_ptr(), probs.data_ptr(), _stream()), "ym_gate_router")
-    _count(3)
+    _count(4)
     return idx, w, probs
 
 
@@ -591,7 +591,7 @@ def zero_cost_router(x, fc, temperature, cx_w, cx_b, topk):
     _lib.check(lib().ym_zero_cost_router(x.data_ptr(), pitch(x), B, H, W, Cc, fc.data_ptr(), E, float(temperature), cx_w.data_ptr(),
                                          float(cx_b), topk, scratch.data_ptr(), w.data_ptr(), idx.data_ptr(), probs.data_ptr(), _stream()),
                "ym_zero_cost_router")
-    _count(2)
+    _count(3)
     return idx, w, probs
 
 
@@ -615,11 +615,11 @@ def gated_select(fo, idx, w, gamma, beta, E, oc, G, eps=1e-5, out=None):
     k = idx.shape[1]
     if out is None:
         out = new_act(B, H, W, oc, fo.device)
-    scratch = torch.empty((2 * B * k * oc,), dtype=torch.float32, device=fo.device)
+    scratch = torch.empty((lib().ym_gated_select_scratch_floats(B, k, oc),), dtype=torch.float32, device=fo.device)
     _lib.check(lib().ym_gated_select(fo.data_ptr(), pitch(fo), B, H * W, E, oc, G, eps, idx.data_ptr(), w.data_ptr(), k,
                                      gamma.data_ptr(), beta.data_ptr(), scratch.data_ptr(), out.data_ptr(), pitch(out), _stream()),
                "ym_gated_select")
-    _count(2)
+    _count(3)
     return out
 
 
@@ -679,7 +679,7 @@ def pixel_router(x, pk, topk, w_min=0.01):
                                      pk["gn1_b"].data_ptr(), pk["G1"], pk["pw1"].data_ptr(), R, pk["gn2_w"].data_ptr(), pk["gn2_b"].data_ptr(),
                                      pk["G2"], pk["pw2"].data_ptr(), pk["b2"].data_ptr(), E, pk["eps"], pk["temperature"], float(w_min), topk,
                                      scratch.data_ptr(), w.data_ptr(), idx.data_ptr(), probs.data_ptr(), _stream()), "ym_pixel_router")
-    _count(3)
+    _count(4)
     return idx, w, probs
 
 
