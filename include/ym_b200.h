@@ -222,8 +222,8 @@ int ym_obb_finish(int nl, const void* const* angle, const int* hs, const int* ws
  *   round(c*topk) best ranks and renormalises.  DualStreamGateRouterV2 (gated.py:181-260, v0_11 / v0_12 zoos): ln_w / ln_b fp32 [2C]
  *   (nullable pair) = LayerNorm over the statistics in front of global_fc, prior fp32 [E] (nullable) added to the blended logits
  *   before the clamp.  Outputs: w fp32 [B][topk], idx int32 [B][topk], probs fp32 [B][E] (nullable).
- *   scratch: ym_gate_router_scratch_floats() floats.  Four kernels (slab statistics, their merge, local stream, finish), no host
- *   synchronisation.
+ *   scratch: ym_gate_router_scratch_floats() floats.  Six small kernels (slab statistics and their merge; the local stream as depthwise + GN partials,
+ *   GN + 1x1 + GN partials on pixel slabs, then its head per image; finish), no host synchronisation.
  * ym_fc_gate: out[b][o] = offset + scale * sigmoid(b2[o] + w2[o] . silu(w1 . v[b]))   v fp16 [B][ldv] (a 1x1 adaptive average pool):
  *   se_gate gated.py:325-332 (scale 1), feature_gate moe/hooks.py:50-57 (scale = tanh(refine_scale)), CrossPathGate gated.py:2396-2412
  *   (offset 0.5, scale 0.5*tanh(gate_scale), v0_15 zoo); consumed by ym_ew_nhwc op 4.

@@ -8,6 +8,26 @@
 
 using namespace ym::gated;
 
+// gate_r1a / r1b / r1c kernels as launch_r1 in gated.cu issues them.
+static void host_r1(R1Args& a, int B, std::vector<float>& p12) {
+    r1_geom(a.Hp * a.Wp, a.C, &a.S1, &a.PS1, &a.S2, &a.PS2);
+    p12.assign((size_t)B * (a.S1 + a.S2) * 2 * MAXG, 0.f);
+    a.p1 = p12.data();
+    a.p2 = a.p1 + (size_t)B * a.S1 * 2 * MAXG;
+    std::vector<float> sm(r1a_smem_floats(a.C, NTHR) + r1b_smem_floats(a.C, a.R, a.PS2) + r1_smem_floats(a.R, a.E, NTHR));
+    for (int b = 0; b < B; ++b)
+        for (int s = 0; s < a.S1; ++s)
+            for (int ph = 0; ph < R1A_PHASES; ++ph)
+                for (int t = 0; t < NTHR; ++t) r1a_phase(ph, a, b, s, t, NTHR, sm.data());
+    for (int b = 0; b < B; ++b)
+        for (int s = 0; s < a.S2; ++s)
+            for (int ph = 0; ph < R1B_PHASES; ++ph)
+                for (int t = 0; t < NTHR; ++t) r1b_phase(ph, a, b, s, t, NTHR, sm.data());
+    for (int b = 0; b < B; ++b)
+        for (int ph = 0; ph < R1_TAIL_PHASES; ++ph)
+            for (int t = 0; t < NTHR; ++t) r1_tail_phase(ph, a, b, t, NTHR, sm.data());
+}
+
 // gate_r0_kernel (grid = slabs x images) followed by gate_r0m_kernel (grid = images), as launch_r0 in gated.cu issues them.
 static void host_r0(R0Args& a, int B, std::vector<float>& part, float* sm) {
     r0_slabs(a.Hp, &a.S, &a.PR);
@@ -42,12 +62,8 @@ extern "C" int host_gate_router(const void* x, int ldx, int B, int H, int W, int
     a1.pooled = pooled.data(); a1.t1 = t1.data(); a1.t2 = t2.data(); a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E;
     a1.G1 = G1; a1.G2 = G2; a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w;
     a1.g2b = gn2_b; a1.pw2 = pw2; a1.b2 = b2; a1.ll = ll.data(); a1.pixel_softmax = 0; a1.inv_temp = 1.f;
-    for (int b = 0; b < B; ++b) {
-        for (int ph = 0; ph < R1_PHASES; ++ph)
-            for (int t = 0; t < NTHR; ++t) r1_phase(ph, a1, b, t, NTHR, sm.data());
-        for (int ph = 0; ph < R1_TAIL_PHASES; ++ph)
-            for (int t = 0; t < NTHR; ++t) r1_tail_phase(ph, a1, b, t, NTHR, sm.data());
-    }
+    std::vector<float> p12;
+    host_r1(a1, B, p12);
     R2Args a2;
     a2.stats = stats.data(); a2.ll = ll.data(); a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha;
     a2.inv_temp = 1.f / temperature; a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.w_min = 0.f; a2.cx = cx.data(); a2.w = w_out;
@@ -75,12 +91,8 @@ extern "C" int host_pixel_router(const void* x, int ldx, int B, int H, int W, in
     a1.g2b = gn2_b; a1.pw2 = pw2; a1.b2 = b2; a1.ll = ll.data(); a1.pixel_softmax = 1; a1.inv_temp = 1.f / temperature;
     std::vector<float> part;
     host_r0(a0, B, part, sm.data());
-    for (int b = 0; b < B; ++b) {
-        for (int ph = 0; ph < R1_PHASES; ++ph)
-            for (int t = 0; t < NTHR; ++t) r1_phase(ph, a1, b, t, NTHR, sm.data());
-        for (int ph = 0; ph < R1_TAIL_PHASES; ++ph)
-            for (int t = 0; t < NTHR; ++t) r1_tail_phase(ph, a1, b, t, NTHR, sm.data());
-    }
+    std::vector<float> p12;
+    host_r1(a1, B, p12);
     R2Args a2;
     a2.stats = stats.data(); a2.ll = ll.data(); a2.wg = nullptr; a2.wc = nullptr; a2.bc = 0.f; a2.alpha = 0.f; a2.inv_temp = 1.f;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 2; a2.w_min = w_min; a2.cx = nullptr; a2.w = w_out; a2.probs = probs_out;

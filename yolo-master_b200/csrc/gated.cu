@@ -29,16 +29,38 @@ static void launch_r0(R0Args& a, int B, float* part, cudaStream_t st) {
     YM_LAUNCH(gate_r0m_kernel, B, NTHR, 0, st, a);
 }
 
-__global__ void __launch_bounds__(NTHR) gate_r1_kernel(const R1Args a) {
+__global__ void __launch_bounds__(NTHR) gate_r1a_kernel(const R1Args a) {   // grid = (S1, B)
     YM_DYN_SMEM(float, sm);
-    for (int ph = 0; ph < R1_PHASES; ++ph) {
-        r1_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
+    for (int ph = 0; ph < R1A_PHASES; ++ph) {
+        r1a_phase(ph, a, blockIdx.y, blockIdx.x, threadIdx.x, NTHR, sm);
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(NTHR) gate_r1b_kernel(const R1Args a) {   // grid = (S2, B)
+    YM_DYN_SMEM(float, sm);
+    for (int ph = 0; ph < R1B_PHASES; ++ph) {
+        r1b_phase(ph, a, blockIdx.y, blockIdx.x, threadIdx.x, NTHR, sm);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(NTHR) gate_r1c_kernel(const R1Args a) {   // grid = B
+    YM_DYN_SMEM(float, sm);
     for (int ph = 0; ph < R1_TAIL_PHASES; ++ph) {
         r1_tail_phase(ph, a, blockIdx.x, threadIdx.x, NTHR, sm);
         __syncthreads();
     }
+}
+
+// Local stream of every image: depthwise + GN1 partials, GN1 + 1x1 + GN2 partials, GN2 + head + spatial mean.
+static void launch_r1(R1Args& a, int B, float* p1, cudaStream_t st) {
+    r1_geom(a.Hp * a.Wp, a.C, &a.S1, &a.PS1, &a.S2, &a.PS2);
+    a.p1 = p1;
+    a.p2 = p1 + (long long)B * a.S1 * 2 * MAXG;
+    YM_LAUNCH(gate_r1a_kernel, dim3(a.S1, B), NTHR, r1a_smem_floats(a.C, NTHR) * sizeof(float), st, a);
+    YM_LAUNCH(gate_r1b_kernel, dim3(a.S2, B), NTHR, r1b_smem_floats(a.C, a.R, a.PS2) * sizeof(float), st, a);
+    YM_LAUNCH(gate_r1c_kernel, B, NTHR, r1_smem_floats(a.R, a.E, NTHR) * sizeof(float), st, a);
 }
 
 __global__ void __launch_bounds__(NTHR) gate_r2_kernel(const R2Args a) {
@@ -146,7 +168,9 @@ extern "C" long long ym_gate_router_scratch_floats(int B, int H, int W, int C, i
     int Hp, Wp, eff;
     pooled_dims(H, W, pool, &Hp, &Wp, &eff);
     const long long N = (long long)Hp * Wp;
-    return (long long)B * (2LL * C + N * C * 2 + N * R + E + 1 + 2LL * R0_MAX_SLABS * C);
+    int S1, PS1, S2, PS2;
+    r1_geom((int)N, C, &S1, &PS1, &S2, &PS2);
+    return (long long)B * (2LL * C + N * C * 2 + N * R + E + 1 + 2LL * R0_MAX_SLABS * C + 2LL * MAXG * (S1 + S2));
 }
 
 extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* global_fc,
@@ -165,6 +189,11 @@ extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C
     int Hp, Wp, eff;
     pooled_dims(H, W, pool, &Hp, &Wp, &eff);
     const long long N = (long long)Hp * Wp;
+    {
+        int S1, PS1, S2, PS2;
+        r1_geom((int)N, C, &S1, &PS1, &S2, &PS2);
+        YM_CHECK_ARG(r1b_smem_floats(C, R, PS2) <= 12288 && r1a_smem_floats(C, NTHR) <= 12288, "%s: the local stream does not fit 48 KB of shared memory", "ym_gate_router");
+    }
     float* stats = scratch;
     float* pooled = stats + (long long)B * 2 * C;
     float* t1 = pooled + (long long)B * N * C;
@@ -181,7 +210,7 @@ extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C
     a1.pooled = pooled; a1.t1 = t1; a1.t2 = t2; a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E; a1.G1 = G1; a1.G2 = G2;
     a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w; a1.g2b = gn2_b; a1.pw2 = pw2;
     a1.b2 = b2; a1.ll = ll; a1.pixel_softmax = 0; a1.inv_temp = 1.f;
-    YM_LAUNCH(gate_r1_kernel, B, NTHR, r1_smem_floats(R, E, NTHR) * sizeof(float), st, a1);
+    launch_r1(a1, B, part + (long long)B * 2 * R0_MAX_SLABS * C, st);
     R2Args a2;
     a2.stats = stats; a2.ll = ll; a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha; a2.inv_temp = 1.f / temperature;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.w_min = 0.f; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
@@ -204,6 +233,11 @@ extern "C" int ym_pixel_router(const void* x, int ldx, int B, int H, int W, int 
     int Hp, Wp, eff;
     pooled_dims(H, W, pool, &Hp, &Wp, &eff);
     const long long N = (long long)Hp * Wp;
+    {
+        int S1, PS1, S2, PS2;
+        r1_geom((int)N, C, &S1, &PS1, &S2, &PS2);
+        YM_CHECK_ARG(r1b_smem_floats(C, R, PS2) <= 12288 && r1a_smem_floats(C, NTHR) <= 12288, "%s: the local stream does not fit 48 KB of shared memory", "ym_pixel_router");
+    }
     float* stats = scratch;
     float* pooled = stats + (long long)B * 2 * C;
     float* t1 = pooled + (long long)B * N * C;
@@ -219,7 +253,7 @@ extern "C" int ym_pixel_router(const void* x, int ldx, int B, int H, int W, int 
     a1.pooled = pooled; a1.t1 = t1; a1.t2 = t2; a1.Hp = Hp; a1.Wp = Wp; a1.C = C; a1.R = R; a1.E = E; a1.G1 = G1; a1.G2 = G2;
     a1.eps = gn_eps; a1.dw = dw; a1.g1w = gn1_w; a1.g1b = gn1_b; a1.pw1 = pw1; a1.g2w = gn2_w; a1.g2b = gn2_b; a1.pw2 = pw2;
     a1.b2 = b2; a1.ll = ll; a1.pixel_softmax = 1; a1.inv_temp = 1.f / temperature;
-    YM_LAUNCH(gate_r1_kernel, B, NTHR, r1_smem_floats(R, E, NTHR) * sizeof(float), st, a1);
+    launch_r1(a1, B, part + (long long)B * 2 * R0_MAX_SLABS * C, st);
     R2Args a2;
     a2.stats = stats; a2.ll = ll; a2.wg = nullptr; a2.wc = nullptr; a2.bc = 0.f; a2.alpha = 0.f; a2.inv_temp = 1.f;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 2; a2.w_min = w_min; a2.cx = nullptr; a2.w = w_out; a2.probs = probs_out;

@@ -176,35 +176,6 @@ YM_HD void r0m_phase(const R0Args& a, int img, int tid, int nthr) {
     }
 }
 
-// GroupNorm statistics of a [N][Cc] fp32 map in two passes; element e belongs to group (e % Cc) / cpg.
-// pass 0: per-thread partial sums -> part[tid*MAXG + g];   pass 1: partial sums of (v - mean[g])^2.
-YM_HD void gn_partials(const float* t, int N, int Cc, int cpg, const float* mean, int tid, int nthr, float* part) {
-    float acc[MAXG];
-#pragma unroll
-    for (int g = 0; g < MAXG; ++g) acc[g] = 0.f;
-    const int n = N * Cc;
-    for (int e = tid; e < n; e += nthr) {
-        const int g = (e % Cc) / cpg;
-        float v = t[e];
-        if (mean) {
-            float m = 0.f;
-#pragma unroll
-            for (int gg = 0; gg < MAXG; ++gg) m = g == gg ? mean[gg] : m;
-            v = (v - m) * (v - m);
-        }
-#pragma unroll
-        for (int gg = 0; gg < MAXG; ++gg) acc[gg] += g == gg ? v : 0.f;
-    }
-#pragma unroll
-    for (int g = 0; g < MAXG; ++g) part[tid * MAXG + g] = acc[g];
-}
-// Fixed-order reduction of the partials by thread g: returns sum / count.
-YM_HD float gn_reduce(const float* part, int g, int nthr, float count) {
-    float s = 0.f;
-    for (int t = 0; t < nthr; ++t) s += part[t * MAXG + g];
-    return s / count;
-}
-
 // --------------------------------------------------------------------------------------------------------------------
 // R1: local stream on the pooled map (gated.py:109-118,144-145): dw3x3 -> GN -> SiLU -> 1x1 -> GN -> SiLU -> 1x1 + bias -> mean.
 struct R1Args {
@@ -220,68 +191,176 @@ struct R1Args {
     float* ll;             // [B][E] local logits (pixel_softmax: the spatial mean of the per-pixel expert probabilities)
     int pixel_softmax;     // 1: UltraEfficientRouter routers.py:104-118 - per-pixel clamp(+-30) / T -> softmax over experts, THEN the mean
     float inv_temp;
+    float *p1, *p2;        // GroupNorm slab partials [B][S1][2*G1], [B][S2][2*G2]: slab mean | slab M2 per group
+    int S1, PS1, S2, PS2;  // pixel slabs of the depthwise kernel / of the 1x1 kernel, pixels per slab
 };
-constexpr int R1_PHASES = 10;
 constexpr int MAXR = 64;       // reduced channels of the local stream (max(C / 16, 4))
-YM_HD int r1_part_floats(int E, int nthr) { return nthr * (E > MAXG ? E : MAXG); }      // per-thread partials: GN groups, or experts
+constexpr int R1A_PHASES = 6, R1B_PHASES = 7;
+// Slab geometry of the local stream: ~16 pixels per depthwise CTA (at most 32 slabs), and for the 1x1 as many pixels as keep the
+// activated [pixels][C+1] tile within 32 KB of shared memory (at most 32).
+YM_HD void r1_geom(int N, int C, int* S1, int* PS1, int* S2, int* PS2) {
+    int want = (N + 15) / 16;
+    want = want < 1 ? 1 : (want > 32 ? 32 : want);
+    *PS1 = (N + want - 1) / want;
+    *S1 = (N + *PS1 - 1) / *PS1;
+    int ps = 8192 / (C + 1);
+    ps = ps < 1 ? 1 : (ps > 32 ? 32 : ps);
+    ps = ps > N ? N : ps;
+    *PS2 = ps;
+    *S2 = (N + ps - 1) / ps;
+}
+YM_HD int r1a_smem_floats(int C, int nthr) { return col_lane_floats(C, nthr) + C + MAXG; }
+YM_HD int r1b_smem_floats(int C, int R, int PS2) { return PS2 * (C + 1) + PS2 * R + R + 3 * MAXG; }
+YM_HD int r1_part_floats(int E, int nthr) { return nthr * (E > MAXG ? E : MAXG); }      // per-thread partials per expert (pixel softmax)
 YM_HD int r1_smem_floats(int R, int E, int nthr) { return r1_part_floats(E, nthr) + 2 * MAXG + col_lane_floats(R, nthr); }
 
-YM_HD void r1_phase(int ph, const R1Args& a, int img, int tid, int nthr, float* sm) {
-    const int N = a.Hp * a.Wp, C = a.C, R = a.R;
+// Slab partials [S][2G] of group g merged in slab order (Chan): slab s holds min(PS, N - s*PS) pixels x cpg channels.
+YM_HD void slab_merge(const float* part, int S, int G, int g, int N, int PS, int cpg, float* mean, float* var) {
+    float cnt = 0.f, mu = 0.f, m2 = 0.f;
+    for (int s = 0; s < S; ++s) {
+        const int n = N - s * PS < PS ? N - s * PS : PS;
+        const float ns = (float)n * cpg, tot = cnt + ns, delta = part[s * 2 * G + g] - mu;
+        mu += delta * (ns / tot);
+        m2 += part[s * 2 * G + G + g] + delta * delta * (cnt * ns / tot);
+        cnt = tot;
+    }
+    *mean = mu;
+    *var = m2 / cnt;
+}
+
+// R1a, CTA (slab, image): depthwise 3x3 (zero padding) of the slab's pixels -> t1, and the slab's GroupNorm-1 partials.
+YM_HD void r1a_phase(int ph, const R1Args& a, int img, int slab, int tid, int nthr, float* sm) {
+    const int N = a.Hp * a.Wp, C = a.C, cpg = C / a.G1;
+    const int p0 = slab * a.PS1, p1 = p0 + a.PS1 < N ? p0 + a.PS1 : N, n = p1 - p0;
     const float* src = a.pooled + (long long)img * N * C;
     float* t1 = a.t1 + (long long)img * N * C;
-    float* t2 = a.t2 + (long long)img * N * R;
-    float* part = sm;
-    float* mean = sm + r1_part_floats(a.E, nthr);
-    float* rstd = mean + MAXG;
-    const int cpg1 = C / a.G1, cpg2 = R / a.G2;
-    switch (ph) {
-        case 0: {   // depthwise 3x3, zero padding
-            for (int e = tid; e < N * C; e += nthr) {
-                const int c = e % C, p = e / C, y = p / a.Wp, x = p % a.Wp;
-                float s = 0.f;
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int yy = y + ky - 1;
-                    if (yy < 0 || yy >= a.Hp) continue;
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const int xx = x + kx - 1;
-                        if (xx < 0 || xx >= a.Wp) continue;
-                        s += a.dw[c * 9 + ky * 3 + kx] * src[(long long)(yy * a.Wp + xx) * C + c];
+    float* part = sm;                                  // [lanes][C]
+    float* chs = sm + col_lane_floats(C, nthr);        // [C]
+    float* mean = chs + C;                             // [G1]
+    float* out = a.p1 + ((long long)img * a.S1 + slab) * 2 * a.G1;
+    const ColLane cl(C, tid, nthr);
+    if (ph == 0 || ph == 3) {
+        if (!cl.active()) return;
+        for (int c = cl.c0; c < C; c += cl.Cg) {
+            float acc = 0.f;
+            if (ph == 0) {
+                float w[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) w[k] = a.dw[c * 9 + k];
+                for (int p = p0 + cl.pl; p < p1; p += cl.NL) {
+                    const int y = p / a.Wp, x = p % a.Wp;
+                    float s = 0.f;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int yy = y + ky - 1;
+                        if (yy < 0 || yy >= a.Hp) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int xx = x + kx - 1;
+                            if (xx < 0 || xx >= a.Wp) continue;
+                            s += w[ky * 3 + kx] * src[(long long)(yy * a.Wp + xx) * C + c];
+                        }
                     }
+                    t1[(long long)p * C + c] = s;
+                    acc += s;
                 }
-                t1[e] = s;
+            } else {
+                const float m = mean[c / cpg];
+                for (int p = p0 + cl.pl; p < p1; p += cl.NL) {
+                    const float d = t1[(long long)p * C + c] - m;
+                    acc += d * d;
+                }
+            }
+            part[cl.pl * C + c] = acc;
+        }
+    } else if (ph == 1 || ph == 4) {
+        for (int c = tid; c < C; c += nthr) {
+            float s = 0.f;
+            for (int l = 0; l < cl.NL; ++l) s += part[l * C + c];
+            chs[c] = s;
+        }
+    } else if (tid < a.G1) {
+        float s = 0.f;
+        for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) s += chs[c];
+        if (ph == 2) {
+            s /= (float)n * cpg;
+            mean[tid] = s;
+            out[tid] = s;
+        } else {
+            out[a.G1 + tid] = s;
+        }
+    }
+}
+
+// R1b, CTA (slab, image): GroupNorm-1 (merged partials) + SiLU of the slab's pixels into a shared tile, the 1x1 C -> R from the tile
+// -> t2, and the slab's GroupNorm-2 partials.  Lanes of a warp walk the pixels of one output channel: the weight row is a broadcast,
+// the tile rows are one bank apart (pitch C + 1).
+YM_HD void r1b_phase(int ph, const R1Args& a, int img, int slab, int tid, int nthr, float* sm) {
+    const int N = a.Hp * a.Wp, C = a.C, R = a.R, cpg1 = C / a.G1, cpg2 = R / a.G2, TP = C + 1;
+    const int p0 = slab * a.PS2, p1 = p0 + a.PS2 < N ? p0 + a.PS2 : N, n = p1 - p0;
+    const float* t1 = a.t1 + ((long long)img * N + p0) * C;
+    float* t2 = a.t2 + ((long long)img * N + p0) * R;
+    float* tile = sm;                          // [PS2][C+1]
+    float* o2 = tile + a.PS2 * TP;             // [PS2][R]
+    float* chs = o2 + a.PS2 * R;               // [R]
+    float* mean1 = chs + R;
+    float* rstd1 = mean1 + MAXG;
+    float* mean2 = rstd1 + MAXG;
+    float* out = a.p2 + ((long long)img * a.S2 + slab) * 2 * a.G2;
+    switch (ph) {
+        case 0:
+            if (tid < a.G1) {
+                float mu, var;
+                slab_merge(a.p1 + (long long)img * a.S1 * 2 * a.G1, a.S1, a.G1, tid, N, a.PS1, cpg1, &mu, &var);
+                mean1[tid] = mu;
+                rstd1[tid] = 1.f / sqrtf(var + a.eps);
             }
             break;
-        }
-        case 1: gn_partials(t1, N, C, cpg1, nullptr, tid, nthr, part); break;
-        case 2: if (tid < a.G1) mean[tid] = gn_reduce(part, tid, nthr, (float)N * cpg1); break;
-        case 3: gn_partials(t1, N, C, cpg1, mean, tid, nthr, part); break;
-        case 4: if (tid < a.G1) rstd[tid] = 1.f / sqrtf(gn_reduce(part, tid, nthr, (float)N * cpg1) + a.eps); break;
-        case 5: {   // GN1 apply + SiLU in place, then nothing else reads the raw t1
-            for (int e = tid; e < N * C; e += nthr) {
-                const int c = e % C, g = c / cpg1;
-                t1[e] = silu_f32((t1[e] - mean[g]) * rstd[g] * a.g1w[c] + a.g1b[c]);
+        case 1:
+            for (int e = tid; e < n * C; e += nthr) {
+                const int c = e % C, p = e / C, g = c / cpg1;
+                tile[p * TP + c] = silu_f32((t1[e] - mean1[g]) * rstd1[g] * a.g1w[c] + a.g1b[c]);
             }
             break;
-        }
-        case 6: {   // 1x1: C -> R
-            for (int e = tid; e < N * R; e += nthr) {
-                const int r = e % R, p = e / R;
-                const float* row = t1 + (long long)p * C;
+        case 2:
+            for (int e = tid; e < n * R; e += nthr) {
+                const int p = e % n, r = e / n;
+                const float* row = tile + p * TP;
                 const float* w = a.pw1 + (long long)r * C;
                 float s = 0.f;
                 for (int c = 0; c < C; ++c) s += w[c] * row[c];
-                t2[e] = s;
+                t2[(long long)p * R + r] = s;
+                o2[p * R + r] = s;
             }
             break;
-        }
-        case 7: gn_partials(t2, N, R, cpg2, nullptr, tid, nthr, part); break;
-        case 8: if (tid < a.G2) mean[tid] = gn_reduce(part, tid, nthr, (float)N * cpg2); break;
-        case 9: gn_partials(t2, N, R, cpg2, mean, tid, nthr, part); break;
-        default: break;
+        case 3:
+        case 5:
+            for (int r = tid; r < R; r += nthr) {
+                const float m = ph == 5 ? mean2[r / cpg2] : 0.f;
+                float s = 0.f;
+                for (int p = 0; p < n; ++p) {
+                    const float d = o2[p * R + r] - m;
+                    s += ph == 5 ? d * d : d;
+                }
+                chs[r] = s;
+            }
+            break;
+        default:   // 4: slab mean of group tid, 6: slab M2
+            if (tid < a.G2) {
+                float s = 0.f;
+                for (int r = tid * cpg2; r < (tid + 1) * cpg2; ++r) s += chs[r];
+                if (ph == 4) {
+                    s /= (float)n * cpg2;
+                    mean2[tid] = s;
+                    out[tid] = s;
+                } else {
+                    out[a.G2 + tid] = s;
+                }
+            }
+            break;
     }
 }
-// The tail needs two more barriers; kept separate so that R1_PHASES stays a plain loop bound.
+// R1c, CTA (image): GroupNorm-2 from the merged partials, SiLU, the last 1x1 and the spatial mean (or the per-pixel softmax variant).
 constexpr int R1_TAIL_PHASES = 3;
 YM_HD void r1_tail_phase(int ph, const R1Args& a, int img, int tid, int nthr, float* sm) {
     const int N = a.Hp * a.Wp, R = a.R;
@@ -292,7 +371,12 @@ YM_HD void r1_tail_phase(int ph, const R1Args& a, int img, int tid, int nthr, fl
     float* colp = rstd + MAXG;
     const int cpg2 = R / a.G2;
     if (ph == 0) {
-        if (tid < a.G2) rstd[tid] = 1.f / sqrtf(gn_reduce(part, tid, nthr, (float)N * cpg2) + a.eps);
+        if (tid < a.G2) {
+            float mu, var;
+            slab_merge(a.p2 + (long long)img * a.S2 * 2 * a.G2, a.S2, a.G2, tid, N, a.PS2, cpg2, &mu, &var);
+            mean[tid] = mu;
+            rstd[tid] = 1.f / sqrtf(var + a.eps);
+        }
     } else if (ph == 1 && a.pixel_softmax) {   // per pixel: SiLU(GN2) -> 1x1 + bias -> clamp -> / T -> softmax; per-thread sums per expert
         float acc[MAXE];
         for (int e = 0; e < a.E; ++e) acc[e] = 0.f;

@@ -576,7 +576,7 @@ def gate_router(x, pk, topk):
                                     None if ln is None else ln[0].data_ptr(), None if ln is None else ln[1].data_ptr(),
                                     0.0 if ln is None else ln[2], None if prior is None else prior.data_ptr(),
                                     scratch.data_ptr(), w.data_ptr(), idx.data_ptr(), probs.data_ptr(), _stream()), "ym_gate_router")
-    _count(4)
+    _count(6)
     return idx, w, probs
 
 
@@ -679,7 +679,7 @@ def pixel_router(x, pk, topk, w_min=0.01):
                                      pk["gn1_b"].data_ptr(), pk["G1"], pk["pw1"].data_ptr(), R, pk["gn2_w"].data_ptr(), pk["gn2_b"].data_ptr(),
                                      pk["G2"], pk["pw2"].data_ptr(), pk["b2"].data_ptr(), E, pk["eps"], pk["temperature"], float(w_min), topk,
                                      scratch.data_ptr(), w.data_ptr(), idx.data_ptr(), probs.data_ptr(), _stream()), "ym_pixel_router")
-    _count(4)
+    _count(6)
     return idx, w, probs
 
 
