@@ -191,6 +191,17 @@ def test_slab_statistics_merge(emu):
     rw, ri, rp = O.zero_cost_router({"m." + k_: v.float() for k_, v in sd.items()}, "m.routing", xd.float(), 2, 2.0)
     assert torch.equal(idx.long(), ri)
     torch.testing.assert_close(probs, rp, atol=5e-6, rtol=2e-4)
+    from yolo_master_b200.nn.modules.gated import VisualEnhancedAdaptiveGateMoE
+    mv = VisualEnhancedAdaptiveGateMoE(128, 128, 8, 2, 0.5)
+    sdv = mv.state_dict()
+    fill_state_dict_(sdv, 11)
+    mv.load_state_dict(sdv)
+    sdm = {"m." + k_: v.float() for k_, v in sdv.items()}
+    xv = (torch.randn((2, 64, 40, 44), generator=g) + 1.5).half()                 # pooled 10 x 11: depthwise slabs 7 x 16 (ragged), 1x1 slabs 4 x 32
+    idx, w, probs = ops.gate_router(xv.permute(0, 2, 3, 1).contiguous(), mv.eval().get_pack()["router"], 2)
+    rw, ri, rp = O.dual_stream_gate_router(sdm, "m.routing", xv.float(), 2, 1.2)
+    assert torch.equal(idx.long(), ri)
+    torch.testing.assert_close(probs, rp, atol=5e-6, rtol=2e-4)
     B, H, W, E, oc, G = 2, 27, 23, 4, 32, 8                                        # 621 pixels -> 3 slabs of 207
     buf = (torch.randn((B, H, W, E * oc), generator=g) * 0.5 + 4.0).half()
     idx = torch.tensor([[2, 0], [1, 3]], dtype=torch.int32)
