@@ -28,7 +28,7 @@ static void host_r1(R1Args& a, int B, std::vector<float>& p12) {
             for (int t = 0; t < NTHR; ++t) r1_tail_phase(ph, a, b, t, NTHR, sm.data());
 }
 
-// gate_r0_kernel (grid = slabs x images) followed by gate_r0m_kernel (grid = images), as launch_r0 in gated.cu issues them.
+// gate_r0_kernel (grid = slabs x images), as launch_r0 in gated.cu issues it.
 static void host_r0(R0Args& a, int B, std::vector<float>& part, float* sm) {
     r0_slabs(a.Hp, &a.S, &a.PR);
     part.assign((size_t)B * a.S * 2 * a.C, 0.f);
@@ -37,8 +37,21 @@ static void host_r0(R0Args& a, int B, std::vector<float>& part, float* sm) {
         for (int s = 0; s < a.S; ++s)
             for (int ph = 0; ph < R0_PHASES; ++ph)
                 for (int t = 0; t < NTHR; ++t) r0_phase(ph, a, b, s, t, NTHR, sm);
-    for (int b = 0; b < B; ++b)
-        for (int t = 0; t < NTHR; ++t) r0m_phase(a, b, t, NTHR);
+}
+
+// gate_r0m_kernel (merge + global stream, grid = images) and gate_r2_kernel (one CTA), as launch_finish in gated.cu issues them.
+static void host_finish(const R0Args& a0, R2Args& a2, std::vector<float>& gl) {
+    gl.assign((size_t)a2.B * a2.E, 0.f);
+    a2.gl = gl.data();
+    std::vector<float> sm(g_smem_floats(a2.C, a2.E, NTHR) + 16);
+    if (a2.zero_cost != 2)
+        for (int b = 0; b < a2.B; ++b) {
+            for (int t = 0; t < NTHR; ++t) r0m_phase(a0, b, t, NTHR);
+            for (int ph = 0; ph < G_PHASES; ++ph)
+                for (int t = 0; t < NTHR; ++t) g_phase(ph, a2, b, t, NTHR, sm.data());
+        }
+    for (int ph = 0; ph < R2_PHASES; ++ph)
+        for (int t = 0; t < NTHR; ++t) r2_phase(ph, a2, t, NTHR, sm.data());
 }
 
 extern "C" int host_gate_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* global_fc,
@@ -68,8 +81,8 @@ extern "C" int host_gate_router(const void* x, int ldx, int B, int H, int W, int
     a2.stats = stats.data(); a2.ll = ll.data(); a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha;
     a2.inv_temp = 1.f / temperature; a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.w_min = 0.f; a2.cx = cx.data(); a2.w = w_out;
     a2.probs = probs_out; a2.idx = idx_out; a2.ln_w = ln_w; a2.ln_b = ln_b; a2.ln_eps = ln_eps; a2.prior = prior;
-    for (int ph = 0; ph < R2_PHASES; ++ph)
-        for (int t = 0; t < NTHR; ++t) r2_phase(ph, a2, t, NTHR, sm.data());
+    std::vector<float> gl;
+    host_finish(a0, a2, gl);
     return 0;
 }
 
@@ -97,8 +110,8 @@ extern "C" int host_pixel_router(const void* x, int ldx, int B, int H, int W, in
     a2.stats = stats.data(); a2.ll = ll.data(); a2.wg = nullptr; a2.wc = nullptr; a2.bc = 0.f; a2.alpha = 0.f; a2.inv_temp = 1.f;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 2; a2.w_min = w_min; a2.cx = nullptr; a2.w = w_out; a2.probs = probs_out;
     a2.idx = idx_out; a2.ln_w = nullptr; a2.ln_b = nullptr; a2.ln_eps = 0.f; a2.prior = nullptr;
-    for (int ph = 0; ph < R2_PHASES; ++ph)
-        for (int t = 0; t < NTHR; ++t) r2_phase(ph, a2, t, NTHR, sm.data());
+    std::vector<float> gl;
+    host_finish(a0, a2, gl);
     return 0;
 }
 
@@ -114,8 +127,8 @@ extern "C" int host_zero_cost_router(const void* x, int ldx, int B, int H, int W
     a2.stats = stats.data(); a2.ll = nullptr; a2.wg = fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = 1.f; a2.inv_temp = 1.f / temperature;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.w_min = 0.f; a2.cx = cx.data(); a2.w = w_out; a2.probs = probs_out;
     a2.idx = idx_out; a2.ln_w = nullptr; a2.ln_b = nullptr; a2.ln_eps = 0.f; a2.prior = nullptr;
-    for (int ph = 0; ph < R2_PHASES; ++ph)
-        for (int t = 0; t < NTHR; ++t) r2_phase(ph, a2, t, NTHR, sm.data());
+    std::vector<float> gl;
+    host_finish(a0, a2, gl);
     return 0;
 }
 

@@ -19,14 +19,21 @@ __global__ void __launch_bounds__(NTHR) gate_r0_kernel(const R0Args a) {   // gr
     }
 }
 
-__global__ void __launch_bounds__(NTHR) gate_r0m_kernel(const R0Args a) { r0m_phase(a, blockIdx.x, threadIdx.x, NTHR); }
+__global__ void __launch_bounds__(NTHR) gate_r0m_kernel(const R0Args a, const R2Args r) {   // grid = B: merge, then the global stream
+    YM_DYN_SMEM(float, sm);
+    r0m_phase(a, blockIdx.x, threadIdx.x, NTHR);
+    __syncthreads();
+    for (int ph = 0; ph < G_PHASES; ++ph) {
+        g_phase(ph, r, blockIdx.x, threadIdx.x, NTHR, sm);
+        __syncthreads();
+    }
+}
 
-// Statistics + pooled map of every image: slab kernel, then the per-image merge.
+// Slab statistics + pooled map of every image.
 static void launch_r0(R0Args& a, int B, float* part, cudaStream_t st) {
     a.part = part;
     r0_slabs(a.Hp, &a.S, &a.PR);
     YM_LAUNCH(gate_r0_kernel, dim3(a.S, B), NTHR, r0_smem_floats(a.C, NTHR) * sizeof(float), st, a);
-    YM_LAUNCH(gate_r0m_kernel, B, NTHR, 0, st, a);
 }
 
 __global__ void __launch_bounds__(NTHR) gate_r1a_kernel(const R1Args a) {   // grid = (S1, B)
@@ -69,6 +76,12 @@ __global__ void __launch_bounds__(NTHR) gate_r2_kernel(const R2Args a) {
         r2_phase(ph, a, threadIdx.x, NTHR, sm);
         __syncthreads();
     }
+}
+
+// Per image: merge of the slab statistics, global stream logits and complexity; then the batch-level finish.
+static void launch_finish(const R0Args& a0, const R2Args& a2, cudaStream_t st) {
+    if (a2.zero_cost != 2) YM_LAUNCH(gate_r0m_kernel, a2.B, NTHR, g_smem_floats(a2.C, a2.E, NTHR) * sizeof(float), st, a0, a2);
+    YM_LAUNCH(gate_r2_kernel, 1, NTHR, 0, st, a2);
 }
 
 __global__ void __launch_bounds__(NTHR) fc_gate_kernel(const FcArgs a) {
@@ -170,7 +183,7 @@ extern "C" long long ym_gate_router_scratch_floats(int B, int H, int W, int C, i
     const long long N = (long long)Hp * Wp;
     int S1, PS1, S2, PS2;
     r1_geom((int)N, C, &S1, &PS1, &S2, &PS2);
-    return (long long)B * (2LL * C + N * C * 2 + N * R + E + 1 + 2LL * R0_MAX_SLABS * C + 2LL * MAXG * (S1 + S2));
+    return (long long)B * (2LL * C + N * C * 2 + N * R + E + 1 + 2LL * R0_MAX_SLABS * C + 2LL * MAXG * (S1 + S2) + E);
 }
 
 extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* global_fc,
@@ -214,8 +227,9 @@ extern "C" int ym_gate_router(const void* x, int ldx, int B, int H, int W, int C
     R2Args a2;
     a2.stats = stats; a2.ll = ll; a2.wg = global_fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = alpha; a2.inv_temp = 1.f / temperature;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 0; a2.w_min = 0.f; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
+    a2.gl = a1.p2 + (long long)B * a1.S2 * 2 * MAXG;
     a2.ln_w = ln_w; a2.ln_b = ln_b; a2.ln_eps = ln_eps; a2.prior = prior;
-    YM_LAUNCH(gate_r2_kernel, 1, NTHR, 0, st, a2);
+    launch_finish(a0, a2, st);
     YM_CHECK_LAUNCH("gate_router");
     return YM_OK;
 }
@@ -257,13 +271,14 @@ extern "C" int ym_pixel_router(const void* x, int ldx, int B, int H, int W, int 
     R2Args a2;
     a2.stats = stats; a2.ll = ll; a2.wg = nullptr; a2.wc = nullptr; a2.bc = 0.f; a2.alpha = 0.f; a2.inv_temp = 1.f;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 2; a2.w_min = w_min; a2.cx = nullptr; a2.w = w_out; a2.probs = probs_out;
+    a2.gl = nullptr;
     a2.idx = idx_out; a2.ln_w = nullptr; a2.ln_b = nullptr; a2.ln_eps = 0.f; a2.prior = nullptr;
-    YM_LAUNCH(gate_r2_kernel, 1, NTHR, 0, st, a2);
+    launch_finish(a0, a2, st);
     YM_CHECK_LAUNCH("pixel_router");
     return YM_OK;
 }
 
-extern "C" long long ym_zero_cost_router_scratch_floats(int B, int C) { return (long long)B * (2LL * C + 1 + 2LL * R0_MAX_SLABS * C); }
+extern "C" long long ym_zero_cost_router_scratch_floats(int B, int C) { return (long long)B * (2LL * C + 1 + 2LL * R0_MAX_SLABS * C + MAXE); }
 
 extern "C" int ym_zero_cost_router(const void* x, int ldx, int B, int H, int W, int C, const float* fc, int E, float temperature,
                                    const float* cx_w, float cx_b, int topk, float* scratch, float* w_out, int* idx_out,
@@ -284,8 +299,9 @@ extern "C" int ym_zero_cost_router(const void* x, int ldx, int B, int H, int W, 
     R2Args a2;
     a2.stats = stats; a2.ll = nullptr; a2.wg = fc; a2.wc = cx_w; a2.bc = cx_b; a2.alpha = 1.f; a2.inv_temp = 1.f / temperature;
     a2.B = B; a2.C = C; a2.E = E; a2.topk = topk; a2.zero_cost = 1; a2.w_min = 0.f; a2.cx = cx; a2.w = w_out; a2.probs = probs_out; a2.idx = idx_out;
+    a2.gl = part + (long long)B * 2 * R0_MAX_SLABS * C;
     a2.ln_w = nullptr; a2.ln_b = nullptr; a2.ln_eps = 0.f; a2.prior = nullptr;
-    YM_LAUNCH(gate_r2_kernel, 1, NTHR, 0, st, a2);
+    launch_finish(a0, a2, st);
     YM_CHECK_LAUNCH("zero_cost_router");
     return YM_OK;
 }

@@ -449,22 +449,84 @@ struct R2Args {
                           // 2: `ll` already holds expert probabilities (UltraEfficientRouter): top-k, w / max(sum, 1e-6), no complexity,
                           //    weights <= w_min zeroed (BatchedExpertComputation's eval threshold, moe/utils.py:172-173)
     float w_min;
-    float* cx;            // scratch [B]
+    float* cx;            // scratch [B]: per-image complexity, written by g_phase
+    float* gl;            // scratch [B][E]: global-stream logits, written by g_phase
     float *w, *probs;     // [B][topk], [B][E] (probs nullable)
     int* idx;             // [B][topk]
 };
-constexpr int R2_PHASES = 3;
+constexpr int R2_PHASES = 2;
 YM_HD int r2_smem_floats() { return 4; }
+
+// G, CTA (image), runs behind the statistics merge in the same kernel: the optional LayerNorm of the [mean | std] row, the global
+// stream's E dot products of length 2C and the complexity estimator's dot product of length C.  One output row per warp-sized group
+// of 32 threads (coalesced weight rows), partials reduced through shared memory in lane order.
+constexpr int G_PHASES = 7;
+YM_HD int g_smem_floats(int C, int E, int nthr) { return nthr + 2 + 2 * C + (E + 1) * 32; }
+
+YM_HD void g_phase(int ph, const R2Args& a, int img, int tid, int nthr, float* sm) {
+    const int C2 = 2 * a.C;
+    const float* st = a.stats + (long long)img * C2;
+    float* part = sm;              // [nthr]
+    float* lnp = sm + nthr;        // mean, rstd of the row
+    float* row = lnp + 2;          // [2C] the (normalised) statistics
+    float* rowp = row + C2;        // [(E+1)][32]
+    const bool ln = a.ln_w != nullptr;
+    switch (ph) {
+        case 0:
+        case 2: {
+            if (!ln) return;
+            const float m = ph == 2 ? lnp[0] : 0.f;
+            float s = 0.f;
+            for (int j = tid; j < C2; j += nthr) {
+                const float d = st[j] - m;
+                s += ph == 2 ? d * d : d;
+            }
+            part[tid] = s;
+            break;
+        }
+        case 1:
+        case 3: {
+            if (!ln || tid != 0) return;
+            float s = 0.f;
+            for (int t = 0; t < nthr; ++t) s += part[t];
+            s /= (float)C2;
+            if (ph == 1) lnp[0] = s;
+            else lnp[1] = 1.f / sqrtf(s + a.ln_eps);
+            break;
+        }
+        case 4:
+            for (int j = tid; j < C2; j += nthr) row[j] = ln ? (st[j] - lnp[0]) * lnp[1] * a.ln_w[j] + a.ln_b[j] : st[j];
+            break;
+        case 5: {
+            const int lane = tid & 31, nrow = nthr >> 5;
+            for (int r = tid >> 5; r <= a.E; r += nrow) {
+                float s = 0.f;
+                if (r < a.E) {
+                    if (a.wg)
+                        for (int j = lane; j < C2; j += 32) s += a.wg[(long long)r * C2 + j] * row[j];
+                } else if (a.wc) {
+                    for (int c = lane; c < a.C; c += 32) s += a.wc[c] * st[c];
+                }
+                rowp[r * 32 + lane] = s;
+            }
+            break;
+        }
+        default: {
+            if (tid > a.E) return;
+            float s = 0.f;
+            for (int l = 0; l < 32; ++l) s += rowp[tid * 32 + l];
+            if (tid < a.E) {
+                if (a.wg) a.gl[(long long)img * a.E + tid] = s;
+            } else if (a.wc) {
+                a.cx[img] = sigmoid_f(a.bc + s);
+            }
+            break;
+        }
+    }
+}
 
 YM_HD void r2_phase(int ph, const R2Args& a, int tid, int nthr, float* sm) {
     if (ph == 0) {
-        if (a.zero_cost == 2) return;
-        for (int b = tid; b < a.B; b += nthr) {
-            float s = a.bc;
-            for (int c = 0; c < a.C; ++c) s += a.wc[c] * a.stats[(long long)b * 2 * a.C + c];
-            a.cx[b] = sigmoid_f(s);
-        }
-    } else if (ph == 1) {
         if (tid != 0 || a.zero_cost == 2) return;
         float s = 0.f;
         for (int b = 0; b < a.B; ++b) s += a.cx[b];
@@ -502,22 +564,8 @@ YM_HD void r2_phase(int ph, const R2Args& a, int tid, int nthr, float* sm) {
                 continue;
             }
             float mx = -3.0e38f;
-            const float* st = a.stats + (long long)b * 2 * a.C;
-            float lm = 0.f, lr = 1.f;
-            if (a.ln_w) {                                             // LayerNorm statistics of this image's [mean | std] row
-                for (int j = 0; j < 2 * a.C; ++j) lm += st[j];
-                lm /= (float)(2 * a.C);
-                float v = 0.f;
-                for (int j = 0; j < 2 * a.C; ++j) v += (st[j] - lm) * (st[j] - lm);
-                lr = 1.f / sqrtf(v / (float)(2 * a.C) + a.ln_eps);
-            }
             for (int e = 0; e < a.E; ++e) {
-                float gl = 0.f;
-                const float* w = a.wg + (long long)e * 2 * a.C;
-                if (a.ln_w)
-                    for (int j = 0; j < 2 * a.C; ++j) gl += w[j] * ((st[j] - lm) * lr * a.ln_w[j] + a.ln_b[j]);
-                else
-                    for (int j = 0; j < 2 * a.C; ++j) gl += w[j] * st[j];
+                const float gl = a.gl[(long long)b * a.E + e];
                 float l = a.zero_cost ? gl : a.alpha * gl + (1.f - a.alpha) * a.ll[(long long)b * a.E + e];
                 if (a.prior) l += a.prior[e];
                 if (!a.zero_cost) {
