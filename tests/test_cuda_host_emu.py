@@ -285,5 +285,5 @@ def test_global_average_pool_kernel(emu):
     ops.gap(x, out=wide[..., 64:96])
     torch.testing.assert_close(wide[..., 64:96].float(), x.float().mean((1, 2), keepdim=True), atol=1e-3, rtol=1e-3)
     assert not wide[..., :64].any()
-    with pytest.raises(RuntimeError, match="multiple of 8"):
+    with pytest.raises(RuntimeError, match="multiples of 8"):
         ops.gap(torch.zeros((1, 2, 2, 12), dtype=torch.float16))

@@ -320,7 +320,7 @@ extern "C" int ym_fc_gate(const void* v, int ldv, int B, int Cin, const float* w
 
 extern "C" int ym_gap_nhwc(const void* x, int ldx, int B, int HW, int C, void* out, int ldo, void* stream) {
     YM_CHECK_ARG(x && out, "ym_gap_nhwc: null pointer");
-    YM_CHECK_ARG(B > 0 && B <= 65535 && HW > 0 && C > 0 && C % 8 == 0 && ldx >= C && ldo >= C, "ym_gap_nhwc: bad sizes (C multiple of 8)");
+    YM_CHECK_ARG(B > 0 && B <= 65535 && HW > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldx >= C && ldo >= C, "ym_gap_nhwc: bad sizes (C and the pitch multiples of 8)");
     GapArgs a;
     a.x = (const __half*)x; a.ldx = ldx; a.HW = HW; a.C = C; a.out = (__half*)out; a.ldo = ldo;
     YM_LAUNCH(gap_kernel, dim3((C + GAP_SLAB - 1) / GAP_SLAB, B), NTHR, gap_smem_floats(NTHR) * sizeof(float), (cudaStream_t)stream, a);

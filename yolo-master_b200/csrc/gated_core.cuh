@@ -679,10 +679,11 @@ YM_HD void gap_phase(int ph, const GapArgs& a, int img, int slab, int tid, int n
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
         if (c < a.C) {
             const ym_half* base = a.x + (long long)img * a.HW * a.ldx + c;
+            float v[8];
             for (int p = lane; p < a.HW; p += nl) {
-                const ym_half* v = base + (long long)p * a.ldx;
+                ym_load8(base + (long long)p * a.ldx, v);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += ym_h2f(v[j]);
+                for (int j = 0; j < 8; ++j) acc[j] += v[j];
             }
         }
 #pragma unroll

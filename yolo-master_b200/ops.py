@@ -679,7 +679,7 @@ def pixel_router(x, pk, topk, w_min=0.01):
                                      pk["gn1_b"].data_ptr(), pk["G1"], pk["pw1"].data_ptr(), R, pk["gn2_w"].data_ptr(), pk["gn2_b"].data_ptr(),
                                      pk["G2"], pk["pw2"].data_ptr(), pk["b2"].data_ptr(), E, pk["eps"], pk["temperature"], float(w_min), topk,
                                      scratch.data_ptr(), w.data_ptr(), idx.data_ptr(), probs.data_ptr(), _stream()), "ym_pixel_router")
-    _count(6)
+    _count(5)
     return idx, w, probs
 
 
