@@ -211,6 +211,27 @@ int ym_kpts_decode(int nl, const void* const* kpt, const int* hs, const int* ws,
 int ym_obb_finish(int nl, const void* const* angle, const int* hs, const int* ws, const float* strides, int B, int nc,
                   const float* yin, float* yout, void* stream);
 
+/* ---- Segment / OBB post-processing (csrc/postproc.cu) ------------------------------------------------
+ * ym_process_mask: ops.process_mask(protos, masks_in, bboxes, shape, upsample) ultralytics/utils/ops.py:500-528 (+ crop_mask :477-497)
+ *   for the detections of one image.  protos [nm][mh][mw] fp16 (proto_dtype 1) or fp32 (2); dets fp32 rows of pitch ld with the xyxy
+ *   box (in `shape` = (in_h, in_w) coordinates) at columns 0..3 and the nm mask coefficients from column coef_col (NMS rows: 6).
+ *   logits = coefficients @ prototypes (fp32), bilinear upsampling to (in_h, in_w) as F.interpolate(align_corners=False) when
+ *   upsample, crop x1 <= col < x2, y1 <= row < y2 (boxes scaled by (mw/in_w, mh/in_h) when not upsample), > 0.
+ *   out uint8 [n][in_h][in_w] (upsample) or [n][mh][mw].  scratch: ym_process_mask_scratch_bytes(n, mh, mw).  n == 0 is a no-op. */
+long long ym_process_mask_scratch_bytes(int n, int mh, int mw);
+int ym_process_mask(const void* protos, int proto_dtype, int nm, int mh, int mw, const float* dets, int ld, int n, int coef_col,
+                    int in_h, int in_w, int upsample, unsigned char* out, void* scratch, void* stream);
+
+/* ym_nms_rotated: non_max_suppression(..., rotated=True) ultralytics/utils/nms.py:13-171 - TorchNMS.fast_nms :193-242 with
+ *   batch_probiou utils/metrics.py:293-326: candidate j (score order, ties towards the lower anchor) survives iff no candidate i < j
+ *   has ProbIoU >= iou_thres; class offset cls * max_wh on the centre; the first max_nms candidates by score enter, the first max_det
+ *   survivors leave.  pred fp32 [B][4+nc+1][A] = xywh, class scores, angle (ym_obb_finish's output).
+ *   out fp32 [B][max_det][7] = x, y, w, h, conf, cls, angle; out_count int32 [B]; out_idx int32 [B][max_det] (-1 past the count).
+ *   scratch: ym_nms_rotated_scratch_bytes(B, A). */
+long long ym_nms_rotated_scratch_bytes(int B, int A);
+int ym_nms_rotated(const float* pred, int B, int nc, int A, float conf_thres, float iou_thres, int max_det, int max_nms, float max_wh,
+                   float* out, int* out_count, int* out_idx, void* scratch, void* stream);
+
 /* ---- Gated MoE family (VisualEnhancedAdaptiveGateMoE, nn/modules/moe/gated.py) ----------------------
  * ym_gate_router: DualStreamGateRouter.forward gated.py:129-151 (fp32 throughout, as the reference's FP32RouterMixin) followed by
  *   AdaptiveGateMoE._safe_complexity / _apply_complexity_gate gated.py:455-490.  x: fp16 [B][H*W][ldx] (the dynamic channel half).

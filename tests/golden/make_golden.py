@@ -13,6 +13,7 @@ import json
 import os
 import sys
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -239,6 +240,55 @@ def nms_golden():
     torch.save({"cases": cases}, f"{OUT}/nms.golden.pt")
 
 
+def synth_obb_predictions(B, nc, A, seed):
+    """Seeded (B, 4+nc+1, A) OBB-head style predictions: clustered xywh boxes, class scores, angle in [-pi/4, 3pi/4)."""
+    g = torch.Generator().manual_seed(seed)
+    pred = synth_predictions(B, nc, A, seed)
+    pred[:, 2:4] *= torch.exp(torch.randn((B, 2, A), generator=g) * 0.4)            # elongated boxes: the angle matters
+    ncl = max(A // 12, 1)
+    base = (torch.rand((B, ncl), generator=g) - 0.25) * torch.pi
+    which = torch.randint(0, ncl, (B, A), generator=g)
+    ang = torch.gather(base, 1, which) + torch.randn((B, A), generator=g) * 0.15
+    return torch.cat([pred, ang[:, None, :]], 1).contiguous()
+
+
+def postproc_golden():
+    """Reference ops.process_mask (both branches) and non_max_suppression(rotated=True) on seeded inputs (inputs stored)."""
+    from ultralytics.utils import ops
+    from ultralytics.utils.nms import non_max_suppression
+    masks = []
+    for seed, (nm, mh, mw, n, shape) in enumerate([(32, 80, 80, 7, (320, 320)), (32, 24, 40, 5, (96, 160)), (8, 20, 12, 9, (77, 50)),
+                                                    (32, 40, 40, 0, (160, 160)), (16, 28, 28, 17, (112, 112))]):
+        g = torch.Generator().manual_seed(900 + seed)
+        protos = (torch.randn((nm, mh, mw), generator=g) * 0.7).half().float()      # fp16-representable: the head emits fp16
+        for _ in range(2):                                                          # smooth, so that the masks have structure
+            protos = torch.nn.functional.avg_pool2d(protos[None], 3, 1, 1)[0]
+        protos = protos.half().float()
+        coef = torch.randn((n, nm), generator=g)
+        cxy = torch.rand((n, 2), generator=g) * torch.tensor([shape[1], shape[0]])
+        wh = torch.rand((n, 2), generator=g) * torch.tensor([shape[1], shape[0]]) * 0.6 + 2
+        boxes = torch.cat([cxy - wh / 2, cxy + wh / 2], 1)
+        if n:
+            boxes[0] = torch.tensor([-5.0, -3.0, shape[1] + 4.0, shape[0] + 9.0])   # a box past every edge
+        case = {"protos": protos, "coef": coef, "boxes": boxes, "shape": shape}
+        for up in (True, False):
+            m = ops.process_mask(protos.clone(), coef.clone(), boxes.clone(), shape, upsample=up)
+            assert m.dtype == torch.uint8 and int(m.max()) <= 1 if m.numel() else True
+            key = "up" if up else "native"                                          # 0 / 1 masks, stored as packed bits
+            case[key + "_shape"], case[key + "_bits"] = tuple(m.shape), torch.from_numpy(np.packbits(m.numpy().reshape(-1)))
+            print("mask case", seed, key, tuple(m.shape), int(m.sum()))
+        masks.append(case)
+    nms = []
+    for seed, (B, nc, A, conf, iou, max_det, max_nms) in enumerate([(2, 15, 2100, 0.25, 0.45, 300, 30000), (2, 3, 600, 0.05, 0.3, 25, 30000),
+                                                                     (1, 15, 1500, 0.01, 0.6, 300, 400), (1, 4, 300, 0.999, 0.45, 300, 30000)]):
+        pred = synth_obb_predictions(B, nc, A, 950 + seed)
+        out, keep = non_max_suppression(pred.clone(), conf, iou, nc=nc, max_det=max_det, max_nms=max_nms, rotated=True, return_idxs=True)
+        nms.append({"pred": pred, "nc": nc, "conf": conf, "iou": iou, "max_det": max_det, "max_nms": max_nms,
+                    "out": [o.clone() for o in out], "keep": [k.clone().long().view(-1) for k in keep]})
+        print("rotated nms case", seed, [len(o) for o in out])
+    torch.save({"masks": masks, "nms": nms}, f"{OUT}/postproc.golden.pt")
+
+
 ESMOE_CASES = [(64, 4, 2, 20, 24, 6), (32, 4, 2, 9, 7, 5), (128, 4, 2, 10, 10, 4)]   # C, E, top_k, H, W, B
 
 
@@ -401,10 +451,10 @@ def gated_family_golden():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["main", "dispatch", "nms", "esmoe", "letterbox", "gated_family", "cls", *EXTRA_MODELS]
+    which = sys.argv[1:] or ["main", "dispatch", "nms", "postproc", "esmoe", "letterbox", "gated_family", "cls", *EXTRA_MODELS]
     for w in which:
         if w in EXTRA_MODELS:
             extra_model_golden(w)
         else:
-            {"main": main, "dispatch": dispatch_golden, "nms": nms_golden, "esmoe": esmoe_golden, "letterbox": letterbox_golden,
+            {"main": main, "dispatch": dispatch_golden, "nms": nms_golden, "postproc": postproc_golden, "esmoe": esmoe_golden, "letterbox": letterbox_golden,
              "gated_family": gated_family_golden, "cls": cls_golden}[w]()

@@ -1,5 +1,5 @@
 """The extern "C" entry points written after round 1's GPU budget, exercised END TO END without a GPU: the real .cu translation units
-(preproc.cu, gated.cu, nms_large.cu, mix.cu) are compiled with g++ against tests/native/cuda_host_emu.h - a CUDA execution model on
+(preproc.cu, gated.cu, nms_large.cu, mix.cu, postproc.cu) are compiled with g++ against tests/native/cuda_host_emu.h - a CUDA execution model on
 host threads (one OS thread per CUDA thread of a block, std::barrier for __syncthreads, thread_local blockIdx / threadIdx) - and
 called through the real `yolo_master_b200.ops` wrappers with CPU tensors.  Unlike the phase / per-element harnesses this covers
 the argument checks, the launch geometry, the shared-memory sizing, the grid-stride loops and the vectorised stores of the kernels
@@ -17,14 +17,16 @@ import torch.nn.functional as F
 from _util import GOLD, ROOT
 from oracle import letterbox_oracle as L
 from oracle import nms_oracle as N
+from oracle import postproc_oracle as PP
 from oracle import yolo_master_oracle as O
 from yolo_master_b200 import _lib, ops
 
 CSRC = os.path.join(ROOT, "yolo-master_b200", "csrc")
-UNITS = ["preproc.cu", "gated.cu", "nms_large.cu", "mix.cu"]
+UNITS = ["preproc.cu", "gated.cu", "nms_large.cu", "mix.cu", "postproc.cu"]
 SYMBOLS = ["ym_letterbox_u8", "ym_scale_boxes", "ym_kpts_decode", "ym_obb_finish", "ym_gate_router", "ym_gate_router_scratch_floats",
            "ym_zero_cost_router", "ym_zero_cost_router_scratch_floats", "ym_pixel_router", "ym_latent_router", "ym_fc_gate", "ym_classify_head", "ym_gated_select", "ym_gated_select_scratch_floats",
-           "ym_ctx_mean3", "ym_gap_nhwc", "ym_nms_batched_large", "ym_nms_large_scratch_bytes", "ym_ew_nhwc", "ym_last_error"]
+           "ym_ctx_mean3", "ym_gap_nhwc", "ym_nms_batched_large", "ym_nms_large_scratch_bytes", "ym_ew_nhwc", "ym_last_error",
+           "ym_process_mask", "ym_process_mask_scratch_bytes", "ym_nms_rotated", "ym_nms_rotated_scratch_bytes"]
 
 
 @pytest.fixture(scope="module")
@@ -287,3 +289,93 @@ def test_global_average_pool_kernel(emu):
     assert not wide[..., :64].any()
     with pytest.raises(RuntimeError, match="multiples of 8"):
         ops.gap(torch.zeros((1, 2, 2, 12), dtype=torch.float16))
+
+
+def _unpack_bits(case, key):
+    shape = tuple(case[key + "_shape"])
+    return torch.from_numpy(np.unpackbits(case[key + "_bits"].numpy())[:int(np.prod(shape))].reshape(shape))
+
+
+def assert_masks_match(got, want, field, keep, what, tol=1e-4):
+    """Bit-exact except where the thresholded fp32 field is within `tol` of zero (another summation order may land on the other
+    side); the crop itself (keep) is integer-exact."""
+    assert got.shape == want.shape and got.dtype == torch.uint8, what
+    bad = got != want
+    assert not (bad & ~keep).any(), (what, "mask pixels outside the crop")
+    assert not (bad & (field.abs() > tol)).any(), (what, int(bad.sum()), float(field[bad].abs().max()) if bad.any() else 0.0)
+    assert bad.float().mean().item() < 1e-3, (what, "too many marginal pixels")
+
+
+def test_process_mask_kernels_match_reference_goldens(emu):
+    """ym_process_mask (both kernels, vector and scalar stores, fp16 and fp32 prototypes) against the REFERENCE's ops.process_mask."""
+    G = torch.load(os.path.join(GOLD, "postproc.golden.pt"))
+    for i, c in enumerate(G["masks"]):
+        n, nm = c["coef"].shape
+        dets = torch.cat([c["boxes"], torch.zeros((n, 2)), c["coef"]], 1).contiguous()
+        for key, up in (("up", True), ("native", False)):
+            want = _unpack_bits(c, key)
+            for protos in (c["protos"], c["protos"].half()):                      # the goldens' prototypes are fp16-representable
+                got = ops.process_mask(protos, dets, c["shape"], upsample=up)
+                if n == 0:
+                    assert got.shape == want.shape
+                    continue
+                field = PP.mask_field(c["protos"], c["coef"], c["shape"], up)
+                mh, mw = c["protos"].shape[1:]
+                boxes = c["boxes"] if up else c["boxes"] * torch.tensor([[mw / c["shape"][1], mh / c["shape"][0]] * 2])
+                assert_masks_match(got, want, field, PP.crop_keep(boxes, *field.shape[1:]), (i, key, str(protos.dtype)))
+    with pytest.raises(RuntimeError, match="row pitch"):
+        ops.process_mask(torch.zeros((32, 4, 4)), torch.zeros((1, 10)), (16, 16))
+    with pytest.raises(RuntimeError, match="nm <= 64"):
+        ops.process_mask(torch.zeros((65, 4, 4)), torch.zeros((1, 80)), (16, 16))
+
+
+def test_process_mask_more_than_one_detection_group_and_ragged_width(emu):
+    g = torch.Generator().manual_seed(4)
+    protos = torch.randn((5, 9, 7), generator=g)
+    n = 19                                                                        # three groups of 8 detections, the last ragged
+    coef = torch.randn((n, 5), generator=g)
+    boxes = torch.tensor([[3.0, 2.0, 20.0, 30.0]]).repeat(n, 1) + torch.rand((n, 4), generator=g) * 3
+    dets = torch.cat([boxes, torch.zeros((n, 3)), coef, torch.zeros((n, 2))], 1).contiguous()   # coefficients at column 7, pitch 14
+    for up, shape in ((True, (37, 27)), (True, (36, 28)), (False, (36, 28))):      # ow % 4 != 0 -> scalar stores
+        got = ops.process_mask(protos, dets, shape, upsample=up, coef_col=7)
+        want = PP.process_mask(protos, coef, boxes, shape, upsample=up)
+        field = PP.mask_field(protos, coef, shape, up)
+        bx = boxes if up else boxes * torch.tensor([[7 / shape[1], 9 / shape[0]] * 2])
+        assert_masks_match(got, want, field, PP.crop_keep(bx, *field.shape[1:]), (up, shape))
+
+
+def test_rotated_nms_kernels_match_reference_goldens(emu):
+    """ym_nms_rotated (best class, sort, tiled fast-NMS sweep, ordered emit) against the REFERENCE's non_max_suppression(rotated=True)."""
+    G = torch.load(os.path.join(GOLD, "postproc.golden.pt"))
+    for i, c in enumerate(G["nms"]):
+        _, _, margin = PP.non_max_suppression_rotated(c["pred"], c["conf"], c["iou"], c["max_det"], c["max_nms"])
+        assert margin > 1e-5, (i, margin)                                        # every suppression decision is clear of fp32 noise
+        out, cnt, idx = ops.nms_rotated(c["pred"], c["conf"], c["iou"], c["max_det"], c["max_nms"])
+        for b in range(c["pred"].shape[0]):
+            k = int(cnt[b])
+            assert k == len(c["keep"][b]), (i, b, k, len(c["keep"][b]))
+            assert torch.equal(idx[b, :k].long(), c["keep"][b]), (i, b)
+            assert torch.equal(out[b, :k], c["out"][b]), (i, b)
+            assert (idx[b, k:] == -1).all() and (out[b, k:] == 0).all()
+
+
+def test_rotated_nms_ties_caps_and_empty(emu):
+    nc, A = 2, 40
+    pred = torch.zeros((1, 4 + nc + 1, A))
+    pred[0, 0] = torch.arange(A) * 100.0                                          # far apart: nothing suppresses
+    pred[0, 1] = 50.0
+    pred[0, 2], pred[0, 3] = 8.0, 4.0
+    pred[0, 4] = 0.5                                                              # all scores tie: anchor order
+    pred[0, 5] = 0.1
+    out, cnt, idx = ops.nms_rotated(pred, 0.25, 0.45, max_det=7, max_nms=25)
+    assert int(cnt[0]) == 7 and idx[0].tolist() == list(range(7))
+    out, cnt, idx = ops.nms_rotated(pred, 0.9, 0.45)
+    assert int(cnt[0]) == 0 and (idx == -1).all()
+    pred[0, 0] = 50.0                                                             # identical boxes, same class: only the first survives
+    out, cnt, idx = ops.nms_rotated(pred, 0.25, 0.45)
+    assert int(cnt[0]) == 1 and int(idx[0, 0]) == 0
+    pred[0, 5, 1::2] = 0.9                                                        # odd anchors switch class (and score): two survivors
+    out, cnt, idx = ops.nms_rotated(pred, 0.25, 0.45)
+    assert int(cnt[0]) == 2 and idx[0, :2].tolist() == [1, 0] and out[0, 0, 5] == 1 and out[0, 1, 5] == 0
+    want, keep, _ = PP.non_max_suppression_rotated(pred, 0.25, 0.45)
+    assert torch.equal(out[0, :2], want[0]) and torch.equal(idx[0, :2].long(), keep[0])

@@ -5,7 +5,7 @@
 # Results land in gpurun_out/round2_first_call.log and gpurun_out/models_r2.json.
 mkdir -p gpurun_out
 {
-  for f in tests/test_gpu_zz_predictor.py tests/test_gpu_zz_nms_large.py tests/test_gpu_zz_model_v0_1.py tests/test_gpu_zz_pose.py tests/test_gpu_zz_segment.py tests/test_gpu_zz_obb.py tests/test_gpu_zz_classify.py tests/test_gpu_zz_latent.py tests/test_gpu_zz_gated.py; do
+  for f in tests/test_gpu_zz_predictor.py tests/test_gpu_zz_nms_large.py tests/test_gpu_zz_model_v0_1.py tests/test_gpu_zz_pose.py tests/test_gpu_zz_segment.py tests/test_gpu_zz_obb.py tests/test_gpu_zz_classify.py tests/test_gpu_zz_postproc.py tests/test_gpu_zz_latent.py tests/test_gpu_zz_gated.py; do
     echo "=== $f"
     timeout 600 python -m pytest "$f" -q -rxXf --tb=short -p no:cacheprovider 2>&1 | tail -60
   done

@@ -78,6 +78,10 @@ SIGNATURES = {
     "ym_classify_head": (ci, [vp, ci, ci, ci, vp, vp, ci, vp, vp, vp]),
     "ym_obb_finish": (ci, [ci, C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, vp, vp, vp]),
     "ym_kpts_decode": (ci, [ci, C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp]),
+    "ym_process_mask_scratch_bytes": (cll, [ci, ci, ci]),
+    "ym_process_mask": (ci, [vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, ci, vp, vp, vp]),
+    "ym_nms_rotated_scratch_bytes": (cll, [ci, ci]),
+    "ym_nms_rotated": (ci, [vp, ci, ci, ci, cf, cf, ci, ci, cf, vp, vp, vp, vp, vp]),
     "ym_letterbox_u8": (ci, [vp, cll, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, ci, ci, ci, ci, vp]),
     "ym_scale_boxes": (ci, [vp, ci, cll, ci, vp, ci, vp, ci, ci, vp]),
     "ym_detect_topk": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp, vp, vp]),

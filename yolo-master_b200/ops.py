@@ -341,6 +341,45 @@ def nms_batched_large(pred, conf_thres, iou_thres, max_det=300, max_nms=30000, m
     return out, cnt, idx
 
 
+def process_mask(protos, dets, shape, upsample=True, coef_col=6):
+    """ym_process_mask.  protos: (nm, mh, mw) fp16 / fp32; dets: fp32 (n, >= coef_col + nm) rows with the xyxy box (in `shape`
+    coordinates) at columns 0..3 and the mask coefficients from `coef_col` -> uint8 (n, *shape) when upsample else (n, mh, mw)."""
+    if protos.dim() != 3 or protos.dtype not in (torch.float16, torch.float32) or not _dev(protos):
+        raise ValueError("process_mask: expected fp16 / fp32 CUDA prototypes of shape (nm, mh, mw)")
+    if dets.dim() != 2 or dets.dtype != torch.float32 or not _dev(dets) or dets.stride(-1) != 1:
+        raise ValueError("process_mask: expected fp32 CUDA detection rows (n, >= coef_col + nm)")
+    nm, mh, mw = protos.shape
+    n = dets.shape[0]
+    oh, ow = (int(shape[0]), int(shape[1])) if upsample else (mh, mw)
+    out = torch.empty((n, oh, ow), dtype=torch.uint8, device=protos.device)
+    if n == 0:
+        return out
+    protos = protos.contiguous()
+    scratch = torch.empty((lib().ym_process_mask_scratch_bytes(n, mh, mw),), dtype=torch.uint8, device=protos.device)
+    _lib.check(lib().ym_process_mask(protos.data_ptr(), 1 if protos.dtype == torch.float16 else 2, nm, mh, mw, dets.data_ptr(),
+                                     dets.stride(0), n, coef_col, int(shape[0]), int(shape[1]), 1 if upsample else 0, out.data_ptr(),
+                                     scratch.data_ptr(), _stream()), "ym_process_mask")
+    _count(2)
+    return out
+
+
+def nms_rotated(pred, conf_thres, iou_thres, max_det=300, max_nms=30000, max_wh=7680.0):
+    """ym_nms_rotated.  pred: fp32 (B, 4+nc+1, A) xywh + class scores + angle.  Returns (out (B,max_det,7), count (B,) int32,
+    idx (B,max_det) int32)."""
+    if pred.dtype != torch.float32 or not _dev(pred) or pred.dim() != 3 or pred.shape[1] < 6:
+        raise ValueError("nms_rotated: expected an fp32 CUDA tensor of shape (B, 4+nc+1, A)")
+    pred = pred.contiguous()
+    B, no, A = pred.shape
+    out = torch.empty((B, max_det, 7), dtype=torch.float32, device=pred.device)
+    cnt = torch.empty((B,), dtype=torch.int32, device=pred.device)
+    idx = torch.empty((B, max_det), dtype=torch.int32, device=pred.device)
+    scratch = torch.empty((lib().ym_nms_rotated_scratch_bytes(B, A),), dtype=torch.uint8, device=pred.device)
+    _lib.check(lib().ym_nms_rotated(pred.data_ptr(), B, no - 5, A, float(conf_thres), float(iou_thres), max_det, max_nms, float(max_wh),
+                                    out.data_ptr(), cnt.data_ptr(), idx.data_ptr(), scratch.data_ptr(), _stream()), "ym_nms_rotated")
+    _count(4)
+    return out, cnt, idx
+
+
 def esmoe_forward(x, pack, topk, dyn_thr, out=None):
     """ES_MOE eval forward on the C ABI (ym_esmoe_route / _dwconv / _pointwise / _combine).  x: (B,H,W,C) fp16 view."""
     B, H, W, Cc = x.shape

@@ -29,8 +29,16 @@ def non_max_suppression(prediction, conf_thres: float = 0.25, iou_thres: float =
             output.append(pred[idx])
             keepi.append(idx)
         return (output, keepi) if return_idxs else output
-    if classes is not None or agnostic or multi_label or rotated or len(labels):
-        raise NotImplementedError("non_max_suppression: classes / agnostic / multi_label / rotated / labels are not on the B200 path")
+    if classes is not None or agnostic or multi_label or len(labels):
+        raise NotImplementedError("non_max_suppression: classes / agnostic / multi_label / labels are not on the B200 path")
+    if rotated:
+        # OBB rows (B, 4 + nc + 1, A): xywh stays (nms.py:90), fast-NMS on ProbIoU (nms.py:148-152); rows (x, y, w, h, conf, cls, angle)
+        if cluster or (nc and prediction.shape[1] - 4 - nc != 1):
+            raise NotImplementedError("non_max_suppression(rotated=True): expects (B, 4 + nc + 1, A) predictions, no cluster mode")
+        out, cnt, idx = ops.nms_rotated(prediction.float(), conf_thres, iou_thres, max_det, max_nms, float(max_wh))
+        counts = cnt.tolist()
+        output = [out[b, :n] for b, n in enumerate(counts)]
+        return (output, [idx[b, :n].long() for b, n in enumerate(counts)]) if return_idxs else output
     extra = None
     if nc and prediction.shape[1] - 4 != nc:      # rows past 4 + nc (keypoints, mask coefficients) ride along with the kept anchors
         if cluster:

@@ -64,3 +64,10 @@ def clip_boxes(boxes, shape):
         return boxes
     p = torch.tensor([[1.0, 0.0, 0.0, shape[1], shape[0]]], dtype=torch.float32)
     return _k.scale_boxes(boxes, p, rows_per_img=boxes.numel() // boxes.shape[-1], padding=False, xywh=False)
+
+
+def process_mask(protos, masks_in, bboxes, shape, upsample: bool = False):
+    """utils/ops.py:500-528: (mask_dim, mh, mw) prototypes x (N, mask_dim) coefficients -> uint8 (N, H, W) masks cropped to the
+    xyxy `bboxes` (given in `shape` coordinates); H, W = `shape` when upsample else the prototype resolution."""
+    dets = torch.cat([bboxes.float(), masks_in.float()], 1).contiguous()
+    return _k.process_mask(protos, dets, shape, upsample=upsample, coef_col=4)
