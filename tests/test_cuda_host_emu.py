@@ -379,3 +379,73 @@ def test_rotated_nms_ties_caps_and_empty(emu):
     assert int(cnt[0]) == 2 and idx[0, :2].tolist() == [1, 0] and out[0, 0, 5] == 1 and out[0, 1, 5] == 0
     want, keep, _ = PP.non_max_suppression_rotated(pred, 0.25, 0.45)
     assert torch.equal(out[0, :2], want[0]) and torch.equal(idx[0, :2].long(), keep[0])
+
+
+class _TaskStub(torch.nn.Module):
+    def __init__(self, out, nc):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(1))
+        self.out, self.stride, self.names = out, torch.tensor([8.0, 16.0, 32.0]), {i: str(i) for i in range(nc)}
+
+    def forward(self, x):
+        return self.out
+
+
+def test_obb_predictor_postprocess_end_to_end(emu):
+    """OBBPredictor.postprocess: ym_nms_rotated -> (x, y, w, h, angle, conf, cls) rows with ym_scale_boxes(xywh) - against the
+    reference's own NMS output (golden) followed by the oracle rescale, exactly."""
+    from yolo_master_b200.engine import OBBPredictor
+    c = torch.load(os.path.join(GOLD, "postproc.golden.pt"))["nms"][0]
+    B = c["pred"].shape[0]
+    pred = OBBPredictor(_TaskStub((c["pred"], {}), c["nc"]), imgsz=640, conf=c["conf"], iou=c["iou"], max_det=c["max_det"], device="cpu")
+    frames = [np.zeros((480, 640, 3), np.uint8), np.zeros((360, 500, 3), np.uint8)][:B]
+    res = pred.postprocess((c["pred"], {}), torch.zeros((B, 3, 640, 640)), frames)
+    for b, r in enumerate(res):
+        ref = c["out"][b]
+        want = torch.cat([torch.from_numpy(L.scale_boxes((640, 640), ref[:, :4].numpy(), frames[b].shape, xywh=True)), ref[:, 6:7], ref[:, 4:6]], 1)
+        assert r.boxes is None and r.masks is None and len(r) == len(ref)
+        assert torch.equal(r.obb.data, want), b
+        assert torch.equal(r.obb.xywhr, want[:, :5]) and torch.equal(r.obb.conf, ref[:, 4]) and torch.equal(r.obb.cls, ref[:, 5])
+        assert r.obb.xyxyxyxy.shape == (len(ref), 4, 2) and torch.allclose(r.obb.xyxyxyxy.mean(1), want[:, :2], atol=1e-2)
+        assert len(r[:3].obb) == 3 and r.cpu().obb.data.shape == want.shape
+
+
+def test_segmentation_predictor_postprocess_end_to_end(emu, monkeypatch):
+    """SegmentationPredictor.postprocess: NMS rows carrying the coefficients -> ym_process_mask (boxes / coefficients read in place
+    from the (n, 6 + nm) rows) -> ym_scale_boxes -> mask-less rows dropped.  The shared-memory NMS kernel (nms.cu, warp intrinsics) is
+    not part of the emulated units: its place is taken by the NMS oracle here; everything after it is the product path."""
+    from yolo_master_b200.engine import SegmentationPredictor
+    from yolo_master_b200.utils import nms as host_nms
+    g = torch.Generator().manual_seed(21)
+    B, nc, nm, A = 2, 5, 8, 300
+    y = torch.zeros((B, 4 + nc + nm, A))
+    y[:, 0:2] = torch.rand((B, 2, A), generator=g) * 140 + 10
+    y[:, 2:4] = torch.rand((B, 2, A), generator=g) * 60 + 6
+    y[:, 4:4 + nc] = torch.rand((B, nc, A), generator=g) ** 3
+    y[:, 4 + nc:] = torch.randn((B, nm, A), generator=g)
+    y[0, 4 + nc:, :] -= 100.0 * (torch.arange(A) % 3 == 0)                      # some detections with an all-negative field: dropped
+    protos = torch.nn.functional.avg_pool2d(torch.randn((B, nm, 40, 40), generator=g), 3, 1, 1).abs().half()
+
+    def oracle_nms(prediction, conf_thres, iou_thres, classes=None, agnostic=False, max_det=300, nc=0, **kw):
+        outs, idxs = N.non_max_suppression(prediction[:, :4 + nc].float(), conf_thres, iou_thres, max_det)
+        return [torch.cat([o, prediction[b, 4 + nc:, i].t().float()], 1) for b, (o, i) in enumerate(zip(outs, idxs))]
+
+    monkeypatch.setattr(host_nms, "non_max_suppression", oracle_nms)
+    pred = SegmentationPredictor(_TaskStub(((y, protos), {}), nc), imgsz=160, conf=0.3, iou=0.5, device="cpu")
+    frames = [np.zeros((120, 160, 3), np.uint8), np.zeros((300, 200, 3), np.uint8)]
+    res = pred.postprocess(((y, protos), {}), torch.zeros((B, 3, 160, 160)), frames)
+    dropped = 0
+    for b, r in enumerate(res):
+        rows = oracle_nms(y, 0.3, 0.5, nc=nc)[b]
+        masks = PP.process_mask(protos[b].float(), rows[:, 6:], rows[:, :4], (160, 160), upsample=True)
+        keep = masks.amax((-2, -1)) > 0
+        dropped += int((~keep).sum())
+        want = rows[keep][:, :6].clone()
+        want[:, :4] = torch.from_numpy(L.scale_boxes((160, 160), want[:, :4].numpy(), frames[b].shape))
+        assert torch.equal(r.boxes.data, want), b
+        field = PP.mask_field(protos[b].float(), rows[:, 6:], (160, 160), True)[keep]
+        assert_masks_match(r.masks.data, masks[keep], field, PP.crop_keep(rows[keep][:, :4], 160, 160), b)
+        assert r.masks.shape == (int(keep.sum()), 160, 160) and len(r) == int(keep.sum())
+    assert dropped > 0
+    with pytest.raises(NotImplementedError):
+        SegmentationPredictor(_TaskStub(None, nc), retina_masks=True, device="cpu")

@@ -106,3 +106,25 @@ def test_rotated_nms_full_size_properties(A):
         again[0, 4:4 + nc].scatter_(0, o[:, 5].long()[None], o[None, :, 4])
         o2, k2 = non_max_suppression(again.to(DEV), 0.25, 0.45, nc=nc, max_det=300, rotated=True, return_idxs=True)
         assert k2[0].cpu().tolist() == list(range(len(o))) and torch.equal(o2[0].cpu(), o)
+
+
+def test_obb_predictor_on_the_reference_golden():
+    """OBBPredictor.postprocess on the device: ym_nms_rotated + ym_scale_boxes(xywh) against the reference's rows + oracle rescale."""
+    from oracle import letterbox_oracle as L
+    from yolo_master_b200.engine import OBBPredictor
+
+    class Stub(torch.nn.Module):
+        def __init__(self, nc):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self.stride, self.names = torch.tensor([8.0, 16.0, 32.0]), {i: str(i) for i in range(nc)}
+
+    c = G["nms"][0]
+    B = c["pred"].shape[0]
+    pred = OBBPredictor(Stub(c["nc"]).to(DEV), imgsz=640, conf=c["conf"], iou=c["iou"], max_det=c["max_det"])
+    frames = [np.zeros((480, 640, 3), np.uint8), np.zeros((360, 500, 3), np.uint8)][:B]
+    res = pred.postprocess((c["pred"].to(DEV), {}), torch.zeros((B, 3, 640, 640), device=DEV), frames)
+    for b, r in enumerate(res):
+        ref = c["out"][b]
+        want = torch.cat([torch.from_numpy(L.scale_boxes((640, 640), ref[:, :4].numpy(), frames[b].shape, xywh=True)), ref[:, 6:7], ref[:, 4:6]], 1)
+        assert torch.equal(r.obb.data.cpu(), want), b

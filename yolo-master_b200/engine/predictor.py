@@ -12,6 +12,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .. import ops as _k
 from ..data.augment import LetterBox
 from ..utils import nms, ops
 from .results import Results
@@ -24,6 +25,8 @@ class DetectionPredictor:
     `rect`, `half`, `cluster`, `sigma`).  `half=None` (default) feeds the model the uint8 batch - its first convolution scales
     by 1/255 while loading (same arithmetic as `im.half() / 255`); `half=True/False` reproduce the reference's fp16/fp32 tensor.
     """
+
+    task = "detect"
 
     def __init__(self, model, imgsz=640, conf: float = 0.25, iou: float = 0.7, max_det: int = 300, classes=None,
                  agnostic_nms: bool = False, rect: bool = False, half=None, cluster: bool = False, sigma: float = 0.1, device=None):
@@ -90,22 +93,29 @@ class DetectionPredictor:
         return self.model(im)
 
     # ------------------------------------------------------------------------------------------ after the forward pass
+    def _nc(self) -> int:
+        """detect/predict.py:62: 0 for the detect task, else the class count (rows past 4 + nc ride along with the kept anchors)."""
+        if self.task == "detect":
+            return 0
+        names = getattr(self.model, "names", None)
+        return len(names) if names else int(self.model.model[-1].nc)
+
     def postprocess(self, preds, img, orig_imgs, **kwargs):
         """detect/predict.py:32-74: NMS (or the end2end confidence filter), then boxes back to the original frames."""
         if isinstance(preds, (list, tuple)):
             preds = preds[0]
-        end2end = bool(getattr(self.model, "end2end", False)) or preds.shape[-1] == 6
+        end2end = (bool(getattr(self.model, "end2end", False)) or preds.shape[-1] == 6) and self.task == "detect"
         frame_wh = (img.shape[3], img.shape[2]) if self.cluster else None
         dets = nms.non_max_suppression(preds, self.conf, kwargs.pop("iou", self.iou), self.classes, self.agnostic_nms,
-                                       max_det=self.max_det, end2end=end2end, cluster=self.cluster and not end2end,
-                                       sigma=self.sigma, frame_wh=frame_wh)
+                                       max_det=self.max_det, nc=self._nc(), end2end=end2end, rotated=self.task == "obb",
+                                       cluster=self.cluster and not end2end, sigma=self.sigma, frame_wh=frame_wh)
         if self.cluster and not end2end:   # CW-NMS rows are (x, y, w, h): back to corners before rescaling
             for d in dets:
                 d[:, 2:4] += d[:, 0:2]
         if isinstance(orig_imgs, torch.Tensor):   # tensor source: the "original" frames are the batch itself (predict.py:63-64)
             as_float = orig_imgs.float() / 255 if orig_imgs.dtype == torch.uint8 else orig_imgs.float()
             orig_imgs = list(ops.convert_torch2numpy_batch(as_float)[..., ::-1])
-        return self.construct_results(dets, img, orig_imgs)
+        return self.construct_results(dets, img, orig_imgs, **kwargs)
 
     def construct_results(self, preds, img, orig_imgs):
         """detect/predict.py:91-125 with the per-image `scale_boxes` calls folded into one launch over the ragged rows."""
@@ -140,3 +150,56 @@ class DetectionPredictor:
             im = self.preprocess(frames)
             preds = self.inference(im)
             return self.postprocess(preds, im, frames)
+
+
+class SegmentationPredictor(DetectionPredictor):
+    """ultralytics/models/yolo/segment/predict.py:11-113: NMS carrying the mask coefficients, then `ops.process_mask` per image
+    (`ym_process_mask`: logits, x4 bilinear upsampling, crop and threshold without a float (n, H, W) intermediate in HBM)."""
+
+    task = "segment"
+
+    def __init__(self, *args, retina_masks: bool = False, **kwargs):
+        super().__init__(*args, **kwargs)
+        if retina_masks:
+            raise NotImplementedError("SegmentationPredictor(retina_masks=True) (ops.process_mask_native) is not on the B200 path")
+
+    def postprocess(self, preds, img, orig_imgs, **kwargs):
+        """segment/predict.py:50-66: the model returns ((y, proto), aux) (or (y, proto) when exported)."""
+        protos = preds[0][1] if isinstance(preds[0], (tuple, list)) else preds[1]
+        return super().postprocess(preds[0], img, orig_imgs, protos=protos)
+
+    def construct_results(self, preds, img, orig_imgs, protos):
+        """segment/predict.py:68-84."""
+        paths = self.batch[0] if self.batch else [None] * len(preds)
+        return [self.construct_result(p, img, o, pth, proto) for p, o, pth, proto in zip(preds, orig_imgs, paths, protos)]
+
+    def construct_result(self, pred, img, orig_img, img_path, proto):
+        """segment/predict.py:86-111."""
+        pred = pred.float().contiguous()
+        if pred.shape[0] == 0:
+            masks = None
+        else:
+            masks = _k.process_mask(proto, pred, img.shape[2:], upsample=True, coef_col=6)   # boxes / coefficients read in place
+            ops.scale_boxes(img.shape[2:], pred[:, :4], orig_img.shape)
+            keep = masks.amax((-2, -1)) > 0                              # only keep predictions with masks
+            if not bool(keep.all()):
+                pred, masks = pred[keep], masks[keep]
+        return Results(orig_img, path=img_path, names=getattr(self.model, "names", None), boxes=pred[:, :6], masks=masks)
+
+
+class OBBPredictor(DetectionPredictor):
+    """ultralytics/models/yolo/obb/predict.py:10-58: rotated NMS (`ym_nms_rotated`), centres / sizes back to the original frame."""
+
+    task = "obb"
+
+    def construct_results(self, preds, img, orig_imgs):
+        paths = self.batch[0] if self.batch else [None] * len(preds)
+        return [self.construct_result(p, img, o, pth) for p, o, pth in zip(preds, orig_imgs, paths)]
+
+    def construct_result(self, pred, img, orig_img, img_path):
+        """obb/predict.py:41-58.  pred rows: (x, y, w, h, conf, cls, angle) -> obb rows (x, y, w, h, angle, conf, cls)."""
+        pred = pred.float()
+        rboxes = torch.cat([pred[:, :4], pred[:, -1:]], dim=-1).contiguous()
+        ops.scale_boxes(img.shape[2:], rboxes[:, :4], orig_img.shape, xywh=True)
+        obb = torch.cat([rboxes, pred[:, 4:6]], dim=-1)
+        return Results(orig_img, path=img_path, names=getattr(self.model, "names", None), obb=obb)

@@ -1,4 +1,4 @@
-"""`Results` / `Boxes` containers with the attribute names of ultralytics/engine/results.py:184-300,860-1100 (detection subset).
+"""`Results` / `Boxes` containers with the attribute names of ultralytics/engine/results.py:184-300,860-1100 (detection, segmentation and oriented-box subset).
 Plain holders: the tensors stay wherever the predictor produced them (CUDA) until `.cpu()` / `.numpy()` is asked for."""
 from __future__ import annotations
 
@@ -85,14 +85,108 @@ class Boxes:
         return b
 
 
-class Results:
-    """One image's detections (results.py:184-300): `orig_img`, `orig_shape`, `boxes`, `names`, `path`, `speed`."""
+class Masks:
+    """(n, H, W) uint8 masks at the network input size (results.py:1080-1150): `data`, `orig_shape`, `shape`."""
 
-    def __init__(self, orig_img, path=None, names=None, boxes=None, speed=None):
+    def __init__(self, masks, orig_shape):
+        if masks.ndim == 2:
+            masks = masks[None, :]
+        self.data = masks
+        self.orig_shape = tuple(orig_shape)
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        return Masks(self.data[idx], self.orig_shape)
+
+    def cpu(self):
+        return Masks(self.data.cpu(), self.orig_shape)
+
+    def cuda(self):
+        return Masks(self.data.cuda(), self.orig_shape)
+
+    def to(self, *args, **kwargs):
+        return Masks(self.data.to(*args, **kwargs), self.orig_shape)
+
+    def numpy(self):
+        return Masks(self.data.cpu().numpy(), self.orig_shape)
+
+
+class OBB:
+    """(n, 7) rows (x, y, w, h, angle, conf, cls) in pixels of the original frame (results.py:1380-1560)."""
+
+    def __init__(self, boxes, orig_shape):
+        if boxes.ndim == 1:
+            boxes = boxes[None, :]
+        if boxes.shape[-1] not in (7, 8):
+            raise ValueError(f"expected 7 or 8 values but got {boxes.shape[-1]}")
+        self.data = boxes
+        self.orig_shape = tuple(orig_shape)
+        self.is_track = boxes.shape[-1] == 8
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    @property
+    def xywhr(self):
+        return self.data[:, :5]
+
+    @property
+    def conf(self):
+        return self.data[:, -2]
+
+    @property
+    def cls(self):
+        return self.data[:, -1]
+
+    @property
+    def id(self):
+        return self.data[:, -3] if self.is_track else None
+
+    @property
+    def xyxyxyxy(self):
+        """utils/ops.py xywhr2xyxyxyxy: the four corners, (n, 4, 2)."""
+        ctr, w, h, ang = self.data[:, :2], self.data[:, 2:3], self.data[:, 3:4], self.data[:, 4:5]
+        cos, sin = torch.cos(ang), torch.sin(ang)
+        v1 = torch.cat([w / 2 * cos, w / 2 * sin], -1)
+        v2 = torch.cat([-h / 2 * sin, h / 2 * cos], -1)
+        return torch.stack([ctr + v1 + v2, ctr + v1 - v2, ctr - v1 - v2, ctr - v1 + v2], -2)
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        return OBB(self.data[idx], self.orig_shape)
+
+    def cpu(self):
+        return OBB(self.data.cpu(), self.orig_shape)
+
+    def cuda(self):
+        return OBB(self.data.cuda(), self.orig_shape)
+
+    def to(self, *args, **kwargs):
+        return OBB(self.data.to(*args, **kwargs), self.orig_shape)
+
+    def numpy(self):
+        return OBB(self.data.cpu().numpy(), self.orig_shape)
+
+
+class Results:
+    """One image's detections (results.py:184-300): `orig_img`, `orig_shape`, `boxes`, `masks`, `obb`, `names`, `path`, `speed`."""
+
+    def __init__(self, orig_img, path=None, names=None, boxes=None, speed=None, masks=None, obb=None):
         self.orig_img = orig_img
         self.orig_shape = tuple(orig_img.shape[:2])
         self.boxes = Boxes(boxes, self.orig_shape) if boxes is not None else None
-        self.masks = self.probs = self.keypoints = self.obb = None
+        self.probs = self.keypoints = None
+        self.masks = Masks(masks, self.orig_shape) if masks is not None else None
+        self.obb = OBB(obb, self.orig_shape) if obb is not None else None
         self.speed = speed if speed is not None else {"preprocess": None, "inference": None, "postprocess": None}
         self.names = names
         self.path = path
@@ -100,15 +194,22 @@ class Results:
         self._keys = ("boxes",)
 
     def __len__(self):
-        return 0 if self.boxes is None else len(self.boxes)
+        for k in ("boxes", "masks", "obb"):                           # results.py:262-274: the first non-empty field
+            v = getattr(self, k)
+            if v is not None:
+                return len(v)
+        return 0
 
     def __getitem__(self, idx):
-        return Results(self.orig_img, self.path, self.names, None if self.boxes is None else self.boxes.data[idx], self.speed)
+        return Results(self.orig_img, self.path, self.names, None if self.boxes is None else self.boxes.data[idx], self.speed,
+                       None if self.masks is None else self.masks.data[idx], None if self.obb is None else self.obb.data[idx])
 
     def _apply(self, fn, *args, **kwargs):
         r = Results(self.orig_img, self.path, self.names, None, self.speed)
-        if self.boxes is not None:
-            r.boxes = getattr(self.boxes, fn)(*args, **kwargs)
+        for k in ("boxes", "masks", "obb"):
+            v = getattr(self, k)
+            if v is not None:
+                setattr(r, k, getattr(v, fn)(*args, **kwargs))
         return r
 
     def cpu(self):
