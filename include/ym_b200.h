@@ -211,6 +211,17 @@ int ym_kpts_decode(int nl, const void* const* kpt, const int* hs, const int* ws,
 int ym_obb_finish(int nl, const void* const* angle, const int* hs, const int* ws, const float* strides, int B, int nc,
                   const float* yin, float* yout, void* stream);
 
+/* ---- DiversifiedExpertGroup (moe/gated.py:2214-2333, v0_14 zoo; csrc/mix.cu) ---------------------------------------------------
+ * ym_dwconv3_routed_nhwc: dw_layers[e][0] for e = route[b * route_stride]: depthwise 3x3 whose taps (w fp16 [E][9][C], tap-major) AND
+ *   dilation (dil int32 [E] on the device; padding = dilation) are chosen per image by the router, without a host round trip
+ *   (the reference loops over torch.unique(indices).tolist()).  x fp16 [B][H][W][ldx] -> out fp16 [B][H][W][ldo]; fp32 accumulation.
+ * ym_route_affine: in place on (scale, shift) fp32 [B][C] = (rstd, -mean * rstd) from ym_groupnorm_stats with unit gamma:
+ *   scale *= gamma[e], shift = shift * gamma[e] + beta[e]  (gamma, beta fp32 [E][C]): the per-expert GroupNorm dw_layers[e][1]. */
+int ym_dwconv3_routed_nhwc(const void* x, int ldx, const void* w, const int* route, int route_stride, const int* dil, int E, int B, int H,
+                           int W, int C, void* out, int ldo, void* stream);
+int ym_route_affine(float* scale, float* shift, const float* gamma, const float* beta, const int* route, int route_stride, int E, int B,
+                    int C, void* stream);
+
 /* ---- Segment / OBB post-processing (csrc/postproc.cu) ------------------------------------------------
  * ym_process_mask: ops.process_mask(protos, masks_in, bboxes, shape, upsample) ultralytics/utils/ops.py:500-528 (+ crop_mask :477-497)
  *   for the detections of one image.  protos [nm][mh][mw] fp16 (proto_dtype 1) or fp32 (2); dets fp32 rows of pitch ld with the xyxy

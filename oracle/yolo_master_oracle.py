@@ -1219,6 +1219,27 @@ def shared_inverted_expert_group(sd, p, x, w, idx, num_experts, out_channels):
     return _st(out)
 
 
+def diversified_expert_group(sd, p, x, w, idx, num_experts, out_channels):
+    """`DiversifiedExpertGroup.forward` moe/gated.py:2297-2333 (v0_14): shared expand 1x1 -> GN -> SiLU, then per ACTIVE expert e a
+    depthwise 3x3 with dilation 1 + e // 2 (:2270-2276; the `dw_dilations` parameters are stored but never read) -> GN -> SiLU,
+    1x1 + GN projection, weighted index_add (routes with weight <= 0 are dropped)."""
+    B, C, H, W = x.shape
+    t = F.conv2d(x, _w(sd[p + ".shared_expand.0.weight"]))
+    hid = t.shape[1]
+    feat = _st(F.silu(_gn(sd, p + ".shared_expand.1", t, get_safe_groups(hid, 8))))
+    out = torch.zeros(B, out_channels, H, W)
+    valid = w > 0.0
+    for e in torch.unique(idx[valid]).tolist():
+        d = 1 + e // 2
+        bi, ki = torch.where((idx == e) & valid)
+        t = F.conv2d(feat[bi], _w(sd[f"{p}.dw_layers.{e}.0.weight"]), None, 1, d, d, hid)
+        t = _st(F.silu(_gn(sd, f"{p}.dw_layers.{e}.1", _st(t), get_safe_groups(hid, 8))))
+        y = _gn(sd, f"{p}.expert_projections.{e}.1", F.conv2d(t, _w(sd[f"{p}.expert_projections.{e}.0.weight"])),
+                get_safe_groups(out_channels, 8))
+        out.index_add_(0, bi, _st(y) * w[bi, ki].view(-1, 1, 1, 1))
+    return _st(out)
+
+
 def pyramid_context_mixer(sd, p, x, groups=8, pool_scales=(2, 4)):
     """`PyramidContextMixer.forward` gated.py:1210-1221."""
     B, C, H, W = x.shape
@@ -1276,7 +1297,9 @@ def gated_moe_forward(sd, p, x, c1, c2, num_experts, top_k, split_ratio, num_gro
     cx = cx.clamp(0.3, 1.5) if bool(torch.isfinite(cx)) else torch.tensor(1.0)
     w, idx, probs = dual_stream_gate_router(sd, p + ".routing", xd, top_k, max(float(temperature), 1e-3))
     w = complexity_gate(w, cx)
-    if backend == "low_rank_fused":
+    if p + ".fused_experts.dw_layers.0.0.weight" in sd:     # DiversifiedExpertMoE gated.py:2552-2560 (v0_14): group replaced
+        out_d = diversified_expert_group(sd, p + ".fused_experts", xd, w, idx, num_experts, out_dyn)
+    elif backend == "low_rank_fused":
         out_d = low_rank_fused_expert_group(sd, p + ".fused_experts", xd, w, idx, num_experts, out_dyn, num_groups)
     elif backend == "fused":
         out_d = fused_expert_group(sd, p + ".fused_experts", xd, w, idx, num_experts, out_dyn, num_groups)
@@ -1314,6 +1337,7 @@ GATED_VARIANTS = {
     "HybridAdaptiveGateMoEv2": (1.2, True, False, True, ()),                 # v0.11: v0.6 + DualStreamGateRouterV2 (keys in the sd)
     "OptimalHybridGateMoE": (1.2, True, False, True, ("light_refine",)),     # v0.12: + depthwise refinement
     "MultiHeadRouterMoE": (1.2, True, False, True, ("light_refine",)),       # v0.13: v0.12 + MultiHeadRouterV3 (keys in the sd)
+    "DiversifiedExpertMoE": (1.2, True, False, True, ("light_refine",)),     # v0.14: v0.12 + DiversifiedExpertGroup (keys in the sd)
     "GatedFusionMoE": (1.2, True, False, True, ("light_refine",)),           # v0.15: v0.12 + CrossPathGate (keys in the sd)
     "SharedExpertMoE": (1.2, True, True, True, ()),       # moe/shared_expert_moe.py: v0.7 blocks sharing one expert group per pool_id
 }

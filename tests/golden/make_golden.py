@@ -413,12 +413,15 @@ def gated_family_golden():
     (c1 = c2 = 64, top-2 of 4 and of 16 experts, key-seeded weights) on a seeded (2, 64, 12, 12) input -> output, router decisions
     before the complexity gate, and the state-dict key table."""
     from ultralytics.nn.modules.moe import gated as G
-    out = {}
+    path = f"{OUT}/gated_family.golden.pt"
+    out = torch.load(path) if os.path.exists(path) and not os.environ.get("GATED_REGEN") else {}
     from ultralytics.nn.modules.moe import modules as MM
-    for ci, name in enumerate(GATED_FAMILY + ["UltimateOptimizedMoE", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE", "MultiHeadRouterMoE", "GatedFusionMoE", "UltraOptimizedMoE"]):
+    for ci, name in enumerate(GATED_FAMILY + ["UltimateOptimizedMoE", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE", "MultiHeadRouterMoE", "GatedFusionMoE", "UltraOptimizedMoE", "DiversifiedExpertMoE"]):
         for E in (4, 16):
+            if f"{name}/E{E}" in out:                    # entries are deterministic; GATED_REGEN=1 recomputes them all
+                continue
             torch.manual_seed(0)
-            split = 0.375 if (E == 16 and name in ("HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE", "MultiHeadRouterMoE", "GatedFusionMoE")) else 0.5   # the v0_11 / v0_12 P5 setting
+            split = 0.375 if (E == 16 and name in ("HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE", "MultiHeadRouterMoE", "GatedFusionMoE", "DiversifiedExpertMoE")) else 0.5   # the v0_11 / v0_12 P5 setting
             if name == "UltraOptimizedMoE":          # (in, out, num_experts, top_k): no channel split
                 m = MM.UltraOptimizedMoE(64, 64, E, 2).eval()
             else:

@@ -26,7 +26,7 @@ UNITS = ["preproc.cu", "gated.cu", "nms_large.cu", "mix.cu", "postproc.cu"]
 SYMBOLS = ["ym_letterbox_u8", "ym_scale_boxes", "ym_kpts_decode", "ym_obb_finish", "ym_gate_router", "ym_gate_router_scratch_floats",
            "ym_zero_cost_router", "ym_zero_cost_router_scratch_floats", "ym_pixel_router", "ym_latent_router", "ym_fc_gate", "ym_classify_head", "ym_gated_select", "ym_gated_select_scratch_floats",
            "ym_ctx_mean3", "ym_gap_nhwc", "ym_nms_batched_large", "ym_nms_large_scratch_bytes", "ym_ew_nhwc", "ym_last_error",
-           "ym_process_mask", "ym_process_mask_scratch_bytes", "ym_nms_rotated", "ym_nms_rotated_scratch_bytes"]
+           "ym_dwconv3_routed_nhwc", "ym_route_affine", "ym_process_mask", "ym_process_mask_scratch_bytes", "ym_nms_rotated", "ym_nms_rotated_scratch_bytes"]
 
 
 @pytest.fixture(scope="module")
@@ -449,3 +449,32 @@ def test_segmentation_predictor_postprocess_end_to_end(emu, monkeypatch):
     assert dropped > 0
     with pytest.raises(NotImplementedError):
         SegmentationPredictor(_TaskStub(None, nc), retina_masks=True, device="cpu")
+
+
+def test_routed_dilated_depthwise_and_route_affine_kernels(emu):
+    """ym_dwconv3_routed_nhwc (taps and dilation chosen per image on the device, dilations 1 ... 8 as the 16-expert v0_14 block uses,
+    on a sliced view with a pitch) and ym_route_affine against torch: F.conv2d(dilation=d) per image / gathered gamma, beta."""
+    g = torch.Generator().manual_seed(8)
+    B, H, W, C, E = 5, 11, 9, 24, 16
+    buf = torch.randn((B, H, W, C + 8), generator=g).half()
+    x = buf[..., 8:]                                                              # channel-sliced view: pitch 32, 24 channels
+    w = (torch.randn((E, 9, C), generator=g) * 0.3).half()
+    dil = torch.tensor([1 + e // 2 for e in range(E)], dtype=torch.int32)
+    routes = torch.tensor([[0, 3], [15, 1], [6, 6], [9, 14], [2, 11]], dtype=torch.int32)   # (B, top_k): column views have stride 2
+    for j in range(2):
+        got = ops.dwconv3_routed(x, w, routes[:, j], dil)
+        for b in range(B):
+            e = int(routes[b, j])
+            d = int(dil[e])
+            want = F.conv2d(x[b:b + 1].float().permute(0, 3, 1, 2), w[e].float().t().reshape(C, 1, 3, 3), None, 1, d, d, C)[0].permute(1, 2, 0)
+            assert torch.equal(got[b], want.half()) or float((got[b].float() - want).abs().max()) < 2e-3, (j, b)   # fp32 sums, one fp16 rounding
+    sc, sh = torch.rand((B, C), generator=g) + 0.5, torch.randn((B, C), generator=g)
+    gamma, beta = torch.randn((E, C), generator=g), torch.randn((E, C), generator=g)
+    r = routes[:, 1]
+    want_sc, want_sh = sc * gamma[r.long()], sh * gamma[r.long()] + beta[r.long()]
+    ops.route_affine(sc, sh, gamma, beta, r)
+    torch.testing.assert_close(sc, want_sc, atol=1e-6, rtol=1e-6)
+    torch.testing.assert_close(sh, want_sh, atol=1e-6, rtol=1e-6)
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        ops.dwconv3_routed(torch.zeros((1, 2, 2, 12), dtype=torch.float16), torch.zeros((2, 9, 12), dtype=torch.float16),
+                           torch.zeros((1,), dtype=torch.int32), torch.ones((2,), dtype=torch.int32))

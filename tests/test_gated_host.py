@@ -230,7 +230,8 @@ def test_gated_zoo_yamls_build():
         assert DetectionModel(f"master/{ver}/det/yolo-master-s.yaml").model[5].in_channels == 256
     assert type(DetectionModel("yolo-master-n.yaml").model[3]).__name__ == "ES_MOE"        # a bare name still resolves to the v0 zoo
     for cfg, cls in (("master/v0_12/det/yolo-master-n.yaml", "OptimalHybridGateMoE"), ("master/exp/yolo-master-v0_11.yaml", "HybridAdaptiveGateMoEv2"),
-                     ("master/v0_13/det/yolo-master-n.yaml", "MultiHeadRouterMoE"), ("master/v0_15/det/yolo-master-n.yaml", "GatedFusionMoE")):
+                     ("master/v0_13/det/yolo-master-n.yaml", "MultiHeadRouterMoE"), ("master/v0_15/det/yolo-master-n.yaml", "GatedFusionMoE"),
+                     ("master/v0_14/det/yolo-master-n.yaml", "DiversifiedExpertMoE")):
         m = DetectionModel(cfg)
         assert [type(m.model[i]).__name__ for i in (5, 8, 11)] == [cls] * 3 and m.model[11].dynamic_channels == 96
         assert type(m.model[5].routing).__name__ == ("MultiHeadRouterV3" if cls == "MultiHeadRouterMoE" else "DualStreamGateRouterV2")

@@ -93,7 +93,7 @@ def test_model_host_wiring_matches_reference_golden(emu, name, cfg, tag):
 ZOO = ["master/v0_1/det/yolo-master-n-uomoe.yaml", "master/v0_8/det/yolo-master-moe-mot-shared-n.yaml", "master/v0_3/det/yolo-master-n.yaml", "master/v0_4/det/yolo-master-n.yaml", "master/v0_5/det/yolo-master-n.yaml",
        "master/v0_6/det/yolo-master-n.yaml", "master/v0_7/det/yolo-master-n.yaml", "master/v0_8/det/yolo-master-n.yaml",
        "master/v0_9/det/yolo-master-n.yaml", "master/exp/yolo-master-v0_11.yaml", "master/v0_12/det/yolo-master-n.yaml",
-       "master/v0_13/det/yolo-master-n.yaml", "master/v0_15/det/yolo-master-n.yaml"]
+       "master/v0_13/det/yolo-master-n.yaml", "master/v0_14/det/yolo-master-n.yaml", "master/v0_15/det/yolo-master-n.yaml"]
 
 
 @pytest.mark.parametrize("cfg", ZOO, ids=[c.split("/")[1] + ("-uomoe" if "uomoe" in c else "-shared" if "shared" in c else "") for c in ZOO])

@@ -431,7 +431,27 @@ def install_model():
     conv.Conv.forward = conv.Conv.forward_fuse = conv_forward
 
 
+def dwconv3_routed(x, w_taps, route, dil):
+    """Torch restatement of ym_dwconv3_routed_nhwc (checked against the kernel itself in tests/test_cuda_host_emu.py)."""
+    B, H, W, C = x.shape
+    y = torch.empty((B, C, H, W))
+    for b in range(B):
+        e = int(route[b])
+        d = int(dil[e])
+        y[b] = F.conv2d(x[b:b + 1].float().permute(0, 3, 1, 2), w_taps[e].float().t().reshape(C, 1, 3, 3), None, 1, d, d, C)[0]
+    return _out(y.permute(0, 2, 3, 1), None)
+
+
+def route_affine(scale, shift, gamma, beta, route):
+    g, bt = gamma[route.long()], beta[route.long()]
+    scale.mul_(g)
+    shift.mul_(g).add_(bt)
+    return scale, shift
+
+
 def install():
+    for name, fn in dict(dwconv3_routed=dwconv3_routed, route_affine=route_affine).items():
+        setattr(ops, name, fn)
     for name, fn in dict(conv2d=conv2d, dwconv=dwconv, ew=ew, groupnorm_stats=groupnorm_stats, layernorm=layernorm, attn_small=attn_small,
                          attn_window=attn_window, deform_sample=deform_sample, token_router=token_router, linear_attn=linear_attn,
                          adaptive_avgpool=adaptive_avgpool, gap=gap).items():

@@ -92,6 +92,69 @@ __global__ void __launch_bounds__(256) ew_kernel(const __half* __restrict__ a, i
     }
 }
 
+
+// Routed, dilated depthwise 3x3 (DiversifiedExpertGroup.dw_layers, moe/gated.py:2267-2280, v0_14 zoo): image b runs the taps AND the
+// dilation of expert e = route[b] (dilation 1 + e / 2 in the reference, passed as a table), zero padding = dilation.  One thread per
+// pixel and 8 channels, 16-byte loads of the activation and of the tap row, fp32 accumulation in tap order, fp16 output.
+__global__ void __launch_bounds__(256) dw3_routed_kernel(const __half* __restrict__ x, int ldx, const __half* __restrict__ w,
+                                                         const int* __restrict__ route, int route_stride,
+                                                         const int* __restrict__ dil, int E, int B, int H, int W, int C,
+                                                         __half* __restrict__ out, int ldo) {
+    const int cv = C >> 3;
+    const long long total = (long long)B * H * W * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / cv;
+        const int c = (int)(i - pix * cv) << 3;
+        const int b = (int)(pix / ((long long)H * W));
+        const int rem = (int)(pix - (long long)b * H * W);
+        const int y = rem / W, xx = rem - y * W;
+        int e = route[(long long)b * route_stride];
+        e = e < 0 ? 0 : (e >= E ? E - 1 : e);
+        const int d = dil[e];
+        const __half* wt = w + (long long)e * 9 * C + c;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int sy = y + (ky - 1) * d;
+            if (sy < 0 || sy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int sx = xx + (kx - 1) * d;
+                if (sx < 0 || sx >= W) continue;
+                const Half8 hv = *reinterpret_cast<const Half8*>(x + (((long long)b * H + sy) * W + sx) * ldx + c);
+                const Half8 hw = *reinterpret_cast<const Half8*>(wt + (ky * 3 + kx) * C);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 fv = __half22float2(hv.v[j]), fw = __half22float2(hw.v[j]);
+                    acc[2 * j] = fmaf(fv.x, fw.x, acc[2 * j]);
+                    acc[2 * j + 1] = fmaf(fv.y, fw.y, acc[2 * j + 1]);
+                }
+            }
+        }
+        Half8 o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o.v[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+        *reinterpret_cast<Half8*>(out + pix * ldo + c) = o;
+    }
+}
+
+// Per-image normalisation (scale = rstd, shift = -mean * rstd from ym_groupnorm_stats with unit gamma) -> the routed expert's affine:
+// scale' = scale * gamma[e], shift' = shift * gamma[e] + beta[e], e = route[b]  (the per-expert GroupNorm of dw_layers[e][1]).
+__global__ void __launch_bounds__(256) route_affine_kernel(float* __restrict__ scale, float* __restrict__ shift,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const int* __restrict__ route, int route_stride, int E, int B, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * C) return;
+    const int b = (int)(i / C), c = (int)(i - (long long)b * C);
+    int e = route[(long long)b * route_stride];
+    e = e < 0 ? 0 : (e >= E ? E - 1 : e);
+    const float g = gamma[(long long)e * C + c];
+    scale[i] = scale[i] * g;
+    shift[i] = fmaf(shift[i], g, beta[(long long)e * C + c]);
+}
+
 }  // namespace ym
 
 using namespace ym;
@@ -136,5 +199,35 @@ extern "C" int ym_ew_nhwc(int op, const void* a, int lda, const void* b, int ldb
     }
 #undef EW_LAUNCH
     YM_CHECK_LAUNCH("ew_nhwc");
+    return YM_OK;
+}
+
+// DiversifiedExpertGroup.dw_layers[e][0] (moe/gated.py:2272-2277) for e = route[b * route_stride]: x fp16 [B][H][W][ldx] ->
+// out fp16 [B][H][W][ldo], w fp16 [E][9][C] tap-major, dil int32 [E] (device).  C, ldx, ldo multiples of 8.
+extern "C" int ym_dwconv3_routed_nhwc(const void* x, int ldx, const void* w, const int* route, int route_stride, const int* dil, int E,
+                                      int B, int H, int W, int C, void* out, int ldo, void* stream) {
+    YM_CHECK_ARG(x && w && route && dil && out, "ym_dwconv3_routed_nhwc: null pointer");
+    YM_CHECK_ARG(C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && ldx >= C && ldo >= C, "ym_dwconv3_routed_nhwc: multiples of 8");
+    YM_CHECK_ARG(E >= 1 && B >= 0 && H > 0 && W > 0 && route_stride >= 1, "ym_dwconv3_routed_nhwc: sizes");
+    if (B == 0) return YM_OK;
+    const long long total = (long long)B * H * W * (C / 8);
+    long long nb = (total + 255) / 256;
+    if (nb > 148LL * 16) nb = 148LL * 16;
+    YM_LAUNCH(dw3_routed_kernel, (int)nb, 256, 0, (cudaStream_t)stream, (const __half*)x, ldx, (const __half*)w, route, route_stride, dil,
+              E, B, H, W, C, (__half*)out, ldo);
+    YM_CHECK_LAUNCH("dwconv3_routed");
+    return YM_OK;
+}
+
+// In place on scale / shift fp32 [B][C]: the routed expert's GroupNorm affine (gamma, beta fp32 [E][C]).
+extern "C" int ym_route_affine(float* scale, float* shift, const float* gamma, const float* beta, const int* route, int route_stride,
+                               int E, int B, int C, void* stream) {
+    YM_CHECK_ARG(scale && shift && gamma && beta && route, "ym_route_affine: null pointer");
+    YM_CHECK_ARG(E >= 1 && B >= 0 && C > 0 && route_stride >= 1, "ym_route_affine: sizes");
+    if (B == 0) return YM_OK;
+    const long long total = (long long)B * C;
+    YM_LAUNCH(route_affine_kernel, (int)((total + 255) / 256), 256, 0, (cudaStream_t)stream, scale, shift, gamma, beta, route,
+              route_stride, E, B, C);
+    YM_CHECK_LAUNCH("route_affine");
     return YM_OK;
 }

@@ -6,7 +6,7 @@ from .gated import (AdaptiveGateMoE, ContextRefinedLowRankHybridAdaptiveGateMoE,
                     LowRankHybridAdaptiveGateMoE, PyramidContextMixer, RefinedLowRankHybridAdaptiveGateMoE, SharedInvertedExpertGroup,
                     UltimateOptimizedMoE, VisualDetailGate, VisualEnhancedAdaptiveGateMoE, ZeroCostRouter, DualStreamGateRouterV2,
                     HybridAdaptiveGateMoEv2, OptimalHybridGateMoE, MultiHeadRouterMoE, GatedFusionMoE, MultiHeadRouterV3, CrossPathGate,
-                    SharedExpertMoE)
+                    SharedExpertMoE, DiversifiedExpertGroup, DiversifiedExpertMoE)
 from .head import DFL, OBB, Classify, Detect, Pose, Proto, Segment
 from .latent import DenseChannelExpert, LatentMixture, LatentRouter
 from .moa import C2fMoA, MoABlock
@@ -26,6 +26,6 @@ __all__ = (
     "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
     "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE", "ContextRefinedLowRankHybridAdaptiveGateMoE",
     "VisualEnhancedAdaptiveGateMoE", "UltimateOptimizedMoE", "ZeroCostRouter", "DualStreamGateRouterV2", "HybridAdaptiveGateMoEv2",
-    "OptimalHybridGateMoE", "MultiHeadRouterMoE", "GatedFusionMoE", "SharedExpertMoE", "MultiHeadRouterV3", "CrossPathGate", "DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup",
+    "OptimalHybridGateMoE", "MultiHeadRouterMoE", "GatedFusionMoE", "SharedExpertMoE", "DiversifiedExpertMoE", "DiversifiedExpertGroup", "MultiHeadRouterV3", "CrossPathGate", "DualStreamGateRouter", "FusedExpertGroup", "LowRankFusedExpertGroup", "SharedInvertedExpertGroup",
     "VisualDetailGate", "PyramidContextMixer",
 )

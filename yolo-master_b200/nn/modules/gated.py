@@ -225,6 +225,28 @@ class SharedInvertedExpertGroup(nn.Module):
             nn.Sequential(nn.Conv2d(hidden, out_channels, 1, bias=False), _gn(out_channels)) for _ in range(num_experts))
 
 
+class DiversifiedExpertGroup(nn.Module):
+    """`DiversifiedExpertGroup(in_channels, out_channels, num_experts, expand_ratio=2.0, top_k=2, weight_threshold=0.0, num_groups=8)`
+    (gated.py:2214-2333, v0_14): shared expand, then per expert a depthwise 3x3 with dilation 1 + e // 2 and a 1x1 projection.  The
+    `dw_dilations` parameters exist for state-dict parity; like the reference's forward, nothing reads them."""
+
+    def __init__(self, in_channels, out_channels, num_experts, expand_ratio=2.0, top_k=2, weight_threshold=0.0, num_groups=8):
+        super().__init__()
+        self.in_channels, self.out_channels, self.num_experts = in_channels, out_channels, num_experts
+        self.top_k, self.weight_threshold = top_k, weight_threshold
+        hidden = max(1, int(in_channels * expand_ratio))
+        self.shared_expand = nn.Sequential(nn.Conv2d(in_channels, hidden, 1, bias=False), _gn(hidden, num_groups), nn.SiLU(inplace=False))
+        self.dw_layers = nn.ModuleList()
+        self.dw_dilations = nn.ParameterList()
+        for i in range(num_experts):
+            d = 1 + (i // 2)
+            self.dw_layers.append(nn.Sequential(nn.Conv2d(hidden, hidden, 3, padding=d, dilation=d, groups=hidden, bias=False),
+                                                _gn(hidden, num_groups), nn.SiLU(inplace=False)))
+            self.dw_dilations.append(nn.Parameter(torch.tensor(float(d))))
+        self.expert_projections = nn.ModuleList(
+            nn.Sequential(nn.Conv2d(hidden, out_channels, 1, bias=False), _gn(out_channels, num_groups)) for _ in range(num_experts))
+
+
 class VisualDetailGate(nn.Module):
     """`VisualDetailGate(channels, num_groups=8, reduction=8)` (gated.py:1154-1178)."""
 
@@ -357,15 +379,29 @@ class _GatedMoE(nn.Module, PackCache):
         r["cx_w"], r["cx_b"] = _f32(ce.weight).reshape(-1).contiguous(), float(ce.bias.detach().float())
         pk["router"] = r
         fe = self.fused_experts
-        if self.expert_backend == "low_rank_fused":
+        if isinstance(fe, DiversifiedExpertGroup):
+            se = fe.shared_expand
+            hid = se[0].weight.shape[0]
+            pk["sf0"], pk["sf1"] = _pack_linear(se[0].weight), _gn_args(se[1])
+            pk["div_dw"] = torch.stack([_pack_dw(l[0].weight) for l in fe.dw_layers]).contiguous()             # fp16 [E][9][hid]
+            pk["div_dil"] = torch.tensor([int(l[0].dilation[0]) for l in fe.dw_layers], dtype=torch.int32, device=dev)
+            pk["div_gamma"] = torch.stack([_f32(l[1].weight) for l in fe.dw_layers]).contiguous()
+            pk["div_beta"] = torch.stack([_f32(l[1].bias) for l in fe.dw_layers]).contiguous()
+            pk["div_G"], pk["div_eps"] = fe.dw_layers[0][1].num_groups, float(fe.dw_layers[0][1].eps)
+            pk["div_one"] = torch.ones(hid, dtype=torch.float32, device=dev)
+            pk["div_zero"] = torch.zeros(hid, dtype=torch.float32, device=dev)
+        elif self.expert_backend == "low_rank_fused":
             pk["bn0"], pk["bn1"] = _pack_linear(fe.bottleneck[0].weight), _gn_args(fe.bottleneck[1])
-        if self.expert_backend in ("low_rank_fused", "fused"):
+        if isinstance(fe, DiversifiedExpertGroup):
+            pass
+        elif self.expert_backend in ("low_rank_fused", "fused"):
             fused = fe.fused if self.expert_backend == "low_rank_fused" else fe
             pk["fused_w"] = pack_gemm_weight(fused.dense_weight())
             pk["fused_gamma"], pk["fused_beta"] = _f32(fused.expert_norm_weight), _f32(fused.expert_norm_bias)
         else:
             sf = fe.shared_feature
             pk["sf0"], pk["sf1"], pk["sf3"], pk["sf4"] = _pack_linear(sf[0].weight), _gn_args(sf[1]), _pack_dw(sf[3].weight), _gn_args(sf[4])
+        if hasattr(fe, "expert_projections"):
             pk["proj_w"] = torch.stack([pack_gemm_weight(p[0].weight.detach().float()) for p in fe.expert_projections]).contiguous()
             pk["proj_gamma"] = torch.stack([_f32(p[1].weight) for p in fe.expert_projections]).contiguous()
             pk["proj_beta"] = torch.stack([_f32(p[1].bias) for p in fe.expert_projections]).contiguous()
@@ -400,6 +436,24 @@ class _GatedMoE(nn.Module, PackCache):
     def _experts(self, xd, idx, w, pk, out):
         B, H, W, _ = xd.shape
         fe = self.fused_experts
+        if isinstance(fe, DiversifiedExpertGroup):
+            # shared expand once; per routing rank the ROUTED depthwise (taps and dilation of expert idx[b, j], chosen on the device),
+            # its per-expert GroupNorm + SiLU, the grouped projection GEMM and the weighted accumulation (gated.py:2297-2333)
+            hid = pk["sf0"][0].shape[0]
+            h = _norm(ops.conv2d(xd, *pk["sf0"], hid, 1, 1, 1, 0, False), pk["sf1"], act=True)
+            oc, G, HW = self.out_dynamic, pk["proj_G"], H * W
+            acc = None
+            for j in range(idx.shape[1]):
+                rj, wj = idx[:, j].contiguous(), w[:, j].contiguous()
+                d = ops.dwconv3_routed(h, pk["div_dw"], rj, pk["div_dil"])
+                sc, sh = ops.groupnorm_stats(d, pk["div_G"], pk["div_one"], pk["div_zero"], pk["div_eps"])
+                ops.route_affine(sc, sh, pk["div_gamma"], pk["div_beta"], rj)
+                feat = ops.ew(ops.EW_AFFINE, a=d, p0=sc, p1=sh, rows_per_img=HW, act=True)
+                o, st = ops.moe_expert_gemm(feat, ops.pitch(feat), 1, B, HW, hid, pk["proj_w"], rj, oc, groups=G)
+                sc2, sh2 = ops.gn_finalize(st, B, HW, G, oc, HW * (oc // G), pk["proj_eps"], pk["proj_gamma"], pk["proj_beta"], rj, route_w=wj)
+                last = j == idx.shape[1] - 1
+                acc = ops.ew(ops.EW_AFFINE, a=o.view(B, H, W, oc), b=acc, p0=sc2, p1=sh2, rows_per_img=HW, act=False, out=out if last else None)
+            return acc
         if self.expert_backend in ("low_rank_fused", "fused"):
             t, fused = xd, fe
             if self.expert_backend == "low_rank_fused":
@@ -622,6 +676,16 @@ class OptimalHybridGateMoE(HybridAdaptiveGateMoEv2):
     """`OptimalHybridGateMoE(..., fused_expert_threshold=8, shuffle_groups=2, refine=True, refine_reduction=8)` (gated.py:1846-2023,
     v0_12): v0_11 plus a depthwise refinement gated by a global SE vector."""
     HOOKS = ("light_refine",)
+
+
+class DiversifiedExpertMoE(OptimalHybridGateMoE):
+    """`DiversifiedExpertMoE(..., fused_expert_threshold=8, shuffle_groups=2, refine=True, refine_reduction=8)` (gated.py:2499-2561,
+    v0_14): `OptimalHybridGateMoE` whose expert group is replaced by a `DiversifiedExpertGroup` (expand_ratio 2, threshold 0)."""
+
+    def __init__(self, in_channels, out_channels, num_experts=4, top_k=2, split_ratio=0.5, num_groups=8, *args, **kwargs):
+        super().__init__(in_channels, out_channels, num_experts, top_k, split_ratio, num_groups, *args, **kwargs)
+        self.fused_experts = DiversifiedExpertGroup(self.dynamic_channels, self.out_dynamic, num_experts, expand_ratio=2.0, top_k=top_k,
+                                                    weight_threshold=0.0, num_groups=num_groups)
 
 
 class MultiHeadRouterMoE(_GatedMoE):

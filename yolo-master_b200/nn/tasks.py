@@ -29,7 +29,7 @@ MIXTURE_MODULES.update({n: getattr(M, n) for n in (          # the AdaptiveGateM
     "AdaptiveGateMoE", "FusedAdaptiveGateMoE", "HybridAdaptiveGateMoE", "LowRankHybridAdaptiveGateMoE",
     "RefinedLowRankHybridAdaptiveGateMoE", "DetailAwareLowRankHybridAdaptiveGateMoE", "ContextRefinedLowRankHybridAdaptiveGateMoE",
     "VisualEnhancedAdaptiveGateMoE", "UltimateOptimizedMoE", "HybridAdaptiveGateMoEv2", "OptimalHybridGateMoE", "MultiHeadRouterMoE",
-    "GatedFusionMoE", "SharedExpertMoE")})                                      # + the v0_3 zoo block
+    "GatedFusionMoE", "SharedExpertMoE", "DiversifiedExpertMoE")})                                      # + the v0_3 zoo block
 BASE_MODULES = frozenset({M.Conv, M.DWConv, M.Bottleneck, M.SPPF, M.C2PSA, M.C2f, M.C3k2, M.C3, M.A2C2f, M.Classify})
 REPEAT_MODULES = frozenset({M.C2f, M.C3k2, M.C3, M.C2PSA, M.A2C2f})
 MIXTURE_BASE_MODULES = frozenset(MIXTURE_MODULES.values())

@@ -341,6 +341,29 @@ def nms_batched_large(pred, conf_thres, iou_thres, max_det=300, max_nms=30000, m
     return out, cnt, idx
 
 
+def dwconv3_routed(x, w_taps, route, dil):
+    """ym_dwconv3_routed_nhwc.  x: (B,H,W,C) fp16 view; w_taps fp16 [E,9,C]; route int32 (B,) view (image -> expert); dil int32 [E]."""
+    B, H, W, Cc = x.shape
+    E = w_taps.shape[0]
+    if route.dtype != torch.int32 or route.dim() != 1 or route.shape[0] != B or dil.dtype != torch.int32 or dil.numel() != E:
+        raise ValueError("dwconv3_routed: route int32 (B,), dil int32 (E,)")
+    out = new_act(B, H, W, Cc, x.device)
+    _lib.check(lib().ym_dwconv3_routed_nhwc(x.data_ptr(), pitch(x), w_taps.data_ptr(), route.data_ptr(), max(route.stride(0), 1),
+                                            dil.data_ptr(), E, B, H, W, Cc, out.data_ptr(), pitch(out), _stream()),
+               "ym_dwconv3_routed_nhwc")
+    _count()
+    return out
+
+
+def route_affine(scale, shift, gamma, beta, route):
+    """ym_route_affine, in place: (scale, shift) fp32 (B, C) from unit-gamma GroupNorm statistics -> expert route[b]'s affine."""
+    B, Cc = scale.shape
+    _lib.check(lib().ym_route_affine(scale.data_ptr(), shift.data_ptr(), gamma.data_ptr(), beta.data_ptr(), route.data_ptr(),
+                                     max(route.stride(0), 1), gamma.shape[0], B, Cc, _stream()), "ym_route_affine")
+    _count()
+    return scale, shift
+
+
 def process_mask(protos, dets, shape, upsample=True, coef_col=6):
     """ym_process_mask.  protos: (nm, mh, mw) fp16 / fp32; dets: fp32 (n, >= coef_col + nm) rows with the xyxy box (in `shape`
     coordinates) at columns 0..3 and the mask coefficients from `coef_col` -> uint8 (n, *shape) when upsample else (n, mh, mw)."""
