@@ -211,6 +211,10 @@ int ym_kpts_decode(int nl, const void* const* kpt, const int* hs, const int* ws,
 int ym_obb_finish(int nl, const void* const* angle, const int* hs, const int* ws, const float* strides, int B, int nc,
                   const float* yin, float* yout, void* stream);
 
+/* ops.scale_coords + clip_coords utils/ops.py:596-631,204-225, in place, for the points of one image (PosePredictor.construct_result
+ * models/yolo/pose/predict.py:62-66): coords fp32 rows of pitch ld >= 2, (x, y) first; params_host = (gain, pad_x, pad_y, w0, h0). */
+int ym_scale_coords(float* coords, int ld, long long n, const float* params_host, int padding, int normalize, void* stream);
+
 /* ---- DiversifiedExpertGroup (moe/gated.py:2214-2333, v0_14 zoo; csrc/mix.cu) ---------------------------------------------------
  * ym_dwconv3_routed_nhwc: dw_layers[e][0] for e = route[b * route_stride]: depthwise 3x3 whose taps (w fp16 [E][9][C], tap-major) AND
  *   dilation (dil int32 [E] on the device; padding = dilation) are chosen per image by the router, without a host round trip

@@ -110,3 +110,24 @@ def scale_boxes(img1_shape, boxes: np.ndarray, img0_shape, padding=True, xywh=Fa
         b[..., [0, 2]] = b[..., [0, 2]].clip(0, w)
         b[..., [1, 3]] = b[..., [1, 3]].clip(0, h)
     return b
+
+
+def scale_coords(img1_shape, coords: np.ndarray, img0_shape, normalize=False, padding=True) -> np.ndarray:
+    """`ops.scale_coords` + `clip_coords` utils/ops.py:596-631,204-225 on fp32 points (..., >= 2); returns a new array (fp32 arithmetic
+    in the reference's order: subtract the integer padding, divide by float32(gain), clamp, optional normalisation)."""
+    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+    pad_x = round((img1_shape[1] - round(img0_shape[1] * gain)) / 2 - 0.1)
+    pad_y = round((img1_shape[0] - round(img0_shape[0] * gain)) / 2 - 0.1)
+    c = coords.astype(np.float32).copy()
+    if padding:
+        c[..., 0] -= np.float32(pad_x)
+        c[..., 1] -= np.float32(pad_y)
+    c[..., 0] = c[..., 0] / np.float32(gain)
+    c[..., 1] = c[..., 1] / np.float32(gain)
+    h, w = img0_shape[:2]
+    c[..., 0] = c[..., 0].clip(0, w)
+    c[..., 1] = c[..., 1].clip(0, h)
+    if normalize:
+        c[..., 0] = c[..., 0] / np.float32(w)
+        c[..., 1] = c[..., 1] / np.float32(h)
+    return c

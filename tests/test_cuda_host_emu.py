@@ -23,7 +23,7 @@ from yolo_master_b200 import _lib, ops
 
 CSRC = os.path.join(ROOT, "yolo-master_b200", "csrc")
 UNITS = ["preproc.cu", "gated.cu", "nms_large.cu", "mix.cu", "postproc.cu"]
-SYMBOLS = ["ym_letterbox_u8", "ym_scale_boxes", "ym_kpts_decode", "ym_obb_finish", "ym_gate_router", "ym_gate_router_scratch_floats",
+SYMBOLS = ["ym_letterbox_u8", "ym_scale_boxes", "ym_scale_coords", "ym_kpts_decode", "ym_obb_finish", "ym_gate_router", "ym_gate_router_scratch_floats",
            "ym_zero_cost_router", "ym_zero_cost_router_scratch_floats", "ym_pixel_router", "ym_latent_router", "ym_fc_gate", "ym_classify_head", "ym_gated_select", "ym_gated_select_scratch_floats",
            "ym_ctx_mean3", "ym_gap_nhwc", "ym_nms_batched_large", "ym_nms_large_scratch_bytes", "ym_ew_nhwc", "ym_last_error",
            "ym_dwconv3_routed_nhwc", "ym_route_affine", "ym_process_mask", "ym_process_mask_scratch_bytes", "ym_nms_rotated", "ym_nms_rotated_scratch_bytes"]
@@ -478,3 +478,29 @@ def test_routed_dilated_depthwise_and_route_affine_kernels(emu):
     with pytest.raises(RuntimeError, match="multiples of 8"):
         ops.dwconv3_routed(torch.zeros((1, 2, 2, 12), dtype=torch.float16), torch.zeros((2, 9, 12), dtype=torch.float16),
                            torch.zeros((1,), dtype=torch.int32), torch.ones((2,), dtype=torch.int32))
+
+
+def test_scale_coords_kernel_and_pose_predictor(emu):
+    """ym_scale_coords bit-exact against the oracle (which test_scale_coords_oracle_matches_reference pins to ops.scale_coords), and
+    PosePredictor.construct_result: boxes through ym_scale_boxes, keypoints (n, 17, 3) through ym_scale_coords, visibility untouched."""
+    from yolo_master_b200.engine import PosePredictor
+    from yolo_master_b200.utils import ops as box_ops
+    g = torch.Generator().manual_seed(6)
+    for shape0 in ((480, 640), (1080, 1920), (100, 37)):
+        for last in (2, 3):
+            k = torch.rand((9, 17, last), generator=g) * 700 - 30
+            for norm in (False, True):
+                got = box_ops.scale_coords((640, 640), k.clone(), shape0, normalize=norm)
+                assert np.array_equal(got.numpy(), L.scale_coords((640, 640), k.numpy(), shape0, normalize=norm)), (shape0, last, norm)
+    assert box_ops.scale_coords((640, 640), torch.zeros((0, 17, 3)), (480, 640)).shape == (0, 17, 3)
+    stub = _TaskStub(None, 1)
+    stub.kpt_shape = (17, 3)
+    pred = PosePredictor(stub, imgsz=640, device="cpu")
+    rows = torch.cat([torch.rand((5, 4), generator=g) * 600, torch.rand((5, 1), generator=g), torch.zeros((5, 1)),
+                      torch.rand((5, 51), generator=g) * 600], 1)
+    frame = np.zeros((360, 500, 3), np.uint8)
+    r = pred.construct_result(rows.clone(), torch.zeros((1, 3, 640, 640)), frame, None)
+    want_k = L.scale_coords((640, 640), rows[:, 6:].reshape(5, 17, 3).numpy(), frame.shape)
+    assert np.array_equal(r.keypoints.data.numpy(), want_k) and np.array_equal(want_k[..., 2], rows[:, 6:].reshape(5, 17, 3)[..., 2].numpy())
+    assert np.array_equal(r.boxes.data[:, :4].numpy(), L.scale_boxes((640, 640), rows[:, :4].numpy(), frame.shape))
+    assert r.keypoints.xy.shape == (5, 17, 2) and r.keypoints.conf.shape == (5, 17) and len(r[:2].keypoints) == 2

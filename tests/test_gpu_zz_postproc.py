@@ -128,3 +128,16 @@ def test_obb_predictor_on_the_reference_golden():
         ref = c["out"][b]
         want = torch.cat([torch.from_numpy(L.scale_boxes((640, 640), ref[:, :4].numpy(), frames[b].shape, xywh=True)), ref[:, 6:7], ref[:, 4:6]], 1)
         assert torch.equal(r.obb.data.cpu(), want), b
+
+
+def test_scale_coords_on_device_bit_exact():
+    """ym_scale_coords through utils.ops.scale_coords against the oracle (pinned to ops.scale_coords), (n, 17, 2 | 3) keypoints."""
+    from oracle import letterbox_oracle as L
+    from yolo_master_b200.utils.ops import scale_coords
+    g = torch.Generator().manual_seed(6)
+    for shape0 in ((480, 640), (1080, 1920), (100, 37)):
+        for last in (2, 3):
+            k = torch.rand((300, 17, last), generator=g) * 700 - 30
+            for norm in (False, True):
+                got = scale_coords((640, 640), k.clone().to(DEV), shape0, normalize=norm).cpu()
+                assert np.array_equal(got.numpy(), L.scale_coords((640, 640), k.numpy(), shape0, normalize=norm)), (shape0, last, norm)

@@ -66,3 +66,24 @@ def test_scale_boxes_oracle_matches_reference(case):
     b = torch.rand((64, 6), generator=g) * torch.tensor([img1[1], img1[0], img1[1], img1[0], 1, 80]) * 1.1 - 8.0
     out = L.scale_boxes(img1, b[:, :4].numpy(), case["img0"], xywh=case["xywh"])
     assert np.array_equal(out, case["out"].numpy())
+
+
+def test_scale_coords_oracle_matches_reference():
+    """oracle scale_coords == the reference's ops.scale_coords, bit for bit (needs /root/reference: build container only)."""
+    import os
+    import sys
+    import numpy as np
+    import pytest
+    import torch
+    if not os.path.isdir("/root/reference/ultralytics"):
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, "/root/reference")
+    os.environ.setdefault("YOLO_CONFIG_DIR", "/tmp/ulcfg")
+    from ultralytics.utils import ops as R
+    from oracle import letterbox_oracle as L
+    g = torch.Generator().manual_seed(12)
+    for shape0 in ((480, 640), (1080, 1920), (100, 37), (640, 640)):
+        for norm in (False, True):
+            k = torch.rand((7, 17, 3), generator=g) * 800 - 60
+            want = R.scale_coords((640, 640), k.clone(), shape0, normalize=norm)
+            assert np.array_equal(L.scale_coords((640, 640), k.numpy(), shape0, normalize=norm), want.numpy()), (shape0, norm)

@@ -85,6 +85,7 @@ SIGNATURES = {
     "ym_nms_rotated_scratch_bytes": (cll, [ci, ci]),
     "ym_nms_rotated": (ci, [vp, ci, ci, ci, cf, cf, ci, ci, cf, vp, vp, vp, vp, vp]),
     "ym_letterbox_u8": (ci, [vp, cll, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, ci, ci, ci, ci, vp]),
+    "ym_scale_coords": (ci, [vp, ci, cll, vp, ci, ci, vp]),
     "ym_scale_boxes": (ci, [vp, ci, cll, ci, vp, ci, vp, ci, ci, vp]),
     "ym_detect_topk": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp, vp, vp]),
     "ym_detect_dense": (ci, [ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, ci, vp, vp]),

@@ -84,6 +84,16 @@ __global__ void __launch_bounds__(256) scale_boxes_kernel(float* __restrict__ bo
     scale_box(boxes + i * ld, sp.p[img], padding, xywh, DivRn());
 }
 
+struct ScaleCoordParams {
+    float p[5];
+};
+__global__ void __launch_bounds__(256) scale_coords_kernel(float* __restrict__ coords, int ld, long long n, int padding, int normalize,
+                                                           const ScaleCoordParams sp) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    scale_coord(coords + i * ld, sp.p, padding, normalize, DivRn());
+}
+
 constexpr int KPT_MAX_LEVELS = 8;
 struct KptLevels {
     const float* kpt[KPT_MAX_LEVELS];   // fp32 [B][h][w][nk]
@@ -234,5 +244,18 @@ extern "C" int ym_scale_boxes(float* boxes, int ld, long long n, int rows_per_im
     YM_LAUNCH(scale_boxes_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, boxes, ld, n, rows_per_img, row_img, padding,
               xywh, sp);
     YM_CHECK_LAUNCH("scale_boxes");
+    return YM_OK;
+}
+
+// ops.scale_coords (utils/ops.py:596-631) in place for the points of ONE image: coords fp32 rows of pitch ld >= 2 with (x, y) in the
+// first two columns (keypoints (n, nk, 2 | 3): ld = 2 | 3, rows = n * nk); params_host = (gain, pad_x, pad_y, w0, h0).
+extern "C" int ym_scale_coords(float* coords, int ld, long long n, const float* params_host, int padding, int normalize, void* stream) {
+    YM_CHECK_ARG(n == 0 || coords, "ym_scale_coords: null coords");
+    YM_CHECK_ARG(ld >= 2 && n >= 0 && params_host, "ym_scale_coords: row pitch >= 2");
+    if (n == 0) return YM_OK;
+    ScaleCoordParams sp;
+    memcpy(sp.p, params_host, sizeof(sp.p));
+    YM_LAUNCH(scale_coords_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, coords, ld, n, padding, normalize, sp);
+    YM_CHECK_LAUNCH("scale_coords");
     return YM_OK;
 }

@@ -98,6 +98,26 @@ YM_HD void scale_box(float* b, const float* p, int padding, int xywh, Div div) {
     b[3] = y2;
 }
 
+// ops.scale_coords + clip_coords (utils/ops.py:596-631,204-225) for one point (x, y[, ...]): p = (gain, pad_x, pad_y, w0, h0).
+template <typename Div>
+YM_HD void scale_coord(float* c, const float* p, int padding, int normalize, Div div) {
+    float x = c[0], y = c[1];
+    if (padding) {
+        x -= p[1];
+        y -= p[2];
+    }
+    x = div(x, p[0]);
+    y = div(y, p[0]);
+    x = x < 0.f ? 0.f : (x > p[3] ? p[3] : x);      // clamp_(0, w) keeps NaN
+    y = y < 0.f ? 0.f : (y > p[4] ? p[4] : y);
+    if (normalize) {
+        x = div(x, p[3]);
+        y = div(y, p[4]);
+    }
+    c[0] = x;
+    c[1] = y;
+}
+
 // Pose.kpts_decode head.py:644-664 for one output element y[b][k][a] (k = keypoint*ndim + d): x / y are (v*2 + grid coordinate) *
 // stride (the reference's anchor - 0.5 IS the integer grid coordinate), the optional visibility channel is a sigmoid.
 // v points at the level's fp32 NHWC tower output [B][h][w][nk]; (gx, gy) is the anchor's cell, `sig` an IEEE-accurate sigmoid.

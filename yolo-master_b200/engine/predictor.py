@@ -203,3 +203,23 @@ class OBBPredictor(DetectionPredictor):
         ops.scale_boxes(img.shape[2:], rboxes[:, :4], orig_img.shape, xywh=True)
         obb = torch.cat([rboxes, pred[:, 4:6]], dim=-1)
         return Results(orig_img, path=img_path, names=getattr(self.model, "names", None), obb=obb)
+
+
+class PosePredictor(DetectionPredictor):
+    """ultralytics/models/yolo/pose/predict.py:9-66: NMS carrying the keypoint columns, boxes and keypoints back to the original frame
+    (`ym_scale_boxes`, `ym_scale_coords`)."""
+
+    task = "pose"
+
+    def construct_results(self, preds, img, orig_imgs):
+        paths = self.batch[0] if self.batch else [None] * len(preds)
+        return [self.construct_result(p, img, o, pth) for p, o, pth in zip(preds, orig_imgs, paths)]
+
+    def construct_result(self, pred, img, orig_img, img_path):
+        """pose/predict.py:43-66."""
+        result = super().construct_result(pred, img, orig_img, img_path)
+        kpt_shape = tuple(getattr(self.model, "kpt_shape", None) or self.model.model[-1].kpt_shape)
+        kpts = pred[:, 6:].float().reshape(pred.shape[0], *kpt_shape).contiguous()
+        ops.scale_coords(img.shape[2:], kpts, orig_img.shape)
+        result.keypoints = type(result)(orig_img, keypoints=kpts).keypoints
+        return result

@@ -117,6 +117,47 @@ class Masks:
         return Masks(self.data.cpu().numpy(), self.orig_shape)
 
 
+class Keypoints:
+    """(n, nk, 2 | 3) keypoints in pixels of the original frame (results.py:1180-1290): `data`, `xy`, `conf`, `has_visible`."""
+
+    def __init__(self, keypoints, orig_shape):
+        if keypoints.ndim == 2:
+            keypoints = keypoints[None, :]
+        self.data = keypoints
+        self.orig_shape = tuple(orig_shape)
+        self.has_visible = self.data.shape[-1] == 3
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    @property
+    def xy(self):
+        return self.data[..., :2]
+
+    @property
+    def conf(self):
+        return self.data[..., 2] if self.has_visible else None
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        return Keypoints(self.data[idx], self.orig_shape)
+
+    def cpu(self):
+        return Keypoints(self.data.cpu(), self.orig_shape)
+
+    def cuda(self):
+        return Keypoints(self.data.cuda(), self.orig_shape)
+
+    def to(self, *args, **kwargs):
+        return Keypoints(self.data.to(*args, **kwargs), self.orig_shape)
+
+    def numpy(self):
+        return Keypoints(self.data.cpu().numpy(), self.orig_shape)
+
+
 class OBB:
     """(n, 7) rows (x, y, w, h, angle, conf, cls) in pixels of the original frame (results.py:1380-1560)."""
 
@@ -180,11 +221,12 @@ class OBB:
 class Results:
     """One image's detections (results.py:184-300): `orig_img`, `orig_shape`, `boxes`, `masks`, `obb`, `names`, `path`, `speed`."""
 
-    def __init__(self, orig_img, path=None, names=None, boxes=None, speed=None, masks=None, obb=None):
+    def __init__(self, orig_img, path=None, names=None, boxes=None, speed=None, masks=None, obb=None, keypoints=None):
         self.orig_img = orig_img
         self.orig_shape = tuple(orig_img.shape[:2])
         self.boxes = Boxes(boxes, self.orig_shape) if boxes is not None else None
-        self.probs = self.keypoints = None
+        self.probs = None
+        self.keypoints = Keypoints(keypoints, self.orig_shape) if keypoints is not None else None
         self.masks = Masks(masks, self.orig_shape) if masks is not None else None
         self.obb = OBB(obb, self.orig_shape) if obb is not None else None
         self.speed = speed if speed is not None else {"preprocess": None, "inference": None, "postprocess": None}
@@ -202,11 +244,12 @@ class Results:
 
     def __getitem__(self, idx):
         return Results(self.orig_img, self.path, self.names, None if self.boxes is None else self.boxes.data[idx], self.speed,
-                       None if self.masks is None else self.masks.data[idx], None if self.obb is None else self.obb.data[idx])
+                       None if self.masks is None else self.masks.data[idx], None if self.obb is None else self.obb.data[idx],
+                       None if self.keypoints is None else self.keypoints.data[idx])
 
     def _apply(self, fn, *args, **kwargs):
         r = Results(self.orig_img, self.path, self.names, None, self.speed)
-        for k in ("boxes", "masks", "obb"):
+        for k in ("boxes", "masks", "obb", "keypoints"):
             v = getattr(self, k)
             if v is not None:
                 setattr(r, k, getattr(v, fn)(*args, **kwargs))

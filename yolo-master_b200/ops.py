@@ -617,6 +617,18 @@ def scale_boxes(boxes, params, rows_per_img=0, row_img=None, padding=True, xywh=
     return boxes
 
 
+def scale_coords(coords, params, padding=True, normalize=False):
+    """ym_scale_coords, in place.  coords: fp32 CUDA contiguous (..., 2 | 3) points of ONE image; params: fp32 HOST (5,) row."""
+    if not _dev(coords) or coords.dtype != torch.float32 or not coords.is_contiguous() or coords.shape[-1] < 2:
+        raise ValueError("scale_coords: expected a contiguous fp32 CUDA tensor (..., >= 2)")
+    if params.is_cuda or params.dtype != torch.float32 or params.numel() != 5 or not params.is_contiguous():
+        raise ValueError("scale_coords: params must be a contiguous fp32 HOST tensor of 5 values")
+    _lib.check(lib().ym_scale_coords(coords.data_ptr(), coords.shape[-1], coords.numel() // coords.shape[-1], params.data_ptr(),
+                                     1 if padding else 0, 1 if normalize else 0, _stream()), "ym_scale_coords")
+    _count()
+    return coords
+
+
 EW_SIGMOID, EW_MUL_GATE, EW_MUL = 6, 7, 8
 
 

@@ -71,3 +71,11 @@ def process_mask(protos, masks_in, bboxes, shape, upsample: bool = False):
     xyxy `bboxes` (given in `shape` coordinates); H, W = `shape` when upsample else the prototype resolution."""
     dets = torch.cat([bboxes.float(), masks_in.float()], 1).contiguous()
     return _k.process_mask(protos, dets, shape, upsample=upsample, coef_col=4)
+
+
+def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None, normalize: bool = False, padding: bool = True):
+    """utils/ops.py:596-631: rescale (..., 2 | 3) points from the letterboxed `img1_shape` to `img0_shape` and clip them, in place."""
+    if coords.numel() == 0:
+        return coords
+    return _k.scale_coords(coords, box_params(img1_shape, [img0_shape], None if ratio_pad is None else [ratio_pad]).reshape(5).contiguous(),
+                           padding=padding, normalize=normalize)
