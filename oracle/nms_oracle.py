@@ -5,8 +5,11 @@
   tests/golden/make_golden.py -> nms.golden.pt (tests/test_nms_oracle.py).
 * `cw_nms` restates the ONLY executable specification of CW-NMS in the reference snapshot, the C++ deployment code
   `examples/YOLO-Master-Cross-Platform-Edge-Deployment/cpp/src/common.cpp:56-198` (`box_iou`, `nms_greedy`, `nms_and_cap`),
-  in float64 like the C++.  **Parity unpinned**: the reference has no test, golden vector or Python implementation of
-  CW-NMS; the known-answer cases in tests/test_nms_oracle.py were derived by hand from the C++ formulae.
+  in float64 like the C++.  **Pinned** to the reference's own C++: oracle/Makefile compiles common.cpp as it lies (against
+  oracle/cv_shim, a stand-in for the few cv:: value types; there is no OpenCV in this image) into oracle/_ref/libcwnms_ref.so,
+  tests/golden/make_cwnms_golden.py runs its `decode` (= decode_candidates + nms_and_cap) into tests/golden/cwnms.golden.pt and
+  tests/test_nms_oracle.py holds `cw_nms` to it: survivor set / order / score / class exact, boxes to one fp32 ulp (incl. the
+  > 3000-candidate pool cap, Standard mode, max_det cap and frame clipping).  Hand-derived known answers are kept beside it.
 """
 from __future__ import annotations
 

@@ -12,7 +12,7 @@ from yolo_master_b200 import ops
 from yolo_master_b200.nn.tasks import ClassificationModel
 from yolo_master_b200.utils.synth import synth_images
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run of ym_classify_head / the cls model")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 NAME, CFG = "yolo-master-cls-n-v0_1", "master/v0_1/cls/yolo-master-cls-n.yaml"
 

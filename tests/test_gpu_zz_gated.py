@@ -19,8 +19,7 @@ from yolo_master_b200.nn.modules.gated import VisualEnhancedAdaptiveGateMoE
 from yolo_master_b200.nn.tasks import DetectionModel
 from yolo_master_b200.utils.synth import fill_state_dict_, synth_images
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run of the gated-MoE kernels (host-verified only)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 CFG = "master/v0_10/det/yolo-master-n.yaml"
 NAME = "yolo-master-n-v0_10"

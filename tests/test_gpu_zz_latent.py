@@ -11,7 +11,7 @@ from oracle import yolo_master_oracle as O
 from yolo_master_b200.nn.tasks import DetectionModel
 from yolo_master_b200.utils.synth import synth_images
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run of ym_latent_router / the latent model")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 NAME, CFG = "yolo26-master-latent-n", "26/yolo26-master-latent-n-resinit010.yaml"
 

@@ -14,7 +14,7 @@ from oracle import yolo_master_oracle as O
 from yolo_master_b200.nn.tasks import DetectionModel
 from yolo_master_b200.utils.synth import synth_images
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run of the v0_1 model composition")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 NAME, CFG = "yolo-master-n-v0_1", "master/v0_1/det/yolo-master-n.yaml"
 

@@ -11,7 +11,7 @@ from oracle import nms_oracle as N
 from yolo_master_b200 import ops
 from yolo_master_b200.utils.nms import non_max_suppression
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run of ym_nms_batched_large (host-verified only)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 

@@ -11,7 +11,7 @@ from oracle import yolo_master_oracle as O
 from yolo_master_b200.nn.tasks import OBBModel
 from yolo_master_b200.utils.synth import synth_images
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run of ym_obb_finish / the obb model")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 NAME, CFG = "yolo-master-obb-n-v0_1", "master/v0_1/obb/yolo-master-obb-n.yaml"
 

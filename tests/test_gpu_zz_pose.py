@@ -16,7 +16,7 @@ from yolo_master_b200.nn.tasks import PoseModel
 from yolo_master_b200.utils.nms import non_max_suppression
 from yolo_master_b200.utils.synth import synth_images
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run of ym_kpts_decode / the pose model")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 NAME, CFG = "yolo-master-pose-n-v0_1", "master/v0_1/pose/yolo-master-pose-n.yaml"
 

@@ -17,7 +17,7 @@ from oracle import postproc_oracle as PP
 from yolo_master_b200.utils.nms import non_max_suppression
 from yolo_master_b200.utils.ops import process_mask
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run of ym_process_mask / ym_nms_rotated")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 G = torch.load(os.path.join(GOLD, "postproc.golden.pt"))
 

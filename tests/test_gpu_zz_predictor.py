@@ -20,8 +20,7 @@ from yolo_master_b200.engine import DetectionPredictor
 from yolo_master_b200.nn.tasks import DetectionModel
 from yolo_master_b200.utils import ops as box_ops
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run of ym_letterbox_u8 / ym_scale_boxes (host-verified only)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 GOLDEN = torch.load(os.path.join(GOLD, "letterbox.golden.pt"))
 

@@ -14,7 +14,7 @@ from yolo_master_b200.nn.modules.head import Proto
 from yolo_master_b200.nn.tasks import SegmentationModel
 from yolo_master_b200.utils.synth import fill_state_dict_, synth_images
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run of the Segment head / Proto composition")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 NAME, CFG = "yolo-master-seg-n-v0_1", "master/v0_1/seg/yolo-master-seg-n.yaml"
 

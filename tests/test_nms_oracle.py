@@ -1,4 +1,5 @@
-"""NMS oracle pinned to the real reference function; CW-NMS oracle (parity unpinned) checked on hand-derived answers."""
+"""NMS oracle pinned to the real reference function; CW-NMS oracle pinned to the reference's own C++ (`nms_and_cap`, common.cpp:127-205,
+compiled as it lies by oracle/Makefile -> tests/golden/cwnms.golden.pt) and checked on hand-derived answers."""
 import importlib.util
 import math
 import os
@@ -65,3 +66,46 @@ def test_cw_nms_clip_cap_and_threshold_edges():
     np.testing.assert_allclose(dets[1, :4], [630, 630, 10, 10])
     dets, kept = N.cw_nms(boxes, scores, cls, 0.25, 0.5, 0.1, 1, 640, 640)
     assert kept == [0]                       # max_det cap counts emitted detections
+
+
+def _cw_oracle_image(pred_img, c):
+    """oracle.cw_nms on one raw (4 + nc, A) prediction, candidates decoded like decode_candidates (common.cpp:93-125) with an
+    identity letterbox: first-max class, top-left xywh in fp32."""
+    p = pred_img
+    sc, cl = p[4:].max(0)
+    cx, cy, w, h = p[0], p[1], p[2], p[3]
+    boxes = torch.stack([cx - 0.5 * w, cy - 0.5 * h, w, h], 1).numpy()
+    return N.cw_nms(boxes, sc.numpy(), cl.numpy(), c["conf"], c["iou"], c["sigma"], c["max_det"], c["frame_w"], c["frame_h"],
+                    cluster=bool(c["cluster"]))
+
+
+def test_cw_nms_oracle_matches_reference_cpp_golden():
+    """The restatement against the reference's own compiled `decode` = decode_candidates + nms_and_cap: same survivors in the same
+    order (score / class columns exact), boxes equal to the last fp32 bit or one ulp of it (libm exp vs numpy exp in float64)."""
+    g = torch.load(os.path.join(GOLD, "cwnms.golden.pt"))
+    for c in g["cases"]:
+        pred = synth_predictions(c["B"], c["nc"], c["A"], c["seed"], c["dense"])
+        for b in range(c["B"]):
+            dets, _ = _cw_oracle_image(pred[b], c)
+            ref = c["dets"][b].numpy()
+            assert dets.shape == ref.shape, (c["seed"], b, dets.shape, ref.shape)
+            assert np.array_equal(dets[:, 4:], ref[:, 4:]), "survivor set / order differs from the reference C++"
+            np.testing.assert_allclose(dets[:, :4], ref[:, :4], rtol=3e-7, atol=2e-5)
+
+
+def test_cw_nms_reference_library_live():
+    """When oracle/_ref/libcwnms_ref.so is present (build container, or shipped to the GPU box), the golden is what it produces NOW."""
+    import pytest
+    so = os.path.join(os.path.dirname(GOLD), "..", "oracle", "_ref", "libcwnms_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libcwnms_ref.so not built (make -C oracle needs /root/reference)")
+    spec = importlib.util.spec_from_file_location("make_cwnms_golden", os.path.join(GOLD, "make_cwnms_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    f = mk.load_ref()
+    g = torch.load(os.path.join(GOLD, "cwnms.golden.pt"))
+    for c in g["cases"][:3]:
+        pred = synth_predictions(c["B"], c["nc"], c["A"], c["seed"], c["dense"])
+        for b in range(c["B"]):
+            d = mk.reference_dets(f, pred[b], c["nc"], c["conf"], c["iou"], c["max_det"], c["cluster"], c["sigma"], c["frame_w"], c["frame_h"])
+            assert torch.equal(d, c["dets"][b])
