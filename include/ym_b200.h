@@ -74,6 +74,16 @@ int ym_set_attention_poly(int every);
  *      (default: removes 50 of the 74 KB per KV tile that crossed the 128 B/clk shared-memory pipe; 1.005 -> 0.922 ms)
  *   3  1 + 2 */
 int ym_set_attention_chunked(int mode);
+/* Same contract, warp-specialised (tc_attention2.cu; the default of ym_attention_fwd): one CTA = two 128-row query tiles of one
+ * (image, head) sharing every K / V tile, K / V / Q by TMA (4-D tensor maps over the packed qkv buffer: d, token, head, image) into a
+ * 6-stage ring, one thread issuing all TMA + tcgen05.mma, eight softmax warps (thread = query row) that hand S / P / O over through
+ * mbarriers only - no __syncthreads in the key loop, QK(t+1) issued while softmax(t) runs.  Same arithmetic as ym_attention_fwd_tc
+ * (lazy rescale, P in tensor memory, TS-mode PV).  `_supported`: tensor-map strides must be multiples of 16 bytes. */
+int ym_attention_fwd_tc2(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
+                         int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream);
+int ym_attention_fwd_tc2_supported(int heads, int head_stride, int ld);
+/* Kernel behind ym_attention_fwd: 2 = ym_attention_fwd_tc2 (default), 1 = ym_attention_fwd_tc, 0 = mma.sync kernel.  Returns the
+ * previous setting (A/B baselines for tests and profiles; nothing in the package changes it). */
 int ym_set_attention_impl(int impl);
 
 /* EfficientSpatialRouter.forward + BaseRouter._process_logits (eval)  moe/routers.py:283-304, :185-265.
@@ -220,11 +230,13 @@ int ym_scale_coords(float* coords, int ld, long long n, const float* params_host
  *   dilation (dil int32 [E] on the device; padding = dilation) are chosen per image by the router, without a host round trip
  *   (the reference loops over torch.unique(indices).tolist()).  x fp16 [B][H][W][ldx] -> out fp16 [B][H][W][ldo]; fp32 accumulation.
  * ym_route_affine: in place on (scale, shift) fp32 [B][C] = (rstd, -mean * rstd) from ym_groupnorm_stats with unit gamma:
- *   scale *= gamma[e], shift = shift * gamma[e] + beta[e]  (gamma, beta fp32 [E][C]): the per-expert GroupNorm dw_layers[e][1]. */
+ *   scale *= gamma[e], shift = shift * gamma[e] + beta[e]  (gamma, beta fp32 [E][C]): the per-expert GroupNorm dw_layers[e][1];
+ *   optional route_w fp32 [B]: both are then multiplied by the image's routing weight (the routed projection of the gated family when
+ *   its GroupNorm groups are narrower than the 8-channel statistics granule of ym_moe_expert_gemm's epilogue). */
 int ym_dwconv3_routed_nhwc(const void* x, int ldx, const void* w, const int* route, int route_stride, const int* dil, int E, int B, int H,
                            int W, int C, void* out, int ldo, void* stream);
 int ym_route_affine(float* scale, float* shift, const float* gamma, const float* beta, const int* route, int route_stride, int E, int B,
-                    int C, void* stream);
+                    int C, const float* route_w, void* stream);
 
 /* ---- Segment / OBB post-processing (csrc/postproc.cu) ------------------------------------------------
  * ym_process_mask: ops.process_mask(protos, masks_in, bboxes, shape, upsample) ultralytics/utils/ops.py:500-528 (+ crop_mask :477-497)

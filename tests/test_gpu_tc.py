@@ -114,6 +114,66 @@ def test_tc_attention_large_logits_lazy_rescale(softmax_mode):
     assert_close(out, ref, what="tc attention lazy rescale")
 
 
+def _attn_ref(qkv, batch, N, heads, hs, dv):
+    t = qkv.float().view(batch, N, heads, hs).permute(0, 2, 1, 3)
+    q, k, v = t[..., :32], t[..., 32:64], t[..., 64:]
+    return (torch.softmax((q * 32 ** -0.5) @ k.transpose(-1, -2), -1) @ v).permute(0, 2, 1, 3).reshape(batch, N, 1, heads * dv)
+
+
+@pytest.mark.parametrize("N,heads,dv,batch", [(64, 1, 32, 1), (128, 2, 32, 2), (256, 2, 32, 1), (257, 2, 32, 2), (400, 2, 32, 3), (1600, 2, 32, 2),
+                                              (221, 4, 32, 2), (400, 2, 64, 2), (100, 2, 64, 1), (6400, 2, 32, 2), (40, 1, 32, 1), (17, 2, 32, 2),
+                                              (129, 1, 32, 1), (385, 3, 32, 1), (449, 2, 64, 2), (3200, 1, 32, 1)])
+def test_tc_attention2_strict(N, heads, dv, batch):
+    """Warp-specialised tcgen05 / TMA attention kernel (ym_attention_fwd_tc2) alone vs fp32 softmax attention, strict tolerance:
+    ragged N (query-tile and key-tile tails, an absent second query tile), one and several heads, d_v = 64, the P3 length."""
+    from yolo_master_b200 import _lib
+    hs = 64 + dv
+    g = torch.Generator().manual_seed(N + dv)
+    qkv = torch.randn((batch, N, 1, heads * hs), generator=g).half()
+    out = torch.full((batch, N, 1, heads * dv), float("nan"), dtype=torch.float16, device=DEV)
+    _lib.check(_lib.load().ym_attention_fwd_tc2(qkv.to(DEV).data_ptr(), heads * hs, batch, N, heads, hs, 0, 32, 64, 32, dv,
+                                                32 ** -0.5, out.data_ptr(), heads * dv, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert_close(out, _attn_ref(qkv, batch, N, heads, hs, dv), what=f"tc attention2 N={N} dv={dv}")
+
+
+def test_tc_attention2_large_logits_lazy_rescale_and_impl_agreement():
+    """Growing row maxima exercise the lazy O rescale; the three kernels behind ym_attention_fwd agree within the strict tolerance."""
+    from yolo_master_b200 import _lib, ops
+    N, heads, dv, hs = 512, 1, 32, 96
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn((1, N, 1, hs), generator=g)
+    qkv[..., 32:64] *= torch.linspace(0.5, 6.0, N).view(1, N, 1, 1)     # key norms increase along the sequence
+    qkv = qkv.half()
+    ref = _attn_ref(qkv, 1, N, heads, hs, dv)
+    outs = []
+    for impl in (2, 1, 0):
+        prev = _lib.load().ym_set_attention_impl(impl)
+        try:
+            outs.append(ops.attention(qkv.to(DEV), 1, N, heads, hs, 0, 32, 64, 32, dv, 32 ** -0.5))
+            torch.cuda.synchronize()
+        finally:
+            _lib.load().ym_set_attention_impl(prev)
+        assert_close(outs[-1].reshape(ref.shape), ref, what=f"attention impl {impl} lazy rescale")
+    assert _lib.load().ym_set_attention_impl(2) == 2, "the warp-specialised kernel is the default behind ym_attention_fwd"
+
+
+def test_tc_attention2_area_layout_interleaved_qkv():
+    """The layout AAttn really uses (block.py:1708-1722): per head [q | k | v] interleaved in one (B, N, heads*3*32) buffer, output written
+    into a channel slice of a wider buffer (pitch > heads*d_v)."""
+    from yolo_master_b200 import _lib
+    B, N, heads, hd = 3, 1600, 2, 32
+    g = torch.Generator().manual_seed(11)
+    qkv = torch.randn((B, N, 1, heads * 3 * hd), generator=g).half()
+    wide = torch.zeros((B, N, 1, 256), dtype=torch.float16, device=DEV)
+    out = wide[..., 64:64 + heads * hd]
+    _lib.check(_lib.load().ym_attention_fwd_tc2(qkv.to(DEV).data_ptr(), heads * 3 * hd, B, N, heads, 3 * hd, 0, hd, 2 * hd, hd, hd,
+                                                hd ** -0.5, out.data_ptr(), 256, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert_close(out, _attn_ref(qkv, B, N, heads, 3 * hd, hd), what="tc attention2 AAttn layout")
+    assert float(wide[..., :64].abs().max()) == 0 and float(wide[..., 128:].abs().max()) == 0, "wrote outside its channel slice"
+
+
 @pytest.mark.parametrize("c1,c2,k,s,act", [
     (64, 64, 1, 1, True), (64, 192, 1, 1, False), (384, 128, 1, 1, True), (48, 64, 1, 1, True), (96, 64, 1, 1, True),
     (16, 32, 3, 2, True), (64, 64, 3, 2, True), (32, 32, 3, 1, True), (16, 8, 3, 1, True), (128, 256, 3, 2, True),

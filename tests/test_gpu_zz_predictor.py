@@ -58,7 +58,9 @@ def test_letterbox_kernel_shapes_dtypes_batches():
         assert np.array_equal(lb.apply_batch(dev)[0].cpu().numpy(), L.letterbox_frame(img, new_shape)), (h, w, new_shape)
         u8 = torch.from_numpy(want).to(DEV)
         assert torch.equal(lb.apply_batch(dev, swap_rb=True, chw=True, dtype=torch.float16)[0], u8.half() / 255)
-        assert torch.equal(lb.apply_batch(dev, swap_rb=True, chw=True, dtype=torch.float32)[0], u8.float() / 255)
+        # fp32: the kernel divides exactly (x / 255 correctly rounded = the reference's CPU `im.float() / 255`); torch's CUDA scalar division
+        # multiplies by the reciprocal instead (1 ulp apart on some values), so the exact reference is computed on the host
+        assert torch.equal(lb.apply_batch(dev, swap_rb=True, chw=True, dtype=torch.float32)[0].cpu(), u8.cpu().float() / 255)
     frames = np.stack([_frame(20 + i, 360, 500) for i in range(5)])
     out = LetterBox((640, 640)).apply_batch(torch.from_numpy(frames).to(DEV), swap_rb=True, chw=True).cpu().numpy()
     for i in range(5):

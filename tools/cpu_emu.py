@@ -442,10 +442,13 @@ def dwconv3_routed(x, w_taps, route, dil):
     return _out(y.permute(0, 2, 3, 1), None)
 
 
-def route_affine(scale, shift, gamma, beta, route):
+def route_affine(scale, shift, gamma, beta, route, route_w=None):
     g, bt = gamma[route.long()], beta[route.long()]
     scale.mul_(g)
     shift.mul_(g).add_(bt)
+    if route_w is not None:
+        scale.mul_(route_w.view(-1, 1))
+        shift.mul_(route_w.view(-1, 1))
     return scale, shift
 
 

@@ -12,13 +12,13 @@ B, N, heads, hd = 32, 6400, 2, 32
 qkv = torch.randn((B, 80, 80, 3 * heads * hd), device="cuda").half()
 out = ops.new_act(B, 80, 80, heads * hd, "cuda")
 L = _lib.load()
-for impl in (0, 1):
+for impl in (1, 2):
     L.ym_set_attention_impl(impl)
     for _ in range(2):
         ops.attention(qkv, B, N, heads, 3 * hd, 0, hd, 2 * hd, hd, hd, hd ** -0.5, out=out)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-for impl in (0, 1):
+for impl in (1, 2):
     L.ym_set_attention_impl(impl)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -24,6 +24,8 @@ SIGNATURES = {
     "ym_concat2_nhwc": (ci, [vp, ci, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, vp]),
     "ym_attention_fwd": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, cf, vp, ci, vp]),
     "ym_attention_fwd_tc": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, cf, vp, ci, vp]),
+    "ym_attention_fwd_tc2": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, cf, vp, ci, vp]),
+    "ym_attention_fwd_tc2_supported": (ci, [ci, ci, ci]),
     "ym_set_attention_impl": (ci, [ci]),
     "ym_set_attention_poly": (ci, [ci]),
     "ym_set_attention_chunked": (ci, [ci]),
@@ -79,7 +81,7 @@ SIGNATURES = {
     "ym_obb_finish": (ci, [ci, C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, vp, vp, vp]),
     "ym_kpts_decode": (ci, [ci, C.POINTER(vp), C.POINTER(ci), C.POINTER(ci), C.POINTER(cf), ci, ci, ci, vp, vp]),
     "ym_dwconv3_routed_nhwc": (ci, [vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, ci, vp, ci, vp]),
-    "ym_route_affine": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "ym_route_affine": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp]),
     "ym_process_mask_scratch_bytes": (cll, [ci, ci, ci]),
     "ym_process_mask": (ci, [vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, ci, vp, vp, vp]),
     "ym_nms_rotated_scratch_bytes": (cll, [ci, ci]),

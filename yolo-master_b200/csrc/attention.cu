@@ -209,10 +209,15 @@ using namespace ym;
 
 extern "C" int ym_attention_fwd_tc(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
                                    int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream);
-static int g_attention_impl = 1;  // 1 = tcgen05/TMEM kernel (tc_attention.cu), 0 = mma.sync kernel (this file)
+extern "C" int ym_attention_fwd_tc2(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
+                                    int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream);
+extern "C" int ym_attention_fwd_tc2_supported(int heads, int head_stride, int ld);
+// 2 = warp-specialised tcgen05 / TMA kernel (tc_attention2.cu, default), 1 = one-tile-per-CTA tcgen05 kernel (tc_attention.cu),
+// 0 = mma.sync kernel (this file).  The older kernels stay selectable as A/B baselines of the same contract.
+static int g_attention_impl = 2;
 extern "C" int ym_set_attention_impl(int impl) {
     const int old = g_attention_impl;
-    if (impl == 0 || impl == 1) g_attention_impl = impl;
+    if (impl >= 0 && impl <= 2) g_attention_impl = impl;
     return old;
 }
 
@@ -227,7 +232,9 @@ extern "C" int ym_attention_fwd(const void* qkv, int ld, int batch, int N, int h
     YM_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0 && ldo % 2 == 0, "ym_attention_fwd: alignment");
     YM_CHECK_ARG(N > 0 && heads > 0 && batch >= 0 && batch < 65536, "ym_attention_fwd: bad sizes");
     if (batch == 0) return YM_OK;
-    if (g_attention_impl == 1 && ((uintptr_t)out & 15) == 0 && ldo % 8 == 0)
+    if (g_attention_impl == 2 && ((uintptr_t)out & 15) == 0 && ldo % 8 == 0 && ym_attention_fwd_tc2_supported(heads, head_stride, ld))
+        return ym_attention_fwd_tc2(qkv, ld, batch, N, heads, head_stride, q_off, k_off, v_off, d_qk, d_v, scale, out, ldo, stream);
+    if (g_attention_impl >= 1 && ((uintptr_t)out & 15) == 0 && ldo % 8 == 0)
         return ym_attention_fwd_tc(qkv, ld, batch, N, heads, head_stride, q_off, k_off, v_off, d_qk, d_v, scale, out, ldo, stream);
     const float sl2 = scale * 1.4426950408889634f;
     dim3 grid((N + ATT_BQ - 1) / ATT_BQ, heads, batch);

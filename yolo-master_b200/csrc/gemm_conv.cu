@@ -231,11 +231,11 @@ __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParam
     for (int ni = 0; ni < NT; ++ni) {
         const int nl = ni * 8 + 2 * t;
         const int n = n0 + nl;
-        const bool nok = n < p.Cout;  // Cout is even -> the pair is in or out together
+        const bool nok = n < p.Cout;  // an odd Cout (1-class heads, the OBB angle) leaves the second channel of the last pair out
         float bias0 = 0.f, bias1 = 0.f;
         if (nok && biasb != nullptr) {
             bias0 = biasb[n];
-            bias1 = biasb[n + 1];
+            if (n + 1 < p.Cout) bias1 = biasb[n + 1];
         }
         float ssum = 0.f, ssq = 0.f;
 #pragma unroll
@@ -393,7 +393,7 @@ extern "C" int ym_conv2d_nhwc(const void* x, int ldx, int B, int H, int W, int C
                               int out_f32, const void* res, int ldr, int act, void* stream) {
     YM_CHECK_ARG(x && w && out, "ym_conv2d_nhwc: null pointer");
     YM_CHECK_ARG(Cin % 8 == 0 && ldx % 8 == 0, "ym_conv2d_nhwc: Cin (%d) and ldx (%d) must be multiples of 8", Cin, ldx);
-    YM_CHECK_ARG(Cout % 2 == 0, "ym_conv2d_nhwc: Cout (%d) must be even", Cout);
+    YM_CHECK_ARG(Cout >= 1, "ym_conv2d_nhwc: Cout (%d) must be positive", Cout);
     YM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, "ym_conv2d_nhwc: x/w must be 16-byte aligned");
     YM_CHECK_ARG(Cout % 8 != 0 || (((uintptr_t)out & 15) == 0 && ldo % (out_f32 ? 4 : 8) == 0),
                  "ym_conv2d_nhwc: out must be 16-byte aligned with a pitch (%d) that keeps rows 16-byte aligned", ldo);

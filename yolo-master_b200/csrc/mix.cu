@@ -144,15 +144,17 @@ __global__ void __launch_bounds__(256) dw3_routed_kernel(const __half* __restric
 // scale' = scale * gamma[e], shift' = shift * gamma[e] + beta[e], e = route[b]  (the per-expert GroupNorm of dw_layers[e][1]).
 __global__ void __launch_bounds__(256) route_affine_kernel(float* __restrict__ scale, float* __restrict__ shift,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           const int* __restrict__ route, int route_stride, int E, int B, int C) {
+                                                           const int* __restrict__ route, int route_stride, int E, int B, int C,
+                                                           const float* __restrict__ route_w) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * C) return;
     const int b = (int)(i / C), c = (int)(i - (long long)b * C);
     int e = route[(long long)b * route_stride];
     e = e < 0 ? 0 : (e >= E ? E - 1 : e);
     const float g = gamma[(long long)e * C + c];
-    scale[i] = scale[i] * g;
-    shift[i] = fmaf(shift[i], g, beta[(long long)e * C + c]);
+    const float rw = route_w != nullptr ? route_w[b] : 1.f;      // routing weight of image b folded into the affine
+    scale[i] = scale[i] * g * rw;
+    shift[i] = fmaf(shift[i], g, beta[(long long)e * C + c]) * rw;
 }
 
 }  // namespace ym
@@ -221,13 +223,13 @@ extern "C" int ym_dwconv3_routed_nhwc(const void* x, int ldx, const void* w, con
 
 // In place on scale / shift fp32 [B][C]: the routed expert's GroupNorm affine (gamma, beta fp32 [E][C]).
 extern "C" int ym_route_affine(float* scale, float* shift, const float* gamma, const float* beta, const int* route, int route_stride,
-                               int E, int B, int C, void* stream) {
+                               int E, int B, int C, const float* route_w, void* stream) {
     YM_CHECK_ARG(scale && shift && gamma && beta && route, "ym_route_affine: null pointer");
     YM_CHECK_ARG(E >= 1 && B >= 0 && C > 0 && route_stride >= 1, "ym_route_affine: sizes");
     if (B == 0) return YM_OK;
     const long long total = (long long)B * C;
     YM_LAUNCH(route_affine_kernel, (int)((total + 255) / 256), 256, 0, (cudaStream_t)stream, scale, shift, gamma, beta, route,
-              route_stride, E, B, C);
+              route_stride, E, B, C, route_w);
     YM_CHECK_LAUNCH("route_affine");
     return YM_OK;
 }

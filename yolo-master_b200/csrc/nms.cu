@@ -165,7 +165,9 @@ __global__ void __launch_bounds__(1024) nms_image_kernel(const float* __restrict
         }
         __syncthreads();
         const int i = s_cur, nk = s_nk;
-        if (i >= n || nk >= max_det) break;
+        // mode 1 (CW-NMS): survivors that clip to nothing are dropped AFTER the sweep and do not count towards max_det
+        // (common.cpp:180-197), so the sweep collects up to the 512-entry survivor table instead of stopping at max_det
+        if (i >= n || nk >= (MODE == 1 ? 512 : max_det)) break;
         const BoxT<T> bi = offbox(i);
         for (int j = i + 1 + tid; j < n; j += blockDim.x) {
             if (!sup[j] && iou(bi, offbox(j)) > (T)iou_thres) sup[j] = 1;
@@ -174,7 +176,8 @@ __global__ void __launch_bounds__(1024) nms_image_kernel(const float* __restrict
         __syncthreads();
     }
     __syncthreads();
-    const int nk = s_nk < max_det ? s_nk : max_det;
+    const int nk_cap = MODE == 1 ? 512 : max_det;
+    const int nk = s_nk < nk_cap ? s_nk : nk_cap;
 
     // ---- emit (mode 1: cluster-weighted refinement, one warp per survivor, then clip / drop empty in survivor order)
     float* ob = out + (long long)b * max_det * 6;

@@ -1,0 +1,330 @@
+// Warp-specialised tcgen05 / TMEM / TMA fused attention forward (sm_100a):  O = softmax((Q*scale) K^T) V, d_qk = 32, d_v in {32, 64}.
+//
+// Same contract and the same arithmetic as tc_attention.cu (reference: AAttn / Attention, block.py:1708-1722 / :1324-1331); what
+// changes is WHO does what, so that the exp unit never waits for a hand-off:
+//
+//   * one CTA owns TWO 128-row query tiles of one (image, head) and walks the keys once for both: every K / V tile is fetched
+//     once per 256 query rows (tc_attention.cu: once per 128) by TMA (one 4-D tensor map per operand: d, token, head, image;
+//     rows past N arrive as zeros) into a 6-stage shared-memory ring in the 64B/128B-swizzled canonical UMMA layout;
+//   * warp 8 lane 0 is the only thread that issues TMA and tcgen05.mma.  Its static order per key tile t is
+//       QK_A(t+1), QK_B(t+1), PV_A(t), PV_B(t), refill of the stage released by tile t-1
+//     with QK(t+1) issued as soon as the softmax warps have READ S(t) out of tensor memory - one whole softmax phase before
+//     they need S(t+1) - so the tensor-core latency is never on the softmax warps' path;
+//   * warps 0-3 (tile A) and 4-7 (tile B) are softmax warps: thread = query row (shuffle-free max / sum), S row read with
+//     tcgen05.ld, exp2 on the MUFU, lazy rescale (O only touched when a row max grows by more than 2^8), packed fp16 P row
+//     written back to tensor memory (tcgen05.st) as the A operand of the TS-mode PV MMA.  They never meet at a __syncthreads:
+//     every hand-off is an mbarrier (S full / S consumed / P full / PV done), arrived on by one lane per warp.
+//
+// With 2 CTAs per SM every SM sub-partition holds 4 softmax warps of 4 independent tiles; a warp's non-exp section per key tile
+// (tensor-memory load, P store, two barrier polls) is ~300 clk against 4 x 512 clk of MUFU work per round, where tc_attention.cu's
+// serial section (S wait -> softmax -> PV wait -> __syncthreads -> MMA issue -> MMA latency) was ~1200 clk and convoyed all
+// four CTAs of an SM into the same phase.
+//
+// Tensor memory per CTA: per query tile S 64 + P 32 + O d_v columns (fp32 / packed fp16 / fp32) -> 256 columns (d_v = 32).
+#include <cuda.h>
+
+#include "tc_common.cuh"
+
+namespace ym {
+
+constexpr int A2_BQ = 128, A2_BKV = 64, A2_STAGES = 6, A2_THREADS = 288;   // 8 softmax warps + 1 TMA / MMA warp
+
+__device__ __forceinline__ float a2_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void a2_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void a2_tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+struct A2Bars {
+    uint64_t q_full;
+    uint64_t kv_full[A2_STAGES], kv_empty[A2_STAGES];
+    uint64_t s_full[2], s_free[2], p_full[2], pv_done[2];
+    uint32_t tmem_slot;
+};
+
+template <int DV>
+__global__ void __launch_bounds__(A2_THREADS, (DV == 32) ? 2 : 1)
+tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_v, int N, float scale_log2, __half* __restrict__ out, int ldo) {
+    constexpr int Q_BYTES = A2_BQ * 64, K_BYTES = A2_BKV * 64, V_BYTES = A2_BKV * DV * 2, STAGE_BYTES = K_BYTES + V_BYTES;
+    constexpr uint32_t QT_COLS = 64 + 32 + DV;                 // tensor-memory columns of one query tile: S | P | O
+    constexpr uint32_t TMEM_COLS = (DV == 32) ? 256 : 512;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* sQ = smem;                                  // 2 x [128 rows x 64 B], SW64
+    unsigned char* sKV = sQ + 2 * Q_BYTES;                     // [STAGES][K tile | V tile]
+    __shared__ A2Bars bars;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * (2 * A2_BQ), h = blockIdx.y, b = blockIdx.z;
+    const bool has_b = q0 + A2_BQ < N;                          // the second query tile holds at least one real row
+    const int T = (N + A2_BKV - 1) / A2_BKV;
+
+    if (tid == 0) {
+        tc::mbar_init(&bars.q_full, 1);
+        for (int s = 0; s < A2_STAGES; ++s) {
+            tc::mbar_init(&bars.kv_full[s], 1);
+            tc::mbar_init(&bars.kv_empty[s], 1);
+        }
+        for (int q = 0; q < 2; ++q) {
+            tc::mbar_init(&bars.s_full[q], 1);
+            tc::mbar_init(&bars.s_free[q], 4);     // one arrive per softmax warp
+            tc::mbar_init(&bars.p_full[q], 4);
+            tc::mbar_init(&bars.pv_done[q], 1);
+        }
+        tc::fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 8) tc::tmem_alloc(&bars.tmem_slot, TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = bars.tmem_slot;
+
+    if (warp == 8) {
+        // ================================================= TMA + MMA issuer (one thread) =========================================
+        if (lane == 0) {
+            const uint32_t idesc_qk = tc::make_idesc_f16(A2_BQ, A2_BKV, 0);
+            const uint32_t idesc_pv = tc::make_idesc_f16(A2_BQ, DV, 1);      // V is MN-major (d_v contiguous)
+            auto load_kv = [&](int t) {
+                const int st = t % A2_STAGES;
+                unsigned char* dK = sKV + st * STAGE_BYTES;
+                a2_expect_tx(&bars.kv_full[st], (uint32_t)STAGE_BYTES);
+                a2_tma_load_4d(dK, &map_k, 0, t * A2_BKV, h, b, &bars.kv_full[st]);
+                a2_tma_load_4d(dK + K_BYTES, &map_v, 0, t * A2_BKV, h, b, &bars.kv_full[st]);
+            };
+            a2_expect_tx(&bars.q_full, (uint32_t)(2 * Q_BYTES));
+            a2_tma_load_4d(sQ, &map_q, 0, q0, h, b, &bars.q_full);           // one 256-row box: tile A then tile B
+            for (int t = 0; t < A2_STAGES && t < T; ++t) load_kv(t);
+
+            auto issue_qk = [&](int q, int t) {
+                const uint64_t qdesc = tc::make_desc(smem_u32(sQ + q * Q_BYTES), 512, 4);
+                const uint64_t kdesc = tc::make_desc(smem_u32(sKV + (t % A2_STAGES) * STAGE_BYTES), 512, 4);
+                const uint32_t t_s = tmem_base + q * QT_COLS;
+                tc::mma_f16_ss(t_s, qdesc, kdesc, idesc_qk, 0u);
+                tc::mma_f16_ss(t_s, qdesc + 2, kdesc + 2, idesc_qk, 1u);
+                tc::mma_commit(&bars.s_full[q]);
+            };
+            auto issue_pv = [&](int q, int t) {
+                const uint32_t va = smem_u32(sKV + (t % A2_STAGES) * STAGE_BYTES + K_BYTES);
+                const uint64_t vdesc = (DV == 32) ? tc::make_desc(va, 512, 4) : tc::make_desc(va, 1024, 2);
+                constexpr uint32_t VSTEP = (16 * DV * 2) >> 4;               // 16 keys per MMA k-step, in 16-byte units
+                const uint32_t t_p = tmem_base + q * QT_COLS + 64, t_o = t_p + 32;
+#pragma unroll
+                for (int k = 0; k < A2_BKV / 16; ++k)
+                    tc::mma_f16_ts(t_o, t_p + 8 * k, vdesc + VSTEP * k, idesc_pv, (t | k) ? 1u : 0u);   // 16 keys = 8 columns of P
+                tc::mma_commit(&bars.pv_done[q]);
+            };
+
+            tc::mbar_wait(&bars.q_full, 0);
+            tc::mbar_wait(&bars.kv_full[0], 0);
+            issue_qk(0, 0);
+            if (has_b) issue_qk(1, 0);
+            for (int t = 0; t < T; ++t) {
+                if (t + 1 < T) {
+                    tc::mbar_wait(&bars.kv_full[(t + 1) % A2_STAGES], ((t + 1) / A2_STAGES) & 1);
+                    tc::mbar_wait(&bars.s_free[0], t & 1);                   // every softmax warp of tile A holds S_A(t) in registers
+                    tc::fence_after_sync();
+                    issue_qk(0, t + 1);
+                    if (has_b) {
+                        tc::mbar_wait(&bars.s_free[1], t & 1);
+                        tc::fence_after_sync();
+                        issue_qk(1, t + 1);
+                    }
+                }
+                tc::mbar_wait(&bars.p_full[0], t & 1);
+                tc::fence_after_sync();
+                issue_pv(0, t);
+                if (has_b) {
+                    tc::mbar_wait(&bars.p_full[1], t & 1);
+                    tc::fence_after_sync();
+                    issue_pv(1, t);
+                }
+                tc::mma_commit(&bars.kv_empty[t % A2_STAGES]);               // every MMA that reads stage t%STAGES has been issued
+                if (t >= 1 && t - 1 + A2_STAGES < T) {                       // refill the stage of tile t-1 (its PVs retired a phase ago)
+                    tc::mbar_wait(&bars.kv_empty[(t - 1) % A2_STAGES], ((t - 1) / A2_STAGES) & 1);
+                    load_kv(t - 1 + A2_STAGES);
+                }
+            }
+        }
+    } else if (warp < 4 || has_b) {
+        // ================================================= softmax warps: thread = query row ======================================
+        const int qt = warp >> 2;                                            // 0 = tile A, 1 = tile B
+        const int row = tid & 127;
+        const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t t_s = tmem_base + qt * QT_COLS + lane_sel, t_p = t_s + 64, t_o = t_s + 96;
+        uint64_t* bar_s_full = &bars.s_full[qt];
+        uint64_t* bar_s_free = &bars.s_free[qt];
+        uint64_t* bar_p_full = &bars.p_full[qt];
+        uint64_t* bar_pv = &bars.pv_done[qt];
+        float m_used = -INFINITY, l_run = 0.f;
+
+        for (int t = 0; t < T; ++t) {
+            tc::mbar_wait(bar_s_full, t & 1);
+            tc::fence_after_sync();
+            uint32_t sr[64];
+            {
+                uint32_t lo[32], hi[32];
+                tc::tmem_ld32(t_s, lo);
+                tc::tmem_ld32(t_s + 32, hi);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { sr[i] = lo[i]; sr[32 + i] = hi[i]; }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(bar_s_free);                      // S(t) is in registers: QK(t+1) may overwrite it
+            const int kv0 = t * A2_BKV;
+            if (kv0 + A2_BKV > N) {               // tail tile only: keys >= N do not exist
+#pragma unroll
+                for (int i = 0; i < 64; ++i)
+                    if (kv0 + i >= N) sr[i] = 0xff800000u;   // -inf
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+            const float m_tile = mx * scale_log2;
+            const bool grow = m_tile > m_used + 8.f;         // also true on the first tile (m_used = -inf)
+            float alpha = 1.f;
+            if (grow) {
+                alpha = a2_exp2(m_used - m_tile);            // 0 on the first tile
+                m_used = m_tile;
+            }
+            uint32_t pk[32];
+            float ls_row[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float p0 = a2_exp2(fmaf(__uint_as_float(sr[2 * i]), scale_log2, -m_used));
+                const float p1 = a2_exp2(fmaf(__uint_as_float(sr[2 * i + 1]), scale_log2, -m_used));
+                pk[i] = pack_half2(p0, p1);
+                ls_row[i & 3] += p0 + p1;                    // four independent partial sums
+            }
+            l_run = l_run * alpha + ((ls_row[0] + ls_row[1]) + (ls_row[2] + ls_row[3]));
+            // ---- PV(t-1) must have retired before its P operand is overwritten or O is rescaled (issued a whole phase ago)
+            if (t > 0) {
+                tc::mbar_wait(bar_pv, (t - 1) & 1);
+                tc::fence_after_sync();
+                if (__any_sync(0xffffffffu, grow)) {         // warp-collective TMEM round trip, lanes that did not grow use 1.0
+#pragma unroll
+                    for (int c0 = 0; c0 < DV; c0 += 32) {
+                        uint32_t o[32];
+                        tc::tmem_ld32(t_o + c0, o);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tc::tmem_st32(t_o + c0, o);
+                    }
+                }
+            }
+            tc::tmem_st32(t_p, pk);                          // A operand of the TS-mode MMA: lane = query row, column c = keys 2c, 2c+1
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(bar_p_full);
+        }
+        // ---- finalise: O / l -> global
+        tc::mbar_wait(bar_pv, (T - 1) & 1);
+        tc::fence_after_sync();
+        const float inv = 1.f / l_run;
+        const int qrow = q0 + qt * A2_BQ + row;
+        __half* orow = out + ((long long)b * N + qrow) * ldo + h * DV;
+#pragma unroll
+        for (int c0 = 0; c0 < DV; c0 += 32) {
+            uint32_t o[32];
+            tc::tmem_ld32(t_o + c0, o);
+            tc::tmem_ld_wait();
+            if (qrow < N) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    Half8 hv;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        hv.v[q] = __floats2half2_rn(__uint_as_float(o[c * 8 + 2 * q]) * inv, __uint_as_float(o[c * 8 + 2 * q + 1]) * inv);
+                    *reinterpret_cast<Half8*>(orow + c0 + c * 8) = hv;
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+typedef CUresult (*A2EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static A2EncodeFn a2_encode() {
+    static A2EncodeFn fn = nullptr;
+    if (!fn) {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult r;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess && r == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<A2EncodeFn>(q);
+    }
+    return fn;
+}
+// (d, token, head, image) view of one operand of the packed qkv buffer; box = d x rows x 1 x 1
+static bool a2_map(CUtensorMap* m, const __half* base, int d, int N, int heads, int batch, int ld, int head_stride, int box_rows) {
+    cuuint64_t gdim[4] = {(cuuint64_t)d, (cuuint64_t)N, (cuuint64_t)heads, (cuuint64_t)batch};
+    cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)head_stride * 2, (cuuint64_t)N * ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)d, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    return a2_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       d == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace ym
+
+using namespace ym;
+
+extern "C" int ym_attention_fwd_tc2_supported(int heads, int head_stride, int ld) {
+    // tensor-map strides are multiples of 16 bytes; a single head needs no head stride
+    return a2_encode() != nullptr && ld % 8 == 0 && (heads == 1 || head_stride % 8 == 0);
+}
+
+extern "C" int ym_attention_fwd_tc2(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
+                                    int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream) {
+    YM_CHECK_ARG(qkv && out, "ym_attention_fwd_tc2: null pointer");
+    YM_CHECK_ARG(d_qk == 32, "ym_attention_fwd_tc2: d_qk must be 32 (got %d)", d_qk);
+    YM_CHECK_ARG(d_v == 32 || d_v == 64, "ym_attention_fwd_tc2: d_v must be 32 or 64 (got %d)", d_v);
+    YM_CHECK_ARG(ld % 8 == 0 && head_stride % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
+                 "ym_attention_fwd_tc2: offsets/pitch must be multiples of 8 halves");
+    YM_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0 && ldo % 8 == 0, "ym_attention_fwd_tc2: alignment");
+    YM_CHECK_ARG(N > 0 && heads > 0 && batch >= 0 && batch < 65536, "ym_attention_fwd_tc2: bad sizes");
+    YM_CHECK_ARG(a2_encode() != nullptr, "ym_attention_fwd_tc2: cuTensorMapEncodeTiled unavailable");
+    if (batch == 0) return YM_OK;
+    const __half* base = (const __half*)qkv;
+    const int hs = heads == 1 ? 8 : head_stride;          // any legal stride for a size-1 dimension
+    CUtensorMap mq, mk, mv;
+    if (!a2_map(&mq, base + q_off, 32, N, heads, batch, ld, hs, 2 * A2_BQ) || !a2_map(&mk, base + k_off, 32, N, heads, batch, ld, hs, A2_BKV) ||
+        !a2_map(&mv, base + v_off, d_v, N, heads, batch, ld, hs, A2_BKV)) {
+        ym_set_error("ym_attention_fwd_tc2: cuTensorMapEncodeTiled failed (N=%d heads=%d batch=%d ld=%d head_stride=%d)", N, heads, batch, ld, hs);
+        return YM_ERR_CUDA;
+    }
+    const float sl2 = scale * 1.4426950408889634f;
+    dim3 grid((N + 2 * A2_BQ - 1) / (2 * A2_BQ), heads, batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)2 * A2_BQ * 64 + A2_STAGES * (A2_BKV * 64 + A2_BKV * d_v * 2) + 1024;
+    cudaError_t e;
+    if (d_v == 32) {
+        e = cudaFuncSetAttribute(tc_attention2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) tc_attention2_kernel<32><<<grid, A2_THREADS, smem, st>>>(mq, mk, mv, N, sl2, (__half*)out, ldo);
+    } else {
+        e = cudaFuncSetAttribute(tc_attention2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) tc_attention2_kernel<64><<<grid, A2_THREADS, smem, st>>>(mq, mk, mv, N, sl2, (__half*)out, ldo);
+    }
+    if (e != cudaSuccess) { ym_set_error("ym_attention_fwd_tc2: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
+    YM_CHECK_LAUNCH("tc_attention2");
+    return YM_OK;
+}

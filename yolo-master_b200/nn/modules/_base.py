@@ -99,3 +99,36 @@ def require_eval(m: nn.Module):
         raise RuntimeError(
             f"{type(m).__name__}: the B200 path implements the inference forward only; call .eval() first "
             "(training is out of scope, SURVEY.md §8)")
+
+
+def fwd_child(m: nn.Module, x: torch.Tensor, out=None, **kw):
+    """`m.fwd_nhwc(x, out=...)` for a child that may be a plain `nn.Sequential` (instances built by the reference's own
+    constructors inside `yolo_master_b200.integration`): the chain is walked here, the last member writes into `out`."""
+    f = getattr(m, "fwd_nhwc", None)
+    if f is not None:
+        return f(x, out=out, **kw)
+    if isinstance(m, nn.Sequential):
+        mods = list(m)
+        for j, mm in enumerate(mods):
+            x = fwd_child(mm, x, out=out if j == len(mods) - 1 else None)
+        return x
+    raise NotImplementedError(f"{type(m).__name__} has no NHWC forward on the B200 path")
+
+
+def plain_conv_fwd(m: nn.Conv2d, x: torch.Tensor, out=None, out_f32=False):
+    """Bare `nn.Conv2d` (bias, no norm / activation: Detect's last 1x1, head.py:104-119) on the GEMM kernel; the folded fp16 pack
+    is cached on the module (same cache as `PlainConv2d`, which mirrors this layer when the model is built by this package)."""
+    from ... import ops
+    f = getattr(m, "fwd_nhwc", None)
+    if f is not None:
+        return f(x, out=out, out_f32=out_f32)
+    if m.groups != 1 or m.dilation != (1, 1) or m.kernel_size[0] != m.kernel_size[1] or m.stride[0] != m.stride[1]:
+        raise NotImplementedError("nn.Conv2d: groups / dilation / non-square geometry is not on the B200 path")
+
+    def build():
+        w, b = fold_bn(m.weight, m.bias, None)
+        return {"w": pack_gemm_weight(w), "bias": b.contiguous()}
+
+    pk = cached_pack(m, "plain", [m.weight] + ([m.bias] if m.bias is not None else []), build)
+    return ops.conv2d(x, pk["w"], pk["bias"], m.out_channels, m.kernel_size[0], m.kernel_size[1], m.stride[0], m.padding[0], False,
+                      out=out, out_f32=out_f32)

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ._base import cached_f32, cached_pack, fold_bn, pack_gemm_weight, require_eval, to_nchw, to_nhwc
+from ._base import cached_f32, cached_pack, fold_bn, fwd_child, pack_gemm_weight, require_eval, to_nchw, to_nhwc
 from .conv import Conv
 
 __all__ = ("Bottleneck", "C2f", "C3", "C3k", "C3k2", "SPPF", "Attention", "PSABlock", "C2PSA", "AAttn", "ABlock", "A2C2f")
@@ -56,7 +56,7 @@ class C2f(_NHWCBlock):
         cat = ops.new_act(B, H, W, (2 + n) * c, x.device)  # [y0 | y1 | m0(y1) | m1(..) ...]
         self.cv1.fwd_nhwc(x, out=cat[..., : 2 * c])
         for j, m in enumerate(self.m):
-            m.fwd_nhwc(cat[..., (1 + j) * c:(2 + j) * c], out=cat[..., (2 + j) * c:(3 + j) * c])
+            fwd_child(m, cat[..., (1 + j) * c:(2 + j) * c], out=cat[..., (2 + j) * c:(3 + j) * c])
         return self.cv2.fwd_nhwc(cat, out=out)
 
 
@@ -295,7 +295,7 @@ class A2C2f(_NHWCBlock):
         cat = ops.new_act(B, H, W, (1 + n) * c_, x.device)
         self.cv1.fwd_nhwc(x, out=cat[..., :c_])
         for j, m in enumerate(self.m):
-            m.fwd_nhwc(cat[..., j * c_:(j + 1) * c_], out=cat[..., (j + 1) * c_:(j + 2) * c_])
+            fwd_child(m, cat[..., j * c_:(j + 1) * c_], out=cat[..., (j + 1) * c_:(j + 2) * c_])
         if self.gamma is not None:      # x + gamma * y  (block.py:1877-1879)
             y = self.cv2.fwd_nhwc(cat)
             return ops.ew(ops.EW_SCALE_RES, a=x, b=y, p0=cached_f32(self, 'gamma', self.gamma, (-1,)), out=out)

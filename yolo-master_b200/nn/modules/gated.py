@@ -406,6 +406,9 @@ class _GatedMoE(nn.Module, PackCache):
             pk["proj_gamma"] = torch.stack([_f32(p[1].weight) for p in fe.expert_projections]).contiguous()
             pk["proj_beta"] = torch.stack([_f32(p[1].bias) for p in fe.expert_projections]).contiguous()
             pk["proj_G"], pk["proj_eps"] = fe.expert_projections[0][1].num_groups, float(fe.expert_projections[0][1].eps)
+            oc_ = pk["proj_gamma"].shape[1]
+            pk["proj_one"] = torch.ones(oc_, dtype=torch.float32, device=pk["proj_gamma"].device)
+            pk["proj_zero"] = torch.zeros(oc_, dtype=torch.float32, device=pk["proj_gamma"].device)
         if hasattr(self, "cross_gate"):   # only the first C of the gate MLP's 2C outputs are used (gated.py:2404-2408)
             cg = self.cross_gate
             pk["xg_w1"], pk["xg_w2"], pk["xg_b2"] = _f32(cg.gate_net[2].weight), _f32(cg.gate_net[4].weight[:C]), _f32(cg.gate_net[4].bias[:C])
@@ -433,6 +436,21 @@ class _GatedMoE(nn.Module, PackCache):
         return pk
 
     # ------------------------------------------------------------------------------------------------------------ forward
+    @staticmethod
+    def _routed_proj(feat, pk, rj, wj, B, H, W, hid, oc, G):
+        """expert_projections[e_b]: grouped 1x1 GEMM of image b with its routed expert + that expert's GroupNorm affine times the
+        routing weight, as (o, scale, shift).  GroupNorm statistics ride in the GEMM epilogue when a group is a whole number of its
+        8-channel granules; narrower groups (n-scale: 32 or 24 output channels in 8 groups) take a statistics pass over o."""
+        HW = H * W
+        wide = (oc // G) % 8 == 0
+        o, st = ops.moe_expert_gemm(feat, ops.pitch(feat), 1, B, HW, hid, pk["proj_w"], rj, oc, groups=G if wide else 0)
+        if wide:
+            sc, sh = ops.gn_finalize(st, B, HW, G, oc, HW * (oc // G), pk["proj_eps"], pk["proj_gamma"], pk["proj_beta"], rj, route_w=wj)
+        else:
+            sc, sh = ops.groupnorm_stats(o.view(B, H, W, oc), G, pk["proj_one"], pk["proj_zero"], pk["proj_eps"])
+            ops.route_affine(sc, sh, pk["proj_gamma"], pk["proj_beta"], rj, route_w=wj)
+        return o, sc, sh
+
     def _experts(self, xd, idx, w, pk, out):
         B, H, W, _ = xd.shape
         fe = self.fused_experts
@@ -449,8 +467,7 @@ class _GatedMoE(nn.Module, PackCache):
                 sc, sh = ops.groupnorm_stats(d, pk["div_G"], pk["div_one"], pk["div_zero"], pk["div_eps"])
                 ops.route_affine(sc, sh, pk["div_gamma"], pk["div_beta"], rj)
                 feat = ops.ew(ops.EW_AFFINE, a=d, p0=sc, p1=sh, rows_per_img=HW, act=True)
-                o, st = ops.moe_expert_gemm(feat, ops.pitch(feat), 1, B, HW, hid, pk["proj_w"], rj, oc, groups=G)
-                sc2, sh2 = ops.gn_finalize(st, B, HW, G, oc, HW * (oc // G), pk["proj_eps"], pk["proj_gamma"], pk["proj_beta"], rj, route_w=wj)
+                o, sc2, sh2 = self._routed_proj(feat, pk, rj, wj, B, H, W, hid, oc, G)
                 last = j == idx.shape[1] - 1
                 acc = ops.ew(ops.EW_AFFINE, a=o.view(B, H, W, oc), b=acc, p0=sc2, p1=sh2, rows_per_img=HW, act=False, out=out if last else None)
             return acc
@@ -468,8 +485,7 @@ class _GatedMoE(nn.Module, PackCache):
         acc = None
         for j in range(idx.shape[1]):                       # one grouped GEMM per routing rank; a zero weight contributes zero
             rj, wj = idx[:, j].contiguous(), w[:, j].contiguous()
-            o, st = ops.moe_expert_gemm(feat, ops.pitch(feat), 1, B, HW, hid, pk["proj_w"], rj, oc, groups=G)
-            sc, sh = ops.gn_finalize(st, B, HW, G, oc, HW * (oc // G), pk["proj_eps"], pk["proj_gamma"], pk["proj_beta"], rj, route_w=wj)
+            o, sc, sh = self._routed_proj(feat, pk, rj, wj, B, H, W, hid, oc, G)
             last = j == idx.shape[1] - 1
             acc = ops.ew(ops.EW_AFFINE, a=o.view(B, H, W, oc), b=acc, p0=sc, p1=sh, rows_per_img=HW, act=False, out=out if last else None)
         return acc

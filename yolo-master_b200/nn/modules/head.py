@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ._base import PackCache, cached_f32, pack_gemm_weight, require_eval, to_nchw, to_nhwc
+from ._base import PackCache, cached_f32, fwd_child, pack_gemm_weight, plain_conv_fwd, require_eval, to_nchw, to_nhwc
 from .conv import Conv, DWConv, PlainConv2d
 
 __all__ = ("Detect", "DFL", "Pose", "Proto", "Segment", "OBB", "Classify")
@@ -89,12 +89,8 @@ class Detect(nn.Module):
     def _tower(seq, x, out_f32=True):
         mods = list(seq)
         for m in mods[:-1]:
-            if isinstance(m, nn.Sequential):
-                for mm in m:
-                    x = mm.fwd_nhwc(x)
-            else:
-                x = m.fwd_nhwc(x)
-        return mods[-1].fwd_nhwc(x, out_f32=out_f32)
+            x = fwd_child(m, x)
+        return plain_conv_fwd(mods[-1], x, out_f32=out_f32)    # PlainConv2d here, a bare nn.Conv2d on reference-built instances
 
     def head_raw(self, feats_nhwc):
         """Per level (boxes fp32 (B,h,w,4*reg_max), logits fp32 (B,h,w,nc)) from the active towers."""
@@ -111,7 +107,7 @@ class Detect(nn.Module):
             if self.end2end:
                 raise NotImplementedError("Detect: end2end top-k with DFL (reg_max > 1) is not on the B200 path")
             ver = self.dfl.conv.weight._version
-            if self._dfl_checked != ver:          # one host read per weight version, never inside a captured forward
+            if getattr(self, "_dfl_checked", None) != ver:          # one host read per weight version, never inside a captured forward
                 self.dfl.check_frozen()
                 self._dfl_checked = ver
         if self.agnostic_nms:

@@ -355,11 +355,13 @@ def dwconv3_routed(x, w_taps, route, dil):
     return out
 
 
-def route_affine(scale, shift, gamma, beta, route):
-    """ym_route_affine, in place: (scale, shift) fp32 (B, C) from unit-gamma GroupNorm statistics -> expert route[b]'s affine."""
+def route_affine(scale, shift, gamma, beta, route, route_w=None):
+    """ym_route_affine, in place: (scale, shift) fp32 (B, C) from unit-gamma GroupNorm statistics -> expert route[b]'s affine
+    (times the routing weight route_w[b] when given)."""
     B, Cc = scale.shape
     _lib.check(lib().ym_route_affine(scale.data_ptr(), shift.data_ptr(), gamma.data_ptr(), beta.data_ptr(), route.data_ptr(),
-                                     max(route.stride(0), 1), gamma.shape[0], B, Cc, _stream()), "ym_route_affine")
+                                     max(route.stride(0), 1), gamma.shape[0], B, Cc,
+                                     None if route_w is None else route_w.data_ptr(), _stream()), "ym_route_affine")
     _count()
     return scale, shift
 
