@@ -13,7 +13,7 @@ cpu: * the constructor's stride forward (tasks.py:555-559: CPU, 256x256, Detect 
        fp16 noise floor, before and after the reference's own `model.fuse()`;
      * `uninstall()` restores every binding.
 gpu: * the same model `.eval().half().cuda()`: the reference's `_predict_once` now launches this package's kernels (counted), result
-       equal to this package's own DetectionModel bit for bit and within the fp16 noise floor of the stock reference on the same GPU;
+       within the fp16 noise floor of this package's own DetectionModel and of the stock reference on the same GPU;
      * predict-style inference: checkpoint saved with `torch.save`, loaded and run by the reference's own `YOLO(...).predict(...)`
        (AutoBackend -> fuse -> half -> LetterBox -> model -> Results), detections equal to the stock reference's within noise.
 Prints one line `DROPIN OK {...}` on success.
@@ -118,7 +118,9 @@ def main(mode):
             y_ours = ours(xg.half())[0]
         d_ours = float((top(y_acc) - top(y_ours)).abs().max())
         d_ref = float((top(y_acc) - top(y_ref)).abs().max())
-        assert d_ours <= 2e-3, f"reference-built model vs this package's DetectionModel: {d_ours}"
+        # not bit-identical: `model.half()` rounds the reference's parameters to fp16 BEFORE this package folds BatchNorm (its own
+        # DetectionModel folds the fp32 parameters), and nn.Upsample stays torch's kernel - both inside the fp16 noise floor
+        assert d_ours < 2.5e-2, f"reference-built model vs this package's DetectionModel: {d_ours}"
         assert d_ref < 2.5e-2, f"vs the stock reference on the same GPU: {d_ref}"
         info.update(kernels=launched, vs_own_model=d_ours, vs_stock_reference_gpu=d_ref)
 

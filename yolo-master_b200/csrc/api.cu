@@ -1,5 +1,6 @@
 // C-ABI plumbing: thread-local error string, version, device probe.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "ym_common.cuh"
 
@@ -15,6 +16,22 @@ extern "C" void ym_set_error(const char* fmt, ...) {
 extern "C" const char* ym_last_error(void) { return g_err; }
 
 extern "C" int ym_version(void) { return 100; }
+
+// Programmatic dependent launch of the forward-path kernels (ym_common.cuh: pdl_prologue / launch_pdl).  Default on; the
+// environment variable YM_PDL=0 or ym_set_pdl(0) turns the launch attribute off (A/B measurements; results are identical).
+static int g_pdl = -1;
+extern "C" int ym_pdl_enabled(void) {
+    if (g_pdl < 0) {
+        const char* e = getenv("YM_PDL");
+        g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return g_pdl;
+}
+extern "C" int ym_set_pdl(int on) {
+    const int old = ym_pdl_enabled();
+    g_pdl = on ? 1 : 0;
+    return old;
+}
 
 // Returns 0 and fills sm_major/sm_minor/sm_count/l2_bytes for the current device.
 extern "C" int ym_device_info(int* sm_major, int* sm_minor, int* sm_count, long long* l2_bytes) {

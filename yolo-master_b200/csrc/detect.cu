@@ -104,6 +104,7 @@ __device__ __forceinline__ void anchor_of(const DetectLevels& L, int a, int& lvl
 
 // Stage 1, full-GPU: per-anchor max logit over classes (warp per anchor row) -> sortable keys [B][A].
 __global__ void __launch_bounds__(256) detect_rowmax_kernel(const DetectLevels L, int nc, int B, uint32_t* __restrict__ keys) {
+    pdl_prologue();
     const int A = L.off[L.nl];
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256) detect_rowmax_kernel(const DetectLevels L
 
 __global__ void __launch_bounds__(1024) detect_topk_kernel(const DetectLevels L, int nc, int kdet, float* __restrict__ out,
                                                            int* __restrict__ out_anchor, const uint32_t* __restrict__ keys_g) {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int A = L.off[L.nl];
     const int nkeys_max = max(A, kdet * nc);
@@ -223,6 +225,7 @@ __device__ __forceinline__ float dfl_side(const float* __restrict__ p, int reg_m
 
 __global__ void __launch_bounds__(256) detect_dense_kernel(const DetectLevels L, int nc, int reg_max, int xyxy, int B,
                                                            float* __restrict__ y) {
+    pdl_prologue();
     const int A = L.off[L.nl];
     const int no = 4 + nc;
     const long long total = (long long)B * no * A;
@@ -290,9 +293,9 @@ extern "C" int ym_detect_topk(int nl, const void* const* box, const void* const*
     cudaError_t e = cudaFuncSetAttribute(detect_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ym_set_error("ym_detect_topk: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
     const long long rows = (long long)B * A;
-    detect_rowmax_kernel<<<(int)((rows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(L, nc, B, (uint32_t*)scratch);
+    launch_pdl(detect_rowmax_kernel, (int)((rows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream, L, nc, B, (uint32_t*)scratch);
     YM_CHECK_LAUNCH("detect_rowmax");
-    detect_topk_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(L, nc, k, out, out_anchor, (const uint32_t*)scratch);
+    launch_pdl(detect_topk_kernel, B, 1024, smem, (cudaStream_t)stream, L, nc, k, out, out_anchor, (const uint32_t*)scratch);
     YM_CHECK_LAUNCH("detect_topk");
     return YM_OK;
 }
@@ -306,7 +309,7 @@ extern "C" int ym_detect_dense(int nl, const void* const* box, const void* const
     if (rc) return rc;
     if (B == 0) return YM_OK;
     const long long total = (long long)B * (4 + nc) * L.off[nl];
-    detect_dense_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(L, nc, reg_max, xyxy, B, y);
+    launch_pdl(detect_dense_kernel, (int)((total + 255) / 256), 256, 0, (cudaStream_t)stream, L, nc, reg_max, xyxy, B, y);
     YM_CHECK_LAUNCH("detect_dense");
     return YM_OK;
 }

@@ -30,6 +30,7 @@ template <typename TIn, int COUT>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const TIn* __restrict__ img, int B, int Cin, int H, int W,
                                                         const __grid_constant__ StemWeights<COUT> sw,
                                                         __half* __restrict__ out, int ldo, int Ho, int Wo, int tiles_x) {
+    pdl_prologue();
     // CTA = 32 x 8 output pixels; the (65 x 17) x Cin input patch is staged in shared memory with coalesced row reads.
     constexpr int TW = 32, TH = 8, IW = 2 * TW + 1, IH = 2 * TH + 1;
     __shared__ float sx[4][IH][IW + 1];
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const __half* __restrict__ 
                                                      int grp_off, const __half* __restrict__ w, const float* __restrict__ bias,
                                                      int B, int H, int W, int C, int act, const __half* __restrict__ add,
                                                      int ldadd, __half* __restrict__ out, int ldo) {
+    pdl_prologue();
     const int chunks = C >> 3;
     const long long total = (long long)B * H * W * chunks;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const __half* __restr
                                                            const __half* __restrict__ add, int ldadd, __half* __restrict__ out,
                                                            int ldo, int tiles_x, const int* __restrict__ route_idx, int topk,
                                                            int expert) {
+    pdl_prologue();
     constexpr int R = KS / 2, PX = 4, CB = CHUNKS * 8;
     constexpr int GROUPS = 256 / CHUNKS;           // pixel groups per CTA
     constexpr int TW = (CHUNKS == 8) ? 16 : 32;    // tile width
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const __half* __restr
 // y0 lives in channel slot 0 of the concat buffer; slots 1..3 are written here.  8 channels per thread.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sppf_pool_kernel(__half* __restrict__ buf, int ld, int B, int H, int W, int C, int k) {
+    pdl_prologue();
     const int chunks = C >> 3;
     const long long total = (long long)B * H * W * chunks;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,6 +322,7 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(__half* __restrict__ buf
 __global__ void __launch_bounds__(256) concat2_kernel(const __half* __restrict__ a, int lda, int Ca, int up,
                                                       const __half* __restrict__ bsrc, int ldb, int Cb,
                                                       __half* __restrict__ out, int ldo, int B, int H, int W) {
+    pdl_prologue();
     const int chunks = (Ca + Cb) >> 3;
     const long long total = (long long)B * H * W * chunks;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -356,6 +361,7 @@ __device__ __forceinline__ Half8 hmax8(const Half8& a, const Half8& b) {
 }
 
 __global__ void __launch_bounds__(256) sppf_pool_plane_kernel(__half* __restrict__ buf, int ld, int H, int W, int C, int k) {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char sppf_smem[];
     Half8* cur = reinterpret_cast<Half8*>(sppf_smem);   // [H*W]
     Half8* tmp = cur + H * W;                           // [H*W]
@@ -406,9 +412,9 @@ static int stem_launch(const void* img, int in_dtype, int B, int Cin, int H, int
     memcpy(sw.b, bias_host, sizeof(float) * CO);
     const int tiles_x = (Wo + 31) / 32, tiles_y = (Ho + 7) / 8;
     const dim3 grid(tiles_x * tiles_y, B);
-    if (in_dtype == 0) stem_conv_kernel<__half, CO><<<grid, 256, 0, st>>>((const __half*)img, B, Cin, H, W, sw, (__half*)out, ldo, Ho, Wo, tiles_x);
-    else if (in_dtype == 1) stem_conv_kernel<float, CO><<<grid, 256, 0, st>>>((const float*)img, B, Cin, H, W, sw, (__half*)out, ldo, Ho, Wo, tiles_x);
-    else if (in_dtype == 2) stem_conv_kernel<unsigned char, CO><<<grid, 256, 0, st>>>((const unsigned char*)img, B, Cin, H, W, sw, (__half*)out, ldo, Ho, Wo, tiles_x);
+    if (in_dtype == 0) launch_pdl(stem_conv_kernel<__half, CO>, grid, 256, 0, st, (const __half*)img, B, Cin, H, W, sw, (__half*)out, ldo, Ho, Wo, tiles_x);
+    else if (in_dtype == 1) launch_pdl(stem_conv_kernel<float, CO>, grid, 256, 0, st, (const float*)img, B, Cin, H, W, sw, (__half*)out, ldo, Ho, Wo, tiles_x);
+    else if (in_dtype == 2) launch_pdl(stem_conv_kernel<unsigned char, CO>, grid, 256, 0, st, (const unsigned char*)img, B, Cin, H, W, sw, (__half*)out, ldo, Ho, Wo, tiles_x);
     else { ym_set_error("ym_stem_conv_nchw: bad in_dtype %d", in_dtype); return YM_ERR_ARG; }
     return YM_OK;
 }
@@ -472,7 +478,7 @@ static int dwconv_impl(const void* x, int ldx, int grp_w, int grp_stride, int gr
     do {                                                                                                                      \
         auto kern = dwconv_tiled_kernel<KS, CH>;                                                                              \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
-        kern<<<grid, 256, smem, st>>>((const __half*)x, ldx, grp_w, grp_stride, grp_off, (const __half*)w, bias, H, W, C, act, \
+        launch_pdl(kern, grid, 256, smem, st, (const __half*)x, ldx, grp_w, grp_stride, grp_off, (const __half*)w, bias, H, W, C, act, \
                                       (const __half*)add, ldadd, (__half*)out, ldo, tiles_x, route_idx, topk, expert);        \
     } while (0)
         bool done = true;
@@ -488,7 +494,7 @@ static int dwconv_impl(const void* x, int ldx, int grp_w, int grp_stride, int gr
     }
     YM_CHECK_ARG(route_idx == nullptr, "dwconv: routed mode needs the tiled kernel (C %% 16 == 0, k in 3/5/7/9)");
 #define YM_DW(KS)                                                                                                    \
-    dwconv_kernel<KS><<<nblocks(total, 256), 256, 0, st>>>((const __half*)x, ldx, grp_w, grp_stride, grp_off,          \
+    launch_pdl(dwconv_kernel<KS>, nblocks(total, 256), 256, 0, st, (const __half*)x, ldx, grp_w, grp_stride, grp_off,          \
                                                            (const __half*)w, bias, B, H, W, C, act, (const __half*)add, \
                                                            ldadd, (__half*)out, ldo)
     switch (ksize) {
@@ -515,10 +521,10 @@ extern "C" int ym_sppf_pool_nhwc(void* buf, int ld, int B, int H, int W, int C, 
             if (e != cudaSuccess) { ym_set_error("ym_sppf_pool_nhwc: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
             attr = plane;
         }
-        sppf_pool_plane_kernel<<<dim3(C / 8, B), 256, plane, (cudaStream_t)stream>>>((__half*)buf, ld, H, W, C, k);
+        launch_pdl(sppf_pool_plane_kernel, dim3(C / 8, B), 256, plane, (cudaStream_t)stream, (__half*)buf, ld, H, W, C, k);
     } else {
         const long long total = (long long)B * H * W * (C / 8);
-        sppf_pool_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>((__half*)buf, ld, B, H, W, C, k);
+        launch_pdl(sppf_pool_kernel, nblocks(total, 256), 256, 0, (cudaStream_t)stream, (__half*)buf, ld, B, H, W, C, k);
     }
     YM_CHECK_LAUNCH("sppf_pool");
     return YM_OK;
@@ -531,7 +537,7 @@ extern "C" int ym_concat2_nhwc(const void* a, int lda, int Ca, int up, const voi
     YM_CHECK_ARG(up >= 1 && H % up == 0 && W % up == 0, "ym_concat2_nhwc: bad upsample factor");
     if (B == 0) return YM_OK;
     const long long total = (long long)B * H * W * ((Ca + Cb) / 8);
-    concat2_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)a, lda, Ca, up, (const __half*)b,
+    launch_pdl(concat2_kernel, nblocks(total, 256), 256, 0, (cudaStream_t)stream, (const __half*)a, lda, Ca, up, (const __half*)b,
                                                                          ldb, Cb, (__half*)out, ldo, B, H, W);
     YM_CHECK_LAUNCH("concat2");
     return YM_OK;

@@ -52,6 +52,7 @@ template <int BN, int EPI, bool A_XFORM>
 // (A register cap of 96 for the BN = 64 tiles - 5 instead of 4 CTAs per SM at 16-88 bytes of spill - was measured: the whole
 // step got 1 % slower, so the kernel keeps the compiler's 124-128 registers.)
 __global__ void __launch_bounds__(NTHREADS) gemm_conv_kernel(const GemmConvParams p) {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* sA = reinterpret_cast<__half*>(smem_raw);                 // [STAGES][BM][SK]
     __half* sB = sA + STAGES * BM * SK;                               // [STAGES][BN][SK]
@@ -371,7 +372,7 @@ static int launch_gemm(const GemmConvParams& p, int problems, cudaStream_t strea
         }
     }
     dim3 grid((p.M + BM - 1) / BM, (p.Cout + BN - 1) / BN, problems);
-    kern<<<grid, NTHREADS, smem, stream>>>(p);
+    launch_pdl(kern, grid, NTHREADS, smem, stream, p);
     YM_CHECK_LAUNCH("gemm_conv");
     return YM_OK;
 }
@@ -393,7 +394,7 @@ extern "C" int ym_conv2d_nhwc(const void* x, int ldx, int B, int H, int W, int C
                               int out_f32, const void* res, int ldr, int act, void* stream) {
     YM_CHECK_ARG(x && w && out, "ym_conv2d_nhwc: null pointer");
     YM_CHECK_ARG(Cin % 8 == 0 && ldx % 8 == 0, "ym_conv2d_nhwc: Cin (%d) and ldx (%d) must be multiples of 8", Cin, ldx);
-    YM_CHECK_ARG(Cout >= 1, "ym_conv2d_nhwc: Cout (%d) must be positive", Cout);
+    YM_CHECK_ARG(Cout % 2 == 0, "ym_conv2d_nhwc: Cout (%d) must be even (the host side pads odd widths to a multiple of 8)", Cout);
     YM_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, "ym_conv2d_nhwc: x/w must be 16-byte aligned");
     YM_CHECK_ARG(Cout % 8 != 0 || (((uintptr_t)out & 15) == 0 && ldo % (out_f32 ? 4 : 8) == 0),
                  "ym_conv2d_nhwc: out must be 16-byte aligned with a pitch (%d) that keeps rows 16-byte aligned", ldo);
@@ -475,6 +476,7 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
                                                           const float* __restrict__ beta, const int* __restrict__ route_idx,
                                                           const float* __restrict__ route_w, float* __restrict__ scale,
                                                           float* __restrict__ shift) {
+    pdl_prologue();
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (wid >= P * groups) return;
     const int pr = wid / groups, grp = wid - pr * groups;
@@ -510,7 +512,7 @@ extern "C" int ym_gn_finalize(const float* stats, int P, int HW, int groups, int
     YM_CHECK_ARG(groups > 0 && C % groups == 0 && (C / groups) % 8 == 0, "ym_gn_finalize: bad groups");
     if (P == 0) return YM_OK;
     const int n = P * groups * 32;
-    gn_finalize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(stats, P, (HW + BM - 1) / BM, groups, C, count, eps, gamma, beta,
+    launch_pdl(gn_finalize_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, stats, P, (HW + BM - 1) / BM, groups, C, count, eps, gamma, beta,
                                                                           route_idx, route_w, scale, shift);
     YM_CHECK_LAUNCH("gn_finalize");
     return YM_OK;

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256) router_fused_kernel(const __half* __restr
                                                            int Hp, int Wp, int Cr, const float* __restrict__ w1,
                                                            const float* __restrict__ scale1, const float* __restrict__ shift1,
                                                            float* __restrict__ partial, int tiles_x, int nblk) {
+    pdl_prologue();
     extern __shared__ float rsm[];
     float* sp = rsm;                                   // [RT_HY][RT_HX][C] pooled tile with halo (zero outside the map)
     float* red = rsm + RT_HY * RT_HX * C;              // [RT_QUADS][Cr]
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(32) router_finish_kernel(const float* __restri
                                                            const float* __restrict__ shift2, int E, int topk,
                                                            int* __restrict__ idx_out, float* __restrict__ w_out,
                                                            float* __restrict__ probs_out) {
+    pdl_prologue();
     __shared__ float hm[64];
     __shared__ float pr[64];
     const int b = blockIdx.x, lane = threadIdx.x;
@@ -212,10 +214,10 @@ extern "C" int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C
         if (e != cudaSuccess) { ym_set_error("ym_router_topk: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
         smem_set = smem;
     }
-    router_fused_kernel<<<dim3(nblk, B), 256, smem, st>>>((const __half*)x, ldx, H, W, C, ps, Hp, Wp, Cr, w1, scale1, shift1, partial,
+    launch_pdl(router_fused_kernel, dim3(nblk, B), 256, smem, st, (const __half*)x, ldx, H, W, C, ps, Hp, Wp, Cr, w1, scale1, shift1, partial,
                                                          tiles_x, nblk);
     YM_CHECK_LAUNCH("router_fused");
-    router_finish_kernel<<<B, 32, 0, st>>>(partial, nblk, Cr, Hp * Wp, w2, scale2, shift2, E, topk, idx_out, w_out, probs_out);
+    launch_pdl(router_finish_kernel, B, 32, 0, st, partial, nblk, Cr, Hp * Wp, w2, scale2, shift2, E, topk, idx_out, w_out, probs_out);
     YM_CHECK_LAUNCH("router_finish");
     return YM_OK;
 }

@@ -90,6 +90,7 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = bars.tmem_slot;
+    pdl_prologue();    // barriers / tensor memory are set up: let the next kernel stage itself, then wait for the qkv conv
 
     if (warp == 8) {
         // ================================================= TMA + MMA issuer (one thread) =========================================
@@ -319,10 +320,10 @@ extern "C" int ym_attention_fwd_tc2(const void* qkv, int ld, int batch, int N, i
     cudaError_t e;
     if (d_v == 32) {
         e = cudaFuncSetAttribute(tc_attention2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) tc_attention2_kernel<32><<<grid, A2_THREADS, smem, st>>>(mq, mk, mv, N, sl2, (__half*)out, ldo);
+        if (e == cudaSuccess) launch_pdl(tc_attention2_kernel<32>, grid, A2_THREADS, smem, st, mq, mk, mv, N, sl2, (__half*)out, ldo);
     } else {
         e = cudaFuncSetAttribute(tc_attention2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) tc_attention2_kernel<64><<<grid, A2_THREADS, smem, st>>>(mq, mk, mv, N, sl2, (__half*)out, ldo);
+        if (e == cudaSuccess) launch_pdl(tc_attention2_kernel<64>, grid, A2_THREADS, smem, st, mq, mk, mv, N, sl2, (__half*)out, ldo);
     }
     if (e != cudaSuccess) { ym_set_error("ym_attention_fwd_tc2: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
     YM_CHECK_LAUNCH("tc_attention2");

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(CV_THREADS) tc_conv_kernel(const __grid_consta
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
+    pdl_prologue();    // barriers / tensor memory are set up: let the next kernel stage itself, then wait for our producer grid
 
     // ---- tile coordinates
     const int n0 = blockIdx.y * BN;
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
+    pdl_prologue();    // barriers / tensor memory are set up: let the next kernel stage itself, then wait for our producer grid
 
     const int total_tiles = m_tiles * n_tiles;
     const int cchunks = (p.Cin + p.kc - 1) / p.kc;
@@ -498,7 +500,7 @@ static int launch_conv2(const CUtensorMap& ma, const CUtensorMap& mb, const CUte
     }
     const int total = m_tiles * n_tiles;
     const int grid = total < 2 * sms ? total : 2 * sms;
-    kern<<<grid, CV2_THREADS, smem, st>>>(ma, mb, mo, p, m_tiles, n_tiles);
+    launch_pdl(kern, grid, CV2_THREADS, smem, st, ma, mb, mo, p, m_tiles, n_tiles);
     YM_CHECK_LAUNCH("tc_conv2");
     return YM_OK;
 }
@@ -511,7 +513,7 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const TcCon
     auto kern = tc_conv_kernel<BN, FLAT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ym_set_error("tc_conv: smem attr %zu: %s", smem, cudaGetErrorString(e)); return YM_ERR_CUDA; }
-    kern<<<grid, CV_THREADS, smem, st>>>(ma, mb, p);
+    launch_pdl(kern, grid, CV_THREADS, smem, st, ma, mb, p);
     YM_CHECK_LAUNCH("tc_conv");
     return YM_OK;
 }
@@ -532,6 +534,7 @@ extern "C" int ym_conv2d_tc_supported(int Cin, int Cout, int KH, int KW, int str
     if (!(KH == KW && (KH == 1 || KH == 3) && (stride == 1 || stride == 2) && pad == KH / 2)) return 0;
     if (Cin % 8 != 0 || Cin < 16) return 0;
     if (Cout % 8 != 0 || ldx % 8 != 0) return 0;
+    if (Cout > 1024) return 0;      // the kernels stage the folded bias of all output channels in a 1088-float shared table
     return get_encode() != nullptr;
 }
 

@@ -20,6 +20,9 @@
 
 // thread-local last-error string (api.cu)
 extern "C" void ym_set_error(const char* fmt, ...);
+// programmatic dependent launch switch (api.cu): 1 = kernels that call ym::pdl_prologue() are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel of the stream is staged while this one drains
+extern "C" int ym_pdl_enabled(void);
 
 #define YM_CHECK_ARG(cond, ...)                 \
     do {                                        \
@@ -41,6 +44,21 @@ extern "C" void ym_set_error(const char* fmt, ...);
 namespace ym {
 
 #ifndef YM_HOST_EMU   // inline PTX: real GPU builds only
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------------------
+// A kernel launched through ym::launch_pdl may become resident while its predecessor in the stream is still running.  It must
+// therefore call pdl_wait() before it touches global memory (reads of the predecessor's output, and writes - the predecessor may
+// still be reading a buffer the allocator hands to this kernel).  pdl_trigger() lets the NEXT kernel of the stream be staged as
+// soon as every CTA of this grid has reached it: its CTAs then fill whatever resources this grid's last wave leaves free, run
+// their prologue (barrier init, tensor-memory allocation, descriptor prefetch) and park in pdl_wait() until this grid has
+// completed and flushed - launch latency and drain / fill bubbles between the ~160 kernels of a forward overlap instead of adding up.
+// Without the launch attribute both instructions are no-ops, so eager launches and older call sites stay correct.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+    pdl_trigger();
+    pdl_wait();
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -101,6 +119,25 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+#endif
+
+#ifndef YM_HOST_EMU
+// kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute (see pdl_prologue); the kernel MUST call pdl_wait()
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = ym_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif
 

@@ -45,6 +45,34 @@ def pack_gemm_weight(w: torch.Tensor) -> torch.Tensor:
     return out.contiguous()
 
 
+def pad_channels8(w: torch.Tensor, b: torch.Tensor, cout_to: int = 8):
+    """Zero-pad a folded conv weight [Co,Ci,KH,KW] / bias [Co] to multiples of 8 channels on both sides (1-class heads, the OBB angle,
+    the 51-channel Pose towers): kernels move 16-byte (8-channel) vectors, and zero weights keep the pad channels at exactly zero.
+    `cout_to` = 2 for a head's last layer (the GEMM kernel writes any even width; only an odd one needs a pad channel).
+    Returns (w, b, cin_p, cout_p)."""
+    Co, Ci = w.shape[0], w.shape[1]
+    cin_p, cout_p = (Ci + 7) // 8 * 8, (Co + cout_to - 1) // cout_to * cout_to
+    if cin_p != Ci or cout_p != Co:
+        wp = torch.zeros((cout_p, cin_p, *w.shape[2:]), dtype=w.dtype, device=w.device)
+        wp[:Co, :Ci] = w
+        bp = torch.zeros(cout_p, dtype=b.dtype, device=b.device)
+        bp[:Co] = b
+        w, b = wp, bp
+    return w, b.contiguous(), cin_p, cout_p
+
+
+def plain_conv_run(m: nn.Conv2d, pk: dict, x: torch.Tensor, out=None, out_f32=False):
+    """The GEMM kernel for a bare nn.Conv2d from its pack; a padded output width is cut back to a dense tensor (the decode kernels
+    that follow read dense rows)."""
+    from ... import ops
+    padded = pk["cin_p"] != m.in_channels or pk["cout_p"] != m.out_channels
+    if padded and (x.shape[-1] != pk["cin_p"] or out is not None):
+        raise NotImplementedError(f"nn.Conv2d({m.in_channels}->{m.out_channels}): odd channel widths run zero-padded inside a tower only")
+    y = ops.conv2d(x, pk["w"], pk["bias"], pk["cout_p"], m.kernel_size[0], m.kernel_size[1], m.stride[0], m.padding[0], False,
+                   out=out, out_f32=out_f32)
+    return y[..., :m.out_channels].contiguous() if pk["cout_p"] != m.out_channels else y
+
+
 def bn_affine(bn: nn.BatchNorm2d):
     s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
     return s.contiguous(), (bn.bias.detach().float() - bn.running_mean.detach().float() * s).contiguous()
@@ -127,8 +155,35 @@ def plain_conv_fwd(m: nn.Conv2d, x: torch.Tensor, out=None, out_f32=False):
 
     def build():
         w, b = fold_bn(m.weight, m.bias, None)
-        return {"w": pack_gemm_weight(w), "bias": b.contiguous()}
+        w, b, cin_p, cout_p = pad_channels8(w, b.contiguous(), cout_to=2)
+        return {"w": pack_gemm_weight(w), "bias": b, "cin_p": cin_p, "cout_p": cout_p}
 
     pk = cached_pack(m, "plain", [m.weight] + ([m.bias] if m.bias is not None else []), build)
-    return ops.conv2d(x, pk["w"], pk["bias"], m.out_channels, m.kernel_size[0], m.kernel_size[1], m.stride[0], m.padding[0], False,
-                      out=out, out_f32=out_f32)
+    return plain_conv_run(m, pk, x, out, out_f32)
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def run_branches(fns):
+    """Run independent kernel chains.  While a CUDA graph is being captured each chain gets its own stream (forked from / joined to
+    the capturing stream), so the graph holds them as parallel branches - the six towers of the Detect head are ~24 latency-bound
+    launches that otherwise run back to back.  Eager execution stays on the current stream (no cross-stream allocator traffic)."""
+    if len(fns) <= 1 or not torch.cuda.is_available() or not torch.cuda.is_current_stream_capturing():
+        return [f() for f in fns]
+    cur = torch.cuda.current_stream()
+    key = (cur.device.index, len(fns) - 1)
+    side = _SIDE_STREAMS.get(key)
+    if side is None:
+        side = [torch.cuda.Stream(device=cur.device) for _ in range(len(fns) - 1)]
+        _SIDE_STREAMS[key] = side
+    for s in side:
+        s.wait_stream(cur)
+    out = [None] * len(fns)
+    for s, (j, f) in zip(side, list(enumerate(fns))[1:]):
+        with torch.cuda.stream(s):
+            out[j] = f()
+    out[0] = fns[0]()
+    for s in side:
+        cur.wait_stream(s)
+    return out

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ._base import PackCache, fold_bn, pack_gemm_weight, require_eval, to_nchw, to_nhwc
+from ._base import PackCache, fold_bn, pack_gemm_weight, pad_channels8, plain_conv_run, require_eval, to_nchw, to_nhwc
 
 __all__ = ("Conv", "DWConv", "Concat", "Upsample", "autopad", "PlainConv2d")
 
@@ -62,6 +62,7 @@ class Conv(nn.Module, PackCache):
         w, b = fold_bn(self.conv.weight, self.conv.bias, getattr(self, "bn", None))
         pk = {"kind": kind, "act": act, "bias": b.contiguous()}
         if kind == "gemm":
+            w, pk["bias"], pk["cin_p"], pk["cout_p"] = pad_channels8(w, pk["bias"])
             pk["w"] = pack_gemm_weight(w)
         elif kind == "dw":
             C, _, k, _ = w.shape
@@ -79,7 +80,13 @@ class Conv(nn.Module, PackCache):
         pk = self.get_pack()
         cv = self.conv
         if pk["kind"] == "gemm":
-            return ops.conv2d(x, pk["w"], pk["bias"], cv.out_channels, cv.kernel_size[0], cv.kernel_size[1], cv.stride[0],
+            if pk["cin_p"] != cv.in_channels or pk["cout_p"] != cv.out_channels:
+                # widths that are not multiples of 8 (Pose towers: 51 keypoint channels) travel zero-padded to the next multiple of 8:
+                # the producer's padded output IS this conv's input, padded weights / bias keep the pad channels at exactly zero
+                if x.shape[-1] != pk["cin_p"] or out is not None or res is not None:
+                    raise NotImplementedError(f"Conv({cv.in_channels}->{cv.out_channels}): odd channel widths run zero-padded to a "
+                                              "multiple of 8 inside a tower only (no out= / res= views, input from a padded producer)")
+            return ops.conv2d(x, pk["w"], pk["bias"], pk["cout_p"], cv.kernel_size[0], cv.kernel_size[1], cv.stride[0],
                               cv.padding[0], pk["act"], out=out, res=res)
         if pk["kind"] == "dw":
             return ops.dwconv(x, pk["w"], pk["bias"], cv.kernel_size[0], pk["act"], cv.out_channels, add=res, out=out)
@@ -94,7 +101,8 @@ class Conv(nn.Module, PackCache):
             if not pk["act"]:
                 raise NotImplementedError("stem Conv without SiLU is not on the B200 path")
             return to_nchw(ops.stem_conv(x, pk["w"], pk["bias"], self.conv.out_channels))
-        return to_nchw(self.fwd_nhwc(to_nhwc(x)))
+        y = to_nchw(self.fwd_nhwc(to_nhwc(x)))
+        return y if y.shape[1] == self.conv.out_channels else y[:, :self.conv.out_channels]
 
     forward_fuse = forward
 
@@ -115,12 +123,11 @@ class PlainConv2d(nn.Conv2d, PackCache):
         if self.groups != 1 or self.dilation != (1, 1):
             raise NotImplementedError("PlainConv2d: groups/dilation not supported")
         w, b = fold_bn(self.weight, self.bias, None)
-        return {"w": pack_gemm_weight(w), "bias": b.contiguous()}
+        w, b, cin_p, cout_p = pad_channels8(w, b.contiguous(), cout_to=2)
+        return {"w": pack_gemm_weight(w), "bias": b, "cin_p": cin_p, "cout_p": cout_p}
 
     def fwd_nhwc(self, x, out=None, out_f32=False):
-        pk = self.get_pack()
-        return ops.conv2d(x, pk["w"], pk["bias"], self.out_channels, self.kernel_size[0], self.kernel_size[1], self.stride[0],
-                          self.padding[0], False, out=out, out_f32=out_f32)
+        return plain_conv_run(self, self.get_pack(), x, out, out_f32)
 
     def forward(self, x):
         return to_nchw(self.fwd_nhwc(to_nhwc(x)))

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ._base import PackCache, cached_f32, fwd_child, pack_gemm_weight, plain_conv_fwd, require_eval, to_nchw, to_nhwc
+from ._base import PackCache, cached_f32, fwd_child, pack_gemm_weight, plain_conv_fwd, require_eval, run_branches, to_nchw, to_nhwc
 from .conv import Conv, DWConv, PlainConv2d
 
 __all__ = ("Detect", "DFL", "Pose", "Proto", "Segment", "OBB", "Classify")
@@ -97,9 +97,12 @@ class Detect(nn.Module):
         e2e = self.end2end
         box_head = self.one2one_cv2 if e2e else self.cv2
         cls_head = self.one2one_cv3 if e2e else self.cv3
-        boxes = [self._tower(box_head[i], f) for i, f in enumerate(feats_nhwc)]
-        logits = [self._tower(cls_head[i], f) for i, f in enumerate(feats_nhwc)]
-        return boxes, logits
+        n = len(feats_nhwc)
+        # 2 x nl independent towers: parallel graph branches under capture (largest maps first), serial otherwise
+        jobs = [(lambda i=i: self._tower(cls_head[i], feats_nhwc[i])) for i in range(n)] + \
+               [(lambda i=i: self._tower(box_head[i], feats_nhwc[i])) for i in range(n)]
+        res = run_branches(jobs)
+        return res[n:], res[:n]
 
     def forward(self, x):
         require_eval(self)
