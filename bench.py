@@ -33,6 +33,9 @@ UNIT = "images/s"
 IMG = 640
 FLOPS_PER_IMAGE = 30.23e9      # conv 7.67 G + attention bmm 22.57 G (2*MAC)
 BYTES_PER_IMAGE = 139e6        # SURVEY.md §8d algorithmic fp16 bytes (unfused layer I/O + attention streams)
+# one ex2 per attention score: AAttn at P3 / P4 / P5 (two ABlockMoE each, 2 heads) + C2PSA's Attention at P5 (2 heads)
+EXPS_PER_IMAGE = 2 * 2 * (6400.0 ** 2 + 1600.0 ** 2 + 400.0 ** 2) + 2 * 400.0 ** 2
+SM_CLOCK_HZ = 1.965e9          # clocks.max.sm of the pool's B200s (the bench records the clock it saw under load)
 
 
 def peaks():
@@ -197,25 +200,42 @@ def time_attention_kernel(dev, batch, pk):
     ms = e0.elapsed_time(e1) / reps
     flops = 4.0 * N * N * hd * heads * batch
     algo_bytes = 4.0 * N * hd * heads * batch * 2
-    ach = flops / (ms * 1e-3) / 1e12
+    tf = flops / (ms * 1e-3) / 1e12
     traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["tc_attention_kernel<32>"]
+    try:   # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/, read - not measured - here)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["tc_attention2_kernel<32>"]
         if batch == 32:
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]   # per launch, from the committed ncu --set full capture
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     except Exception:
         pass
     exps = float(N) * N * heads * batch
-    return {"kernel": "tc_attention_kernel<32> (tcgen05: S = QK^T SS-mode, O += PV TS-mode with P in tensor memory; AAttn P3: N=6400, "
-                      "2 heads x d32, whole batch)", "bound": "tensor",
-            "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": ach / pk["tflops_burst"], "traffic": traffic,
+    texp = exps / (ms * 1e-3) / 1e12
+    exp_peak = 148 * 16 * SM_CLOCK_HZ / 1e12          # 16 ex2 per clock per SM on the MUFU (B300_MICROARCH.md), at the measured clock
+    return {"kernel": "tc_attention2_kernel<32> (warp-specialised tcgen05: S = QK^T SS-mode, O += PV TS-mode with P in tensor memory, TMA K/V ring; "
+                      "AAttn P3: N=6400, 2 heads x d32, whole batch)",
+            "bound": "exp", "achieved": texp, "peak": exp_peak, "unit": "Texp/s", "frac": texp / exp_peak,
+            "tensor": {"achieved": tf, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": tf / pk["tflops_burst"]},
+            "traffic": traffic, "traffic_source": "profiles/r02_traffic.json (ncu --set full of the same launch; committed, not measured in this run)",
             "ms_per_launch": ms, "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": algo_bytes,
-            "exp_per_launch": exps, "gexp_per_s": exps / (ms * 1e-3) / 1e9,
-            "mufu_frac": exps / (ms * 1e-3) / (148 * 16 * 1.965e9),
-            "note": "d=32 attention has two equal non-tensor ceilings of 16 scores/clk/SM (4.65 T scores/s): one ex2 per score on "
-                    "the MUFU (16 lanes/clk/SM) and one fp32 score read back from tensor memory (tcgen05.ld: 64 B/clk/SM); "
-                    "mufu_frac is the fraction of that ceiling (an FMA-pipe exp2 offload was measured and gives no gain, "
-                    "profiles/r01_attention_poly_sweep.json); peak = cuBLAS bf16 burst " + pk["source"]}
+            "exp_per_launch": exps,
+            "note": "softmax attention at d=32 is bound by one ex2 per score on the MUFU (16 lanes/clk/SM -> 4.65 T scores/s at 1965 MHz), "
+                    "not by the tensor pipe (128 FLOP per score -> 27 % of the bf16 peak AT that ceiling) nor by HBM (K/V are L2-resident); "
+                    "`frac` is therefore achieved / MUFU ceiling and `tensor.frac` is reported beside it (SURVEY.md 8d); peaks " + pk["source"]}
+
+
+def model_roofline(images_per_s_per_gpu, pk):
+    """Whole-forward lower bounds per image and where the measured step sits against the binding one."""
+    t_hbm = BYTES_PER_IMAGE / (pk["hbm_gbs"] * 1e9)
+    t_tensor = FLOPS_PER_IMAGE / (pk["tflops_sustained"] * 1e12)
+    t_exp = EXPS_PER_IMAGE / (148 * 16 * SM_CLOCK_HZ)
+    bound = max((t_exp, "exp"), (t_hbm, "hbm"), (t_tensor, "tensor"))
+    t_img = 1.0 / images_per_s_per_gpu
+    return {"flops_per_image": FLOPS_PER_IMAGE, "bytes_per_image": BYTES_PER_IMAGE, "exps_per_image": EXPS_PER_IMAGE,
+            "lower_bound_us_per_image": {"hbm": t_hbm * 1e6, "tensor": t_tensor * 1e6, "exp": t_exp * 1e6},
+            "bound": bound[1], "achieved": bound[0] / t_img, "unit": "fraction of the binding lower bound (max of the three) per image",
+            "us_per_image": t_img * 1e6,
+            "tflops": FLOPS_PER_IMAGE * images_per_s_per_gpu / 1e12, "algorithmic_gbs": BYTES_PER_IMAGE * images_per_s_per_gpu / 1e9,
+            "hbm_frac": t_hbm / t_img, "tensor_frac": t_tensor / t_img, "exp_frac": t_exp / t_img}
 
 
 def time_dispatch(dev, pk, B=64, baseline=True):
@@ -443,11 +463,7 @@ def run_ours(args):
             "kernels_per_step": kernels_per_step,
             "clocks": clocks,
             "roofline": roof,
-            "model_roofline": {"flops_per_image": FLOPS_PER_IMAGE, "bytes_per_image": BYTES_PER_IMAGE,
-                               "tflops": FLOPS_PER_IMAGE * value / world / 1e12,
-                               "algorithmic_gbs": BYTES_PER_IMAGE * value / world / 1e9,
-                               "hbm_frac": BYTES_PER_IMAGE * value / world / 1e9 / pk["hbm_gbs"],
-                               "tensor_frac": FLOPS_PER_IMAGE * value / world / 1e12 / pk["tflops_sustained"]},
+            "model_roofline": model_roofline(value / world, pk),
             "dispatch": disp,
             "torch_eager_gpu": eager,
             "cpu_baseline": cpu_base,

@@ -82,9 +82,37 @@ int ym_set_attention_chunked(int mode);
 int ym_attention_fwd_tc2(const void* qkv, int ld, int batch, int N, int heads, int head_stride, int q_off, int k_off,
                          int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream);
 int ym_attention_fwd_tc2_supported(int heads, int head_stride, int ld);
+/* ym_attention_fwd_tc2, d_v = 32: every `every`-th exponential of a score row is computed on the FMA pipe (degree-3 polynomial,
+ * |rel err| < 7.5e-5) instead of the MUFU, whose 16 ex2 / clk / SM is the kernel's ceiling (0 = MUFU only; 2 / 3 / 4 / 6).  Returns the
+ * previous setting; ym_attention2_poly reads it. */
+int ym_set_attention2_poly(int every);
+int ym_attention2_poly(void);
 /* Kernel behind ym_attention_fwd: 2 = ym_attention_fwd_tc2 (default), 1 = ym_attention_fwd_tc, 0 = mma.sync kernel.  Returns the
  * previous setting (A/B baselines for tests and profiles; nothing in the package changes it). */
 int ym_set_attention_impl(int impl);
+
+/* ---- routed expert FFN on tcgen05 with the hidden activation kept on chip (csrc/tc_moe.cu) --------------------------------------
+ * SimpleExpert (moe/experts.py:73-88: 1x1 -> GroupNorm -> SiLU -> 1x1 -> GroupNorm) of the top-k experts of every image inside
+ * OptimizedMOEImproved.forward (moe/modules.py:1128-1157).  Problem p = (image p / topk, rank p % topk), expert route_idx[p].
+ *   x  fp16 [B][HW][ldx] (C channels used), w1 fp16 [E][HID][C], w2 fp16 [E][C][HID], (C, HID) = (64, 128) or (128, 256)
+ *   stage 1: stats[P][strips][HID/8][2] = GroupNorm-1 partial sums (sum, sum of squares per 8-channel slice) of h = x W1[e]^T, h
+ *            rounded to fp16 as the reference's fp16 execution stores it; h itself is never written
+ *   ym_gn_finalize_tiles(stats, P, strips, groups, HID, HW * HID / groups, eps, gamma, beta, route_idx, NULL, a_scale, a_shift)
+ *   stage 2: out[P][HW][C] = SiLU(h * a_scale + a_shift) W2[e]^T in fp16 (h recomputed, normalised and fed to the second tcgen05.mma from
+ *            tensor memory) and stats[P][strips][C/8][2] = GroupNorm-2 partial sums of out
+ * `strips` = ym_moe_ffn_strips(HW, P) row strips per problem (one CTA each); a dropped route (route_idx < 0) writes zero statistics. */
+int ym_moe_ffn_supported(int C, int HID, int ldx);
+int ym_moe_ffn_strips(int HW, int P);
+long long ym_moe_ffn_stats_floats(int P, int strips, int N);
+int ym_moe_ffn(int stage, const void* x, int ldx, int B, int HW, int C, int HID, int topk, const void* w1, const void* w2, int E,
+               const int* route_idx, const float* a_scale, const float* a_shift, void* out, float* stats, int strips, void* stream);
+/* ym_gn_finalize with an explicit number of partial-sum tiles per problem. */
+int ym_gn_finalize_tiles(const float* stats, int P, int tiles, int groups, int C, float count, float eps, const float* gamma,
+                         const float* beta, const int* route_idx, const float* route_w, float* scale, float* shift, void* stream);
+/* Programmatic dependent launch of the forward-path kernels (default on; YM_PDL=0 in the environment or ym_set_pdl(0) turns the launch
+ * attribute off - results are identical, only launch overlap changes).  ym_set_pdl returns the previous setting. */
+int ym_pdl_enabled(void);
+int ym_set_pdl(int on);
 
 /* EfficientSpatialRouter.forward + BaseRouter._process_logits (eval)  moe/routers.py:283-304, :185-265.
  * w1: fp32 [9][C/4][Cr][4] (tap-major, float4 over channels), scale1/shift1: folded BN1 [Cr]; w2: fp32 [E][Cr], scale2/shift2: folded BN2 [E].

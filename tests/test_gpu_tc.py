@@ -174,6 +174,77 @@ def test_tc_attention2_area_layout_interleaved_qkv():
     assert float(wide[..., :64].abs().max()) == 0 and float(wide[..., 128:].abs().max()) == 0, "wrote outside its channel slice"
 
 
+@pytest.mark.parametrize("B,HW,C,HID,E,topk", [(4, 6400, 64, 128, 4, 2), (3, 1600, 64, 128, 8, 2), (5, 400, 128, 256, 16, 2), (2, 100, 64, 128, 4, 1),
+                                               (1, 129, 128, 256, 4, 2), (7, 37, 64, 128, 4, 2)])
+def test_moe_ffn_tc_matches_fp32_chain(B, HW, C, HID, E, topk):
+    """ym_moe_ffn (tcgen05, hidden kept in tensor memory) stage by stage against fp32 torch on the same fp16 inputs: GroupNorm-1 affine
+    from the stage-1 statistics, o = SiLU(GN1(h)) W2^T and the GroupNorm-2 affine from the stage-2 statistics (strict tolerance), ragged
+    HW (row-tile tails, empty trailing strips), both width pairs, a channel-slice input view."""
+    from yolo_master_b200 import ops
+    g = torch.Generator().manual_seed(HW + C)
+    wide = torch.randn((B, HW, 1, C + 64), generator=g).half().to(DEV)
+    x = wide[..., 32:32 + C]                                                  # pitch C + 64, 64-byte offset
+    w1 = (torch.randn((E, HID, C), generator=g) / C ** 0.5).half().to(DEV)
+    w2 = (torch.randn((E, C, HID), generator=g) / HID ** 0.5).half().to(DEV)
+    ridx = torch.stack([torch.randperm(E, generator=g)[:topk] for _ in range(B)]).int().view(-1).to(DEV)
+    rw = torch.rand((B * topk,), generator=g).to(DEV)
+    G1, G2, eps = 8, 8, 1e-5
+    ga1, be1 = (0.6 + 0.8 * torch.rand((E, HID), generator=g)).to(DEV), (0.2 * torch.randn((E, HID), generator=g)).to(DEV)
+    ga2, be2 = (0.6 + 0.8 * torch.rand((E, C), generator=g)).to(DEV), (0.2 * torch.randn((E, C), generator=g)).to(DEV)
+    P = B * topk
+    st1, strips = ops.moe_ffn_stats(x, topk, w1, ridx)
+    sc1, sh1 = ops.gn_finalize_tiles(st1, P, strips, G1, HID, HW * (HID // G1), eps, ga1, be1, ridx)
+    o, st2 = ops.moe_ffn_fused(x, topk, w1, w2, ridx, sc1, sh1, strips)
+    sc2, sh2 = ops.gn_finalize_tiles(st2, P, strips, G2, C, HW * (C // G2), eps, ga2, be2, ridx, route_w=rw)
+    torch.cuda.synchronize()
+    xf = x.float().reshape(B, HW, C)
+    for p in range(P):
+        e = int(ridx[p])
+        h = (xf[p // topk] @ w1[e].float().t()).half().float()                 # the fp16 hidden of the reference's fp16 execution
+        hg = h.view(HW, G1, HID // G1)
+        mean, var = hg.mean((0, 2)), hg.var((0, 2), unbiased=False)
+        rstd = 1.0 / torch.sqrt(var + eps)
+        s1 = rstd.repeat_interleave(HID // G1) * ga1[e]
+        t1 = be1[e] - mean.repeat_interleave(HID // G1) * s1
+        assert_close(sc1[p], s1, atol=1e-4, rtol=1e-3, what=f"GN1 scale p={p}")
+        assert_close(sh1[p], t1, atol=1e-3, rtol=1e-3, what=f"GN1 shift p={p}")
+        a = torch.nn.functional.silu(h * s1 + t1).half().float()
+        oref = a @ w2[e].float().t()
+        assert_close(o[p], oref, what=f"o p={p}")
+        og = o[p].float().view(HW, G2, C // G2)
+        m2, v2 = og.mean((0, 2)), og.var((0, 2), unbiased=False)
+        r2 = 1.0 / torch.sqrt(v2 + eps)
+        s2 = rw[p] * r2.repeat_interleave(C // G2) * ga2[e]
+        t2 = rw[p] * be2[e] - m2.repeat_interleave(C // G2) * s2
+        assert_close(sc2[p], s2, atol=1e-4, rtol=1e-3, what=f"GN2 scale p={p}")
+        assert_close(sh2[p], t2, atol=1e-3, rtol=1e-3, what=f"GN2 shift p={p}")
+    assert float(wide[..., :32].float().abs().max()) > 0      # the view's neighbours are inputs only - nothing was written there
+
+
+def test_moe_ffn_tc_and_mma_chains_agree_in_the_block():
+    """OptimizedMOEImproved through both expert-FFN implementations (MOE_FFN_IMPL): same routing, block outputs within the strict tolerance
+    of each other (the fp32 accumulation order of the two GEMM engines differs, nothing else)."""
+    from yolo_master_b200.nn.modules import moe as moe_mod
+    from yolo_master_b200.utils.synth import fill_state_dict_
+    m = moe_mod.OptimizedMOEImproved(64, 64, num_experts=4, top_k=2).to(DEV).eval()
+    sd = m.state_dict()
+    fill_state_dict_(sd, 3)
+    m.load_state_dict(sd)
+    x = (torch.randn((4, 40, 40, 64), generator=torch.Generator().manual_seed(1)) * 0.7).half().to(DEV)
+    outs = {}
+    for impl in ("tc", "mma"):
+        moe_mod.MOE_FFN_IMPL = impl
+        try:
+            with torch.no_grad():
+                outs[impl] = m.fwd_nhwc(x).clone()
+                snap = {k: v.clone() for k, v in m.last_routing_snapshot.items()}
+            outs[impl + "_idx"] = snap["topk_indices"]
+        finally:
+            moe_mod.MOE_FFN_IMPL = "tc"
+    assert torch.equal(outs["tc_idx"], outs["mma_idx"])
+    assert_close(outs["tc"], outs["mma"].float(), what="tc vs mma expert FFN chain")
+
+
 @pytest.mark.parametrize("c1,c2,k,s,act", [
     (64, 64, 1, 1, True), (64, 192, 1, 1, False), (384, 128, 1, 1, True), (48, 64, 1, 1, True), (96, 64, 1, 1, True),
     (16, 32, 3, 2, True), (64, 64, 3, 2, True), (32, 32, 3, 1, True), (16, 8, 3, 1, True), (128, 256, 3, 2, True),

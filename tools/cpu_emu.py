@@ -195,6 +195,29 @@ def moe_expert_gemm(a, lda, a_div, P, HW, K, w_all, route_idx, N, a_scale=None, 
     return out, (out if groups else None)
 
 
+def moe_ffn_supported(C, HID, ldx):
+    return (C, HID) in ((64, 128), (128, 256)) and ldx % 8 == 0
+
+
+def moe_ffn_stats(x, topk, w1, route_idx):
+    """Stage 1 of ym_moe_ffn: the "statistics" handle of the emulation is the fp16-rounded hidden activation itself."""
+    B, H, W, Cc = x.shape
+    h, _ = moe_expert_gemm(x, x.shape[-1], topk, B * topk, H * W, Cc, w1, route_idx, w1.shape[1], groups=1)
+    return h, 1
+
+
+def moe_ffn_fused(x, topk, w1, w2, route_idx, a_scale, a_shift, strips):
+    B, H, W, Cc = x.shape
+    P, HW, HID = B * topk, H * W, w1.shape[1]
+    h, _ = moe_expert_gemm(x, x.shape[-1], topk, P, HW, Cc, w1, route_idx, HID, groups=1)
+    o, _ = moe_expert_gemm(h, HID, 1, P, HW, HID, w2, route_idx, Cc, a_scale=a_scale, a_shift=a_shift, groups=1)
+    return o, o
+
+
+def gn_finalize_tiles(stats, P, tiles, G, C_, count, eps, gamma, beta, route_idx, route_w=None):
+    return gn_finalize(stats, P, stats.shape[1], G, C_, count, eps, gamma, beta, route_idx, route_w)
+
+
 def gn_finalize(stats, P, HW, G, C_, count, eps, gamma, beta, route_idx, route_w=None):
     o = stats.float().reshape(P, HW, G, C_ // G)
     mean = o.mean((1, 3))
@@ -415,6 +438,7 @@ def install_model():
     install()
     for name, fn in dict(stem_conv=stem_conv, attention=attention, concat2=concat2, sppf_pool=sppf_pool, router_topk=router_topk,
                          moe_combine=moe_combine, moe_expert_gemm=moe_expert_gemm, gn_finalize=gn_finalize, detect_dense=detect_dense,
+                         moe_ffn_supported=moe_ffn_supported, moe_ffn_stats=moe_ffn_stats, moe_ffn_fused=moe_ffn_fused, gn_finalize_tiles=gn_finalize_tiles,
                          detect_topk=detect_topk, kpts_decode=kpts_decode, obb_finish=obb_finish, latent_router=latent_router).items():
         setattr(ops, name, fn)
     ops.pitch = lambda t, dtype=torch.float16: (t.stride(2) if t.shape[2] > 1 else (t.stride(1) if t.shape[1] > 1 else (t.stride(0) if t.shape[0] > 1 else t.shape[3])))

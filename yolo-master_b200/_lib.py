@@ -26,7 +26,16 @@ SIGNATURES = {
     "ym_attention_fwd_tc": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, cf, vp, ci, vp]),
     "ym_attention_fwd_tc2": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, cf, vp, ci, vp]),
     "ym_attention_fwd_tc2_supported": (ci, [ci, ci, ci]),
+    "ym_set_attention2_poly": (ci, [ci]),
+    "ym_attention2_poly": (ci, []),
     "ym_set_attention_impl": (ci, [ci]),
+    "ym_moe_ffn_supported": (ci, [ci, ci, ci]),
+    "ym_moe_ffn_strips": (ci, [ci, ci]),
+    "ym_moe_ffn_stats_floats": (cll, [ci, ci, ci]),
+    "ym_moe_ffn": (ci, [ci, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp, vp, vp, vp, vp, ci, vp]),
+    "ym_gn_finalize_tiles": (ci, [vp, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp, vp]),
+    "ym_pdl_enabled": (ci, []),
+    "ym_set_pdl": (ci, [ci]),
     "ym_set_attention_poly": (ci, [ci]),
     "ym_set_attention_chunked": (ci, [ci]),
     "ym_router_scratch_floats": (cll, [ci, ci, ci, ci, ci, ci]),

@@ -518,6 +518,19 @@ extern "C" int ym_gn_finalize(const float* stats, int P, int HW, int groups, int
     return YM_OK;
 }
 
+// Same with an explicit number of partial-sum tiles per problem (ym_moe_ffn writes one set per STRIP of row tiles, tc_moe.cu).
+extern "C" int ym_gn_finalize_tiles(const float* stats, int P, int tiles, int groups, int C, float count, float eps, const float* gamma,
+                                    const float* beta, const int* route_idx, const float* route_w, float* scale, float* shift,
+                                    void* stream) {
+    YM_CHECK_ARG(stats && gamma && beta && route_idx && scale && shift, "ym_gn_finalize_tiles: null pointer");
+    YM_CHECK_ARG(groups > 0 && C % groups == 0 && (C / groups) % 8 == 0 && tiles >= 1, "ym_gn_finalize_tiles: bad groups / tiles");
+    if (P == 0) return YM_OK;
+    const int n = P * groups * 32;
+    launch_pdl(gn_finalize_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, stats, P, tiles, groups, C, count, eps, gamma, beta,
+               route_idx, route_w, scale, shift);
+    YM_CHECK_LAUNCH("gn_finalize_tiles");
+    return YM_OK;
+}
 
 // ES_MOE expert pointwise stage: y[p] = route_w[p] * SiLU(t[p] * Wpw[e_p]^T + bias[e_p])  (experts.py:280-296 with BN folded),
 // one problem per (image, k); problems whose route_idx is negative (dropped by the dynamic threshold) are skipped.

@@ -6,10 +6,10 @@
 //   * one CTA owns TWO 128-row query tiles of one (image, head) and walks the keys once for both: every K / V tile is fetched
 //     once per 256 query rows (tc_attention.cu: once per 128) by TMA (one 4-D tensor map per operand: d, token, head, image;
 //     rows past N arrive as zeros) into a 6-stage shared-memory ring in the 64B/128B-swizzled canonical UMMA layout;
-//   * warp 8 lane 0 is the only thread that issues TMA and tcgen05.mma.  Its static order per key tile t is
-//       QK_A(t+1), QK_B(t+1), PV_A(t), PV_B(t), refill of the stage released by tile t-1
-//     with QK(t+1) issued as soon as the softmax warps have READ S(t) out of tensor memory - one whole softmax phase before
-//     they need S(t+1) - so the tensor-core latency is never on the softmax warps' path;
+//   * each query tile has its own issuing thread (warp 8 lane 0: all TMA + tile A's tcgen05.mma; warp 9 lane 0: tile B's).  Per key
+//     tile t it issues QK(t+1) as soon as ITS softmax warps have READ S(t) out of tensor memory - one whole softmax phase before
+//     they need S(t+1) - then PV(t) when P(t) is complete, so the tensor-core latency is never on the softmax warps' path and the
+//     two tiles never wait for each other (they only share the K/V ring, released by one commit-arrive per tile);
 //   * warps 0-3 (tile A) and 4-7 (tile B) are softmax warps: thread = query row (shuffle-free max / sum), S row read with
 //     tcgen05.ld, exp2 on the MUFU, lazy rescale (O only touched when a row max grows by more than 2^8), packed fp16 P row
 //     written back to tensor memory (tcgen05.st) as the A operand of the TS-mode PV MMA.  They never meet at a __syncthreads:
@@ -27,12 +27,24 @@
 
 namespace ym {
 
-constexpr int A2_BQ = 128, A2_BKV = 64, A2_STAGES = 6, A2_THREADS = 288;   // 8 softmax warps + 1 TMA / MMA warp
+constexpr int A2_BQ = 128, A2_BKV = 64, A2_STAGES = 6, A2_THREADS = 320;   // 8 softmax warps + 2 issuer warps (one per query tile)
 
 __device__ __forceinline__ float a2_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
     return y;
+}
+// exp2 on the FMA / ALU pipes (same polynomial as tc_attention.cu): round-to-nearest range reduction by the 1.5*2^23 magic add, degree-3
+// minimax polynomial of 2^f on [-0.5, 0.5] (max relative error 7.5e-5, a sixth of the fp16 rounding of P), exponent inserted by an
+// integer add.  With POLY = n every n-th score of a row takes this path, so the MUFU (16 ex2 / clk / SM) serves (n-1)/n of them.
+__device__ __forceinline__ float a2_exp2_poly(float x) {
+    x = fmaxf(x, -125.f);
+    const float t = x + 12582912.f;
+    const float f = x - (t - 12582912.f);
+    float p = fmaf(0.05517164617776871f, f, 0.2426111251115799f);
+    p = fmaf(p, f, 0.6932609677314758f);
+    p = fmaf(p, f, 0.9999280571937561f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 __device__ __forceinline__ void a2_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -52,7 +64,7 @@ struct A2Bars {
     uint32_t tmem_slot;
 };
 
-template <int DV>
+template <int DV, int POLY>
 __global__ void __launch_bounds__(A2_THREADS, (DV == 32) ? 2 : 1)
 tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, int N, float scale_log2, __half* __restrict__ out, int ldo) {
@@ -74,7 +86,7 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tc::mbar_init(&bars.q_full, 1);
         for (int s = 0; s < A2_STAGES; ++s) {
             tc::mbar_init(&bars.kv_full[s], 1);
-            tc::mbar_init(&bars.kv_empty[s], 1);
+            tc::mbar_init(&bars.kv_empty[s], has_b ? 2 : 1);   // one commit-arrive per query tile that reads the stage
         }
         for (int q = 0; q < 2; ++q) {
             tc::mbar_init(&bars.s_full[q], 1);
@@ -92,9 +104,14 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t tmem_base = bars.tmem_slot;
     pdl_prologue();    // barriers / tensor memory are set up: let the next kernel stage itself, then wait for the qkv conv
 
-    if (warp == 8) {
-        // ================================================= TMA + MMA issuer (one thread) =========================================
-        if (lane == 0) {
+    if (warp >= 8) {
+        // ====================================== issuers: warp 8 = TMA + tile A's MMAs, warp 9 = tile B's MMAs ======================
+        // Each query tile has its OWN issuing thread, so a tile's QK(t+1) is issued the moment ITS softmax warps have read S(t) and
+        // its PV(t) the moment ITS P(t) is complete, whatever the sibling tile is doing.  (One thread serving both tiles in a static
+        // order locked them one key tile apart: tile A's next S was only issued when tile B finished - ~900 clk of s_full polling per
+        // key tile in profiles/r02_attention2_ncu.txt, first capture.)
+        const int q = warp - 8;
+        if (lane == 0 && (q == 0 || has_b)) {
             const uint32_t idesc_qk = tc::make_idesc_f16(A2_BQ, A2_BKV, 0);
             const uint32_t idesc_pv = tc::make_idesc_f16(A2_BQ, DV, 1);      // V is MN-major (d_v contiguous)
             auto load_kv = [&](int t) {
@@ -104,23 +121,23 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 a2_tma_load_4d(dK, &map_k, 0, t * A2_BKV, h, b, &bars.kv_full[st]);
                 a2_tma_load_4d(dK + K_BYTES, &map_v, 0, t * A2_BKV, h, b, &bars.kv_full[st]);
             };
-            a2_expect_tx(&bars.q_full, (uint32_t)(2 * Q_BYTES));
-            a2_tma_load_4d(sQ, &map_q, 0, q0, h, b, &bars.q_full);           // one 256-row box: tile A then tile B
-            for (int t = 0; t < A2_STAGES && t < T; ++t) load_kv(t);
-
-            auto issue_qk = [&](int q, int t) {
-                const uint64_t qdesc = tc::make_desc(smem_u32(sQ + q * Q_BYTES), 512, 4);
+            if (q == 0) {
+                a2_expect_tx(&bars.q_full, (uint32_t)(2 * Q_BYTES));
+                a2_tma_load_4d(sQ, &map_q, 0, q0, h, b, &bars.q_full);       // one 256-row box: tile A then tile B
+                for (int t = 0; t < A2_STAGES && t < T; ++t) load_kv(t);
+            }
+            const uint32_t t_s = tmem_base + q * QT_COLS, t_p = t_s + 64, t_o = t_p + 32;
+            const uint64_t qdesc = tc::make_desc(smem_u32(sQ + q * Q_BYTES), 512, 4);
+            auto issue_qk = [&](int t) {
                 const uint64_t kdesc = tc::make_desc(smem_u32(sKV + (t % A2_STAGES) * STAGE_BYTES), 512, 4);
-                const uint32_t t_s = tmem_base + q * QT_COLS;
                 tc::mma_f16_ss(t_s, qdesc, kdesc, idesc_qk, 0u);
                 tc::mma_f16_ss(t_s, qdesc + 2, kdesc + 2, idesc_qk, 1u);
                 tc::mma_commit(&bars.s_full[q]);
             };
-            auto issue_pv = [&](int q, int t) {
+            auto issue_pv = [&](int t) {
                 const uint32_t va = smem_u32(sKV + (t % A2_STAGES) * STAGE_BYTES + K_BYTES);
                 const uint64_t vdesc = (DV == 32) ? tc::make_desc(va, 512, 4) : tc::make_desc(va, 1024, 2);
                 constexpr uint32_t VSTEP = (16 * DV * 2) >> 4;               // 16 keys per MMA k-step, in 16-byte units
-                const uint32_t t_p = tmem_base + q * QT_COLS + 64, t_o = t_p + 32;
 #pragma unroll
                 for (int k = 0; k < A2_BKV / 16; ++k)
                     tc::mma_f16_ts(t_o, t_p + 8 * k, vdesc + VSTEP * k, idesc_pv, (t | k) ? 1u : 0u);   // 16 keys = 8 columns of P
@@ -129,30 +146,19 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 
             tc::mbar_wait(&bars.q_full, 0);
             tc::mbar_wait(&bars.kv_full[0], 0);
-            issue_qk(0, 0);
-            if (has_b) issue_qk(1, 0);
+            issue_qk(0);
             for (int t = 0; t < T; ++t) {
                 if (t + 1 < T) {
                     tc::mbar_wait(&bars.kv_full[(t + 1) % A2_STAGES], ((t + 1) / A2_STAGES) & 1);
-                    tc::mbar_wait(&bars.s_free[0], t & 1);                   // every softmax warp of tile A holds S_A(t) in registers
+                    tc::mbar_wait(&bars.s_free[q], t & 1);                   // every softmax warp of this tile holds S(t) in registers
                     tc::fence_after_sync();
-                    issue_qk(0, t + 1);
-                    if (has_b) {
-                        tc::mbar_wait(&bars.s_free[1], t & 1);
-                        tc::fence_after_sync();
-                        issue_qk(1, t + 1);
-                    }
+                    issue_qk(t + 1);
                 }
-                tc::mbar_wait(&bars.p_full[0], t & 1);
+                tc::mbar_wait(&bars.p_full[q], t & 1);
                 tc::fence_after_sync();
-                issue_pv(0, t);
-                if (has_b) {
-                    tc::mbar_wait(&bars.p_full[1], t & 1);
-                    tc::fence_after_sync();
-                    issue_pv(1, t);
-                }
-                tc::mma_commit(&bars.kv_empty[t % A2_STAGES]);               // every MMA that reads stage t%STAGES has been issued
-                if (t >= 1 && t - 1 + A2_STAGES < T) {                       // refill the stage of tile t-1 (its PVs retired a phase ago)
+                issue_pv(t);
+                tc::mma_commit(&bars.kv_empty[t % A2_STAGES]);               // this tile's MMAs on stage t%STAGES have been issued (one arrive per tile)
+                if (q == 0 && t >= 1 && t - 1 + A2_STAGES < T) {             // refill the stage of key tile t-1 once BOTH query tiles retired it
                     tc::mbar_wait(&bars.kv_empty[(t - 1) % A2_STAGES], ((t - 1) / A2_STAGES) & 1);
                     load_kv(t - 1 + A2_STAGES);
                 }
@@ -205,8 +211,10 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             float ls_row[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float p0 = a2_exp2(fmaf(__uint_as_float(sr[2 * i]), scale_log2, -m_used));
-                const float p1 = a2_exp2(fmaf(__uint_as_float(sr[2 * i + 1]), scale_log2, -m_used));
+                const float x0 = fmaf(__uint_as_float(sr[2 * i]), scale_log2, -m_used);
+                const float x1 = fmaf(__uint_as_float(sr[2 * i + 1]), scale_log2, -m_used);
+                const float p0 = (POLY > 0 && (2 * i) % POLY == POLY - 1) ? a2_exp2_poly(x0) : a2_exp2(x0);
+                const float p1 = (POLY > 0 && (2 * i + 1) % POLY == POLY - 1) ? a2_exp2_poly(x1) : a2_exp2(x1);
                 pk[i] = pack_half2(p0, p1);
                 ls_row[i & 3] += p0 + p1;                    // four independent partial sums
             }
@@ -289,6 +297,15 @@ static bool a2_map(CUtensorMap* m, const __half* base, int d, int N, int heads, 
 
 using namespace ym;
 
+// Every n-th softmax exponential of the d_v = 32 kernel on the FMA pipe instead of the MUFU (0 = all on the MUFU; 2 / 3 / 4 / 6).
+static int g_attention2_poly = 0;
+extern "C" int ym_attention2_poly(void) { return g_attention2_poly; }
+extern "C" int ym_set_attention2_poly(int every) {
+    const int old = g_attention2_poly;
+    if (every == 0 || every == 2 || every == 3 || every == 4 || every == 6) g_attention2_poly = every;
+    return old;
+}
+
 extern "C" int ym_attention_fwd_tc2_supported(int heads, int head_stride, int ld) {
     // tensor-map strides are multiples of 16 bytes; a single head needs no head stride
     return a2_encode() != nullptr && ld % 8 == 0 && (heads == 1 || head_stride % 8 == 0);
@@ -317,14 +334,25 @@ extern "C" int ym_attention_fwd_tc2(const void* qkv, int ld, int batch, int N, i
     dim3 grid((N + 2 * A2_BQ - 1) / (2 * A2_BQ), heads, batch);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)2 * A2_BQ * 64 + A2_STAGES * (A2_BKV * 64 + A2_BKV * d_v * 2) + 1024;
-    cudaError_t e;
+    cudaError_t e = cudaSuccess;
+#define A2_LAUNCH(DV_, POLY_)                                                                                                        \
+    do {                                                                                                                             \
+        e = cudaFuncSetAttribute(tc_attention2_kernel<DV_, POLY_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+        if (e == cudaSuccess) e = launch_pdl(tc_attention2_kernel<DV_, POLY_>, grid, A2_THREADS, smem, st, mq, mk, mv, N, sl2, (__half*)out, ldo); \
+    } while (0)
+    const int poly = ym_attention2_poly();
     if (d_v == 32) {
-        e = cudaFuncSetAttribute(tc_attention2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) launch_pdl(tc_attention2_kernel<32>, grid, A2_THREADS, smem, st, mq, mk, mv, N, sl2, (__half*)out, ldo);
+        switch (poly) {
+            case 2: A2_LAUNCH(32, 2); break;
+            case 3: A2_LAUNCH(32, 3); break;
+            case 4: A2_LAUNCH(32, 4); break;
+            case 6: A2_LAUNCH(32, 6); break;
+            default: A2_LAUNCH(32, 0); break;
+        }
     } else {
-        e = cudaFuncSetAttribute(tc_attention2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) launch_pdl(tc_attention2_kernel<64>, grid, A2_THREADS, smem, st, mq, mk, mv, N, sl2, (__half*)out, ldo);
+        A2_LAUNCH(64, 0);
     }
+#undef A2_LAUNCH
     if (e != cudaSuccess) { ym_set_error("ym_attention_fwd_tc2: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
     YM_CHECK_LAUNCH("tc_attention2");
     return YM_OK;

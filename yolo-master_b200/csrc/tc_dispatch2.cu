@@ -114,16 +114,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DQ_THREADS, 1)
     const uint32_t rank = dq_ctarank(), cid = dq_clusterid(), ncl = dq_nclusters();
     const int my_units = ((int)cid < p.units) ? (p.units - 1 - (int)cid) / (int)ncl + 1 : 0;   // units cid, cid + ncl, ... (<= DQ_MAXU)
 
-    // routes of every unit this pair will process, read once (the loops below never touch global memory for them)
-    for (int i = tid; i < my_units; i += DQ_THREADS) {
-        const int b = (p.unit0 + (int)cid + i * (int)ncl) / p.upi;
-        int n = 0;
-        for (int j = 0; j < p.topk && j < 2; ++j) {
-            const float wj = p.route_w[b * p.topk + j];
-            if (wj > p.w_min) { s_e[i][n] = p.route_idx[b * p.topk + j]; s_w[i][n] = wj; ++n; }
-        }
-        s_nr[i] = n;
-    }
     if (tid == 0) {
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&a_full[a], 1); tc::mbar_init(&a_empty[a], 1); }
         for (int s = 0; s < DQ_BSTAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
@@ -140,6 +130,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DQ_THREADS, 1)
     dq_cluster_sync();                                      // both CTAs' barriers are initialised before any remote arrive / TMA credit
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
+    // barriers / tensor memory are set up: let the next kernel of the stream stage itself, then wait for the producers of x and of
+    // the routing table (programmatic dependent launch; both are no-ops for an ordinary launch)
+    pdl_prologue();
+    // routes of every unit this pair will process, read once (the loops below never touch global memory for them)
+    for (int i = tid; i < my_units; i += DQ_THREADS) {
+        const int b = (p.unit0 + (int)cid + i * (int)ncl) / p.upi;
+        int n = 0;
+        for (int j = 0; j < p.topk && j < 2; ++j) {
+            const float wj = p.route_w[b * p.topk + j];
+            if (wj > p.w_min) { s_e[i][n] = p.route_idx[b * p.topk + j]; s_w[i][n] = wj; ++n; }
+        }
+        s_nr[i] = n;
+    }
+    __syncthreads();
     if (tid == 0) DQ_TR(3, 1);
     int tr = 0;                                             // per-role trace cursor
 
@@ -429,8 +433,8 @@ extern "C" int ym_moe_dispatch_v3(const void* x, int ldx, int B, int HW, int C, 
         const long long n = total - u0 < (long long)maxcl * DQ_MAXU ? total - u0 : (long long)maxcl * DQ_MAXU;
         p.unit0 = (int)u0; p.units = (int)n;
         const int ncl = n < maxcl ? (int)n : maxcl;
-        if (N == 256) tc_dispatch2_kernel<256><<<2 * ncl, DQ_THREADS, DQ_SMEM, (cudaStream_t)stream>>>(mx, mw, mo, p);
-        else tc_dispatch2_kernel<128><<<2 * ncl, DQ_THREADS, DQ_SMEM, (cudaStream_t)stream>>>(mx, mw, mo, p);
+        if (N == 256) launch_pdl(tc_dispatch2_kernel<256>, 2 * ncl, DQ_THREADS, DQ_SMEM, (cudaStream_t)stream, mx, mw, mo, p);
+        else launch_pdl(tc_dispatch2_kernel<128>, 2 * ncl, DQ_THREADS, DQ_SMEM, (cudaStream_t)stream, mx, mw, mo, p);
         YM_CHECK_LAUNCH("tc_dispatch2");
     }
     return YM_OK;

@@ -1,0 +1,358 @@
+// Routed expert FFN of OptimizedMOEImproved on tcgen05 with the hidden activation kept on chip (sm_100a).
+//
+// Reference: SimpleExpert = 1x1 conv -> GroupNorm -> SiLU -> 1x1 conv -> GroupNorm (moe/experts.py:73-88), applied to image b by its
+// top-k experts and combined (moe/modules.py:1128-1157).  Routing is per IMAGE, so a routed problem p = (image b, rank j) is a plain
+// GEMM chain over that image's HW token rows with expert e = route_idx[p]'s weights - no gather, no permutation.
+//
+// What made the mma.sync version (gemm_conv.cu) slow is traffic, not math: GEMM1 wrote the hidden h [P][HW][HID] (105 MB per P3 block at
+// bs32) and GEMM2 read it back, because GroupNorm-1 needs the statistics of the WHOLE image before any element can be normalised.
+// Here GEMM1 is cheap enough (K = C = 64 / 128) to run twice:
+//   pass 1  ym_moe_ffn_stats  : h = x W1[e]^T per 128-row tile (tcgen05.mma into tensor memory), epilogue = GroupNorm-1 partial sums
+//                               of the fp16-rounded h; nothing but 2 * HID/8 floats per (problem, strip) is written
+//   (ym_gn_finalize_tiles     : partial sums -> per-(problem, channel) scale / shift, unchanged arithmetic)
+//   pass 2  ym_moe_ffn_fused  : h again (bit-identical: same MMA, same operands), epilogue-1 = round to fp16, GroupNorm-1 affine, SiLU,
+//                               pack to fp16 and write it back into TENSOR MEMORY as the A operand of a TS-mode tcgen05.mma
+//                               o = a W2[e]^T; epilogue-2 = o -> fp16 -> global + GroupNorm-2 partial sums.
+// h never exists in global memory: per P3 block the chain moves x (read by both passes, L2-resident between the k ranks) and o.
+//
+// One CTA = one strip of consecutive 128-row tiles of ONE problem (weights fetched once per CTA by TMA), 160 threads:
+//   warp 0 lane 0 : every TMA (x tiles double-buffered, W1 / W2 once) and every tcgen05.mma, static order
+//                   GEMM1(0); per tile i: [P2: wait a(i) -> GEMM2(i)]; GEMM1(i+1); refill x(i+2)
+//   warps 1-4     : epilogue, thread = token row (tensor-memory lane), hand-offs through mbarriers only
+// Partial statistics are accumulated per thread over the strip and reduced once, in a fixed order (bit-reproducible).
+#include <cuda.h>
+
+#include "tc_common.cuh"
+
+namespace ym {
+
+constexpr int MF_BM = 128, MF_THREADS = 160;
+
+__device__ __forceinline__ void mf_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mf_tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void mf_tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+struct MoeFfnParams {
+    const int* route_idx;      // [P] expert of problem p (negative = dropped route: the CTA exits)
+    int a_div;                 // image of problem p = p / a_div (top_k)
+    int HW, mtiles, tiles_per_strip;
+    const float* a_scale;      // pass 2: GroupNorm-1 affine per (problem, hidden channel) [P][HID]
+    const float* a_shift;
+    __half* out;               // pass 2: o [P][HW][C]
+    float* stats;              // partial sums [P][strips][NS/2][2], NS/2 = (pass 1 ? HID : C) / 8 eight-channel slices
+};
+
+struct MfBars {
+    uint64_t w_full, x_full[2], d1_full, a_full, d2_full;
+    uint32_t tmem_slot;
+};
+
+// STAGE 1: statistics of h only.  STAGE 2: the fused chain.
+template <int C, int HID, int STAGE>
+__global__ void __launch_bounds__(MF_THREADS, (HID <= 128) ? 2 : 1)
+moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+               const __grid_constant__ CUtensorMap map_w2, const MoeFfnParams p) {
+    constexpr int KC1 = C / 64;                        // 64-wide k chunks of GEMM1 (K = C)
+    constexpr int KC2 = HID / 64;                      // 64-wide k chunks of GEMM2 (K = HID)
+    constexpr int X_BYTES = MF_BM * C * 2, W1_BYTES = HID * C * 2, W2_BYTES = C * HID * 2;
+    constexpr uint32_t D1_COLS = HID, A_COLS = HID / 2, D2_COLS = C;
+    constexpr uint32_t TMEM_COLS = (STAGE == 1) ? (HID <= 128 ? 128 : 256) : (HID <= 128 ? 256 : 512);
+    constexpr int NS = (STAGE == 1 ? HID : C) / 8 * 2;   // floats of partial statistics per thread / per strip
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* sX = smem;                          // [2][KC1][128 rows x 128 B]
+    unsigned char* sW1 = sX + 2 * X_BYTES;             // [KC1][HID rows x 128 B]
+    unsigned char* sW2 = sW1 + W1_BYTES;               // [KC2][C rows x 128 B]           (pass 2)
+    float* sAff = reinterpret_cast<float*>(sW2 + (STAGE == 2 ? W2_BYTES : 0));   // [2][HID] GroupNorm-1 scale | shift (pass 2)
+    __shared__ MfBars bars;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int prob = blockIdx.y, strip = blockIdx.x;
+    const int t0 = strip * p.tiles_per_strip;
+    const int nt = min(p.tiles_per_strip, p.mtiles - t0);
+
+    if (tid == 0) {
+        tc::mbar_init(&bars.w_full, 1);
+        tc::mbar_init(&bars.x_full[0], 1);
+        tc::mbar_init(&bars.x_full[1], 1);
+        tc::mbar_init(&bars.d1_full, 1);
+        tc::mbar_init(&bars.a_full, 4);                // one arrive per epilogue warp
+        tc::mbar_init(&bars.d2_full, 1);
+        tc::fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(&bars.tmem_slot, TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = bars.tmem_slot;
+    pdl_prologue();                                    // set-up done: stage the next kernel, then wait for the producers of x / routes / affine
+    const int e = p.route_idx[prob];
+    const bool active = e >= 0 && nt > 0;              // CTA-uniform
+    if (active) {
+        const int img = prob / p.a_div;
+        if (STAGE == 2) {
+            for (int i = tid; i < HID; i += MF_THREADS) {
+                sAff[i] = p.a_scale[(long long)prob * HID + i];
+                sAff[HID + i] = p.a_shift[(long long)prob * HID + i];
+            }
+        }
+        __syncthreads();
+        const uint32_t t_d1 = tmem_base, t_a = tmem_base + D1_COLS, t_d2 = tmem_base + D1_COLS + A_COLS;
+
+        if (warp == 0) {
+            if (lane == 0) {
+                // ============================================ TMA + MMA issuer ============================================
+                auto load_x = [&](int i) {
+                    unsigned char* dst = sX + (i & 1) * X_BYTES;
+                    mf_expect_tx(&bars.x_full[i & 1], (uint32_t)X_BYTES);
+#pragma unroll
+                    for (int kc = 0; kc < KC1; ++kc)
+                        mf_tma_load_3d(dst + kc * (MF_BM * 128), &map_x, kc * 64, (t0 + i) * MF_BM, img, &bars.x_full[i & 1]);
+                };
+                mf_expect_tx(&bars.w_full, (uint32_t)(W1_BYTES + (STAGE == 2 ? W2_BYTES : 0)));
+#pragma unroll
+                for (int kc = 0; kc < KC1; ++kc) mf_tma_load_2d(sW1 + kc * (HID * 128), &map_w1, kc * 64, e * HID, &bars.w_full);
+                if (STAGE == 2) {
+#pragma unroll
+                    for (int kc = 0; kc < KC2; ++kc) mf_tma_load_2d(sW2 + kc * (C * 128), &map_w2, kc * 64, e * C, &bars.w_full);
+                }
+                load_x(0);
+                if (nt > 1) load_x(1);
+                const uint32_t idesc1 = tc::make_idesc_f16(MF_BM, HID, 0);
+                const uint32_t idesc2 = tc::make_idesc_f16(MF_BM, C, 0);
+                auto gemm1 = [&](int i) {
+                    const uint32_t xa = smem_u32(sX + (i & 1) * X_BYTES), wa = smem_u32(sW1);
+#pragma unroll
+                    for (int kc = 0; kc < KC1; ++kc) {
+                        const uint64_t ad = tc::make_desc_sw128(xa + kc * (MF_BM * 128)), bd = tc::make_desc_sw128(wa + kc * (HID * 128));
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) tc::mma_f16_ss(t_d1, ad + 2 * ks, bd + 2 * ks, idesc1, (kc | ks) ? 1u : 0u);
+                    }
+                    tc::mma_commit(&bars.d1_full);
+                };
+                tc::mbar_wait(&bars.w_full, 0);
+                tc::mbar_wait(&bars.x_full[0], 0);
+                gemm1(0);
+                for (int i = 0; i < nt; ++i) {
+                    // the epilogue has read D1(i) (and, pass 2, written the A operand): D1 and x buffer i&1 are free
+                    tc::mbar_wait(&bars.a_full, i & 1);
+                    tc::fence_after_sync();
+                    if (STAGE == 2) {
+                        const uint32_t wa = smem_u32(sW2);
+#pragma unroll
+                        for (int kc = 0; kc < KC2; ++kc) {
+                            const uint64_t bd = tc::make_desc_sw128(wa + kc * (C * 128));
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)      // 16 hidden channels = 8 tensor-memory columns of the packed A operand
+                                tc::mma_f16_ts(t_d2, t_a + 8 * (kc * 4 + ks), bd + 2 * ks, idesc2, (kc | ks) ? 1u : 0u);
+                        }
+                        tc::mma_commit(&bars.d2_full);
+                    }
+                    if (i + 1 < nt) {
+                        tc::mbar_wait(&bars.x_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+                        gemm1(i + 1);
+                        if (i + 2 < nt) load_x(i + 2);       // buffer i&1: GEMM1(i) retired before a_full(i)
+                    }
+                }
+            }
+        } else {
+            // ================================================ epilogue warps: thread = token row ==================================
+            const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+            const int row_in_tile = (warp & 3) * 32 + lane;
+            float part[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) part[i] = 0.f;
+            for (int i = 0; i < nt; ++i) {
+                const int row = (t0 + i) * MF_BM + row_in_tile;
+                const bool live = row < p.HW;
+                tc::mbar_wait(&bars.d1_full, i & 1);
+                tc::fence_after_sync();
+#pragma unroll
+                for (int c0 = 0; c0 < HID; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(t_d1 + lane_sel + c0, v);
+                    tc::tmem_ld_wait();
+                    if (STAGE == 1) {
+                        if (live) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                const float2 r = __half22float2(__floats2half2_rn(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])));
+                                const int s = (c0 + 2 * q) >> 3;
+                                part[2 * s] += r.x + r.y;
+                                part[2 * s + 1] += r.x * r.x + r.y * r.y;
+                            }
+                        }
+                    } else {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const float2 r = __half22float2(__floats2half2_rn(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])));
+                            const int c = c0 + 2 * q;
+                            const float a0 = silu_f(fmaf(r.x, sAff[c], sAff[HID + c]));
+                            const float a1 = silu_f(fmaf(r.y, sAff[c + 1], sAff[HID + c + 1]));
+                            pk[q] = pack_half2(a0, a1);
+                        }
+                        tc::tmem_st16(t_a + lane_sel + c0 / 2, pk);
+                    }
+                }
+                if (STAGE == 2) tc::tmem_st_wait();
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.a_full);
+                if (STAGE == 2) {
+                    tc::mbar_wait(&bars.d2_full, i & 1);
+                    tc::fence_after_sync();
+                    __half* orow = p.out + ((long long)prob * p.HW + row) * C;
+#pragma unroll
+                    for (int c0 = 0; c0 < C; c0 += 32) {
+                        uint32_t v[32];
+                        tc::tmem_ld32(t_d2 + lane_sel + c0, v);
+                        tc::tmem_ld_wait();
+                        if (live) {
+#pragma unroll
+                            for (int c8 = 0; c8 < 4; ++c8) {
+                                Half8 hv;
+                                float s = 0.f, q2 = 0.f;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    hv.v[q] = __floats2half2_rn(__uint_as_float(v[c8 * 8 + 2 * q]), __uint_as_float(v[c8 * 8 + 2 * q + 1]));
+                                    const float2 r = __half22float2(hv.v[q]);
+                                    s += r.x + r.y;
+                                    q2 += r.x * r.x + r.y * r.y;
+                                }
+                                const int sl = (c0 >> 3) + c8;
+                                part[2 * sl] += s;
+                                part[2 * sl + 1] += q2;
+                                *reinterpret_cast<Half8*>(orow + c0 + c8 * 8) = hv;
+                            }
+                        }
+                    }
+                    tc::fence_before_sync();       // D2 / the A operand are read out before the next tile's MMAs may overwrite them
+                }
+            }
+            // ---- strip statistics: per-thread partials -> shared memory -> fixed-order column sums (bit-reproducible)
+            // every MMA that read the x buffers has retired (d1_full / d2_full of the last tile were waited on), so sX is free
+            float* red = reinterpret_cast<float*>(sX);
+            const int r = tid - 32;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) red[r * NS + i] = part[i];
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");       // the four epilogue warps only
+            if (r < NS) {
+                float a = 0.f;
+                for (int k = 0; k < 128; ++k) a += red[k * NS + r];
+                p.stats[((long long)prob * gridDim.x + strip) * NS + r] = a;
+            }
+        }
+    } else if (warp >= 1) {
+        // dropped route / empty trailing strip: the statistics slots must still be defined (the finalize kernel sums every strip)
+        const int r = tid - 32;
+        if (r < NS) p.stats[((long long)prob * gridDim.x + strip) * NS + r] = 0.f;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+typedef CUresult (*MfEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static MfEncodeFn mf_encode() {
+    static MfEncodeFn fn = nullptr;
+    if (!fn) {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult r;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess && r == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<MfEncodeFn>(q);
+    }
+    return fn;
+}
+static bool mf_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    cuuint32_t est[3] = {1, 1, 1};
+    return mf_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, est,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int C, int HID, int STAGE>
+static int mf_launch(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mw2, const MoeFfnParams& p, int strips, int P,
+                     cudaStream_t st) {
+    size_t smem = (size_t)2 * MF_BM * C * 2 + (size_t)HID * C * 2 + 1024;
+    if (STAGE == 2) smem += (size_t)C * HID * 2 + 2 * HID * sizeof(float);
+    auto kern = moe_ffn_kernel<C, HID, STAGE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ym_set_error("ym_moe_ffn: smem attr %zu: %s", smem, cudaGetErrorString(e)); return YM_ERR_CUDA; }
+    e = launch_pdl(kern, dim3(strips, P), dim3(MF_THREADS), smem, st, mx, mw1, mw2, p);
+    if (e != cudaSuccess) { ym_set_error("ym_moe_ffn: launch: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
+    return YM_OK;
+}
+
+}  // namespace ym
+
+using namespace ym;
+
+extern "C" int ym_moe_ffn_supported(int C, int HID, int ldx) {
+    return mf_encode() != nullptr && ((C == 64 && HID == 128) || (C == 128 && HID == 256)) && ldx % 8 == 0;
+}
+
+// strips per problem such that the grid is a few waves of resident CTAs and every strip amortises its weight fetch over >= 2 tiles
+extern "C" int ym_moe_ffn_strips(int HW, int P) {
+    const int mtiles = (HW + MF_BM - 1) / MF_BM;
+    int tps = 4;                                             // tiles per strip
+    while (tps > 1 && (long long)P * ((mtiles + tps - 1) / tps) < 2 * 296) --tps;
+    return (mtiles + tps - 1) / tps;
+}
+
+extern "C" long long ym_moe_ffn_stats_floats(int P, int strips, int N) { return (long long)P * strips * (N / 8) * 2; }
+
+// stage 1: stats != null, out == null: GroupNorm-1 partial sums of h = x W1[e]^T           -> stats [P][strips][HID/8][2]
+// stage 2: out  != null              : o = SiLU(GN1(h)) W2[e]^T (fp16) and its partial sums -> out [P][HW][C], stats [P][strips][C/8][2]
+extern "C" int ym_moe_ffn(int stage, const void* x, int ldx, int B, int HW, int C, int HID, int topk, const void* w1, const void* w2, int E,
+                          const int* route_idx, const float* a_scale, const float* a_shift, void* out, float* stats, int strips,
+                          void* stream) {
+    YM_CHECK_ARG(x && w1 && route_idx && stats, "ym_moe_ffn: null pointer");
+    YM_CHECK_ARG(stage == 1 || (stage == 2 && w2 && a_scale && a_shift && out), "ym_moe_ffn: stage %d needs w2 / a_scale / a_shift / out", stage);
+    YM_CHECK_ARG(ym_moe_ffn_supported(C, HID, ldx), "ym_moe_ffn: unsupported shape C=%d HID=%d ldx=%d (64/128 or 128/256)", C, HID, ldx);
+    YM_CHECK_ARG((((uintptr_t)x | (uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)out) & 15) == 0, "ym_moe_ffn: 16-byte alignment");
+    YM_CHECK_ARG(topk >= 1 && E >= 1 && HW >= 1 && strips >= 1, "ym_moe_ffn: bad sizes");
+    if (B == 0) return YM_OK;
+    const int P = B * topk, mtiles = (HW + MF_BM - 1) / MF_BM;
+    YM_CHECK_ARG(P <= 65535, "ym_moe_ffn: too many routed problems (%d)", P);
+    CUtensorMap mx, mw1, mw2;
+    {
+        cuuint64_t d[3] = {(cuuint64_t)C, (cuuint64_t)HW, (cuuint64_t)B}, s[2] = {(cuuint64_t)ldx * 2, (cuuint64_t)HW * ldx * 2};
+        cuuint32_t bx[3] = {64, MF_BM, 1};
+        if (!mf_map(&mx, x, 3, d, s, bx)) { ym_set_error("ym_moe_ffn: tensor map (x) failed"); return YM_ERR_CUDA; }
+    }
+    {
+        cuuint64_t d[2] = {(cuuint64_t)C, (cuuint64_t)E * HID}, s[1] = {(cuuint64_t)C * 2};
+        cuuint32_t bx[2] = {64, (cuuint32_t)HID};
+        if (!mf_map(&mw1, w1, 2, d, s, bx)) { ym_set_error("ym_moe_ffn: tensor map (w1) failed"); return YM_ERR_CUDA; }
+    }
+    if (stage == 2) {
+        cuuint64_t d[2] = {(cuuint64_t)HID, (cuuint64_t)E * C}, s[1] = {(cuuint64_t)HID * 2};
+        cuuint32_t bx[2] = {64, (cuuint32_t)C};
+        if (!mf_map(&mw2, w2, 2, d, s, bx)) { ym_set_error("ym_moe_ffn: tensor map (w2) failed"); return YM_ERR_CUDA; }
+    } else {
+        mw2 = mw1;
+    }
+    MoeFfnParams p;
+    p.route_idx = route_idx; p.a_div = topk; p.HW = HW; p.mtiles = mtiles; p.tiles_per_strip = (mtiles + strips - 1) / strips;
+    p.a_scale = a_scale; p.a_shift = a_shift; p.out = (__half*)out; p.stats = stats;
+    YM_CHECK_ARG((long long)strips * p.tiles_per_strip >= mtiles, "ym_moe_ffn: strips do not cover the tiles");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 64) return stage == 1 ? mf_launch<64, 128, 1>(mx, mw1, mw2, p, strips, P, st) : mf_launch<64, 128, 2>(mx, mw1, mw2, p, strips, P, st);
+    return stage == 1 ? mf_launch<128, 256, 1>(mx, mw1, mw2, p, strips, P, st) : mf_launch<128, 256, 2>(mx, mw1, mw2, p, strips, P, st);
+}

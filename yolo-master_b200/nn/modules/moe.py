@@ -97,6 +97,11 @@ class EfficientSpatialRouter(nn.Module, PackCache):
         return w, idx.long(), {}
 
 
+# "tc": routed expert FFN on the tcgen05 kernels with the hidden kept on chip (csrc/tc_moe.cu) where the widths allow;
+# "mma": the mma.sync implicit-GEMM chain of csrc/gemm_conv.cu (h through global memory) - kept as the A/B baseline
+MOE_FFN_IMPL = "tc"
+
+
 class SimpleExpert(nn.Module):
     """`SimpleExpert(in_channels, out_channels, expand_ratio=2, num_groups=8)`: 1x1 -> GN -> SiLU -> 1x1 -> GN.
 
@@ -180,12 +185,21 @@ class OptimizedMOEImproved(nn.Module, PackCache):
         ridx, rw = idx.view(-1), w.view(-1)
         P, hid = B * k, pk["hid"]
         ldx = ops.pitch(x)
-        # GEMM1: h[p] = x[p // k] @ W1[e_p]^T, GroupNorm-1 statistics in the epilogue
-        h, st1 = ops.moe_expert_gemm(x, ldx, k, P, HW, C, pk["w1"], ridx, hid, groups=pk["G1"])
-        sc1, sh1 = ops.gn_finalize(st1, P, HW, pk["G1"], hid, HW * (hid // pk["G1"]), pk["eps1"], pk["gamma1"], pk["beta1"], ridx)
-        # GEMM2: o[p] = SiLU(GN1(h[p])) @ W2[e_p]^T with GN+SiLU applied on the A-operand load; GN-2 statistics
-        o, st2 = ops.moe_expert_gemm(h, hid, 1, P, HW, hid, pk["w2"], ridx, C, a_scale=sc1, a_shift=sh1, groups=pk["G2"])
-        sc2, sh2 = ops.gn_finalize(st2, P, HW, pk["G2"], C, HW * (C // pk["G2"]), pk["eps2"], pk["gamma2"], pk["beta2"], ridx, route_w=rw)
+        if MOE_FFN_IMPL == "tc" and pk["w1"].shape[2] == C and pk["w2"].shape[2] == hid and (hid // pk["G1"]) % 8 == 0 \
+                and (C // pk["G2"]) % 8 == 0 and ops.moe_ffn_supported(C, hid, ldx):
+            # tcgen05 path (csrc/tc_moe.cu): the hidden activation stays in tensor memory - pass 1 takes GroupNorm-1 statistics of
+            # h = x W1[e]^T without storing it, pass 2 recomputes h, normalises, SiLU, and feeds the second GEMM from tensor memory
+            st1, strips = ops.moe_ffn_stats(x, k, pk["w1"], ridx)
+            sc1, sh1 = ops.gn_finalize_tiles(st1, P, strips, pk["G1"], hid, HW * (hid // pk["G1"]), pk["eps1"], pk["gamma1"], pk["beta1"], ridx)
+            o, st2 = ops.moe_ffn_fused(x, k, pk["w1"], pk["w2"], ridx, sc1, sh1, strips)
+            sc2, sh2 = ops.gn_finalize_tiles(st2, P, strips, pk["G2"], C, HW * (C // pk["G2"]), pk["eps2"], pk["gamma2"], pk["beta2"], ridx, route_w=rw)
+        else:
+            # GEMM1: h[p] = x[p // k] @ W1[e_p]^T, GroupNorm-1 statistics in the epilogue
+            h, st1 = ops.moe_expert_gemm(x, ldx, k, P, HW, C, pk["w1"], ridx, hid, groups=pk["G1"])
+            sc1, sh1 = ops.gn_finalize(st1, P, HW, pk["G1"], hid, HW * (hid // pk["G1"]), pk["eps1"], pk["gamma1"], pk["beta1"], ridx)
+            # GEMM2: o[p] = SiLU(GN1(h[p])) @ W2[e_p]^T with GN+SiLU applied on the A-operand load; GN-2 statistics
+            o, st2 = ops.moe_expert_gemm(h, hid, 1, P, HW, hid, pk["w2"], ridx, C, a_scale=sc1, a_shift=sh1, groups=pk["G2"])
+            sc2, sh2 = ops.gn_finalize(st2, P, HW, pk["G2"], C, HW * (C // pk["G2"]), pk["eps2"], pk["gamma2"], pk["beta2"], ridx, route_w=rw)
         # combine: shared expert GEMM + sum_j w_j*GN2(o_j) (+ residual), fp32 accumulate, one rounding
         add_res = outer_residual or (self.add_residual and self.in_channels == self.out_channels)
         y = ops.moe_combine(x, pk["ws"], pk["bs"], o, sc2, sh2, k, add_residual=add_res, out=out)

@@ -211,6 +211,50 @@ def gn_finalize(stats, P, HW, G, C_, count, eps, gamma, beta, route_idx, route_w
     return scale, shift
 
 
+def moe_ffn_supported(C, HID, ldx) -> bool:
+    """True when the tcgen05 expert-FFN kernels (csrc/tc_moe.cu) serve this width pair."""
+    return bool(lib().ym_moe_ffn_supported(C, HID, ldx))
+
+
+def moe_ffn_stats(x, topk, w1, route_idx):
+    """ym_moe_ffn stage 1.  x: (B,H,W,C) fp16 view; w1 fp16 [E][HID][C]; route_idx int32 [B*topk].
+    Returns (GroupNorm-1 partial sums, strips) - the hidden activation itself is never written."""
+    B, H, W, Cc = x.shape
+    E, HID, _ = w1.shape
+    P = B * topk
+    strips = lib().ym_moe_ffn_strips(H * W, P)
+    stats = torch.empty((lib().ym_moe_ffn_stats_floats(P, strips, HID),), dtype=torch.float32, device=x.device)
+    _lib.check(lib().ym_moe_ffn(1, x.data_ptr(), pitch(x), B, H * W, Cc, HID, topk, w1.data_ptr(), None, E, route_idx.data_ptr(),
+                                None, None, None, stats.data_ptr(), strips, _stream()), "ym_moe_ffn(stats)")
+    _count()
+    return stats, strips
+
+
+def moe_ffn_fused(x, topk, w1, w2, route_idx, a_scale, a_shift, strips):
+    """ym_moe_ffn stage 2: o[p] = SiLU(GN1(x W1[e]^T)) W2[e]^T, fp16 [P][HW][C], + GroupNorm-2 partial sums."""
+    B, H, W, Cc = x.shape
+    E, HID, _ = w1.shape
+    P = B * topk
+    o = torch.empty((P, H * W, Cc), dtype=torch.float16, device=x.device)
+    stats = torch.empty((lib().ym_moe_ffn_stats_floats(P, strips, Cc),), dtype=torch.float32, device=x.device)
+    _lib.check(lib().ym_moe_ffn(2, x.data_ptr(), pitch(x), B, H * W, Cc, HID, topk, w1.data_ptr(), w2.data_ptr(), E, route_idx.data_ptr(),
+                                a_scale.data_ptr(), a_shift.data_ptr(), o.data_ptr(), stats.data_ptr(), strips, _stream()),
+               "ym_moe_ffn(fused)")
+    _count()
+    return o, stats
+
+
+def gn_finalize_tiles(stats, P, tiles, G, C_, count, eps, gamma, beta, route_idx, route_w=None):
+    """ym_gn_finalize_tiles: partial sums [P][tiles][C_/8][2] -> (scale, shift) fp32 [P][C_] of the routed expert's GroupNorm."""
+    scale = torch.empty((P, C_), dtype=torch.float32, device=stats.device)
+    shift = torch.empty((P, C_), dtype=torch.float32, device=stats.device)
+    _lib.check(lib().ym_gn_finalize_tiles(stats.data_ptr(), P, tiles, G, C_, float(count), float(eps), gamma.data_ptr(), beta.data_ptr(),
+                                          route_idx.data_ptr(), None if route_w is None else route_w.data_ptr(),
+                                          scale.data_ptr(), shift.data_ptr(), _stream()), "ym_gn_finalize_tiles")
+    _count()
+    return scale, shift
+
+
 def moe_combine(x, ws_packed, bias_s, o, o_scale, o_shift, topk, add_residual=True, out=None):
     B, H, W, Cc = x.shape
     if out is None:
