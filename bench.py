@@ -337,6 +337,40 @@ def time_torch_eager_gpu(dev, B):
                     "6 steps of the same 32-image batch; the faster of fp16 / fp32 is the headline baseline"}
 
 
+def time_two_streams(model, dev_in, B, steps, warmup, dev):
+    """EXPERIMENT, reported beside the headline, never as it: two CUDA-graph instances of the forward (own activation pools) replayed on
+    two streams, alternate batches to alternate streams - the MUFU-bound attention of one batch can overlap the latency / HBM-bound
+    convolutions of the other.  Same K steps of 32 images; time = first launch to last completion."""
+    from yolo_master_b200.nn.tasks import GraphedForward
+    try:
+        gs = [GraphedForward(model, B, IMG, IMG, torch.float16) for _ in range(2)]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        for j in range(2):
+            gs[j].static_in.copy_(dev_in[j])
+        cur = torch.cuda.current_stream(dev)
+
+        def run(n):
+            for s in streams:
+                s.wait_stream(cur)
+            for i in range(n):
+                with torch.cuda.stream(streams[i & 1]):
+                    gs[i & 1].graph.replay()
+            for s in streams:
+                cur.wait_stream(s)
+        run(warmup)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(steps)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        return {"value": B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+                "note": "two forward graphs on two streams, batches alternate; throughput experiment, not the headline"}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from yolo_master_b200 import ops
@@ -436,6 +470,7 @@ def run_ours(args):
     ms_e2e_sync = timed(lambda i: g8.run_host(host_in[i % 3]), args.steps, args.warmup)   # unpipelined call, for reference
 
     value = world * B * args.steps / (ms_dev * 1e-3)
+    two = time_two_streams(model, dev_in, B, args.steps, args.warmup, dev) if (rank == 0 and args.two_stream) else None
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     roof = time_attention_kernel(dev, B, pk) if rank == 0 else None
     disp = time_dispatch(dev, pk) if rank == 0 else None
@@ -465,6 +500,7 @@ def run_ours(args):
             "roofline": roof,
             "model_roofline": model_roofline(value / world, pk),
             "dispatch": disp,
+            "two_stream": two,
             "torch_eager_gpu": eager,
             "cpu_baseline": cpu_base,
         }
@@ -482,6 +518,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--ref-images", type=int, default=8, help="images per CPU-oracle step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--two-stream", action="store_true", help="also time two forward graphs replayed on two streams (experiment)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly ONE JSON line: libraries that print to the C-level stdout (NCCL prints "NCCL version ..." there on

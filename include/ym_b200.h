@@ -106,6 +106,12 @@ int ym_moe_ffn_strips(int HW, int P);
 long long ym_moe_ffn_stats_floats(int P, int strips, int N);
 int ym_moe_ffn(int stage, const void* x, int ldx, int B, int HW, int C, int HID, int topk, const void* w1, const void* w2, int E,
                const int* route_idx, const float* a_scale, const float* a_shift, void* out, float* stats, int strips, void* stream);
+/* Combine of OptimizedMOEImproved (moe/modules.py:1144-1157) on tcgen05: y[b] = SiLU(x[b] Ws^T + bs) + sum_j (o[b*topk+j] * o_scale +
+ * o_shift) (+ x[b]); ws fp16 [C][C] (BatchNorm folded), o fp16 [B*topk][HW][C], o_scale / o_shift fp32 [B*topk][C] (GroupNorm-2 affine
+ * times the routing weight), C = 64 or 128.  Same arithmetic order as ym_moe_combine (mma.sync), which serves the other widths. */
+int ym_moe_combine_tc_supported(int C, int ldx, int ldo);
+int ym_moe_combine_tc(const void* x, int ldx, int B, int HW, int C, const void* ws, const float* bias_s, const void* o,
+                      const float* o_scale, const float* o_shift, int topk, void* out, int ldo, int add_residual, void* stream);
 /* ym_gn_finalize with an explicit number of partial-sum tiles per problem. */
 int ym_gn_finalize_tiles(const float* stats, int P, int tiles, int groups, int C, float count, float eps, const float* gamma,
                          const float* beta, const int* route_idx, const float* route_w, float* scale, float* shift, void* stream);

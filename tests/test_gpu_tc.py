@@ -221,6 +221,40 @@ def test_moe_ffn_tc_matches_fp32_chain(B, HW, C, HID, E, topk):
     assert float(wide[..., :32].float().abs().max()) > 0      # the view's neighbours are inputs only - nothing was written there
 
 
+@pytest.mark.parametrize("B,HW,C,topk,res", [(3, 6400, 64, 2, True), (4, 1600, 64, 2, True), (5, 400, 128, 2, True), (2, 130, 128, 1, False), (7, 37, 64, 2, True)])
+def test_moe_combine_tc_matches_fp32(B, HW, C, topk, res):
+    """ym_moe_combine_tc (tcgen05 shared expert + routed sum + residual) against fp32 torch, and bit-for-bit layout checks: channel-slice
+    input and output views, ragged HW."""
+    from yolo_master_b200 import ops
+    g = torch.Generator().manual_seed(HW + C + 1)
+    wide = torch.randn((B, HW, 1, C + 32), generator=g).half().to(DEV)
+    x = wide[..., 16:16 + C]
+    ws = (torch.randn((C, C), generator=g) / C ** 0.5).half().to(DEV)
+    bs = (0.2 * torch.randn((C,), generator=g)).to(DEV)
+    o = torch.randn((B * topk, HW, C), generator=g).half().to(DEV)
+    sc = (0.5 * torch.rand((B * topk, C), generator=g)).to(DEV)
+    sh = (0.2 * torch.randn((B * topk, C), generator=g)).to(DEV)
+    owide = torch.zeros((B, HW, 1, C + 64), dtype=torch.float16, device=DEV)
+    out = owide[..., 64:]
+    for impl in ("tc", "mma"):
+        ops.MOE_COMBINE_IMPL = impl
+        try:
+            owide.zero_()
+            ops.moe_combine(x, ws, bs, o, sc, sh, topk, add_residual=res, out=out)
+            torch.cuda.synchronize()
+        finally:
+            ops.MOE_COMBINE_IMPL = "tc"
+        xf = x.float().reshape(B, HW, C)
+        ref = torch.nn.functional.silu(xf @ ws.float().t() + bs)
+        of = o.float().view(B, topk, HW, C)
+        for j in range(topk):
+            ref = ref + of[:, j] * sc.view(B, topk, 1, C)[:, j] + sh.view(B, topk, 1, C)[:, j]
+        if res:
+            ref = ref + xf
+        assert_close(out.reshape(B, HW, C), ref, what=f"moe_combine {impl}")
+        assert float(owide[..., :64].abs().max()) == 0, "wrote outside its channel slice"
+
+
 def test_moe_ffn_tc_and_mma_chains_agree_in_the_block():
     """OptimizedMOEImproved through both expert-FFN implementations (MOE_FFN_IMPL): same routing, block outputs within the strict tolerance
     of each other (the fp32 accumulation order of the two GEMM engines differs, nothing else)."""

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 bash tools/gpu_suite.sh r02d
 timeout 300 python tools/attn_bench.py gpurun_out/attn_bench_r02d.json > gpurun_out/attn_bench_r02d.log 2>&1
-timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_r02d.json 2> gpurun_out/bench_r02d.err
+timeout 600 python bench.py --no-cpu-baseline --two-stream > gpurun_out/bench_r02d.json 2> gpurun_out/bench_r02d.err
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/launch_dram_r02d.csv python tools/profile_forward.py > gpurun_out/profile_forward_r02d.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_attention2 -c 1 -o gpurun_out/attn2_r02d python tools/profile_attention.py > gpurun_out/attn2_ncu_d.log 2>&1
 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:moe_ffn -c 4 -o gpurun_out/moe_ffn_r02d python tools/profile_forward.py > gpurun_out/moe_ffn_ncu_d.log 2>&1

@@ -21,7 +21,10 @@ namespace ym {
 // partial[b, tile, r] = sum over the tile's pixels of SiLU(scale1*conv + shift1); router_finish_kernel is unchanged.
 constexpr int RT_TY = 4, RT_TX = 16, RT_HY = RT_TY + 2, RT_HX = RT_TX + 2, RT_QUADS = RT_TY * (RT_TX / 4);
 
-__global__ void __launch_bounds__(256) router_fused_kernel(const __half* __restrict__ x, int ldx, int H, int W, int C, int ps,
+// The input-channel reduction of an item is split over S = blockDim / (RT_QUADS * Cr) slices (threads of the same (quad, r), different
+// channel ranges; up to 512 threads per CTA): the per-thread chain of weight loads (L2-latency bound: 288 dependent iterations at
+// C = 128) shrinks S-fold, and at Cr = 8 the half of the CTA that had no item gets one.  Slice partials are summed in slice order.
+__global__ void __launch_bounds__(512) router_fused_kernel(const __half* __restrict__ x, int ldx, int H, int W, int C, int ps,
                                                            int Hp, int Wp, int Cr, const float* __restrict__ w1,
                                                            const float* __restrict__ scale1, const float* __restrict__ shift1,
                                                            float* __restrict__ partial, int tiles_x, int nblk) {
@@ -62,41 +65,67 @@ __global__ void __launch_bounds__(256) router_fused_kernel(const __half* __restr
     __syncthreads();
     const int C4 = C >> 2;
     const int nitems = RT_QUADS * Cr;                   // (quad, r)
-    for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
-        const int r = it % Cr, quad = it / Cr;
-        const int qy = quad >> 2, qx = quad & 3;        // pixels (ty0 + qy, tx0 + 4*qx + 0..3)
-        float a[4][4];
+    const int S = max(1, (int)blockDim.x / nitems);     // channel slices per item
+    float* red4 = red + RT_QUADS * Cr;                  // [S][nitems][4] per-slice conv partials of the four pixels
+    for (int wi = threadIdx.x; wi < nitems * S; wi += blockDim.x) {
+        const int it = wi % nitems, slice = wi / nitems;
+        {
+            const int r = it % Cr, quad = it / Cr;
+            const int qy = quad >> 2, qx = quad & 3;        // pixels (ty0 + qy, tx0 + 4*qx + 0..3)
+            const int c4_lo = (int)((long long)C4 * slice / S), c4_hi = (int)((long long)C4 * (slice + 1) / S);
+            float a[4][4];
 #pragma unroll
-        for (int pxl = 0; pxl < 4; ++pxl)
+            for (int pxl = 0; pxl < 4; ++pxl)
 #pragma unroll
-            for (int l = 0; l < 4; ++l) a[pxl][l] = 0.f;
-        const float4* wbase = reinterpret_cast<const float4*>(w1) + r;
-        for (int ky = 0; ky < 3; ++ky) {
-            const float* srow = sp + (size_t)((qy + ky) * RT_HX + 4 * qx) * C;
-            for (int c4 = 0; c4 < C4; ++c4) {
-                float4 xv[6];
+                for (int l = 0; l < 4; ++l) a[pxl][l] = 0.f;
+            const float4* wbase = reinterpret_cast<const float4*>(w1) + r;
+            for (int ky = 0; ky < 3; ++ky) {
+                const float* srow = sp + (size_t)((qy + ky) * RT_HX + 4 * qx) * C;
+#pragma unroll 2
+                for (int c4 = c4_lo; c4 < c4_hi; ++c4) {
+                    float4 wv[3];
 #pragma unroll
-                for (int j = 0; j < 6; ++j) xv[j] = *reinterpret_cast<const float4*>(srow + (size_t)j * C + c4 * 4);
+                    for (int kx = 0; kx < 3; ++kx) wv[kx] = __ldg(wbase + ((long long)(ky * 3 + kx) * C4 + c4) * Cr);
+                    float4 xv[6];
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const float4 wv = __ldg(wbase + ((long long)(ky * 3 + kx) * C4 + c4) * Cr);
+                    for (int j = 0; j < 6; ++j) xv[j] = *reinterpret_cast<const float4*>(srow + (size_t)j * C + c4 * 4);
 #pragma unroll
-                    for (int pxl = 0; pxl < 4; ++pxl) {
-                        a[pxl][0] = fmaf(xv[pxl + kx].x, wv.x, a[pxl][0]);
-                        a[pxl][1] = fmaf(xv[pxl + kx].y, wv.y, a[pxl][1]);
-                        a[pxl][2] = fmaf(xv[pxl + kx].z, wv.z, a[pxl][2]);
-                        a[pxl][3] = fmaf(xv[pxl + kx].w, wv.w, a[pxl][3]);
+                    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                        for (int pxl = 0; pxl < 4; ++pxl) {
+                            a[pxl][0] = fmaf(xv[pxl + kx].x, wv[kx].x, a[pxl][0]);
+                            a[pxl][1] = fmaf(xv[pxl + kx].y, wv[kx].y, a[pxl][1]);
+                            a[pxl][2] = fmaf(xv[pxl + kx].z, wv[kx].z, a[pxl][2]);
+                            a[pxl][3] = fmaf(xv[pxl + kx].w, wv[kx].w, a[pxl][3]);
+                        }
                     }
                 }
             }
+            float4 part;
+            part.x = (a[0][0] + a[0][1]) + (a[0][2] + a[0][3]);
+            part.y = (a[1][0] + a[1][1]) + (a[1][2] + a[1][3]);
+            part.z = (a[2][0] + a[2][1]) + (a[2][2] + a[2][3]);
+            part.w = (a[3][0] + a[3][1]) + (a[3][2] + a[3][3]);
+            reinterpret_cast<float4*>(red4)[slice * nitems + it] = part;
         }
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < nitems; it += blockDim.x) {
+        const int r = it % Cr, quad = it / Cr;
+        const int qy = quad >> 2, qx = quad & 3;
+        float4 acc = reinterpret_cast<const float4*>(red4)[it];
+        for (int sl = 1; sl < S; ++sl) {                  // fixed slice order: deterministic
+            const float4 t = reinterpret_cast<const float4*>(red4)[sl * nitems + it];
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        const float conv[4] = {acc.x, acc.y, acc.z, acc.w};
         const float sc = scale1[r], sh = shift1[r];
         float hsum = 0.f;
 #pragma unroll
         for (int pxl = 0; pxl < 4; ++pxl) {
             const int py = ty0 + qy, px = tx0 + 4 * qx + pxl;
             if (py < Hp && px < Wp) {
-                const float v = fmaf((a[pxl][0] + a[pxl][1]) + (a[pxl][2] + a[pxl][3]), sc, sh);
+                const float v = fmaf(conv[pxl], sc, sh);
                 hsum += v / (1.f + expf(-v));
             }
         }
@@ -206,7 +235,12 @@ extern "C" int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C
     const int tiles_x = (Wp + RT_TX - 1) / RT_TX, tiles_y = (Hp + RT_TY - 1) / RT_TY;
     const int nblk = tiles_x * tiles_y;
     float* partial = scratch;
-    const size_t smem = ((size_t)RT_HY * RT_HX * C + RT_QUADS * (size_t)Cr) * sizeof(float);
+    const int nitems = RT_QUADS * Cr;
+    int threads = nitems;                                    // S channel slices per item, at most 4 and at most 512 threads
+    while (threads * 2 <= 512 && threads * 2 <= 4 * nitems && (C / 4) >= 2 * (threads / nitems) * 2) threads *= 2;
+    if (threads < 256) threads = 256;                        // the pooling phase wants a full CTA (extra threads carry no conv item)
+    const int S = threads / nitems > 0 ? threads / nitems : 1;
+    const size_t smem = ((size_t)RT_HY * RT_HX * C + RT_QUADS * (size_t)Cr + (size_t)S * nitems * 4) * sizeof(float);
     YM_CHECK_ARG(smem <= 200 * 1024, "ym_router_topk: C=%d too wide for the fused router tile", C);
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
@@ -214,7 +248,7 @@ extern "C" int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C
         if (e != cudaSuccess) { ym_set_error("ym_router_topk: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
         smem_set = smem;
     }
-    launch_pdl(router_fused_kernel, dim3(nblk, B), 256, smem, st, (const __half*)x, ldx, H, W, C, ps, Hp, Wp, Cr, w1, scale1, shift1, partial,
+    launch_pdl(router_fused_kernel, dim3(nblk, B), threads, smem, st, (const __half*)x, ldx, H, W, C, ps, Hp, Wp, Cr, w1, scale1, shift1, partial,
                                                          tiles_x, nblk);
     YM_CHECK_LAUNCH("router_fused");
     launch_pdl(router_finish_kernel, B, 32, 0, st, partial, nblk, Cr, Hp * Wp, w2, scale2, shift2, E, topk, idx_out, w_out, probs_out);

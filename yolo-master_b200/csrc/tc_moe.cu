@@ -266,6 +266,166 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---- combine: y = SiLU(x Ws^T + bs) + sum_j (o[b,j] * scale2[b,j] + shift2[b,j]) + x   (moe/modules.py:1144-1157) ------------------
+// shared expert = 1x1 conv + folded BN + SiLU on the tensor core (tcgen05, accumulator double-buffered in tensor memory so the MMA of
+// tile i+1 runs under the epilogue of tile i); the epilogue thread (= token row) adds the routed experts' GroupNorm-2-normalised outputs
+// (routing weight folded into scale2 / shift2 by ym_gn_finalize_tiles) and the residual, one rounding to fp16, one 128 / 256-byte row store.
+struct MoeCombineParams {
+    const __half* x;   int ldx;        // residual read (the GEMM operand comes through TMA)
+    const float* bias;                 // [C] folded BN bias of the shared expert
+    const __half* o;                   // [B*topk][HW][C]
+    const float* o_scale; const float* o_shift;   // [B*topk][C]
+    __half* out;       int ldo;
+    int HW, mtiles, tiles_per_strip, topk, add_residual;
+};
+struct McBars {
+    uint64_t w_full, x_full[2], d_full[2], d_free[2];
+    uint32_t tmem_slot;
+};
+
+template <int C>
+__global__ void __launch_bounds__(MF_THREADS, 2)
+moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const MoeCombineParams p) {
+    constexpr int KC = C / 64;
+    constexpr int X_BYTES = MF_BM * C * 2, W_BYTES = C * C * 2;
+    constexpr uint32_t TMEM_COLS = 2 * C;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* sX = smem;                          // [2][KC][128 rows x 128 B]
+    unsigned char* sW = sX + 2 * X_BYTES;              // [KC][C rows x 128 B]
+    float* sAff = reinterpret_cast<float*>(sW + W_BYTES);   // bias [C] | per rank j: scale [C], shift [C]
+    __shared__ McBars bars;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int img = blockIdx.y, strip = blockIdx.x;
+    const int t0 = strip * p.tiles_per_strip;
+    const int nt = min(p.tiles_per_strip, p.mtiles - t0);
+    if (tid == 0) {
+        tc::mbar_init(&bars.w_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&bars.x_full[i], 1);
+            tc::mbar_init(&bars.d_full[i], 1);
+            tc::mbar_init(&bars.d_free[i], 4);
+        }
+        tc::fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(&bars.tmem_slot, TMEM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = bars.tmem_slot;
+    pdl_prologue();
+    if (nt > 0) {
+        for (int i = tid; i < C; i += MF_THREADS) sAff[i] = p.bias ? p.bias[i] : 0.f;
+        for (int i = tid; i < p.topk * C; i += MF_THREADS) {
+            const int j = i / C, c = i - j * C;
+            sAff[C + (2 * j) * C + c] = p.o_scale[((long long)img * p.topk + j) * C + c];
+            sAff[C + (2 * j + 1) * C + c] = p.o_shift[((long long)img * p.topk + j) * C + c];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            if (lane == 0) {
+                auto load_x = [&](int i) {
+                    unsigned char* dst = sX + (i & 1) * X_BYTES;
+                    mf_expect_tx(&bars.x_full[i & 1], (uint32_t)X_BYTES);
+#pragma unroll
+                    for (int kc = 0; kc < KC; ++kc)
+                        mf_tma_load_3d(dst + kc * (MF_BM * 128), &map_x, kc * 64, (t0 + i) * MF_BM, img, &bars.x_full[i & 1]);
+                };
+                mf_expect_tx(&bars.w_full, (uint32_t)W_BYTES);
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc) mf_tma_load_2d(sW + kc * (C * 128), &map_w, kc * 64, 0, &bars.w_full);
+                load_x(0);
+                if (nt > 1) load_x(1);
+                const uint32_t idesc = tc::make_idesc_f16(MF_BM, C, 0);
+                tc::mbar_wait(&bars.w_full, 0);
+                for (int i = 0; i < nt; ++i) {
+                    const int bf = i & 1;
+                    tc::mbar_wait(&bars.x_full[bf], (i >> 1) & 1);
+                    if (i >= 2) {                            // the epilogue has drained accumulator bf (tile i-2)
+                        tc::mbar_wait(&bars.d_free[bf], ((i >> 1) - 1) & 1);
+                        tc::fence_after_sync();
+                    }
+                    const uint32_t xa = smem_u32(sX + bf * X_BYTES), wa = smem_u32(sW);
+#pragma unroll
+                    for (int kc = 0; kc < KC; ++kc) {
+                        const uint64_t ad = tc::make_desc_sw128(xa + kc * (MF_BM * 128)), bd = tc::make_desc_sw128(wa + kc * (C * 128));
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) tc::mma_f16_ss(tmem_base + bf * C, ad + 2 * ks, bd + 2 * ks, idesc, (kc | ks) ? 1u : 0u);
+                    }
+                    tc::mma_commit(&bars.d_full[bf]);
+                    // x buffer bf is re-filled for tile i+2 once this tile's MMA has retired: the epilogue's d_free(i) arrive implies it
+                    if (i + 2 < nt) {
+                        tc::mbar_wait(&bars.d_full[bf], (i >> 1) & 1);
+                        load_x(i + 2);
+                    }
+                }
+            }
+        } else {
+            const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+            const int row_in_tile = (warp & 3) * 32 + lane;
+            for (int i = 0; i < nt; ++i) {
+                const int bf = i & 1;
+                const int row = (t0 + i) * MF_BM + row_in_tile;
+                const bool live = row < p.HW;
+                tc::mbar_wait(&bars.d_full[bf], (i >> 1) & 1);
+                tc::fence_after_sync();
+                const __half* xrow = p.x + ((long long)img * p.HW + row) * p.ldx;
+                __half* yrow = p.out + ((long long)img * p.HW + row) * p.ldo;
+#pragma unroll
+                for (int c0 = 0; c0 < C; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(tmem_base + bf * C + lane_sel + c0, v);
+                    tc::tmem_ld_wait();
+                    if (live) {
+                        float acc[32];
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) acc[q] = silu_f(__uint_as_float(v[q]) + sAff[c0 + q]);
+                        for (int j = 0; j < p.topk; ++j) {
+                            const __half* orow = p.o + (((long long)img * p.topk + j) * p.HW + row) * C + c0;
+                            const float* sc = sAff + C + (2 * j) * C + c0;
+                            const float* sh = sc + C;
+#pragma unroll
+                            for (int c8 = 0; c8 < 4; ++c8) {
+                                const Half8 ov = *reinterpret_cast<const Half8*>(orow + c8 * 8);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 f = __half22float2(ov.v[q]);
+                                    acc[c8 * 8 + 2 * q] += fmaf(f.x, sc[c8 * 8 + 2 * q], sh[c8 * 8 + 2 * q]);
+                                    acc[c8 * 8 + 2 * q + 1] += fmaf(f.y, sc[c8 * 8 + 2 * q + 1], sh[c8 * 8 + 2 * q + 1]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            Half8 hv;
+                            if (p.add_residual) {
+                                const Half8 rv = *reinterpret_cast<const Half8*>(xrow + c0 + c8 * 8);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 rf = __half22float2(rv.v[q]);
+                                    hv.v[q] = __floats2half2_rn(acc[c8 * 8 + 2 * q] + rf.x, acc[c8 * 8 + 2 * q + 1] + rf.y);
+                                }
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) hv.v[q] = __floats2half2_rn(acc[c8 * 8 + 2 * q], acc[c8 * 8 + 2 * q + 1]);
+                            }
+                            *reinterpret_cast<Half8*>(yrow + c0 + c8 * 8) = hv;
+                        }
+                    }
+                }
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars.d_free[bf]);
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 typedef CUresult (*MfEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -355,4 +515,46 @@ extern "C" int ym_moe_ffn(int stage, const void* x, int ldx, int B, int HW, int 
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 64) return stage == 1 ? mf_launch<64, 128, 1>(mx, mw1, mw2, p, strips, P, st) : mf_launch<64, 128, 2>(mx, mw1, mw2, p, strips, P, st);
     return stage == 1 ? mf_launch<128, 256, 1>(mx, mw1, mw2, p, strips, P, st) : mf_launch<128, 256, 2>(mx, mw1, mw2, p, strips, P, st);
+}
+
+// y[b] = SiLU(x[b] Ws^T + bs) + sum_j (o[b*topk+j] * o_scale + o_shift) (+ x[b]): the combine of OptimizedMOEImproved on tcgen05.
+extern "C" int ym_moe_combine_tc_supported(int C, int ldx, int ldo) { return mf_encode() != nullptr && (C == 64 || C == 128) && ldx % 8 == 0 && ldo % 8 == 0; }
+
+extern "C" int ym_moe_combine_tc(const void* x, int ldx, int B, int HW, int C, const void* ws, const float* bias_s, const void* o,
+                                 const float* o_scale, const float* o_shift, int topk, void* out, int ldo, int add_residual, void* stream) {
+    YM_CHECK_ARG(x && ws && o && o_scale && o_shift && out, "ym_moe_combine_tc: null pointer");
+    YM_CHECK_ARG(ym_moe_combine_tc_supported(C, ldx, ldo), "ym_moe_combine_tc: unsupported shape C=%d ldx=%d ldo=%d", C, ldx, ldo);
+    YM_CHECK_ARG((((uintptr_t)x | (uintptr_t)ws | (uintptr_t)o | (uintptr_t)out) & 15) == 0, "ym_moe_combine_tc: 16-byte alignment");
+    YM_CHECK_ARG(topk >= 1 && topk <= 4 && HW >= 1 && B >= 0 && B <= 65535, "ym_moe_combine_tc: bad sizes");
+    if (B == 0) return YM_OK;
+    const int mtiles = (HW + MF_BM - 1) / MF_BM;
+    int tps = 4;
+    while (tps > 1 && (long long)B * ((mtiles + tps - 1) / tps) < 2 * 296) --tps;
+    const int strips = (mtiles + tps - 1) / tps;
+    CUtensorMap mx, mw;
+    {
+        cuuint64_t d[3] = {(cuuint64_t)C, (cuuint64_t)HW, (cuuint64_t)B}, s[2] = {(cuuint64_t)ldx * 2, (cuuint64_t)HW * ldx * 2};
+        cuuint32_t bx[3] = {64, MF_BM, 1};
+        if (!mf_map(&mx, x, 3, d, s, bx)) { ym_set_error("ym_moe_combine_tc: tensor map (x) failed"); return YM_ERR_CUDA; }
+    }
+    {
+        cuuint64_t d[2] = {(cuuint64_t)C, (cuuint64_t)C}, s[1] = {(cuuint64_t)C * 2};
+        cuuint32_t bx[2] = {64, (cuuint32_t)C};
+        if (!mf_map(&mw, ws, 2, d, s, bx)) { ym_set_error("ym_moe_combine_tc: tensor map (ws) failed"); return YM_ERR_CUDA; }
+    }
+    MoeCombineParams p;
+    p.x = (const __half*)x; p.ldx = ldx; p.bias = bias_s; p.o = (const __half*)o; p.o_scale = o_scale; p.o_shift = o_shift;
+    p.out = (__half*)out; p.ldo = ldo; p.HW = HW; p.mtiles = mtiles; p.tiles_per_strip = tps; p.topk = topk; p.add_residual = add_residual;
+    const size_t smem = (size_t)2 * MF_BM * C * 2 + (size_t)C * C * 2 + (size_t)(1 + 2 * topk) * C * sizeof(float) + 1024;
+    cudaError_t e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 64) {
+        e = cudaFuncSetAttribute(moe_combine_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = launch_pdl(moe_combine_tc_kernel<64>, dim3(strips, B), dim3(MF_THREADS), smem, st, mx, mw, p);
+    } else {
+        e = cudaFuncSetAttribute(moe_combine_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = launch_pdl(moe_combine_tc_kernel<128>, dim3(strips, B), dim3(MF_THREADS), smem, st, mx, mw, p);
+    }
+    if (e != cudaSuccess) { ym_set_error("ym_moe_combine_tc: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
+    return YM_OK;
 }

@@ -17,6 +17,9 @@ from .conv import Conv, DWConv, PlainConv2d
 __all__ = ("Detect", "DFL", "Pose", "Proto", "Segment", "OBB", "Classify")
 
 
+_EARLY_STREAMS: dict = {}
+
+
 class DFL(nn.Module):
     """`DFL(c1=16)` (block.py:63-85): frozen 1x1 conv with weights 0..c1-1 = expectation over the softmaxed bins.
     Only holds the state_dict key (`dfl.conv.weight`); the arithmetic is fused into `ym_detect_dense`."""
@@ -98,11 +101,42 @@ class Detect(nn.Module):
         box_head = self.one2one_cv2 if e2e else self.cv2
         cls_head = self.one2one_cv3 if e2e else self.cv3
         n = len(feats_nhwc)
+        early = self.__dict__.pop("_early", None)
+        if early is not None and len(early["out"]) == n and all(early["src"][i] == feats_nhwc[i].data_ptr() for i in range(n)):
+            # towers were started level by level while the neck was still running (start_level): join their streams
+            cur = torch.cuda.current_stream()
+            for st in early["streams"]:
+                cur.wait_stream(st)
+            return [early["out"][i][0] for i in range(n)], [early["out"][i][1] for i in range(n)]
         # 2 x nl independent towers: parallel graph branches under capture (largest maps first), serial otherwise
         jobs = [(lambda i=i: self._tower(cls_head[i], feats_nhwc[i])) for i in range(n)] + \
                [(lambda i=i: self._tower(box_head[i], feats_nhwc[i])) for i in range(n)]
         res = run_branches(jobs)
         return res[n:], res[:n]
+
+    def start_level(self, level: int, feat_nchw: torch.Tensor) -> bool:
+        """Under CUDA-graph capture: start the box / class towers of pyramid level `level` on two side streams as soon as its feature map
+        exists, so that they overlap the rest of the neck (the P3 towers are the longest chains of the head and their input is ready
+        six layers before the P5 map).  `head_raw` joins the streams.  Returns False (and does nothing) outside a capture."""
+        if not (feat_nchw.is_cuda and torch.cuda.is_current_stream_capturing()) or self.training:
+            return False
+        e2e = self.end2end
+        box_head = self.one2one_cv2 if e2e else self.cv2
+        cls_head = self.one2one_cv3 if e2e else self.cv3
+        f = to_nhwc(feat_nchw)
+        cur = torch.cuda.current_stream()
+        key = ("detect_early", cur.device.index)
+        pool = _EARLY_STREAMS.setdefault(key, [torch.cuda.Stream(device=cur.device) for _ in range(2 * self.nl)])
+        early = self.__dict__.setdefault("_early", {"out": {}, "src": {}, "streams": []})
+        outs = []
+        for j, tower in enumerate((box_head[level], cls_head[level])):
+            st = pool[2 * level + j]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs.append(self._tower(tower, f))
+            early["streams"].append(st)
+        early["out"][level], early["src"][level] = (outs[0], outs[1]), f.data_ptr()
+        return True
 
     def forward(self, x):
         require_eval(self)

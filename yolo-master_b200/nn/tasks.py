@@ -209,6 +209,10 @@ class DetectionModel(nn.Module):
     def _predict_once(self, x):
         y = []
         pending_up = 1
+        head = self.model[-1]
+        # Detect: level l's towers start (on side streams, under graph capture only) the moment layer head.f[l] has produced its map
+        early = {f: l for l, f in enumerate(head.f)} if type(head) is M.Detect and isinstance(head.f, list) else {}
+        head.__dict__.pop("_early", None)
         for i, m in enumerate(self.model):
             if m.f != -1:
                 x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
@@ -222,6 +226,8 @@ class DetectionModel(nn.Module):
             else:
                 x = m(x)
             y.append(x if m.i in self.save else None)
+            if i in early:
+                head.start_level(early[i], x)
         return x
 
     def forward(self, x):

@@ -255,13 +255,23 @@ def gn_finalize_tiles(stats, P, tiles, G, C_, count, eps, gamma, beta, route_idx
     return scale, shift
 
 
+MOE_COMBINE_IMPL = "tc"    # "tc": tcgen05 kernel (csrc/tc_moe.cu) where the width allows; "mma": the mma.sync kernel of csrc/gemm_conv.cu
+
+
 def moe_combine(x, ws_packed, bias_s, o, o_scale, o_shift, topk, add_residual=True, out=None):
     B, H, W, Cc = x.shape
     if out is None:
         out = new_act(B, H, W, Cc, x.device)
-    _lib.check(lib().ym_moe_combine(x.data_ptr(), pitch(x), B, H * W, Cc, ws_packed.data_ptr(), ws_packed.shape[1],
-                                    bias_s.data_ptr(), o.data_ptr(), o.shape[2], o_scale.data_ptr(), o_shift.data_ptr(),
-                                    topk, out.data_ptr(), pitch(out), 1 if add_residual else 0, _stream()),
+    L = lib()
+    if MOE_COMBINE_IMPL == "tc" and ws_packed.shape[1] == Cc and o.shape[2] == Cc and L.ym_moe_combine_tc_supported(Cc, pitch(x), pitch(out)):
+        _lib.check(L.ym_moe_combine_tc(x.data_ptr(), pitch(x), B, H * W, Cc, ws_packed.data_ptr(), bias_s.data_ptr(), o.data_ptr(),
+                                       o_scale.data_ptr(), o_shift.data_ptr(), topk, out.data_ptr(), pitch(out),
+                                       1 if add_residual else 0, _stream()), "ym_moe_combine_tc")
+        _count()
+        return out
+    _lib.check(L.ym_moe_combine(x.data_ptr(), pitch(x), B, H * W, Cc, ws_packed.data_ptr(), ws_packed.shape[1],
+                                bias_s.data_ptr(), o.data_ptr(), o.shape[2], o_scale.data_ptr(), o_shift.data_ptr(),
+                                topk, out.data_ptr(), pitch(out), 1 if add_residual else 0, _stream()),
                "ym_moe_combine")
     _count()
     return out
