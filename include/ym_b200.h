@@ -36,6 +36,9 @@ int ym_conv2d_nhwc(const void* x, int ldx, int B, int H, int W, int Cin, const v
  * parameter block so that every FFMA reads its weight from the constant bank (baked in at capture time under a CUDA graph). */
 int ym_stem_conv_nchw(const void* img, int in_dtype, int B, int Cin, int H, int W, const float* wgt_host,
                       const float* bias_host, int Cout, void* out, int ldo, void* stream);
+/* Kernel behind ym_stem_conv_nchw for Cin <= 3, Cout = 16: 1 = mma.sync implicit GEMM with fp16 operands / fp32 accumulation (default;
+ * inputs rounded to fp16 like the reference's fp16 predictor path), 0 = fp32 FFMA kernel.  Returns the previous setting. */
+int ym_set_stem_impl(int impl);
 
 /* Depthwise k x k (k in 3/5/7/9, stride 1, pad k/2) + bias (+SiLU) (+add).  Replaces DWConv conv.py:185-199,
  * AAttn.pe block.py:1688,1731 and Attention.pe block.py:1311,1331 (reads V in place from the head-interleaved qkv:

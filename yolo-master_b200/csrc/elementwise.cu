@@ -78,6 +78,98 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const TIn* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tensor-core stem (Cin <= 3, Cout = 16): the same 3x3 / stride 2 / pad 1 convolution as an implicit GEMM on mma.sync.m16n8k16.
+// The FFMA kernel above spends 432 FFMA + im2col addressing per output pixel (FFMA-issue bound at 11 % of HBM,
+// profiles/r01_early_layers_ncu.txt); here a pixel costs 6/16 of an HMMA.  K is laid out as (ci, ky) groups of FOUR taps
+// (kx = 0, 1, 2 and a zero-weight pad), 9 groups padded to 12 -> K = 48 = three k16 steps, so that every A-fragment register is ONE
+// aligned 32-bit shared-memory load of two horizontally adjacent fp16 input pixels (the im2col never exists).  Inputs are rounded to
+// fp16 as the reference's own fp16 predictor path does (`im.half()`, then `/ 255` for uint8 frames: engine/predictor.py:173-175);
+// weights are the folded fp16 conv weights, accumulation is fp32.
+// CTA = 8 warps = 8 output rows x 64 output columns; warp = one output row, four 16-pixel groups.
+struct StemTcWeights {
+    uint32_t b[3][2][32][2];      // B fragments per (k step, n tile, lane): {b0, b1} as packed half2
+    float bias[16];
+};
+
+template <typename TIn>
+__device__ __forceinline__ __half stem_to_half(TIn v);
+template <>
+__device__ __forceinline__ __half stem_to_half<__half>(__half v) { return v; }
+template <>
+__device__ __forceinline__ __half stem_to_half<float>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __half stem_to_half<unsigned char>(unsigned char v) { return __float2half_rn(__fdiv_rn((float)v, 255.f)); }
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) stem_conv_tc_kernel(const TIn* __restrict__ img, int B, int Cin, int H, int W,
+                                                           const __grid_constant__ StemTcWeights sw, __half* __restrict__ out, int ldo,
+                                                           int Ho, int Wo, int tiles_x) {
+    pdl_prologue();
+    constexpr int TW = 64, TH = 8, IW = 2 * TW + 2, IH = 2 * TH + 1, RS = IW + 2;    // row stride 132 halves = 66 words
+    __shared__ __align__(16) __half sx[3][IH][RS];
+    __shared__ __align__(16) __half sout[8][16][16];                                 // per warp: 16 pixels x 16 channels staging
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int oy0 = (blockIdx.x / tiles_x) * TH, ox0 = (blockIdx.x % tiles_x) * TW;
+    const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
+    for (int i = tid; i < 3 * IH * IW; i += 256) {
+        const int ci = i / (IH * IW), rem = i - ci * (IH * IW);
+        const int ry = rem / IW, rx = rem - ry * IW;
+        const int iy = iy0 + ry, ix = ix0 + rx;
+        __half v = __float2half_rn(0.f);
+        if (ci < Cin && iy >= 0 && iy < H && ix >= 0 && ix < W) v = stem_to_half<TIn>(img[(((long long)b * Cin + ci) * H + iy) * W + ix]);
+        sx[ci][ry][rx] = v;
+    }
+    __syncthreads();
+    const int oy = oy0 + warp;
+    if (oy >= Ho) return;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t bf[3][2][2];
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) { bf[ks][nt][0] = sw.b[ks][nt][lane][0]; bf[ks][nt][1] = sw.b[ks][nt][lane][1]; }
+    const float bias0 = sw.bias[2 * t], bias1 = sw.bias[2 * t + 1], bias8 = sw.bias[8 + 2 * t], bias9 = sw.bias[8 + 2 * t + 1];
+#pragma unroll 1
+    for (int grp = 0; grp < TW / 16; ++grp) {
+        const int lx = grp * 16 + g;                      // output column (tile-local) of fragment row g; row g+8 = lx + 8
+        float acc[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[nt][q] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+            // k local 2t, 2t+1 -> tap group 4*ks + (t >> 1), pair (t & 1); k local 2t+8, 2t+9 -> group 4*ks + 2 + (t >> 1), same pair
+            uint32_t a[4];
+#pragma unroll
+            for (int hi = 0; hi < 2; ++hi) {
+                const int grpk = 4 * ks + 2 * hi + (t >> 1);          // (ci, ky) group, 9..11 are zero-weight pads
+                const int ci = grpk < 9 ? grpk / 3 : 0, ky = grpk < 9 ? grpk - 3 * (grpk / 3) : 0;
+                const __half* row = &sx[ci][2 * warp + ky][2 * (t & 1)];
+                a[2 * hi + 0] = *reinterpret_cast<const uint32_t*>(row + 2 * lx);            // fragment row g
+                a[2 * hi + 1] = *reinterpret_cast<const uint32_t*>(row + 2 * (lx + 8));      // fragment row g + 8
+            }
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) mma_16816(acc[nt], a, bf[ks][nt][0], bf[ks][nt][1]);
+        }
+        // fragments -> per-warp staging tile -> one 16-byte store per lane (16 pixels x 32 B are contiguous in the NHWC output)
+        __half2* so = reinterpret_cast<__half2*>(&sout[warp][0][0]);
+        so[g * 8 + t] = __floats2half2_rn(silu_f(acc[0][0] + bias0), silu_f(acc[0][1] + bias1));
+        so[g * 8 + 4 + t] = __floats2half2_rn(silu_f(acc[1][0] + bias8), silu_f(acc[1][1] + bias9));
+        so[(g + 8) * 8 + t] = __floats2half2_rn(silu_f(acc[0][2] + bias0), silu_f(acc[0][3] + bias1));
+        so[(g + 8) * 8 + 4 + t] = __floats2half2_rn(silu_f(acc[1][2] + bias8), silu_f(acc[1][3] + bias9));
+        __syncwarp();
+        const int px = lane >> 1, hf = lane & 1;
+        const int ox = ox0 + grp * 16 + px;
+        if (ox < Wo)
+            *reinterpret_cast<Half8*>(out + (((long long)b * Ho + oy) * Wo + ox) * ldo + hf * 8) =
+                *reinterpret_cast<const Half8*>(&sout[warp][px][hf * 8]);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Depthwise k x k (stride 1, pad k/2) + bias (+SiLU) (+add), 8 channels per thread.
 // Source channel for output channel c: (c / grp_w) * grp_stride + grp_off + c % grp_w  -- lets `pe(v)` read V in place
 // from the head-interleaved qkv tensor (block.py:1688,1731; :1311,1331).  Weights tap-major [k*k][C] fp16.
@@ -400,6 +492,14 @@ using namespace ym;
 
 static inline int nblocks(long long total, int bs) { return (int)((total + bs - 1) / bs); }
 
+// 1 = tensor-core stem (mma.sync implicit GEMM, fp16 operands) where Cin <= 3 and Cout = 16; 0 = fp32 FFMA kernel (A/B baseline)
+static int g_stem_impl = 1;
+extern "C" int ym_set_stem_impl(int impl) {
+    const int old = g_stem_impl;
+    if (impl == 0 || impl == 1) g_stem_impl = impl;
+    return old;
+}
+
 // in_dtype: 0 = fp16 NCHW, 1 = fp32 NCHW, 2 = uint8 NCHW (scaled by 1/255).  wgt_host / bias_host are HOST pointers (fp32
 // [Cin*9][Cout] and [Cout]): they are copied into the kernel's parameter block (constant bank) at launch, i.e. at capture
 // time under a CUDA graph.
@@ -410,6 +510,35 @@ static int stem_launch(const void* img, int in_dtype, int B, int Cin, int H, int
     memset(&sw, 0, sizeof(sw));
     memcpy(sw.w, wgt_host, sizeof(float) * (size_t)Cin * 9 * CO);
     memcpy(sw.b, bias_host, sizeof(float) * CO);
+    if (CO == 16 && Cin <= 3 && g_stem_impl == 1) {
+        // tensor-core path: fragment-ordered fp16 weights (K = (ci, ky) groups of four taps, see stem_conv_tc_kernel)
+        StemTcWeights tw;
+        memset(&tw, 0, sizeof(tw));
+        auto wk = [&](int k, int n) -> float {          // weight of GEMM row k (0..47), output channel n
+            const int grp = k >> 2, kx = k & 3;
+            if (grp >= 9 || kx >= 3) return 0.f;
+            const int ci = grp / 3, ky = grp % 3;
+            if (ci >= Cin) return 0.f;
+            return wgt_host[(size_t)((ci * 3 + ky) * 3 + kx) * CO + n];
+        };
+        for (int ks = 0; ks < 3; ++ks)
+            for (int nt = 0; nt < 2; ++nt)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, t = lane & 3, n = nt * 8 + g;
+                    const __half2 b0 = __floats2half2_rn(wk(16 * ks + 2 * t, n), wk(16 * ks + 2 * t + 1, n));
+                    const __half2 b1 = __floats2half2_rn(wk(16 * ks + 2 * t + 8, n), wk(16 * ks + 2 * t + 9, n));
+                    memcpy(&tw.b[ks][nt][lane][0], &b0, 4);
+                    memcpy(&tw.b[ks][nt][lane][1], &b1, 4);
+                }
+        memcpy(tw.bias, bias_host, sizeof(float) * 16);
+        const int tx = (Wo + 63) / 64, ty = (Ho + 7) / 8;
+        const dim3 gridt(tx * ty, B);
+        if (in_dtype == 0) launch_pdl(stem_conv_tc_kernel<__half>, gridt, 256, 0, st, (const __half*)img, B, Cin, H, W, tw, (__half*)out, ldo, Ho, Wo, tx);
+        else if (in_dtype == 1) launch_pdl(stem_conv_tc_kernel<float>, gridt, 256, 0, st, (const float*)img, B, Cin, H, W, tw, (__half*)out, ldo, Ho, Wo, tx);
+        else if (in_dtype == 2) launch_pdl(stem_conv_tc_kernel<unsigned char>, gridt, 256, 0, st, (const unsigned char*)img, B, Cin, H, W, tw, (__half*)out, ldo, Ho, Wo, tx);
+        else { ym_set_error("ym_stem_conv_nchw: bad in_dtype %d", in_dtype); return YM_ERR_ARG; }
+        return YM_OK;
+    }
     const int tiles_x = (Wo + 31) / 32, tiles_y = (Ho + 7) / 8;
     const dim3 grid(tiles_x * tiles_y, B);
     if (in_dtype == 0) launch_pdl(stem_conv_kernel<__half, CO>, grid, 256, 0, st, (const __half*)img, B, Cin, H, W, sw, (__half*)out, ldo, Ho, Wo, tiles_x);

@@ -176,18 +176,23 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         uint64_t* bar_pv = &bars.pv_done[qt];
         float m_used = -INFINITY, l_run = 0.f;
 
+        // Software-pipelined by one hand-off: iteration t first issues the tensor-memory read of S(t) (asynchronous), THEN completes the
+        // hand-over of P(t-1) (wait for its store, fence, arrive) while that read is in flight, then consumes S(t).  One read site and one
+        // store site per iteration: nothing is carried around the loop in registers (a variant that prefetched S(t+1) at the end of
+        // iteration t carried 64 registers across the back edge and spilled them).
         for (int t = 0; t < T; ++t) {
-            tc::mbar_wait(bar_s_full, t & 1);
+            uint32_t sv[64];                                                  // S row of key tile t
+            tc::mbar_wait(bar_s_full, t & 1);                                 // QK(t) was issued when s_free(t-1) arrived: long complete
             tc::fence_after_sync();
-            uint32_t sr[64];
-            {
-                uint32_t lo[32], hi[32];
-                tc::tmem_ld32(t_s, lo);
-                tc::tmem_ld32(t_s + 32, hi);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { sr[i] = lo[i]; sr[32 + i] = hi[i]; }
+            tc::tmem_ld32(t_s, *reinterpret_cast<uint32_t (*)[32]>(&sv[0]));
+            tc::tmem_ld32(t_s + 32, *reinterpret_cast<uint32_t (*)[32]>(&sv[32]));
+            if (t > 0) {                                                      // P(t-1): its tcgen05.st was issued at the end of iteration t-1
+                tc::tmem_st_wait();
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(bar_p_full);
             }
+            tc::tmem_ld_wait();
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(bar_s_free);                      // S(t) is in registers: QK(t+1) may overwrite it
@@ -195,11 +200,11 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             if (kv0 + A2_BKV > N) {               // tail tile only: keys >= N do not exist
 #pragma unroll
                 for (int i = 0; i < 64; ++i)
-                    if (kv0 + i >= N) sr[i] = 0xff800000u;   // -inf
+                    if (kv0 + i >= N) sv[i] = 0xff800000u;   // -inf
             }
             float mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
             const float m_tile = mx * scale_log2;
             const bool grow = m_tile > m_used + 8.f;         // also true on the first tile (m_used = -inf)
             float alpha = 1.f;
@@ -211,8 +216,8 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             float ls_row[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float x0 = fmaf(__uint_as_float(sr[2 * i]), scale_log2, -m_used);
-                const float x1 = fmaf(__uint_as_float(sr[2 * i + 1]), scale_log2, -m_used);
+                const float x0 = fmaf(__uint_as_float(sv[2 * i]), scale_log2, -m_used);
+                const float x1 = fmaf(__uint_as_float(sv[2 * i + 1]), scale_log2, -m_used);
                 const float p0 = (POLY > 0 && (2 * i) % POLY == POLY - 1) ? a2_exp2_poly(x0) : a2_exp2(x0);
                 const float p1 = (POLY > 0 && (2 * i + 1) % POLY == POLY - 1) ? a2_exp2_poly(x1) : a2_exp2(x1);
                 pk[i] = pack_half2(p0, p1);
@@ -236,11 +241,11 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 }
             }
             tc::tmem_st32(t_p, pk);                          // A operand of the TS-mode MMA: lane = query row, column c = keys 2c, 2c+1
-            tc::tmem_st_wait();
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(bar_p_full);
         }
+        tc::tmem_st_wait();                                  // hand over P(T-1)
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(bar_p_full);
         // ---- finalise: O / l -> global
         tc::mbar_wait(bar_pv, (T - 1) & 1);
         tc::fence_after_sync();

@@ -76,6 +76,7 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     unsigned char* sW1 = sX + 2 * X_BYTES;             // [KC1][HID rows x 128 B]
     unsigned char* sW2 = sW1 + W1_BYTES;               // [KC2][C rows x 128 B]           (pass 2)
     float* sAff = reinterpret_cast<float*>(sW2 + (STAGE == 2 ? W2_BYTES : 0));   // [2][HID] GroupNorm-1 scale | shift (pass 2)
+    unsigned char* sStage = reinterpret_cast<unsigned char*>(sAff + 2 * HID);     // [4 warps][32 rows][128 B] output staging (pass 2)
     __shared__ MfBars bars;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -215,13 +216,18 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (STAGE == 2) {
                     tc::mbar_wait(&bars.d2_full, i & 1);
                     tc::fence_after_sync();
-                    __half* orow = p.out + ((long long)prob * p.HW + row) * C;
+                    // o rows leave through a warp-private staging tile: a thread owns a token ROW of the accumulator, but 32 row-strided
+                    // 16-byte stores per instruction choke the LSU (lg_throttle 2.25 / issue in the first capture, 118 us per P3 launch);
+                    // staged, every store instruction writes 512 contiguous bytes.
+                    unsigned char* stg = sStage + (warp - 1) * 4096;        // [32 rows][128 B], 16-byte chunks XOR-swizzled by row
+                    const int tile_row0 = (t0 + i) * MF_BM + (warp & 3) * 32;
 #pragma unroll
-                    for (int c0 = 0; c0 < C; c0 += 32) {
-                        uint32_t v[32];
-                        tc::tmem_ld32(t_d2 + lane_sel + c0, v);
-                        tc::tmem_ld_wait();
-                        if (live) {
+                    for (int hc = 0; hc < C / 64; ++hc) {
+#pragma unroll
+                        for (int c0 = 0; c0 < 64; c0 += 32) {
+                            uint32_t v[32];
+                            tc::tmem_ld32(t_d2 + lane_sel + hc * 64 + c0, v);
+                            tc::tmem_ld_wait();
 #pragma unroll
                             for (int c8 = 0; c8 < 4; ++c8) {
                                 Half8 hv;
@@ -233,12 +239,24 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                                     s += r.x + r.y;
                                     q2 += r.x * r.x + r.y * r.y;
                                 }
-                                const int sl = (c0 >> 3) + c8;
-                                part[2 * sl] += s;
-                                part[2 * sl + 1] += q2;
-                                *reinterpret_cast<Half8*>(orow + c0 + c8 * 8) = hv;
+                                if (live) {
+                                    const int sl = ((hc * 64 + c0) >> 3) + c8;
+                                    part[2 * sl] += s;
+                                    part[2 * sl + 1] += q2;
+                                }
+                                const int ch = (c0 >> 3) + c8;
+                                *reinterpret_cast<Half8*>(stg + lane * 128 + ((ch ^ (lane & 7)) << 4)) = hv;
                             }
                         }
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int idx = k * 32 + lane, rr = idx >> 3, ch = idx & 7;
+                            if (tile_row0 + rr < p.HW)
+                                *reinterpret_cast<Half8*>(p.out + ((long long)prob * p.HW + tile_row0 + rr) * C + hc * 64 + ch * 8) =
+                                    *reinterpret_cast<const Half8*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                        }
+                        __syncwarp();
                     }
                     tc::fence_before_sync();       // D2 / the A operand are read out before the next tile's MMAs may overwrite them
                 }
@@ -293,7 +311,8 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char* sX = smem;                          // [2][KC][128 rows x 128 B]
     unsigned char* sW = sX + 2 * X_BYTES;              // [KC][C rows x 128 B]
-    float* sAff = reinterpret_cast<float*>(sW + W_BYTES);   // bias [C] | per rank j: scale [C], shift [C]
+    float* sAff = reinterpret_cast<float*>(sW + W_BYTES);   // bias [C] | per rank j: scale [C], shift [C]   (topk <= 2)
+    float* sStage = sAff + 5 * C;                           // [4 warps][32 rows][64 fp32] staging of SiLU(shared expert)
     __shared__ McBars bars;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -367,53 +386,81 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             const int row_in_tile = (warp & 3) * 32 + lane;
             for (int i = 0; i < nt; ++i) {
                 const int bf = i & 1;
-                const int row = (t0 + i) * MF_BM + row_in_tile;
-                const bool live = row < p.HW;
                 tc::mbar_wait(&bars.d_full[bf], (i >> 1) & 1);
                 tc::fence_after_sync();
-                const __half* xrow = p.x + ((long long)img * p.HW + row) * p.ldx;
-                __half* yrow = p.out + ((long long)img * p.HW + row) * p.ldo;
+                // The accumulator arrives one token ROW per thread; the routed outputs, the residual and y live in global memory as rows of
+                // 128 / 256 bytes.  Row-strided 16-byte accesses (32 sectors per instruction) throttled the LSU in the first version
+                // (130 us per P3 launch), so SiLU(shared) is staged in a warp-private fp32 tile and the sum is formed in (row, 8-channel
+                // chunk) ownership: every global load / store instruction then covers 512 contiguous bytes.
+                float* stg = sStage + (warp - 1) * (32 * 64);               // [32 rows][64 fp32], 16-byte chunks XOR-swizzled by row
+                const int tile_row0 = (t0 + i) * MF_BM + (warp & 3) * 32;
+                const int ch = lane & 7;                                     // this lane's 8-channel chunk in the coalesced phase
 #pragma unroll
-                for (int c0 = 0; c0 < C; c0 += 32) {
-                    uint32_t v[32];
-                    tc::tmem_ld32(tmem_base + bf * C + lane_sel + c0, v);
-                    tc::tmem_ld_wait();
-                    if (live) {
-                        float acc[32];
+                for (int hc = 0; hc < C / 64; ++hc) {
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) acc[q] = silu_f(__uint_as_float(v[q]) + sAff[c0 + q]);
-                        for (int j = 0; j < p.topk; ++j) {
-                            const __half* orow = p.o + (((long long)img * p.topk + j) * p.HW + row) * C + c0;
-                            const float* sc = sAff + C + (2 * j) * C + c0;
-                            const float* sh = sc + C;
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        uint32_t v[32];
+                        tc::tmem_ld32(tmem_base + bf * C + lane_sel + hc * 64 + c0, v);
+                        tc::tmem_ld_wait();
 #pragma unroll
-                            for (int c8 = 0; c8 < 4; ++c8) {
-                                const Half8 ov = *reinterpret_cast<const Half8*>(orow + c8 * 8);
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            float4 f;
+                            f.x = silu_f(__uint_as_float(v[c4 * 4 + 0]) + sAff[hc * 64 + c0 + c4 * 4 + 0]);
+                            f.y = silu_f(__uint_as_float(v[c4 * 4 + 1]) + sAff[hc * 64 + c0 + c4 * 4 + 1]);
+                            f.z = silu_f(__uint_as_float(v[c4 * 4 + 2]) + sAff[hc * 64 + c0 + c4 * 4 + 2]);
+                            f.w = silu_f(__uint_as_float(v[c4 * 4 + 3]) + sAff[hc * 64 + c0 + c4 * 4 + 3]);
+                            const int pos = ((c0 >> 2) + c4) ^ (lane & 7);
+                            *reinterpret_cast<float4*>(stg + lane * 64 + pos * 4) = f;
+                        }
+                    }
+                    __syncwarp();
+                    float sc[2][8], sh[2][8];                                // this lane's channels: GroupNorm-2 affine of each routed rank
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const float2 f = __half22float2(ov.v[q]);
-                                    acc[c8 * 8 + 2 * q] += fmaf(f.x, sc[c8 * 8 + 2 * q], sh[c8 * 8 + 2 * q]);
-                                    acc[c8 * 8 + 2 * q + 1] += fmaf(f.y, sc[c8 * 8 + 2 * q + 1], sh[c8 * 8 + 2 * q + 1]);
-                                }
+                    for (int j = 0; j < 2; ++j) {
+                        if (j < p.topk) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                sc[j][q] = sAff[C + (2 * j) * C + hc * 64 + ch * 8 + q];
+                                sh[j][q] = sAff[C + (2 * j + 1) * C + hc * 64 + ch * 8 + q];
                             }
                         }
+                    }
 #pragma unroll
-                        for (int c8 = 0; c8 < 4; ++c8) {
+                    for (int k = 0; k < 8; ++k) {
+                        const int rr = (k * 32 + lane) >> 3;
+                        const int row = tile_row0 + rr;
+                        if (row < p.HW) {
+                            const float4 a0 = *reinterpret_cast<const float4*>(stg + rr * 64 + (((2 * ch) ^ (rr & 7)) << 2));
+                            const float4 a1 = *reinterpret_cast<const float4*>(stg + rr * 64 + (((2 * ch + 1) ^ (rr & 7)) << 2));
+                            float acc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                if (j < p.topk) {
+                                    const Half8 ov = *reinterpret_cast<const Half8*>(p.o + (((long long)img * p.topk + j) * p.HW + row) * C + hc * 64 + ch * 8);
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float2 f = __half22float2(ov.v[q]);
+                                        acc[2 * q] += fmaf(f.x, sc[j][2 * q], sh[j][2 * q]);
+                                        acc[2 * q + 1] += fmaf(f.y, sc[j][2 * q + 1], sh[j][2 * q + 1]);
+                                    }
+                                }
+                            }
                             Half8 hv;
                             if (p.add_residual) {
-                                const Half8 rv = *reinterpret_cast<const Half8*>(xrow + c0 + c8 * 8);
+                                const Half8 rv = *reinterpret_cast<const Half8*>(p.x + ((long long)img * p.HW + row) * p.ldx + hc * 64 + ch * 8);
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     const float2 rf = __half22float2(rv.v[q]);
-                                    hv.v[q] = __floats2half2_rn(acc[c8 * 8 + 2 * q] + rf.x, acc[c8 * 8 + 2 * q + 1] + rf.y);
+                                    hv.v[q] = __floats2half2_rn(acc[2 * q] + rf.x, acc[2 * q + 1] + rf.y);
                                 }
                             } else {
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) hv.v[q] = __floats2half2_rn(acc[c8 * 8 + 2 * q], acc[c8 * 8 + 2 * q + 1]);
+                                for (int q = 0; q < 4; ++q) hv.v[q] = __floats2half2_rn(acc[2 * q], acc[2 * q + 1]);
                             }
-                            *reinterpret_cast<Half8*>(yrow + c0 + c8 * 8) = hv;
+                            *reinterpret_cast<Half8*>(p.out + ((long long)img * p.HW + row) * p.ldo + hc * 64 + ch * 8) = hv;
                         }
                     }
+                    __syncwarp();
                 }
                 tc::fence_before_sync();
                 __syncwarp();
@@ -450,7 +497,7 @@ template <int C, int HID, int STAGE>
 static int mf_launch(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mw2, const MoeFfnParams& p, int strips, int P,
                      cudaStream_t st) {
     size_t smem = (size_t)2 * MF_BM * C * 2 + (size_t)HID * C * 2 + 1024;
-    if (STAGE == 2) smem += (size_t)C * HID * 2 + 2 * HID * sizeof(float);
+    if (STAGE == 2) smem += (size_t)C * HID * 2 + 2 * HID * sizeof(float) + 4 * 4096;
     auto kern = moe_ffn_kernel<C, HID, STAGE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ym_set_error("ym_moe_ffn: smem attr %zu: %s", smem, cudaGetErrorString(e)); return YM_ERR_CUDA; }
@@ -525,7 +572,7 @@ extern "C" int ym_moe_combine_tc(const void* x, int ldx, int B, int HW, int C, c
     YM_CHECK_ARG(x && ws && o && o_scale && o_shift && out, "ym_moe_combine_tc: null pointer");
     YM_CHECK_ARG(ym_moe_combine_tc_supported(C, ldx, ldo), "ym_moe_combine_tc: unsupported shape C=%d ldx=%d ldo=%d", C, ldx, ldo);
     YM_CHECK_ARG((((uintptr_t)x | (uintptr_t)ws | (uintptr_t)o | (uintptr_t)out) & 15) == 0, "ym_moe_combine_tc: 16-byte alignment");
-    YM_CHECK_ARG(topk >= 1 && topk <= 4 && HW >= 1 && B >= 0 && B <= 65535, "ym_moe_combine_tc: bad sizes");
+    YM_CHECK_ARG(topk >= 1 && topk <= 2 && HW >= 1 && B >= 0 && B <= 65535, "ym_moe_combine_tc: top_k must be 1 or 2 (got %d)", topk);
     if (B == 0) return YM_OK;
     const int mtiles = (HW + MF_BM - 1) / MF_BM;
     int tps = 4;
@@ -545,7 +592,7 @@ extern "C" int ym_moe_combine_tc(const void* x, int ldx, int B, int HW, int C, c
     MoeCombineParams p;
     p.x = (const __half*)x; p.ldx = ldx; p.bias = bias_s; p.o = (const __half*)o; p.o_scale = o_scale; p.o_shift = o_shift;
     p.out = (__half*)out; p.ldo = ldo; p.HW = HW; p.mtiles = mtiles; p.tiles_per_strip = tps; p.topk = topk; p.add_residual = add_residual;
-    const size_t smem = (size_t)2 * MF_BM * C * 2 + (size_t)C * C * 2 + (size_t)(1 + 2 * topk) * C * sizeof(float) + 1024;
+    const size_t smem = (size_t)2 * MF_BM * C * 2 + (size_t)C * C * 2 + (size_t)5 * C * sizeof(float) + 4 * 32 * 64 * sizeof(float) + 1024;
     cudaError_t e;
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 64) {

@@ -263,7 +263,7 @@ def moe_combine(x, ws_packed, bias_s, o, o_scale, o_shift, topk, add_residual=Tr
     if out is None:
         out = new_act(B, H, W, Cc, x.device)
     L = lib()
-    if MOE_COMBINE_IMPL == "tc" and ws_packed.shape[1] == Cc and o.shape[2] == Cc and L.ym_moe_combine_tc_supported(Cc, pitch(x), pitch(out)):
+    if MOE_COMBINE_IMPL == "tc" and topk <= 2 and ws_packed.shape[1] == Cc and o.shape[2] == Cc and L.ym_moe_combine_tc_supported(Cc, pitch(x), pitch(out)):
         _lib.check(L.ym_moe_combine_tc(x.data_ptr(), pitch(x), B, H * W, Cc, ws_packed.data_ptr(), bias_s.data_ptr(), o.data_ptr(),
                                        o_scale.data_ptr(), o_shift.data_ptr(), topk, out.data_ptr(), pitch(out),
                                        1 if add_residual else 0, _stream()), "ym_moe_combine_tc")
