@@ -446,13 +446,33 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    depth = max(1, args.streams)
+    pipe = model.pipelined(B, IMG, IMG, dtype=torch.float16, depth=depth) if depth > 1 else None
+    pipe8 = model.pipelined(B, IMG, IMG, dtype=torch.uint8, depth=depth) if depth > 1 else None
+
+    def timed_pipe(steps, warmup):
+        """K steps through PipelinedForward: `depth` graph instances on `depth` streams, batch i on instance i % depth; the events sit on
+        the calling stream, which run_device joins to the instance streams on both sides."""
+        pipe.run_device(dev_in[i % nrot] for i in range(warmup))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pipe.run_device(dev_in[i % nrot] for i in range(steps))
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
     with ClockSampler(local) as clk:
-        ms_dev = timed(lambda i: g(dev_in[i % nrot]), args.steps, args.warmup)
+        ms_single = timed(lambda i: g(dev_in[i % nrot]), args.steps, args.warmup)
+        ms_dev = timed_pipe(args.steps, args.warmup) if depth > 1 else ms_single
     clocks = clk.summary()
     # e2e: K batches through the public pipelined host-buffer API; every step's H2D (uint8 frames) and D2H ((B,300,6) fp32)
     # are inside the timed region, on copy streams that overlap the neighbouring steps' compute
     def e2e_run(n):
-        for out in g8.stream_host(host_in[i % 3] for i in range(n)):
+        for out in (pipe8 if depth > 1 else g8).stream_host(host_in[i % 3] for i in range(n)):
             pass
     e2e_run(args.warmup)
     barrier()
@@ -470,6 +490,24 @@ def run_ours(args):
     ms_e2e_sync = timed(lambda i: g8.run_host(host_in[i % 3]), args.steps, args.warmup)   # unpipelined call, for reference
 
     value = world * B * args.steps / (ms_dev * 1e-3)
+    sweep = None
+    if rank == 0 and world == 1 and args.depth_sweep:          # how throughput moves with the number of graph instances in flight
+        sweep = {"1": world * B * args.steps / (ms_single * 1e-3), str(depth): value}
+        for d3 in (2, 3, 4):
+            if str(d3) in sweep:
+                continue
+            try:
+                p3 = model.pipelined(B, IMG, IMG, dtype=torch.float16, depth=d3)
+                p3.run_device(dev_in[i % nrot] for i in range(args.warmup))
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                p3.run_device(dev_in[i % nrot] for i in range(args.steps))
+                e1.record()
+                torch.cuda.synchronize(dev)
+                sweep[str(d3)] = B * args.steps / (e0.elapsed_time(e1) * 1e-3)
+            except Exception as e:
+                sweep[str(d3)] = f"{type(e).__name__}: {str(e)[:120]}"
     two = time_two_streams(model, dev_in, B, args.steps, args.warmup, dev) if (rank == 0 and args.two_stream) else None
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     roof = time_attention_kernel(dev, B, pk) if rank == 0 else None
@@ -488,10 +526,14 @@ def run_ours(args):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
             "config": bench_config(world, B),
-            "execution": "CUDA graph of the whole forward",
+            "execution": (f"{depth} CUDA-graph instances of the whole bs{B} forward on {depth} streams, consecutive batches on consecutive "
+                          "instances (PipelinedForward: same kernels and per-batch results as one graph; the exp-bound attention of one batch "
+                          "overlaps the latency / HBM-bound layers of the other)") if depth > 1 else "CUDA graph of the whole forward",
+            "single_stream": {"value": world * B * args.steps / (ms_single * 1e-3), "unit": UNIT, "ms_per_step": ms_single / args.steps,
+                              "note": "one CUDA graph replayed back to back on one stream (the latency of one bs32 forward)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * 3 * IMG * IMG, "d2h_bytes_per_step": B * 300 * 6 * 4,
                     "ms_per_step": ms_e2e / args.steps, "input": "uint8 RGB frames in pinned host memory (x/255 on the device)",
-                    "api": "GraphedForward.stream_host (double-buffered H2D / compute / D2H)",
+                    "api": ("PipelinedForward.stream_host" if depth > 1 else "GraphedForward.stream_host") + " (H2D / forward / D2H of neighbouring batches overlap)",
                     "unpipelined_ms_per_step": ms_e2e_sync / args.steps,
                     "unpipelined_value": world * B * args.steps / (ms_e2e_sync * 1e-3)},
             "gpu_launches": kernels_per_step * args.steps,
@@ -501,6 +543,7 @@ def run_ours(args):
             "model_roofline": model_roofline(value / world, pk),
             "dispatch": disp,
             "two_stream": two,
+            "depth_sweep_images_per_s": sweep,
             "torch_eager_gpu": eager,
             "cpu_baseline": cpu_base,
         }
@@ -518,7 +561,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--ref-images", type=int, default=8, help="images per CPU-oracle step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--two-stream", action="store_true", help="also time two forward graphs replayed on two streams (experiment)")
+    ap.add_argument("--two-stream", action="store_true", help="(legacy experiment leg) also time two raw graph replays on two streams")
+    ap.add_argument("--depth-sweep", action="store_true", help="also time PipelinedForward at depth 1 / 2 / 3 / 4")
+    ap.add_argument("--streams", type=int, default=2, help="graph instances / streams of PipelinedForward (1 = a single graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly ONE JSON line: libraries that print to the C-level stdout (NCCL prints "NCCL version ..." there on

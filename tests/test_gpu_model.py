@@ -167,6 +167,26 @@ def test_stream_host_pipeline_uint8(model_and_sd):
     assert (s8 - s16).abs().max() < 2e-2
 
 
+def test_pipelined_forward_two_instances_bit_identical_and_in_order(model_and_sd):
+    """PipelinedForward (two graph instances on two streams): every batch gets exactly what the single graph returns for it, in order,
+    for the device-resident call and for the host-buffer stream with an odd number of batches (slot reuse, flush)."""
+    m, _ = model_and_sd
+    frames = [(synth_images(2, 256, 256, 60 + i) * 255).round().to(torch.uint8).pin_memory() for i in range(7)]
+    g8 = m.graphed(2, 256, 256, dtype=torch.uint8)
+    want = [g8.run_host(f).clone() for f in frames]
+    pipe = m.pipelined(2, 256, 256, dtype=torch.uint8, depth=2)
+    assert pipe.kernels_per_replay == g8.kernels_per_replay and pipe.depth == 2
+    got = [o.clone() for o in pipe.stream_host(iter(frames))]
+    assert len(got) == len(want)
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert torch.equal(a, b), f"batch {i}"
+    got2 = [o.clone() for o in pipe.stream_host(iter(frames[:3]))]           # second use of the same pipeline, fewer batches
+    assert all(torch.equal(a, b) for a, b in zip(got2, want[:3]))
+    outs = pipe.run_device([f.to(DEV) for f in frames[:2]])
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0].cpu(), want[0]) and torch.equal(outs[1].cpu(), want[1])
+
+
 def test_empty_batch_and_bad_rank(model_and_sd):
     m, _ = model_and_sd
     with torch.no_grad():

@@ -84,10 +84,11 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const TIn* __restrict__ 
 // (kx = 0, 1, 2 and a zero-weight pad), 9 groups padded to 12 -> K = 48 = three k16 steps, so that every A-fragment register is ONE
 // aligned 32-bit shared-memory load of two horizontally adjacent fp16 input pixels (the im2col never exists).  Inputs are rounded to
 // fp16 as the reference's own fp16 predictor path does (`im.half()`, then `/ 255` for uint8 frames: engine/predictor.py:173-175);
-// weights are the folded fp16 conv weights, accumulation is fp32.
+// the folded fp32 weights are split into two fp16 parts (w = hi + lo, lo = the next 11 mantissa bits) and both are multiplied in - the
+// first layer keeps the fp32-weight accuracy of the FFMA kernel for six more HMMAs per 16 pixels; accumulation is fp32.
 // CTA = 8 warps = 8 output rows x 64 output columns; warp = one output row, four 16-pixel groups.
 struct StemTcWeights {
-    uint32_t b[3][2][32][2];      // B fragments per (k step, n tile, lane): {b0, b1} as packed half2
+    uint32_t b[2][3][2][32][2];   // B fragments per (hi | lo part, k step, n tile, lane): {b0, b1} as packed half2
     float bias[16];
 };
 
@@ -112,23 +113,44 @@ __global__ void __launch_bounds__(256) stem_conv_tc_kernel(const TIn* __restrict
     const int b = blockIdx.y;
     const int oy0 = (blockIdx.x / tiles_x) * TH, ox0 = (blockIdx.x % tiles_x) * TW;
     const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
-    for (int i = tid; i < 3 * IH * IW; i += 256) {
-        const int ci = i / (IH * IW), rem = i - ci * (IH * IW);
-        const int ry = rem / IW, rx = rem - ry * IW;
-        const int iy = iy0 + ry, ix = ix0 + rx;
-        __half v = __float2half_rn(0.f);
-        if (ci < Cin && iy >= 0 && iy < H && ix >= 0 && ix < W) v = stem_to_half<TIn>(img[(((long long)b * Cin + ci) * H + iy) * W + ix]);
-        sx[ci][ry][rx] = v;
+    // patch load: 26 elements per thread in two batches of 13 - all loads of a batch are issued before the first shared-memory store, so a
+    // CTA has ~3.3 K loads in flight instead of one per thread (the one-at-a-time loop ran the whole kernel at load latency: 191 us)
+    constexpr int TOT = 3 * IH * IW, PER = (TOT + 255) / 256, BATCH = (PER + 1) / 2;
+#pragma unroll
+    for (int j0 = 0; j0 < PER; j0 += BATCH) {
+        __half vals[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            const int i = tid + 256 * (j0 + j);
+            const int ci = i / (IH * IW), rem = i - ci * (IH * IW);
+            const int ry = rem / IW, rx = rem - ry * IW;
+            const int iy = iy0 + ry, ix = ix0 + rx;
+            __half v = __float2half_rn(0.f);
+            if (j0 + j < PER && i < TOT && ci < Cin && iy >= 0 && iy < H && ix >= 0 && ix < W)
+                v = stem_to_half<TIn>(img[(((long long)b * Cin + ci) * H + iy) * W + ix]);
+            vals[j] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            const int i = tid + 256 * (j0 + j);
+            if (j0 + j < PER && i < TOT) {
+                const int ci = i / (IH * IW), rem = i - ci * (IH * IW);
+                const int ry = rem / IW, rx = rem - ry * IW;
+                sx[ci][ry][rx] = vals[j];
+            }
+        }
     }
     __syncthreads();
     const int oy = oy0 + warp;
     if (oy >= Ho) return;
     const int g = lane >> 2, t = lane & 3;
-    uint32_t bf[3][2][2];
+    uint32_t bf[2][3][2][2];
 #pragma unroll
-    for (int ks = 0; ks < 3; ++ks)
+    for (int part = 0; part < 2; ++part)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) { bf[ks][nt][0] = sw.b[ks][nt][lane][0]; bf[ks][nt][1] = sw.b[ks][nt][lane][1]; }
+        for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) { bf[part][ks][nt][0] = sw.b[part][ks][nt][lane][0]; bf[part][ks][nt][1] = sw.b[part][ks][nt][lane][1]; }
     const float bias0 = sw.bias[2 * t], bias1 = sw.bias[2 * t + 1], bias8 = sw.bias[8 + 2 * t], bias9 = sw.bias[8 + 2 * t + 1];
 #pragma unroll 1
     for (int grp = 0; grp < TW / 16; ++grp) {
@@ -151,7 +173,10 @@ __global__ void __launch_bounds__(256) stem_conv_tc_kernel(const TIn* __restrict
                 a[2 * hi + 1] = *reinterpret_cast<const uint32_t*>(row + 2 * (lx + 8));      // fragment row g + 8
             }
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) mma_16816(acc[nt], a, bf[ks][nt][0], bf[ks][nt][1]);
+            for (int nt = 0; nt < 2; ++nt) {
+                mma_16816(acc[nt], a, bf[1][ks][nt][0], bf[1][ks][nt][1]);      // low part first: small terms enter the fp32 sum early
+                mma_16816(acc[nt], a, bf[0][ks][nt][0], bf[0][ks][nt][1]);
+            }
         }
         // fragments -> per-warp staging tile -> one 16-byte store per lane (16 pixels x 32 B are contiguous in the NHWC output)
         __half2* so = reinterpret_cast<__half2*>(&sout[warp][0][0]);
@@ -521,15 +546,20 @@ static int stem_launch(const void* img, int in_dtype, int B, int Cin, int H, int
             if (ci >= Cin) return 0.f;
             return wgt_host[(size_t)((ci * 3 + ky) * 3 + kx) * CO + n];
         };
-        for (int ks = 0; ks < 3; ++ks)
-            for (int nt = 0; nt < 2; ++nt)
-                for (int lane = 0; lane < 32; ++lane) {
-                    const int g = lane >> 2, t = lane & 3, n = nt * 8 + g;
-                    const __half2 b0 = __floats2half2_rn(wk(16 * ks + 2 * t, n), wk(16 * ks + 2 * t + 1, n));
-                    const __half2 b1 = __floats2half2_rn(wk(16 * ks + 2 * t + 8, n), wk(16 * ks + 2 * t + 9, n));
-                    memcpy(&tw.b[ks][nt][lane][0], &b0, 4);
-                    memcpy(&tw.b[ks][nt][lane][1], &b1, 4);
-                }
+        auto part_of = [&](float w, int part) -> float {       // part 0: fp16(w), part 1: fp16(w - fp16(w))
+            const float hi = __half2float(__float2half_rn(w));
+            return part == 0 ? hi : (w - hi);
+        };
+        for (int part = 0; part < 2; ++part)
+            for (int ks = 0; ks < 3; ++ks)
+                for (int nt = 0; nt < 2; ++nt)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int g = lane >> 2, t = lane & 3, n = nt * 8 + g;
+                        const __half2 b0 = __floats2half2_rn(part_of(wk(16 * ks + 2 * t, n), part), part_of(wk(16 * ks + 2 * t + 1, n), part));
+                        const __half2 b1 = __floats2half2_rn(part_of(wk(16 * ks + 2 * t + 8, n), part), part_of(wk(16 * ks + 2 * t + 9, n), part));
+                        memcpy(&tw.b[part][ks][nt][lane][0], &b0, 4);
+                        memcpy(&tw.b[part][ks][nt][lane][1], &b1, 4);
+                    }
         memcpy(tw.bias, bias_host, sizeof(float) * 16);
         const int tx = (Wo + 63) / 64, ty = (Ho + 7) / 8;
         const dim3 gridt(tx * ty, B);

@@ -15,10 +15,12 @@
 //                               o = a W2[e]^T; epilogue-2 = o -> fp16 -> global + GroupNorm-2 partial sums.
 // h never exists in global memory: per P3 block the chain moves x (read by both passes, L2-resident between the k ranks) and o.
 //
-// One CTA = one strip of consecutive 128-row tiles of ONE problem (weights fetched once per CTA by TMA), 160 threads:
+// One CTA = one strip of consecutive 128-row tiles of ONE problem (weights fetched once per CTA by TMA), 288 threads:
 //   warp 0 lane 0 : every TMA (x tiles double-buffered, W1 / W2 once) and every tcgen05.mma, static order
 //                   GEMM1(0); per tile i: [P2: wait a(i) -> GEMM2(i)]; GEMM1(i+1); refill x(i+2)
-//   warps 1-4     : epilogue, thread = token row (tensor-memory lane), hand-offs through mbarriers only
+//   warps 1-8     : epilogue, thread = token row (tensor-memory lane) x one HALF of the columns: warps w and w+4 share a lane quarter and
+//                   split the columns (four epilogue warps per CTA left two warps per SM sub-partition: 14 % warp occupancy, latency-bound
+//                   at 72 / 86 us per P3 launch in the second capture); hand-offs through mbarriers only
 // Partial statistics are accumulated per thread over the strip and reduced once, in a fixed order (bit-reproducible).
 #include <cuda.h>
 
@@ -26,7 +28,7 @@
 
 namespace ym {
 
-constexpr int MF_BM = 128, MF_THREADS = 160;
+constexpr int MF_BM = 128, MF_THREADS = 288;   // warp 0: TMA + MMA issuer; warps 1-8: epilogue (two per tensor-memory lane quarter)
 
 __device__ __forceinline__ void mf_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -61,7 +63,7 @@ struct MfBars {
 
 // STAGE 1: statistics of h only.  STAGE 2: the fused chain.
 template <int C, int HID, int STAGE>
-__global__ void __launch_bounds__(MF_THREADS, (HID <= 128) ? 2 : 1)
+__global__ void __maxnreg__((HID <= 128) ? 112 : 224)
 moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                const __grid_constant__ CUtensorMap map_w2, const MoeFfnParams p) {
     constexpr int KC1 = C / 64;                        // 64-wide k chunks of GEMM1 (K = C)
@@ -76,7 +78,7 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     unsigned char* sW1 = sX + 2 * X_BYTES;             // [KC1][HID rows x 128 B]
     unsigned char* sW2 = sW1 + W1_BYTES;               // [KC2][C rows x 128 B]           (pass 2)
     float* sAff = reinterpret_cast<float*>(sW2 + (STAGE == 2 ? W2_BYTES : 0));   // [2][HID] GroupNorm-1 scale | shift (pass 2)
-    unsigned char* sStage = reinterpret_cast<unsigned char*>(sAff + 2 * HID);     // [4 warps][32 rows][128 B] output staging (pass 2)
+    unsigned char* sStage = reinterpret_cast<unsigned char*>(sAff + 2 * HID);     // [8 warps][32 rows][64 B] output staging (pass 2)
     __shared__ MfBars bars;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -89,7 +91,7 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         tc::mbar_init(&bars.x_full[0], 1);
         tc::mbar_init(&bars.x_full[1], 1);
         tc::mbar_init(&bars.d1_full, 1);
-        tc::mbar_init(&bars.a_full, 4);                // one arrive per epilogue warp
+        tc::mbar_init(&bars.a_full, 8);                // one arrive per epilogue warp
         tc::mbar_init(&bars.d2_full, 1);
         tc::fence_mbar_init();
     }
@@ -170,30 +172,34 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 }
             }
         } else {
-            // ================================================ epilogue warps: thread = token row ==================================
+            // ====================================== epilogue warps: thread = token row x one half of the columns ======================
             const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+            const int half = (warp - 1) >> 2;                               // 0: lower half of the columns, 1: upper half
             const int row_in_tile = (warp & 3) * 32 + lane;
-            float part[NS];
+            constexpr int NSH = NS / 2;                                     // statistics slots of this thread (its half of the columns)
+            constexpr int H1 = HID / 2, H2 = C / 2;                         // columns per half: GEMM1 / GEMM2 accumulator
+            float part[NSH];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) part[i] = 0.f;
+            for (int i = 0; i < NSH; ++i) part[i] = 0.f;
             for (int i = 0; i < nt; ++i) {
                 const int row = (t0 + i) * MF_BM + row_in_tile;
                 const bool live = row < p.HW;
                 tc::mbar_wait(&bars.d1_full, i & 1);
                 tc::fence_after_sync();
 #pragma unroll
-                for (int c0 = 0; c0 < HID; c0 += 32) {
+                for (int c0 = 0; c0 < H1; c0 += 32) {
+                    const int cb = half * H1 + c0;                          // first hidden channel of this 32-column chunk
                     uint32_t v[32];
-                    tc::tmem_ld32(t_d1 + lane_sel + c0, v);
+                    tc::tmem_ld32(t_d1 + lane_sel + cb, v);
                     tc::tmem_ld_wait();
                     if (STAGE == 1) {
                         if (live) {
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
                                 const float2 r = __half22float2(__floats2half2_rn(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])));
-                                const int s = (c0 + 2 * q) >> 3;
-                                part[2 * s] += r.x + r.y;
-                                part[2 * s + 1] += r.x * r.x + r.y * r.y;
+                                const int sl = (c0 + 2 * q) >> 3;
+                                part[2 * sl] += r.x + r.y;
+                                part[2 * sl + 1] += r.x * r.x + r.y * r.y;
                             }
                         }
                     } else {
@@ -201,12 +207,12 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
                         for (int q = 0; q < 16; ++q) {
                             const float2 r = __half22float2(__floats2half2_rn(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])));
-                            const int c = c0 + 2 * q;
+                            const int c = cb + 2 * q;
                             const float a0 = silu_f(fmaf(r.x, sAff[c], sAff[HID + c]));
                             const float a1 = silu_f(fmaf(r.y, sAff[c + 1], sAff[HID + c + 1]));
                             pk[q] = pack_half2(a0, a1);
                         }
-                        tc::tmem_st16(t_a + lane_sel + c0 / 2, pk);
+                        tc::tmem_st16(t_a + lane_sel + cb / 2, pk);
                     }
                 }
                 if (STAGE == 2) tc::tmem_st_wait();
@@ -216,45 +222,40 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (STAGE == 2) {
                     tc::mbar_wait(&bars.d2_full, i & 1);
                     tc::fence_after_sync();
-                    // o rows leave through a warp-private staging tile: a thread owns a token ROW of the accumulator, but 32 row-strided
-                    // 16-byte stores per instruction choke the LSU (lg_throttle 2.25 / issue in the first capture, 118 us per P3 launch);
-                    // staged, every store instruction writes 512 contiguous bytes.
-                    unsigned char* stg = sStage + (warp - 1) * 4096;        // [32 rows][128 B], 16-byte chunks XOR-swizzled by row
+                    // o rows leave through a warp-private staging tile (thread = token row of the accumulator, but row-strided 16-byte
+                    // stores choke the LSU: lg_throttle 2.25 / issue in the first capture); staged, every store instruction writes full sectors
+                    unsigned char* stg = sStage + (warp - 1) * 2048;        // [32 rows][64 B]: one 32-column chunk at a time
                     const int tile_row0 = (t0 + i) * MF_BM + (warp & 3) * 32;
 #pragma unroll
-                    for (int hc = 0; hc < C / 64; ++hc) {
+                    for (int c0 = 0; c0 < H2; c0 += 32) {
+                        uint32_t v[32];
+                        tc::tmem_ld32(t_d2 + lane_sel + half * H2 + c0, v);
+                        tc::tmem_ld_wait();
 #pragma unroll
-                        for (int c0 = 0; c0 < 64; c0 += 32) {
-                            uint32_t v[32];
-                            tc::tmem_ld32(t_d2 + lane_sel + hc * 64 + c0, v);
-                            tc::tmem_ld_wait();
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            Half8 hv;
+                            float sm = 0.f, q2 = 0.f;
 #pragma unroll
-                            for (int c8 = 0; c8 < 4; ++c8) {
-                                Half8 hv;
-                                float s = 0.f, q2 = 0.f;
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    hv.v[q] = __floats2half2_rn(__uint_as_float(v[c8 * 8 + 2 * q]), __uint_as_float(v[c8 * 8 + 2 * q + 1]));
-                                    const float2 r = __half22float2(hv.v[q]);
-                                    s += r.x + r.y;
-                                    q2 += r.x * r.x + r.y * r.y;
-                                }
-                                if (live) {
-                                    const int sl = ((hc * 64 + c0) >> 3) + c8;
-                                    part[2 * sl] += s;
-                                    part[2 * sl + 1] += q2;
-                                }
-                                const int ch = (c0 >> 3) + c8;
-                                *reinterpret_cast<Half8*>(stg + lane * 128 + ((ch ^ (lane & 7)) << 4)) = hv;
+                            for (int q = 0; q < 4; ++q) {
+                                hv.v[q] = __floats2half2_rn(__uint_as_float(v[c8 * 8 + 2 * q]), __uint_as_float(v[c8 * 8 + 2 * q + 1]));
+                                const float2 r = __half22float2(hv.v[q]);
+                                sm += r.x + r.y;
+                                q2 += r.x * r.x + r.y * r.y;
                             }
+                            if (live) {
+                                const int sl = (c0 >> 3) + c8;
+                                part[2 * sl] += sm;
+                                part[2 * sl + 1] += q2;
+                            }
+                            *reinterpret_cast<Half8*>(stg + lane * 64 + ((c8 ^ ((lane >> 1) & 3)) << 4)) = hv;
                         }
                         __syncwarp();
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int idx = k * 32 + lane, rr = idx >> 3, ch = idx & 7;
+                        for (int k = 0; k < 4; ++k) {
+                            const int idx = k * 32 + lane, rr = idx >> 2, ch = idx & 3;
                             if (tile_row0 + rr < p.HW)
-                                *reinterpret_cast<Half8*>(p.out + ((long long)prob * p.HW + tile_row0 + rr) * C + hc * 64 + ch * 8) =
-                                    *reinterpret_cast<const Half8*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                                *reinterpret_cast<Half8*>(p.out + ((long long)prob * p.HW + tile_row0 + rr) * C + half * H2 + c0 + ch * 8) =
+                                    *reinterpret_cast<const Half8*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
                         }
                         __syncwarp();
                     }
@@ -264,13 +265,14 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             // ---- strip statistics: per-thread partials -> shared memory -> fixed-order column sums (bit-reproducible)
             // every MMA that read the x buffers has retired (d1_full / d2_full of the last tile were waited on), so sX is free
             float* red = reinterpret_cast<float*>(sX);
-            const int r = tid - 32;
+            const int r = tid - 32;                                         // 0..255: [half][row]
 #pragma unroll
-            for (int i = 0; i < NS; ++i) red[r * NS + i] = part[i];
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");       // the four epilogue warps only
+            for (int i = 0; i < NSH; ++i) red[r * NSH + i] = part[i];
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");       // the eight epilogue warps only
             if (r < NS) {
+                const int h2 = r / NSH, jj = r - h2 * NSH;                  // statistics slot r belongs to column half h2
                 float a = 0.f;
-                for (int k = 0; k < 128; ++k) a += red[k * NS + r];
+                for (int k = 0; k < 128; ++k) a += red[(h2 * 128 + k) * NSH + jj];
                 p.stats[((long long)prob * gridDim.x + strip) * NS + r] = a;
             }
         }
@@ -302,7 +304,7 @@ struct McBars {
 };
 
 template <int C>
-__global__ void __launch_bounds__(MF_THREADS, 2)
+__global__ void __maxnreg__(112)
 moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const MoeCombineParams p) {
     constexpr int KC = C / 64;
     constexpr int X_BYTES = MF_BM * C * 2, W_BYTES = C * C * 2;
@@ -312,7 +314,7 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     unsigned char* sX = smem;                          // [2][KC][128 rows x 128 B]
     unsigned char* sW = sX + 2 * X_BYTES;              // [KC][C rows x 128 B]
     float* sAff = reinterpret_cast<float*>(sW + W_BYTES);   // bias [C] | per rank j: scale [C], shift [C]   (topk <= 2)
-    float* sStage = sAff + 5 * C;                           // [4 warps][32 rows][64 fp32] staging of SiLU(shared expert)
+    float* sStage = sAff + 5 * C;                           // [8 warps][32 rows][32 fp32] staging of SiLU(shared expert)
     __shared__ McBars bars;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -324,7 +326,7 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&bars.x_full[i], 1);
             tc::mbar_init(&bars.d_full[i], 1);
-            tc::mbar_init(&bars.d_free[i], 4);
+            tc::mbar_init(&bars.d_free[i], 8);
         }
         tc::fence_mbar_init();
     }
@@ -383,35 +385,33 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             }
         } else {
             const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-            const int row_in_tile = (warp & 3) * 32 + lane;
+            const int half = (warp - 1) >> 2;                               // this warp's half of the channels
+            constexpr int H = C / 2;
             for (int i = 0; i < nt; ++i) {
                 const int bf = i & 1;
                 tc::mbar_wait(&bars.d_full[bf], (i >> 1) & 1);
                 tc::fence_after_sync();
                 // The accumulator arrives one token ROW per thread; the routed outputs, the residual and y live in global memory as rows of
                 // 128 / 256 bytes.  Row-strided 16-byte accesses (32 sectors per instruction) throttled the LSU in the first version
-                // (130 us per P3 launch), so SiLU(shared) is staged in a warp-private fp32 tile and the sum is formed in (row, 8-channel
-                // chunk) ownership: every global load / store instruction then covers 512 contiguous bytes.
-                float* stg = sStage + (warp - 1) * (32 * 64);               // [32 rows][64 fp32], 16-byte chunks XOR-swizzled by row
+                // (130 us per P3 launch), so SiLU(shared) is staged in a warp-private fp32 tile, 32 channels at a time, and the sum is formed
+                // in (row, 8-channel group) ownership: every global load / store instruction then covers whole 32-byte sectors.
+                float* stg = sStage + (warp - 1) * (32 * 32);               // [32 rows][32 fp32], 16-byte chunks XOR-swizzled by row
                 const int tile_row0 = (t0 + i) * MF_BM + (warp & 3) * 32;
-                const int ch = lane & 7;                                     // this lane's 8-channel chunk in the coalesced phase
+                const int cg = lane & 3;                                     // this lane's 8-channel group in the coalesced phase
 #pragma unroll
-                for (int hc = 0; hc < C / 64; ++hc) {
+                for (int c0 = 0; c0 < H; c0 += 32) {
+                    const int cb = half * H + c0;                            // first channel of this chunk
+                    uint32_t v[32];
+                    tc::tmem_ld32(tmem_base + bf * C + lane_sel + cb, v);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 32) {
-                        uint32_t v[32];
-                        tc::tmem_ld32(tmem_base + bf * C + lane_sel + hc * 64 + c0, v);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) {
-                            float4 f;
-                            f.x = silu_f(__uint_as_float(v[c4 * 4 + 0]) + sAff[hc * 64 + c0 + c4 * 4 + 0]);
-                            f.y = silu_f(__uint_as_float(v[c4 * 4 + 1]) + sAff[hc * 64 + c0 + c4 * 4 + 1]);
-                            f.z = silu_f(__uint_as_float(v[c4 * 4 + 2]) + sAff[hc * 64 + c0 + c4 * 4 + 2]);
-                            f.w = silu_f(__uint_as_float(v[c4 * 4 + 3]) + sAff[hc * 64 + c0 + c4 * 4 + 3]);
-                            const int pos = ((c0 >> 2) + c4) ^ (lane & 7);
-                            *reinterpret_cast<float4*>(stg + lane * 64 + pos * 4) = f;
-                        }
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        float4 f;
+                        f.x = silu_f(__uint_as_float(v[c4 * 4 + 0]) + sAff[cb + c4 * 4 + 0]);
+                        f.y = silu_f(__uint_as_float(v[c4 * 4 + 1]) + sAff[cb + c4 * 4 + 1]);
+                        f.z = silu_f(__uint_as_float(v[c4 * 4 + 2]) + sAff[cb + c4 * 4 + 2]);
+                        f.w = silu_f(__uint_as_float(v[c4 * 4 + 3]) + sAff[cb + c4 * 4 + 3]);
+                        *reinterpret_cast<float4*>(stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = f;
                     }
                     __syncwarp();
                     float sc[2][8], sh[2][8];                                // this lane's channels: GroupNorm-2 affine of each routed rank
@@ -420,23 +420,23 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                         if (j < p.topk) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
-                                sc[j][q] = sAff[C + (2 * j) * C + hc * 64 + ch * 8 + q];
-                                sh[j][q] = sAff[C + (2 * j + 1) * C + hc * 64 + ch * 8 + q];
+                                sc[j][q] = sAff[C + (2 * j) * C + cb + cg * 8 + q];
+                                sh[j][q] = sAff[C + (2 * j + 1) * C + cb + cg * 8 + q];
                             }
                         }
                     }
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int rr = (k * 32 + lane) >> 3;
+                    for (int k = 0; k < 4; ++k) {
+                        const int rr = (k * 32 + lane) >> 2;
                         const int row = tile_row0 + rr;
                         if (row < p.HW) {
-                            const float4 a0 = *reinterpret_cast<const float4*>(stg + rr * 64 + (((2 * ch) ^ (rr & 7)) << 2));
-                            const float4 a1 = *reinterpret_cast<const float4*>(stg + rr * 64 + (((2 * ch + 1) ^ (rr & 7)) << 2));
+                            const float4 a0 = *reinterpret_cast<const float4*>(stg + rr * 32 + (((2 * cg) ^ (rr & 7)) << 2));
+                            const float4 a1 = *reinterpret_cast<const float4*>(stg + rr * 32 + (((2 * cg + 1) ^ (rr & 7)) << 2));
                             float acc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 if (j < p.topk) {
-                                    const Half8 ov = *reinterpret_cast<const Half8*>(p.o + (((long long)img * p.topk + j) * p.HW + row) * C + hc * 64 + ch * 8);
+                                    const Half8 ov = *reinterpret_cast<const Half8*>(p.o + (((long long)img * p.topk + j) * p.HW + row) * C + cb + cg * 8);
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) {
                                         const float2 f = __half22float2(ov.v[q]);
@@ -447,7 +447,7 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                             }
                             Half8 hv;
                             if (p.add_residual) {
-                                const Half8 rv = *reinterpret_cast<const Half8*>(p.x + ((long long)img * p.HW + row) * p.ldx + hc * 64 + ch * 8);
+                                const Half8 rv = *reinterpret_cast<const Half8*>(p.x + ((long long)img * p.HW + row) * p.ldx + cb + cg * 8);
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     const float2 rf = __half22float2(rv.v[q]);
@@ -457,7 +457,7 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) hv.v[q] = __floats2half2_rn(acc[2 * q], acc[2 * q + 1]);
                             }
-                            *reinterpret_cast<Half8*>(p.out + ((long long)img * p.HW + row) * p.ldo + hc * 64 + ch * 8) = hv;
+                            *reinterpret_cast<Half8*>(p.out + ((long long)img * p.HW + row) * p.ldo + cb + cg * 8) = hv;
                         }
                     }
                     __syncwarp();
@@ -497,7 +497,7 @@ template <int C, int HID, int STAGE>
 static int mf_launch(const CUtensorMap& mx, const CUtensorMap& mw1, const CUtensorMap& mw2, const MoeFfnParams& p, int strips, int P,
                      cudaStream_t st) {
     size_t smem = (size_t)2 * MF_BM * C * 2 + (size_t)HID * C * 2 + 1024;
-    if (STAGE == 2) smem += (size_t)C * HID * 2 + 2 * HID * sizeof(float) + 4 * 4096;
+    if (STAGE == 2) smem += (size_t)C * HID * 2 + 2 * HID * sizeof(float) + (size_t)8 * 2048;
     auto kern = moe_ffn_kernel<C, HID, STAGE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ym_set_error("ym_moe_ffn: smem attr %zu: %s", smem, cudaGetErrorString(e)); return YM_ERR_CUDA; }
@@ -514,11 +514,25 @@ extern "C" int ym_moe_ffn_supported(int C, int HID, int ldx) {
     return mf_encode() != nullptr && ((C == 64 && HID == 128) || (C == 128 && HID == 256)) && ldx % 8 == 0;
 }
 
-// strips per problem such that the grid is a few waves of resident CTAs and every strip amortises its weight fetch over >= 2 tiles
+// Row tiles per CTA: the smallest strip length whose grid fits ONE wave of resident CTAs (2 per SM).  A CTA's fixed cost (tensor-memory
+// allocation, barrier set-up, the expert's weights by TMA, pipeline fill: ~5 us) is then paid once per SM slot instead of once per tile -
+// at P4 / P5 (13 / 4 row tiles per problem) one-tile CTAs in three waves spent most of their life in that prologue.
+static int mf_tiles_per_strip(long long units, int mtiles) {
+    static int slots = 0;
+    if (!slots) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        slots = 2 * (sms > 0 ? sms : 148);
+    }
+    for (int tps = 1; tps < mtiles; ++tps)
+        if (units * ((mtiles + tps - 1) / tps) <= slots) return tps;
+    return mtiles;
+}
+
 extern "C" int ym_moe_ffn_strips(int HW, int P) {
     const int mtiles = (HW + MF_BM - 1) / MF_BM;
-    int tps = 4;                                             // tiles per strip
-    while (tps > 1 && (long long)P * ((mtiles + tps - 1) / tps) < 2 * 296) --tps;
+    const int tps = mf_tiles_per_strip(P, mtiles);
     return (mtiles + tps - 1) / tps;
 }
 
@@ -575,8 +589,7 @@ extern "C" int ym_moe_combine_tc(const void* x, int ldx, int B, int HW, int C, c
     YM_CHECK_ARG(topk >= 1 && topk <= 2 && HW >= 1 && B >= 0 && B <= 65535, "ym_moe_combine_tc: top_k must be 1 or 2 (got %d)", topk);
     if (B == 0) return YM_OK;
     const int mtiles = (HW + MF_BM - 1) / MF_BM;
-    int tps = 4;
-    while (tps > 1 && (long long)B * ((mtiles + tps - 1) / tps) < 2 * 296) --tps;
+    const int tps = mf_tiles_per_strip(B, mtiles);
     const int strips = (mtiles + tps - 1) / tps;
     CUtensorMap mx, mw;
     {
@@ -592,7 +605,7 @@ extern "C" int ym_moe_combine_tc(const void* x, int ldx, int B, int HW, int C, c
     MoeCombineParams p;
     p.x = (const __half*)x; p.ldx = ldx; p.bias = bias_s; p.o = (const __half*)o; p.o_scale = o_scale; p.o_shift = o_shift;
     p.out = (__half*)out; p.ldo = ldo; p.HW = HW; p.mtiles = mtiles; p.tiles_per_strip = tps; p.topk = topk; p.add_residual = add_residual;
-    const size_t smem = (size_t)2 * MF_BM * C * 2 + (size_t)C * C * 2 + (size_t)5 * C * sizeof(float) + 4 * 32 * 64 * sizeof(float) + 1024;
+    const size_t smem = (size_t)2 * MF_BM * C * 2 + (size_t)C * C * 2 + (size_t)5 * C * sizeof(float) + 8 * 32 * 32 * sizeof(float) + 1024;
     cudaError_t e;
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 64) {
