@@ -89,6 +89,9 @@ int ym_attention_fwd_tc2_supported(int heads, int head_stride, int ld);
  * |rel err| < 7.5e-5) instead of the MUFU, whose 16 ex2 / clk / SM is the kernel's ceiling (0 = MUFU only; 2 / 3 / 4 / 6).  Returns the
  * previous setting; ym_attention2_poly reads it. */
 int ym_set_attention2_poly(int every);
+/* Query tiles (128 rows) per CTA of ym_attention_fwd_tc2: 0 = chosen by wave fit (two tiles share every K / V tile; one tile per CTA when
+ * the grid is below two waves and splits better), 1 / 2 = forced.  Results are bit-identical either way.  Returns the previous setting. */
+int ym_set_attention2_qtiles(int n);
 int ym_attention2_poly(void);
 /* Kernel behind ym_attention_fwd: 2 = ym_attention_fwd_tc2 (default), 1 = ym_attention_fwd_tc, 0 = mma.sync kernel.  Returns the
  * previous setting (A/B baselines for tests and profiles; nothing in the package changes it). */

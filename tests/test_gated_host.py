@@ -228,7 +228,9 @@ def test_gated_zoo_yamls_build():
         if nparam:
             assert sum(p.numel() for p in m.parameters()) == nparam
         assert DetectionModel(f"master/{ver}/det/yolo-master-s.yaml").model[5].in_channels == 256
-    assert type(DetectionModel("yolo-master-n.yaml").model[3]).__name__ == "ES_MOE"        # a bare name still resolves to the v0 zoo
+    assert type(DetectionModel("master/v0/det/yolo-master-n.yaml").model[3]).__name__ == "ES_MOE"
+    with pytest.raises(FileNotFoundError, match="Multiple files match"):       # 16 zoo versions ship this file name: like check_yaml
+        DetectionModel("yolo-master-n.yaml")
     for cfg, cls in (("master/v0_12/det/yolo-master-n.yaml", "OptimalHybridGateMoE"), ("master/exp/yolo-master-v0_11.yaml", "HybridAdaptiveGateMoEv2"),
                      ("master/v0_13/det/yolo-master-n.yaml", "MultiHeadRouterMoE"), ("master/v0_15/det/yolo-master-n.yaml", "GatedFusionMoE"),
                      ("master/v0_14/det/yolo-master-n.yaml", "DiversifiedExpertMoE")):

@@ -61,7 +61,7 @@ def test_config2_s_mot_moa_bs64_640_cwnms():
 def test_config3_l_1280_shard():
     """configs[3]: YOLO-Master-L @ 1280x1280, one rank's shard of the 8-GPU batch (16 images per GPU; 4 here to bound test time),
     dense DFL output (B, 84, 33600) + NMS."""
-    m = _model("yolo-master-l-v0", "yolo-master-l.yaml")
+    m = _model("yolo-master-l-v0", "master/v0/det/yolo-master-l.yaml")
     x = synth_images(4, 1280, 1280, 78).half().to(DEV)
     with torch.no_grad():
         y = m(x)[0]

@@ -125,16 +125,25 @@ def _attn_ref(qkv, batch, N, heads, hs, dv):
                                               (129, 1, 32, 1), (385, 3, 32, 1), (449, 2, 64, 2), (3200, 1, 32, 1)])
 def test_tc_attention2_strict(N, heads, dv, batch):
     """Warp-specialised tcgen05 / TMA attention kernel (ym_attention_fwd_tc2) alone vs fp32 softmax attention, strict tolerance:
-    ragged N (query-tile and key-tile tails, an absent second query tile), one and several heads, d_v = 64, the P3 length."""
+    ragged N (query-tile and key-tile tails, an absent second query tile), one and several heads, d_v = 64, the P3 length - with one
+    and with two query tiles per CTA (bit-identical to each other: a row sees the same keys in the same order)."""
     from yolo_master_b200 import _lib
     hs = 64 + dv
     g = torch.Generator().manual_seed(N + dv)
     qkv = torch.randn((batch, N, 1, heads * hs), generator=g).half()
-    out = torch.full((batch, N, 1, heads * dv), float("nan"), dtype=torch.float16, device=DEV)
-    _lib.check(_lib.load().ym_attention_fwd_tc2(qkv.to(DEV).data_ptr(), heads * hs, batch, N, heads, hs, 0, 32, 64, 32, dv,
-                                                32 ** -0.5, out.data_ptr(), heads * dv, torch.cuda.current_stream().cuda_stream))
-    torch.cuda.synchronize()
-    assert_close(out, _attn_ref(qkv, batch, N, heads, hs, dv), what=f"tc attention2 N={N} dv={dv}")
+    outs = []
+    for qt in (2, 1):
+        prev = _lib.load().ym_set_attention2_qtiles(qt)
+        try:
+            out = torch.full((batch, N, 1, heads * dv), float("nan"), dtype=torch.float16, device=DEV)
+            _lib.check(_lib.load().ym_attention_fwd_tc2(qkv.to(DEV).data_ptr(), heads * hs, batch, N, heads, hs, 0, 32, 64, 32, dv,
+                                                        32 ** -0.5, out.data_ptr(), heads * dv, torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+        finally:
+            _lib.load().ym_set_attention2_qtiles(prev)
+        assert_close(out, _attn_ref(qkv, batch, N, heads, hs, dv), what=f"tc attention2 N={N} dv={dv} q_tiles={qt}")
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]), "one / two query tiles per CTA must agree bit for bit"
 
 
 def test_tc_attention2_large_logits_lazy_rescale_and_impl_agreement():

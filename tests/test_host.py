@@ -93,7 +93,7 @@ def test_product_does_not_import_oracle():
 
 
 @pytest.mark.parametrize("name,cfg,scale", [
-    ("yolo-master-n-v0", "yolo-master-n.yaml", None), ("yolo-master-l-v0", "yolo-master-l.yaml", None),
+    ("yolo-master-n-v0", "master/v0/det/yolo-master-n.yaml", None), ("yolo-master-l-v0", "master/v0/det/yolo-master-l.yaml", None),
     ("yolo26-master-moa-mot-n", "yolo26-master-moa-mot-n.yaml", None), ("yolo26-master-moa-mot-s", "yolo26-master-moa-mot-n.yaml", [0.50, 0.50, 1024])])
 def test_state_dict_keys_match_reference_all_families(name, cfg, scale):
     """Stock YAMLs of the v0 (ES_MOE / A2C2f / DFL) and MoT + MoA families build with the reference's exact state_dict layout

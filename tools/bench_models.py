@@ -28,8 +28,8 @@ def moamot(scale):
 
 
 CASES = [("yolo26-master-n", "yolo26-master-n.yaml", "yolo26-master-n", B0, 640),
-         ("yolo-master-n-v0", "yolo-master-n.yaml", "yolo-master-n-v0", B0, 640),
-         ("yolo-master-l-v0 @1280 (configs[3] shard)", "yolo-master-l.yaml", "yolo-master-l-v0", 16, 1280),
+         ("yolo-master-n-v0", "master/v0/det/yolo-master-n.yaml", "yolo-master-n-v0", B0, 640),
+         ("yolo-master-l-v0 @1280 (configs[3] shard)", "master/v0/det/yolo-master-l.yaml", "yolo-master-l-v0", 16, 1280),
          ("yolo26-master-moa-mot-n", moamot(False), "yolo26-master-moa-mot-n", B0, 640),
          ("yolo26-master-moa-mot-s bs64 (configs[2])", moamot(True), "yolo26-master-moa-mot-s", 64, 640),
          # families added after round 1's GPU budget (first hardware numbers pending): v0_1 ModularRouterExpertMoE, v0_10 gated MoE

@@ -22,8 +22,8 @@ if which in ("moamot", "moamots"):
         cfg["scale"] = "s"
     keys = "yolo26-master-moa-mot-s" if which == "moamots" else "yolo26-master-moa-mot-n"
 else:
-    cfg, keys = {"n": ("yolo26-master-n.yaml", "yolo26-master-n"), "v0n": ("yolo-master-n.yaml", "yolo-master-n-v0"),
-                 "v0l": ("yolo-master-l.yaml", "yolo-master-l-v0")}[which]
+    cfg, keys = {"n": ("yolo26-master-n.yaml", "yolo26-master-n"), "v0n": ("master/v0/det/yolo-master-n.yaml", "yolo-master-n-v0"),
+                 "v0l": ("master/v0/det/yolo-master-l.yaml", "yolo-master-l-v0")}[which]
 m = DetectionModel(cfg)
 m.load_state_dict(synth_sd_from_keys(0, keys))
 m.to("cuda").eval()

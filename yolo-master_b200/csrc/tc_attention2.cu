@@ -67,7 +67,7 @@ struct A2Bars {
 template <int DV, int POLY>
 __global__ void __launch_bounds__(A2_THREADS, (DV == 32) ? 2 : 1)
 tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                     const __grid_constant__ CUtensorMap map_v, int N, float scale_log2, __half* __restrict__ out, int ldo) {
+                     const __grid_constant__ CUtensorMap map_v, int N, float scale_log2, __half* __restrict__ out, int ldo, int q_tiles) {
     constexpr int Q_BYTES = A2_BQ * 64, K_BYTES = A2_BKV * 64, V_BYTES = A2_BKV * DV * 2, STAGE_BYTES = K_BYTES + V_BYTES;
     constexpr uint32_t QT_COLS = 64 + 32 + DV;                 // tensor-memory columns of one query tile: S | P | O
     constexpr uint32_t TMEM_COLS = (DV == 32) ? 256 : 512;
@@ -78,8 +78,8 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     __shared__ A2Bars bars;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.x * (2 * A2_BQ), h = blockIdx.y, b = blockIdx.z;
-    const bool has_b = q0 + A2_BQ < N;                          // the second query tile holds at least one real row
+    const int q0 = blockIdx.x * (q_tiles * A2_BQ), h = blockIdx.y, b = blockIdx.z;
+    const bool has_b = q_tiles == 2 && q0 + A2_BQ < N;          // the second query tile is in use and holds at least one real row
     const int T = (N + A2_BKV - 1) / A2_BKV;
 
     if (tid == 0) {
@@ -311,6 +311,14 @@ extern "C" int ym_set_attention2_poly(int every) {
     return old;
 }
 
+// Query tiles per CTA: 0 = by wave fit (default), 1 / 2 = forced (tests exercise both code paths on small grids).
+static int g_attention2_qtiles = 0;
+extern "C" int ym_set_attention2_qtiles(int n) {
+    const int old = g_attention2_qtiles;
+    if (n >= 0 && n <= 2) g_attention2_qtiles = n;
+    return old;
+}
+
 extern "C" int ym_attention_fwd_tc2_supported(int heads, int head_stride, int ld) {
     // tensor-map strides are multiples of 16 bytes; a single head needs no head stride
     return a2_encode() != nullptr && ld % 8 == 0 && (heads == 1 || head_stride % 8 == 0);
@@ -336,14 +344,28 @@ extern "C" int ym_attention_fwd_tc2(const void* qkv, int ld, int batch, int N, i
         return YM_ERR_CUDA;
     }
     const float sl2 = scale * 1.4426950408889634f;
-    dim3 grid((N + 2 * A2_BQ - 1) / (2 * A2_BQ), heads, batch);
+    // Two query tiles per CTA halve the K / V traffic, but on a small grid the second wave of long CTAs is mostly empty (P4: 448 CTAs on
+    // 296 slots = two waves of 2-tile CTAs against three of 1-tile CTAs): below two waves the tile count per CTA follows the wave fit.
+    static int slots = 0;
+    if (!slots) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        slots = 2 * (sms > 0 ? sms : 148);
+    }
+    const long long ctas2 = (long long)((N + 2 * A2_BQ - 1) / (2 * A2_BQ)) * heads * batch;
+    const long long ctas1 = (long long)((N + A2_BQ - 1) / A2_BQ) * heads * batch;
+    int q_tiles = 2;
+    if (d_v == 32 && ctas2 < 2LL * slots && (ctas1 + slots - 1) / slots < 2 * ((ctas2 + slots - 1) / slots)) q_tiles = 1;
+    if (g_attention2_qtiles) q_tiles = g_attention2_qtiles;
+    dim3 grid((N + q_tiles * A2_BQ - 1) / (q_tiles * A2_BQ), heads, batch);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)2 * A2_BQ * 64 + A2_STAGES * (A2_BKV * 64 + A2_BKV * d_v * 2) + 1024;
     cudaError_t e = cudaSuccess;
 #define A2_LAUNCH(DV_, POLY_)                                                                                                        \
     do {                                                                                                                             \
         e = cudaFuncSetAttribute(tc_attention2_kernel<DV_, POLY_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-        if (e == cudaSuccess) e = launch_pdl(tc_attention2_kernel<DV_, POLY_>, grid, A2_THREADS, smem, st, mq, mk, mv, N, sl2, (__half*)out, ldo); \
+        if (e == cudaSuccess) e = launch_pdl(tc_attention2_kernel<DV_, POLY_>, grid, A2_THREADS, smem, st, mq, mk, mv, N, sl2, (__half*)out, ldo, q_tiles); \
     } while (0)
     const int poly = ym_attention2_poly();
     if (d_v == 32) {

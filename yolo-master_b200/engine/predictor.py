@@ -31,6 +31,12 @@ class DetectionPredictor:
     def __init__(self, model, imgsz=640, conf: float = 0.25, iou: float = 0.7, max_det: int = 300, classes=None,
                  agnostic_nms: bool = False, rect: bool = False, half=None, cluster: bool = False, sigma: float = 0.1, device=None):
         self.model = model
+        end2end = bool(getattr(model, "end2end", False))
+        if (classes is not None or agnostic_nms) and not end2end:
+            # `non_max_suppression` would only refuse after the letterbox and the forward have run: fail at construction instead
+            raise NotImplementedError("DetectionPredictor: classes= / agnostic_nms= are not on the B200 NMS path (end2end heads filter classes)")
+        if not 1 <= int(max_det) <= 512:
+            raise ValueError(f"DetectionPredictor: max_det must be in 1..512 (the NMS kernels keep a 512-entry survivor table), got {max_det}")
         self.imgsz = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
         self.conf, self.iou, self.max_det = conf, iou, max_det
         self.classes, self.agnostic_nms, self.rect = classes, agnostic_nms, rect

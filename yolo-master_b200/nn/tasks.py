@@ -47,14 +47,18 @@ def yaml_model_load(path):
     if not os.path.exists(path):
         if os.path.exists(os.path.join(_CFG_ROOT, path)):          # 'master/v0_10/det/yolo-master-n.yaml'
             path = os.path.join(_CFG_ROOT, path)
-        else:                                                     # bare name: first match of a sorted walk (v0 before v0_10)
+        else:                                                     # bare name: must be unique in the tree (the reference's check_yaml raises too)
+            hits = []
             for root, dirs, files in os.walk(_CFG_ROOT):
                 dirs.sort()
                 if os.path.basename(path) in files:
-                    path = os.path.join(root, os.path.basename(path))
-                    break
-            else:
+                    hits.append(os.path.join(root, os.path.basename(path)))
+            if not hits:
                 raise FileNotFoundError(path)
+            if len(hits) > 1:
+                rel = [os.path.relpath(h, _CFG_ROOT) for h in hits]
+                raise FileNotFoundError(f"Multiple files match '{path}', specify the path below cfg/models: {rel}")
+            path = hits[0]
     with open(path) as f:
         d = yaml.safe_load(f)
     d["yaml_file"] = path

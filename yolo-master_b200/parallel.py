@@ -23,9 +23,16 @@ def broadcast_module_state(module: torch.nn.Module, src: int = 0) -> int:
     n = 0
     if not is_dist():
         return n
-    for t in list(module.parameters()) + list(module.buffers()):
-        dist.broadcast(t.data, src=src)
-        n += 1
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src)
+            t.add_(0)        # an in-place op on the tensor itself bumps `_version`: `.data` writes do not, and the weight-pack caches of
+            n += 1           # the modules (PackCache / cached_f32 / cached_pack) key on (data_ptr, _version, device)
+    for m in module.modules():      # belt and braces: drop derived packs and captured graphs built before the broadcast
+        for k in ("_ym_pack", "_ym_packs", "_ym_f32"):
+            m.__dict__.pop(k, None)
+        if isinstance(m.__dict__.get("_graphs"), dict):
+            m.__dict__["_graphs"].clear()
     return n
 
 
