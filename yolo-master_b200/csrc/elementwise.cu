@@ -113,30 +113,35 @@ __global__ void __launch_bounds__(256) stem_conv_tc_kernel(const TIn* __restrict
     const int b = blockIdx.y;
     const int oy0 = (blockIdx.x / tiles_x) * TH, ox0 = (blockIdx.x % tiles_x) * TW;
     const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
-    // patch load: 26 elements per thread in two batches of 13 - all loads of a batch are issued before the first shared-memory store, so a
-    // CTA has ~3.3 K loads in flight instead of one per thread (the one-at-a-time loop ran the whole kernel at load latency: 191 us)
-    constexpr int TOT = 3 * IH * IW, PER = (TOT + 255) / 256, BATCH = (PER + 1) / 2;
+    // patch load: the 3 x 17 (channel, row) lines of 130 pixels are dealt to the 8 warps, a lane takes pixels lane, lane + 32, ... of its
+    // lines; ALL loads of a thread (<= 35) are issued before the first shared-memory store, with adds as the only index arithmetic
+    // (a one-element-at-a-time loop ran the kernel at load latency, and a flat index with two divisions per element at integer-ALU rate)
+    constexpr int LINES = 3 * IH, LPW = (LINES + 7) / 8, CPL = (IW + 31) / 32;
+    __half vals[LPW][CPL];
 #pragma unroll
-    for (int j0 = 0; j0 < PER; j0 += BATCH) {
-        __half vals[BATCH];
+    for (int li = 0; li < LPW; ++li) {
+        const int line = warp + 8 * li;
+        const int ci = line / IH, ry = line - ci * IH;
+        const int iy = iy0 + ry;
+        const bool row_ok = line < LINES && ci < Cin && iy >= 0 && iy < H;
+        const TIn* src = img + (((long long)b * Cin + (row_ok ? ci : 0)) * H + (row_ok ? iy : 0)) * W;
 #pragma unroll
-        for (int j = 0; j < BATCH; ++j) {
-            const int i = tid + 256 * (j0 + j);
-            const int ci = i / (IH * IW), rem = i - ci * (IH * IW);
-            const int ry = rem / IW, rx = rem - ry * IW;
-            const int iy = iy0 + ry, ix = ix0 + rx;
+        for (int k = 0; k < CPL; ++k) {
+            const int rx = lane + 32 * k, ix = ix0 + rx;
             __half v = __float2half_rn(0.f);
-            if (j0 + j < PER && i < TOT && ci < Cin && iy >= 0 && iy < H && ix >= 0 && ix < W)
-                v = stem_to_half<TIn>(img[(((long long)b * Cin + ci) * H + iy) * W + ix]);
-            vals[j] = v;
+            if (row_ok && rx < IW && ix >= 0 && ix < W) v = stem_to_half<TIn>(src[ix]);
+            vals[li][k] = v;
         }
+    }
 #pragma unroll
-        for (int j = 0; j < BATCH; ++j) {
-            const int i = tid + 256 * (j0 + j);
-            if (j0 + j < PER && i < TOT) {
-                const int ci = i / (IH * IW), rem = i - ci * (IH * IW);
-                const int ry = rem / IW, rx = rem - ry * IW;
-                sx[ci][ry][rx] = vals[j];
+    for (int li = 0; li < LPW; ++li) {
+        const int line = warp + 8 * li;
+        if (line < LINES) {
+            const int ci = line / IH, ry = line - ci * IH;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const int rx = lane + 32 * k;
+                if (rx < IW) sx[ci][ry][rx] = vals[li][k];
             }
         }
     }

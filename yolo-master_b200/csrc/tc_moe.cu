@@ -73,7 +73,7 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     constexpr uint32_t TMEM_COLS = (STAGE == 1) ? (HID <= 128 ? 128 : 256) : (HID <= 128 ? 256 : 512);
     constexpr int NS = (STAGE == 1 ? HID : C) / 8 * 2;   // floats of partial statistics per thread / per strip
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     unsigned char* sX = smem;                          // [2][KC1][128 rows x 128 B]
     unsigned char* sW1 = sX + 2 * X_BYTES;             // [KC1][HID rows x 128 B]
     unsigned char* sW2 = sW1 + W1_BYTES;               // [KC2][C rows x 128 B]           (pass 2)
@@ -205,12 +205,13 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     } else {
                         uint32_t pk[16];
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            const float2 r = __half22float2(__floats2half2_rn(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])));
-                            const int c = cb + 2 * q;
-                            const float a0 = silu_f(fmaf(r.x, sAff[c], sAff[HID + c]));
-                            const float a1 = silu_f(fmaf(r.y, sAff[c + 1], sAff[HID + c + 1]));
-                            pk[q] = pack_half2(a0, a1);
+                        for (int q4 = 0; q4 < 8; ++q4) {          // four channels per step: one 16-byte broadcast read each of scale / shift
+                            const float4 sc4 = *reinterpret_cast<const float4*>(sAff + cb + 4 * q4);
+                            const float4 sh4 = *reinterpret_cast<const float4*>(sAff + HID + cb + 4 * q4);
+                            const float2 r0 = __half22float2(__floats2half2_rn(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1])));
+                            const float2 r1 = __half22float2(__floats2half2_rn(__uint_as_float(v[4 * q4 + 2]), __uint_as_float(v[4 * q4 + 3])));
+                            pk[2 * q4] = pack_half2(silu_f(fmaf(r0.x, sc4.x, sh4.x)), silu_f(fmaf(r0.y, sc4.y, sh4.y)));
+                            pk[2 * q4 + 1] = pack_half2(silu_f(fmaf(r1.x, sc4.z, sh4.z)), silu_f(fmaf(r1.y, sc4.w, sh4.w)));
                         }
                         tc::tmem_st16(t_a + lane_sel + cb / 2, pk);
                     }
@@ -247,15 +248,15 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                                 part[2 * sl] += sm;
                                 part[2 * sl + 1] += q2;
                             }
-                            *reinterpret_cast<Half8*>(stg + lane * 64 + ((c8 ^ ((lane >> 1) & 3)) << 4)) = hv;
+                            *reinterpret_cast<uint4*>(stg + lane * 64 + ((c8 ^ ((lane >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(&hv);
                         }
                         __syncwarp();
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const int idx = k * 32 + lane, rr = idx >> 2, ch = idx & 3;
                             if (tile_row0 + rr < p.HW)
-                                *reinterpret_cast<Half8*>(p.out + ((long long)prob * p.HW + tile_row0 + rr) * C + half * H2 + c0 + ch * 8) =
-                                    *reinterpret_cast<const Half8*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+                                *reinterpret_cast<uint4*>(p.out + ((long long)prob * p.HW + tile_row0 + rr) * C + half * H2 + c0 + ch * 8) =
+                                    *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
                         }
                         __syncwarp();
                     }
@@ -310,7 +311,7 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     constexpr int X_BYTES = MF_BM * C * 2, W_BYTES = C * C * 2;
     constexpr uint32_t TMEM_COLS = 2 * C;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
     unsigned char* sX = smem;                          // [2][KC][128 rows x 128 B]
     unsigned char* sW = sX + 2 * X_BYTES;              // [KC][C rows x 128 B]
     float* sAff = reinterpret_cast<float*>(sW + W_BYTES);   // bias [C] | per rank j: scale [C], shift [C]   (topk <= 2)
@@ -406,11 +407,12 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(sAff + cb + c4 * 4);
                         float4 f;
-                        f.x = silu_f(__uint_as_float(v[c4 * 4 + 0]) + sAff[cb + c4 * 4 + 0]);
-                        f.y = silu_f(__uint_as_float(v[c4 * 4 + 1]) + sAff[cb + c4 * 4 + 1]);
-                        f.z = silu_f(__uint_as_float(v[c4 * 4 + 2]) + sAff[cb + c4 * 4 + 2]);
-                        f.w = silu_f(__uint_as_float(v[c4 * 4 + 3]) + sAff[cb + c4 * 4 + 3]);
+                        f.x = silu_f(__uint_as_float(v[c4 * 4 + 0]) + b4.x);
+                        f.y = silu_f(__uint_as_float(v[c4 * 4 + 1]) + b4.y);
+                        f.z = silu_f(__uint_as_float(v[c4 * 4 + 2]) + b4.z);
+                        f.w = silu_f(__uint_as_float(v[c4 * 4 + 3]) + b4.w);
                         *reinterpret_cast<float4*>(stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) = f;
                     }
                     __syncwarp();
@@ -436,7 +438,8 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 if (j < p.topk) {
-                                    const Half8 ov = *reinterpret_cast<const Half8*>(p.o + (((long long)img * p.topk + j) * p.HW + row) * C + cb + cg * 8);
+                                    const uint4 ovq = *reinterpret_cast<const uint4*>(p.o + (((long long)img * p.topk + j) * p.HW + row) * C + cb + cg * 8);
+                                    const Half8 ov = *reinterpret_cast<const Half8*>(&ovq);
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) {
                                         const float2 f = __half22float2(ov.v[q]);
@@ -447,7 +450,8 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                             }
                             Half8 hv;
                             if (p.add_residual) {
-                                const Half8 rv = *reinterpret_cast<const Half8*>(p.x + ((long long)img * p.HW + row) * p.ldx + cb + cg * 8);
+                                const uint4 rvq = *reinterpret_cast<const uint4*>(p.x + ((long long)img * p.HW + row) * p.ldx + cb + cg * 8);
+                                const Half8 rv = *reinterpret_cast<const Half8*>(&rvq);
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     const float2 rf = __half22float2(rv.v[q]);
@@ -457,7 +461,7 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) hv.v[q] = __floats2half2_rn(acc[2 * q], acc[2 * q + 1]);
                             }
-                            *reinterpret_cast<Half8*>(p.out + ((long long)img * p.HW + row) * p.ldo + cb + cg * 8) = hv;
+                            *reinterpret_cast<uint4*>(p.out + ((long long)img * p.HW + row) * p.ldo + cb + cg * 8) = *reinterpret_cast<const uint4*>(&hv);
                         }
                     }
                     __syncwarp();
@@ -525,9 +529,14 @@ static int mf_tiles_per_strip(long long units, int mtiles) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         slots = 2 * (sms > 0 ? sms : 148);
     }
-    for (int tps = 1; tps < mtiles; ++tps)
-        if (units * ((mtiles + tps - 1) / tps) <= slots) return tps;
-    return mtiles;
+    int best = 1;
+    long long best_cost = -1;
+    for (int tps = 1; tps <= mtiles; ++tps) {          // makespan ~ waves x (tiles per CTA + ~one tile of CTA prologue); ties -> more CTAs
+        const long long ctas = units * ((mtiles + tps - 1) / tps);
+        const long long cost = ((ctas + slots - 1) / slots) * (tps + 1);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = tps; }
+    }
+    return best;
 }
 
 extern "C" int ym_moe_ffn_strips(int HW, int P) {

@@ -141,8 +141,20 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 }
 #endif
 
+// Eight fp16 values = one 16-byte memory transaction.  __half2 has user-provided copy operations, so the implicit copy of this struct is
+// FOUR member copies: every `*reinterpret_cast<Half8*>(p) = h` / `h = *reinterpret_cast<const Half8*>(p)` in the code base compiled
+// to four 32-bit LDG / STG (cuobjdump: 1865 LDG.E, no LDG.E.128 in elementwise.o) - a quarter of the bytes per memory instruction and
+// four times the LSU work in every bandwidth-bound kernel.  The explicit copy operations below move the 16 bytes as one uint4.
 struct alignas(16) Half8 {
     __half2 v[4];
+#ifndef YM_HOST_EMU
+    __device__ __forceinline__ Half8() {}
+    __device__ __forceinline__ Half8(const Half8& o) { *reinterpret_cast<uint4*>(this) = *reinterpret_cast<const uint4*>(&o); }
+    __device__ __forceinline__ Half8& operator=(const Half8& o) {
+        *reinterpret_cast<uint4*>(this) = *reinterpret_cast<const uint4*>(&o);
+        return *this;
+    }
+#endif
 };
 
 }  // namespace ym
