@@ -86,13 +86,17 @@ int ym_attention_fwd_tc2(const void* qkv, int ld, int batch, int N, int heads, i
                          int v_off, int d_qk, int d_v, float scale, void* out, int ldo, void* stream);
 int ym_attention_fwd_tc2_supported(int heads, int head_stride, int ld);
 /* ym_attention_fwd_tc2, d_v = 32: every `every`-th exponential of a score row is computed on the FMA pipe (degree-3 polynomial,
- * |rel err| < 7.5e-5) instead of the MUFU, whose 16 ex2 / clk / SM is the kernel's ceiling (0 = MUFU only; 2 / 3 / 4 / 6).  Returns the
+ * |rel err| < 7.5e-5) instead of the MUFU, whose 16 ex2 / clk / SM is the kernel's ceiling (0 = MUFU only; 4).  Returns the
  * previous setting; ym_attention2_poly reads it. */
 int ym_set_attention2_poly(int every);
 /* Query tiles (128 rows) per CTA of ym_attention_fwd_tc2: 0 = chosen by wave fit (two tiles share every K / V tile; one tile per CTA when
  * the grid is below two waves and splits better), 1 / 2 = forced.  Results are bit-identical either way.  Returns the previous setting. */
 int ym_set_attention2_qtiles(int n);
 int ym_attention2_poly(void);
+/* Scheduling variants of ym_attention_fwd_tc2 (bit 0: row maximum as four independent chains, bit 1: K / V ring refilled three key tiles
+ * behind the consumers, bit 2: issuing threads sleep between barrier polls).  Results are bit-identical for every value.  Returns the
+ * previous setting. */
+int ym_set_attention2_variant(int bits);
 /* Kernel behind ym_attention_fwd: 2 = ym_attention_fwd_tc2 (default), 1 = ym_attention_fwd_tc, 0 = mma.sync kernel.  Returns the
  * previous setting (A/B baselines for tests and profiles; nothing in the package changes it). */
 int ym_set_attention_impl(int impl);

@@ -22,7 +22,7 @@ def models():
     out = {}
     for name, cfg in MODELS.items():
         sd = synth_sd_from_keys(0, name)
-        m = DetectionModel(os.path.basename(cfg))
+        m = DetectionModel(cfg)
         missing, unexpected = m.load_state_dict(sd, strict=True)
         out[name] = (m.to(DEV).eval(), sd, O.parse_spec(yaml_of(cfg)))
     return out

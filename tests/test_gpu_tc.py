@@ -132,8 +132,9 @@ def test_tc_attention2_strict(N, heads, dv, batch):
     g = torch.Generator().manual_seed(N + dv)
     qkv = torch.randn((batch, N, 1, heads * hs), generator=g).half()
     outs = []
-    for qt in (2, 1):
+    for qt, variant in ((2, None), (1, None), (2, 0), (2, 7)):
         prev = _lib.load().ym_set_attention2_qtiles(qt)
+        prev_var = _lib.load().ym_set_attention2_variant(variant) if variant is not None else None
         try:
             out = torch.full((batch, N, 1, heads * dv), float("nan"), dtype=torch.float16, device=DEV)
             _lib.check(_lib.load().ym_attention_fwd_tc2(qkv.to(DEV).data_ptr(), heads * hs, batch, N, heads, hs, 0, 32, 64, 32, dv,
@@ -141,9 +142,11 @@ def test_tc_attention2_strict(N, heads, dv, batch):
             torch.cuda.synchronize()
         finally:
             _lib.load().ym_set_attention2_qtiles(prev)
-        assert_close(out, _attn_ref(qkv, batch, N, heads, hs, dv), what=f"tc attention2 N={N} dv={dv} q_tiles={qt}")
+            if prev_var is not None:
+                _lib.load().ym_set_attention2_variant(prev_var)
+        assert_close(out, _attn_ref(qkv, batch, N, heads, hs, dv), what=f"tc attention2 N={N} dv={dv} q_tiles={qt} variant={variant}")
         outs.append(out)
-    assert torch.equal(outs[0], outs[1]), "one / two query tiles per CTA must agree bit for bit"
+    assert all(torch.equal(outs[0], o) for o in outs[1:]), "query tiles per CTA / scheduling variants must agree bit for bit"
 
 
 def test_tc_attention2_large_logits_lazy_rescale_and_impl_agreement():

@@ -29,6 +29,7 @@ SIGNATURES = {
     "ym_attention_fwd_tc2_supported": (ci, [ci, ci, ci]),
     "ym_set_attention2_poly": (ci, [ci]),
     "ym_set_attention2_qtiles": (ci, [ci]),
+    "ym_set_attention2_variant": (ci, [ci]),
     "ym_attention2_poly": (ci, []),
     "ym_set_attention_impl": (ci, [ci]),
     "ym_moe_ffn_supported": (ci, [ci, ci, ci]),

@@ -31,20 +31,31 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const TIn* __restrict__ 
                                                         const __grid_constant__ StemWeights<COUT> sw,
                                                         __half* __restrict__ out, int ldo, int Ho, int Wo, int tiles_x) {
     pdl_prologue();
-    // CTA = 32 x 8 output pixels; the (65 x 17) x Cin input patch is staged in shared memory with coalesced row reads.
+    // CTA = 32 x 8 output pixels; the (65 x 17) x Cin input patch is staged in shared memory one image line per warp pass (lane =
+    // column: coalesced, no per-element div / mod - the flat-index loop it replaces spent more instructions on addressing than the
+    // 432 FFMAs), even and odd columns in separate planes so that the stride-2 reads of the taps are bank-conflict free.
     constexpr int TW = 32, TH = 8, IW = 2 * TW + 1, IH = 2 * TH + 1;
-    __shared__ float sx[4][IH][IW + 1];
-    const int tid = threadIdx.x;
+    __shared__ float se[4][IH][TW + 1 + 3];   // columns rx = 0, 2, ... 64  (taps kx = 0 and kx = 2)
+    __shared__ float so[4][IH][TW + 4];       // columns rx = 1, 3, ... 63  (tap kx = 1)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
     const int oy0 = (blockIdx.x / tiles_x) * TH, ox0 = (blockIdx.x % tiles_x) * TW;
     const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
-    for (int i = tid; i < Cin * IH * IW; i += 256) {
-        const int ci = i / (IH * IW), rem = i % (IH * IW);
-        const int ry = rem / IW, rx = rem % IW;
-        const int iy = iy0 + ry, ix = ix0 + rx;
-        float v = 0.f;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = load_px<TIn>(img + (((long long)b * Cin + ci) * H + iy) * W + ix);
-        sx[ci][ry][rx] = v;
+    for (int line = warp; line < Cin * IH; line += 8) {
+        const int ci = line / IH, ry = line - ci * IH;
+        const int iy = iy0 + ry;
+        const bool row_ok = iy >= 0 && iy < H;
+        const TIn* src = img + (((long long)b * Cin + ci) * H + (row_ok ? iy : 0)) * W;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int rx = lane + 32 * j;
+            if (rx < IW) {
+                const int ix = ix0 + rx;
+                const float v = (row_ok && ix >= 0 && ix < W) ? load_px<TIn>(src + ix) : 0.f;
+                if (rx & 1) so[ci][ry][rx >> 1] = v;
+                else se[ci][ry][rx >> 1] = v;
+            }
+        }
     }
     __syncthreads();
     const int lx = tid % TW, ly = tid / TW;
@@ -60,7 +71,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const TIn* __restrict__ 
             for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    const float v = sx[ci][2 * ly + ky][2 * lx + kx];
+                    const float v = (kx == 1) ? so[ci][2 * ly + ky][lx] : se[ci][2 * ly + ky][lx + (kx >> 1)];
 #pragma unroll
                     for (int c = 0; c < COUT; ++c) acc[c] = fmaf(v, sw.w[((ci * 3 + ky) * 3 + kx) * COUT + c], acc[c]);
                 }
@@ -441,31 +452,40 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(__half* __restrict__ buf
 // ---------------------------------------------------------------------------------------------
 // out[..., 0:Ca] = a (optionally nearest-upsampled by `up`), out[..., Ca:Ca+Cb] = b     (nn.Upsample + Concat)
 // ---------------------------------------------------------------------------------------------
+// Four 16-byte items per thread, all four loads issued before the first store (one item per thread with 64-bit div / mod moved 1.8 TB/s:
+// profiles/r02_launch_roofline.txt, r02g); 32-bit index arithmetic (the host checks the item count fits).
 __global__ void __launch_bounds__(256) concat2_kernel(const __half* __restrict__ a, int lda, int Ca, int up,
                                                       const __half* __restrict__ bsrc, int ldb, int Cb,
                                                       __half* __restrict__ out, int ldo, int B, int H, int W) {
     pdl_prologue();
-    const int chunks = (Ca + Cb) >> 3;
-    const long long total = (long long)B * H * W * chunks;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int ch = (int)(idx % chunks);
-    const long long pix = idx / chunks;
-    const int c = ch * 8;
-    Half8 v;
-    if (c < Ca) {
-        long long sp = pix;
-        if (up > 1) {
-            const int ox = (int)(pix % W);
-            const int oy = (int)((pix / W) % H);
-            const int b = (int)(pix / ((long long)W * H));
-            sp = ((long long)b * (H / up) + oy / up) * (W / up) + ox / up;
+    const unsigned chunks = (unsigned)(Ca + Cb) >> 3, ca_chunks = (unsigned)Ca >> 3;
+    const unsigned total = (unsigned)B * H * W * chunks;
+    const unsigned base = blockIdx.x * 1024u + threadIdx.x;
+    uint4 v[4];
+    unsigned pix[4], ch[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned idx = base + j * 256u;
+        v[j] = make_uint4(0u, 0u, 0u, 0u);
+        pix[j] = idx / chunks;
+        ch[j] = idx - pix[j] * chunks;
+        if (idx < total) {
+            if (ch[j] < ca_chunks) {
+                unsigned sp = pix[j];
+                if (up > 1) {
+                    const unsigned row = pix[j] / (unsigned)W, ox = pix[j] - row * (unsigned)W;       // row = b * H + oy
+                    const unsigned b = row / (unsigned)H, oy = row - b * (unsigned)H;
+                    sp = (b * (unsigned)(H / up) + oy / (unsigned)up) * (unsigned)(W / up) + ox / (unsigned)up;
+                }
+                v[j] = *reinterpret_cast<const uint4*>(a + (long long)sp * lda + ch[j] * 8);
+            } else {
+                v[j] = *reinterpret_cast<const uint4*>(bsrc + (long long)pix[j] * ldb + (ch[j] - ca_chunks) * 8);
+            }
         }
-        v = *reinterpret_cast<const Half8*>(a + sp * lda + c);
-    } else {
-        v = *reinterpret_cast<const Half8*>(bsrc + pix * ldb + (c - Ca));
     }
-    *reinterpret_cast<Half8*>(out + pix * ldo + c) = v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (base + j * 256u < total) *reinterpret_cast<uint4*>(out + (long long)pix[j] * ldo + ch[j] * 8) = v[j];
 }
 
 }  // namespace ym
@@ -523,7 +543,7 @@ using namespace ym;
 static inline int nblocks(long long total, int bs) { return (int)((total + bs - 1) / bs); }
 
 // 1 = tensor-core stem (mma.sync implicit GEMM, fp16 operands) where Cin <= 3 and Cout = 16; 0 = fp32 FFMA kernel (A/B baseline)
-static int g_stem_impl = 1;
+static int g_stem_impl = 0;   // 0 = FFMA kernel (181 us at bs32 / 640, r02g), 1 = mma.sync kernel (226 us: shared-memory queue bound)
 extern "C" int ym_set_stem_impl(int impl) {
     const int old = g_stem_impl;
     if (impl == 0 || impl == 1) g_stem_impl = impl;
@@ -701,7 +721,8 @@ extern "C" int ym_concat2_nhwc(const void* a, int lda, int Ca, int up, const voi
     YM_CHECK_ARG(up >= 1 && H % up == 0 && W % up == 0, "ym_concat2_nhwc: bad upsample factor");
     if (B == 0) return YM_OK;
     const long long total = (long long)B * H * W * ((Ca + Cb) / 8);
-    launch_pdl(concat2_kernel, nblocks(total, 256), 256, 0, (cudaStream_t)stream, (const __half*)a, lda, Ca, up, (const __half*)b,
+    YM_CHECK_ARG(total < (1LL << 31), "ym_concat2_nhwc: %lld 16-byte items exceed the 32-bit index range", total);
+    launch_pdl(concat2_kernel, nblocks(total, 1024), 256, 0, (cudaStream_t)stream, (const __half*)a, lda, Ca, up, (const __half*)b,
                                                                          ldb, Cb, (__half*)out, ldo, B, H, W);
     YM_CHECK_LAUNCH("concat2");
     return YM_OK;

@@ -27,7 +27,7 @@
 
 namespace ym {
 
-constexpr int A2_BQ = 128, A2_BKV = 64, A2_STAGES = 6, A2_THREADS = 320;   // 8 softmax warps + 2 issuer warps (one per query tile)
+constexpr int A2_BQ = 128, A2_BKV = 64, A2_STAGES = 8, A2_THREADS = 320;   // 8 softmax warps + 2 issuer warps (one per query tile)
 
 __device__ __forceinline__ float a2_exp2(float x) {
     float y;
@@ -64,10 +64,10 @@ struct A2Bars {
     uint32_t tmem_slot;
 };
 
-template <int DV, int POLY>
+template <int DV, int POLY, int VAR>
 __global__ void __launch_bounds__(A2_THREADS, (DV == 32) ? 2 : 1)
 tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                     const __grid_constant__ CUtensorMap map_v, int N, float scale_log2, __half* __restrict__ out, int ldo, int q_tiles) {
+                     const __grid_constant__ CUtensorMap map_v, int N, float scale_log2, __half* __restrict__ out, int ldo, int q_tiles, int var_flags) {
     constexpr int Q_BYTES = A2_BQ * 64, K_BYTES = A2_BKV * 64, V_BYTES = A2_BKV * DV * 2, STAGE_BYTES = K_BYTES + V_BYTES;
     constexpr uint32_t QT_COLS = 64 + 32 + DV;                 // tensor-memory columns of one query tile: S | P | O
     constexpr uint32_t TMEM_COLS = (DV == 32) ? 256 : 512;
@@ -111,6 +111,12 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         // order locked them one key tile apart: tile A's next S was only issued when tile B finished - ~900 clk of s_full polling per
         // key tile in profiles/r02_attention2_ncu.txt, first capture.)
         const int q = warp - 8;
+        const int refill_lag = (var_flags & 2) ? 3 : 1;
+        const bool relax = (var_flags & 4) != 0;
+        auto iwait = [&](uint64_t* bar, uint32_t parity) {
+            if (relax) tc::mbar_wait_sleep(bar, parity, 32);
+            else tc::mbar_wait(bar, parity);
+        };
         if (lane == 0 && (q == 0 || has_b)) {
             const uint32_t idesc_qk = tc::make_idesc_f16(A2_BQ, A2_BKV, 0);
             const uint32_t idesc_pv = tc::make_idesc_f16(A2_BQ, DV, 1);      // V is MN-major (d_v contiguous)
@@ -144,23 +150,25 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 tc::mma_commit(&bars.pv_done[q]);
             };
 
-            tc::mbar_wait(&bars.q_full, 0);
-            tc::mbar_wait(&bars.kv_full[0], 0);
+            iwait(&bars.q_full, 0);
+            iwait(&bars.kv_full[0], 0);
             issue_qk(0);
             for (int t = 0; t < T; ++t) {
                 if (t + 1 < T) {
-                    tc::mbar_wait(&bars.kv_full[(t + 1) % A2_STAGES], ((t + 1) / A2_STAGES) & 1);
-                    tc::mbar_wait(&bars.s_free[q], t & 1);                   // every softmax warp of this tile holds S(t) in registers
+                    iwait(&bars.kv_full[(t + 1) % A2_STAGES], ((t + 1) / A2_STAGES) & 1);
+                    iwait(&bars.s_free[q], t & 1);                   // every softmax warp of this tile holds S(t) in registers
                     tc::fence_after_sync();
                     issue_qk(t + 1);
                 }
-                tc::mbar_wait(&bars.p_full[q], t & 1);
+                iwait(&bars.p_full[q], t & 1);
                 tc::fence_after_sync();
                 issue_pv(t);
                 tc::mma_commit(&bars.kv_empty[t % A2_STAGES]);               // this tile's MMAs on stage t%STAGES have been issued (one arrive per tile)
-                if (q == 0 && t >= 1 && t - 1 + A2_STAGES < T) {             // refill the stage of key tile t-1 once BOTH query tiles retired it
-                    tc::mbar_wait(&bars.kv_empty[(t - 1) % A2_STAGES], ((t - 1) / A2_STAGES) & 1);
-                    load_kv(t - 1 + A2_STAGES);
+                // refill the stage of key tile t-lag once BOTH query tiles retired it.  lag = 1 keeps the ring full but parks tile A's issuer
+                // behind tile B's PV(t-1); lag = 3 lets the two tiles drift three key tiles apart before either issuer waits on the other.
+                if (q == 0 && t >= refill_lag && t - refill_lag + A2_STAGES < T) {
+                    iwait(&bars.kv_empty[(t - refill_lag) % A2_STAGES], ((t - refill_lag) / A2_STAGES) & 1);
+                    load_kv(t - refill_lag + A2_STAGES);
                 }
             }
         }
@@ -202,9 +210,19 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 for (int i = 0; i < 64; ++i)
                     if (kv0 + i >= N) sv[i] = 0xff800000u;   // -inf
             }
-            float mx = -INFINITY;
+            float mx;
+            if (VAR & 1) {                        // four independent chains: 8 dependent FMNMX3 instead of 32 before the first exponential can issue
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+                for (int i = 0; i < 16; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) m4[c] = fmaxf(m4[c], __uint_as_float(sv[c * 16 + i]));
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            } else {
+                mx = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            }
             const float m_tile = mx * scale_log2;
             const bool grow = m_tile > m_used + 8.f;         // also true on the first tile (m_used = -inf)
             float alpha = 1.f;
@@ -302,12 +320,21 @@ static bool a2_map(CUtensorMap* m, const __half* base, int d, int N, int heads, 
 
 using namespace ym;
 
-// Every n-th softmax exponential of the d_v = 32 kernel on the FMA pipe instead of the MUFU (0 = all on the MUFU; 2 / 3 / 4 / 6).
+// Every n-th softmax exponential of the d_v = 32 kernel on the FMA pipe instead of the MUFU (0 = all on the MUFU; 4).
 static int g_attention2_poly = 0;
 extern "C" int ym_attention2_poly(void) { return g_attention2_poly; }
 extern "C" int ym_set_attention2_poly(int every) {
     const int old = g_attention2_poly;
-    if (every == 0 || every == 2 || every == 3 || every == 4 || every == 6) g_attention2_poly = every;
+    if (every == 0 || every == 4) g_attention2_poly = every;
+    return old;
+}
+
+// Kernel variant bits (measurement knob): bit 0 = row maximum as four independent chains, bit 1 = K / V ring refilled three key tiles
+// behind the consumer instead of one, bit 2 = the issuing threads sleep between barrier polls.
+static int g_attention2_variant = 0;
+extern "C" int ym_set_attention2_variant(int bits) {
+    const int old = g_attention2_variant;
+    if (bits >= 0 && bits <= 7) g_attention2_variant = bits;
     return old;
 }
 
@@ -362,22 +389,18 @@ extern "C" int ym_attention_fwd_tc2(const void* qkv, int ld, int batch, int N, i
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)2 * A2_BQ * 64 + A2_STAGES * (A2_BKV * 64 + A2_BKV * d_v * 2) + 1024;
     cudaError_t e = cudaSuccess;
-#define A2_LAUNCH(DV_, POLY_)                                                                                                        \
+#define A2_LAUNCH(DV_, POLY_, VAR_)                                                                                                        \
     do {                                                                                                                             \
-        e = cudaFuncSetAttribute(tc_attention2_kernel<DV_, POLY_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-        if (e == cudaSuccess) e = launch_pdl(tc_attention2_kernel<DV_, POLY_>, grid, A2_THREADS, smem, st, mq, mk, mv, N, sl2, (__half*)out, ldo, q_tiles); \
+        e = cudaFuncSetAttribute(tc_attention2_kernel<DV_, POLY_, VAR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+        if (e == cudaSuccess) e = launch_pdl(tc_attention2_kernel<DV_, POLY_, VAR_>, grid, A2_THREADS, smem, st, mq, mk, mv, N, sl2, (__half*)out, ldo, q_tiles, lag); \
     } while (0)
     const int poly = ym_attention2_poly();
+    const int tree = g_attention2_variant & 1, lag = g_attention2_variant & 6;
     if (d_v == 32) {
-        switch (poly) {
-            case 2: A2_LAUNCH(32, 2); break;
-            case 3: A2_LAUNCH(32, 3); break;
-            case 4: A2_LAUNCH(32, 4); break;
-            case 6: A2_LAUNCH(32, 6); break;
-            default: A2_LAUNCH(32, 0); break;
-        }
+        if (poly == 4) { if (tree) A2_LAUNCH(32, 4, 1); else A2_LAUNCH(32, 4, 0); }
+        else { if (tree) A2_LAUNCH(32, 0, 1); else A2_LAUNCH(32, 0, 0); }
     } else {
-        A2_LAUNCH(64, 0);
+        if (tree) A2_LAUNCH(64, 0, 1); else A2_LAUNCH(64, 0, 0);
     }
 #undef A2_LAUNCH
     if (e != cudaSuccess) { ym_set_error("ym_attention_fwd_tc2: smem attr: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }

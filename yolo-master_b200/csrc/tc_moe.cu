@@ -63,7 +63,9 @@ struct MfBars {
 
 // STAGE 1: statistics of h only.  STAGE 2: the fused chain.
 template <int C, int HID, int STAGE>
-__global__ void __maxnreg__((HID <= 128) ? 112 : 224)
+// 9 warps are allocated as 10 (pairs): two CTAs per SM leave 65536 / (20 * 32) = 102 -> 96 registers per thread.  (__maxnreg__(112) fitted the
+// code without spills but silently halved the occupancy: 14 % warps active in profiles/r02_moe_ncu.txt, second capture.)
+__global__ void __launch_bounds__(MF_THREADS, (HID <= 128) ? 2 : 1)
 moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                const __grid_constant__ CUtensorMap map_w2, const MoeFfnParams p) {
     constexpr int KC1 = C / 64;                        // 64-wide k chunks of GEMM1 (K = C)
@@ -292,11 +294,11 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 // tile i+1 runs under the epilogue of tile i); the epilogue thread (= token row) adds the routed experts' GroupNorm-2-normalised outputs
 // (routing weight folded into scale2 / shift2 by ym_gn_finalize_tiles) and the residual, one rounding to fp16, one 128 / 256-byte row store.
 struct MoeCombineParams {
-    const __half* x;   int ldx;        // residual read (the GEMM operand comes through TMA)
-    const float* bias;                 // [C] folded BN bias of the shared expert
-    const __half* o;                   // [B*topk][HW][C]
-    const float* o_scale; const float* o_shift;   // [B*topk][C]
-    __half* out;       int ldo;
+    const __half* __restrict__ x;   int ldx;        // residual read (the GEMM operand comes through TMA)
+    const float* __restrict__ bias;                 // [C] folded BN bias of the shared expert
+    const __half* __restrict__ o;                   // [B*topk][HW][C]
+    const float* __restrict__ o_scale; const float* __restrict__ o_shift;   // [B*topk][C]
+    __half* __restrict__ out;       int ldo;
     int HW, mtiles, tiles_per_strip, topk, add_residual;
 };
 struct McBars {
@@ -305,7 +307,7 @@ struct McBars {
 };
 
 template <int C>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(MF_THREADS, (C <= 64) ? 2 : 1)   // C = 128 holds 131 KB of shared memory: one CTA per SM either way
 moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const MoeCombineParams p) {
     constexpr int KC = C / 64;
     constexpr int X_BYTES = MF_BM * C * 2, W_BYTES = C * C * 2;
@@ -427,8 +429,26 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                             }
                         }
                     }
+                    // all global reads of the four row groups first (12 independent 16-byte loads in flight per lane), then the arithmetic:
+                    // in program order every load sat behind the previous group's store and paid its full latency (60 % of the samples)
+                    #pragma unroll
+                    for (int kb = 0; kb < 4; kb += 2) {          // two row groups at a time: 6 loads in flight, 24 registers
+                    uint4 oq[2][2], xq[2];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k2 = 0; k2 < 2; ++k2) {
+                        const int k = kb + k2;
+                        const int row = tile_row0 + ((k * 32 + lane) >> 2);
+                        const bool ok = row < p.HW;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            oq[k2][j] = (ok && j < p.topk) ? *reinterpret_cast<const uint4*>(p.o + (((long long)img * p.topk + j) * p.HW + row) * C + cb + cg * 8)
+                                                          : make_uint4(0u, 0u, 0u, 0u);
+                        xq[k2] = (ok && p.add_residual) ? *reinterpret_cast<const uint4*>(p.x + ((long long)img * p.HW + row) * p.ldx + cb + cg * 8)
+                                                       : make_uint4(0u, 0u, 0u, 0u);
+                    }
+#pragma unroll
+                    for (int k2 = 0; k2 < 2; ++k2) {
+                        const int k = kb + k2;
                         const int rr = (k * 32 + lane) >> 2;
                         const int row = tile_row0 + rr;
                         if (row < p.HW) {
@@ -438,8 +458,7 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 if (j < p.topk) {
-                                    const uint4 ovq = *reinterpret_cast<const uint4*>(p.o + (((long long)img * p.topk + j) * p.HW + row) * C + cb + cg * 8);
-                                    const Half8 ov = *reinterpret_cast<const Half8*>(&ovq);
+                                    const Half8 ov = *reinterpret_cast<const Half8*>(&oq[k2][j]);
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) {
                                         const float2 f = __half22float2(ov.v[q]);
@@ -450,8 +469,7 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                             }
                             Half8 hv;
                             if (p.add_residual) {
-                                const uint4 rvq = *reinterpret_cast<const uint4*>(p.x + ((long long)img * p.HW + row) * p.ldx + cb + cg * 8);
-                                const Half8 rv = *reinterpret_cast<const Half8*>(&rvq);
+                                const Half8 rv = *reinterpret_cast<const Half8*>(&xq[k2]);
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     const float2 rf = __half22float2(rv.v[q]);
@@ -463,6 +481,7 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                             }
                             *reinterpret_cast<uint4*>(p.out + ((long long)img * p.HW + row) * p.ldo + cb + cg * 8) = *reinterpret_cast<const uint4*>(&hv);
                         }
+                    }
                     }
                     __syncwarp();
                 }
