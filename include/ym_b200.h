@@ -29,6 +29,9 @@ int ym_device_info(int* sm_major, int* sm_minor, int* sm_count, long long* l2_by
 int ym_conv2d_nhwc(const void* x, int ldx, int B, int H, int W, int Cin, const void* w, int Kpad, const float* bias,
                    int Cout, int KH, int KW, int stride, int pad, void* out, int ldo, int out_f32, const void* res,
                    int ldr, int act, void* stream);
+/* Kernel behind ym_conv2d_nhwc for 3x3 / pad 1 layers with Cin in {8, 16}, Cout in {8, 16, 32}, fp16 output: 1 = patch-staged kernel
+ * (csrc/small_conv.cu, default), 0 = the implicit GEMM every other shape takes.  Returns the previous setting. */
+int ym_set_small_conv_impl(int impl);
 
 /* model.0 stem: Conv(Cin<=4 -> Cout in {16,32,64}, k3 s2 p1) + bias + SiLU reading the NCHW image (conv.py:69-89).
  * in_dtype: 0 fp16, 1 fp32, 2 uint8 (x/255, engine/predictor.py:175).  out NHWC fp16.

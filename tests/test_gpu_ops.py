@@ -47,8 +47,9 @@ def _run(mod, x):
 @pytest.mark.parametrize("c1,c2,k,s,act", [
     (16, 32, 3, 2, True), (64, 64, 3, 2, True), (32, 32, 1, 1, True), (16, 8, 3, 1, True), (8, 16, 3, 1, True),
     (384, 128, 1, 1, True), (64, 192, 1, 1, False), (128, 256, 3, 2, True), (48, 64, 1, 1, True), (256, 80, 1, 1, True),
+    (16, 16, 3, 1, True), (16, 16, 3, 2, False), (8, 8, 3, 2, True), (8, 32, 3, 1, True), (16, 8, 3, 2, True), (8, 16, 3, 2, True),
 ])
-@pytest.mark.parametrize("hw", [(20, 20), (37, 23)])
+@pytest.mark.parametrize("hw", [(20, 20), (37, 23), (70, 41)])
 def test_conv(c1, c2, k, s, act, hw):
     m = M.Conv(c1, c2, k, s, act=act)
     sd = _prep(m, seed=c1 * 7 + c2)
@@ -61,9 +62,55 @@ def test_conv(c1, c2, k, s, act, hw):
     assert_close(y, O.conv_block(sd, "m", x.float(), s, 1, act), max_bad_frac=1e-4, what="vs fp32-weight oracle")
 
 
+@pytest.mark.parametrize("c1,c2,s", [(16, 32, 2), (16, 8, 1), (8, 16, 1), (16, 16, 1), (8, 8, 2), (16, 32, 1)])
+def test_small_conv_matches_implicit_gemm_and_adds_the_residual(c1, c2, s):
+    """The patch-staged 3x3 kernel behind ym_conv2d_nhwc (Cin 8 / 16) against the implicit-GEMM kernel it replaces, on a multi-tile
+    ragged image with and without the residual operand (the Bottleneck shortcut), and against the fp32 oracle."""
+    from yolo_master_b200 import _lib, ops
+    m = M.Conv(c1, c2, 3, s)
+    sd = _prep(m, seed=c1 + 3 * c2 + s)
+    x = _x(3, c1, 75, 133, seed=11).to(DEV).contiguous(memory_format=torch.channels_last)
+    outs = {}
+    for impl in (1, 0):
+        prev = _lib.load().ym_set_small_conv_impl(impl)
+        try:
+            with torch.no_grad():
+                outs[impl] = m(x)
+            torch.cuda.synchronize()
+        finally:
+            _lib.load().ym_set_small_conv_impl(prev)
+    ref = O.conv_block(sd, "m", x.float().cpu(), s, 1, True)
+    assert_close(outs[1], ref, what=f"small conv {c1}->{c2} s{s}")
+    assert float((outs[1].float() - outs[0].float()).abs().max()) <= 2e-3 * max(1.0, float(outs[0].float().abs().max()))
+    if c1 == c2 and s == 1:
+        b = M.Bottleneck(c1, c1, shortcut=True, e=0.5 if c1 == 16 else 1.0)
+        _prep(b, seed=5)
+        res = {}
+        for impl in (1, 0):
+            prev = _lib.load().ym_set_small_conv_impl(impl)
+            try:
+                with torch.no_grad():
+                    res[impl] = b(x)
+                torch.cuda.synchronize()
+            finally:
+                _lib.load().ym_set_small_conv_impl(prev)
+        assert float((res[1].float() - res[0].float()).abs().max()) <= 4e-3 * max(1.0, float(res[0].float().abs().max()))
+
+
+@pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.uint8])
-@pytest.mark.parametrize("hw", [(64, 64), (63, 65)])
-def test_stem_conv_reads_nchw_image(dtype, hw):
+@pytest.mark.parametrize("hw", [(64, 64), (63, 65), (200, 136)])
+def test_stem_conv_reads_nchw_image(dtype, hw, impl):
+    """Both stem kernels (0 = FFMA, 1 = mma.sync with split fp16 weights) on even, odd and multi-tile image sizes."""
+    from yolo_master_b200 import _lib
+    prev = _lib.load().ym_set_stem_impl(impl)
+    try:
+        _stem_case(dtype, hw)
+    finally:
+        _lib.load().ym_set_stem_impl(prev)
+
+
+def _stem_case(dtype, hw):
     m = M.Conv(3, 16, 3, 2)
     sd = _prep(m, seed=1)
     g = torch.Generator().manual_seed(5)

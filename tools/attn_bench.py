@@ -40,34 +40,27 @@ for name, (B, N, heads, hd, dv) in {"P3": (32, 6400, 2, 32, 32), "P4": (32, 1600
         res[f"{name}_impl{impl}"] = {"ms": ms, "Tscores_per_s": scores / (ms * 1e-3) / 1e12, "mufu_frac": scores / (ms * 1e-3) / (148 * 16 * 1.965e9),
                                     "tflops": 4 * scores * hd / (ms * 1e-3) / 1e12 if dv == hd else None, "max_abs_dev_vs_impl2": dev}
         print(name, "impl", impl, res[f"{name}_impl{impl}"], flush=True)
-# scheduling variants of the warp-specialised kernel (ym_set_attention2_variant bits: 1 = four max chains, 2 = refill lag 3, 4 = issuer
-# sleeps between polls) with and without every 4th exponential on the FMA pipe (ym_set_attention2_poly)
-for name, (B, N, heads, hd) in {"P3": (32, 6400, 2, 32), "P4": (32, 1600, 2, 32)}.items():
-    qkv = torch.randn((B, N, 1, heads * 3 * hd), device="cuda").half()
-    out = torch.empty((B, N, 1, heads * hd), device="cuda", dtype=torch.float16)
-    base = None
-    for every in (0, 4):
-        for variant in range(8):
-            L.ym_set_attention2_poly(every)
-            old_var = L.ym_set_attention2_variant(variant)
-            reps = 20 if name == "P3" else 50
-            for _ in range(3):
-                ops.attention(qkv, B, N, heads, 3 * hd, 0, hd, 2 * hd, hd, hd, hd ** -0.5, out=out)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(reps):
-                ops.attention(qkv, B, N, heads, 3 * hd, 0, hd, 2 * hd, hd, hd, hd ** -0.5, out=out)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / reps
-            L.ym_set_attention2_variant(old_var)
-            if base is None:
-                base = out.clone()
-            scores = float(N) * N * heads * B
-            res[f"{name}_poly{every}_var{variant}"] = {"ms": ms, "mufu_ceiling_frac": scores / (ms * 1e-3) / (148 * 16 * 1.965e9),
-                                                     "max_abs_dev_vs_first": float((out.float() - base.float()).abs().max())}
-            print(name, "poly", every, "variant", variant, res[f"{name}_poly{every}_var{variant}"], flush=True)
+# query tiles per CTA forced to 1 / 2 (ym_set_attention2_qtiles; 0 = the launcher's wave-fit rule) at the small pyramid levels
+for name, (B, N, heads, hd, dv) in {"P3": (32, 6400, 2, 32, 32), "P4": (32, 1600, 2, 32, 32), "P5": (32, 400, 2, 32, 32), "PSA": (32, 400, 2, 32, 64)}.items():
+    hs = 2 * hd + dv
+    qkv = torch.randn((B, N, 1, heads * hs), device="cuda").half()
+    out = torch.empty((B, N, 1, heads * dv), device="cuda", dtype=torch.float16)
+    for qt in (0, 1, 2):
+        old = L.ym_set_attention2_qtiles(qt)
+        reps = 20 if name == "P3" else 50
+        for _ in range(3):
+            ops.attention(qkv, B, N, heads, hs, 0, hd, 2 * hd, hd, dv, hd ** -0.5, out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            ops.attention(qkv, B, N, heads, hs, 0, hd, 2 * hd, hd, dv, hd ** -0.5, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        L.ym_set_attention2_qtiles(old)
+        ms = e0.elapsed_time(e1) / reps
+        res[f"{name}_qtiles{qt}"] = {"ms": ms, "mufu_ceiling_frac": float(N) * N * heads * B / (ms * 1e-3) / (148 * 16 * 1.965e9)}
+        print(name, "q_tiles", qt, res[f"{name}_qtiles{qt}"], flush=True)
 L.ym_set_attention2_poly(0)
 if len(sys.argv) > 1:
     json.dump(res, open(sys.argv[1], "w"), indent=1)

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const TIn* __restrict__ 
 // fp16 as the reference's own fp16 predictor path does (`im.half()`, then `/ 255` for uint8 frames: engine/predictor.py:173-175);
 // the folded fp32 weights are split into two fp16 parts (w = hi + lo, lo = the next 11 mantissa bits) and both are multiplied in - the
 // first layer keeps the fp32-weight accuracy of the FFMA kernel for six more HMMAs per 16 pixels; accumulation is fp32.
-// CTA = 8 warps = 8 output rows x 64 output columns; warp = one output row, four 16-pixel groups.
+// CTA = 8 warps = 16 output rows x 64 output columns; warp = two output rows, four 16-pixel groups each.
 struct StemTcWeights {
     uint32_t b[2][3][2][32][2];   // B fragments per (hi | lo part, k step, n tile, lane): {b0, b1} as packed half2
     float bias[16];
@@ -117,48 +117,57 @@ __global__ void __launch_bounds__(256) stem_conv_tc_kernel(const TIn* __restrict
                                                            const __grid_constant__ StemTcWeights sw, __half* __restrict__ out, int ldo,
                                                            int Ho, int Wo, int tiles_x) {
     pdl_prologue();
-    constexpr int TW = 64, TH = 8, IW = 2 * TW + 2, IH = 2 * TH + 1, RS = IW + 2;    // row stride 132 halves = 66 words
+    constexpr int TW = 64, TH = 16, IW = 2 * TW + 2, IH = 2 * TH + 1, RS = IW + 2;   // row stride 132 halves = 66 words
     __shared__ __align__(16) __half sx[3][IH][RS];
     __shared__ __align__(16) __half sout[8][16][16];                                 // per warp: 16 pixels x 16 channels staging
+    __shared__ __align__(8) uint32_t sbf[12 * 32 * 2];                               // B fragments, [(part, ks, nt)][lane][2]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
     const int oy0 = (blockIdx.x / tiles_x) * TH, ox0 = (blockIdx.x % tiles_x) * TW;
     const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
-    // patch load: the 3 x 17 (channel, row) lines of 130 pixels are dealt to the 8 warps, a lane takes pixels lane, lane + 32, ... of its
-    // lines; ALL loads of a thread (<= 35) are issued before the first shared-memory store, with adds as the only index arithmetic
-    // (a one-element-at-a-time loop ran the kernel at load latency, and a flat index with two divisions per element at integer-ALU rate)
-    constexpr int LINES = 3 * IH, LPW = (LINES + 7) / 8, CPL = (IW + 31) / 32;
-    __half vals[LPW][CPL];
+    // B fragments: kernel parameter -> shared memory once per CTA (3 words per thread), then ONE conflict-free 8-byte read per fragment.
+    // Read straight from the parameter bank they are lane-indexed constant loads, which the constant cache serves one address at a time:
+    // 12 LDC.64 x 32 lanes per warp were 42 % of the kernel's stall samples (profiles/r02_moe_stem_ncu.txt).
+    {
+        const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(&sw.b[0][0][0][0][0]);
 #pragma unroll
-    for (int li = 0; li < LPW; ++li) {
-        const int line = warp + 8 * li;
-        const int ci = line / IH, ry = line - ci * IH;
-        const int iy = iy0 + ry;
-        const bool row_ok = line < LINES && ci < Cin && iy >= 0 && iy < H;
-        const TIn* src = img + (((long long)b * Cin + (row_ok ? ci : 0)) * H + (row_ok ? iy : 0)) * W;
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-            const int rx = lane + 32 * k, ix = ix0 + rx;
-            __half v = __float2half_rn(0.f);
-            if (row_ok && rx < IW && ix >= 0 && ix < W) v = stem_to_half<TIn>(src[ix]);
-            vals[li][k] = v;
-        }
+        for (int i = 0; i < 3; ++i) sbf[tid + 256 * i] = wsrc[tid + 256 * i];
     }
+    // patch load: the 3 x 33 (channel, row) lines of 130 pixels are dealt to the 8 warps, a lane takes pixels lane, lane + 32, ... of its
+    // lines; the loads of a batch of lines are all issued before the first shared-memory store, with adds as the only index arithmetic
+    constexpr int LINES = 3 * IH, LPW = (LINES + 7) / 8, CPL = (IW + 31) / 32, LB = 5;
+#pragma unroll 1
+    for (int l0 = 0; l0 < LPW; l0 += LB) {
+        __half vals[LB][CPL];
 #pragma unroll
-    for (int li = 0; li < LPW; ++li) {
-        const int line = warp + 8 * li;
-        if (line < LINES) {
+        for (int li = 0; li < LB; ++li) {
+            const int line = warp + 8 * (l0 + li);
             const int ci = line / IH, ry = line - ci * IH;
+            const int iy = iy0 + ry;
+            const bool row_ok = line < LINES && ci < Cin && iy >= 0 && iy < H;
+            const TIn* src = img + (((long long)b * Cin + (row_ok ? ci : 0)) * H + (row_ok ? iy : 0)) * W;
 #pragma unroll
             for (int k = 0; k < CPL; ++k) {
-                const int rx = lane + 32 * k;
-                if (rx < IW) sx[ci][ry][rx] = vals[li][k];
+                const int rx = lane + 32 * k, ix = ix0 + rx;
+                __half v = __float2half_rn(0.f);
+                if (row_ok && rx < IW && ix >= 0 && ix < W) v = stem_to_half<TIn>(src[ix]);
+                vals[li][k] = v;
+            }
+        }
+#pragma unroll
+        for (int li = 0; li < LB; ++li) {
+            const int line = warp + 8 * (l0 + li);
+            if (line < LINES) {
+                const int ci = line / IH, ry = line - ci * IH;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    const int rx = lane + 32 * k;
+                    if (rx < IW) sx[ci][ry][rx] = vals[li][k];
+                }
             }
         }
     }
     __syncthreads();
-    const int oy = oy0 + warp;
-    if (oy >= Ho) return;
     const int g = lane >> 2, t = lane & 3;
     uint32_t bf[2][3][2][2];
 #pragma unroll
@@ -166,10 +175,17 @@ __global__ void __launch_bounds__(256) stem_conv_tc_kernel(const TIn* __restrict
 #pragma unroll
         for (int ks = 0; ks < 3; ++ks)
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) { bf[part][ks][nt][0] = sw.b[part][ks][nt][lane][0]; bf[part][ks][nt][1] = sw.b[part][ks][nt][lane][1]; }
+            for (int nt = 0; nt < 2; ++nt) {
+                const uint2 w2 = *reinterpret_cast<const uint2*>(&sbf[((((part * 3 + ks) * 2 + nt) * 32) + lane) * 2]);
+                bf[part][ks][nt][0] = w2.x;
+                bf[part][ks][nt][1] = w2.y;
+            }
     const float bias0 = sw.bias[2 * t], bias1 = sw.bias[2 * t + 1], bias8 = sw.bias[8 + 2 * t], bias9 = sw.bias[8 + 2 * t + 1];
 #pragma unroll 1
-    for (int grp = 0; grp < TW / 16; ++grp) {
+    for (int it = 0; it < 2 * (TW / 16); ++it) {
+        const int wr = 2 * warp + (it >> 2), grp = it & 3;   // tile row of this warp (two per warp), 16-pixel group
+        const int oy = oy0 + wr;
+        if (oy >= Ho) break;
         const int lx = grp * 16 + g;                      // output column (tile-local) of fragment row g; row g+8 = lx + 8
         float acc[2][4];
 #pragma unroll
@@ -184,7 +200,7 @@ __global__ void __launch_bounds__(256) stem_conv_tc_kernel(const TIn* __restrict
             for (int hi = 0; hi < 2; ++hi) {
                 const int grpk = 4 * ks + 2 * hi + (t >> 1);          // (ci, ky) group, 9..11 are zero-weight pads
                 const int ci = grpk < 9 ? grpk / 3 : 0, ky = grpk < 9 ? grpk - 3 * (grpk / 3) : 0;
-                const __half* row = &sx[ci][2 * warp + ky][2 * (t & 1)];
+                const __half* row = &sx[ci][2 * wr + ky][2 * (t & 1)];
                 a[2 * hi + 0] = *reinterpret_cast<const uint32_t*>(row + 2 * lx);            // fragment row g
                 a[2 * hi + 1] = *reinterpret_cast<const uint32_t*>(row + 2 * (lx + 8));      // fragment row g + 8
             }
@@ -543,7 +559,7 @@ using namespace ym;
 static inline int nblocks(long long total, int bs) { return (int)((total + bs - 1) / bs); }
 
 // 1 = tensor-core stem (mma.sync implicit GEMM, fp16 operands) where Cin <= 3 and Cout = 16; 0 = fp32 FFMA kernel (A/B baseline)
-static int g_stem_impl = 0;   // 0 = FFMA kernel (181 us at bs32 / 640, r02g), 1 = mma.sync kernel (226 us: shared-memory queue bound)
+static int g_stem_impl = 1;   // 1 = mma.sync kernel (112 us at bs32 / 640, r02i), 0 = FFMA kernel (176 us)
 extern "C" int ym_set_stem_impl(int impl) {
     const int old = g_stem_impl;
     if (impl == 0 || impl == 1) g_stem_impl = impl;
@@ -586,7 +602,7 @@ static int stem_launch(const void* img, int in_dtype, int B, int Cin, int H, int
                         memcpy(&tw.b[part][ks][nt][lane][1], &b1, 4);
                     }
         memcpy(tw.bias, bias_host, sizeof(float) * 16);
-        const int tx = (Wo + 63) / 64, ty = (Ho + 7) / 8;
+        const int tx = (Wo + 63) / 64, ty = (Ho + 15) / 16;
         const dim3 gridt(tx * ty, B);
         if (in_dtype == 0) launch_pdl(stem_conv_tc_kernel<__half>, gridt, 256, 0, st, (const __half*)img, B, Cin, H, W, tw, (__half*)out, ldo, Ho, Wo, tx);
         else if (in_dtype == 1) launch_pdl(stem_conv_tc_kernel<float>, gridt, 256, 0, st, (const float*)img, B, Cin, H, W, tw, (__half*)out, ldo, Ho, Wo, tx);

@@ -385,6 +385,11 @@ static int dispatch_bn(const GemmConvParams& p, int problems, cudaStream_t strea
     return launch_gemm<64, EPI, A_XFORM>(p, problems, stream);
 }
 
+// small_conv.cu: patch-staged kernel for 3x3 layers over 8 / 16 input channels
+int small_conv3_supported(int Cin, int Cout, int KH, int KW, int stride, int pad, int Kpad, int out_f32, int B);
+int small_conv3_run(const void* x, int ldx, int B, int H, int W, int Cin, const void* w, int Kpad, const float* bias, int Cout, int stride,
+                    void* out, int ldo, const void* res, int ldr, int act, cudaStream_t st);
+
 }  // namespace ym
 
 using namespace ym;
@@ -402,6 +407,12 @@ extern "C" int ym_conv2d_nhwc(const void* x, int ldx, int B, int H, int W, int C
     YM_CHECK_ARG(stride >= 1 && KH >= 1 && KW >= 1 && pad >= 0, "ym_conv2d_nhwc: bad geometry");
     YM_CHECK_ARG(res == nullptr || (ldr % 8 == 0 && ((uintptr_t)res & 15) == 0), "ym_conv2d_nhwc: residual must be 16-byte aligned");
     if (B == 0) return YM_OK;
+    if (small_conv3_supported(Cin, Cout, KH, KW, stride, pad, Kpad, out_f32, B)) {
+        const int rc = small_conv3_run(x, ldx, B, H, W, Cin, w, Kpad, bias, Cout, stride, out, ldo, res, ldr, act, (cudaStream_t)stream);
+        if (rc) return rc;
+        YM_CHECK_LAUNCH("small_conv3");
+        return YM_OK;
+    }
     GemmConvParams p;
     memset(&p, 0, sizeof(p));
     p.x = (const __half*)x; p.ldx = ldx; p.w = (const __half*)w; p.Kpad = Kpad; p.bias = bias;
