@@ -1,6 +1,6 @@
 """GPU parity of the Classify head (`ym_classify_head`) and the v0_1 classification model (`ClassificationModel`: BatchNorm eps 1e-5,
-unlike detection models) against the reference golden and the CPU oracle.  Written after round 1's GPU budget was spent (kernel body
-under g++, whole model on CPU emulation): xfail(strict=False) until its first hardware run, like the other zz suites."""
+unlike detection models) against the reference golden and the CPU oracle.  The kernel body also runs under g++ and the whole model on CPU
+emulation in the CPU suite; on the B200 since round 2 (profiles/r02_gpu_suite.txt)."""
 import os
 
 import pytest

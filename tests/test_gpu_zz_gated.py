@@ -2,10 +2,8 @@
 the new `ym_ew_nhwc` ops and the `VisualEnhancedAdaptiveGateMoE` block / the v0_10 yolo-master-n model against the oracle and
 the reference goldens, through the public API.
 
-Written after round 1's GPU budget was spent: the kernel bodies and the host wiring are verified on the host
-(tests/test_gated_host.py runs the same phase functions under g++ and the block against the oracle), the CUDA launches have not
-run on hardware yet.  Until they have, the module is marked xfail(strict=False) - XPASS means the marker can go - and the file
-name sorts it after the verified suites."""
+The kernel bodies and the host wiring are also verified on the host (tests/test_gated_host.py runs the same phase functions under g++
+and the block against the oracle); the CUDA launches run on the B200 since round 2 (profiles/r02_gpu_suite.txt)."""
 import os
 
 import pytest

@@ -1,6 +1,6 @@
 """GPU parity of LatentMixture (the yolo26-master-latent-n* zoo): `ym_latent_router` and the whole model against the
-reference golden and the CPU oracle.  Written after round 1's GPU budget was spent (kernel verified on the CUDA-on-host emulation,
-whole model on emulated ops): xfail(strict=False) until its first hardware run, like the other zz suites."""
+reference golden and the CPU oracle.  The kernel also runs on the CUDA-on-host emulation and the whole model on
+emulated ops in the CPU suite; on the B200 since round 2 (profiles/r02_gpu_suite.txt)."""
 import os
 
 import pytest

@@ -2,8 +2,7 @@
 owns its residual, A2C2f area attention, DFL Detect) against the reference golden and the CPU oracle, through the public API.
 
 Every kernel on this path is verified on hardware by the other suites (the MoE-FFN chain inside A2C2fMoE, test_gpu_ops.py); this
-model-level composition was added after round 1's GPU budget was spent, so the module follows the same convention as the other
-test_gpu_zz_* files: xfail(strict=False) until its first hardware run (XPASS = drop the marker)."""
+is the model-level composition (on the B200 since round 2, profiles/r02_gpu_suite.txt)."""
 import os
 
 import pytest

@@ -1,9 +1,8 @@
 """GPU parity of the large-candidate NMS path (`ym_nms_batched_large`, SURVEY.md 8(f) rank 3: validation at conf 0.001) against the
 NMS oracle, against the shared-memory kernel where both apply, and through `non_max_suppression`'s automatic switch.
 
-Written after round 1's GPU budget was spent: the algorithm is verified on the host (tests/test_nms_large_host.py runs the same
-per-image function under g++, bit-exact against the oracle); the CUDA launch has not run on hardware yet, hence the same
-xfail(strict=False) convention as the other test_gpu_zz_* files (XPASS = drop the marker)."""
+The algorithm is also verified on the host (tests/test_nms_large_host.py runs the same per-image function under g++, bit-exact
+against the oracle); the CUDA launch runs on the B200 since round 2 (profiles/r02_gpu_suite.txt)."""
 import pytest
 import torch
 

@@ -1,6 +1,6 @@
 """GPU parity of the OBB head: angle towers + `ym_obb_finish` and the v0_1 obb model against the reference
-golden and the CPU oracle.  Written after round 1's GPU budget was spent (per-anchor function checked under g++, whole model on CPU
-emulation): xfail(strict=False) until its first hardware run, like the other zz suites."""
+golden and the CPU oracle.  The per-anchor function is also checked under g++ and the whole model on CPU
+emulation in the CPU suite; on the B200 since round 2 (profiles/r02_gpu_suite.txt)."""
 import os
 
 import pytest

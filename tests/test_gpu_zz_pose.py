@@ -1,8 +1,8 @@
 """GPU parity of the Pose head: `ym_kpts_decode` and the v0_1 pose model (`PoseModel`, ModularRouterExpertMoE
 backbone) against the reference golden and the CPU oracle, plus NMS carrying the keypoint columns.
 
-Written after round 1's GPU budget was spent (kernel body checked under g++ in tests/test_preproc_host.py, whole-model wiring on
-CPU emulation in tests/test_host_model_wiring.py): xfail(strict=False) until its first hardware run, like the other zz suites."""
+The kernel body is also checked under g++ in tests/test_preproc_host.py and the whole-model wiring on CPU emulation in
+tests/test_host_model_wiring.py; on the B200 since round 2 (profiles/r02_gpu_suite.txt)."""
 import os
 
 import pytest

@@ -1,8 +1,8 @@
 """GPU parity of the Segment / OBB post-processing: `ym_process_mask` and `ym_nms_rotated` through the host
 mirrors `utils.ops.process_mask` / `utils.nms.non_max_suppression(rotated=True)` against the reference goldens
 (tests/golden/postproc.golden.pt) and the CPU oracle, plus size-independent properties at full size (640 x 640 masks, 8400 and
-33 600 anchors).  Written after round 1's GPU budget was spent (both translation-unit kernels verified under the CUDA-on-host
-emulation, tests/test_cuda_host_emu.py): xfail(strict=False) until its first hardware run, like the other zz suites.
+33 600 anchors).  Both translation-unit kernels also run under the CUDA-on-host emulation
+(tests/test_cuda_host_emu.py); on the B200 since round 2 (profiles/r02_gpu_suite.txt).
 
 Tolerances: masks are bit-exact except pixels whose fp32 field (the value compared with 0) lies within 1e-4 of zero; rotated NMS is
 exact (kept anchors, order, rows) on inputs whose closest ProbIoU-to-threshold distance exceeds 1e-5 (asserted on the oracle)."""

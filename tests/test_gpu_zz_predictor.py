@@ -2,10 +2,8 @@
 `ym_scale_boxes` through the public mirror (LetterBox, DetectionPredictor, utils.ops.scale_boxes), bit-exact against the oracle
 (pinned to the real LetterBox + cv2 and ops.scale_boxes by tests/test_letterbox_oracle.py) and the reference goldens.
 
-These two kernels were written after round 1's GPU budget was spent: their arithmetic is verified on the host
-(tests/test_preproc_host.py compiles the same per-pixel code with g++), but the CUDA launch itself has not run on hardware yet.
-Until it has, the module is marked xfail(strict=False) - an XPASS in the report means the kernels are good and the marker can
-go - and the file name sorts it after the verified suites."""
+Their arithmetic is also verified on the host (tests/test_preproc_host.py compiles the same per-pixel code with g++); the CUDA launches
+run on the B200 since round 2 (profiles/r02_gpu_suite.txt)."""
 import os
 import zlib
 

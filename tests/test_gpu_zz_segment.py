@@ -1,7 +1,6 @@
 """GPU parity of the Segment head: mask-coefficient towers, prototype branch (the 2x2 stride-2 transposed
 convolution as a 1x1 convolution + depth-to-space) and the v0_1 seg model against the reference golden and the CPU oracle.
-Written after round 1's GPU budget was spent (whole-model wiring verified on CPU emulation): xfail(strict=False) until its first
-hardware run, like the other zz suites."""
+The whole-model wiring is also verified on CPU emulation; on the B200 since round 2 (profiles/r02_gpu_suite.txt)."""
 import os
 
 import pytest

@@ -92,12 +92,13 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const TIn* __restrict__ 
 // Tensor-core stem (Cin <= 3, Cout = 16): the same 3x3 / stride 2 / pad 1 convolution as an implicit GEMM on mma.sync.m16n8k16.
 // The FFMA kernel above spends 432 FFMA + im2col addressing per output pixel (FFMA-issue bound at 11 % of HBM,
 // profiles/r01_early_layers_ncu.txt); here a pixel costs 6/16 of an HMMA.  K is laid out as (ci, ky) groups of FOUR taps
-// (kx = 0, 1, 2 and a zero-weight pad), 9 groups padded to 12 -> K = 48 = three k16 steps, so that every A-fragment register is ONE
+// (a zero-weight pad and kx = 0, 1, 2), 9 groups padded to 12 -> K = 48 = three k16 steps, so that every A-fragment register is ONE
 // aligned 32-bit shared-memory load of two horizontally adjacent fp16 input pixels (the im2col never exists).  Inputs are rounded to
 // fp16 as the reference's own fp16 predictor path does (`im.half()`, then `/ 255` for uint8 frames: engine/predictor.py:173-175);
 // the folded fp32 weights are split into two fp16 parts (w = hi + lo, lo = the next 11 mantissa bits) and both are multiplied in - the
 // first layer keeps the fp32-weight accuracy of the FFMA kernel for six more HMMAs per 16 pixels; accumulation is fp32.
 // CTA = 8 warps = 16 output rows x 64 output columns; warp = two output rows, four 16-pixel groups each.
+// K slot order inside a (ci, ky) group is {zero, kx = 0, kx = 1, kx = 2} (see the kernel's patch layout).
 struct StemTcWeights {
     uint32_t b[2][3][2][32][2];   // B fragments per (hi | lo part, k step, n tile, lane): {b0, b1} as packed half2
     float bias[16];
@@ -112,19 +113,22 @@ __device__ __forceinline__ __half stem_to_half<float>(float v) { return __float2
 template <>
 __device__ __forceinline__ __half stem_to_half<unsigned char>(unsigned char v) { return __float2half_rn(__fdiv_rn((float)v, 255.f)); }
 
-template <typename TIn>
+template <typename TIn, bool VEC>
 __global__ void __launch_bounds__(256) stem_conv_tc_kernel(const TIn* __restrict__ img, int B, int Cin, int H, int W,
                                                            const __grid_constant__ StemTcWeights sw, __half* __restrict__ out, int ldo,
                                                            int Ho, int Wo, int tiles_x) {
     pdl_prologue();
-    constexpr int TW = 64, TH = 16, IW = 2 * TW + 2, IH = 2 * TH + 1, RS = IW + 2;   // row stride 132 halves = 66 words
+    // patch column j <-> image column 2 * ox0 - 2 + j: the four K slots of a (ci, ky) group are {zero weight, kx = 0, kx = 1, kx = 2}, so
+    // both fragment pairs of an output pixel - columns (2 lx, 2 lx + 1) and (2 lx + 2, 2 lx + 3) - are aligned 32-bit words AND start on
+    // an even image column: fp16 images with even W are staged with 32-bit loads and stores.  Row stride 144 halves = 72 words (8 mod 32).
+    constexpr int TW = 64, TH = 16, IW = 2 * TW + 4, IH = 2 * TH + 1, RS = 144;
     __shared__ __align__(16) __half sx[3][IH][RS];
     __shared__ __align__(16) __half sout[8][16][16];                                 // per warp: 16 pixels x 16 channels staging
     __shared__ __align__(8) uint32_t sbf[12 * 32 * 2];                               // B fragments, [(part, ks, nt)][lane][2]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
     const int oy0 = (blockIdx.x / tiles_x) * TH, ox0 = (blockIdx.x % tiles_x) * TW;
-    const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 1;
+    const int iy0 = oy0 * 2 - 1, ix0 = ox0 * 2 - 2;
     // B fragments: kernel parameter -> shared memory once per CTA (3 words per thread), then ONE conflict-free 8-byte read per fragment.
     // Read straight from the parameter bank they are lane-indexed constant loads, which the constant cache serves one address at a time:
     // 12 LDC.64 x 32 lanes per warp were 42 % of the kernel's stall samples (profiles/r02_moe_stem_ncu.txt).
@@ -133,36 +137,73 @@ __global__ void __launch_bounds__(256) stem_conv_tc_kernel(const TIn* __restrict
 #pragma unroll
         for (int i = 0; i < 3; ++i) sbf[tid + 256 * i] = wsrc[tid + 256 * i];
     }
-    // patch load: the 3 x 33 (channel, row) lines of 130 pixels are dealt to the 8 warps, a lane takes pixels lane, lane + 32, ... of its
-    // lines; the loads of a batch of lines are all issued before the first shared-memory store, with adds as the only index arithmetic
-    constexpr int LINES = 3 * IH, LPW = (LINES + 7) / 8, CPL = (IW + 31) / 32, LB = 5;
+    // patch load: the 3 x 33 (channel, row) lines are dealt to the 8 warps; the loads of a batch of lines are all issued before the first
+    // shared-memory store, with adds as the only index arithmetic (scalar loads with per-element bounds tests executed 38 M of the
+    // kernel's 69 M instructions: profiles/r02_small_stem_ncu.txt)
+    constexpr int LINES = 3 * IH, LPW = (LINES + 7) / 8, LB = 5;
+    if (VEC) {
+        constexpr int PPL = IW / 2, CPL = (PPL + 31) / 32;       // 66 pixel pairs per line, 3 per lane
 #pragma unroll 1
-    for (int l0 = 0; l0 < LPW; l0 += LB) {
-        __half vals[LB][CPL];
+        for (int l0 = 0; l0 < LPW; l0 += LB) {
+            uint32_t vals[LB][CPL];
 #pragma unroll
-        for (int li = 0; li < LB; ++li) {
-            const int line = warp + 8 * (l0 + li);
-            const int ci = line / IH, ry = line - ci * IH;
-            const int iy = iy0 + ry;
-            const bool row_ok = line < LINES && ci < Cin && iy >= 0 && iy < H;
-            const TIn* src = img + (((long long)b * Cin + (row_ok ? ci : 0)) * H + (row_ok ? iy : 0)) * W;
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-                const int rx = lane + 32 * k, ix = ix0 + rx;
-                __half v = __float2half_rn(0.f);
-                if (row_ok && rx < IW && ix >= 0 && ix < W) v = stem_to_half<TIn>(src[ix]);
-                vals[li][k] = v;
-            }
-        }
-#pragma unroll
-        for (int li = 0; li < LB; ++li) {
-            const int line = warp + 8 * (l0 + li);
-            if (line < LINES) {
+            for (int li = 0; li < LB; ++li) {
+                const int line = warp + 8 * (l0 + li);
                 const int ci = line / IH, ry = line - ci * IH;
+                const int iy = iy0 + ry;
+                const bool row_ok = line < LINES && ci < Cin && iy >= 0 && iy < H;
+                const TIn* src = img + (((long long)b * Cin + (row_ok ? ci : 0)) * H + (row_ok ? iy : 0)) * W;
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
-                    const int rx = lane + 32 * k;
-                    if (rx < IW) sx[ci][ry][rx] = vals[li][k];
+                    const int m = lane + 32 * k, ix = ix0 + 2 * m;          // even: the pair is inside or outside the image as a whole
+                    uint32_t v = 0u;
+                    if (row_ok && m < PPL && ix >= 0 && ix < W) v = *reinterpret_cast<const uint32_t*>(src + ix);
+                    vals[li][k] = v;
+                }
+            }
+#pragma unroll
+            for (int li = 0; li < LB; ++li) {
+                const int line = warp + 8 * (l0 + li);
+                if (line < LINES) {
+                    const int ci = line / IH, ry = line - ci * IH;
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        const int m = lane + 32 * k;
+                        if (m < PPL) *reinterpret_cast<uint32_t*>(&sx[ci][ry][2 * m]) = vals[li][k];
+                    }
+                }
+            }
+        }
+    } else {
+        constexpr int CPL = (IW + 31) / 32;
+#pragma unroll 1
+        for (int l0 = 0; l0 < LPW; l0 += LB) {
+            __half vals[LB][CPL];
+#pragma unroll
+            for (int li = 0; li < LB; ++li) {
+                const int line = warp + 8 * (l0 + li);
+                const int ci = line / IH, ry = line - ci * IH;
+                const int iy = iy0 + ry;
+                const bool row_ok = line < LINES && ci < Cin && iy >= 0 && iy < H;
+                const TIn* src = img + (((long long)b * Cin + (row_ok ? ci : 0)) * H + (row_ok ? iy : 0)) * W;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    const int rx = lane + 32 * k, ix = ix0 + rx;
+                    __half v = __float2half_rn(0.f);
+                    if (row_ok && rx < IW && ix >= 0 && ix < W) v = stem_to_half<TIn>(src[ix]);
+                    vals[li][k] = v;
+                }
+            }
+#pragma unroll
+            for (int li = 0; li < LB; ++li) {
+                const int line = warp + 8 * (l0 + li);
+                if (line < LINES) {
+                    const int ci = line / IH, ry = line - ci * IH;
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        const int rx = lane + 32 * k;
+                        if (rx < IW) sx[ci][ry][rx] = vals[li][k];
+                    }
                 }
             }
         }
@@ -581,8 +622,8 @@ static int stem_launch(const void* img, int in_dtype, int B, int Cin, int H, int
         StemTcWeights tw;
         memset(&tw, 0, sizeof(tw));
         auto wk = [&](int k, int n) -> float {          // weight of GEMM row k (0..47), output channel n
-            const int grp = k >> 2, kx = k & 3;
-            if (grp >= 9 || kx >= 3) return 0.f;
+            const int grp = k >> 2, kx = (k & 3) - 1;          // slots of a (ci, ky) group: {zero, kx = 0, kx = 1, kx = 2}
+            if (grp >= 9 || kx < 0) return 0.f;
             const int ci = grp / 3, ky = grp % 3;
             if (ci >= Cin) return 0.f;
             return wgt_host[(size_t)((ci * 3 + ky) * 3 + kx) * CO + n];
@@ -604,9 +645,11 @@ static int stem_launch(const void* img, int in_dtype, int B, int Cin, int H, int
         memcpy(tw.bias, bias_host, sizeof(float) * 16);
         const int tx = (Wo + 63) / 64, ty = (Ho + 15) / 16;
         const dim3 gridt(tx * ty, B);
-        if (in_dtype == 0) launch_pdl(stem_conv_tc_kernel<__half>, gridt, 256, 0, st, (const __half*)img, B, Cin, H, W, tw, (__half*)out, ldo, Ho, Wo, tx);
-        else if (in_dtype == 1) launch_pdl(stem_conv_tc_kernel<float>, gridt, 256, 0, st, (const float*)img, B, Cin, H, W, tw, (__half*)out, ldo, Ho, Wo, tx);
-        else if (in_dtype == 2) launch_pdl(stem_conv_tc_kernel<unsigned char>, gridt, 256, 0, st, (const unsigned char*)img, B, Cin, H, W, tw, (__half*)out, ldo, Ho, Wo, tx);
+        const bool vec = in_dtype == 0 && W % 2 == 0 && ((uintptr_t)img & 3) == 0;      // every image row then starts on a 4-byte boundary
+        if (vec) launch_pdl(stem_conv_tc_kernel<__half, true>, gridt, 256, 0, st, (const __half*)img, B, Cin, H, W, tw, (__half*)out, ldo, Ho, Wo, tx);
+        else if (in_dtype == 0) launch_pdl(stem_conv_tc_kernel<__half, false>, gridt, 256, 0, st, (const __half*)img, B, Cin, H, W, tw, (__half*)out, ldo, Ho, Wo, tx);
+        else if (in_dtype == 1) launch_pdl(stem_conv_tc_kernel<float, false>, gridt, 256, 0, st, (const float*)img, B, Cin, H, W, tw, (__half*)out, ldo, Ho, Wo, tx);
+        else if (in_dtype == 2) launch_pdl(stem_conv_tc_kernel<unsigned char, false>, gridt, 256, 0, st, (const unsigned char*)img, B, Cin, H, W, tw, (__half*)out, ldo, Ho, Wo, tx);
         else { ym_set_error("ym_stem_conv_nchw: bad in_dtype %d", in_dtype); return YM_ERR_ARG; }
         return YM_OK;
     }

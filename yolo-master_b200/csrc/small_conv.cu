@@ -32,15 +32,15 @@ template <int CIN, int S, int COUT>
 struct SmallConvCfg {
     static constexpr int TW = 32, TH = 8;
     static constexpr int IH = (TH - 1) * S + 3, IW = (TW - 1) * S + 3;
-    static constexpr int PW = (IW + S - 1) / S + 1;           // pixels per plane row (+1: the last tap of the last pixel)
+    static constexpr int PW = (IW + S - 1) / S;               // pixels per plane row
     static constexpr int PP = CIN == 16 ? 48 : 16;            // bytes between neighbouring pixels of a plane row
     static constexpr int ROWB = PW * PP;
     static constexpr int PATCH_BYTES = IH * S * ROWB;
     static constexpr int CH = CIN / 8;                        // 16-byte chunks per pixel
     static constexpr int SLICES = 9 * CH, KSTEPS = (SLICES + 1) / 2;
     static constexpr int NT = COUT / 8;
-    static constexpr int SP = COUT + 8;                       // staging pitch in floats
-    static constexpr int STG_BYTES = 8 * 16 * SP * 4;
+    static constexpr int SP = COUT + 8;                       // staging pitch in halves: 16-byte rows stay aligned, (SP / 2) % 8 == 4
+    static constexpr int STG_BYTES = 8 * 16 * SP * 2;
 };
 
 // byte offset of (patch row ry, patch column rx, chunk c8)
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) small_conv3_kernel(const SmallConvParams 
     unsigned char* patch = sc_smem;
     const int wpitch = (p.Kpad + 8) * 2;                      // bytes per weight row: (Kpad + 8) / 2 words == 4 mod 8 for Kpad = 96 / 160
     unsigned char* sW = patch + Cfg::PATCH_BYTES;
-    float* stg_all = reinterpret_cast<float*>(sW + ((COUT * wpitch + 127) & ~127));
+    __half* stg_all = reinterpret_cast<__half*>(sW + ((COUT * wpitch + 127) & ~127));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
@@ -73,15 +73,19 @@ __global__ void __launch_bounds__(256) small_conv3_kernel(const SmallConvParams 
     }
     pdl_prologue();
     {
-        constexpr int TOTAL = Cfg::IH * Cfg::IW * Cfg::CH;
+        // chunk i = (row ry, column-chunk rem) with rem = rx * CH + c8: each thread walks i = tid, tid + 256, ... by carrying (ry, rem)
+        constexpr int RC = Cfg::IW * Cfg::CH, DQ = 256 / RC, DR = 256 % RC;
         const __half* xb = p.x + (long long)b * p.H * p.W * p.ldx;
-        for (int i = tid; i < TOTAL; i += 256) {
-            const int ry = i / (Cfg::IW * Cfg::CH), rem = i - ry * (Cfg::IW * Cfg::CH);
+        int ry = tid / RC, rem = tid - ry * RC;
+        while (ry < Cfg::IH) {
             const int rx = rem / Cfg::CH, c8 = rem - rx * Cfg::CH;
             const int gy = iy0 + ry, gx = ix0 + rx;
             const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
             const __half* src = ok ? xb + ((long long)gy * p.W + gx) * p.ldx + c8 * 8 : p.x;
             cp_async16(patch + patch_off<Cfg, S>(ry, rx, c8), src, ok ? 16 : 0);
+            ry += DQ;
+            rem += DR;
+            if (rem >= RC) { rem -= RC; ++ry; }
         }
     }
     cp_async_commit();
@@ -129,49 +133,42 @@ __global__ void __launch_bounds__(256) small_conv3_kernel(const SmallConvParams 
         }
     }
 
-    // ---- epilogue: fragments -> warp-private fp32 staging tile -> one 16-byte (8-channel) chunk of an output pixel per lane
-    float* stg = stg_all + warp * 16 * Cfg::SP;
-    constexpr int RPI = 32 / Cfg::NT;                          // pixels per pass (Cout 32: 8, 16: 16, 8: 32 -> one pass covers 16 twice)
+    // ---- epilogue: bias, SiLU and the residual in fragment layout, rounded ONCE to fp16 into a warp-private staging tile, then one
+    // 16-byte (8-channel) chunk of an output pixel per lane to global memory
+    __half* stg = stg_all + warp * 16 * Cfg::SP;
+    constexpr int RPI = 32 / Cfg::NT;                          // pixels per pass (Cout 32: 8, 16: 16, 8: 32)
     const int ch = lane % Cfg::NT, rsub = lane / Cfg::NT;
-    float bias8[8];
+    float bias2[Cfg::NT][2];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) bias8[q] = p.bias != nullptr ? p.bias[ch * 8 + q] : 0.f;
+    for (int nt = 0; nt < Cfg::NT; ++nt) {
+        bias2[nt][0] = p.bias != nullptr ? p.bias[nt * 8 + 2 * t] : 0.f;
+        bias2[nt][1] = p.bias != nullptr ? p.bias[nt * 8 + 2 * t + 1] : 0.f;
+    }
+    const long long row_pix = ((long long)b * p.Ho + oy) * p.Wo;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
-        for (int nt = 0; nt < Cfg::NT; ++nt) {
-            *reinterpret_cast<float2*>(stg + g * Cfg::SP + nt * 8 + 2 * t) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
-            *reinterpret_cast<float2*>(stg + (g + 8) * Cfg::SP + nt * 8 + 2 * t) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+        for (int hf = 0; hf < 2; ++hf) {
+            const int r = g + hf * 8, ox = ox0 + mt * 16 + r;
+#pragma unroll
+            for (int nt = 0; nt < Cfg::NT; ++nt) {
+                float v0 = acc[mt][nt][2 * hf] + bias2[nt][0], v1 = acc[mt][nt][2 * hf + 1] + bias2[nt][1];
+                if (p.act == 1) { v0 = silu_f(v0); v1 = silu_f(v1); }
+                if (p.res != nullptr && ox < p.Wo) {
+                    const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(p.res + (row_pix + ox) * p.ldr + nt * 8 + 2 * t));
+                    v0 += rf.x;
+                    v1 += rf.y;
+                }
+                *reinterpret_cast<__half2*>(stg + r * Cfg::SP + nt * 8 + 2 * t) = __floats2half2_rn(v0, v1);
+            }
         }
         __syncwarp();
 #pragma unroll
         for (int it = 0; it < (16 + RPI - 1) / RPI; ++it) {
             const int r = it * RPI + rsub;
             const int ox = ox0 + mt * 16 + r;
-            if (r < 16 && ox < p.Wo) {
-                const float4 v0 = *reinterpret_cast<const float4*>(stg + r * Cfg::SP + ch * 8);
-                const float4 v1 = *reinterpret_cast<const float4*>(stg + r * Cfg::SP + ch * 8 + 4);
-                float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    v[q] += bias8[q];
-                    if (p.act == 1) v[q] = silu_f(v[q]);
-                }
-                const long long pix = ((long long)b * p.Ho + oy) * p.Wo + ox;
-                if (p.res != nullptr) {
-                    const Half8 rv = *reinterpret_cast<const Half8*>(p.res + pix * p.ldr + ch * 8);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float2 rf = __half22float2(rv.v[q]);
-                        v[2 * q] += rf.x;
-                        v[2 * q + 1] += rf.y;
-                    }
-                }
-                Half8 o;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) o.v[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
-                *reinterpret_cast<Half8*>(p.out + pix * p.ldo + ch * 8) = o;
-            }
+            if (r < 16 && ox < p.Wo)
+                *reinterpret_cast<uint4*>(p.out + (row_pix + ox) * p.ldo + ch * 8) = *reinterpret_cast<const uint4*>(stg + r * Cfg::SP + ch * 8);
         }
         __syncwarp();
     }

@@ -371,19 +371,18 @@ extern "C" int ym_attention_fwd_tc2(const void* qkv, int ld, int batch, int N, i
         return YM_ERR_CUDA;
     }
     const float sl2 = scale * 1.4426950408889634f;
-    // Two query tiles per CTA halve the K / V traffic, but on a small grid the second wave of long CTAs is mostly empty (P4: 448 CTAs on
-    // 296 slots = two waves of 2-tile CTAs against three of 1-tile CTAs): below two waves the tile count per CTA follows the wave fit.
-    static int slots = 0;
-    if (!slots) {
+    // Two query tiles per CTA keep all eight softmax warps of a CTA busy and halve the K / V traffic; a one-tile CTA leaves half of its
+    // threads and tensor memory idle, so it only pays when the two-tile grid would not even put one CTA on every SM (P5: 128 CTAs).
+    // Measured at bs32 (profiles/r02_attention_qtiles.json): P4 77 us with two tiles against 97 us with one, P5 11.9 against 11.1 us.
+    static int sm_count = 0;
+    if (!sm_count) {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        slots = 2 * (sms > 0 ? sms : 148);
+        sm_count = sms > 0 ? sms : 148;
     }
     const long long ctas2 = (long long)((N + 2 * A2_BQ - 1) / (2 * A2_BQ)) * heads * batch;
-    const long long ctas1 = (long long)((N + A2_BQ - 1) / A2_BQ) * heads * batch;
-    int q_tiles = 2;
-    if (d_v == 32 && ctas2 < 2LL * slots && (ctas1 + slots - 1) / slots < 2 * ((ctas2 + slots - 1) / slots)) q_tiles = 1;
+    int q_tiles = (d_v == 32 && ctas2 < sm_count) ? 1 : 2;
     if (g_attention2_qtiles) q_tiles = g_attention2_qtiles;
     dim3 grid((N + q_tiles * A2_BQ - 1) / (q_tiles * A2_BQ), heads, batch);
     cudaStream_t st = (cudaStream_t)stream;
