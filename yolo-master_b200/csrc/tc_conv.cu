@@ -31,6 +31,8 @@ struct TcConvParams {
     int M;             // flat mode: B*H*W rows
     int act;
     int stages;        // operand ring depth of the persistent kernel (set by launch_conv2)
+    int direct_store;  // persistent kernel: 1 = the epilogue warps copy the staged tile to global memory themselves, 0 = one TMA store
+    int dbg;           // timing experiments: bit 0 no TMA store, bit 1 no epilogue arithmetic / staging, bit 2 no tensor-memory read, bit 3 weights loaded for the first tile only
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -145,13 +147,44 @@ __global__ void __launch_bounds__(CV_THREADS) tc_conv_kernel(const __grid_consta
     }
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     constexpr int NCHUNK = BN < 16 ? 1 : BN / 16;
+    // fp32 outputs (the class-logit convs of the Detect towers) in FLAT mode: a thread's 16 floats of a chunk go through a warp-private
+    // shared-memory strip (pitch 20 floats: conflict-free float4 accesses) so that one store instruction covers eight rows x 64
+    // contiguous bytes.  Row-per-thread float4 stores touched 32 half-used sectors per instruction (59 us for the P3 logits, 44 MB).
+    __shared__ __align__(16) float f32_stg[CV_THREADS / 32][32][20];
+    const bool staged_f32 = FLAT && p.out_f32 && p.res == nullptr && (p.ldo % 4 == 0);
 #pragma unroll 1
     for (int ci = 0; ci < NCHUNK; ++ci) {
         uint32_t rr[16];
         tc::tmem_ld16(lane_addr + ci * 16, rr);
         tc::tmem_ld_wait();
         const int n = n0 + ci * 16;
-        if (!rowok || n >= p.Cout) continue;
+        if (n >= p.Cout) continue;                  // uniform across the CTA
+        if (staged_f32 && n + 16 <= p.Cout) {
+            float4* mine = reinterpret_cast<float4*>(&f32_stg[warp][lane][0]);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                float x[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    x[e] = __uint_as_float(rr[4 * q4 + e]);
+                    if (p.bias != nullptr) x[e] += p.bias[n + 4 * q4 + e];
+                    if (p.act == 1) x[e] = silu_f(x[e]);
+                }
+                mine[q4] = make_float4(x[0], x[1], x[2], x[3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int rl = it * 8 + (lane >> 2), c4 = lane & 3;
+                const long long m = (long long)m0 + warp * 32 + rl;
+                if (m < p.M)
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldo + n + 4 * c4) =
+                        *reinterpret_cast<const float4*>(&f32_stg[warp][rl][4 * c4]);
+            }
+            __syncwarp();
+            continue;
+        }
+        if (!rowok) continue;
         float v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
@@ -324,14 +357,15 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
                     tc::mbar_wait(&empty_bar[s], ph ^ 1);
                     unsigned char* st = smem + s * stage_bytes;
                     const int tap = it / cchunks, c0 = (it - tap * cchunks) * p.kc;
-                    mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + b_bytes));
+                    const bool load_b = !(p.dbg & 8) || tile == (int)blockIdx.x;
+                    mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + (load_b ? b_bytes : 0)));
                     if (FLAT) {
                         tma_load_2d(st, &map_a, c0, m0, &full_bar[s]);
                     } else {
                         const int ky = tap / p.KW, kx = tap - ky * p.KW;
                         tma_load_4d(st, &map_a, c0, ox0 * p.stride + kx - p.pad, oy0 * p.stride + ky - p.pad, b, &full_bar[s]);
                     }
-                    tma_load_2d(st + a_bytes, &map_b, tap * p.Cin + c0, n0, &full_bar[s]);
+                    if (load_b) tma_load_2d(st + a_bytes, &map_b, tap * p.Cin + c0, n0, &full_bar[s]);
                     if (++s == nst) { s = 0; ph ^= 1; }
                 }
             }
@@ -395,14 +429,20 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
             tc::mbar_wait(&tfull_bar[acc], (titer >> 1) & 1);
             tc::fence_after_sync();
             uint32_t rr[NC];
-            if constexpr (NC == 32) tc::tmem_ld32(lane_addr + acc * BN, rr);
-            else if constexpr (NC == 16) tc::tmem_ld16(lane_addr + acc * BN, rr);
-            else tc::tmem_ld8(lane_addr + acc * BN, rr);
-            tc::tmem_ld_wait();
+            if (!(p.dbg & 4)) {
+                if constexpr (NC == 32) tc::tmem_ld32(lane_addr + acc * BN, rr);
+                else if constexpr (NC == 16) tc::tmem_ld16(lane_addr + acc * BN, rr);
+                else tc::tmem_ld8(lane_addr + acc * BN, rr);
+                tc::tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) rr[j] = 0u;
+            }
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);   // accumulator drained: the MMAs of tile i+2 may start
             constexpr int CH = NC < 16 ? NC : 16;          // process 8 / 16 columns at a time (register budget: 2 CTAs/SM)
+            if (p.dbg & 2) continue;
 #pragma unroll
             for (int c0 = 0; c0 < NC; c0 += CH) {
                 float v[CH];
@@ -443,16 +483,57 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
                     *reinterpret_cast<uint4*>(sbuf + off) = w;
                 }
             }
-            tc::fence_proxy_async();                       // staged tile -> visible to the TMA store
-            if (elected) tma_store_wait_read0();           // the previous tile's store has released the other buffer
-            epi_barrier();
-            if (elected) {
-                if (FLAT) tma_store_2d(&map_o, sbuf, n0, m0);
-                else tma_store_4d(&map_o, sbuf, n0, ox0, oy0, b);
-                tma_store_commit();
+            if (p.direct_store) {
+                // The TMA unit of an SM moves ~16 bytes per clock in this kernel, loads and stores together (4 launches of
+                // profiles/r02_tcconv2_ncu.txt: 14-17 B/clk/SM whatever the shape), and on the K <= 64 layers the output tile is 40 %
+                // of that traffic: here the epilogue warps write the staged tile out themselves, 16 bytes per thread, a warp
+                // instruction covering 4 (BN = 64) ... 16 (BN = 16) whole output rows.
+                epi_barrier();                             // tile staged (generic-proxy writes: the barrier orders them)
+                constexpr int CPR = BN / 8;                // 16-byte chunks per row
+                const int et = tid - 64;                   // 0..255
+#pragma unroll
+                for (int k = 0; k < (CV_BM * CPR) / CV2_EPI_THREADS; ++k) {
+                    const int c = et + k * CV2_EPI_THREADS;
+                    const int row = c / CPR, ch = c - row * CPR;
+                    uint32_t off;
+                    if (OUT_ROW == 128) off = tc::sw128_offset(row, ch);
+                    else if (OUT_ROW == 64) off = tc::sw64_offset(row, ch);
+                    else off = (uint32_t)(row * 32 + ((ch ^ ((row >> 2) & 1)) << 4));
+                    long long gp;
+                    bool ok;
+                    if (FLAT) {
+                        gp = (long long)m0 + row;
+                        ok = gp < p.M;
+                    } else {
+                        const int ty = row / p.TW, tx = row - ty * p.TW;
+                        const int oy = oy0 + ty, ox = ox0 + tx;
+                        ok = ty < p.TH && oy < p.Ho && ox < p.Wo;
+                        gp = ((long long)b * p.Ho + oy) * p.Wo + ox;
+                    }
+                    const int nn = n0 + ch * 8;
+                    if (ok && nn < p.Cout) {
+                        __half* dst = reinterpret_cast<__half*>(p.out) + gp * p.ldo + nn;
+                        const uint4 w = *reinterpret_cast<const uint4*>(sbuf + off);
+                        if (nn + 8 <= p.Cout) {
+                            *reinterpret_cast<uint4*>(dst) = w;
+                        } else {
+                            const __half* hw = reinterpret_cast<const __half*>(&w);
+                            for (int e = 0; nn + e < p.Cout; ++e) dst[e] = hw[e];
+                        }
+                    }
+                }
+            } else {
+                tc::fence_proxy_async();                   // staged tile -> visible to the TMA store
+                if (elected) tma_store_wait_read0();       // the previous tile's store has released the other buffer
+                epi_barrier();
+                if (elected && !(p.dbg & 1)) {
+                    if (FLAT) tma_store_2d(&map_o, sbuf, n0, m0);
+                    else tma_store_4d(&map_o, sbuf, n0, ox0, oy0, b);
+                    tma_store_commit();
+                }
             }
         }
-        if (elected) tma_store_wait_all();
+        if (elected && !p.direct_store) tma_store_wait_all();
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -480,6 +561,9 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
     return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+static int g_conv2_direct_store = 0;   // measured slower on every layer shape (profiles/r02_op_bench.json): the epilogue warps are the critical resource
+static int g_conv2_debug = 0;          // timing experiments only (ym_set_conv2_debug): results are invalid when non-zero
+
 template <int BN, bool FLAT>
 static int launch_conv2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const TcConvParams& p_in, int m_tiles,
                         int n_tiles, cudaStream_t st) {
@@ -487,6 +571,9 @@ static int launch_conv2(const CUtensorMap& ma, const CUtensorMap& mb, const CUte
     const int row_bytes = p.kc * 2;
     const int stage = ((CV_BM * row_bytes + BN * row_bytes + 1023) / 1024) * 1024;
     p.stages = cv2_stages(stage);
+    p.direct_store = g_conv2_direct_store;
+    p.dbg = g_conv2_debug & 15;
+    if ((g_conv2_debug >> 4) & 15) p.stages = (g_conv2_debug >> 4) & 15;
     const size_t smem = (size_t)p.stages * stage + 2 * (size_t)CV_BM * BN * 2 + 1024;
     auto kern = tc_conv2_kernel<BN, FLAT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -655,4 +742,20 @@ extern "C" int ym_conv2d_tc(const void* x, int ldx, int B, int H, int W, int Cin
         default: return YM_LC(128);
     }
 #undef YM_LC
+}
+
+// Output path of the persistent tcgen05 conv kernel: 1 = the epilogue warps store the staged tile (default), 0 = TMA store.  Returns the
+// previous setting (A/B measurements and tests; results are bit-identical).
+extern "C" int ym_set_conv2_direct_store(int on) {
+    const int old = g_conv2_direct_store;
+    if (on == 0 || on == 1) g_conv2_direct_store = on;
+    return old;
+}
+
+// Timing experiments on the persistent kernel (tools/conv2_probe.py): bits 0-3 switch parts of it off (TcConvParams::dbg), bits 4-7
+// override the operand ring depth.  Outputs are INVALID while non-zero; nothing in the package sets it.  Returns the previous value.
+extern "C" int ym_set_conv2_debug(int flags) {
+    const int old = g_conv2_debug;
+    if (flags >= 0 && flags < 256) g_conv2_debug = flags;
+    return old;
 }
