@@ -32,11 +32,11 @@ int ym_conv2d_nhwc(const void* x, int ldx, int B, int H, int W, int Cin, const v
 /* Kernel behind ym_conv2d_nhwc for 3x3 / pad 1 layers with Cin in {8, 16}, Cout in {8, 16, 32}, fp16 output: 1 = patch-staged kernel
  * (csrc/small_conv.cu, default), 0 = the implicit GEMM every other shape takes.  Returns the previous setting. */
 int ym_set_small_conv_impl(int impl);
-/* Output path of the persistent tcgen05 convolution kernel behind ym_conv2d_tc: 1 = its epilogue warps copy the staged tile to global
- * memory with 16-byte stores (default), 0 = one TMA store per tile.  Bit-identical results.  Returns the previous setting. */
-int ym_set_conv2_direct_store(int on);
+/* Epilogue organisation of the persistent tcgen05 convolution kernel behind ym_conv2d_tc: 2 = two groups of four warps take alternate
+ * tiles (default), 1 = all eight warps work on every tile.  Bit-identical results.  Returns the previous setting. */
+int ym_set_conv2_epi_groups(int n);
 /* Timing experiments on the persistent tcgen05 convolution kernel (tools/conv2_probe.py): bit 0 no TMA store, bit 1 no epilogue
- * arithmetic / staging, bit 2 no tensor-memory read, bit 3 weights loaded for a CTA's first tile only, bits 4-7 operand ring depth.
+ * arithmetic / staging, bit 2 no tensor-memory read, bit 3 weights loaded for a CTA's first tile only, bit 4 no proxy fence, bit 5 no epilogue barrier, bit 6 no staging writes, bits 8-11 operand ring depth.
  * Outputs are INVALID while the value is non-zero; the package never sets it.  Returns the previous value. */
 int ym_set_conv2_debug(int flags);
 

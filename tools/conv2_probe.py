@@ -40,9 +40,9 @@ def timed(fn, reps=20):
     return e0.elapsed_time(e1) / (5 * reps) * 1e3
 
 
-FLAGS = [("full kernel", 0), ("no TMA store", 1), ("no epilogue arithmetic / staging / store", 3), ("no tensor-memory read either", 7),
-         ("weights once per CTA", 8), ("weights once + no store", 9), ("ring 2", 2 << 4), ("ring 4", 4 << 4), ("ring 6 (one CTA per SM)", 6 << 4),
-         ("ring 8 (one CTA per SM)", 8 << 4)]
+FLAGS = [("full kernel", 0), ("no TMA store", 1), ("no store, no proxy fence", 1 | 16), ("no store, no fence, no barrier", 1 | 16 | 32),
+         ("no store / fence / barrier / staging writes (arithmetic only)", 1 | 16 | 32 | 64), ("no epilogue arithmetic / staging / store", 3),
+         ("no tensor-memory read either", 7), ("weights once per CTA", 8), ("ring 2", 2 << 8), ("ring 4 (one CTA per SM)", 4 << 8)]
 res = {}
 for (c1, c2, k, st, hw, act) in [(64, 192, 1, 1, 80, False), (48, 64, 1, 1, 160, True), (192, 64, 1, 1, 80, True), (32, 64, 3, 2, 160, True)]:
     conv = M.Conv(c1, c2, k, st, act=act).cuda().eval()

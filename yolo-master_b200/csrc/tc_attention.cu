@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(TA_THREADS) tc_attention_kernel(const __half* 
     // TMEM columns: S [0,64), O [64,64+DV), L (row sums, 16 cols) [64+DV, 80+DV)
     constexpr uint32_t TMEM_COLS = (DV == 32) ? 128 : 256;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS, not generic ST)
     unsigned char* sQ = smem;
     unsigned char* sP = sQ + Q_BYTES;
     unsigned char* sK = sP + P_BYTES;                      // [STAGES][K_BYTES]

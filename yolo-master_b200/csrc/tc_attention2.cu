@@ -72,7 +72,7 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     constexpr uint32_t QT_COLS = 64 + 32 + DV;                 // tensor-memory columns of one query tile: S | P | O
     constexpr uint32_t TMEM_COLS = (DV == 32) ? 256 : 512;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS, not generic ST)
     unsigned char* sQ = smem;                                  // 2 x [128 rows x 64 B], SW64
     unsigned char* sKV = sQ + 2 * Q_BYTES;                     // [STAGES][K tile | V tile]
     __shared__ A2Bars bars;

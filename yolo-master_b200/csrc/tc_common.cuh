@@ -18,8 +18,16 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;                                   // the common case costs three instructions
     long long t0 = 0;
-    for (uint32_t it = 0; !done; ++it) {
+    for (uint32_t it = 1; !done; ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -27,7 +35,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
-        if (!done && (it & 63u) == 63u) {
+        if (!done && (it & 255u) == 0u) {               // watchdog: a protocol error traps after ~1 s instead of hanging the GPU
             const long long now = clock64();
             if (t0 == 0) t0 = now;
             else if (now - t0 > 2000000000LL) __trap();

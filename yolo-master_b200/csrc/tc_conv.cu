@@ -31,7 +31,7 @@ struct TcConvParams {
     int M;             // flat mode: B*H*W rows
     int act;
     int stages;        // operand ring depth of the persistent kernel (set by launch_conv2)
-    int direct_store;  // persistent kernel: 1 = the epilogue warps copy the staged tile to global memory themselves, 0 = one TMA store
+    int epi_groups;    // persistent kernel: 1 = eight epilogue warps per tile, 2 = two groups of four on alternate tiles
     int dbg;           // timing experiments: bit 0 no TMA store, bit 1 no epilogue arithmetic / staging, bit 2 no tensor-memory read, bit 3 weights loaded for the first tile only
 };
 
@@ -56,7 +56,7 @@ template <int BN, bool FLAT>
 __global__ void __launch_bounds__(CV_THREADS) tc_conv_kernel(const __grid_constant__ CUtensorMap map_a,
                                                              const __grid_constant__ CUtensorMap map_b, const TcConvParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS, not generic ST)
     const int row_bytes = p.kc * 2;                       // 32 / 64 / 128
     const int a_bytes = CV_BM * row_bytes, b_bytes = BN * row_bytes;
     const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
@@ -285,13 +285,16 @@ __device__ __forceinline__ void silu_array(float (&v)[NC]) {
     for (int j = 0; j < NC; ++j) v[j] *= e[j];
 }
 
-template <int BN, bool FLAT>
+template <int BN, bool FLAT, bool DBG>
 __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                const __grid_constant__ CUtensorMap map_b,
                                                                const __grid_constant__ CUtensorMap map_o, const TcConvParams p,
                                                                int m_tiles, int n_tiles) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET arithmetic: a round trip through uintptr_t loses the shared address space and every staging store
+    // below became a generic ST.E.128 with 64-bit address arithmetic and a MEMBAR before the proxy fence (SASS of round-2 call 12)
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    const int dbg = DBG ? p.dbg : 0;                       // timing probe (tools/conv2_probe.py): compiled out of the production kernels
     const int row_bytes = p.kc * 2;
     const int a_bytes = CV_BM * row_bytes, b_bytes = BN * row_bytes;
     const int stage_bytes = ((a_bytes + b_bytes + 1023) / 1024) * 1024;
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
     constexpr int OUT_BYTES = CV_BM * OUT_ROW;
     const int nst = p.stages;
     unsigned char* stg = smem + nst * stage_bytes;         // [2][OUT_BYTES], 1024-aligned
-    __shared__ uint64_t full_bar[CV2_MAX_STAGES], empty_bar[CV2_MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint64_t full_bar[CV2_MAX_STAGES], empty_bar[CV2_MAX_STAGES], tfull_bar[2], tempty_bar[2], sfree_bar[2];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float sbias[1024 + 64];       // folded-BN bias, zero padded past Cout
     constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
@@ -313,7 +316,8 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(&tfull_bar[a], 1);
-            tc::mbar_init(&tempty_bar[a], 8);          // one arrive per epilogue warp
+            tc::mbar_init(&tempty_bar[a], p.epi_groups == 2 ? 4 : 8);   // one arrive per epilogue warp working on that accumulator
+            tc::mbar_init(&sfree_bar[a], 1);          // two-group epilogue: the group's staging buffer has been read by its last store
         }
         tc::fence_mbar_init();
     }
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
                     tc::mbar_wait(&empty_bar[s], ph ^ 1);
                     unsigned char* st = smem + s * stage_bytes;
                     const int tap = it / cchunks, c0 = (it - tap * cchunks) * p.kc;
-                    const bool load_b = !(p.dbg & 8) || tile == (int)blockIdx.x;
+                    const bool load_b = !(dbg & 8) || tile == (int)blockIdx.x;
                     mbar_expect_tx(&full_bar[s], (uint32_t)(a_bytes + (load_b ? b_bytes : 0)));
                     if (FLAT) {
                         tma_load_2d(st, &map_a, c0, m0, &full_bar[s]);
@@ -394,20 +398,38 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
             }
         }
     } else {
-        // ===== 8 epilogue warps: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4
-        constexpr int NC = BN / 2;                 // columns per thread: 8 / 16 / 32
+        // ===== 8 epilogue warps: TMEM lane quarter = warp % 4 (hardware rule).
+        // p.epi_groups == 1: all eight work on the same tile, column half = (warp - 2) / 4.
+        // p.epi_groups == 2: warps 2-5 and 6-9 are two independent groups that take ALTERNATE tiles (group g owns accumulator g, staging
+        //   buffer g and named barrier 1 + g); a thread then handles every column of its row in two passes.  One tile's chain - wait for
+        //   the accumulator, tensor-memory read, bias / SiLU (2 MUFU per value: the busiest unit of these kernels), staging, barrier,
+        //   store - no longer holds all epilogue warps of the CTA: with the timing probe (profiles/r02_conv2_probe.json) the arithmetic
+        //   and the CTA-wide barrier were 29 + 10 us of a 61 us layer whose loads alone take 18 us.
+        constexpr int NC = BN / 2;                 // columns per thread and pass: 8 / 16 / 32
+        const int ngrp = p.epi_groups, grp = ngrp == 2 ? (warp - 2) >> 2 : 0;
         const int q = warp & 3, half = (warp - 2) >> 2;
+        const int npass = ngrp == 2 ? 2 : 1;
         const int r = q * 32 + lane;
-        const int cbase = half * NC;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + cbase;
-        const bool elected = (warp == 2 && lane == 0);
-        uint32_t titer = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++titer) {
-            int n0, m0, b, oy0, ox0;
-            tile_coords(tile, n0, m0, b, oy0, ox0);
-            const uint32_t acc = titer & 1;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool elected = ((ngrp == 2 ? (warp & 3) == 2 : warp == 2) && lane == 0);
+        uint32_t titer = 0;                        // this group's tile counter
+        // (m tile, n tile) of the group's current tile, advanced by carry instead of a division per tile
+        const int tstep = ngrp * (int)gridDim.x, step_mt = tstep / n_tiles, step_nt = tstep - step_mt * n_tiles;
+        int cur_mt = (int)(blockIdx.x + grp * gridDim.x) / n_tiles, cur_nt = (int)(blockIdx.x + grp * gridDim.x) - cur_mt * n_tiles;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += tstep, ++titer) {
+            int n0, m0, b = 0, oy0 = 0, ox0 = 0;
+            if (FLAT) {
+                n0 = cur_nt * BN;
+                m0 = cur_mt * CV_BM;
+                cur_nt += step_nt;
+                cur_mt += step_mt;
+                if (cur_nt >= n_tiles) { cur_nt -= n_tiles; ++cur_mt; }
+            } else {
+                tile_coords(tile, n0, m0, b, oy0, ox0);
+            }
+            const uint32_t acc = ngrp == 2 ? (uint32_t)grp : (titer & 1);
+            const uint32_t acc_phase = ngrp == 2 ? (titer & 1) : ((titer >> 1) & 1);
             unsigned char* sbuf = stg + acc * OUT_BYTES;
-            const int n = n0 + cbase;
             long long opix;
             bool rowok;
             if (FLAT) {
@@ -419,121 +441,108 @@ __global__ void __launch_bounds__(CV2_THREADS, 2) tc_conv2_kernel(const __grid_c
                 rowok = oy < p.Ho && ox < p.Wo;
                 opix = ((long long)b * p.Ho + oy) * p.Wo + ox;
             }
-            // residual slice of this thread's row: issued before waiting for the accumulator, lands while the MMAs run
-            Half8 rv[NC / 8];
-            const bool has_res = p.res != nullptr && rowok && n + NC <= p.Cout;
-            if (has_res) {
-#pragma unroll
-                for (int c = 0; c < NC / 8; ++c) rv[c] = *reinterpret_cast<const Half8*>(p.res + opix * p.ldr + n + c * 8);
-            }
-            tc::mbar_wait(&tfull_bar[acc], (titer >> 1) & 1);
-            tc::fence_after_sync();
-            uint32_t rr[NC];
-            if (!(p.dbg & 4)) {
-                if constexpr (NC == 32) tc::tmem_ld32(lane_addr + acc * BN, rr);
-                else if constexpr (NC == 16) tc::tmem_ld16(lane_addr + acc * BN, rr);
-                else tc::tmem_ld8(lane_addr + acc * BN, rr);
-                tc::tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int j = 0; j < NC; ++j) rr[j] = 0u;
-            }
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);   // accumulator drained: the MMAs of tile i+2 may start
-            constexpr int CH = NC < 16 ? NC : 16;          // process 8 / 16 columns at a time (register budget: 2 CTAs/SM)
-            if (p.dbg & 2) continue;
-#pragma unroll
-            for (int c0 = 0; c0 < NC; c0 += CH) {
-                float v[CH];
-#pragma unroll
-                for (int j = 0; j < CH; j += 4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(&sbias[n + c0 + j]);
-                    v[j] = __uint_as_float(rr[c0 + j]) + bb.x;
-                    v[j + 1] = __uint_as_float(rr[c0 + j + 1]) + bb.y;
-                    v[j + 2] = __uint_as_float(rr[c0 + j + 2]) + bb.z;
-                    v[j + 3] = __uint_as_float(rr[c0 + j + 3]) + bb.w;
-                }
-                if (p.act == 1) silu_array<CH>(v);
+            bool waited = false;
+            for (int pass = 0; pass < npass; ++pass) {
+                const int cbase = (ngrp == 2 ? pass : half) * NC;
+                const int n = n0 + cbase;
+                // residual slice of this thread's row: issued before waiting for the accumulator, lands while the MMAs run
+                Half8 rv[NC / 8];
+                const bool has_res = p.res != nullptr && rowok && n + NC <= p.Cout;
                 if (has_res) {
 #pragma unroll
-                    for (int c = 0; c < CH / 8; ++c)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f = __half22float2(rv[c0 / 8 + c].v[j]);
-                            v[c * 8 + 2 * j] += f.x;
-                            v[c * 8 + 2 * j + 1] += f.y;
-                        }
-                } else if (p.res != nullptr && rowok) {
-                    for (int j = 0; j < CH && n + c0 + j < p.Cout; ++j) v[j] += __half2float(p.res[opix * p.ldr + n + c0 + j]);
+                    for (int c = 0; c < NC / 8; ++c) rv[c] = *reinterpret_cast<const Half8*>(p.res + opix * p.ldr + n + c * 8);
                 }
-                // staged row r, 16-byte chunks of this thread's column half, swizzled as the TMA store map expects
+                if (!waited) {
+                    tc::mbar_wait(&tfull_bar[acc], acc_phase);
+                    tc::fence_after_sync();
+                    waited = true;
+                }
+                uint32_t rr[NC];
+                if (!(dbg & 4)) {
+                    const uint32_t ta = lane_base + acc * BN + cbase;
+                    if constexpr (NC == 32) tc::tmem_ld32(ta, rr);
+                    else if constexpr (NC == 16) tc::tmem_ld16(ta, rr);
+                    else tc::tmem_ld8(ta, rr);
+                    tc::tmem_ld_wait();
+                } else {
 #pragma unroll
-                for (int c = 0; c < CH / 8; ++c) {
-                    uint4 w;
-                    w.x = pack_half2(v[8 * c + 0], v[8 * c + 1]);
-                    w.y = pack_half2(v[8 * c + 2], v[8 * c + 3]);
-                    w.z = pack_half2(v[8 * c + 4], v[8 * c + 5]);
-                    w.w = pack_half2(v[8 * c + 6], v[8 * c + 7]);
-                    const int ch = (cbase + c0) / 8 + c;
-                    uint32_t off;
-                    if (OUT_ROW == 128) off = tc::sw128_offset(r, ch);
-                    else if (OUT_ROW == 64) off = tc::sw64_offset(r, ch);
-                    else off = (uint32_t)(r * 32 + ((ch ^ ((r >> 2) & 1)) << 4));   // 32-byte swizzle
-                    *reinterpret_cast<uint4*>(sbuf + off) = w;
+                    for (int j = 0; j < NC; ++j) rr[j] = 0u;
+                }
+                if (pass == npass - 1) {
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&tempty_bar[acc]);   // accumulator drained: the MMAs of the next tile on it may start
+                }
+                constexpr int CH = NC < 16 ? NC : 16;      // process 8 / 16 columns at a time (register budget: 2 CTAs/SM)
+                if (dbg & 2) continue;
+                if (ngrp == 2 && pass == 0) {
+                    // a group has ONE staging buffer: the TMA store of its previous tile must have read it before anyone writes again.
+                    // The store was issued a whole accumulator wait + tensor-memory read ago, so this rarely blocks.
+                    if (elected) {
+                        tma_store_wait_read0();
+                        tc::mbar_arrive(&sfree_bar[grp]);
+                    }
+                    tc::mbar_wait(&sfree_bar[grp], titer & 1);
+                }
+#pragma unroll
+                for (int c0 = 0; c0 < NC; c0 += CH) {
+                    float v[CH];
+#pragma unroll
+                    for (int j = 0; j < CH; j += 4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(&sbias[n + c0 + j]);
+                        v[j] = __uint_as_float(rr[c0 + j]) + bb.x;
+                        v[j + 1] = __uint_as_float(rr[c0 + j + 1]) + bb.y;
+                        v[j + 2] = __uint_as_float(rr[c0 + j + 2]) + bb.z;
+                        v[j + 3] = __uint_as_float(rr[c0 + j + 3]) + bb.w;
+                    }
+                    if (p.act == 1) silu_array<CH>(v);
+                    if (has_res) {
+#pragma unroll
+                        for (int c = 0; c < CH / 8; ++c)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = __half22float2(rv[c0 / 8 + c].v[j]);
+                                v[c * 8 + 2 * j] += f.x;
+                                v[c * 8 + 2 * j + 1] += f.y;
+                            }
+                    } else if (p.res != nullptr && rowok) {    // ragged channel tail: static indices (a runtime-bounded loop put v[] in local memory)
+#pragma unroll
+                        for (int j = 0; j < CH; ++j)
+                            if (n + c0 + j < p.Cout) v[j] += __half2float(p.res[opix * p.ldr + n + c0 + j]);
+                    }
+                    // staged row r, 16-byte chunks of this thread's columns, swizzled as the TMA store map expects
+#pragma unroll
+                    for (int c = 0; c < CH / 8; ++c) {
+                        uint4 w;
+                        w.x = pack_half2(v[8 * c + 0], v[8 * c + 1]);
+                        w.y = pack_half2(v[8 * c + 2], v[8 * c + 3]);
+                        w.z = pack_half2(v[8 * c + 4], v[8 * c + 5]);
+                        w.w = pack_half2(v[8 * c + 6], v[8 * c + 7]);
+                        const int ch = (cbase + c0) / 8 + c;
+                        uint32_t off;
+                        if (OUT_ROW == 128) off = tc::sw128_offset(r, ch);
+                        else if (OUT_ROW == 64) off = tc::sw64_offset(r, ch);
+                        else off = (uint32_t)(r * 32 + ((ch ^ ((r >> 2) & 1)) << 4));   // 32-byte swizzle
+                        if (!(dbg & 64)) *reinterpret_cast<uint4*>(sbuf + off) = w;
+                        else if (w.x == 0x7fc07fc0u) sbuf[off] = 1;   // keeps the arithmetic alive
+                    }
                 }
             }
-            if (p.direct_store) {
-                // The TMA unit of an SM moves ~16 bytes per clock in this kernel, loads and stores together (4 launches of
-                // profiles/r02_tcconv2_ncu.txt: 14-17 B/clk/SM whatever the shape), and on the K <= 64 layers the output tile is 40 %
-                // of that traffic: here the epilogue warps write the staged tile out themselves, 16 bytes per thread, a warp
-                // instruction covering 4 (BN = 64) ... 16 (BN = 16) whole output rows.
-                epi_barrier();                             // tile staged (generic-proxy writes: the barrier orders them)
-                constexpr int CPR = BN / 8;                // 16-byte chunks per row
-                const int et = tid - 64;                   // 0..255
-#pragma unroll
-                for (int k = 0; k < (CV_BM * CPR) / CV2_EPI_THREADS; ++k) {
-                    const int c = et + k * CV2_EPI_THREADS;
-                    const int row = c / CPR, ch = c - row * CPR;
-                    uint32_t off;
-                    if (OUT_ROW == 128) off = tc::sw128_offset(row, ch);
-                    else if (OUT_ROW == 64) off = tc::sw64_offset(row, ch);
-                    else off = (uint32_t)(row * 32 + ((ch ^ ((row >> 2) & 1)) << 4));
-                    long long gp;
-                    bool ok;
-                    if (FLAT) {
-                        gp = (long long)m0 + row;
-                        ok = gp < p.M;
-                    } else {
-                        const int ty = row / p.TW, tx = row - ty * p.TW;
-                        const int oy = oy0 + ty, ox = ox0 + tx;
-                        ok = ty < p.TH && oy < p.Ho && ox < p.Wo;
-                        gp = ((long long)b * p.Ho + oy) * p.Wo + ox;
-                    }
-                    const int nn = n0 + ch * 8;
-                    if (ok && nn < p.Cout) {
-                        __half* dst = reinterpret_cast<__half*>(p.out) + gp * p.ldo + nn;
-                        const uint4 w = *reinterpret_cast<const uint4*>(sbuf + off);
-                        if (nn + 8 <= p.Cout) {
-                            *reinterpret_cast<uint4*>(dst) = w;
-                        } else {
-                            const __half* hw = reinterpret_cast<const __half*>(&w);
-                            for (int e = 0; nn + e < p.Cout; ++e) dst[e] = hw[e];
-                        }
-                    }
-                }
-            } else {
-                tc::fence_proxy_async();                   // staged tile -> visible to the TMA store
-                if (elected) tma_store_wait_read0();       // the previous tile's store has released the other buffer
-                epi_barrier();
-                if (elected && !(p.dbg & 1)) {
-                    if (FLAT) tma_store_2d(&map_o, sbuf, n0, m0);
-                    else tma_store_4d(&map_o, sbuf, n0, ox0, oy0, b);
-                    tma_store_commit();
-                }
+            if (dbg & 2) continue;
+            if (!(dbg & 16)) tc::fence_proxy_async();       // staged tile -> visible to the TMA store
+            if (elected && ngrp == 1) tma_store_wait_read0();   // one group: the previous tile's store has released the OTHER buffer
+            if (!(dbg & 32)) {                           // literal barrier ids: a register id makes ptxas reserve all sixteen
+                if (ngrp == 1) epi_barrier();
+                else if (grp == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                else asm volatile("bar.sync 2, 128;\n" ::: "memory");
+            }
+            if (elected && !(dbg & 1)) {
+                if (FLAT) tma_store_2d(&map_o, sbuf, n0, m0);
+                else tma_store_4d(&map_o, sbuf, n0, ox0, oy0, b);
+                tma_store_commit();
             }
         }
-        if (elected && !p.direct_store) tma_store_wait_all();
+        if (elected) tma_store_wait_all();
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -561,21 +570,21 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
     return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-static int g_conv2_direct_store = 0;   // measured slower on every layer shape (profiles/r02_op_bench.json): the epilogue warps are the critical resource
+static int g_conv2_epi_groups = 2;
 static int g_conv2_debug = 0;          // timing experiments only (ym_set_conv2_debug): results are invalid when non-zero
 
-template <int BN, bool FLAT>
-static int launch_conv2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const TcConvParams& p_in, int m_tiles,
+template <int BN, bool FLAT, bool DBG>
+static int launch_conv2_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const TcConvParams& p_in, int m_tiles,
                         int n_tiles, cudaStream_t st) {
     TcConvParams p = p_in;
     const int row_bytes = p.kc * 2;
     const int stage = ((CV_BM * row_bytes + BN * row_bytes + 1023) / 1024) * 1024;
     p.stages = cv2_stages(stage);
-    p.direct_store = g_conv2_direct_store;
-    p.dbg = g_conv2_debug & 15;
-    if ((g_conv2_debug >> 4) & 15) p.stages = (g_conv2_debug >> 4) & 15;
+    p.epi_groups = g_conv2_epi_groups;
+    p.dbg = g_conv2_debug & 255;
+    if ((g_conv2_debug >> 8) & 15) p.stages = (g_conv2_debug >> 8) & 15;
     const size_t smem = (size_t)p.stages * stage + 2 * (size_t)CV_BM * BN * 2 + 1024;
-    auto kern = tc_conv2_kernel<BN, FLAT>;
+    auto kern = tc_conv2_kernel<BN, FLAT, DBG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ym_set_error("tc_conv2: smem attr %zu: %s", smem, cudaGetErrorString(e)); return YM_ERR_CUDA; }
     static int sms = 0;
@@ -590,6 +599,13 @@ static int launch_conv2(const CUtensorMap& ma, const CUtensorMap& mb, const CUte
     launch_pdl(kern, grid, CV2_THREADS, smem, st, ma, mb, mo, p, m_tiles, n_tiles);
     YM_CHECK_LAUNCH("tc_conv2");
     return YM_OK;
+}
+
+template <int BN, bool FLAT>
+static int launch_conv2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const TcConvParams& p, int m_tiles, int n_tiles,
+                        cudaStream_t st) {
+    if (g_conv2_debug & 255) return launch_conv2_t<BN, FLAT, true>(ma, mb, mo, p, m_tiles, n_tiles, st);
+    return launch_conv2_t<BN, FLAT, false>(ma, mb, mo, p, m_tiles, n_tiles, st);
 }
 
 template <int BN, bool FLAT>
@@ -744,18 +760,18 @@ extern "C" int ym_conv2d_tc(const void* x, int ldx, int B, int H, int W, int Cin
 #undef YM_LC
 }
 
-// Output path of the persistent tcgen05 conv kernel: 1 = the epilogue warps store the staged tile (default), 0 = TMA store.  Returns the
-// previous setting (A/B measurements and tests; results are bit-identical).
-extern "C" int ym_set_conv2_direct_store(int on) {
-    const int old = g_conv2_direct_store;
-    if (on == 0 || on == 1) g_conv2_direct_store = on;
+// Epilogue organisation of the persistent tcgen05 conv kernel: 2 = two groups of four warps on alternate tiles (default), 1 = all eight
+// warps on every tile.  Bit-identical results.  Returns the previous setting (A/B measurements and tests).
+extern "C" int ym_set_conv2_epi_groups(int n) {
+    const int old = g_conv2_epi_groups;
+    if (n == 1 || n == 2) g_conv2_epi_groups = n;
     return old;
 }
 
-// Timing experiments on the persistent kernel (tools/conv2_probe.py): bits 0-3 switch parts of it off (TcConvParams::dbg), bits 4-7
-// override the operand ring depth.  Outputs are INVALID while non-zero; nothing in the package sets it.  Returns the previous value.
+// Timing experiments on the persistent kernel (tools/conv2_probe.py): bits 0-3 switch parts of it off (TcConvParams::dbg), bit 4 no proxy fence, bit 5 no epilogue barrier, bit 6 no staging
+// writes; bits 8-11 override the operand ring depth.  Outputs are INVALID while non-zero; nothing in the package sets it.  Returns the previous value.
 extern "C" int ym_set_conv2_debug(int flags) {
     const int old = g_conv2_debug;
-    if (flags >= 0 && flags < 256) g_conv2_debug = flags;
+    if (flags >= 0 && flags < 4096) g_conv2_debug = flags;
     return old;
 }

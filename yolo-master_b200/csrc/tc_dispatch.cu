@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) tc_dispatch_kernel(const __grid
                                                                     const __grid_constant__ CUtensorMap map_w,
                                                                     const __grid_constant__ CUtensorMap map_o, const DispatchParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS, not generic ST)
     constexpr int A_CHUNK = DP_BM * 128, A_TILE = 4 * A_CHUNK, B_TILE = DP_BN * 128, STG_HALF = DP_BM * 128;
     const int kchunks = p.K / DP_KC;                       // <= 4
     unsigned char* sA = smem;                              // [2 tiles][4][A_CHUNK]  128 KB: the next x tile lands while this one is multiplied

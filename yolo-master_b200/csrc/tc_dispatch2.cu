@@ -98,7 +98,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DQ_THREADS, 1)
     tc_dispatch2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                         const __grid_constant__ CUtensorMap map_o, const Dispatch2Params p) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS, not generic ST)
     constexpr int A_CHUNK = DQ_BM * 128, A_TILE = 4 * A_CHUNK, B_SLOT = 128 * 128, B_BYTES = (NI / 2) * 128, NCT = NI / 2;
     const int kchunks = p.K / DQ_KC;                       // <= 4
     unsigned char* sA = smem;                              // [2 tiles][4][A_CHUNK]  128 KB

@@ -47,7 +47,7 @@ template <int BN, bool GROUPED>
 __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const TcGemmParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned operand ring
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS, not generic ST)
     constexpr int A_BYTES = TC_BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
     __shared__ uint64_t mma_bar[TC_STAGES];
     __shared__ uint64_t done_bar;
