@@ -24,7 +24,7 @@ constexpr int RT_TY = 4, RT_TX = 16, RT_HY = RT_TY + 2, RT_HX = RT_TX + 2, RT_QU
 // The input-channel reduction of an item is split over S = blockDim / (RT_QUADS * Cr) slices (threads of the same (quad, r), different
 // channel ranges; up to 512 threads per CTA): the per-thread chain of weight loads (L2-latency bound: 288 dependent iterations at
 // C = 128) shrinks S-fold, and at Cr = 8 the half of the CTA that had no item gets one.  Slice partials are summed in slice order.
-__global__ void __launch_bounds__(512) router_fused_kernel(const __half* __restrict__ x, int ldx, int H, int W, int C, int ps,
+__global__ void __launch_bounds__(512, 2) router_fused_kernel(const __half* __restrict__ x, int ldx, int H, int W, int C, int ps,
                                                            int Hp, int Wp, int Cr, const float* __restrict__ w1,
                                                            const float* __restrict__ scale1, const float* __restrict__ shift1,
                                                            float* __restrict__ partial, int tiles_x, int nblk) {
