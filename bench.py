@@ -615,7 +615,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--two-stream", action="store_true", help="(legacy experiment leg) also time two raw graph replays on two streams")
     ap.add_argument("--depth-sweep", action="store_true", help="also time PipelinedForward at depth 1 / 2 / 3 / 4")
-    ap.add_argument("--streams", type=int, default=2, help="graph instances / streams of PipelinedForward (1 = a single graph)")
+    ap.add_argument("--streams", type=int, default=4, help="graph instances / streams of PipelinedForward (1 = a single graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly ONE JSON line: libraries that print to the C-level stdout (NCCL prints "NCCL version ..." there on

@@ -126,6 +126,26 @@ def _stem_case(dtype, hw):
     assert_close(y, ref, what="stem")
 
 
+@pytest.mark.parametrize("c,hw,act", [(64, (80, 80), False), (32, (37, 23), True), (128, (40, 40), False), (64, (16, 16), False), (96, (21, 50), True)])
+def test_dwconv7_tensor_core_kernel_matches_ffma_kernel_and_oracle(c, hw, act):
+    """Depthwise 7x7 as Toeplitz GEMMs on mma.sync (csrc/dwconv_tc.cu) against the FFMA kernel it replaces and the fp32 oracle: whole and
+    ragged tiles, several channel blocks, SiLU, and the fused residual (DWConv inside a shortcut)."""
+    from yolo_master_b200 import _lib
+    m = M.Conv(c, c, 7, 1, None, g=c, act=act)
+    sd = _prep(m, seed=c + 7)
+    x = _x(2, c, *hw, seed=13)
+    outs = {}
+    for impl in (1, 0):
+        prev = _lib.load().ym_set_dwconv_tc(impl)
+        try:
+            outs[impl] = _run(m, x)
+        finally:
+            _lib.load().ym_set_dwconv_tc(prev)
+    ref = O.conv_block(sd, "m", x.float(), 1, c, act)
+    assert_close(outs[1], ref, what=f"dwconv7 tc C={c}")
+    assert float((outs[1].float() - outs[0].float()).abs().max()) <= 2e-3 * max(1.0, float(outs[0].float().abs().max()))
+
+
 @pytest.mark.parametrize("c,k,act", [(64, 3, True), (80, 3, True), (64, 7, False), (128, 7, False)])
 def test_dwconv(c, k, act):
     m = M.Conv(c, c, k, 1, None, g=c, act=act) if k == 7 else M.DWConv(c, c, k, act=act)

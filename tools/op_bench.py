@@ -61,6 +61,18 @@ if us:
     mb = (a.numel() + b.numel() + out.numel()) * 2 / 1e6
     res["concat2_p3"] = {"us": us, "GBps": mb / us * 1e3}
     print("concat2 P3", res["concat2_p3"], flush=True)
+# depthwise 7x7 (the pe convs of the area-attention blocks): Toeplitz-GEMM kernel (1) against the FFMA kernel (0)
+for (c, hw) in [(64, 80), (128, 40), (256, 20)]:
+    conv = M.Conv(c, c, 7, 1, None, g=c, act=False).cuda().eval()
+    xin = torch.randn((32, c, hw, hw), device="cuda").half().contiguous(memory_format=torch.channels_last)
+    for impl in (1, 0):
+        prev = L.ym_set_dwconv_tc(impl)
+        with torch.no_grad():
+            us = timed(lambda: conv(xin))
+        L.ym_set_dwconv_tc(prev)
+        mb = 2 * xin.numel() * 2 / 1e6
+        res[f"dwconv7_{c}_{hw}_impl{impl}"] = {"us": us, "GBps": mb / us * 1e3}
+        print("dwconv7", c, hw, "impl", impl, res[f"dwconv7_{c}_{hw}_impl{impl}"], flush=True)
 # 3x3 layers over 8 / 16 input channels: patch-staged kernel (1) against the implicit GEMM (0)
 for (c1, c2, st, hw) in [(16, 32, 2, 320), (16, 8, 1, 160), (8, 16, 1, 160), (16, 16, 1, 80), (16, 16, 1, 160)]:
     conv = M.Conv(c1, c2, 3, st).cuda().eval()

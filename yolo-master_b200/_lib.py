@@ -21,6 +21,7 @@ SIGNATURES = {
     "ym_stem_conv_nchw": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, vp, ci, vp]),
     "ym_set_stem_impl": (ci, [ci]),
     "ym_set_small_conv_impl": (ci, [ci]),
+    "ym_set_dwconv_tc": (ci, [ci]),
     "ym_set_conv2_epi_groups": (ci, [ci]),
     "ym_set_conv2_debug": (ci, [ci]),
     "ym_dwconv_nhwc": (ci, [vp, ci, ci, ci, ci, vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, vp, ci, vp]),

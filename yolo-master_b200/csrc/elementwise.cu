@@ -684,6 +684,11 @@ extern "C" int ym_stem_conv_nchw(const void* img, int in_dtype, int B, int Cin, 
 static int dwconv_impl(const void* x, int ldx, int grp_w, int grp_stride, int grp_off, const void* w, const float* bias, int B,
                        int H, int W, int C, int ksize, int act, const void* add, int ldadd, void* out, int ldo,
                        const int* route_idx, int topk, int expert, void* stream);
+namespace ym {   // dwconv_tc.cu: depthwise 7x7 as Toeplitz GEMMs on mma.sync
+int dwconv7_tc_supported(int C, int ksize, int grp_w, int B, const void* route_idx);
+int dwconv7_tc_run(const void* x, int ldx, int grp_w, int grp_stride, int grp_off, const void* w, const float* bias, int B, int H, int W, int C,
+                   int act, const void* add, int ldadd, void* out, int ldo, cudaStream_t st);
+}
 
 extern "C" int ym_dwconv_nhwc(const void* x, int ldx, int grp_w, int grp_stride, int grp_off, const void* w,
                               const float* bias, int B, int H, int W, int C, int ksize, int act, const void* add, int ldadd,
@@ -711,6 +716,12 @@ static int dwconv_impl(const void* x, int ldx, int grp_w, int grp_stride, int gr
     if (B == 0) return YM_OK;
     const long long total = (long long)B * H * W * (C / 8);
     cudaStream_t st = (cudaStream_t)stream;
+    if (ym::dwconv7_tc_supported(C, ksize, grp_w, B, route_idx)) {
+        const int rc = ym::dwconv7_tc_run(x, ldx, grp_w, grp_stride, grp_off, w, bias, B, H, W, C, act, add, ldadd, out, ldo, st);
+        if (rc) return rc;
+        YM_CHECK_LAUNCH("dwconv7_tc");
+        return YM_OK;
+    }
     const int chunks = (C % 64 == 0) ? 8 : ((C % 16 == 0) ? 2 : 0);  // source mapping is per 8-channel chunk
     if (chunks && B <= 65535) {
         const int TW = chunks == 8 ? 16 : 32, TH = chunks == 8 ? 8 : 16, CB = chunks * 8, R = ksize / 2;

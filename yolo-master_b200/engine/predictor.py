@@ -45,6 +45,7 @@ class DetectionPredictor:
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         self.stride = int(max(model.stride.tolist())) if hasattr(model, "stride") else 32
         self._letterbox = {}
+        self._staging = {}
         self.batch = None
 
     # ------------------------------------------------------------------------------------------ before the forward pass
@@ -84,7 +85,14 @@ class DetectionPredictor:
         for i, s in enumerate(shapes):
             groups.setdefault(s, []).append(i)
         for s, idxs in groups.items():   # one upload + one launch per group of same-sized frames
-            host = torch.empty((len(idxs), *s), dtype=torch.uint8, pin_memory=self.device.type == "cuda")
+            # pinned staging buffer, kept per (count, frame shape): allocating 88 MB of page-locked memory per call costs more than
+            # the copy it serves.  Reuse is safe: every call ends with a host read of the detection counts, i.e. after its H2D.
+            key = (len(idxs), s)
+            host = self._staging.get(key)
+            if host is None:
+                if len(self._staging) >= 8:
+                    self._staging.clear()
+                host = self._staging[key] = torch.empty((len(idxs), *s), dtype=torch.uint8, pin_memory=self.device.type == "cuda")
             for j, i in enumerate(idxs):
                 frame = im[i]
                 host[j].copy_(torch.from_numpy(np.ascontiguousarray(frame)) if isinstance(frame, np.ndarray) else frame)
