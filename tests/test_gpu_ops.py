@@ -141,8 +141,10 @@ def test_dwconv7_tensor_core_kernel_matches_ffma_kernel_and_oracle(c, hw, act):
             outs[impl] = _run(m, x)
         finally:
             _lib.load().ym_set_dwconv_tc(prev)
-    ref = O.conv_block(sd, "m", x.float(), 1, c, act)
+    with O.fp16_weights():   # the deployed weights: BN folded, rounded to fp16
+        ref = O.conv_block(sd, "m", x.float(), 1, c, act)
     assert_close(outs[1], ref, what=f"dwconv7 tc C={c}")
+    assert_close(outs[1], O.conv_block(sd, "m", x.float(), 1, c, act), max_bad_frac=1e-4, what="vs fp32-weight oracle")
     assert float((outs[1].float() - outs[0].float()).abs().max()) <= 2e-3 * max(1.0, float(outs[0].float().abs().max()))
 
 

@@ -8,9 +8,10 @@
 // is a 16 x 32 Toeplitz matrix times a 32 x (rows) matrix of input pixels, the SAME T for every output row y of the channel.  So per
 // channel:  D[16 px][8 rows] += T_ky[16][32] * In_ky[32][8 rows]  over the 7 filter rows = 14 mma.sync.m16n8k16 for 128 outputs x 49
 // taps (196 FFMA warp-instructions of arithmetic in the other kernel).  fp16 operands, fp32 accumulation: the same arithmetic precision.
-//   * A (Toeplitz) fragments: element (m, k) depends on k - m only, so a thread's registers are pairs (w[d], w[d+1]) at five offsets per
-//     filter row; a warp builds, per channel, a small table of all aligned pairs of the zero-extended filter row (both parities) in
-//     shared memory and every lane then reads its 35 words.
+//   * A (Toeplitz) fragments: element (m, k) depends on k - m only, so a thread's registers are pairs (w[d], w[d+1]) at the five offsets
+//     d0 - 8, d0, d0 + 8, d0 + 16, d0 + 24 (d0 = 2t - g) per filter row - and since the filter is 7 wide exactly ONE of them overlaps it.
+//     The CTA builds the eight non-trivial pairs (d = -1 .. 6) of every (channel, filter row) once in shared memory (7 KB); a lane reads
+//     its one word per filter row and places it with selects (which of the five slots is a property of the lane, not of the channel).
 //   * B (input) fragments: the CTA stages its haloed input tile TRANSPOSED, [channel][row][x] with x contiguous (16-byte global loads,
 //     2-byte shared-memory scatter), so one ldmatrix.x4 delivers both k-steps of a filter row for 8 output rows; the fourth 8-column
 //     segment (k 24..31) points at a zero strip, columns 22-23 of each row are zero.
@@ -25,7 +26,7 @@ constexpr int DT_HH = DT_TH + 2 * DT_R;          // 22 input rows
 constexpr int DT_HW = DT_TW + 2 * DT_R;          // 22 input columns
 constexpr int DT_RP = 24;                        // row pitch in halves (48 B): 22 pixels + 2 zeros; 8 rows fall in 8 distinct 16-byte bank groups
 constexpr int DT_CH_HALVES = DT_HH * DT_RP;      // 528 halves per channel
-constexpr int DT_TABW = 24;                      // words per (parity, ky) table row
+constexpr int DT_PAIRS = 8;                      // pairs (w[d], w[d+1]), d = -1 .. 6, per (channel, filter row)
 constexpr int DT_PIXP = 36;                      // staging: floats per pixel (32 channels + 4)
 constexpr int DT_ROWP = DT_TW * DT_PIXP + 4;     // staging: floats per row (580)
 
@@ -43,8 +44,8 @@ __global__ void __launch_bounds__(256, 2) dwconv7_tc_kernel(const DwTcParams p) 
     extern __shared__ __align__(16) unsigned char dt_smem[];
     __half* sIn = reinterpret_cast<__half*>(dt_smem);                                   // [32][22][24]
     __half* sW = sIn + DT_CB * DT_CH_HALVES;                                            // [49][32]
-    uint32_t* sTab = reinterpret_cast<uint32_t*>(sW + 49 * DT_CB);                      // [8 warps][2][7][24]
-    float* sOut = reinterpret_cast<float*>(sTab + 8 * 2 * DT_K * DT_TABW);              // [16 rows][580]
+    uint32_t* sTab = reinterpret_cast<uint32_t*>(sW + 49 * DT_CB);                      // [32 ch][7 ky][8 pairs]
+    float* sOut = reinterpret_cast<float*>(sTab + DT_CB * DT_K * DT_PAIRS);             // [16 rows][580]
     __half* sZero = reinterpret_cast<__half*>(sOut + DT_TH * DT_ROWP);                   // 8 rows x 16 B of zeros (one ldmatrix segment)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -61,53 +62,71 @@ __global__ void __launch_bounds__(256, 2) dwconv7_tc_kernel(const DwTcParams p) 
         *reinterpret_cast<uint32_t*>(sIn + i * DT_RP + DT_HW) = 0u;
     pdl_prologue();
 
-    // ---- haloed input tile, transposed to [channel][row][x]
+    // ---- haloed input tile, transposed to [channel][row][x].  Item = (8-channel group, pixel) with the pixel fastest: the 2-byte scatter of a
+    // warp then lands on consecutive x of one row and channel (conflict-free); the 16-byte global reads of a warp touch 32 pixels.
     {
         const __half* xb = p.x + (long long)b * p.H * p.W * p.ldx;
-        for (int i = tid; i < DT_HH * DT_HW * (DT_CB / 8); i += 256) {
-            const int c8 = i & 3, pp = i >> 2;
+        constexpr int NPIX = DT_HH * DT_HW, ITEMS = NPIX * (DT_CB / 8), ITERS = (ITEMS + 255) / 256;
+        // all (up to eight) 16-byte loads of a thread are in flight before the first scatter: behind one another each paid the full L2 / HBM
+        // latency (the first version of this kernel was no faster than the FFMA one for that reason alone)
+        uint4 v[ITERS];
+#pragma unroll
+        for (int k = 0; k < ITERS; ++k) {
+            const int i = tid + k * 256;
+            const int c8 = i / NPIX, pp = i - c8 * NPIX;
             const int hy = pp / DT_HW, hx = pp - hy * DT_HW;
             const int iy = ty0 + hy - DT_R, ix = tx0 + hx - DT_R;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+            v[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < ITEMS && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
                 const int c = cb0 + c8 * 8;
                 const int csrc = (c / p.grp_w) * p.grp_stride + p.grp_off + (c % p.grp_w);
-                v = *reinterpret_cast<const uint4*>(xb + ((long long)iy * p.W + ix) * p.ldx + csrc);
+                v[k] = *reinterpret_cast<const uint4*>(xb + ((long long)iy * p.W + ix) * p.ldx + csrc);
             }
-            const __half* hv = reinterpret_cast<const __half*>(&v);
-            __half* dst = sIn + (c8 * 8) * DT_CH_HALVES + hy * DT_RP + hx;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j * DT_CH_HALVES] = hv[j];
         }
+#pragma unroll
+        for (int k = 0; k < ITERS; ++k) {
+            const int i = tid + k * 256;
+            if (i < ITEMS) {
+                const int c8 = i / NPIX, pp = i - c8 * NPIX;
+                const int hy = pp / DT_HW, hx = pp - hy * DT_HW;
+                const __half* hv = reinterpret_cast<const __half*>(&v[k]);
+                __half* dst = sIn + (c8 * 8) * DT_CH_HALVES + hy * DT_RP + hx;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j * DT_CH_HALVES] = hv[j];
+            }
+        }
+    }
+    __syncthreads();                                              // sW is complete: build the pair table
+    for (int i = tid; i < DT_CB * DT_K * DT_PAIRS; i += 256) {
+        const int cl = i / (DT_K * DT_PAIRS), rem = i - cl * (DT_K * DT_PAIRS);
+        const int ky = rem / DT_PAIRS, d = rem - ky * DT_PAIRS - 1;             // d = -1 .. 6
+        const unsigned short lo = d >= 0 ? __half_as_ushort(sW[(ky * DT_K + d) * DT_CB + cl]) : (unsigned short)0;
+        const unsigned short hi = d + 1 < DT_K ? __half_as_ushort(sW[(ky * DT_K + d + 1) * DT_CB + cl]) : (unsigned short)0;
+        sTab[i] = (uint32_t)lo | ((uint32_t)hi << 16);
     }
     __syncthreads();
 
     const int g = lane >> 2, t = lane & 3;
-    const int par = g & 1;
-    const int i0 = (2 * t - g - par + 16) >> 1;                     // 4 .. 11
-    uint32_t* tab = sTab + warp * (2 * DT_K * DT_TABW);
+    // the lane's five pair offsets are d0 - 8 + 8 j (j = 0 .. 4), d0 = 2t - g in [-7, 6]: exactly one lies in [-1, 6]
+    const int d0 = 2 * t - g;
+    const int jstar = d0 >= -1 ? 1 : 2;                            // d0 in [-1, 6] -> slot 1 (d0 itself); d0 in [-7, -2] -> slot 2 (d0 + 8)
+    const int dstar = d0 >= -1 ? d0 : d0 + 8;                      // in [-1, 6]
     // ldmatrix row address of this lane: matrix = lane / 8 (k segment), row = lane % 8
     const int seg = lane >> 3, lrow = lane & 7;
 
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int cl = warp * 4 + cc;                               // CTA-local channel
-        // ---- table of aligned pairs of the zero-extended filter rows of this channel: word i of (parity q, ky) = (w[d], w[d+1]), d = 2i + q - 16
-        for (int idx = lane; idx < 2 * DT_K * DT_TABW; idx += 32) {
-            const int q = idx / (DT_K * DT_TABW), rem = idx - q * (DT_K * DT_TABW);
-            const int ky = rem / DT_TABW, i = rem - ky * DT_TABW;
-            const int d = 2 * i + q - 16;
-            const unsigned short lo = (d >= 0 && d < DT_K) ? __half_as_ushort(sW[(ky * DT_K + d) * DT_CB + cl]) : (unsigned short)0;
-            const unsigned short hi = (d + 1 >= 0 && d + 1 < DT_K) ? __half_as_ushort(sW[(ky * DT_K + d + 1) * DT_CB + cl]) : (unsigned short)0;
-            tab[idx] = (uint32_t)lo | ((uint32_t)hi << 16);
+        uint32_t aw[DT_K][5];                                       // pairs at d0-8, d0, d0+8, d0+16, d0+24
+#pragma unroll
+        for (int ky = 0; ky < DT_K; ++ky) {
+            const uint32_t wv = sTab[(cl * DT_K + ky) * DT_PAIRS + dstar + 1];
+            aw[ky][0] = 0u;
+            aw[ky][1] = jstar == 1 ? wv : 0u;
+            aw[ky][2] = jstar == 2 ? wv : 0u;
+            aw[ky][3] = 0u;
+            aw[ky][4] = 0u;
         }
-        __syncwarp();
-        uint32_t aw[DT_K][5];                                       // words i0-4, i0, i0+4, i0+8, i0+12 of this lane's parity
-#pragma unroll
-        for (int ky = 0; ky < DT_K; ++ky)
-#pragma unroll
-            for (int j = 0; j < 5; ++j) aw[ky][j] = tab[(par * DT_K + ky) * DT_TABW + i0 - 4 + 4 * j];
-        __syncwarp();                                               // the table is rebuilt for the next channel
         const float bias = p.bias != nullptr ? p.bias[cb0 + cl] : 0.f;
         const uint32_t in_base = smem_u32(sIn + cl * DT_CH_HALVES);
         const uint32_t zero_addr = smem_u32(sZero) + (uint32_t)(lrow * 16);
@@ -178,7 +197,7 @@ int dwconv7_tc_run(const void* x, int ldx, int grp_w, int grp_stride, int grp_of
     p.w = (const __half*)w; p.bias = bias; p.add = (const __half*)add; p.ldadd = ldadd; p.out = (__half*)out; p.ldo = ldo;
     p.H = H; p.W = W; p.C = C; p.act = act; p.tiles_x = (W + DT_TW - 1) / DT_TW;
     const int tiles_y = (H + DT_TH - 1) / DT_TH;
-    const size_t smem = (size_t)DT_CB * DT_CH_HALVES * 2 + 49 * DT_CB * 2 + (size_t)8 * 2 * DT_K * DT_TABW * 4 + (size_t)DT_TH * DT_ROWP * 4 + 128;
+    const size_t smem = (size_t)DT_CB * DT_CH_HALVES * 2 + 49 * DT_CB * 2 + (size_t)DT_CB * DT_K * DT_PAIRS * 4 + (size_t)DT_TH * DT_ROWP * 4 + 128;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(dwconv7_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
