@@ -56,8 +56,8 @@ int ym_set_stem_impl(int impl);
 int ym_dwconv_nhwc(const void* x, int ldx, int grp_w, int grp_stride, int grp_off, const void* w, const float* bias,
                    int B, int H, int W, int C, int ksize, int act, const void* add, int ldadd, void* out, int ldo,
                    void* stream);
-/* Depthwise 7x7 layers with C % 32 == 0 behind ym_dwconv_nhwc: 1 = Toeplitz-GEMM kernel on mma.sync (csrc/dwconv_tc.cu, default),
- * 0 = the FFMA kernel every other depthwise shape takes.  Returns the previous setting. */
+/* Depthwise 7x7 layers with C % 32 == 0 behind ym_dwconv_nhwc: 1 = Toeplitz-GEMM kernel on mma.sync (csrc/dwconv_tc.cu: half the
+ * instructions, the same time at bs32), 0 = the FFMA kernel every other depthwise shape takes (default).  Returns the previous setting. */
 int ym_set_dwconv_tc(int on);
 
 /* SPPF pooling: slots 1..3 of the [.., 4C] concat buffer = MaxPool(k) chained 1..3 times of slot 0 (block.py:237-242). */

@@ -184,7 +184,10 @@ __global__ void __launch_bounds__(256, 2) dwconv7_tc_kernel(const DwTcParams p) 
     }
 }
 
-static int g_dwconv_tc = 1;
+// Measured at bs32 (profiles/r02_dwconv_ncu.txt, profiles/r02_op_bench.json): 25.8 M instructions against the FFMA kernel's 43.6 M, but the same
+// 56 us per P3 launch - a CTA is four barrier-separated phases (load, pair table, MMAs, store) of ~2 us each and only two CTAs fit an SM
+// (81 KB of shared memory), so it runs at the latency of its phases.  Kept selectable (ym_set_dwconv_tc); the FFMA kernel stays the default.
+static int g_dwconv_tc = 0;
 
 int dwconv7_tc_supported(int C, int ksize, int grp_w, int B, const void* route_idx) {
     return g_dwconv_tc == 1 && ksize == 7 && C % DT_CB == 0 && grp_w % 8 == 0 && route_idx == nullptr && B <= 65535 && C / DT_CB <= 65535;
@@ -210,7 +213,7 @@ int dwconv7_tc_run(const void* x, int ldx, int grp_w, int grp_stride, int grp_of
 
 }  // namespace ym
 
-// 1 = depthwise 7x7 layers with C % 32 == 0 run on the mma.sync Toeplitz kernel (default), 0 = the FFMA kernel.  Returns the previous setting.
+// 1 = depthwise 7x7 layers with C % 32 == 0 run on the mma.sync Toeplitz kernel, 0 = the FFMA kernel (default).  Returns the previous setting.
 extern "C" int ym_set_dwconv_tc(int on) {
     const int old = ym::g_dwconv_tc;
     if (on == 0 || on == 1) ym::g_dwconv_tc = on;
