@@ -49,6 +49,13 @@ class DetectionPredictor:
         self.batch = None
 
     # ------------------------------------------------------------------------------------------ before the forward pass
+    def _copy_pool(self):
+        pool = self.__dict__.get("_pool")
+        if pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = self.__dict__["_pool"] = ThreadPoolExecutor(max_workers=8, thread_name_prefix="ym-stage")
+        return pool
+
     def _get_letterbox(self, auto: bool) -> LetterBox:
         lb = self._letterbox.get(auto)
         if lb is None:
@@ -93,9 +100,18 @@ class DetectionPredictor:
                 if len(self._staging) >= 8:
                     self._staging.clear()
                 host = self._staging[key] = torch.empty((len(idxs), *s), dtype=torch.uint8, pin_memory=self.device.type == "cuda")
-            for j, i in enumerate(idxs):
+            def stage(ji, host=host):
+                j, i = ji
                 frame = im[i]
                 host[j].copy_(torch.from_numpy(np.ascontiguousarray(frame)) if isinstance(frame, np.ndarray) else frame)
+
+            if len(idxs) >= 8 and host[0].numel() >= (1 << 20):
+                # 32 frames of 720p are 88 MB of pageable -> pinned copies: one thread moves ~10 GB/s, i.e. as long as the whole forward.
+                # The copies are independent and release the GIL: spread them over a small pool.
+                list(self._copy_pool().map(stage, enumerate(idxs)))
+            else:
+                for ji in enumerate(idxs):
+                    stage(ji)
             dev = host.to(self.device, non_blocking=True)
             contiguous_run = idxs == list(range(idxs[0], idxs[0] + len(idxs)))
             res = lb.apply_batch(dev, swap_rb=True, chw=True, dtype=out_dtype, out=out[idxs[0]:idxs[0] + len(idxs)] if contiguous_run else None)
