@@ -21,7 +21,7 @@
 
 namespace ym {
 
-constexpr int DT_TW = 16, DT_TH = 16, DT_CB = 32, DT_R = 3, DT_K = 7;
+constexpr int DT_TW = 16, DT_TH = 16, DT_CB = 32, DT_R = 3, DT_K = 7;  // (TH = 8 fits four CTAs per SM but loads 2.4x instead of 1.9x the tile: 68 us against 56)
 constexpr int DT_HH = DT_TH + 2 * DT_R;          // 22 input rows
 constexpr int DT_HW = DT_TW + 2 * DT_R;          // 22 input columns
 constexpr int DT_RP = 24;                        // row pitch in halves (48 B): 22 pixels + 2 zeros; 8 rows fall in 8 distinct 16-byte bank groups
@@ -42,7 +42,7 @@ struct DwTcParams {
 
 __global__ void __launch_bounds__(256, 2) dwconv7_tc_kernel(const DwTcParams p) {
     extern __shared__ __align__(16) unsigned char dt_smem[];
-    __half* sIn = reinterpret_cast<__half*>(dt_smem);                                   // [32][22][24]
+    __half* sIn = reinterpret_cast<__half*>(dt_smem);                                   // [32 ch][22 rows][24]
     __half* sW = sIn + DT_CB * DT_CH_HALVES;                                            // [49][32]
     uint32_t* sTab = reinterpret_cast<uint32_t*>(sW + 49 * DT_CB);                      // [32 ch][7 ky][8 pairs]
     float* sOut = reinterpret_cast<float*>(sTab + DT_CB * DT_K * DT_PAIRS);             // [16 rows][580]
@@ -185,8 +185,9 @@ __global__ void __launch_bounds__(256, 2) dwconv7_tc_kernel(const DwTcParams p) 
 }
 
 // Measured at bs32 (profiles/r02_dwconv_ncu.txt, profiles/r02_op_bench.json): 25.8 M instructions against the FFMA kernel's 43.6 M, but the same
-// 56 us per P3 launch - a CTA is four barrier-separated phases (load, pair table, MMAs, store) of ~2 us each and only two CTAs fit an SM
-// (81 KB of shared memory), so it runs at the latency of its phases.  Kept selectable (ym_set_dwconv_tc); the FFMA kernel stays the default.
+// 56 us per P3 launch - the time went from the FFMAs into the TRANSPOSING load of the input tile ([row][x][channel] in memory, [channel][row][x]
+// for ldmatrix): eight 2-byte scatters per 16-byte load, and the tile is read 1.9x with its halo.  An 8-row tile (four CTAs per SM instead of
+// two) reads 2.4x and takes 68 us: the kernel scales with the bytes it transposes, not with its occupancy.  Kept selectable (ym_set_dwconv_tc); the FFMA kernel stays the default.
 static int g_dwconv_tc = 0;
 
 int dwconv7_tc_supported(int C, int ksize, int grp_w, int B, const void* route_idx) {
