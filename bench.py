@@ -429,6 +429,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.kernel_priority:
+        from yolo_master_b200 import _lib
+        _lib.load().ym_set_kernel_priority(args.kernel_priority)     # read at launch (capture) time by every kernel but attention
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
@@ -614,6 +617,8 @@ def main():
     ap.add_argument("--ref-images", type=int, default=8, help="images per CPU-oracle step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--two-stream", action="store_true", help="(legacy experiment leg) also time two raw graph replays on two streams")
+    ap.add_argument("--kernel-priority", type=int, default=0,
+                    help="launch priority (0 = off, -1 .. -8) of every kernel except the attention kernels (ym_set_kernel_priority)")
     ap.add_argument("--depth-sweep", action="store_true", help="also time PipelinedForward at depth 1 / 2 / 3 / 4")
     ap.add_argument("--streams", type=int, default=4, help="graph instances / streams of PipelinedForward (1 = a single graph)")
     args = ap.parse_args()

@@ -142,6 +142,11 @@ int ym_gn_finalize_tiles(const float* stats, int P, int tiles, int groups, int C
  * attribute off - results are identical, only launch overlap changes).  ym_set_pdl returns the previous setting. */
 int ym_pdl_enabled(void);
 int ym_set_pdl(int on);
+/* Launch priority of every forward-path kernel EXCEPT the attention kernels (those stay at 0, the lowest): 0 = off, -1 .. -8 are passed to
+ * cudaLaunchAttributePriority.  With several graph instances in flight the slots a long attention kernel frees then go to the other
+ * instances' short kernels first.  Takes effect at launch (capture) time.  Returns the previous value. */
+int ym_kernel_priority(void);
+int ym_set_kernel_priority(int prio);
 
 /* EfficientSpatialRouter.forward + BaseRouter._process_logits (eval)  moe/routers.py:283-304, :185-265.
  * w1: fp32 [9][C/4][Cr][4] (tap-major, float4 over channels), scale1/shift1: folded BN1 [Cr]; w2: fp32 [E][Cr], scale2/shift2: folded BN2 [E].

@@ -20,6 +20,8 @@ SIGNATURES = {
     "ym_conv2d_tc": (ci, [vp, ci, ci, ci, ci, ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, ci, ci, vp, ci, ci, vp]),
     "ym_stem_conv_nchw": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, vp, ci, vp]),
     "ym_set_stem_impl": (ci, [ci]),
+    "ym_kernel_priority": (ci, []),
+    "ym_set_kernel_priority": (ci, [ci]),
     "ym_set_small_conv_impl": (ci, [ci]),
     "ym_set_dwconv_tc": (ci, [ci]),
     "ym_set_conv2_epi_groups": (ci, [ci]),

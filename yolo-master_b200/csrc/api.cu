@@ -47,3 +47,15 @@ extern "C" int ym_device_info(int* sm_major, int* sm_minor, int* sm_count, long 
     if (l2_bytes) *l2_bytes = (long long)prop.l2CacheSize;
     return YM_OK;
 }
+
+// Launch priority of the forward-path kernels relative to the long exp-bound attention kernels (which always launch at priority 0, the
+// lowest): with several graph instances in flight, the CTA slots an attention kernel frees then go first to the short kernels of the
+// other instances instead of to its own remaining CTAs.  0 = off (every kernel at the default priority); a negative value is passed to
+// cudaLaunchAttributePriority (numerically lower = scheduled first).  Returns the previous value.
+static int g_kernel_priority = 0;
+extern "C" int ym_kernel_priority(void) { return g_kernel_priority; }
+extern "C" int ym_set_kernel_priority(int prio) {
+    const int old = g_kernel_priority;
+    if (prio <= 8 && prio >= -8) g_kernel_priority = prio;   // > 0: the ATTENTION kernels launch at -prio and everything else at the default
+    return old;
+}

@@ -391,7 +391,7 @@ extern "C" int ym_attention_fwd_tc2(const void* qkv, int ld, int batch, int N, i
 #define A2_LAUNCH(DV_, POLY_, VAR_)                                                                                                        \
     do {                                                                                                                             \
         e = cudaFuncSetAttribute(tc_attention2_kernel<DV_, POLY_, VAR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-        if (e == cudaSuccess) e = launch_pdl(tc_attention2_kernel<DV_, POLY_, VAR_>, grid, A2_THREADS, smem, st, mq, mk, mv, N, sl2, (__half*)out, ldo, q_tiles, lag); \
+        if (e == cudaSuccess) e = launch_pdl_prio(ym_kernel_priority() > 0 ? -ym_kernel_priority() : 0, tc_attention2_kernel<DV_, POLY_, VAR_>, grid, A2_THREADS, smem, st, mq, mk, mv, N, sl2, (__half*)out, ldo, q_tiles, lag); \
     } while (0)
     const int poly = ym_attention2_poly();
     const int tree = g_attention2_variant & 1, lag = g_attention2_variant & 6;

@@ -23,6 +23,7 @@ extern "C" void ym_set_error(const char* fmt, ...);
 // programmatic dependent launch switch (api.cu): 1 = kernels that call ym::pdl_prologue() are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel of the stream is staged while this one drains
 extern "C" int ym_pdl_enabled(void);
+extern "C" int ym_kernel_priority(void);
 
 #define YM_CHECK_ARG(cond, ...)                 \
     do {                                        \
@@ -123,21 +124,29 @@ __device__ __forceinline__ float warp_max(float v) {
 #endif
 
 #ifndef YM_HOST_EMU
-// kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute (see pdl_prologue); the kernel MUST call pdl_wait()
+// kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute (see pdl_prologue); the kernel MUST call pdl_wait().
+// `prio` is the launch priority (cudaLaunchAttributePriority; 0 = default, lower = earlier): launch_pdl uses ym_kernel_priority().
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+static inline cudaError_t launch_pdl_prio(int prio, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = ym_pdl_enabled() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributePriority;
+    attr[1].val.priority = prio;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = ym_kernel_priority() != 0 ? 2 : 1;        // feature off: exactly the launch it always was
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    const int kp = ym_kernel_priority();
+    return launch_pdl_prio(kp < 0 ? kp : 0, kernel, grid, block, smem, stream, args...);
 }
 #endif
 
