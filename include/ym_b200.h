@@ -135,6 +135,17 @@ int ym_moe_ffn(int stage, const void* x, int ldx, int B, int HW, int C, int HID,
 int ym_moe_combine_tc_supported(int C, int ldx, int ldo);
 int ym_moe_combine_tc(const void* x, int ldx, int B, int HW, int C, const void* ws, const float* bias_s, const void* o,
                       const float* o_scale, const float* o_shift, int topk, void* out, int ldo, int add_residual, void* stream);
+/* The same two kernels finalising their GroupNorm THEMSELVES from the partial sums of the kernel before (no ym_gn_finalize_tiles launch in
+ * between; bit-identical to the two-launch form): pass 2 of ym_moe_ffn with GroupNorm-1 given as (partial sums of pass 1, groups, element
+ * count per group, eps, gamma / beta fp32 [E][HID]); the combine with GroupNorm-2 given the same way (partial sums of pass 2 over
+ * `gn2_tiles` = strips, gamma / beta fp32 [E][C]) plus the routing table and weights (route_w [B*topk] is folded into the affine). */
+int ym_moe_ffn_gn(const void* x, int ldx, int B, int HW, int C, int HID, int topk, const void* w1, const void* w2, int E, const int* route_idx,
+                  const float* gn1_stats, int gn1_groups, float gn1_count, float gn1_eps, const float* gamma1, const float* beta1, void* out,
+                  float* stats, int strips, void* stream);
+int ym_moe_combine_tc_gn(const void* x, int ldx, int B, int HW, int C, const void* ws, const float* bias_s, const void* o,
+                         const float* gn2_stats, int gn2_tiles, int gn2_groups, float gn2_count, float gn2_eps, const float* gamma2,
+                         const float* beta2, const int* route_idx, const float* route_w, int topk, void* out, int ldo, int add_residual,
+                         void* stream);
 /* ym_gn_finalize with an explicit number of partial-sum tiles per problem. */
 int ym_gn_finalize_tiles(const float* stats, int P, int tiles, int groups, int C, float count, float eps, const float* gamma,
                          const float* beta, const int* route_idx, const float* route_w, float* scale, float* shift, void* stream);

@@ -359,3 +359,26 @@ def test_tc_conv_slices_residual_f32():
     ref32 = torch.nn.functional.conv2d(x.float().cpu().permute(0, 3, 1, 2), w.half().float(), bias.cpu(), 1, 1).permute(0, 2, 3, 1)
     assert y32.dtype == torch.float32
     assert_close(y32, ref32, what="tc_conv f32 out")
+
+
+def test_moe_groupnorm_finalised_in_the_consumer_kernels_is_bit_identical():
+    """ym_moe_ffn_gn / ym_moe_combine_tc_gn (GroupNorm-1 / -2 finalised inside pass 2 / the combine from the partial sums) against the
+    three-launch form with ym_gn_finalize_tiles in between: the same bits, on both width pairs and a ragged map."""
+    from yolo_master_b200.nn.modules import moe as moe_mod
+    from yolo_master_b200.nn import modules as M
+    for C, hw in ((64, (20, 20)), (128, (13, 9))):
+        torch.manual_seed(C)
+        m = M.OptimizedMOEImproved(C, C, num_experts=4, top_k=2).to(DEV).eval()
+        for prm in m.parameters():
+            prm.data.normal_(0, 0.2)
+        x = torch.randn((3, C, *hw), device=DEV).half().contiguous(memory_format=torch.channels_last)
+        outs = {}
+        for fold in (True, False):
+            prev = moe_mod.MOE_GN_FOLD
+            moe_mod.MOE_GN_FOLD = fold
+            try:
+                with torch.no_grad():
+                    outs[fold] = m(x).clone()
+            finally:
+                moe_mod.MOE_GN_FOLD = prev
+        assert torch.equal(outs[True], outs[False]), f"C={C}: folded GroupNorm finalisation must not change a bit"

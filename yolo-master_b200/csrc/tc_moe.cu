@@ -46,6 +46,40 @@ __device__ __forceinline__ void mf_tma_load_3d(void* dst, const CUtensorMap* map
                  : "memory");
 }
 
+// GroupNorm partial sums that the CONSUMER kernel finalises itself (one launch less per GroupNorm): [problems][tiles][Cn / 8][2] as
+// written by the statistics epilogues, with the routed expert's gamma / beta tables [E][Cn].  stats == nullptr: the caller passes
+// finished scale / shift arrays instead (ym_gn_finalize_tiles).
+struct GnRaw {
+    const float* stats; int tiles, groups; float count, eps;
+    const float* gamma; const float* beta;
+    const float* route_w;      // optional per-problem factor folded into the affine (the routing weight before the combine)
+};
+
+// One warp: scale / shift of channel group `grp` of problem `pr` - the arithmetic of gn_finalize_kernel (gemm_conv.cu) operation for
+// operation, so both ways of finalising give the same bits.
+__device__ __forceinline__ void gn_group_affine(const GnRaw& g, int Cn, int pr, int e, int grp, int lane, float* scale_out, float* shift_out) {
+    const int cpg = Cn / g.groups, tpg = cpg / 8, nt8 = Cn / 8;
+    float s = 0.f, q = 0.f;
+    for (int i = lane; i < g.tiles * tpg; i += 32) {
+        const int mt = i / tpg, t = grp * tpg + i % tpg;
+        const float* src = g.stats + (((long long)pr * g.tiles + mt) * nt8 + t) * 2;
+        s += src[0];
+        q += src[1];
+    }
+    s = ym::warp_sum(s);
+    q = ym::warp_sum(q);
+    const float mean = s / g.count;
+    const float var = fmaxf(q / g.count - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + g.eps);
+    const float rw = g.route_w ? g.route_w[pr] : 1.f;
+    for (int j = lane; j < cpg; j += 32) {
+        const int c = grp * cpg + j;
+        const float gm = g.gamma[e * Cn + c], bt = g.beta[e * Cn + c];
+        scale_out[c] = rw * rstd * gm;
+        shift_out[c] = rw * (bt - mean * rstd * gm);
+    }
+}
+
 struct MoeFfnParams {
     const int* route_idx;      // [P] expert of problem p (negative = dropped route: the CTA exits)
     int a_div;                 // image of problem p = p / a_div (top_k)
@@ -54,6 +88,7 @@ struct MoeFfnParams {
     const float* a_shift;
     __half* out;               // pass 2: o [P][HW][C]
     float* stats;              // partial sums [P][strips][NS/2][2], NS/2 = (pass 1 ? HID : C) / 8 eight-channel slices
+    GnRaw gn1;                 // pass 2: GroupNorm-1 finalised here when gn1.stats != nullptr (a_scale / a_shift unused)
 };
 
 struct MfBars {
@@ -109,9 +144,13 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (active) {
         const int img = prob / p.a_div;
         if (STAGE == 2) {
-            for (int i = tid; i < HID; i += MF_THREADS) {
-                sAff[i] = p.a_scale[(long long)prob * HID + i];
-                sAff[HID + i] = p.a_shift[(long long)prob * HID + i];
+            if (p.gn1.stats != nullptr) {
+                for (int grp = warp; grp < p.gn1.groups; grp += MF_THREADS / 32) gn_group_affine(p.gn1, HID, prob, e, grp, lane, sAff, sAff + HID);
+            } else {
+                for (int i = tid; i < HID; i += MF_THREADS) {
+                    sAff[i] = p.a_scale[(long long)prob * HID + i];
+                    sAff[HID + i] = p.a_shift[(long long)prob * HID + i];
+                }
             }
         }
         __syncthreads();
@@ -299,6 +338,8 @@ struct MoeCombineParams {
     const __half* __restrict__ o;                   // [B*topk][HW][C]
     const float* __restrict__ o_scale; const float* __restrict__ o_shift;   // [B*topk][C]
     __half* __restrict__ out;       int ldo;
+    GnRaw gn2;                                      // GroupNorm-2 finalised here when gn2.stats != nullptr (o_scale / o_shift unused)
+    const int* __restrict__ route_idx;              // with gn2: expert of problem img * topk + j
     int HW, mtiles, tiles_per_strip, topk, add_residual;
 };
 struct McBars {
@@ -342,10 +383,17 @@ moe_combine_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     pdl_prologue();
     if (nt > 0) {
         for (int i = tid; i < C; i += MF_THREADS) sAff[i] = p.bias ? p.bias[i] : 0.f;
-        for (int i = tid; i < p.topk * C; i += MF_THREADS) {
-            const int j = i / C, c = i - j * C;
-            sAff[C + (2 * j) * C + c] = p.o_scale[((long long)img * p.topk + j) * C + c];
-            sAff[C + (2 * j + 1) * C + c] = p.o_shift[((long long)img * p.topk + j) * C + c];
+        if (p.gn2.stats != nullptr) {
+            for (int pg = warp; pg < p.topk * p.gn2.groups; pg += MF_THREADS / 32) {
+                const int j = pg / p.gn2.groups, grp = pg - j * p.gn2.groups, pr = img * p.topk + j;
+                gn_group_affine(p.gn2, C, pr, p.route_idx[pr], grp, lane, sAff + C + (2 * j) * C, sAff + C + (2 * j + 1) * C);
+            }
+        } else {
+            for (int i = tid; i < p.topk * C; i += MF_THREADS) {
+                const int j = i / C, c = i - j * C;
+                sAff[C + (2 * j) * C + c] = p.o_scale[((long long)img * p.topk + j) * C + c];
+                sAff[C + (2 * j + 1) * C + c] = p.o_shift[((long long)img * p.topk + j) * C + c];
+            }
         }
         __syncthreads();
         if (warp == 0) {
@@ -568,11 +616,11 @@ extern "C" long long ym_moe_ffn_stats_floats(int P, int strips, int N) { return 
 
 // stage 1: stats != null, out == null: GroupNorm-1 partial sums of h = x W1[e]^T           -> stats [P][strips][HID/8][2]
 // stage 2: out  != null              : o = SiLU(GN1(h)) W2[e]^T (fp16) and its partial sums -> out [P][HW][C], stats [P][strips][C/8][2]
-extern "C" int ym_moe_ffn(int stage, const void* x, int ldx, int B, int HW, int C, int HID, int topk, const void* w1, const void* w2, int E,
-                          const int* route_idx, const float* a_scale, const float* a_shift, void* out, float* stats, int strips,
-                          void* stream) {
+static int moe_ffn_impl(int stage, const void* x, int ldx, int B, int HW, int C, int HID, int topk, const void* w1, const void* w2, int E,
+                        const int* route_idx, const float* a_scale, const float* a_shift, const GnRaw& gn1, void* out, float* stats, int strips,
+                        void* stream) {
     YM_CHECK_ARG(x && w1 && route_idx && stats, "ym_moe_ffn: null pointer");
-    YM_CHECK_ARG(stage == 1 || (stage == 2 && w2 && a_scale && a_shift && out), "ym_moe_ffn: stage %d needs w2 / a_scale / a_shift / out", stage);
+    YM_CHECK_ARG(stage == 1 || (stage == 2 && w2 && ((a_scale && a_shift) || gn1.stats) && out), "ym_moe_ffn: stage %d needs w2 / GroupNorm-1 affine or statistics / out", stage);
     YM_CHECK_ARG(ym_moe_ffn_supported(C, HID, ldx), "ym_moe_ffn: unsupported shape C=%d HID=%d ldx=%d (64/128 or 128/256)", C, HID, ldx);
     YM_CHECK_ARG((((uintptr_t)x | (uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)out) & 15) == 0, "ym_moe_ffn: 16-byte alignment");
     YM_CHECK_ARG(topk >= 1 && E >= 1 && HW >= 1 && strips >= 1, "ym_moe_ffn: bad sizes");
@@ -599,19 +647,43 @@ extern "C" int ym_moe_ffn(int stage, const void* x, int ldx, int B, int HW, int 
     }
     MoeFfnParams p;
     p.route_idx = route_idx; p.a_div = topk; p.HW = HW; p.mtiles = mtiles; p.tiles_per_strip = (mtiles + strips - 1) / strips;
-    p.a_scale = a_scale; p.a_shift = a_shift; p.out = (__half*)out; p.stats = stats;
+    p.a_scale = a_scale; p.a_shift = a_shift; p.out = (__half*)out; p.stats = stats; p.gn1 = gn1;
     YM_CHECK_ARG((long long)strips * p.tiles_per_strip >= mtiles, "ym_moe_ffn: strips do not cover the tiles");
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 64) return stage == 1 ? mf_launch<64, 128, 1>(mx, mw1, mw2, p, strips, P, st) : mf_launch<64, 128, 2>(mx, mw1, mw2, p, strips, P, st);
     return stage == 1 ? mf_launch<128, 256, 1>(mx, mw1, mw2, p, strips, P, st) : mf_launch<128, 256, 2>(mx, mw1, mw2, p, strips, P, st);
 }
 
+static bool gn_raw_ok(const GnRaw& g, int Cn) {
+    return g.stats && g.gamma && g.beta && g.tiles >= 1 && g.groups >= 1 && Cn % g.groups == 0 && (Cn / g.groups) % 8 == 0 && g.count > 0.f;
+}
+
+extern "C" int ym_moe_ffn(int stage, const void* x, int ldx, int B, int HW, int C, int HID, int topk, const void* w1, const void* w2, int E,
+                          const int* route_idx, const float* a_scale, const float* a_shift, void* out, float* stats, int strips,
+                          void* stream) {
+    GnRaw none;
+    memset(&none, 0, sizeof(none));
+    return moe_ffn_impl(stage, x, ldx, B, HW, C, HID, topk, w1, w2, E, route_idx, a_scale, a_shift, none, out, stats, strips, stream);
+}
+
+// Stage 2 with GroupNorm-1 finalised inside the kernel from stage 1's partial sums (no ym_gn_finalize_tiles launch in between).
+extern "C" int ym_moe_ffn_gn(const void* x, int ldx, int B, int HW, int C, int HID, int topk, const void* w1, const void* w2, int E,
+                             const int* route_idx, const float* gn1_stats, int gn1_groups, float gn1_count, float gn1_eps, const float* gamma1,
+                             const float* beta1, void* out, float* stats, int strips, void* stream) {
+    GnRaw g;
+    memset(&g, 0, sizeof(g));
+    g.stats = gn1_stats; g.tiles = strips; g.groups = gn1_groups; g.count = gn1_count; g.eps = gn1_eps; g.gamma = gamma1; g.beta = beta1;
+    YM_CHECK_ARG(gn_raw_ok(g, HID), "ym_moe_ffn_gn: bad GroupNorm-1 description (groups %d over %d channels)", gn1_groups, HID);
+    return moe_ffn_impl(2, x, ldx, B, HW, C, HID, topk, w1, w2, E, route_idx, nullptr, nullptr, g, out, stats, strips, stream);
+}
+
 // y[b] = SiLU(x[b] Ws^T + bs) + sum_j (o[b*topk+j] * o_scale + o_shift) (+ x[b]): the combine of OptimizedMOEImproved on tcgen05.
 extern "C" int ym_moe_combine_tc_supported(int C, int ldx, int ldo) { return mf_encode() != nullptr && (C == 64 || C == 128) && ldx % 8 == 0 && ldo % 8 == 0; }
 
-extern "C" int ym_moe_combine_tc(const void* x, int ldx, int B, int HW, int C, const void* ws, const float* bias_s, const void* o,
-                                 const float* o_scale, const float* o_shift, int topk, void* out, int ldo, int add_residual, void* stream) {
-    YM_CHECK_ARG(x && ws && o && o_scale && o_shift && out, "ym_moe_combine_tc: null pointer");
+static int moe_combine_tc_impl(const void* x, int ldx, int B, int HW, int C, const void* ws, const float* bias_s, const void* o,
+                               const float* o_scale, const float* o_shift, const GnRaw& gn2, const int* route_idx, int topk, void* out, int ldo,
+                               int add_residual, void* stream) {
+    YM_CHECK_ARG(x && ws && o && ((o_scale && o_shift) || (gn2.stats && route_idx)) && out, "ym_moe_combine_tc: null pointer");
     YM_CHECK_ARG(ym_moe_combine_tc_supported(C, ldx, ldo), "ym_moe_combine_tc: unsupported shape C=%d ldx=%d ldo=%d", C, ldx, ldo);
     YM_CHECK_ARG((((uintptr_t)x | (uintptr_t)ws | (uintptr_t)o | (uintptr_t)out) & 15) == 0, "ym_moe_combine_tc: 16-byte alignment");
     YM_CHECK_ARG(topk >= 1 && topk <= 2 && HW >= 1 && B >= 0 && B <= 65535, "ym_moe_combine_tc: top_k must be 1 or 2 (got %d)", topk);
@@ -633,6 +705,7 @@ extern "C" int ym_moe_combine_tc(const void* x, int ldx, int B, int HW, int C, c
     MoeCombineParams p;
     p.x = (const __half*)x; p.ldx = ldx; p.bias = bias_s; p.o = (const __half*)o; p.o_scale = o_scale; p.o_shift = o_shift;
     p.out = (__half*)out; p.ldo = ldo; p.HW = HW; p.mtiles = mtiles; p.tiles_per_strip = tps; p.topk = topk; p.add_residual = add_residual;
+    p.gn2 = gn2; p.route_idx = route_idx;
     const size_t smem = (size_t)2 * MF_BM * C * 2 + (size_t)C * C * 2 + (size_t)5 * C * sizeof(float) + 8 * 32 * 32 * sizeof(float) + 1024;
     cudaError_t e;
     cudaStream_t st = (cudaStream_t)stream;
@@ -645,4 +718,24 @@ extern "C" int ym_moe_combine_tc(const void* x, int ldx, int B, int HW, int C, c
     }
     if (e != cudaSuccess) { ym_set_error("ym_moe_combine_tc: %s", cudaGetErrorString(e)); return YM_ERR_CUDA; }
     return YM_OK;
+}
+
+extern "C" int ym_moe_combine_tc(const void* x, int ldx, int B, int HW, int C, const void* ws, const float* bias_s, const void* o,
+                                 const float* o_scale, const float* o_shift, int topk, void* out, int ldo, int add_residual, void* stream) {
+    GnRaw none;
+    memset(&none, 0, sizeof(none));
+    return moe_combine_tc_impl(x, ldx, B, HW, C, ws, bias_s, o, o_scale, o_shift, none, nullptr, topk, out, ldo, add_residual, stream);
+}
+
+// The combine with GroupNorm-2 (times the routing weight) finalised inside the kernel from pass 2's partial sums.
+extern "C" int ym_moe_combine_tc_gn(const void* x, int ldx, int B, int HW, int C, const void* ws, const float* bias_s, const void* o,
+                                    const float* gn2_stats, int gn2_tiles, int gn2_groups, float gn2_count, float gn2_eps, const float* gamma2,
+                                    const float* beta2, const int* route_idx, const float* route_w, int topk, void* out, int ldo,
+                                    int add_residual, void* stream) {
+    GnRaw g;
+    memset(&g, 0, sizeof(g));
+    g.stats = gn2_stats; g.tiles = gn2_tiles; g.groups = gn2_groups; g.count = gn2_count; g.eps = gn2_eps; g.gamma = gamma2; g.beta = beta2;
+    g.route_w = route_w;
+    YM_CHECK_ARG(gn_raw_ok(g, C) && route_idx, "ym_moe_combine_tc_gn: bad GroupNorm-2 description (groups %d over %d channels)", gn2_groups, C);
+    return moe_combine_tc_impl(x, ldx, B, HW, C, ws, bias_s, o, nullptr, nullptr, g, route_idx, topk, out, ldo, add_residual, stream);
 }

@@ -100,6 +100,9 @@ class EfficientSpatialRouter(nn.Module, PackCache):
 # "tc": routed expert FFN on the tcgen05 kernels with the hidden kept on chip (csrc/tc_moe.cu) where the widths allow;
 # "mma": the mma.sync implicit-GEMM chain of csrc/gemm_conv.cu (h through global memory) - kept as the A/B baseline
 MOE_FFN_IMPL = "tc"
+# GroupNorm-1 / GroupNorm-2 of the tcgen05 expert chain finalised inside the consumer kernels (ym_moe_ffn_gn, ym_moe_combine_tc_gn)
+# instead of by two ym_gn_finalize_tiles launches per block: same bits, 12 launches less per yolo26-master-n forward
+MOE_GN_FOLD = True
 
 
 class SimpleExpert(nn.Module):
@@ -190,8 +193,19 @@ class OptimizedMOEImproved(nn.Module, PackCache):
             # tcgen05 path (csrc/tc_moe.cu): the hidden activation stays in tensor memory - pass 1 takes GroupNorm-1 statistics of
             # h = x W1[e]^T without storing it, pass 2 recomputes h, normalises, SiLU, and feeds the second GEMM from tensor memory
             st1, strips = ops.moe_ffn_stats(x, k, pk["w1"], ridx)
-            sc1, sh1 = ops.gn_finalize_tiles(st1, P, strips, pk["G1"], hid, HW * (hid // pk["G1"]), pk["eps1"], pk["gamma1"], pk["beta1"], ridx)
-            o, st2 = ops.moe_ffn_fused(x, k, pk["w1"], pk["w2"], ridx, sc1, sh1, strips)
+            if MOE_GN_FOLD:
+                # both GroupNorms are finalised by their consumer kernels from the partial sums (two launches less per block, same bits)
+                o, st2 = ops.moe_ffn_fused_gn(x, k, pk["w1"], pk["w2"], ridx, st1, strips, pk["G1"], HW * (hid // pk["G1"]), pk["eps1"],
+                                              pk["gamma1"], pk["beta1"])
+                add_res = outer_residual or (self.add_residual and self.in_channels == self.out_channels)
+                if ops.moe_combine_gn_supported(x, pk["ws"], o, k, out):
+                    y = ops.moe_combine_gn(x, pk["ws"], pk["bs"], o, st2, strips, pk["G2"], HW * (C // pk["G2"]), pk["eps2"], pk["gamma2"],
+                                           pk["beta2"], ridx, rw, k, add_residual=add_res, out=out)
+                    self.last_routing_snapshot = {"topk_indices": idx, "topk_weights": w, "router_probs": probs}  # device tensors, lazy
+                    return y
+            else:
+                sc1, sh1 = ops.gn_finalize_tiles(st1, P, strips, pk["G1"], hid, HW * (hid // pk["G1"]), pk["eps1"], pk["gamma1"], pk["beta1"], ridx)
+                o, st2 = ops.moe_ffn_fused(x, k, pk["w1"], pk["w2"], ridx, sc1, sh1, strips)
             sc2, sh2 = ops.gn_finalize_tiles(st2, P, strips, pk["G2"], C, HW * (C // pk["G2"]), pk["eps2"], pk["gamma2"], pk["beta2"], ridx, route_w=rw)
         else:
             # GEMM1: h[p] = x[p // k] @ W1[e_p]^T, GroupNorm-1 statistics in the epilogue

@@ -244,6 +244,39 @@ def moe_ffn_fused(x, topk, w1, w2, route_idx, a_scale, a_shift, strips):
     return o, stats
 
 
+def moe_ffn_fused_gn(x, topk, w1, w2, route_idx, st1, strips, G1, count1, eps1, gamma1, beta1):
+    """ym_moe_ffn_gn: stage 2 with GroupNorm-1 finalised inside the kernel from stage 1's partial sums `st1`."""
+    B, H, W, Cc = x.shape
+    E, HID, _ = w1.shape
+    P = B * topk
+    o = torch.empty((P, H * W, Cc), dtype=torch.float16, device=x.device)
+    stats = torch.empty((lib().ym_moe_ffn_stats_floats(P, strips, Cc),), dtype=torch.float32, device=x.device)
+    _lib.check(lib().ym_moe_ffn_gn(x.data_ptr(), pitch(x), B, H * W, Cc, HID, topk, w1.data_ptr(), w2.data_ptr(), E, route_idx.data_ptr(),
+                                   st1.data_ptr(), G1, float(count1), float(eps1), gamma1.data_ptr(), beta1.data_ptr(), o.data_ptr(),
+                                   stats.data_ptr(), strips, _stream()), "ym_moe_ffn_gn")
+    _count()
+    return o, stats
+
+
+def moe_combine_gn_supported(x, ws_packed, o, topk, out=None) -> bool:
+    Cc = x.shape[3]
+    return (MOE_COMBINE_IMPL == "tc" and topk <= 2 and ws_packed.shape[1] == Cc and o.shape[2] == Cc
+            and bool(lib().ym_moe_combine_tc_supported(Cc, pitch(x), pitch(x) if out is None else pitch(out))))
+
+
+def moe_combine_gn(x, ws_packed, bias_s, o, st2, strips, G2, count2, eps2, gamma2, beta2, route_idx, route_w, topk, add_residual=True, out=None):
+    """ym_moe_combine_tc_gn: the combine with GroupNorm-2 (times the routing weight) finalised inside the kernel from `st2`."""
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = new_act(B, H, W, Cc, x.device)
+    _lib.check(lib().ym_moe_combine_tc_gn(x.data_ptr(), pitch(x), B, H * W, Cc, ws_packed.data_ptr(), bias_s.data_ptr(), o.data_ptr(),
+                                          st2.data_ptr(), strips, G2, float(count2), float(eps2), gamma2.data_ptr(), beta2.data_ptr(),
+                                          route_idx.data_ptr(), route_w.data_ptr(), topk, out.data_ptr(), pitch(out),
+                                          1 if add_residual else 0, _stream()), "ym_moe_combine_tc_gn")
+    _count()
+    return out
+
+
 def gn_finalize_tiles(stats, P, tiles, G, C_, count, eps, gamma, beta, route_idx, route_w=None):
     """ym_gn_finalize_tiles: partial sums [P][tiles][C_/8][2] -> (scale, shift) fp32 [P][C_] of the routed expert's GroupNorm."""
     scale = torch.empty((P, C_), dtype=torch.float32, device=stats.device)
