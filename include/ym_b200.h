@@ -139,6 +139,11 @@ int ym_moe_combine_tc(const void* x, int ldx, int B, int HW, int C, const void* 
  * between; bit-identical to the two-launch form): pass 2 of ym_moe_ffn with GroupNorm-1 given as (partial sums of pass 1, groups, element
  * count per group, eps, gamma / beta fp32 [E][HID]); the combine with GroupNorm-2 given the same way (partial sums of pass 2 over
  * `gn2_tiles` = strips, gamma / beta fp32 [E][C]) plus the routing table and weights (route_w [B*topk] is folded into the affine). */
+/* Pass 1 of ym_moe_ffn with the router's finish in its prologue: idx_out / w_out (/ probs_out) are OUTPUTS (same values as
+ * ym_router_topk writes), used by this kernel for its weight selection and by the kernels after it. */
+int ym_moe_ffn_routed(const void* x, int ldx, int B, int HW, int C, int HID, int topk, const void* w1, int E, const float* partial, int nblk,
+                      int Cr, int npix, const float* rw2, const float* rscale2, const float* rshift2, int* idx_out, float* w_out,
+                      float* probs_out, float* stats, int strips, void* stream);
 int ym_moe_ffn_gn(const void* x, int ldx, int B, int HW, int C, int HID, int topk, const void* w1, const void* w2, int E, const int* route_idx,
                   const float* gn1_stats, int gn1_groups, float gn1_count, float gn1_eps, const float* gamma1, const float* beta1, void* out,
                   float* stats, int strips, void* stream);
@@ -166,6 +171,12 @@ long long ym_router_scratch_floats(int B, int H, int W, int C, int Cr, int pool)
 int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* w1, int Cr,
                    const float* scale1, const float* shift1, const float* w2, const float* scale2, const float* shift2,
                    int E, int topk, float* scratch, int* idx_out, float* w_out, float* probs_out, void* stream);
+/* The two halves of ym_router_topk: ym_router_partial runs the fused pool + conv3x3 + BN + SiLU pass and leaves per-tile partial sums
+ * [B][nblk][Cr] at the start of `scratch` (nblk = ym_router_blocks(H, W, pool, &npix)); the finish (mean -> logits -> softmax -> top-k)
+ * then runs either as its own launch (ym_router_topk) or in the prologue of ym_moe_ffn_routed. */
+int ym_router_blocks(int H, int W, int pool, int* npix);
+int ym_router_partial(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* w1, int Cr, const float* scale1,
+                      const float* shift1, float* scratch, void* stream);
 
 /* Routed expert GEMM, one problem per (image, k): replaces the per-expert Python loop + x[batch_idx] gather of
  * OptimizedMOEImproved.forward moe/modules.py:1128-1142 for SimpleExpert's two 1x1 convs (moe/experts.py:79-85).

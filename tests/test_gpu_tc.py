@@ -374,11 +374,15 @@ def test_moe_groupnorm_finalised_in_the_consumer_kernels_is_bit_identical():
         x = torch.randn((3, C, *hw), device=DEV).half().contiguous(memory_format=torch.channels_last)
         outs = {}
         for fold in (True, False):
-            prev = moe_mod.MOE_GN_FOLD
-            moe_mod.MOE_GN_FOLD = fold
+            prev = moe_mod.MOE_GN_FOLD, moe_mod.MOE_ROUTER_FOLD
+            moe_mod.MOE_GN_FOLD = moe_mod.MOE_ROUTER_FOLD = fold
             try:
                 with torch.no_grad():
                     outs[fold] = m(x).clone()
+                    snap = m.last_routing_snapshot
+                    outs[(fold, "route")] = (snap["topk_indices"].clone(), snap["topk_weights"].clone(), snap["router_probs"].clone())
             finally:
-                moe_mod.MOE_GN_FOLD = prev
-        assert torch.equal(outs[True], outs[False]), f"C={C}: folded GroupNorm finalisation must not change a bit"
+                moe_mod.MOE_GN_FOLD, moe_mod.MOE_ROUTER_FOLD = prev
+        assert torch.equal(outs[True], outs[False]), f"C={C}: folded GroupNorm / router finalisation must not change a bit"
+        for a, b in zip(outs[(True, "route")], outs[(False, "route")]):
+            assert torch.equal(a, b), "routing table published by the statistics pass must equal ym_router_topk's"

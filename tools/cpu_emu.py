@@ -218,6 +218,16 @@ def gn_finalize_tiles(stats, P, tiles, G, C_, count, eps, gamma, beta, route_idx
     return gn_finalize(stats, P, stats.shape[1], G, C_, count, eps, gamma, beta, route_idx, route_w)
 
 
+def router_partial(x, pack, pool=4):
+    return (x, pack, pool), 0, 0                  # the emulation finishes the routing in moe_ffn_stats_routed
+
+
+def moe_ffn_stats_routed(x, topk, w1, rpack, partial, nblk, npix):
+    idx, w, probs = router_topk(x, rpack, topk, partial[2])
+    st1, strips = moe_ffn_stats(x, topk, w1, idx.view(-1))
+    return idx, w, probs, st1, strips
+
+
 def moe_ffn_fused_gn(x, topk, w1, w2, route_idx, st1, strips, G1, count1, eps1, gamma1, beta1):
     P, HID = x.shape[0] * topk, w1.shape[1]
     sc1, sh1 = gn_finalize_tiles(st1, P, strips, G1, HID, count1, eps1, gamma1, beta1, route_idx)
@@ -455,7 +465,7 @@ def install_model():
     for name, fn in dict(stem_conv=stem_conv, attention=attention, concat2=concat2, sppf_pool=sppf_pool, router_topk=router_topk,
                          moe_combine=moe_combine, moe_expert_gemm=moe_expert_gemm, gn_finalize=gn_finalize, detect_dense=detect_dense,
                          moe_ffn_supported=moe_ffn_supported, moe_ffn_stats=moe_ffn_stats, moe_ffn_fused=moe_ffn_fused, gn_finalize_tiles=gn_finalize_tiles,
-                         moe_ffn_fused_gn=moe_ffn_fused_gn, moe_combine_gn_supported=moe_combine_gn_supported, moe_combine_gn=moe_combine_gn,
+                         moe_ffn_fused_gn=moe_ffn_fused_gn, router_partial=router_partial, moe_ffn_stats_routed=moe_ffn_stats_routed, moe_combine_gn_supported=moe_combine_gn_supported, moe_combine_gn=moe_combine_gn,
                          detect_topk=detect_topk, kpts_decode=kpts_decode, obb_finish=obb_finish, latent_router=latent_router).items():
         setattr(ops, name, fn)
     ops.pitch = lambda t, dtype=torch.float16: (t.stride(2) if t.shape[2] > 1 else (t.stride(1) if t.shape[1] > 1 else (t.stride(0) if t.shape[0] > 1 else t.shape[3])))

@@ -44,6 +44,9 @@ SIGNATURES = {
     "ym_moe_ffn": (ci, [ci, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp, vp, vp, vp, vp, ci, vp]),
     "ym_moe_combine_tc_supported": (ci, [ci, ci, ci]),
     "ym_moe_combine_tc": (ci, [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp, ci, vp, ci, ci, vp]),
+    "ym_router_blocks": (ci, [ci, ci, ci, vp]),
+    "ym_router_partial": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, ci, vp, vp, vp, vp]),
+    "ym_moe_ffn_routed": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, ci, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]),
     "ym_moe_ffn_gn": (ci, [vp, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp, vp, vp, ci, vp]),
     "ym_moe_combine_tc_gn": (ci, [vp, ci, ci, ci, ci, vp, vp, vp, vp, ci, ci, cf, cf, vp, vp, vp, vp, ci, vp, ci, ci, vp]),
     "ym_gn_finalize_tiles": (ci, [vp, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, vp, vp, vp]),

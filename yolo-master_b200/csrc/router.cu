@@ -8,6 +8,7 @@
 // Replaces ~10 launches + 3 host syncs (routers.py:51,295,301) with 2 small launches and no sync: routing stays on
 // the device as an index table consumed by ym_moe_expert_gemm.
 #include "ym_common.cuh"
+#include "router_core.cuh"
 
 namespace ym {
 
@@ -139,69 +140,14 @@ __global__ void __launch_bounds__(512, 2) router_fused_kernel(const __half* __re
     }
 }
 
-// One warp per image: mean hidden -> logits -> softmax -> top-k (lowest index wins ties) -> renormalise.
-__global__ void __launch_bounds__(32) router_finish_kernel(const float* __restrict__ partial, int nblk, int Cr, int npix,
-                                                           const float* __restrict__ w2,      // [E][Cr]
-                                                           const float* __restrict__ scale2,  // [E]
-                                                           const float* __restrict__ shift2, int E, int topk,
-                                                           int* __restrict__ idx_out, float* __restrict__ w_out,
-                                                           float* __restrict__ probs_out) {
+// One warp per image: mean hidden -> logits -> softmax -> top-k (lowest index wins ties) -> renormalise (router_core.cuh).
+__global__ void __launch_bounds__(32) router_finish_kernel(const RouterFin r) {
     pdl_prologue();
     __shared__ float hm[64];
     __shared__ float pr[64];
-    const int b = blockIdx.x, lane = threadIdx.x;
-    for (int r = lane; r < Cr; r += 32) {
-        float s = 0.f;
-        for (int i = 0; i < nblk; ++i) s += partial[((long long)b * nblk + i) * Cr + r];
-        hm[r] = s / (float)npix;
-    }
-    __syncwarp();
-    float mx = -INFINITY;
-    for (int e = lane; e < E; e += 32) {
-        float acc = 0.f;
-        for (int r = 0; r < Cr; ++r) acc = fmaf(w2[e * Cr + r], hm[r], acc);
-        const float lg = fmaf(acc, scale2[e], shift2[e]);
-        pr[e] = lg;
-        mx = fmaxf(mx, lg);
-    }
-    mx = warp_max(mx);
-    __syncwarp();
-    float sum = 0.f;
-    for (int e = lane; e < E; e += 32) {
-        const float v = expf(pr[e] - mx);
-        pr[e] = v;
-        sum += v;
-    }
-    sum = warp_sum(sum);
-    __syncwarp();
-    for (int e = lane; e < E; e += 32) {
-        pr[e] = pr[e] / sum;
-        if (probs_out) probs_out[(long long)b * E + e] = pr[e];
-    }
-    __syncwarp();
-    if (lane == 0) {
-        float vals[8];
-        int ids[8];
-        unsigned long long taken = 0ull;
-        float tot = 0.f;
-        for (int j = 0; j < topk; ++j) {
-            int best = -1;
-            float bv = -INFINITY;
-            for (int e = 0; e < E; ++e) {
-                if ((taken >> e) & 1ull) continue;
-                if (pr[e] > bv) { bv = pr[e]; best = e; }
-            }
-            taken |= 1ull << best;
-            vals[j] = bv;
-            ids[j] = best;
-            tot += bv;
-        }
-        tot = fmaxf(tot, 1e-6f);
-        for (int j = 0; j < topk; ++j) {
-            idx_out[b * topk + j] = ids[j];
-            w_out[b * topk + j] = vals[j] / tot;
-        }
-    }
+    int ids[8];
+    float vals[8];
+    router_finish_warp(r, blockIdx.x, threadIdx.x, hm, pr, ids, vals, true);
 }
 
 }  // namespace ym
@@ -217,14 +163,22 @@ extern "C" long long ym_router_scratch_floats(int B, int H, int W, int C, int Cr
     return (long long)B * Hp * Wp * C + (long long)B * nblk * Cr;
 }
 
-extern "C" int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* w1, int Cr,
-                              const float* scale1, const float* shift1, const float* w2, const float* scale2,
-                              const float* shift2, int E, int topk, float* scratch, int* idx_out, float* w_out,
-                              float* probs_out, void* stream) {
-    YM_CHECK_ARG(x && w1 && scale1 && shift1 && w2 && scale2 && shift2 && scratch && idx_out && w_out,
-                 "ym_router_topk: null pointer");
+// Tile grid of router_fused_kernel over the pooled map (also the number of partial-sum blocks per image); *npix = pooled pixels.
+extern "C" int ym_router_blocks(int H, int W, int pool, int* npix) {
+    const bool do_pool = H > pool && W > pool;  // routers.py:289-292
+    const int ps = do_pool ? pool : 1;
+    const int Hp = H / ps, Wp = W / ps;
+    if (npix) *npix = Hp * Wp;
+    return ((Wp + RT_TX - 1) / RT_TX) * ((Hp + RT_TY - 1) / RT_TY);
+}
+
+// First half of ym_router_topk: the fused pool + conv3x3 + BN + SiLU pass, leaving per-tile partial sums [B][nblk][Cr] at the start of
+// `scratch`.  The second half (router_finish_warp) runs either as its own launch (ym_router_topk) or inside the prologue of the
+// consumer (ym_moe_ffn_routed).
+extern "C" int ym_router_partial(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* w1, int Cr, const float* scale1,
+                                 const float* shift1, float* scratch, void* stream) {
+    YM_CHECK_ARG(x && w1 && scale1 && shift1 && scratch, "ym_router_partial: null pointer");
     YM_CHECK_ARG(Cr == 8 || Cr == 16 || Cr == 32 || Cr == 64, "ym_router_topk: reduced channels must be 8/16/32/64 (got %d)", Cr);
-    YM_CHECK_ARG(E >= 1 && E <= 64 && topk >= 1 && topk <= 8 && topk <= E, "ym_router_topk: need 1<=topk<=min(8,E), E<=64");
     YM_CHECK_ARG(pool >= 1, "ym_router_topk: pool");
     if (B == 0) return YM_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -251,7 +205,23 @@ extern "C" int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C
     launch_pdl(router_fused_kernel, dim3(nblk, B), threads, smem, st, (const __half*)x, ldx, H, W, C, ps, Hp, Wp, Cr, w1, scale1, shift1, partial,
                                                          tiles_x, nblk);
     YM_CHECK_LAUNCH("router_fused");
-    launch_pdl(router_finish_kernel, B, 32, 0, st, partial, nblk, Cr, Hp * Wp, w2, scale2, shift2, E, topk, idx_out, w_out, probs_out);
+    return YM_OK;
+}
+
+extern "C" int ym_router_topk(const void* x, int ldx, int B, int H, int W, int C, int pool, const float* w1, int Cr,
+                              const float* scale1, const float* shift1, const float* w2, const float* scale2,
+                              const float* shift2, int E, int topk, float* scratch, int* idx_out, float* w_out,
+                              float* probs_out, void* stream) {
+    YM_CHECK_ARG(x && w1 && scale1 && shift1 && w2 && scale2 && shift2 && scratch && idx_out && w_out,
+                 "ym_router_topk: null pointer");
+    YM_CHECK_ARG(E >= 1 && E <= 64 && topk >= 1 && topk <= 8 && topk <= E, "ym_router_topk: need 1<=topk<=min(8,E), E<=64");
+    if (B == 0) return YM_OK;
+    const int rc = ym_router_partial(x, ldx, B, H, W, C, pool, w1, Cr, scale1, shift1, scratch, stream);
+    if (rc) return rc;
+    RouterFin r;
+    r.partial = scratch; r.nblk = ym_router_blocks(H, W, pool, &r.npix); r.Cr = Cr; r.w2 = w2; r.scale2 = scale2; r.shift2 = shift2;
+    r.E = E; r.topk = topk; r.idx_out = idx_out; r.w_out = w_out; r.probs_out = probs_out;
+    launch_pdl(router_finish_kernel, B, 32, 0, (cudaStream_t)stream, r);
     YM_CHECK_LAUNCH("router_finish");
     return YM_OK;
 }

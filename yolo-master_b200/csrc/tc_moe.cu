@@ -25,6 +25,7 @@
 #include <cuda.h>
 
 #include "tc_common.cuh"
+#include "router_core.cuh"
 
 namespace ym {
 
@@ -89,6 +90,7 @@ struct MoeFfnParams {
     __half* out;               // pass 2: o [P][HW][C]
     float* stats;              // partial sums [P][strips][NS/2][2], NS/2 = (pass 1 ? HID : C) / 8 eight-channel slices
     GnRaw gn1;                 // pass 2: GroupNorm-1 finalised here when gn1.stats != nullptr (a_scale / a_shift unused)
+    RouterFin rf;              // pass 1: the router's finish runs in the prologue when rf.partial != nullptr (route_idx is then an OUTPUT)
 };
 
 struct MfBars {
@@ -139,7 +141,24 @@ moe_ffn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     tc::fence_after_sync();
     const uint32_t tmem_base = bars.tmem_slot;
     pdl_prologue();                                    // set-up done: stage the next kernel, then wait for the producers of x / routes / affine
-    const int e = p.route_idx[prob];
+    int e;
+    if (STAGE == 1 && p.rf.partial != nullptr) {
+        // the router's finish (spatial mean -> logits -> softmax -> top-k) for this CTA's image, by warp 0 of EVERY CTA of the image: a few
+        // hundred flops instead of a launch; strip 0 of route 0 publishes idx / w / probs for the kernels that follow
+        __shared__ float rf_hm[64], rf_pr[64];
+        __shared__ int rf_e;
+        if (warp == 0) {
+            int ids[8];
+            float vals[8];
+            const int img_r = prob / p.a_div, jr = prob - img_r * p.a_div;
+            router_finish_warp(p.rf, img_r, lane, rf_hm, rf_pr, ids, vals, strip == 0 && jr == 0);
+            if (lane == 0) rf_e = ids[jr];
+        }
+        __syncthreads();
+        e = rf_e;
+    } else {
+        e = p.route_idx[prob];
+    }
     const bool active = e >= 0 && nt > 0;              // CTA-uniform
     if (active) {
         const int img = prob / p.a_div;
@@ -617,9 +636,9 @@ extern "C" long long ym_moe_ffn_stats_floats(int P, int strips, int N) { return 
 // stage 1: stats != null, out == null: GroupNorm-1 partial sums of h = x W1[e]^T           -> stats [P][strips][HID/8][2]
 // stage 2: out  != null              : o = SiLU(GN1(h)) W2[e]^T (fp16) and its partial sums -> out [P][HW][C], stats [P][strips][C/8][2]
 static int moe_ffn_impl(int stage, const void* x, int ldx, int B, int HW, int C, int HID, int topk, const void* w1, const void* w2, int E,
-                        const int* route_idx, const float* a_scale, const float* a_shift, const GnRaw& gn1, void* out, float* stats, int strips,
-                        void* stream) {
-    YM_CHECK_ARG(x && w1 && route_idx && stats, "ym_moe_ffn: null pointer");
+                        const int* route_idx, const float* a_scale, const float* a_shift, const GnRaw& gn1, const RouterFin& rf, void* out,
+                        float* stats, int strips, void* stream) {
+    YM_CHECK_ARG(x && w1 && (route_idx || rf.partial) && stats, "ym_moe_ffn: null pointer");
     YM_CHECK_ARG(stage == 1 || (stage == 2 && w2 && ((a_scale && a_shift) || gn1.stats) && out), "ym_moe_ffn: stage %d needs w2 / GroupNorm-1 affine or statistics / out", stage);
     YM_CHECK_ARG(ym_moe_ffn_supported(C, HID, ldx), "ym_moe_ffn: unsupported shape C=%d HID=%d ldx=%d (64/128 or 128/256)", C, HID, ldx);
     YM_CHECK_ARG((((uintptr_t)x | (uintptr_t)w1 | (uintptr_t)w2 | (uintptr_t)out) & 15) == 0, "ym_moe_ffn: 16-byte alignment");
@@ -647,7 +666,7 @@ static int moe_ffn_impl(int stage, const void* x, int ldx, int B, int HW, int C,
     }
     MoeFfnParams p;
     p.route_idx = route_idx; p.a_div = topk; p.HW = HW; p.mtiles = mtiles; p.tiles_per_strip = (mtiles + strips - 1) / strips;
-    p.a_scale = a_scale; p.a_shift = a_shift; p.out = (__half*)out; p.stats = stats; p.gn1 = gn1;
+    p.a_scale = a_scale; p.a_shift = a_shift; p.out = (__half*)out; p.stats = stats; p.gn1 = gn1; p.rf = rf;
     YM_CHECK_ARG((long long)strips * p.tiles_per_strip >= mtiles, "ym_moe_ffn: strips do not cover the tiles");
     cudaStream_t st = (cudaStream_t)stream;
     if (C == 64) return stage == 1 ? mf_launch<64, 128, 1>(mx, mw1, mw2, p, strips, P, st) : mf_launch<64, 128, 2>(mx, mw1, mw2, p, strips, P, st);
@@ -662,8 +681,27 @@ extern "C" int ym_moe_ffn(int stage, const void* x, int ldx, int B, int HW, int 
                           const int* route_idx, const float* a_scale, const float* a_shift, void* out, float* stats, int strips,
                           void* stream) {
     GnRaw none;
+    RouterFin norf;
     memset(&none, 0, sizeof(none));
-    return moe_ffn_impl(stage, x, ldx, B, HW, C, HID, topk, w1, w2, E, route_idx, a_scale, a_shift, none, out, stats, strips, stream);
+    memset(&norf, 0, sizeof(norf));
+    return moe_ffn_impl(stage, x, ldx, B, HW, C, HID, topk, w1, w2, E, route_idx, a_scale, a_shift, none, norf, out, stats, strips, stream);
+}
+
+// Pass 1 (GroupNorm-1 statistics) with the router's finish in its prologue: `partial` are the per-tile sums of ym_router_partial
+// ([B][nblk][Cr]), (w2, scale2, shift2) the router's second layer; idx_out / w_out (/ probs_out) are WRITTEN here, for this kernel's own
+// weight selection and for the kernels that follow.  Same results as ym_router_topk + ym_moe_ffn(1, ...), one launch less.
+extern "C" int ym_moe_ffn_routed(const void* x, int ldx, int B, int HW, int C, int HID, int topk, const void* w1, int E, const float* partial,
+                                 int nblk, int Cr, int npix, const float* rw2, const float* rscale2, const float* rshift2, int* idx_out,
+                                 float* w_out, float* probs_out, float* stats, int strips, void* stream) {
+    YM_CHECK_ARG(partial && rw2 && rscale2 && rshift2 && idx_out && w_out, "ym_moe_ffn_routed: null pointer");
+    YM_CHECK_ARG(nblk >= 1 && npix >= 1 && Cr >= 1 && Cr <= 64 && E >= 1 && E <= 64 && topk >= 1 && topk <= 8 && topk <= E,
+                 "ym_moe_ffn_routed: need Cr <= 64, 1 <= topk <= min(8, E), E <= 64");
+    GnRaw none;
+    RouterFin rf;
+    memset(&none, 0, sizeof(none));
+    rf.partial = partial; rf.nblk = nblk; rf.Cr = Cr; rf.npix = npix; rf.w2 = rw2; rf.scale2 = rscale2; rf.shift2 = rshift2;
+    rf.E = E; rf.topk = topk; rf.idx_out = idx_out; rf.w_out = w_out; rf.probs_out = probs_out;
+    return moe_ffn_impl(1, x, ldx, B, HW, C, HID, topk, w1, nullptr, E, nullptr, nullptr, nullptr, none, rf, nullptr, stats, strips, stream);
 }
 
 // Stage 2 with GroupNorm-1 finalised inside the kernel from stage 1's partial sums (no ym_gn_finalize_tiles launch in between).
@@ -674,7 +712,9 @@ extern "C" int ym_moe_ffn_gn(const void* x, int ldx, int B, int HW, int C, int H
     memset(&g, 0, sizeof(g));
     g.stats = gn1_stats; g.tiles = strips; g.groups = gn1_groups; g.count = gn1_count; g.eps = gn1_eps; g.gamma = gamma1; g.beta = beta1;
     YM_CHECK_ARG(gn_raw_ok(g, HID), "ym_moe_ffn_gn: bad GroupNorm-1 description (groups %d over %d channels)", gn1_groups, HID);
-    return moe_ffn_impl(2, x, ldx, B, HW, C, HID, topk, w1, w2, E, route_idx, nullptr, nullptr, g, out, stats, strips, stream);
+    RouterFin norf;
+    memset(&norf, 0, sizeof(norf));
+    return moe_ffn_impl(2, x, ldx, B, HW, C, HID, topk, w1, w2, E, route_idx, nullptr, nullptr, g, norf, out, stats, strips, stream);
 }
 
 // y[b] = SiLU(x[b] Ws^T + bs) + sum_j (o[b*topk+j] * o_scale + o_shift) (+ x[b]): the combine of OptimizedMOEImproved on tcgen05.

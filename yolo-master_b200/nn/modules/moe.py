@@ -103,6 +103,8 @@ MOE_FFN_IMPL = "tc"
 # GroupNorm-1 / GroupNorm-2 of the tcgen05 expert chain finalised inside the consumer kernels (ym_moe_ffn_gn, ym_moe_combine_tc_gn)
 # instead of by two ym_gn_finalize_tiles launches per block: same bits, 12 launches less per yolo26-master-n forward
 MOE_GN_FOLD = True
+# the router's finish inside the prologue of the statistics pass (ym_moe_ffn_routed) instead of its own launch: 6 launches less per forward
+MOE_ROUTER_FOLD = True
 
 
 class SimpleExpert(nn.Module):
@@ -184,15 +186,25 @@ class OptimizedMOEImproved(nn.Module, PackCache):
         B, H, W, C = x.shape
         HW, k = H * W, self.top_k
         pk = self.get_pack()
-        idx, w, probs = self.routing.route_nhwc(x, k)           # device index table, no host sync
-        ridx, rw = idx.view(-1), w.view(-1)
         P, hid = B * k, pk["hid"]
         ldx = ops.pitch(x)
-        if MOE_FFN_IMPL == "tc" and pk["w1"].shape[2] == C and pk["w2"].shape[2] == hid and (hid // pk["G1"]) % 8 == 0 \
-                and (C // pk["G2"]) % 8 == 0 and ops.moe_ffn_supported(C, hid, ldx):
+        tc = MOE_FFN_IMPL == "tc" and pk["w1"].shape[2] == C and pk["w2"].shape[2] == hid and (hid // pk["G1"]) % 8 == 0 \
+            and (C // pk["G2"]) % 8 == 0 and ops.moe_ffn_supported(C, hid, ldx)
+        st1 = None
+        if tc and MOE_ROUTER_FOLD and 1 <= k <= min(8, self.num_experts):
+            # the router's finish (mean -> logits -> softmax -> top-k) runs in the prologue of the expert FFN's statistics pass, which
+            # publishes idx / w / probs for the kernels after it: one launch less per block, same values
+            rpack = self.routing.get_pack()
+            partial, nblk, npix = ops.router_partial(x, rpack, self.routing.pool_scale)
+            idx, w, probs, st1, strips = ops.moe_ffn_stats_routed(x, k, pk["w1"], rpack, partial, nblk, npix)
+        else:
+            idx, w, probs = self.routing.route_nhwc(x, k)       # device index table, no host sync
+        ridx, rw = idx.view(-1), w.view(-1)
+        if tc:
             # tcgen05 path (csrc/tc_moe.cu): the hidden activation stays in tensor memory - pass 1 takes GroupNorm-1 statistics of
             # h = x W1[e]^T without storing it, pass 2 recomputes h, normalises, SiLU, and feeds the second GEMM from tensor memory
-            st1, strips = ops.moe_ffn_stats(x, k, pk["w1"], ridx)
+            if st1 is None:
+                st1, strips = ops.moe_ffn_stats(x, k, pk["w1"], ridx)
             if MOE_GN_FOLD:
                 # both GroupNorms are finalised by their consumer kernels from the partial sums (two launches less per block, same bits)
                 o, st2 = ops.moe_ffn_fused_gn(x, k, pk["w1"], pk["w2"], ridx, st1, strips, pk["G1"], HW * (hid // pk["G1"]), pk["eps1"],

@@ -185,6 +185,40 @@ def router_topk(x, pack, topk, pool=4):
     return idx, w, probs
 
 
+def router_partial(x, pack, pool=4):
+    """ym_router_partial: the fused pool + conv + BN + SiLU pass of the router.  Returns (partial sums, nblk, npix) for
+    `moe_ffn_stats_routed`, whose prologue finishes the routing."""
+    B, H, W, Cc = x.shape
+    Cr = pack["Cr"]
+    n = lib().ym_router_scratch_floats(B, H, W, Cc, Cr, pool)
+    scratch = torch.empty((n,), dtype=torch.float32, device=x.device)
+    npix = C.c_int(0)
+    nblk = lib().ym_router_blocks(H, W, pool, C.addressof(npix))
+    _lib.check(lib().ym_router_partial(x.data_ptr(), pitch(x), B, H, W, Cc, pool, pack["w1"].data_ptr(), Cr, pack["scale1"].data_ptr(),
+                                       pack["shift1"].data_ptr(), scratch.data_ptr(), _stream()), "ym_router_partial")
+    _count()
+    return scratch, nblk, npix.value
+
+
+def moe_ffn_stats_routed(x, topk, w1, rpack, partial, nblk, npix):
+    """ym_moe_ffn_routed: stage 1 of the expert FFN with the router's finish in its prologue.
+    Returns (idx int32 [B,k], w fp32 [B,k], probs fp32 [B,E], GroupNorm-1 partial sums, strips)."""
+    B, H, W, Cc = x.shape
+    E, HID, _ = w1.shape
+    P = B * topk
+    strips = lib().ym_moe_ffn_strips(H * W, P)
+    stats = torch.empty((lib().ym_moe_ffn_stats_floats(P, strips, HID),), dtype=torch.float32, device=x.device)
+    idx = torch.empty((B, topk), dtype=torch.int32, device=x.device)
+    w = torch.empty((B, topk), dtype=torch.float32, device=x.device)
+    probs = torch.empty((B, E), dtype=torch.float32, device=x.device)
+    _lib.check(lib().ym_moe_ffn_routed(x.data_ptr(), pitch(x), B, H * W, Cc, HID, topk, w1.data_ptr(), E, partial.data_ptr(), nblk,
+                                       rpack["Cr"], npix, rpack["w2"].data_ptr(), rpack["scale2"].data_ptr(), rpack["shift2"].data_ptr(),
+                                       idx.data_ptr(), w.data_ptr(), probs.data_ptr(), stats.data_ptr(), strips, _stream()),
+               "ym_moe_ffn_routed")
+    _count()
+    return idx, w, probs, stats, strips
+
+
 def moe_expert_gemm(a, lda, a_div, P, HW, K, w_all, route_idx, N, a_scale=None, a_shift=None, groups=0):
     """ym_moe_expert_gemm.  Returns (out fp16 [P,HW,N], partial GroupNorm stats fp32 or None)."""
     dev = route_idx.device
