@@ -130,3 +130,32 @@ def test_mixture_module_signatures_match_reference():
     for name, params in expect.items():
         got = [p for p in inspect.signature(getattr(M, name).__init__).parameters if p != "self"]
         assert got == params, (name, got)
+
+
+def test_host_side_helpers_of_the_c_abi_need_no_gpu():
+    """Pure host entry points: the router's tile grid (ym_router_blocks, routers.py:289-292 pooling rule), the A/B switches (set returns the
+    previous value and rejects out-of-range arguments), the expert-FFN strip count."""
+    import ctypes as C
+    from yolo_master_b200 import _lib
+    L = _lib.load()
+    for (H, W, pool) in [(80, 80, 4), (40, 40, 4), (20, 20, 4), (4, 4, 4), (37, 23, 4), (160, 96, 2)]:
+        do_pool = H > pool and W > pool
+        ps = pool if do_pool else 1
+        Hp, Wp = H // ps, W // ps
+        npix = C.c_int(0)
+        nblk = L.ym_router_blocks(H, W, pool, C.addressof(npix))
+        assert npix.value == Hp * Wp and nblk == ((Wp + 15) // 16) * ((Hp + 3) // 4), (H, W, pool, nblk, npix.value)
+    for setter, good, bad in [(L.ym_set_small_conv_impl, (0, 1), 2), (L.ym_set_stem_impl, (0, 1), 5), (L.ym_set_dwconv_tc, (0, 1), -1),
+                              (L.ym_set_conv2_epi_groups, (1, 2), 3), (L.ym_set_attention2_qtiles, (0, 1, 2), 3),
+                              (L.ym_set_attention2_variant, tuple(range(8)), 8), (L.ym_set_kernel_priority, (0, -3, 3), 9)]:
+        first = setter(good[0])
+        try:
+            for v in good:
+                prev = setter(v)
+                assert setter(bad) == v and setter(v) == v, (setter, v)      # a rejected value leaves the setting alone
+                assert prev in good or prev == first
+        finally:
+            setter(first)
+    for HW, P in [(6400, 64), (1600, 64), (400, 64), (117, 6)]:
+        strips = L.ym_moe_ffn_strips(HW, P)
+        assert 1 <= strips <= (HW + 127) // 128
